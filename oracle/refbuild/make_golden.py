@@ -1,0 +1,230 @@
+"""ORACLE INFRASTRUCTURE: generates tests/golden/*.npz by running the
+REFERENCE ITSELF (the stub-built copy in oracle/_ref, see build_reference.sh).
+
+    PYTHONPATH=oracle/_ref python oracle/refbuild/make_golden.py
+
+Every array below is an output of reference code (PyNucleus, nl/ and fem/);
+nothing here is computed by this repository's own oracle or product.  The only
+substitution is the 2D regular triangle rule family (oracle/triangle_rules.py,
+provided through the modepy stand-in), see SURVEY.md section 8c.
+
+The fixtures are committed; this script only needs to be re-run when a new
+fixture is added.
+"""
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
+OUT = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+
+from PyNucleus_fem.mesh import simpleInterval, uniform_disc  # noqa: E402
+from PyNucleus_fem.DoFMaps import P1_DoFMap  # noqa: E402
+from PyNucleus_nl.kernels import getFractionalKernel  # noqa: E402
+from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder  # noqa: E402
+from PyNucleus_nl.fractionalOrders import constFractionalOrder  # noqa: E402
+from PyNucleus_base.myTypes import REAL  # noqa: E402
+
+
+def mesh_arrays(mesh, dm):
+    out = dict(vertices=np.array(mesh.vertices), cells=np.array(mesh.cells),
+               dofs=np.array(dm.dofs), num_dofs=dm.num_dofs,
+               hVector=np.array(mesh.hVector), volVector=np.array(mesh.volVector),
+               h=mesh.h, hmin=mesh.hmin, diam=mesh.diam)
+    if mesh.dim == 2:
+        out['boundaryEdges'] = np.array(mesh.boundaryEdges)
+    else:
+        out['boundaryVertices'] = np.array(mesh.boundaryVertices)
+    return out
+
+
+def rule_arrays(prefix, qr):
+    return {prefix+'_nodes': np.array(qr.nodes), prefix+'_weights': np.array(qr.weights)}
+
+
+def pair_dump(builder, mesh, pairs):
+    """panel type, permutations and local matrix for the given cell pairs"""
+    lm = builder.local_matrix
+    nloc = np.array(builder.contrib).shape[0] if hasattr(builder, 'contrib') else None
+    dpe = builder.dm.dofs_per_element
+    nloc = (2*dpe)*(2*dpe+1)//2
+    nv = mesh.cells.shape[1]
+    panels = np.zeros(len(pairs), dtype=np.int32)
+    perm1 = np.zeros((len(pairs), nv), dtype=np.int32)
+    perm2 = np.zeros((len(pairs), nv), dtype=np.int32)
+    perm = np.zeros((len(pairs), 2*dpe), dtype=np.int32)
+    contribs = np.zeros((len(pairs), nloc))
+    contrib = np.zeros((nloc, 1), dtype=REAL)
+    for n, (c1, c2) in enumerate(pairs):
+        lm.setCell1_py(int(c1))
+        lm.setCell2_py(int(c2))
+        p = lm.getPanelType()
+        panels[n] = p
+        perm1[n] = np.array(lm.perm1)
+        perm2[n] = np.array(lm.perm2)
+        pp = np.array(lm.perm)
+        perm[n, :pp.shape[0]] = pp
+        lm.eval_py(contrib, p)
+        contribs[n] = contrib[:, 0]
+    return dict(pairs=np.array(pairs, dtype=np.int32), panels=panels, perm1=perm1, perm2=perm2,
+                perm=perm, contribs=contribs)
+
+
+def boundary_dump(builder, mesh, pairs):
+    lm = builder.local_matrix_zeroExterior
+    surface = mesh.get_surface_mesh()
+    lm.setMesh2_py(surface)
+    dpe = builder.dm.dofs_per_element
+    nloc = dpe*(dpe+1)//2
+    panels = np.zeros(len(pairs), dtype=np.int32)
+    contribs = np.zeros((len(pairs), nloc))
+    contrib = np.zeros((nloc, 1), dtype=REAL)
+    for n, (c1, c2) in enumerate(pairs):
+        lm.setCell1_py(int(c1))
+        lm.setCell2_py(int(c2))
+        p = lm.getPanelType()
+        panels[n] = p
+        lm.eval_py(contrib, p)
+        contribs[n] = contrib[:, 0]
+    return dict(bpairs=np.array(pairs, dtype=np.int32), bpanels=panels, bcontribs=contribs,
+                surface_cells=np.array(surface.cells))
+
+
+def all_panels(builder, mesh):
+    lm = builder.local_matrix
+    nc = mesh.num_cells
+    P = np.zeros((nc, nc), dtype=np.int8)
+    for c1 in range(nc):
+        lm.setCell1_py(c1)
+        for c2 in range(c1, nc):
+            lm.setCell2_py(c2)
+            P[c1, c2] = lm.getPanelType()
+    return P
+
+
+def interval_case(noRef, s, name):
+    mesh = simpleInterval(-1, 1)
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    kernel = getFractionalKernel(1, constFractionalOrder(s), np.inf)
+    b = nonlocalBuilder(dm, kernel, {})
+    A = np.array(b.getDense().data)
+    b0 = nonlocalBuilder(dm, kernel, {}, zeroExterior=False)
+    A0 = np.array(b0.getDense().data)
+    out = mesh_arrays(mesh, dm)
+    out.update(A=A, A_interior=A0, s=s, scaling=kernel.scalingValue,
+               boundary_scaling=b.local_matrix_zeroExterior.kernel.scalingValue,
+               target_order=b.local_matrix.target_order,
+               quad_order_diagonal=b.local_matrix.quad_order_diagonal,
+               boundary_target_order=b.local_matrix_zeroExterior.target_order,
+               boundary_quad_order_diagonal=b.local_matrix_zeroExterior.quad_order_diagonal)
+    out.update(rule_arrays('qrId', b.local_matrix.qrId))
+    out.update(rule_arrays('qrVertex', b.local_matrix.qrVertex))
+    out.update(rule_arrays('bqrVertex', b.local_matrix_zeroExterior.qrVertex))
+    out['panels'] = all_panels(b, mesh)
+    nc = mesh.num_cells
+    pairs = [(c1, c2) for c1 in range(nc) for c2 in range(c1, nc)]
+    if len(pairs) > 600:
+        rng = np.random.RandomState(0)
+        near = [(c1, c2) for (c1, c2) in pairs if c2-c1 <= 2]
+        idx = rng.choice(len(pairs), 300, replace=False)
+        pairs = near + [pairs[i] for i in idx]
+    out.update(pair_dump(b, mesh, pairs))
+    nb = mesh.get_surface_mesh().num_cells
+    out.update(boundary_dump(b, mesh, [(c1, e) for c1 in range(nc) for e in range(nb)]))
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, A.shape)
+
+
+def disc_case(noRef, s, name, full_pairs=False, with_A=True):
+    mesh = uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    out = mesh_arrays(mesh, dm)
+    if with_A:
+        kernel = getFractionalKernel(2, constFractionalOrder(s), np.inf)
+        params = {'target_order': 0.5}
+        b = nonlocalBuilder(dm, kernel, params)
+        A = np.array(b.getDense().data)
+        b0 = nonlocalBuilder(dm, kernel, params, zeroExterior=False)
+        A0 = np.array(b0.getDense().data)
+        out.update(A=A, A_interior=A0, s=s, scaling=kernel.scalingValue,
+                   boundary_scaling=b.local_matrix_zeroExterior.kernel.scalingValue,
+                   target_order=b.local_matrix.target_order,
+                   quad_order_diagonal=b.local_matrix.quad_order_diagonal,
+                   quad_order_diagonalV=b.local_matrix.quad_order_diagonalV,
+                   boundary_quad_order_diagonal=b.local_matrix_zeroExterior.quad_order_diagonal)
+        out.update(rule_arrays('qrId', b.local_matrix.qrId))
+        out.update(rule_arrays('qrEdge', b.local_matrix.qrEdge))
+        out.update(rule_arrays('qrVertex', b.local_matrix.qrVertex))
+        out.update(rule_arrays('bqrEdge', b.local_matrix_zeroExterior.qrEdge))
+        out.update(rule_arrays('bqrVertex', b.local_matrix_zeroExterior.qrVertex))
+        P = all_panels(b, mesh)
+        out['panels'] = P
+        nc = mesh.num_cells
+        rng = np.random.RandomState(1)
+        touching = [(c1, c2) for c1 in range(nc) for c2 in range(c1, nc) if P[c1, c2] < 0]
+        distant = [(c1, c2) for c1 in range(nc) for c2 in range(c1, nc) if P[c1, c2] > 0]
+        if not full_pairs:
+            if len(touching) > 400:
+                idx = rng.choice(len(touching), 400, replace=False)
+                touching = [touching[i] for i in idx]
+            # keep every order present plus a random sample
+            byorder = {}
+            for pr in distant:
+                byorder.setdefault(int(P[pr]), []).append(pr)
+            sample = []
+            for o, lst in sorted(byorder.items()):
+                idx = rng.choice(len(lst), min(len(lst), 12), replace=False)
+                sample += [lst[i] for i in idx]
+            distant = sample
+        out.update(pair_dump(b, mesh, touching+distant))
+        nb = mesh.get_surface_mesh().num_cells
+        bp = [(c1, e) for c1 in range(nc) for e in range(nb)]
+        if len(bp) > 700:
+            idx = rng.choice(len(bp), 700, replace=False)
+            bp = [bp[i] for i in idx]
+        out.update(boundary_dump(b, mesh, bp))
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, out['cells'].shape, out.get('A', np.zeros((0, 0))).shape)
+
+
+def kernel_values():
+    """closed-form style spot values straight from the reference kernels"""
+    rng = np.random.RandomState(2)
+    out = {}
+    for dim in (1, 2):
+        x = rng.rand(20, dim)
+        y = rng.rand(20, dim)+1.5
+        for s in (0.25, 0.75):
+            k = getFractionalKernel(dim, constFractionalOrder(s), np.inf)
+            kb = k.getBoundaryKernel()
+            out['x_%dd' % dim] = x
+            out['y_%dd' % dim] = y
+            out['k_%dd_s%g' % (dim, s)] = np.array([k(x[i], y[i]) for i in range(20)])
+            out['kb_%dd_s%g' % (dim, s)] = np.array([kb(x[i], y[i]) for i in range(20)])
+            out['C_%dd_s%g' % (dim, s)] = k.scalingValue
+            out['Cb_%dd_s%g' % (dim, s)] = kb.scalingValue
+    np.savez_compressed(os.path.join(OUT, 'kernel_values'), **out)
+    print('kernel_values')
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['all']
+    if 'all' in which or 'interval' in which:
+        interval_case(3, 0.25, 'interval_s0.25_r3')
+        interval_case(6, 0.25, 'interval_s0.25_r6')
+        interval_case(5, 0.75, 'interval_s0.75_r5')
+    if 'all' in which or 'disc' in which:
+        disc_case(0, 0.75, 'disc_mesh_r0', with_A=False)
+        disc_case(1, 0.75, 'disc_s0.75_r1', full_pairs=True)
+        disc_case(2, 0.75, 'disc_s0.75_r2')
+        disc_case(3, 0.75, 'disc_s0.75_r3')
+        disc_case(2, 0.25, 'disc_s0.25_r2')
+        disc_case(4, 0.75, 'disc_mesh_r4', with_A=False)
+    if 'all' in which or 'kernels' in which:
+        kernel_values()

@@ -1,0 +1,148 @@
+"""The oracle (oracle/) against the REFERENCE's own outputs.
+
+tests/golden/*.npz were produced by the stub-built reference
+(oracle/refbuild/make_golden.py): panel types, vertex permutations, local
+matrices and assembled dense matrices.  These tests pin the C/numpy
+restatement before anything else is compared against it.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import meshes, tables
+
+CASES_2D = ['disc_s0.75_r1', 'disc_s0.75_r2', 'disc_s0.25_r2', 'disc_s0.75_r3']
+CASES_1D = ['interval_s0.25_r3', 'interval_s0.25_r6', 'interval_s0.75_r5']
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name+'.npz'))
+
+
+def problem_from_golden(g):
+    dim = g['vertices'].shape[1]
+    to = float(g['target_order']) if dim == 2 else None
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices'].reshape(-1, 1)
+    return oracle.Problem(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), float(g['s']),
+                          bfacets=bf, target_order=to, hVector=g['hVector'], volVector=g['volVector'],
+                          hmin=float(g['hmin']), diam=float(g['diam']))
+
+
+@pytest.mark.parametrize('r', [0, 4])
+def test_disc_mesh_matches_reference(golden_dir, r):
+    g = load(golden_dir, 'disc_mesh_r%d' % r)
+    m = meshes.disc(r)
+    assert np.array_equal(m.cells, g['cells'])
+    assert np.abs(m.vertices-g['vertices']).max() < 1e-15
+    dofs, n = meshes.p1_dofs(m)
+    assert n == int(g['num_dofs'])
+    assert np.array_equal(np.where(dofs >= 0, dofs, -1), np.where(g['dofs'] >= 0, g['dofs'], -1))
+    assert set(map(tuple, m.boundary_facets())) == set(map(tuple, g['boundaryEdges']))
+    assert np.allclose(m.hVector, g['hVector'], rtol=1e-14)
+    assert np.allclose(m.volVector, g['volVector'], rtol=1e-13)
+
+
+def test_interval_mesh_matches_reference(golden_dir):
+    g = load(golden_dir, 'interval_s0.25_r6')
+    m = meshes.interval(-1., 1., 6)
+    assert np.array_equal(m.cells, g['cells'])
+    assert np.array_equal(m.vertices, g['vertices'])
+    dofs, n = meshes.p1_dofs(m)
+    assert n == 63
+    assert np.array_equal(np.where(dofs >= 0, dofs, -1), np.where(g['dofs'] >= 0, g['dofs'], -1))
+
+
+@pytest.mark.parametrize('name', CASES_2D)
+def test_singular_tables_2d(golden_dir, name):
+    g = load(golden_dir, name)
+    s = float(g['s'])
+    H0 = float(g['diam'])/np.sqrt(8.)
+    o = tables.diag_orders(2, -2-2*s, -1-2*s, float(g['hmin']), H0, int(g['num_dofs']), 0.5)
+    assert o['qod'] == int(g['quad_order_diagonal'])
+    assert o['qodV'] == int(g['quad_order_diagonalV'])
+    assert o['b_qod'] == int(g['boundary_quad_order_diagonal'])
+    R = tables.near_rules(2, -2-2*s, -1-2*s, o)
+    for nm, key in (('qrId', ('interior', -3)), ('qrEdge', ('interior', -2)), ('qrVertex', ('interior', -1)),
+                    ('bqrEdge', ('boundary', -2)), ('bqrVertex', ('boundary', -1))):
+        b, w = R[key]
+        assert b.shape == g[nm+'_nodes'].shape
+        assert np.abs(b-g[nm+'_nodes']).max() < 1e-15
+        assert np.allclose(w, g[nm+'_weights'], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize('name', CASES_1D)
+def test_singular_tables_1d(golden_dir, name):
+    g = load(golden_dir, name)
+    s = float(g['s'])
+    H0 = float(g['diam'])/np.sqrt(8.)
+    o = tables.diag_orders(1, -1-2*s, -2*s, float(g['hmin']), H0, int(g['num_dofs']))
+    assert o['qod'] == int(g['quad_order_diagonal'])
+    assert o['b_qod'] == int(g['boundary_quad_order_diagonal'])
+    assert o['target_order'] == float(g['target_order'])
+    R = tables.near_rules(1, -1-2*s, -2*s, o)
+    for nm, key in (('qrId', ('interior', -2)), ('qrVertex', ('interior', -1)), ('bqrVertex', ('boundary', -1))):
+        b, w = R[key]
+        assert b.shape == g[nm+'_nodes'].shape
+        assert np.abs(b-g[nm+'_nodes']).max() < 1e-15
+        assert np.allclose(w, g[nm+'_weights'], rtol=1e-14, atol=0)
+
+
+def test_scaling_constants(golden_dir):
+    g = load(golden_dir, 'kernel_values')
+    for dim in (1, 2):
+        for s in (0.25, 0.75):
+            C = tables.fractional_scaling(dim, s)
+            assert np.isclose(C, float(g['C_%dd_s%g' % (dim, s)]), rtol=1e-15)
+            assert np.isclose(C/s, float(g['Cb_%dd_s%g' % (dim, s)]), rtol=1e-15)
+            x, y = g['x_%dd' % dim], g['y_%dd' % dim]
+            d2 = ((x-y)**2).sum(axis=1)
+            assert np.allclose(C*d2**(-dim/2.-s), g['k_%dd_s%g' % (dim, s)], rtol=1e-14)
+            assert np.allclose(C/s*d2**(-(dim-1)/2.-s), g['kb_%dd_s%g' % (dim, s)], rtol=1e-14)
+
+
+@pytest.mark.parametrize('name', CASES_2D+CASES_1D)
+def test_pairs_and_dense_match_reference(golden_dir, name):
+    g = load(golden_dir, name)
+    P = problem_from_golden(g)
+    panels, p1, p2, C = P.pairs(g['pairs'])
+    # bit-exact classification, panel order and permutations
+    assert np.array_equal(panels, g['panels_pairs'] if 'panels_pairs' in g else g['panels'][g['pairs'][:, 0], g['pairs'][:, 1]])
+    touching = panels < 0
+    assert np.array_equal(p1[touching], g['perm1'][touching])
+    assert np.array_equal(p2[touching], g['perm2'][touching])
+    # local matrices: same algorithm, same summation order
+    scale = np.abs(g['contribs']).max(axis=1, keepdims=True)
+    assert (np.abs(C-g['contribs'])/scale).max() < 1e-14
+    bpan, bC = P.boundary_pairs(g['bpairs'])
+    assert np.array_equal(bpan, g['bpanels'])
+    scale = np.abs(g['bcontribs']).max(axis=1, keepdims=True)
+    assert (np.abs(bC-g['bcontribs'])/scale).max() < 1e-14
+    # assembled matrices (thread-private partial sums: order differs)
+    A = P.dense(True)
+    A0 = P.dense(False)
+    nz = np.abs(g['A']) > 0
+    assert (np.abs(A-g['A'])[nz]/np.abs(g['A'])[nz]).max() < 1e-12
+    assert np.abs(A0-g['A_interior']).max()/np.abs(g['A_interior']).max() < 1e-13
+
+
+def test_all_pair_panels_match_reference(golden_dir):
+    """every pair c1<=c2 of the r=2 disc and the r=6 interval"""
+    for name in ('disc_s0.75_r2', 'interval_s0.25_r6'):
+        g = load(golden_dir, name)
+        P = problem_from_golden(g)
+        nc = g['cells'].shape[0]
+        iu = np.triu_indices(nc)
+        pairs = np.stack(iu, axis=1).astype(np.int32)
+        panels = P.pairs(pairs, with_contrib=False)[0]
+        assert np.array_equal(panels, g['panels'][iu])
+
+
+def test_slices_add_up():
+    """rank slices of the cell loop sum to the full matrix (the reference's Allreduce)"""
+    P = oracle.disc_problem(2)
+    A = P.dense(True)
+    nc = P.P.nc
+    B = sum(P.dense(True, start=a, end=b) for a, b in ((0, 30), (30, 61), (61, nc)))
+    assert np.abs(A-B).max()/np.abs(A).max() < 1e-14
