@@ -124,7 +124,7 @@ def interval_case(noRef, s, name):
     out.update(rule_arrays('qrId', b.local_matrix.qrId))
     out.update(rule_arrays('qrVertex', b.local_matrix.qrVertex))
     out.update(rule_arrays('bqrVertex', b.local_matrix_zeroExterior.qrVertex))
-    out['panels'] = all_panels(b, mesh)
+    out['panel_matrix'] = all_panels(b, mesh)
     nc = mesh.num_cells
     pairs = [(c1, c2) for c1 in range(nc) for c2 in range(c1, nc)]
     if len(pairs) > 600:
@@ -164,7 +164,7 @@ def disc_case(noRef, s, name, full_pairs=False, with_A=True):
         out.update(rule_arrays('bqrEdge', b.local_matrix_zeroExterior.qrEdge))
         out.update(rule_arrays('bqrVertex', b.local_matrix_zeroExterior.qrVertex))
         P = all_panels(b, mesh)
-        out['panels'] = P
+        out['panel_matrix'] = P
         nc = mesh.num_cells
         rng = np.random.RandomState(1)
         touching = [(c1, c2) for c1 in range(nc) for c2 in range(c1, nc) if P[c1, c2] < 0]
