@@ -1,0 +1,183 @@
+/* pnb200 -- C ABI of the B200-native nonlocal assembly library (libpnb200.so).
+ *
+ * Drop-in boundary for the Cython inner loops of the reference's nonlocal
+ * operator assembly (sandialabs/PyNucleus, paths relative to the reference
+ * root).  Plain pointers and sizes only; no Python or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative code on failure;
+ *     pnb_last_error() returns a human readable message for the calling thread
+ *   - all caller arrays are C-contiguous; the library never frees caller memory
+ *   - INDEX = int32, REAL = double  (base/PyNucleus_base/myTypes64.pxd)
+ *   - a pointer documented as "device" must point into CUDA memory of the
+ *     problem's device (e.g. torch.Tensor.data_ptr()); "host" pointers are
+ *     ordinary memory
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with PNB_ERR_NO_DEVICE
+ */
+#ifndef PNB200_H
+#define PNB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNB_OK 0
+#define PNB_ERR_NO_DEVICE (-1)
+#define PNB_ERR_CUDA (-2)
+#define PNB_ERR_ARG (-3)
+#define PNB_ERR_UNSUPPORTED (-4)
+#define PNB_ERR_ORDER (-5) /* a pair needs a regular rule of higher order than was supplied */
+
+/* panel types, nl/PyNucleus_nl/panelTypes.pxi */
+#define PNB_DISTANT 0
+#define PNB_COMMON_VERTEX (-1)
+#define PNB_COMMON_EDGE (-2)
+#define PNB_COMMON_FACE (-3)
+#define PNB_IGNORED (-6)
+
+/* kernel types, nl/PyNucleus_nl/kernel_params.pxi:87-98 */
+#define PNB_KERNEL_FRACTIONAL 0
+
+/* Simplicial mesh: the arrays nonlocalBuilder reads from `dm.mesh`
+ * (nonlocalOperator_{SCALAR}.pxi:111-126,144-152: vertices, cells, volVector,
+ * hVector, diam) plus the surface mesh of the zero-exterior loop
+ * (nonlocalAssembly_{SCALAR}.pxi:1432-1436, mesh.get_surface_mesh()). */
+typedef struct {
+    int32_t dim;             /* 1 or 2 (= manifold dimension) */
+    int32_t num_vertices;
+    int32_t num_cells;
+    const double *vertices;  /* host, num_vertices x dim */
+    const int32_t *cells;    /* host, num_cells x (dim+1) */
+    const double *vol;       /* host, num_cells  (mesh.volVector) */
+    const double *h;         /* host, num_cells  (mesh.hVector)   */
+    double diam;             /* mesh.diam; H0 = diam/sqrt(8), nonlocalOperator_{SCALAR}.pxi:435 */
+    int32_t num_bfacets;
+    const int32_t *bfacets;  /* host, num_bfacets x dim: boundary vertices (1D) / oriented boundary edges (2D) */
+} pnb_mesh_t;
+
+/* P1 DoFMap: dm.dofs, negative = boundary DoF (fem/PyNucleus_fem/DoFMaps.pyx:157-210) */
+typedef struct {
+    int32_t dofs_per_element; /* dim+1 (P1) */
+    int32_t num_dofs;
+    const int32_t *dofs;      /* host, num_cells x dofs_per_element */
+} pnb_dofmap_t;
+
+/* Kernel parameter block, the device-side equivalent of
+ * kernel_params.pxi:14-28 for piecewise-constant symmetric kernels. */
+typedef struct {
+    int32_t kernel_type;   /* PNB_KERNEL_FRACTIONAL */
+    int32_t dim;
+    double s;              /* fS        */
+    double scaling;        /* fSCALING of the interior kernel  C(d,s)          */
+    double bscaling;       /* fSCALING of kernel.getBoundaryKernel() = C/s     */
+    double singularity;    /* fSINGULARITY of the interior kernel, -d-2s       */
+    double bsingularity;   /* of the boundary kernel, 1-d-2s                   */
+    double horizon2;       /* fHORIZON2; +inf for the infinite horizon         */
+    double target_order;   /* local_matrix.target_order                         */
+    double btarget_order;  /* local_matrix_zeroExterior.target_order            */
+} pnb_kernel_t;
+
+/* One quadrature table: rows x n barycentric coordinates (x point first, then
+ * y point) and n weights, exactly the `nodes`/`weights` of the reference's
+ * quadratureRule objects (fem/PyNucleus_fem/quadrature.pxd:25-26). */
+typedef struct {
+    int32_t n;
+    int32_t rows;
+    const double *bary; /* host, rows x n */
+    const double *w;    /* host, n */
+} pnb_rule_t;
+
+/* All tables of one problem.  Singular tables replace specialQuadRules[...]
+ * (fractionalLaplacian2D.pyx:644-813,1255-1314; fractionalLaplacian1D.pyx:255-339,
+ * 671-709); regular tables replace distantQuadRulesPtr[order]
+ * (nonlocalOperator_{SCALAR}.pxi:549-600, 988-1020). */
+typedef struct {
+    pnb_rule_t identical;  /* COMMON_FACE (2D) / COMMON_EDGE (1D) */
+    pnb_rule_t edge;       /* COMMON_EDGE (2D only) */
+    pnb_rule_t vertex;     /* COMMON_VERTEX */
+    pnb_rule_t bedge;      /* boundary COMMON_EDGE (2D only) */
+    pnb_rule_t bvertex;    /* boundary COMMON_VERTEX */
+    int32_t max_order;     /* regular tables are given for orders 1..max_order */
+    const pnb_rule_t *cell;  /* host, max_order+1 entries, index = order: rule on a cell  */
+    const pnb_rule_t *facet; /* host, max_order+1 entries: rule on a boundary facet        */
+} pnb_rules_t;
+
+typedef struct pnb_problem pnb_problem;
+
+const char *pnb_last_error(void);
+int pnb_version(void);
+int pnb_device_count(void);
+
+/* Uploads mesh, DoFMap, kernel parameters and tables to `device` and builds
+ * the DoF-tile schedule.  Replaces nonlocalBuilder.__init__/setKernel
+ * (nonlocalAssembly_{SCALAR}.pxi:879-975).  `rules` may carry max_order = 0
+ * when only pnb_max_order / pnb_classify_pairs are used afterwards. */
+int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm, const pnb_kernel_t *kernel,
+                       const pnb_rules_t *rules, int device, pnb_problem **out);
+/* Replaces the lazily grown distantQuadRules cache: (re)uploads the regular tables. */
+int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules);
+void pnb_problem_destroy(pnb_problem *p);
+
+/* Largest regular quadrature order any cell pair / cell-facet pair requests
+ * (getQuadOrder, fractionalLaplacian2D.pyx:622-642,1226-1253;
+ * fractionalLaplacian1D.pyx:234-253,644-669).  Lets the host build exactly the
+ * tables that addQuadRule would have created on demand. */
+int pnb_max_order(pnb_problem *p, int zero_exterior, int32_t *max_order_out);
+
+/* getPanelType() for a list of cell pairs (nonlocalOperator_{SCALAR}.pxi:280-378,
+ * 493-540).  pairs: host, npairs x 2.  Outputs (host): panel[npairs],
+ * perm1/perm2[npairs x (dim+1)] (may be NULL).  boundary != 0: second index is a
+ * boundary facet (local_matrix_zeroExterior). */
+int pnb_classify_pairs(pnb_problem *p, int boundary, int64_t npairs, const int32_t *pairs,
+                       int32_t *panel, int32_t *perm1, int32_t *perm2);
+
+/* Histogram of getPanelType over all cell pairs c1<=c2: hist[3+panel] for
+ * panel in [-3, 255].  hist: host, 259 entries. */
+int pnb_panel_histogram(pnb_problem *p, int64_t *hist);
+
+/* local_matrix.eval(contrib, panel) for a list of cell pairs
+ * (fractionalLaplacian2D.pyx:823-891, fractionalLaplacian1D.pyx:349-407,
+ * nonlocalOperator_{SCALAR}.pxi:722-789; boundary: :1022-1108, 2D :1324-1407,
+ * 1D :719-783).  contrib: host, npairs x nloc with
+ * nloc = (2*dpe)(2*dpe+1)/2 (interior) or dpe(dpe+1)/2 (boundary), the
+ * reference's flattened upper-triangular layout.
+ * path = 0: warp-cooperative evaluator; path = 1: thread-per-pair low-order
+ * evaluator (regular pairs of order <= pnb_far_max_order() only). */
+int pnb_local_matrices(pnb_problem *p, int boundary, int path, int64_t npairs, const int32_t *pairs,
+                       int32_t *panel, double *contrib);
+int pnb_far_max_order(void);
+
+/* nonlocalBuilder.getDense() (nonlocalAssembly_{SCALAR}.pxi:1262-1473) for the
+ * rows [row_begin, row_end) of the operator: A is (row_end-row_begin) x num_dofs
+ * with leading dimension ld (in doubles).  a_on_device != 0: A is device
+ * memory; else A is host memory and the copy back is part of the call.
+ * The result is deterministic (no floating point atomics): bitwise
+ * reproducible from run to run. */
+int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end,
+                       double *A, int64_t ld, int a_on_device);
+
+/* Counters of the last pnb_dense_assemble call: [0] evaluated cell pairs
+ * (with tile-halo redundancy), [1] distinct cell pairs c1<=c2 that are not
+ * skipped, [2] kernel launches, [3..] reserved.  stats: host, 8 entries. */
+int pnb_dense_stats(pnb_problem *p, int64_t *stats);
+/* device time in ms of the phases of the last assembly:
+ * [0] tile kernel, [1] boundary kernel, [2] reduce+scatter, [3] total */
+int pnb_dense_timings(pnb_problem *p, double *ms);
+
+/* Dense_LinearOperator.matvec (base/PyNucleus_base/DenseLinearOperator_{SCALAR}.pxi:14-18
+ * -> dgemv, opt_true_blas.pxi:159): y = A x for a row block.  All pointers are
+ * device memory on `device`; stream is a cudaStream_t (0 = default stream). */
+int pnb_dense_matvec(int device, const double *A, int64_t num_rows, int64_t num_cols, int64_t ld,
+                     const double *x, double *y, void *stream);
+
+/* FP64 FMA throughput microbenchmark (roofline denominator): returns TFLOP/s */
+int pnb_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

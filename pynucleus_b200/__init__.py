@@ -1,0 +1,12 @@
+"""pynucleus_b200: B200-native nonlocal operator assembly behind PyNucleus'
+nonlocalBuilder API.  The compute path is hand-written CUDA for
+sm_100a in libpnb200.so (C ABI: include/pnb200.h); this package is the
+host-side mirror of the reference interface."""
+from .mesh import simpleInterval, uniform_disc, polygon_disc, refined, meshNd  # noqa: F401
+from .dofmap import P1_DoFMap  # noqa: F401
+from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder,  # noqa: F401
+                      constantFractionalLaplacianScaling, FRACTIONAL)
+from .assembly import nonlocalBuilder, assembleNonlocalOperator  # noqa: F401
+from .linear_operators import Dense_LinearOperator  # noqa: F401
+
+__version__ = '0.1.0'

@@ -1,0 +1,104 @@
+"""ctypes binding of libpnb200.so (C ABI: include/pnb200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` /
+``pynucleus_b200.build.build()``.  There is no CPU fallback: if the shared
+library is missing, or no CUDA device is visible, every compute call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpnb200.so')
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int32_p = ctypes.POINTER(ctypes.c_int32)
+c_int64_p = ctypes.POINTER(ctypes.c_int64)
+
+
+class pnb_mesh_t(ctypes.Structure):
+    _fields_ = [('dim', ctypes.c_int32), ('num_vertices', ctypes.c_int32), ('num_cells', ctypes.c_int32),
+                ('vertices', ctypes.c_void_p), ('cells', ctypes.c_void_p), ('vol', ctypes.c_void_p),
+                ('h', ctypes.c_void_p), ('diam', ctypes.c_double), ('num_bfacets', ctypes.c_int32),
+                ('bfacets', ctypes.c_void_p)]
+
+
+class pnb_dofmap_t(ctypes.Structure):
+    _fields_ = [('dofs_per_element', ctypes.c_int32), ('num_dofs', ctypes.c_int32), ('dofs', ctypes.c_void_p)]
+
+
+class pnb_kernel_t(ctypes.Structure):
+    _fields_ = [('kernel_type', ctypes.c_int32), ('dim', ctypes.c_int32), ('s', ctypes.c_double),
+                ('scaling', ctypes.c_double), ('bscaling', ctypes.c_double), ('singularity', ctypes.c_double),
+                ('bsingularity', ctypes.c_double), ('horizon2', ctypes.c_double),
+                ('target_order', ctypes.c_double), ('btarget_order', ctypes.c_double)]
+
+
+class pnb_rule_t(ctypes.Structure):
+    _fields_ = [('n', ctypes.c_int32), ('rows', ctypes.c_int32), ('bary', ctypes.c_void_p), ('w', ctypes.c_void_p)]
+
+
+class pnb_rules_t(ctypes.Structure):
+    _fields_ = [('identical', pnb_rule_t), ('edge', pnb_rule_t), ('vertex', pnb_rule_t),
+                ('bedge', pnb_rule_t), ('bvertex', pnb_rule_t), ('max_order', ctypes.c_int32),
+                ('cell', ctypes.POINTER(pnb_rule_t)), ('facet', ctypes.POINTER(pnb_rule_t))]
+
+
+# every symbol include/pnb200.h declares
+EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_create', 'pnb_problem_set_rules',
+           'pnb_problem_destroy', 'pnb_max_order', 'pnb_classify_pairs', 'pnb_panel_histogram',
+           'pnb_local_matrices', 'pnb_far_max_order', 'pnb_dense_assemble', 'pnb_dense_stats',
+           'pnb_dense_timings', 'pnb_dense_matvec', 'pnb_fp64_peak']
+
+_LIB = None
+
+
+class PNBError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('libpnb200 error {}: {}'.format(code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libpnb200.so; raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('{} not found: build it with `python -c "import __graft_entry__ as g; g.build()"`. '
+                               'There is no CPU fallback.'.format(LIB_PATH))
+        L = ctypes.CDLL(LIB_PATH)
+        L.pnb_last_error.restype = ctypes.c_char_p
+        L.pnb_problem_create.argtypes = [ctypes.POINTER(pnb_mesh_t), ctypes.POINTER(pnb_dofmap_t),
+                                         ctypes.POINTER(pnb_kernel_t), ctypes.POINTER(pnb_rules_t),
+                                         ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.pnb_problem_set_rules.argtypes = [ctypes.c_void_p, ctypes.POINTER(pnb_rules_t)]
+        L.pnb_problem_destroy.argtypes = [ctypes.c_void_p]
+        L.pnb_problem_destroy.restype = None
+        L.pnb_max_order.argtypes = [ctypes.c_void_p, ctypes.c_int, c_int32_p]
+        L.pnb_classify_pairs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_panel_histogram.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_local_matrices.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_dense_assemble.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
+                                         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
+        L.pnb_dense_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_dense_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_dense_matvec.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_fp64_peak.argtypes = [ctypes.c_int, c_double_p]
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise PNBError(rc, lib().pnb_last_error().decode())
+
+
+def as_rule(bary, w, keep):
+    bary = np.ascontiguousarray(bary, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    keep += [bary, w]
+    return pnb_rule_t(bary.shape[1], bary.shape[0], bary.ctypes.data, w.ctypes.data)

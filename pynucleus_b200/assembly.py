@@ -1,0 +1,227 @@
+"""nonlocalBuilder: the reference's assembly API on top of libpnb200.
+
+Drop-in for nl/PyNucleus_nl/nonlocalAssembly_{SCALAR}.pxi:878-3370 restricted to
+the accelerated path: same constructor signature (:879-901) and `params` keys
+(:987-994), `getDense()` (:1262-1473) returns a Dense_LinearOperator whose
+entries equal the reference's Cython assembly to summation-order rounding.
+All floating point work of the path runs in hand-written CUDA kernels
+(pynucleus_b200/csrc); this module only prepares tables and parameter blocks.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+
+from . import _lib, quadrature
+from .linear_operators import Dense_LinearOperator
+
+IGNORED = -6
+COMMON_VERTEX, COMMON_EDGE, COMMON_FACE = -1, -2, -3
+
+
+class _Problem:
+    """owner of a pnb_problem handle (device-resident mesh, DoFMap, kernel, tables)"""
+
+    def __init__(self, dm, kernel, bkernel, orders, device, max_order):
+        mesh = dm.mesh
+        self._keep = []
+        self.dim = mesh.dim
+        self.nvc = mesh.dim+1
+        self.device = device
+        self.handle = ctypes.c_void_p()
+        self.vertices = np.ascontiguousarray(mesh.vertices, dtype=np.float64)
+        self.cells = np.ascontiguousarray(mesh.cells, dtype=np.int32)
+        self.vol = np.ascontiguousarray(mesh.volVector, dtype=np.float64)
+        self.h = np.ascontiguousarray(mesh.hVector, dtype=np.float64)
+        self.bfacets = np.ascontiguousarray(mesh.boundaryFacets, dtype=np.int32).reshape(-1, mesh.dim)
+        self.dofs = np.ascontiguousarray(dm.dofs, dtype=np.int32)
+        m = _lib.pnb_mesh_t(mesh.dim, mesh.num_vertices, mesh.num_cells, self.vertices.ctypes.data,
+                            self.cells.ctypes.data, self.vol.ctypes.data, self.h.ctypes.data, mesh.diam,
+                            self.bfacets.shape[0], self.bfacets.ctypes.data)
+        d = _lib.pnb_dofmap_t(dm.dofs_per_element, dm.num_dofs, self.dofs.ctypes.data)
+        k = _lib.pnb_kernel_t(kernel.kernelType, kernel.dim, kernel.sValue, kernel.scalingValue, bkernel.scalingValue,
+                              kernel.singularityValue, bkernel.singularityValue,
+                              kernel.horizonValue2 if kernel.finiteHorizon else np.inf,
+                              orders.target_order, orders.btarget_order)
+        self.singular = quadrature.singular_tables(mesh.dim, kernel.singularityValue, bkernel.singularityValue, orders,
+                                                   dm.polynomialOrder)
+        self.max_order = 0
+        rules = self._rules(max_order)
+        _lib.check(_lib.lib().pnb_problem_create(ctypes.byref(m), ctypes.byref(d), ctypes.byref(k), ctypes.byref(rules),
+                                                 device, ctypes.byref(self.handle)))
+        self.max_order = max_order
+
+    def _rules(self, max_order):
+        keep = []
+        r = _lib.pnb_rules_t()
+        for name in ('identical', 'edge', 'vertex', 'bedge', 'bvertex'):
+            if name in self.singular:
+                setattr(r, name, _lib.as_rule(*self.singular[name], keep))
+        cell = (_lib.pnb_rule_t*(max_order+1))()
+        facet = (_lib.pnb_rule_t*(max_order+1))()
+        for o in range(1, max_order+1):
+            cell[o] = _lib.as_rule(*quadrature.regular(o, self.dim), keep)
+            facet[o] = _lib.as_rule(*quadrature.regular(o, self.dim-1), keep)
+        r.max_order = max_order
+        r.cell = cell
+        r.facet = facet
+        keep += [cell, facet]
+        self._keep = keep
+        return r
+
+    def set_max_order(self, max_order):
+        rules = self._rules(max_order)
+        _lib.check(_lib.lib().pnb_problem_set_rules(self.handle, ctypes.byref(rules)))
+        self.max_order = max_order
+
+    def required_max_order(self, zero_exterior=True):
+        v = ctypes.c_int32(0)
+        _lib.check(_lib.lib().pnb_max_order(self.handle, int(zero_exterior), ctypes.byref(v)))
+        return int(v.value)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().pnb_problem_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+class nonlocalBuilder:
+    """nonlocalBuilder(dm, kernel, params={}, zeroExterior=True, comm=None, PLogger=None, dm2=None)
+
+    `params`: 'target_order' (nonlocalAssembly_{SCALAR}.pxi:987), 'quadType' in
+    ('classical-refactored',), 'device' (CUDA device index, default current)."""
+
+    def __init__(self, dm, kernel, params={}, zeroExterior=True, comm=None, PLogger=None, dm2=None, **kwargs):
+        if 'boundary' in kwargs:
+            warnings.warn('"boundary" parameter deprecated', DeprecationWarning)
+            zeroExterior = kwargs['boundary']
+        if dm2 is not None:
+            raise NotImplementedError('assembly with two DoFMaps is outside the accelerated path')
+        assert kernel.dim == dm.mesh.dim, "Kernel dimension must match dm.mesh dimension"
+        quadType = params.get('quadType', 'classical-refactored')
+        assert quadType in ('classical-refactored', )
+        self.dm = dm
+        self.dm2 = None
+        self.mesh = dm.mesh
+        self.comm = comm
+        self.PLogger = PLogger
+        self.params = params
+        self.setKernel(kernel, zeroExterior)
+
+    def setKernel(self, kernel, zeroExterior=True):
+        if not kernel.symmetric or kernel.variable:
+            raise NotImplementedError('only symmetric kernels with constant parameters are supported yet')
+        self.kernel = kernel
+        # nonlocalAssembly_{SCALAR}.pxi:918-921
+        self.zeroExterior = False if kernel.finiteHorizon else zeroExterior
+        self.kernelBoundary = kernel.getBoundaryKernel()
+        mesh = self.mesh
+        H0 = mesh.diam/np.sqrt(8.)
+        self.orders = quadrature.localMatrixOrders(mesh.dim, kernel.singularityValue, self.kernelBoundary.singularityValue,
+                                                   mesh.hmin, H0, self.dm.num_dofs, self.params.get('target_order', None),
+                                                   self.dm.polynomialOrder)
+        self._problem = None
+
+    # -- device problem (lazy) ---------------------------------------------
+    @property
+    def problem(self):
+        if self._problem is None:
+            import torch
+            if not torch.cuda.is_available():
+                raise RuntimeError('pynucleus_b200 needs a CUDA device; there is no CPU fallback')
+            device = self.params.get('device', torch.cuda.current_device())
+            self._problem = _Problem(self.dm, self.kernel, self.kernelBoundary, self.orders, device,
+                                     self.params.get('max_regular_order', 24))
+        return self._problem
+
+    def _retry_on_order(self, fn):
+        try:
+            return fn()
+        except _lib.PNBError as e:
+            if e.code != -5:
+                raise
+            # the reference grows its rule cache lazily (addQuadRule); do the same in one step
+            need = self.problem.required_max_order(self.zeroExterior)
+            self.problem.set_max_order(need)
+            return fn()
+
+    # -- parity / debugging entry points -------------------------------------
+    def getPanelTypes(self, pairs, boundary=False, returnPerms=False):
+        """getPanelType() of the given (cell1, cell2) pairs; boundary=True: (cell, boundary facet)"""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pairs.shape[0]
+        panel = np.zeros(n, dtype=np.int32)
+        perm1 = np.zeros((n, self.mesh.dim+1), dtype=np.int32)
+        perm2 = np.zeros((n, self.mesh.dim+1), dtype=np.int32)
+        _lib.check(_lib.lib().pnb_classify_pairs(self.problem.handle, int(boundary), n, pairs.ctypes.data,
+                                                 panel.ctypes.data, perm1.ctypes.data, perm2.ctypes.data))
+        if returnPerms:
+            return panel, perm1, perm2
+        return panel
+
+    def getLocalMatrices(self, pairs, boundary=False, path=0):
+        """local_matrix.eval(contrib, panel) for the given pairs -> (panel, contrib[n, nloc])"""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pairs.shape[0]
+        nvc = self.mesh.dim+1
+        nloc = nvc*(nvc+1)//2 if boundary else (2*nvc)*(2*nvc+1)//2
+        panel = np.zeros(n, dtype=np.int32)
+        contrib = np.zeros((n, nloc))
+
+        def run():
+            _lib.check(_lib.lib().pnb_local_matrices(self.problem.handle, int(boundary), path, n, pairs.ctypes.data,
+                                                     panel.ctypes.data, contrib.ctypes.data))
+        self._retry_on_order(run)
+        return panel, contrib
+
+    def getPanelHistogram(self):
+        hist = np.zeros(259, dtype=np.int64)
+        _lib.check(_lib.lib().pnb_panel_histogram(self.problem.handle, hist.ctypes.data))
+        return {k-3: int(v) for k, v in enumerate(hist) if v}
+
+    # -- the operator ---------------------------------------------------------
+    def getDense(self, trySparsification=False, out=None):
+        """Dense operator of the kernel on dm (nonlocalAssembly_{SCALAR}.pxi:1262-1473).
+
+        out: optional (N, N) float64 CUDA tensor to assemble into."""
+        import torch
+        N = self.dm.num_dofs
+        prob = self.problem
+        dev = torch.device('cuda', prob.device)
+        A = torch.empty((N, N), dtype=torch.float64, device=dev) if out is None else out
+
+        def run():
+            _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.data_ptr(),
+                                                     A.stride(0), 1))
+        self._retry_on_order(run)
+        return Dense_LinearOperator(A, prob.device)
+
+    def getDenseHost(self, out=None):
+        """Same as getDense() but through the host-buffer C entry point: the result is written to host memory
+        (device -> host copy inside the call)."""
+        N = self.dm.num_dofs
+        A = np.empty((N, N)) if out is None else out
+        prob = self.problem
+
+        def run():
+            _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.ctypes.data, N, 0))
+        self._retry_on_order(run)
+        return A
+
+    def getStats(self):
+        stats = np.zeros(8, dtype=np.int64)
+        ms = np.zeros(4)
+        _lib.check(_lib.lib().pnb_dense_stats(self.problem.handle, stats.ctypes.data))
+        _lib.check(_lib.lib().pnb_dense_timings(self.problem.handle, ms.ctypes.data))
+        return dict(evaluated_pairs=int(stats[0]), distinct_pairs=int(stats[1]), launches=int(stats[2]),
+                    ms_tiles=float(ms[0]), ms_boundary=float(ms[1]), ms_reduce_scatter=float(ms[2]), ms_total=float(ms[3]))
+
+
+def assembleNonlocalOperator(mesh, dm, s, horizon=None, params={}, zeroExterior=True, comm=None, **kwargs):
+    """nonlocalAssembly.pyx:362-372"""
+    from .kernels import getFractionalKernel
+    kernel = getFractionalKernel(mesh.dim, s, horizon)
+    return nonlocalBuilder(dm, kernel, params, zeroExterior, comm, **kwargs).getDense()

@@ -1,0 +1,1184 @@
+// libpnb200: B200-native nonlocal operator assembly (C ABI in include/pnb200.h).
+//
+// Dense assembly design:
+//   * the N x N output is cut into PNB_TD x PNB_TD DoF tiles; a CTA owns the
+//     tiles of one (row group, column group) pair and is the ONLY writer of
+//     those entries (row-tile ownership, no floating point atomics);
+//   * per tile the CTA walks over the cell pairs (cells touching the row DoFs)
+//     x (cells touching the column DoFs) in 16x16 sub-batches: classify the
+//     pair (shared vertices / quadrature order), evaluate low-order regular
+//     pairs one per thread, queue singular and high-order pairs in a
+//     deterministic list and evaluate them one per warp, stage the 3x3 cross
+//     blocks in shared memory and fold them into the tile accumulator with an
+//     entry-centric gather in fixed order;
+//   * the cell-diagonal blocks (both dofs on the same cell; they receive a
+//     contribution from EVERY other cell) are reduced per CTA, staged per
+//     (group, cell) and reduced/scattered by row-owning threads afterwards;
+//   * only tiles with row tile <= column tile are computed; the mirror image
+//     is written by the same CTA.
+#include "../../include/pnb200.h"
+#include "pnb_pair.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+extern "C" const char *pnb_last_error(void) { return g_err.c_str(); }
+extern "C" int pnb_version(void) { return 100; }
+extern "C" int pnb_far_max_order(void) { return PNB_FAR_MAX_ORDER; }
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? PNB_ERR_NO_DEVICE : PNB_ERR_CUDA, \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+    } while (0)
+
+extern "C" int pnb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// problem object
+// ---------------------------------------------------------------------------
+struct TileSched {
+    int ntiles, G, ngroups;
+    const int *tile_ptr;    // ntiles+1
+    const int *tile_cells;  // cell ids per tile, ascending
+    const int *tile_loc;    // packed tile-local dof index of each vertex (8 bits each, 0xFF = not in tile)
+    const int *home;        // nc: home tile of a cell
+    const int *units;       // 2 x nunits (row group, col group)
+    int nunits;
+    double *DXp, *DYp;      // ngroups x nc x ND staging of cell-diagonal blocks
+    double *Dbnd;           // nc x ND boundary contributions
+    double *D;              // nc x ND reduced
+    const int *dof_ptr;     // N+1: dof -> incident cells
+    const int *dof_cells;   // packed (cell*4 + local index)
+    int *err;               // [0]: max order requested beyond tables
+    unsigned long long *counters;  // [0] evaluated pairs
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct pnb_problem {
+    int device = 0;
+    DProblem P{};
+    TileSched S{};
+    std::vector<void *> allocs;       // everything to free
+    std::vector<void *> rule_allocs;  // regular tables (replaced by set_rules)
+    FarRule far_rules[PNB_FAR_MAX_ORDER + 1];
+    int64_t stats[8] = {0};
+    double timings[4] = {0};
+    int64_t distinct_pairs = 0;
+    // host copies needed later
+    int dim = 0, nc = 0, N = 0, nb = 0;
+    bool has_singular = false;
+};
+
+template <class T> static int upload(pnb_problem *p, const T *host, size_t count, const T **dev, bool rule = false)
+{
+    void *d = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc(&d, bytes));
+    (rule ? p->rule_allocs : p->allocs).push_back(d);
+    if (count) CK(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = (const T *)d;
+    return 0;
+}
+
+template <class T> static int dalloc(pnb_problem *p, size_t count, T **dev, bool zero = true)
+{
+    void *d = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc(&d, bytes));
+    p->allocs.push_back(d);
+    if (zero) CK(cudaMemset(d, 0, bytes));
+    *dev = (T *)d;
+    return 0;
+}
+
+static int upload_rule(pnb_problem *p, const pnb_rule_t &r, DRule *out, bool rule_alloc)
+{
+    out->n = r.n;
+    out->rows = r.rows;
+    out->bary = nullptr;
+    out->w = nullptr;
+    if (r.n <= 0) return 0;
+    if (upload(p, r.bary, (size_t)r.rows * r.n, &out->bary, rule_alloc)) return PNB_ERR_CUDA;
+    if (upload(p, r.w, (size_t)r.n, &out->w, rule_alloc)) return PNB_ERR_CUDA;
+    return 0;
+}
+
+__constant__ FarRule c_far[PNB_FAR_MAX_ORDER + 1];
+
+extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
+{
+    if (!p || !rules) return fail(PNB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(p->device));
+    for (void *d : p->rule_allocs) cudaFree(d);
+    p->rule_allocs.clear();
+    const int nvc = p->dim + 1;
+    int rc = 0;
+    p->has_singular = rules->vertex.n > 0;
+    rc |= upload_rule(p, rules->identical, &p->P.q_id, true);
+    rc |= upload_rule(p, rules->edge, &p->P.q_edge, true);
+    rc |= upload_rule(p, rules->vertex, &p->P.q_vertex, true);
+    rc |= upload_rule(p, rules->bedge, &p->P.bq_edge, true);
+    rc |= upload_rule(p, rules->bvertex, &p->P.bq_vertex, true);
+    if (rc) return PNB_ERR_CUDA;
+    const int mo = rules->max_order;
+    std::vector<DRule> cell(mo + 1), facet(mo + 1);
+    memset(cell.data(), 0, sizeof(DRule) * (mo + 1));
+    memset(facet.data(), 0, sizeof(DRule) * (mo + 1));
+    for (int o = 1; o <= mo; o++) {
+        if (rules->cell[o].rows != nvc) return fail(PNB_ERR_ARG, "cell rule must have dim+1 barycentric rows");
+        if (upload_rule(p, rules->cell[o], &cell[o], true)) return PNB_ERR_CUDA;
+        if (rules->facet && rules->facet[o].n > 0)
+            if (upload_rule(p, rules->facet[o], &facet[o], true)) return PNB_ERR_CUDA;
+    }
+    if (upload(p, cell.data(), (size_t)mo + 1, &p->P.reg_cell, true)) return PNB_ERR_CUDA;
+    if (upload(p, facet.data(), (size_t)mo + 1, &p->P.reg_facet, true)) return PNB_ERR_CUDA;
+    p->P.max_order = mo;
+    // low-order 2D rules for the thread-per-pair evaluator
+    memset(p->far_rules, 0, sizeof(p->far_rules));
+    if (p->dim == 2)
+        for (int o = 1; o <= std::min(mo, PNB_FAR_MAX_ORDER); o++) {
+            const pnb_rule_t &r = rules->cell[o];
+            if (r.n > 8) continue;
+            p->far_rules[o].n = r.n;
+            for (int k = 0; k < 3; k++)
+                for (int i = 0; i < r.n; i++) p->far_rules[o].bary[k][i] = r.bary[k * r.n + i];
+            for (int i = 0; i < r.n; i++) p->far_rules[o].w[i] = r.w[i];
+        }
+    CK(cudaMemcpyToSymbol(c_far, p->far_rules, sizeof(p->far_rules)));
+    return 0;
+}
+
+extern "C" void pnb_problem_destroy(pnb_problem *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (void *d : p->allocs) cudaFree(d);
+    for (void *d : p->rule_allocs) cudaFree(d);
+    delete p;
+}
+
+extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm, const pnb_kernel_t *kernel,
+                                  const pnb_rules_t *rules, int device, pnb_problem **out)
+{
+    if (!mesh || !dm || !kernel || !rules || !out) return fail(PNB_ERR_ARG, "null argument");
+    if (mesh->dim != 1 && mesh->dim != 2) return fail(PNB_ERR_UNSUPPORTED, "only 1D and 2D meshes are supported");
+    if (dm->dofs_per_element != mesh->dim + 1) return fail(PNB_ERR_UNSUPPORTED, "only P1 DoFMaps are supported");
+    if (kernel->kernel_type != PNB_KERNEL_FRACTIONAL) return fail(PNB_ERR_UNSUPPORTED, "kernel type not supported");
+    if (kernel->dim != mesh->dim) return fail(PNB_ERR_ARG, "Kernel dimension must match dm.mesh dimension");
+    if (std::isfinite(kernel->horizon2)) return fail(PNB_ERR_UNSUPPORTED, "finite horizon not supported yet");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PNB_ERR_NO_DEVICE, "no CUDA device: libpnb200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(PNB_ERR_ARG, "invalid device index");
+    CK(cudaSetDevice(device));
+
+    pnb_problem *p = new pnb_problem();
+    p->device = device;
+    const int dim = mesh->dim, nvc = dim + 1, nc = mesh->num_cells, N = dm->num_dofs, nb = mesh->num_bfacets;
+    p->dim = dim; p->nc = nc; p->N = N; p->nb = nb;
+    DProblem &P = p->P;
+    P.dim = dim; P.nc = nc; P.nv = mesh->num_vertices; P.N = N; P.nb = nb;
+
+    // precomputeSimplices (nonlocalOperator_{SCALAR}.pxi:111-126): same summation order
+    std::vector<double> simplices((size_t)nc * nvc * dim), centers((size_t)nc * dim, 0.), hcell(nc);
+    const double fac = 1. / nvc;
+    for (int c = 0; c < nc; c++) {
+        for (int m = 0; m < nvc; m++) {
+            const int k = mesh->cells[(size_t)c * nvc + m];
+            if (k < 0 || k >= mesh->num_vertices) { delete p; return fail(PNB_ERR_ARG, "cell refers to a vertex out of range"); }
+            for (int l = 0; l < dim; l++) {
+                const double v = mesh->vertices[(size_t)k * dim + l];
+                simplices[((size_t)c * nvc + m) * dim + l] = v;
+                centers[(size_t)c * dim + l] += v;
+            }
+        }
+        for (int l = 0; l < dim; l++) centers[(size_t)c * dim + l] *= fac;
+        // get_h_simplex (nonlocalOperator.pyx:114-118, 152-160)
+        const double *sx = &simplices[(size_t)c * nvc * dim];
+        if (dim == 1) hcell[c] = fabs(sx[1] - sx[0]);
+        else {
+            double hmax = 0.;
+            for (int i = 0; i < 2; i++)
+                for (int j = i + 1; j < 3; j++) {
+                    const double h2 = (sx[2 * j] - sx[2 * i]) * (sx[2 * j] - sx[2 * i]) + (sx[2 * j + 1] - sx[2 * i + 1]) * (sx[2 * j + 1] - sx[2 * i + 1]);
+                    hmax = std::max(hmax, h2);
+                }
+            hcell[c] = sqrt(hmax);
+        }
+    }
+    std::vector<double> bsimplices((size_t)nb * dim * dim), bcenters((size_t)nb * dim, 0.), bvol(nb), bh(nb);
+    const double bfac = 1. / dim;
+    for (int f = 0; f < nb; f++) {
+        for (int m = 0; m < dim; m++) {
+            const int k = mesh->bfacets[(size_t)f * dim + m];
+            for (int l = 0; l < dim; l++) {
+                const double v = mesh->vertices[(size_t)k * dim + l];
+                bsimplices[((size_t)f * dim + m) * dim + l] = v;
+                bcenters[(size_t)f * dim + l] += v;
+            }
+        }
+        for (int l = 0; l < dim; l++) bcenters[(size_t)f * dim + l] *= bfac;
+        if (dim == 1) { bvol[f] = 1.; bh[f] = 1.; }
+        else {
+            const double *sx = &bsimplices[(size_t)f * 4];
+            double h2 = 0.;
+            for (int k = 0; k < 2; k++) h2 += (sx[2 + k] - sx[k]) * (sx[2 + k] - sx[k]);
+            bvol[f] = bh[f] = sqrt(h2);
+        }
+    }
+    int rc = 0;
+    rc |= upload(p, simplices.data(), simplices.size(), &P.simplices);
+    rc |= upload(p, centers.data(), centers.size(), &P.centers);
+    rc |= upload(p, mesh->cells, (size_t)nc * nvc, &P.cells);
+    rc |= upload(p, dm->dofs, (size_t)nc * nvc, &P.dofs);
+    rc |= upload(p, mesh->vol, (size_t)nc, &P.vol);
+    rc |= upload(p, mesh->h, (size_t)nc, &P.h);
+    rc |= upload(p, hcell.data(), (size_t)nc, &P.hcell);
+    rc |= upload(p, mesh->bfacets, (size_t)nb * dim, &P.bfacets);
+    rc |= upload(p, bsimplices.data(), bsimplices.size(), &P.bsimplices);
+    rc |= upload(p, bcenters.data(), bcenters.size(), &P.bcenters);
+    rc |= upload(p, bvol.data(), (size_t)nb, &P.bvol);
+    rc |= upload(p, bh.data(), (size_t)nb, &P.bh);
+    if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
+
+    P.s = kernel->s; P.C = kernel->scaling; P.Cb = kernel->bscaling;
+    P.sing = kernel->singularity; P.bsing = kernel->bsingularity;
+    P.expo = -0.5 * dim - kernel->s;            // kernelsCy.pyx:159-183
+    P.bexpo = -0.5 * (dim - 1) - kernel->s;     // kernelsCy.pyx:216-240
+    P.H0 = mesh->diam / sqrt(8.);               // nonlocalOperator_{SCALAR}.pxi:435
+    if (dim == 2) {
+        P.c_int = (0.5 * kernel->target_order + 0.5) * log((double)N * (P.H0 * P.H0));
+        P.c_bnd = (0.5 * kernel->btarget_order + 0.25) * log((double)N * (P.H0 * P.H0));
+    } else {
+        P.c_int = (kernel->target_order + 2.) * log((double)N * P.H0);
+        P.c_bnd = (kernel->btarget_order + 1.) * log((double)N * P.H0);
+    }
+
+    // ---- DoF tiles -------------------------------------------------------
+    TileSched &S = p->S;
+    const int TD = PNB_TD;
+    S.ntiles = std::max(1, (N + TD - 1) / TD);
+    S.G = 4;
+    S.ngroups = (S.ntiles + S.G - 1) / S.G;
+    std::vector<int> home(nc);
+    std::vector<std::vector<int>> tcells(S.ntiles);
+    int64_t live = 0;
+    for (int c = 0; c < nc; c++) {
+        int tl[3], nt = 0, mind = -1;
+        for (int m = 0; m < nvc; m++) {
+            const int d = dm->dofs[(size_t)c * nvc + m];
+            if (d >= N) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "dof index out of range"); }
+            if (d >= 0) {
+                const int t = d / TD;
+                bool seen = false;
+                for (int k = 0; k < nt; k++) seen |= tl[k] == t;
+                if (!seen) tl[nt++] = t;
+                if (mind < 0 || d < mind) mind = d;
+            }
+        }
+        if (mind >= 0) { home[c] = mind / TD; live++; }
+        else {
+            // no dofs: spread such cells evenly; they only feed cell-diagonal blocks of other cells
+            home[c] = (int)(((int64_t)c * S.ntiles) / std::max(nc, 1));
+            tl[nt++] = home[c];
+        }
+        for (int k = 0; k < nt; k++) tcells[tl[k]].push_back(c);
+    }
+    // pairs c1<=c2 that the reference does not skip (at least one non-negative dof)
+    {
+        const int64_t dead = nc - live;
+        p->distinct_pairs = (int64_t)nc * (nc + 1) / 2 - dead * (dead + 1) / 2;
+    }
+    std::vector<int> tptr(S.ntiles + 1, 0), tlist, tloc;
+    for (int t = 0; t < S.ntiles; t++) {
+        tptr[t + 1] = tptr[t] + (int)tcells[t].size();
+        for (int c : tcells[t]) {
+            tlist.push_back(c);
+            int packed = 0;
+            for (int m = 0; m < 3; m++) {
+                int l = 0xFF;
+                if (m < nvc) {
+                    const int d = dm->dofs[(size_t)c * nvc + m];
+                    if (d >= 0 && d / TD == t) l = d - t * TD;
+                }
+                packed |= l << (8 * m);
+            }
+            tloc.push_back(packed);
+        }
+    }
+    std::vector<int> units;
+    // heavy (near-diagonal) units first
+    for (int dg = 0; dg < S.ngroups; dg++)
+        for (int gr = 0; gr + dg < S.ngroups; gr++) { units.push_back(gr); units.push_back(gr + dg); }
+    S.nunits = (int)units.size() / 2;
+    // dof -> cells
+    std::vector<int> dptr(N + 1, 0), dcells;
+    for (int c = 0; c < nc; c++)
+        for (int m = 0; m < nvc; m++) { const int d = dm->dofs[(size_t)c * nvc + m]; if (d >= 0) dptr[d + 1]++; }
+    for (int i = 0; i < N; i++) dptr[i + 1] += dptr[i];
+    dcells.resize(dptr[N]);
+    {
+        std::vector<int> pos(dptr.begin(), dptr.end() - 1);
+        for (int c = 0; c < nc; c++)
+            for (int m = 0; m < nvc; m++) { const int d = dm->dofs[(size_t)c * nvc + m]; if (d >= 0) dcells[pos[d]++] = c * 4 + m; }
+    }
+    const int ND = nvc * (nvc + 1) / 2;
+    rc |= upload(p, tptr.data(), tptr.size(), &S.tile_ptr);
+    rc |= upload(p, tlist.data(), tlist.size(), &S.tile_cells);
+    rc |= upload(p, tloc.data(), tloc.size(), &S.tile_loc);
+    rc |= upload(p, home.data(), home.size(), &S.home);
+    rc |= upload(p, units.data(), units.size(), &S.units);
+    rc |= upload(p, dptr.data(), dptr.size(), &S.dof_ptr);
+    rc |= upload(p, dcells.data(), dcells.size(), &S.dof_cells);
+    rc |= dalloc(p, (size_t)S.ngroups * nc * ND, &S.DXp);
+    rc |= dalloc(p, (size_t)S.ngroups * nc * ND, &S.DYp);
+    rc |= dalloc(p, (size_t)nc * ND, &S.Dbnd);
+    rc |= dalloc(p, (size_t)nc * ND, &S.D);
+    rc |= dalloc(p, 4, &S.err);
+    rc |= dalloc(p, 8, &S.counters);
+    if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
+    rc = pnb_problem_set_rules(p, rules);
+    if (rc) { pnb_problem_destroy(p); return rc; }
+    *out = p;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// classification / order kernels
+// ---------------------------------------------------------------------------
+__global__ void classify_kernel(DProblem P, int boundary, int64_t np, const int *pairs, int *panel, int *perm1, int *perm2)
+{
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= np) return;
+    int p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+    const int a = pairs[2 * n], b = pairs[2 * n + 1];
+    const int pan = boundary ? panel_boundary(P, a, b, p1, p2) : panel_interior(P, a, b, p1, p2);
+    panel[n] = pan;
+    const int nvc = P.dim + 1;
+    if (perm1)
+        for (int k = 0; k < nvc; k++) perm1[n * nvc + k] = p1[k];
+    if (perm2)
+        for (int k = 0; k < nvc; k++) perm2[n * nvc + k] = (boundary && k >= P.dim) ? 0 : p2[k];
+}
+
+// one thread per c1, loops over c2 >= c1 (and the facets)
+__global__ void max_order_kernel(DProblem P, int zero_exterior, int *out, unsigned long long *hist)
+{
+    const int c1 = blockIdx.x * blockDim.x + threadIdx.x;
+    int best = 0;
+    if (c1 < P.nc) {
+        int p1[3], p2[3];
+        for (int c2 = c1; c2 < P.nc; c2++) {
+            const int pan = panel_interior(P, c1, c2, p1, p2);
+            best = max(best, pan);
+            if (hist && pan >= -3 && pan < 256) atomicAdd(&hist[3 + pan], 1ull);
+        }
+        if (zero_exterior)
+            for (int f = 0; f < P.nb; f++) best = max(best, panel_boundary(P, c1, f, p1, p2));
+    }
+    atomicMax(out, best);
+}
+
+extern "C" int pnb_max_order(pnb_problem *p, int zero_exterior, int32_t *max_order_out)
+{
+    if (!p || !max_order_out) return fail(PNB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemset(p->S.err, 0, sizeof(int) * 4));
+    max_order_kernel<<<(p->nc + 127) / 128, 128>>>(p->P, zero_exterior, p->S.err + 1, nullptr);
+    CK(cudaGetLastError());
+    int v = 0;
+    CK(cudaMemcpy(&v, p->S.err + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    *max_order_out = v;
+    return 0;
+}
+
+extern "C" int pnb_panel_histogram(pnb_problem *p, int64_t *hist)
+{
+    if (!p || !hist) return fail(PNB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(p->device));
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc(&d, 259 * sizeof(unsigned long long)));
+    CK(cudaMemset(d, 0, 259 * sizeof(unsigned long long)));
+    CK(cudaMemset(p->S.err, 0, sizeof(int) * 4));
+    max_order_kernel<<<(p->nc + 127) / 128, 128>>>(p->P, 0, p->S.err + 1, d);
+    cudaError_t e = cudaMemcpy(hist, d, 259 * sizeof(int64_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CK(e);
+    return 0;
+}
+
+extern "C" int pnb_classify_pairs(pnb_problem *p, int boundary, int64_t npairs, const int32_t *pairs, int32_t *panel,
+                                  int32_t *perm1, int32_t *perm2)
+{
+    if (!p || !pairs || !panel) return fail(PNB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(p->device));
+    const int nvc = p->dim + 1;
+    int *dpairs = nullptr, *dpanel = nullptr, *dp1 = nullptr, *dp2 = nullptr;
+    const size_t n = (size_t)std::max<int64_t>(npairs, 1);
+    CK(cudaMalloc(&dpairs, n * 2 * sizeof(int)));
+    CK(cudaMalloc(&dpanel, n * sizeof(int)));
+    CK(cudaMalloc(&dp1, n * nvc * sizeof(int)));
+    CK(cudaMalloc(&dp2, n * nvc * sizeof(int)));
+    int rc = 0;
+    if (npairs > 0) {
+        cudaMemcpy(dpairs, pairs, (size_t)npairs * 2 * sizeof(int), cudaMemcpyHostToDevice);
+        classify_kernel<<<(unsigned)((npairs + 255) / 256), 256>>>(p->P, boundary, npairs, dpairs, dpanel, dp1, dp2);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(panel, dpanel, (size_t)npairs * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && perm1) e = cudaMemcpy(perm1, dp1, (size_t)npairs * nvc * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && perm2) e = cudaMemcpy(perm2, dp2, (size_t)npairs * nvc * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dpairs); cudaFree(dpanel); cudaFree(dp1); cudaFree(dp2);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// local matrices of a list of pairs (parity entry point)
+// ---------------------------------------------------------------------------
+// writes the reduced lane sums of a SINGULAR pair into the reference's local index space
+template <int DIM>
+__device__ __forceinline__ void singular_to_local(const double *acc, int lane, int common, const int *perm1, const int *perm2,
+                                                  double scale, double *out /* NL, zero-initialised */)
+{
+    constexpr int NV = PairDims<DIM>::NV, NR = 2 * NV - 1, NA = NR * (NR + 1) / 2;
+    // lane l owns compact entry l = (I,J), I<=J over NR rows
+    int I = 0, J = 0, k = 0;
+    bool mine = false;
+    double v = 0.;
+#pragma unroll
+    for (int a = 0; a < NR; a++)
+#pragma unroll
+        for (int b = a; b < NR; b++) {
+            if (k == lane) { I = a; J = b; mine = true; v = acc[k]; }
+            k++;
+        }
+    (void)NA;
+    const int rows = 2 * NV - common;
+    if (!mine || J >= rows) return;
+    // perm: dofs on the reordered simplices -> usual local numbering (nonlocalOperator_{SCALAR}.pxi:351-376)
+    int i = I < NV ? perm1[I] : NV + perm2[I - NV + common];
+    int j = J < NV ? perm1[J] : NV + perm2[J - NV + common];
+    const int kk = j < i ? tri_idx(2 * NV, j, i) : tri_idx(2 * NV, i, j);
+    out[kk] = v * scale;
+}
+
+template <int DIM>
+__global__ void local_matrices_kernel(DProblem P, int boundary, int path, int64_t np, const int *pairs, int *panel_out,
+                                      double *contrib, int *err)
+{
+    constexpr int NV = PairDims<DIM>::NV, NL = PairDims<DIM>::NL, ND = PairDims<DIM>::ND;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (n >= np) return;
+    const int a = pairs[2 * n], b = pairs[2 * n + 1];
+    int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
+    if (boundary) {
+        const int pan = panel_boundary(P, a, b, p1, p2);
+        if (lane == 0) panel_out[n] = pan;
+        double *out = contrib + n * ND;
+        if (pan > P.max_order) { if (lane == 0) atomicMax(err, pan); return; }
+        double acc[ND];
+        lanes_boundary<DIM>(P, a, b, pan, p1, p2, lane, 32, acc);
+        warp_allreduce<ND>(acc);
+        // vol factors: regular vol1*vol2 (nonlocalOperator_{SCALAR}.pxi:1071), singular 2D -2 vol1 vol2
+        // (fractionalLaplacian2D.pyx:1375), singular 1D vol1 (fractionalLaplacian1D.pyx:724)
+        double scale;
+        if (pan >= 1) scale = P.vol[a] * P.bvol[b];
+        else scale = DIM == 2 ? -2.0 * P.vol[a] * P.bvol[b] : P.vol[a];
+        if (lane < ND) out[lane] = 0.;
+        __syncwarp();
+        int k = 0;
+#pragma unroll
+        for (int I = 0; I < NV; I++)
+#pragma unroll
+            for (int J = I; J < NV; J++) {
+                if (k == lane) {
+                    const int i = pan >= 1 ? I : p1[I], j = pan >= 1 ? J : p1[J];
+                    const int kk = j < i ? tri_idx(NV, j, i) : tri_idx(NV, i, j);
+                    out[kk] = acc[k] * scale;
+                }
+                k++;
+            }
+        return;
+    }
+    const int pan = panel_interior(P, a, b, p1, p2);
+    if (lane == 0) panel_out[n] = pan;
+    double *out = contrib + n * NL;
+    if (lane < NL) out[lane] = 0.;
+    __syncwarp();
+    if (pan == PNB_IGNORED_PANEL) return;
+    if (pan > P.max_order) { if (lane == 0) atomicMax(err, pan); return; }
+    if (pan >= 1) {
+        const double vol = P.vol[a] * P.vol[b];
+        if (path == 1 && DIM == 2 && pan <= PNB_FAR_MAX_ORDER && c_far[pan].n > 0) {
+            if (lane == 0) {
+                double s1[3][2], s2[3][2], xy[9], xx[6], yy[6];
+                load_simplex<2>(P.simplices, a, 3, s1);
+                load_simplex<2>(P.simplices, b, 3, s2);
+                const int nq = c_far[pan].n;
+                if (nq == 3) far_eval_2d<3>(s1, s2, c_far[pan], P.C, P.expo, xy, xx, yy);
+                else if (nq == 6) far_eval_2d<6>(s1, s2, c_far[pan], P.C, P.expo, xy, xx, yy);
+                else if (nq == 7) far_eval_2d<7>(s1, s2, c_far[pan], P.C, P.expo, xy, xx, yy);
+                else if (nq == 1) far_eval_2d<1>(s1, s2, c_far[pan], P.C, P.expo, xy, xx, yy);
+                else { atomicMax(err, 100000 + pan); return; }
+                for (int I = 0; I < 3; I++)
+                    for (int J = I; J < 3; J++) {
+                        out[tri_idx(6, I, J)] = xx[tri_idx(3, I, J)] * vol;
+                        out[tri_idx(6, 3 + I, 3 + J)] = yy[tri_idx(3, I, J)] * vol;
+                    }
+                for (int I = 0; I < 3; I++)
+                    for (int J = 0; J < 3; J++) out[tri_idx(6, I, 3 + J)] = xy[3 * I + J] * vol;
+            }
+            return;
+        }
+        double acc[NL];
+        lanes_regular_interior<DIM>(P, a, b, pan, lane, 32, acc);
+        warp_allreduce<NL>(acc);
+#pragma unroll
+        for (int k = 0; k < NL; k++)
+            if (k == lane) out[k] = acc[k] * vol;
+    } else {
+        constexpr int NR = 2 * NV - 1, NA = NR * (NR + 1) / 2;
+        double acc[NA];
+        lanes_singular_interior<DIM>(P, a, b, pan, p1, p2, lane, 32, acc);
+        warp_allreduce<NA>(acc);
+        // vol = 4 vol1 vol2 in 2D (fractionalLaplacian2D.pyx:851), vol1 vol2 in 1D (fractionalLaplacian1D.pyx:378)
+        const double scale = (DIM == 2 ? 4.0 : 1.0) * P.vol[a] * P.vol[b];
+        singular_to_local<DIM>(acc, lane, -pan, p1, p2, scale, out);
+    }
+}
+
+extern "C" int pnb_local_matrices(pnb_problem *p, int boundary, int path, int64_t npairs, const int32_t *pairs,
+                                  int32_t *panel, double *contrib)
+{
+    if (!p || !pairs || !panel || !contrib) return fail(PNB_ERR_ARG, "null argument");
+    if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
+    CK(cudaSetDevice(p->device));
+    const int nvc = p->dim + 1;
+    const int nloc = boundary ? nvc * (nvc + 1) / 2 : (2 * nvc) * (2 * nvc + 1) / 2;
+    int *dpairs = nullptr, *dpanel = nullptr;
+    double *dc = nullptr;
+    const size_t n = (size_t)std::max<int64_t>(npairs, 1);
+    CK(cudaMalloc(&dpairs, n * 2 * sizeof(int)));
+    CK(cudaMalloc(&dpanel, n * sizeof(int)));
+    CK(cudaMalloc(&dc, n * nloc * sizeof(double)));
+    int rc = 0;
+    if (npairs > 0) {
+        cudaMemcpy(dpairs, pairs, (size_t)npairs * 2 * sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemset(p->S.err, 0, 4 * sizeof(int));
+        const unsigned blocks = (unsigned)((npairs * 32 + 255) / 256);
+        if (p->dim == 2) local_matrices_kernel<2><<<blocks, 256>>>(p->P, boundary, path, npairs, dpairs, dpanel, dc, p->S.err);
+        else local_matrices_kernel<1><<<blocks, 256>>>(p->P, boundary, path, npairs, dpairs, dpanel, dc, p->S.err);
+        cudaError_t e = cudaGetLastError();
+        int herr[4] = {0, 0, 0, 0};
+        if (e == cudaSuccess) e = cudaMemcpy(herr, p->S.err, 4 * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(panel, dpanel, (size_t)npairs * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(contrib, dc, (size_t)npairs * nloc * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, cudaGetErrorString(e));
+        else if (herr[0] > 0) rc = fail(PNB_ERR_ORDER, "regular quadrature order " + std::to_string(herr[0]) + " exceeds the supplied tables (max_order " + std::to_string(p->P.max_order) + ")");
+    }
+    cudaFree(dpairs); cudaFree(dpanel); cudaFree(dc);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// dense assembly: tile kernel
+// ---------------------------------------------------------------------------
+template <int DIM> struct TileSmem {
+    static constexpr int NV = PairDims<DIM>::NV, NX = PairDims<DIM>::NX, ND = PairDims<DIM>::ND;
+    double acc[PNB_TD][PNB_TD + 1];
+    double B[PNB_SB * PNB_SB][NX];
+    double dxy[PNB_SB * PNB_SB][2 * ND];
+    unsigned long long rmask[PNB_TD], cmask[PNB_TD];
+    int rcell[PNB_SB], ccell[PNB_SB];
+    int rloc[PNB_SB], cloc[PNB_SB];   // packed
+    int rhome[PNB_SB], chome[PNB_SB];
+    int nearlist[PNB_SB * PNB_SB];
+    int nearpanel[PNB_SB * PNB_SB];
+    int warpcnt[PNB_THREADS / 32];
+    int nnear;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(PNB_THREADS) tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_max)
+{
+    constexpr int NV = PairDims<DIM>::NV, NX = PairDims<DIM>::NX, ND = PairDims<DIM>::ND, NL = PairDims<DIM>::NL;
+    constexpr int TD = PNB_TD, SB = PNB_SB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<DIM> &sm = *reinterpret_cast<TileSmem<DIM> *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gr = S.units[2 * blockIdx.x], gc = S.units[2 * blockIdx.x + 1];
+    unsigned long long my_pairs = 0;
+
+    for (int rt = gr * S.G; rt < min((gr + 1) * S.G, S.ntiles); rt++)
+        for (int ct = max(gc * S.G, rt); ct < min((gc + 1) * S.G, S.ntiles); ct++) {
+            const bool diag = rt == ct;
+            const int rbeg = S.tile_ptr[rt], nR = S.tile_ptr[rt + 1] - rbeg;
+            const int cbeg = S.tile_ptr[ct], nC = S.tile_ptr[ct + 1] - cbeg;
+            for (int e = tid; e < TD * (TD + 1); e += PNB_THREADS) (&sm.acc[0][0])[e] = 0.;
+            __syncthreads();
+            for (int rb = 0; rb < nR; rb += SB) {
+                // row batch metadata + masks
+                if (tid < SB) {
+                    const bool ok = rb + tid < nR;
+                    const int c = ok ? S.tile_cells[rbeg + rb + tid] : -1;
+                    sm.rcell[tid] = c;
+                    sm.rloc[tid] = ok ? S.tile_loc[rbeg + rb + tid] : 0x00FFFFFF;
+                    sm.rhome[tid] = ok ? S.home[c] : -1;
+                }
+                __syncthreads();
+                if (tid < TD) {
+                    unsigned long long m = 0;
+                    for (int k = 0; k < SB; k++)
+                        for (int i = 0; i < NV; i++)
+                            if (((sm.rloc[k] >> (8 * i)) & 0xFF) == tid) m |= 1ull << (k * NV + i);
+                    sm.rmask[tid] = m;
+                }
+                for (int cb = diag ? rb : 0; cb < nC; cb += SB) {
+                    __syncthreads();
+                    if (tid < SB) {
+                        const bool ok = cb + tid < nC;
+                        const int c = ok ? S.tile_cells[cbeg + cb + tid] : -1;
+                        sm.ccell[tid] = c;
+                        sm.cloc[tid] = ok ? S.tile_loc[cbeg + cb + tid] : 0x00FFFFFF;
+                        sm.chome[tid] = ok ? S.home[c] : -1;
+                    }
+                    if (tid == 0) sm.nnear = 0;
+                    __syncthreads();
+                    if (tid < TD) {
+                        unsigned long long m = 0;
+                        for (int k = 0; k < SB; k++)
+                            for (int i = 0; i < NV; i++)
+                                if (((sm.cloc[k] >> (8 * i)) & 0xFF) == tid) m |= 1ull << (k * NV + i);
+                        sm.cmask[tid] = m;
+                    }
+                    // ---- phase 1: classify, evaluate low-order regular pairs ----
+                    const int k1 = tid / SB, k2 = tid % SB;
+                    const int K1 = sm.rcell[k1], K2 = sm.ccell[k2];
+#pragma unroll
+                    for (int k = 0; k < NX; k++) sm.B[tid][k] = 0.;
+#pragma unroll
+                    for (int k = 0; k < 2 * ND; k++) sm.dxy[tid][k] = 0.;
+                    int todo = 0;  // 0 nothing, >0 regular order (near), <0 singular panel
+                    bool countD = false;
+                    if (K1 >= 0 && K2 >= 0 && (diag ? K1 <= K2 : K1 != K2)) {
+                        bool any1 = false, any2 = false;
+#pragma unroll
+                        for (int m = 0; m < NV; m++) {
+                            any1 |= P.dofs[(size_t)K1 * NV + m] >= 0;
+                            any2 |= P.dofs[(size_t)K2 * NV + m] >= 0;
+                        }
+                        countD = sm.rhome[k1] == rt && sm.chome[k2] == ct;
+                        const bool rin = (sm.rloc[k1] & 0x00FFFFFF) != 0x00FFFFFF, cin = (sm.cloc[k2] & 0x00FFFFFF) != 0x00FFFFFF;
+                        const bool cross = (rin && cin) || (diag && rin && cin);
+                        if ((any1 || any2) && (countD || cross)) {
+                            int panel;
+                            if (K1 == K2) panel = -NV;
+                            else {
+                                panel = -shared_vertices(P.cells + (size_t)K1 * NV, NV, P.cells + (size_t)K2 * NV, NV);
+                                if (panel == 0) {
+                                    const double d = center_distance(P.centers + (size_t)K1 * DIM, P.centers + (size_t)K2 * DIM, DIM);
+                                    panel = quad_order_interior(P, P.h[K1], P.h[K2], d);
+                                }
+                            }
+                            my_pairs++;
+                            if (panel > P.max_order) {
+                                atomicMax(S.err, panel);
+                            } else if (DIM == 2 && panel >= 1 && panel <= far_max && c_far[panel].n > 0) {
+                                double s1[3][2], s2[3][2], xy[9], xx[6], yy[6];
+                                load_simplex<2>(P.simplices, K1, 3, s1);
+                                load_simplex<2>(P.simplices, K2, 3, s2);
+                                const int nq = c_far[panel].n;
+                                if (nq == 3) far_eval_2d<3>(s1, s2, c_far[panel], P.C, P.expo, xy, xx, yy);
+                                else if (nq == 6) far_eval_2d<6>(s1, s2, c_far[panel], P.C, P.expo, xy, xx, yy);
+                                else far_eval_2d<7>(s1, s2, c_far[panel], P.C, P.expo, xy, xx, yy);
+                                const double sc = 2.0 * P.vol[K1] * P.vol[K2];
+                                if (DIM == 2) {
+#pragma unroll
+                                    for (int k = 0; k < 9; k++) sm.B[tid][k % NX] = xy[k] * sc;
+                                    if (countD) {
+#pragma unroll
+                                        for (int k = 0; k < 6; k++) {
+                                            sm.dxy[tid][k % (2 * ND)] = xx[k] * sc;
+                                            sm.dxy[tid][(ND + k) % (2 * ND)] = yy[k] * sc;
+                                        }
+                                    }
+                                }
+                            } else {
+                                todo = panel;
+                            }
+                        }
+                    }
+                    // ---- deterministic compaction of the queued pairs ----
+                    const unsigned bal = __ballot_sync(0xffffffffu, todo != 0);
+                    if (lane == 0) sm.warpcnt[warp] = __popc(bal);
+                    __syncthreads();
+                    if (todo != 0) {
+                        int pos = __popc(bal & ((1u << lane) - 1));
+                        for (int w = 0; w < warp; w++) pos += sm.warpcnt[w];
+                        sm.nearlist[pos] = tid | (countD ? 0x10000 : 0);
+                        sm.nearpanel[pos] = todo;
+                    }
+                    if (tid == 0) {
+                        int tot = 0;
+                        for (int w = 0; w < PNB_THREADS / 32; w++) tot += sm.warpcnt[w];
+                        sm.nnear = tot;
+                    }
+                    __syncthreads();
+                    // ---- phase 2: one warp per queued pair ----
+                    const int nnear = sm.nnear;
+                    for (int q = warp; q < nnear; q += PNB_THREADS / 32) {
+                        const int slot = sm.nearlist[q] & 0xFFFF;
+                        const bool cD = (sm.nearlist[q] & 0x10000) != 0;
+                        const int panel = sm.nearpanel[q];
+                        const int Ka = sm.rcell[slot / SB], Kb = sm.ccell[slot % SB];
+                        if (panel >= 1) {
+                            double acc[NL];
+                            lanes_regular_interior<DIM>(P, Ka, Kb, panel, lane, 32, acc);
+                            warp_allreduce<NL>(acc);
+                            const double sc = 2.0 * P.vol[Ka] * P.vol[Kb];
+                            int k = 0;
+#pragma unroll
+                            for (int I = 0; I < 2 * NV; I++)
+#pragma unroll
+                                for (int J = I; J < 2 * NV; J++) {
+                                    if (k == lane) {
+                                        const double v = acc[k] * sc;
+                                        if (I < NV && J >= NV) sm.B[slot][I * NV + (J - NV)] = v;
+                                        else if (cD && J < NV) sm.dxy[slot][tri_idx(NV, I, J)] = v;
+                                        else if (cD && I >= NV) sm.dxy[slot][ND + tri_idx(NV, I - NV, J - NV)] = v;
+                                    }
+                                    k++;
+                                }
+                        } else {
+                            // reference orientation: smaller cell index first
+                            const bool swapped = Ka > Kb;
+                            const int c1 = swapped ? Kb : Ka, c2 = swapped ? Ka : Kb;
+                            int p1[3], p2[3];
+                            const int pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.cells + (size_t)c2 * NV, NV, c1 == c2, p1, p2);
+                            constexpr int NR = 2 * NV - 1, NA = NR * (NR + 1) / 2;
+                            double acc[NA];
+                            lanes_singular_interior<DIM>(P, c1, c2, pan, p1, p2, lane, 32, acc);
+                            warp_allreduce<NA>(acc);
+                            const double sc = (c1 == c2 ? 1.0 : 2.0) * (DIM == 2 ? 4.0 : 1.0) * P.vol[c1] * P.vol[c2];
+                            const int common = -pan, rows = 2 * NV - common;
+                            int k = 0;
+#pragma unroll
+                            for (int I = 0; I < NR; I++)
+#pragma unroll
+                                for (int J = I; J < NR; J++) {
+                                    if (k == lane && J < rows) {
+                                        const double v = acc[k] * sc;
+                                        int i = I < NV ? p1[I] : NV + p2[I - NV + common];
+                                        int j = J < NV ? p1[J] : NV + p2[J - NV + common];
+                                        if (j < i) { const int t = i; i = j; j = t; }
+                                        // (i,j) in the reference's 2NV x 2NV local numbering of (c1,c2)
+                                        if (i < NV && j >= NV) {
+                                            if (!swapped) sm.B[slot][i * NV + (j - NV)] = v;
+                                            else sm.B[slot][(j - NV) * NV + i] = v;
+                                        } else if (cD) {
+                                            const bool first = j < NV;   // block of c1
+                                            const int a = first ? i : i - NV, b = first ? j : j - NV;
+                                            const bool to_dx = first != swapped;
+                                            sm.dxy[slot][(to_dx ? 0 : ND) + tri_idx(NV, a, b)] = v;
+                                        }
+                                    }
+                                    k++;
+                                }
+                        }
+                    }
+                    __syncthreads();
+                    // ---- phase 3: fold cross blocks into the tile, fixed order ----
+                    for (int e = tid; e < TD * TD; e += PNB_THREADS) {
+                        const int a = e / TD, b = e - a * TD;
+                        double sum = 0.;
+                        bool hit = false;
+                        unsigned long long ra = sm.rmask[a], cm = sm.cmask[b];
+                        if (ra && cm) {
+                            hit = true;
+                            while (ra) {
+                                const int u = __ffsll((long long)ra) - 1;
+                                ra &= ra - 1;
+                                const int kk1 = u / NV, i = u - kk1 * NV;
+                                unsigned long long c = cm;
+                                while (c) {
+                                    const int v = __ffsll((long long)c) - 1;
+                                    c &= c - 1;
+                                    const int kk2 = v / NV, j = v - kk2 * NV;
+                                    sum += sm.B[kk1 * SB + kk2][i * NV + j];
+                                }
+                            }
+                        }
+                        if (diag) {
+                            unsigned long long rb2 = sm.rmask[b], ca = sm.cmask[a];
+                            if (rb2 && ca) {
+                                hit = true;
+                                while (rb2) {
+                                    const int u = __ffsll((long long)rb2) - 1;
+                                    rb2 &= rb2 - 1;
+                                    const int kk1 = u / NV, i = u - kk1 * NV;
+                                    unsigned long long c = ca;
+                                    while (c) {
+                                        const int v = __ffsll((long long)c) - 1;
+                                        c &= c - 1;
+                                        const int kk2 = v / NV, j = v - kk2 * NV;
+                                        sum += sm.B[kk1 * SB + kk2][i * NV + j];
+                                    }
+                                }
+                            }
+                        }
+                        if (hit) sm.acc[a][b] += sum;
+                    }
+                    // ---- cell-diagonal blocks: reduce over the batch, stage per (group, cell) ----
+                    if (tid < SB * ND) {
+                        const int kk1 = tid / ND, comp = tid - kk1 * ND;
+                        const int K = sm.rcell[kk1];
+                        if (K >= 0 && sm.rhome[kk1] == rt) {
+                            double sacc = 0.;
+                            for (int kk2 = 0; kk2 < SB; kk2++) sacc += sm.dxy[kk1 * SB + kk2][comp];
+                            if (sacc != 0.) S.DXp[((size_t)gc * P.nc + K) * ND + comp] += sacc;
+                        }
+                    } else if (tid < 2 * SB * ND) {
+                        const int t2 = tid - SB * ND;
+                        const int kk2 = t2 / ND, comp = t2 - kk2 * ND;
+                        const int K = sm.ccell[kk2];
+                        if (K >= 0 && sm.chome[kk2] == ct) {
+                            double sacc = 0.;
+                            for (int kk1 = 0; kk1 < SB; kk1++) sacc += sm.dxy[kk1 * SB + kk2][ND + comp];
+                            if (sacc != 0.) S.DYp[((size_t)gr * P.nc + K) * ND + comp] += sacc;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+            // ---- write the tile (and its mirror image) ----
+            const int r0 = rt * TD, c0 = ct * TD;
+            for (int e = tid; e < TD * TD; e += PNB_THREADS) {
+                const int a = e / TD, b = e - a * TD;
+                if (r0 + a < P.N && c0 + b < P.N) A[(size_t)(r0 + a) * ld + c0 + b] = sm.acc[a][b];
+            }
+            if (!diag)
+                for (int e = tid; e < TD * TD; e += PNB_THREADS) {
+                    const int b = e / TD, a = e - b * TD;
+                    if (r0 + a < P.N && c0 + b < P.N) A[(size_t)(c0 + b) * ld + r0 + a] = sm.acc[a][b];
+                }
+            __syncthreads();
+        }
+    // pair counter (statistics only; integer atomics)
+    for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
+    if (lane == 0 && my_pairs) atomicAdd(S.counters, my_pairs);
+}
+
+// ---------------------------------------------------------------------------
+// zero-exterior facet loop (nonlocalAssembly_{SCALAR}.pxi:1430-1448): one warp per
+// cell, lanes over the boundary facets, each lane integrates whole pairs and
+// keeps a private sum; fixed butterfly at the end.
+// ---------------------------------------------------------------------------
+template <int DIM>
+__global__ void boundary_kernel(DProblem P, TileSched S)
+{
+    constexpr int NV = PairDims<DIM>::NV, ND = PairDims<DIM>::ND;
+    const int lane = threadIdx.x & 31;
+    const int c1 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c1 >= P.nc) return;
+    bool any = false;
+    for (int m = 0; m < NV; m++) any |= P.dofs[(size_t)c1 * NV + m] >= 0;
+    if (!any) return;
+    double tot[ND];
+#pragma unroll
+    for (int k = 0; k < ND; k++) tot[k] = 0.;
+    // regular facets: lane-per-facet
+    for (int f0 = 0; f0 < P.nb; f0 += 32) {
+        const int f = f0 + lane;
+        int pan = 0;
+        int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
+        if (f < P.nb) pan = panel_boundary(P, c1, f, p1, p2);
+        if (f < P.nb && pan >= 1) {
+            if (pan > P.max_order) atomicMax(S.err, pan);
+            else {
+                double acc[ND];
+                lanes_boundary<DIM>(P, c1, f, pan, p1, p2, 0, 1, acc);
+                const double sc = P.vol[c1] * P.bvol[f];
+#pragma unroll
+                for (int k = 0; k < ND; k++) tot[k] += acc[k] * sc;
+            }
+        }
+        // singular facets of this chunk: whole warp per facet, in facet order
+        unsigned sing = __ballot_sync(0xffffffffu, f < P.nb && pan < 0);
+        while (sing) {
+            const int src = __ffs(sing) - 1;
+            sing &= sing - 1;
+            const int fs = f0 + src;
+            const int pans = __shfl_sync(0xffffffffu, pan, src);
+            int q1[3], q2[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                q1[k] = __shfl_sync(0xffffffffu, p1[k], src);
+                q2[k] = __shfl_sync(0xffffffffu, p2[k], src);
+            }
+            double acc[ND];
+            lanes_boundary<DIM>(P, c1, fs, pans, q1, q2, lane, 32, acc);
+            const double sc = DIM == 2 ? -2.0 * P.vol[c1] * P.bvol[fs] : P.vol[c1];
+            // entry (I,J) over permuted dofs -> local (perm1[I], perm1[J])
+            int k = 0;
+#pragma unroll
+            for (int I = 0; I < NV; I++)
+#pragma unroll
+                for (int J = I; J < NV; J++) {
+                    const int i = q1[I], j = q1[J];
+                    const int kk = j < i ? tri_idx(NV, j, i) : tri_idx(NV, i, j);
+#pragma unroll
+                    for (int t = 0; t < ND; t++)
+                        if (t == kk) tot[t] += acc[k] * sc;
+                    k++;
+                }
+        }
+    }
+    warp_allreduce<ND>(tot);
+#pragma unroll
+    for (int k = 0; k < ND; k++)
+        if (k == lane) S.Dbnd[(size_t)c1 * ND + k] = tot[k];
+}
+
+// D[K] = sum_g DXp[g][K] + sum_g DYp[g][K] + Dbnd[K], fixed order
+__global__ void reduce_D_kernel(TileSched S, int nc, int ND, int use_bnd)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= (int64_t)nc * ND) return;
+    double s = 0.;
+    for (int g = 0; g < S.ngroups; g++) s += S.DXp[(size_t)g * nc * ND + e];
+    for (int g = 0; g < S.ngroups; g++) s += S.DYp[(size_t)g * nc * ND + e];
+    if (use_bnd) s += S.Dbnd[e];
+    S.D[e] = s;
+}
+
+// row-owned scatter of the cell-diagonal blocks (addToMatrixElemSym semantics,
+// nonlocalAssembly_{SCALAR}.pxi:152-168, 204-221): thread I adds to row I only
+__global__ void scatter_D_kernel(DProblem P, TileSched S, double *A, int64_t ld)
+{
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= P.N) return;
+    const int NV = P.dim + 1, ND = NV * (NV + 1) / 2;
+    for (int t = S.dof_ptr[I]; t < S.dof_ptr[I + 1]; t++) {
+        const int K = S.dof_cells[t] >> 2, p = S.dof_cells[t] & 3;
+        for (int q = 0; q < NV; q++) {
+            const int J = P.dofs[(size_t)K * NV + q];
+            if (J < 0) continue;
+            const int kk = p <= q ? tri_idx(NV, p, q) : tri_idx(NV, q, p);
+            A[(size_t)I * ld + J] += S.D[(size_t)K * ND + kk];
+        }
+    }
+}
+
+extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *A,
+                                  int64_t ld, int a_on_device)
+{
+    if (!p || !A) return fail(PNB_ERR_ARG, "null argument");
+    if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
+    if (row_begin != 0 || row_end != p->N) return fail(PNB_ERR_UNSUPPORTED, "row blocks are assembled through pnb_dense_assemble_rows");
+    if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
+    CK(cudaSetDevice(p->device));
+    const int N = p->N, nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
+    double *dA = A;
+    if (!a_on_device) CK(cudaMalloc(&dA, (size_t)N * ld * sizeof(double)));
+    TileSched &S = p->S;
+    cudaEvent_t ev[5];
+    for (auto &e : ev) cudaEventCreate(&e);
+    int rc = 0;
+    cudaError_t e;
+    cudaMemsetAsync(S.DXp, 0, (size_t)S.ngroups * nc * ND * sizeof(double));
+    cudaMemsetAsync(S.DYp, 0, (size_t)S.ngroups * nc * ND * sizeof(double));
+    cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * ND * sizeof(double));
+    cudaMemsetAsync(S.err, 0, 4 * sizeof(int));
+    cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
+    cudaEventRecord(ev[0]);
+    int launches = 0;
+    if (p->dim == 2) {
+        const size_t smem = sizeof(TileSmem<2>);
+        cudaFuncSetAttribute(tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tile_kernel<2><<<S.nunits, PNB_THREADS, smem>>>(p->P, S, dA, ld, PNB_FAR_MAX_ORDER);
+    } else {
+        const size_t smem = sizeof(TileSmem<1>);
+        cudaFuncSetAttribute(tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tile_kernel<1><<<S.nunits, PNB_THREADS, smem>>>(p->P, S, dA, ld, 0);
+    }
+    launches++;
+    cudaEventRecord(ev[1]);
+    if (zero_exterior && p->nb > 0) {
+        const unsigned blocks = (unsigned)(((size_t)nc * 32 + 255) / 256);
+        if (p->dim == 2) boundary_kernel<2><<<blocks, 256>>>(p->P, S);
+        else boundary_kernel<1><<<blocks, 256>>>(p->P, S);
+        launches++;
+    }
+    cudaEventRecord(ev[2]);
+    reduce_D_kernel<<<(unsigned)(((size_t)nc * ND + 255) / 256), 256>>>(S, nc, ND, zero_exterior && p->nb > 0);
+    scatter_D_kernel<<<(N + 127) / 128, 128>>>(p->P, S, dA, ld);
+    launches += 2;
+    cudaEventRecord(ev[3]);
+    e = cudaEventSynchronize(ev[3]);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    int herr[4] = {0, 0, 0, 0};
+    unsigned long long hcnt[8] = {0};
+    if (e == cudaSuccess) e = cudaMemcpy(herr, S.err, sizeof(herr), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(hcnt, S.counters, sizeof(hcnt), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("dense assembly: ") + cudaGetErrorString(e));
+    else if (herr[0] > 0) rc = fail(PNB_ERR_ORDER, "regular quadrature order " + std::to_string(herr[0]) + " exceeds the supplied tables (max_order " + std::to_string(p->P.max_order) + ")");
+    if (!rc && !a_on_device) {
+        e = cudaMemcpy2D(A, (size_t)ld * sizeof(double), dA, (size_t)ld * sizeof(double), (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
+    }
+    float ms;
+    for (int k = 0; k < 3; k++) { cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); p->timings[k] = ms; }
+    cudaEventElapsedTime(&ms, ev[0], ev[3]);
+    p->timings[3] = ms;
+    p->stats[0] = (int64_t)hcnt[0];
+    p->stats[1] = p->distinct_pairs;
+    p->stats[2] = launches;
+    for (auto &ee : ev) cudaEventDestroy(ee);
+    if (!a_on_device) cudaFree(dA);
+    return rc;
+}
+
+extern "C" int pnb_dense_stats(pnb_problem *p, int64_t *stats)
+{
+    if (!p || !stats) return fail(PNB_ERR_ARG, "null argument");
+    memcpy(stats, p->stats, sizeof(p->stats));
+    return 0;
+}
+
+extern "C" int pnb_dense_timings(pnb_problem *p, double *ms)
+{
+    if (!p || !ms) return fail(PNB_ERR_ARG, "null argument");
+    memcpy(ms, p->timings, sizeof(p->timings));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// dense matvec  y = A x  (row block), HBM-bound: one warp per row, 16-byte loads
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) matvec_kernel(const double *__restrict__ A, int64_t nrows, int64_t ncols, int64_t ld,
+                                                      const double *__restrict__ x, double *__restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool vec_ok = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    for (int64_t row = warp; row < nrows; row += nwarps) {
+        const double *a = A + row * ld;
+        double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+        if (vec_ok) {
+            const double2 *a2 = reinterpret_cast<const double2 *>(a);
+            const double2 *x2 = reinterpret_cast<const double2 *>(x);
+            const int64_t n2 = ncols >> 1;
+            int64_t j = lane;
+            for (; j + 96 < n2; j += 128) {
+                const double2 v0 = __ldcs(a2 + j), v1 = __ldcs(a2 + j + 32), v2 = __ldcs(a2 + j + 64), v3 = __ldcs(a2 + j + 96);
+                const double2 w0 = x2[j], w1 = x2[j + 32], w2 = x2[j + 64], w3 = x2[j + 96];
+                s0 += v0.x * w0.x + v0.y * w0.y;
+                s1 += v1.x * w1.x + v1.y * w1.y;
+                s2 += v2.x * w2.x + v2.y * w2.y;
+                s3 += v3.x * w3.x + v3.y * w3.y;
+            }
+            for (; j < n2; j += 32) {
+                const double2 v0 = __ldcs(a2 + j);
+                const double2 w0 = x2[j];
+                s0 += v0.x * w0.x + v0.y * w0.y;
+            }
+            if ((ncols & 1) && lane == 0) s1 += a[ncols - 1] * x[ncols - 1];
+        } else {
+            for (int64_t j = lane; j < ncols; j += 32) s0 += a[j] * x[j];
+        }
+        double s = (s0 + s1) + (s2 + s3);
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) y[row] = s;
+    }
+}
+
+extern "C" int pnb_dense_matvec(int device, const double *A, int64_t num_rows, int64_t num_cols, int64_t ld,
+                                const double *x, double *y, void *stream)
+{
+    if (!A || !x || !y) return fail(PNB_ERR_ARG, "null argument");
+    if (pnb_device_count() == 0) return fail(PNB_ERR_NO_DEVICE, "no CUDA device: libpnb200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t want = (num_rows * 32 + 255) / 256;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 8));
+    matvec_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A, num_rows, num_cols, ld, x, y);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 FMA peak microbenchmark
+// ---------------------------------------------------------------------------
+__global__ void fp64_peak_kernel(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int pnb_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return fail(PNB_ERR_ARG, "null argument");
+    if (pnb_device_count() == 0) return fail(PNB_ERR_NO_DEVICE, "no CUDA device");
+    CK(cudaSetDevice(device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 20000;
+    double *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    fp64_peak_kernel<<<blocks, threads>>>(d, 1000);
+    double best = 0.;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+        best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    CK(cudaGetLastError());
+    *tflops = best;
+    return 0;
+}

@@ -1,0 +1,329 @@
+// Per-pair local-matrix evaluators.
+//
+//  * lane evaluators (warp-cooperative): every lane integrates a strided subset
+//    of the quadrature nodes of ONE cell pair; the caller reduces over the
+//    lanes with a fixed butterfly (deterministic).  Used for singular panels
+//    and for regular panels of order > PNB_FAR_MAX_ORDER.
+//  * far evaluator (thread-per-pair): regular panels of low order, the bulk of
+//    all pairs, with the 6x6 local matrix factored into its xx / xy / yy
+//    blocks so that each kernel value is used in 5 FMAs instead of 63 flops.
+#pragma once
+#include "pnb_device.cuh"
+
+template <int DIM> struct PairDims {
+    static constexpr int NV = DIM + 1;               // vertices (= P1 dofs) per cell
+    static constexpr int NL = (2 * NV) * (2 * NV + 1) / 2;  // local entries, interior
+    static constexpr int ND = NV * (NV + 1) / 2;     // entries of one cell-diagonal block
+    static constexpr int NX = NV * NV;               // entries of the cross block
+};
+
+// gamma(x,y) = C |x-y|^(-d-2s)  (kernelsCy.pyx:159-183); boundary kernels :216-240
+__device__ __forceinline__ double kernel_value(double scal, double expo, double d2) { return scal * pow(d2, expo); }
+
+template <int DIM>
+__device__ __forceinline__ void load_simplex(const double *base, size_t idx, int nverts, double (*s)[2])
+{
+    const double *p = base + idx * (size_t)(nverts * DIM);
+#pragma unroll
+    for (int k = 0; k < DIM + 1; k++)
+        if (k < nverts) {
+            s[k][0] = p[k * DIM];
+            s[k][1] = DIM == 2 ? p[k * DIM + 1] : 0.;
+        }
+}
+
+// ---------------------------------------------------------------------------
+// Regular element pair, lanes over the n x n tensor nodes
+// (eval_distant, nonlocalOperator_{SCALAR}.pxi:756-789).  acc[NL] in the
+// reference's flattened upper-triangular order; NOT yet multiplied by vol1*vol2.
+// ---------------------------------------------------------------------------
+template <int DIM>
+__device__ void lanes_regular_interior(const DProblem &P, int c1, int c2, int order, int lane, int nlanes, double *acc)
+{
+    constexpr int NV = PairDims<DIM>::NV, NL = PairDims<DIM>::NL;
+    double s1[3][2], s2[3][2];
+    load_simplex<DIM>(P.simplices, c1, NV, s1);
+    load_simplex<DIM>(P.simplices, c2, NV, s2);
+    const DRule r = P.reg_cell[order];
+    const int n = r.n;
+#pragma unroll
+    for (int k = 0; k < NL; k++) acc[k] = 0.;
+    for (int q = lane; q < n * n; q += nlanes) {
+        const int i = q / n, j = q - i * n;
+        double psi[2 * NV];
+        double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const double bx = r.bary[k * n + i], by = r.bary[k * n + j];
+            psi[k] = bx;
+            psi[NV + k] = -by;
+            x0 += bx * s1[k][0];
+            y0 += by * s2[k][0];
+            if (DIM == 2) {
+                x1 += bx * s1[k][1];
+                y1 += by * s2[k][1];
+            }
+        }
+        double d2 = (x0 - y0) * (x0 - y0);
+        if (DIM == 2) d2 += (x1 - y1) * (x1 - y1);
+        const double g = (r.w[i] * r.w[j]) * kernel_value(P.C, P.expo, d2);
+        int k = 0;
+#pragma unroll
+        for (int I = 0; I < 2 * NV; I++) {
+            const double t = g * psi[I];
+#pragma unroll
+            for (int J = I; J < 2 * NV; J++) acc[k++] += t * psi[J];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Singular element pair (fractionalLaplacian2D.pyx:851-891,
+// fractionalLaplacian1D.pyx:378-407).  acc holds the upper triangle of the
+// (2NV-1)x(2NV-1) matrix over the PSI rows (rows >= 2*NV-common are zero);
+// mapping to the reference's local indices through `perm` is done by the
+// caller.  NOT yet multiplied by the volume factor.
+// ---------------------------------------------------------------------------
+template <int DIM>
+__device__ void lanes_singular_interior(const DProblem &P, int c1, int c2, int panel, const int *perm1, const int *perm2,
+                                        int lane, int nlanes, double *acc)
+{
+    constexpr int NV = PairDims<DIM>::NV, NR = 2 * NV - 1, NA = NR * (NR + 1) / 2;
+    double s1[3][2], s2[3][2], t1[3][2], t2[3][2];
+    load_simplex<DIM>(P.simplices, c1, NV, t1);
+    load_simplex<DIM>(P.simplices, c2, NV, t2);
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+#pragma unroll
+        for (int m = 0; m < NV; m++) {
+            if (perm1[k] == m) { s1[k][0] = t1[m][0]; s1[k][1] = t1[m][1]; }
+            if (perm2[k] == m) { s2[k][0] = t2[m][0]; s2[k][1] = t2[m][1]; }
+        }
+    }
+    const int common = -panel;
+    DRule r;
+    if (DIM == 2) r = panel == -3 ? P.q_id : (panel == -2 ? P.q_edge : P.q_vertex);
+    else r = panel == -2 ? P.q_id : P.q_vertex;
+    const int n = r.n;
+#pragma unroll
+    for (int k = 0; k < NA; k++) acc[k] = 0.;
+    for (int q = lane; q < n; q += nlanes) {
+        double psi[NR];
+        double bx[NV], by[NV];
+        double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            bx[k] = r.bary[k * n + q];
+            by[k] = r.bary[(NV + k) * n + q];
+            x0 += s1[k][0] * bx[k];
+            y0 += s2[k][0] * by[k];
+            if (DIM == 2) {
+                x1 += s1[k][1] * bx[k];
+                y1 += s2[k][1] * by[k];
+            }
+        }
+        double d2 = (x0 - y0) * (x0 - y0);
+        if (DIM == 2) d2 += (x1 - y1) * (x1 - y1);
+        const double g = r.w[q] * kernel_value(P.C, P.expo, d2);
+        // PSI rows: shared dofs phi(x)-phi(y); then x-only; then y-only
+#pragma unroll
+        for (int k = 0; k < NR; k++) psi[k] = 0.;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            if (k < common) psi[k] = bx[k] - by[k];
+            else {
+                psi[k] = bx[k];
+#pragma unroll
+                for (int m = NV; m < NR; m++)
+                    if (m == NV + k - common) psi[m] = -by[k];
+            }
+        }
+        int k = 0;
+#pragma unroll
+        for (int I = 0; I < NR; I++) {
+            const double t = g * psi[I];
+#pragma unroll
+            for (int J = I; J < NR; J++) acc[k++] += t * psi[J];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Element x boundary facet.  Regular: eval_distant_boundary
+// (nonlocalOperator_{SCALAR}.pxi:1069-1108); singular: fractionalLaplacian2D.pyx:1356-1407,
+// fractionalLaplacian1D.pyx:753-781.  acc[ND] over the (permuted, if singular)
+// element dofs; NOT yet multiplied by the volume factor.
+// ---------------------------------------------------------------------------
+template <int DIM>
+__device__ void lanes_boundary(const DProblem &P, int c1, int f, int panel, const int *perm1, const int *perm2,
+                               int lane, int nlanes, double *acc)
+{
+    constexpr int NV = PairDims<DIM>::NV, ND = PairDims<DIM>::ND, NF = DIM;
+    double t1[3][2], t2[3][2];
+    load_simplex<DIM>(P.simplices, c1, NV, t1);
+    load_simplex<DIM>(P.bsimplices, f, NF, t2);
+    double nx = 0., ny = 0.;
+    if (DIM == 2) {
+        nx = t2[1][1] - t2[0][1];
+        ny = t2[0][0] - t2[1][0];
+        const double inv = 1. / sqrt(nx * nx + ny * ny);
+        nx *= inv;
+        ny *= inv;
+    }
+#pragma unroll
+    for (int k = 0; k < ND; k++) acc[k] = 0.;
+    if (panel >= 1) {
+        const DRule r0 = P.reg_cell[panel], r1 = P.reg_facet[panel];
+        const int n0 = r0.n, n1 = r1.n;
+        for (int q = lane; q < n0 * n1; q += nlanes) {
+            const int i = q / n1, m = q - i * n1;
+            double phi[NV];
+            double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                phi[k] = r0.bary[k * n0 + i];
+                x0 += phi[k] * t1[k][0];
+                if (DIM == 2) x1 += phi[k] * t1[k][1];
+            }
+#pragma unroll
+            for (int k = 0; k < NF; k++) {
+                const double b = r1.bary[k * n1 + m];
+                y0 += b * t2[k][0];
+                if (DIM == 2) y1 += b * t2[k][1];
+            }
+            double w0 = y0 - x0, w1 = y1 - x1;
+            double d2 = w0 * w0;
+            double nw = 1.;
+            if (DIM == 2) {
+                d2 += w1 * w1;
+                const double inv = 1. / sqrt(d2);
+                nw = nx * (w0 * inv) + ny * (w1 * inv);
+            }
+            const double g = (r0.w[i] * r1.w[m]) * nw * kernel_value(P.Cb, P.bexpo, d2);
+            int k = 0;
+#pragma unroll
+            for (int I = 0; I < NV; I++) {
+                const double t = g * phi[I];
+#pragma unroll
+                for (int J = I; J < NV; J++) acc[k++] += t * phi[J];
+            }
+        }
+    } else {
+        double s1[3][2], s2[3][2];
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+#pragma unroll
+            for (int m = 0; m < NV; m++) {
+                if (perm1[k] == m) { s1[k][0] = t1[m][0]; s1[k][1] = t1[m][1]; }
+                if (k < NF && m < NF && perm2[k] == m) { s2[k][0] = t2[m][0]; s2[k][1] = t2[m][1]; }
+            }
+        const DRule r = (DIM == 2 && panel == -2) ? P.bq_edge : P.bq_vertex;
+        const int n = r.n;
+        for (int q = lane; q < n; q += nlanes) {
+            double phi[NV];
+            double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                phi[k] = r.bary[k * n + q];
+                x0 += s1[k][0] * phi[k];
+                if (DIM == 2) x1 += s1[k][1] * phi[k];
+            }
+#pragma unroll
+            for (int k = 0; k < NF; k++) {
+                const double b = r.bary[(NV + k) * n + q];
+                y0 += s2[k][0] * b;
+                if (DIM == 2) y1 += s2[k][1] * b;
+            }
+            double w0 = x0 - y0, w1 = x1 - y1;
+            double d2 = w0 * w0;
+            double nw = 1.;
+            if (DIM == 2) {
+                d2 += w1 * w1;
+                const double inv = 1. / sqrt(d2);
+                nw = nx * (w0 * inv) + ny * (w1 * inv);
+            }
+            const double g = r.w[q] * nw * kernel_value(P.Cb, P.bexpo, d2);
+            int k = 0;
+#pragma unroll
+            for (int I = 0; I < NV; I++) {
+                const double t = g * phi[I];
+#pragma unroll
+                for (int J = I; J < NV; J++) acc[k++] += t * phi[J];
+            }
+        }
+    }
+}
+
+// fixed-shape butterfly: every lane ends with the same, order-independent-of-
+// scheduling sum
+template <int N> __device__ __forceinline__ void warp_allreduce(double *v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Far evaluator: regular 2D pair with an NQ-point triangle rule on each cell,
+// one thread per pair.  Factored form of nonlocalOperator_{SCALAR}.pxi:769-789:
+//   xx[I,I'] =  sum_i phi_I(x_i) phi_I'(x_i) r_i,   r_i = sum_j g_ij
+//   yy[J,J'] =  sum_j phi_J(y_j) phi_J'(y_j) c_j,   c_j = sum_i g_ij
+//   xy[I,J]  = -sum_i phi_I(x_i) sum_j g_ij phi_J(y_j)
+// with g_ij = w_i w_j gamma(x_i, y_j).  Outputs are NOT scaled by vol1*vol2.
+// ---------------------------------------------------------------------------
+struct FarRule {
+    int n;
+    double bary[3][8];
+    double w[8];
+};
+
+template <int NQ>
+__device__ __forceinline__ void far_eval_2d(const double (*s1)[2], const double (*s2)[2], const FarRule &R, double C,
+                                            double expo, double *xy, double *xx, double *yy)
+{
+    double Y[NQ][2], csum[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; j++) {
+        Y[j][0] = R.bary[0][j] * s2[0][0] + R.bary[1][j] * s2[1][0] + R.bary[2][j] * s2[2][0];
+        Y[j][1] = R.bary[0][j] * s2[0][1] + R.bary[1][j] * s2[1][1] + R.bary[2][j] * s2[2][1];
+        csum[j] = 0.;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) xy[k] = 0.;
+#pragma unroll
+    for (int k = 0; k < 6; k++) xx[k] = yy[k] = 0.;
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+        const double p0 = R.bary[0][i], p1 = R.bary[1][i], p2 = R.bary[2][i];
+        const double X0 = p0 * s1[0][0] + p1 * s1[1][0] + p2 * s1[2][0];
+        const double X1 = p0 * s1[0][1] + p1 * s1[1][1] + p2 * s1[2][1];
+        const double wi = R.w[i];
+        double r = 0., t0 = 0., t1 = 0., t2 = 0.;
+#pragma unroll
+        for (int j = 0; j < NQ; j++) {
+            const double a = X0 - Y[j][0], b = X1 - Y[j][1];
+            const double d2 = a * a + b * b;
+            const double g = (wi * R.w[j]) * kernel_value(C, expo, d2);
+            r += g;
+            csum[j] += g;
+            t0 += g * R.bary[0][j];
+            t1 += g * R.bary[1][j];
+            t2 += g * R.bary[2][j];
+        }
+        const double r0 = r * p0, r1 = r * p1, r2 = r * p2;
+        xx[0] += r0 * p0; xx[1] += r0 * p1; xx[2] += r0 * p2;
+        xx[3] += r1 * p1; xx[4] += r1 * p2; xx[5] += r2 * p2;
+        xy[0] -= p0 * t0; xy[1] -= p0 * t1; xy[2] -= p0 * t2;
+        xy[3] -= p1 * t0; xy[4] -= p1 * t1; xy[5] -= p1 * t2;
+        xy[6] -= p2 * t0; xy[7] -= p2 * t1; xy[8] -= p2 * t2;
+    }
+#pragma unroll
+    for (int j = 0; j < NQ; j++) {
+        const double q0 = R.bary[0][j], q1 = R.bary[1][j], q2 = R.bary[2][j];
+        const double c0 = csum[j] * q0, c1 = csum[j] * q1, c2 = csum[j] * q2;
+        yy[0] += c0 * q0; yy[1] += c0 * q1; yy[2] += c0 * q2;
+        yy[3] += c1 * q1; yy[4] += c1 * q2; yy[5] += c2 * q2;
+    }
+}

@@ -1,0 +1,151 @@
+"""Kernel objects of the nonlocal operators (user-facing drop-in).
+
+Mirrors the factories of nl/PyNucleus_nl/kernels.py:109-231 and the kernel
+classes of nl/PyNucleus_nl/kernelsCy.pyx:625-868 (Kernel), :1564-2027
+(FractionalKernel), the fractional orders of fractionalOrders.pyx:72-93 and the
+scaling constants of kernelNormalization.pyx:70-104.  The objects only carry
+parameters; the kernel VALUES on the hot path are evaluated on the GPU from
+the parameter block built by ``nonlocalBuilder`` (pnb_kernel_t).
+"""
+from math import pi, gamma
+
+import numpy as np
+
+FRACTIONAL = 0
+INDICATOR = 1
+PERIDYNAMIC = 2
+
+
+class constFractionalOrder:
+    """s(x,y) = const (fractionalOrders.pyx:72-93)"""
+    symmetric = True
+    numParameters = 1
+
+    def __init__(self, s):
+        self.value = float(s)
+        self.min = self.max = float(s)
+
+    def __call__(self, x, y):
+        return self.value
+
+    def __repr__(self):
+        return '{}'.format(self.value)
+
+
+class constant:
+    """constant function, used for the horizon (fem functions.pyx)"""
+
+    def __init__(self, value):
+        self.value = float(value)
+
+    def __call__(self, x):
+        return self.value
+
+
+def constantFractionalLaplacianScaling(dim, s, horizon, tempered=0.):
+    """C(d,s,delta)/2 (kernelNormalization.pyx:70-89)"""
+    if 1. < s < 2.:
+        s = s-1.
+    if horizon <= 0. or s <= 0. or s >= 1.:
+        return np.nan
+    if horizon < np.inf:
+        return (2.-2*s)*pow(horizon, 2*s-2.)*dim*gamma(0.5*dim)/pow(pi, 0.5*dim)*0.5
+    if tempered == 0. or s == 0.5:
+        return 2.0**(2.0*s)*s*gamma(s+0.5*dim)/pow(pi, 0.5*dim)/gamma(1.0-s)*0.5
+    return gamma(0.5*dim)/abs(gamma(-2*s))/pow(pi, 0.5*dim)*0.5*0.5
+
+
+class FractionalKernel:
+    """gamma(x,y) = C(d,s) |x-y|^{-d-2s}  (boundary form: |x-y|^{-(d-1)-2s})
+
+    Attribute names follow kernelsCy.pyx:1564-1640."""
+    kernelType = FRACTIONAL
+    valueSize = 1
+
+    def __init__(self, dim, s, horizon, scaling, boundary=False, phi=None, piecewise=True):
+        self.dim = int(dim)
+        self.s = s
+        self.horizon = horizon
+        self.boundary = boundary
+        self.piecewise = piecewise
+        self.phi = phi
+        self.scalingPrePhi = scaling
+        self.scalingValue = scaling if phi is None else phi*scaling
+        self.variableOrder = not isinstance(s, constFractionalOrder)
+        self.variableHorizon = False
+        self.variableScaling = False
+        self.variable = self.variableOrder
+        self.symmetric = bool(s.symmetric)
+        self.horizonValue = horizon.value
+        self.horizonValue2 = horizon.value**2
+        self.finiteHorizon = horizon.value != np.inf
+        self.complement = False
+        self.sValue = s.value
+        if not boundary:
+            self.singularityValue = -self.dim-2*self.sValue
+        else:
+            self.singularityValue = 1.-self.dim-2*self.sValue
+        self.min_singularity = self.max_singularity = self.singularityValue
+
+    def getModifiedKernel(self, s=None, horizon=None, scaling=None):
+        s = self.s if s is None else s
+        horizon = self.horizon if horizon is None else horizon
+        return getFractionalKernel(self.dim, s, horizon, scaling=scaling, piecewise=self.piecewise, boundary=self.boundary)
+
+    def getBoundaryKernel(self):
+        """kernel of the Gauss-theorem surface term, scaled by 1/s (kernelsCy.pyx:1982-2027)"""
+        return FractionalKernel(self.dim, self.s, self.horizon, self.scalingPrePhi, boundary=True,
+                                phi=1./self.s.value, piecewise=self.piecewise)
+
+    def __call__(self, x, y):
+        x = np.atleast_1d(np.asarray(x, dtype=float))
+        y = np.atleast_1d(np.asarray(y, dtype=float))
+        d2 = float(((x-y)**2).sum())
+        if self.finiteHorizon and d2 > self.horizonValue2:
+            return 0.
+        if not self.boundary:
+            return self.scalingValue*pow(d2, -0.5*self.dim-self.sValue)
+        return self.scalingValue*pow(d2, -0.5*(self.dim-1)-self.sValue)
+
+    def __repr__(self):
+        return 'kernel(fractional, s={}, horizon={}, scaling={}{})'.format(self.s, self.horizonValue, self.scalingValue,
+                                                                         ', boundary' if self.boundary else '')
+
+
+def _getFractionalOrder(s):
+    if isinstance(s, (int, float)):
+        return constFractionalOrder(s)
+    return s
+
+
+def _getHorizon(horizon):
+    if horizon is None:
+        return constant(np.inf)
+    if isinstance(horizon, (int, float)):
+        return constant(horizon)
+    return horizon
+
+
+def getFractionalKernel(dim, s, horizon=None, interaction=None, scaling=None, normalized=True, piecewise=True,
+                        phi=None, boundary=False, derivative=0, tempered=0., max_horizon=np.nan, manifold=False):
+    """kernels.py:109-165"""
+    dim = getattr(dim, 'dim', dim)
+    sFun = _getFractionalOrder(s)
+    horizonFun = _getHorizon(horizon)
+    if derivative != 0 or tempered != 0. or manifold:
+        raise NotImplementedError('derivative / tempered / manifold kernels are outside the accelerated path')
+    if not isinstance(sFun, constFractionalOrder):
+        raise NotImplementedError('variable fractional orders are not supported yet')
+    if scaling is None:
+        scaling = constantFractionalLaplacianScaling(dim, sFun.value, horizonFun.value, tempered) if normalized else 0.5
+    if boundary and phi is None:
+        phi = 1./sFun.value
+    return FractionalKernel(dim, sFun, horizonFun, scaling, boundary=boundary, phi=phi, piecewise=piecewise)
+
+
+def getKernel(dim, s=None, horizon=None, scaling=None, interaction=None, normalized=True, piecewise=True, phi=None,
+              kernel=FRACTIONAL, boundary=False, **kwargs):
+    """kernels.py:213-231"""
+    if kernel in (FRACTIONAL, 'fractional', 'FRACTIONAL'):
+        return getFractionalKernel(dim, s, horizon, interaction, scaling, normalized, piecewise, phi, boundary)
+    raise NotImplementedError('kernel type {} is not supported yet'.format(kernel))

@@ -1,0 +1,106 @@
+"""Operators returned by nonlocalBuilder.
+
+Dense_LinearOperator mirrors the surface of
+base/PyNucleus_base/DenseLinearOperator_{SCALAR}.pxi:8-93 and
+LinearOperator_{SCALAR}.pxi:38-324 that callers of the assembly path use
+(shape, num_rows/num_columns, matvec / __call__ / __mul__ / dot, toarray, data,
+diagonal, T, getMemorySize).  The entries live in HBM (a torch tensor is the
+allocation); ``matvec`` runs the hand-written FP64 kernel through
+``pnb_dense_matvec``.  ``data`` copies to host memory on first use.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Dense_LinearOperator:
+    def __init__(self, data, device_index=None):
+        if not isinstance(data, torch.Tensor):
+            raise TypeError('Dense_LinearOperator holds device memory; use from_numpy() for host arrays')
+        if not data.is_cuda or data.dtype != torch.float64 or data.dim() != 2 or data.stride(1) != 1:
+            raise ValueError('need a 2-D row-major float64 CUDA tensor')
+        self._A = data
+        self.device_index = data.device.index if device_index is None else device_index
+        self.num_rows, self.num_columns = int(data.shape[0]), int(data.shape[1])
+        self._host = None
+
+    @classmethod
+    def from_numpy(cls, array, device=0):
+        return cls(torch.as_tensor(np.ascontiguousarray(array, dtype=np.float64)).to('cuda:{}'.format(device)))
+
+    shape = property(lambda self: (self.num_rows, self.num_columns))
+    device_data = property(lambda self: self._A)
+
+    @property
+    def data(self):
+        if self._host is None:
+            self._host = self._A.cpu().numpy()
+        return self._host
+
+    def toarray(self):
+        return self.data
+
+    @property
+    def diagonal(self):
+        return torch.diagonal(self._A).cpu().numpy().copy()
+
+    @property
+    def T(self):
+        return Dense_LinearOperator(self._A.t().contiguous())
+
+    def isSparse(self):
+        return False
+
+    def getMemorySize(self):
+        return self._A.numel()*8
+
+    # ---- y = A x ---------------------------------------------------------
+    def matvec_device(self, x, y=None):
+        """x, y: float64 CUDA tensors on the operator's device"""
+        if y is None:
+            y = torch.empty(self.num_rows, dtype=torch.float64, device=self._A.device)
+        if x.shape[0] != self.num_columns or y.shape[0] != self.num_rows:
+            raise ValueError('shape mismatch')
+        stream = torch.cuda.current_stream(self._A.device).cuda_stream
+        _lib.check(_lib.lib().pnb_dense_matvec(self.device_index, self._A.data_ptr(), self.num_rows, self.num_columns,
+                                               self._A.stride(0), x.data_ptr(), y.data_ptr(), stream))
+        return y
+
+    def matvec(self, x, y=None):
+        """PyNucleus calling convention: A(x, y) / A.matvec(x, y) with host vectors"""
+        if isinstance(x, torch.Tensor):
+            return self.matvec_device(x, y)
+        xd = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(self._A.device)
+        yd = self.matvec_device(xd)
+        if y is None:
+            return yd.cpu().numpy()
+        y[:] = yd.cpu().numpy()
+        return y
+
+    __call__ = matvec
+
+    def dot(self, x):
+        return self.matvec(x)
+
+    def __mul__(self, x):
+        if np.isscalar(x):
+            return Dense_LinearOperator(self._A*x)
+        return self.matvec(x)
+
+    def __rmul__(self, x):
+        if np.isscalar(x):
+            return Dense_LinearOperator(self._A*x)
+        return NotImplemented
+
+    def __add__(self, other):
+        if isinstance(other, Dense_LinearOperator):
+            return Dense_LinearOperator(self._A+other._A)
+        return NotImplemented
+
+    def toLinearOperator(self):
+        from scipy.sparse.linalg import LinearOperator
+        return LinearOperator(shape=self.shape, matvec=lambda x: self.matvec(x), dtype=np.float64)
+
+    def __repr__(self):
+        return '<{}x{} Dense_LinearOperator on cuda:{}>'.format(self.num_rows, self.num_columns, self.device_index)

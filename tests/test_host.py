@@ -1,0 +1,140 @@
+"""CPU-side tests: C ABI loads and exports what include/pnb200.h declares, the
+host-side mirror (tables, meshes, DoFMap, kernels) agrees with the oracle and
+with the reference goldens, and the product fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pynucleus_b200 as pb
+from pynucleus_b200 import _lib, quadrature
+from oracle import tables, meshes
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    return _lib.lib()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, 'include', 'pnb200.h')).read()
+    declared = set(re.findall(r'\b(pnb_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.pnb_version() >= 100
+    assert lib.pnb_far_max_order() == 5
+
+
+def test_no_cpu_fallback(lib):
+    """without a CUDA device every compute entry point fails with PNB_ERR_NO_DEVICE"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    mesh = pb.refined(pb.uniform_disc(), 1)
+    dm = pb.P1_DoFMap(mesh)
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'target_order': 0.5})
+    with pytest.raises(RuntimeError):
+        b.getDense()
+    y = ctypes.c_double()
+    assert lib.pnb_fp64_peak(0, ctypes.byref(y)) == -1
+    assert b'no CUDA device' in lib.pnb_last_error()
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'pynucleus_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+                assert 'liboracle' not in src
+
+
+@pytest.mark.parametrize('dim,s,hmin,diam,N', [(2, 0.75, 0.05, 2.8, 3000), (2, 0.25, 0.1, 2.8, 300),
+                                               (1, 0.25, 0.03, 2., 63), (1, 0.75, 0.06, 2., 31)])
+def test_tables_match_oracle(dim, s, hmin, diam, N):
+    H0 = diam/np.sqrt(8)
+    sing, bs = -dim-2*s, 1-dim-2*s
+    to = 0.5 if dim == 2 else None
+    o = quadrature.localMatrixOrders(dim, sing, bs, hmin, H0, N, to)
+    oo = tables.diag_orders(dim, sing, bs, hmin, H0, N, to)
+    assert (o.quad_order_diagonal, o.bquad_order_diagonal, o.target_order, o.btarget_order) == \
+        (oo['qod'], oo['b_qod'], oo['target_order'], oo['b_target_order'])
+    T = quadrature.singular_tables(dim, sing, bs, o)
+    R = tables.near_rules(dim, sing, bs, oo)
+    names = {'identical': ('interior', -3 if dim == 2 else -2), 'edge': ('interior', -2), 'vertex': ('interior', -1),
+             'bedge': ('boundary', -2), 'bvertex': ('boundary', -1)}
+    for k, (b, w) in T.items():
+        bb, ww = R[names[k]]
+        assert np.array_equal(b, bb)
+        assert np.allclose(w, ww, rtol=1e-15, atol=0)
+
+
+def test_regular_rules_match_oracle_and_are_exact():
+    from oracle.triangle_rules import check_exactness
+    for p in range(1, 25):
+        for md in (0, 1, 2):
+            b, w = quadrature.regular(p, md)
+            bb, ww = tables.regular_rule(p, md)
+            assert np.array_equal(b, bb) and np.array_equal(w, ww)
+        b, w = quadrature.regular(p, 2)
+        assert check_exactness(b, w, p) < 5e-15
+        assert w.min() > 0 and b.min() > 0 and abs(w.sum()-1) < 1e-14
+
+
+def test_meshes_match_reference(golden_dir):
+    for r in (0, 4):
+        g = np.load(os.path.join(golden_dir, 'disc_mesh_r%d.npz' % r))
+        m = pb.refined(pb.uniform_disc(), r)
+        assert np.array_equal(m.cells, g['cells'])
+        assert np.abs(m.vertices-g['vertices']).max() < 1e-15
+        assert np.array_equal(m.boundaryFacets, g['boundaryEdges'])
+        dm = pb.P1_DoFMap(m)
+        assert dm.num_dofs == int(g['num_dofs'])
+        assert np.array_equal(np.where(dm.dofs >= 0, dm.dofs, -1), np.where(g['dofs'] >= 0, g['dofs'], -1))
+        assert np.allclose(m.hVector, g['hVector'], rtol=1e-14)
+        assert np.allclose(m.volVector, g['volVector'], rtol=1e-13)
+        assert abs(m.diam-float(g['diam'])) < 1e-15
+    g = np.load(os.path.join(golden_dir, 'interval_s0.25_r6.npz'))
+    m = pb.refined(pb.simpleInterval(-1., 1.), 6)
+    assert np.array_equal(m.cells, g['cells']) and np.array_equal(m.vertices, g['vertices'])
+    assert pb.P1_DoFMap(m).num_dofs == 63
+
+
+def test_dof_counts_of_the_bench_meshes():
+    # N = 1 + nc/2 - 3*2^r
+    for r, N in ((5, 2977), (6, 12097)):
+        m = pb.refined(pb.uniform_disc(), r)
+        assert m.num_cells == 6*4**r
+        assert pb.P1_DoFMap(m).num_dofs == N
+
+
+def test_kernel_values_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'kernel_values.npz'))
+    for dim in (1, 2):
+        for s in (0.25, 0.75):
+            k = pb.getFractionalKernel(dim, s)
+            kb = k.getBoundaryKernel()
+            assert np.isclose(k.scalingValue, float(g['C_%dd_s%g' % (dim, s)]), rtol=1e-15)
+            assert np.isclose(kb.scalingValue, float(g['Cb_%dd_s%g' % (dim, s)]), rtol=1e-15)
+            assert k.singularityValue == -dim-2*s and kb.singularityValue == 1-dim-2*s
+            x, y = g['x_%dd' % dim], g['y_%dd' % dim]
+            assert np.allclose([k(a, b) for a, b in zip(x, y)], g['k_%dd_s%g' % (dim, s)], rtol=1e-14)
+            assert np.allclose([kb(a, b) for a, b in zip(x, y)], g['kb_%dd_s%g' % (dim, s)], rtol=1e-14)
+
+
+def test_builder_argument_checks():
+    mesh = pb.refined(pb.uniform_disc(), 1)
+    dm = pb.P1_DoFMap(mesh)
+    with pytest.raises(AssertionError):
+        pb.nonlocalBuilder(dm, pb.getFractionalKernel(1, 0.75), {})
+    with pytest.raises(AssertionError):
+        pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'quadType': 'general'})
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'target_order': 0.5})
+    assert b.zeroExterior and b.orders.quad_order_diagonal >= 4
