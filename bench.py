@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the nonlocal dense assembly hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU assembly on the host cores
+
+A step = one full getDense() of the 2D fractional Laplacian (s=0.75, P1,
+infinite horizon, zero exterior) on a synthetic disc mesh.  One JSON line is
+printed by rank 0.  See DESIGN.md (Measurement) for how every field is formed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'matrix entries assembled/sec (2D frac. Laplacian P1, FP64)'
+UNIT = 'entries/s'
+S_ORDER = 0.75
+TARGET_ORDER = 0.5
+
+# workload: name -> (polygon sides, refinements).  N = 1 + nc/2 - sides*2^r/2
+WORKLOADS = {
+    'disc20k': (10, 6),    # 40 960 cells, 20 161 DoFs, 3.25 GB   (BASELINE.json configs[1])
+    'disc12k': (6, 6),     # hexagon r=6: 24 576 cells, 12 097 DoFs
+    'disc49k': (6, 7),     # hexagon r=7: 98 304 cells, 48 769 DoFs, 19 GB
+    'disc3k': (6, 5),      # hexagon r=5: 2 977 DoFs
+    'disc105k': (13, 7),   # 212 992 cells, ~105.7k DoFs, 89 GB
+}
+
+
+def make_mesh(workload):
+    import pynucleus_b200 as pb
+    sides, noRef = WORKLOADS[workload]
+    mesh = pb.refined(pb.polygon_disc(sides), noRef)
+    dm = pb.P1_DoFMap(mesh)
+    return mesh, dm
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu=0):
+        self.gpu = gpu
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu='+self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(', '))
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.strip() == 'Active':
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------
+# algorithmic work
+# --------------------------------------------------------------------------
+def algorithmic_flops(hist, builder):
+    """sum over the panel histogram of nq * (F_map + 7 + 3*ne) FP64 flops; pow counted separately"""
+    from pynucleus_b200 import quadrature
+    sing = builder.problem.singular
+    flops = 0.
+    pows = 0.
+    for panel, count in hist.items():
+        if panel >= 1:
+            n = quadrature.regular(panel, 2)[1].shape[0]
+            nq, per = n*n, 70.
+        elif panel == -3:
+            nq, per = sing['identical'][1].shape[0], 24+7+3*6
+        elif panel == -2:
+            nq, per = sing['edge'][1].shape[0], 24+7+3*10
+        elif panel == -1:
+            nq, per = sing['vertex'][1].shape[0], 24+7+3*15
+        else:
+            continue
+        flops += count*nq*per
+        pows += count*nq
+    return flops, pows
+
+
+# --------------------------------------------------------------------------
+# CPU reference arm: the reference's own getDense on the host cores
+# --------------------------------------------------------------------------
+def _ref_worker(args):
+    workload, rank, size = args
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', '_ref'))
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    import numpy as np
+    from mpi4py import MPI
+    from PyNucleus_fem.mesh import mesh2d
+    from PyNucleus_fem.DoFMaps import P1_DoFMap
+    from PyNucleus_nl.kernels import getFractionalKernel
+    from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder
+    from PyNucleus_nl.fractionalOrders import constFractionalOrder
+    mesh0, _ = make_mesh(workload)
+    mesh = mesh2d(mesh0.vertices.copy(), mesh0.cells.copy())
+    dm = P1_DoFMap(mesh)
+    kernel = getFractionalKernel(2, constFractionalOrder(S_ORDER), np.inf)
+    comm = MPI.fakeComm(rank, size)
+    b = nonlocalBuilder(dm, kernel, {'target_order': TARGET_ORDER}, comm=comm)
+    nc = mesh.num_cells
+    start, end = int(np.ceil(nc*rank/size)), int(np.ceil(nc*(rank+1)/size))
+    pairs = sum(nc-c for c in range(start, end))
+    t = time.time()
+    b.getDense()
+    t = time.time()-t
+    return pairs, t, dm.num_dofs, nc
+
+
+def reference_throughput(workload, target_seconds=15., cores=None):
+    """entries/s of the reference's Cython getDense on `cores` host processes, each assembling one rank slice of
+    a `size`-rank cell partition of the SAME mesh (nonlocalAssembly_{SCALAR}.pxi:1280-1285)"""
+    import multiprocessing as mp
+    if not os.path.isdir(os.path.join(ROOT, 'oracle', '_ref', 'PyNucleus_nl')):
+        return None
+    cores = cores or len(os.sched_getaffinity(0))
+    sides, noRef = WORKLOADS[workload]
+    nc = sides*4**noRef
+    per_pair = 2.5e-6     # s per cell pair of the reference on one core (measured: ~2.2 us here)
+    size = max(cores, int(np.ceil(nc*(nc+1)/2*per_pair/target_seconds)))
+    ranks = [int(i*size/cores) for i in range(cores)]
+    ctx = mp.get_context('spawn')
+    t0 = time.time()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(workload, r, size) for r in ranks])
+    wall = time.time()-t0
+    pairs = sum(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    N, nc = res[0][2], res[0][3]
+    entries_per_pair = N*N/(nc*(nc+1)/2.)
+    return {'value': pairs*entries_per_pair/tmax, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+            'sample': '{} of {} rank slices (ranks i*{}//{}) of the reference cell partition of the same mesh '
+                      '({} of {} cell pairs); slowest slice {:.1f} s, wall {:.1f} s incl. import/mesh'.format(
+                          cores, size, size, cores, pairs, nc*(nc+1)//2, tmax, wall),
+            'seconds': tmax}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals = []
+    last = None
+    for _ in range(args.warmup_ref+args.steps_ref):
+        last = reference_throughput(args.workload, target_seconds=args.ref_seconds)
+        if last is None:
+            print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref (stub-built reference) is missing'}))
+            return
+        vals.append(last)
+    vals = vals[args.warmup_ref:]
+    v = float(np.mean([x['value'] for x in vals]))
+    mesh, dm = make_mesh(args.workload)
+    N = dm.num_dofs
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps_ref, 'warmup': args.warmup_ref, 'ms_per_step': 1e3*N*N/v, 'higher_is_better': True,
+            'scaling': 'weak' if args.gpus > 1 else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': '{}: 2D disc, s=0.75, P1, dense, N={} ({} cells)'.format(args.workload, N, mesh.num_cells),
+                       'note': 'CPU: reference Cython getDense (stub-built, oracle/_ref); ms_per_step extrapolated from '
+                               'the sampled slices to the full matrix'},
+            'cpu_baseline': dict(last, value=v),
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    import pynucleus_b200 as pb
+    from pynucleus_b200 import _lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+
+    mesh, dm = make_mesh(args.workload)
+    N = dm.num_dofs
+    kernel = pb.getFractionalKernel(2, S_ORDER)
+    params = {'target_order': TARGET_ORDER, 'device': local_rank}
+    builder = pb.nonlocalBuilder(dm, kernel, params)
+    if world > 1:
+        raise NotImplementedError('row-sharded multi-GPU assembly: see bench_sharded in a later commit')
+
+    A = torch.empty((N, N), dtype=torch.float64, device=dev)
+    flush = torch.empty(64*1024*1024, dtype=torch.float64, device=dev)   # 512 MB > L2
+    peak = 0.
+    pk = np.zeros(1)
+    _lib.check(_lib.lib().pnb_fp64_peak(local_rank, pk.ctypes.data_as(_lib.c_double_p)))
+    peak = float(pk[0])
+
+    def step():
+        builder.getDense(out=A)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    tile_ms, launches = [], 0
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+        torch.cuda.synchronize()
+        st = builder.getStats()
+        tile_ms.append(st['ms_tiles'])
+        launches += st['launches']
+    clocks = sampler.stop()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    ms_step = float(np.mean(ms))
+    st = builder.getStats()
+    value = N*float(N)/(ms_step*1e-3)
+
+    # end to end through the host-buffer C entry point: problem upload + assembly + copy back, every step
+    host = torch.empty((N, N), dtype=torch.float64).pin_memory()
+    hA = host.numpy()
+    e2e_ms = []
+    h2d = (mesh.vertices.nbytes+mesh.cells.nbytes+dm.dofs.nbytes+mesh.volVector.nbytes+mesh.hVector.nbytes
+           + mesh.boundaryFacets.nbytes)
+    for k in range(max(1, min(args.steps, 3))+1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b2 = pb.nonlocalBuilder(dm, kernel, params)
+        b2.getDenseHost(out=hA)
+        checksum = float(hA[0, 0])
+        e2e_ms.append((time.perf_counter()-t0)*1e3)
+        del b2
+    e2e_ms = e2e_ms[1:]
+    e2e_value = N*float(N)/(float(np.mean(e2e_ms))*1e-3)
+
+    # roofline of the dominant kernel (tile kernel): algorithmic FP64 flops / measured device time
+    hist = builder.getPanelHistogram()
+    flops, pows = algorithmic_flops(hist, builder)
+    t_tile = float(np.mean(tile_ms))*1e-3
+    achieved = flops/t_tile/1e12
+    roofline = {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved/peak if peak else None,
+                'traffic': None,
+                'note': 'algorithmic flops (SURVEY 8d: 70/node-pair regular, 49/61/76 singular; pow excluded) of all '
+                        'distinct cell pairs / tile-kernel time; peak = DFMA microbenchmark run in this process; '
+                        'pow evaluations/s = {:.3e}; tile-halo redundancy {:.3f}x; kernel share of step {:.3f}'.format(
+                            pows/t_tile, st['evaluated_pairs']/max(st['distinct_pairs'], 1), t_tile*1e3/ms_step)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = reference_throughput(args.workload, target_seconds=args.ref_seconds)
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': '{}: 2D disc ({}-gon fan, {} radial refinements), s={}, P1, infinite horizon, zero exterior, '
+                                   'dense, N={} ({} cells), target_order={}'.format(args.workload, WORKLOADS[args.workload][0],
+                                                                                  WORKLOADS[args.workload][1], S_ORDER, N,
+                                                                                  mesh.num_cells, TARGET_ORDER),
+                       'l2': 'output ({:.2f} GB/step) exceeds L2; 512 MB flush written between steps (untimed)'.format(N*N*8/1e9),
+                       'parallelism': 'single GPU' if world == 1 else 'row blocks x{}'.format(world)},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(N*N*8),
+                    'ms_per_step': float(np.mean(e2e_ms)), 'checksum_A00': checksum},
+            'gpu_launches': int(launches),
+            'roofline': roofline,
+            'cpu_baseline': cpu,
+            'phases_ms': {'tiles': st['ms_tiles'], 'boundary': st['ms_boundary'], 'reduce_scatter': st['ms_reduce_scatter']},
+            'pairs': {'distinct': st['distinct_pairs'], 'evaluated': st['evaluated_pairs']}}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
+    ap.add_argument('--workload', default='disc20k', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-seconds', type=float, default=15.)
+    args = ap.parse_args()
+    # the reference arm is bounded: a few sampled slices per step
+    args.steps_ref = min(args.steps, 2)
+    args.warmup_ref = min(args.warmup, 0)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == '__main__':
+    main()

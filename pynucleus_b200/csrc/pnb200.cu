@@ -819,7 +819,9 @@ __global__ void __launch_bounds__(PNB_THREADS) tile_kernel(DProblem P, TileSched
                     // ---- phase 3: fold cross blocks into the tile, fixed order ----
                     for (int e = tid; e < TD * TD; e += PNB_THREADS) {
                         const int a = e / TD, b = e - a * TD;
-                        double sum = 0.;
+                        // direct and mirrored parts are summed separately so that acc[a][b] and acc[b][a]
+                        // of a diagonal tile are bitwise equal (sd+sm == sm+sd)
+                        double sum = 0., summ = 0.;
                         bool hit = false;
                         unsigned long long ra = sm.rmask[a], cm = sm.cmask[b];
                         if (ra && cm) {
@@ -850,11 +852,12 @@ __global__ void __launch_bounds__(PNB_THREADS) tile_kernel(DProblem P, TileSched
                                         const int v = __ffsll((long long)c) - 1;
                                         c &= c - 1;
                                         const int kk2 = v / NV, j = v - kk2 * NV;
-                                        sum += sm.B[kk1 * SB + kk2][i * NV + j];
+                                        summ += sm.B[kk1 * SB + kk2][i * NV + j];
                                     }
                                 }
                             }
                         }
+                        sum += summ;
                         if (hit) sm.acc[a][b] += sum;
                     }
                     // ---- cell-diagonal blocks: reduce over the batch, stage per (group, cell) ----
