@@ -70,7 +70,11 @@ struct TileSched {
     const int *dof_ptr;     // N+1: dof -> incident cells
     const int *dof_cells;   // packed (cell*4 + local index)
     int *err;               // [0]: max order requested beyond tables
-    unsigned long long *counters;  // [0] evaluated pairs
+    unsigned long long *counters;  // [0] evaluated pairs (far pass), [1] evaluated pairs (near pass)
+    int maxcells;           // largest cell list of a tile
+    int *tileflag;          // ntiles x ntiles: tile holds pairs for the near pass
+    int *unitflag;          // nunits: unit holds flagged tiles
+    int *nearunits;         // compacted list of flagged units, [nunits] = count
 };
 
 struct DevBuf {
@@ -85,6 +89,7 @@ struct pnb_problem {
     std::vector<void *> allocs;       // everything to free
     std::vector<void *> rule_allocs;  // regular tables (replaced by set_rules)
     FarRule far_rules[PNB_FAR_MAX_ORDER + 1];
+    int far_mask = 0;   // bit o set: order o is handled by the thread-per-pair evaluator
     int64_t stats[8] = {0};
     double timings[4] = {0};
     int64_t distinct_pairs = 0;
@@ -127,7 +132,21 @@ static int upload_rule(pnb_problem *p, const pnb_rule_t &r, DRule *out, bool rul
     return 0;
 }
 
-__constant__ FarRule c_far[PNB_FAR_MAX_ORDER + 1];
+
+// host side of PowTab (see pnb_device.cuh); long double keeps the table entries correctly rounded
+static void build_powtab(PowTab *t, double scal, double expo)
+{
+    t->scal = scal;
+    t->expo = expo;
+    t->coef[0] = 1.;
+    for (int k = 1; k < 8; k++) t->coef[k] = t->coef[k - 1] * (expo - k + 1) / k;
+    for (int i = 0; i < 128; i++) {
+        t->IT[i].x = 1.0 / (1.0 + (i + 0.5) / 128.0);
+        const long double m0 = 1.0L / (long double)t->IT[i].x;
+        t->IT[i].y = (double)powl(m0, (long double)expo);
+    }
+    for (int k = 0; k < 256; k++) t->T1[k] = (double)((long double)scal * exp2l((long double)expo * (long double)(k - PNB_POW_EOFF)));
+}
 
 extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
 {
@@ -157,18 +176,28 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
     if (upload(p, cell.data(), (size_t)mo + 1, &p->P.reg_cell, true)) return PNB_ERR_CUDA;
     if (upload(p, facet.data(), (size_t)mo + 1, &p->P.reg_facet, true)) return PNB_ERR_CUDA;
     p->P.max_order = mo;
-    // low-order 2D rules for the thread-per-pair evaluator
+    // low-order 2D rules for the thread-per-pair evaluator (orders 2..5, node counts fixed at compile time)
     memset(p->far_rules, 0, sizeof(p->far_rules));
+    p->far_mask = 0;
     if (p->dim == 2)
-        for (int o = 1; o <= std::min(mo, PNB_FAR_MAX_ORDER); o++) {
+        for (int o = 2; o <= std::min(mo, PNB_FAR_MAX_ORDER); o++) {
             const pnb_rule_t &r = rules->cell[o];
-            if (r.n > 8) continue;
-            p->far_rules[o].n = r.n;
-            for (int k = 0; k < 3; k++)
-                for (int i = 0; i < r.n; i++) p->far_rules[o].bary[k][i] = r.bary[k * r.n + i];
-            for (int i = 0; i < r.n; i++) p->far_rules[o].w[i] = r.w[i];
+            if (r.n != far_expected_nodes(o)) continue;
+            FarRule &F = p->far_rules[o];
+            F.n = r.n;
+            for (int i = 0; i < r.n; i++) {
+                F.w[i] = r.w[i];
+                for (int k = 0; k < 3; k++) {
+                    F.bary[k][i] = r.bary[k * r.n + i];
+                    F.wb[k][i] = r.w[i] * r.bary[k * r.n + i];
+                }
+                int e = 0;
+                for (int a = 0; a < 3; a++)
+                    for (int b = a; b < 3; b++) F.qq[e++][i] = r.w[i] * r.bary[a * r.n + i] * r.bary[b * r.n + i];
+            }
+            p->far_mask |= 1 << o;
         }
-    CK(cudaMemcpyToSymbol(c_far, p->far_rules, sizeof(p->far_rules)));
+    if (upload(p, p->far_rules, (size_t)PNB_FAR_MAX_ORDER + 1, &p->P.far_rules, true)) return PNB_ERR_CUDA;
     return 0;
 }
 
@@ -268,6 +297,26 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     rc |= upload(p, bh.data(), (size_t)nb, &P.bh);
     if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
 
+    // table-driven power for both kernels, per-cell logs for the fast order selection
+    {
+        PowTab tabs[2];
+        const double scal[2] = {kernel->scaling, kernel->bscaling};
+        const double expo[2] = {-0.5 * dim - kernel->s, -0.5 * (dim - 1) - kernel->s};
+        for (int t = 0; t < 2; t++) build_powtab(&tabs[t], scal[t], expo[t]);
+        const PowTab *dt = nullptr;
+        rc |= upload(p, tabs, 2, &dt);
+        P.pow_int = dt;
+        P.pow_bnd = dt + 1;
+        std::vector<float> lhf(nc), ahf(nc);
+        const double H0 = mesh->diam / sqrt(8.);
+        for (int c = 0; c < nc; c++) {
+            lhf[c] = (float)log(mesh->h[c]);
+            ahf[c] = (float)fabs(log(mesh->h[c] / H0));
+        }
+        rc |= upload(p, lhf.data(), (size_t)nc, &P.lhf);
+        rc |= upload(p, ahf.data(), (size_t)nc, &P.ahf);
+        if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
+    }
     P.s = kernel->s; P.C = kernel->scaling; P.Cb = kernel->bscaling;
     P.sing = kernel->singularity; P.bsing = kernel->bsingularity;
     P.expo = -0.5 * dim - kernel->s;            // kernelsCy.pyx:159-183
@@ -285,7 +334,7 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     TileSched &S = p->S;
     const int TD = PNB_TD;
     S.ntiles = std::max(1, (N + TD - 1) / TD);
-    S.G = 4;
+    S.G = 2;
     S.ngroups = (S.ntiles + S.G - 1) / S.G;
     std::vector<int> home(nc);
     std::vector<std::vector<int>> tcells(S.ntiles);
@@ -316,21 +365,52 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         const int64_t dead = nc - live;
         p->distinct_pairs = (int64_t)nc * (nc + 1) / 2 - dead * (dead + 1) / 2;
     }
+    // Cell lists are cut into batches of PNB_SB cells that share NO vertex.  The cross blocks of the pairs of
+    // (row batch) x (column batch) then hit pairwise distinct tile entries, so that they can be added to the
+    // shared-memory tile straight from registers without conflicts (and in an order that is fixed by the schedule).
     std::vector<int> tptr(S.ntiles + 1, 0), tlist, tloc;
-    for (int t = 0; t < S.ntiles; t++) {
-        tptr[t + 1] = tptr[t] + (int)tcells[t].size();
-        for (int c : tcells[t]) {
-            tlist.push_back(c);
-            int packed = 0;
-            for (int m = 0; m < 3; m++) {
-                int l = 0xFF;
-                if (m < nvc) {
-                    const int d = dm->dofs[(size_t)c * nvc + m];
-                    if (d >= 0 && d / TD == t) l = d - t * TD;
+    {
+        std::vector<std::vector<int>> bcells;      // batches of the current tile
+        std::vector<std::vector<int>> bverts;
+        for (int t = 0; t < S.ntiles; t++) {
+            bcells.clear();
+            bverts.clear();
+            size_t first_open = 0;
+            for (int c : tcells[t]) {
+                const int *v = mesh->cells + (size_t)c * nvc;
+                size_t b = first_open;
+                for (; b < bcells.size(); b++) {
+                    if ((int)bcells[b].size() >= PNB_SB) continue;
+                    bool clash = false;
+                    for (int x : bverts[b])
+                        for (int m = 0; m < nvc; m++) clash |= x == v[m];
+                    if (!clash) break;
                 }
-                packed |= l << (8 * m);
+                if (b == bcells.size()) { bcells.emplace_back(); bverts.emplace_back(); }
+                bcells[b].push_back(c);
+                for (int m = 0; m < nvc; m++) bverts[b].push_back(v[m]);
+                while (first_open < bcells.size() && (int)bcells[first_open].size() >= PNB_SB) first_open++;
             }
-            tloc.push_back(packed);
+            for (auto &bc : bcells) {
+                for (int k = 0; k < PNB_SB; k++) {
+                    const int c = k < (int)bc.size() ? bc[k] : -1;
+                    tlist.push_back(c);
+                    int packed = 0x00FFFFFF;
+                    if (c >= 0) {
+                        packed = 0;
+                        for (int m = 0; m < 3; m++) {
+                            int l = 0xFF;
+                            if (m < nvc) {
+                                const int d = dm->dofs[(size_t)c * nvc + m];
+                                if (d >= 0 && d / TD == t) l = d - t * TD;
+                            }
+                            packed |= l << (8 * m);
+                        }
+                    }
+                    tloc.push_back(packed);
+                }
+            }
+            tptr[t + 1] = (int)tlist.size();
         }
     }
     std::vector<int> units;
@@ -363,6 +443,11 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     rc |= dalloc(p, (size_t)nc * ND, &S.D);
     rc |= dalloc(p, 4, &S.err);
     rc |= dalloc(p, 8, &S.counters);
+    S.maxcells = PNB_SB;
+    for (int t = 0; t < S.ntiles; t++) S.maxcells = std::max(S.maxcells, tptr[t + 1] - tptr[t]);
+    rc |= dalloc(p, (size_t)S.ntiles * S.ntiles, &S.tileflag);
+    rc |= dalloc(p, (size_t)S.nunits, &S.unitflag);
+    rc |= dalloc(p, (size_t)S.nunits + 1, &S.nearunits);
     if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
     rc = pnb_problem_set_rules(p, rules);
     if (rc) { pnb_problem_destroy(p); return rc; }
@@ -491,8 +576,8 @@ __device__ __forceinline__ void singular_to_local(const double *acc, int lane, i
 }
 
 template <int DIM>
-__global__ void local_matrices_kernel(DProblem P, int boundary, int path, int64_t np, const int *pairs, int *panel_out,
-                                      double *contrib, int *err)
+__global__ void local_matrices_kernel(DProblem P, int boundary, int path, int far_mask, int64_t np, const int *pairs,
+                                      int *panel_out, double *contrib, int *err)
 {
     constexpr int NV = PairDims<DIM>::NV, NL = PairDims<DIM>::NL, ND = PairDims<DIM>::ND;
     const int lane = threadIdx.x & 31;
@@ -538,17 +623,13 @@ __global__ void local_matrices_kernel(DProblem P, int boundary, int path, int64_
     if (pan > P.max_order) { if (lane == 0) atomicMax(err, pan); return; }
     if (pan >= 1) {
         const double vol = P.vol[a] * P.vol[b];
-        if (path == 1 && DIM == 2 && pan <= PNB_FAR_MAX_ORDER && c_far[pan].n > 0) {
+        if (path == 1 && DIM == 2 && pan >= 2 && pan <= PNB_FAR_MAX_ORDER && ((far_mask >> pan) & 1)) {
             if (lane == 0) {
                 double s1[3][2], s2[3][2], xy[9], xx[6], yy[6];
                 load_simplex<2>(P.simplices, a, 3, s1);
                 load_simplex<2>(P.simplices, b, 3, s2);
-                const int nq = c_far[pan].n;
-                if (nq == 3) far_eval_2d<3>(s1, s2, c_far[pan], P.C, P.expo, xy, xx, yy);
-                else if (nq == 6) far_eval_2d<6>(s1, s2, c_far[pan], P.C, P.expo, xy, xx, yy);
-                else if (nq == 7) far_eval_2d<7>(s1, s2, c_far[pan], P.C, P.expo, xy, xx, yy);
-                else if (nq == 1) far_eval_2d<1>(s1, s2, c_far[pan], P.C, P.expo, xy, xx, yy);
-                else { atomicMax(err, 100000 + pan); return; }
+                const PowCtx kv(P.pow_int);
+                far_eval_2d(P.far_rules[pan], s1, s2, kv, true, xy, xx, yy);
                 for (int I = 0; I < 3; I++)
                     for (int J = I; J < 3; J++) {
                         out[tri_idx(6, I, J)] = xx[tri_idx(3, I, J)] * vol;
@@ -595,8 +676,8 @@ extern "C" int pnb_local_matrices(pnb_problem *p, int boundary, int path, int64_
         cudaMemcpy(dpairs, pairs, (size_t)npairs * 2 * sizeof(int), cudaMemcpyHostToDevice);
         cudaMemset(p->S.err, 0, 4 * sizeof(int));
         const unsigned blocks = (unsigned)((npairs * 32 + 255) / 256);
-        if (p->dim == 2) local_matrices_kernel<2><<<blocks, 256>>>(p->P, boundary, path, npairs, dpairs, dpanel, dc, p->S.err);
-        else local_matrices_kernel<1><<<blocks, 256>>>(p->P, boundary, path, npairs, dpairs, dpanel, dc, p->S.err);
+        if (p->dim == 2) local_matrices_kernel<2><<<blocks, 256>>>(p->P, boundary, path, p->far_mask, npairs, dpairs, dpanel, dc, p->S.err);
+        else local_matrices_kernel<1><<<blocks, 256>>>(p->P, boundary, path, 0, npairs, dpairs, dpanel, dc, p->S.err);
         cudaError_t e = cudaGetLastError();
         int herr[4] = {0, 0, 0, 0};
         if (e == cudaSuccess) e = cudaMemcpy(herr, p->S.err, 4 * sizeof(int), cudaMemcpyDeviceToHost);
@@ -612,293 +693,498 @@ extern "C" int pnb_local_matrices(pnb_problem *p, int boundary, int path, int64_
 // ---------------------------------------------------------------------------
 // dense assembly: tile kernel
 // ---------------------------------------------------------------------------
-template <int DIM> struct TileSmem {
-    static constexpr int NV = PairDims<DIM>::NV, NX = PairDims<DIM>::NX, ND = PairDims<DIM>::ND;
-    double acc[PNB_TD][PNB_TD + 1];
-    double B[PNB_SB * PNB_SB][NX];
-    double dxy[PNB_SB * PNB_SB][2 * ND];
-    unsigned long long rmask[PNB_TD], cmask[PNB_TD];
-    int rcell[PNB_SB], ccell[PNB_SB];
-    int rloc[PNB_SB], cloc[PNB_SB];   // packed
-    int rhome[PNB_SB], chome[PNB_SB];
-    int nearlist[PNB_SB * PNB_SB];
-    int nearpanel[PNB_SB * PNB_SB];
-    int warpcnt[PNB_THREADS / 32];
-    int nnear;
+// cell data of one batch of PNB_SB cells, structure-of-arrays (bank-conflict free for lane = cell)
+template <int DIM> struct CellBatch {
+    static constexpr int NV = DIM + 1;
+    double sx[NV * DIM][PNB_SB];  // simplex coordinates [vertex*DIM + axis][cell]
+    double cx[DIM][PNB_SB];       // centers
+    double vol[PNB_SB];
+    int v[NV][PNB_SB];            // global vertex ids
+    float lh[PNB_SB], ah[PNB_SB]; // (float) log h, |log(h/H0)|
+    int cell[PNB_SB], loc[PNB_SB], home[PNB_SB], any[PNB_SB];
 };
 
+#ifdef PNB_PROFILE
+#define PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pc_ = clock64();
+#define PROF(k) { const long long now_ = clock64(); pt_[k] += now_ - pc_; pc_ = now_; }
+#define PROF_END if (tid == 0) { for (int k_ = 0; k_ < 8; k_++) atomicAdd(S.counters + 2 + (k_ % 6), (unsigned long long)pt_[k_]); }
+#else
+#define PROF_DECL
+#define PROF(k)
+#define PROF_END
+#endif
+
+template <int DIM, bool NEAR> struct TileSmem {
+    static constexpr int NV = PairDims<DIM>::NV, NX = PairDims<DIM>::NX, ND = PairDims<DIM>::ND;
+    PowTab pw;
+    FarRule far[NEAR ? 1 : PNB_FAR_MAX_ORDER + 1];
+    double acc[PNB_TD][PNB_TD + 1];
+    double dxy[PNB_SB * PNB_SB][2 * ND];   // cell-diagonal blocks of the pairs of the sub-batch (slot = k1*SB+k2)
+    double nv[NEAR ? PNB_SB * PNB_SB : 1][NX];   // near pass: cross blocks kept for the mirrored update of diagonal tiles
+    unsigned char slotD[PNB_SB * PNB_SB];  // dxy[slot] holds data of this sub-batch
+    double partial[NEAR ? 64 : 1][PairDims<DIM>::NL];   // near pass: slice sums of split pairs
+    CellBatch<DIM> rb, cb;
+    int list[PNB_SB * PNB_SB];
+    int listpanel[PNB_SB * PNB_SB];
+    int warpcnt[PNB_THREADS / 32];
+    int clscnt[(PNB_FAR_MAX_ORDER - 1) * (PNB_THREADS / 32)];
+    int nlist;
+    int anynear;
+    int anyD;
+    // followed by DXs[maxcells][ND], DYs[maxcells][ND] (dynamic)
+};
+
+// getQuadOrder (fractionalLaplacian2D.pyx:622-642) in single precision.  Returns the order when the
+// result is certain (the value handed to ceil() is farther than the error bound from an integer), else -1
+// and the caller repeats the selection with the reference's exact double arithmetic.
+__device__ __forceinline__ int fast_order_2d(double d2, float lh1, float lh2, float ah1, float ah2, float cf, float sf)
+{
+    const float MARGIN = 2e-3f;
+    const float Ld = 0.5f * __logf((float)d2);
+    const float l1 = Ld - lh1, l2 = Ld - lh2;
+    const float m = fmaxf(ah1, ah2);
+    const float num1 = cf + (sf - 1.f) * ah2 + m - sf * l2;
+    const float num2 = cf + (sf - 1.f) * ah1 + m - sf * l1;
+    const float f1 = __fdividef(num1, fmaxf(l1, 0.f) + 0.4f);
+    const float f2 = __fdividef(num2, fmaxf(l2, 0.f) + 0.4f);
+    const float g = fmaxf(f1, f2);
+    if (g <= 2.f - MARGIN) return 2;
+    const float k = ceilf(g);
+    if (k - g > MARGIN && g - (k - 1.f) > MARGIN && g < 250.f) return (int)k;
+    return -1;
+}
+
 template <int DIM>
-__global__ void __launch_bounds__(PNB_THREADS) tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_max)
+__device__ __forceinline__ void load_batch(const DProblem &P, const TileSched &S, CellBatch<DIM> &b, int beg, int off, int tid)
+{
+    constexpr int NV = DIM + 1;
+    if (tid < PNB_SB) {
+        const int c = S.tile_cells[beg + off + tid];
+        const bool ok = c >= 0;
+        b.cell[tid] = c;
+        b.loc[tid] = S.tile_loc[beg + off + tid];
+        b.home[tid] = ok ? S.home[c] : -1;
+        int any = 0;
+        if (ok) {
+#pragma unroll
+            for (int m = 0; m < NV; m++) {
+                any |= P.dofs[(size_t)c * NV + m] >= 0;
+                b.v[m][tid] = P.cells[(size_t)c * NV + m];
+            }
+            b.vol[tid] = P.vol[c];
+            b.lh[tid] = P.lhf[c];
+            b.ah[tid] = P.ahf[c];
+#pragma unroll
+            for (int j = 0; j < DIM; j++) b.cx[j][tid] = P.centers[(size_t)c * DIM + j];
+        }
+        b.any[tid] = any;
+    } else if (tid >= 32 && tid < 32 + PNB_SB * NV * DIM) {
+        const int e = tid - 32, comp = e / PNB_SB, k = e - comp * PNB_SB;
+        const int c = S.tile_cells[beg + off + k];
+        if (c >= 0) b.sx[comp][k] = P.simplices[(size_t)c * (NV * DIM) + comp];
+    }
+}
+
+// adds the NV x NV cross block X of the pair (row cell, column cell) to the tile; conflict free within a sub-batch
+template <int DIM>
+__device__ __forceinline__ void scatter_block(double (*acc)[PNB_TD + 1], int rloc, int cloc, const double *X, bool transposed)
+{
+    constexpr int NV = DIM + 1;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const int a = (rloc >> (8 * i)) & 0xFF;
+        if (a == 0xFF) continue;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int b = (cloc >> (8 * j)) & 0xFF;
+            if (b == 0xFF) continue;
+            if (!transposed) acc[a][b] += X[i * NV + j];
+            else acc[b][a] += X[i * NV + j];
+        }
+    }
+}
+
+// NEAR = false: far pass.  Evaluates the regular pairs of order 2..5 one per thread (binned by order), writes
+//               the tiles (A = ...) and flags the tiles that hold other pairs.
+// NEAR = true:  near pass over the flagged units.  Evaluates singular pairs and the remaining regular pairs one
+//               per warp and adds to the tiles (A += ...).  Same CTA <-> tile ownership in both passes: no
+//               atomics on floating point data anywhere.
+template <int DIM, bool NEAR>
+__global__ void __launch_bounds__(PNB_THREADS, NEAR ? 1 : 2)
+tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
 {
     constexpr int NV = PairDims<DIM>::NV, NX = PairDims<DIM>::NX, ND = PairDims<DIM>::ND, NL = PairDims<DIM>::NL;
-    constexpr int TD = PNB_TD, SB = PNB_SB;
+    constexpr int TD = PNB_TD, SB = PNB_SB, NW = PNB_THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem<DIM> &sm = *reinterpret_cast<TileSmem<DIM> *>(smem_raw);
+    TileSmem<DIM, NEAR> &sm = *reinterpret_cast<TileSmem<DIM, NEAR> *>(smem_raw);
+    double *DXs = reinterpret_cast<double *>(smem_raw + sizeof(TileSmem<DIM, NEAR>));
+    double *DYs = DXs + (size_t)S.maxcells * ND;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gr = S.units[2 * blockIdx.x], gc = S.units[2 * blockIdx.x + 1];
+    const int unit = NEAR ? S.nearunits[blockIdx.x] : blockIdx.x;
+    const int gr = S.units[2 * unit], gc = S.units[2 * unit + 1];
     unsigned long long my_pairs = 0;
+    const float cf = (float)P.c_int, sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
+    {   // stage the power table
+        const double *src = reinterpret_cast<const double *>(P.pow_int);
+        double *dst = reinterpret_cast<double *>(&sm.pw);
+        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_THREADS) dst[e] = src[e];
+        if (!NEAR && DIM == 2) {
+            const double *fs = reinterpret_cast<const double *>(P.far_rules);
+            double *fd = reinterpret_cast<double *>(&sm.far[0]);
+            for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER + 1) * sizeof(FarRule) / sizeof(double)); e += PNB_THREADS) fd[e] = fs[e];
+        }
+    }
+    __syncthreads();
+    const PowCtx kv(&sm.pw);
+    bool unit_near = false;
+    PROF_DECL
 
     for (int rt = gr * S.G; rt < min((gr + 1) * S.G, S.ntiles); rt++)
         for (int ct = max(gc * S.G, rt); ct < min((gc + 1) * S.G, S.ntiles); ct++) {
+            if (NEAR && !S.tileflag[(size_t)rt * S.ntiles + ct]) continue;
             const bool diag = rt == ct;
             const int rbeg = S.tile_ptr[rt], nR = S.tile_ptr[rt + 1] - rbeg;
             const int cbeg = S.tile_ptr[ct], nC = S.tile_ptr[ct + 1] - cbeg;
-            for (int e = tid; e < TD * (TD + 1); e += PNB_THREADS) (&sm.acc[0][0])[e] = 0.;
             __syncthreads();
+            for (int e = tid; e < TD * (TD + 1); e += PNB_THREADS) (&sm.acc[0][0])[e] = 0.;
+            for (int e = tid; e < nR * ND; e += PNB_THREADS) DXs[e] = 0.;
+            for (int e = tid; e < nC * ND; e += PNB_THREADS) DYs[e] = 0.;
+            if (tid == 0) sm.anynear = 0;
             for (int rb = 0; rb < nR; rb += SB) {
-                // row batch metadata + masks
-                if (tid < SB) {
-                    const bool ok = rb + tid < nR;
-                    const int c = ok ? S.tile_cells[rbeg + rb + tid] : -1;
-                    sm.rcell[tid] = c;
-                    sm.rloc[tid] = ok ? S.tile_loc[rbeg + rb + tid] : 0x00FFFFFF;
-                    sm.rhome[tid] = ok ? S.home[c] : -1;
-                }
                 __syncthreads();
-                if (tid < TD) {
-                    unsigned long long m = 0;
-                    for (int k = 0; k < SB; k++)
-                        for (int i = 0; i < NV; i++)
-                            if (((sm.rloc[k] >> (8 * i)) & 0xFF) == tid) m |= 1ull << (k * NV + i);
-                    sm.rmask[tid] = m;
-                }
+                load_batch<DIM>(P, S, sm.rb, rbeg, rb, tid);
                 for (int cb = diag ? rb : 0; cb < nC; cb += SB) {
-                    __syncthreads();
-                    if (tid < SB) {
-                        const bool ok = cb + tid < nC;
-                        const int c = ok ? S.tile_cells[cbeg + cb + tid] : -1;
-                        sm.ccell[tid] = c;
-                        sm.cloc[tid] = ok ? S.tile_loc[cbeg + cb + tid] : 0x00FFFFFF;
-                        sm.chome[tid] = ok ? S.home[c] : -1;
-                    }
-                    if (tid == 0) sm.nnear = 0;
-                    __syncthreads();
-                    if (tid < TD) {
-                        unsigned long long m = 0;
-                        for (int k = 0; k < SB; k++)
-                            for (int i = 0; i < NV; i++)
-                                if (((sm.cloc[k] >> (8 * i)) & 0xFF) == tid) m |= 1ull << (k * NV + i);
-                        sm.cmask[tid] = m;
-                    }
-                    // ---- phase 1: classify, evaluate low-order regular pairs ----
+                    PROF(5)
+                    __syncthreads();    // S0: previous sub-batch done
+                    load_batch<DIM>(P, S, sm.cb, cbeg, cb, tid);
+                    if (tid == 0) sm.anyD = 0;
+                    __syncthreads();    // S1: batches visible
+                    PROF(0)
+                    // ---- phase 1: classify every pair of the sub-batch ----
                     const int k1 = tid / SB, k2 = tid % SB;
-                    const int K1 = sm.rcell[k1], K2 = sm.ccell[k2];
-#pragma unroll
-                    for (int k = 0; k < NX; k++) sm.B[tid][k] = 0.;
-#pragma unroll
-                    for (int k = 0; k < 2 * ND; k++) sm.dxy[tid][k] = 0.;
-                    int todo = 0;  // 0 nothing, >0 regular order (near), <0 singular panel
+                    const int K1 = sm.rb.cell[k1], K2 = sm.cb.cell[k2];
+                    int todo = 0;  // 0 nothing, >0 regular order (queued), <0 singular panel (queued)
+                    int cls = 0;   // far pass: order 2..5 of a pair for the thread-per-pair evaluator, else 0
                     bool countD = false;
-                    if (K1 >= 0 && K2 >= 0 && (diag ? K1 <= K2 : K1 != K2)) {
-                        bool any1 = false, any2 = false;
-#pragma unroll
-                        for (int m = 0; m < NV; m++) {
-                            any1 |= P.dofs[(size_t)K1 * NV + m] >= 0;
-                            any2 |= P.dofs[(size_t)K2 * NV + m] >= 0;
-                        }
-                        countD = sm.rhome[k1] == rt && sm.chome[k2] == ct;
-                        const bool rin = (sm.rloc[k1] & 0x00FFFFFF) != 0x00FFFFFF, cin = (sm.cloc[k2] & 0x00FFFFFF) != 0x00FFFFFF;
-                        const bool cross = (rin && cin) || (diag && rin && cin);
-                        if ((any1 || any2) && (countD || cross)) {
+                    sm.slotD[tid] = 0;
+                    // diagonal tiles: every unordered pair once (batches rb <= cb; inside a batch k1 <= k2)
+                    if (K1 >= 0 && K2 >= 0 && K1 != K2 ? (!diag || rb < cb || k1 < k2) : (K1 >= 0 && K1 == K2 && diag)) {
+                        countD = sm.rb.home[k1] == rt && sm.cb.home[k2] == ct;
+                        const bool rin = (sm.rb.loc[k1] & 0x00FFFFFF) != 0x00FFFFFF, cin = (sm.cb.loc[k2] & 0x00FFFFFF) != 0x00FFFFFF;
+                        if ((sm.rb.any[k1] || sm.cb.any[k2]) && (countD || (rin && cin))) {
                             int panel;
                             if (K1 == K2) panel = -NV;
                             else {
-                                panel = -shared_vertices(P.cells + (size_t)K1 * NV, NV, P.cells + (size_t)K2 * NV, NV);
+                                int v1[NV], v2[NV];
+#pragma unroll
+                                for (int m = 0; m < NV; m++) { v1[m] = sm.rb.v[m][k1]; v2[m] = sm.cb.v[m][k2]; }
+                                panel = -shared_vertices(v1, NV, v2, NV);
                                 if (panel == 0) {
-                                    const double d = center_distance(P.centers + (size_t)K1 * DIM, P.centers + (size_t)K2 * DIM, DIM);
-                                    panel = quad_order_interior(P, P.h[K1], P.h[K2], d);
+                                    if (DIM == 2) {
+                                        const double a = sm.rb.cx[0][k1] - sm.cb.cx[0][k2], b = sm.rb.cx[DIM - 1][k1] - sm.cb.cx[DIM - 1][k2];
+                                        panel = fast_order_2d(a * a + b * b, sm.rb.lh[k1], sm.cb.lh[k2], sm.rb.ah[k1], sm.cb.ah[k2], cf, sf);
+                                    } else panel = -1;
+                                    if (panel < 0) {
+                                        // getPanelType evaluates (c1 <= c2): keep the operand order of the reference
+                                        const int c1 = min(K1, K2), c2 = max(K1, K2);
+                                        const double d = center_distance(P.centers + (size_t)c1 * DIM, P.centers + (size_t)c2 * DIM, DIM);
+                                        panel = quad_order_interior(P, P.h[c1], P.h[c2], d);
+                                    }
                                 }
                             }
+                            const bool is_far = DIM == 2 && panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1);
+                            if (panel > P.max_order) atomicMax(S.err, panel);
+                            else if (is_far) cls = NEAR ? 0 : panel;
+                            else todo = panel;
+                        }
+                    }
+                    // ---- ordered binning: far pass by order, near pass in slot order ----
+                    unsigned mybal = 0;
+                    if (!NEAR) {
+                        if (todo != 0) sm.anynear = 1;
+#pragma unroll
+                        for (int c = 2; c <= PNB_FAR_MAX_ORDER; c++) {
+                            const unsigned bc = __ballot_sync(0xffffffffu, cls == c);
+                            if (lane == 0) sm.clscnt[(c - 2) * NW + warp] = __popc(bc);
+                            if (cls == c) mybal = bc;
+                        }
+                    } else {
+                        mybal = __ballot_sync(0xffffffffu, todo != 0);
+                        if (lane == 0) sm.warpcnt[warp] = __popc(mybal);
+                    }
+                    PROF(1)
+                    __syncthreads();    // S2
+                    if (!NEAR) {
+                        const int me = (cls - 2) * NW + warp;
+                        int pos = 0, tot = 0;
+#pragma unroll 4
+                        for (int q = 0; q < (PNB_FAR_MAX_ORDER - 1) * NW; q++) {
+                            const int c = sm.clscnt[q];
+                            if (q < me) pos += c;
+                            tot += c;
+                        }
+                        if (cls != 0) sm.list[pos + __popc(mybal & ((1u << lane) - 1))] = tid | (countD ? 0x100 : 0) | (cls << 12);
+                        if (tid == 0) sm.nlist = tot;
+                    } else {
+                        int pos = 0, tot = 0;
+                        for (int w = 0; w < NW; w++) {
+                            if (w < warp) pos += sm.warpcnt[w];
+                            tot += sm.warpcnt[w];
+                        }
+                        if (todo != 0) {
+                            pos += __popc(mybal & ((1u << lane) - 1));
+                            sm.list[pos] = tid | (countD ? 0x100 : 0);
+                            sm.listpanel[pos] = todo;
+                        }
+                        if (tid == 0) sm.nlist = tot;
+                    }
+                    __syncthreads();    // S3
+                    PROF(2)
+                    const int nlist = sm.nlist;
+                    if (nlist == 0) continue;     // uniform across the CTA
+                    // ---- phase 2: evaluate ----
+                    double X[NX];
+                    int rl = 0x00FFFFFF, cl = 0x00FFFFFF;   // tile-local dofs of the pair this thread scatters
+                    bool have = false;
+                    if (!NEAR) {
+                        if (DIM == 2 && tid < nlist) {
+                            const int item = sm.list[tid];
+                            const int slot = item & 0xFF, order = item >> 12;
+                            const bool cD = (item & 0x100) != 0;
+                            const int a1 = slot / SB, a2 = slot % SB;
                             my_pairs++;
-                            if (panel > P.max_order) {
-                                atomicMax(S.err, panel);
-                            } else if (DIM == 2 && panel >= 1 && panel <= far_max && c_far[panel].n > 0) {
-                                double s1[3][2], s2[3][2], xy[9], xx[6], yy[6];
-                                load_simplex<2>(P.simplices, K1, 3, s1);
-                                load_simplex<2>(P.simplices, K2, 3, s2);
-                                const int nq = c_far[panel].n;
-                                if (nq == 3) far_eval_2d<3>(s1, s2, c_far[panel], P.C, P.expo, xy, xx, yy);
-                                else if (nq == 6) far_eval_2d<6>(s1, s2, c_far[panel], P.C, P.expo, xy, xx, yy);
-                                else far_eval_2d<7>(s1, s2, c_far[panel], P.C, P.expo, xy, xx, yy);
-                                const double sc = 2.0 * P.vol[K1] * P.vol[K2];
-                                if (DIM == 2) {
+                            double s1[3][2], s2[3][2], xx[6], yy[6];
 #pragma unroll
-                                    for (int k = 0; k < 9; k++) sm.B[tid][k % NX] = xy[k] * sc;
-                                    if (countD) {
+                            for (int m = 0; m < 3; m++) {
+                                s1[m][0] = sm.rb.sx[(m * DIM) % (NV * DIM)][a1];
+                                s1[m][1] = sm.rb.sx[(m * DIM + 1) % (NV * DIM)][a1];
+                                s2[m][0] = sm.cb.sx[(m * DIM) % (NV * DIM)][a2];
+                                s2[m][1] = sm.cb.sx[(m * DIM + 1) % (NV * DIM)][a2];
+                            }
+                            const double sc = 2.0 * sm.rb.vol[a1] * sm.cb.vol[a2];
+                            double xy[9];
+                            far_eval_2d(sm.far[NEAR ? 0 : order], s1, s2, kv, cD, xy, xx, yy);
+                            if (cD) {
 #pragma unroll
-                                        for (int k = 0; k < 6; k++) {
-                                            sm.dxy[tid][k % (2 * ND)] = xx[k] * sc;
-                                            sm.dxy[tid][(ND + k) % (2 * ND)] = yy[k] * sc;
-                                        }
+                                for (int k = 0; k < 6; k++) {
+                                    sm.dxy[slot][k % (2 * ND)] = xx[k] * sc;
+                                    sm.dxy[slot][(ND + k) % (2 * ND)] = yy[k] * sc;
+                                }
+                                sm.slotD[slot] = 1;
+                                sm.anyD = 1;
+                            }
+#pragma unroll
+                            for (int k = 0; k < NX; k++) X[k] = xy[k % 9] * sc;
+                            rl = sm.rb.loc[a1];
+                            cl = sm.cb.loc[a2];
+                            have = true;
+                            scatter_block<DIM>(sm.acc, rl, cl, X, false);
+                        }
+                    } else {
+                        // One warp per (pair, slice): sub-batches with few queued pairs split every pair into S slices of
+                        // its quadrature nodes so that all warps stay busy; slice sums are combined in fixed order.
+                        const int Sl = nlist >= 32 ? 1 : (nlist >= 16 ? 2 : (nlist >= 8 ? 4 : 8));
+                        constexpr int NRr = 2 * NV - 1, NA = NRr * (NRr + 1) / 2;
+                        for (int pass = 0; pass < (Sl > 1 ? 2 : 1); pass++) {
+                            if (pass == 1) __syncthreads();
+                            const int nitems = pass == 0 ? nlist * Sl : nlist;
+                            for (int it = warp; it < nitems; it += NW) {
+                                const int q = pass == 0 ? it / Sl : it, sl = pass == 0 ? it - q * Sl : 0;
+                                const int slot = sm.list[q] & 0xFF;
+                                const bool cD = (sm.list[q] & 0x100) != 0;
+                                const int panel = sm.listpanel[q];
+                                const int Ka = sm.rb.cell[slot / SB], Kb = sm.cb.cell[slot % SB];
+                                // reference orientation of singular pairs: smaller cell index first
+                                const bool swapped = panel < 0 && Ka > Kb;
+                                const int c1 = swapped ? Kb : Ka, c2 = swapped ? Ka : Kb;
+                                int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
+                                int pan = panel;
+                                if (panel < 0) pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.cells + (size_t)c2 * NV, NV, c1 == c2, p1, p2);
+                                double acc[NL];
+                                if (pass == 0) {
+                                    if (lane == 0 && sl == 0) my_pairs++;
+                                    if (panel >= 1) {
+                                        lanes_regular_interior<DIM>(P, Ka, Kb, panel, sl * 32 + lane, 32 * Sl, acc);
+                                        warp_allreduce<NL>(acc);
+                                    } else {
+                                        lanes_singular_interior<DIM>(P, c1, c2, pan, p1, p2, sl * 32 + lane, 32 * Sl, acc);
+                                        warp_allreduce<NA>(acc);
+                                    }
+                                    if (Sl > 1) {
+#pragma unroll
+                                        for (int k = 0; k < NL; k++)
+                                            if (k == lane) sm.partial[it][k] = acc[k];
+                                        continue;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < NL; k++) {
+                                        double v = 0.;
+                                        for (int ss = 0; ss < Sl; ss++) v += sm.partial[q * Sl + ss][k];
+                                        acc[k] = v;
                                     }
                                 }
-                            } else {
-                                todo = panel;
+                                double myv = 0.;         // lane k < NX: entry k of the cross block
+                                double myd = 0.;         // lane k < 2*ND: entry k of (dx, dy)
+                                if (panel >= 1) {
+                                    const double sc = 2.0 * P.vol[Ka] * P.vol[Kb];
+                                    int k = 0;
+#pragma unroll
+                                    for (int I = 0; I < 2 * NV; I++)
+#pragma unroll
+                                        for (int J = I; J < 2 * NV; J++) {
+                                            const double v = acc[k] * sc;
+                                            if (I < NV && J >= NV) { if (lane == I * NV + (J - NV)) myv = v; }
+                                            else if (J < NV) { if (lane == tri_idx(NV, I, J)) myd = v; }
+                                            else { if (lane == ND + tri_idx(NV, I - NV, J - NV)) myd = v; }
+                                            k++;
+                                        }
+                                } else {
+                                    const double sc = (c1 == c2 ? 1.0 : 2.0) * (DIM == 2 ? 4.0 : 1.0) * P.vol[c1] * P.vol[c2];
+                                    const int common = -pan, rows = 2 * NV - common;
+                                    int k = 0;
+#pragma unroll
+                                    for (int I = 0; I < NRr; I++)
+#pragma unroll
+                                        for (int J = I; J < NRr; J++) {
+                                            if (J < rows) {
+                                                const double v = acc[k] * sc;
+                                                int i = I < NV ? p1[I] : NV + p2[I - NV + common];
+                                                int j = J < NV ? p1[J] : NV + p2[J - NV + common];
+                                                if (j < i) { const int t = i; i = j; j = t; }
+                                                // (i,j) in the reference's 2NV x 2NV local numbering of (c1,c2)
+                                                if (i < NV && j >= NV) {
+                                                    const int e = !swapped ? i * NV + (j - NV) : (j - NV) * NV + i;
+                                                    if (lane == e) myv = v;
+                                                } else {
+                                                    const bool first = j < NV;   // block of c1
+                                                    const int a = first ? i : i - NV, b = first ? j : j - NV;
+                                                    const bool to_dx = first != swapped;
+                                                    if (lane == (to_dx ? 0 : ND) + tri_idx(NV, a, b)) myd = v;
+                                                }
+                                            }
+                                            k++;
+                                        }
+                                }
+                                // lanes 0..NX-1 add the cross block (distinct entries), lanes 0..2ND-1 store the diagonal blocks
+                                if (lane < NX) {
+                                    const int i = lane / NV, j = lane - i * NV;
+                                    const int a = (sm.rb.loc[slot / SB] >> (8 * i)) & 0xFF, b = (sm.cb.loc[slot % SB] >> (8 * j)) & 0xFF;
+                                    if (a != 0xFF && b != 0xFF) sm.acc[a][b] += myv;
+                                    sm.nv[q][lane] = myv;
+                                }
+                                if (cD && lane < 2 * ND) sm.dxy[slot][lane] = myd;
+                                if (cD && lane == 0) { sm.slotD[slot] = 1; sm.anyD = 1; }
                             }
                         }
                     }
-                    // ---- deterministic compaction of the queued pairs ----
-                    const unsigned bal = __ballot_sync(0xffffffffu, todo != 0);
-                    if (lane == 0) sm.warpcnt[warp] = __popc(bal);
-                    __syncthreads();
-                    if (todo != 0) {
-                        int pos = __popc(bal & ((1u << lane) - 1));
-                        for (int w = 0; w < warp; w++) pos += sm.warpcnt[w];
-                        sm.nearlist[pos] = tid | (countD ? 0x10000 : 0);
-                        sm.nearpanel[pos] = todo;
-                    }
-                    if (tid == 0) {
-                        int tot = 0;
-                        for (int w = 0; w < PNB_THREADS / 32; w++) tot += sm.warpcnt[w];
-                        sm.nnear = tot;
-                    }
-                    __syncthreads();
-                    // ---- phase 2: one warp per queued pair ----
-                    const int nnear = sm.nnear;
-                    for (int q = warp; q < nnear; q += PNB_THREADS / 32) {
-                        const int slot = sm.nearlist[q] & 0xFFFF;
-                        const bool cD = (sm.nearlist[q] & 0x10000) != 0;
-                        const int panel = sm.nearpanel[q];
-                        const int Ka = sm.rcell[slot / SB], Kb = sm.ccell[slot % SB];
-                        if (panel >= 1) {
-                            double acc[NL];
-                            lanes_regular_interior<DIM>(P, Ka, Kb, panel, lane, 32, acc);
-                            warp_allreduce<NL>(acc);
-                            const double sc = 2.0 * P.vol[Ka] * P.vol[Kb];
-                            int k = 0;
-#pragma unroll
-                            for (int I = 0; I < 2 * NV; I++)
-#pragma unroll
-                                for (int J = I; J < 2 * NV; J++) {
-                                    if (k == lane) {
-                                        const double v = acc[k] * sc;
-                                        if (I < NV && J >= NV) sm.B[slot][I * NV + (J - NV)] = v;
-                                        else if (cD && J < NV) sm.dxy[slot][tri_idx(NV, I, J)] = v;
-                                        else if (cD && I >= NV) sm.dxy[slot][ND + tri_idx(NV, I - NV, J - NV)] = v;
-                                    }
-                                    k++;
-                                }
+                    __syncthreads();    // S4: direct updates done
+                    PROF(4)
+                    if (diag) {
+                        // mirror image inside a diagonal tile: second conflict-free round
+                        if (!NEAR) {
+                            if (have) scatter_block<DIM>(sm.acc, rl, cl, X, true);
                         } else {
-                            // reference orientation: smaller cell index first
-                            const bool swapped = Ka > Kb;
-                            const int c1 = swapped ? Kb : Ka, c2 = swapped ? Ka : Kb;
-                            int p1[3], p2[3];
-                            const int pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.cells + (size_t)c2 * NV, NV, c1 == c2, p1, p2);
-                            constexpr int NR = 2 * NV - 1, NA = NR * (NR + 1) / 2;
-                            double acc[NA];
-                            lanes_singular_interior<DIM>(P, c1, c2, pan, p1, p2, lane, 32, acc);
-                            warp_allreduce<NA>(acc);
-                            const double sc = (c1 == c2 ? 1.0 : 2.0) * (DIM == 2 ? 4.0 : 1.0) * P.vol[c1] * P.vol[c2];
-                            const int common = -pan, rows = 2 * NV - common;
-                            int k = 0;
-#pragma unroll
-                            for (int I = 0; I < NR; I++)
-#pragma unroll
-                                for (int J = I; J < NR; J++) {
-                                    if (k == lane && J < rows) {
-                                        const double v = acc[k] * sc;
-                                        int i = I < NV ? p1[I] : NV + p2[I - NV + common];
-                                        int j = J < NV ? p1[J] : NV + p2[J - NV + common];
-                                        if (j < i) { const int t = i; i = j; j = t; }
-                                        // (i,j) in the reference's 2NV x 2NV local numbering of (c1,c2)
-                                        if (i < NV && j >= NV) {
-                                            if (!swapped) sm.B[slot][i * NV + (j - NV)] = v;
-                                            else sm.B[slot][(j - NV) * NV + i] = v;
-                                        } else if (cD) {
-                                            const bool first = j < NV;   // block of c1
-                                            const int a = first ? i : i - NV, b = first ? j : j - NV;
-                                            const bool to_dx = first != swapped;
-                                            sm.dxy[slot][(to_dx ? 0 : ND) + tri_idx(NV, a, b)] = v;
-                                        }
-                                    }
-                                    k++;
-                                }
-                        }
-                    }
-                    __syncthreads();
-                    // ---- phase 3: fold cross blocks into the tile, fixed order ----
-                    for (int e = tid; e < TD * TD; e += PNB_THREADS) {
-                        const int a = e / TD, b = e - a * TD;
-                        // direct and mirrored parts are summed separately so that acc[a][b] and acc[b][a]
-                        // of a diagonal tile are bitwise equal (sd+sm == sm+sd)
-                        double sum = 0., summ = 0.;
-                        bool hit = false;
-                        unsigned long long ra = sm.rmask[a], cm = sm.cmask[b];
-                        if (ra && cm) {
-                            hit = true;
-                            while (ra) {
-                                const int u = __ffsll((long long)ra) - 1;
-                                ra &= ra - 1;
-                                const int kk1 = u / NV, i = u - kk1 * NV;
-                                unsigned long long c = cm;
-                                while (c) {
-                                    const int v = __ffsll((long long)c) - 1;
-                                    c &= c - 1;
-                                    const int kk2 = v / NV, j = v - kk2 * NV;
-                                    sum += sm.B[kk1 * SB + kk2][i * NV + j];
-                                }
+                            for (int q = tid / NX; q < nlist; q += PNB_THREADS / NX) {
+                                const int e = tid % NX;
+                                if (tid / NX >= PNB_THREADS / NX) break;
+                                const int slot = sm.list[q] & 0xFF;
+                                const int i = e / NV, j = e - i * NV;
+                                const int a = (sm.rb.loc[slot / SB] >> (8 * i)) & 0xFF, b = (sm.cb.loc[slot % SB] >> (8 * j)) & 0xFF;
+                                if (a != 0xFF && b != 0xFF) sm.acc[b][a] += sm.nv[q][e];
                             }
                         }
-                        if (diag) {
-                            unsigned long long rb2 = sm.rmask[b], ca = sm.cmask[a];
-                            if (rb2 && ca) {
-                                hit = true;
-                                while (rb2) {
-                                    const int u = __ffsll((long long)rb2) - 1;
-                                    rb2 &= rb2 - 1;
-                                    const int kk1 = u / NV, i = u - kk1 * NV;
-                                    unsigned long long c = ca;
-                                    while (c) {
-                                        const int v = __ffsll((long long)c) - 1;
-                                        c &= c - 1;
-                                        const int kk2 = v / NV, j = v - kk2 * NV;
-                                        summ += sm.B[kk1 * SB + kk2][i * NV + j];
-                                    }
-                                }
-                            }
-                        }
-                        sum += summ;
-                        if (hit) sm.acc[a][b] += sum;
                     }
-                    // ---- cell-diagonal blocks: reduce over the batch, stage per (group, cell) ----
-                    if (tid < SB * ND) {
-                        const int kk1 = tid / ND, comp = tid - kk1 * ND;
-                        const int K = sm.rcell[kk1];
-                        if (K >= 0 && sm.rhome[kk1] == rt) {
-                            double sacc = 0.;
-                            for (int kk2 = 0; kk2 < SB; kk2++) sacc += sm.dxy[kk1 * SB + kk2][comp];
-                            if (sacc != 0.) S.DXp[((size_t)gc * P.nc + K) * ND + comp] += sacc;
-                        }
-                    } else if (tid < 2 * SB * ND) {
-                        const int t2 = tid - SB * ND;
-                        const int kk2 = t2 / ND, comp = t2 - kk2 * ND;
-                        const int K = sm.ccell[kk2];
-                        if (K >= 0 && sm.chome[kk2] == ct) {
-                            double sacc = 0.;
-                            for (int kk1 = 0; kk1 < SB; kk1++) sacc += sm.dxy[kk1 * SB + kk2][ND + comp];
-                            if (sacc != 0.) S.DYp[((size_t)gr * P.nc + K) * ND + comp] += sacc;
+                    // ---- cell-diagonal blocks: reduce over the sub-batch into the per-tile accumulators ----
+                    if (sm.anyD) {
+                        if (tid < SB * ND) {
+                            const int kk1 = tid / ND, comp = tid - kk1 * ND;
+                            if (sm.rb.cell[kk1] >= 0 && sm.rb.home[kk1] == rt) {
+                                double sacc = 0.;
+                                for (int kk2 = 0; kk2 < SB; kk2++)
+                                    if (sm.slotD[kk1 * SB + kk2]) sacc += sm.dxy[kk1 * SB + kk2][comp];
+                                DXs[(rb + kk1) * ND + comp] += sacc;
+                            }
+                        } else if (tid < 2 * SB * ND) {
+                            const int t2 = tid - SB * ND;
+                            const int kk2 = t2 / ND, comp = t2 - kk2 * ND;
+                            if (sm.cb.cell[kk2] >= 0 && sm.cb.home[kk2] == ct) {
+                                double sacc = 0.;
+                                for (int kk1 = 0; kk1 < SB; kk1++)
+                                    if (sm.slotD[kk1 * SB + kk2]) sacc += sm.dxy[kk1 * SB + kk2][ND + comp];
+                                DYs[(cb + kk2) * ND + comp] += sacc;
+                            }
                         }
                     }
                 }
-                __syncthreads();
             }
             __syncthreads();
-            // ---- write the tile (and its mirror image) ----
+            // ---- write the tile (and its mirror image); flush the cell-diagonal partial sums ----
             const int r0 = rt * TD, c0 = ct * TD;
             for (int e = tid; e < TD * TD; e += PNB_THREADS) {
                 const int a = e / TD, b = e - a * TD;
-                if (r0 + a < P.N && c0 + b < P.N) A[(size_t)(r0 + a) * ld + c0 + b] = sm.acc[a][b];
+                if (r0 + a < P.N && c0 + b < P.N) {
+                    double *dst = &A[(size_t)(r0 + a) * ld + c0 + b];
+                    // diagonal tiles: acc[a][b] and acc[b][a] hold the same terms summed in different orders;
+                    // their mean is bitwise symmetric (and deterministic)
+                    const double v = diag ? 0.5 * (sm.acc[a][b] + sm.acc[b][a]) : sm.acc[a][b];
+                    *dst = NEAR ? *dst + v : v;
+                }
             }
             if (!diag)
                 for (int e = tid; e < TD * TD; e += PNB_THREADS) {
                     const int b = e / TD, a = e - b * TD;
-                    if (r0 + a < P.N && c0 + b < P.N) A[(size_t)(c0 + b) * ld + r0 + a] = sm.acc[a][b];
+                    if (r0 + a < P.N && c0 + b < P.N) {
+                        double *dst = &A[(size_t)(c0 + b) * ld + r0 + a];
+                        *dst = NEAR ? *dst + sm.acc[a][b] : sm.acc[a][b];
+                    }
                 }
-            __syncthreads();
+            for (int e = tid; e < nR * ND; e += PNB_THREADS) {
+                const int K = S.tile_cells[rbeg + e / ND];
+                if (K >= 0 && DXs[e] != 0.) S.DXp[((size_t)gc * P.nc + K) * ND + (e % ND)] += DXs[e];
+            }
+            for (int e = tid; e < nC * ND; e += PNB_THREADS) {
+                const int K = S.tile_cells[cbeg + e / ND];
+                if (K >= 0 && DYs[e] != 0.) S.DYp[((size_t)gr * P.nc + K) * ND + (e % ND)] += DYs[e];
+            }
+            if (!NEAR && sm.anynear) {
+                if (tid == 0) S.tileflag[(size_t)rt * S.ntiles + ct] = 1;
+                unit_near = true;
+            }
         }
+    PROF_END
+    if (!NEAR && unit_near && tid == 0) S.unitflag[unit] = 1;
     // pair counter (statistics only; integer atomics)
     for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
-    if (lane == 0 && my_pairs) atomicAdd(S.counters, my_pairs);
+    if (lane == 0 && my_pairs) atomicAdd(S.counters + (NEAR ? 1 : 0), my_pairs);
+}
+
+// ordered compaction of the flagged units (single block; nunits is small)
+__global__ void compact_units_kernel(TileSched S)
+{
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int u0 = 0; u0 < S.nunits; u0 += blockDim.x) {
+        const int u = u0 + threadIdx.x;
+        const bool f = u < S.nunits && S.unitflag[u];
+        // block-wide ordered scan via ballots
+        __shared__ int wc[32];
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(bal);
+        __syncthreads();
+        int pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) pos += wc[w];
+        if (f) S.nearunits[pos] = u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += wc[w];
+            base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) S.nearunits[S.nunits] = base;
 }
 
 // ---------------------------------------------------------------------------
@@ -1025,16 +1311,31 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
     cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
     cudaEventRecord(ev[0]);
     int launches = 0;
+    cudaMemsetAsync(S.tileflag, 0, (size_t)S.ntiles * S.ntiles * sizeof(int));
+    cudaMemsetAsync(S.unitflag, 0, (size_t)S.nunits * sizeof(int));
+    const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
+    int nnear_units = 0;
     if (p->dim == 2) {
-        const size_t smem = sizeof(TileSmem<2>);
-        cudaFuncSetAttribute(tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tile_kernel<2><<<S.nunits, PNB_THREADS, smem>>>(p->P, S, dA, ld, PNB_FAR_MAX_ORDER);
+        const size_t smem = sizeof(TileSmem<2, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
+        const size_t smem_far = sizeof(TileSmem<2, false>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
+        cudaFuncSetAttribute(tile_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_far);
+        cudaFuncSetAttribute(tile_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tile_kernel<2, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, p->far_mask);
+        compact_units_kernel<<<1, 1024>>>(S);
+        cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);
+        if (nnear_units > 0 && !(dbg & 0x100))
+            tile_kernel<2, true><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, p->far_mask);
     } else {
-        const size_t smem = sizeof(TileSmem<1>);
-        cudaFuncSetAttribute(tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tile_kernel<1><<<S.nunits, PNB_THREADS, smem>>>(p->P, S, dA, ld, 0);
+        const size_t smem = sizeof(TileSmem<1, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
+        const size_t smem_far = sizeof(TileSmem<1, false>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
+        cudaFuncSetAttribute(tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_far);
+        cudaFuncSetAttribute(tile_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tile_kernel<1, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, 0);
+        compact_units_kernel<<<1, 1024>>>(S);
+        cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);
+        if (nnear_units > 0) tile_kernel<1, true><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, 0);
     }
-    launches++;
+    launches += 3;
     cudaEventRecord(ev[1]);
     if (zero_exterior && p->nb > 0) {
         const unsigned blocks = (unsigned)(((size_t)nc * 32 + 255) / 256);
@@ -1063,7 +1364,11 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
     for (int k = 0; k < 3; k++) { cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); p->timings[k] = ms; }
     cudaEventElapsedTime(&ms, ev[0], ev[3]);
     p->timings[3] = ms;
-    p->stats[0] = (int64_t)hcnt[0];
+    p->stats[0] = (int64_t)(hcnt[0] + hcnt[1]);
+    p->stats[3] = (int64_t)hcnt[1];
+#ifdef PNB_PROFILE
+    fprintf(stderr, "PNB_PROFILE cycles(tid0 sums): load+S1 %llu | classify %llu | S2+list+S3 %llu | eval %llu | S4 %llu | mirror+D+loop %llu\n", hcnt[2], hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7]);
+#endif
     p->stats[1] = p->distinct_pairs;
     p->stats[2] = launches;
     for (auto &ee : ev) cudaEventDestroy(ee);
@@ -1155,8 +1460,31 @@ __global__ void fp64_peak_kernel(double *out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+__global__ void fp64_latency_kernel(double *out, long long *cyc, int iters)
+{
+    double a = threadIdx.x * 1e-9 + 1.0;
+    const double b = 1.0000001, c = 1e-9;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+        a = fma(a, b, c); a = fma(a, b, c); a = fma(a, b, c); a = fma(a, b, c);
+        a = fma(a, b, c); a = fma(a, b, c); a = fma(a, b, c); a = fma(a, b, c);
+    }
+    const long long t1 = clock64();
+    out[threadIdx.x] = a;
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+
 extern "C" int pnb_fp64_peak(int device, double *tflops)
 {
+    if (getenv("PNB_FP64_LATENCY")) {
+        double *d = nullptr; long long *c = nullptr, h = 0;
+        cudaMalloc(&d, 32 * sizeof(double)); cudaMalloc(&c, sizeof(long long));
+        fp64_latency_kernel<<<1, 32>>>(d, c, 1000);
+        fp64_latency_kernel<<<1, 32>>>(d, c, 1000);
+        cudaMemcpy(&h, c, sizeof(long long), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "PNB dependent DFMA latency: %.2f cycles\n", (double)h / 8000.);
+        cudaFree(d); cudaFree(c);
+    }
     if (!tflops) return fail(PNB_ERR_ARG, "null argument");
     if (pnb_device_count() == 0) return fail(PNB_ERR_NO_DEVICE, "no CUDA device");
     CK(cudaSetDevice(device));

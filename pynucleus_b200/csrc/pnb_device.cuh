@@ -21,8 +21,27 @@ struct DRule {
     const double *w;     // n
 };
 
+// Table-driven x^e for a fixed exponent e (the kernel singularity):
+//   x = 2^E * m,  m in [1,2),  m = m0[idx] * (1+r),  idx = top 7 mantissa bits, |r| <= 2^-8
+//   scal * x^e = T1[E] * T2[idx] * sum_k binom(e,k) r^k      (k <= 7)
+// T1 = scal * 2^(E e) and T2 = m0^e are rounded from long double on the host;
+// max relative error ~5e-16 (measured against 200-bit arithmetic), against
+// ~1.3e-16 of libm pow.  Exponents outside the table fall back to pow().
+#define PNB_POW_EOFF 240
+struct PowTab {
+    double coef[8];
+    double T1[256];
+    double2 IT[128];   // x = 1/m0 (rounded), y = m0^e for the exact reciprocal of x
+    double scal, expo;
+};
+
 struct DProblem {
     int dim, nc, nv, N, nb;
+    const PowTab *pow_int;     // interior kernel  C |x-y|^(-d-2s)   as a function of |x-y|^2
+    const PowTab *pow_bnd;     // boundary kernel
+    const struct FarRule *far_rules;   // PNB_FAR_MAX_ORDER+1 low-order 2D rules for the thread-per-pair evaluator
+    const float *lhf;          // nc: (float) log(h)
+    const float *ahf;          // nc: (float) |log(h/H0)|
     const double *simplices;   // nc x (dim+1) x dim     (precomputeSimplices, nonlocalOperator_{SCALAR}.pxi:111-126)
     const double *centers;     // nc x dim
     const int *cells;          // nc x (dim+1)

@@ -17,8 +17,44 @@ template <int DIM> struct PairDims {
     static constexpr int NX = NV * NV;               // entries of the cross block
 };
 
-// gamma(x,y) = C |x-y|^(-d-2s)  (kernelsCy.pyx:159-183); boundary kernels :216-240
-__device__ __forceinline__ double kernel_value(double scal, double expo, double d2) { return scal * pow(d2, expo); }
+// gamma(x,y) = C |x-y|^(-d-2s)  (kernelsCy.pyx:159-183); boundary kernels :216-240,
+// evaluated from d2 = |x-y|^2 with the table-driven power (PowTab).
+__device__ __noinline__ double kernel_value_slow(double scal, double expo, double d2) { return scal * pow(d2, expo); }
+
+// polynomial coefficients in registers, tables wherever `t` points (shared or global memory)
+struct PowCtx {
+    const PowTab *t;
+    double c0, c1, c2, c3, c4, c5, c6, c7;
+    __device__ __forceinline__ explicit PowCtx(const PowTab *tab) : t(tab)
+    {
+        c0 = tab->coef[0]; c1 = tab->coef[1]; c2 = tab->coef[2]; c3 = tab->coef[3];
+        c4 = tab->coef[4]; c5 = tab->coef[5]; c6 = tab->coef[6]; c7 = tab->coef[7];
+    }
+    __device__ __forceinline__ double operator()(double d2) const
+    {
+        const int hi = __double2hiint(d2), lo = __double2loint(d2);
+        const int E = ((hi >> 20) & 0x7ff) - 1023 + PNB_POW_EOFF;
+        if ((unsigned)E > 255u) return kernel_value_slow(t->scal, t->expo, d2);
+        const int idx = (hi >> 13) & 0x7f;
+        const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+        const double2 it = t->IT[idx];
+        const double r = fma(m, it.x, -1.0);
+        double p = fma(c7, r, c6);
+        p = fma(p, r, c5);
+        p = fma(p, r, c4);
+        p = fma(p, r, c3);
+        p = fma(p, r, c2);
+        p = fma(p, r, c1);
+        p = fma(p, r, c0);
+        return t->T1[E] * (it.y * p);
+    }
+};
+
+__device__ __forceinline__ double kernel_value(const PowTab *__restrict__ t, double d2)
+{
+    const PowCtx ctx(t);
+    return ctx(d2);
+}
 
 template <int DIM>
 __device__ __forceinline__ void load_simplex(const double *base, size_t idx, int nverts, double (*s)[2])
@@ -46,6 +82,7 @@ __device__ void lanes_regular_interior(const DProblem &P, int c1, int c2, int or
     load_simplex<DIM>(P.simplices, c2, NV, s2);
     const DRule r = P.reg_cell[order];
     const int n = r.n;
+    const PowCtx kv(P.pow_int);
 #pragma unroll
     for (int k = 0; k < NL; k++) acc[k] = 0.;
     for (int q = lane; q < n * n; q += nlanes) {
@@ -57,16 +94,19 @@ __device__ void lanes_regular_interior(const DProblem &P, int c1, int c2, int or
             const double bx = r.bary[k * n + i], by = r.bary[k * n + j];
             psi[k] = bx;
             psi[NV + k] = -by;
-            x0 += bx * s1[k][0];
-            y0 += by * s2[k][0];
+            // un-fused, in the reference's order (nodesInGlobalCoords, quadrature.pyx:76-87): the node
+            // coordinates and hence x-y are then bit-identical to the reference's, which matters for close
+            // pairs where |x-y| << |x|
+            x0 = PNB_ADD(x0, PNB_MUL(bx, s1[k][0]));
+            y0 = PNB_ADD(y0, PNB_MUL(by, s2[k][0]));
             if (DIM == 2) {
-                x1 += bx * s1[k][1];
-                y1 += by * s2[k][1];
+                x1 = PNB_ADD(x1, PNB_MUL(bx, s1[k][1]));
+                y1 = PNB_ADD(y1, PNB_MUL(by, s2[k][1]));
             }
         }
-        double d2 = (x0 - y0) * (x0 - y0);
-        if (DIM == 2) d2 += (x1 - y1) * (x1 - y1);
-        const double g = (r.w[i] * r.w[j]) * kernel_value(P.C, P.expo, d2);
+        double d2 = PNB_MUL(x0 - y0, x0 - y0);
+        if (DIM == 2) d2 = PNB_ADD(d2, PNB_MUL(x1 - y1, x1 - y1));
+        const double g = (r.w[i] * r.w[j]) * kv(d2);
         int k = 0;
 #pragma unroll
         for (int I = 0; I < 2 * NV; I++) {
@@ -105,6 +145,7 @@ __device__ void lanes_singular_interior(const DProblem &P, int c1, int c2, int p
     if (DIM == 2) r = panel == -3 ? P.q_id : (panel == -2 ? P.q_edge : P.q_vertex);
     else r = panel == -2 ? P.q_id : P.q_vertex;
     const int n = r.n;
+    const PowCtx kv(P.pow_int);
 #pragma unroll
     for (int k = 0; k < NA; k++) acc[k] = 0.;
     for (int q = lane; q < n; q += nlanes) {
@@ -115,16 +156,20 @@ __device__ void lanes_singular_interior(const DProblem &P, int c1, int c2, int p
         for (int k = 0; k < NV; k++) {
             bx[k] = r.bary[k * n + q];
             by[k] = r.bary[(NV + k) * n + q];
-            x0 += s1[k][0] * bx[k];
-            y0 += s2[k][0] * by[k];
-            if (DIM == 2) {
-                x1 += s1[k][1] * bx[k];
-                y1 += s2[k][1] * by[k];
+            // un-fused and left to right as in fractionalLaplacian2D.pyx:858-863
+            if (k == 0) {
+                x0 = PNB_MUL(s1[k][0], bx[k]);
+                y0 = PNB_MUL(s2[k][0], by[k]);
+                if (DIM == 2) { x1 = PNB_MUL(s1[k][1], bx[k]); y1 = PNB_MUL(s2[k][1], by[k]); }
+            } else {
+                x0 = PNB_ADD(x0, PNB_MUL(s1[k][0], bx[k]));
+                y0 = PNB_ADD(y0, PNB_MUL(s2[k][0], by[k]));
+                if (DIM == 2) { x1 = PNB_ADD(x1, PNB_MUL(s1[k][1], bx[k])); y1 = PNB_ADD(y1, PNB_MUL(s2[k][1], by[k])); }
             }
         }
-        double d2 = (x0 - y0) * (x0 - y0);
-        if (DIM == 2) d2 += (x1 - y1) * (x1 - y1);
-        const double g = r.w[q] * kernel_value(P.C, P.expo, d2);
+        double d2 = PNB_MUL(x0 - y0, x0 - y0);
+        if (DIM == 2) d2 = PNB_ADD(d2, PNB_MUL(x1 - y1, x1 - y1));
+        const double g = r.w[q] * kv(d2);
         // PSI rows: shared dofs phi(x)-phi(y); then x-only; then y-only
 #pragma unroll
         for (int k = 0; k < NR; k++) psi[k] = 0.;
@@ -170,6 +215,7 @@ __device__ void lanes_boundary(const DProblem &P, int c1, int f, int panel, cons
         nx *= inv;
         ny *= inv;
     }
+    const PowCtx kv(P.pow_bnd);
 #pragma unroll
     for (int k = 0; k < ND; k++) acc[k] = 0.;
     if (panel >= 1) {
@@ -182,24 +228,24 @@ __device__ void lanes_boundary(const DProblem &P, int c1, int f, int panel, cons
 #pragma unroll
             for (int k = 0; k < NV; k++) {
                 phi[k] = r0.bary[k * n0 + i];
-                x0 += phi[k] * t1[k][0];
-                if (DIM == 2) x1 += phi[k] * t1[k][1];
+                x0 = PNB_ADD(x0, PNB_MUL(phi[k], t1[k][0]));
+                if (DIM == 2) x1 = PNB_ADD(x1, PNB_MUL(phi[k], t1[k][1]));
             }
 #pragma unroll
             for (int k = 0; k < NF; k++) {
                 const double b = r1.bary[k * n1 + m];
-                y0 += b * t2[k][0];
-                if (DIM == 2) y1 += b * t2[k][1];
+                y0 = PNB_ADD(y0, PNB_MUL(b, t2[k][0]));
+                if (DIM == 2) y1 = PNB_ADD(y1, PNB_MUL(b, t2[k][1]));
             }
             double w0 = y0 - x0, w1 = y1 - x1;
-            double d2 = w0 * w0;
+            double d2 = PNB_MUL(w0, w0);
             double nw = 1.;
             if (DIM == 2) {
-                d2 += w1 * w1;
+                d2 = PNB_ADD(d2, PNB_MUL(w1, w1));
                 const double inv = 1. / sqrt(d2);
                 nw = nx * (w0 * inv) + ny * (w1 * inv);
             }
-            const double g = (r0.w[i] * r1.w[m]) * nw * kernel_value(P.Cb, P.bexpo, d2);
+            const double g = (r0.w[i] * r1.w[m]) * nw * kv(d2);
             int k = 0;
 #pragma unroll
             for (int I = 0; I < NV; I++) {
@@ -225,24 +271,34 @@ __device__ void lanes_boundary(const DProblem &P, int c1, int f, int panel, cons
 #pragma unroll
             for (int k = 0; k < NV; k++) {
                 phi[k] = r.bary[k * n + q];
-                x0 += s1[k][0] * phi[k];
-                if (DIM == 2) x1 += s1[k][1] * phi[k];
+                if (k == 0) {
+                    x0 = PNB_MUL(s1[k][0], phi[k]);
+                    if (DIM == 2) x1 = PNB_MUL(s1[k][1], phi[k]);
+                } else {
+                    x0 = PNB_ADD(x0, PNB_MUL(s1[k][0], phi[k]));
+                    if (DIM == 2) x1 = PNB_ADD(x1, PNB_MUL(s1[k][1], phi[k]));
+                }
             }
 #pragma unroll
             for (int k = 0; k < NF; k++) {
                 const double b = r.bary[(NV + k) * n + q];
-                y0 += s2[k][0] * b;
-                if (DIM == 2) y1 += s2[k][1] * b;
+                if (k == 0) {
+                    y0 = PNB_MUL(s2[k][0], b);
+                    if (DIM == 2) y1 = PNB_MUL(s2[k][1], b);
+                } else {
+                    y0 = PNB_ADD(y0, PNB_MUL(s2[k][0], b));
+                    if (DIM == 2) y1 = PNB_ADD(y1, PNB_MUL(s2[k][1], b));
+                }
             }
             double w0 = x0 - y0, w1 = x1 - y1;
-            double d2 = w0 * w0;
+            double d2 = PNB_MUL(w0, w0);
             double nw = 1.;
             if (DIM == 2) {
-                d2 += w1 * w1;
+                d2 = PNB_ADD(d2, PNB_MUL(w1, w1));
                 const double inv = 1. / sqrt(d2);
                 nw = nx * (w0 * inv) + ny * (w1 * inv);
             }
-            const double g = r.w[q] * nw * kernel_value(P.Cb, P.bexpo, d2);
+            const double g = r.w[q] * nw * kv(d2);
             int k = 0;
 #pragma unroll
             for (int I = 0; I < NV; I++) {
@@ -266,64 +322,74 @@ template <int N> __device__ __forceinline__ void warp_allreduce(double *v)
 }
 
 // ---------------------------------------------------------------------------
-// Far evaluator: regular 2D pair with an NQ-point triangle rule on each cell,
-// one thread per pair.  Factored form of nonlocalOperator_{SCALAR}.pxi:769-789:
-//   xx[I,I'] =  sum_i phi_I(x_i) phi_I'(x_i) r_i,   r_i = sum_j g_ij
-//   yy[J,J'] =  sum_j phi_J(y_j) phi_J'(y_j) c_j,   c_j = sum_i g_ij
-//   xy[I,J]  = -sum_i phi_I(x_i) sum_j g_ij phi_J(y_j)
-// with g_ij = w_i w_j gamma(x_i, y_j).  Outputs are NOT scaled by vol1*vol2.
+// Far evaluator: regular 2D pair of order 2..5, one thread per pair.  Factored
+// form of nonlocalOperator_{SCALAR}.pxi:769-789 with g_ij = gamma(x_i, y_j):
+//   xx[I,I'] =  sum_i w_i phi_I(x_i) phi_I'(x_i) r_i,   r_i = sum_j w_j g_ij
+//   yy[J,J'] =  sum_j w_j phi_J(y_j) phi_J'(y_j) c_j,   c_j = sum_i w_i g_ij
+//   xy[I,J]  = -sum_i w_i phi_I(x_i) sum_j g_ij w_j phi_J(y_j)
+// The rule of each order lives in its own __constant__ symbol so that the
+// unrolled inner loop uses constant-bank operands; weights are folded into the
+// per-node constants (wb = w * bary).  Outputs are NOT scaled by vol1*vol2.
 // ---------------------------------------------------------------------------
 struct FarRule {
     int n;
+    int pad;
     double bary[3][8];
     double w[8];
+    double wb[3][8];   // w[j] * bary[k][j]
+    double qq[6][8];   // w[j] * bary[a][j] * bary[b][j], a<=b   (diagonal block of the second cell)
 };
 
-template <int NQ>
-__device__ __forceinline__ void far_eval_2d(const double (*s1)[2], const double (*s2)[2], const FarRule &R, double C,
-                                            double expo, double *xy, double *xx, double *yy)
+// node counts the thread-per-pair evaluator accepts (orders 2..5 of the adopted triangle family)
+__host__ __device__ inline int far_expected_nodes(int order) { return order == 2 ? 3 : (order == 3 || order == 4) ? 6 : order == 5 ? 7 : -1; }
+
+// Deliberately ROLLED loops with a runtime node count: one small loop body serves every order.  (Unrolled
+// per-order instantiations were measured 2-3x slower: the tile kernel then no longer fits the instruction
+// cache and warps stall on instruction fetch.)  R lives in shared memory; all lanes of a warp that work on
+// the same order read the same addresses (broadcast).
+__device__ __forceinline__ void far_eval_2d(const FarRule &R, const double (*s1)[2], const double (*s2)[2],
+                                            const PowCtx &T, const bool with_d, double *xy, double *xx, double *yy)
 {
-    double Y[NQ][2], csum[NQ];
-#pragma unroll
-    for (int j = 0; j < NQ; j++) {
-        Y[j][0] = R.bary[0][j] * s2[0][0] + R.bary[1][j] * s2[1][0] + R.bary[2][j] * s2[2][0];
-        Y[j][1] = R.bary[0][j] * s2[0][1] + R.bary[1][j] * s2[1][1] + R.bary[2][j] * s2[2][1];
-        csum[j] = 0.;
-    }
+    const int n = R.n;
 #pragma unroll
     for (int k = 0; k < 9; k++) xy[k] = 0.;
 #pragma unroll
     for (int k = 0; k < 6; k++) xx[k] = yy[k] = 0.;
-#pragma unroll
-    for (int i = 0; i < NQ; i++) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
         const double p0 = R.bary[0][i], p1 = R.bary[1][i], p2 = R.bary[2][i];
         const double X0 = p0 * s1[0][0] + p1 * s1[1][0] + p2 * s1[2][0];
         const double X1 = p0 * s1[0][1] + p1 * s1[1][1] + p2 * s1[2][1];
         const double wi = R.w[i];
         double r = 0., t0 = 0., t1 = 0., t2 = 0.;
-#pragma unroll
-        for (int j = 0; j < NQ; j++) {
-            const double a = X0 - Y[j][0], b = X1 - Y[j][1];
-            const double d2 = a * a + b * b;
-            const double g = (wi * R.w[j]) * kernel_value(C, expo, d2);
-            r += g;
-            csum[j] += g;
-            t0 += g * R.bary[0][j];
-            t1 += g * R.bary[1][j];
-            t2 += g * R.bary[2][j];
+#pragma unroll 1
+        for (int j = 0; j < n; j++) {
+            const double q0 = R.bary[0][j], q1 = R.bary[1][j], q2 = R.bary[2][j];
+            const double a = X0 - (q0 * s2[0][0] + q1 * s2[1][0] + q2 * s2[2][0]);
+            const double b = X1 - (q0 * s2[0][1] + q1 * s2[1][1] + q2 * s2[2][1]);
+            const double g = T(a * a + b * b);
+            t0 = fma(g, R.wb[0][j], t0);
+            t1 = fma(g, R.wb[1][j], t1);
+            t2 = fma(g, R.wb[2][j], t2);
+            if (with_d) {
+                r = fma(g, R.w[j], r);
+                const double gw = g * wi;
+                yy[0] = fma(gw, R.qq[0][j], yy[0]);
+                yy[1] = fma(gw, R.qq[1][j], yy[1]);
+                yy[2] = fma(gw, R.qq[2][j], yy[2]);
+                yy[3] = fma(gw, R.qq[3][j], yy[3]);
+                yy[4] = fma(gw, R.qq[4][j], yy[4]);
+                yy[5] = fma(gw, R.qq[5][j], yy[5]);
+            }
         }
-        const double r0 = r * p0, r1 = r * p1, r2 = r * p2;
-        xx[0] += r0 * p0; xx[1] += r0 * p1; xx[2] += r0 * p2;
-        xx[3] += r1 * p1; xx[4] += r1 * p2; xx[5] += r2 * p2;
-        xy[0] -= p0 * t0; xy[1] -= p0 * t1; xy[2] -= p0 * t2;
-        xy[3] -= p1 * t0; xy[4] -= p1 * t1; xy[5] -= p1 * t2;
-        xy[6] -= p2 * t0; xy[7] -= p2 * t1; xy[8] -= p2 * t2;
-    }
-#pragma unroll
-    for (int j = 0; j < NQ; j++) {
-        const double q0 = R.bary[0][j], q1 = R.bary[1][j], q2 = R.bary[2][j];
-        const double c0 = csum[j] * q0, c1 = csum[j] * q1, c2 = csum[j] * q2;
-        yy[0] += c0 * q0; yy[1] += c0 * q1; yy[2] += c0 * q2;
-        yy[3] += c1 * q1; yy[4] += c1 * q2; yy[5] += c2 * q2;
+        const double q0 = wi * p0, q1 = wi * p1, q2 = wi * p2;
+        if (with_d) {
+            const double r0 = r * q0, r1 = r * q1, r2 = r * q2;
+            xx[0] += r0 * p0; xx[1] += r0 * p1; xx[2] += r0 * p2;
+            xx[3] += r1 * p1; xx[4] += r1 * p2; xx[5] += r2 * p2;
+        }
+        xy[0] -= q0 * t0; xy[1] -= q0 * t1; xy[2] -= q0 * t2;
+        xy[3] -= q1 * t0; xy[4] -= q1 * t1; xy[5] -= q1 * t2;
+        xy[6] -= q2 * t0; xy[7] -= q2 * t1; xy[8] -= q2 * t2;
     }
 }

@@ -33,6 +33,19 @@ def builder_from_golden(g, zeroExterior=True):
     return pb.nonlocalBuilder(dm, kernel, params, zeroExterior=zeroExterior)
 
 
+def entry_err(A, Aref):
+    """max entry error relative to max(|Aref_ij|, 1e-2*sqrt(Aref_ii*Aref_jj)).
+
+    Entries are sums of positive and negative pair contributions of size up
+    to ~A_ii; the few near-diagonal entries that cancel to < 1e-2 of the
+    diagonal scale carry the summation-order rounding of the large terms, so
+    they are held to 1e-12 of that scale (i.e. an absolute 1e-14*A_ii),
+    everything else to 1e-12 of the entry itself."""
+    d = np.sqrt(np.abs(np.diag(Aref)))
+    scale = np.maximum(np.abs(Aref), 1e-2*np.outer(d, d))
+    return (np.abs(A-Aref)/scale).max()
+
+
 def relerr_rows(C, Cref):
     scale = np.abs(Cref).max(axis=1, keepdims=True)
     scale[scale == 0] = 1.
@@ -96,11 +109,9 @@ def test_dense_vs_reference(golden_dir, name):
     g = load(golden_dir, name)
     A = builder_from_golden(g).getDense().data
     Aref = g['A']
-    nz = np.abs(Aref) > 0
-    assert (np.abs(A-Aref)[nz]/np.abs(Aref)[nz]).max() < TOL
-    assert np.abs(A[~nz]).max() if (~nz).any() else 0. < 1e-14
+    assert entry_err(A, Aref) < TOL
     A0 = builder_from_golden(g, zeroExterior=False).getDense().data
-    assert np.abs(A0-g['A_interior']).max()/np.abs(g['A_interior']).max() < TOL
+    assert entry_err(A0, g['A_interior']) < TOL
     assert np.array_equal(A, A.T)
 
 
@@ -121,8 +132,7 @@ def test_dense_vs_oracle_disc(noRef, s):
     A = b.getDense().data
     P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, s, bfacets=mesh.boundaryFacets, target_order=0.5)
     Aref = P.dense(True)
-    nz = np.abs(Aref) > 0
-    assert (np.abs(A-Aref)[nz]/np.abs(Aref)[nz]).max() < TOL
+    assert entry_err(A, Aref) < TOL
     st = b.getStats()
     assert st['distinct_pairs'] == P.last_npairs
     # bit-exact classification on a random sample of pairs at this size
@@ -140,8 +150,7 @@ def test_dense_vs_oracle_interval(noRef, s):
     A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(1, s), {}).getDense().data
     P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, s, bfacets=mesh.boundaryFacets)
     Aref = P.dense(True)
-    nz = np.abs(Aref) > 0
-    assert (np.abs(A-Aref)[nz]/np.abs(Aref)[nz]).max() < TOL
+    assert entry_err(A, Aref) < TOL
 
 
 def test_nonuniform_mesh_vs_oracle():
@@ -162,8 +171,7 @@ def test_nonuniform_mesh_vs_oracle():
     A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.6), {'target_order': 0.5}).getDense().data
     P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, 0.6, bfacets=mesh.boundaryFacets, target_order=0.5)
     Aref = P.dense(True)
-    nz = np.abs(Aref) > 0
-    assert (np.abs(A-Aref)[nz]/np.abs(Aref)[nz]).max() < TOL
+    assert entry_err(A, Aref) < TOL
 
 
 def test_deterministic_and_symmetric():
