@@ -228,10 +228,10 @@ def run_cuda(args):
     kernel = pb.getFractionalKernel(2, S_ORDER)
     params = {'target_order': TARGET_ORDER, 'device': local_rank}
     builder = pb.nonlocalBuilder(dm, kernel, params)
-    if world > 1:
-        raise NotImplementedError('row-sharded multi-GPU assembly: see bench_sharded in a later commit')
+    from pynucleus_b200.assembly import row_partition
+    r0, r1 = row_partition(N, world, _lib.lib().pnb_row_granularity())[rank]
 
-    A = torch.empty((N, N), dtype=torch.float64, device=dev)
+    A = torch.empty((max(r1-r0, 1), N), dtype=torch.float64, device=dev)
     flush = torch.empty(64*1024*1024, dtype=torch.float64, device=dev)   # 512 MB > L2
     peak = 0.
     pk = np.zeros(1)
@@ -239,7 +239,10 @@ def run_cuda(args):
     peak = float(pk[0])
 
     def step():
-        builder.getDense(out=A)
+        if world == 1:
+            builder.getDense(out=A)
+        else:
+            builder.getDenseRowBlock(r0, r1, out=A)
 
     for _ in range(args.warmup):
         step()
@@ -251,6 +254,8 @@ def run_cuda(args):
     torch.cuda.synchronize()
     for k in range(args.steps):
         flush.zero_()
+        if world > 1:
+            dist.barrier()
         ev[k][0].record()
         step()
         ev[k][1].record()
@@ -260,23 +265,40 @@ def run_cuda(args):
         launches += st['launches']
     clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
+    if world > 1:
+        # device time of a step = max over ranks
+        t = torch.tensor(ms, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.cpu().tolist()
     ms_step = float(np.mean(ms))
     st = builder.getStats()
     value = N*float(N)/(ms_step*1e-3)
 
     # end to end through the host-buffer C entry point: problem upload + assembly + copy back, every step
-    host = torch.empty((N, N), dtype=torch.float64).pin_memory()
+    host = torch.empty((max(r1-r0, 1), N), dtype=torch.float64).pin_memory()
     hA = host.numpy()
     e2e_ms = []
     h2d = (mesh.vertices.nbytes+mesh.cells.nbytes+dm.dofs.nbytes+mesh.volVector.nbytes+mesh.hVector.nbytes
            + mesh.boundaryFacets.nbytes)
     for k in range(max(1, min(args.steps, 3))+1):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        b2 = pb.nonlocalBuilder(dm, kernel, params)
-        b2.getDenseHost(out=hA)
+        b2 = pb.nonlocalBuilder(dm, kernel, params)      # uploads mesh, DoFMap, tables (host -> device)
+        if world == 1:
+            b2.getDenseHost(out=hA)                       # assembly + device -> host copy inside the C call
+        else:
+            b2.getDenseRowBlock(r0, r1, out=A)
+            host.copy_(A)
+            torch.cuda.synchronize()
         checksum = float(hA[0, 0])
-        e2e_ms.append((time.perf_counter()-t0)*1e3)
+        dt = (time.perf_counter()-t0)*1e3
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_ms.append(dt)
         del b2
     e2e_ms = e2e_ms[1:]
     e2e_value = N*float(N)/(float(np.mean(e2e_ms))*1e-3)
@@ -294,7 +316,7 @@ def run_cuda(args):
                             pows/t_tile, st['evaluated_pairs']/max(st['distinct_pairs'], 1), t_tile*1e3/ms_step)}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
         cpu = reference_throughput(args.workload, target_seconds=args.ref_seconds)
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
@@ -306,7 +328,7 @@ def run_cuda(args):
                        'l2': 'output ({:.2f} GB/step) exceeds L2; 512 MB flush written between steps (untimed)'.format(N*N*8/1e9),
                        'parallelism': 'single GPU' if world == 1 else 'row blocks x{}'.format(world)},
             'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(N*N*8),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d)*world, 'd2h_bytes_per_step': int(N*N*8),
                     'ms_per_step': float(np.mean(e2e_ms)), 'checksum_A00': checksum},
             'gpu_launches': int(launches),
             'roofline': roofline,

@@ -160,6 +160,21 @@ int pnb_far_max_order(void);
 int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end,
                        double *A, int64_t ld, int a_on_device);
 
+/* Row-block (multi-GPU) form of pnb_dense_assemble: one problem instance per GPU assembles the rows
+ * [row_begin, row_end) (multiples of pnb_row_granularity(), or num_dofs) into device memory A_rows of
+ * (row_end-row_begin) x num_dofs.  Replaces the reference's cell-range split + Allreduce of the full matrix
+ * (nonlocalAssembly_{SCALAR}.pxi:1280-1285, 1449-1450): every entry is written by exactly one GPU.
+ *   1. pnb_dense_rows_begin   all pair integrals that touch the owned rows
+ *   2. the caller sums the buffers returned by pnb_dense_cell_blocks over all row blocks (NCCL allreduce;
+ *      supports are disjoint, so the sum is exact and order independent).  Not needed for a single block.
+ *   3. pnb_dense_rows_end     adds the cell-diagonal blocks to the owned rows */
+int pnb_row_granularity(void);
+int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *A_rows, int64_t ld);
+int pnb_dense_cell_blocks(pnb_problem *p, double **device_ptr, int64_t *count);
+/* copy between that buffer and caller device memory of `count` doubles (to_problem != 0: caller -> problem) */
+int pnb_dense_cell_blocks_copy(pnb_problem *p, double *device_buf, int to_problem);
+int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row_end, double *A_rows, int64_t ld);
+
 /* Counters of the last pnb_dense_assemble call: [0] evaluated cell pairs
  * (with tile-halo redundancy), [1] distinct cell pairs c1<=c2 that are not
  * skipped, [2] kernel launches, [3..] reserved.  stats: host, 8 entries. */

@@ -199,6 +199,38 @@ class nonlocalBuilder:
         self._retry_on_order(run)
         return Dense_LinearOperator(A, prob.device)
 
+    def getDenseRowBlock(self, row_begin, row_end, out=None, process_group=None):
+        """Rows [row_begin, row_end) of getDense() on this process' GPU (row-block sharding over GPUs).
+
+        The reference splits the cell loop over MPI ranks and Allreduces the whole matrix
+        (nonlocalAssembly_{SCALAR}.pxi:1280-1285, 1449-1450); here every rank owns a row block and the only
+        exchange is the sum of the per-cell diagonal blocks (num_cells x 6 doubles) over `process_group`.
+        Returns a (row_end-row_begin) x N Dense_LinearOperator."""
+        import torch
+        N = self.dm.num_dofs
+        prob = self.problem
+        dev = torch.device('cuda', prob.device)
+        A = torch.empty((row_end-row_begin, N), dtype=torch.float64, device=dev) if out is None else out
+        L = _lib.lib()
+        nvc = self.mesh.dim+1
+        empty = row_end <= row_begin
+
+        def run():
+            import torch.distributed as dist
+            D = None
+            if not empty:
+                _lib.check(L.pnb_dense_rows_begin(prob.handle, int(self.zeroExterior), row_begin, row_end, A.data_ptr(), A.stride(0)))
+            if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+                # sum of the per-cell diagonal blocks over the row blocks (disjoint supports: exact)
+                D = exchange_cell_blocks(self.mesh.num_cells*(nvc*(nvc+1)//2), dev, process_group,
+                                         None if empty else (lambda buf: _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, buf.data_ptr(), 0))))
+            if not empty:
+                if D is not None:
+                    _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, D.data_ptr(), 1))
+                _lib.check(L.pnb_dense_rows_end(prob.handle, row_begin, row_end, A.data_ptr(), A.stride(0)))
+        self._retry_on_order(run)
+        return Dense_LinearOperator(A, prob.device) if not empty else None
+
     def getDenseHost(self, out=None):
         """Same as getDense() but through the host-buffer C entry point: the result is written to host memory
         (device -> host copy inside the call)."""
@@ -218,6 +250,25 @@ class nonlocalBuilder:
         _lib.check(_lib.lib().pnb_dense_timings(self.problem.handle, ms.ctypes.data))
         return dict(evaluated_pairs=int(stats[0]), distinct_pairs=int(stats[1]), launches=int(stats[2]),
                     ms_tiles=float(ms[0]), ms_boundary=float(ms[1]), ms_reduce_scatter=float(ms[2]), ms_total=float(ms[3]))
+
+
+def exchange_cell_blocks(count, device, process_group=None, fill=None):
+    """All-reduce (sum) of the per-cell diagonal blocks.  `fill(buf)` writes this rank's blocks (zeros where
+    the rank does not own the cell) into the float64 buffer; ranks without rows contribute zeros."""
+    import torch
+    import torch.distributed as dist
+    D = torch.zeros(count, dtype=torch.float64, device=device)
+    if fill is not None:
+        fill(D)
+    dist.all_reduce(D, op=dist.ReduceOp.SUM, group=process_group)
+    return D
+
+
+def row_partition(num_dofs, world_size, granularity=64):
+    """contiguous row blocks [begin, end) per rank, aligned to the tile granularity of the device code"""
+    ntiles = (num_dofs+granularity-1)//granularity
+    bounds = [min(num_dofs, ((ntiles*r)//world_size)*granularity) for r in range(world_size)]+[num_dofs]
+    return [(bounds[r], bounds[r+1]) for r in range(world_size)]
 
 
 def assembleNonlocalOperator(mesh, dm, s, horizon=None, params={}, zeroExterior=True, comm=None, **kwargs):

@@ -64,6 +64,7 @@ struct TileSched {
     const int *home;        // nc: home tile of a cell
     const int *units;       // 2 x nunits (row group, col group)
     int nunits;
+    int nunits_all;         // capacity of the unit buffers
     double *DXp, *DYp;      // ngroups x nc x ND staging of cell-diagonal blocks
     double *Dbnd;           // nc x ND boundary contributions
     double *D;              // nc x ND reduced
@@ -71,6 +72,7 @@ struct TileSched {
     const int *dof_cells;   // packed (cell*4 + local index)
     int *err;               // [0]: max order requested beyond tables
     unsigned long long *counters;  // [0] evaluated pairs (far pass), [1] evaluated pairs (near pass)
+    int own_t0, own_t1;     // row tiles [own_t0, own_t1) are owned (written) by this problem instance
     int maxcells;           // largest cell list of a tile
     int *tileflag;          // ntiles x ntiles: tile holds pairs for the near pass
     int *unitflag;          // nunits: unit holds flagged tiles
@@ -91,6 +93,7 @@ struct pnb_problem {
     FarRule far_rules[PNB_FAR_MAX_ORDER + 1];
     int far_mask = 0;   // bit o set: order o is handled by the thread-per-pair evaluator
     int64_t stats[8] = {0};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double timings[4] = {0};
     int64_t distinct_pairs = 0;
     // host copies needed later
@@ -207,6 +210,7 @@ extern "C" void pnb_problem_destroy(pnb_problem *p)
     cudaSetDevice(p->device);
     for (void *d : p->allocs) cudaFree(d);
     for (void *d : p->rule_allocs) cudaFree(d);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
 }
 
@@ -418,6 +422,9 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     for (int dg = 0; dg < S.ngroups; dg++)
         for (int gr = 0; gr + dg < S.ngroups; gr++) { units.push_back(gr); units.push_back(gr + dg); }
     S.nunits = (int)units.size() / 2;
+    S.nunits_all = S.nunits;
+    S.own_t0 = 0;
+    S.own_t1 = S.ntiles;
     // dof -> cells
     std::vector<int> dptr(N + 1, 0), dcells;
     for (int c = 0; c < nc; c++)
@@ -843,6 +850,10 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
         for (int ct = max(gc * S.G, rt); ct < min((gc + 1) * S.G, S.ntiles); ct++) {
             if (NEAR && !S.tileflag[(size_t)rt * S.ntiles + ct]) continue;
             const bool diag = rt == ct;
+            // row-block ownership: the direct image belongs to the owner of row tile rt, the mirror image to the
+            // owner of row tile ct; tiles that touch no owned row are not computed by this GPU
+            const bool own_r = rt >= S.own_t0 && rt < S.own_t1, own_c = ct >= S.own_t0 && ct < S.own_t1;
+            if (!own_r && !own_c) continue;
             const int rbeg = S.tile_ptr[rt], nR = S.tile_ptr[rt + 1] - rbeg;
             const int cbeg = S.tile_ptr[ct], nC = S.tile_ptr[ct + 1] - cbeg;
             __syncthreads();
@@ -1123,19 +1134,19 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
             const int r0 = rt * TD, c0 = ct * TD;
             for (int e = tid; e < TD * TD; e += PNB_THREADS) {
                 const int a = e / TD, b = e - a * TD;
-                if (r0 + a < P.N && c0 + b < P.N) {
-                    double *dst = &A[(size_t)(r0 + a) * ld + c0 + b];
+                if (own_r && r0 + a < P.N && c0 + b < P.N) {
+                    double *dst = &A[(size_t)(r0 + a - S.own_t0 * TD) * ld + c0 + b];
                     // diagonal tiles: acc[a][b] and acc[b][a] hold the same terms summed in different orders;
                     // their mean is bitwise symmetric (and deterministic)
                     const double v = diag ? 0.5 * (sm.acc[a][b] + sm.acc[b][a]) : sm.acc[a][b];
                     *dst = NEAR ? *dst + v : v;
                 }
             }
-            if (!diag)
+            if (!diag && own_c)
                 for (int e = tid; e < TD * TD; e += PNB_THREADS) {
                     const int b = e / TD, a = e - b * TD;
                     if (r0 + a < P.N && c0 + b < P.N) {
-                        double *dst = &A[(size_t)(c0 + b) * ld + r0 + a];
+                        double *dst = &A[(size_t)(c0 + b - S.own_t0 * TD) * ld + r0 + a];
                         *dst = NEAR ? *dst + sm.acc[a][b] : sm.acc[a][b];
                     }
                 }
@@ -1202,6 +1213,7 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
     bool any = false;
     for (int m = 0; m < NV; m++) any |= P.dofs[(size_t)c1 * NV + m] >= 0;
     if (!any) return;
+    if (S.home[c1] < S.own_t0 || S.home[c1] >= S.own_t1) return;
     double tot[ND];
 #pragma unroll
     for (int k = 0; k < ND; k++) tot[k] = 0.;
@@ -1263,6 +1275,10 @@ __global__ void reduce_D_kernel(TileSched S, int nc, int ND, int use_bnd)
 {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= (int64_t)nc * ND) return;
+    // only cells whose home tile is owned have seen all their partners; the others are completed by the
+    // owner of their home tile (exchanged by the caller between pnb_dense_rows_begin and _end)
+    const int hm = S.home[e / ND];
+    if (hm < S.own_t0 || hm >= S.own_t1) { S.D[e] = 0.; return; }
     double s = 0.;
     for (int g = 0; g < S.ngroups; g++) s += S.DXp[(size_t)g * nc * ND + e];
     for (int g = 0; g < S.ngroups; g++) s += S.DYp[(size_t)g * nc * ND + e];
@@ -1274,8 +1290,9 @@ __global__ void reduce_D_kernel(TileSched S, int nc, int ND, int use_bnd)
 // nonlocalAssembly_{SCALAR}.pxi:152-168, 204-221): thread I adds to row I only
 __global__ void scatter_D_kernel(DProblem P, TileSched S, double *A, int64_t ld)
 {
-    const int I = blockIdx.x * blockDim.x + threadIdx.x;
-    if (I >= P.N) return;
+    const int I = blockIdx.x * blockDim.x + threadIdx.x + S.own_t0 * PNB_TD;
+    if (I >= P.N || I >= S.own_t1 * PNB_TD) return;
+    A -= (size_t)S.own_t0 * PNB_TD * ld;
     const int NV = P.dim + 1, ND = NV * (NV + 1) / 2;
     for (int t = S.dof_ptr[I]; t < S.dof_ptr[I + 1]; t++) {
         const int K = S.dof_cells[t] >> 2, p = S.dof_cells[t] & 3;
@@ -1288,31 +1305,50 @@ __global__ void scatter_D_kernel(DProblem P, TileSched S, double *A, int64_t ld)
     }
 }
 
-extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *A,
-                                  int64_t ld, int a_on_device)
+static int check_rows(pnb_problem *p, int32_t row_begin, int32_t row_end)
 {
-    if (!p || !A) return fail(PNB_ERR_ARG, "null argument");
+    if (row_begin < 0 || row_end > p->N || row_begin >= row_end) return fail(PNB_ERR_ARG, "invalid row range");
+    if (row_begin % PNB_TD != 0 || (row_end % PNB_TD != 0 && row_end != p->N))
+        return fail(PNB_ERR_ARG, "row blocks must start and end at multiples of " + std::to_string(PNB_TD) + " (pnb_row_granularity)");
+    return 0;
+}
+
+extern "C" int pnb_row_granularity(void) { return PNB_TD; }
+
+// tile passes + boundary kernel + reduction of the cell-diagonal blocks of the owned cells
+extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *dA, int64_t ld)
+{
+    if (!p || !dA) return fail(PNB_ERR_ARG, "null argument");
     if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
-    if (row_begin != 0 || row_end != p->N) return fail(PNB_ERR_UNSUPPORTED, "row blocks are assembled through pnb_dense_assemble_rows");
+    if (check_rows(p, row_begin, row_end)) return PNB_ERR_ARG;
     if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
     CK(cudaSetDevice(p->device));
-    const int N = p->N, nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
-    double *dA = A;
-    if (!a_on_device) CK(cudaMalloc(&dA, (size_t)N * ld * sizeof(double)));
+    const int nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
     TileSched &S = p->S;
-    cudaEvent_t ev[5];
-    for (auto &e : ev) cudaEventCreate(&e);
-    int rc = 0;
-    cudaError_t e;
+    S.own_t0 = row_begin / PNB_TD;
+    S.own_t1 = (row_end + PNB_TD - 1) / PNB_TD;
+    // units: group pairs (gr <= gc) that hold a tile touching an owned row tile, near-diagonal first
+    {
+        const int g0 = S.own_t0 / S.G, g1 = (S.own_t1 - 1) / S.G;
+        std::vector<int> units;
+        for (int dg = 0; dg < S.ngroups; dg++)
+            for (int gr = 0; gr + dg < S.ngroups; gr++) {
+                const int gc = gr + dg;
+                if ((gr >= g0 && gr <= g1) || (gc >= g0 && gc <= g1)) { units.push_back(gr); units.push_back(gc); }
+            }
+        S.nunits = (int)units.size() / 2;
+        CK(cudaMemcpy(const_cast<int *>(S.units), units.data(), units.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    for (auto &e : p->ev) if (!e) cudaEventCreate(&e);
     cudaMemsetAsync(S.DXp, 0, (size_t)S.ngroups * nc * ND * sizeof(double));
     cudaMemsetAsync(S.DYp, 0, (size_t)S.ngroups * nc * ND * sizeof(double));
     cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * ND * sizeof(double));
     cudaMemsetAsync(S.err, 0, 4 * sizeof(int));
     cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
-    cudaEventRecord(ev[0]);
-    int launches = 0;
     cudaMemsetAsync(S.tileflag, 0, (size_t)S.ntiles * S.ntiles * sizeof(int));
-    cudaMemsetAsync(S.unitflag, 0, (size_t)S.nunits * sizeof(int));
+    cudaMemsetAsync(S.unitflag, 0, (size_t)S.nunits_all * sizeof(int));
+    cudaEventRecord(p->ev[0]);
+    int launches = 0;
     const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
     int nnear_units = 0;
     if (p->dim == 2) {
@@ -1335,34 +1371,74 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
         cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);
         if (nnear_units > 0) tile_kernel<1, true><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, 0);
     }
-    launches += 3;
-    cudaEventRecord(ev[1]);
+    launches += nnear_units > 0 ? 3 : 2;
+    cudaEventRecord(p->ev[1]);
     if (zero_exterior && p->nb > 0) {
         const unsigned blocks = (unsigned)(((size_t)nc * 32 + 255) / 256);
         if (p->dim == 2) boundary_kernel<2><<<blocks, 256>>>(p->P, S);
         else boundary_kernel<1><<<blocks, 256>>>(p->P, S);
         launches++;
     }
-    cudaEventRecord(ev[2]);
+    cudaEventRecord(p->ev[2]);
     reduce_D_kernel<<<(unsigned)(((size_t)nc * ND + 255) / 256), 256>>>(S, nc, ND, zero_exterior && p->nb > 0);
-    scatter_D_kernel<<<(N + 127) / 128, 128>>>(p->P, S, dA, ld);
-    launches += 2;
-    cudaEventRecord(ev[3]);
-    e = cudaEventSynchronize(ev[3]);
+    launches++;
+    cudaEventRecord(p->ev[3]);
+    p->stats[2] = launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// device buffer of the cell-diagonal blocks: num_cells x (dim+1)(dim+2)/2 doubles.  After _begin it holds the
+// complete blocks of the cells whose home row tile is owned and zeros elsewhere; with several row blocks the
+// caller sums the buffers of all owners (disjoint supports: the sum is exact) before calling _end.
+extern "C" int pnb_dense_cell_blocks(pnb_problem *p, double **dptr, int64_t *count)
+{
+    if (!p || !dptr || !count) return fail(PNB_ERR_ARG, "null argument");
+    const int nvc = p->dim + 1;
+    *dptr = p->S.D;
+    *count = (int64_t)p->nc * (nvc * (nvc + 1) / 2);
+    return 0;
+}
+
+// copies between the cell-block buffer and a caller device buffer (direction != 0: caller -> problem)
+extern "C" int pnb_dense_cell_blocks_copy(pnb_problem *p, double *device_buf, int to_problem)
+{
+    if (!p || !device_buf) return fail(PNB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(p->device));
+    const int nvc = p->dim + 1;
+    const size_t bytes = (size_t)p->nc * (nvc * (nvc + 1) / 2) * sizeof(double);
+    if (to_problem) CK(cudaMemcpyAsync(p->S.D, device_buf, bytes, cudaMemcpyDeviceToDevice));
+    else CK(cudaMemcpyAsync(device_buf, p->S.D, bytes, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
+// scatter of the cell-diagonal blocks into the owned rows; collects errors, counters and timings
+extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row_end, double *dA, int64_t ld)
+{
+    if (!p || !dA) return fail(PNB_ERR_ARG, "null argument");
+    if (check_rows(p, row_begin, row_end)) return PNB_ERR_ARG;
+    CK(cudaSetDevice(p->device));
+    TileSched &S = p->S;
+    if (S.own_t0 != row_begin / PNB_TD) return fail(PNB_ERR_ARG, "pnb_dense_rows_end does not match pnb_dense_rows_begin");
+    const int nrows = row_end - row_begin;
+    scatter_D_kernel<<<(nrows + 127) / 128, 128>>>(p->P, S, dA, ld);
+    p->stats[2] += 1;
+    cudaEventRecord(p->ev[4]);
+    cudaError_t e = cudaEventSynchronize(p->ev[4]);
     if (e == cudaSuccess) e = cudaGetLastError();
     int herr[4] = {0, 0, 0, 0};
     unsigned long long hcnt[8] = {0};
     if (e == cudaSuccess) e = cudaMemcpy(herr, S.err, sizeof(herr), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(hcnt, S.counters, sizeof(hcnt), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("dense assembly: ") + cudaGetErrorString(e));
-    else if (herr[0] > 0) rc = fail(PNB_ERR_ORDER, "regular quadrature order " + std::to_string(herr[0]) + " exceeds the supplied tables (max_order " + std::to_string(p->P.max_order) + ")");
-    if (!rc && !a_on_device) {
-        e = cudaMemcpy2D(A, (size_t)ld * sizeof(double), dA, (size_t)ld * sizeof(double), (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
-    }
+    if (e != cudaSuccess) return fail(PNB_ERR_CUDA, std::string("dense assembly: ") + cudaGetErrorString(e));
+    if (herr[0] > 0) return fail(PNB_ERR_ORDER, "regular quadrature order " + std::to_string(herr[0]) + " exceeds the supplied tables (max_order " + std::to_string(p->P.max_order) + ")");
     float ms;
-    for (int k = 0; k < 3; k++) { cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); p->timings[k] = ms; }
-    cudaEventElapsedTime(&ms, ev[0], ev[3]);
+    for (int k = 0; k < 2; k++) { cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]); p->timings[k] = ms; }
+    cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]);
+    float ms2;
+    cudaEventElapsedTime(&ms2, p->ev[3], p->ev[4]);
+    p->timings[2] = ms + ms2;      // reduce + (exchange by the caller) + scatter
+    cudaEventElapsedTime(&ms, p->ev[0], p->ev[4]);
     p->timings[3] = ms;
     p->stats[0] = (int64_t)(hcnt[0] + hcnt[1]);
     p->stats[3] = (int64_t)hcnt[1];
@@ -1370,8 +1446,26 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
     fprintf(stderr, "PNB_PROFILE cycles(tid0 sums): load+S1 %llu | classify %llu | S2+list+S3 %llu | eval %llu | S4 %llu | mirror+D+loop %llu\n", hcnt[2], hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7]);
 #endif
     p->stats[1] = p->distinct_pairs;
-    p->stats[2] = launches;
-    for (auto &ee : ev) cudaEventDestroy(ee);
+    return 0;
+}
+
+extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *A,
+                                  int64_t ld, int a_on_device)
+{
+    if (!p || !A) return fail(PNB_ERR_ARG, "null argument");
+    if (row_begin != 0 || row_end != p->N)
+        return fail(PNB_ERR_ARG, "pnb_dense_assemble builds the whole operator; row blocks go through pnb_dense_rows_begin/_end");
+    if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
+    CK(cudaSetDevice(p->device));
+    const int N = p->N;
+    double *dA = A;
+    if (!a_on_device) CK(cudaMalloc(&dA, (size_t)N * ld * sizeof(double)));
+    int rc = pnb_dense_rows_begin(p, zero_exterior, 0, N, dA, ld);
+    if (!rc) rc = pnb_dense_rows_end(p, 0, N, dA, ld);
+    if (!rc && !a_on_device) {
+        cudaError_t e = cudaMemcpy2D(A, (size_t)ld * sizeof(double), dA, (size_t)ld * sizeof(double), (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
+    }
     if (!a_on_device) cudaFree(dA);
     return rc;
 }

@@ -1,0 +1,61 @@
+"""Host-side logic of the row-block (multi-GPU) path on CPU with gloo, world_size 2: the row partition and the
+exchange of the per-cell diagonal blocks (sum over ranks of arrays with disjoint supports)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pynucleus_b200.assembly import row_partition, exchange_cell_blocks
+    N, nc = 721, 1536
+    blocks = row_partition(N, world, 64)
+    a, b = blocks[rank]
+    # every rank "owns" the cells whose index falls into its share; supports are disjoint
+    mine = np.zeros(nc*6)
+    own = np.arange(nc) % world == rank
+    mine.reshape(nc, 6)[own] = np.arange(nc*6).reshape(nc, 6)[own]+1.
+
+    def fill(buf):
+        buf.copy_(torch.from_numpy(mine))
+    D = exchange_cell_blocks(nc*6, torch.device('cpu'), None, fill)
+    ok = np.array_equal(D.numpy(), np.arange(nc*6)+1.)
+    q.put((rank, (a, b), ok))
+    dist.destroy_process_group()
+
+
+def test_partition_and_exchange_gloo():
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500+os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[2] for r in res)
+    (a0, b0), (a1, b1) = res[0][1], res[1][1]
+    assert a0 == 0 and b0 == a1 and b1 == 721 and b0 % 64 == 0
+
+
+def test_row_partition_properties():
+    from pynucleus_b200.assembly import row_partition
+    for N in (1, 37, 64, 65, 721, 20161, 105_000):
+        for world in (1, 2, 3, 4, 8):
+            blocks = row_partition(N, world, 64)
+            assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == N
+            for (a, b), (c, d) in zip(blocks[:-1], blocks[1:]):
+                assert b == c and a <= b
+            assert all(a % 64 == 0 for a, _ in blocks)

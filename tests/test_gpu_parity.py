@@ -220,3 +220,37 @@ def test_energy_known_answer_interval():
     energy = b.dot(u)
     exact = 2.**(-2.*s)*np.pi/(gamma(0.5+s)*gamma(s+1.5))
     assert abs(energy-exact)/exact < 0.02
+
+
+@pytest.mark.parametrize('nblocks', [2, 3])
+def test_row_blocks_equal_full_operator(nblocks):
+    """row-block (multi-GPU) assembly on one GPU: several problem instances, each owning a row block; the
+    per-cell diagonal blocks are summed by hand (what the NCCL all-reduce does across ranks)"""
+    import torch
+    import pynucleus_b200 as pb
+    from pynucleus_b200 import _lib
+    from pynucleus_b200.assembly import row_partition
+    mesh = pb.refined(pb.uniform_disc(), 4)
+    dm = pb.P1_DoFMap(mesh)
+    N = dm.num_dofs
+    kernel = pb.getFractionalKernel(2, 0.75)
+    full = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense().data
+    L = _lib.lib()
+    blocks = row_partition(N, nblocks, L.pnb_row_granularity())
+    builders = [pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}) for _ in blocks]
+    outs = [torch.empty((b-a, N), dtype=torch.float64, device='cuda') for a, b in blocks]
+    Dsum = torch.zeros(mesh.num_cells*6, dtype=torch.float64, device='cuda')
+    for bld, (a, b), out in zip(builders, blocks, outs):
+        _lib.check(L.pnb_dense_rows_begin(bld.problem.handle, 1, a, b, out.data_ptr(), out.stride(0)))
+        D = torch.empty_like(Dsum)
+        _lib.check(L.pnb_dense_cell_blocks_copy(bld.problem.handle, D.data_ptr(), 0))
+        torch.cuda.synchronize()
+        # disjoint supports
+        assert int(((D != 0) & (Dsum != 0)).sum()) == 0
+        Dsum += D
+    for bld, (a, b), out in zip(builders, blocks, outs):
+        _lib.check(L.pnb_dense_cell_blocks_copy(bld.problem.handle, Dsum.data_ptr(), 1))
+        _lib.check(L.pnb_dense_rows_end(bld.problem.handle, a, b, out.data_ptr(), out.stride(0)))
+    A = torch.cat(outs, dim=0).cpu().numpy()
+    assert entry_err(A, full) < TOL
+    assert np.array_equal(A, A.T)
