@@ -286,8 +286,12 @@ def run_cuda(args):
             dist.barrier()
         t0 = time.perf_counter()
         b2 = pb.nonlocalBuilder(dm, kernel, params)      # uploads mesh, DoFMap, tables (host -> device)
+        b2.problem
+        t1 = time.perf_counter()
         if world == 1:
             b2.getDenseHost(out=hA)                       # assembly + device -> host copy inside the C call
+            if rank == 0 and os.environ.get('PNB_BENCH_VERBOSE'):
+                print('e2e: setup %.1f ms, assemble+copy %.1f ms' % ((t1-t0)*1e3, (time.perf_counter()-t1)*1e3), file=sys.stderr)
         else:
             b2.getDenseRowBlock(r0, r1, out=A)
             host.copy_(A)

@@ -29,6 +29,8 @@
 // error handling
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
+struct pnb_problem;
+static pnb_problem *g_bench_problem = nullptr;   // last created problem (debug micro-benchmarks only)
 extern "C" const char *pnb_last_error(void) { return g_err.c_str(); }
 extern "C" int pnb_version(void) { return 100; }
 extern "C" int pnb_far_max_order(void) { return PNB_FAR_MAX_ORDER; }
@@ -211,6 +213,7 @@ extern "C" void pnb_problem_destroy(pnb_problem *p)
     for (void *d : p->allocs) cudaFree(d);
     for (void *d : p->rule_allocs) cudaFree(d);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (g_bench_problem == p) g_bench_problem = nullptr;
     delete p;
 }
 
@@ -459,6 +462,7 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     rc = pnb_problem_set_rules(p, rules);
     if (rc) { pnb_problem_destroy(p); return rc; }
     *out = p;
+    g_bench_problem = p;
     return 0;
 }
 
@@ -1554,6 +1558,36 @@ __global__ void fp64_peak_kernel(double *out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// micro-benchmark of the thread-per-pair evaluator in isolation (debug aid, PNB_FAREVAL_BENCH)
+__global__ void __launch_bounds__(256, 2) fareval_bench_kernel(DProblem P, int order, int with_d, int iters, double *out)
+{
+    __shared__ PowTab pw;
+    __shared__ FarRule far[PNB_FAR_MAX_ORDER + 1];
+    const int tid = threadIdx.x;
+    {
+        const double *src = reinterpret_cast<const double *>(P.pow_int);
+        double *dst = reinterpret_cast<double *>(&pw);
+        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += 256) dst[e] = src[e];
+        const double *fs = reinterpret_cast<const double *>(P.far_rules);
+        double *fd = reinterpret_cast<double *>(&far[0]);
+        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER + 1) * sizeof(FarRule) / sizeof(double)); e += 256) fd[e] = fs[e];
+    }
+    __syncthreads();
+    const PowCtx kv(&pw);
+    const int g = blockIdx.x * 256 + tid;
+    double s1[3][2], s2[3][2];
+    load_simplex<2>(P.simplices, g % P.nc, 3, s1);
+    load_simplex<2>(P.simplices, (g * 7 + P.nc / 2) % P.nc, 3, s2);
+    double acc = 0.;
+    for (int it = 0; it < iters; it++) {
+        double xy[9], xx[6], yy[6];
+        far_eval_2d(far[order], s1, s2, kv, with_d != 0, xy, xx, yy);
+        acc += xy[0] + xy[4] + xy[8] + xx[0] + yy[5];
+        s2[0][0] += 1e-9;
+    }
+    out[g] = acc;
+}
+
 __global__ void fp64_latency_kernel(double *out, long long *cyc, int iters)
 {
     double a = threadIdx.x * 1e-9 + 1.0;
@@ -1570,6 +1604,30 @@ __global__ void fp64_latency_kernel(double *out, long long *cyc, int iters)
 
 extern "C" int pnb_fp64_peak(int device, double *tflops)
 {
+    if (getenv("PNB_FAREVAL_BENCH") && g_bench_problem) {
+        pnb_problem *p = g_bench_problem;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        double *d = nullptr;
+        const int blocks = sms * 2 * 8, iters = 200;
+        cudaMalloc(&d, (size_t)blocks * 256 * sizeof(double));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int order = 2; order <= 5; order++)
+            for (int wd = 0; wd < 2; wd++) {
+                fareval_bench_kernel<<<blocks, 256>>>(p->P, order, wd, 10, d);
+                cudaEventRecord(e0);
+                fareval_bench_kernel<<<blocks, 256>>>(p->P, order, wd, iters, d);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                const double pairs = (double)blocks * 256 * iters;
+                const int n = p->far_rules[order].n;
+                fprintf(stderr, "PNB fareval order %d with_d %d: %.3f ms, %.3e pairs/s, %.3e node pairs/s (%s)\n", order, wd, ms, pairs / (ms * 1e-3), pairs * n * n / (ms * 1e-3), cudaGetErrorString(cudaGetLastError()));
+            }
+        cudaFree(d);
+    }
     if (getenv("PNB_FP64_LATENCY")) {
         double *d = nullptr; long long *c = nullptr, h = 0;
         cudaMalloc(&d, 32 * sizeof(double)); cudaMalloc(&c, sizeof(long long));

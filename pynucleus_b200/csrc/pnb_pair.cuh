@@ -331,6 +331,10 @@ template <int N> __device__ __forceinline__ void warp_allreduce(double *v)
 // unrolled inner loop uses constant-bank operands; weights are folded into the
 // per-node constants (wb = w * bary).  Outputs are NOT scaled by vol1*vol2.
 // ---------------------------------------------------------------------------
+#ifndef PNB_FAR_UNROLL
+#define PNB_FAR_UNROLL 1
+#endif
+static constexpr int kFarUnroll = PNB_FAR_UNROLL;
 struct FarRule {
     int n;
     int pad;
@@ -362,7 +366,7 @@ __device__ __forceinline__ void far_eval_2d(const FarRule &R, const double (*s1)
         const double X1 = p0 * s1[0][1] + p1 * s1[1][1] + p2 * s1[2][1];
         const double wi = R.w[i];
         double r = 0., t0 = 0., t1 = 0., t2 = 0.;
-#pragma unroll 1
+#pragma unroll kFarUnroll
         for (int j = 0; j < n; j++) {
             const double q0 = R.bary[0][j], q1 = R.bary[1][j], q2 = R.bary[2][j];
             const double a = X0 - (q0 * s2[0][0] + q1 * s2[1][0] + q2 * s2[2][0]);
