@@ -183,6 +183,17 @@ int pnb_dense_stats(pnb_problem *p, int64_t *stats);
  * [0] tile kernel, [1] boundary kernel, [2] reduce+scatter, [3] total */
 int pnb_dense_timings(pnb_problem *p, double *ms);
 
+/* H2 far-field kernel blocks, assembleFarFieldInteractions (nl/PyNucleus_nl/clusterMethodCy.pyx:2153-2238):
+ * for each admissible cluster pair b an m1^d x m2^d block  -2 gamma(xi_i, xi_j)  at the tensor Chebyshev
+ * nodes of the two cluster boxes (boxes: nblk x d x 2 = [lo, hi] per axis; multi-index with the last
+ * dimension fastest).  eta / eta_ptr: the 1D Chebyshev nodes cos((2(m-p)-1)pi/(2m)), p = 0..m-1, for every
+ * m <= max_m, stored back to back (eta_ptr[m] = start of the m nodes; eta_ptr has max_m+2 entries) -- computed
+ * by the caller exactly as the reference does (np.cos) so that the node coordinates are bit-identical.
+ * offsets: nblk+1 prefix sums of the block sizes; out: host, offsets[nblk] doubles.  All inputs host memory. */
+int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, const double *boxes2,
+                        const int32_t *m1, const int32_t *m2, int32_t max_m, const double *eta,
+                        const int32_t *eta_ptr, const int64_t *offsets, double *out);
+
 /* Dense_LinearOperator.matvec (base/PyNucleus_base/DenseLinearOperator_{SCALAR}.pxi:14-18
  * -> dgemv, opt_true_blas.pxi:159): y = A x for a row block.  All pointers are
  * device memory on `device`; stream is a cudaStream_t (0 = default stream). */

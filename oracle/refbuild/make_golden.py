@@ -193,6 +193,89 @@ def disc_case(noRef, s, name, full_pairs=False, with_A=True):
     print(name, out['cells'].shape, out.get('A', np.zeros((0, 0))).shape)
 
 
+def varconst_case(noRef, s, name):
+    """variable-order code path of the reference with s(x,y) = const (config 4): dense matrix only"""
+    from PyNucleus_nl.fractionalOrders import variableConstFractionalOrder
+    mesh = uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    kernel = getFractionalKernel(2, variableConstFractionalOrder(s), np.inf)
+    assert kernel.variable
+    b = nonlocalBuilder(dm, kernel, {'target_order': 0.5})
+    A = np.array(b.getDense().data)
+    out = mesh_arrays(mesh, dm)
+    out.update(A=A, s=s, target_order=0.5)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, A.shape)
+
+
+def h2_case(dim, noRef, s, name, max_far=60):
+    """getH2 of the reference: cluster tree, admissible / near pairs, far-field kernel blocks
+    (clusterMethodCy.pyx:2153-2238), near-field CSR matrix, and H2 matvec of a fixed vector"""
+    if dim == 2:
+        mesh = uniform_disc()
+        params = {'target_order': 0.5}
+    else:
+        mesh = simpleInterval(-1, 1)
+        params = {}
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    kernel = getFractionalKernel(dim, constFractionalOrder(s), np.inf)
+    b = nonlocalBuilder(dm, kernel, params)
+    H, Pnear = b.getH2(returnNearField=True)
+    out = mesh_arrays(mesh, dm)
+    out.update(s=s, target_order=params.get('target_order', np.nan), repr=str(H))
+    # tree
+    nodes = list(H.tree.get_tree_nodes())
+    ids = np.array([n.id for n in nodes], dtype=np.int64)
+    out['tree_ids'] = ids
+    out['tree_boxes'] = np.array([np.array(n.box) for n in nodes])
+    out['tree_parent'] = np.array([n.parent.id if n.parent is not None else -1 for n in nodes], dtype=np.int64)
+    out['tree_isleaf'] = np.array([n.isLeaf for n in nodes], dtype=bool)
+    out['tree_level'] = np.array([n.levelNo for n in nodes], dtype=np.int32)
+    out['tree_order'] = np.array([n.interpolation_order for n in nodes], dtype=np.int32)
+    dofptr = [0]
+    dofs = []
+    for n in nodes:
+        d = np.sort(np.array(n.dofs.toArray()))
+        dofs.append(d)
+        dofptr.append(dofptr[-1]+d.shape[0])
+    out['tree_dofptr'] = np.array(dofptr, dtype=np.int64)
+    out['tree_dofs'] = np.concatenate(dofs).astype(np.int32)
+    out['near_pairs'] = np.array([(cP.n1.id, cP.n2.id) for cP in Pnear], dtype=np.int64)
+    far = []
+    for lvl in sorted(H.Pfar):
+        for cP in H.Pfar[lvl]:
+            far.append((lvl, cP))
+    out['far_pairs'] = np.array([(lvl, cP.n1.id, cP.n2.id) for lvl, cP in far], dtype=np.int64)
+    rng = np.random.RandomState(3)
+    sel = np.sort(rng.choice(len(far), min(max_far, len(far)), replace=False))
+    out['far_sel'] = sel
+    out['far_box1'] = np.array([np.array(far[i][1].n1.box) for i in sel])
+    out['far_box2'] = np.array([np.array(far[i][1].n2.box) for i in sel])
+    out['far_m1'] = np.array([far[i][1].n1.interpolation_order for i in sel], dtype=np.int32)
+    out['far_m2'] = np.array([far[i][1].n2.interpolation_order for i in sel], dtype=np.int32)
+    blocks = [np.array(far[i][1].kernelInterpolant).ravel() for i in sel]
+    out['far_ptr'] = np.concatenate(([0], np.cumsum([b_.shape[0] for b_ in blocks]))).astype(np.int64)
+    out['far_blocks'] = np.concatenate(blocks)
+    An = H.Anear
+    out['Anear_indptr'] = np.array(An.indptr)
+    out['Anear_indices'] = np.array(An.indices)
+    out['Anear_data'] = np.array(An.data)
+    if hasattr(An, 'diagonal') and An.__class__.__name__.startswith('SSS'):
+        out['Anear_diagonal'] = np.array(An.diagonal)
+    out['Anear_type'] = An.__class__.__name__
+    x = np.sin(np.arange(dm.num_dofs)*0.37)+0.1
+    out['x'] = x
+    out['Hx'] = H*x
+    A = np.array(b.getDense().data)
+    out['Ax'] = A.dot(x)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, H)
+
+
 def kernel_values():
     """closed-form style spot values straight from the reference kernels"""
     rng = np.random.RandomState(2)
@@ -226,5 +309,11 @@ if __name__ == '__main__':
         disc_case(3, 0.75, 'disc_s0.75_r3')
         disc_case(2, 0.25, 'disc_s0.25_r2')
         disc_case(4, 0.75, 'disc_mesh_r4', with_A=False)
+    if 'all' in which or 'varconst' in which:
+        varconst_case(2, 0.75, 'disc_varconst0.75_r2')
+        varconst_case(3, 0.4, 'disc_varconst0.4_r3')
+    if 'all' in which or 'h2' in which:
+        h2_case(2, 4, 0.75, 'h2_disc_s0.75_r4')
+        h2_case(1, 8, 0.25, 'h2_interval_s0.25_r8')
     if 'all' in which or 'kernels' in which:
         kernel_values()

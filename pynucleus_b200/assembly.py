@@ -112,8 +112,9 @@ class nonlocalBuilder:
         self.setKernel(kernel, zeroExterior)
 
     def setKernel(self, kernel, zeroExterior=True):
-        if not kernel.symmetric or kernel.variable:
-            raise NotImplementedError('only symmetric kernels with constant parameters are supported yet')
+        from .kernels import constFractionalOrder
+        if not kernel.symmetric or not isinstance(kernel.s, constFractionalOrder):
+            raise NotImplementedError('only symmetric kernels whose order is constant in space are supported yet')
         self.kernel = kernel
         # nonlocalAssembly_{SCALAR}.pxi:918-921
         self.zeroExterior = False if kernel.finiteHorizon else zeroExterior
@@ -242,6 +243,32 @@ class nonlocalBuilder:
             _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.ctypes.data, N, 0))
         self._retry_on_order(run)
         return A
+
+    def getFarFieldBlocks(self, boxes1, boxes2, m1, m2):
+        """kernelInterpolant blocks of admissible cluster pairs (assembleFarFieldInteractions,
+        clusterMethodCy.pyx:2153-2238): list of (m1^d x m2^d) arrays  -2 gamma(xi_i, xi_j)."""
+        dim = self.mesh.dim
+        boxes1 = np.ascontiguousarray(boxes1, dtype=np.float64).reshape(-1, dim, 2)
+        boxes2 = np.ascontiguousarray(boxes2, dtype=np.float64).reshape(-1, dim, 2)
+        m1 = np.ascontiguousarray(m1, dtype=np.int32)
+        m2 = np.ascontiguousarray(m2, dtype=np.int32)
+        nblk = m1.shape[0]
+        max_m = int(max(m1.max(), m2.max())) if nblk else 1
+        # 1D Chebyshev nodes, evaluated with numpy exactly as the reference does (clusterMethodCy.pyx:2178, 2194)
+        eta_ptr = np.zeros(max_m+2, dtype=np.int32)
+        etas = []
+        for m in range(max_m+1):
+            eta_ptr[m] = sum(e.shape[0] for e in etas)
+            etas.append(np.cos((2.0*np.arange(m, 0, -1)-1.0)/(2.0*m)*np.pi) if m > 0 else np.zeros(0))
+        eta_ptr[max_m+1] = sum(e.shape[0] for e in etas)
+        eta = np.ascontiguousarray(np.concatenate(etas)) if etas else np.zeros(1)
+        sizes = (m1.astype(np.int64)**dim)*(m2.astype(np.int64)**dim)
+        offsets = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+        out = np.empty(int(offsets[-1]))
+        _lib.check(_lib.lib().pnb_farfield_blocks(self.problem.handle, nblk, boxes1.ctypes.data, boxes2.ctypes.data,
+                                                  m1.ctypes.data, m2.ctypes.data, max_m, eta.ctypes.data,
+                                                  eta_ptr.ctypes.data, offsets.ctypes.data, out.ctypes.data))
+        return [out[offsets[b]:offsets[b+1]].reshape(int(m1[b])**dim, int(m2[b])**dim) for b in range(nblk)]
 
     def getStats(self):
         stats = np.zeros(8, dtype=np.int64)

@@ -96,6 +96,8 @@ struct pnb_problem {
     int far_mask = 0;   // bit o set: order o is handled by the thread-per-pair evaluator
     int64_t stats[8] = {0};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *stage = nullptr;      // device staging of the host-output entry point
+    size_t stage_bytes = 0;
     double timings[4] = {0};
     int64_t distinct_pairs = 0;
     // host copies needed later
@@ -213,6 +215,7 @@ extern "C" void pnb_problem_destroy(pnb_problem *p)
     for (void *d : p->allocs) cudaFree(d);
     for (void *d : p->rule_allocs) cudaFree(d);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stage) cudaFree(p->stage);
     if (g_bench_problem == p) g_bench_problem = nullptr;
     delete p;
 }
@@ -1463,14 +1466,27 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
     CK(cudaSetDevice(p->device));
     const int N = p->N;
     double *dA = A;
-    if (!a_on_device) CK(cudaMalloc(&dA, (size_t)N * ld * sizeof(double)));
-    int rc = pnb_dense_rows_begin(p, zero_exterior, 0, N, dA, ld);
-    if (!rc) rc = pnb_dense_rows_end(p, 0, N, dA, ld);
+    if (!a_on_device) {
+        // device staging buffer, kept for the life of the problem
+        const size_t need = (size_t)N * N * sizeof(double);
+        if (p->stage_bytes < need) {
+            if (p->stage) cudaFree(p->stage);
+            p->stage = nullptr;
+            p->stage_bytes = 0;
+            CK(cudaMalloc(&p->stage, need));
+            p->stage_bytes = need;
+        }
+        dA = (double *)p->stage;
+    }
+    const int64_t dld = a_on_device ? ld : N;
+    int rc = pnb_dense_rows_begin(p, zero_exterior, 0, N, dA, dld);
+    if (!rc) rc = pnb_dense_rows_end(p, 0, N, dA, dld);
     if (!rc && !a_on_device) {
-        cudaError_t e = cudaMemcpy2D(A, (size_t)ld * sizeof(double), dA, (size_t)ld * sizeof(double), (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost);
+        cudaError_t e;
+        if (ld == N) e = cudaMemcpy(A, dA, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost);
+        else e = cudaMemcpy2D(A, (size_t)ld * sizeof(double), dA, (size_t)N * sizeof(double), (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
     }
-    if (!a_on_device) cudaFree(dA);
     return rc;
 }
 
@@ -1486,6 +1502,82 @@ extern "C" int pnb_dense_timings(pnb_problem *p, double *ms)
     if (!p || !ms) return fail(PNB_ERR_ARG, "null argument");
     memcpy(ms, p->timings, sizeof(p->timings));
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// H2 far-field kernel blocks (assembleFarFieldInteractions, clusterMethodCy.pyx:2153-2238):
+// block b holds -2 gamma(xi_i, xi_j) at the tensor Chebyshev nodes of the two cluster boxes,
+// xi = (hi-lo)*0.5*(eta_p+1) + lo with the 1D nodes eta supplied by the host (np.cos as in the
+// reference), multi-index with the last dimension fastest (productIterator, :2120-2151).
+// One CTA per block, threads over the m1^d x m2^d entries.
+// ---------------------------------------------------------------------------
+__global__ void farfield_kernel(const PowTab *__restrict__ tab, int dim, const double *__restrict__ boxes1,
+                                const double *__restrict__ boxes2, const int *__restrict__ m1s, const int *__restrict__ m2s,
+                                const double *__restrict__ eta, const int *__restrict__ eta_ptr,
+                                const long long *__restrict__ offsets, double *__restrict__ out)
+{
+    const int b = blockIdx.x;
+    const int m1 = m1s[b], m2 = m2s[b];
+    const int n1 = dim == 1 ? m1 : m1 * m1, n2 = dim == 1 ? m2 : m2 * m2;
+    const double *e1 = eta + eta_ptr[m1], *e2 = eta + eta_ptr[m2];
+    const double *bx = boxes1 + (size_t)b * dim * 2, *by = boxes2 + (size_t)b * dim * 2;
+    const PowCtx kv(tab);
+    double *o = out + offsets[b];
+    for (int e = threadIdx.x; e < n1 * n2; e += blockDim.x) {
+        const int i = e / n2, j = e - i * n2;
+        double d2 = 0.;
+        for (int a = 0; a < dim; a++) {
+            const int pi = dim == 1 ? i : (a == 0 ? i / m1 : i % m1);
+            const int pj = dim == 1 ? j : (a == 0 ? j / m2 : j % m2);
+            const double x = PNB_ADD(PNB_MUL(PNB_MUL(PNB_SUB(bx[2 * a + 1], bx[2 * a]), 0.5), PNB_ADD(e1[pi], 1.0)), bx[2 * a]);
+            const double y = PNB_ADD(PNB_MUL(PNB_MUL(PNB_SUB(by[2 * a + 1], by[2 * a]), 0.5), PNB_ADD(e2[pj], 1.0)), by[2 * a]);
+            const double t = PNB_SUB(x, y);
+            d2 = a == 0 ? PNB_MUL(t, t) : PNB_ADD(d2, PNB_MUL(t, t));
+        }
+        o[e] = kv(d2) * -2.0;
+    }
+}
+
+extern "C" int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, const double *boxes2,
+                                   const int32_t *m1, const int32_t *m2, int32_t max_m, const double *eta,
+                                   const int32_t *eta_ptr, const int64_t *offsets, double *out)
+{
+    if (!p || !boxes1 || !boxes2 || !m1 || !m2 || !eta || !eta_ptr || !offsets || !out) return fail(PNB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(p->device));
+    if (nblk == 0) return 0;
+    const int dim = p->dim;
+    const int64_t total = offsets[nblk];
+    double *db1 = nullptr, *db2 = nullptr, *deta = nullptr, *dout = nullptr;
+    int *dm1 = nullptr, *dm2 = nullptr, *dptr = nullptr;
+    long long *doff = nullptr;
+    const size_t nb = (size_t)nblk, neta = (size_t)eta_ptr[max_m + 1];
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+#define FF(call) if (e == cudaSuccess) e = (call)
+    FF(cudaMalloc(&db1, nb * dim * 2 * sizeof(double)));
+    FF(cudaMalloc(&db2, nb * dim * 2 * sizeof(double)));
+    FF(cudaMalloc(&dm1, nb * sizeof(int)));
+    FF(cudaMalloc(&dm2, nb * sizeof(int)));
+    FF(cudaMalloc(&deta, neta * sizeof(double)));
+    FF(cudaMalloc(&dptr, ((size_t)max_m + 2) * sizeof(int)));
+    FF(cudaMalloc(&doff, (nb + 1) * sizeof(long long)));
+    FF(cudaMalloc(&dout, (size_t)total * sizeof(double)));
+    FF(cudaMemcpy(db1, boxes1, nb * dim * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    FF(cudaMemcpy(db2, boxes2, nb * dim * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    FF(cudaMemcpy(dm1, m1, nb * sizeof(int), cudaMemcpyHostToDevice));
+    FF(cudaMemcpy(dm2, m2, nb * sizeof(int), cudaMemcpyHostToDevice));
+    FF(cudaMemcpy(deta, eta, neta * sizeof(double), cudaMemcpyHostToDevice));
+    FF(cudaMemcpy(dptr, eta_ptr, ((size_t)max_m + 2) * sizeof(int), cudaMemcpyHostToDevice));
+    FF(cudaMemcpy(doff, offsets, (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    if (e == cudaSuccess) {
+        farfield_kernel<<<(unsigned)nblk, 256>>>(p->P.pow_int, dim, db1, db2, dm1, dm2, deta, dptr, doff, dout);
+        e = cudaGetLastError();
+    }
+    FF(cudaMemcpy(out, dout, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost));
+#undef FF
+    if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("far-field blocks: ") + cudaGetErrorString(e));
+    cudaFree(db1); cudaFree(db2); cudaFree(dm1); cudaFree(dm2); cudaFree(deta); cudaFree(dptr); cudaFree(doff); cudaFree(dout);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

@@ -32,6 +32,15 @@ class constFractionalOrder:
         return '{}'.format(self.value)
 
 
+class variableConstFractionalOrder(constFractionalOrder):
+    """s(x,y) = const declared as a *variable* order (fractionalOrders.pyx:203-220).  The reference then runs
+    its variable-kernel code path (per-pair evalParams, lazily built singular rules, NO.pxi:509-513, 534-535),
+    whose result equals the constant-order one to rounding (4.5e-16, tests/golden/disc_varconst*.npz).  On the
+    device the order is a constant, so the kernel is assembled by the same kernels; only the host-side flags
+    (`kernel.variable`, `kernel.variableOrder`) differ."""
+    pass
+
+
 class constant:
     """constant function, used for the horizon (fem functions.pyx)"""
 
@@ -71,7 +80,7 @@ class FractionalKernel:
         self.phi = phi
         self.scalingPrePhi = scaling
         self.scalingValue = scaling if phi is None else phi*scaling
-        self.variableOrder = not isinstance(s, constFractionalOrder)
+        self.variableOrder = isinstance(s, variableConstFractionalOrder) or not isinstance(s, constFractionalOrder)
         self.variableHorizon = False
         self.variableScaling = False
         self.variable = self.variableOrder

@@ -254,3 +254,35 @@ def test_row_blocks_equal_full_operator(nblocks):
     A = torch.cat(outs, dim=0).cpu().numpy()
     assert entry_err(A, full) < TOL
     assert np.array_equal(A, A.T)
+
+
+@pytest.mark.parametrize('name', ['disc_varconst0.75_r2', 'disc_varconst0.4_r3'])
+def test_varconst_kernel_vs_reference(golden_dir, name):
+    """BASELINE config 4: the reference's variable-order code path with s(x,y) = const"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'])
+    dm = pb.P1_DoFMap(mesh)
+    kernel = pb.getFractionalKernel(2, pb.variableConstFractionalOrder(float(g['s'])))
+    assert kernel.variable and kernel.symmetric
+    A = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense().data
+    assert entry_err(A, g['A']) < TOL
+
+
+@pytest.mark.parametrize('name', ['h2_disc_s0.75_r4', 'h2_interval_s0.25_r8'])
+def test_farfield_blocks_vs_reference(golden_dir, name):
+    """H2 far-field Chebyshev kernel blocks (clusterMethodCy.pyx:2153-2238) against the reference's kernelInterpolant"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    dim = g['vertices'].shape[1]
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices'].reshape(-1, 1)
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=bf)
+    dm = pb.P1_DoFMap(mesh)
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, float(g['s'])), {'target_order': 0.5} if dim == 2 else {})
+    blocks = b.getFarFieldBlocks(g['far_box1'], g['far_box2'], g['far_m1'], g['far_m2'])
+    ptr = g['far_ptr']
+    worst = 0.
+    for k, blk in enumerate(blocks):
+        ref = g['far_blocks'][ptr[k]:ptr[k+1]].reshape(blk.shape)
+        worst = max(worst, (np.abs(blk-ref)/np.abs(ref)).max())
+    assert worst < 1e-14

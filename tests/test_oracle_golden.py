@@ -146,3 +146,15 @@ def test_slices_add_up():
     nc = P.P.nc
     B = sum(P.dense(True, start=a, end=b) for a, b in ((0, 30), (30, 61), (61, nc)))
     assert np.abs(A-B).max()/np.abs(A).max() < 1e-14
+
+
+@pytest.mark.parametrize('name', ['h2_disc_s0.75_r4', 'h2_interval_s0.25_r8'])
+def test_farfield_blocks_match_reference(golden_dir, name):
+    from oracle import h2
+    g = load(golden_dir, name)
+    dim = g['vertices'].shape[1]
+    ptr = g['far_ptr']
+    for k in range(g['far_m1'].shape[0]):
+        blk = h2.farfield_block(dim, float(g['s']), g['far_box1'][k], g['far_box2'][k], g['far_m1'][k], g['far_m2'][k])
+        ref = g['far_blocks'][ptr[k]:ptr[k+1]].reshape(blk.shape)
+        assert (np.abs(blk-ref)/np.abs(ref)).max() < 1e-14
