@@ -135,7 +135,7 @@ class nonlocalBuilder:
                 raise RuntimeError('pynucleus_b200 needs a CUDA device; there is no CPU fallback')
             device = self.params.get('device', torch.cuda.current_device())
             self._problem = _Problem(self.dm, self.kernel, self.kernelBoundary, self.orders, device,
-                                     self.params.get('max_regular_order', 24))
+                                     self.params.get('max_regular_order', 32))
         return self._problem
 
     def _retry_on_order(self, fn):
@@ -144,6 +144,9 @@ class nonlocalBuilder:
         except _lib.PNBError as e:
             if e.code != -5:
                 raise
+            import os, sys
+            if os.environ.get('PNB_BENCH_VERBOSE'):
+                print('retry:', e, file=sys.stderr)
             # the reference grows its rule cache lazily (addQuadRule); do the same in one step
             need = self.problem.required_max_order(self.zeroExterior)
             self.problem.set_max_order(need)

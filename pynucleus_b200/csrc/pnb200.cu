@@ -20,6 +20,7 @@
 #include "pnb_pair.cuh"
 
 #include <algorithm>
+#include <time.h>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -1479,14 +1480,20 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
         dA = (double *)p->stage;
     }
     const int64_t dld = a_on_device ? ld : N;
+    const bool verbose = getenv("PNB_BENCH_VERBOSE") != nullptr;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t0 = now();
     int rc = pnb_dense_rows_begin(p, zero_exterior, 0, N, dA, dld);
+    const double t1 = now();
     if (!rc) rc = pnb_dense_rows_end(p, 0, N, dA, dld);
+    const double t2 = now();
     if (!rc && !a_on_device) {
         cudaError_t e;
         if (ld == N) e = cudaMemcpy(A, dA, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost);
         else e = cudaMemcpy2D(A, (size_t)ld * sizeof(double), dA, (size_t)N * sizeof(double), (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
     }
+    if (verbose) fprintf(stderr, "pnb_dense_assemble: begin %.1f ms, end %.1f ms, copy %.1f ms (device timers: tiles %.1f)\n", t1 - t0, t2 - t1, now() - t2, p->timings[0]);
     return rc;
 }
 
