@@ -319,6 +319,33 @@ def run_cuda(args):
                         'pow evaluations/s = {:.3e}; tile-halo redundancy {:.3f}x; kernel share of step {:.3f}'.format(
                             pows/t_tile, st['evaluated_pairs']/max(st['distinct_pairs'], 1), t_tile*1e3/ms_step)}
 
+    # second kernel of the path: y = A x on the assembled rows (HBM-bound, reads the matrix once)
+    matvec = None
+    if r1 > r0:
+        Aop = pb.Dense_LinearOperator(A[:r1-r0], local_rank)
+        xv = torch.ones(N, dtype=torch.float64, device=dev)
+        yv = torch.empty(r1-r0, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            Aop.matvec_device(xv, yv)
+        mv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in mv:
+            flush.zero_()
+            a.record()
+            Aop.matvec_device(xv, yv)
+            b.record()
+        torch.cuda.synchronize()
+        mv_ms = float(np.median([a.elapsed_time(b) for a, b in mv]))
+        hbm_peak = None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'MEASURED_PEAKS.json')) as f:
+                hbm_peak = float(json.load(f)['hbm_gbs'])
+        except Exception:
+            pass
+        gbs = ((r1-r0)*N*8+N*8+(r1-r0)*8)/(mv_ms*1e-3)/1e9
+        matvec = {'kernel': 'matvec_kernel', 'bound': 'hbm', 'ms': mv_ms, 'achieved': gbs, 'unit': 'GB/s',
+                  'peak': hbm_peak, 'frac': gbs/hbm_peak if hbm_peak else None,
+                  'note': 'algorithmic bytes = 8*(rows*N + N + rows); L2 flushed between launches; peak = MEASURED_PEAKS.json hbm_gbs'}
+
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
         cpu = reference_throughput(args.workload, target_seconds=args.ref_seconds)
@@ -336,6 +363,7 @@ def run_cuda(args):
                     'ms_per_step': float(np.mean(e2e_ms)), 'checksum_A00': checksum},
             'gpu_launches': int(launches),
             'roofline': roofline,
+            'matvec': matvec,
             'cpu_baseline': cpu,
             'phases_ms': {'tiles': st['ms_tiles'], 'boundary': st['ms_boundary'], 'reduce_scatter': st['ms_reduce_scatter']},
             'pairs': {'distinct': st['distinct_pairs'], 'evaluated': st['evaluated_pairs']}}

@@ -193,6 +193,25 @@ def disc_case(noRef, s, name, full_pairs=False, with_A=True):
     print(name, out['cells'].shape, out.get('A', np.zeros((0, 0))).shape)
 
 
+def rows_case(noRef, s, name, nrows=12):
+    """Larger mesh (N = 2977 at noRef 5): the full matrix is too big to commit, keep sampled rows, the diagonal,
+    and products with seeded vectors."""
+    mesh = uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    out = mesh_arrays(mesh, dm)
+    kernel = getFractionalKernel(2, constFractionalOrder(s), np.inf)
+    A = np.array(nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense().data)
+    rng = np.random.default_rng(7)
+    rows = np.sort(rng.choice(dm.num_dofs, nrows, replace=False))
+    x = rng.standard_normal(dm.num_dofs)
+    out.update(s=s, rows=rows, A_rows=A[rows], diagonal=np.diag(A).copy(), x=x, Ax=A.dot(x),
+               ones_Ax=A.dot(np.ones(dm.num_dofs)), frobenius=np.linalg.norm(A))
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, dm.num_dofs)
+
+
 def varconst_case(noRef, s, name):
     """variable-order code path of the reference with s(x,y) = const (config 4): dense matrix only"""
     from PyNucleus_nl.fractionalOrders import variableConstFractionalOrder
@@ -309,6 +328,8 @@ if __name__ == '__main__':
         disc_case(3, 0.75, 'disc_s0.75_r3')
         disc_case(2, 0.25, 'disc_s0.25_r2')
         disc_case(4, 0.75, 'disc_mesh_r4', with_A=False)
+    if 'all' in which or 'rows' in which:
+        rows_case(5, 0.75, 'disc_s0.75_r5_rows')
     if 'all' in which or 'varconst' in which:
         varconst_case(2, 0.75, 'disc_varconst0.75_r2')
         varconst_case(3, 0.4, 'disc_varconst0.4_r3')

@@ -235,6 +235,20 @@ class nonlocalBuilder:
         self._retry_on_order(run)
         return Dense_LinearOperator(A, prob.device) if not empty else None
 
+    def getDenseDistributed(self, process_group=None):
+        """getDense() sharded by rows over the ranks of `process_group` (one process per GPU): returns a
+        DistributedDenseOperator whose matvec all-gathers the product (the reference's distributed operators
+        Allreduce instead, clusterMethodCy.pyx:3136-3142)."""
+        import torch.distributed as dist
+        from .solvers import DistributedDenseOperator
+        world = dist.get_world_size(process_group)
+        rank = dist.get_rank(process_group)
+        N = self.dm.num_dofs
+        blocks = row_partition(N, world, int(_lib.lib().pnb_row_granularity()))
+        a, b = blocks[rank]
+        rows = self.getDenseRowBlock(a, b, process_group=process_group)
+        return DistributedDenseOperator(rows, a, b, N, blocks, process_group)
+
     def getDenseHost(self, out=None):
         """Same as getDense() but through the host-buffer C entry point: the result is written to host memory
         (device -> host copy inside the call)."""

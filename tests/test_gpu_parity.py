@@ -286,3 +286,98 @@ def test_farfield_blocks_vs_reference(golden_dir, name):
         ref = g['far_blocks'][ptr[k]:ptr[k+1]].reshape(blk.shape)
         worst = max(worst, (np.abs(blk-ref)/np.abs(ref)).max())
     assert worst < 1e-14
+
+
+def _p1_load_vector(mesh, dm, fun=None, rule=None):
+    """b_i = int f phi_i (f = 1 when fun is None, exact); rule = (bary[nvc, n], w[n])"""
+    nvc = mesh.dim+1
+    b = np.zeros(dm.num_dofs)
+    bary, w = rule if rule is not None else (None, None)
+    for k in range(nvc):
+        m = dm.dofs[:, k] >= 0
+        if fun is None:
+            val = mesh.volVector/nvc
+        else:
+            pts = np.einsum('qk,ckd->cqd', bary.T, mesh.vertices[mesh.cells])      # cells x nodes x dim
+            val = mesh.volVector*np.einsum('q,cq->c', w*bary[k], fun(pts))
+        np.add.at(b, dm.dofs[m, k], val[m])
+    return b
+
+
+def _p1_mass(mesh, dm):
+    nvc = mesh.dim+1
+    M = np.zeros((dm.num_dofs, dm.num_dofs))
+    for a in range(nvc):
+        for c in range(nvc):
+            m = (dm.dofs[:, a] >= 0) & (dm.dofs[:, c] >= 0)
+            fac = 2. if a == c else 1.
+            np.add.at(M, (dm.dofs[m, a], dm.dofs[m, c]), fac*mesh.volVector[m]/((nvc)*(nvc+1)))
+    return M
+
+
+def test_driver_golden_disc_constant_forcing():
+    """Driver-level known answers of the reference (tests/cache_runFractional.py--domaindisc--sconst(0.75)--
+    problemconstant--elementP1--solvercg-mg--matrixFormatdense, noRef 5 -> 2977 DoFs): Hs error 0.0603196,
+    L2 error 0.00225634, compared with the reference's own tolerance rTol = 3e-2
+    (nl/PyNucleus_nl/discretizedProblems.py:225-241).  Error definitions: discretizedProblems.py:77-110,
+    exact values nonlocalProblems.py:741-749.  Solved with CG on the device (dense matvec kernel)."""
+    from scipy.special import gamma
+    import pynucleus_b200 as pb
+    s = 0.75
+    mesh = pb.refined(pb.uniform_disc(), 5)
+    dm = pb.P1_DoFMap(mesh)
+    assert dm.num_dofs == 2977
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, s), {'target_order': 0.5}).getDense()
+    b = _p1_load_vector(mesh, dm)
+    u, its, res = pb.cg(A, b, tol=1e-10, maxiter=2000)
+    assert res[-1] <= 1e-10
+    C = 2.**(-2.*s)*gamma(1.)/gamma(1.+s)/gamma(1.+s)
+    exactHs2 = C*np.pi/(s+1)
+    Hs_error = np.sqrt(abs(b.dot(u)-exactHs2))
+    assert abs(Hs_error-0.060319591944560894) <= 3e-2*0.060319591944560894
+
+    def u_exact(x):
+        return C*np.maximum(1.-(x**2).sum(axis=-1), 0.)**s
+    # the reference integrates z with its default P1 rule, the edge-midpoint rule (fem/PyNucleus_fem/femCy.pyx:2648-2650,
+    # quadrature.pyx:279-282); the L2 number it caches includes that quadrature error, so use the same rule
+    midpoints = (np.array([[0.5, 0.0, 0.5], [0.5, 0.5, 0.0], [0.0, 0.5, 0.5]]), np.full(3, 1./3.))
+    z = _p1_load_vector(mesh, dm, u_exact, rule=midpoints)
+    M = _p1_mass(mesh, dm)
+    L2_ex2 = C**2*np.pi/(1+2*s)
+    L2_error = np.sqrt(abs(L2_ex2-2*z.dot(u)+u.dot(M.dot(u))))
+    assert abs(L2_error-0.002256341047519089) <= 3e-2*0.002256341047519089
+    # energy known answer of the reference's tests/test_fracLapl.py:60-77 (disc): 2 pi 2^{-2s} / (Gamma(1+s)^2 2(s+1))
+    assert abs(b.dot(u)-2*np.pi*2.**(-2*s)/(gamma(1+s)**2*2*(s+1))) < 0.35*exactHs2
+
+
+def test_sampled_rows_at_2977_dofs(golden_dir):
+    """disc, 5 refinements (N = 2977, the reference's driver-test size): CUDA assembly against sampled rows,
+    the diagonal, and seeded products of the reference's own getDense output."""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, 'disc_s0.75_r5_rows')
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'])
+    dm = pb.P1_DoFMap(mesh)
+    Aop = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, float(g['s'])), {'target_order': 0.5}).getDense()
+    A = Aop.toarray()
+    d = np.sqrt(g['diagonal'])
+    scale = np.maximum(np.abs(g['A_rows']), 1e-2*np.outer(d[g['rows']], d))
+    assert (np.abs(A[g['rows']]-g['A_rows'])/scale).max() < TOL
+    assert np.abs(np.diag(A)/g['diagonal']-1).max() < TOL
+    assert np.abs(Aop*g['x']-g['Ax']).max() < TOL*np.abs(g['Ax']).max()
+    assert np.abs(A.dot(np.ones(A.shape[0]))-g['ones_Ax']).max() < TOL*np.abs(g['diagonal']).max()
+    assert abs(np.linalg.norm(A)/float(g['frobenius'])-1) < TOL
+
+
+def test_two_gpus_row_blocks_matvec_cg():
+    """N > 1 on real GPUs (skipped on a one-GPU box): tests/multi_gpu_worker.py under torchrun, NCCL"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', str(29800+os.getpid() % 100),
+           os.path.join(here, 'multi_gpu_worker.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and 'OK' in out.stdout, out.stdout[-2000:]+out.stderr[-4000:]

@@ -158,3 +158,20 @@ def test_farfield_blocks_match_reference(golden_dir, name):
         blk = h2.farfield_block(dim, float(g['s']), g['far_box1'][k], g['far_box2'][k], g['far_m1'][k], g['far_m2'][k])
         ref = g['far_blocks'][ptr[k]:ptr[k+1]].reshape(blk.shape)
         assert (np.abs(blk-ref)/np.abs(ref)).max() < 1e-14
+
+
+def test_sampled_rows_at_2977_dofs(golden_dir):
+    """disc, 5 refinements (the size of the reference's driver test): sampled rows, the diagonal and products
+    with seeded vectors of the reference's getDense output."""
+    g = load(golden_dir, 'disc_s0.75_r5_rows')
+    P = oracle.Problem(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), float(g['s']),
+                       bfacets=g['boundaryEdges'], target_order=0.5, hVector=g['hVector'], volVector=g['volVector'],
+                       hmin=float(g['hmin']), diam=float(g['diam']))
+    A = P.dense(True)
+    d = np.sqrt(g['diagonal'])
+    scale = np.maximum(np.abs(g['A_rows']), 1e-2*np.outer(d[g['rows']], d))
+    assert (np.abs(A[g['rows']]-g['A_rows'])/scale).max() < 1e-12
+    assert np.abs(np.diag(A)/g['diagonal']-1).max() < 1e-13
+    assert np.abs(A.dot(g['x'])-g['Ax']).max() < 1e-12*np.abs(g['Ax']).max()
+    assert np.abs(A.dot(np.ones(A.shape[0]))-g['ones_Ax']).max() < 1e-12*np.abs(g['diagonal']).max()
+    assert abs(np.linalg.norm(A)/float(g['frobenius'])-1) < 1e-13
