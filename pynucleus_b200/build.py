@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'pnb200.cu')
 OUT = os.path.join(HERE, 'libpnb200.so')
 DEPS = [SRC, os.path.join(HERE, 'csrc', 'pnb_device.cuh'), os.path.join(HERE, 'csrc', 'pnb_pair.cuh'),
+        os.path.join(HERE, 'csrc', 'pnb_group.cuh'),
         os.path.join(HERE, '..', 'include', 'pnb200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

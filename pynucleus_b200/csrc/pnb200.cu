@@ -87,8 +87,14 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+struct GroupSched;
+struct GroupHost;
 struct pnb_problem {
     int device = 0;
+    GroupSched *G = nullptr;          // 2D cell-group path (pnb_group.cuh)
+    GroupHost *gh = nullptr;
+    std::vector<int> h_cells, h_dofs; // host copies for the lazy group schedule
+    std::vector<double> h_centers, h_h;
     DProblem P{};
     TileSched S{};
     std::vector<void *> allocs;       // everything to free
@@ -209,6 +215,7 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
     return 0;
 }
 
+static void destroy_group_host(pnb_problem *p);
 extern "C" void pnb_problem_destroy(pnb_problem *p)
 {
     if (!p) return;
@@ -218,6 +225,7 @@ extern "C" void pnb_problem_destroy(pnb_problem *p)
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stage) cudaFree(p->stage);
     if (g_bench_problem == p) g_bench_problem = nullptr;
+    destroy_group_host(p);
     delete p;
 }
 
@@ -292,6 +300,12 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
             for (int k = 0; k < 2; k++) h2 += (sx[2 + k] - sx[k]) * (sx[2 + k] - sx[k]);
             bvol[f] = bh[f] = sqrt(h2);
         }
+    }
+    if (dim == 2) {
+        p->h_cells.assign(mesh->cells, mesh->cells + (size_t)nc * nvc);
+        p->h_dofs.assign(dm->dofs, dm->dofs + (size_t)nc * nvc);
+        p->h_centers = centers;
+        p->h_h.assign(mesh->h, mesh->h + nc);
     }
     int rc = 0;
     rc |= upload(p, simplices.data(), simplices.size(), &P.simplices);
@@ -1513,6 +1527,385 @@ __global__ void scatter_D_kernel(DProblem P, TileSched S, double *A, int64_t ld)
     }
 }
 
+
+#include "pnb_group.cuh"
+
+// ---------------------------------------------------------------------------
+// cell-group schedule (host)
+// ---------------------------------------------------------------------------
+struct GroupHost {
+    bool ready = false;
+    int GC = 0;
+    std::vector<GUnit> f2_units, mix_units, near_units;   // f2 / mix sorted by phase
+    std::vector<int> f2_off, mix_off;                     // phase offsets
+    const GUnit *d_f2 = nullptr, *d_mix = nullptr, *d_near = nullptr;
+    size_t smem_f2 = 0, smem_mix = 0, smem_near = 0;
+    int nphase = 0;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> evs;
+};
+
+static uint64_t hilbert_index(uint32_t x, uint32_t y)
+{
+    uint64_t d = 0;
+    for (uint32_t s = 32768; s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+        d += (uint64_t)s * s * ((3 * rx) ^ ry);
+        if (!ry) {
+            if (rx) { x = 65535 - x; y = 65535 - y; }
+            const uint32_t t = x; x = y; y = t;
+        }
+    }
+    return d;
+}
+
+// upper bound of the real-valued quadrature order (the argument of ceil in getQuadOrder,
+// fractionalLaplacian2D.pyx:622-642) over all pairs with d >= dmin, h1 in group 1, h2 in group 2
+static double order_upper_bound(const DProblem &P, double dmin, double h1max, double h2max, double a1min, double a1max,
+                                double a2min, double a2max)
+{
+    if (!(dmin > 0.)) return 1e30;
+    const double s = fmax(-0.5 * (P.sing + 2), 0.);
+    const double amax = fmax(a1max, a2max);
+    auto f = [&](double hthis_max, double ath_min, double ath_max, double hother_max) {
+        // num = c + (s-1) |log(h_this/H0)| + max(|log h1/H0|, |log h2/H0|) - s log(d/h_this);  den = max(log(d/h_other),0) + 0.4
+        const double num = P.c_int + (s - 1. < 0. ? (s - 1.) * ath_min : (s - 1.) * ath_max) + amax - s * log(dmin / hthis_max);
+        const double den = fmax(log(dmin / hother_max), 0.) + 0.4;
+        return num <= 0. ? 0. : num / den;
+    };
+    return fmax(f(h2max, a2min, a2max, h1max), f(h1max, a1min, a1max, h2max));
+}
+
+
+// ---------------------------------------------------------------------------
+// cell-group path: schedule construction and launch sequence
+// ---------------------------------------------------------------------------
+struct GroupGeom {
+    std::vector<int> gptr, gcells, gloc, gdptr, gdofs, color;
+    std::vector<std::vector<int>> adj;     // groups sharing a vertex (sorted, includes self)
+    std::vector<double> box;               // per group: xmin, xmax, ymin, ymax, hmax, amin, amax
+    int ngroups = 0, cap = 0, maxld = 0, ncolors = 0;
+};
+
+static void build_group_geometry(const pnb_problem *p, int GC, const std::vector<int> &order, GroupGeom &gg)
+{
+    const int nc = p->nc;
+    const int *cells = p->h_cells.data(), *dofs = p->h_dofs.data();
+    gg = GroupGeom();
+    gg.ngroups = std::max(1, (nc + GC - 1) / GC);
+    gg.gptr.assign(1, 0);
+    gg.gdptr.assign(1, 0);
+    std::vector<int> grp(nc, 0);
+    std::vector<std::vector<int>> bcells;
+    std::vector<std::vector<int>> bverts;
+    for (int g = 0; g < gg.ngroups; g++) {
+        const int c0 = g * GC, c1 = std::min(nc, c0 + GC);
+        // local dofs
+        std::vector<int> ld;
+        for (int k = c0; k < c1; k++)
+            for (int m = 0; m < 3; m++) { const int d = dofs[(size_t)order[k] * 3 + m]; if (d >= 0) ld.push_back(d); }
+        std::sort(ld.begin(), ld.end());
+        ld.erase(std::unique(ld.begin(), ld.end()), ld.end());
+        gg.maxld = std::max(gg.maxld, (int)ld.size());
+        // batches of <= PNB_SB cells sharing no vertex; balanced fill (the fullest batches decide the padding)
+        const int B0 = std::max(1, (c1 - c0 + PNB_SB - 1) / PNB_SB);
+        bcells.assign(B0, std::vector<int>());
+        bverts.assign(B0, std::vector<int>());
+        for (int k = c0; k < c1; k++) {
+            const int c = order[k];
+            grp[c] = g;
+            const int *v = cells + (size_t)c * 3;
+            int best = -1;
+            for (int b = 0; b < (int)bcells.size(); b++) {
+                if ((int)bcells[b].size() >= PNB_SB) continue;
+                bool clash = false;
+                for (int x : bverts[b]) clash |= x == v[0] || x == v[1] || x == v[2];
+                if (!clash && (best < 0 || bcells[b].size() < bcells[best].size())) best = b;
+            }
+            if (best < 0) { bcells.emplace_back(); bverts.emplace_back(); best = (int)bcells.size() - 1; }
+            bcells[best].push_back(c);
+            for (int m = 0; m < 3; m++) bverts[best].push_back(v[m]);
+        }
+        // fullest batches first
+        std::stable_sort(bcells.begin(), bcells.end(), [](const std::vector<int> &a, const std::vector<int> &b) { return a.size() > b.size(); });
+        for (auto &bc : bcells) {
+            if (bc.empty()) continue;
+            for (int k = 0; k < PNB_SB; k++) {
+                const int c = k < (int)bc.size() ? bc[k] : -1;
+                gg.gcells.push_back(c);
+                int packed = 0x00FFFFFF;
+                if (c >= 0) {
+                    packed = 0;
+                    for (int m = 0; m < 3; m++) {
+                        const int d = dofs[(size_t)c * 3 + m];
+                        int l = 0xFF;
+                        if (d >= 0) l = (int)(std::lower_bound(ld.begin(), ld.end(), d) - ld.begin());
+                        packed |= l << (8 * m);
+                    }
+                }
+                gg.gloc.push_back(packed);
+            }
+        }
+        gg.gptr.push_back((int)gg.gcells.size());
+        gg.cap = std::max(gg.cap, gg.gptr[g + 1] - gg.gptr[g]);
+        gg.gdofs.insert(gg.gdofs.end(), ld.begin(), ld.end());
+        gg.gdptr.push_back((int)gg.gdofs.size());
+    }
+    // adjacency through shared vertices
+    gg.adj.assign(gg.ngroups, std::vector<int>());
+    {
+        std::vector<std::vector<int>> vg(p->P.nv);
+        for (int c = 0; c < nc; c++)
+            for (int m = 0; m < 3; m++) vg[cells[(size_t)c * 3 + m]].push_back(grp[c]);
+        for (auto &l : vg) {
+            std::sort(l.begin(), l.end());
+            l.erase(std::unique(l.begin(), l.end()), l.end());
+            for (int a : l)
+                for (int b : l) gg.adj[a].push_back(b);
+        }
+        for (int g = 0; g < gg.ngroups; g++) {
+            auto &l = gg.adj[g];
+            l.push_back(g);
+            std::sort(l.begin(), l.end());
+            l.erase(std::unique(l.begin(), l.end()), l.end());
+        }
+    }
+    // greedy colouring
+    gg.color.assign(gg.ngroups, -1);
+    for (int g = 0; g < gg.ngroups; g++) {
+        unsigned long long used = 0;
+        for (int a : gg.adj[g]) if (a != g && gg.color[a] >= 0) used |= 1ull << gg.color[a];
+        int c = 0;
+        while ((used >> c) & 1) c++;
+        gg.color[g] = c;
+        gg.ncolors = std::max(gg.ncolors, c + 1);
+    }
+    // boxes of the cell centers, extreme mesh sizes
+    gg.box.assign((size_t)gg.ngroups * 7, 0.);
+    for (int g = 0; g < gg.ngroups; g++) {
+        double *b = &gg.box[(size_t)g * 7];
+        b[0] = b[2] = 1e300; b[1] = b[3] = -1e300; b[4] = 0.; b[5] = 1e300; b[6] = 0.;
+        for (int k = g * GC; k < std::min(nc, (g + 1) * GC); k++) {
+            const int c = order[k];
+            const double x = p->h_centers[(size_t)c * 2], y = p->h_centers[(size_t)c * 2 + 1], h = p->h_h[c];
+            const double a = fabs(log(h / p->P.H0));
+            b[0] = std::min(b[0], x); b[1] = std::max(b[1], x);
+            b[2] = std::min(b[2], y); b[3] = std::max(b[3], y);
+            b[4] = std::max(b[4], h); b[5] = std::min(b[5], a); b[6] = std::max(b[6], a);
+        }
+    }
+}
+
+struct GroupHostFull : GroupHost {
+    GroupGeom gg;
+    int far_mask = -1, max_order = -1;
+    std::vector<void *> unit_allocs;
+    size_t ns_slots = 0;
+};
+
+static int build_group_schedule(pnb_problem *p)
+{
+    const int nc = p->nc;
+    if (!p->gh) p->gh = new GroupHostFull();
+    if (!p->G) p->G = new GroupSched();
+    GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+    GroupSched &G = *p->G;
+    int smem_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device);
+    if (smem_sm <= 0) smem_sm = 228 * 1024;
+    const size_t budget = (size_t)smem_sm / 2 - 1024;     // two CTAs per SM
+    if (!gh->ready) {
+        // Hilbert order of the cell centers
+        double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+        for (int c = 0; c < nc; c++)
+            for (int l = 0; l < 2; l++) { lo[l] = std::min(lo[l], p->h_centers[(size_t)c * 2 + l]); hi[l] = std::max(hi[l], p->h_centers[(size_t)c * 2 + l]); }
+        std::vector<uint64_t> key(nc);
+        for (int c = 0; c < nc; c++) {
+            uint32_t q[2];
+            for (int l = 0; l < 2; l++) {
+                const double t = hi[l] > lo[l] ? (p->h_centers[(size_t)c * 2 + l] - lo[l]) / (hi[l] - lo[l]) : 0.;
+                q[l] = (uint32_t)std::min(65535., std::max(0., t * 65535.));
+            }
+            key[c] = hilbert_index(q[0], q[1]);
+        }
+        std::vector<int> order(nc);
+        for (int c = 0; c < nc; c++) order[c] = c;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+        const int forced = getenv("PNB_GC") ? atoi(getenv("PNB_GC")) : 0;
+        const int cand[] = {128, 112, 96, 80, 64, 48, 32};
+        for (int GC : cand) {
+            if (forced > 0) GC = forced;
+            build_group_geometry(p, GC, order, gh->gg);
+            gh->GC = GC;
+            const int ldS = gh->gg.maxld + 1;
+            if (forced > 0 || (gmix_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS, false) <= budget && gh->gg.maxld < 255)) break;
+        }
+        const GroupGeom &gg = gh->gg;
+        if (gg.maxld >= 255) return fail(PNB_ERR_UNSUPPORTED, "cell group with more than 254 local dofs");
+        G.ngroups = gg.ngroups; G.cap = gg.cap; G.maxld = gg.maxld; G.ldS = gg.maxld + 1; G.ncolors = gg.ncolors;
+        G.nparts = 4;
+        int rc = 0;
+        rc |= upload(p, gg.gptr.data(), gg.gptr.size(), &G.gptr);
+        rc |= upload(p, gg.gcells.data(), gg.gcells.size(), &G.gcells);
+        rc |= upload(p, gg.gloc.data(), gg.gloc.size(), &G.gloc);
+        rc |= upload(p, gg.gdptr.data(), gg.gdptr.size(), &G.gdptr);
+        rc |= upload(p, gg.gdofs.data(), gg.gdofs.size(), &G.gdofs);
+        rc |= dalloc(p, (size_t)gg.ngroups * nc * 6, &G.Dp);
+        if (rc) return PNB_ERR_CUDA;
+        G.err = p->S.err;
+        G.counters = p->S.counters;
+        G.nsstride = (size_t)G.maxld * G.maxld + 2 * (size_t)G.cap * 6;
+        gh->smem_f2 = gf2_smem_bytes(G.cap, G.maxld, G.ldS);
+        gh->smem_mix = gmix_smem_bytes(G.cap, G.maxld, G.ldS, false);
+        gh->smem_near = gmix_smem_bytes(G.cap, G.maxld, G.ldS, true);
+        for (auto &s : gh->st) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        gh->ready = true;
+        if (getenv("PNB_BENCH_VERBOSE"))
+            fprintf(stderr, "group path: GC %d, %d groups, cap %d, maxld %d, %d colours, smem f2/mix/near %zu/%zu/%zu\n", gh->GC,
+                    gg.ngroups, gg.cap, gg.maxld, gg.ncolors, gh->smem_f2, gh->smem_mix, gh->smem_near);
+    }
+    if (gh->far_mask == p->far_mask && gh->max_order == p->P.max_order) return 0;
+    // ---- unit kinds (depend on the tables) ----
+    const GroupGeom &gg = gh->gg;
+    const bool far_full = (p->far_mask & 0x3C) == 0x3C && p->P.max_order >= PNB_FAR_MAX_ORDER;
+    const bool far_2 = (p->far_mask & 4) && p->P.max_order >= 2;
+    const int ncol = gg.ncolors;
+    gh->nphase = ncol * ncol;
+    std::vector<std::vector<GUnit>> f2(gh->nphase), mix(gh->nphase);
+    gh->near_units.clear();
+    int nslots = 0;
+    for (int I = 0; I < gg.ngroups; I++) {
+        const double *b1 = &gg.box[(size_t)I * 7];
+        for (int J = I; J < gg.ngroups; J++) {
+            const double *b2 = &gg.box[(size_t)J * 7];
+            int kind = 2;
+            if (!std::binary_search(gg.adj[I].begin(), gg.adj[I].end(), J)) {
+                const double dx = std::max(0., std::max(b2[0] - b1[1], b1[0] - b2[1]));
+                const double dy = std::max(0., std::max(b2[2] - b1[3], b1[2] - b2[3]));
+                const double ub = order_upper_bound(p->P, sqrt(dx * dx + dy * dy), b1[4], b2[4], b1[5], b1[6], b2[5], b2[6]);
+                if (far_2 && ub <= 2. - 1e-6) kind = 0;
+                else if (far_full && ub <= PNB_FAR_MAX_ORDER - 1e-6) kind = 1;
+            }
+            GUnit u{I, J, kind, -1};
+            const int ph = gg.color[I] * ncol + gg.color[J];
+            if (kind == 2) { u.slot = nslots++; gh->near_units.push_back(u); }
+            (kind == 0 ? f2 : mix)[ph].push_back(u);
+        }
+    }
+    gh->f2_units.clear(); gh->mix_units.clear();
+    gh->f2_off.assign(1, 0); gh->mix_off.assign(1, 0);
+    for (int ph = 0; ph < gh->nphase; ph++) {
+        // near units first: they are the longest
+        std::stable_sort(mix[ph].begin(), mix[ph].end(), [](const GUnit &a, const GUnit &b) { return a.kind > b.kind; });
+        gh->f2_units.insert(gh->f2_units.end(), f2[ph].begin(), f2[ph].end());
+        gh->mix_units.insert(gh->mix_units.end(), mix[ph].begin(), mix[ph].end());
+        gh->f2_off.push_back((int)gh->f2_units.size());
+        gh->mix_off.push_back((int)gh->mix_units.size());
+    }
+    for (void *d : gh->unit_allocs) cudaFree(d);
+    gh->unit_allocs.clear();
+    auto up = [&](const std::vector<GUnit> &v, const GUnit **dev) -> int {
+        void *d = nullptr;
+        CK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(GUnit)));
+        gh->unit_allocs.push_back(d);
+        if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(GUnit), cudaMemcpyHostToDevice));
+        *dev = (const GUnit *)d;
+        return 0;
+    };
+    if (up(gh->f2_units, &gh->d_f2) || up(gh->mix_units, &gh->d_mix) || up(gh->near_units, &gh->d_near)) return PNB_ERR_CUDA;
+    if ((size_t)nslots > gh->ns_slots) {
+        void *d = nullptr;
+        CK(cudaMalloc(&d, std::max<size_t>((size_t)nslots * G.nparts * G.nsstride, 1) * sizeof(double)));
+        p->allocs.push_back(d);     // older, smaller buffers stay until the problem is destroyed
+        G.NS = (double *)d;
+        gh->ns_slots = nslots;
+    }
+    gh->far_mask = p->far_mask;
+    gh->max_order = p->P.max_order;
+    if (getenv("PNB_BENCH_VERBOSE"))
+        fprintf(stderr, "group path: units f2 %zu, mix %zu (near %zu), phases %d\n", gh->f2_units.size(), gh->mix_units.size(),
+                gh->near_units.size(), gh->nphase);
+    return 0;
+}
+
+static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t ld)
+{
+    if (build_group_schedule(p)) return PNB_ERR_CUDA;
+    GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+    GroupSched &G = *p->G;
+    TileSched &S = p->S;
+    const int nc = p->nc, N = p->N;
+    S.own_t0 = 0;
+    S.own_t1 = S.ntiles;
+    for (auto &e : p->ev) if (!e) cudaEventCreate(&e);
+    cudaFuncSetAttribute(gf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_f2);
+    cudaFuncSetAttribute(gmix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_mix);
+    cudaFuncSetAttribute(gmix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_near);
+    F2Rule R;
+    {
+        const FarRule &F = p->far_rules[2];
+        for (int q = 0; q < 3; q++) {
+            R.w[q] = F.w[q];
+            for (int k = 0; k < 3; k++) { R.bary[k][q] = F.bary[k][q]; R.wphi[q][k] = F.wb[k][q]; }
+            for (int e = 0; e < 6; e++) R.qq[e][q] = F.qq[e][q];
+        }
+        R.c[0] = 1.;
+        for (int k = 1; k < 8; k++) R.c[k] = R.c[k - 1] * (p->P.expo - k + 1) / k;
+    }
+    cudaMemsetAsync(S.err, 0, 4 * sizeof(int));
+    cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * 6 * sizeof(double));
+    cudaEventRecord(p->ev[0]);
+    cudaMemset2DAsync(dA, (size_t)ld * sizeof(double), 0, (size_t)N * sizeof(double), N);
+    int launches = 0;
+    const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
+    if (!gh->near_units.empty() && !(dbg & 0x100)) {
+        gmix_kernel<true><<<(unsigned)(gh->near_units.size() * G.nparts), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, dA, ld, p->far_mask);
+        launches++;
+    }
+    for (int ph = 0; ph < gh->nphase; ph++) {
+        const int nm = gh->mix_off[ph + 1] - gh->mix_off[ph], nf = gh->f2_off[ph + 1] - gh->f2_off[ph];
+        if (nm > 0 && !(dbg & 0x200)) {
+            gmix_kernel<false><<<nm, PNB_THREADS, gh->smem_mix>>>(p->P, G, gh->d_mix + gh->mix_off[ph], dA, ld, p->far_mask);
+            launches++;
+        }
+        if (nf > 0 && !(dbg & 0x1000)) {
+            gf2_kernel<<<nf, PNB_THREADS, gh->smem_f2>>>(p->P, G, gh->d_f2 + gh->f2_off[ph], dA, ld, R);
+            launches++;
+        }
+    }
+    {
+        const unsigned nt = (unsigned)((N + 31) / 32);
+        symmetrize_kernel<<<dim3(nt, nt), 256>>>(dA, ld, N);
+        launches++;
+    }
+    cudaEventRecord(p->ev[1]);
+    if (zero_exterior && p->nb > 0) {
+        boundary_kernel<2><<<(unsigned)(((size_t)nc * 32 + 255) / 256), 256>>>(p->P, S);
+        launches++;
+    }
+    cudaEventRecord(p->ev[2]);
+    greduce_D_kernel<<<(unsigned)(((size_t)nc * 6 + 255) / 256), 256>>>(G, S.D, S.Dbnd, nc, zero_exterior && p->nb > 0);
+    launches++;
+    cudaEventRecord(p->ev[3]);
+    p->stats[2] = launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static void destroy_group_host(pnb_problem *p)
+{
+    if (p->gh) {
+        GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+        for (void *d : gh->unit_allocs) cudaFree(d);
+        for (auto &s : gh->st) if (s) cudaStreamDestroy(s);
+        delete gh;
+        p->gh = nullptr;
+    }
+    delete p->G;
+    p->G = nullptr;
+}
+
 static int check_rows(pnb_problem *p, int32_t row_begin, int32_t row_end)
 {
     if (row_begin < 0 || row_end > p->N || row_begin >= row_end) return fail(PNB_ERR_ARG, "invalid row range");
@@ -1533,6 +1926,9 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     CK(cudaSetDevice(p->device));
     const int nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
     TileSched &S = p->S;
+    // 2D, whole operator: cell-group path (PNB_DEBUG bit 0x800 forces the DoF-tile path)
+    if (p->dim == 2 && row_begin == 0 && row_end == p->N && !((getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0) & 0x800))
+        return run_group_path(p, zero_exterior, dA, ld);
     S.own_t0 = row_begin / PNB_TD;
     S.own_t1 = (row_end + PNB_TD - 1) / PNB_TD;
     // units: group pairs (gr <= gc) that hold a tile touching an owned row tile, near-diagonal first
@@ -1645,6 +2041,7 @@ extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row
     if (e == cudaSuccess) e = cudaMemcpy(hcnt, S.counters, sizeof(hcnt), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return fail(PNB_ERR_CUDA, std::string("dense assembly: ") + cudaGetErrorString(e));
     if (herr[0] > 0) return fail(PNB_ERR_ORDER, "regular quadrature order " + std::to_string(herr[0]) + " exceeds the supplied tables (max_order " + std::to_string(p->P.max_order) + ")");
+    if (herr[1] > 0) return fail(PNB_ERR_CUDA, "internal error: a unit classified as far holds a near pair");
     float ms;
     for (int k = 0; k < 2; k++) { cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]); p->timings[k] = ms; }
     cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]);
