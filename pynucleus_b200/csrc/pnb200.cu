@@ -1699,8 +1699,10 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
 struct GroupHostFull : GroupHost {
     GroupGeom gg;
     int far_mask = -1, max_order = -1;
-    std::vector<void *> unit_allocs;
-    size_t ns_slots = 0;
+    std::vector<void *> unit_allocs, near_allocs;
+    const int2 *d_items = nullptr;
+    double *d_R = nullptr;
+    int nitems = 0, npairs = 0;
 };
 
 static int build_group_schedule(pnb_problem *p)
@@ -1738,12 +1740,12 @@ static int build_group_schedule(pnb_problem *p)
             build_group_geometry(p, GC, order, gh->gg);
             gh->GC = GC;
             const int ldS = gh->gg.maxld + 1;
-            if (forced > 0 || (gmix_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS, false) <= budget && gh->gg.maxld < 255)) break;
+            if (forced > 0 || (gmix_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS) <= budget && gh->gg.maxld < 255)) break;
         }
         const GroupGeom &gg = gh->gg;
         if (gg.maxld >= 255) return fail(PNB_ERR_UNSUPPORTED, "cell group with more than 254 local dofs");
         G.ngroups = gg.ngroups; G.cap = gg.cap; G.maxld = gg.maxld; G.ldS = gg.maxld + 1; G.ncolors = gg.ncolors;
-        G.nparts = 4;
+        G.nbmax = gg.cap / PNB_SB;
         int rc = 0;
         rc |= upload(p, gg.gptr.data(), gg.gptr.size(), &G.gptr);
         rc |= upload(p, gg.gcells.data(), gg.gcells.size(), &G.gcells);
@@ -1754,10 +1756,9 @@ static int build_group_schedule(pnb_problem *p)
         if (rc) return PNB_ERR_CUDA;
         G.err = p->S.err;
         G.counters = p->S.counters;
-        G.nsstride = (size_t)G.maxld * G.maxld + 2 * (size_t)G.cap * 6;
         gh->smem_f2 = gf2_smem_bytes(G.cap, G.maxld, G.ldS);
-        gh->smem_mix = gmix_smem_bytes(G.cap, G.maxld, G.ldS, false);
-        gh->smem_near = gmix_smem_bytes(G.cap, G.maxld, G.ldS, true);
+        gh->smem_mix = gmix_smem_bytes(G.cap, G.maxld, G.ldS);
+        gh->smem_near = gnear_list_smem_bytes(G.cap);
         for (auto &s : gh->st) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         gh->ready = true;
         if (getenv("PNB_BENCH_VERBOSE"))
@@ -1813,18 +1814,48 @@ static int build_group_schedule(pnb_problem *p)
         return 0;
     };
     if (up(gh->f2_units, &gh->d_f2) || up(gh->mix_units, &gh->d_mix) || up(gh->near_units, &gh->d_near)) return PNB_ERR_CUDA;
-    if ((size_t)nslots > gh->ns_slots) {
-        void *d = nullptr;
-        CK(cudaMalloc(&d, std::max<size_t>((size_t)nslots * G.nparts * G.nsstride, 1) * sizeof(double)));
-        p->allocs.push_back(d);     // older, smaller buffers stay until the problem is destroyed
-        G.NS = (double *)d;
-        gh->ns_slots = nslots;
+    // ---- near pair list: count, allocate, fill (depends on mesh and tables only; reused by every assembly) ----
+    for (void *d : gh->near_allocs) cudaFree(d);
+    gh->near_allocs.clear();
+    gh->nitems = 0;
+    if (!gh->near_units.empty()) {
+        int *cursor = nullptr;
+        CK(cudaMalloc((void **)&cursor, 4 * sizeof(int)));
+        gh->near_allocs.push_back(cursor);
+        CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
+        CK(cudaMemset(p->S.err, 0, 4 * sizeof(int)));
+        cudaFuncSetAttribute(gnear_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_near);
+        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 0, cursor, nullptr, nullptr, nullptr);
+        int tot[2] = {0, 0};
+        CK(cudaMemcpy(tot, cursor, sizeof(tot), cudaMemcpyDeviceToHost));
+        int4 *pairs = nullptr;
+        int2 *items = nullptr;
+        int *nearbase = nullptr;
+        double *R = nullptr;
+        CK(cudaMalloc((void **)&pairs, std::max<size_t>(tot[0], 1) * sizeof(int4)));
+        gh->near_allocs.push_back(pairs);
+        CK(cudaMalloc((void **)&items, std::max<size_t>(tot[1], 1) * sizeof(int2)));
+        gh->near_allocs.push_back(items);
+        CK(cudaMalloc((void **)&nearbase, (size_t)nslots * G.nbmax * G.nbmax * sizeof(int)));
+        gh->near_allocs.push_back(nearbase);
+        CK(cudaMalloc((void **)&R, std::max<size_t>(tot[1], 1) * PairDims<2>::NL * sizeof(double)));
+        gh->near_allocs.push_back(R);
+        CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
+        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 1, cursor, pairs, items, nearbase);
+        CK(cudaDeviceSynchronize());
+        G.npairs = pairs;
+        G.nearbase = nearbase;
+        G.R = R;
+        gh->d_items = items;
+        gh->d_R = R;
+        gh->nitems = tot[1];
+        gh->npairs = tot[0];
     }
     gh->far_mask = p->far_mask;
     gh->max_order = p->P.max_order;
     if (getenv("PNB_BENCH_VERBOSE"))
-        fprintf(stderr, "group path: units f2 %zu, mix %zu (near %zu), phases %d\n", gh->f2_units.size(), gh->mix_units.size(),
-                gh->near_units.size(), gh->nphase);
+        fprintf(stderr, "group path: units f2 %zu, mix %zu (near %zu), phases %d; near pairs %d in %d items\n", gh->f2_units.size(),
+                gh->mix_units.size(), gh->near_units.size(), gh->nphase, gh->npairs, gh->nitems);
     return 0;
 }
 
@@ -1839,8 +1870,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     S.own_t1 = S.ntiles;
     for (auto &e : p->ev) if (!e) cudaEventCreate(&e);
     cudaFuncSetAttribute(gf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_f2);
-    cudaFuncSetAttribute(gmix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_mix);
-    cudaFuncSetAttribute(gmix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_near);
+    cudaFuncSetAttribute(gmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_mix);
     F2Rule R;
     {
         const FarRule &F = p->far_rules[2];
@@ -1859,14 +1889,15 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     cudaMemset2DAsync(dA, (size_t)ld * sizeof(double), 0, (size_t)N * sizeof(double), N);
     int launches = 0;
     const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
-    if (!gh->near_units.empty() && !(dbg & 0x100)) {
-        gmix_kernel<true><<<(unsigned)(gh->near_units.size() * G.nparts), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, dA, ld, p->far_mask);
+    if (gh->nitems > 0 && !(dbg & 0x100)) {
+        const int wpb = PNB_THREADS / 32;
+        gnear_eval_kernel<<<(unsigned)((gh->nitems + wpb - 1) / wpb), PNB_THREADS>>>(p->P, G.npairs, gh->d_items, gh->nitems, gh->d_R);
         launches++;
     }
     for (int ph = 0; ph < gh->nphase; ph++) {
         const int nm = gh->mix_off[ph + 1] - gh->mix_off[ph], nf = gh->f2_off[ph + 1] - gh->f2_off[ph];
         if (nm > 0 && !(dbg & 0x200)) {
-            gmix_kernel<false><<<nm, PNB_THREADS, gh->smem_mix>>>(p->P, G, gh->d_mix + gh->mix_off[ph], dA, ld, p->far_mask);
+            gmix_kernel<<<nm, PNB_THREADS, gh->smem_mix>>>(p->P, G, gh->d_mix + gh->mix_off[ph], dA, ld, p->far_mask);
             launches++;
         }
         if (nf > 0 && !(dbg & 0x1000)) {
@@ -1898,6 +1929,7 @@ static void destroy_group_host(pnb_problem *p)
     if (p->gh) {
         GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
         for (void *d : gh->unit_allocs) cudaFree(d);
+        for (void *d : gh->near_allocs) cudaFree(d);
         for (auto &s : gh->st) if (s) cudaStreamDestroy(s);
         delete gh;
         p->gh = nullptr;

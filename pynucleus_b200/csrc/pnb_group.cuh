@@ -12,23 +12,26 @@
 // Three kernels (unit kinds are decided on the host from bounding boxes with a rigorous bound on getQuadOrder):
 //   gf2_kernel   units whose pairs all have order 2 (3-node rule): no classification, unrolled 3x3 evaluation
 //   gmix_kernel  every other unit: classification, binning by order, thread-per-pair evaluation of orders
-//                2..5; for units that may hold other pairs it adds the blocks staged by gnear_kernel
-//   gnear_kernel (runs first) singular pairs and regular pairs of order > 5 of the near units, warp per
-//                (pair, slice); a unit is split into parts (row batches) that are staged separately
+//                2..5; pairs it does not take (touching pairs, higher orders) are fetched from the results of
+//   gnear_eval_kernel (runs first): singular pairs and regular pairs of order > 5, one warp per slice of at
+//                most PNB_NEAR_ITEM quadrature nodes of a pair, from a pair list built once per problem
+//                (gnear_list_kernel); equal-sized items keep all SMs busy
 // Cell-diagonal blocks (xx / yy of nonlocalOperator_{SCALAR}.pxi:769-789) are staged per (partner group, cell):
 // slot Dp[g][c] has exactly one writer, the unit (group(c), g).
 #pragma once
 
 struct GroupSched {
-    int ngroups, cap, maxld, ldS, ncolors, nparts;
+    int ngroups, cap, maxld, ldS, ncolors;
     const int *gptr;     // ngroups+1: first cell slot of a group (multiples of PNB_SB)
     const int *gcells;   // cell id per slot, -1 = padding; batches of PNB_SB slots share no vertex
     const int *gloc;     // packed group-local dof index of the 3 vertices (8 bits each, 0xFF = no dof)
     const int *gdptr;    // ngroups+1
     const int *gdofs;    // group-local dof -> global dof
     double *Dp;          // ngroups x nc x ND
-    double *NS;          // near staging [slot][part][nsstride]: block (maxld x maxld), DX (cap x ND), DY (cap x ND)
-    size_t nsstride;
+    int nbmax;           // largest number of batches of a group
+    const int4 *npairs;  // near pair list: (row cell, column cell, panel, first item)
+    const int *nearbase; // [near slot][row batch][column batch]: position of the first pair of the sub-batch
+    const double *R;     // results of the near items, NL doubles each
     int *err;
     unsigned long long *counters;
 };
@@ -254,7 +257,250 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
 }
 
 // -------------------------------------------------------------------------------------------------
-// mixed units (orders 2..5 by thread-per-pair evaluation, binned by order) and near parts
+// classification of one slot pair of a sub-batch (shared by the list builder and the unit kernel).
+// Returns the panel (order >= 1, or -(shared vertices) for touching pairs), 0 when the slot holds no pair.
+// -------------------------------------------------------------------------------------------------
+struct GCls {
+    const double *cxI, *cxJ;      // [2][cap]
+    const float *lhI, *ahI, *lhJ, *ahJ;
+    const int *cellI, *locI, *cellJ, *locJ;
+    int cap;
+    float cf, sf;
+};
+
+__device__ __forceinline__ int g_classify(const DProblem &P, const GCls &c, bool diag, bool maybe_touching, int rb, int cb, int k1, int k2)
+{
+    const int s1 = rb + k1, s2 = cb + k2;
+    const int K1 = c.cellI[s1], K2 = c.cellJ[s2];
+    // diagonal units: every unordered pair once (batches rb <= cb; inside a batch k1 <= k2)
+    if (!(K1 >= 0 && K2 >= 0 && K1 != K2 ? (!diag || rb < cb || k1 < k2) : (K1 >= 0 && K1 == K2 && diag))) return 0;
+    // the reference skips pairs of cells without any dof
+    if ((c.locI[s1] & 0x00FFFFFF) == 0x00FFFFFF && (c.locJ[s2] & 0x00FFFFFF) == 0x00FFFFFF) return 0;
+    if (K1 == K2) return -3;
+    int panel = 0;
+    if (maybe_touching) {
+        int v1[3], v2[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) { v1[m] = P.cells[(size_t)K1 * 3 + m]; v2[m] = P.cells[(size_t)K2 * 3 + m]; }
+        panel = -shared_vertices(v1, 3, v2, 3);
+    }
+    if (panel == 0) {
+        const double a = c.cxI[s1] - c.cxJ[s2], b = c.cxI[c.cap + s1] - c.cxJ[c.cap + s2];
+        panel = fast_order_2d(a * a + b * b, c.lhI[s1], c.lhJ[s2], c.ahI[s1], c.ahJ[s2], c.cf, c.sf);
+        if (panel < 0) {
+            // getPanelType evaluates (c1 <= c2): keep the operand order of the reference
+            const int c1 = min(K1, K2), c2 = max(K1, K2);
+            const double d = center_distance(P.centers + (size_t)c1 * 2, P.centers + (size_t)c2 * 2, 2);
+            panel = quad_order_interior(P, P.h[c1], P.h[c2], d);
+        }
+    }
+    return panel;
+}
+
+// work items of a near pair: slices of at most PNB_NEAR_ITEM quadrature nodes, one warp each
+#define PNB_NEAR_ITEM 2048
+__device__ __forceinline__ int near_slices(const DProblem &P, int panel)
+{
+    int nodes;
+    if (panel >= 1) { const int n = P.reg_cell[panel].n; nodes = n * n; }
+    else nodes = panel == -3 ? P.q_id.n : (panel == -2 ? P.q_edge.n : P.q_vertex.n);
+    return max(1, (nodes + PNB_NEAR_ITEM - 1) / PNB_NEAR_ITEM);
+}
+
+__device__ __forceinline__ void g_load_cls_side(const DProblem &P, const GroupSched &G, int g, int *cell, int *loc, double *cx, float *lh, float *ah,
+                                                int cap, int tid)
+{
+    const int beg = G.gptr[g], n = G.gptr[g + 1] - beg;
+    for (int s = tid; s < n; s += PNB_THREADS) {
+        const int c = G.gcells[beg + s];
+        cell[s] = c;
+        loc[s] = G.gloc[beg + s];
+        if (c >= 0) {
+            cx[s] = P.centers[(size_t)c * 2];
+            cx[cap + s] = P.centers[(size_t)c * 2 + 1];
+            lh[s] = P.lhf[c];
+            ah[s] = P.ahf[c];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// near pair list (built once per problem and table set): one CTA per near unit.  Pairs that the
+// thread-per-pair evaluator does not take (touching pairs, orders outside far_mask) are appended in sub-batch /
+// slot order to a segment of the global list (segments are reserved with an integer atomic: their order does
+// not matter, results are addressed through nearbase).  fill == 0 only counts.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PNB_THREADS)
+gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int far_mask, int fill, int *cursor, int4 *pairs, int2 *items,
+                  int *nearbase)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *sp = smem_raw;
+    const int cap = G.cap;
+    double *cxs = reinterpret_cast<double *>(carve(sp, (size_t)4 * cap * 8));
+    float *lhs = reinterpret_cast<float *>(carve(sp, (size_t)4 * cap * 4));
+    int *ints = reinterpret_cast<int *>(carve(sp, (size_t)4 * cap * 4));
+    __shared__ int wcnt[PNB_THREADS / 32], wits[PNB_THREADS / 32], tot[2], base[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GUnit u = units[blockIdx.x];
+    const int I = u.I, J = u.J;
+    const bool diag = I == J;
+    const int nI = G.gptr[I + 1] - G.gptr[I], nJ = G.gptr[J + 1] - G.gptr[J];
+    GCls c;
+    c.cxI = cxs; c.cxJ = cxs + 2 * cap;
+    c.lhI = lhs; c.ahI = lhs + cap; c.lhJ = lhs + 2 * cap; c.ahJ = lhs + 3 * cap;
+    c.cellI = ints; c.locI = ints + cap; c.cellJ = ints + 2 * cap; c.locJ = ints + 3 * cap;
+    c.cap = cap;
+    c.cf = (float)P.c_int; c.sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
+    g_load_cls_side(P, G, I, ints, ints + cap, cxs, lhs, lhs + cap, cap, tid);
+    g_load_cls_side(P, G, J, ints + 2 * cap, ints + 3 * cap, cxs + 2 * cap, lhs + 2 * cap, lhs + 3 * cap, cap, tid);
+    if (tid < 2) tot[tid] = 0;
+    __syncthreads();
+    const int k1 = tid / PNB_SB, k2 = tid % PNB_SB;
+    int run_pairs = 0, run_items = 0;
+    for (int pass = 0; pass < (fill ? 2 : 1); pass++) {
+        for (int rb = 0; rb < nI; rb += PNB_SB)
+            for (int cb = diag ? rb : 0; cb < nJ; cb += PNB_SB) {
+                const int panel = g_classify(P, c, diag, true, rb, cb, k1, k2);
+                if (panel > P.max_order) atomicMax(G.err, panel);
+                const bool is_far = panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1);
+                const bool near = panel != 0 && !is_far && panel <= P.max_order;
+                const int sl = near ? near_slices(P, panel) : 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, near);
+                // inclusive warp scan of the slice counts
+                int inc = sl;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, off);
+                    if (lane >= off) inc += t;
+                }
+                if (pass == 0) {
+                    if (lane == 31) { atomicAdd(&tot[0], __popc(bal)); atomicAdd(&tot[1], inc); }
+                    continue;
+                }
+                if (lane == 31) { wcnt[warp] = __popc(bal); wits[warp] = inc; }
+                __syncthreads();
+                int pp = 0, pi = 0, tp = 0, ti = 0;
+                for (int w = 0; w < PNB_THREADS / 32; w++) {
+                    if (w < warp) { pp += wcnt[w]; pi += wits[w]; }
+                    tp += wcnt[w]; ti += wits[w];
+                }
+                if (tid == 0) nearbase[((size_t)u.slot * G.nbmax + rb / PNB_SB) * G.nbmax + cb / PNB_SB] = base[0] + run_pairs;
+                if (near) {
+                    const int pos = base[0] + run_pairs + pp + __popc(bal & ((1u << lane) - 1));
+                    const int it0 = base[1] + run_items + pi + inc - sl;
+                    pairs[pos] = make_int4(c.cellI[rb + k1], c.cellJ[cb + k2], panel, it0);
+                    for (int q = 0; q < sl; q++) items[it0 + q] = make_int2(pos, q);
+                }
+                run_pairs += tp;
+                run_items += ti;
+                __syncthreads();
+            }
+        if (pass == 0) {
+            __syncthreads();
+            if (tid == 0) {
+                base[0] = atomicAdd(cursor, tot[0]);
+                base[1] = atomicAdd(cursor + 1, tot[1]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// one warp per item: slice `q` of the quadrature nodes of a near pair; 21 partial sums per item
+__global__ void __launch_bounds__(PNB_THREADS)
+gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__restrict__ items, int nitems, double *__restrict__ R)
+{
+    constexpr int NV = 3, NL = PairDims<2>::NL, NRr = 2 * NV - 1, NA = NRr * (NRr + 1) / 2;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (PNB_THREADS / 32) + (threadIdx.x >> 5);
+    if (item >= nitems) return;
+    const int2 it = items[item];
+    const int4 pr = pairs[it.x];
+    const int Ka = pr.x, Kb = pr.y, panel = pr.z;
+    const int Sl = near_slices(P, panel);
+    double acc[NL];
+    if (panel >= 1) {
+        lanes_regular_interior<2>(P, Ka, Kb, panel, it.y * 32 + lane, 32 * Sl, acc);
+        warp_allreduce<NL>(acc);
+    } else {
+        // reference orientation of singular pairs: smaller cell index first
+        const int c1 = min(Ka, Kb), c2 = max(Ka, Kb);
+        int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
+        const int pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.cells + (size_t)c2 * NV, NV, c1 == c2, p1, p2);
+#pragma unroll
+        for (int k = 0; k < NL; k++) acc[k] = 0.;
+        lanes_singular_interior<2>(P, c1, c2, pan, p1, p2, it.y * 32 + lane, 32 * Sl, acc);
+        warp_allreduce<NA>(acc);
+    }
+#pragma unroll
+    for (int k = 0; k < NL; k++)
+        if (k == lane) R[(size_t)item * NL + k] = acc[k];
+}
+
+// sums the slices of a near pair and maps the 21 values to the cross block and the two cell-diagonal blocks
+// of (row cell Ka, column cell Kb).  Deliberately not inlined (keeps the registers of the unit kernel low).
+__device__ __noinline__ void near_fetch(const DProblem &P, const double *__restrict__ R, int4 pr, double *xy, double *dxy)
+{
+    constexpr int NV = 3, ND = 6, NL = PairDims<2>::NL, NRr = 2 * NV - 1;
+    const int Ka = pr.x, Kb = pr.y, panel = pr.z;
+    const int Sl = near_slices(P, panel);
+    double acc[NL];
+#pragma unroll
+    for (int k = 0; k < NL; k++) acc[k] = 0.;
+    for (int q = 0; q < Sl; q++) {
+        const double *r = R + (size_t)(pr.w + q) * NL;
+#pragma unroll
+        for (int k = 0; k < NL; k++) acc[k] += r[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) xy[k] = 0.;
+#pragma unroll
+    for (int k = 0; k < 12; k++) dxy[k] = 0.;
+    if (panel >= 1) {
+        const double sc = 2.0 * P.vol[Ka] * P.vol[Kb];
+        int k = 0;
+#pragma unroll
+        for (int II = 0; II < 2 * NV; II++)
+#pragma unroll
+            for (int JJ = II; JJ < 2 * NV; JJ++) {
+                const double v = acc[k] * sc;
+                if (II < NV && JJ >= NV) xy[II * NV + (JJ - NV)] = v;
+                else if (JJ < NV) dxy[tri_idx(NV, II, JJ)] = v;
+                else dxy[ND + tri_idx(NV, II - NV, JJ - NV)] = v;
+                k++;
+            }
+    } else {
+        const bool swapped = Ka > Kb;
+        const int c1 = swapped ? Kb : Ka, c2 = swapped ? Ka : Kb;
+        int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
+        const int pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.cells + (size_t)c2 * NV, NV, c1 == c2, p1, p2);
+        const double sc = (c1 == c2 ? 1.0 : 2.0) * 4.0 * P.vol[c1] * P.vol[c2];
+        const int common = -pan, rows = 2 * NV - common;
+        int k = 0;
+        for (int II = 0; II < NRr; II++)
+            for (int JJ = II; JJ < NRr; JJ++) {
+                if (JJ < rows) {
+                    const double v = acc[k] * sc;
+                    int i = II < NV ? p1[II] : NV + p2[II - NV + common];
+                    int j = JJ < NV ? p1[JJ] : NV + p2[JJ - NV + common];
+                    if (j < i) { const int t = i; i = j; j = t; }
+                    // (i,j) in the reference's 2NV x 2NV local numbering of (c1,c2)
+                    if (i < NV && j >= NV) xy[!swapped ? i * NV + (j - NV) : (j - NV) * NV + i] = v;
+                    else {
+                        const bool first = j < NV;   // block of c1
+                        const int a = first ? i : i - NV, b = first ? j : j - NV;
+                        dxy[((first != swapped) ? 0 : ND) + tri_idx(NV, a, b)] = v;
+                    }
+                }
+                k++;
+            }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// unit kernel: regular pairs of order 2..5 thread-per-pair (binned by order); every other pair was evaluated by
+// gnear_eval_kernel and is fetched here, so that all contributions of a unit are added in one fixed order
 // -------------------------------------------------------------------------------------------------
 struct GMixFixed {
     PowTab pw;
@@ -266,17 +512,12 @@ struct GMixFixed {
     int warpcnt[PNB_THREADS / 32];
     int nlist, anyD;
 };
-struct GNearExtra {
-    double partial[64][PairDims<2>::NL];     // slice sums of split pairs
-    int listpanel[PNB_SB * PNB_SB];
-};
 
-inline size_t gmix_smem_bytes(int cap, int maxld, int ldS, bool nearpart)
+inline size_t gmix_smem_bytes(int cap, int maxld, int ldS)
 {
     size_t b = 0;
     auto add = [&](size_t x) { b += (x + 15) & ~(size_t)15; };
     add(sizeof(GMixFixed));
-    if (nearpart) add(sizeof(GNearExtra));
     add((size_t)maxld * ldS * 8);
     add((size_t)2 * 6 * cap * 8);     // sx
     add((size_t)2 * 2 * cap * 8);     // cx
@@ -287,17 +528,24 @@ inline size_t gmix_smem_bytes(int cap, int maxld, int ldS, bool nearpart)
     return b;
 }
 
-// NEARPART = false: one CTA per unit, far pairs; NEARPART = true: one CTA per (near unit, part), other pairs
-template <bool NEARPART>
-__global__ void __launch_bounds__(PNB_THREADS, NEARPART ? 1 : 2)
+inline size_t gnear_list_smem_bytes(int cap)
+{
+    size_t b = 0;
+    auto add = [&](size_t x) { b += (x + 15) & ~(size_t)15; };
+    add((size_t)4 * cap * 8);
+    add((size_t)4 * cap * 4);
+    add((size_t)4 * cap * 4);
+    return b;
+}
+
+__global__ void __launch_bounds__(PNB_THREADS, 2)
 gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__restrict__ A, int64_t ld, int far_mask)
 {
-    constexpr int NV = 3, NX = 9, ND = 6, NL = PairDims<2>::NL, SB = PNB_SB, NW = PNB_THREADS / 32;
+    constexpr int NV = 3, ND = 6, SB = PNB_SB, NW = PNB_THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
     const int cap = G.cap, ldS = G.ldS;
     GMixFixed &sm = *reinterpret_cast<GMixFixed *>(carve(sp, sizeof(GMixFixed)));
-    GNearExtra &nx = *reinterpret_cast<GNearExtra *>(NEARPART ? carve(sp, sizeof(GNearExtra)) : sp);
     double *S = reinterpret_cast<double *>(carve(sp, (size_t)G.maxld * ldS * 8));
     double *sx = reinterpret_cast<double *>(carve(sp, (size_t)2 * 6 * cap * 8));
     double *cxs = reinterpret_cast<double *>(carve(sp, (size_t)2 * 2 * cap * 8));
@@ -306,46 +554,42 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
     int *ints = reinterpret_cast<int *>(carve(sp, (size_t)2 * 2 * cap * 4));
     double *DYs = reinterpret_cast<double *>(carve(sp, (size_t)cap * 6 * 8));
     // side 0 = rows (I), side 1 = columns (J)
-    double *sxI = sx, *sxJ = sx + 6 * cap, *cxI = cxs, *cxJ = cxs + 2 * cap, *volI = vols, *volJ = vols + cap;
-    float *lhI = lhs, *ahI = lhs + cap, *lhJ = lhs + 2 * cap, *ahJ = lhs + 3 * cap;
+    double *sxI = sx, *sxJ = sx + 6 * cap, *volI = vols, *volJ = vols + cap;
     int *cellI = ints, *locI = ints + cap, *cellJ = ints + 2 * cap, *locJ = ints + 3 * cap;
+    GCls c;
+    c.cxI = cxs; c.cxJ = cxs + 2 * cap;
+    c.lhI = lhs; c.ahI = lhs + cap; c.lhJ = lhs + 2 * cap; c.ahJ = lhs + 3 * cap;
+    c.cellI = cellI; c.locI = locI; c.cellJ = cellJ; c.locJ = locJ;
+    c.cap = cap;
+    c.cf = (float)P.c_int; c.sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const GUnit u = units[NEARPART ? blockIdx.x / G.nparts : blockIdx.x];
-    const int part = NEARPART ? blockIdx.x % G.nparts : 0;
+    const GUnit u = units[blockIdx.x];
     const int I = u.I, J = u.J;
-    const bool diag = I == J;
+    const bool diag = I == J, nearunit = u.kind == 2;
     const int ibeg = G.gptr[I], nI = G.gptr[I + 1] - ibeg, jbeg = G.gptr[J], nJ = G.gptr[J + 1] - jbeg;
     const int dI = G.gdptr[I], nldI = G.gdptr[I + 1] - dI, dJ = G.gdptr[J], nldJ = G.gdptr[J + 1] - dJ;
-    const float cf = (float)P.c_int, sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
-    unsigned long long my_pairs = 0;
+    unsigned long long my_pairs = 0, my_near = 0;
     {
         const double *src = reinterpret_cast<const double *>(P.pow_int);
         double *dst = reinterpret_cast<double *>(&sm.pw);
         for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_THREADS) dst[e] = src[e];
-        if (!NEARPART) {
-            const double *fs = reinterpret_cast<const double *>(P.far_rules + 2);
-            double *fd = reinterpret_cast<double *>(&sm.far[0]);
-            for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_THREADS) fd[e] = fs[e];
-        }
+        const double *fs = reinterpret_cast<const double *>(P.far_rules + 2);
+        double *fd = reinterpret_cast<double *>(&sm.far[0]);
+        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_THREADS) fd[e] = fs[e];
         for (int e = tid; e < nldI * ldS; e += PNB_THREADS) S[e] = 0.;
         for (int e = tid; e < cap * 6; e += PNB_THREADS) DYs[e] = 0.;
+        g_load_cls_side(P, G, I, cellI, locI, cxs, lhs, lhs + cap, cap, tid);
+        g_load_cls_side(P, G, J, cellJ, locJ, cxs + 2 * cap, lhs + 2 * cap, lhs + 3 * cap, cap, tid);
         for (int e = tid; e < nI + nJ; e += PNB_THREADS) {
             const bool first = e < nI;
             const int s = first ? e : e - nI;
-            const int c = G.gcells[(first ? ibeg : jbeg) + s];
-            (first ? cellI : cellJ)[s] = c;
-            const int lc = G.gloc[(first ? ibeg : jbeg) + s];
-            (first ? locI : locJ)[s] = lc;
-            if (c >= 0) {
+            const int cc = G.gcells[(first ? ibeg : jbeg) + s];
+            if (cc >= 0) {
                 double *d = first ? sxI : sxJ;
 #pragma unroll
-                for (int k = 0; k < 6; k++) d[k * cap + s] = P.simplices[(size_t)c * 6 + k];
-                (first ? cxI : cxJ)[s] = P.centers[(size_t)c * 2];
-                (first ? cxI : cxJ)[cap + s] = P.centers[(size_t)c * 2 + 1];
-                (first ? volI : volJ)[s] = P.vol[c];
-                (first ? lhI : lhJ)[s] = P.lhf[c];
-                (first ? ahI : ahJ)[s] = P.ahf[c];
+                for (int k = 0; k < 6; k++) d[k * cap + s] = P.simplices[(size_t)cc * 6 + k];
+                (first ? volI : volJ)[s] = P.vol[cc];
             }
         }
     }
@@ -353,116 +597,110 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
     const PowCtx kv(&sm.pw);
     const int k1 = tid / SB, k2 = tid % SB;
 
-    const double *nsrc = (!NEARPART && u.kind == 2) ? G.NS + (size_t)u.slot * G.nparts * G.nsstride : nullptr;
-    const size_t doff = (size_t)G.maxld * G.maxld;
-    for (int rb = NEARPART ? part * SB : 0; rb < nI; rb += NEARPART ? G.nparts * SB : SB) {
+    for (int rb = 0; rb < nI; rb += SB) {
         double dxacc = 0.;      // threads tid < SB*ND: entry (tid % ND) of the block of row cell rb + tid / ND
         for (int cb = diag ? rb : 0; cb < nJ; cb += SB) {
             // ---- classify every pair of the sub-batch ----
-            const int s1 = rb + k1, s2 = cb + k2;
-            const int K1 = cellI[s1], K2 = cellJ[s2];
-            int todo = 0, cls = 0;
+            int cls = 0, todo = 0;
             sm.slotD[tid] = 0;
             if (tid == 0) sm.anyD = 0;
-            // diagonal units: every unordered pair once (batches rb <= cb; inside a batch k1 <= k2)
-            if (K1 >= 0 && K2 >= 0 && K1 != K2 ? (!diag || rb < cb || k1 < k2) : (K1 >= 0 && K1 == K2 && diag)) {
-                if ((locI[s1] & 0x00FFFFFF) != 0x00FFFFFF || (locJ[s2] & 0x00FFFFFF) != 0x00FFFFFF) {
-                    int panel;
-                    if (K1 == K2) panel = -NV;
-                    else {
-                        panel = 0;
-                        if (u.kind == 2) {
-                            int v1[NV], v2[NV];
-#pragma unroll
-                            for (int m = 0; m < NV; m++) { v1[m] = P.cells[(size_t)K1 * NV + m]; v2[m] = P.cells[(size_t)K2 * NV + m]; }
-                            panel = -shared_vertices(v1, NV, v2, NV);
-                        }
-                        if (panel == 0) {
-                            const double a = cxI[s1] - cxJ[s2], b = cxI[cap + s1] - cxJ[cap + s2];
-                            panel = fast_order_2d(a * a + b * b, lhI[s1], lhJ[s2], ahI[s1], ahJ[s2], cf, sf);
-                            if (panel < 0) {
-                                // getPanelType evaluates (c1 <= c2): keep the operand order of the reference
-                                const int c1 = min(K1, K2), c2 = max(K1, K2);
-                                const double d = center_distance(P.centers + (size_t)c1 * 2, P.centers + (size_t)c2 * 2, 2);
-                                panel = quad_order_interior(P, P.h[c1], P.h[c2], d);
-                            }
-                        }
-                    }
+            {
+                const int panel = g_classify(P, c, diag, nearunit, rb, cb, k1, k2);
+                if (panel != 0) {
                     const bool is_far = panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1);
                     if (panel > P.max_order) atomicMax(G.err, panel);
-                    else if (is_far) cls = NEARPART ? 0 : panel;
-                    else {
-                        todo = NEARPART ? panel : 0;
-                        if (!NEARPART && u.kind != 2) atomicMax(G.err + 1, 1);   // host bound violated (never expected)
-                    }
+                    else if (is_far) cls = panel;
+                    else if (nearunit) todo = panel;
+                    else atomicMax(G.err + 1, 1);   // host bound violated (never expected)
                 }
             }
-            // ---- ordered binning: far pairs by order, other pairs in slot order ----
+            // ---- ordered binning of the far pairs by order; rank of the other pairs in slot order ----
             unsigned mybal = 0;
-            if (!NEARPART) {
 #pragma unroll
-                for (int c = 2; c <= PNB_FAR_MAX_ORDER; c++) {
-                    const unsigned bc = __ballot_sync(0xffffffffu, cls == c);
-                    if (lane == 0) sm.clscnt[(c - 2) * NW + warp] = __popc(bc);
-                    if (cls == c) mybal = bc;
-                }
-            } else {
-                mybal = __ballot_sync(0xffffffffu, todo != 0);
-                if (lane == 0) sm.warpcnt[warp] = __popc(mybal);
+            for (int o = 2; o <= PNB_FAR_MAX_ORDER; o++) {
+                const unsigned bc = __ballot_sync(0xffffffffu, cls == o);
+                if (lane == 0) sm.clscnt[(o - 2) * NW + warp] = __popc(bc);
+                if (cls == o) mybal = bc;
+            }
+            unsigned nbal = 0;
+            if (nearunit) {
+                nbal = __ballot_sync(0xffffffffu, todo != 0);
+                if (lane == 0) sm.warpcnt[warp] = __popc(nbal);
             }
             __syncthreads();    // B1
-            if (!NEARPART) {
+            int nnear = 0, npos = 0;
+            {
                 const int me = (cls - 2) * NW + warp;
                 int pos = 0, tot = 0;
 #pragma unroll 4
                 for (int q = 0; q < (PNB_FAR_MAX_ORDER - 1) * NW; q++) {
-                    const int c = sm.clscnt[q];
-                    if (q < me) pos += c;
-                    tot += c;
+                    const int cc = sm.clscnt[q];
+                    if (q < me) pos += cc;
+                    tot += cc;
                 }
                 if (cls != 0) sm.list[pos + __popc(mybal & ((1u << lane) - 1))] = tid | (cls << 12);
                 if (tid == 0) sm.nlist = tot;
-            } else {
-                int pos = 0, tot = 0;
-                for (int w = 0; w < NW; w++) {
-                    if (w < warp) pos += sm.warpcnt[w];
-                    tot += sm.warpcnt[w];
+                if (nearunit) {
+                    for (int w = 0; w < NW; w++) {
+                        if (w < warp) npos += sm.warpcnt[w];
+                        nnear += sm.warpcnt[w];
+                    }
+                    npos += __popc(nbal & ((1u << lane) - 1));
                 }
-                if (todo != 0) {
-                    pos += __popc(mybal & ((1u << lane) - 1));
-                    sm.list[pos] = tid;
-                    nx.listpanel[pos] = todo;
-                }
-                if (tid == 0) sm.nlist = tot;
             }
             __syncthreads();    // B2
             const int nlist = sm.nlist;
-            if (nlist == 0) continue;     // uniform across the CTA
-            // ---- evaluate ----
-            if (!NEARPART) {
-                if (tid < nlist) {
-                    const int item = sm.list[tid];
-                    const int slot = item & 0xFF, order = item >> 12;
-                    const int a1 = rb + slot / SB, a2 = cb + slot % SB;
-                    my_pairs++;
-                    double s1v[3][2], s2v[3][2], xx[6], yy[6], xy[9];
+            if (nlist == 0 && nnear == 0) continue;     // uniform across the CTA
+            // ---- evaluate the far pairs ----
+            if (tid < nlist) {
+                const int item = sm.list[tid];
+                const int slot = item & 0xFF, order = item >> 12;
+                const int a1 = rb + slot / SB, a2 = cb + slot % SB;
+                my_pairs++;
+                double s1v[3][2], s2v[3][2], xx[6], yy[6], xy[9];
 #pragma unroll
-                    for (int m = 0; m < 3; m++) {
-                        s1v[m][0] = sxI[(2 * m) * cap + a1];
-                        s1v[m][1] = sxI[(2 * m + 1) * cap + a1];
-                        s2v[m][0] = sxJ[(2 * m) * cap + a2];
-                        s2v[m][1] = sxJ[(2 * m + 1) * cap + a2];
-                    }
-                    const double sc = 2.0 * volI[a1] * volJ[a2];
-                    far_eval_2d(sm.far[order - 2], s1v, s2v, kv, true, xy, xx, yy);
+                for (int m = 0; m < 3; m++) {
+                    s1v[m][0] = sxI[(2 * m) * cap + a1];
+                    s1v[m][1] = sxI[(2 * m + 1) * cap + a1];
+                    s2v[m][0] = sxJ[(2 * m) * cap + a2];
+                    s2v[m][1] = sxJ[(2 * m + 1) * cap + a2];
+                }
+                const double sc = 2.0 * volI[a1] * volJ[a2];
+                far_eval_2d(sm.far[order - 2], s1v, s2v, kv, true, xy, xx, yy);
 #pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        sm.dxy[slot][k] = xx[k] * sc;
-                        sm.dxy[slot][6 + k] = yy[k] * sc;
+                for (int k = 0; k < 6; k++) {
+                    sm.dxy[slot][k] = xx[k] * sc;
+                    sm.dxy[slot][6 + k] = yy[k] * sc;
+                }
+                sm.slotD[slot] = 1;
+                sm.anyD = 1;
+                const int rl = locI[a1], cl = locJ[a2];
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    const int a = (rl >> (8 * i)) & 0xFF;
+                    if (a == 0xFF) continue;
+#pragma unroll
+                    for (int j = 0; j < NV; j++) {
+                        const int b = (cl >> (8 * j)) & 0xFF;
+                        if (b == 0xFF) continue;
+                        S[a * ldS + b] += xy[i * NV + j] * sc;
                     }
-                    sm.slotD[slot] = 1;
+                }
+            }
+            // ---- fetch the other pairs (distinct slots, distinct entries of S) ----
+            if (todo != 0) {
+                const int pos = G.nearbase[((size_t)u.slot * G.nbmax + rb / SB) * G.nbmax + cb / SB] + npos;
+                const int4 pr = G.npairs[pos];
+                if (pr.x != cellI[rb + k1] || pr.y != cellJ[cb + k2] || pr.z != todo) atomicMax(G.err + 1, 2);
+                else {
+                    double xy[9], d12[12];
+                    near_fetch(P, G.R, pr, xy, d12);
+                    my_near++;
+#pragma unroll
+                    for (int k = 0; k < 12; k++) sm.dxy[tid][k] = d12[k];
+                    sm.slotD[tid] = 1;
                     sm.anyD = 1;
-                    const int rl = locI[a1], cl = locJ[a2];
+                    const int rl = locI[rb + k1], cl = locJ[cb + k2];
 #pragma unroll
                     for (int i = 0; i < NV; i++) {
                         const int a = (rl >> (8 * i)) & 0xFF;
@@ -471,104 +709,8 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
                         for (int j = 0; j < NV; j++) {
                             const int b = (cl >> (8 * j)) & 0xFF;
                             if (b == 0xFF) continue;
-                            S[a * ldS + b] += xy[i * NV + j] * sc;
+                            S[a * ldS + b] += xy[i * NV + j];
                         }
-                    }
-                }
-            } else {
-                // One warp per (pair, slice): sub-batches with few queued pairs split every pair into slices of its
-                // quadrature nodes so that all warps stay busy; slice sums are combined in fixed order.
-                const int Sl = nlist >= 32 ? 1 : (nlist >= 16 ? 2 : (nlist >= 8 ? 4 : 8));
-                constexpr int NRr = 2 * NV - 1, NA = NRr * (NRr + 1) / 2;
-                for (int pass = 0; pass < (Sl > 1 ? 2 : 1); pass++) {
-                    if (pass == 1) __syncthreads();
-                    const int nitems = pass == 0 ? nlist * Sl : nlist;
-                    for (int it = warp; it < nitems; it += NW) {
-                        const int q = pass == 0 ? it / Sl : it, sl = pass == 0 ? it - q * Sl : 0;
-                        const int slot = sm.list[q] & 0xFF;
-                        const int panel = nx.listpanel[q];
-                        const int a1 = rb + slot / SB, a2 = cb + slot % SB;
-                        const int Ka = cellI[a1], Kb = cellJ[a2];
-                        // reference orientation of singular pairs: smaller cell index first
-                        const bool swapped = panel < 0 && Ka > Kb;
-                        const int c1 = swapped ? Kb : Ka, c2 = swapped ? Ka : Kb;
-                        int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
-                        int pan = panel;
-                        if (panel < 0) pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.cells + (size_t)c2 * NV, NV, c1 == c2, p1, p2);
-                        double acc[NL];
-                        if (pass == 0) {
-                            if (lane == 0 && sl == 0) my_pairs++;
-                            if (panel >= 1) {
-                                lanes_regular_interior<2>(P, Ka, Kb, panel, sl * 32 + lane, 32 * Sl, acc);
-                                warp_allreduce<NL>(acc);
-                            } else {
-                                lanes_singular_interior<2>(P, c1, c2, pan, p1, p2, sl * 32 + lane, 32 * Sl, acc);
-                                warp_allreduce<NA>(acc);
-                            }
-                            if (Sl > 1) {
-#pragma unroll
-                                for (int k = 0; k < NL; k++)
-                                    if (k == lane) nx.partial[it][k] = acc[k];
-                                continue;
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < NL; k++) {
-                                double v = 0.;
-                                for (int ss = 0; ss < Sl; ss++) v += nx.partial[q * Sl + ss][k];
-                                acc[k] = v;
-                            }
-                        }
-                        double myv = 0.;         // lane k < NX: entry k of the cross block
-                        double myd = 0.;         // lane k < 2*ND: entry k of (dx, dy)
-                        if (panel >= 1) {
-                            const double sc = 2.0 * P.vol[Ka] * P.vol[Kb];
-                            int k = 0;
-#pragma unroll
-                            for (int II = 0; II < 2 * NV; II++)
-#pragma unroll
-                                for (int JJ = II; JJ < 2 * NV; JJ++) {
-                                    const double v = acc[k] * sc;
-                                    if (II < NV && JJ >= NV) { if (lane == II * NV + (JJ - NV)) myv = v; }
-                                    else if (JJ < NV) { if (lane == tri_idx(NV, II, JJ)) myd = v; }
-                                    else { if (lane == ND + tri_idx(NV, II - NV, JJ - NV)) myd = v; }
-                                    k++;
-                                }
-                        } else {
-                            const double sc = (c1 == c2 ? 1.0 : 2.0) * 4.0 * P.vol[c1] * P.vol[c2];
-                            const int common = -pan, rows = 2 * NV - common;
-                            int k = 0;
-#pragma unroll
-                            for (int II = 0; II < NRr; II++)
-#pragma unroll
-                                for (int JJ = II; JJ < NRr; JJ++) {
-                                    if (JJ < rows) {
-                                        const double v = acc[k] * sc;
-                                        int i = II < NV ? p1[II] : NV + p2[II - NV + common];
-                                        int j = JJ < NV ? p1[JJ] : NV + p2[JJ - NV + common];
-                                        if (j < i) { const int t = i; i = j; j = t; }
-                                        // (i,j) in the reference's 2NV x 2NV local numbering of (c1,c2)
-                                        if (i < NV && j >= NV) {
-                                            const int e = !swapped ? i * NV + (j - NV) : (j - NV) * NV + i;
-                                            if (lane == e) myv = v;
-                                        } else {
-                                            const bool first = j < NV;   // block of c1
-                                            const int a = first ? i : i - NV, b = first ? j : j - NV;
-                                            const bool to_dx = first != swapped;
-                                            if (lane == (to_dx ? 0 : ND) + tri_idx(NV, a, b)) myd = v;
-                                        }
-                                    }
-                                    k++;
-                                }
-                        }
-                        // lanes 0..NX-1 add the cross block (distinct entries), lanes 0..2ND-1 store the diagonal blocks
-                        if (lane < NX) {
-                            const int i = lane / NV, j = lane - i * NV;
-                            const int a = (locI[a1] >> (8 * i)) & 0xFF, b = (locJ[a2] >> (8 * j)) & 0xFF;
-                            if (a != 0xFF && b != 0xFF) S[a * ldS + b] += myv;
-                        }
-                        if (lane < 2 * ND) sm.dxy[slot][lane] = myd;
-                        if (lane == 0) { sm.slotD[slot] = 1; sm.anyD = 1; }
                     }
                 }
             }
@@ -594,44 +736,28 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
         }
         if (tid < SB * ND) {
             const int kk1 = tid / ND, comp = tid - kk1 * ND;
-            const int c = cellI[rb + kk1];
-            if (NEARPART) {
-                G.NS[((size_t)u.slot * G.nparts + part) * G.nsstride + doff + (size_t)(rb + kk1) * ND + comp] = dxacc;
-            } else if (c >= 0) {
-                // near units: the part that owns this row batch staged the sum of the remaining pairs
-                if (nsrc) dxacc += nsrc[(size_t)((rb / SB) % G.nparts) * G.nsstride + doff + (size_t)(rb + kk1) * ND + comp];
-                G.Dp[((size_t)J * P.nc + c) * ND + comp] = dxacc;
-            }
+            const int cc = cellI[rb + kk1];
+            if (cc >= 0) G.Dp[((size_t)J * P.nc + cc) * ND + comp] = dxacc;
         }
     }
     __syncthreads();
-    if (NEARPART) {
-        // stage the block and the column-cell sums of this part (row-cell sums were staged per row batch)
-        double *dst = G.NS + ((size_t)u.slot * G.nparts + part) * G.nsstride;
-        for (int e = tid; e < nldI * nldJ; e += PNB_THREADS) dst[e] = S[(e / nldJ) * ldS + (e % nldJ)];
-        double *dd = dst + doff + (size_t)cap * ND;
-        for (int e = tid; e < nJ * ND; e += PNB_THREADS) dd[e] = DYs[e];
-    } else {
-        for (int e = tid; e < nldI * nldJ; e += PNB_THREADS) {
-            const int a = e / nldJ, b = e - a * nldJ;
-            double v = S[a * ldS + b];
-            if (nsrc)
-                for (int pp = 0; pp < G.nparts; pp++) v += nsrc[(size_t)pp * G.nsstride + e];
-            A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]] += v;
-        }
-        // column-cell sums; same group on both sides: slot Dp[I][c] takes the row sums (written above) and these
-        for (int e = tid; e < nJ * ND; e += PNB_THREADS) {
-            const int c = cellJ[e / ND];
-            if (c < 0) continue;
-            double v = DYs[e];
-            if (nsrc)
-                for (int pp = 0; pp < G.nparts; pp++) v += nsrc[(size_t)pp * G.nsstride + doff + (size_t)cap * ND + e];
-            double *dp = &G.Dp[((size_t)I * P.nc + c) * ND + (e % ND)];
-            *dp = diag ? *dp + v : v;
-        }
+    for (int e = tid; e < nldI * nldJ; e += PNB_THREADS) {
+        const int a = e / nldJ, b = e - a * nldJ;
+        A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]] += S[a * ldS + b];
     }
-    for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
-    if (lane == 0 && my_pairs) atomicAdd(G.counters + (NEARPART ? 1 : 0), my_pairs);
+    // column-cell sums; same group on both sides: slot Dp[I][c] takes the row sums (written above) and these
+    for (int e = tid; e < nJ * ND; e += PNB_THREADS) {
+        const int cc = cellJ[e / ND];
+        if (cc < 0) continue;
+        double *dp = &G.Dp[((size_t)I * P.nc + cc) * ND + (e % ND)];
+        *dp = diag ? *dp + DYs[e] : DYs[e];
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
+        my_near += __shfl_xor_sync(0xffffffffu, my_near, off);
+    }
+    if (lane == 0 && my_pairs) atomicAdd(G.counters, my_pairs);
+    if (lane == 0 && my_near) atomicAdd(G.counters + 1, my_near);
 }
 
 // F = U + U^T in place, 32 x 32 tiles; bitwise symmetric by construction
