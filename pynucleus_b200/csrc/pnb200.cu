@@ -190,6 +190,25 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
     if (upload(p, cell.data(), (size_t)mo + 1, &p->P.reg_cell, true)) return PNB_ERR_CUDA;
     if (upload(p, facet.data(), (size_t)mo + 1, &p->P.reg_facet, true)) return PNB_ERR_CUDA;
     p->P.max_order = mo;
+    p->P.reg_derived = nullptr; p->P.reg_doff = nullptr; p->P.reg_nmax = 0;
+    if (p->dim == 2) {
+        std::vector<int> doff(mo + 2, 0);
+        std::vector<double> der;
+        for (int o = 1; o <= mo; o++) {
+            const pnb_rule_t &r = rules->cell[o];
+            doff[o] = (int)(der.size() / 10);
+            p->P.reg_nmax = std::max(p->P.reg_nmax, r.n);
+            for (int i = 0; i < r.n; i++) {
+                der.push_back(r.w[i]);
+                for (int k = 0; k < 3; k++) der.push_back(r.w[i] * r.bary[k * r.n + i]);
+                for (int a = 0; a < 3; a++)
+                    for (int b = a; b < 3; b++) der.push_back(r.w[i] * r.bary[a * r.n + i] * r.bary[b * r.n + i]);
+            }
+        }
+        doff[mo + 1] = (int)(der.size() / 10);
+        if (upload(p, der.data(), der.size(), &p->P.reg_derived, true)) return PNB_ERR_CUDA;
+        if (upload(p, doff.data(), doff.size(), &p->P.reg_doff, true)) return PNB_ERR_CUDA;
+    }
     // low-order 2D rules for the thread-per-pair evaluator (orders 2..5, node counts fixed at compile time)
     memset(p->far_rules, 0, sizeof(p->far_rules));
     p->far_mask = 0;
@@ -1715,7 +1734,9 @@ static int build_group_schedule(pnb_problem *p)
     int smem_sm = 0;
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device);
     if (smem_sm <= 0) smem_sm = 228 * 1024;
-    const size_t budget = (size_t)smem_sm / 2 - 1024;     // two CTAs per SM
+    int smem_blk = 0;
+    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+    const size_t budget = smem_blk > 0 ? (size_t)smem_blk : (size_t)smem_sm - 1024;     // one 512-thread CTA per SM
     if (!gh->ready) {
         // Hilbert order of the cell centers
         double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
@@ -1734,7 +1755,7 @@ static int build_group_schedule(pnb_problem *p)
         for (int c = 0; c < nc; c++) order[c] = c;
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
         const int forced = getenv("PNB_GC") ? atoi(getenv("PNB_GC")) : 0;
-        const int cand[] = {128, 112, 96, 80, 64, 48, 32};
+        const int cand[] = {144, 128, 112, 96, 80, 64, 48, 32};
         for (int GC : cand) {
             if (forced > 0) GC = forced;
             build_group_geometry(p, GC, order, gh->gg);
@@ -1891,17 +1912,19 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
     if (gh->nitems > 0 && !(dbg & 0x100)) {
         const int wpb = PNB_THREADS / 32;
-        gnear_eval_kernel<<<(unsigned)((gh->nitems + wpb - 1) / wpb), PNB_THREADS>>>(p->P, G.npairs, gh->d_items, gh->nitems, gh->d_R);
+        const size_t smem_eval = sizeof(PowTab) + (size_t)wpb * 4 * p->P.reg_nmax * sizeof(double);
+        cudaFuncSetAttribute(gnear_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval);
+        gnear_eval_kernel<<<(unsigned)((gh->nitems + wpb - 1) / wpb), PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->nitems, gh->d_R);
         launches++;
     }
     for (int ph = 0; ph < gh->nphase; ph++) {
         const int nm = gh->mix_off[ph + 1] - gh->mix_off[ph], nf = gh->f2_off[ph + 1] - gh->f2_off[ph];
         if (nm > 0 && !(dbg & 0x200)) {
-            gmix_kernel<<<nm, PNB_THREADS, gh->smem_mix>>>(p->P, G, gh->d_mix + gh->mix_off[ph], dA, ld, p->far_mask);
+            gmix_kernel<<<nm, PNB_GT, gh->smem_mix>>>(p->P, G, gh->d_mix + gh->mix_off[ph], dA, ld, p->far_mask);
             launches++;
         }
         if (nf > 0 && !(dbg & 0x1000)) {
-            gf2_kernel<<<nf, PNB_THREADS, gh->smem_f2>>>(p->P, G, gh->d_f2 + gh->f2_off[ph], dA, ld, R);
+            gf2_kernel<<<nf, PNB_GT, gh->smem_f2>>>(p->P, G, gh->d_f2 + gh->f2_off[ph], dA, ld, R);
             launches++;
         }
     }

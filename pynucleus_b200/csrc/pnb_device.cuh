@@ -60,6 +60,10 @@ struct DProblem {
     int max_order;
     const DRule *reg_cell;
     const DRule *reg_facet;
+    // 2D cell rules, per node 10 doubles: w, w*bary[0..2], w*bary[a]*bary[b] (a<=b); rule o starts at node reg_doff[o]
+    const double *reg_derived;
+    const int *reg_doff;
+    int reg_nmax;              // largest node count of a cell rule
 };
 
 __host__ __device__ inline int tri_idx(int n, int i, int j) { return n * i - ((i * (i + 1)) >> 1) + j; }

@@ -74,8 +74,14 @@ __device__ __forceinline__ unsigned char *carve(unsigned char *&p, size_t bytes)
 }
 
 // -------------------------------------------------------------------------------------------------
-// uniform order 2
+// uniform order 2.  PNB_GT threads: two column batches per step (sub-batch = tid / 256), so that 16 warps
+// hide the latency of the dependent FP64 chains although the unit block limits the SM to one CTA.  The
+// evaluation needs no ordering; the two sub-batches add to the block one after the other.
+// Cell-diagonal blocks: xx[e] = sum_i qq[e][i] r_i and yy[e] = sum_j qq[e][j] c_j are linear in the row sums
+// r_i / column sums c_j of the kernel matrix, so only those (3 + 3 values per pair) are reduced over the
+// partner cells; qq is applied once per cell at the end.
 // -------------------------------------------------------------------------------------------------
+#define PNB_GT 512
 inline size_t gf2_smem_bytes(int cap, int maxld, int ldS)
 {
     size_t b = 0;
@@ -85,12 +91,13 @@ inline size_t gf2_smem_bytes(int cap, int maxld, int ldS)
     add((size_t)12 * cap * 8);        // nodes of both sides
     add((size_t)2 * cap * 8);         // vol
     add((size_t)4 * cap * 4);         // cell, loc (both sides)
-    add((size_t)2 * 8 * 16 * 6 * 8);  // Yw
-    add((size_t)cap * 6 * 8);         // DYs
+    add((size_t)2 * 8 * 16 * 3 * 8);  // Yw
+    add((size_t)cap * 3 * 8);         // column sums
+    add((size_t)16 * 3 * 8);          // row sums of the second sub-batch
     return b;
 }
 
-__global__ void __launch_bounds__(PNB_THREADS, 2)
+__global__ void __launch_bounds__(PNB_GT, 1)
 gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__restrict__ A, int64_t ld, F2Rule R)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -104,8 +111,9 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
     double *volj = voli + cap;
     int *celli = reinterpret_cast<int *>(carve(sp, (size_t)4 * cap * 4));
     int *cellj = celli + cap, *loci = celli + 2 * cap, *locj = celli + 3 * cap;
-    double *Yw = reinterpret_cast<double *>(carve(sp, (size_t)2 * 8 * 16 * 6 * 8));
-    double *DYs = reinterpret_cast<double *>(carve(sp, (size_t)cap * 6 * 8));
+    double *Yw = reinterpret_cast<double *>(carve(sp, (size_t)2 * 8 * 16 * 3 * 8));
+    double *CYs = reinterpret_cast<double *>(carve(sp, (size_t)cap * 3 * 8));
+    double *RX1 = reinterpret_cast<double *>(carve(sp, (size_t)16 * 3 * 8));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const GUnit u = units[blockIdx.x];
@@ -115,10 +123,10 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
     {
         const double *src = reinterpret_cast<const double *>(P.pow_int);
         double *dst = reinterpret_cast<double *>(pw);
-        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_THREADS) dst[e] = src[e];
-        for (int e = tid; e < nldI * ldS; e += PNB_THREADS) S[e] = 0.;
-        for (int e = tid; e < nJ * 6; e += PNB_THREADS) DYs[e] = 0.;
-        for (int e = tid; e < nI + nJ; e += PNB_THREADS) {
+        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_GT) dst[e] = src[e];
+        for (int e = tid; e < nldI * ldS; e += PNB_GT) S[e] = 0.;
+        for (int e = tid; e < cap * 3; e += PNB_GT) CYs[e] = 0.;
+        for (int e = tid; e < nI + nJ; e += PNB_GT) {
             const bool first = e < nI;
             const int s = first ? e : e - nI;
             const int c = G.gcells[(first ? ibeg : jbeg) + s];
@@ -137,9 +145,8 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
         }
     }
     __syncthreads();
-    const int k1 = tid >> 4, k2 = tid & 15;
+    const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15, wsub = warp & 7;
     unsigned long long my_pairs = 0;
-    int step = 0;
     for (int rb = 0; rb < nI; rb += PNB_SB) {
         const int s1 = rb + k1;
         const int c1 = celli[s1];
@@ -148,12 +155,14 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
 #pragma unroll
         for (int q = 0; q < 3; q++) { x[q][0] = xi[(2 * q) * cap + s1]; x[q][1] = xi[(2 * q + 1) * cap + s1]; }
         const double v1 = c1 >= 0 ? 2.0 * voli[s1] : 0.;
-        double xx[6] = {0., 0., 0., 0., 0., 0.};
-        for (int cb = 0; cb < nJ; cb += PNB_SB, step++) {
+        double rx[3] = {0., 0., 0.};
+        for (int cb0 = 0; cb0 < nJ; cb0 += 2 * PNB_SB) {
+            const int cb = cb0 + sub * PNB_SB;
             const int s2 = cb + k2;
-            const int c2 = cellj[s2];
-            const int l2 = locj[s2];
-            double yy[6] = {0., 0., 0., 0., 0., 0.};
+            const int c2 = cb < nJ ? cellj[s2] : -1;
+            const int l2 = cb < nJ ? locj[s2] : 0x00FFFFFF;
+            double cy[3] = {0., 0., 0.};
+            double X[9];
             // a pair is skipped only when neither cell carries a dof (as the reference does)
             const bool live = c1 >= 0 && c2 >= 0 && !((l1 & 0x00FFFFFF) == 0x00FFFFFF && (l2 & 0x00FFFFFF) == 0x00FFFFFF);
             if (live) {
@@ -169,7 +178,6 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
                     }
                 }
                 const double sc = v1 * volj[s2];
-                double X[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) X[k] = 0.;
 #pragma unroll
@@ -182,6 +190,7 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
                         t2 = fma(g[i][j], R.wphi[j][2], t2);
                         r = fma(g[i][j], R.w[j], r);
                     }
+                    t0 *= sc; t1 *= sc; t2 *= sc;
 #pragma unroll
                     for (int a = 0; a < 3; a++) {
                         const double q = R.wphi[i][a];
@@ -189,20 +198,26 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
                         X[a * 3 + 1] = fma(-q, t1, X[a * 3 + 1]);
                         X[a * 3 + 2] = fma(-q, t2, X[a * 3 + 2]);
                     }
-                    r *= sc;
-#pragma unroll
-                    for (int e = 0; e < 6; e++) xx[e] = fma(R.qq[e][i], r, xx[e]);
+                    rx[i] = fma(r, sc, rx[i]);
                 }
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
                     double c = 0.;
 #pragma unroll
                     for (int i = 0; i < 3; i++) c = fma(g[i][j], R.w[i], c);
-                    c *= sc;
-#pragma unroll
-                    for (int e = 0; e < 6; e++) yy[e] = fma(R.qq[e][j], c, yy[e]);
+                    cy[j] = c * sc;
                 }
-                // conflict free: the 16 row cells share no vertex, neither do the 16 column cells
+            }
+            // column sums: the two half-warps, then the 8 warps of the sub-batch through shared memory
+#pragma unroll
+            for (int e = 0; e < 3; e++) cy[e] += __shfl_xor_sync(0xffffffffu, cy[e], 16);
+            if (lane < 16) {
+#pragma unroll
+                for (int e = 0; e < 3; e++) Yw[((sub * 8 + wsub) * 16 + k2) * 3 + e] = cy[e];
+            }
+            __syncthreads();     // orders the block updates of the previous step, publishes Yw
+            // conflict free inside a sub-batch: the 16 row cells share no vertex, neither do the 16 column cells
+            if (live && sub == 0) {
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     const int ra = (l1 >> (8 * a)) & 0xFF;
@@ -211,46 +226,63 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
                     for (int b = 0; b < 3; b++) {
                         const int cbk = (l2 >> (8 * b)) & 0xFF;
                         if (cbk == 0xFF) continue;
-                        S[ra * ldS + cbk] += X[a * 3 + b] * sc;
+                        S[ra * ldS + cbk] += X[a * 3 + b];
                     }
                 }
             }
-            // column-cell blocks: sum over the 16 row cells (two half-warps, then 8 warps through shared memory)
-            double *yw = Yw + (size_t)(step & 1) * (8 * 16 * 6);
+            if (tid < 96) {
+                const int sb = tid / 48, t = tid - sb * 48, kk2 = t / 3, e = t - kk2 * 3;
+                if (cb0 + sb * PNB_SB < nJ) {
+                    double s = 0.;
 #pragma unroll
-            for (int e = 0; e < 6; e++) yy[e] += __shfl_xor_sync(0xffffffffu, yy[e], 16);
-            if (lane < 16) {
-#pragma unroll
-                for (int e = 0; e < 6; e++) yw[(warp * 16 + k2) * 6 + e] = yy[e];
+                    for (int w = 0; w < 8; w++) s += Yw[((sb * 8 + w) * 16 + kk2) * 3 + e];
+                    CYs[(cb0 + sb * PNB_SB + kk2) * 3 + e] += s;
+                }
             }
             __syncthreads();
-            if (tid < 96) {
-                const int kk2 = tid / 6, e = tid - kk2 * 6;
-                double s = 0.;
+            if (live && sub == 1) {
 #pragma unroll
-                for (int w = 0; w < 8; w++) s += yw[(w * 16 + kk2) * 6 + e];
-                DYs[(cb + kk2) * 6 + e] += s;
+                for (int a = 0; a < 3; a++) {
+                    const int ra = (l1 >> (8 * a)) & 0xFF;
+                    if (ra == 0xFF) continue;
+#pragma unroll
+                    for (int b = 0; b < 3; b++) {
+                        const int cbk = (l2 >> (8 * b)) & 0xFF;
+                        if (cbk == 0xFF) continue;
+                        S[ra * ldS + cbk] += X[a * 3 + b];
+                    }
+                }
             }
         }
-        // row-cell blocks: sum over the column cells of the whole group (16 lanes, fixed tree)
+        // row sums: over the 16 lanes (fixed tree), then the two sub-batches
 #pragma unroll
         for (int off = 8; off > 0; off >>= 1) {
 #pragma unroll
-            for (int e = 0; e < 6; e++) xx[e] += __shfl_xor_sync(0xffffffffu, xx[e], off);
+            for (int e = 0; e < 3; e++) rx[e] += __shfl_xor_sync(0xffffffffu, rx[e], off);
         }
-        if (k2 == 0 && c1 >= 0) {
+        if (sub == 1 && k2 == 0) {
 #pragma unroll
-            for (int e = 0; e < 6; e++) G.Dp[((size_t)J * P.nc + c1) * 6 + e] = xx[e];
+            for (int e = 0; e < 3; e++) RX1[k1 * 3 + e] = rx[e];
+        }
+        __syncthreads();
+        if (sub == 0 && k2 == 0 && c1 >= 0) {
+#pragma unroll
+            for (int e = 0; e < 3; e++) rx[e] += RX1[k1 * 3 + e];
+#pragma unroll
+            for (int e = 0; e < 6; e++)
+                G.Dp[((size_t)J * P.nc + c1) * 6 + e] = R.qq[e][0] * rx[0] + R.qq[e][1] * rx[1] + R.qq[e][2] * rx[2];
         }
     }
     __syncthreads();
-    for (int e = tid; e < nldI * nldJ; e += PNB_THREADS) {
+    for (int e = tid; e < nldI * nldJ; e += PNB_GT) {
         const int a = e / nldJ, b = e - a * nldJ;
         A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]] += S[a * ldS + b];
     }
-    for (int e = tid; e < nJ * 6; e += PNB_THREADS) {
-        const int c2 = cellj[e / 6];
-        if (c2 >= 0) G.Dp[((size_t)I * P.nc + c2) * 6 + (e % 6)] = DYs[e];
+    for (int e = tid; e < nJ * 6; e += PNB_GT) {
+        const int s2 = e / 6, k = e - s2 * 6;
+        const int c2 = cellj[s2];
+        if (c2 >= 0)
+            G.Dp[((size_t)I * P.nc + c2) * 6 + k] = R.qq[k][0] * CYs[s2 * 3] + R.qq[k][1] * CYs[s2 * 3 + 1] + R.qq[k][2] * CYs[s2 * 3 + 2];
     }
     for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
     if (lane == 0 && my_pairs) atomicAdd(G.counters, my_pairs);
@@ -407,11 +439,106 @@ gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int
     }
 }
 
-// one warp per item: slice `q` of the quadrature nodes of a near pair; 21 partial sums per item
-__global__ void __launch_bounds__(PNB_THREADS)
+// Regular near pair, one slice of its n x n node pairs per warp.  The node coordinates of both cells are
+// computed once per item (un-fused, in the reference's order, see lanes_regular_interior) and kept in shared
+// memory; every lane takes a contiguous run of the row-major node pairs, so that the row sums of
+// nonlocalOperator_{SCALAR}.pxi:769-789 can be factored out (27 instead of ~60 FP64 operations per node pair).
+__device__ __forceinline__ void near_regular_item(const DProblem &P, const PowCtx &kv, int Ka, int Kb, int order, int slice, int nsl,
+                                                  double *xs, int lane, double *acc)
+{
+    const int nmax = P.reg_nmax;
+    const DRule r = P.reg_cell[order];
+    const int n = r.n;
+    const double *der = P.reg_derived + (size_t)P.reg_doff[order] * 10;
+    {
+        double s1[3][2], s2[3][2];
+        load_simplex<2>(P.simplices, Ka, 3, s1);
+        load_simplex<2>(P.simplices, Kb, 3, s2);
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) {
+            double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const double b = r.bary[m * n + k];
+                x0 = PNB_ADD(x0, PNB_MUL(b, s1[m][0]));
+                x1 = PNB_ADD(x1, PNB_MUL(b, s1[m][1]));
+                y0 = PNB_ADD(y0, PNB_MUL(b, s2[m][0]));
+                y1 = PNB_ADD(y1, PNB_MUL(b, s2[m][1]));
+            }
+            xs[k] = x0; xs[nmax + k] = x1; xs[2 * nmax + k] = y0; xs[3 * nmax + k] = y1;
+        }
+        __syncwarp();
+    }
+    const int total = n * n, per = (total + nsl - 1) / nsl;
+    const int q0 = slice * per, q1 = min(total, q0 + per);
+    const int L = (max(q1 - q0, 0) + 31) / 32;
+    const int qa = q0 + lane * L, qb = min(q1, qa + L);
+    double xy[9], xx[6], yy[6];
+#pragma unroll
+    for (int k = 0; k < 9; k++) xy[k] = 0.;
+#pragma unroll
+    for (int k = 0; k < 6; k++) xx[k] = yy[k] = 0.;
+    if (qa < qb) {
+        int i = qa / n, j = qa - i * n;
+        double X0 = xs[i], X1 = xs[nmax + i], wi = der[(size_t)i * 10];
+        double t0 = 0., t1 = 0., t2 = 0., rs = 0.;
+#pragma unroll 1
+        for (int q = qa; q < qb; q++) {
+            const double a = X0 - xs[2 * nmax + j], b = X1 - xs[3 * nmax + j];
+            const double g = kv(PNB_ADD(PNB_MUL(a, a), PNB_MUL(b, b)));
+            const double *dj = der + (size_t)j * 10;
+            rs = fma(g, dj[0], rs);
+            t0 = fma(g, dj[1], t0);
+            t1 = fma(g, dj[2], t1);
+            t2 = fma(g, dj[3], t2);
+            const double gw = g * wi;
+#pragma unroll
+            for (int e = 0; e < 6; e++) yy[e] = fma(gw, dj[4 + e], yy[e]);
+            j++;
+            if (j == n || q + 1 == qb) {
+                const double *di = der + (size_t)i * 10;
+#pragma unroll
+                for (int aa = 0; aa < 3; aa++) {
+                    const double wp = di[1 + aa];
+                    xy[aa * 3 + 0] = fma(-wp, t0, xy[aa * 3 + 0]);
+                    xy[aa * 3 + 1] = fma(-wp, t1, xy[aa * 3 + 1]);
+                    xy[aa * 3 + 2] = fma(-wp, t2, xy[aa * 3 + 2]);
+                }
+#pragma unroll
+                for (int e = 0; e < 6; e++) xx[e] = fma(di[4 + e], rs, xx[e]);
+                t0 = t1 = t2 = rs = 0.;
+                if (j == n && q + 1 < qb) {
+                    j = 0;
+                    i++;
+                    X0 = xs[i]; X1 = xs[nmax + i]; wi = der[(size_t)i * 10];
+                }
+            }
+        }
+    }
+    // the reference's flattened upper triangle of the 6 x 6 local matrix over (dofs of cell 1, dofs of cell 2)
+    int k = 0;
+#pragma unroll
+    for (int II = 0; II < 6; II++)
+#pragma unroll
+        for (int JJ = II; JJ < 6; JJ++) {
+            acc[k++] = (II < 3 && JJ >= 3) ? xy[II * 3 + (JJ - 3)] : (JJ < 3 ? xx[tri_idx(3, II, JJ)] : yy[tri_idx(3, II - 3, JJ - 3)]);
+        }
+}
+
+// one warp per item: slice of the quadrature nodes of a near pair; 21 partial sums per item
+__global__ void __launch_bounds__(PNB_THREADS, 2)
 gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__restrict__ items, int nitems, double *__restrict__ R)
 {
     constexpr int NV = 3, NL = PairDims<2>::NL, NRr = 2 * NV - 1, NA = NRr * (NRr + 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PowTab *pw = reinterpret_cast<PowTab *>(smem_raw);
+    double *xs = reinterpret_cast<double *>(smem_raw + sizeof(PowTab)) + (size_t)(threadIdx.x >> 5) * 4 * P.reg_nmax;
+    {
+        const double *src = reinterpret_cast<const double *>(P.pow_int);
+        double *dst = reinterpret_cast<double *>(pw);
+        for (int e = threadIdx.x; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_THREADS) dst[e] = src[e];
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * (PNB_THREADS / 32) + (threadIdx.x >> 5);
     if (item >= nitems) return;
@@ -421,7 +548,8 @@ gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__rest
     const int Sl = near_slices(P, panel);
     double acc[NL];
     if (panel >= 1) {
-        lanes_regular_interior<2>(P, Ka, Kb, panel, it.y * 32 + lane, 32 * Sl, acc);
+        const PowCtx kv(pw);
+        near_regular_item(P, kv, Ka, Kb, panel, it.y, Sl, xs, lane, acc);
         warp_allreduce<NL>(acc);
     } else {
         // reference orientation of singular pairs: smaller cell index first
@@ -505,11 +633,11 @@ __device__ __noinline__ void near_fetch(const DProblem &P, const double *__restr
 struct GMixFixed {
     PowTab pw;
     FarRule far[PNB_FAR_MAX_ORDER - 1];      // orders 2..PNB_FAR_MAX_ORDER
-    double dxy[PNB_SB * PNB_SB][12];
-    unsigned char slotD[PNB_SB * PNB_SB];
-    int list[PNB_SB * PNB_SB];
-    int clscnt[(PNB_FAR_MAX_ORDER - 1) * (PNB_THREADS / 32)];
-    int warpcnt[PNB_THREADS / 32];
+    double dxy[2 * PNB_SB * PNB_SB][12];
+    unsigned char slotD[2 * PNB_SB * PNB_SB];
+    int list[2 * PNB_SB * PNB_SB];
+    int clscnt[(PNB_FAR_MAX_ORDER - 1) * (PNB_GT / 32)];
+    int warpcnt[PNB_GT / 32];
     int nlist, anyD;
 };
 
@@ -538,10 +666,28 @@ inline size_t gnear_list_smem_bytes(int cap)
     return b;
 }
 
-__global__ void __launch_bounds__(PNB_THREADS, 2)
+// adds the 3 x 3 cross block of a pair to the unit block
+__device__ __forceinline__ void g_scatter(double *S, int ldS, int rl, int cl, const double *xy)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int a = (rl >> (8 * i)) & 0xFF;
+        if (a == 0xFF) continue;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int b = (cl >> (8 * j)) & 0xFF;
+            if (b == 0xFF) continue;
+            S[a * ldS + b] += xy[i * 3 + j];
+        }
+    }
+}
+
+// PNB_GT threads, two column batches per step (sub-batch = slot / 256): classification, binning and evaluation
+// run over both; the block updates of the two sub-batches are separated by a barrier.
+__global__ void __launch_bounds__(PNB_GT, 1)
 gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__restrict__ A, int64_t ld, int far_mask)
 {
-    constexpr int NV = 3, ND = 6, SB = PNB_SB, NW = PNB_THREADS / 32;
+    constexpr int ND = 6, SB = PNB_SB, NW = PNB_GT / 32, NSL = 2 * SB * SB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
     const int cap = G.cap, ldS = G.ldS;
@@ -573,15 +719,17 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
     {
         const double *src = reinterpret_cast<const double *>(P.pow_int);
         double *dst = reinterpret_cast<double *>(&sm.pw);
-        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_THREADS) dst[e] = src[e];
+        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_GT) dst[e] = src[e];
         const double *fs = reinterpret_cast<const double *>(P.far_rules + 2);
         double *fd = reinterpret_cast<double *>(&sm.far[0]);
-        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_THREADS) fd[e] = fs[e];
-        for (int e = tid; e < nldI * ldS; e += PNB_THREADS) S[e] = 0.;
-        for (int e = tid; e < cap * 6; e += PNB_THREADS) DYs[e] = 0.;
-        g_load_cls_side(P, G, I, cellI, locI, cxs, lhs, lhs + cap, cap, tid);
-        g_load_cls_side(P, G, J, cellJ, locJ, cxs + 2 * cap, lhs + 2 * cap, lhs + 3 * cap, cap, tid);
-        for (int e = tid; e < nI + nJ; e += PNB_THREADS) {
+        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_GT) fd[e] = fs[e];
+        for (int e = tid; e < nldI * ldS; e += PNB_GT) S[e] = 0.;
+        for (int e = tid; e < cap * 6; e += PNB_GT) DYs[e] = 0.;
+        if (tid < PNB_THREADS) {
+            g_load_cls_side(P, G, I, cellI, locI, cxs, lhs, lhs + cap, cap, tid);
+            g_load_cls_side(P, G, J, cellJ, locJ, cxs + 2 * cap, lhs + 2 * cap, lhs + 3 * cap, cap, tid);
+        }
+        for (int e = tid; e < nI + nJ; e += PNB_GT) {
             const bool first = e < nI;
             const int s = first ? e : e - nI;
             const int cc = G.gcells[(first ? ibeg : jbeg) + s];
@@ -595,16 +743,17 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
     }
     __syncthreads();
     const PowCtx kv(&sm.pw);
-    const int k1 = tid / SB, k2 = tid % SB;
+    const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15;
 
     for (int rb = 0; rb < nI; rb += SB) {
         double dxacc = 0.;      // threads tid < SB*ND: entry (tid % ND) of the block of row cell rb + tid / ND
-        for (int cb = diag ? rb : 0; cb < nJ; cb += SB) {
-            // ---- classify every pair of the sub-batch ----
+        for (int cb0 = diag ? rb : 0; cb0 < nJ; cb0 += 2 * SB) {
+            const int cb = cb0 + sub * SB;
+            // ---- classify every pair of the two sub-batches ----
             int cls = 0, todo = 0;
             sm.slotD[tid] = 0;
             if (tid == 0) sm.anyD = 0;
-            {
+            if (cb < nJ) {
                 const int panel = g_classify(P, c, diag, nearunit, rb, cb, k1, k2);
                 if (panel != 0) {
                     const bool is_far = panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1);
@@ -641,8 +790,9 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
                 if (cls != 0) sm.list[pos + __popc(mybal & ((1u << lane) - 1))] = tid | (cls << 12);
                 if (tid == 0) sm.nlist = tot;
                 if (nearunit) {
+                    // rank inside the own sub-batch (the list builder numbers every sub-batch separately)
                     for (int w = 0; w < NW; w++) {
-                        if (w < warp) npos += sm.warpcnt[w];
+                        if (w < warp && (w >> 3) == sub) npos += sm.warpcnt[w];
                         nnear += sm.warpcnt[w];
                     }
                     npos += __popc(nbal & ((1u << lane) - 1));
@@ -651,13 +801,16 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
             __syncthreads();    // B2
             const int nlist = sm.nlist;
             if (nlist == 0 && nnear == 0) continue;     // uniform across the CTA
-            // ---- evaluate the far pairs ----
+            // ---- evaluate the far pairs (no ordering needed) ----
+            double xy[9];
+            int frl = 0x00FFFFFF, fcl = 0x00FFFFFF, fsub = -1;
             if (tid < nlist) {
                 const int item = sm.list[tid];
-                const int slot = item & 0xFF, order = item >> 12;
-                const int a1 = rb + slot / SB, a2 = cb + slot % SB;
+                const int slot = item & 0x1FF, order = item >> 12;
+                fsub = slot >> 8;
+                const int a1 = rb + ((slot >> 4) & 15), a2 = cb0 + fsub * SB + (slot & 15);
                 my_pairs++;
-                double s1v[3][2], s2v[3][2], xx[6], yy[6], xy[9];
+                double s1v[3][2], s2v[3][2], xx[6], yy[6];
 #pragma unroll
                 for (int m = 0; m < 3; m++) {
                     s1v[m][0] = sxI[(2 * m) * cap + a1];
@@ -672,67 +825,59 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
                     sm.dxy[slot][k] = xx[k] * sc;
                     sm.dxy[slot][6 + k] = yy[k] * sc;
                 }
+#pragma unroll
+                for (int k = 0; k < 9; k++) xy[k] *= sc;
                 sm.slotD[slot] = 1;
                 sm.anyD = 1;
-                const int rl = locI[a1], cl = locJ[a2];
-#pragma unroll
-                for (int i = 0; i < NV; i++) {
-                    const int a = (rl >> (8 * i)) & 0xFF;
-                    if (a == 0xFF) continue;
-#pragma unroll
-                    for (int j = 0; j < NV; j++) {
-                        const int b = (cl >> (8 * j)) & 0xFF;
-                        if (b == 0xFF) continue;
-                        S[a * ldS + b] += xy[i * NV + j] * sc;
-                    }
-                }
+                frl = locI[a1];
+                fcl = locJ[a2];
             }
-            // ---- fetch the other pairs (distinct slots, distinct entries of S) ----
-            if (todo != 0) {
-                const int pos = G.nearbase[((size_t)u.slot * G.nbmax + rb / SB) * G.nbmax + cb / SB] + npos;
-                const int4 pr = G.npairs[pos];
-                if (pr.x != cellI[rb + k1] || pr.y != cellJ[cb + k2] || pr.z != todo) atomicMax(G.err + 1, 2);
-                else {
-                    double xy[9], d12[12];
-                    near_fetch(P, G.R, pr, xy, d12);
-                    my_near++;
+            // ---- block updates: sub-batch 0, barrier, sub-batch 1; pairs of one sub-batch hit distinct entries ----
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ph++) {
+                if (ph == 1) __syncthreads();
+                if (fsub == ph) g_scatter(S, ldS, frl, fcl, xy);
+                if (todo != 0 && sub == ph) {
+                    // pairs evaluated by gnear_eval_kernel
+                    const int pos = G.nearbase[((size_t)u.slot * G.nbmax + rb / SB) * G.nbmax + cb / SB] + npos;
+                    const int4 pr = G.npairs[pos];
+                    if (pr.x != cellI[rb + k1] || pr.y != cellJ[cb + k2] || pr.z != todo) atomicMax(G.err + 1, 2);
+                    else {
+                        double nxy[9], d12[12];
+                        near_fetch(P, G.R, pr, nxy, d12);
+                        my_near++;
 #pragma unroll
-                    for (int k = 0; k < 12; k++) sm.dxy[tid][k] = d12[k];
-                    sm.slotD[tid] = 1;
-                    sm.anyD = 1;
-                    const int rl = locI[rb + k1], cl = locJ[cb + k2];
-#pragma unroll
-                    for (int i = 0; i < NV; i++) {
-                        const int a = (rl >> (8 * i)) & 0xFF;
-                        if (a == 0xFF) continue;
-#pragma unroll
-                        for (int j = 0; j < NV; j++) {
-                            const int b = (cl >> (8 * j)) & 0xFF;
-                            if (b == 0xFF) continue;
-                            S[a * ldS + b] += xy[i * NV + j];
-                        }
+                        for (int k = 0; k < 12; k++) sm.dxy[tid][k] = d12[k];
+                        sm.slotD[tid] = 1;
+                        sm.anyD = 1;
+                        g_scatter(S, ldS, locI[rb + k1], locJ[cb + k2], nxy);
                     }
                 }
             }
             __syncthreads();    // B3
-            // ---- cell-diagonal blocks: reduce over the sub-batch ----
+            // ---- cell-diagonal blocks: reduce over the two sub-batches ----
             if (sm.anyD) {
                 if (tid < SB * ND) {
                     const int kk1 = tid / ND, comp = tid - kk1 * ND;
                     double sacc = 0.;
-                    for (int kk2 = 0; kk2 < SB; kk2++)
-                        if (sm.slotD[kk1 * SB + kk2]) sacc += sm.dxy[kk1 * SB + kk2][comp];
+                    for (int q = 0; q < 2 * SB; q++) {
+                        const int slot = (q >> 4) * (SB * SB) + kk1 * SB + (q & 15);
+                        if (sm.slotD[slot]) sacc += sm.dxy[slot][comp];
+                    }
                     dxacc += sacc;
-                } else if (tid < 2 * SB * ND) {
+                } else if (tid < 3 * SB * ND) {
                     const int t2 = tid - SB * ND;
-                    const int kk2 = t2 / ND, comp = t2 - kk2 * ND;
+                    const int sb = t2 / (SB * ND), t3 = t2 - sb * (SB * ND);
+                    const int kk2 = t3 / ND, comp = t3 - kk2 * ND;
                     double sacc = 0.;
-                    for (int kk1 = 0; kk1 < SB; kk1++)
-                        if (sm.slotD[kk1 * SB + kk2]) sacc += sm.dxy[kk1 * SB + kk2][ND + comp];
-                    DYs[(cb + kk2) * ND + comp] += sacc;
+                    for (int kk1 = 0; kk1 < SB; kk1++) {
+                        const int slot = sb * (SB * SB) + kk1 * SB + kk2;
+                        if (sm.slotD[slot]) sacc += sm.dxy[slot][ND + comp];
+                    }
+                    if (cb0 + sb * SB < nJ) DYs[(cb0 + sb * SB + kk2) * ND + comp] += sacc;
                 }
             }
-            __syncthreads();    // B4: slotD / dxy reused by the next sub-batch
+            __syncthreads();    // B4: slotD / dxy reused by the next step
         }
         if (tid < SB * ND) {
             const int kk1 = tid / ND, comp = tid - kk1 * ND;
@@ -741,12 +886,12 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
         }
     }
     __syncthreads();
-    for (int e = tid; e < nldI * nldJ; e += PNB_THREADS) {
+    for (int e = tid; e < nldI * nldJ; e += PNB_GT) {
         const int a = e / nldJ, b = e - a * nldJ;
         A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]] += S[a * ldS + b];
     }
     // column-cell sums; same group on both sides: slot Dp[I][c] takes the row sums (written above) and these
-    for (int e = tid; e < nJ * ND; e += PNB_THREADS) {
+    for (int e = tid; e < nJ * ND; e += PNB_GT) {
         const int cc = cellJ[e / ND];
         if (cc < 0) continue;
         double *dp = &G.Dp[((size_t)I * P.nc + cc) * ND + (e % ND)];
@@ -758,6 +903,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
     }
     if (lane == 0 && my_pairs) atomicAdd(G.counters, my_pairs);
     if (lane == 0 && my_near) atomicAdd(G.counters + 1, my_near);
+    (void)NSL;
 }
 
 // F = U + U^T in place, 32 x 32 tiles; bitwise symmetric by construction
