@@ -779,14 +779,20 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
             __syncthreads();    // B1
             int nnear = 0, npos = 0;
             {
+                // exclusive prefix over the (order, warp) counters: 64 entries, two per lane, warp scan
+                static_assert((PNB_FAR_MAX_ORDER - 1) * NW == 64, "counter scan assumes 64 entries");
                 const int me = (cls - 2) * NW + warp;
-                int pos = 0, tot = 0;
-#pragma unroll 4
-                for (int q = 0; q < (PNB_FAR_MAX_ORDER - 1) * NW; q++) {
-                    const int cc = sm.clscnt[q];
-                    if (q < me) pos += cc;
-                    tot += cc;
+                const int v0 = sm.clscnt[2 * lane], v1 = sm.clscnt[2 * lane + 1];
+                int incl = v0 + v1;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += t;
                 }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                const int src = (me >> 1) & 31;
+                const int ex = __shfl_sync(0xffffffffu, incl - v0 - v1, src), a0 = __shfl_sync(0xffffffffu, v0, src);
+                const int pos = ex + ((me & 1) ? a0 : 0);
                 if (cls != 0) sm.list[pos + __popc(mybal & ((1u << lane) - 1))] = tid | (cls << 12);
                 if (tid == 0) sm.nlist = tot;
                 if (nearunit) {
