@@ -95,6 +95,7 @@ struct pnb_problem {
     GroupHost *gh = nullptr;
     std::vector<int> h_cells, h_dofs; // host copies for the lazy group schedule
     std::vector<double> h_centers, h_h;
+    std::vector<int4> h_grid;         // lane grids of the near evaluator per order
     DProblem P{};
     TileSched S{};
     std::vector<void *> allocs;       // everything to free
@@ -190,24 +191,52 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
     if (upload(p, cell.data(), (size_t)mo + 1, &p->P.reg_cell, true)) return PNB_ERR_CUDA;
     if (upload(p, facet.data(), (size_t)mo + 1, &p->P.reg_facet, true)) return PNB_ERR_CUDA;
     p->P.max_order = mo;
-    p->P.reg_derived = nullptr; p->P.reg_doff = nullptr; p->P.reg_nmax = 0;
+    p->P.reg_derived = nullptr; p->P.reg_doff = nullptr; p->P.reg_nmax = 0; p->P.reg_grid = nullptr;
     if (p->dim == 2) {
+        // per node: w, w*bary[0..2], w*bary[a]*bary[b] (a<=b), bary[0..2]
         std::vector<int> doff(mo + 2, 0);
         std::vector<double> der;
         for (int o = 1; o <= mo; o++) {
             const pnb_rule_t &r = rules->cell[o];
-            doff[o] = (int)(der.size() / 10);
+            doff[o] = (int)(der.size() / 13);
             p->P.reg_nmax = std::max(p->P.reg_nmax, r.n);
             for (int i = 0; i < r.n; i++) {
                 der.push_back(r.w[i]);
                 for (int k = 0; k < 3; k++) der.push_back(r.w[i] * r.bary[k * r.n + i]);
                 for (int a = 0; a < 3; a++)
                     for (int b = a; b < 3; b++) der.push_back(r.w[i] * r.bary[a * r.n + i] * r.bary[b * r.n + i]);
+                for (int k = 0; k < 3; k++) der.push_back(r.bary[k * r.n + i]);
             }
         }
-        doff[mo + 1] = (int)(der.size() / 10);
+        doff[mo + 1] = (int)(der.size() / 13);
+        // lane grid of the near evaluator per order: the smallest lane group (8, 16, 32) whose best RS x CS grid
+        // keeps >= 84 % of the lanes busy with <= 192 node pairs per lane, else the best grid found
+        std::vector<int4> grid(mo + 1, make_int4(32, 1, 32, 0));
+        for (int o = 1; o <= mo; o++) {
+            const int n = rules->cell[o].n;
+            if (n <= 0) continue;
+            const int nsl = std::max(1, (n * n + 2047) / 2048), ncols = (n + nsl - 1) / nsl;
+            double best = -1.;
+            bool found = false;
+            for (int LPI = 8; LPI <= 32 && !found; LPI *= 2) {
+                if ((int64_t)n * (32 / LPI) > p->P.reg_nmax) continue;
+                double bu = -1.;
+                int4 bg = make_int4(LPI, 1, LPI, 0);
+                for (int RS = 1; RS <= LPI; RS++) {
+                    const int CS = LPI / RS;
+                    const int rp = (n + RS - 1) / RS, cp = (ncols + CS - 1) / CS;
+                    if (rp * cp > (LPI == 32 ? 1 << 30 : 192)) continue;
+                    const double u = ((double)n / (rp * RS)) * ((double)ncols / (cp * CS)) * ((double)RS * CS / LPI);
+                    if (u > bu) { bu = u; bg = make_int4(RS, CS, LPI, 0); }
+                }
+                if (bu > best) { best = bu; grid[o] = bg; }
+                if (bu >= 0.84) found = true;
+            }
+        }
         if (upload(p, der.data(), der.size(), &p->P.reg_derived, true)) return PNB_ERR_CUDA;
         if (upload(p, doff.data(), doff.size(), &p->P.reg_doff, true)) return PNB_ERR_CUDA;
+        if (upload(p, grid.data(), grid.size(), &p->P.reg_grid, true)) return PNB_ERR_CUDA;
+        p->h_grid = grid;
     }
     // low-order 2D rules for the thread-per-pair evaluator (orders 2..5, node counts fixed at compile time)
     memset(p->far_rules, 0, sizeof(p->far_rules));
@@ -1752,8 +1781,10 @@ struct GroupHostFull : GroupHost {
     int far_mask = -1, max_order = -1;
     std::vector<void *> unit_allocs, near_allocs;
     const int2 *d_items = nullptr;
+    const int *d_perm = nullptr;
+    const int4 *d_chunks = nullptr;
     double *d_R = nullptr;
-    int nitems = 0, npairs = 0;
+    int nitems = 0, npairs = 0, nchunks = 0;
 };
 
 static int build_group_schedule(pnb_problem *p)
@@ -1878,24 +1909,55 @@ static int build_group_schedule(pnb_problem *p)
         CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
         CK(cudaMemset(p->S.err, 0, 4 * sizeof(int)));
         cudaFuncSetAttribute(gnear_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_near);
-        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 0, cursor, nullptr, nullptr, nullptr);
+        int *bins = nullptr, *binbase = nullptr, *perm = nullptr;
+        CK(cudaMalloc((void **)&bins, 128 * sizeof(int)));
+        gh->near_allocs.push_back(bins);
+        CK(cudaMalloc((void **)&binbase, 64 * sizeof(int)));
+        gh->near_allocs.push_back(binbase);
+        CK(cudaMemset(bins, 0, 128 * sizeof(int)));
+        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 0, cursor, nullptr, nullptr, nullptr, bins, nullptr, nullptr);
         int tot[2] = {0, 0};
         CK(cudaMemcpy(tot, cursor, sizeof(tot), cudaMemcpyDeviceToHost));
+        int hb[64], hbase[64];
+        CK(cudaMemcpy(hb, bins, sizeof(hb), cudaMemcpyDeviceToHost));
+        // processing order: highest orders first (longest items), singular pairs last; chunks of 8 warps
+        std::vector<int4> chunks;
+        {
+            int off = 0;
+            for (int t = 63; t >= 0; t--) {
+                const int key = t;
+                hbase[key] = off;
+                const int K = key >= 1 ? 32 / (key < (int)p->h_grid.size() ? p->h_grid[key].z : 32) : 1;
+                const int per = (PNB_THREADS / 32) * K;
+                for (int q = 0; q < hb[key]; q += per) chunks.push_back(make_int4(key, off + q, std::min(per, hb[key] - q), 0));
+                off += hb[key];
+            }
+        }
+        CK(cudaMemcpy(binbase, hbase, sizeof(hbase), cudaMemcpyHostToDevice));
         int4 *pairs = nullptr;
         int2 *items = nullptr;
         int *nearbase = nullptr;
         double *R = nullptr;
+        int4 *dchunks = nullptr;
         CK(cudaMalloc((void **)&pairs, std::max<size_t>(tot[0], 1) * sizeof(int4)));
         gh->near_allocs.push_back(pairs);
         CK(cudaMalloc((void **)&items, std::max<size_t>(tot[1], 1) * sizeof(int2)));
         gh->near_allocs.push_back(items);
+        CK(cudaMalloc((void **)&perm, std::max<size_t>(tot[1], 1) * sizeof(int)));
+        gh->near_allocs.push_back(perm);
         CK(cudaMalloc((void **)&nearbase, (size_t)nslots * G.nbmax * G.nbmax * sizeof(int)));
         gh->near_allocs.push_back(nearbase);
         CK(cudaMalloc((void **)&R, std::max<size_t>(tot[1], 1) * PairDims<2>::NL * sizeof(double)));
         gh->near_allocs.push_back(R);
+        CK(cudaMalloc((void **)&dchunks, std::max<size_t>(chunks.size(), 1) * sizeof(int4)));
+        gh->near_allocs.push_back(dchunks);
+        if (!chunks.empty()) CK(cudaMemcpy(dchunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
         CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
-        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 1, cursor, pairs, items, nearbase);
+        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 1, cursor, pairs, items, nearbase, bins, binbase, perm);
         CK(cudaDeviceSynchronize());
+        gh->d_perm = perm;
+        gh->d_chunks = dchunks;
+        gh->nchunks = (int)chunks.size();
         G.npairs = pairs;
         G.nearbase = nearbase;
         G.R = R;
@@ -1944,9 +2006,12 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
     if (gh->nitems > 0 && !(dbg & 0x100)) {
         const int wpb = PNB_THREADS / 32;
-        const size_t smem_eval = sizeof(PowTab) + (size_t)wpb * 4 * p->P.reg_nmax * sizeof(double);
+        const size_t smem_eval = sizeof(PowTab) + ((size_t)13 + (size_t)wpb * 4) * p->P.reg_nmax * sizeof(double);
         cudaFuncSetAttribute(gnear_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval);
-        gnear_eval_kernel<<<(unsigned)((gh->nitems + wpb - 1) / wpb), PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->nitems, gh->d_R);
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
+        const int grid = std::min(gh->nchunks, 2 * nsm);
+        gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R);
         launches++;
     }
     for (int ph = 0; ph < gh->nphase; ph++) {

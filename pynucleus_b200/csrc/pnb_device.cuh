@@ -64,6 +64,7 @@ struct DProblem {
     const double *reg_derived;
     const int *reg_doff;
     int reg_nmax;              // largest node count of a cell rule
+    const int4 *reg_grid;      // per order: lane grid of the near evaluator (row lanes, column lanes, lanes per pair, 0)
 };
 
 __host__ __device__ inline int tri_idx(int n, int i, int j) { return n * i - ((i * (i + 1)) >> 1) + j; }

@@ -364,7 +364,7 @@ __device__ __forceinline__ void g_load_cls_side(const DProblem &P, const GroupSc
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PNB_THREADS)
 gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int far_mask, int fill, int *cursor, int4 *pairs, int2 *items,
-                  int *nearbase)
+                  int *nearbase, int *bins, const int *binbase, int *perm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
@@ -408,6 +408,8 @@ gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int
                 }
                 if (pass == 0) {
                     if (lane == 31) { atomicAdd(&tot[0], __popc(bal)); atomicAdd(&tot[1], inc); }
+                    // items per evaluation key (regular: the order, singular: 0), counted once (fill == 0)
+                    if (near && !fill) atomicAdd(bins + (panel >= 1 ? min(panel, 63) : 0), sl);
                     continue;
                 }
                 if (lane == 31) { wcnt[warp] = __popc(bal); wits[warp] = inc; }
@@ -422,7 +424,12 @@ gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int
                     const int pos = base[0] + run_pairs + pp + __popc(bal & ((1u << lane) - 1));
                     const int it0 = base[1] + run_items + pi + inc - sl;
                     pairs[pos] = make_int4(c.cellI[rb + k1], c.cellJ[cb + k2], panel, it0);
-                    for (int q = 0; q < sl; q++) items[it0 + q] = make_int2(pos, q);
+                    const int key = panel >= 1 ? min(panel, 63) : 0;
+                    for (int q = 0; q < sl; q++) {
+                        items[it0 + q] = make_int2(pos, q);
+                        // processing order: grouped by key; the order inside a key does not matter
+                        perm[binbase[key] + atomicAdd(bins + 64 + key, 1)] = it0 + q;
+                    }
                 }
                 run_pairs += tp;
                 run_items += ti;
@@ -439,80 +446,74 @@ gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int
     }
 }
 
-// Regular near pair, one slice of its n x n node pairs per warp.  The node coordinates of both cells are
-// computed once per item (un-fused, in the reference's order, see lanes_regular_interior) and kept in shared
-// memory; every lane takes a contiguous run of the row-major node pairs, so that the row sums of
-// nonlocalOperator_{SCALAR}.pxi:769-789 can be factored out (27 instead of ~60 FP64 operations per node pair).
-__device__ __forceinline__ void near_regular_item(const DProblem &P, const PowCtx &kv, int Ka, int Kb, int order, int slice, int nsl,
-                                                  double *xs, int lane, double *acc)
+// Regular near pair: one column slice of its n x n node pairs per lane group of LPI = 8, 16 or 32 lanes
+// (small rules: several pairs per warp).  Inside the group the lanes form an RS x CS grid: lane (ri, cj) takes
+// the rows i = ri, ri + RS, ... and the columns j = j0 + cj, j0 + cj + CS, ...; all lanes of a column group
+// read the same column data (shared-memory broadcast), and the row sums of
+// nonlocalOperator_{SCALAR}.pxi:769-789 are factored out (27 instead of ~60 FP64 operations per node pair).
+// The node coordinates are computed once per item, un-fused and in the reference's order (see
+// lanes_regular_interior), and kept in shared memory.
+__device__ __forceinline__ void near_regular_group(const DProblem &P, const PowCtx &kv, const double *__restrict__ der, int n, int Ka, int Kb,
+                                                   int slice, int nsl, double *xs, int gl, int4 grid, bool valid, double *acc)
 {
-    const int nmax = P.reg_nmax;
-    const DRule r = P.reg_cell[order];
-    const int n = r.n;
-    const double *der = P.reg_derived + (size_t)P.reg_doff[order] * 10;
-    {
+    const int RS = grid.x, CS = grid.y, LPI = grid.z;
+    const int per = (n + nsl - 1) / nsl;
+    const int j0 = slice * per, j1 = min(n, j0 + per);
+    if (valid) {
         double s1[3][2], s2[3][2];
         load_simplex<2>(P.simplices, Ka, 3, s1);
         load_simplex<2>(P.simplices, Kb, 3, s2);
-        __syncwarp();
-        for (int k = lane; k < n; k += 32) {
-            double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
-#pragma unroll
-            for (int m = 0; m < 3; m++) {
-                const double b = r.bary[m * n + k];
-                x0 = PNB_ADD(x0, PNB_MUL(b, s1[m][0]));
-                x1 = PNB_ADD(x1, PNB_MUL(b, s1[m][1]));
-                y0 = PNB_ADD(y0, PNB_MUL(b, s2[m][0]));
-                y1 = PNB_ADD(y1, PNB_MUL(b, s2[m][1]));
+        for (int k = gl; k < n; k += LPI) {
+            // barycentric coordinates from the derived table: bary[m] = (w bary[m]) / w is not bit-exact, so the
+            // table keeps the plain coordinates in slots 10..12
+            const double b0 = der[(size_t)k * 13 + 10], b1 = der[(size_t)k * 13 + 11], b2 = der[(size_t)k * 13 + 12];
+            double x0 = PNB_MUL(b0, s1[0][0]), x1 = PNB_MUL(b0, s1[0][1]);
+            x0 = PNB_ADD(x0, PNB_MUL(b1, s1[1][0])); x1 = PNB_ADD(x1, PNB_MUL(b1, s1[1][1]));
+            x0 = PNB_ADD(x0, PNB_MUL(b2, s1[2][0])); x1 = PNB_ADD(x1, PNB_MUL(b2, s1[2][1]));
+            xs[k] = x0; xs[n + k] = x1;
+            if (k >= j0 && k < j1) {
+                double y0 = PNB_MUL(b0, s2[0][0]), y1 = PNB_MUL(b0, s2[0][1]);
+                y0 = PNB_ADD(y0, PNB_MUL(b1, s2[1][0])); y1 = PNB_ADD(y1, PNB_MUL(b1, s2[1][1]));
+                y0 = PNB_ADD(y0, PNB_MUL(b2, s2[2][0])); y1 = PNB_ADD(y1, PNB_MUL(b2, s2[2][1]));
+                xs[2 * n + k] = y0; xs[3 * n + k] = y1;
             }
-            xs[k] = x0; xs[nmax + k] = x1; xs[2 * nmax + k] = y0; xs[3 * nmax + k] = y1;
         }
-        __syncwarp();
     }
-    const int total = n * n, per = (total + nsl - 1) / nsl;
-    const int q0 = slice * per, q1 = min(total, q0 + per);
-    const int L = (max(q1 - q0, 0) + 31) / 32;
-    const int qa = q0 + lane * L, qb = min(q1, qa + L);
+    __syncwarp();
     double xy[9], xx[6], yy[6];
 #pragma unroll
     for (int k = 0; k < 9; k++) xy[k] = 0.;
 #pragma unroll
     for (int k = 0; k < 6; k++) xx[k] = yy[k] = 0.;
-    if (qa < qb) {
-        int i = qa / n, j = qa - i * n;
-        double X0 = xs[i], X1 = xs[nmax + i], wi = der[(size_t)i * 10];
-        double t0 = 0., t1 = 0., t2 = 0., rs = 0.;
-#pragma unroll 1
-        for (int q = qa; q < qb; q++) {
-            const double a = X0 - xs[2 * nmax + j], b = X1 - xs[3 * nmax + j];
-            const double g = kv(PNB_ADD(PNB_MUL(a, a), PNB_MUL(b, b)));
-            const double *dj = der + (size_t)j * 10;
-            rs = fma(g, dj[0], rs);
-            t0 = fma(g, dj[1], t0);
-            t1 = fma(g, dj[2], t1);
-            t2 = fma(g, dj[3], t2);
-            const double gw = g * wi;
+    if (valid && gl < RS * CS) {
+        const int ri = gl % RS, cj = gl / RS;
+        for (int i = ri; i < n; i += RS) {
+            const double X0 = xs[i], X1 = xs[n + i];
+            const double *di = der + (size_t)i * 13;
+            const double wi = di[0];
+            double t0 = 0., t1 = 0., t2 = 0., rs = 0.;
+#pragma unroll 2
+            for (int j = j0 + cj; j < j1; j += CS) {
+                const double a = X0 - xs[2 * n + j], b = X1 - xs[3 * n + j];
+                const double g = kv(PNB_ADD(PNB_MUL(a, a), PNB_MUL(b, b)));
+                const double *dj = der + (size_t)j * 13;
+                rs = fma(g, dj[0], rs);
+                t0 = fma(g, dj[1], t0);
+                t1 = fma(g, dj[2], t1);
+                t2 = fma(g, dj[3], t2);
+                const double gw = g * wi;
 #pragma unroll
-            for (int e = 0; e < 6; e++) yy[e] = fma(gw, dj[4 + e], yy[e]);
-            j++;
-            if (j == n || q + 1 == qb) {
-                const double *di = der + (size_t)i * 10;
-#pragma unroll
-                for (int aa = 0; aa < 3; aa++) {
-                    const double wp = di[1 + aa];
-                    xy[aa * 3 + 0] = fma(-wp, t0, xy[aa * 3 + 0]);
-                    xy[aa * 3 + 1] = fma(-wp, t1, xy[aa * 3 + 1]);
-                    xy[aa * 3 + 2] = fma(-wp, t2, xy[aa * 3 + 2]);
-                }
-#pragma unroll
-                for (int e = 0; e < 6; e++) xx[e] = fma(di[4 + e], rs, xx[e]);
-                t0 = t1 = t2 = rs = 0.;
-                if (j == n && q + 1 < qb) {
-                    j = 0;
-                    i++;
-                    X0 = xs[i]; X1 = xs[nmax + i]; wi = der[(size_t)i * 10];
-                }
+                for (int e = 0; e < 6; e++) yy[e] = fma(gw, dj[4 + e], yy[e]);
             }
+#pragma unroll
+            for (int aa = 0; aa < 3; aa++) {
+                const double wp = di[1 + aa];
+                xy[aa * 3 + 0] = fma(-wp, t0, xy[aa * 3 + 0]);
+                xy[aa * 3 + 1] = fma(-wp, t1, xy[aa * 3 + 1]);
+                xy[aa * 3 + 2] = fma(-wp, t2, xy[aa * 3 + 2]);
+            }
+#pragma unroll
+            for (int e = 0; e < 6; e++) xx[e] = fma(di[4 + e], rs, xx[e]);
         }
     }
     // the reference's flattened upper triangle of the 6 x 6 local matrix over (dofs of cell 1, dofs of cell 2)
@@ -525,45 +526,81 @@ __device__ __forceinline__ void near_regular_item(const DProblem &P, const PowCt
         }
 }
 
-// one warp per item: slice of the quadrature nodes of a near pair; 21 partial sums per item
+// Persistent CTAs over chunks of items of one key (regular: the order; 0: singular pairs).  A chunk holds up to
+// 8 x (32 / LPI) items, one lane group each; the derived rule table of the key is staged in shared memory.
 __global__ void __launch_bounds__(PNB_THREADS, 2)
-gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__restrict__ items, int nitems, double *__restrict__ R)
+gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__restrict__ items, const int *__restrict__ perm,
+                  const int4 *__restrict__ chunks, int nchunks, double *__restrict__ R)
 {
     constexpr int NV = 3, NL = PairDims<2>::NL, NRr = 2 * NV - 1, NA = NRr * (NRr + 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PowTab *pw = reinterpret_cast<PowTab *>(smem_raw);
-    double *xs = reinterpret_cast<double *>(smem_raw + sizeof(PowTab)) + (size_t)(threadIdx.x >> 5) * 4 * P.reg_nmax;
+    double *der = reinterpret_cast<double *>(smem_raw + sizeof(PowTab));
+    double *xsw = der + (size_t)13 * P.reg_nmax + (size_t)(threadIdx.x >> 5) * 4 * P.reg_nmax;
     {
         const double *src = reinterpret_cast<const double *>(P.pow_int);
         double *dst = reinterpret_cast<double *>(pw);
         for (int e = threadIdx.x; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_THREADS) dst[e] = src[e];
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * (PNB_THREADS / 32) + (threadIdx.x >> 5);
-    if (item >= nitems) return;
-    const int2 it = items[item];
-    const int4 pr = pairs[it.x];
-    const int Ka = pr.x, Kb = pr.y, panel = pr.z;
-    const int Sl = near_slices(P, panel);
-    double acc[NL];
-    if (panel >= 1) {
-        const PowCtx kv(pw);
-        near_regular_item(P, kv, Ka, Kb, panel, it.y, Sl, xs, lane, acc);
-        warp_allreduce<NL>(acc);
-    } else {
-        // reference orientation of singular pairs: smaller cell index first
-        const int c1 = min(Ka, Kb), c2 = max(Ka, Kb);
-        int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
-        const int pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.cells + (size_t)c2 * NV, NV, c1 == c2, p1, p2);
+    const PowCtx kv(pw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int staged = -1;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int4 c = chunks[ch];
+        const int key = c.x;
+        if (key >= 1 && key != staged) {
+            __syncthreads();      // everybody is done with the previous table
+            const int n = P.reg_cell[key].n;
+            const double *src = P.reg_derived + (size_t)P.reg_doff[key] * 13;
+            for (int e = threadIdx.x; e < n * 13; e += PNB_THREADS) der[e] = src[e];
+            staged = key;
+            __syncthreads();
+        }
+        if (key >= 1) {
+            const int4 grid = P.reg_grid[key];
+            const int LPI = grid.z, K = 32 / LPI, g = lane / LPI, gl = lane - g * LPI;
+            const int idx = warp * K + g;
+            const bool valid = idx < c.z;
+            const int item = valid ? perm[c.y + idx] : 0;
+            const int2 it = items[item];
+            const int4 pr = pairs[it.x];
+            const int n = P.reg_cell[key].n;
+            double acc[NL];
+            __syncwarp();
+            near_regular_group(P, kv, der, n, pr.x, pr.y, it.y, near_slices(P, key), xsw + (size_t)g * 4 * n, gl, grid, valid, acc);
+            for (int off = LPI >> 1; off > 0; off >>= 1) {
 #pragma unroll
-        for (int k = 0; k < NL; k++) acc[k] = 0.;
-        lanes_singular_interior<2>(P, c1, c2, pan, p1, p2, it.y * 32 + lane, 32 * Sl, acc);
-        warp_allreduce<NA>(acc);
+                for (int k = 0; k < NL; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+            }
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < NL; k++)
+                    if ((k % LPI) == gl) R[(size_t)item * NL + k] = acc[k];
+            }
+        } else {
+            const int idx = warp;
+            if (idx < c.z) {
+                const int item = perm[c.y + idx];
+                const int2 it = items[item];
+                const int4 pr = pairs[it.x];
+                const int Ka = pr.x, Kb = pr.y;
+                const int Sl = near_slices(P, pr.z);
+                // reference orientation of singular pairs: smaller cell index first
+                const int c1 = min(Ka, Kb), c2 = max(Ka, Kb);
+                int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
+                const int pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.cells + (size_t)c2 * NV, NV, c1 == c2, p1, p2);
+                double acc[NL];
+#pragma unroll
+                for (int k = 0; k < NL; k++) acc[k] = 0.;
+                lanes_singular_interior<2>(P, c1, c2, pan, p1, p2, it.y * 32 + lane, 32 * Sl, acc);
+                warp_allreduce<NA>(acc);
+#pragma unroll
+                for (int k = 0; k < NL; k++)
+                    if (k == lane) R[(size_t)item * NL + k] = acc[k];
+            }
+        }
     }
-#pragma unroll
-    for (int k = 0; k < NL; k++)
-        if (k == lane) R[(size_t)item * NL + k] = acc[k];
 }
 
 // sums the slices of a near pair and maps the 21 values to the cross block and the two cell-diagonal blocks
