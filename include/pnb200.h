@@ -160,6 +160,14 @@ int pnb_far_max_order(void);
 int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end,
                        double *A, int64_t ld, int a_on_device);
 
+/* 2D, several GPUs: exploits the symmetry across GPUs (the reference splits the cell loop over ranks and
+ * Allreduces the matrix, nonlocalAssembly_{SCALAR}.pxi:1280-1285, 1449-1450).  Instance `part` of `nparts`
+ * evaluates its share of the cell pairs into the full N x N device scratch dU (this share of the operator
+ * without the cell-diagonal blocks).  The caller sums rows [row_begin,row_end) of all shares on their owner,
+ * sums the cell-block buffers and calls pnb_dense_rows_end on the summed rows. */
+int pnb_dense_partial_begin(pnb_problem *p, int zero_exterior, int part, int nparts, int32_t row_begin, int32_t row_end,
+                            double *dU, int64_t ld);
+
 /* Row-block (multi-GPU) form of pnb_dense_assemble: one problem instance per GPU assembles the rows
  * [row_begin, row_end) (multiples of pnb_row_granularity(), or num_dofs) into device memory A_rows of
  * (row_end-row_begin) x num_dofs.  Replaces the reference's cell-range split + Allreduce of the full matrix
@@ -202,6 +210,11 @@ int pnb_dense_matvec(int device, const double *A, int64_t num_rows, int64_t num_
 
 /* FP64 FMA throughput microbenchmark (roofline denominator): returns TFLOP/s */
 int pnb_fp64_peak(int device, double *tflops);
+
+/* Device buffers of destroyed problems are cached for the next problem (the reference allocates its
+ * matrices per call, nonlocalAssembly_{SCALAR}.pxi:1286-1290; cudaMalloc of GB-sized buffers is slow).
+ * Returns the cached buffers to the driver.  PNB_POOL_LIMIT_GB bounds the cache (default 48). */
+int pnb_release_cached_memory(void);
 
 #ifdef __cplusplus
 }

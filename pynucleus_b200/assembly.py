@@ -219,8 +219,36 @@ class nonlocalBuilder:
         nvc = self.mesh.dim+1
         empty = row_end <= row_begin
 
+        import torch.distributed as dist
+        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        gran = int(L.pnb_row_granularity())
+        blocks = row_partition(N, world, gran) if world > 1 else []
+        shared = self.mesh.dim == 2 and world > 1 and blocks[rank] == (row_begin, row_end)
+
+        def run_shared():
+            # 2D, standard partition: every rank evaluates 1/world of the cell pairs (each pair once over all ranks)
+            # into a full-size scratch, the owners of the rows sum the shares over NVLink (NCCL reduce)
+            U = self._scratch(N, dev)
+            _lib.check(L.pnb_dense_partial_begin(prob.handle, int(self.zeroExterior), rank, world, row_begin, row_end, U.data_ptr(), N))
+            works = []
+            for k, (a, b) in enumerate(blocks):
+                if b > a:
+                    dst = dist.get_global_rank(process_group, k) if process_group is not None else k
+                    works.append(dist.reduce(U[a:b], dst=dst, op=dist.ReduceOp.SUM, group=process_group, async_op=True))
+            for w in works:
+                w.wait()
+            if not empty:
+                A.copy_(U[row_begin:row_end])
+            D = exchange_cell_blocks(self.mesh.num_cells*(nvc*(nvc+1)//2), dev, process_group,
+                                     lambda buf: _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, buf.data_ptr(), 0)))
+            if not empty:
+                _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, D.data_ptr(), 1))
+                _lib.check(L.pnb_dense_rows_end(prob.handle, row_begin, row_end, A.data_ptr(), A.stride(0)))
+
         def run():
-            import torch.distributed as dist
+            if shared:
+                return run_shared()
             D = None
             if not empty:
                 _lib.check(L.pnb_dense_rows_begin(prob.handle, int(self.zeroExterior), row_begin, row_end, A.data_ptr(), A.stride(0)))
@@ -234,6 +262,13 @@ class nonlocalBuilder:
                 _lib.check(L.pnb_dense_rows_end(prob.handle, row_begin, row_end, A.data_ptr(), A.stride(0)))
         self._retry_on_order(run)
         return Dense_LinearOperator(A, prob.device) if not empty else None
+
+    def _scratch(self, N, dev):
+        import torch
+        U = getattr(self, '_U', None)
+        if U is None or U.shape[0] != N or U.device != dev:
+            U = self._U = torch.empty((N, N), dtype=torch.float64, device=dev)
+        return U
 
     def getDenseDistributed(self, process_group=None):
         """getDense() sharded by rows over the ranks of `process_group` (one process per GPU): returns a

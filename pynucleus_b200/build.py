@@ -11,7 +11,7 @@ DEPS = [SRC, os.path.join(HERE, 'csrc', 'pnb_device.cuh'), os.path.join(HERE, 'c
         os.path.join(HERE, '..', 'include', 'pnb200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC', '-shared', '-lpthread']
 
 
 def build(force=False, verbose=False):

@@ -56,6 +56,88 @@ extern "C" int pnb_device_count(void)
     return n;
 }
 
+
+// ---------------------------------------------------------------------------
+// caching device allocator: problems are created and destroyed per assembly in the end-to-end path, and
+// cudaMalloc / cudaFree of the multi-GB staging buffers cost ~100 ms each.  Freed blocks are kept (per
+// device) and handed out again; pnb_release_cached_memory() returns them to the driver.
+// ---------------------------------------------------------------------------
+#include <mutex>
+#include <map>
+#include <thread>
+struct PoolBlock { void *p; size_t bytes; int dev; };
+static std::mutex g_pool_mu;
+static std::vector<PoolBlock> g_pool_free;
+static std::map<void *, PoolBlock> g_pool_used;
+static size_t g_pool_cached = 0;
+
+static void pool_trim_locked(size_t limit, int dev_only)
+{
+    for (size_t i = 0; i < g_pool_free.size() && g_pool_cached > limit;) {
+        if (dev_only >= 0 && g_pool_free[i].dev != dev_only) { i++; continue; }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(g_pool_free[i].dev);
+        cudaFree(g_pool_free[i].p);
+        cudaSetDevice(cur);
+        g_pool_cached -= g_pool_free[i].bytes;
+        g_pool_free.erase(g_pool_free.begin() + i);
+    }
+}
+
+static cudaError_t pool_malloc(void **out, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t want = bytes <= (1u << 20) ? ((bytes + 255) & ~(size_t)255) : ((bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1));
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool_free.size(); i++) {
+        const PoolBlock &b = g_pool_free[i];
+        if (b.dev != dev || b.bytes < want || b.bytes > want + want / 4 + (1u << 20)) continue;
+        if (best < 0 || b.bytes < g_pool_free[best].bytes) best = i;
+    }
+    if (best >= 0) {
+        PoolBlock b = g_pool_free[best];
+        g_pool_free.erase(g_pool_free.begin() + best);
+        g_pool_cached -= b.bytes;
+        g_pool_used[b.p] = b;
+        *out = b.p;
+        return cudaSuccess;
+    }
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim_locked(0, dev);      // give the cached blocks of this device back and retry
+        e = cudaMalloc(&d, want);
+        if (e != cudaSuccess) return e;
+    }
+    g_pool_used[d] = PoolBlock{d, want, dev};
+    *out = d;
+    return cudaSuccess;
+}
+
+static void pool_free(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    auto it = g_pool_used.find(p);
+    if (it == g_pool_used.end()) { cudaFree(p); return; }
+    g_pool_free.push_back(it->second);
+    g_pool_cached += it->second.bytes;
+    g_pool_used.erase(it);
+    static const size_t limit = (size_t)(getenv("PNB_POOL_LIMIT_GB") ? atof(getenv("PNB_POOL_LIMIT_GB")) : 48.) << 30;
+    pool_trim_locked(limit, -1);
+}
+
+extern "C" int pnb_release_cached_memory(void)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    pool_trim_locked(0, -1);
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // problem object
 // ---------------------------------------------------------------------------
@@ -96,6 +178,7 @@ struct pnb_problem {
     std::vector<int> h_cells, h_dofs; // host copies for the lazy group schedule
     std::vector<double> h_centers, h_h;
     std::vector<int4> h_grid;         // lane grids of the near evaluator per order
+    int part = 0, nparts = 1;         // share of the units this problem instance evaluates (multi-GPU)
     DProblem P{};
     TileSched S{};
     std::vector<void *> allocs;       // everything to free
@@ -117,7 +200,7 @@ template <class T> static int upload(pnb_problem *p, const T *host, size_t count
 {
     void *d = nullptr;
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    CK(cudaMalloc(&d, bytes));
+    CK(pool_malloc(&d, bytes));
     (rule ? p->rule_allocs : p->allocs).push_back(d);
     if (count) CK(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
     *dev = (const T *)d;
@@ -128,7 +211,7 @@ template <class T> static int dalloc(pnb_problem *p, size_t count, T **dev, bool
 {
     void *d = nullptr;
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    CK(cudaMalloc(&d, bytes));
+    CK(pool_malloc(&d, bytes));
     p->allocs.push_back(d);
     if (zero) CK(cudaMemset(d, 0, bytes));
     *dev = (T *)d;
@@ -167,7 +250,7 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
 {
     if (!p || !rules) return fail(PNB_ERR_ARG, "null argument");
     CK(cudaSetDevice(p->device));
-    for (void *d : p->rule_allocs) cudaFree(d);
+    for (void *d : p->rule_allocs) pool_free(d);
     p->rule_allocs.clear();
     const int nvc = p->dim + 1;
     int rc = 0;
@@ -268,10 +351,10 @@ extern "C" void pnb_problem_destroy(pnb_problem *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    for (void *d : p->allocs) cudaFree(d);
-    for (void *d : p->rule_allocs) cudaFree(d);
+    for (void *d : p->allocs) pool_free(d);
+    for (void *d : p->rule_allocs) pool_free(d);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
-    if (p->stage) cudaFree(p->stage);
+    if (p->stage) pool_free(p->stage);
     if (g_bench_problem == p) g_bench_problem = nullptr;
     destroy_group_host(p);
     delete p;
@@ -1644,8 +1727,11 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
     gg.gptr.assign(1, 0);
     gg.gdptr.assign(1, 0);
     std::vector<int> grp(nc, 0);
-    std::vector<std::vector<int>> bcells;
-    for (int g = 0; g < gg.ngroups; g++) {
+    struct PerGroup { std::vector<int> gcells, gloc, ld; };
+    std::vector<PerGroup> pg(gg.ngroups);
+    auto do_group = [&](int g) {
+        std::vector<std::vector<int>> bcells;
+        PerGroup &out = pg[g];
         const int c0 = g * GC, c1 = std::min(nc, c0 + GC);
         // local dofs
         std::vector<int> ld;
@@ -1653,7 +1739,6 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
             for (int m = 0; m < 3; m++) { const int d = dofs[(size_t)order[k] * 3 + m]; if (d >= 0) ld.push_back(d); }
         std::sort(ld.begin(), ld.end());
         ld.erase(std::unique(ld.begin(), ld.end()), ld.end());
-        gg.maxld = std::max(gg.maxld, (int)ld.size());
         // batches of <= PNB_SB cells sharing no vertex.  Most-constrained-first (DSATUR-like) assignment to the
         // emptiest admissible batch: reaches the minimum number of batches (full batches, no padding) on
         // triangulations, where first-fit leaves ~15-25 % of the slots empty.
@@ -1712,7 +1797,7 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
             if (bc.empty()) continue;
             for (int k = 0; k < PNB_SB; k++) {
                 const int c = k < (int)bc.size() ? bc[k] : -1;
-                gg.gcells.push_back(c);
+                out.gcells.push_back(c);
                 int packed = 0x00FFFFFF;
                 if (c >= 0) {
                     packed = 0;
@@ -1723,12 +1808,27 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
                         packed |= l << (8 * m);
                     }
                 }
-                gg.gloc.push_back(packed);
+                out.gloc.push_back(packed);
             }
         }
+        out.ld.swap(ld);
+    };
+    {
+        // groups are independent: a few host threads (the colouring is quadratic in the group size)
+        const int nt = std::max(1, std::min(8, std::min((int)std::thread::hardware_concurrency(), gg.ngroups / 8)));
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t]() { for (int g = t; g < gg.ngroups; g += nt) do_group(g); });
+        for (auto &x : th) x.join();
+    }
+    for (int g = 0; g < gg.ngroups; g++) {
+        const PerGroup &o = pg[g];
+        gg.maxld = std::max(gg.maxld, (int)o.ld.size());
+        gg.gcells.insert(gg.gcells.end(), o.gcells.begin(), o.gcells.end());
+        gg.gloc.insert(gg.gloc.end(), o.gloc.begin(), o.gloc.end());
         gg.gptr.push_back((int)gg.gcells.size());
         gg.cap = std::max(gg.cap, gg.gptr[g + 1] - gg.gptr[g]);
-        gg.gdofs.insert(gg.gdofs.end(), ld.begin(), ld.end());
+        gg.gdofs.insert(gg.gdofs.end(), o.ld.begin(), o.ld.end());
         gg.gdptr.push_back((int)gg.gdofs.size());
     }
     // adjacency through shared vertices
@@ -1778,7 +1878,7 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
 
 struct GroupHostFull : GroupHost {
     GroupGeom gg;
-    int far_mask = -1, max_order = -1;
+    int far_mask = -1, max_order = -1, part = -1, nparts = -1;
     std::vector<void *> unit_allocs, near_allocs;
     const int2 *d_items = nullptr;
     const int *d_perm = nullptr;
@@ -1787,9 +1887,17 @@ struct GroupHostFull : GroupHost {
     int nitems = 0, npairs = 0, nchunks = 0;
 };
 
+static double wall_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int build_group_schedule(pnb_problem *p)
 {
     const int nc = p->nc;
+    const double tw0 = wall_ms();
     if (!p->gh) p->gh = new GroupHostFull();
     if (!p->G) p->G = new GroupSched();
     GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
@@ -1849,7 +1957,8 @@ static int build_group_schedule(pnb_problem *p)
             fprintf(stderr, "group path: GC %d, %d groups, cap %d, maxld %d, %d colours, smem f2/mix/near %zu/%zu/%zu\n", gh->GC,
                     gg.ngroups, gg.cap, gg.maxld, gg.ncolors, gh->smem_f2, gh->smem_mix, gh->smem_near);
     }
-    if (gh->far_mask == p->far_mask && gh->max_order == p->P.max_order) return 0;
+    if (gh->far_mask == p->far_mask && gh->max_order == p->P.max_order && gh->part == p->part && gh->nparts == p->nparts) return 0;
+    const double tw1 = wall_ms();
     // ---- unit kinds (depend on the tables) ----
     const GroupGeom &gg = gh->gg;
     const bool far_full = (p->far_mask & 0x3C) == 0x3C && p->P.max_order >= PNB_FAR_MAX_ORDER;
@@ -1859,6 +1968,8 @@ static int build_group_schedule(pnb_problem *p)
     std::vector<std::vector<GUnit>> f2(gh->nphase), mix(gh->nphase);
     gh->near_units.clear();
     int nslots = 0;
+    // several GPUs: the units of every (phase, kind) are dealt out round-robin
+    std::vector<int> dealt((size_t)gh->nphase * 3, 0);
     for (int I = 0; I < gg.ngroups; I++) {
         const double *b1 = &gg.box[(size_t)I * 7];
         for (int J = I; J < gg.ngroups; J++) {
@@ -1873,6 +1984,7 @@ static int build_group_schedule(pnb_problem *p)
             }
             GUnit u{I, J, kind, -1};
             const int ph = gg.color[I] * ncol + gg.color[J];
+            if ((dealt[(size_t)ph * 3 + kind]++ % p->nparts) != p->part) continue;
             if (kind == 2) { u.slot = nslots++; gh->near_units.push_back(u); }
             (kind == 0 ? f2 : mix)[ph].push_back(u);
         }
@@ -1887,32 +1999,33 @@ static int build_group_schedule(pnb_problem *p)
         gh->f2_off.push_back((int)gh->f2_units.size());
         gh->mix_off.push_back((int)gh->mix_units.size());
     }
-    for (void *d : gh->unit_allocs) cudaFree(d);
+    for (void *d : gh->unit_allocs) pool_free(d);
     gh->unit_allocs.clear();
     auto up = [&](const std::vector<GUnit> &v, const GUnit **dev) -> int {
         void *d = nullptr;
-        CK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(GUnit)));
+        CK(pool_malloc(&d, std::max<size_t>(v.size(), 1) * sizeof(GUnit)));
         gh->unit_allocs.push_back(d);
         if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(GUnit), cudaMemcpyHostToDevice));
         *dev = (const GUnit *)d;
         return 0;
     };
     if (up(gh->f2_units, &gh->d_f2) || up(gh->mix_units, &gh->d_mix) || up(gh->near_units, &gh->d_near)) return PNB_ERR_CUDA;
+    const double tw2 = wall_ms();
     // ---- near pair list: count, allocate, fill (depends on mesh and tables only; reused by every assembly) ----
-    for (void *d : gh->near_allocs) cudaFree(d);
+    for (void *d : gh->near_allocs) pool_free(d);
     gh->near_allocs.clear();
     gh->nitems = 0;
     if (!gh->near_units.empty()) {
         int *cursor = nullptr;
-        CK(cudaMalloc((void **)&cursor, 4 * sizeof(int)));
+        CK(pool_malloc((void **)&cursor, 4 * sizeof(int)));
         gh->near_allocs.push_back(cursor);
         CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
         CK(cudaMemset(p->S.err, 0, 4 * sizeof(int)));
         cudaFuncSetAttribute(gnear_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_near);
         int *bins = nullptr, *binbase = nullptr, *perm = nullptr;
-        CK(cudaMalloc((void **)&bins, 128 * sizeof(int)));
+        CK(pool_malloc((void **)&bins, 128 * sizeof(int)));
         gh->near_allocs.push_back(bins);
-        CK(cudaMalloc((void **)&binbase, 64 * sizeof(int)));
+        CK(pool_malloc((void **)&binbase, 64 * sizeof(int)));
         gh->near_allocs.push_back(binbase);
         CK(cudaMemset(bins, 0, 128 * sizeof(int)));
         gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 0, cursor, nullptr, nullptr, nullptr, bins, nullptr, nullptr);
@@ -1939,17 +2052,17 @@ static int build_group_schedule(pnb_problem *p)
         int *nearbase = nullptr;
         double *R = nullptr;
         int4 *dchunks = nullptr;
-        CK(cudaMalloc((void **)&pairs, std::max<size_t>(tot[0], 1) * sizeof(int4)));
+        CK(pool_malloc((void **)&pairs, std::max<size_t>(tot[0], 1) * sizeof(int4)));
         gh->near_allocs.push_back(pairs);
-        CK(cudaMalloc((void **)&items, std::max<size_t>(tot[1], 1) * sizeof(int2)));
+        CK(pool_malloc((void **)&items, std::max<size_t>(tot[1], 1) * sizeof(int2)));
         gh->near_allocs.push_back(items);
-        CK(cudaMalloc((void **)&perm, std::max<size_t>(tot[1], 1) * sizeof(int)));
+        CK(pool_malloc((void **)&perm, std::max<size_t>(tot[1], 1) * sizeof(int)));
         gh->near_allocs.push_back(perm);
-        CK(cudaMalloc((void **)&nearbase, (size_t)nslots * G.nbmax * G.nbmax * sizeof(int)));
+        CK(pool_malloc((void **)&nearbase, (size_t)nslots * G.nbmax * G.nbmax * sizeof(int)));
         gh->near_allocs.push_back(nearbase);
-        CK(cudaMalloc((void **)&R, std::max<size_t>(tot[1], 1) * PairDims<2>::NL * sizeof(double)));
+        CK(pool_malloc((void **)&R, std::max<size_t>(tot[1], 1) * PairDims<2>::NL * sizeof(double)));
         gh->near_allocs.push_back(R);
-        CK(cudaMalloc((void **)&dchunks, std::max<size_t>(chunks.size(), 1) * sizeof(int4)));
+        CK(pool_malloc((void **)&dchunks, std::max<size_t>(chunks.size(), 1) * sizeof(int4)));
         gh->near_allocs.push_back(dchunks);
         if (!chunks.empty()) CK(cudaMemcpy(dchunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
         CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
@@ -1968,21 +2081,30 @@ static int build_group_schedule(pnb_problem *p)
     }
     gh->far_mask = p->far_mask;
     gh->max_order = p->P.max_order;
+    gh->part = p->part;
+    gh->nparts = p->nparts;
     if (getenv("PNB_BENCH_VERBOSE"))
-        fprintf(stderr, "group path: units f2 %zu, mix %zu (near %zu), phases %d; near pairs %d in %d items\n", gh->f2_units.size(),
-                gh->mix_units.size(), gh->near_units.size(), gh->nphase, gh->npairs, gh->nitems);
+        fprintf(stderr, "group path: units f2 %zu, mix %zu (near %zu), phases %d; near pairs %d in %d items; host ms: groups %.1f, units %.1f, near list %.1f\n",
+                gh->f2_units.size(), gh->mix_units.size(), gh->near_units.size(), gh->nphase, gh->npairs, gh->nitems, tw1 - tw0, tw2 - tw1, wall_ms() - tw2);
     return 0;
 }
 
-static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t ld)
+// part / nparts: share of the units evaluated by this instance (nparts > 1: dA is a full N x N scratch that holds
+// this share of U + U^T afterwards; the caller sums the shares of all instances).  own tiles: cells whose home
+// tile is owned get their boundary terms here.
+static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t ld, int part = 0, int nparts = 1, int own_t0 = 0, int own_t1 = -1)
 {
+    p->part = part;
+    p->nparts = nparts;
     if (build_group_schedule(p)) return PNB_ERR_CUDA;
     GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
     GroupSched &G = *p->G;
     TileSched &S = p->S;
     const int nc = p->nc, N = p->N;
-    S.own_t0 = 0;
-    S.own_t1 = S.ntiles;
+    S.own_t0 = own_t0;
+    S.own_t1 = own_t1 < 0 ? S.ntiles : own_t1;
+    // unit slots of the other instances stay untouched: start from zero
+    if (nparts > 1) cudaMemsetAsync(G.Dp, 0, (size_t)G.ngroups * nc * 6 * sizeof(double));
     for (auto &e : p->ev) if (!e) cudaEventCreate(&e);
     cudaFuncSetAttribute(gf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_f2);
     cudaFuncSetAttribute(gmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_mix);
@@ -2048,8 +2170,8 @@ static void destroy_group_host(pnb_problem *p)
 {
     if (p->gh) {
         GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
-        for (void *d : gh->unit_allocs) cudaFree(d);
-        for (void *d : gh->near_allocs) cudaFree(d);
+        for (void *d : gh->unit_allocs) pool_free(d);
+        for (void *d : gh->near_allocs) pool_free(d);
         for (auto &s : gh->st) if (s) cudaStreamDestroy(s);
         delete gh;
         p->gh = nullptr;
@@ -2149,6 +2271,24 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     return 0;
 }
 
+// Several GPUs, 2D: instance `part` of `nparts` evaluates its share of the group units (dealt out round-robin per
+// phase and kind, so that every pair is still evaluated exactly once over all instances) into the FULL N x N
+// device scratch dU, which afterwards holds this share of U + U^T.  The caller sums the rows [row_begin,
+// row_end) of all shares on the owner of those rows (reduce over NVLink), sums the cell-block buffers
+// (pnb_dense_cell_blocks_copy) and finishes with pnb_dense_rows_end on the summed rows.
+extern "C" int pnb_dense_partial_begin(pnb_problem *p, int zero_exterior, int part, int nparts, int32_t row_begin, int32_t row_end,
+                                       double *dU, int64_t ld)
+{
+    if (!p || !dU) return fail(PNB_ERR_ARG, "null argument");
+    if (p->dim != 2) return fail(PNB_ERR_UNSUPPORTED, "pnb_dense_partial_begin: 2D only (1D problems use row blocks)");
+    if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(PNB_ERR_ARG, "invalid part");
+    if (row_begin != row_end && check_rows(p, row_begin, row_end)) return PNB_ERR_ARG;
+    if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
+    CK(cudaSetDevice(p->device));
+    return run_group_path(p, zero_exterior, dU, ld, part, nparts, row_begin / PNB_TD, (row_end + PNB_TD - 1) / PNB_TD);
+}
+
 // device buffer of the cell-diagonal blocks: num_cells x (dim+1)(dim+2)/2 doubles.  After _begin it holds the
 // complete blocks of the cells whose home row tile is owned and zeros elsewhere; with several row blocks the
 // caller sums the buffers of all owners (disjoint supports: the sum is exact) before calling _end.
@@ -2225,10 +2365,10 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
         // device staging buffer, kept for the life of the problem
         const size_t need = (size_t)N * N * sizeof(double);
         if (p->stage_bytes < need) {
-            if (p->stage) cudaFree(p->stage);
+            if (p->stage) pool_free(p->stage);
             p->stage = nullptr;
             p->stage_bytes = 0;
-            CK(cudaMalloc(&p->stage, need));
+            CK(pool_malloc(&p->stage, need));
             p->stage_bytes = need;
         }
         dA = (double *)p->stage;

@@ -862,7 +862,10 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
                     s2v[m][1] = sxJ[(2 * m + 1) * cap + a2];
                 }
                 const double sc = 2.0 * volI[a1] * volJ[a2];
-                far_eval_2d(sm.far[order - 2], s1v, s2v, kv, true, xy, xx, yy);
+                // node counts of the adopted rule family (far_expected_nodes): 3, 6, 6, 7
+                if (order == 2) far_eval_n<3>(sm.far[0], s1v, s2v, kv, xy, xx, yy);
+                else if (order == 5) far_eval_n<7>(sm.far[3], s1v, s2v, kv, xy, xx, yy);
+                else far_eval_n<6>(sm.far[order - 2], s1v, s2v, kv, xy, xx, yy);
 #pragma unroll
                 for (int k = 0; k < 6; k++) {
                     sm.dxy[slot][k] = xx[k] * sc;

@@ -23,15 +23,20 @@ def main():
     op = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5, 'device': local}).getDenseDistributed()
     A = full.device_data
     mine = op.A_rows.device_data
-    # row blocks are computed by the same kernels in the same order: bitwise equal to the single-GPU rows
-    assert torch.equal(mine, A[op.row_begin:op.row_end]), 'row block differs from the single-GPU operator'
+    # every rank evaluates a share of the cell pairs and the shares are summed over NVLink: same terms as on
+    # one GPU, different summation order -> 1e-12 relative to the entry / diagonal scale
+    d = torch.sqrt(torch.diagonal(A))
+    scale = torch.maximum(A[op.row_begin:op.row_end].abs(), 1e-2*torch.outer(d[op.row_begin:op.row_end], d))
+    err = float(((mine-A[op.row_begin:op.row_end]).abs()/scale).max())
+    assert err < 1e-12, 'row block differs from the single-GPU operator: %g' % err
     x = torch.from_numpy(np.random.default_rng(3).standard_normal(dm.num_dofs)).cuda()
     y = op.matvec_device(x)
-    assert torch.equal(y, full.matvec_device(x)), 'distributed matvec differs'
+    y1 = full.matvec_device(x)
+    assert float((y-y1).abs().max()) < 1e-12*float(y1.abs().max()), 'distributed matvec differs'
     b = torch.full((dm.num_dofs,), 1e-3, dtype=torch.float64, device='cuda')
     u, its, res = pb.cg(op, b, tol=1e-12)
     u1, its1, res1 = pb.cg(full, b, tol=1e-12)
-    assert its == its1 and torch.equal(u, u1), 'CG iterates differ'
+    assert abs(its-its1) <= 1 and float((u-u1).abs().max()) < 1e-9*float(u1.abs().max()), 'CG solutions differ'
     assert float((full.matvec_device(u)-b).abs().max()) < 1e-11
     dist.barrier()
     if rank == 0:
