@@ -1945,6 +1945,16 @@ static int build_group_schedule(pnb_problem *p)
         rc |= upload(p, gg.gdptr.data(), gg.gdptr.size(), &G.gdptr);
         rc |= upload(p, gg.gdofs.data(), gg.gdofs.size(), &G.gdofs);
         rc |= dalloc(p, (size_t)gg.ngroups * nc * 6, &G.Dp);
+        {
+            std::vector<int> aptr(1, 0), alist;
+            for (int g = 0; g < gg.ngroups; g++) {
+                alist.insert(alist.end(), gg.adj[g].begin(), gg.adj[g].end());
+                aptr.push_back((int)alist.size());
+            }
+            rc |= upload(p, aptr.data(), aptr.size(), &G.adjptr);
+            rc |= upload(p, alist.data(), alist.size(), &G.adj);
+            rc |= dalloc(p, 4, &G.counters_i);
+        }
         if (rc) return PNB_ERR_CUDA;
         G.err = p->S.err;
         G.counters = p->S.counters;
@@ -2010,6 +2020,22 @@ static int build_group_schedule(pnb_problem *p)
         return 0;
     };
     if (up(gh->f2_units, &gh->d_f2) || up(gh->mix_units, &gh->d_mix) || up(gh->near_units, &gh->d_near)) return PNB_ERR_CUDA;
+    {
+        // list positions of the units (phase-major order: neighbours in the list never touch the same entries of U)
+        std::vector<int> ticket((size_t)gg.ngroups * gg.ngroups, -1);
+        for (size_t k = 0; k < gh->f2_units.size(); k++) ticket[(size_t)gh->f2_units[k].I * gg.ngroups + gh->f2_units[k].J] = (int)k;
+        for (size_t k = 0; k < gh->mix_units.size(); k++)
+            ticket[(size_t)gh->mix_units[k].I * gg.ngroups + gh->mix_units[k].J] = (int)k | (1 << 30);
+        void *d = nullptr;
+        CK(pool_malloc(&d, ticket.size() * sizeof(int)));
+        gh->unit_allocs.push_back(d);
+        CK(cudaMemcpy(d, ticket.data(), ticket.size() * sizeof(int), cudaMemcpyHostToDevice));
+        G.ticket = (const int *)d;
+        CK(pool_malloc(&d, std::max<size_t>(gh->f2_units.size() + gh->mix_units.size(), 1) * sizeof(int)));
+        gh->unit_allocs.push_back(d);
+        G.done = (int *)d;
+        G.nlist0 = (int)gh->f2_units.size();
+    }
     const double tw2 = wall_ms();
     // ---- near pair list: count, allocate, fill (depends on mesh and tables only; reused by every assembly) ----
     for (void *d : gh->near_allocs) pool_free(d);
@@ -2136,14 +2162,20 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R);
         launches++;
     }
-    for (int ph = 0; ph < gh->nphase; ph++) {
-        const int nm = gh->mix_off[ph + 1] - gh->mix_off[ph], nf = gh->f2_off[ph + 1] - gh->f2_off[ph];
-        if (nm > 0 && !(dbg & 0x200)) {
-            gmix_kernel<<<nm, PNB_GT, gh->smem_mix>>>(p->P, G, gh->d_mix + gh->mix_off[ph], dA, ld, p->far_mask);
+    {
+        // one persistent launch per unit list; the units take tickets in list order and order their updates of U
+        // among themselves (g_wait_predecessors)
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
+        const int nf = (int)gh->f2_units.size(), nm = (int)gh->mix_units.size();
+        cudaMemsetAsync(G.counters_i, 0, 4 * sizeof(int));
+        cudaMemsetAsync(G.done, 0, std::max<size_t>((size_t)nf + nm, 1) * sizeof(int));
+        if (nf > 0 && !(dbg & 0x1000)) {
+            gf2_kernel<<<std::min(nf, nsm), PNB_GT, gh->smem_f2>>>(p->P, G, gh->d_f2, nf, dA, ld, R);
             launches++;
         }
-        if (nf > 0 && !(dbg & 0x1000)) {
-            gf2_kernel<<<nf, PNB_GT, gh->smem_f2>>>(p->P, G, gh->d_f2 + gh->f2_off[ph], dA, ld, R);
+        if (nm > 0 && !(dbg & 0x200)) {
+            gmix_kernel<<<std::min(nm, nsm), PNB_GT, gh->smem_mix>>>(p->P, G, gh->d_mix, nm, dA, ld, p->far_mask);
             launches++;
         }
     }

@@ -32,6 +32,14 @@ struct GroupSched {
     const int4 *npairs;  // near pair list: (row cell, column cell, panel, first item)
     const int *nearbase; // [near slot][row batch][column batch]: position of the first pair of the sub-batch
     const double *R;     // results of the near items, NL doubles each
+    // ordered updates of U: every unit list is processed by persistent CTAs in list order (tickets); a unit adds
+    // its block to U only after all units of smaller ticket that touch the same entries have done so
+    const int *adjptr;   // ngroups+1: groups sharing a vertex (sorted, includes the group itself)
+    const int *adj;
+    const int *ticket;   // ngroups x ngroups: list position | (list << 30) of unit (I <= J), -1 = not evaluated here
+    int *done;           // completion flags: list 0 (f2) at [0, nf2), list 1 (mix) at [nf2, nf2 + nmix)
+    int *counters_i;     // [0], [1]: next ticket of list 0 / 1
+    int nlist0;
     int *err;
     unsigned long long *counters;
 };
@@ -73,6 +81,47 @@ __device__ __forceinline__ unsigned char *carve(unsigned char *&p, size_t bytes)
     return r;
 }
 
+
+// ---- ordered update of U -------------------------------------------------------------------------
+// Unit (I,J) writes U[dofs(I), dofs(J)].  It shares entries exactly with the units (a,b), a <= b, whose row group a
+// touches I and whose column group b touches J.  Tickets are handed out in list order, so a waiting CTA only
+// waits for CTAs that are already running or done: no deadlock, and the order of the additions to every entry of
+// U is the list order (bitwise reproducible).
+__device__ __forceinline__ void g_wait_predecessors(const GroupSched &G, int listid, int myticket, int I, int J, int tid, int nthreads)
+{
+    const int a0 = G.adjptr[I], na = G.adjptr[I + 1] - a0, b0 = G.adjptr[J], nb = G.adjptr[J + 1] - b0;
+    const volatile int *done = G.done + (listid ? G.nlist0 : 0);
+    for (int idx = tid; idx < na * nb; idx += nthreads) {
+        const int a = G.adj[a0 + idx / nb], b = G.adj[b0 + idx % nb];
+        if (a > b) continue;
+        const int tk = G.ticket[(size_t)a * G.ngroups + b];
+        if (tk < 0 || (tk >> 30) != listid) continue;
+        const int t = tk & 0x3FFFFFFF;
+        if (t >= myticket) continue;
+        while (done[t] == 0) __nanosleep(64);
+    }
+    __threadfence();
+    __syncthreads();
+}
+
+__device__ __forceinline__ void g_signal_done(const GroupSched &G, int listid, int myticket, int tid)
+{
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *((volatile int *)(G.done + (listid ? G.nlist0 : 0) + myticket)) = 1;
+}
+
+// adds the unit block to U (L2 operations: other SMs update neighbouring entries of the same lines)
+__device__ __forceinline__ void g_flush_block(const GroupSched &G, const double *S, int ldS, int dI, int nldI, int dJ, int nldJ, double *A,
+                                              int64_t ld, int tid, int nthreads)
+{
+    for (int e = tid; e < nldI * nldJ; e += nthreads) {
+        const int a = e / nldJ, b = e - a * nldJ;
+        double *dst = &A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]];
+        __stcg(dst, __ldcg(dst) + S[a * ldS + b]);
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // uniform order 2.  PNB_GT threads: two column batches per step (sub-batch = tid / 256), so that 16 warps
 // hide the latency of the dependent FP64 chains although the unit block limits the SM to one CTA.  The
@@ -98,7 +147,7 @@ inline size_t gf2_smem_bytes(int cap, int maxld, int ldS)
 }
 
 __global__ void __launch_bounds__(PNB_GT, 1)
-gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__restrict__ A, int64_t ld, F2Rule R)
+gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits, double *__restrict__ A, int64_t ld, F2Rule R)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
@@ -116,14 +165,24 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
     double *RX1 = reinterpret_cast<double *>(carve(sp, (size_t)16 * 3 * 8));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const GUnit u = units[blockIdx.x];
-    const int I = u.I, J = u.J;
-    const int ibeg = G.gptr[I], nI = G.gptr[I + 1] - ibeg, jbeg = G.gptr[J], nJ = G.gptr[J + 1] - jbeg;
-    const int dI = G.gdptr[I], nldI = G.gdptr[I + 1] - dI, dJ = G.gdptr[J], nldJ = G.gdptr[J + 1] - dJ;
+    __shared__ int s_ticket;
     {
         const double *src = reinterpret_cast<const double *>(P.pow_int);
         double *dst = reinterpret_cast<double *>(pw);
         for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_GT) dst[e] = src[e];
+    }
+    unsigned long long my_pairs = 0;
+    for (;;) {
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(G.counters_i, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    if (ticket >= nunits) break;
+    const GUnit u = units[ticket];
+    const int I = u.I, J = u.J;
+    const int ibeg = G.gptr[I], nI = G.gptr[I + 1] - ibeg, jbeg = G.gptr[J], nJ = G.gptr[J + 1] - jbeg;
+    const int dI = G.gdptr[I], nldI = G.gdptr[I + 1] - dI, dJ = G.gdptr[J], nldJ = G.gdptr[J + 1] - dJ;
+    {
         for (int e = tid; e < nldI * ldS; e += PNB_GT) S[e] = 0.;
         for (int e = tid; e < cap * 3; e += PNB_GT) CYs[e] = 0.;
         for (int e = tid; e < nI + nJ; e += PNB_GT) {
@@ -146,7 +205,6 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
     }
     __syncthreads();
     const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15, wsub = warp & 7;
-    unsigned long long my_pairs = 0;
     for (int rb = 0; rb < nI; rb += PNB_SB) {
         const int s1 = rb + k1;
         const int c1 = celli[s1];
@@ -274,15 +332,15 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__
         }
     }
     __syncthreads();
-    for (int e = tid; e < nldI * nldJ; e += PNB_GT) {
-        const int a = e / nldJ, b = e - a * nldJ;
-        A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]] += S[a * ldS + b];
-    }
     for (int e = tid; e < nJ * 6; e += PNB_GT) {
         const int s2 = e / 6, k = e - s2 * 6;
         const int c2 = cellj[s2];
         if (c2 >= 0)
             G.Dp[((size_t)I * P.nc + c2) * 6 + k] = R.qq[k][0] * CYs[s2 * 3] + R.qq[k][1] * CYs[s2 * 3 + 1] + R.qq[k][2] * CYs[s2 * 3 + 2];
+    }
+    g_wait_predecessors(G, 0, ticket, I, J, tid, PNB_GT);
+    g_flush_block(G, S, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_GT);
+    g_signal_done(G, 0, ticket, tid);
     }
     for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
     if (lane == 0 && my_pairs) atomicAdd(G.counters, my_pairs);
@@ -722,7 +780,7 @@ __device__ __forceinline__ void g_scatter(double *S, int ldS, int rl, int cl, co
 // PNB_GT threads, two column batches per step (sub-batch = slot / 256): classification, binning and evaluation
 // run over both; the block updates of the two sub-batches are separated by a barrier.
 __global__ void __launch_bounds__(PNB_GT, 1)
-gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *__restrict__ A, int64_t ld, int far_mask)
+gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits, double *__restrict__ A, int64_t ld, int far_mask)
 {
     constexpr int ND = 6, SB = PNB_SB, NW = PNB_GT / 32, NSL = 2 * SB * SB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -747,12 +805,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
     c.cf = (float)P.c_int; c.sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const GUnit u = units[blockIdx.x];
-    const int I = u.I, J = u.J;
-    const bool diag = I == J, nearunit = u.kind == 2;
-    const int ibeg = G.gptr[I], nI = G.gptr[I + 1] - ibeg, jbeg = G.gptr[J], nJ = G.gptr[J + 1] - jbeg;
-    const int dI = G.gdptr[I], nldI = G.gdptr[I + 1] - dI, dJ = G.gdptr[J], nldJ = G.gdptr[J + 1] - dJ;
-    unsigned long long my_pairs = 0, my_near = 0;
+    __shared__ int s_ticket;
     {
         const double *src = reinterpret_cast<const double *>(P.pow_int);
         double *dst = reinterpret_cast<double *>(&sm.pw);
@@ -760,6 +813,23 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
         const double *fs = reinterpret_cast<const double *>(P.far_rules + 2);
         double *fd = reinterpret_cast<double *>(&sm.far[0]);
         for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_GT) fd[e] = fs[e];
+    }
+    unsigned long long my_pairs = 0, my_near = 0;
+    __syncthreads();        // the power table is complete before its coefficients go to registers
+    const PowCtx kv(&sm.pw);
+    const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15;
+    for (;;) {
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(G.counters_i + 1, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    if (ticket >= nunits) break;
+    const GUnit u = units[ticket];
+    const int I = u.I, J = u.J;
+    const bool diag = I == J, nearunit = u.kind == 2;
+    const int ibeg = G.gptr[I], nI = G.gptr[I + 1] - ibeg, jbeg = G.gptr[J], nJ = G.gptr[J + 1] - jbeg;
+    const int dI = G.gdptr[I], nldI = G.gdptr[I + 1] - dI, dJ = G.gdptr[J], nldJ = G.gdptr[J + 1] - dJ;
+    {
         for (int e = tid; e < nldI * ldS; e += PNB_GT) S[e] = 0.;
         for (int e = tid; e < cap * 6; e += PNB_GT) DYs[e] = 0.;
         if (tid < PNB_THREADS) {
@@ -779,8 +849,6 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
         }
     }
     __syncthreads();
-    const PowCtx kv(&sm.pw);
-    const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15;
 
     for (int rb = 0; rb < nI; rb += SB) {
         double dxacc = 0.;      // threads tid < SB*ND: entry (tid % ND) of the block of row cell rb + tid / ND
@@ -932,16 +1000,16 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, double *_
         }
     }
     __syncthreads();
-    for (int e = tid; e < nldI * nldJ; e += PNB_GT) {
-        const int a = e / nldJ, b = e - a * nldJ;
-        A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]] += S[a * ldS + b];
-    }
     // column-cell sums; same group on both sides: slot Dp[I][c] takes the row sums (written above) and these
     for (int e = tid; e < nJ * ND; e += PNB_GT) {
         const int cc = cellJ[e / ND];
         if (cc < 0) continue;
         double *dp = &G.Dp[((size_t)I * P.nc + cc) * ND + (e % ND)];
         *dp = diag ? *dp + DYs[e] : DYs[e];
+    }
+    g_wait_predecessors(G, 1, ticket, I, J, tid, PNB_GT);
+    g_flush_block(G, S, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_GT);
+    g_signal_done(G, 1, ticket, tid);
     }
     for (int off = 16; off > 0; off >>= 1) {
         my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
