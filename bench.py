@@ -186,7 +186,7 @@ def run_reference(args):
     for _ in range(args.warmup_ref+args.steps_ref):
         last = reference_throughput(args.workload, target_seconds=args.ref_seconds)
         if last is None:
-            print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref (stub-built reference) is missing'}))
+            emit({'impl': 'reference', 'unavailable': 'oracle/_ref (stub-built reference) is missing'})
             return
         vals.append(last)
     vals = vals[args.warmup_ref:]
@@ -201,7 +201,7 @@ def run_reference(args):
                                'the sampled slices to the full matrix'},
             'cpu_baseline': dict(last, value=v),
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -311,12 +311,16 @@ def run_cuda(args):
     hist = builder.getPanelHistogram()
     flops, pows = algorithmic_flops(hist, builder)
     t_tile = float(np.mean(tile_ms))*1e-3
+    # several GPUs: this rank evaluated its share of the pairs; the roofline is per GPU
+    share = st['evaluated_pairs']/max(st['distinct_pairs'], 1) if world > 1 else 1.
+    flops, pows = flops*share, pows*share
     achieved = flops/t_tile/1e12
     roofline = {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved/peak if peak else None,
                 'traffic': None,
-                'note': 'algorithmic flops (SURVEY 8d: 70/node-pair regular, 49/61/76 singular; pow excluded) of all '
-                        'distinct cell pairs / tile-kernel time; peak = DFMA microbenchmark run in this process; '
-                        'pow evaluations/s = {:.3e}; tile-halo redundancy {:.3f}x; kernel share of step {:.3f}'.format(
+                'note': 'algorithmic flops (SURVEY 8d: 70/node-pair regular, 49/61/76 singular; pow excluded) of the '
+                        'distinct cell pairs this GPU evaluates / device time of the pair kernels (near evaluator + unit '
+                        'kernels + symmetrisation, CUDA events); peak = DFMA microbenchmark run in this process; '
+                        'pow evaluations/s = {:.3e}; evaluated/distinct pairs {:.3f}; kernel share of step {:.3f}'.format(
                             pows/t_tile, st['evaluated_pairs']/max(st['distinct_pairs'], 1), t_tile*1e3/ms_step)}
 
     # second kernel of the path: y = A x on the assembled rows (HBM-bound, reads the matrix once)
@@ -368,12 +372,31 @@ def run_cuda(args):
             'phases_ms': {'tiles': st['ms_tiles'], 'boundary': st['ms_boundary'], 'reduce_scatter': st['ms_reduce_scatter']},
             'pairs': {'distinct': st['distinct_pairs'], 'evaluated': st['evaluated_pairs']}}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line, on the real stdout"""
+    data = (json.dumps(line)+'\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries (NCCL: "NCCL version ..." with NCCL_DEBUG set) write to stdout; the contract is ONE JSON line there,
+    # so everything else is sent to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
