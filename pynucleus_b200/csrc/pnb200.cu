@@ -471,6 +471,13 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         }
         rc |= upload(p, lhf.data(), (size_t)nc, &P.lhf);
         rc |= upload(p, ahf.data(), (size_t)nc, &P.ahf);
+        std::vector<float> lhc(nc), ahc(nc), lhb(nb), ahb(nb);
+        for (int c = 0; c < nc; c++) { lhc[c] = (float)log(hcell[c]); ahc[c] = (float)fabs(log(hcell[c] / H0)); }
+        for (int f = 0; f < nb; f++) { lhb[f] = (float)log(bh[f]); ahb[f] = (float)fabs(log(bh[f] / H0)); }
+        rc |= upload(p, lhc.data(), (size_t)nc, &P.lhcf);
+        rc |= upload(p, ahc.data(), (size_t)nc, &P.ahcf);
+        rc |= upload(p, lhb.data(), (size_t)nb, &P.lhbf);
+        rc |= upload(p, ahb.data(), (size_t)nb, &P.ahbf);
         if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
     }
     P.s = kernel->s; P.C = kernel->scaling; P.Cb = kernel->bscaling;
@@ -1556,6 +1563,23 @@ __global__ void compact_units_kernel(TileSched S)
 // cell, lanes over the boundary facets, each lane integrates whole pairs and
 // keeps a private sum; fixed butterfly at the end.
 // ---------------------------------------------------------------------------
+// getQuadOrder of the boundary class (fractionalLaplacian2D.pyx:1226-1253) in single precision; -1 when the value
+// handed to ceil() is within the error bound of an integer (the caller then repeats it in double precision)
+__device__ __forceinline__ int fast_order_boundary_2d(double d2, float lh1, float lh2, float ah1, float ah2, float cb, float sf)
+{
+    const float MARGIN = 2e-3f;
+    const float Ld = 0.5f * __logf((float)d2);
+    const float l1 = fmaxf(Ld - lh1, 0.f), l2 = fmaxf(Ld - lh2, 0.f);
+    const float m = fmaxf(ah1, ah2);
+    const float num1 = cb + m + (sf - 1.f) * ah2 - sf * l2;
+    const float num2 = cb + m + (sf - 1.f) * ah1 - sf * l1;
+    const float g = fmaxf(__fdividef(num1, l1 + 0.35f), __fdividef(num2, l2 + 0.35f));
+    if (g <= 2.f - MARGIN) return 2;
+    const float k = ceilf(g);
+    if (k - g > MARGIN && g - (k - 1.f) > MARGIN && g < 250.f) return (int)k;
+    return -1;
+}
+
 template <int DIM>
 __global__ void boundary_kernel(DProblem P, TileSched S)
 {
@@ -1575,7 +1599,17 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
         const int f = f0 + lane;
         int pan = 0;
         int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
-        if (f < P.nb) pan = panel_boundary(P, c1, f, p1, p2);
+        if (f < P.nb) {
+            if (DIM == 2) {
+                pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.bfacets + (size_t)f * 2, 2, false, p1, p2);
+                if (pan == 0) {
+                    const double a = P.centers[(size_t)c1 * 2] - P.bcenters[(size_t)f * 2], b = P.centers[(size_t)c1 * 2 + 1] - P.bcenters[(size_t)f * 2 + 1];
+                    pan = fast_order_boundary_2d(a * a + b * b, P.lhcf[c1], P.lhbf[f], P.ahcf[c1], P.ahbf[f], (float)P.c_bnd,
+                                                 (float)fmax(0.5 * (-P.bsing - 1.), 0.));
+                    if (pan < 0) pan = panel_boundary(P, c1, f, p1, p2);
+                }
+            } else pan = panel_boundary(P, c1, f, p1, p2);
+        }
         if (f < P.nb && pan >= 1) {
             if (pan > P.max_order) atomicMax(S.err, pan);
             else {

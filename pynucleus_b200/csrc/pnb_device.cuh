@@ -42,6 +42,8 @@ struct DProblem {
     const struct FarRule *far_rules;   // PNB_FAR_MAX_ORDER+1 low-order 2D rules for the thread-per-pair evaluator
     const float *lhf;          // nc: (float) log(h)
     const float *ahf;          // nc: (float) |log(h/H0)|
+    const float *lhcf, *ahcf;  // nc: the same for get_h_simplex (boundary class)
+    const float *lhbf, *ahbf;  // nb: the same for the boundary facets
     const double *simplices;   // nc x (dim+1) x dim     (precomputeSimplices, nonlocalOperator_{SCALAR}.pxi:111-126)
     const double *centers;     // nc x dim
     const int *cells;          // nc x (dim+1)

@@ -381,3 +381,64 @@ def test_two_gpus_row_blocks_matvec_cg():
            os.path.join(here, 'multi_gpu_worker.py')]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and 'OK' in out.stdout, out.stdout[-2000:]+out.stderr[-4000:]
+
+
+@pytest.mark.parametrize('nparts', [2, 3])
+def test_unit_shares_sum_to_full_operator(nparts):
+    """several GPUs, 2D (pnb_dense_partial_begin), emulated on one GPU: every instance evaluates its share of the
+    cell pairs into a full-size scratch; the row owners sum the shares (what the NCCL reduce does) and add the
+    summed cell-diagonal blocks.  Every pair is evaluated exactly once over all instances."""
+    import torch
+    import pynucleus_b200 as pb
+    from pynucleus_b200 import _lib
+    from pynucleus_b200.assembly import row_partition
+    mesh = pb.refined(pb.uniform_disc(), 4)
+    dm = pb.P1_DoFMap(mesh)
+    N = dm.num_dofs
+    kernel = pb.getFractionalKernel(2, 0.75)
+    ref = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5})
+    full = ref.getDense().data
+    distinct = ref.getStats()['distinct_pairs']
+    L = _lib.lib()
+    blocks = row_partition(N, nparts, L.pnb_row_granularity())
+    builders = [pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}) for _ in blocks]
+    Usum = torch.zeros((N, N), dtype=torch.float64, device='cuda')
+    Dsum = torch.zeros(mesh.num_cells*6, dtype=torch.float64, device='cuda')
+    evaluated = 0
+    for k, (bld, (a, b)) in enumerate(zip(builders, blocks)):
+        U = torch.empty((N, N), dtype=torch.float64, device='cuda')
+        _lib.check(L.pnb_dense_partial_begin(bld.problem.handle, 1, k, nparts, a, b, U.data_ptr(), N))
+        D = torch.empty_like(Dsum)
+        _lib.check(L.pnb_dense_cell_blocks_copy(bld.problem.handle, D.data_ptr(), 0))
+        torch.cuda.synchronize()
+        Usum += U
+        Dsum += D
+    outs = []
+    for bld, (a, b) in zip(builders, blocks):
+        out = Usum[a:b].clone()
+        _lib.check(L.pnb_dense_cell_blocks_copy(bld.problem.handle, Dsum.data_ptr(), 1))
+        _lib.check(L.pnb_dense_rows_end(bld.problem.handle, a, b, out.data_ptr(), out.stride(0)))
+        evaluated += bld.getStats()['evaluated_pairs']
+        outs.append(out)
+    A = torch.cat(outs, dim=0).cpu().numpy()
+    assert evaluated == distinct
+    assert entry_err(A, full) < TOL
+    assert np.abs(A-A.T).max() <= 1e-13*np.abs(A).max()
+
+
+def test_group_path_equals_tile_path(monkeypatch):
+    """2D: the cell-group kernels (default) against the DoF-tile kernels (PNB_DEBUG bit 0x800), which share only the
+    per-pair evaluators: same operator to rounding, both bitwise symmetric"""
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.polygon_disc(7), 3)
+    mesh.vertices[:] = mesh.vertices*np.array([1.3, 0.8])      # anisotropic: several mesh sizes and orders
+    mesh = pb.meshNd(mesh.vertices, mesh.cells)
+    dm = pb.P1_DoFMap(mesh)
+    kernel = pb.getFractionalKernel(2, 0.4)
+    A = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense().data
+    monkeypatch.setenv('PNB_DEBUG', '2048')
+    b = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5})
+    B = b.getDense().data
+    assert b.getStats()['evaluated_pairs'] > b.getStats()['distinct_pairs']      # the tile path ran (halo pairs)
+    assert entry_err(A, B) < TOL
+    assert np.array_equal(A, A.T) and np.array_equal(B, B.T)
