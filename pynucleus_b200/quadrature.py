@@ -10,6 +10,7 @@ Tables hold barycentric coordinates (x point rows first, then y point rows);
 P1 shape functions are the barycentric coordinates, so PSI/PHI tables
 (fractionalLaplacian2D.pyx:644-813) are formed on the device.
 """
+from functools import lru_cache
 from math import ceil, log
 
 import numpy as np
@@ -42,6 +43,7 @@ def _join(parts, weights):
     return np.ascontiguousarray(np.hstack([np.vstack(p) for p in parts])), np.concatenate(weights)
 
 
+@lru_cache(maxsize=256)
 def singular2d(panel, sg, qod, qodV):
     if panel == COMMON_FACE:
         (a, b, c, d), w = tensor_gauss_jacobi(((1, 3+sg, 0), (1, 2+sg, 0), (1, 1+sg, 0), (qod, 0, 0)))
@@ -66,6 +68,7 @@ def singular2d(panel, sg, qod, qodV):
     raise NotImplementedError(panel)
 
 
+@lru_cache(maxsize=256)
 def singular2d_boundary(panel, sg, qod):
     if panel == COMMON_EDGE:
         (a, b, c), w = tensor_gauss_jacobi(((qod, 1.+sg, 1.), (qod, 0., 0.), (qod, 0., 0.)))
@@ -83,6 +86,7 @@ def singular2d_boundary(panel, sg, qod):
     raise NotImplementedError(panel)
 
 
+@lru_cache(maxsize=256)
 def singular1d(panel, sg, qod, qor):
     if panel == COMMON_EDGE:
         (a, b), w = tensor_gauss_jacobi(((qor, 1+sg, 0), (qor, 0+sg, 0)))
@@ -94,11 +98,13 @@ def singular1d(panel, sg, qod, qor):
     raise NotImplementedError(panel)
 
 
+@lru_cache(maxsize=256)
 def singular1d_boundary(sg, qod):
     (a, ), w = tensor_gauss_jacobi(((qod, sg, 0), ))
     return np.ascontiguousarray(np.vstack((1-a, a, np.ones_like(a)))), w*a**(-sg)
 
 
+@lru_cache(maxsize=256)
 def regular(order, manifold_dim):
     """rule of integer `order` on a simplex of dimension `manifold_dim`"""
     if manifold_dim == 0:
