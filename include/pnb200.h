@@ -79,6 +79,9 @@ typedef struct {
     double horizon2;       /* fHORIZON2; +inf for the infinite horizon         */
     double target_order;   /* local_matrix.target_order                         */
     double btarget_order;  /* local_matrix_zeroExterior.target_order            */
+    int32_t order_num_dofs; /* num_dofs entering getQuadOrder (local_matrix.num_dofs, fractionalLaplacian2D.pyx:629);
+                             * 0 = dm.num_dofs.  Differs when two DoFMaps are combined
+                             * (nonlocalAssembly_{SCALAR}.pxi:1366-1378: the local matrix keeps the first map's count) */
 } pnb_kernel_t;
 
 /* One quadrature table: rows x n barycentric coordinates (x point first, then

@@ -36,7 +36,7 @@ class _Problem(ctypes.Structure):
                 ('qr_face', _Rule), ('qr_edge', _Rule), ('qr_vertex', _Rule),
                 ('bqr_edge', _Rule), ('bqr_vertex', _Rule),
                 ('max_order', ctypes.c_int),
-                ('reg_cell', ctypes.c_void_p), ('reg_facet', ctypes.c_void_p)]
+                ('reg_cell', ctypes.c_void_p), ('reg_facet', ctypes.c_void_p), ('order_num_dofs', ctypes.c_int)]
 
 
 def build():
@@ -64,7 +64,7 @@ class Problem:
     """One (mesh, P1 DoFMap, constant-order fractional kernel) assembly problem."""
 
     def __init__(self, vertices, cells, dofs, num_dofs, s, bfacets=None, target_order=None,
-                 hVector=None, volVector=None, hmin=None, diam=None, max_order=None):
+                 hVector=None, volVector=None, hmin=None, diam=None, max_order=None, order_num_dofs=None):
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         self.dofs = np.ascontiguousarray(dofs, dtype=np.int32)
@@ -84,8 +84,10 @@ class Problem:
         self.bsingularity = 1.-dim-2*s
         self.C = tables.fractional_scaling(dim, s)
         self.Cb = self.C*(1./s)      # phi = 1/s, kernels.py:151-160, kernelsCy.pyx:1990-1995
+        # two DoFMaps: the local matrices (orders, getQuadOrder) keep the DoF count of the first map
+        self.order_num_dofs = int(order_num_dofs) if order_num_dofs else self.num_dofs
         self.orders = tables.diag_orders(dim, self.singularity, self.bsingularity, hmin, self.H0,
-                                         self.num_dofs, target_order)
+                                         self.order_num_dofs, target_order)
         self.near = tables.near_rules(dim, self.singularity, self.bsingularity, self.orders)
         self._keep = []
         P = _Problem()
@@ -97,6 +99,7 @@ class Problem:
         P.h = self.h.ctypes.data
         P.dofs = self.dofs.ctypes.data
         P.num_dofs = self.num_dofs
+        P.order_num_dofs = self.order_num_dofs
         P.nb = self.bfacets.shape[0]
         P.bfacets = self.bfacets.ctypes.data
         P.H0 = self.H0

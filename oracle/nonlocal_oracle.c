@@ -61,7 +61,12 @@ typedef struct {
     int max_order;
     const orc_rule *reg_cell;   /* rule on a cell       */
     const orc_rule *reg_facet;  /* rule on a boundary facet */
+    /* num_dofs entering getQuadOrder; 0 = num_dofs.  Two DoFMaps (NA.pxi:1366-1378): the local matrices keep the
+     * count of the first map while the assembly runs over the combined map */
+    int order_num_dofs;
 } orc_problem;
+#define ORDN(P) ((P)->order_num_dofs > 0 ? (P)->order_num_dofs : (P)->num_dofs)
+
 
 /* ---------------------------------------------------------------------- */
 /* classification: shared-vertex count and vertex permutations             */
@@ -117,7 +122,7 @@ static int quad_order_interior(const orc_problem *P, double h1, double h2, doubl
     double logdh1 = log(d / h1), logdh2 = log(d / h2);
     double p1, p2;
     if (P->dim == 2) {
-        double c = (0.5 * P->target_order + 0.5) * log(P->num_dofs * (P->H0 * P->H0));
+        double c = (0.5 * P->target_order + 0.5) * log(ORDN(P) * (P->H0 * P->H0));
         double logh1H0 = fabs(log(h1 / P->H0)), logh2H0 = fabs(log(h2 / P->H0));
         double loghminH0 = maxd(logh1H0, logh2H0);
         double s = maxd(-0.5 * (P->singularity + 2), 0.);
@@ -125,7 +130,7 @@ static int quad_order_interior(const orc_problem *P, double h1, double h2, doubl
         p2 = maxd(ceil((c + (s - 1.) * logh1H0 + loghminH0 - s * logdh1) / (maxd(logdh2, 0) + 0.4)), 2);
     } else {
         double s = maxd(-0.5 * (P->singularity + 1), 0.);
-        double c = (P->target_order + 2.) * log(P->num_dofs * P->H0);
+        double c = (P->target_order + 2.) * log(ORDN(P) * P->H0);
         p1 = maxd(ceil((c + (2. * s - 1.) * fabs(log(h2 / P->H0)) - 2. * s * logdh2) / (maxd(logdh1, 0) + 0.8)), 2);
         p2 = maxd(ceil((c + (2. * s - 1.) * fabs(log(h1 / P->H0)) - 2. * s * logdh1) / (maxd(logdh2, 0) + 0.8)), 2);
     }
@@ -142,13 +147,13 @@ static int quad_order_boundary(const orc_problem *P, double h1, double h2, doubl
         double logh1H0 = fabs(log(h1 / P->H0)), logh2H0 = fabs(log(h2 / P->H0));
         double loghminH0 = maxd(logh1H0, logh2H0);
         double s = maxd(0.5 * (-P->bsingularity - 1.), 0.);
-        double c = (0.5 * P->btarget_order + 0.25) * log(P->num_dofs * (P->H0 * P->H0));
+        double c = (0.5 * P->btarget_order + 0.25) * log(ORDN(P) * (P->H0 * P->H0));
         p1 = maxd(ceil((c + loghminH0 + (s - 1.) * logh2H0 - s * logdh2) / (maxd(logdh1, 0) + 0.35)), 2);
         p2 = maxd(ceil((c + loghminH0 + (s - 1.) * logh1H0 - s * logdh1) / (maxd(logdh2, 0) + 0.35)), 2);
     } else {
         double logdh1 = maxd(log(d / h1), 0.), logdh2 = maxd(log(d / h2), 0.);
         double s = maxd(0.5 * (-P->bsingularity - 1.), 0.);
-        double c = (P->btarget_order + 1.) * log(P->num_dofs * P->H0);
+        double c = (P->btarget_order + 1.) * log(ORDN(P) * P->H0);
         p1 = maxd(ceil((c + (2. * s - 1.) * fabs(log(h2 / P->H0)) - 2. * s * log(d / h2)) / (logdh1 + 0.8)), 2);
         p2 = maxd(ceil((c + (2. * s - 1.) * fabs(log(h1 / P->H0)) - 2. * s * log(d / h1)) / (logdh2 + 0.8)), 2);
     }

@@ -212,6 +212,24 @@ def rows_case(noRef, s, name, nrows=12):
     print(name, dm.num_dofs)
 
 
+def dm2_case(noRef, s, name):
+    """two DoFMaps (rows: interior DoFs, columns: the complementary boundary DoFs), NA.pxi:1366-1378"""
+    mesh = uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    dm2 = dm.getComplementDoFMap()
+    out = mesh_arrays(mesh, dm)
+    kernel = getFractionalKernel(2, constFractionalOrder(s), np.inf)
+    b = nonlocalBuilder(dm, kernel, {'target_order': 0.5}, dm2=dm2)
+    A = np.array(b.getDense().data)
+    b0 = nonlocalBuilder(dm, kernel, {'target_order': 0.5}, zeroExterior=False, dm2=dm2)
+    A0 = np.array(b0.getDense().data)
+    out.update(s=s, dofs2=np.array(dm2.dofs), num_dofs2=dm2.num_dofs, A_bc=A, A_bc_interior=A0)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, A.shape)
+
+
 def varconst_case(noRef, s, name):
     """variable-order code path of the reference with s(x,y) = const (config 4): dense matrix only"""
     from PyNucleus_nl.fractionalOrders import variableConstFractionalOrder
@@ -330,6 +348,9 @@ if __name__ == '__main__':
         disc_case(4, 0.75, 'disc_mesh_r4', with_A=False)
     if 'all' in which or 'rows' in which:
         rows_case(5, 0.75, 'disc_s0.75_r5_rows')
+    if 'all' in which or 'dm2' in which:
+        dm2_case(2, 0.75, 'disc_dm2_s0.75_r2')
+        dm2_case(3, 0.25, 'disc_dm2_s0.25_r3')
     if 'all' in which or 'varconst' in which:
         varconst_case(2, 0.75, 'disc_varconst0.75_r2')
         varconst_case(3, 0.4, 'disc_varconst0.4_r3')

@@ -22,7 +22,7 @@ COMMON_VERTEX, COMMON_EDGE, COMMON_FACE = -1, -2, -3
 class _Problem:
     """owner of a pnb_problem handle (device-resident mesh, DoFMap, kernel, tables)"""
 
-    def __init__(self, dm, kernel, bkernel, orders, device, max_order):
+    def __init__(self, dm, kernel, bkernel, orders, device, max_order, order_num_dofs=0):
         mesh = dm.mesh
         self._keep = []
         self.dim = mesh.dim
@@ -42,7 +42,7 @@ class _Problem:
         k = _lib.pnb_kernel_t(kernel.kernelType, kernel.dim, kernel.sValue, kernel.scalingValue, bkernel.scalingValue,
                               kernel.singularityValue, bkernel.singularityValue,
                               kernel.horizonValue2 if kernel.finiteHorizon else np.inf,
-                              orders.target_order, orders.btarget_order)
+                              orders.target_order, orders.btarget_order, order_num_dofs)
         self.singular = quadrature.singular_tables(mesh.dim, kernel.singularityValue, bkernel.singularityValue, orders,
                                                    dm.polynomialOrder)
         self.max_order = 0
@@ -98,13 +98,14 @@ class nonlocalBuilder:
         if 'boundary' in kwargs:
             warnings.warn('"boundary" parameter deprecated', DeprecationWarning)
             zeroExterior = kwargs['boundary']
-        if dm2 is not None:
-            raise NotImplementedError('assembly with two DoFMaps is outside the accelerated path')
         assert kernel.dim == dm.mesh.dim, "Kernel dimension must match dm.mesh dimension"
         quadType = params.get('quadType', 'classical-refactored')
         assert quadType in ('classical-refactored', )
         self.dm = dm
-        self.dm2 = None
+        # two DoFMaps (rows: dm, columns: dm2; nonlocalAssembly_{SCALAR}.pxi:1366-1378): the reference assembles over the
+        # combined map and keeps the block rows [0, N) x columns [N, N+N2); so do we, on the device
+        self.dm2 = dm2
+        self._dm_assembly = dm if dm2 is None else dm.combine(dm2)
         self.mesh = dm.mesh
         self.comm = comm
         self.PLogger = PLogger
@@ -134,8 +135,9 @@ class nonlocalBuilder:
             if not torch.cuda.is_available():
                 raise RuntimeError('pynucleus_b200 needs a CUDA device; there is no CPU fallback')
             device = self.params.get('device', torch.cuda.current_device())
-            self._problem = _Problem(self.dm, self.kernel, self.kernelBoundary, self.orders, device,
-                                     self.params.get('max_regular_order', 32))
+            self._problem = _Problem(self._dm_assembly, self.kernel, self.kernelBoundary, self.orders, device,
+                                     self.params.get('max_regular_order', 32),
+                                     order_num_dofs=self.dm.num_dofs if self.dm2 is not None else 0)
         return self._problem
 
     def _retry_on_order(self, fn):
@@ -192,16 +194,25 @@ class nonlocalBuilder:
 
         out: optional (N, N) float64 CUDA tensor to assemble into."""
         import torch
-        N = self.dm.num_dofs
+        N = self._dm_assembly.num_dofs
         prob = self.problem
         dev = torch.device('cuda', prob.device)
+        if self.dm2 is not None and out is not None:
+            raise ValueError('out= is not supported together with dm2')
         A = torch.empty((N, N), dtype=torch.float64, device=dev) if out is None else out
 
         def run():
             _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.data_ptr(),
                                                      A.stride(0), 1))
         self._retry_on_order(run)
+        if self.dm2 is not None:
+            n1 = self.dm.num_dofs
+            return Dense_LinearOperator(A[:n1, n1:].contiguous(), prob.device)
         return Dense_LinearOperator(A, prob.device)
+
+    def _no_dm2(self):
+        if self.dm2 is not None:
+            raise NotImplementedError('only getDense() supports two DoFMaps')
 
     def getDenseRowBlock(self, row_begin, row_end, out=None, process_group=None):
         """Rows [row_begin, row_end) of getDense() on this process' GPU (row-block sharding over GPUs).
@@ -211,6 +222,7 @@ class nonlocalBuilder:
         exchange is the sum of the per-cell diagonal blocks (num_cells x 6 doubles) over `process_group`.
         Returns a (row_end-row_begin) x N Dense_LinearOperator."""
         import torch
+        self._no_dm2()
         N = self.dm.num_dofs
         prob = self.problem
         dev = torch.device('cuda', prob.device)
@@ -287,6 +299,7 @@ class nonlocalBuilder:
     def getDenseHost(self, out=None):
         """Same as getDense() but through the host-buffer C entry point: the result is written to host memory
         (device -> host copy inside the call)."""
+        self._no_dm2()
         N = self.dm.num_dofs
         A = np.empty((N, N)) if out is None else out
         prob = self.problem

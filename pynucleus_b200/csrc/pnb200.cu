@@ -342,6 +342,9 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
             }
             p->far_mask |= 1 << o;
         }
+    // experiments: PNB_FAR_MASK restricts the orders taken by the thread-per-pair evaluator (the others go to the
+    // near evaluator)
+    if (getenv("PNB_FAR_MASK")) p->far_mask &= atoi(getenv("PNB_FAR_MASK"));
     if (upload(p, p->far_rules, (size_t)PNB_FAR_MAX_ORDER + 1, &p->P.far_rules, true)) return PNB_ERR_CUDA;
     return 0;
 }
@@ -485,12 +488,13 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     P.expo = -0.5 * dim - kernel->s;            // kernelsCy.pyx:159-183
     P.bexpo = -0.5 * (dim - 1) - kernel->s;     // kernelsCy.pyx:216-240
     P.H0 = mesh->diam / sqrt(8.);               // nonlocalOperator_{SCALAR}.pxi:435
+    const double Nord = kernel->order_num_dofs > 0 ? kernel->order_num_dofs : N;
     if (dim == 2) {
-        P.c_int = (0.5 * kernel->target_order + 0.5) * log((double)N * (P.H0 * P.H0));
-        P.c_bnd = (0.5 * kernel->btarget_order + 0.25) * log((double)N * (P.H0 * P.H0));
+        P.c_int = (0.5 * kernel->target_order + 0.5) * log(Nord * (P.H0 * P.H0));
+        P.c_bnd = (0.5 * kernel->btarget_order + 0.25) * log(Nord * (P.H0 * P.H0));
     } else {
-        P.c_int = (kernel->target_order + 2.) * log((double)N * P.H0);
-        P.c_bnd = (kernel->btarget_order + 1.) * log((double)N * P.H0);
+        P.c_int = (kernel->target_order + 2.) * log(Nord * P.H0);
+        P.c_bnd = (kernel->btarget_order + 1.) * log(Nord * P.H0);
     }
 
     // ---- DoF tiles -------------------------------------------------------
@@ -2005,8 +2009,11 @@ static int build_group_schedule(pnb_problem *p)
     const double tw1 = wall_ms();
     // ---- unit kinds (depend on the tables) ----
     const GroupGeom &gg = gh->gg;
-    const bool far_full = (p->far_mask & 0x3C) == 0x3C && p->P.max_order >= PNB_FAR_MAX_ORDER;
-    const bool far_2 = (p->far_mask & 4) && p->P.max_order >= 2;
+    // far_top: all orders 2..far_top are taken by the thread-per-pair evaluator
+    int far_top = 1;
+    while (far_top < PNB_FAR_MAX_ORDER && far_top < p->P.max_order && ((p->far_mask >> (far_top + 1)) & 1)) far_top++;
+    const bool far_full = far_top >= 3;
+    const bool far_2 = far_top >= 2;
     const int ncol = gg.ncolors;
     gh->nphase = ncol * ncol;
     std::vector<std::vector<GUnit>> f2(gh->nphase), mix(gh->nphase);
@@ -2024,7 +2031,7 @@ static int build_group_schedule(pnb_problem *p)
                 const double dy = std::max(0., std::max(b2[2] - b1[3], b1[2] - b2[3]));
                 const double ub = order_upper_bound(p->P, sqrt(dx * dx + dy * dy), b1[4], b2[4], b1[5], b1[6], b2[5], b2[6]);
                 if (far_2 && ub <= 2. - 1e-6) kind = 0;
-                else if (far_full && ub <= PNB_FAR_MAX_ORDER - 1e-6) kind = 1;
+                else if (far_full && ub <= far_top - 1e-6) kind = 1;
             }
             GUnit u{I, J, kind, -1};
             const int ph = gg.color[I] * ncol + gg.color[J];

@@ -29,12 +29,37 @@ class P1_DoFMap:
         interior = order[~isb[order]]
         num = np.empty(nv, dtype=np.int64)
         num[interior] = np.arange(interior.shape[0])
-        bv = np.nonzero(isb)[0]
+        # boundary DoFs: -1, -2, ... in the order of mesh.boundaryVertices (DoFMaps.pyx:158-163)
+        bv = np.asarray(mesh.boundaryVertices) if tag is None else np.nonzero(isb)[0]
         num[bv] = -1-np.arange(bv.shape[0])
         self.dofs = np.ascontiguousarray(num[mesh.cells], dtype=INDEX)
         self.num_dofs = int(interior.shape[0])
         self.num_boundary_dofs = int(bv.shape[0])
         self._vertex2dof = num
+
+    def getComplementDoFMap(self):
+        """DoFs and boundary DoFs swapped (fem/PyNucleus_fem/DoFMaps.pyx:1170-1184)"""
+        from copy import copy
+        bdm = copy(self)
+        bdm.dofs = np.ascontiguousarray(-self.dofs-1, dtype=INDEX)
+        bdm.num_dofs, bdm.num_boundary_dofs = self.num_boundary_dofs, self.num_dofs
+        bdm._vertex2dof = -self._vertex2dof-1
+        return bdm
+
+    def combine(self, other):
+        """all DoFs of two complementary maps, the second map's DoFs after the first's (DoFMaps.pyx:1563-1588)"""
+        from copy import copy
+        assert type(self) is type(other), "Cannot combine DoFMaps of different type"
+        assert self.mesh is other.mesh, "Both DoFMaps need to have the same mesh"
+        assert self.num_dofs == other.num_boundary_dofs and self.num_boundary_dofs == other.num_dofs, "DoFMaps need to be complementary"
+        if np.any((self.dofs >= 0) == (other.dofs >= 0)):
+            raise NotImplementedError()
+        dmc = copy(self)
+        dmc.dofs = np.ascontiguousarray(np.where(self.dofs >= 0, self.dofs, self.num_dofs+other.dofs), dtype=INDEX)
+        dmc.num_dofs = self.num_dofs+other.num_dofs
+        dmc.num_boundary_dofs = 0
+        dmc._vertex2dof = np.where(self._vertex2dof >= 0, self._vertex2dof, self.num_dofs+other._vertex2dof)
+        return dmc
 
     def __repr__(self):
         return 'P1 DoFMap with {} DoFs and {} boundary DoFs.'.format(self.num_dofs, self.num_boundary_dofs)

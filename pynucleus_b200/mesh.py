@@ -15,13 +15,16 @@ REAL = np.float64
 
 
 class meshNd:
-    def __init__(self, vertices, cells, boundary=None, radial=False):
+    def __init__(self, vertices, cells, boundary=None, radial=False, boundaryVertices=None):
         self.vertices = np.ascontiguousarray(vertices, dtype=REAL)
         self.cells = np.ascontiguousarray(cells, dtype=INDEX)
         self.dim = self.vertices.shape[1]
         self.manifold_dim = self.cells.shape[1]-1
         self.radial = radial
         self._boundary = None if boundary is None else np.ascontiguousarray(boundary, dtype=INDEX)
+        # order of the boundary vertices = order of the negative DoF numbers (DoFMaps.pyx:158-163); the reference
+        # appends the midpoints of the boundary edges in edge order when it refines (meshCy.pyx:534-555)
+        self._bvertices = None if boundaryVertices is None else np.ascontiguousarray(boundaryVertices, dtype=INDEX)
         self._h = self._vol = None
 
     num_vertices = property(lambda self: self.vertices.shape[0])
@@ -81,6 +84,8 @@ class meshNd:
 
     @property
     def boundaryVertices(self):
+        if self._bvertices is not None:
+            return self._bvertices
         return np.unique(self.boundaryFacets.ravel()).astype(INDEX)
 
     def get_surface_mesh(self):
@@ -97,7 +102,7 @@ class meshNd:
             newc = np.empty((2*nc, 2), dtype=INDEX)
             newc[0::2, 0], newc[0::2, 1] = c[:, 0], m
             newc[1::2, 0], newc[1::2, 1] = m, c[:, 1]
-            return meshNd(newv, newc, self._boundary, self.radial)
+            return meshNd(newv, newc, self._boundary, self.radial, self._bvertices)
         # edges in sweep order (c0c1), (c0c2), (c1c2) per cell; numbered at first appearance
         e = np.empty((nc, 3, 2), dtype=np.int64)
         e[:, 0], e[:, 1], e[:, 2] = c[:, [0, 1]], c[:, [0, 2]], c[:, [1, 2]]
@@ -133,7 +138,7 @@ class meshNd:
         newb = np.empty((2*be.shape[0], 2), dtype=INDEX)
         newb[0::2, 0], newb[0::2, 1] = be[:, 0], bm
         newb[1::2, 0], newb[1::2, 1] = bm, be[:, 1]
-        return meshNd(newv, newc, newb, self.radial)
+        return meshNd(newv, newc, newb, self.radial, np.concatenate((self.boundaryVertices, bm)))
 
 
 class surfaceMesh:

@@ -442,3 +442,25 @@ def test_group_path_equals_tile_path(monkeypatch):
     assert b.getStats()['evaluated_pairs'] > b.getStats()['distinct_pairs']      # the tile path ran (halo pairs)
     assert entry_err(A, B) < TOL
     assert np.array_equal(A, A.T) and np.array_equal(B, B.T)
+
+
+@pytest.mark.parametrize('name', ['disc_dm2_s0.75_r2', 'disc_dm2_s0.25_r3'])
+def test_two_dofmaps_vs_reference(golden_dir, name):
+    """nonlocalBuilder(dm, kernel, dm2=dm.getComplementDoFMap()).getDense(): the interior x boundary block that the
+    drivers use for inhomogeneous Dirichlet data (nonlocalAssembly_{SCALAR}.pxi:1366-1378)"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    # boundary vertices in the reference's order (= order of the negative DoF numbers)
+    neg = g['dofs'] < 0
+    bv = np.empty(int(g['num_dofs2']), dtype=np.int32)
+    bv[-g['dofs'][neg]-1] = g['cells'][neg]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'], boundaryVertices=bv)
+    dm = pb.P1_DoFMap(mesh)
+    assert np.array_equal(dm.dofs, g['dofs'])
+    dm2 = dm.getComplementDoFMap()
+    assert np.array_equal(dm2.dofs, g['dofs2']) and dm2.num_dofs == int(g['num_dofs2'])
+    kernel = pb.getFractionalKernel(2, float(g['s']))
+    for ze, key in ((True, 'A_bc'), (False, 'A_bc_interior')):
+        A = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}, zeroExterior=ze, dm2=dm2).getDense()
+        assert A.shape == g[key].shape
+        assert np.abs(A.data-g[key]).max() < TOL*np.abs(g[key]).max()

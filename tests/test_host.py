@@ -138,3 +138,22 @@ def test_builder_argument_checks():
         pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'quadType': 'general'})
     b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'target_order': 0.5})
     assert b.zeroExterior and b.orders.quad_order_diagonal >= 4
+
+
+def test_complement_and_combined_dofmaps(golden_dir):
+    """getComplementDoFMap / combine (fem/PyNucleus_fem/DoFMaps.pyx:1170-1184, 1563-1588) against the reference's arrays"""
+    import pynucleus_b200 as pb
+    g = np.load(os.path.join(golden_dir, 'disc_dm2_s0.75_r2.npz'))
+    # boundary vertices in the reference's order (= order of the negative DoF numbers)
+    neg = g['dofs'] < 0
+    bv = np.empty(int(g['num_dofs2']), dtype=np.int32)
+    bv[-g['dofs'][neg]-1] = g['cells'][neg]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'], boundaryVertices=bv)
+    dm = pb.P1_DoFMap(mesh)
+    assert np.array_equal(dm.dofs, g['dofs'])
+    dm2 = dm.getComplementDoFMap()
+    assert np.array_equal(dm2.dofs, g['dofs2']) and dm2.num_dofs == int(g['num_dofs2'])
+    dmc = dm.combine(dm2)
+    assert dmc.num_dofs == dm.num_dofs+dm2.num_dofs and dmc.dofs.min() == 0
+    assert np.array_equal(np.sort(np.unique(dmc.dofs)), np.arange(dmc.num_dofs))
+    assert np.array_equal(dmc.dofs[dm.dofs >= 0], dm.dofs[dm.dofs >= 0])

@@ -175,3 +175,19 @@ def test_sampled_rows_at_2977_dofs(golden_dir):
     assert np.abs(A.dot(g['x'])-g['Ax']).max() < 1e-12*np.abs(g['Ax']).max()
     assert np.abs(A.dot(np.ones(A.shape[0]))-g['ones_Ax']).max() < 1e-12*np.abs(g['diagonal']).max()
     assert abs(np.linalg.norm(A)/float(g['frobenius'])-1) < 1e-13
+
+
+@pytest.mark.parametrize('name', ['disc_dm2_s0.75_r2', 'disc_dm2_s0.25_r3'])
+def test_two_dofmaps_match_reference(golden_dir, name):
+    """rows: interior DoFs, columns: the complementary (boundary) DoFs; the reference assembles over the combined
+    map and keeps that block (nonlocalAssembly_{SCALAR}.pxi:1366-1378)"""
+    g = load(golden_dir, name)
+    n1, n2 = int(g['num_dofs']), int(g['num_dofs2'])
+    combined = np.where(g['dofs'] >= 0, g['dofs'], n1+g['dofs2'])
+    P = oracle.Problem(g['vertices'], g['cells'], combined, n1+n2, float(g['s']), bfacets=g['boundaryEdges'], target_order=0.5,
+                       hVector=g['hVector'], volVector=g['volVector'], hmin=float(g['hmin']), diam=float(g['diam']),
+                       order_num_dofs=n1)
+    for ze, key in ((True, 'A_bc'), (False, 'A_bc_interior')):
+        A = P.dense(ze)[:n1, n1:]
+        assert A.shape == g[key].shape
+        assert np.abs(A-g[key]).max() < 1e-13*np.abs(g[key]).max()
