@@ -3,7 +3,7 @@ sys.path.insert(0,'.')
 from scipy.special import gamma
 import oracle
 import pynucleus_b200 as pb
-sys.path.insert(0,"tests")
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "tests"))
 from test_gpu_parity import _p1_load_vector, _p1_mass
 s=0.75
 mesh = pb.refined(pb.uniform_disc(), 5)

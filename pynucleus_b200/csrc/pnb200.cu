@@ -1334,206 +1334,6 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
     if (lane == 0 && my_pairs) atomicAdd(S.counters + (NEAR ? 1 : 0), my_pairs);
 }
 
-// ---------------------------------------------------------------------------
-// Far pass, 2D (the bulk of all pairs).  One barrier per 16x16 sub-batch, no shared-memory staging:
-//   * the cells of the row tile and of the column tile are loaded into shared memory once per tile;
-//   * half-warp h owns row cell row[rb][h], lane j owns column cell col[cb][j]; thread (h,j) classifies the
-//     pair, evaluates it if it is a regular pair of order 2..5 and adds its 3x3 cross block to the tile
-//     straight from registers.  Row cells of a batch share no vertex, neither do column cells, so the 256
-//     updates of a sub-batch hit pairwise distinct tile entries; the barrier before the next row batch orders
-//     the updates of cells that do share vertices (fixed order -> bitwise reproducible);
-//   * cell-diagonal blocks: the block of the row cell is reduced over the 16 lanes with a fixed shuffle tree,
-//     the block of the column cell accumulates in registers over the row batches (the column cell of a
-//     thread is fixed during the inner loop) and is reduced over the half-warps once per column batch.
-// Everything else (singular pairs, regular pairs of higher order) is left to the near pass: the tile is flagged.
-// ---------------------------------------------------------------------------
-struct FarSmem {
-    PowTab pw;
-    FarRule far[PNB_FAR_MAX_ORDER + 1];
-    double acc[PNB_TD][PNB_TD + 1];
-    double dyred[PNB_SB][PNB_SB][6];
-    int anynear;
-    // followed by: DXs[maxcells][6], DYs[maxcells][6] (dynamic)
-};
-
-__global__ void __launch_bounds__(PNB_THREADS, 2) far_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
-{
-    constexpr int TD = PNB_TD, SB = PNB_SB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FarSmem &sm = *reinterpret_cast<FarSmem *>(smem_raw);
-    double *DXs = reinterpret_cast<double *>(smem_raw + sizeof(FarSmem));
-    double *DYs = DXs + (size_t)S.maxcells * 6;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int h = tid / SB, j = tid % SB;
-    const int unit = blockIdx.x;
-    const int gr = S.units[2 * unit], gc = S.units[2 * unit + 1];
-    unsigned long long my_pairs = 0;
-    const float cf = (float)P.c_int, sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
-    {
-        const double *src = reinterpret_cast<const double *>(P.pow_int);
-        double *dst = reinterpret_cast<double *>(&sm.pw);
-        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_THREADS) dst[e] = src[e];
-        const double *fs = reinterpret_cast<const double *>(P.far_rules);
-        double *fd = reinterpret_cast<double *>(&sm.far[0]);
-        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER + 1) * sizeof(FarRule) / sizeof(double)); e += PNB_THREADS) fd[e] = fs[e];
-    }
-    __syncthreads();
-    const PowCtx kv(&sm.pw);
-    bool unit_near = false;
-
-    for (int rt = gr * S.G; rt < min((gr + 1) * S.G, S.ntiles); rt++)
-        for (int ct = max(gc * S.G, rt); ct < min((gc + 1) * S.G, S.ntiles); ct++) {
-            const bool diag = rt == ct;
-            const bool own_r = rt >= S.own_t0 && rt < S.own_t1, own_c = ct >= S.own_t0 && ct < S.own_t1;
-            if (!own_r && !own_c) continue;
-            const int rbeg = S.tile_ptr[rt], nR = S.tile_ptr[rt + 1] - rbeg;
-            const int cbeg = S.tile_ptr[ct], nC = S.tile_ptr[ct + 1] - cbeg;
-            __syncthreads();
-            for (int e = tid; e < TD * (TD + 1); e += PNB_THREADS) (&sm.acc[0][0])[e] = 0.;
-            for (int e = tid; e < nR * 6; e += PNB_THREADS) DXs[e] = 0.;
-            for (int e = tid; e < nC * 6; e += PNB_THREADS) DYs[e] = 0.;
-            if (tid == 0) sm.anynear = 0;
-            __syncthreads();
-            for (int cb = 0; cb < nC; cb += SB) {
-                // column cell of this thread: fixed during the inner loop (read once from global / L1)
-                const int K2 = S.tile_cells[cbeg + cb + j];
-                const int cl = S.tile_loc[cbeg + cb + j];
-                const bool cin = (cl & 0x00FFFFFF) != 0x00FFFFFF;
-                double s2[3][2] = {{0., 0.}, {0., 0.}, {0., 0.}};
-                int v2[3] = {-1, -2, -3};
-                int chome = -1, cany = 0;
-                double vol2 = 0.;
-                float lh2 = 0.f, ah2 = 0.f;
-                if (K2 >= 0) {
-                    chome = S.home[K2];
-#pragma unroll
-                    for (int m = 0; m < 3; m++) {
-                        s2[m][0] = P.simplices[(size_t)K2 * 6 + 2 * m];
-                        s2[m][1] = P.simplices[(size_t)K2 * 6 + 2 * m + 1];
-                        v2[m] = P.cells[(size_t)K2 * 3 + m];
-                        cany |= P.dofs[(size_t)K2 * 3 + m] >= 0;
-                    }
-                    vol2 = P.vol[K2];
-                    lh2 = P.lhf[K2];
-                    ah2 = P.ahf[K2];
-                }
-                const double c2x = (s2[0][0] + s2[1][0] + s2[2][0]) * (1. / 3.), c2y = (s2[0][1] + s2[1][1] + s2[2][1]) * (1. / 3.);
-                double yyacc[6] = {0., 0., 0., 0., 0., 0.};
-                bool anyD = false;
-                const int rb_end = diag ? cb + SB : nR;     // diagonal tiles: batches rb <= cb only
-                for (int rb = 0; rb < rb_end; rb += SB) {
-                    const int K1 = S.tile_cells[rbeg + rb + h];
-                    const int rl = S.tile_loc[rbeg + rb + h];
-                    double xy[9], xx[6], yy[6];
-                    bool evaluated = false, countD = false;
-                    if (K1 >= 0 && K2 >= 0 && K1 != K2 && (!diag || rb < cb || h < j)) {
-                        countD = S.home[K1] == rt && chome == ct;
-                        const bool rin = (rl & 0x00FFFFFF) != 0x00FFFFFF;
-                        int v1[3], rany = 0;
-#pragma unroll
-                        for (int m = 0; m < 3; m++) {
-                            v1[m] = P.cells[(size_t)K1 * 3 + m];
-                            rany |= P.dofs[(size_t)K1 * 3 + m] >= 0;
-                        }
-                        if ((rany || cany) && (countD || (rin && cin))) {
-                            double s1[3][2];
-#pragma unroll
-                            for (int m = 0; m < 3; m++) {
-                                s1[m][0] = P.simplices[(size_t)K1 * 6 + 2 * m];
-                                s1[m][1] = P.simplices[(size_t)K1 * 6 + 2 * m + 1];
-                            }
-                            int panel = -shared_vertices(v1, 3, v2, 3);
-                            if (panel == 0) {
-                                const double a = (s1[0][0] + s1[1][0] + s1[2][0]) * (1. / 3.) - c2x, b = (s1[0][1] + s1[1][1] + s1[2][1]) * (1. / 3.) - c2y;
-                                panel = fast_order_2d(a * a + b * b, P.lhf[K1], lh2, P.ahf[K1], ah2, cf, sf);
-                                if (panel < 0) {
-                                    const int c1 = min(K1, K2), c2 = max(K1, K2);
-                                    const double d = center_distance(P.centers + (size_t)c1 * 2, P.centers + (size_t)c2 * 2, 2);
-                                    panel = quad_order_interior(P, P.h[c1], P.h[c2], d);
-                                }
-                            }
-                            if (panel > P.max_order) atomicMax(S.err, panel);
-                            else if (panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1)) {
-                                far_eval_2d(sm.far[panel], s1, s2, kv, countD, xy, xx, yy);
-                                const double sc = 2.0 * P.vol[K1] * vol2;
-#pragma unroll
-                                for (int k = 0; k < 9; k++) xy[k] *= sc;
-                                if (countD) {
-#pragma unroll
-                                    for (int k = 0; k < 6; k++) { xx[k] *= sc; yyacc[k] += yy[k] * sc; }
-                                    anyD = true;
-                                }
-                                evaluated = true;
-                                my_pairs++;
-                                scatter_block<2>(sm.acc, rl, cl, xy, false);
-                            } else sm.anynear = 1;
-                        }
-                    } else if (K1 >= 0 && K1 == K2 && diag) sm.anynear = 1;     // identical pair: near pass
-                    // cell-diagonal block of the row cell: fixed shuffle tree over the 16 lanes of the half-warp
-                    if (__any_sync(0xffffffffu, evaluated && countD)) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) {
-                            double v = (evaluated && countD) ? xx[k] : 0.;
-                            v += __shfl_xor_sync(0xffffffffu, v, 8);
-                            v += __shfl_xor_sync(0xffffffffu, v, 4);
-                            v += __shfl_xor_sync(0xffffffffu, v, 2);
-                            v += __shfl_xor_sync(0xffffffffu, v, 1);
-                            if (j == 0 && v != 0.) DXs[(rb + h) * 6 + k] += v;
-                        }
-                    }
-                    if (diag) {
-                        // mirror image inside a diagonal tile: second conflict-free round, from registers
-                        __syncthreads();
-                        if (evaluated) scatter_block<2>(sm.acc, rl, cl, xy, true);
-                    }
-                    __syncthreads();    // the next row batch may share vertices with this one
-                }
-                // cell-diagonal blocks of the column cells: reduce the register sums over the 16 half-warps
-                if (__syncthreads_or(anyD)) {
-#pragma unroll
-                    for (int k = 0; k < 6; k++) sm.dyred[h][j][k] = yyacc[k];
-                    __syncthreads();
-                    if (tid < SB * 6) {
-                        const int jj = tid / 6, k = tid - jj * 6;
-                        double v = 0.;
-                        for (int hh = 0; hh < SB; hh++) v += sm.dyred[hh][jj][k];
-                        DYs[(cb + jj) * 6 + k] += v;
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- write the tile (and its mirror image); flush the cell-diagonal partial sums ----
-            const int r0 = rt * TD, c0 = ct * TD;
-            for (int e = tid; e < TD * TD; e += PNB_THREADS) {
-                const int a = e / TD, b = e - a * TD;
-                if (own_r && r0 + a < P.N && c0 + b < P.N) {
-                    const double v = diag ? 0.5 * (sm.acc[a][b] + sm.acc[b][a]) : sm.acc[a][b];
-                    A[(size_t)(r0 + a - S.own_t0 * TD) * ld + c0 + b] = v;
-                }
-            }
-            if (!diag && own_c)
-                for (int e = tid; e < TD * TD; e += PNB_THREADS) {
-                    const int b = e / TD, a = e - b * TD;
-                    if (r0 + a < P.N && c0 + b < P.N) A[(size_t)(c0 + b - S.own_t0 * TD) * ld + r0 + a] = sm.acc[a][b];
-                }
-            for (int e = tid; e < nR * 6; e += PNB_THREADS) {
-                const int K = S.tile_cells[rbeg + e / 6];
-                if (K >= 0 && DXs[e] != 0.) S.DXp[((size_t)gc * P.nc + K) * 6 + (e % 6)] += DXs[e];
-            }
-            for (int e = tid; e < nC * 6; e += PNB_THREADS) {
-                const int K = S.tile_cells[cbeg + e / 6];
-                if (K >= 0 && DYs[e] != 0.) S.DYp[((size_t)gr * P.nc + K) * 6 + (e % 6)] += DYs[e];
-            }
-            if (sm.anynear) {
-                if (tid == 0) S.tileflag[(size_t)rt * S.ntiles + ct] = 1;
-                unit_near = true;
-            }
-        }
-    if (unit_near && tid == 0) S.unitflag[unit] = 1;
-    for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
-    if (lane == 0 && my_pairs) atomicAdd(S.counters, my_pairs);
-}
-
 // ordered compaction of the flagged units (single block; nunits is small)
 __global__ void compact_units_kernel(TileSched S)
 {
@@ -2305,14 +2105,9 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     if (p->dim == 2) {
         const size_t smem = sizeof(TileSmem<2, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
         const size_t smem_far = sizeof(TileSmem<2, false>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
-        const size_t smem_far2 = sizeof(FarSmem) + 2 * (size_t)S.maxcells * 6 * sizeof(double);
-        cudaFuncSetAttribute(far_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_far2);
         cudaFuncSetAttribute(tile_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_far);
         cudaFuncSetAttribute(tile_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        // PNB_DEBUG=1024 selects the experimental barrier-light far kernel (no binning, one barrier per sub-batch);
-        // measured 18 % slower than the binned one on the bench mesh (divergence), kept for the next round
-        if (dbg & 0x400) far_kernel<<<S.nunits, PNB_THREADS, smem_far2>>>(p->P, S, dA, ld, p->far_mask);
-        else tile_kernel<2, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, p->far_mask);
+        tile_kernel<2, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, p->far_mask);
         compact_units_kernel<<<1, 1024>>>(S);
         cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);
         if (nnear_units > 0 && !(dbg & 0x100))
