@@ -1,4 +1,4 @@
-import numpy as np, sys, time
+import numpy as np, sys, time, os
 sys.path.insert(0,'.')
 from scipy.special import gamma
 import oracle
