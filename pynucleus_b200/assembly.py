@@ -309,6 +309,49 @@ class nonlocalBuilder:
         self._retry_on_order(run)
         return A
 
+    # -- H2 format ----------------------------------------------------------------
+    def getTree(self):
+        """root of the cluster tree (nonlocalAssembly_{SCALAR}.pxi:2541-2664, serial branch)"""
+        from .cluster_tree import build_tree
+        self._no_dm2()
+        return build_tree(self.mesh, self.dm, self.kernel, self.orders.target_order, self.params)
+
+    def getH2(self, returnNearField=False, returnTree=False):
+        """H2 operator (nonlocalAssembly_{SCALAR}.pxi:3094-3219): cluster tree, admissible pairs, leaf moments and transfer
+        operators as in the reference (node for node), far-field kernel blocks from the CUDA kernel.  The near field
+        is taken from the dense operator on the near cluster pairs (see h2.nearFromDense): the reference's
+        cluster-union near-field quadrature is not restated yet, so this does not save assembly work.
+        Falls back to getDense() when there is no admissible pair, like the reference (:3200-3209)."""
+        import torch
+        from .cluster_tree import admissible_clusters
+        from . import h2
+        root = self.getTree()
+        Pnear, Pfar_nodes = admissible_clusters(root, trim=self.params.get('trim', True))
+        if sum(len(v) for v in Pfar_nodes.values()) == 0:
+            H = self.getDense()
+        else:
+            for n in root.get_tree_nodes():
+                if n.isLeaf:
+                    n.value = h2.leaf_values(n, self.mesh, self.dm)
+                if n.parent is not None:
+                    n.transferOperator = h2.transfer_operator(n.parent, n)
+            levels = sorted(Pfar_nodes)
+            pairs = [(lvl, a, b) for lvl in levels for a, b in Pfar_nodes[lvl]]
+            blocks = self.getFarFieldBlocks(np.array([a.box for _, a, _ in pairs]), np.array([b.box for _, _, b in pairs]),
+                                            [a.interpolation_order for _, a, _ in pairs], [b.interpolation_order for _, _, b in pairs])
+            Pfar = {}
+            for (lvl, a, b), K in zip(pairs, blocks):
+                Pfar.setdefault(lvl, []).append(h2.farFieldClusterPair(a, b, K))
+            dense = self.getDense()
+            dev = torch.device('cuda', self.problem.device)
+            H = h2.H2Matrix(root, Pfar, h2.nearFromDense(dense, Pnear), self.dm.num_dofs, dev)
+        out = (H, )
+        if returnNearField:
+            out += (Pnear, )
+        if returnTree:
+            out += (root, )
+        return out[0] if len(out) == 1 else out
+
     def getFarFieldBlocks(self, boxes1, boxes2, m1, m2):
         """kernelInterpolant blocks of admissible cluster pairs (assembleFarFieldInteractions,
         clusterMethodCy.pyx:2153-2238): list of (m1^d x m2^d) arrays  -2 gamma(xi_i, xi_j)."""

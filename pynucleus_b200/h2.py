@@ -1,0 +1,199 @@
+"""H2 operator: cluster basis (leaf moments, transfer operators), far-field blocks and the three-pass matvec.
+
+Restates, on top of `cluster_tree`:
+  * tree_node.enterLeafValues        clusterMethodCy.pyx:1205-1325   V[dof, alpha] = int phi_dof(x) L_alpha(x) dx
+  * transferMatrixBuilder.build      clusterMethodCy.pyx:2010-2072   T[alpha_parent, alpha_child] = L^P_alpha(xi^C_beta)
+  * upwardPass / downwardPass        clusterMethodCy.pyx:1093-1176
+  * H2Matrix.matvec                  clusterMethodCy.pyx:2269-2295   y = Anear x + sum_far V1 K12 V2^T x
+  * far-field blocks                 nonlocalBuilder.getFarFieldBlocks (CUDA kernel, pnb_farfield_blocks)
+
+The cluster bases are small dense blocks (m^d <= a few hundred columns); they are built on the host with numpy and
+kept as float64 CUDA tensors, the passes run as torch matrix products on the device.  The near field of the reference
+(assembleClusters: cluster-union quadrature with surface terms, nonlocalAssembly_{SCALAR}.pxi:1663-2160) is NOT restated
+yet; `nearFromDense` fills the near pattern from the dense operator instead (validation / moderate sizes only).
+"""
+import numpy as np
+
+from . import quadrature
+
+
+def chebyshev(box, m):
+    """tensor-factor Chebyshev nodes of a box, [m, dim] (clusterMethodCy.pyx:1259-1262)"""
+    eta = np.cos((2.0*np.arange(m, 0, -1)-1.0)/(2.0*m)*np.pi)
+    return (box[:, 1]-box[:, 0])[None, :]*0.5*(eta[:, None]+1.0)+box[None, :, 0]
+
+
+def _multi_index(m, dim):
+    """productIterator order: last dimension fastest"""
+    if dim == 1:
+        return np.arange(m).reshape(-1, 1)
+    i, j = np.meshgrid(np.arange(m), np.arange(m), indexing='ij')
+    return np.stack((i.ravel(), j.ravel()), axis=1)
+
+
+def leaf_values(node, mesh, dm):
+    """V[local dof, alpha] of a leaf cluster"""
+    dim = mesh.dim
+    m = node.interpolation_order
+    dofs = node.dofs
+    pos = -np.ones(dm.num_dofs, dtype=np.int64)
+    pos[dofs] = np.arange(dofs.shape[0])
+    bary, w = quadrature.regular(m+2, dim)          # P1: quadOrder = order+2 (Sauter/Schwab p. 428)
+    xi = chebyshev(node.box, m)                     # [m, dim]
+    diff = xi[:, None, :]-xi[None, :, :]
+    diff[np.arange(m), np.arange(m), :] = 1.
+    beta = diff.prod(axis=1)                        # [m, dim]
+    incell = (dm.dofs >= 0) & (pos[np.where(dm.dofs >= 0, dm.dofs, 0)] >= 0)
+    cells = np.nonzero(incell.any(axis=1))[0]          # cells around the DoFs of the cluster, ascending
+    V = np.zeros((dofs.shape[0], m**dim))
+    idx = _multi_index(m, dim)
+    for c in cells:
+        simplex = mesh.vertices[mesh.cells[c]]      # [dim+1, dim]
+        x = bary.T.dot(simplex)                     # [nq, dim]
+        vol = mesh.volVector[c]
+        d = x[:, None, :]-xi[None, :, :]            # [nq, m, dim]
+        omega = np.empty((x.shape[0], m, dim))
+        for l in range(m):
+            dd = d.copy()
+            dd[:, l, :] = 1.
+            omega[:, l, :] = dd.prod(axis=1)
+        close = np.abs(d) <= 1e-9
+        omega = np.where(close, beta[None, :, :], omega)
+        # L_alpha(x_j) = prod_q omega[j, alpha_q, q] / prod_q beta[alpha_q, q]
+        om = np.ones((x.shape[0], idx.shape[0]))
+        be = np.ones(idx.shape[0])
+        for q in range(dim):
+            om = om*omega[:, idx[:, q], q]
+            be = be*beta[idx[:, q], q]
+        L = om/be[None, :]
+        for k in range(dim+1):
+            dof = dm.dofs[c, k]
+            if dof < 0 or pos[dof] < 0:
+                continue
+            V[pos[dof]] += (vol*L*(bary[k]*w)[:, None]).sum(axis=0)
+    return V
+
+
+def transfer_operator(parent, child):
+    dim = parent.dim
+    mC, mP = child.interpolation_order, parent.interpolation_order
+    xiC, xiP = chebyshev(child.box, mC), chebyshev(parent.box, mP)
+    omega = (xiC[:, None, :]-xiP[None, :, :]).prod(axis=1)            # [mC, dim]
+    diff = xiP[:, None, :]-xiP[None, :, :]
+    diff[np.arange(mP), np.arange(mP), :] = 1.
+    beta = diff.prod(axis=1)                                          # [mP, dim]
+    I, J = _multi_index(mP, dim), _multi_index(mC, dim)
+    T = np.ones((I.shape[0], J.shape[0]))
+    for l in range(dim):
+        i, j = I[:, l][:, None], J[:, l][None, :]
+        far = np.abs(xiP[i, l]-xiC[j, l]) > 1e-8
+        with np.errstate(divide='ignore', invalid='ignore'):
+            f = omega[j, l]/(xiC[j, l]-xiP[i, l])/beta[i, l]
+        T = T*np.where(far, f, 1.)
+    return T
+
+
+class farFieldClusterPair:
+    def __init__(self, n1, n2, kernelInterpolant):
+        self.n1, self.n2, self.kernelInterpolant = n1, n2, kernelInterpolant
+
+
+class H2Matrix:
+    """y = Anear x + far field; `Anear` any object with a device matvec (or None), x / y float64 CUDA tensors"""
+
+    def __init__(self, tree, Pfar, Anear, num_dofs, device):
+        import torch
+        self.tree, self.Pfar, self.Anear = tree, Pfar, Anear
+        self.num_rows = self.num_columns = num_dofs
+        self.device = device
+        self._dev = {}
+        for n in tree.get_tree_nodes():
+            n._dofs_t = torch.as_tensor(n.dofs, device=device) if n.isLeaf else None
+
+    shape = property(lambda self: (self.num_rows, self.num_columns))
+
+    def _t(self, key, array):
+        import torch
+        if key not in self._dev:
+            self._dev[key] = torch.as_tensor(np.ascontiguousarray(array), device=self.device)
+        return self._dev[key]
+
+    def farfield_device(self, x):
+        """sum over the admissible cluster pairs, three passes on the device"""
+        import torch
+        y = torch.zeros(self.num_rows, dtype=torch.float64, device=self.device)
+
+        def up(n):
+            if n.isLeaf:
+                n.coefficientsUp = self._t(('V', n.id), n.value).t().mv(x[n._dofs_t])
+            else:
+                acc = torch.zeros(n.interpolation_order**n.dim, dtype=torch.float64, device=self.device)
+                for c in n.children:
+                    up(c)
+                    acc += self._t(('T', c.id), c.transferOperator).mv(c.coefficientsUp)
+                n.coefficientsUp = acc
+            n.coefficientsDown = torch.zeros(n.interpolation_order**n.dim, dtype=torch.float64, device=self.device)
+        up(self.tree)
+        for lvl in self.Pfar:
+            for k, cp in enumerate(self.Pfar[lvl]):
+                cp.n1.coefficientsDown += self._t(('K', lvl, k), cp.kernelInterpolant).mv(cp.n2.coefficientsUp)
+
+        def down(n):
+            if n.isLeaf:
+                y[n._dofs_t] += self._t(('V', n.id), n.value).mv(n.coefficientsDown)
+            else:
+                for c in n.children:
+                    c.coefficientsDown += self._t(('T', c.id), c.transferOperator).t().mv(n.coefficientsDown)
+                    down(c)
+        down(self.tree)
+        return y
+
+    def matvec_device(self, x, y=None):
+        out = self.farfield_device(x)
+        if self.Anear is not None:
+            out += self.Anear.matvec_device(x)
+        if y is not None:
+            y.copy_(out)
+            return y
+        return out
+
+    def matvec(self, x, y=None):
+        import torch
+        if isinstance(x, torch.Tensor):
+            return self.matvec_device(x, y)
+        r = self.matvec_device(torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=self.device)).cpu().numpy()
+        if y is None:
+            return r
+        y[:] = r
+        return y
+
+    __call__ = matvec
+
+    def __mul__(self, x):
+        return self.matvec(x)
+
+    def dot(self, x):
+        return self.matvec(x)
+
+    def __repr__(self):
+        nfar = sum(len(v) for v in self.Pfar.values())
+        return '<{}x{} H2Matrix {} tree nodes, {} far-field cluster pairs>'.format(self.num_rows, self.num_columns,
+                                                                                     len(list(self.tree.get_tree_nodes())), nfar)
+
+
+class nearFromDense:
+    """near-field stand-in: the entries of the dense operator on the near cluster pairs (all other entries zero)"""
+
+    def __init__(self, dense, Pnear):
+        import torch
+        A = dense.device_data
+        mask = torch.zeros_like(A, dtype=torch.bool)
+        for n1, n2 in Pnear:
+            d1 = torch.as_tensor(n1.dofs, device=A.device)
+            d2 = torch.as_tensor(n2.dofs, device=A.device)
+            mask[d1[:, None], d2[None, :]] = True
+        self.nnz = int(mask.sum())
+        self._A = torch.where(mask, A, torch.zeros((), dtype=A.dtype, device=A.device))
+
+    def matvec_device(self, x):
+        return self._A.mv(x)

@@ -464,3 +464,26 @@ def test_two_dofmaps_vs_reference(golden_dir, name):
         A = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}, zeroExterior=ze, dm2=dm2).getDense()
         assert A.shape == g[key].shape
         assert np.abs(A.data-g[key]).max() < TOL*np.abs(g[key]).max()
+
+
+@pytest.mark.parametrize('name', ['h2_interval_s0.25_r8', 'h2_disc_s0.75_r4'])
+def test_h2_operator(golden_dir, name):
+    """getH2: far-field part against the reference's H2 matvec (H x - Anear x of its getH2), whole operator against
+    the dense one (the near field here is the dense operator on the near cluster pairs)"""
+    import scipy.sparse as sp
+    import torch
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    b = builder_from_golden(g)
+    H, Pnear, tree = b.getH2(returnNearField=True, returnTree=True)
+    assert np.array_equal(np.array([(a.id, c.id) for a, c in Pnear]), g['near_pairs'])
+    x = torch.as_tensor(g['x']).cuda()
+    N = b.dm.num_dofs
+    low = sp.csr_matrix((g['Anear_data'], g['Anear_indices'], g['Anear_indptr']), shape=(N, N))
+    ref_far = g['Hx']-(low+low.T+sp.diags(g['Anear_diagonal'])).dot(g['x'])
+    yfar = H.farfield_device(x).cpu().numpy()
+    assert np.abs(yfar-ref_far).max() < 1e-11*np.abs(ref_far).max()
+    A = b.getDense()
+    err = np.abs(H*g['x']-A*g['x']).max()/np.abs(A*g['x']).max()
+    ref_err = np.abs(g['Hx']-g['Ax']).max()/np.abs(g['Ax']).max()
+    assert err < max(10*ref_err, 1e-6)

@@ -157,3 +157,47 @@ def test_complement_and_combined_dofmaps(golden_dir):
     assert dmc.num_dofs == dm.num_dofs+dm2.num_dofs and dmc.dofs.min() == 0
     assert np.array_equal(np.sort(np.unique(dmc.dofs)), np.arange(dmc.num_dofs))
     assert np.array_equal(dmc.dofs[dm.dofs >= 0], dm.dofs[dm.dofs >= 0])
+
+
+@pytest.mark.parametrize('name', ['h2_interval_s0.25_r8', 'h2_disc_s0.75_r4'])
+def test_cluster_tree_and_farfield_chain_match_reference(golden_dir, name):
+    """H2 structure node for node, and the far-field part of the reference's H2 matvec
+    (leaf moments, transfer operators, three passes): H x - Anear x of the reference's getH2"""
+    import scipy.sparse as sp
+    import torch
+    from pynucleus_b200 import cluster_tree as ct, h2
+    from oracle import h2 as oracle_h2
+    g = np.load(os.path.join(golden_dir, name+'.npz'))
+    dim = g['vertices'].shape[1]
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices'].reshape(-1, 1)
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=bf)
+    dm = pb.P1_DoFMap(mesh)
+    kernel = pb.getFractionalKernel(dim, float(g['s']))
+    b = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5} if dim == 2 else {})
+    root = ct.build_tree(mesh, dm, kernel, b.orders.target_order)
+    Pnear, Pfar = ct.admissible_clusters(root)
+    nodes = list(root.get_tree_nodes())
+    assert np.array_equal([n.id for n in nodes], g['tree_ids'])
+    assert np.array_equal(np.array([n.box for n in nodes]), g['tree_boxes'])
+    assert np.array_equal([n.parent.id if n.parent else -1 for n in nodes], g['tree_parent'])
+    assert np.array_equal([n.isLeaf for n in nodes], g['tree_isleaf'])
+    assert np.array_equal([n.levelNo for n in nodes], g['tree_level'])
+    assert np.array_equal([n.interpolation_order for n in nodes], g['tree_order'])
+    assert np.array_equal(np.concatenate([np.sort(n.dofs) for n in nodes]), g['tree_dofs'])
+    assert np.array_equal(np.array([(a.id, c.id) for a, c in Pnear]), g['near_pairs'])
+    assert np.array_equal(np.array([(lvl, a.id, c.id) for lvl in sorted(Pfar) for a, c in Pfar[lvl]]), g['far_pairs'])
+    # far-field chain on the CPU (torch), kernel blocks from the oracle
+    for n in nodes:
+        if n.isLeaf:
+            n.value = h2.leaf_values(n, mesh, dm)
+        if n.parent is not None:
+            n.transferOperator = h2.transfer_operator(n.parent, n)
+    P = {lvl: [h2.farFieldClusterPair(a, c, oracle_h2.farfield_block(dim, float(g['s']), a.box, c.box, a.interpolation_order,
+                                                                      c.interpolation_order)) for a, c in Pfar[lvl]]
+         for lvl in sorted(Pfar)}
+    H = h2.H2Matrix(root, P, None, dm.num_dofs, 'cpu')
+    yfar = H.farfield_device(torch.as_tensor(g['x'])).numpy()
+    N = dm.num_dofs
+    low = sp.csr_matrix((g['Anear_data'], g['Anear_indices'], g['Anear_indptr']), shape=(N, N))   # SSS: strict lower + diagonal
+    ref = g['Hx']-(low+low.T+sp.diags(g['Anear_diagonal'])).dot(g['x'])
+    assert np.abs(yfar-ref).max() < 1e-11*np.abs(ref).max()
