@@ -316,11 +316,16 @@ class nonlocalBuilder:
         self._no_dm2()
         return build_tree(self.mesh, self.dm, self.kernel, self.orders.target_order, self.params)
 
+    def assembleClusters(self, Pnear):
+        """near-field blocks of the near cluster pairs (nonlocalAssembly_{SCALAR}.pxi:1663-1889), see h2.assemble_clusters"""
+        from . import h2
+        self._no_dm2()
+        return h2.assemble_clusters(self, Pnear)
+
     def getH2(self, returnNearField=False, returnTree=False):
         """H2 operator (nonlocalAssembly_{SCALAR}.pxi:3094-3219): cluster tree, admissible pairs, leaf moments and transfer
-        operators as in the reference (node for node), far-field kernel blocks from the CUDA kernel.  The near field
-        is taken from the dense operator on the near cluster pairs (see h2.nearFromDense): the reference's
-        cluster-union near-field quadrature is not restated yet, so this does not save assembly work.
+        operators as in the reference (node for node), far-field kernel blocks from the CUDA kernel, near field per
+        near cluster pair from the dense device path on the cluster-union sub-mesh (h2.assemble_clusters).
         Falls back to getDense() when there is no admissible pair, like the reference (:3200-3209)."""
         import torch
         from .cluster_tree import admissible_clusters
@@ -342,9 +347,8 @@ class nonlocalBuilder:
             Pfar = {}
             for (lvl, a, b), K in zip(pairs, blocks):
                 Pfar.setdefault(lvl, []).append(h2.farFieldClusterPair(a, b, K))
-            dense = self.getDense()
             dev = torch.device('cuda', self.problem.device)
-            H = h2.H2Matrix(root, Pfar, h2.nearFromDense(dense, Pnear), self.dm.num_dofs, dev)
+            H = h2.H2Matrix(root, Pfar, self.assembleClusters(Pnear), self.dm.num_dofs, dev)
         out = (H, )
         if returnNearField:
             out += (Pnear, )

@@ -197,3 +197,91 @@ class nearFromDense:
 
     def matvec_device(self, x):
         return self._A.mv(x)
+
+
+class _SubDoFMap:
+    """P1 DoFMap of a cluster pair: the DoFs of the two clusters in local numbering, everything else Dirichlet"""
+    polynomialOrder = 1
+
+    def __init__(self, mesh, dofs, num_dofs):
+        self.mesh, self.dofs, self.num_dofs = mesh, dofs, num_dofs
+        self.dofs_per_element = dofs.shape[1]
+        self.dim = mesh.dim
+
+
+class nearFieldBlocks:
+    """Near field as one dense block per near cluster pair, y[dofs(n1)] += B x[dofs(n2)]  (device tensors)."""
+
+    def __init__(self, num_dofs, device):
+        self.num_dofs, self.device = num_dofs, device
+        self.blocks = []        # (rows tensor, cols tensor, block tensor)
+        self.nnz = 0
+
+    def add(self, rows, cols, block):
+        import torch
+        self.blocks.append((torch.as_tensor(rows, device=self.device), torch.as_tensor(cols, device=self.device), block))
+        self.nnz += block.numel()
+
+    def matvec_device(self, x):
+        import torch
+        y = torch.zeros(self.num_dofs, dtype=torch.float64, device=self.device)
+        for r, c, B in self.blocks:
+            y[r] += B.mv(x[c])
+        return y
+
+    def toarray(self):
+        import torch
+        A = torch.zeros((self.num_dofs, self.num_dofs), dtype=torch.float64, device=self.device)
+        for r, c, B in self.blocks:
+            A[r[:, None], c[None, :]] += B
+        return A.cpu().numpy()
+
+
+def assemble_clusters(builder, Pnear):
+    """Near field of the H2 operator (assembleClusters, nonlocalAssembly_{SCALAR}.pxi:1663-1889, constant kernel).
+
+    For a near cluster pair (n1, n2) the reference integrates the bilinear form over D x D, D = the cells around the
+    DoFs of n1 and n2, and replaces the rest of the space by a surface integral over the boundary of D
+    (:1840-1889); it keeps the entries (i in n1, j in n2).  That is the dense operator of the sub-mesh D with the
+    zero-exterior surface terms on its own boundary, with the quadrature parameters of the whole problem, so the
+    dense device path assembles it: one small problem per cluster pair, block rows n1 / columns n2 kept."""
+    import torch
+    from .assembly import _Problem
+    from .linear_operators import Dense_LinearOperator
+    from .mesh import meshNd
+    from . import _lib
+    mesh, dm = builder.mesh, builder.dm
+    if not builder.zeroExterior:
+        raise NotImplementedError('near field of the regional operator (zeroExterior=False)')
+    dev_index = builder.problem.device
+    dev = torch.device('cuda', dev_index)
+    out = nearFieldBlocks(dm.num_dofs, dev)
+    touch = dm.dofs >= 0
+    cache = {}
+    for n1, n2 in Pnear:
+        key = (n2.id, n1.id)
+        if key in cache:
+            # the local matrices are symmetric: block (n2, n1)^T
+            out.add(n1.dofs, n2.dofs, cache[key].t().contiguous())
+            continue
+        d1, d2 = n1.dofs, n2.dofs
+        union = np.union1d(d1, d2)
+        loc = -np.ones(dm.num_dofs, dtype=np.int64)
+        loc[union] = np.arange(union.shape[0])
+        local = np.where(touch, loc[np.where(touch, dm.dofs, 0)], -1)
+        cells = np.nonzero((local >= 0).any(axis=1))[0]              # cellsUnion
+        sub = meshNd(mesh.vertices, mesh.cells[cells])
+        sdofs = np.ascontiguousarray(np.where(local[cells] >= 0, local[cells], -1), dtype=np.int32)
+        sdm = _SubDoFMap(sub, sdofs, union.shape[0])
+        prob = _Problem(sdm, builder.kernel, builder.kernelBoundary, builder.orders, dev_index,
+                        builder.problem.max_order, order_num_dofs=dm.num_dofs)
+        n = union.shape[0]
+        A = torch.empty((n, n), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, 1, 0, n, A.data_ptr(), A.stride(0), 1))
+        r = torch.as_tensor(loc[d1], device=dev)
+        c = torch.as_tensor(loc[d2], device=dev)
+        B = A[r[:, None], c[None, :]].contiguous()
+        cache[(n1.id, n2.id)] = B
+        out.add(d1, d2, B)
+        del prob
+    return out
