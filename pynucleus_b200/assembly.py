@@ -348,7 +348,10 @@ class nonlocalBuilder:
             for (lvl, a, b), K in zip(pairs, blocks):
                 Pfar.setdefault(lvl, []).append(h2.farFieldClusterPair(a, b, K))
             dev = torch.device('cuda', self.problem.device)
-            H = h2.H2Matrix(root, Pfar, self.assembleClusters(Pnear), self.dm.num_dofs, dev)
+            near = self.assembleClusters(Pnear)
+            near.compile()
+            H = h2.H2Matrix(root, Pfar, near, self.dm.num_dofs, dev)
+            H.compile()
         out = (H, )
         if returnNearField:
             out += (Pnear, )

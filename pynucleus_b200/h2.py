@@ -93,6 +93,17 @@ def transfer_operator(parent, child):
     return T
 
 
+def _csr(rows, cols, vals, shape, device):
+    """device CSR matrix from COO triplets (duplicates summed)"""
+    import warnings
+    import torch
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        A = torch.sparse_coo_tensor(torch.as_tensor(np.vstack((rows, cols)), device=device), torch.as_tensor(vals, device=device),
+                                    size=shape, dtype=torch.float64, device=device, check_invariants=False)
+        return A.coalesce().to_sparse_csr()
+
+
 class farFieldClusterPair:
     def __init__(self, n1, n2, kernelInterpolant):
         self.n1, self.n2, self.kernelInterpolant = n1, n2, kernelInterpolant
@@ -148,8 +159,56 @@ class H2Matrix:
         down(self.tree)
         return y
 
+    # ---- batched form: the passes as a handful of sparse matrix-vector products --------------------------------
+    def compile(self):
+        """Stacks the coefficient vectors of all tree nodes into one vector and turns the three passes into sparse
+        matrices over it: basis B (coefficients x dofs, leaf moments), one transfer matrix per level, the
+        far-field matrix F.  y = B^T (down pass)(F (up pass)(B x)); a dozen SpMVs instead of thousands of tiny
+        products."""
+        import torch
+        nodes = list(self.tree.get_tree_nodes())
+        off = {}
+        tot = 0
+        for n in nodes:
+            off[n.id] = tot
+            tot += n.interpolation_order**n.dim
+        self._ncoef = tot
+
+        def coo(blocks, shape):
+            if not blocks:
+                return None
+            r = np.concatenate([np.repeat(r0+np.arange(B.shape[0]), B.shape[1]) for r0, c0, B in blocks])
+            c = np.concatenate([np.tile(c0 if isinstance(c0, np.ndarray) else c0+np.arange(B.shape[1]), B.shape[0]) for r0, c0, B in blocks])
+            v = np.concatenate([np.asarray(B).ravel() for r0, c0, B in blocks])
+            return _csr(r, c, v, shape, self.device)
+        self._B = coo([(off[n.id], n.dofs, n.value.T) for n in nodes if n.isLeaf], (tot, self.num_rows))
+        levels = {}
+        for n in nodes:
+            if n.parent is not None:
+                levels.setdefault(n.parent.levelNo, []).append((off[n.parent.id], off[n.id], n.transferOperator))
+        self._U = [(lvl, coo(levels[lvl], (tot, tot))) for lvl in sorted(levels, reverse=True)]
+        self._Ut = [(lvl, coo([(c0, r0, np.ascontiguousarray(T.T)) for r0, c0, T in levels[lvl]], (tot, tot))) for lvl in sorted(levels)]
+        self._F = coo([(off[cp.n1.id], off[cp.n2.id], cp.kernelInterpolant) for lvl in self.Pfar for cp in self.Pfar[lvl]], (tot, tot))
+        # B^T: rows are dofs (scattered), columns the coefficient slots of the leaf
+        lb = [(n.dofs, off[n.id], n.value) for n in nodes if n.isLeaf]
+        r = np.concatenate([np.repeat(d, V.shape[1]) for d, c0, V in lb])
+        c = np.concatenate([np.tile(c0+np.arange(V.shape[1]), V.shape[0]) for d, c0, V in lb])
+        v = np.concatenate([V.ravel() for d, c0, V in lb])
+        self._Bt = _csr(r, c, v, (self.num_rows, tot), self.device)
+        self._compiled = True
+
+    def farfield_compiled(self, x):
+        import torch
+        up = torch.mv(self._B, x)
+        for _, U in self._U:            # deepest parents first
+            up = up+torch.mv(U, up)
+        down = torch.mv(self._F, up)
+        for _, Ut in self._Ut:          # root first
+            down = down+torch.mv(Ut, down)
+        return torch.mv(self._Bt, down)
+
     def matvec_device(self, x, y=None):
-        out = self.farfield_device(x)
+        out = self.farfield_compiled(x) if getattr(self, '_compiled', False) else self.farfield_device(x)
         if self.Anear is not None:
             out += self.Anear.matvec_device(x)
         if y is not None:
@@ -222,8 +281,22 @@ class nearFieldBlocks:
         self.blocks.append((torch.as_tensor(rows, device=self.device), torch.as_tensor(cols, device=self.device), block))
         self.nnz += block.numel()
 
+    def compile(self):
+        """one CSR matrix on the device"""
+        import torch
+        r = torch.cat([rr.repeat_interleave(cc.numel()) for rr, cc, B in self.blocks])
+        c = torch.cat([cc.repeat(rr.numel()) for rr, cc, B in self.blocks])
+        v = torch.cat([B.reshape(-1) for rr, cc, B in self.blocks])
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            self._csr = torch.sparse_coo_tensor(torch.stack((r, c)), v, size=(self.num_dofs, self.num_dofs),
+                                                check_invariants=False).coalesce().to_sparse_csr()
+
     def matvec_device(self, x):
         import torch
+        if getattr(self, '_csr', None) is not None:
+            return torch.mv(self._csr, x)
         y = torch.zeros(self.num_dofs, dtype=torch.float64, device=self.device)
         for r, c, B in self.blocks:
             y[r] += B.mv(x[c])
