@@ -29,6 +29,13 @@
 // ---------------------------------------------------------------------------
 // error handling
 // ---------------------------------------------------------------------------
+static double wall_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static thread_local std::string g_err;
 struct pnb_problem;
 static pnb_problem *g_bench_problem = nullptr;   // last created problem (debug micro-benchmarks only)
@@ -175,7 +182,8 @@ struct pnb_problem {
     int device = 0;
     GroupSched *G = nullptr;          // 2D cell-group path (pnb_group.cuh)
     GroupHost *gh = nullptr;
-    std::vector<int> h_cells, h_dofs; // host copies for the lazy group schedule
+    std::vector<int> h_cells, h_dofs, h_home; // host copies for the lazily built schedules
+    bool tiles_ready = false;
     std::vector<double> h_centers, h_h;
     std::vector<int4> h_grid;         // lane grids of the near evaluator per order
     int part = 0, nparts = 1;         // share of the units this problem instance evaluates (multi-GPU)
@@ -363,6 +371,100 @@ extern "C" void pnb_problem_destroy(pnb_problem *p)
     delete p;
 }
 
+// Cell lists of the DoF tiles, cut into batches of PNB_SB cells that share NO vertex.  The cross blocks of the pairs of
+// (row batch) x (column batch) then hit pairwise distinct tile entries, so that they can be added to the
+// shared-memory tile straight from registers without conflicts (and in an order that is fixed by the schedule).
+static int build_tile_schedule(pnb_problem *p)
+{
+    if (p->tiles_ready) return 0;
+    TileSched &S = p->S;
+    const int nc = p->nc, N = p->N, nvc = p->dim + 1, TD = PNB_TD;
+    const int *cells = p->h_cells.data(), *dofs = p->h_dofs.data();
+    std::vector<std::vector<int>> tcells(S.ntiles);
+    for (int c = 0; c < nc; c++) {
+        int tl[3], nt = 0;
+        for (int m = 0; m < nvc; m++) {
+            const int d = dofs[(size_t)c * nvc + m];
+            if (d >= 0) {
+                const int t = d / TD;
+                bool seen = false;
+                for (int k = 0; k < nt; k++) seen |= tl[k] == t;
+                if (!seen) tl[nt++] = t;
+            }
+        }
+        if (nt == 0) tl[nt++] = p->h_home[c];
+        for (int k = 0; k < nt; k++) tcells[tl[k]].push_back(c);
+    }
+    std::vector<int> tptr(S.ntiles + 1, 0), tlist, tloc;
+    {
+        std::vector<std::vector<int>> bcells;      // batches of the current tile
+        std::vector<std::vector<int>> bverts;
+        for (int t = 0; t < S.ntiles; t++) {
+            bcells.clear();
+            bverts.clear();
+            size_t first_open = 0;
+            for (int c : tcells[t]) {
+                const int *v = cells + (size_t)c * nvc;
+                size_t b = first_open;
+                for (; b < bcells.size(); b++) {
+                    if ((int)bcells[b].size() >= PNB_SB) continue;
+                    bool clash = false;
+                    for (int x : bverts[b])
+                        for (int m = 0; m < nvc; m++) clash |= x == v[m];
+                    if (!clash) break;
+                }
+                if (b == bcells.size()) { bcells.emplace_back(); bverts.emplace_back(); }
+                bcells[b].push_back(c);
+                for (int m = 0; m < nvc; m++) bverts[b].push_back(v[m]);
+                while (first_open < bcells.size() && (int)bcells[first_open].size() >= PNB_SB) first_open++;
+            }
+            for (auto &bc : bcells) {
+                for (int k = 0; k < PNB_SB; k++) {
+                    const int c = k < (int)bc.size() ? bc[k] : -1;
+                    tlist.push_back(c);
+                    int packed = 0x00FFFFFF;
+                    if (c >= 0) {
+                        packed = 0;
+                        for (int m = 0; m < 3; m++) {
+                            int l = 0xFF;
+                            if (m < nvc) {
+                                const int d = dofs[(size_t)c * nvc + m];
+                                if (d >= 0 && d / TD == t) l = d - t * TD;
+                            }
+                            packed |= l << (8 * m);
+                        }
+                    }
+                    tloc.push_back(packed);
+                }
+            }
+            tptr[t + 1] = (int)tlist.size();
+        }
+    }
+    std::vector<int> units;
+    // heavy (near-diagonal) units first
+    for (int dg = 0; dg < S.ngroups; dg++)
+        for (int gr = 0; gr + dg < S.ngroups; gr++) { units.push_back(gr); units.push_back(gr + dg); }
+    S.nunits = (int)units.size() / 2;
+    S.nunits_all = S.nunits;
+    const int ND = nvc * (nvc + 1) / 2;
+    int rc = 0;
+    rc |= upload(p, tptr.data(), tptr.size(), &S.tile_ptr);
+    rc |= upload(p, tlist.data(), tlist.size(), &S.tile_cells);
+    rc |= upload(p, tloc.data(), tloc.size(), &S.tile_loc);
+    rc |= upload(p, units.data(), units.size(), &S.units);
+    rc |= dalloc(p, (size_t)S.ngroups * nc * ND, &S.DXp);
+    rc |= dalloc(p, (size_t)S.ngroups * nc * ND, &S.DYp);
+    S.maxcells = PNB_SB;
+    for (int t = 0; t < S.ntiles; t++) S.maxcells = std::max(S.maxcells, tptr[t + 1] - tptr[t]);
+    rc |= dalloc(p, (size_t)S.ntiles * S.ntiles, &S.tileflag);
+    rc |= dalloc(p, (size_t)S.nunits, &S.unitflag);
+    rc |= dalloc(p, (size_t)S.nunits + 1, &S.nearunits);
+    if (rc) return PNB_ERR_CUDA;
+    p->tiles_ready = true;
+    (void)N;
+    return 0;
+}
+
 extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm, const pnb_kernel_t *kernel,
                                   const pnb_rules_t *rules, int device, pnb_problem **out)
 {
@@ -381,6 +483,7 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     if (device < 0 || device >= ndev) return fail(PNB_ERR_ARG, "invalid device index");
     CK(cudaSetDevice(device));
 
+    const double tc0 = wall_ms();
     pnb_problem *p = new pnb_problem();
     p->device = device;
     const int dim = mesh->dim, nvc = dim + 1, nc = mesh->num_cells, N = dm->num_dofs, nb = mesh->num_bfacets;
@@ -435,9 +538,9 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
             bvol[f] = bh[f] = sqrt(h2);
         }
     }
+    p->h_cells.assign(mesh->cells, mesh->cells + (size_t)nc * nvc);
+    p->h_dofs.assign(dm->dofs, dm->dofs + (size_t)nc * nvc);
     if (dim == 2) {
-        p->h_cells.assign(mesh->cells, mesh->cells + (size_t)nc * nvc);
-        p->h_dofs.assign(dm->dofs, dm->dofs + (size_t)nc * nvc);
         p->h_centers = centers;
         p->h_h.assign(mesh->h, mesh->h + nc);
     }
@@ -497,95 +600,31 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         P.c_bnd = (kernel->btarget_order + 1.) * log(Nord * P.H0);
     }
 
-    // ---- DoF tiles -------------------------------------------------------
+    const double tc1 = wall_ms();
+    // ---- DoF tiles: ownership of cells and of the cell-diagonal blocks (both assembly paths) ----------------
     TileSched &S = p->S;
     const int TD = PNB_TD;
     S.ntiles = std::max(1, (N + TD - 1) / TD);
     S.G = 2;
     S.ngroups = (S.ntiles + S.G - 1) / S.G;
     std::vector<int> home(nc);
-    std::vector<std::vector<int>> tcells(S.ntiles);
     int64_t live = 0;
     for (int c = 0; c < nc; c++) {
-        int tl[3], nt = 0, mind = -1;
+        int mind = -1;
         for (int m = 0; m < nvc; m++) {
             const int d = dm->dofs[(size_t)c * nvc + m];
             if (d >= N) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "dof index out of range"); }
-            if (d >= 0) {
-                const int t = d / TD;
-                bool seen = false;
-                for (int k = 0; k < nt; k++) seen |= tl[k] == t;
-                if (!seen) tl[nt++] = t;
-                if (mind < 0 || d < mind) mind = d;
-            }
+            if (d >= 0 && (mind < 0 || d < mind)) mind = d;
         }
         if (mind >= 0) { home[c] = mind / TD; live++; }
-        else {
-            // no dofs: spread such cells evenly; they only feed cell-diagonal blocks of other cells
-            home[c] = (int)(((int64_t)c * S.ntiles) / std::max(nc, 1));
-            tl[nt++] = home[c];
-        }
-        for (int k = 0; k < nt; k++) tcells[tl[k]].push_back(c);
+        // no dofs: spread such cells evenly; they only feed cell-diagonal blocks of other cells
+        else home[c] = (int)(((int64_t)c * S.ntiles) / std::max(nc, 1));
     }
     // pairs c1<=c2 that the reference does not skip (at least one non-negative dof)
     {
         const int64_t dead = nc - live;
         p->distinct_pairs = (int64_t)nc * (nc + 1) / 2 - dead * (dead + 1) / 2;
     }
-    // Cell lists are cut into batches of PNB_SB cells that share NO vertex.  The cross blocks of the pairs of
-    // (row batch) x (column batch) then hit pairwise distinct tile entries, so that they can be added to the
-    // shared-memory tile straight from registers without conflicts (and in an order that is fixed by the schedule).
-    std::vector<int> tptr(S.ntiles + 1, 0), tlist, tloc;
-    {
-        std::vector<std::vector<int>> bcells;      // batches of the current tile
-        std::vector<std::vector<int>> bverts;
-        for (int t = 0; t < S.ntiles; t++) {
-            bcells.clear();
-            bverts.clear();
-            size_t first_open = 0;
-            for (int c : tcells[t]) {
-                const int *v = mesh->cells + (size_t)c * nvc;
-                size_t b = first_open;
-                for (; b < bcells.size(); b++) {
-                    if ((int)bcells[b].size() >= PNB_SB) continue;
-                    bool clash = false;
-                    for (int x : bverts[b])
-                        for (int m = 0; m < nvc; m++) clash |= x == v[m];
-                    if (!clash) break;
-                }
-                if (b == bcells.size()) { bcells.emplace_back(); bverts.emplace_back(); }
-                bcells[b].push_back(c);
-                for (int m = 0; m < nvc; m++) bverts[b].push_back(v[m]);
-                while (first_open < bcells.size() && (int)bcells[first_open].size() >= PNB_SB) first_open++;
-            }
-            for (auto &bc : bcells) {
-                for (int k = 0; k < PNB_SB; k++) {
-                    const int c = k < (int)bc.size() ? bc[k] : -1;
-                    tlist.push_back(c);
-                    int packed = 0x00FFFFFF;
-                    if (c >= 0) {
-                        packed = 0;
-                        for (int m = 0; m < 3; m++) {
-                            int l = 0xFF;
-                            if (m < nvc) {
-                                const int d = dm->dofs[(size_t)c * nvc + m];
-                                if (d >= 0 && d / TD == t) l = d - t * TD;
-                            }
-                            packed |= l << (8 * m);
-                        }
-                    }
-                    tloc.push_back(packed);
-                }
-            }
-            tptr[t + 1] = (int)tlist.size();
-        }
-    }
-    std::vector<int> units;
-    // heavy (near-diagonal) units first
-    for (int dg = 0; dg < S.ngroups; dg++)
-        for (int gr = 0; gr + dg < S.ngroups; gr++) { units.push_back(gr); units.push_back(gr + dg); }
-    S.nunits = (int)units.size() / 2;
-    S.nunits_all = S.nunits;
     S.own_t0 = 0;
     S.own_t1 = S.ntiles;
     // dof -> cells
@@ -600,27 +639,22 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
             for (int m = 0; m < nvc; m++) { const int d = dm->dofs[(size_t)c * nvc + m]; if (d >= 0) dcells[pos[d]++] = c * 4 + m; }
     }
     const int ND = nvc * (nvc + 1) / 2;
-    rc |= upload(p, tptr.data(), tptr.size(), &S.tile_ptr);
-    rc |= upload(p, tlist.data(), tlist.size(), &S.tile_cells);
-    rc |= upload(p, tloc.data(), tloc.size(), &S.tile_loc);
     rc |= upload(p, home.data(), home.size(), &S.home);
-    rc |= upload(p, units.data(), units.size(), &S.units);
     rc |= upload(p, dptr.data(), dptr.size(), &S.dof_ptr);
     rc |= upload(p, dcells.data(), dcells.size(), &S.dof_cells);
-    rc |= dalloc(p, (size_t)S.ngroups * nc * ND, &S.DXp);
-    rc |= dalloc(p, (size_t)S.ngroups * nc * ND, &S.DYp);
     rc |= dalloc(p, (size_t)nc * ND, &S.Dbnd);
     rc |= dalloc(p, (size_t)nc * ND, &S.D);
     rc |= dalloc(p, 4, &S.err);
     rc |= dalloc(p, 8, &S.counters);
-    S.maxcells = PNB_SB;
-    for (int t = 0; t < S.ntiles; t++) S.maxcells = std::max(S.maxcells, tptr[t + 1] - tptr[t]);
-    rc |= dalloc(p, (size_t)S.ntiles * S.ntiles, &S.tileflag);
-    rc |= dalloc(p, (size_t)S.nunits, &S.unitflag);
-    rc |= dalloc(p, (size_t)S.nunits + 1, &S.nearunits);
     if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
+    p->h_home = home;
+    // the tile cell lists are only needed by the DoF-tile kernels (1D, row ranges): built on first use in 2D
+    if (dim == 1 && build_tile_schedule(p)) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
+    const double tc2 = wall_ms();
     rc = pnb_problem_set_rules(p, rules);
     if (rc) { pnb_problem_destroy(p); return rc; }
+    if (getenv("PNB_BENCH_VERBOSE"))
+        fprintf(stderr, "pnb_problem_create: mesh + upload %.1f ms, tile schedule %.1f ms, tables %.1f ms\n", tc1 - tc0, tc2 - tc1, wall_ms() - tc2);
     *out = p;
     g_bench_problem = p;
     return 0;
@@ -1723,14 +1757,8 @@ struct GroupHostFull : GroupHost {
     const int4 *d_chunks = nullptr;
     double *d_R = nullptr;
     int nitems = 0, npairs = 0, nchunks = 0;
+    bool near_ready = false;
 };
-
-static double wall_ms()
-{
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-}
 
 static int build_group_schedule(pnb_problem *p)
 {
@@ -1877,6 +1905,25 @@ static int build_group_schedule(pnb_problem *p)
         G.done = (int *)d;
         G.nlist0 = (int)gh->f2_units.size();
     }
+    gh->near_ready = false;
+    gh->far_mask = p->far_mask;
+    gh->max_order = p->P.max_order;
+    gh->part = p->part;
+    gh->nparts = p->nparts;
+    if (getenv("PNB_BENCH_VERBOSE"))
+        fprintf(stderr, "group path: units f2 %zu, mix %zu (near %zu), phases %d; host ms: groups %.1f, units %.1f\n",
+                gh->f2_units.size(), gh->mix_units.size(), gh->near_units.size(), gh->nphase, tw1 - tw0, wall_ms() - tw1);
+    return 0;
+}
+
+// second half of the schedule: the near pair list.  Built after the f2 kernel has been launched, so that the host work
+// and the two list kernels overlap with it (the list depends on mesh and tables only and is reused by later assemblies)
+static int build_near_list(pnb_problem *p)
+{
+    GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+    GroupSched &G = *p->G;
+    if (gh->near_ready) return 0;
+    const int nslots = (int)gh->near_units.size();
     const double tw2 = wall_ms();
     // ---- near pair list: count, allocate, fill (depends on mesh and tables only; reused by every assembly) ----
     for (void *d : gh->near_allocs) pool_free(d);
@@ -1887,7 +1934,6 @@ static int build_group_schedule(pnb_problem *p)
         CK(pool_malloc((void **)&cursor, 4 * sizeof(int)));
         gh->near_allocs.push_back(cursor);
         CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
-        CK(cudaMemset(p->S.err, 0, 4 * sizeof(int)));
         cudaFuncSetAttribute(gnear_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_near);
         int *bins = nullptr, *binbase = nullptr, *perm = nullptr;
         CK(pool_malloc((void **)&bins, 128 * sizeof(int)));
@@ -1946,13 +1992,9 @@ static int build_group_schedule(pnb_problem *p)
         gh->nitems = tot[1];
         gh->npairs = tot[0];
     }
-    gh->far_mask = p->far_mask;
-    gh->max_order = p->P.max_order;
-    gh->part = p->part;
-    gh->nparts = p->nparts;
+    gh->near_ready = true;
     if (getenv("PNB_BENCH_VERBOSE"))
-        fprintf(stderr, "group path: units f2 %zu, mix %zu (near %zu), phases %d; near pairs %d in %d items; host ms: groups %.1f, units %.1f, near list %.1f\n",
-                gh->f2_units.size(), gh->mix_units.size(), gh->near_units.size(), gh->nphase, gh->npairs, gh->nitems, tw1 - tw0, tw2 - tw1, wall_ms() - tw2);
+        fprintf(stderr, "group path: near pairs %d in %d items; host ms: near list %.1f\n", gh->npairs, gh->nitems, wall_ms() - tw2);
     return 0;
 }
 
@@ -1993,16 +2035,6 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     cudaMemset2DAsync(dA, (size_t)ld * sizeof(double), 0, (size_t)N * sizeof(double), N);
     int launches = 0;
     const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
-    if (gh->nitems > 0 && !(dbg & 0x100)) {
-        const int wpb = PNB_THREADS / 32;
-        const size_t smem_eval = sizeof(PowTab) + ((size_t)13 + (size_t)wpb * 4) * p->P.reg_nmax * sizeof(double);
-        cudaFuncSetAttribute(gnear_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval);
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
-        const int grid = std::min(gh->nchunks, 2 * nsm);
-        gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R);
-        launches++;
-    }
     {
         // one persistent launch per unit list; the units take tickets in list order and order their updates of U
         // among themselves (g_wait_predecessors)
@@ -2013,6 +2045,18 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         cudaMemsetAsync(G.done, 0, std::max<size_t>((size_t)nf + nm, 1) * sizeof(int));
         if (nf > 0 && !(dbg & 0x1000)) {
             gf2_kernel<<<std::min(nf, nsm), PNB_GT, gh->smem_f2>>>(p->P, G, gh->d_f2, nf, dA, ld, R);
+            launches++;
+        }
+        // the near pair list is built (first assembly only) while the f2 kernel runs; its results feed the mix kernel
+        if (build_near_list(p)) return PNB_ERR_CUDA;
+        if (gh->nitems > 0 && !(dbg & 0x100)) {
+            const int wpb = PNB_THREADS / 32;
+            const size_t smem_eval = sizeof(PowTab) + ((size_t)13 + (size_t)wpb * 4) * p->P.reg_nmax * sizeof(double);
+            cudaFuncSetAttribute(gnear_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval);
+            int nsm = 148;
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
+            const int grid = std::min(gh->nchunks, 2 * nsm);
+            gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R);
             launches++;
         }
         if (nm > 0 && !(dbg & 0x200)) {
@@ -2076,6 +2120,7 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     // 2D, whole operator: cell-group path (PNB_DEBUG bit 0x800 forces the DoF-tile path)
     if (p->dim == 2 && row_begin == 0 && row_end == p->N && !((getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0) & 0x800))
         return run_group_path(p, zero_exterior, dA, ld);
+    if (build_tile_schedule(p)) return PNB_ERR_CUDA;
     S.own_t0 = row_begin / PNB_TD;
     S.own_t1 = (row_end + PNB_TD - 1) / PNB_TD;
     // units: group pairs (gr <= gc) that hold a tile touching an owned row tile, near-diagonal first
