@@ -251,6 +251,7 @@ def run_cuda(args):
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     tile_ms, launches = [], 0
+    kms = {'f2': [], 'near': [], 'mix': [], 'symmetrize': []}
     torch.cuda.synchronize()
     for k in range(args.steps):
         flush.zero_()
@@ -263,6 +264,8 @@ def run_cuda(args):
         st = builder.getStats()
         tile_ms.append(st['ms_tiles'])
         launches += st['launches']
+        for key in kms:
+            kms[key].append(st['ms_'+key])
     clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
     if world > 1:
@@ -307,21 +310,40 @@ def run_cuda(args):
     e2e_ms = e2e_ms[1:]
     e2e_value = N*float(N)/(float(np.mean(e2e_ms))*1e-3)
 
-    # roofline of the dominant kernel (tile kernel): algorithmic FP64 flops / measured device time
+    # roofline: algorithmic FP64 flops / device time measured with CUDA events inside the C call.
+    # Headline object = the dominant kernel (gmix_kernel: the units that are not uniformly of order 2); the other pair
+    # kernels and their sum are listed beside it.
     hist = builder.getPanelHistogram()
-    flops, pows = algorithmic_flops(hist, builder)
-    t_tile = float(np.mean(tile_ms))*1e-3
-    # several GPUs: this rank evaluated its share of the pairs; the roofline is per GPU
-    share = st['evaluated_pairs']/max(st['distinct_pairs'], 1) if world > 1 else 1.
-    flops, pows = flops*share, pows*share
-    achieved = flops/t_tile/1e12
-    roofline = {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved/peak if peak else None,
-                'traffic': None,
-                'note': 'algorithmic flops (SURVEY 8d: 70/node-pair regular, 49/61/76 singular; pow excluded) of the '
-                        'distinct cell pairs this GPU evaluates / device time of the pair kernels (near evaluator + unit '
-                        'kernels + symmetrisation, CUDA events); peak = DFMA microbenchmark run in this process; '
-                        'pow evaluations/s = {:.3e}; evaluated/distinct pairs {:.3f}; kernel share of step {:.3f}'.format(
-                            pows/t_tile, st['evaluated_pairs']/max(st['distinct_pairs'], 1), t_tile*1e3/ms_step)}
+    share = st['evaluated_pairs']/max(st['distinct_pairs'], 1) if world > 1 else 1.   # several GPUs: this rank's share
+    flops_all, pows_all = algorithmic_flops(hist, builder)
+    near_hist = {k: v for k, v in hist.items() if k < 0 or k > 5}
+    flops_near, pows_near = algorithmic_flops(near_hist, builder)
+    flops_f2, pows_f2 = st['f2_pairs']*9*70., st['f2_pairs']*9.
+    flops_mix = (flops_all-flops_near)*share-flops_f2
+    pows_mix = (pows_all-pows_near)*share-pows_f2
+    t_all = float(np.mean(tile_ms))*1e-3
+    t = {key: float(np.mean(v))*1e-3 for key, v in kms.items()}
+    per_kernel = {
+        'gmix_kernel': {'ms': t['mix']*1e3, 'tflops': flops_mix/max(t['mix'], 1e-9)/1e12},
+        'gnear_eval_kernel': {'ms': t['near']*1e3, 'tflops': flops_near*share/max(t['near'], 1e-9)/1e12},
+        'gf2_kernel': {'ms': t['f2']*1e3, 'tflops': flops_f2/max(t['f2'], 1e-9)/1e12},
+        'all pair kernels': {'ms': t_all*1e3, 'tflops': flops_all*share/t_all/1e12}}
+    dominant = max(('gmix_kernel', 'gnear_eval_kernel', 'gf2_kernel'), key=lambda k: per_kernel[k]['ms'])
+    achieved = per_kernel[dominant]['tflops']
+    # dram bytes of one launch from the committed ncu --set full captures (profiles/r1_final_ncu_full_*.txt, disc20k)
+    ncu_traffic = {'gmix_kernel': 4.571e9+2.993e9, 'gnear_eval_kernel': 0.770e9+0.001e9, 'gf2_kernel': 4.148e9+3.215e9}
+    roofline = {'bound': 'fp64', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': achieved/peak if peak else None,
+                'traffic': ncu_traffic.get(dominant) if args.workload == 'disc20k' and world == 1 else None,
+                'kernels': per_kernel,
+                'frac_all_pair_kernels': per_kernel['all pair kernels']['tflops']/peak if peak else None,
+                'note': 'algorithmic flops (SURVEY 8d: 70/node-pair regular, 49/61/76 singular; pow excluded) of the cell pairs '
+                        'the kernel evaluates / its device time (CUDA events around the launch inside the C call, averaged '
+                        'over the timed steps); peak = DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no '
+                        'FP64 figure); traffic = dram read+write bytes of one launch from the committed ncu capture; '
+                        'pow evaluations/s over all pair kernels = {:.3e}; evaluated/distinct pairs {:.3f}; pair-kernel share '
+                        'of step {:.3f}'.format(pows_all*share/t_all, st['evaluated_pairs']/max(st['distinct_pairs'], 1),
+                                                t_all*1e3/ms_step)}
 
     # second kernel of the path: y = A x on the assembled rows (HBM-bound, reads the matrix once)
     matvec = None

@@ -193,6 +193,9 @@ int pnb_dense_stats(pnb_problem *p, int64_t *stats);
 /* device time in ms of the phases of the last assembly:
  * [0] tile kernel, [1] boundary kernel, [2] reduce+scatter, [3] total */
 int pnb_dense_timings(pnb_problem *p, double *ms);
+/* device milliseconds of the last 2D assembly per kernel: [0] uniform order-2 units, [1] near pair list (first
+ * assembly only) + near evaluator, [2] all other units, [3] symmetrisation */
+int pnb_dense_kernel_timings(pnb_problem *p, double *ms);
 
 /* H2 far-field kernel blocks, assembleFarFieldInteractions (nl/PyNucleus_nl/clusterMethodCy.pyx:2153-2238):
  * for each admissible cluster pair b an m1^d x m2^d block  -2 gamma(xi_i, xi_j)  at the tensor Chebyshev

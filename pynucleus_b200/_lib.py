@@ -51,7 +51,7 @@ EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_cre
            'pnb_local_matrices', 'pnb_far_max_order', 'pnb_dense_assemble', 'pnb_dense_stats',
            'pnb_dense_timings', 'pnb_dense_matvec', 'pnb_fp64_peak', 'pnb_row_granularity', 'pnb_dense_rows_begin',
            'pnb_dense_cell_blocks', 'pnb_dense_cell_blocks_copy', 'pnb_dense_rows_end', 'pnb_farfield_blocks',
-           'pnb_release_cached_memory', 'pnb_dense_partial_begin']
+           'pnb_release_cached_memory', 'pnb_dense_partial_begin', 'pnb_dense_kernel_timings']
 
 _LIB = None
 
@@ -97,6 +97,7 @@ def lib():
                                           ctypes.c_void_p]
         L.pnb_dense_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.pnb_dense_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_dense_kernel_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.pnb_dense_matvec.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.pnb_fp64_peak.argtypes = [ctypes.c_int, c_double_p]

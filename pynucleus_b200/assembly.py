@@ -390,8 +390,12 @@ class nonlocalBuilder:
         ms = np.zeros(4)
         _lib.check(_lib.lib().pnb_dense_stats(self.problem.handle, stats.ctypes.data))
         _lib.check(_lib.lib().pnb_dense_timings(self.problem.handle, ms.ctypes.data))
+        kms = np.zeros(4)
+        _lib.check(_lib.lib().pnb_dense_kernel_timings(self.problem.handle, kms.ctypes.data))
         return dict(evaluated_pairs=int(stats[0]), distinct_pairs=int(stats[1]), launches=int(stats[2]),
-                    ms_tiles=float(ms[0]), ms_boundary=float(ms[1]), ms_reduce_scatter=float(ms[2]), ms_total=float(ms[3]))
+                    near_pairs=int(stats[3]), f2_pairs=int(stats[4]),
+                    ms_tiles=float(ms[0]), ms_boundary=float(ms[1]), ms_reduce_scatter=float(ms[2]), ms_total=float(ms[3]),
+                    ms_f2=float(kms[0]), ms_near=float(kms[1]), ms_mix=float(kms[2]), ms_symmetrize=float(kms[3]))
 
 
 def exchange_cell_blocks(count, device, process_group=None, fill=None):

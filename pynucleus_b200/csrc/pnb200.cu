@@ -198,6 +198,8 @@ struct pnb_problem {
     void *stage = nullptr;      // device staging of the host-output entry point
     size_t stage_bytes = 0;
     double timings[4] = {0};
+    cudaEvent_t kev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // group path: f2 | near list + evaluator | mix | symmetrize
+    double ktimings[4] = {0};
     int64_t distinct_pairs = 0;
     // host copies needed later
     int dim = 0, nc = 0, N = 0, nb = 0;
@@ -365,6 +367,7 @@ extern "C" void pnb_problem_destroy(pnb_problem *p)
     for (void *d : p->allocs) pool_free(d);
     for (void *d : p->rule_allocs) pool_free(d);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : p->kev) if (e) cudaEventDestroy(e);
     if (p->stage) pool_free(p->stage);
     if (g_bench_problem == p) g_bench_problem = nullptr;
     destroy_group_host(p);
@@ -2043,10 +2046,13 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         const int nf = (int)gh->f2_units.size(), nm = (int)gh->mix_units.size();
         cudaMemsetAsync(G.counters_i, 0, 4 * sizeof(int));
         cudaMemsetAsync(G.done, 0, std::max<size_t>((size_t)nf + nm, 1) * sizeof(int));
+        for (auto &e : p->kev) if (!e) cudaEventCreate(&e);
+        cudaEventRecord(p->kev[0]);
         if (nf > 0 && !(dbg & 0x1000)) {
             gf2_kernel<<<std::min(nf, nsm), PNB_GT, gh->smem_f2>>>(p->P, G, gh->d_f2, nf, dA, ld, R);
             launches++;
         }
+        cudaEventRecord(p->kev[1]);
         // the near pair list is built (first assembly only) while the f2 kernel runs; its results feed the mix kernel
         if (build_near_list(p)) return PNB_ERR_CUDA;
         if (gh->nitems > 0 && !(dbg & 0x100)) {
@@ -2059,16 +2065,19 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
             gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R);
             launches++;
         }
+        cudaEventRecord(p->kev[2]);
         if (nm > 0 && !(dbg & 0x200)) {
             gmix_kernel<<<std::min(nm, nsm), PNB_GT, gh->smem_mix>>>(p->P, G, gh->d_mix, nm, dA, ld, p->far_mask);
             launches++;
         }
     }
+    cudaEventRecord(p->kev[3]);
     {
         const unsigned nt = (unsigned)((N + 31) / 32);
         symmetrize_kernel<<<dim3(nt, nt), 256>>>(dA, ld, N);
         launches++;
     }
+    cudaEventRecord(p->kev[4]);
     cudaEventRecord(p->ev[1]);
     if (zero_exterior && p->nb > 0) {
         boundary_kernel<2><<<(unsigned)(((size_t)nc * 32 + 255) / 256), 256>>>(p->P, S);
@@ -2255,8 +2264,16 @@ extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row
     p->timings[2] = ms + ms2;      // reduce + (exchange by the caller) + scatter
     cudaEventElapsedTime(&ms, p->ev[0], p->ev[4]);
     p->timings[3] = ms;
-    p->stats[0] = (int64_t)(hcnt[0] + hcnt[1]);
-    p->stats[3] = (int64_t)hcnt[1];
+    p->stats[0] = (int64_t)(hcnt[0] + hcnt[1] + hcnt[2]);
+    p->stats[3] = (int64_t)hcnt[1];      // pairs of the near evaluator / near pass
+    p->stats[4] = (int64_t)hcnt[2];      // pairs of the uniform order-2 units
+    if (p->kev[0]) {
+        for (int k = 0; k < 4; k++) {
+            float kms = 0.f;
+            if (cudaEventElapsedTime(&kms, p->kev[k], p->kev[k + 1]) == cudaSuccess) p->ktimings[k] = kms;
+            else { cudaGetLastError(); p->ktimings[k] = 0.; }
+        }
+    }
 #ifdef PNB_PROFILE
     fprintf(stderr, "PNB_PROFILE cycles(tid0 sums): load+S1 %llu | classify %llu | S2+list+S3 %llu | eval %llu | S4 %llu | mirror+D+loop %llu\n", hcnt[2], hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7]);
 #endif
@@ -2308,6 +2325,15 @@ extern "C" int pnb_dense_stats(pnb_problem *p, int64_t *stats)
 {
     if (!p || !stats) return fail(PNB_ERR_ARG, "null argument");
     memcpy(stats, p->stats, sizeof(p->stats));
+    return 0;
+}
+
+// 2D group path: device time of the last assembly per kernel: [0] uniform order-2 units, [1] near pair list (first
+// assembly) + near evaluator, [2] all other units, [3] symmetrisation
+extern "C" int pnb_dense_kernel_timings(pnb_problem *p, double *ms)
+{
+    if (!p || !ms) return fail(PNB_ERR_ARG, "null argument");
+    memcpy(ms, p->ktimings, sizeof(p->ktimings));
     return 0;
 }
 

@@ -343,7 +343,7 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits
     g_signal_done(G, 0, ticket, tid);
     }
     for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
-    if (lane == 0 && my_pairs) atomicAdd(G.counters, my_pairs);
+    if (lane == 0 && my_pairs) atomicAdd(G.counters + 2, my_pairs);
 }
 
 // -------------------------------------------------------------------------------------------------
