@@ -2275,7 +2275,8 @@ extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row
         }
     }
 #ifdef PNB_PROFILE
-    fprintf(stderr, "PNB_PROFILE cycles(tid0 sums): load+S1 %llu | classify %llu | S2+list+S3 %llu | eval %llu | S4 %llu | mirror+D+loop %llu\n", hcnt[2], hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7]);
+    if (p->kev[0]) fprintf(stderr, "PNB_PROFILE gmix cycles (thread 0 of every CTA, summed): unit setup %llu | classify+bin %llu | evaluate %llu | block update+D %llu | flush %llu\n", hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7]);
+    else fprintf(stderr, "PNB_PROFILE cycles(tid0 sums): load+S1 %llu | classify %llu | S2+list+S3 %llu | eval %llu | S4 %llu | mirror+D+loop %llu\n", hcnt[2], hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7]);
 #endif
     p->stats[1] = p->distinct_pairs;
     return 0;

@@ -815,6 +815,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
         for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_GT) fd[e] = fs[e];
     }
     unsigned long long my_pairs = 0, my_near = 0;
+    PROF_DECL
     __syncthreads();        // the power table is complete before its coefficients go to registers
     const PowCtx kv(&sm.pw);
     const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15;
@@ -849,6 +850,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
         }
     }
     __syncthreads();
+    PROF(0)
 
     for (int rb = 0; rb < nI; rb += SB) {
         double dxacc = 0.;      // threads tid < SB*ND: entry (tid % ND) of the block of row cell rb + tid / ND
@@ -910,6 +912,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
                 }
             }
             __syncthreads();    // B2
+            PROF(1)
             const int nlist = sm.nlist;
             if (nlist == 0 && nnear == 0) continue;     // uniform across the CTA
             // ---- evaluate the far pairs (no ordering needed) ----
@@ -946,6 +949,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
                 frl = locI[a1];
                 fcl = locJ[a2];
             }
+            PROF(2)
             // ---- block updates: sub-batch 0, barrier, sub-batch 1; pairs of one sub-batch hit distinct entries ----
 #pragma unroll 1
             for (int ph = 0; ph < 2; ph++) {
@@ -992,6 +996,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
                 }
             }
             __syncthreads();    // B4: slotD / dxy reused by the next step
+            PROF(3)
         }
         if (tid < SB * ND) {
             const int kk1 = tid / ND, comp = tid - kk1 * ND;
@@ -1010,7 +1015,11 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
     g_wait_predecessors(G, 1, ticket, I, J, tid, PNB_GT);
     g_flush_block(G, S, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_GT);
     g_signal_done(G, 1, ticket, tid);
+    PROF(4)
     }
+#ifdef PNB_PROFILE
+    if (tid == 0) { for (int k_ = 0; k_ < 5; k_++) atomicAdd(G.counters + 3 + k_, (unsigned long long)pt_[k_]); }
+#endif
     for (int off = 16; off > 0; off >>= 1) {
         my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
         my_near += __shfl_xor_sync(0xffffffffu, my_near, off);
