@@ -195,7 +195,7 @@ def run_reference(args):
     N = dm.num_dofs
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps_ref, 'warmup': args.warmup_ref, 'ms_per_step': 1e3*N*N/v, 'higher_is_better': True,
-            'scaling': 'strong' if args.gpus > 1 else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': '{}: 2D disc, s=0.75, P1, dense, N={} ({} cells)'.format(args.workload, N, mesh.num_cells),
                        'note': 'CPU: reference Cython getDense (stub-built, oracle/_ref); ms_per_step extrapolated from '
                                'the sampled slices to the full matrix'},
