@@ -335,9 +335,10 @@ class nonlocalBuilder:
         if sum(len(v) for v in Pfar_nodes.values()) == 0:
             H = self.getDense()
         else:
+            d2c = h2.dof_to_cells(self.dm)
             for n in root.get_tree_nodes():
                 if n.isLeaf:
-                    n.value = h2.leaf_values(n, self.mesh, self.dm)
+                    n.value = h2.leaf_values(n, self.mesh, self.dm, d2c)
                 if n.parent is not None:
                     n.transferOperator = h2.transfer_operator(n.parent, n)
             levels = sorted(Pfar_nodes)

@@ -31,47 +31,62 @@ def _multi_index(m, dim):
     return np.stack((i.ravel(), j.ravel()), axis=1)
 
 
-def leaf_values(node, mesh, dm):
-    """V[local dof, alpha] of a leaf cluster"""
+def leaf_values(node, mesh, dm, d2c=None):
+    """V[local dof, alpha] of a leaf cluster (all cells of the cluster at once)"""
     dim = mesh.dim
     m = node.interpolation_order
     dofs = node.dofs
-    pos = -np.ones(dm.num_dofs, dtype=np.int64)
-    pos[dofs] = np.arange(dofs.shape[0])
     bary, w = quadrature.regular(m+2, dim)          # P1: quadOrder = order+2 (Sauter/Schwab p. 428)
     xi = chebyshev(node.box, m)                     # [m, dim]
     diff = xi[:, None, :]-xi[None, :, :]
     diff[np.arange(m), np.arange(m), :] = 1.
     beta = diff.prod(axis=1)                        # [m, dim]
-    incell = (dm.dofs >= 0) & (pos[np.where(dm.dofs >= 0, dm.dofs, 0)] >= 0)
-    cells = np.nonzero(incell.any(axis=1))[0]          # cells around the DoFs of the cluster, ascending
-    V = np.zeros((dofs.shape[0], m**dim))
+    cells = cells_of_dofs(dm, dofs, d2c)            # cells around the DoFs of the cluster, ascending
     idx = _multi_index(m, dim)
-    for c in cells:
-        simplex = mesh.vertices[mesh.cells[c]]      # [dim+1, dim]
-        x = bary.T.dot(simplex)                     # [nq, dim]
-        vol = mesh.volVector[c]
-        d = x[:, None, :]-xi[None, :, :]            # [nq, m, dim]
-        omega = np.empty((x.shape[0], m, dim))
-        for l in range(m):
-            dd = d.copy()
-            dd[:, l, :] = 1.
-            omega[:, l, :] = dd.prod(axis=1)
-        close = np.abs(d) <= 1e-9
-        omega = np.where(close, beta[None, :, :], omega)
-        # L_alpha(x_j) = prod_q omega[j, alpha_q, q] / prod_q beta[alpha_q, q]
-        om = np.ones((x.shape[0], idx.shape[0]))
-        be = np.ones(idx.shape[0])
-        for q in range(dim):
-            om = om*omega[:, idx[:, q], q]
-            be = be*beta[idx[:, q], q]
-        L = om/be[None, :]
-        for k in range(dim+1):
-            dof = dm.dofs[c, k]
-            if dof < 0 or pos[dof] < 0:
-                continue
-            V[pos[dof]] += (vol*L*(bary[k]*w)[:, None]).sum(axis=0)
+    x = np.einsum('kq,ckd->cqd', bary, mesh.vertices[mesh.cells[cells]])      # [nc, nq, dim]
+    d = x[:, :, None, :]-xi[None, None, :, :]                                   # [nc, nq, m, dim]
+    omega = np.empty_like(d)
+    for l in range(m):
+        dd = d.copy()
+        dd[:, :, l, :] = 1.
+        omega[:, :, l, :] = dd.prod(axis=2)
+    omega = np.where(np.abs(d) <= 1e-9, beta[None, None, :, :], omega)
+    # L_alpha(x_j) = prod_q omega[j, alpha_q, q] / prod_q beta[alpha_q, q]
+    om = np.ones(x.shape[:2]+(idx.shape[0], ))
+    be = np.ones(idx.shape[0])
+    for q in range(dim):
+        om = om*omega[:, :, idx[:, q], q]
+        be = be*beta[idx[:, q], q]
+    L = om/be[None, None, :]                                                    # [nc, nq, m^dim]
+    vol = mesh.volVector[cells]
+    V = np.zeros((dofs.shape[0], m**dim))
+    sub = dm.dofs[cells]
+    pos = np.searchsorted(dofs, np.maximum(sub, 0))
+    pos = np.minimum(pos, dofs.shape[0]-1)
+    ok = (sub >= 0) & (dofs[pos] == sub)
+    for k in range(dim+1):
+        contrib = vol[:, None]*np.einsum('cqa,q->ca', L, bary[k]*w)             # [nc, m^dim]
+        np.add.at(V, pos[ok[:, k], k], contrib[ok[:, k]])
     return V
+
+
+def dof_to_cells(dm):
+    """CSR dof -> cells around it (ascending)"""
+    m = dm.dofs >= 0
+    d = dm.dofs[m]
+    c = np.nonzero(m)[0]
+    order = np.lexsort((c, d))
+    d, c = d[order], c[order]
+    ptr = np.zeros(dm.num_dofs+1, dtype=np.int64)
+    np.add.at(ptr, d+1, 1)
+    return np.cumsum(ptr), c
+
+
+def cells_of_dofs(dm, dofs, d2c=None):
+    ptr, cells = dof_to_cells(dm) if d2c is None else d2c
+    cnt = ptr[dofs+1]-ptr[dofs]
+    start = np.repeat(ptr[dofs]-np.concatenate(([0], np.cumsum(cnt)[:-1])), cnt)
+    return np.unique(cells[start+np.arange(cnt.sum())])
 
 
 def transfer_operator(parent, child):
@@ -329,8 +344,14 @@ def assemble_clusters(builder, Pnear):
     dev_index = builder.problem.device
     dev = torch.device('cuda', dev_index)
     out = nearFieldBlocks(dm.num_dofs, dev)
-    touch = dm.dofs >= 0
+    d2c = dof_to_cells(dm)
+    node_cells = {}
     cache = {}
+
+    def cells_of(n):
+        if n.id not in node_cells:
+            node_cells[n.id] = cells_of_dofs(dm, n.dofs, d2c)
+        return node_cells[n.id]
     for n1, n2 in Pnear:
         key = (n2.id, n1.id)
         if key in cache:
@@ -339,20 +360,20 @@ def assemble_clusters(builder, Pnear):
             continue
         d1, d2 = n1.dofs, n2.dofs
         union = np.union1d(d1, d2)
-        loc = -np.ones(dm.num_dofs, dtype=np.int64)
-        loc[union] = np.arange(union.shape[0])
-        local = np.where(touch, loc[np.where(touch, dm.dofs, 0)], -1)
-        cells = np.nonzero((local >= 0).any(axis=1))[0]              # cellsUnion
+        cells = np.union1d(cells_of(n1), cells_of(n2))                 # cellsUnion
+        gd = dm.dofs[cells]
+        pos = np.minimum(np.searchsorted(union, np.maximum(gd, 0)), union.shape[0]-1)
+        inside = (gd >= 0) & (union[pos] == gd)
         sub = meshNd(mesh.vertices, mesh.cells[cells])
-        sdofs = np.ascontiguousarray(np.where(local[cells] >= 0, local[cells], -1), dtype=np.int32)
+        sdofs = np.ascontiguousarray(np.where(inside, pos, -1), dtype=np.int32)
         sdm = _SubDoFMap(sub, sdofs, union.shape[0])
         prob = _Problem(sdm, builder.kernel, builder.kernelBoundary, builder.orders, dev_index,
                         builder.problem.max_order, order_num_dofs=dm.num_dofs)
         n = union.shape[0]
         A = torch.empty((n, n), dtype=torch.float64, device=dev)
         _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, 1, 0, n, A.data_ptr(), A.stride(0), 1))
-        r = torch.as_tensor(loc[d1], device=dev)
-        c = torch.as_tensor(loc[d2], device=dev)
+        r = torch.as_tensor(np.searchsorted(union, d1), device=dev)
+        c = torch.as_tensor(np.searchsorted(union, d2), device=dev)
         B = A[r[:, None], c[None, :]].contiguous()
         cache[(n1.id, n2.id)] = B
         out.add(d1, d2, B)
