@@ -10,7 +10,8 @@ DEPS = [SRC, os.path.join(HERE, 'csrc', 'pnb_device.cuh'), os.path.join(HERE, 'c
         os.path.join(HERE, 'csrc', 'pnb_group.cuh'),
         os.path.join(HERE, '..', 'include', 'pnb200.h')]
 
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+# per-thread default streams: host threads that assemble independent problems (H2 near field) overlap on the device
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--default-stream', 'per-thread',
               '-Xcompiler', '-fPIC', '-shared', '-lpthread']
 
 

@@ -145,6 +145,25 @@ extern "C" int pnb_release_cached_memory(void)
     return 0;
 }
 
+
+// Dynamic shared memory opt-in: function attributes are process-wide state, so concurrent host threads must not
+// set problem-dependent values; every kernel is opted in once per device to the device maximum.
+template <class K> static void smem_optin(K kernel, int device)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, bool> done;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair((const void *)kernel, device);
+    if (done.count(key)) return;
+    int smem_blk = 0;
+    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaFuncAttributes attr;
+    if (smem_blk > 0 && cudaFuncGetAttributes(&attr, kernel) == cudaSuccess)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_blk - (int)attr.sharedSizeBytes);
+    cudaGetLastError();
+    done[key] = true;
+}
+
 // ---------------------------------------------------------------------------
 // problem object
 // ---------------------------------------------------------------------------
@@ -1937,7 +1956,7 @@ static int build_near_list(pnb_problem *p)
         CK(pool_malloc((void **)&cursor, 4 * sizeof(int)));
         gh->near_allocs.push_back(cursor);
         CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
-        cudaFuncSetAttribute(gnear_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_near);
+        smem_optin(gnear_list_kernel, p->device);
         int *bins = nullptr, *binbase = nullptr, *perm = nullptr;
         CK(pool_malloc((void **)&bins, 128 * sizeof(int)));
         gh->near_allocs.push_back(bins);
@@ -2018,8 +2037,8 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     // unit slots of the other instances stay untouched: start from zero
     if (nparts > 1) cudaMemsetAsync(G.Dp, 0, (size_t)G.ngroups * nc * 6 * sizeof(double));
     for (auto &e : p->ev) if (!e) cudaEventCreate(&e);
-    cudaFuncSetAttribute(gf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_f2);
-    cudaFuncSetAttribute(gmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gh->smem_mix);
+    smem_optin(gf2_kernel, p->device);
+    smem_optin(gmix_kernel, p->device);
     F2Rule R;
     {
         const FarRule &F = p->far_rules[2];
@@ -2058,7 +2077,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         if (gh->nitems > 0 && !(dbg & 0x100)) {
             const int wpb = PNB_THREADS / 32;
             const size_t smem_eval = sizeof(PowTab) + ((size_t)13 + (size_t)wpb * 4) * p->P.reg_nmax * sizeof(double);
-            cudaFuncSetAttribute(gnear_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eval);
+            smem_optin(gnear_eval_kernel, p->device);
             int nsm = 148;
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
             const int grid = std::min(gh->nchunks, 2 * nsm);
@@ -2159,8 +2178,8 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     if (p->dim == 2) {
         const size_t smem = sizeof(TileSmem<2, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
         const size_t smem_far = sizeof(TileSmem<2, false>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
-        cudaFuncSetAttribute(tile_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_far);
-        cudaFuncSetAttribute(tile_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_optin(tile_kernel<2, false>, p->device);
+        smem_optin(tile_kernel<2, true>, p->device);
         tile_kernel<2, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, p->far_mask);
         compact_units_kernel<<<1, 1024>>>(S);
         cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);
@@ -2169,8 +2188,8 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     } else {
         const size_t smem = sizeof(TileSmem<1, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
         const size_t smem_far = sizeof(TileSmem<1, false>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
-        cudaFuncSetAttribute(tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_far);
-        cudaFuncSetAttribute(tile_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_optin(tile_kernel<1, false>, p->device);
+        smem_optin(tile_kernel<1, true>, p->device);
         tile_kernel<1, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, 0);
         compact_units_kernel<<<1, 1024>>>(S);
         cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);

@@ -352,15 +352,22 @@ def assemble_clusters(builder, Pnear):
         if n.id not in node_cells:
             node_cells[n.id] = cells_of_dofs(dm, n.dofs, d2c)
         return node_cells[n.id]
+    # one small problem per unordered cluster pair; a few host threads keep several of them in flight (the C calls
+    # release the GIL and run on per-thread CUDA streams)
+    todo, seen = [], set()
     for n1, n2 in Pnear:
-        key = (n2.id, n1.id)
-        if key in cache:
-            # the local matrices are symmetric: block (n2, n1)^T
-            out.add(n1.dofs, n2.dofs, cache[key].t().contiguous())
-            continue
+        if (n2.id, n1.id) not in seen and (n1.id, n2.id) not in seen:
+            seen.add((n1.id, n2.id))
+            todo.append((n1, n2))
+    for n1, n2 in todo:
+        cells_of(n1)
+        cells_of(n2)
+
+    def work(pair):
+        n1, n2 = pair
         d1, d2 = n1.dofs, n2.dofs
         union = np.union1d(d1, d2)
-        cells = np.union1d(cells_of(n1), cells_of(n2))                 # cellsUnion
+        cells = np.union1d(node_cells[n1.id], node_cells[n2.id])       # cellsUnion
         gd = dm.dofs[cells]
         pos = np.minimum(np.searchsorted(union, np.maximum(gd, 0)), union.shape[0]-1)
         inside = (gd >= 0) & (union[pos] == gd)
@@ -370,12 +377,33 @@ def assemble_clusters(builder, Pnear):
         prob = _Problem(sdm, builder.kernel, builder.kernelBoundary, builder.orders, dev_index,
                         builder.problem.max_order, order_num_dofs=dm.num_dofs)
         n = union.shape[0]
-        A = torch.empty((n, n), dtype=torch.float64, device=dev)
-        _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, 1, 0, n, A.data_ptr(), A.stride(0), 1))
-        r = torch.as_tensor(np.searchsorted(union, d1), device=dev)
-        c = torch.as_tensor(np.searchsorted(union, d2), device=dev)
-        B = A[r[:, None], c[None, :]].contiguous()
-        cache[(n1.id, n2.id)] = B
-        out.add(d1, d2, B)
+        # torch work of this thread on its own stream (the legacy default stream would serialise all threads); the C
+        # call returns after its kernels have finished, so no further ordering is needed
+        import threading
+        tl = threading.current_thread()
+        if not hasattr(tl, '_pnb_stream'):
+            tl._pnb_stream = torch.cuda.Stream(dev)
+        with torch.cuda.device(dev), torch.cuda.stream(tl._pnb_stream):
+            A = torch.empty((n, n), dtype=torch.float64, device=dev)
+            _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, 1, 0, n, A.data_ptr(), A.stride(0), 1))
+            r = torch.as_tensor(np.searchsorted(union, d1), device=dev)
+            c = torch.as_tensor(np.searchsorted(union, d2), device=dev)
+            B = A[r[:, None], c[None, :]].contiguous()
+            tl._pnb_stream.synchronize()
         del prob
+        return (n1.id, n2.id), B
+    nthreads = int(builder.params.get('near_field_threads', 8))
+    if nthreads > 1 and len(todo) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(nthreads) as ex:
+            cache = dict(ex.map(work, todo))
+    else:
+        cache = dict(map(work, todo))
+    torch.cuda.synchronize(dev)
+    for n1, n2 in Pnear:
+        B = cache.get((n1.id, n2.id))
+        if B is None:
+            # the local matrices are symmetric: block (n2, n1)^T
+            B = cache[(n2.id, n1.id)].t().contiguous()
+        out.add(n1.dofs, n2.dofs, B)
     return out
