@@ -495,3 +495,19 @@ def test_h2_operator(golden_dir, name):
     err = np.abs(Hx-A*g['x']).max()/np.abs(A*g['x']).max()
     ref_err = np.abs(g['Hx']-g['Ax']).max()/np.abs(g['Ax']).max()
     assert err < 2*ref_err+1e-12
+
+
+def test_h2_against_dense_operator_larger_mesh():
+    """a size the reference's golden does not cover (N = 2977): H2 matvec against the dense matvec (interpolation error only),
+    near-field entries equal to the dense entries there where the near pattern is a full cluster block on the diagonal"""
+    import torch
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.uniform_disc(), 5)
+    dm = pb.P1_DoFMap(mesh)
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'target_order': 0.5})
+    H, Pnear = b.getH2(returnNearField=True)
+    A = b.getDense()
+    x = torch.as_tensor(np.sin(np.arange(dm.num_dofs)*0.37)+0.1).cuda()
+    y, yd = H.matvec_device(x), A.matvec_device(x)
+    assert float((y-yd).abs().max()) < 1e-4*float(yd.abs().max())
+    assert H.Anear.nnz < 0.3*dm.num_dofs**2 and sum(len(v) for v in H.Pfar.values()) > 100
