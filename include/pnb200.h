@@ -82,6 +82,14 @@ typedef struct {
     int32_t order_num_dofs; /* num_dofs entering getQuadOrder (local_matrix.num_dofs, fractionalLaplacian2D.pyx:629);
                              * 0 = dm.num_dofs.  Differs when two DoFMaps are combined
                              * (nonlocalAssembly_{SCALAR}.pxi:1366-1378: the local matrix keeps the first map's count) */
+    /* Piecewise constant variable kernels (kernel.evalParams at the cell centres per cell pair,
+     * nonlocalOperator_{SCALAR}.pxi:509-513; leftRightFractionalOrder, fractionalOrders.pyx:285-335): the parameters above
+     * hold for the cell pairs whose label pair maps to active_class; the other pairs are skipped (they belong to the
+     * problem instance of their own class; the operator is the sum over the classes).  cell_labels == NULL: constant kernel. */
+    const uint8_t *cell_labels;    /* host, num_cells, values 0..3 */
+    const uint8_t *bfacet_labels;  /* host, num_bfacets */
+    int32_t active_class;
+    uint8_t pair_class[16];        /* [label1 * 4 + label2] -> class */
 } pnb_kernel_t;
 
 /* One quadrature table: rows x n barycentric coordinates (x point first, then

@@ -36,7 +36,9 @@ class _Problem(ctypes.Structure):
                 ('qr_face', _Rule), ('qr_edge', _Rule), ('qr_vertex', _Rule),
                 ('bqr_edge', _Rule), ('bqr_vertex', _Rule),
                 ('max_order', ctypes.c_int),
-                ('reg_cell', ctypes.c_void_p), ('reg_facet', ctypes.c_void_p), ('order_num_dofs', ctypes.c_int)]
+                ('reg_cell', ctypes.c_void_p), ('reg_facet', ctypes.c_void_p), ('order_num_dofs', ctypes.c_int),
+                ('labels', ctypes.c_void_p), ('blabels', ctypes.c_void_p), ('active_class', ctypes.c_int),
+                ('pair_class', ctypes.c_ubyte*16)]
 
 
 def build():
@@ -64,7 +66,8 @@ class Problem:
     """One (mesh, P1 DoFMap, constant-order fractional kernel) assembly problem."""
 
     def __init__(self, vertices, cells, dofs, num_dofs, s, bfacets=None, target_order=None,
-                 hVector=None, volVector=None, hmin=None, diam=None, max_order=None, order_num_dofs=None):
+                 hVector=None, volVector=None, hmin=None, diam=None, max_order=None, order_num_dofs=None,
+                 s_max=None, labels=None, blabels=None, pair_class=None, active_class=0):
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         self.dofs = np.ascontiguousarray(dofs, dtype=np.int32)
@@ -86,7 +89,9 @@ class Problem:
         self.Cb = self.C*(1./s)      # phi = 1/s, kernels.py:151-160, kernelsCy.pyx:1990-1995
         # two DoFMaps: the local matrices (orders, getQuadOrder) keep the DoF count of the first map
         self.order_num_dofs = int(order_num_dofs) if order_num_dofs else self.num_dofs
-        self.orders = tables.diag_orders(dim, self.singularity, self.bsingularity, hmin, self.H0,
+        # variable kernels: the singular quadrature orders follow the largest order s.max (fractionalLaplacian2D.pyx:606)
+        sm = self.s if s_max is None else float(s_max)
+        self.orders = tables.diag_orders(dim, -dim-2*sm, 1.-dim-2*sm, hmin, self.H0,
                                          self.order_num_dofs, target_order)
         self.near = tables.near_rules(dim, self.singularity, self.bsingularity, self.orders)
         self._keep = []
@@ -100,6 +105,14 @@ class Problem:
         P.dofs = self.dofs.ctypes.data
         P.num_dofs = self.num_dofs
         P.order_num_dofs = self.order_num_dofs
+        if labels is not None:
+            self._labels = np.ascontiguousarray(labels, dtype=np.uint8)
+            self._blabels = np.ascontiguousarray(blabels, dtype=np.uint8)
+            P.labels = self._labels.ctypes.data
+            P.blabels = self._blabels.ctypes.data
+            P.active_class = int(active_class)
+            for i, v in enumerate(np.asarray(pair_class, dtype=np.uint8).ravel()):
+                P.pair_class[i] = int(v)
         P.nb = self.bfacets.shape[0]
         P.bfacets = self.bfacets.ctypes.data
         P.H0 = self.H0

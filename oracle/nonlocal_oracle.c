@@ -64,6 +64,13 @@ typedef struct {
     /* num_dofs entering getQuadOrder; 0 = num_dofs.  Two DoFMaps (NA.pxi:1366-1378): the local matrices keep the
      * count of the first map while the assembly runs over the combined map */
     int order_num_dofs;
+    /* piecewise constant variable kernels (kernel.evalParams at the cell centres, NO.pxi:509-513): the kernel
+     * parameters of this problem hold for the pairs whose label pair maps to active_class; all other pairs belong to
+     * another problem instance (the operator is the sum over the classes).  labels == NULL: constant kernel */
+    const unsigned char *labels;   /* nc */
+    const unsigned char *blabels;  /* nb */
+    int active_class;
+    unsigned char pair_class[16];  /* [label1 * 4 + label2] */
 } orc_problem;
 #define ORDN(P) ((P)->order_num_dofs > 0 ? (P)->order_num_dofs : (P)->num_dofs)
 
@@ -588,6 +595,7 @@ int64_t orc_dense(const orc_problem *P, int start, int end, int zero_exterior, d
                     skip = skip && ldofs[k] < 0 && ldofs[nvc + k] < 0;
                 }
                 if (skip) continue;
+                if (P->labels && P->pair_class[P->labels[c1] * 4 + P->labels[c2]] != P->active_class) continue;
                 panel = orc_panel_interior(P, c1, c2, p1, p2);
                 if (panel == IGNORED) continue;
                 orc_local_interior(P, c1, c2, panel, p1, p2, contrib);
@@ -625,7 +633,9 @@ int64_t orc_dense(const orc_problem *P, int start, int end, int zero_exterior, d
             if (zero_exterior) {
                 for (k = 0; k < nvc; k++) ldofs[k] = P->dofs[(size_t)c1 * nvc + k];
                 for (f = 0; f < P->nb; f++) {
-                    int panel = orc_panel_boundary(P, c1, f, p1, p2);
+                    int panel;
+                    if (P->labels && P->pair_class[P->labels[c1] * 4 + P->blabels[f]] != P->active_class) continue;
+                    panel = orc_panel_boundary(P, c1, f, p1, p2);
                     orc_local_boundary(P, c1, f, panel, p1, p2, bcontrib);
                     if (use_atomic) {
                         int p, q, kk = 0;

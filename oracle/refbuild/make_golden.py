@@ -247,6 +247,28 @@ def varconst_case(noRef, s, name):
     print(name, A.shape)
 
 
+def leftright_case(noRef, sll, srr, slr, name):
+    """piecewise constant, symmetric variable order s(x,y) (leftRightFractionalOrder, fractionalOrders.pyx:285-335):
+    the kernel parameters change per cell pair (kernel.evalParams at the cell centres, NO.pxi:509-513)"""
+    from PyNucleus_nl.fractionalOrders import leftRightFractionalOrder
+    mesh = uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    kernel = getFractionalKernel(2, leftRightFractionalOrder(sll, srr, slr, slr, 0.), np.inf)
+    assert kernel.variable and kernel.symmetric
+    b = nonlocalBuilder(dm, kernel, {'target_order': 0.5})
+    A = np.array(b.getDense().data)
+    b0 = nonlocalBuilder(dm, kernel, {'target_order': 0.5}, zeroExterior=False)
+    A0 = np.array(b0.getDense().data)
+    out = mesh_arrays(mesh, dm)
+    out.update(A=A, A_interior=A0, sll=sll, srr=srr, slr=slr, interface=0., target_order=0.5,
+               quad_order_diagonal=b.local_matrix.quad_order_diagonal, quad_order_diagonalV=b.local_matrix.quad_order_diagonalV,
+               boundary_quad_order_diagonal=b.local_matrix_zeroExterior.quad_order_diagonal)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, A.shape)
+
+
 def h2_case(dim, noRef, s, name, max_far=60):
     """getH2 of the reference: cluster tree, admissible / near pairs, far-field kernel blocks
     (clusterMethodCy.pyx:2153-2238), near-field CSR matrix, and H2 matvec of a fixed vector"""
@@ -348,6 +370,9 @@ if __name__ == '__main__':
         disc_case(4, 0.75, 'disc_mesh_r4', with_A=False)
     if 'all' in which or 'rows' in which:
         rows_case(5, 0.75, 'disc_s0.75_r5_rows')
+    if 'all' in which or 'leftright' in which:
+        leftright_case(2, 0.25, 0.75, 0.5, 'disc_leftright_r2')
+        leftright_case(3, 0.4, 0.8, 0.3, 'disc_leftright_r3')
     if 'all' in which or 'dm2' in which:
         dm2_case(2, 0.75, 'disc_dm2_s0.75_r2')
         dm2_case(3, 0.25, 'disc_dm2_s0.25_r3')

@@ -4,7 +4,7 @@ sm_100a in libpnb200.so (C ABI: include/pnb200.h); this package is the
 host-side mirror of the reference interface."""
 from .mesh import simpleInterval, uniform_disc, polygon_disc, refined, meshNd  # noqa: F401
 from .dofmap import P1_DoFMap  # noqa: F401
-from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder, variableConstFractionalOrder,  # noqa: F401
+from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder, variableConstFractionalOrder, leftRightFractionalOrder,  # noqa: F401
                       constantFractionalLaplacianScaling, FRACTIONAL)
 from .assembly import nonlocalBuilder, assembleNonlocalOperator  # noqa: F401
 from .linear_operators import Dense_LinearOperator  # noqa: F401

@@ -32,7 +32,9 @@ class pnb_kernel_t(ctypes.Structure):
     _fields_ = [('kernel_type', ctypes.c_int32), ('dim', ctypes.c_int32), ('s', ctypes.c_double),
                 ('scaling', ctypes.c_double), ('bscaling', ctypes.c_double), ('singularity', ctypes.c_double),
                 ('bsingularity', ctypes.c_double), ('horizon2', ctypes.c_double),
-                ('target_order', ctypes.c_double), ('btarget_order', ctypes.c_double), ('order_num_dofs', ctypes.c_int32)]
+                ('target_order', ctypes.c_double), ('btarget_order', ctypes.c_double), ('order_num_dofs', ctypes.c_int32),
+                ('cell_labels', ctypes.c_void_p), ('bfacet_labels', ctypes.c_void_p), ('active_class', ctypes.c_int32),
+                ('pair_class', ctypes.c_uint8*16)]
 
 
 class pnb_rule_t(ctypes.Structure):

@@ -22,7 +22,8 @@ COMMON_VERTEX, COMMON_EDGE, COMMON_FACE = -1, -2, -3
 class _Problem:
     """owner of a pnb_problem handle (device-resident mesh, DoFMap, kernel, tables)"""
 
-    def __init__(self, dm, kernel, bkernel, orders, device, max_order, order_num_dofs=0):
+    def __init__(self, dm, kernel, bkernel, orders, device, max_order, order_num_dofs=0, labels=None, blabels=None,
+                 pair_class=None, active_class=0):
         mesh = dm.mesh
         self._keep = []
         self.dim = mesh.dim
@@ -43,6 +44,15 @@ class _Problem:
                               kernel.singularityValue, bkernel.singularityValue,
                               kernel.horizonValue2 if kernel.finiteHorizon else np.inf,
                               orders.target_order, orders.btarget_order, order_num_dofs)
+        if labels is not None:
+            # piecewise constant variable kernel: this instance takes the cell pairs of one class
+            self.labels = np.ascontiguousarray(labels, dtype=np.uint8)
+            self.blabels = np.ascontiguousarray(blabels, dtype=np.uint8)
+            k.cell_labels = self.labels.ctypes.data
+            k.bfacet_labels = self.blabels.ctypes.data
+            k.active_class = int(active_class)
+            for i, v in enumerate(np.asarray(pair_class, dtype=np.uint8).ravel()):
+                k.pair_class[i] = int(v)
         self.singular = quadrature.singular_tables(mesh.dim, kernel.singularityValue, bkernel.singularityValue, orders,
                                                    dm.polynomialOrder)
         self.max_order = 0
@@ -113,9 +123,33 @@ class nonlocalBuilder:
         self.setKernel(kernel, zeroExterior)
 
     def setKernel(self, kernel, zeroExterior=True):
-        from .kernels import constFractionalOrder
+        from .kernels import constFractionalOrder, getFractionalKernel
+        self._classes = None
+        if kernel.symmetric and hasattr(kernel.s, 'classes'):
+            # piecewise constant order s(x,y): one constant-order problem instance per class of cell pairs, the
+            # operator is their sum; quadrature orders follow s.max like the reference's setKernel
+            # (fractionalLaplacian2D.pyx:606-611, 1217-1219)
+            if self.dm2 is not None:
+                raise NotImplementedError('two DoFMaps with a variable order')
+            svals, pair_class = kernel.s.classes()
+            mesh = self.mesh
+            centers = mesh.vertices[mesh.cells].mean(axis=1)
+            bf = np.asarray(mesh.boundaryFacets).reshape(-1, mesh.dim)
+            bcenters = mesh.vertices[bf].mean(axis=1)
+            self._classes = dict(kernels=[getFractionalKernel(mesh.dim, sv) for sv in svals], pair_class=pair_class,
+                                 labels=kernel.s.labels(centers), blabels=kernel.s.labels(bcenters), problems=None)
+            self.kernel = kernel
+            self.zeroExterior = zeroExterior
+            kmax = getFractionalKernel(mesh.dim, kernel.s.max)
+            self.kernelBoundary = kernel.getBoundaryKernel()
+            H0 = mesh.diam/np.sqrt(8.)
+            self.orders = quadrature.localMatrixOrders(mesh.dim, kmax.singularityValue, kmax.getBoundaryKernel().singularityValue,
+                                                       mesh.hmin, H0, self.dm.num_dofs, self.params.get('target_order', None),
+                                                       self.dm.polynomialOrder)
+            self._problem = None
+            return
         if not kernel.symmetric or not isinstance(kernel.s, constFractionalOrder):
-            raise NotImplementedError('only symmetric kernels whose order is constant in space are supported yet')
+            raise NotImplementedError('only symmetric kernels whose order is constant or piecewise constant (leftRight) are supported yet')
         self.kernel = kernel
         # nonlocalAssembly_{SCALAR}.pxi:918-921
         self.zeroExterior = False if kernel.finiteHorizon else zeroExterior
@@ -130,6 +164,8 @@ class nonlocalBuilder:
     # -- device problem (lazy) ---------------------------------------------
     @property
     def problem(self):
+        if self._classes is not None:
+            raise NotImplementedError('only getDense() supports piecewise variable orders')
         if self._problem is None:
             import torch
             if not torch.cuda.is_available():
@@ -194,6 +230,8 @@ class nonlocalBuilder:
 
         out: optional (N, N) float64 CUDA tensor to assemble into."""
         import torch
+        if self._classes is not None:
+            return self._getDenseClasses(out)
         N = self._dm_assembly.num_dofs
         prob = self.problem
         dev = torch.device('cuda', prob.device)
@@ -209,6 +247,42 @@ class nonlocalBuilder:
             n1 = self.dm.num_dofs
             return Dense_LinearOperator(A[:n1, n1:].contiguous(), prob.device)
         return Dense_LinearOperator(A, prob.device)
+
+    def _getDenseClasses(self, out=None):
+        """piecewise constant variable order: sum over the classes of cell pairs, each assembled by the constant-order
+        kernels restricted to its pairs"""
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError('pynucleus_b200 needs a CUDA device; there is no CPU fallback')
+        C = self._classes
+        device = self.params.get('device', torch.cuda.current_device())
+        dev = torch.device('cuda', device)
+        N = self.dm.num_dofs
+        if C['problems'] is None:
+            C['problems'] = [_Problem(self.dm, k, k.getBoundaryKernel(), self.orders, device, self.params.get('max_regular_order', 32),
+                                      labels=C['labels'], blabels=C['blabels'], pair_class=C['pair_class'], active_class=i)
+                             for i, k in enumerate(C['kernels'])]
+        A = torch.empty((N, N), dtype=torch.float64, device=dev) if out is None else out
+        tmp = None
+        for i, prob in enumerate(C['problems']):
+            target = A
+            if i > 0:
+                tmp = torch.empty_like(A) if tmp is None else tmp
+                target = tmp
+
+            def run():
+                _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, target.data_ptr(),
+                                                         target.stride(0), 1))
+            try:
+                run()
+            except _lib.PNBError as e:
+                if e.code != -5:
+                    raise
+                prob.set_max_order(max(prob.required_max_order(self.zeroExterior), prob.max_order+1))
+                run()
+            if i > 0:
+                A += tmp
+        return Dense_LinearOperator(A, device)
 
     def _no_dm2(self):
         if self.dm2 is not None:

@@ -202,6 +202,7 @@ struct pnb_problem {
     GroupSched *G = nullptr;          // 2D cell-group path (pnb_group.cuh)
     GroupHost *gh = nullptr;
     std::vector<int> h_cells, h_dofs, h_home; // host copies for the lazily built schedules
+    std::vector<unsigned char> h_labels;      // cell labels of piecewise variable kernels (empty: constant kernel)
     bool tiles_ready = false;
     std::vector<double> h_centers, h_h;
     std::vector<int4> h_grid;         // lane grids of the near evaluator per order
@@ -607,6 +608,18 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         rc |= upload(p, lhb.data(), (size_t)nb, &P.lhbf);
         rc |= upload(p, ahb.data(), (size_t)nb, &P.ahbf);
         if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
+    }
+    P.labels = nullptr; P.blabels = nullptr; P.active_class = 0;
+    for (int l = 0; l < 4; l++) P.pair_class[l] = 0;
+    if (kernel->cell_labels) {
+        if (nb > 0 && !kernel->bfacet_labels) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "cell labels without boundary facet labels"); }
+        rc |= upload(p, kernel->cell_labels, (size_t)nc, &P.labels);
+        rc |= upload(p, kernel->bfacet_labels, (size_t)nb, &P.blabels);
+        if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
+        P.active_class = kernel->active_class;
+        for (int l1 = 0; l1 < 4; l1++)
+            for (int l2 = 0; l2 < 4; l2++) P.pair_class[l1] |= (unsigned)kernel->pair_class[l1 * 4 + l2] << (8 * l2);
+        p->h_labels.assign(kernel->cell_labels, kernel->cell_labels + nc);
     }
     P.s = kernel->s; P.C = kernel->scaling; P.Cb = kernel->bscaling;
     P.sing = kernel->singularity; P.bsing = kernel->bsingularity;
@@ -1102,7 +1115,8 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                     if (K1 >= 0 && K2 >= 0 && K1 != K2 ? (!diag || rb < cb || k1 < k2) : (K1 >= 0 && K1 == K2 && diag)) {
                         countD = sm.rb.home[k1] == rt && sm.cb.home[k2] == ct;
                         const bool rin = (sm.rb.loc[k1] & 0x00FFFFFF) != 0x00FFFFFF, cin = (sm.cb.loc[k2] & 0x00FFFFFF) != 0x00FFFFFF;
-                        if ((sm.rb.any[k1] || sm.cb.any[k2]) && (countD || (rin && cin))) {
+                        if ((sm.rb.any[k1] || sm.cb.any[k2]) && (countD || (rin && cin)) &&
+                            (!P.labels || pnb_class_active(P, P.labels[K1], P.labels[K2]))) {
                             int panel;
                             if (K1 == K2) panel = -NV;
                             else {
@@ -1459,7 +1473,8 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
         const int f = f0 + lane;
         int pan = 0;
         int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
-        if (f < P.nb) {
+        const bool mine = f < P.nb && (!P.labels || pnb_class_active(P, P.labels[c1], P.blabels[f]));
+        if (mine) {
             if (DIM == 2) {
                 pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.bfacets + (size_t)f * 2, 2, false, p1, p2);
                 if (pan == 0) {
@@ -1470,7 +1485,7 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
                 }
             } else pan = panel_boundary(P, c1, f, p1, p2);
         }
-        if (f < P.nb && pan >= 1) {
+        if (mine && pan >= 1) {
             if (pan > P.max_order) atomicMax(S.err, pan);
             else {
                 double acc[ND];
@@ -1481,7 +1496,7 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
             }
         }
         // singular facets of this chunk: whole warp per facet, in facet order
-        unsigned sing = __ballot_sync(0xffffffffu, f < P.nb && pan < 0);
+        unsigned sing = __ballot_sync(0xffffffffu, mine && pan < 0);
         while (sing) {
             const int src = __ffs(sing) - 1;
             sing &= sing - 1;
@@ -1609,6 +1624,7 @@ struct GroupGeom {
     std::vector<int> gptr, gcells, gloc, gdptr, gdofs, color;
     std::vector<std::vector<int>> adj;     // groups sharing a vertex (sorted, includes self)
     std::vector<double> box;               // per group: xmin, xmax, ymin, ymax, hmax, amin, amax
+    std::vector<int> labelrange;           // per group: smallest and largest cell label (piecewise variable kernels)
     int ngroups = 0, cap = 0, maxld = 0, ncolors = 0;
 };
 
@@ -1754,6 +1770,17 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
         gg.color[g] = c;
         gg.ncolors = std::max(gg.ncolors, c + 1);
     }
+    gg.labelrange.assign((size_t)gg.ngroups * 2, 0);
+    if (!p->h_labels.empty())
+        for (int g = 0; g < gg.ngroups; g++) {
+            int lo = 255, hi = 0;
+            for (int k = g * GC; k < std::min(nc, (g + 1) * GC); k++) {
+                lo = std::min(lo, (int)p->h_labels[order[k]]);
+                hi = std::max(hi, (int)p->h_labels[order[k]]);
+            }
+            gg.labelrange[(size_t)g * 2] = lo;
+            gg.labelrange[(size_t)g * 2 + 1] = hi;
+        }
     // boxes of the cell centers, extreme mesh sizes
     gg.box.assign((size_t)gg.ngroups * 7, 0.);
     for (int g = 0; g < gg.ngroups; g++) {
@@ -1882,6 +1909,12 @@ static int build_group_schedule(pnb_problem *p)
                 const double ub = order_upper_bound(p->P, sqrt(dx * dx + dy * dy), b1[4], b2[4], b1[5], b1[6], b2[5], b2[6]);
                 if (far_2 && ub <= 2. - 1e-6) kind = 0;
                 else if (far_full && ub <= far_top - 1e-6) kind = 1;
+            }
+            if (!p->h_labels.empty()) {
+                const int *lI = &gg.labelrange[(size_t)I * 2], *lJ = &gg.labelrange[(size_t)J * 2];
+                if (lI[0] == lI[1] && lJ[0] == lJ[1]) {
+                    if (!pnb_class_active(p->P, lI[0], lJ[0])) continue;      // no pair of this unit belongs to the class
+                } else if (kind == 0) kind = 1;                                // mixed labels: classified pair by pair
             }
             GUnit u{I, J, kind, -1};
             const int ph = gg.color[I] * ncol + gg.color[J];

@@ -67,7 +67,18 @@ struct DProblem {
     const int *reg_doff;
     int reg_nmax;              // largest node count of a cell rule
     const int4 *reg_grid;      // per order: lane grid of the near evaluator (row lanes, column lanes, lanes per pair, 0)
+    // piecewise constant variable kernels: this problem instance takes the pairs of one class (see pnb_kernel_t)
+    const unsigned char *labels;   // nc, nullptr = constant kernel
+    const unsigned char *blabels;  // nb
+    int active_class;
+    unsigned int pair_class[4];    // packed: byte l2 of word l1
 };
+
+// does the pair of labels belong to this problem instance?
+__host__ __device__ inline bool pnb_class_active(const DProblem &P, int l1, int l2)
+{
+    return (int)((P.pair_class[l1 & 3] >> (8 * (l2 & 3))) & 0xFF) == P.active_class;
+}
 
 __host__ __device__ inline int tri_idx(int n, int i, int j) { return n * i - ((i * (i + 1)) >> 1) + j; }
 

@@ -366,6 +366,8 @@ __device__ __forceinline__ int g_classify(const DProblem &P, const GCls &c, bool
     if (!(K1 >= 0 && K2 >= 0 && K1 != K2 ? (!diag || rb < cb || k1 < k2) : (K1 >= 0 && K1 == K2 && diag))) return 0;
     // the reference skips pairs of cells without any dof
     if ((c.locI[s1] & 0x00FFFFFF) == 0x00FFFFFF && (c.locJ[s2] & 0x00FFFFFF) == 0x00FFFFFF) return 0;
+    // piecewise variable kernels: pairs of other classes belong to another problem instance
+    if (P.labels && !pnb_class_active(P, P.labels[K1], P.labels[K2])) return 0;
     if (K1 == K2) return -3;
     int panel = 0;
     if (maybe_touching) {

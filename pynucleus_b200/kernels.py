@@ -41,6 +41,46 @@ class variableConstFractionalOrder(constFractionalOrder):
     pass
 
 
+class leftRightFractionalOrder:
+    """s(x,y) piecewise constant with an interface x_0 = const (fractionalOrders.pyx:285-335): sll / srr for both points
+    left / right of it, slr (= srl for a symmetric kernel) across.  A piecewise order: the reference evaluates it at the
+    cell centres, once per cell pair (kernel.evalParams, nonlocalOperator_{SCALAR}.pxi:509-513).
+
+    `labels(points)` / `classes()` describe it to the device path: cells get the label 0 (left) or 1 (right), the pair
+    class of two labels selects one of the constant orders."""
+    numParameters = 1
+
+    def __init__(self, sll, srr, slr=np.nan, srl=np.nan, interface=0.):
+        if not np.isfinite(slr):
+            slr = 0.5*(sll+srr)
+        if not np.isfinite(srl):
+            srl = 0.5*(sll+srr)
+        self.sll, self.srr, self.slr, self.srl, self.interface = float(sll), float(srr), float(slr), float(srl), float(interface)
+        self.symmetric = self.slr == self.srl
+        self.min = min(self.sll, self.srr, self.slr, self.srl)
+        self.max = max(self.sll, self.srr, self.slr, self.srl)
+
+    def __call__(self, x, y):
+        x0, y0 = np.atleast_1d(x)[0], np.atleast_1d(y)[0]
+        if x0 < self.interface:
+            return self.sll if y0 < self.interface else self.slr
+        return self.srl if y0 < self.interface else self.srr
+
+    def labels(self, points):
+        return (np.asarray(points)[:, 0] >= self.interface).astype(np.uint8)
+
+    def classes(self):
+        """(orders per class, pair_class[4][4])"""
+        pc = np.zeros((4, 4), dtype=np.uint8)
+        pc[0, 1] = pc[1, 0] = 1
+        pc[1, 1] = 2
+        return [self.sll, self.slr, self.srr], pc
+
+    def __repr__(self):
+        return 'leftRightFractionalOrder(ll={},rr={},lr={},rl={},interface={},sym={})'.format(self.sll, self.srr, self.slr, self.srl,
+                                                                                            self.interface, int(self.symmetric))
+
+
 class constant:
     """constant function, used for the horizon (fem functions.pyx)"""
 
@@ -89,12 +129,18 @@ class FractionalKernel:
         self.horizonValue2 = horizon.value**2
         self.finiteHorizon = horizon.value != np.inf
         self.complement = False
-        self.sValue = s.value
-        if not boundary:
-            self.singularityValue = -self.dim-2*self.sValue
+        off = 1. if boundary else 0.
+        if hasattr(s, 'value'):
+            self.sValue = s.value
+            self.singularityValue = off-self.dim-2*self.sValue
         else:
-            self.singularityValue = 1.-self.dim-2*self.sValue
-        self.min_singularity = self.max_singularity = self.singularityValue
+            # piecewise variable order: the current values are set per cell pair (evalParams); they start out as nan
+            # (kernelsCy.pyx:1606-1611)
+            self.sValue = np.nan
+            self.singularityValue = np.nan
+            self.variableScaling = True
+        self.min_singularity = off-self.dim-2*s.min
+        self.max_singularity = off-self.dim-2*s.max
 
     def getModifiedKernel(self, s=None, horizon=None, scaling=None):
         s = self.s if s is None else s
@@ -103,8 +149,9 @@ class FractionalKernel:
 
     def getBoundaryKernel(self):
         """kernel of the Gauss-theorem surface term, scaled by 1/s (kernelsCy.pyx:1982-2027)"""
+        phi = 1./self.s.value if hasattr(self.s, 'value') else None
         return FractionalKernel(self.dim, self.s, self.horizon, self.scalingPrePhi, boundary=True,
-                                phi=1./self.s.value, piecewise=self.piecewise)
+                                phi=phi, piecewise=self.piecewise)
 
     def __call__(self, x, y):
         x = np.atleast_1d(np.asarray(x, dtype=float))
@@ -143,8 +190,14 @@ def getFractionalKernel(dim, s, horizon=None, interaction=None, scaling=None, no
     horizonFun = _getHorizon(horizon)
     if derivative != 0 or tempered != 0. or manifold:
         raise NotImplementedError('derivative / tempered / manifold kernels are outside the accelerated path')
+    if isinstance(sFun, leftRightFractionalOrder):
+        if not sFun.symmetric or horizonFun.value != np.inf or not normalized or scaling is not None:
+            raise NotImplementedError('piecewise orders: symmetric, infinite horizon, normalised kernels only')
+        # the scaling is a function of s(x,y) (variableFractionalLaplacianScaling, kernelNormalization.pyx:421-499):
+        # evaluated per class by the builder
+        return FractionalKernel(dim, sFun, horizonFun, np.nan, boundary=boundary, phi=phi, piecewise=piecewise)
     if not isinstance(sFun, constFractionalOrder):
-        raise NotImplementedError('variable fractional orders are not supported yet')
+        raise NotImplementedError('this variable fractional order is not supported yet')
     if scaling is None:
         scaling = constantFractionalLaplacianScaling(dim, sFun.value, horizonFun.value, tempered) if normalized else 0.5
     if boundary and phi is None:

@@ -511,3 +511,39 @@ def test_h2_against_dense_operator_larger_mesh():
     y, yd = H.matvec_device(x), A.matvec_device(x)
     assert float((y-yd).abs().max()) < 1e-4*float(yd.abs().max())
     assert H.Anear.nnz < 0.3*dm.num_dofs**2 and sum(len(v) for v in H.Pfar.values()) > 100
+
+
+@pytest.mark.parametrize('name', ['disc_leftright_r2', 'disc_leftright_r3'])
+def test_piecewise_variable_order_vs_reference(golden_dir, name):
+    """getDense with leftRightFractionalOrder: per cell pair the order of its label class, assembled as a
+    sum of constant-order passes restricted to the pairs of each class"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'])
+    dm = pb.P1_DoFMap(mesh)
+    s = pb.leftRightFractionalOrder(float(g['sll']), float(g['srr']), float(g['slr']), float(g['slr']), float(g['interface']))
+    kernel = pb.getFractionalKernel(2, s)
+    assert kernel.variable and kernel.symmetric
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        A = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}, zeroExterior=ze).getDense().data
+        assert entry_err(A, g[key]) < TOL
+        assert np.array_equal(A, A.T)
+
+
+def test_piecewise_variable_order_larger_mesh_vs_oracle():
+    """a mesh with uniformly far units on both sides of the interface (all kernels, label-uniform and mixed groups)"""
+    import oracle
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.polygon_disc(7), 4)
+    dm = pb.P1_DoFMap(mesh)
+    s = pb.leftRightFractionalOrder(0.3, 0.7, 0.45, 0.45, 0.1)
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, s), {'target_order': 0.5}).getDense().data
+    svals, pc = s.classes()
+    labels = s.labels(mesh.vertices[mesh.cells].mean(axis=1))
+    blabels = s.labels(mesh.vertices[mesh.boundaryFacets].mean(axis=1))
+    ref = 0.
+    for k, sv in enumerate(svals):
+        P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, sv, bfacets=mesh.boundaryFacets, target_order=0.5,
+                           s_max=max(svals), labels=labels, blabels=blabels, pair_class=pc, active_class=k, max_order=40)
+        ref = ref+P.dense(True)
+    assert entry_err(A, ref) < TOL

@@ -191,3 +191,27 @@ def test_two_dofmaps_match_reference(golden_dir, name):
         A = P.dense(ze)[:n1, n1:]
         assert A.shape == g[key].shape
         assert np.abs(A-g[key]).max() < 1e-13*np.abs(g[key]).max()
+
+
+@pytest.mark.parametrize('name', ['disc_leftright_r2', 'disc_leftright_r3'])
+def test_piecewise_variable_order_matches_reference(golden_dir, name):
+    """leftRightFractionalOrder (fractionalOrders.pyx:285-335): the kernel parameters are set per cell pair from the cell
+    centres (NO.pxi:509-513).  Restated as a sum over the classes of label pairs, each with its constant order; the
+    singular quadrature orders follow s.max (fractionalLaplacian2D.pyx:606-611)."""
+    g = load(golden_dir, name)
+    svals = [float(g['sll']), float(g['slr']), float(g['srr'])]
+    labels = (g['vertices'][g['cells']].mean(axis=1)[:, 0] >= float(g['interface'])).astype(np.uint8)
+    blabels = (g['vertices'][g['boundaryEdges']].mean(axis=1)[:, 0] >= float(g['interface'])).astype(np.uint8)
+    pc = np.zeros((4, 4), dtype=np.uint8)
+    pc[0, 1] = pc[1, 0] = 1
+    pc[1, 1] = 2
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        A = 0.
+        for k, s in enumerate(svals):
+            P = oracle.Problem(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), s, bfacets=g['boundaryEdges'],
+                               target_order=0.5, hVector=g['hVector'], volVector=g['volVector'], hmin=float(g['hmin']),
+                               diam=float(g['diam']), s_max=max(svals), labels=labels, blabels=blabels, pair_class=pc,
+                               active_class=k, max_order=40)
+            assert P.orders['qod'] == int(g['quad_order_diagonal']) and P.orders['qodV'] == int(g['quad_order_diagonalV'])
+            A = A+P.dense(ze)
+        assert np.abs(A-g[key]).max() < 1e-13*np.abs(g[key]).max()
