@@ -547,3 +547,17 @@ def test_piecewise_variable_order_larger_mesh_vs_oracle():
                            s_max=max(svals), labels=labels, blabels=blabels, pair_class=pc, active_class=k, max_order=40)
         ref = ref+P.dense(True)
     assert entry_err(A, ref) < TOL
+
+
+@pytest.mark.parametrize('noRef', [0, 1])
+def test_tiny_meshes_vs_oracle(noRef):
+    """one and seven DoFs: a single cell group, every pair touching or near"""
+    import oracle
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.uniform_disc(), noRef)
+    dm = pb.P1_DoFMap(mesh)
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'target_order': 0.5}).getDense().data
+    P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, 0.75, bfacets=mesh.boundaryFacets, target_order=0.5)
+    ref = P.dense(True)
+    assert A.shape == ref.shape == (dm.num_dofs, dm.num_dofs)
+    assert np.abs(A-ref).max() < TOL*np.abs(ref).max()
