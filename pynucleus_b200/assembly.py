@@ -23,7 +23,7 @@ class _Problem:
     """owner of a pnb_problem handle (device-resident mesh, DoFMap, kernel, tables)"""
 
     def __init__(self, dm, kernel, bkernel, orders, device, max_order, order_num_dofs=0, labels=None, blabels=None,
-                 pair_class=None, active_class=0):
+                 pair_class=None, active_class=0, tables_from=None):
         mesh = dm.mesh
         self._keep = []
         self.dim = mesh.dim
@@ -53,10 +53,18 @@ class _Problem:
             k.active_class = int(active_class)
             for i, v in enumerate(np.asarray(pair_class, dtype=np.uint8).ravel()):
                 k.pair_class[i] = int(v)
-        self.singular = quadrature.singular_tables(mesh.dim, kernel.singularityValue, bkernel.singularityValue, orders,
-                                                   dm.polynomialOrder)
-        self.max_order = 0
-        rules = self._rules(max_order)
+        if tables_from is not None:
+            # same kernel, orders and table range as another problem (H2 near field: one problem per cluster pair):
+            # share its host-side table structure instead of converting the tables again
+            self.singular = tables_from.singular
+            self._keep = tables_from._keep
+            rules = tables_from._rules_struct
+        else:
+            self.singular = quadrature.singular_tables(mesh.dim, kernel.singularityValue, bkernel.singularityValue, orders,
+                                                       dm.polynomialOrder)
+            self.max_order = 0
+            rules = self._rules(max_order)
+        self._rules_struct = rules
         _lib.check(_lib.lib().pnb_problem_create(ctypes.byref(m), ctypes.byref(d), ctypes.byref(k), ctypes.byref(rules),
                                                  device, ctypes.byref(self.handle)))
         self.max_order = max_order
@@ -80,7 +88,7 @@ class _Problem:
         return r
 
     def set_max_order(self, max_order):
-        rules = self._rules(max_order)
+        rules = self._rules_struct = self._rules(max_order)
         _lib.check(_lib.lib().pnb_problem_set_rules(self.handle, ctypes.byref(rules)))
         self.max_order = max_order
 

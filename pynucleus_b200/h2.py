@@ -363,6 +363,8 @@ def assemble_clusters(builder, Pnear):
         cells_of(n1)
         cells_of(n2)
 
+    template = [builder.problem]      # same kernel, orders and tables: the sub-problems share its table structures
+
     def work(pair):
         n1, n2 = pair
         d1, d2 = n1.dofs, n2.dofs
@@ -375,7 +377,7 @@ def assemble_clusters(builder, Pnear):
         sdofs = np.ascontiguousarray(np.where(inside, pos, -1), dtype=np.int32)
         sdm = _SubDoFMap(sub, sdofs, union.shape[0])
         prob = _Problem(sdm, builder.kernel, builder.kernelBoundary, builder.orders, dev_index,
-                        builder.problem.max_order, order_num_dofs=dm.num_dofs)
+                        builder.problem.max_order, order_num_dofs=dm.num_dofs, tables_from=template[0])
         n = union.shape[0]
         # torch work of this thread on its own stream (the legacy default stream would serialise all threads); the C
         # call returns after its kernels have finished, so no further ordering is needed
