@@ -123,8 +123,9 @@ const char *pnb_last_error(void);
 int pnb_version(void);
 int pnb_device_count(void);
 
-/* Uploads mesh, DoFMap, kernel parameters and tables to `device` and builds
- * the DoF-tile schedule.  Replaces nonlocalBuilder.__init__/setKernel
+/* Uploads mesh, DoFMap, kernel parameters and tables to `device`; the assembly
+ * schedules (cell groups, unit lists, near pair list; DoF tiles) are built on the
+ * first assembly.  Replaces nonlocalBuilder.__init__/setKernel
  * (nonlocalAssembly_{SCALAR}.pxi:879-975).  `rules` may carry max_order = 0
  * when only pnb_max_order / pnb_classify_pairs are used afterwards. */
 int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm, const pnb_kernel_t *kernel,
@@ -167,7 +168,8 @@ int pnb_far_max_order(void);
  * with leading dimension ld (in doubles).  a_on_device != 0: A is device
  * memory; else A is host memory and the copy back is part of the call.
  * The result is deterministic (no floating point atomics): bitwise
- * reproducible from run to run. */
+ * reproducible from run to run, and bitwise symmetric.  2D, whole operator: cell-group kernels (every cell pair
+ * evaluated once, U + U^T); 1D and row ranges: DoF-tile kernels. */
 int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end,
                        double *A, int64_t ld, int a_on_device);
 
@@ -194,12 +196,14 @@ int pnb_dense_cell_blocks(pnb_problem *p, double **device_ptr, int64_t *count);
 int pnb_dense_cell_blocks_copy(pnb_problem *p, double *device_buf, int to_problem);
 int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row_end, double *A_rows, int64_t ld);
 
-/* Counters of the last pnb_dense_assemble call: [0] evaluated cell pairs
- * (with tile-halo redundancy), [1] distinct cell pairs c1<=c2 that are not
- * skipped, [2] kernel launches, [3..] reserved.  stats: host, 8 entries. */
+/* Counters of the last pnb_dense_assemble call: [0] evaluated cell pairs (2D whole-operator path: every pair
+ * once; DoF-tile path: with tile-halo redundancy), [1] distinct cell pairs c1<=c2 that are not skipped,
+ * [2] kernel launches, [3] pairs of the near evaluator, [4] pairs of the uniform order-2 units, [5..] reserved.
+ * stats: host, 8 entries. */
 int pnb_dense_stats(pnb_problem *p, int64_t *stats);
 /* device time in ms of the phases of the last assembly:
- * [0] tile kernel, [1] boundary kernel, [2] reduce+scatter, [3] total */
+ * [0] pair kernels (2D: near evaluator + unit kernels + symmetrisation; 1D / row ranges: tile kernels),
+ * [1] boundary kernel, [2] reduce+scatter of the cell-diagonal blocks, [3] total */
 int pnb_dense_timings(pnb_problem *p, double *ms);
 /* device milliseconds of the last 2D assembly per kernel: [0] uniform order-2 units, [1] near pair list (first
  * assembly only) + near evaluator, [2] all other units, [3] symmetrisation */

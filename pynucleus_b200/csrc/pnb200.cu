@@ -1577,12 +1577,9 @@ struct GroupHost {
     bool ready = false;
     int GC = 0;
     std::vector<GUnit> f2_units, mix_units, near_units;   // f2 / mix sorted by phase
-    std::vector<int> f2_off, mix_off;                     // phase offsets
     const GUnit *d_f2 = nullptr, *d_mix = nullptr, *d_near = nullptr;
     size_t smem_f2 = 0, smem_mix = 0, smem_near = 0;
     int nphase = 0;
-    cudaStream_t st[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> evs;
 };
 
 static uint64_t hilbert_index(uint32_t x, uint32_t y)
@@ -1876,7 +1873,6 @@ static int build_group_schedule(pnb_problem *p)
         gh->smem_f2 = gf2_smem_bytes(G.cap, G.maxld, G.ldS);
         gh->smem_mix = gmix_smem_bytes(G.cap, G.maxld, G.ldS);
         gh->smem_near = gnear_list_smem_bytes(G.cap);
-        for (auto &s : gh->st) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         gh->ready = true;
         if (getenv("PNB_BENCH_VERBOSE"))
             fprintf(stderr, "group path: GC %d, %d groups, cap %d, maxld %d, %d colours, smem f2/mix/near %zu/%zu/%zu\n", gh->GC,
@@ -1924,14 +1920,11 @@ static int build_group_schedule(pnb_problem *p)
         }
     }
     gh->f2_units.clear(); gh->mix_units.clear();
-    gh->f2_off.assign(1, 0); gh->mix_off.assign(1, 0);
     for (int ph = 0; ph < gh->nphase; ph++) {
         // near units first: they are the longest
         std::stable_sort(mix[ph].begin(), mix[ph].end(), [](const GUnit &a, const GUnit &b) { return a.kind > b.kind; });
         gh->f2_units.insert(gh->f2_units.end(), f2[ph].begin(), f2[ph].end());
         gh->mix_units.insert(gh->mix_units.end(), mix[ph].begin(), mix[ph].end());
-        gh->f2_off.push_back((int)gh->f2_units.size());
-        gh->mix_off.push_back((int)gh->mix_units.size());
     }
     for (void *d : gh->unit_allocs) pool_free(d);
     gh->unit_allocs.clear();
@@ -2150,7 +2143,6 @@ static void destroy_group_host(pnb_problem *p)
         GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
         for (void *d : gh->unit_allocs) pool_free(d);
         for (void *d : gh->near_allocs) pool_free(d);
-        for (auto &s : gh->st) if (s) cudaStreamDestroy(s);
         delete gh;
         p->gh = nullptr;
     }
