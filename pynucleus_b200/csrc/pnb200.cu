@@ -1801,7 +1801,7 @@ struct GroupHostFull : GroupHost {
     const int2 *d_items = nullptr;
     const int *d_perm = nullptr;
     const int4 *d_chunks = nullptr;
-    double *d_R = nullptr;
+    double *d_R = nullptr, *d_F = nullptr;
     int nitems = 0, npairs = 0, nchunks = 0;
     bool near_ready = false;
 };
@@ -2023,6 +2023,11 @@ static int build_near_list(pnb_problem *p)
         gh->near_allocs.push_back(nearbase);
         CK(pool_malloc((void **)&R, std::max<size_t>(tot[1], 1) * PairDims<2>::NL * sizeof(double)));
         gh->near_allocs.push_back(R);
+        double *F = nullptr;
+        CK(pool_malloc((void **)&F, std::max<size_t>(tot[0], 1) * 21 * sizeof(double)));
+        gh->near_allocs.push_back(F);
+        G.F = F;
+        gh->d_F = F;
         CK(pool_malloc((void **)&dchunks, std::max<size_t>(chunks.size(), 1) * sizeof(int4)));
         gh->near_allocs.push_back(dchunks);
         if (!chunks.empty()) CK(cudaMemcpy(dchunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
@@ -2108,7 +2113,8 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
             const int grid = std::min(gh->nchunks, 2 * nsm);
             gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R);
-            launches++;
+            gnear_finalize_kernel<<<(gh->npairs + 255) / 256, 256>>>(p->P, G.npairs, gh->npairs, gh->d_R, gh->d_F);
+            launches += 2;
         }
         cudaEventRecord(p->kev[2]);
         if (nm > 0 && !(dbg & 0x200)) {

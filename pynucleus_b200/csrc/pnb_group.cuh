@@ -32,6 +32,7 @@ struct GroupSched {
     const int4 *npairs;  // near pair list: (row cell, column cell, panel, first item)
     const int *nearbase; // [near slot][row batch][column batch]: position of the first pair of the sub-batch
     const double *R;     // results of the near items, NL doubles each
+    const double *F;     // per near pair: finished cross block (9) and cell-diagonal blocks (6 + 6)
     // ordered updates of U: every unit list is processed by persistent CTAs in list order (tickets); a unit adds
     // its block to U only after all units of smaller ticket that touch the same entries have done so
     const int *adjptr;   // ngroups+1: groups sharing a vertex (sorted, includes the group itself)
@@ -665,7 +666,7 @@ gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__rest
 
 // sums the slices of a near pair and maps the 21 values to the cross block and the two cell-diagonal blocks
 // of (row cell Ka, column cell Kb).  Deliberately not inlined (keeps the registers of the unit kernel low).
-__device__ __noinline__ void near_fetch(const DProblem &P, const double *__restrict__ R, int4 pr, double *xy, double *dxy)
+__device__ __forceinline__ void near_fetch(const DProblem &P, const double *__restrict__ R, int4 pr, double *xy, double *dxy)
 {
     constexpr int NV = 3, ND = 6, NL = PairDims<2>::NL, NRr = 2 * NV - 1;
     const int Ka = pr.x, Kb = pr.y, panel = pr.z;
@@ -721,6 +722,21 @@ __device__ __noinline__ void near_fetch(const DProblem &P, const double *__restr
                 k++;
             }
     }
+}
+
+// one thread per near pair: slices summed and mapped once, so that the unit kernel only reads 21 finished values
+// (cross block 9, row-cell block 6, column-cell block 6) per near pair
+__global__ void __launch_bounds__(256) gnear_finalize_kernel(DProblem P, const int4 *__restrict__ pairs, int npairs,
+                                                             const double *__restrict__ R, double *__restrict__ F)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npairs) return;
+    double xy[9], d12[12];
+    near_fetch(P, R, pairs[q], xy, d12);
+#pragma unroll
+    for (int k = 0; k < 9; k++) F[(size_t)q * 21 + k] = xy[k];
+#pragma unroll
+    for (int k = 0; k < 12; k++) F[(size_t)q * 21 + 9 + k] = d12[k];
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -963,11 +979,13 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
                     const int4 pr = G.npairs[pos];
                     if (pr.x != cellI[rb + k1] || pr.y != cellJ[cb + k2] || pr.z != todo) atomicMax(G.err + 1, 2);
                     else {
-                        double nxy[9], d12[12];
-                        near_fetch(P, G.R, pr, nxy, d12);
+                        const double *f = G.F + (size_t)pos * 21;
+                        double nxy[9];
+#pragma unroll
+                        for (int k = 0; k < 9; k++) nxy[k] = __ldg(f + k);
                         my_near++;
 #pragma unroll
-                        for (int k = 0; k < 12; k++) sm.dxy[tid][k] = d12[k];
+                        for (int k = 0; k < 12; k++) sm.dxy[tid][k] = __ldg(f + 9 + k);
                         sm.slotD[tid] = 1;
                         sm.anyD = 1;
                         g_scatter(S, ldS, locI[rb + k1], locJ[cb + k2], nxy);
