@@ -230,6 +230,33 @@ def dm2_case(noRef, s, name):
     print(name, A.shape)
 
 
+def entry_case(dim, noRef, s, name, nsample=10):
+    """nonlocalBuilder.getEntry / getDiagonal (NA.pxi:1539-1660, 2269-2289): single entries integrated over the patch
+    of the two basis functions, the rest of the space replaced by a surface integral around the patch"""
+    mesh = simpleInterval(-1, 1) if dim == 1 else uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    out = mesh_arrays(mesh, dm)
+    kernel = getFractionalKernel(dim, constFractionalOrder(s), np.inf)
+    b = nonlocalBuilder(dm, kernel, {'target_order': 0.5})
+    rng = np.random.default_rng(11)
+    IJ = [(int(i), int(i)) for i in rng.choice(dm.num_dofs, nsample, replace=False)]
+    IJ += [(int(i), int(j)) for i, j in rng.integers(0, dm.num_dofs, (nsample, 2))]
+    # neighbouring DoFs (sharing a cell)
+    dofs = np.array(dm.dofs)
+    for c in rng.choice(mesh.num_cells, nsample, replace=False):
+        d = dofs[c][dofs[c] >= 0]
+        if d.shape[0] >= 2:
+            IJ.append((int(d[0]), int(d[1])))
+    IJ = np.array(IJ, dtype=np.int64)
+    vals = np.array([b.getEntry(int(i), int(j)) for i, j in IJ])
+    diag = np.array(b.getDiagonal().data)
+    out.update(s=s, target_order=0.5, IJ=IJ, entries=vals, diagonal=diag)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, dm.num_dofs, vals[:3], diag[:3])
+
+
 def varconst_case(noRef, s, name):
     """variable-order code path of the reference with s(x,y) = const (config 4): dense matrix only"""
     from PyNucleus_nl.fractionalOrders import variableConstFractionalOrder
@@ -376,6 +403,9 @@ if __name__ == '__main__':
     if 'all' in which or 'dm2' in which:
         dm2_case(2, 0.75, 'disc_dm2_s0.75_r2')
         dm2_case(3, 0.25, 'disc_dm2_s0.25_r3')
+    if 'all' in which or 'entry' in which:
+        entry_case(2, 3, 0.75, 'entry_disc_s0.75_r3')
+        entry_case(1, 6, 0.25, 'entry_interval_s0.25_r6')
     if 'all' in which or 'varconst' in which:
         varconst_case(2, 0.75, 'disc_varconst0.75_r2')
         varconst_case(3, 0.4, 'disc_varconst0.4_r3')

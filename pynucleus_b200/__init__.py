@@ -7,7 +7,7 @@ from .dofmap import P1_DoFMap  # noqa: F401
 from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder, variableConstFractionalOrder, leftRightFractionalOrder,  # noqa: F401
                       constantFractionalLaplacianScaling, FRACTIONAL)
 from .assembly import nonlocalBuilder, assembleNonlocalOperator  # noqa: F401
-from .linear_operators import Dense_LinearOperator  # noqa: F401
+from .linear_operators import Dense_LinearOperator, diagonalOperator  # noqa: F401
 from .solvers import cg, DistributedDenseOperator  # noqa: F401
 
 __version__ = '0.1.0'

@@ -404,6 +404,37 @@ class nonlocalBuilder:
         self._no_dm2()
         return h2.assemble_clusters(self, Pnear)
 
+    def getEntry(self, I, J):
+        """single entry a(phi_I, phi_J) (nonlocalAssembly_{SCALAR}.pxi:1539-1660, constant kernel): the bilinear form
+        over (supp phi_I u supp phi_J)^2 plus the surface integral around that patch instead of the rest of the space
+        -- the near-field block of the cluster pair ({I}, {J}), assembled by the device path on the patch sub-mesh."""
+        return float(self.getEntries(np.array([[I, J]]))[0])
+
+    def getEntries(self, IJ):
+        """getEntry for many (I, J) pairs at once, returns a numpy vector"""
+        IJ = np.asarray(IJ, dtype=np.int64).reshape(-1, 2)
+        if IJ.size and (IJ.min() < 0 or IJ.max() >= self.dm.num_dofs):
+            raise IndexError('DoF index out of range')
+
+        class _single:
+            # single-DoF cluster; ids are unique per DoF so that patches are built once
+            def __init__(self, i):
+                self.id, self.dofs = int(i), np.array([i], dtype=np.int64)
+        nodes = {}
+        Pnear = [(nodes.setdefault(int(i), _single(i)), nodes.setdefault(int(j), _single(j))) for i, j in IJ]
+        near = self.assembleClusters(Pnear)
+        import torch
+        if not near.blocks:
+            return np.zeros(0)
+        return torch.cat([B.reshape(-1) for _, _, B in near.blocks]).cpu().numpy()
+
+    def getDiagonal(self):
+        """diagonal of the operator entry by entry (nonlocalAssembly_{SCALAR}.pxi:2269-2289); like the reference's it is
+        integrated patch-wise (getEntry) and differs from diag(getDense()) by the quadrature error only"""
+        from .linear_operators import diagonalOperator
+        idx = np.arange(self.dm.num_dofs)
+        return diagonalOperator(self.getEntries(np.stack((idx, idx), axis=1)))
+
     def getH2(self, returnNearField=False, returnTree=False):
         """H2 operator (nonlocalAssembly_{SCALAR}.pxi:3094-3219): cluster tree, admissible pairs, leaf moments and transfer
         operators as in the reference (node for node), far-field kernel blocks from the CUDA kernel, near field per

@@ -104,3 +104,43 @@ class Dense_LinearOperator:
 
     def __repr__(self):
         return '<{}x{} Dense_LinearOperator on cuda:{}>'.format(self.num_rows, self.num_columns, self.device_index)
+
+
+class diagonalOperator:
+    """Diagonal operator (base/PyNucleus_base/LinearOperator_{SCALAR}.pxi, diagonalOperator): ``data`` is the diagonal.
+    Returned by nonlocalBuilder.getDiagonal(); N numbers, kept on the host (Jacobi scaling for the Krylov solvers)."""
+
+    def __init__(self, diagonal):
+        self.data = np.ascontiguousarray(diagonal, dtype=np.float64)
+        self.num_rows = self.num_columns = int(self.data.shape[0])
+
+    shape = property(lambda self: (self.num_rows, self.num_columns))
+    diagonal = property(lambda self: self.data)
+
+    def matvec(self, x, y=None):
+        if isinstance(x, torch.Tensor):
+            r = torch.as_tensor(self.data, device=x.device)*x
+            if y is not None:
+                y.copy_(r)
+            return r if y is None else y
+        r = self.data*np.asarray(x)
+        if y is not None:
+            y[:] = r
+            return y
+        return r
+
+    __call__ = matvec
+    dot = matvec
+    __mul__ = matvec
+
+    def toarray(self):
+        return np.diag(self.data)
+
+    def getEntry(self, i, j):
+        return float(self.data[i]) if i == j else 0.
+
+    def isSparse(self):
+        return True
+
+    def getMemorySize(self):
+        return self.data.nbytes

@@ -561,3 +561,26 @@ def test_tiny_meshes_vs_oracle(noRef):
     ref = P.dense(True)
     assert A.shape == ref.shape == (dm.num_dofs, dm.num_dofs)
     assert np.abs(A-ref).max() < TOL*np.abs(ref).max()
+
+
+@pytest.mark.parametrize('name', ['entry_disc_s0.75_r3', 'entry_interval_s0.25_r6'])
+def test_single_entries_and_diagonal_vs_reference(golden_dir, name):
+    """getEntry / getDiagonal (nonlocalAssembly_{SCALAR}.pxi:1539-1660, 2269-2289) against the reference's values"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    dim = g['vertices'].shape[1]
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices'].reshape(-1, 1)
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=bf)
+    dm = pb.P1_DoFMap(mesh)
+    assert np.array_equal(np.where(dm.dofs >= 0, dm.dofs, -1), np.where(g['dofs'] >= 0, g['dofs'], -1))
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, float(g['s'])), {'target_order': float(g['target_order'])})
+    scale = np.abs(g['diagonal']).max()
+    vals = b.getEntries(g['IJ'])
+    assert (np.abs(vals-g['entries'])/np.maximum(np.abs(g['entries']), 1e-2*scale)).max() < TOL
+    I, J = (int(v) for v in g['IJ'][-1])
+    assert abs(b.getEntry(I, J)-g['entries'][-1]) < TOL*max(abs(g['entries'][-1]), 1e-2*scale)
+    D = b.getDiagonal()
+    assert D.shape == (dm.num_dofs, dm.num_dofs)
+    assert np.abs(D.data/g['diagonal']-1).max() < TOL
+    x = np.arange(1., dm.num_dofs+1)
+    assert np.array_equal(D*x, D.data*x)

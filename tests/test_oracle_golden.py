@@ -215,3 +215,25 @@ def test_piecewise_variable_order_matches_reference(golden_dir, name):
             assert P.orders['qod'] == int(g['quad_order_diagonal']) and P.orders['qodV'] == int(g['quad_order_diagonalV'])
             A = A+P.dense(ze)
         assert np.abs(A-g[key]).max() < 1e-13*np.abs(g[key]).max()
+
+
+@pytest.mark.parametrize('name', ['entry_disc_s0.75_r3', 'entry_interval_s0.25_r6'])
+def test_single_entries_match_reference(golden_dir, name):
+    """getEntry / getDiagonal (nonlocalAssembly_{SCALAR}.pxi:1539-1660, 2269-2289): the form over the patch of the two
+    basis functions plus the surface integral around the patch.  Restated as the dense operator of the patch sub-mesh
+    with the quadrature parameters (hmin, diam, DoF count) of the whole problem."""
+    g = load(golden_dir, name)
+    dofs, N = g['dofs'], int(g['num_dofs'])
+
+    def entry(I, J):
+        patch = np.where(((dofs == I) | (dofs == J)).any(axis=1))[0]
+        sub = np.where(dofs[patch] == I, 0, np.where(dofs[patch] == J, 1, -1))
+        P = oracle.Problem(g['vertices'], g['cells'][patch], sub, 2, float(g['s']), target_order=float(g['target_order']),
+                           hVector=g['hVector'][patch], volVector=g['volVector'][patch], hmin=float(g['hmin']),
+                           diam=float(g['diam']), order_num_dofs=N)
+        return P.dense(True)[0, 0 if I == J else 1]
+    scale = np.abs(g['diagonal']).max()
+    for (I, J), ref in zip(g['IJ'], g['entries']):
+        assert abs(entry(I, J)-ref) < 1e-12*max(abs(ref), 1e-2*scale)
+    for I in range(0, N, max(1, N//8)):
+        assert abs(entry(I, I)/g['diagonal'][I]-1) < 1e-12
