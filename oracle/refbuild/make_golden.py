@@ -257,6 +257,49 @@ def entry_case(dim, noRef, s, name, nsample=10):
     print(name, dm.num_dofs, vals[:3], diag[:3])
 
 
+def solver_case(noRef, s, name):
+    """Krylov solvers of the reference (base/PyNucleus_base/solvers.pyx: cg_solver :329-445, gmres_solver :458-660) with
+    the Jacobi preconditioner (invDiagonal) on the assembled operator: solutions and residual histories"""
+    from PyNucleus_base.solvers import cg_solver, gmres_solver
+    from PyNucleus_base.linear_operators import invDiagonal
+    mesh = uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    out = mesh_arrays(mesh, dm)
+    kernel = getFractionalKernel(2, constFractionalOrder(s), np.inf)
+    A = nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense()
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(dm.num_dofs)
+    out.update(s=s, target_order=0.5, b=b)
+    for tag, prec in (('', True), ('_noprec', False)):
+        cg = cg_solver(A)
+        if prec:
+            cg.setPreconditioner(invDiagonal(A))
+        cg.tolerance = 1e-10
+        cg.maxIter = 200
+        cg.setup()
+        x = np.zeros(dm.num_dofs)
+        its = cg(b, x)
+        out.update({'cg_x'+tag: x.copy(), 'cg_iterations'+tag: its, 'cg_residuals'+tag: np.array(cg.residuals)})
+        for left in (True, False):
+            gm = gmres_solver(A)
+            if prec:
+                gm.setPreconditioner(invDiagonal(A), left)
+            gm.tolerance = 1e-10
+            gm.maxIter = 12
+            gm.restarts = 20
+            gm.setup()
+            x = np.zeros(dm.num_dofs)
+            its = gm(b, x)
+            key = 'gmres_'+('left' if left else 'right')+tag
+            out.update({key+'_x': x.copy(), key+'_iterations': its, key+'_residuals': np.array(gm.residuals)})
+            print(key, its, len(gm.residuals), gm.residuals[-1])
+        print('cg'+tag, its, len(cg.residuals), cg.residuals[-1])
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, dm.num_dofs)
+
+
 def varconst_case(noRef, s, name):
     """variable-order code path of the reference with s(x,y) = const (config 4): dense matrix only"""
     from PyNucleus_nl.fractionalOrders import variableConstFractionalOrder
@@ -406,6 +449,8 @@ if __name__ == '__main__':
     if 'all' in which or 'entry' in which:
         entry_case(2, 3, 0.75, 'entry_disc_s0.75_r3')
         entry_case(1, 6, 0.25, 'entry_interval_s0.25_r6')
+    if 'all' in which or 'solvers' in which:
+        solver_case(3, 0.75, 'solvers_disc_s0.75_r3')
     if 'all' in which or 'varconst' in which:
         varconst_case(2, 0.75, 'disc_varconst0.75_r2')
         varconst_case(3, 0.4, 'disc_varconst0.4_r3')

@@ -8,6 +8,6 @@ from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFra
                       constantFractionalLaplacianScaling, FRACTIONAL)
 from .assembly import nonlocalBuilder, assembleNonlocalOperator  # noqa: F401
 from .linear_operators import Dense_LinearOperator, diagonalOperator  # noqa: F401
-from .solvers import cg, DistributedDenseOperator  # noqa: F401
+from .solvers import cg, gmres, DistributedDenseOperator  # noqa: F401
 
 __version__ = '0.1.0'

@@ -231,6 +231,12 @@ class H2Matrix:
             return y
         return out
 
+    def diagonal_device(self):
+        """diagonal of the operator = diagonal of the near field (H2Matrix.diagonal, clusterMethodCy.pyx)"""
+        return self.Anear.diagonal_device()
+
+    diagonal = property(lambda self: self.diagonal_device().cpu().numpy())
+
     def matvec(self, x, y=None):
         import torch
         if isinstance(x, torch.Tensor):
@@ -305,8 +311,18 @@ class nearFieldBlocks:
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
-            self._csr = torch.sparse_coo_tensor(torch.stack((r, c)), v, size=(self.num_dofs, self.num_dofs),
-                                                check_invariants=False).coalesce().to_sparse_csr()
+            coo = torch.sparse_coo_tensor(torch.stack((r, c)), v, size=(self.num_dofs, self.num_dofs),
+                                          check_invariants=False).coalesce()
+            self._csr = coo.to_sparse_csr()
+        idx, val = coo.indices(), coo.values()
+        on = idx[0] == idx[1]
+        self._diag = torch.zeros(self.num_dofs, dtype=torch.float64, device=self.device)
+        self._diag[idx[0][on]] = val[on]
+
+    def diagonal_device(self):
+        if getattr(self, '_diag', None) is None:
+            self.compile()
+        return self._diag
 
     def matvec_device(self, x):
         import torch

@@ -52,31 +52,149 @@ class DistributedDenseOperator:
         return d
 
 
-def cg(A, b, x0=None, tol=1e-8, maxiter=1000, jacobi=True):
-    """Preconditioned conjugate gradients, x and b float64 CUDA tensors (or numpy arrays, copied).
-    Returns (x, iterations, residual norms)."""
+def _device_of(A):
+    return A.device_data.device if hasattr(A, 'device_data') else A.device
+
+
+def _jacobi(A, dev):
+    """1/diag(A) on the device (jacobi_solver / invDiagonal, base/PyNucleus_base/solvers.pyx:229-246)"""
+    if hasattr(A, 'diagonal_device'):
+        d = A.diagonal_device()
+    elif hasattr(A, 'device_data'):
+        d = torch.diagonal(A.device_data).clone()
+    else:
+        d = torch.as_tensor(np.ascontiguousarray(A.diagonal, dtype=np.float64)).to(dev)
+    return 1.0/d
+
+
+def _setup(A, b, x0, precond, jacobi):
     host = not isinstance(b, torch.Tensor)
-    dev = A.device_data.device if hasattr(A, 'device_data') else A.device
+    dev = _device_of(A)
     bt = torch.as_tensor(np.ascontiguousarray(b, dtype=np.float64)).to(dev) if host else b
-    x = torch.zeros_like(bt) if x0 is None else (torch.as_tensor(x0).to(dev) if host else x0.clone())
-    if jacobi:
-        d = A.diagonal_device() if hasattr(A, 'diagonal_device') else torch.diagonal(A.device_data).clone()
-        Minv = 1.0/d
-    r = bt-A.matvec_device(x)
-    z = Minv*r if jacobi else r
-    p = z.clone()
-    rz = torch.dot(r, z)
-    res = [float(torch.sqrt(torch.abs(rz)))]
-    it = 0
-    while it < maxiter and res[-1] > tol:
-        Ap = A.matvec_device(p)
-        alpha = rz/torch.dot(p, Ap)
-        x += alpha*p
-        r -= alpha*Ap
-        z = Minv*r if jacobi else r
-        rz_new = torch.dot(r, z)
-        p = z+(rz_new/rz)*p
-        rz = rz_new
-        res.append(float(torch.sqrt(torch.abs(rz))))
-        it += 1
-    return (x.cpu().numpy() if host else x), it, res
+    if x0 is None:
+        x = torch.zeros_like(bt)
+    else:
+        x = torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64)).to(dev) if not isinstance(x0, torch.Tensor) else x0.clone()
+    if precond is None and jacobi:
+        Minv = _jacobi(A, dev)
+        precond = lambda v: Minv*v        # noqa: E731
+    return host, bt, x, precond
+
+
+def cg(A, b, x0=None, tol=1e-8, maxiter=1000, jacobi=True, relative=False, use2norm=False, precond=None):
+    """Preconditioned conjugate gradients on the device, following cg_solver.solve step by step
+    (base/PyNucleus_base/solvers.pyx:364-445): stopping rule on sqrt(<r, M^-1 r>) (or the 2-norm with use2norm),
+    absolute tolerance or relative to the initial residual (relative=True, :296-301), residual recomputed every 50
+    iterations.  b, x0: float64 CUDA tensors or numpy arrays (copied); precond: callable on device vectors (default:
+    Jacobi when jacobi=True).  Returns (x, iterations, residuals) with the reference's return value and history."""
+    host, bt, x, precond = _setup(A, b, x0, precond, jacobi)
+    r = bt-A.matvec_device(x) if x0 is not None else bt.clone()
+    if relative:
+        tol = tol*float(torch.linalg.vector_norm(r))
+    if precond is None:
+        p = r.clone()
+        beta_old = torch.dot(r, p)
+        crit = float(torch.sqrt(beta_old))
+    else:
+        p = precond(r)
+        beta_old = torch.dot(r, p)
+        crit = float(torch.linalg.vector_norm(r)) if use2norm else float(torch.sqrt(torch.abs(beta_old)))
+    res = [crit]
+    its, k = maxiter, 0
+    if crit <= tol:
+        its = 0
+    else:
+        for i in range(maxiter):
+            Ap = A.matvec_device(p)
+            alpha = beta_old/torch.dot(p, Ap)
+            x += alpha*p
+            r -= alpha*Ap
+            if k == 50:
+                r = bt-A.matvec_device(x)
+                k = 0
+            if precond is None:
+                nr = torch.linalg.vector_norm(r)
+                crit = float(nr)
+                beta = nr*nr
+                z = r
+            else:
+                z = precond(r)
+                beta = torch.dot(r, z)
+                crit = float(torch.linalg.vector_norm(r)) if use2norm else float(torch.sqrt(torch.abs(beta)))
+            res.append(crit)
+            if crit <= tol:
+                its = i
+                break
+            p = z+(beta/beta_old)*p
+            beta_old = beta
+            k += 1
+    return (x.cpu().numpy() if host else x), its, res
+
+
+def gmres(A, b, x0=None, tol=1e-8, maxiter=30, restarts=1, jacobi=True, left=True, relative=False, precond=None):
+    """Restarted GMRES on the device, following gmres_solver.solve (base/PyNucleus_base/solvers.pyx:504-660): modified
+    Gram-Schmidt Arnoldi, Givens rotations, left or right preconditioning, residual history |gamma_i|, the same
+    iteration count (sum over the cycles of the last Arnoldi index).  The Krylov basis and the operator stay on the
+    device; the (maxiter+1) x maxiter Hessenberg matrix is rotated on the host (one transfer of a column per step).
+    Returns (x, iterations, residuals)."""
+    host, bt, x, precond = _setup(A, b, x0, precond, jacobi)
+    dev, n = bt.device, bt.shape[0]
+    do_l = precond is not None and left
+    do_r = precond is not None and not left
+    if relative:
+        tol = tol*float(torch.linalg.vector_norm(bt-A.matvec_device(x) if x0 is not None else bt))
+    eps = 1e-15
+    Q = torch.empty((maxiter+1, n), dtype=torch.float64, device=dev)
+    H = np.ones((maxiter+1, maxiter))
+    c, s_, gamma, y = np.zeros(maxiter), np.zeros(maxiter), np.zeros(maxiter+1), np.zeros(maxiter+1)
+    res, all_iter, breakout = [], 0, False
+    for _ in range(restarts):
+        if breakout:
+            break
+        r = bt-A.matvec_device(x)
+        if do_l:
+            r = precond(r)
+        gamma[0] = float(torch.linalg.vector_norm(r))
+        if not res:
+            res.append(abs(gamma[0]))
+        if abs(gamma[0]) < tol:
+            break
+        Q[0] = r/gamma[0]
+        i = -1
+        for i in range(maxiter):
+            if do_l:
+                r = precond(A.matvec_device(Q[i]))
+            elif do_r:
+                r = A.matvec_device(precond(Q[i]))
+            else:
+                r = A.matvec_device(Q[i]).clone()
+            h = torch.empty(i+2, dtype=torch.float64, device=dev)
+            for j in range(i+1):
+                h[j] = torch.dot(Q[j], r)
+                r -= h[j]*Q[j]
+            h[i+1] = torch.linalg.vector_norm(r)
+            H[:i+2, i] = h.cpu().numpy()
+            if abs(H[i+1, i]) > eps:
+                Q[i+1] = r/H[i+1, i]
+            else:
+                breakout = True
+                break
+            for j in range(i):
+                rho, sigma = H[j, i], H[j+1, i]
+                H[j, i] = c[j]*rho+s_[j]*sigma
+                H[j+1, i] = -s_[j]*rho+c[j]*sigma
+            beta = np.sqrt(H[i, i]**2+H[i+1, i]**2)
+            c[i], s_[i] = H[i, i]/beta, H[i+1, i]/beta
+            H[i, i] = beta
+            gamma[i+1] = -s_[i]*gamma[i]
+            gamma[i] = c[i]*gamma[i]
+            res.append(abs(gamma[i+1]))
+            if abs(gamma[i+1]) < tol:
+                breakout = True
+                break
+        all_iter += i
+        for j in range(i, -1, -1):
+            y[j] = (gamma[j]-H[j, j+1:i+1].dot(y[j+1:i+1]))/H[j, j]
+        upd = torch.as_tensor(y[:i+1], device=dev) @ Q[:i+1]
+        x += precond(upd) if do_r else upd
+    return (x.cpu().numpy() if host else x), all_iter, res

@@ -93,6 +93,10 @@ def _cg_worker(rank, world, port, q):
     rhs = torch.from_numpy(rng.standard_normal(N))
     u, its, res = cg(op, rhs, tol=1e-12, maxiter=500)
     ok_cg = float((A.mv(u)-rhs).abs().max()) < 1e-9
+    from pynucleus_b200.solvers import gmres
+    for left in (True, False):
+        v, gits, gres = gmres(op, rhs, tol=1e-11, maxiter=20, restarts=30, left=left)
+        ok_cg = ok_cg and float((A.mv(v)-rhs).abs().max()) < 1e-8 and float((u-v).abs().max()) < 1e-9
     q.put((rank, bool(ok_mv), bool(ok_diag), bool(ok_cg), its))
     dist.destroy_process_group()
 
@@ -111,3 +115,33 @@ def test_distributed_matvec_and_cg_gloo():
         p.join(timeout=60)
     assert all(r[1] and r[2] and r[3] for r in res), res
     assert res[0][4] == res[1][4]
+
+
+class _HostOperator:
+    """dense operator on the CPU with the interface the Krylov loops use (the CUDA matvec cannot run here)"""
+
+    def __init__(self, A):
+        self.device_data = torch.from_numpy(np.ascontiguousarray(A))
+
+    def matvec_device(self, x, y=None):
+        return torch.mv(self.device_data, x)
+
+
+def test_krylov_loops_follow_the_reference(golden_dir):
+    """cg / gmres (solvers.py) against the residual histories, iteration counts and solutions of the reference's
+    cg_solver / gmres_solver (base/PyNucleus_base/solvers.pyx:329-660) on the reference's own operator"""
+    from pynucleus_b200.solvers import cg, gmres
+    g = np.load(os.path.join(golden_dir, 'solvers_disc_s0.75_r3.npz'))
+    A = _HostOperator(np.load(os.path.join(golden_dir, 'disc_s0.75_r3.npz'))['A'])
+    b = torch.from_numpy(g['b'])
+    for tag, jac in (('', True), ('_noprec', False)):
+        x, its, res = cg(A, b, tol=1e-10, maxiter=200, jacobi=jac)
+        assert its == int(g['cg_iterations'+tag]) and len(res) == len(g['cg_residuals'+tag])
+        assert np.abs(np.array(res)/g['cg_residuals'+tag]-1).max() < 1e-6
+        assert np.abs(x.numpy()-g['cg_x'+tag]).max() < 1e-10*np.abs(g['cg_x'+tag]).max()
+        for left in (True, False):
+            key = 'gmres_'+('left' if left else 'right')+tag
+            x, its, res = gmres(A, b, tol=1e-10, maxiter=12, restarts=20, jacobi=jac, left=left)
+            assert its == int(g[key+'_iterations']) and len(res) == len(g[key+'_residuals'])
+            assert np.abs(np.array(res)/g[key+'_residuals']-1).max() < 1e-6
+            assert np.abs(x.numpy()-g[key+'_x']).max() < 1e-10*np.abs(g[key+'_x']).max()

@@ -584,3 +584,37 @@ def test_single_entries_and_diagonal_vs_reference(golden_dir, name):
     assert np.abs(D.data/g['diagonal']-1).max() < TOL
     x = np.arange(1., dm.num_dofs+1)
     assert np.array_equal(D*x, D.data*x)
+
+
+def test_krylov_loops_on_device(golden_dir):
+    """device CG / GMRES on the assembled operators: residual histories, iteration counts and solutions
+    of the reference's cg_solver / gmres_solver (base/PyNucleus_base/solvers.pyx:329-660); then the same loops on the
+    H2 operator"""
+    import torch
+    import pynucleus_b200 as pb
+    g = load(golden_dir, 'solvers_disc_s0.75_r3')
+    b = builder_from_golden(load(golden_dir, 'disc_s0.75_r3'))
+    A = b.getDense()
+    rhs = torch.as_tensor(g['b']).cuda()
+    for tag, jac in (('', True), ('_noprec', False)):
+        x, its, res = pb.cg(A, rhs, tol=1e-10, maxiter=200, jacobi=jac)
+        assert its == int(g['cg_iterations'+tag]) and len(res) == len(g['cg_residuals'+tag])
+        assert np.abs(np.array(res)/g['cg_residuals'+tag]-1).max() < 1e-6
+        assert np.abs(x.cpu().numpy()-g['cg_x'+tag]).max() < 1e-10*np.abs(g['cg_x'+tag]).max()
+        for left in (True, False):
+            key = 'gmres_'+('left' if left else 'right')+tag
+            x, its, res = pb.gmres(A, rhs, tol=1e-10, maxiter=12, restarts=20, jacobi=jac, left=left)
+            assert its == int(g[key+'_iterations']) and len(res) == len(g[key+'_residuals'])
+            assert np.abs(np.array(res)/g[key+'_residuals']-1).max() < 1e-6
+            assert np.abs(x.cpu().numpy()-g[key+'_x']).max() < 1e-10*np.abs(g[key+'_x']).max()
+    # H2 operator of the r=4 mesh: Jacobi from the near-field diagonal; solution close to the dense solve
+    g4 = load(golden_dir, 'h2_disc_s0.75_r4')
+    b4 = builder_from_golden(g4)
+    H, A4 = b4.getH2(), b4.getDense()
+    assert np.abs(H.diagonal/A4.diagonal-1).max() < 1e-3
+    rhs = torch.as_tensor(g4['x']).cuda()
+    xd, _, _ = pb.cg(A4, rhs, tol=1e-10, maxiter=500)
+    xh, its, res = pb.cg(H, rhs, tol=1e-10, maxiter=500)
+    xg, _, _ = pb.gmres(H, rhs, tol=1e-10, maxiter=30, restarts=20)
+    assert float((xh-xd).abs().max()) < 1e-3*float(xd.abs().max())
+    assert float((xh-xg).abs().max()) < 1e-7*float(xd.abs().max())
