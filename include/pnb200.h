@@ -196,6 +196,12 @@ int pnb_dense_cell_blocks(pnb_problem *p, double **device_ptr, int64_t *count);
 int pnb_dense_cell_blocks_copy(pnb_problem *p, double *device_buf, int to_problem);
 int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row_end, double *A_rows, int64_t ld);
 
+/* Zero-exterior surface terms alone (the facet loop nonlocalAssembly_{SCALAR}.pxi:1430-1448 without the cell pairs):
+ * per cell the upper triangle (row-major) of its symmetric (dim+1) x (dim+1) block, num_cells x (dim+1)(dim+2)/2
+ * doubles written to HOST memory.  The H2 near field of the regional operator (zeroExterior=False) subtracts them
+ * (assembleClusters, nonlocalAssembly_{SCALAR}.pxi:1889-1912). */
+int pnb_boundary_cell_blocks(pnb_problem *p, double *host_out);
+
 /* Counters of the last pnb_dense_assemble call: [0] evaluated cell pairs (2D whole-operator path: every pair
  * once; DoF-tile path: with tile-halo redundancy), [1] distinct cell pairs c1<=c2 that are not skipped,
  * [2] kernel launches, [3] pairs of the near evaluator, [4] pairs of the uniform order-2 units, [5..] reserved.

@@ -405,6 +405,47 @@ def h2_case(dim, noRef, s, name, max_far=60):
     print(name, H)
 
 
+def h2_regional_case(dim, noRef, s, name):
+    """regional operator (zeroExterior=False): near field of getH2 (assembleClusters :1840-1912: surface terms around the
+    cluster unions minus the surface terms of the domain boundary), H2 / dense matvec, and getEntry values"""
+    if dim == 2:
+        mesh = uniform_disc()
+        params = {'target_order': 0.5}
+    else:
+        mesh = simpleInterval(-1, 1)
+        params = {}
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    kernel = getFractionalKernel(dim, constFractionalOrder(s), np.inf)
+    b = nonlocalBuilder(dm, kernel, params, zeroExterior=False)
+    H, Pnear = b.getH2(returnNearField=True)
+    out = mesh_arrays(mesh, dm)
+    out.update(s=s, target_order=params.get('target_order', np.nan), repr=str(H))
+    out['near_pairs'] = np.array([(cP.n1.id, cP.n2.id) for cP in Pnear], dtype=np.int64)
+    An = H.Anear
+    out['Anear_indptr'] = np.array(An.indptr)
+    out['Anear_indices'] = np.array(An.indices)
+    out['Anear_data'] = np.array(An.data)
+    out['Anear_diagonal'] = np.array(An.diagonal)
+    out['Anear_type'] = An.__class__.__name__
+    x = np.sin(np.arange(dm.num_dofs)*0.37)+0.1
+    out['x'] = x
+    out['Hx'] = H*x
+    out['Ax'] = np.array(b.getDense().data).dot(x)
+    rng = np.random.default_rng(5)
+    IJ = [(int(i), int(i)) for i in rng.choice(dm.num_dofs, 6, replace=False)]
+    dofs = np.array(dm.dofs)
+    for c in rng.choice(mesh.num_cells, 6, replace=False):
+        d = dofs[c][dofs[c] >= 0]
+        if d.shape[0] >= 2:
+            IJ.append((int(d[0]), int(d[1])))
+    out['IJ'] = np.array(IJ, dtype=np.int64)
+    out['entries'] = np.array([b.getEntry(i, j) for i, j in IJ])
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, H, An.__class__.__name__)
+
+
 def kernel_values():
     """closed-form style spot values straight from the reference kernels"""
     rng = np.random.RandomState(2)
@@ -457,5 +498,8 @@ if __name__ == '__main__':
     if 'all' in which or 'h2' in which:
         h2_case(2, 4, 0.75, 'h2_disc_s0.75_r4')
         h2_case(1, 8, 0.25, 'h2_interval_s0.25_r8')
+    if 'all' in which or 'h2regional' in which:
+        h2_regional_case(2, 4, 0.75, 'h2_regional_disc_s0.75_r4')
+        h2_regional_case(1, 8, 0.25, 'h2_regional_interval_s0.25_r8')
     if 'all' in which or 'kernels' in which:
         kernel_values()

@@ -53,7 +53,8 @@ EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_cre
            'pnb_local_matrices', 'pnb_far_max_order', 'pnb_dense_assemble', 'pnb_dense_stats',
            'pnb_dense_timings', 'pnb_dense_matvec', 'pnb_fp64_peak', 'pnb_row_granularity', 'pnb_dense_rows_begin',
            'pnb_dense_cell_blocks', 'pnb_dense_cell_blocks_copy', 'pnb_dense_rows_end', 'pnb_farfield_blocks',
-           'pnb_release_cached_memory', 'pnb_dense_partial_begin', 'pnb_dense_kernel_timings']
+           'pnb_release_cached_memory', 'pnb_dense_partial_begin', 'pnb_dense_kernel_timings',
+           'pnb_boundary_cell_blocks']
 
 _LIB = None
 
@@ -94,6 +95,7 @@ def lib():
         L.pnb_dense_rows_end.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64]
         L.pnb_dense_cell_blocks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), c_int64_p]
         L.pnb_dense_cell_blocks_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.pnb_boundary_cell_blocks.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.pnb_farfield_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p]

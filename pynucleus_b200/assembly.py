@@ -422,7 +422,9 @@ class nonlocalBuilder:
                 self.id, self.dofs = int(i), np.array([i], dtype=np.int64)
         nodes = {}
         Pnear = [(nodes.setdefault(int(i), _single(i)), nodes.setdefault(int(j), _single(j))) for i, j in IJ]
-        near = self.assembleClusters(Pnear)
+        from . import h2
+        self._no_dm2()
+        near = h2.assemble_clusters(self, Pnear, entries=True)
         import torch
         if not near.blocks:
             return np.zeros(0)

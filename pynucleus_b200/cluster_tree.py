@@ -114,6 +114,7 @@ class tree_node:
             self.interpolation_order = rp.interpolation_order
         self._num_dofs = dofs.shape[0]
         self.irregularLevelsOffset = 0
+        self._unsplittable = False
 
     isLeaf = property(lambda self: len(self.children) == 0)
     num_dofs = property(lambda self: self._num_dofs)
@@ -161,11 +162,14 @@ class tree_node:
 
     # ---- median bisection -----------------------------------------------------------------------------------
     def refine(self, recursive=True):
+        if self._unsplittable:
+            return
         boxes, coords, hVector, rp = self.data
         dofs = self._dofs
         n0 = dofs.shape[0]
         limit_levels, limit_size = rp.maxLevels, rp.minSize
         if (self.levelNo+1 >= limit_levels) or (n0 <= limit_size):
+            self._unsplittable = True
             return
         dim = self.dim
         if dim == 1:
@@ -191,6 +195,7 @@ class tree_node:
         for k, sel in enumerate((first, ~first)):
             d = dofs[sel]
             if not (d.shape[0] >= rp.minSize and d.shape[0] < n0):
+                self._unsplittable = True         # the admissibility search asks again for every partner cluster
                 return
             c = tree_node(self, d, self.data, mixed_node=self.mixed_node)
             if lvl > 0:

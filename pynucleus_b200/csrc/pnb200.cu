@@ -2285,6 +2285,33 @@ extern "C" int pnb_dense_cell_blocks_copy(pnb_problem *p, double *device_buf, in
     return 0;
 }
 
+// Zero-exterior surface terms alone: per cell the symmetric (dim+1) x (dim+1) block (upper triangle, row-major,
+// num_cells x (dim+1)(dim+2)/2 doubles, host buffer) of sum over the boundary facets.  The H2 near field of the
+// regional operator subtracts these (assembleClusters, nonlocalAssembly_{SCALAR}.pxi:1889-1912).
+extern "C" int pnb_boundary_cell_blocks(pnb_problem *p, double *host_out)
+{
+    if (!p || !host_out) return fail(PNB_ERR_ARG, "null argument");
+    if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
+    CK(cudaSetDevice(p->device));
+    const int nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
+    TileSched &S = p->S;
+    S.own_t0 = 0;
+    S.own_t1 = S.ntiles;
+    CK(cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * ND * sizeof(double)));
+    CK(cudaMemsetAsync(S.err, 0, 4 * sizeof(int)));
+    if (p->nb > 0) {
+        const unsigned blocks = (unsigned)(((size_t)nc * 32 + 255) / 256);
+        if (p->dim == 2) boundary_kernel<2><<<blocks, 256>>>(p->P, S);
+        else boundary_kernel<1><<<blocks, 256>>>(p->P, S);
+        CK(cudaGetLastError());
+    }
+    int herr[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(herr, S.err, sizeof(herr), cudaMemcpyDeviceToHost));
+    if (herr[0] > 0) return fail(PNB_ERR_ORDER, "regular quadrature order " + std::to_string(herr[0]) + " exceeds the supplied tables (max_order " + std::to_string(p->P.max_order) + ")");
+    CK(cudaMemcpy(host_out, S.Dbnd, (size_t)nc * ND * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // scatter of the cell-diagonal blocks into the owned rows; collects errors, counters and timings
 extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row_end, double *dA, int64_t ld)
 {

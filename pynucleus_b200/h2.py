@@ -8,9 +8,10 @@ Restates, on top of `cluster_tree`:
   * far-field blocks                 nonlocalBuilder.getFarFieldBlocks (CUDA kernel, pnb_farfield_blocks)
 
 The cluster bases are small dense blocks (m^d <= a few hundred columns); they are built on the host with numpy and
-kept as float64 CUDA tensors, the passes run as torch matrix products on the device.  The near field of the reference
-(assembleClusters: cluster-union quadrature with surface terms, nonlocalAssembly_{SCALAR}.pxi:1663-2160) is NOT restated
-yet; `nearFromDense` fills the near pattern from the dense operator instead (validation / moderate sizes only).
+kept as float64 CUDA tensors, the passes run as sparse matrix products on the device.  The near field
+(assembleClusters: cluster-union quadrature with surface terms, nonlocalAssembly_{SCALAR}.pxi:1663-2160) is assembled
+per near cluster pair by the dense device path on the cluster-union sub-mesh (`assemble_clusters`); `nearFromDense`
+(the near pattern filled from the dense operator) is kept for validation only.
 """
 import numpy as np
 
@@ -295,6 +296,7 @@ class nearFieldBlocks:
     def __init__(self, num_dofs, device):
         self.num_dofs, self.device = num_dofs, device
         self.blocks = []        # (rows tensor, cols tensor, block tensor)
+        self.correction = None  # (rows, cols, values) of scattered entries added to the blocks
         self.nnz = 0
 
     def add(self, rows, cols, block):
@@ -308,6 +310,11 @@ class nearFieldBlocks:
         r = torch.cat([rr.repeat_interleave(cc.numel()) for rr, cc, B in self.blocks])
         c = torch.cat([cc.repeat(rr.numel()) for rr, cc, B in self.blocks])
         v = torch.cat([B.reshape(-1) for rr, cc, B in self.blocks])
+        if self.correction is not None:
+            # entries added on top of the blocks (only where the pattern has an entry: DoFs of one cell always are
+            # a near pair)
+            cr, cc_, cv = (torch.as_tensor(a, device=self.device) for a in self.correction)
+            r, c, v = torch.cat((r, cr)), torch.cat((c, cc_)), torch.cat((v, cv))
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
@@ -331,6 +338,9 @@ class nearFieldBlocks:
         y = torch.zeros(self.num_dofs, dtype=torch.float64, device=self.device)
         for r, c, B in self.blocks:
             y[r] += B.mv(x[c])
+        if self.correction is not None:
+            cr, cc_, cv = (torch.as_tensor(a, device=self.device) for a in self.correction)
+            y.index_add_(0, cr, cv*x[cc_])
         return y
 
     def toarray(self):
@@ -338,25 +348,29 @@ class nearFieldBlocks:
         A = torch.zeros((self.num_dofs, self.num_dofs), dtype=torch.float64, device=self.device)
         for r, c, B in self.blocks:
             A[r[:, None], c[None, :]] += B
+        if self.correction is not None:
+            cr, cc_, cv = (torch.as_tensor(a, device=self.device) for a in self.correction)
+            A.index_put_((cr, cc_), cv, accumulate=True)
         return A.cpu().numpy()
 
 
-def assemble_clusters(builder, Pnear):
+def assemble_clusters(builder, Pnear, entries=False):
     """Near field of the H2 operator (assembleClusters, nonlocalAssembly_{SCALAR}.pxi:1663-1889, constant kernel).
 
     For a near cluster pair (n1, n2) the reference integrates the bilinear form over D x D, D = the cells around the
     DoFs of n1 and n2, and replaces the rest of the space by a surface integral over the boundary of D
     (:1840-1889); it keeps the entries (i in n1, j in n2).  That is the dense operator of the sub-mesh D with the
     zero-exterior surface terms on its own boundary, with the quadrature parameters of the whole problem, so the
-    dense device path assembles it: one small problem per cluster pair, block rows n1 / columns n2 kept."""
+    dense device path assembles it: one small problem per cluster pair, block rows n1 / columns n2 kept.
+
+    entries=True: the getEntry flavour (:1539-1660) -- for the regional operator (zeroExterior=False) the reference
+    keeps the patch x patch part only, without surface terms and without the correction below."""
     import torch
     from .assembly import _Problem
     from .linear_operators import Dense_LinearOperator
     from .mesh import meshNd
     from . import _lib
     mesh, dm = builder.mesh, builder.dm
-    if not builder.zeroExterior:
-        raise NotImplementedError('near field of the regional operator (zeroExterior=False)')
     dev_index = builder.problem.device
     dev = torch.device('cuda', dev_index)
     out = nearFieldBlocks(dm.num_dofs, dev)
@@ -379,6 +393,7 @@ def assemble_clusters(builder, Pnear):
         cells_of(n1)
         cells_of(n2)
 
+    surface = 0 if (entries and not builder.zeroExterior) else 1
     template = [builder.problem]      # same kernel, orders and tables: the sub-problems share its table structures
 
     def work(pair):
@@ -403,7 +418,7 @@ def assemble_clusters(builder, Pnear):
             tl._pnb_stream = torch.cuda.Stream(dev)
         with torch.cuda.device(dev), torch.cuda.stream(tl._pnb_stream):
             A = torch.empty((n, n), dtype=torch.float64, device=dev)
-            _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, 1, 0, n, A.data_ptr(), A.stride(0), 1))
+            _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, surface, 0, n, A.data_ptr(), A.stride(0), 1))
             r = torch.as_tensor(np.searchsorted(union, d1), device=dev)
             c = torch.as_tensor(np.searchsorted(union, d2), device=dev)
             B = A[r[:, None], c[None, :]].contiguous()
@@ -424,4 +439,22 @@ def assemble_clusters(builder, Pnear):
             # the local matrices are symmetric: block (n2, n1)^T
             B = cache[(n2.id, n1.id)].t().contiguous()
         out.add(n1.dofs, n2.dofs, B)
+    if not builder.zeroExterior and not entries:
+        # regional operator: the blocks above hold the surface terms around the cluster unions, which stand for the
+        # whole complement of the union; take the part Omega^c out again (:1889-1912): minus the surface terms of
+        # the domain boundary, cell by cell, on the entries of the near pattern
+        import ctypes
+        nv = mesh.dim+1
+        D = np.zeros((mesh.num_cells, nv*(nv+1)//2))
+        _lib.check(_lib.lib().pnb_boundary_cell_blocks(builder.problem.handle, D.ctypes.data_as(ctypes.c_void_p)))
+        rows, cols, vals = [], [], []
+        k = 0
+        for p in range(nv):
+            for q in range(p, nv):
+                ok = (dm.dofs[:, p] >= 0) & (dm.dofs[:, q] >= 0) & (D[:, k] != 0)
+                rows.append(dm.dofs[ok, p]); cols.append(dm.dofs[ok, q]); vals.append(-D[ok, k])
+                if p != q:
+                    rows.append(dm.dofs[ok, q]); cols.append(dm.dofs[ok, p]); vals.append(-D[ok, k])
+                k += 1
+        out.correction = (np.concatenate(rows).astype(np.int64), np.concatenate(cols).astype(np.int64), np.concatenate(vals))
     return out

@@ -618,3 +618,27 @@ def test_krylov_loops_on_device(golden_dir):
     xg, _, _ = pb.gmres(H, rhs, tol=1e-10, maxiter=30, restarts=20)
     assert float((xh-xd).abs().max()) < 1e-3*float(xd.abs().max())
     assert float((xh-xg).abs().max()) < 1e-7*float(xd.abs().max())
+
+
+@pytest.mark.parametrize('name', ['h2_regional_interval_s0.25_r8', 'h2_regional_disc_s0.75_r4'])
+def test_h2_regional_operator(golden_dir, name):
+    """zeroExterior=False: the near field carries the surface terms around the cluster unions minus those of the domain
+    boundary (assembleClusters, nonlocalAssembly_{SCALAR}.pxi:1840-1912); getEntry keeps the patch part only"""
+    import scipy.sparse as sp
+    g = load(golden_dir, name)
+    b = builder_from_golden(g, zeroExterior=False)
+    H, Pnear = b.getH2(returnNearField=True)
+    assert np.array_equal(np.array([(a.id, c.id) for a, c in Pnear]), g['near_pairs'])
+    N = b.dm.num_dofs
+    low = sp.csr_matrix((g['Anear_data'], g['Anear_indices'], g['Anear_indptr']), shape=(N, N))
+    ref_near = (low+low.T+sp.diags(g['Anear_diagonal'])).toarray()
+    An = H.Anear.toarray()
+    assert np.array_equal(An != 0, ref_near != 0)
+    assert entry_err(An, ref_near) < TOL
+    Hx = H*g['x']
+    assert np.abs(Hx-g['Hx']).max() < 1e-11*np.abs(g['Hx']).max()
+    A = b.getDense()
+    assert np.abs(A*g['x']-g['Ax']).max() < TOL*np.abs(g['Ax']).max()
+    vals = b.getEntries(g['IJ'])
+    scale = np.abs(g['Anear_diagonal']).max()
+    assert (np.abs(vals-g['entries'])/np.maximum(np.abs(g['entries']), 1e-2*scale)).max() < TOL
