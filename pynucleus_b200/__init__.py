@@ -11,3 +11,4 @@ from .linear_operators import Dense_LinearOperator, diagonalOperator  # noqa: F4
 from .solvers import cg, gmres, DistributedDenseOperator  # noqa: F401
 
 __version__ = '0.1.0'
+from .multigrid import multigrid, hierarchy, buildRestrictionProlongation  # noqa: F401,E402

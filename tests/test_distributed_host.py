@@ -145,3 +145,38 @@ def test_krylov_loops_follow_the_reference(golden_dir):
             assert its == int(g[key+'_iterations']) and len(res) == len(g[key+'_residuals'])
             assert np.abs(np.array(res)/g[key+'_residuals']-1).max() < 1e-6
             assert np.abs(x.numpy()-g[key+'_x']).max() < 1e-10*np.abs(g[key+'_x']).max()
+
+
+def test_multigrid_follows_the_reference(golden_dir):
+    """multigrid / cg-mg host logic (pynucleus_b200/multigrid.py) on CPU stand-ins of the level operators (assembled by
+    the oracle) against the reference's driver run disc / varconst(0.75) / P1 / dense / cg-mg at 3 refinements:
+    level diagonals, V-cycle residual history, preconditioned CG history and solution"""
+    sys.path.insert(0, ROOT)
+    import oracle
+    import pynucleus_b200 as pb
+    from pynucleus_b200.solvers import cg
+    g = np.load(os.path.join(golden_dir, 'mg_disc_varconst0.75_r3.npz'))
+    mesh = pb.uniform_disc()
+    levels = []
+    for k in range(int(g['num_levels'])):
+        if k > 0:
+            mesh = mesh.refine()
+        dm = pb.P1_DoFMap(mesh)
+        P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, 0.75, bfacets=mesh.boundaryFacets, target_order=0.5)
+        A = P.dense(True)
+        assert np.abs(np.diag(A)/g['diag%d' % k]-1).max() < 1e-12
+        lvl = {'A': _HostOperator(A), 'DoFMap': dm}
+        lvl['A'].shape = A.shape
+        if k > 0:
+            lvl['R'], lvl['P'] = pb.buildRestrictionProlongation(levels[-1]['DoFMap'], dm)
+        levels.append(lvl)
+    mg = pb.multigrid(levels)
+    b = torch.from_numpy(g['b'])
+    x, its, res = mg.solve(b, tol=1e-8, maxiter=60)
+    assert its == int(g['mg_iterations']) and len(res) == len(g['mg_residuals'])
+    assert np.abs(np.array(res)/g['mg_residuals']-1).max() < 1e-6
+    assert np.abs(x.numpy()-g['mg_x']).max() < 1e-9*np.abs(g['mg_x']).max()
+    x, its, res = cg(levels[-1]['A'], b, tol=1e-8, maxiter=100, precond=mg.asPreconditioner())
+    assert its == int(g['cg2_iterations']) == int(g['cgmg_iterations'])
+    assert np.abs(np.array(res)/g['cg2_residuals']-1).max() < 1e-6
+    assert np.abs(x.numpy()-g['u']).max() < 1e-8*np.abs(g['u']).max()

@@ -642,3 +642,36 @@ def test_h2_regional_operator(golden_dir, name):
     vals = b.getEntries(g['IJ'])
     scale = np.abs(g['Anear_diagonal']).max()
     assert (np.abs(vals-g['entries'])/np.maximum(np.abs(g['entries']), 1e-2*scale)).max() < TOL
+
+
+def test_cg_mg_driver_config_vs_reference(golden_dir):
+    """BASELINE config 3 (runFractional: disc, s = varconst(0.75), P1, dense, solver cg-mg) at 4 refinements: the
+    hierarchy of dense level operators assembled on the device, V-cycle multigrid (Jacobi 2/3, LU on the coarsest
+    level) and multigrid-preconditioned CG against the reference's driver run: level diagonals 1e-12, iteration
+    counts equal, residual histories 1e-6, solution 1e-8, Hs error of the driver"""
+    import torch
+    from scipy.special import gamma
+    import pynucleus_b200 as pb
+    g = load(golden_dir, 'mg_disc_varconst0.75_r4')
+    kernel = pb.getFractionalKernel(2, pb.variableConstFractionalOrder(0.75))
+    levels = pb.hierarchy(pb.uniform_disc(), int(g['noRef']), kernel, {'target_order': 0.5})
+    assert [lvl['A'].shape[0] for lvl in levels] == list(g['level_num_dofs'])
+    for k, lvl in enumerate(levels):
+        assert np.abs(lvl['A'].diagonal/g['diag%d' % k]-1).max() < TOL
+    mg = pb.multigrid(levels)
+    b = torch.as_tensor(g['b']).cuda()
+    x, its, res = mg.solve(b, tol=1e-8, maxiter=60)
+    assert its == int(g['mg_iterations']) and len(res) == len(g['mg_residuals'])
+    assert np.abs(np.array(res)/g['mg_residuals']-1).max() < 1e-6
+    assert np.abs(x.cpu().numpy()-g['mg_x']).max() < 1e-9*np.abs(g['mg_x']).max()
+    x, its, res = pb.cg(levels[-1]['A'], b, tol=float(g['tol']), maxiter=100, precond=mg.asPreconditioner())
+    assert its == int(g['cgmg_iterations']) and len(res) == len(g['cgmg_residuals'])
+    assert np.abs(np.array(res)/g['cgmg_residuals']-1).max() < 1e-6
+    u = x.cpu().numpy()
+    assert np.abs(u-g['u']).max() < 1e-8*np.abs(g['u']).max()
+    s = 0.75
+    C = 2.**(-2.*s)*gamma(1.)/gamma(1.+s)/gamma(1.+s)
+    Hs_error = np.sqrt(abs(g['b'].dot(u)-C*np.pi/(s+1)))
+    assert abs(Hs_error/float(g['Hs_error'])-1) < 1e-6
+    # the right-hand side of the driver is the P1 load vector of f = 1
+    assert np.abs(_p1_load_vector(levels[-1]['mesh'], levels[-1]['DoFMap'])-g['b']).max() < 1e-14

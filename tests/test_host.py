@@ -201,3 +201,29 @@ def test_cluster_tree_and_farfield_chain_match_reference(golden_dir, name):
     low = sp.csr_matrix((g['Anear_data'], g['Anear_indices'], g['Anear_indptr']), shape=(N, N))   # SSS: strict lower + diagonal
     ref = g['Hx']-(low+low.T+sp.diags(g['Anear_diagonal'])).dot(g['x'])
     assert np.abs(yfar-ref).max() < 1e-11*np.abs(ref).max()
+
+
+def test_restriction_operators_match_reference(golden_dir):
+    """P1 restriction / prolongation of the uniformly refined disc meshes against the hierarchy of the reference's
+    driver (multilevelSolver/PyNucleus_multilevelSolver/restriction_2D_P1.pxi; P = R^T), and the 1D operator against
+    linear interpolation"""
+    import pynucleus_b200 as pb
+    g = np.load(os.path.join(golden_dir, 'mg_disc_varconst0.75_r4.npz'))
+    mesh = pb.uniform_disc()
+    dms = [pb.P1_DoFMap(mesh)]
+    for k in range(1, int(g['num_levels'])):
+        mesh = mesh.refine()
+        dms.append(pb.P1_DoFMap(mesh))
+        R, P = pb.buildRestrictionProlongation(dms[-2], dms[-1])
+        assert R.shape == (dms[-2].num_dofs, dms[-1].num_dofs) == (g['level_num_dofs'][k-1], g['level_num_dofs'][k])
+        assert np.array_equal(R.indptr, g['R%d_indptr' % k]) and np.array_equal(R.indices, g['R%d_indices' % k])
+        assert np.array_equal(R.data, g['R%d_data' % k])
+        assert (P != R.T).nnz == 0
+    m0 = pb.refined(pb.simpleInterval(-1, 1), 3)
+    m1 = m0.refine()
+    d0, d1 = pb.P1_DoFMap(m0), pb.P1_DoFMap(m1)
+    R, P = pb.buildRestrictionProlongation(d0, d1)
+    x0, x1 = d0.getDoFCoordinates()[:, 0], d1.getDoFCoordinates()[:, 0]
+    f = 0.3*x0+0.1            # linear functions vanishing nowhere special: interpolation is exact away from the boundary
+    inner = np.abs(x1) < 1-2*m0.h
+    assert np.abs(P.dot(f)-(0.3*x1+0.1))[inner].max() < 1e-14
