@@ -8,7 +8,7 @@ from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFra
                       constantFractionalLaplacianScaling, FRACTIONAL)
 from .assembly import nonlocalBuilder, assembleNonlocalOperator  # noqa: F401
 from .linear_operators import Dense_LinearOperator, diagonalOperator  # noqa: F401
-from .solvers import cg, gmres, DistributedDenseOperator  # noqa: F401
+from .solvers import cg, gmres, lu, DistributedDenseOperator  # noqa: F401
 
 __version__ = '0.1.0'
 from .multigrid import multigrid, hierarchy, buildRestrictionProlongation  # noqa: F401,E402

@@ -198,3 +198,13 @@ def gmres(A, b, x0=None, tol=1e-8, maxiter=30, restarts=1, jacobi=True, left=Tru
         upd = torch.as_tensor(y[:i+1], device=dev) @ Q[:i+1]
         x += precond(upd) if do_r else upd
     return (x.cpu().numpy() if host else x), all_iter, res
+
+
+def lu(A, b):
+    """direct solve with a dense operator on the device (solver 'lu' of the drivers, base/PyNucleus_base/solvers.pyx:80-120:
+    LU with partial pivoting).  b: float64 CUDA tensor or numpy array (copied); returns x of the same kind."""
+    host = not isinstance(b, torch.Tensor)
+    dev = _device_of(A)
+    bt = torch.as_tensor(np.ascontiguousarray(b, dtype=np.float64)).to(dev) if host else b
+    x = torch.linalg.solve(A.device_data, bt)
+    return x.cpu().numpy() if host else x
