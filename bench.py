@@ -277,6 +277,9 @@ def run_cuda(args):
     st = builder.getStats()
     value = N*float(N)/(ms_step*1e-3)
 
+    builder.releaseScratch()       # several GPUs: the end-to-end builder below brings its own N x N work buffer
+    if world > 1:
+        torch.cuda.empty_cache()
     # end to end through the host-buffer C entry point: problem upload + assembly + copy back, every step
     host = torch.empty((max(r1-r0, 1), N), dtype=torch.float64).pin_memory()
     hA = host.numpy()
@@ -306,6 +309,7 @@ def run_cuda(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e_ms.append(dt)
+        b2.releaseScratch()
         del b2
     e2e_ms = e2e_ms[1:]
     e2e_value = N*float(N)/(float(np.mean(e2e_ms))*1e-3)

@@ -241,6 +241,12 @@ class nonlocalBuilder:
         if self._classes is not None:
             return self._getDenseClasses(out)
         N = self._dm_assembly.num_dofs
+        if N == 0:
+            # no unknowns (e.g. a one-cell interval): empty operator, like the reference
+            if not torch.cuda.is_available():
+                raise RuntimeError('pynucleus_b200 needs a CUDA device; there is no CPU fallback')
+            dev = torch.device('cuda', self.params.get('device', torch.cuda.current_device()))
+            return Dense_LinearOperator(torch.empty((0, 0), dtype=torch.float64, device=dev), dev.index)
         prob = self.problem
         dev = torch.device('cuda', prob.device)
         if self.dm2 is not None and out is not None:
@@ -363,6 +369,10 @@ class nonlocalBuilder:
         if U is None or U.shape[0] != N or U.device != dev:
             U = self._U = torch.empty((N, N), dtype=torch.float64, device=dev)
         return U
+
+    def releaseScratch(self):
+        """frees the N x N work buffer that getDenseRowBlock keeps between calls on several GPUs"""
+        self._U = None
 
     def getDenseDistributed(self, process_group=None):
         """getDense() sharded by rows over the ranks of `process_group` (one process per GPU): returns a

@@ -300,15 +300,15 @@ class nearFieldBlocks:
         self.nnz = 0
 
     def add(self, rows, cols, block):
-        import torch
-        self.blocks.append((torch.as_tensor(rows, device=self.device), torch.as_tensor(cols, device=self.device), block))
+        self.blocks.append((np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64), block))
         self.nnz += block.numel()
 
     def compile(self):
         """one CSR matrix on the device"""
         import torch
-        r = torch.cat([rr.repeat_interleave(cc.numel()) for rr, cc, B in self.blocks])
-        c = torch.cat([cc.repeat(rr.numel()) for rr, cc, B in self.blocks])
+        # index arrays on the host (two uploads instead of thousands of tiny device operations)
+        r = torch.as_tensor(np.concatenate([np.repeat(rr, cc.shape[0]) for rr, cc, B in self.blocks]), device=self.device)
+        c = torch.as_tensor(np.concatenate([np.tile(cc, rr.shape[0]) for rr, cc, B in self.blocks]), device=self.device)
         v = torch.cat([B.reshape(-1) for rr, cc, B in self.blocks])
         if self.correction is not None:
             # entries added on top of the blocks (only where the pattern has an entry: DoFs of one cell always are
@@ -337,7 +337,7 @@ class nearFieldBlocks:
             return torch.mv(self._csr, x)
         y = torch.zeros(self.num_dofs, dtype=torch.float64, device=self.device)
         for r, c, B in self.blocks:
-            y[r] += B.mv(x[c])
+            y[torch.as_tensor(r, device=self.device)] += B.mv(x[torch.as_tensor(c, device=self.device)])
         if self.correction is not None:
             cr, cc_, cv = (torch.as_tensor(a, device=self.device) for a in self.correction)
             y.index_add_(0, cr, cv*x[cc_])
@@ -347,7 +347,7 @@ class nearFieldBlocks:
         import torch
         A = torch.zeros((self.num_dofs, self.num_dofs), dtype=torch.float64, device=self.device)
         for r, c, B in self.blocks:
-            A[r[:, None], c[None, :]] += B
+            A[torch.as_tensor(r, device=self.device)[:, None], torch.as_tensor(c, device=self.device)[None, :]] += B
         if self.correction is not None:
             cr, cc_, cv = (torch.as_tensor(a, device=self.device) for a in self.correction)
             A.index_put_((cr, cc_), cv, accumulate=True)

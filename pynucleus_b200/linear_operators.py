@@ -62,6 +62,8 @@ class Dense_LinearOperator:
             y = torch.empty(self.num_rows, dtype=torch.float64, device=self._A.device)
         if x.shape[0] != self.num_columns or y.shape[0] != self.num_rows:
             raise ValueError('shape mismatch')
+        if self.num_rows == 0 or self.num_columns == 0:
+            return y.zero_()
         stream = torch.cuda.current_stream(self._A.device).cuda_stream
         _lib.check(_lib.lib().pnb_dense_matvec(self.device_index, self._A.data_ptr(), self.num_rows, self.num_columns,
                                                self._A.stride(0), x.data_ptr(), y.data_ptr(), stream))

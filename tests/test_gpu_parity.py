@@ -737,3 +737,14 @@ def test_driver_known_answers(case, ref, tol):
     Hs, L2 = _driver_errors(*case)
     assert abs(Hs/ref[0]-1) < tol[0]
     assert abs(L2/ref[1]-1) < tol[1]
+
+
+def test_mesh_without_unknowns():
+    """a one-cell interval has no interior DoF: empty operator (shape (0, 0)), as the reference returns"""
+    import pynucleus_b200 as pb
+    mesh = pb.simpleInterval(-1, 1)
+    dm = pb.P1_DoFMap(mesh)
+    assert dm.num_dofs == 0
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(1, 0.25), {}).getDense()
+    assert A.shape == (0, 0) and A.data.shape == (0, 0)
+    assert A.matvec(np.zeros(0)).shape == (0, )
