@@ -227,3 +227,30 @@ def test_restriction_operators_match_reference(golden_dir):
     f = 0.3*x0+0.1            # linear functions vanishing nowhere special: interpolation is exact away from the boundary
     inner = np.abs(x1) < 1-2*m0.h
     assert np.abs(P.dot(f)-(0.3*x1+0.1))[inner].max() < 1e-14
+
+
+def test_near_field_container_is_consistent():
+    """nearFieldBlocks (h2.py): block form, compiled CSR form, dense form, diagonal and the scattered correction of
+    the regional operator agree (CPU tensors; the blocks themselves come from the CUDA path)"""
+    import torch
+    from pynucleus_b200.h2 import nearFieldBlocks
+    rng = np.random.default_rng(1)
+    n = 23
+    near = nearFieldBlocks(n, torch.device('cpu'))
+    ref = np.zeros((n, n))
+    for rows, cols in ((np.arange(0, 7), np.arange(0, 7)), (np.arange(0, 7), np.arange(7, 12)), (np.arange(7, 12), np.arange(0, 7)),
+                       (np.arange(7, 23), np.arange(7, 23))):
+        B = rng.standard_normal((rows.shape[0], cols.shape[0]))
+        near.add(rows, cols, torch.from_numpy(B))
+        ref[np.ix_(rows, cols)] += B
+    cr, cc = np.array([0, 3, 3, 22]), np.array([0, 4, 3, 21])
+    cv = rng.standard_normal(4)
+    near.correction = (cr, cc, cv)
+    np.add.at(ref, (cr, cc), cv)
+    x = torch.from_numpy(rng.standard_normal(n))
+    y_blocks = near.matvec_device(x).numpy()
+    assert np.abs(near.toarray()-ref).max() < 1e-15
+    near.compile()
+    assert np.abs(near.matvec_device(x).numpy()-ref.dot(x.numpy())).max() < 1e-13
+    assert np.abs(y_blocks-ref.dot(x.numpy())).max() < 1e-13
+    assert np.abs(near.diagonal_device().numpy()-np.diag(ref)).max() < 1e-15
