@@ -164,9 +164,11 @@ class nonlocalBuilder:
         self.kernelBoundary = kernel.getBoundaryKernel()
         mesh = self.mesh
         H0 = mesh.diam/np.sqrt(8.)
-        self.orders = quadrature.localMatrixOrders(mesh.dim, kernel.singularityValue, self.kernelBoundary.singularityValue,
-                                                   mesh.hmin, H0, self.dm.num_dofs, self.params.get('target_order', None),
-                                                   self.dm.polynomialOrder)
+        # a mesh without unknowns has no quadrature orders (log(num_dofs) in the 1D order formula); getDense() returns
+        # the empty operator
+        self.orders = None if self.dm.num_dofs == 0 else quadrature.localMatrixOrders(
+            mesh.dim, kernel.singularityValue, self.kernelBoundary.singularityValue, mesh.hmin, H0, self.dm.num_dofs,
+            self.params.get('target_order', None), self.dm.polynomialOrder)
         self._problem = None
 
     # -- device problem (lazy) ---------------------------------------------

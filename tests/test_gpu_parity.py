@@ -740,7 +740,7 @@ def test_driver_known_answers(case, ref, tol):
 
 
 def test_mesh_without_unknowns():
-    """a one-cell interval has no interior DoF: empty operator (shape (0, 0)), as the reference returns"""
+    """a one-cell interval has no interior DoF: empty operator of shape (0, 0)"""
     import pynucleus_b200 as pb
     mesh = pb.simpleInterval(-1, 1)
     dm = pb.P1_DoFMap(mesh)
