@@ -204,6 +204,7 @@ struct pnb_problem {
     std::vector<int> h_cells, h_dofs, h_home; // host copies for the lazily built schedules
     std::vector<unsigned char> h_labels;      // cell labels of piecewise variable kernels (empty: constant kernel)
     bool tiles_ready = false;
+    int pow_eoff = 240;      // PowTab::eoff of this problem
     std::vector<double> h_centers, h_h;
     std::vector<int4> h_grid;         // lane grids of the near evaluator per order
     int part = 0, nparts = 1;         // share of the units this problem instance evaluates (multi-GPU)
@@ -262,10 +263,12 @@ static int upload_rule(pnb_problem *p, const pnb_rule_t &r, DRule *out, bool rul
 
 
 // host side of PowTab (see pnb_device.cuh); long double keeps the table entries correctly rounded
-static void build_powtab(PowTab *t, double scal, double expo)
+static void build_powtab(PowTab *t, double scal, double expo, int eoff)
 {
     t->scal = scal;
     t->expo = expo;
+    t->eoff = eoff;
+    t->pad = 0;
     t->coef[0] = 1.;
     for (int k = 1; k < 8; k++) t->coef[k] = t->coef[k - 1] * (expo - k + 1) / k;
     for (int i = 0; i < 128; i++) {
@@ -273,7 +276,7 @@ static void build_powtab(PowTab *t, double scal, double expo)
         const long double m0 = 1.0L / (long double)t->IT[i].x;
         t->IT[i].y = (double)powl(m0, (long double)expo);
     }
-    for (int k = 0; k < 256; k++) t->T1[k] = (double)((long double)scal * exp2l((long double)expo * (long double)(k - PNB_POW_EOFF)));
+    for (int k = 0; k < 256; k++) t->T1[k] = (double)((long double)scal * exp2l((long double)expo * (long double)(k - eoff)));
 }
 
 extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
@@ -587,7 +590,12 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         PowTab tabs[2];
         const double scal[2] = {kernel->scaling, kernel->bscaling};
         const double expo[2] = {-0.5 * dim - kernel->s, -0.5 * (dim - 1) - kernel->s};
-        for (int t = 0; t < 2; t++) build_powtab(&tabs[t], scal[t], expo[t]);
+        // exponent window of the tables: top above 4 diam^2 (no two points of the mesh are further apart than the
+        // diagonal of its bounding box), 256 binary exponents down from there
+        int ex = 0;
+        frexp(4. * mesh->diam * mesh->diam, &ex);
+        p->pow_eoff = 254 - ex;
+        for (int t = 0; t < 2; t++) build_powtab(&tabs[t], scal[t], expo[t], p->pow_eoff);
         const PowTab *dt = nullptr;
         rc |= upload(p, tabs, 2, &dt);
         P.pow_int = dt;
@@ -2080,6 +2088,8 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         }
         R.c[0] = 1.;
         for (int k = 1; k < 8; k++) R.c[k] = R.c[k - 1] * (p->P.expo - k + 1) / k;
+        R.eoff = p->pow_eoff - 1023;
+        R.pad = 0;
     }
     cudaMemsetAsync(S.err, 0, 4 * sizeof(int));
     cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));

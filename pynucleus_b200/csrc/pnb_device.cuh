@@ -26,13 +26,16 @@ struct DRule {
 //   scal * x^e = T1[E] * T2[idx] * sum_k binom(e,k) r^k      (k <= 7)
 // T1 = scal * 2^(E e) and T2 = m0^e are rounded from long double on the host;
 // max relative error ~5e-16 (measured against 200-bit arithmetic), against
-// ~1.3e-16 of libm pow.  Exponents outside the table fall back to pow().
-#define PNB_POW_EOFF 240
+// ~1.3e-16 of libm pow.  T1 covers 256 binary exponents of x; the host places the window (eoff) so that it ends
+// above 4 diam^2 of the mesh (pnb_problem_create), i.e. every |x-y|^2 that can occur down to 2^-250 of the domain
+// size lies inside.  Arguments outside the window (zero distance, NaN) are clamped to its ends: no branch and no
+// call in the evaluation loops (a call there made the compiler keep the loop state in local memory).
 struct PowTab {
     double coef[8];
     double T1[256];
     double2 IT[128];   // x = 1/m0 (rounded), y = m0^e for the exact reciprocal of x
     double scal, expo;
+    int eoff, pad;     // T1[k] = scal * 2^((k - eoff) e)
 };
 
 struct DProblem {

@@ -54,13 +54,13 @@ struct F2Rule {
     double w[3];
     double qq[6][3];     // w[node] * bary[a][node] * bary[b][node], a <= b
     double c[8];         // binomial series of the power function
+    int eoff, pad;       // PowTab::eoff minus the exponent bias
 };
 
 __device__ __forceinline__ double f2_pow(const PowTab *t, const F2Rule &R, double d2)
 {
     const int hi = __double2hiint(d2), lo = __double2loint(d2);
-    const int E = ((hi >> 20) & 0x7ff) - 1023 + PNB_POW_EOFF;
-    if ((unsigned)E > 255u) return kernel_value_slow(t->scal, t->expo, d2);
+    const int E = min(max(((hi >> 20) & 0x7ff) + R.eoff, 0), 255);
     const int idx = (hi >> 13) & 0x7f;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double2 it = t->IT[idx];

@@ -19,22 +19,22 @@ template <int DIM> struct PairDims {
 
 // gamma(x,y) = C |x-y|^(-d-2s)  (kernelsCy.pyx:159-183); boundary kernels :216-240,
 // evaluated from d2 = |x-y|^2 with the table-driven power (PowTab).
-__device__ __noinline__ double kernel_value_slow(double scal, double expo, double d2) { return scal * pow(d2, expo); }
 
 // polynomial coefficients in registers, tables wherever `t` points (shared or global memory)
 struct PowCtx {
     const PowTab *t;
     double c0, c1, c2, c3, c4, c5, c6, c7;
+    int eoff;          // table offset minus the exponent bias
     __device__ __forceinline__ explicit PowCtx(const PowTab *tab) : t(tab)
     {
+        eoff = tab->eoff - 1023;
         c0 = tab->coef[0]; c1 = tab->coef[1]; c2 = tab->coef[2]; c3 = tab->coef[3];
         c4 = tab->coef[4]; c5 = tab->coef[5]; c6 = tab->coef[6]; c7 = tab->coef[7];
     }
     __device__ __forceinline__ double operator()(double d2) const
     {
         const int hi = __double2hiint(d2), lo = __double2loint(d2);
-        const int E = ((hi >> 20) & 0x7ff) - 1023 + PNB_POW_EOFF;
-        if ((unsigned)E > 255u) return kernel_value_slow(t->scal, t->expo, d2);
+        const int E = min(max(((hi >> 20) & 0x7ff) + eoff, 0), 255);
         const int idx = (hi >> 13) & 0x7f;
         const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
         const double2 it = t->IT[idx];
@@ -408,6 +408,7 @@ __device__ __forceinline__ void far_eval_n(const FarRule &R, const double (*s1)[
                                            double *xy, double *xx, double *yy)
 {
     double Y0[N], Y1[N], c[N];
+    const volatile FarRule &RV = R;
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const double q0 = R.bary[0][j], q1 = R.bary[1][j], q2 = R.bary[2][j];
@@ -430,10 +431,12 @@ __device__ __forceinline__ void far_eval_n(const FarRule &R, const double (*s1)[
         for (int j = 0; j < N; j++) {
             const double a = X0 - Y0[j], b = X1 - Y1[j];
             const double g = T(a * a + b * b);
-            t0 = fma(g, R.wb[0][j], t0);
-            t1 = fma(g, R.wb[1][j], t1);
-            t2 = fma(g, R.wb[2][j], t2);
-            r = fma(g, R.w[j], r);
+            // the rule constants are re-read from shared memory (broadcast) in every row: hoisted out of the row loop
+            // they would not fit into the registers and come back from local memory instead
+            t0 = fma(g, RV.wb[0][j], t0);
+            t1 = fma(g, RV.wb[1][j], t1);
+            t2 = fma(g, RV.wb[2][j], t2);
+            r = fma(g, RV.w[j], r);
             c[j] = fma(g, wi, c[j]);
         }
         const double q0 = wi * p0, q1 = wi * p1, q2 = wi * p2;
