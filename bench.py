@@ -335,7 +335,7 @@ def run_cuda(args):
     dominant = max(('gmix_kernel', 'gnear_eval_kernel', 'gf2_kernel'), key=lambda k: per_kernel[k]['ms'])
     achieved = per_kernel[dominant]['tflops']
     # dram bytes of one launch from the committed ncu --set full captures (profiles/r1_final_ncu_full_*.txt, disc20k)
-    ncu_traffic = {'gmix_kernel': 4.031e9+2.555e9, 'gnear_eval_kernel': 0.770e9+0.001e9, 'gf2_kernel': 4.148e9+3.215e9}
+    ncu_traffic = {'gmix_kernel': 3.936e9+2.253e9, 'gnear_eval_kernel': 0.797e9+1.196e9, 'gf2_kernel': 4.148e9+3.215e9}
     roofline = {'bound': 'fp64', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': achieved/peak if peak else None,
                 'traffic': ncu_traffic.get(dominant) if args.workload == 'disc20k' and world == 1 else None,
