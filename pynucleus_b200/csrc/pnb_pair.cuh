@@ -9,6 +9,7 @@
 //    blocks so that each kernel value is used in 5 FMAs instead of 63 flops.
 #pragma once
 #include "pnb_device.cuh"
+#include <type_traits>
 
 template <int DIM> struct PairDims {
     static constexpr int NV = DIM + 1;               // vertices (= P1 dofs) per cell
@@ -408,7 +409,8 @@ __device__ __forceinline__ void far_eval_n(const FarRule &R, const double (*s1)[
                                            double *xy, double *xx, double *yy)
 {
     double Y0[N], Y1[N], c[N];
-    const volatile FarRule &RV = R;
+    // N = 3: the 12 constants stay in registers
+    typename std::conditional<(N > 3), const volatile FarRule &, const FarRule &>::type RV = R;
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const double q0 = R.bary[0][j], q1 = R.bary[1][j], q2 = R.bary[2][j];
