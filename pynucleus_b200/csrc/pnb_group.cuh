@@ -553,7 +553,7 @@ __device__ __forceinline__ void near_regular_group(const DProblem &P, const PowC
             const double *di = der + (size_t)i * 13;
             const double wi = di[0];
             double t0 = 0., t1 = 0., t2 = 0., rs = 0.;
-#pragma unroll 2
+#pragma unroll 4
             for (int j = j0 + cj; j < j1; j += CS) {
                 const double a = X0 - xs[2 * n + j], b = X1 - xs[3 * n + j];
                 const double g = kv(PNB_ADD(PNB_MUL(a, a), PNB_MUL(b, b)));
