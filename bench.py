@@ -244,11 +244,13 @@ def run_cuda(args):
         else:
             builder.getDenseRowBlock(r0, r1, out=A)
 
+    # clocks are sampled from the warm-up on: nvidia-smi needs a few hundred ms for its first line, longer than the
+    # whole timed region of the short multi-GPU runs
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     tile_ms, launches = [], 0
     kms = {'f2': [], 'near': [], 'mix': [], 'symmetrize': []}
@@ -266,13 +268,20 @@ def run_cuda(args):
         launches += st['launches']
         for key in kms:
             kms[key].append(st['ms_'+key])
-    clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
     if world > 1:
         # device time of a step = max over ranks
         t = torch.tensor(ms, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.cpu().tolist()
+    # a timed region shorter than the sampling period: keep the same load up (untimed, same count on every rank)
+    # until the sampler has seen it
+    busy_ms = (args.warmup+args.steps)*float(np.mean(ms))
+    if busy_ms < 1500.:
+        for _ in range(int(np.ceil((1500.-busy_ms)/max(float(np.mean(ms)), 1.)))):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
     ms_step = float(np.mean(ms))
     st = builder.getStats()
     value = N*float(N)/(ms_step*1e-3)
