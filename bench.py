@@ -149,12 +149,29 @@ def _ref_worker(args):
     return pairs, t, dm.num_dofs, nc
 
 
+def _port_worker(args):
+    """the same slice with the CPU restatement (oracle/) -- only used where the stub-built reference is absent"""
+    workload, rank, size = args
+    import numpy as np
+    import oracle
+    mesh, dm = make_mesh(workload)
+    P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, S_ORDER, bfacets=mesh.boundaryFacets,
+                       target_order=TARGET_ORDER)
+    nc = mesh.num_cells
+    start, end = int(np.ceil(nc*rank/size)), int(np.ceil(nc*(rank+1)/size))
+    pairs = sum(nc-c for c in range(start, end))
+    t = time.time()
+    P.dense(True, start, end, wrap=1 << 22)       # entries folded into a 32 MB buffer: the timing needs no N x N matrix
+    t = time.time()-t
+    return pairs, t, dm.num_dofs, nc
+
+
 def reference_throughput(workload, target_seconds=15., cores=None):
     """entries/s of the reference's Cython getDense on `cores` host processes, each assembling one rank slice of
     a `size`-rank cell partition of the SAME mesh (nonlocalAssembly_{SCALAR}.pxi:1280-1285)"""
     import multiprocessing as mp
-    if not os.path.isdir(os.path.join(ROOT, 'oracle', '_ref', 'PyNucleus_nl')):
-        return None
+    have_ref = os.path.isdir(os.path.join(ROOT, 'oracle', '_ref', 'PyNucleus_nl')) and not os.environ.get('PNB_BENCH_FORCE_PORT')
+    worker, kind = (_ref_worker, 'reference') if have_ref else (_port_worker, 'port')
     cores = cores or len(os.sched_getaffinity(0))
     sides, noRef = WORKLOADS[workload]
     nc = sides*4**noRef
@@ -164,13 +181,13 @@ def reference_throughput(workload, target_seconds=15., cores=None):
     ctx = mp.get_context('spawn')
     t0 = time.time()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_ref_worker, [(workload, r, size) for r in ranks])
+        res = pool.map(worker, [(workload, r, size) for r in ranks])
     wall = time.time()-t0
     pairs = sum(r[0] for r in res)
     tmax = max(r[1] for r in res)
     N, nc = res[0][2], res[0][3]
     entries_per_pair = N*N/(nc*(nc+1)/2.)
-    return {'value': pairs*entries_per_pair/tmax, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+    return {'value': pairs*entries_per_pair/tmax, 'unit': UNIT, 'cores': cores, 'kind': kind,
             'sample': '{} of {} rank slices (ranks i*{}//{}) of the reference cell partition of the same mesh '
                       '({} of {} cell pairs); slowest slice {:.1f} s, wall {:.1f} s incl. import/mesh'.format(
                           cores, size, size, cores, pairs, nc*(nc+1)//2, tmax, wall),
@@ -197,8 +214,9 @@ def run_reference(args):
             'steps': args.steps_ref, 'warmup': args.warmup_ref, 'ms_per_step': 1e3*N*N/v, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': '{}: 2D disc, s=0.75, P1, dense, N={} ({} cells)'.format(args.workload, N, mesh.num_cells),
-                       'note': 'CPU: reference Cython getDense (stub-built, oracle/_ref); ms_per_step extrapolated from '
-                               'the sampled slices to the full matrix'},
+                       'note': ('CPU: reference Cython getDense (stub-built, oracle/_ref)' if last['kind'] == 'reference' else
+                                'CPU: C restatement of the reference algorithm (oracle/; oracle/_ref is absent)')
+                               + '; ms_per_step extrapolated from the sampled slices to the full matrix'},
             'cpu_baseline': dict(last, value=v),
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
