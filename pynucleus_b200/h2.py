@@ -46,11 +46,13 @@ def leaf_values(node, mesh, dm, d2c=None):
     idx = _multi_index(m, dim)
     x = np.einsum('kq,ckd->cqd', bary, mesh.vertices[mesh.cells[cells]])      # [nc, nq, dim]
     d = x[:, :, None, :]-xi[None, None, :, :]                                   # [nc, nq, m, dim]
-    omega = np.empty_like(d)
-    for l in range(m):
-        dd = d.copy()
-        dd[:, :, l, :] = 1.
-        omega[:, :, l, :] = dd.prod(axis=2)
+    # omega[.., l, :] = prod_{l' != l} d[.., l', :] from prefix and suffix products (O(m) instead of O(m^2))
+    pre = np.ones_like(d)
+    suf = np.ones_like(d)
+    for l in range(1, m):
+        pre[:, :, l, :] = pre[:, :, l-1, :]*d[:, :, l-1, :]
+        suf[:, :, m-1-l, :] = suf[:, :, m-l, :]*d[:, :, m-l, :]
+    omega = pre*suf
     omega = np.where(np.abs(d) <= 1e-9, beta[None, None, :, :], omega)
     # L_alpha(x_j) = prod_q omega[j, alpha_q, q] / prod_q beta[alpha_q, q]
     om = np.ones(x.shape[:2]+(idx.shape[0], ))
