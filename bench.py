@@ -45,6 +45,15 @@ def make_mesh(workload):
     return mesh, dm
 
 
+def golden_probes(N, nrows, seed=20161):
+    """sampled rows and probe vectors (ones, linspace, two Gaussian) of the size-N goldens in tests/golden/*_rows.npz
+    (oracle/refbuild/make_golden_big.py evaluates the reference's getDense on exactly these)"""
+    rng = np.random.default_rng(seed)
+    rows = np.sort(rng.choice(N, min(nrows, N), replace=False))
+    X = np.stack((np.ones(N), np.linspace(-1., 1., N), rng.standard_normal(N), rng.standard_normal(N)), axis=1)
+    return rows, X
+
+
 # --------------------------------------------------------------------------
 # clocks
 # --------------------------------------------------------------------------
@@ -213,7 +222,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps_ref, 'warmup': args.warmup_ref, 'ms_per_step': 1e3*N*N/v, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{}: 2D disc, s=0.75, P1, dense, N={} ({} cells)'.format(args.workload, N, mesh.num_cells),
+            'config': {'workload': workload_string(args.workload, N, mesh.num_cells),
                        'note': ('CPU: reference Cython getDense (stub-built, oracle/_ref)' if last['kind'] == 'reference' else
                                 'CPU: C restatement of the reference algorithm (oracle/; oracle/_ref is absent)')
                                + '; ms_per_step extrapolated from the sampled slices to the full matrix'},
@@ -225,6 +234,111 @@ def run_reference(args):
 # --------------------------------------------------------------------------
 # CUDA arm
 # --------------------------------------------------------------------------
+def workload_string(workload, N, nc):
+    """the same description in both arms (the driver compares the config of the two lines)"""
+    return ('{}: 2D disc ({}-gon fan, {} radial refinements), s={}, P1, infinite horizon, zero exterior, dense, N={} ({} cells), '
+            'target_order={}'.format(workload, WORKLOADS[workload][0], WORKLOADS[workload][1], S_ORDER, N, nc, TARGET_ORDER))
+
+
+def parity_block(workload, A_rows, rows, dev, world):
+    """max relative entry error of this run's matrix against the REFERENCE's own getDense on the same mesh
+    (tests/golden/<workload>_rows.npz: sampled rows, diagonal, A X for four seeded vectors; generated by
+    oracle/refbuild/make_golden_big.py with the stub-built reference).  Every rank checks the rows it holds; the maxima
+    are reduced over the ranks.  None when there is no golden for the workload."""
+    import torch
+    import torch.distributed as dist
+    path = os.path.join(ROOT, 'tests', 'golden', workload+'_rows.npz')
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    N = int(g['num_dofs'])
+    grows, X = golden_probes(N, g['rows'].shape[0])
+    assert np.array_equal(grows, g['rows'])
+    rows = np.asarray(rows, dtype=np.int64)
+    pos = {int(r): k for k, r in enumerate(rows)}
+    mine = [(k, pos[int(r)]) for k, r in enumerate(grows) if int(r) in pos]
+    d = np.sqrt(np.abs(g['diagonal']))
+    err_rows = 0.
+    if mine:
+        gi = np.array([m[0] for m in mine])
+        li = torch.as_tensor(np.array([m[1] for m in mine]), device=dev)
+        mineA = A_rows[li].cpu().numpy()
+        scale = np.maximum(np.abs(g['A_rows'][gi]), 1e-2*np.outer(d[grows[gi]], d))
+        err_rows = float((np.abs(mineA-g['A_rows'][gi])/scale).max())
+    err_diag = err_ax = 0.
+    if rows.shape[0]:
+        rt = torch.as_tensor(rows, device=dev)
+        diag = A_rows[torch.arange(rows.shape[0], device=dev), rt].cpu().numpy()
+        err_diag = float(np.abs(diag/g['diagonal'][rows]-1).max())
+        Xd = torch.as_tensor(X, device=dev)
+        AX = (A_rows @ Xd).cpu().numpy()
+        bound = (A_rows.abs() @ Xd.abs()).cpu().numpy()
+        err_ax = float((np.abs(AX-g['AX'][rows])/bound).max())
+    errs = torch.tensor([err_rows, err_diag, err_ax, float(len(mine))], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = errs.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        cnt = errs[3:].clone()
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        errs = torch.cat((mx[:3], cnt))
+    e = errs.cpu().tolist()
+    return {'max_rel_err': max(e[:3]), 'rows': e[0], 'diagonal': e[1], 'products': e[2], 'rows_checked': int(e[3]),
+            'golden': 'tests/golden/{}_rows.npz (reference getDense, stub-built, {} slices)'.format(workload, int(g['nslices'])),
+            'bar': 1e-12}
+
+
+# --------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------
+def assemble_steps(builder, world, group, steps, warmup, flush, dev):
+    """warm-up + timed steps of one workload; returns (ms per step list, per-kernel ms, launches, operator, A)"""
+    import torch
+    import torch.distributed as dist
+    state = {'A': None, 'op': None}
+
+    def step():
+        if world == 1:
+            if state['A'] is None:
+                N = builder.dm.num_dofs
+                state['A'] = torch.empty((N, N), dtype=torch.float64, device=dev)
+            state['op'] = builder.getDense(out=state['A'])
+        else:
+            state['op'] = builder.getDenseDistributed(process_group=group, out=state['A'])
+            if state['A'] is None and state['op'].A_rows is not None:
+                state['A'] = state['op'].A_rows.device_data
+
+    cold0 = time.perf_counter()
+    step()
+    torch.cuda.synchronize()
+    cold_ms = (time.perf_counter()-cold0)*1e3
+    for _ in range(max(warmup-1, 0)):
+        step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    tile_ms, launches = [], 0
+    kms = {'f2': [], 'near': [], 'mix': [], 'symmetrize': []}
+    for k in range(steps):
+        flush.zero_()
+        if world > 1:
+            dist.barrier()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+        torch.cuda.synchronize()
+        st = builder.getStats()
+        tile_ms.append(st['ms_tiles'])
+        launches += st['launches']
+        for key in kms:
+            kms[key].append(st['ms_'+key])
+    ms = [a.elapsed_time(b) for a, b in ev]
+    if world > 1:
+        # device time of a step = max over ranks
+        t = torch.tensor(ms, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.cpu().tolist()
+    return ms, tile_ms, kms, launches, cold_ms, state, step
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -246,52 +360,17 @@ def run_cuda(args):
     kernel = pb.getFractionalKernel(2, S_ORDER)
     params = {'target_order': TARGET_ORDER, 'device': local_rank}
     builder = pb.nonlocalBuilder(dm, kernel, params)
-    from pynucleus_b200.assembly import row_partition
-    r0, r1 = row_partition(N, world, _lib.lib().pnb_row_granularity())[rank]
 
-    A = torch.empty((max(r1-r0, 1), N), dtype=torch.float64, device=dev)
     flush = torch.empty(64*1024*1024, dtype=torch.float64, device=dev)   # 512 MB > L2
-    peak = 0.
     pk = np.zeros(1)
     _lib.check(_lib.lib().pnb_fp64_peak(local_rank, pk.ctypes.data_as(_lib.c_double_p)))
     peak = float(pk[0])
-
-    def step():
-        if world == 1:
-            builder.getDense(out=A)
-        else:
-            builder.getDenseRowBlock(r0, r1, out=A)
 
     # clocks are sampled from the warm-up on: nvidia-smi needs a few hundred ms for its first line, longer than the
     # whole timed region of the short multi-GPU runs
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    tile_ms, launches = [], 0
-    kms = {'f2': [], 'near': [], 'mix': [], 'symmetrize': []}
-    torch.cuda.synchronize()
-    for k in range(args.steps):
-        flush.zero_()
-        if world > 1:
-            dist.barrier()
-        ev[k][0].record()
-        step()
-        ev[k][1].record()
-        torch.cuda.synchronize()
-        st = builder.getStats()
-        tile_ms.append(st['ms_tiles'])
-        launches += st['launches']
-        for key in kms:
-            kms[key].append(st['ms_'+key])
-    ms = [a.elapsed_time(b) for a, b in ev]
-    if world > 1:
-        # device time of a step = max over ranks
-        t = torch.tensor(ms, dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.cpu().tolist()
+    ms, tile_ms, kms, launches, cold_ms, state, step = assemble_steps(builder, world, None, args.steps, args.warmup, flush, dev)
     # a timed region shorter than the sampling period: keep the same load up (untimed, same count on every rank)
     # until the sampler has seen it
     busy_ms = (args.warmup+args.steps)*float(np.mean(ms))
@@ -303,16 +382,89 @@ def run_cuda(args):
     ms_step = float(np.mean(ms))
     st = builder.getStats()
     value = N*float(N)/(ms_step*1e-3)
+    op = state['op']
+    A = state['A']
+    rows = np.arange(N) if world == 1 else op.rows
+    nrows = int(rows.shape[0])
 
-    builder.releaseScratch()       # several GPUs: the end-to-end builder below brings its own N x N work buffer
+    # correctness of THIS run's matrix at the benchmarked size, on every rank
+    parity = parity_block(args.workload, A, rows, dev, world)
+
+    # second kernel of the path: y = A x on the assembled rows (HBM-bound, reads the matrix once)
+    matvec = None
+    Aop = xv = yv = None
+    if nrows > 0:
+        Aop = pb.Dense_LinearOperator(A[:nrows], local_rank)
+        xv = torch.ones(N, dtype=torch.float64, device=dev)
+        yv = torch.empty(nrows, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            Aop.matvec_device(xv, yv)
+        mv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in mv:
+            flush.zero_()
+            a.record()
+            Aop.matvec_device(xv, yv)
+            b.record()
+        torch.cuda.synchronize()
+        mv_ms = float(np.median([a.elapsed_time(b) for a, b in mv]))
+        hbm_peak = None
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                hbm_peak = float(json.load(f)['hbm_gbs'])
+        except Exception:
+            pass
+        gbs = (nrows*N*8+N*8+nrows*8)/(mv_ms*1e-3)/1e9
+        matvec = {'kernel': 'matvec_kernel', 'bound': 'hbm', 'ms': mv_ms, 'achieved': gbs, 'unit': 'GB/s',
+                  'peak': hbm_peak, 'frac': gbs/hbm_peak if hbm_peak else None,
+                  'note': 'algorithmic bytes = 8*(rows*N + N + rows); L2 flushed between launches; peak = MEASURED_PEAKS.json hbm_gbs'}
+
+    # roofline: algorithmic FP64 flops (SURVEY 8d) / device time measured with CUDA events inside the C call.
+    # Headline object = the dominant kernel; the other pair kernels and their sum are listed beside it.
+    hist = builder.getPanelHistogram()
+    share = st['evaluated_pairs']/max(st['distinct_pairs'], 1) if world > 1 else 1.   # several GPUs: this rank's share
+    flops_all, pows_all = algorithmic_flops(hist, builder)
+    near_hist = {k: v for k, v in hist.items() if k < 0 or k > 5}
+    flops_near, pows_near = algorithmic_flops(near_hist, builder)
+    flops_f2, pows_f2 = st['f2_pairs']*9*70., st['f2_pairs']*9.
+    flops_mix = (flops_all-flops_near)*share-flops_f2
+    t_all = float(np.mean(tile_ms))*1e-3
+    t = {key: float(np.mean(v))*1e-3 for key, v in kms.items()}
+    per_kernel = {
+        'gmix_kernel': {'ms': t['mix']*1e3, 'tflops': flops_mix/max(t['mix'], 1e-9)/1e12},
+        'gnear_eval_kernel': {'ms': t['near']*1e3, 'tflops': flops_near*share/max(t['near'], 1e-9)/1e12},
+        'gf2_kernel': {'ms': t['f2']*1e3, 'tflops': flops_f2/max(t['f2'], 1e-9)/1e12},
+        'all pair kernels': {'ms': t_all*1e3, 'tflops': flops_all*share/t_all/1e12}}
+    for v in per_kernel.values():
+        v['frac'] = v['tflops']/peak if peak else None
+    dominant = max(('gmix_kernel', 'gnear_eval_kernel', 'gf2_kernel'), key=lambda k: per_kernel[k]['ms'])
+    achieved = per_kernel[dominant]['tflops']
+    roofline = {'bound': 'fp64', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': achieved/peak if peak else None,
+                'traffic': None,
+                'kernels': per_kernel,
+                'frac_all_pair_kernels': per_kernel['all pair kernels']['tflops']/peak if peak else None,
+                'note': 'algorithmic flops (SURVEY 8d: 70/node-pair regular, 49/61/76 singular; pow excluded) of the cell pairs '
+                        'the kernel evaluates / its device time (CUDA events around the launch inside the C call, averaged '
+                        'over the timed steps); peak = DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no '
+                        'FP64 figure); traffic: not measurable in-run (FP64-bound kernels; dram bytes per launch are in the '
+                        'ncu captures under profiles/); pow evaluations/s over all pair kernels = {:.3e}; evaluated/distinct '
+                        'pairs {:.3f}; pair-kernel share of step {:.3f}'.format(
+                            pows_all*share/t_all, st['evaluated_pairs']/max(st['distinct_pairs'], 1), t_all*1e3/ms_step)}
+
+    # end to end through the host-buffer entry point: a NEW builder every step (mesh / DoFMap / table upload, schedules,
+    # near pair list; several GPUs: plan, staging buffers, peer-memory handshake), assembly, copy of the rows to pinned
+    # host memory
+    del op
+    state['op'] = None
+    builder.releaseScratch()
     if world > 1:
         torch.cuda.empty_cache()
-    # end to end through the host-buffer C entry point: problem upload + assembly + copy back, every step
-    host = torch.empty((max(r1-r0, 1), N), dtype=torch.float64).pin_memory()
+    host = torch.empty((max(nrows, 1), N), dtype=torch.float64).pin_memory()
     hA = host.numpy()
     e2e_ms = []
     h2d = (mesh.vertices.nbytes+mesh.cells.nbytes+dm.dofs.nbytes+mesh.volVector.nbytes+mesh.hVector.nbytes
            + mesh.boundaryFacets.nbytes)
+    checksum = None
     for k in range(max(1, min(args.steps, 3))+1):
         torch.cuda.synchronize()
         if world > 1:
@@ -326,82 +478,37 @@ def run_cuda(args):
             if rank == 0 and os.environ.get('PNB_BENCH_VERBOSE'):
                 print('e2e: setup %.1f ms, assemble+copy %.1f ms' % ((t1-t0)*1e3, (time.perf_counter()-t1)*1e3), file=sys.stderr)
         else:
-            b2.getDenseRowBlock(r0, r1, out=A)
-            host.copy_(A)
+            o2 = b2.getDenseDistributed(out=A)
+            if nrows:
+                host[:nrows].copy_(A[:nrows])
             torch.cuda.synchronize()
-        checksum = float(hA[0, 0])
+            del o2
+        if rank == 0:
+            checksum = float(hA[0, 0])
         dt = (time.perf_counter()-t0)*1e3
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
         e2e_ms.append(dt)
         b2.releaseScratch()
         del b2
     e2e_ms = e2e_ms[1:]
     e2e_value = N*float(N)/(float(np.mean(e2e_ms))*1e-3)
 
-    # roofline: algorithmic FP64 flops (SURVEY 8d) / device time measured with CUDA events inside the C call.
-    # Headline object = the dominant kernel (gmix_kernel: the units that are not uniformly of order 2); the other pair
-    # kernels and their sum are listed beside it.
-    hist = builder.getPanelHistogram()
-    share = st['evaluated_pairs']/max(st['distinct_pairs'], 1) if world > 1 else 1.   # several GPUs: this rank's share
-    flops_all, pows_all = algorithmic_flops(hist, builder)
-    near_hist = {k: v for k, v in hist.items() if k < 0 or k > 5}
-    flops_near, pows_near = algorithmic_flops(near_hist, builder)
-    flops_f2, pows_f2 = st['f2_pairs']*9*70., st['f2_pairs']*9.
-    flops_mix = (flops_all-flops_near)*share-flops_f2
-    pows_mix = (pows_all-pows_near)*share-pows_f2
-    t_all = float(np.mean(tile_ms))*1e-3
-    t = {key: float(np.mean(v))*1e-3 for key, v in kms.items()}
-    per_kernel = {
-        'gmix_kernel': {'ms': t['mix']*1e3, 'tflops': flops_mix/max(t['mix'], 1e-9)/1e12},
-        'gnear_eval_kernel': {'ms': t['near']*1e3, 'tflops': flops_near*share/max(t['near'], 1e-9)/1e12},
-        'gf2_kernel': {'ms': t['f2']*1e3, 'tflops': flops_f2/max(t['f2'], 1e-9)/1e12},
-        'all pair kernels': {'ms': t_all*1e3, 'tflops': flops_all*share/t_all/1e12}}
-    dominant = max(('gmix_kernel', 'gnear_eval_kernel', 'gf2_kernel'), key=lambda k: per_kernel[k]['ms'])
-    achieved = per_kernel[dominant]['tflops']
-    # dram bytes of one launch from the committed ncu --set full captures (profiles/r1_final_ncu_full_*.txt, disc20k)
-    ncu_traffic = {'gmix_kernel': 3.936e9+2.253e9, 'gnear_eval_kernel': 0.797e9+1.196e9, 'gf2_kernel': 4.148e9+3.215e9}
-    roofline = {'bound': 'fp64', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': achieved/peak if peak else None,
-                'traffic': ncu_traffic.get(dominant) if args.workload == 'disc20k' and world == 1 else None,
-                'kernels': per_kernel,
-                'frac_all_pair_kernels': per_kernel['all pair kernels']['tflops']/peak if peak else None,
-                'note': 'algorithmic flops (SURVEY 8d: 70/node-pair regular, 49/61/76 singular; pow excluded) of the cell pairs '
-                        'the kernel evaluates / its device time (CUDA events around the launch inside the C call, averaged '
-                        'over the timed steps); peak = DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no '
-                        'FP64 figure); traffic = dram read+write bytes of one launch from the committed ncu capture; '
-                        'pow evaluations/s over all pair kernels = {:.3e}; evaluated/distinct pairs {:.3f}; pair-kernel share '
-                        'of step {:.3f}'.format(pows_all*share/t_all, st['evaluated_pairs']/max(st['distinct_pairs'], 1),
-                                                t_all*1e3/ms_step)}
-
-    # second kernel of the path: y = A x on the assembled rows (HBM-bound, reads the matrix once)
-    matvec = None
-    if r1 > r0:
-        Aop = pb.Dense_LinearOperator(A[:r1-r0], local_rank)
-        xv = torch.ones(N, dtype=torch.float64, device=dev)
-        yv = torch.empty(r1-r0, dtype=torch.float64, device=dev)
-        for _ in range(3):
-            Aop.matvec_device(xv, yv)
-        mv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-        for a, b in mv:
-            flush.zero_()
-            a.record()
-            Aop.matvec_device(xv, yv)
-            b.record()
-        torch.cuda.synchronize()
-        mv_ms = float(np.median([a.elapsed_time(b) for a, b in mv]))
-        hbm_peak = None
+    # BASELINE configs[4] (>= 100k DoFs, the north-star size) in the same line: a few steps of disc105k
+    north = None
+    if args.north_star and args.workload != 'disc105k':
+        del host, hA, A
+        Aop = xv = yv = None       # noqa: F841  (views of the disc20k matrix)
+        state['A'] = None
+        builder = None
+        torch.cuda.empty_cache()
+        _lib.lib().pnb_release_cached_memory()
         try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'MEASURED_PEAKS.json')) as f:
-                hbm_peak = float(json.load(f)['hbm_gbs'])
-        except Exception:
-            pass
-        gbs = ((r1-r0)*N*8+N*8+(r1-r0)*8)/(mv_ms*1e-3)/1e9
-        matvec = {'kernel': 'matvec_kernel', 'bound': 'hbm', 'ms': mv_ms, 'achieved': gbs, 'unit': 'GB/s',
-                  'peak': hbm_peak, 'frac': gbs/hbm_peak if hbm_peak else None,
-                  'note': 'algorithmic bytes = 8*(rows*N + N + rows); L2 flushed between launches; peak = MEASURED_PEAKS.json hbm_gbs'}
+            north = north_star_leg(args, world, rank, local_rank, dev, flush, peak)
+        except Exception as e:       # e.g. out of memory on a small part count: reported, not fatal
+            north = {'workload': 'disc105k', 'error': '{}: {}'.format(type(e).__name__, str(e)[:300])}
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
@@ -409,18 +516,19 @@ def run_cuda(args):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{}: 2D disc ({}-gon fan, {} radial refinements), s={}, P1, infinite horizon, zero exterior, '
-                                   'dense, N={} ({} cells), target_order={}'.format(args.workload, WORKLOADS[args.workload][0],
-                                                                                  WORKLOADS[args.workload][1], S_ORDER, N,
-                                                                                  mesh.num_cells, TARGET_ORDER),
+            'config': {'workload': workload_string(args.workload, N, mesh.num_cells),
                        'l2': 'output ({:.2f} GB/step) exceeds L2; 512 MB flush written between steps (untimed)'.format(N*N*8/1e9),
-                       'parallelism': 'single GPU' if world == 1 else 'row blocks x{}'.format(world)},
+                       'parallelism': 'single GPU' if world == 1 else
+                                      'rows owned by cell groups x{} (peer-memory fragments, no matrix collective)'.format(world)},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d)*world, 'd2h_bytes_per_step': int(N*N*8),
                     'ms_per_step': float(np.mean(e2e_ms)), 'checksum_A00': checksum},
+            'cold_ms_first_assembly': cold_ms,
             'gpu_launches': int(launches),
+            'parity': parity,
             'roofline': roofline,
             'matvec': matvec,
+            'north_star': north,
             'cpu_baseline': cpu,
             'phases_ms': {'tiles': st['ms_tiles'], 'boundary': st['ms_boundary'], 'reduce_scatter': st['ms_reduce_scatter']},
             'pairs': {'distinct': st['distinct_pairs'], 'evaluated': st['evaluated_pairs']}}
@@ -428,6 +536,48 @@ def run_cuda(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def north_star_leg(args, world, rank, local_rank, dev, flush, peak):
+    """disc105k (BASELINE configs[4]: 105 665 DoFs, 212 992 cells, 89 GB of entries) on the same GPUs: device time per
+    assembly, entries/s, structural checks of the result (no golden at this size: symmetric products, positive
+    diagonal, every pair once)"""
+    import torch
+    import torch.distributed as dist
+    import pynucleus_b200 as pb
+    mesh, dm = make_mesh('disc105k')
+    N = dm.num_dofs
+    kernel = pb.getFractionalKernel(2, S_ORDER)
+    builder = pb.nonlocalBuilder(dm, kernel, {'target_order': TARGET_ORDER, 'device': local_rank})
+    steps = 2
+    ms, tile_ms, kms, launches, cold_ms, state, step = assemble_steps(builder, world, None, steps, 1, flush, dev)
+    st = builder.getStats()
+    op, A = state['op'], state['A']
+    rows = np.arange(N) if world == 1 else op.rows
+    nrows = int(rows.shape[0])
+    # structural checks: x^T A y == y^T A x (symmetry through two distributed products), positive diagonal, pairs once
+    rng = np.random.default_rng(11)
+    x = torch.as_tensor(rng.standard_normal(N), device=dev)
+    y = torch.as_tensor(rng.standard_normal(N), device=dev)
+    Aop = op if world > 1 else pb.Dense_LinearOperator(A, local_rank)
+    Ax, Ay = Aop.matvec_device(x).clone(), Aop.matvec_device(y).clone()
+    sym = abs(float(torch.dot(y, Ax)-torch.dot(x, Ay)))/max(abs(float(torch.dot(y, Ax))), 1e-300)
+    dmin = float(Aop.diagonal_device().min()) if world > 1 else float(torch.diagonal(A).min())
+    ev = torch.tensor([float(st['evaluated_pairs'])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ev)
+    ms_step = float(np.mean(ms))
+    t_all = float(np.mean(tile_ms))*1e-3
+    out = {'workload': workload_string('disc105k', N, mesh.num_cells), 'steps': steps, 'warmup': 1, 'ms_per_step': ms_step,
+           'value': N*float(N)/(ms_step*1e-3), 'unit': UNIT, 'rows_this_rank': nrows,
+           'kernels_ms_rank0': {k: float(np.mean(v)) for k, v in kms.items()}, 'pair_kernels_ms_rank0': t_all*1e3,
+           'checks': {'symmetry_rel': sym, 'min_diagonal': dmin, 'pairs_evaluated': int(ev.item()),
+                      'pairs_distinct': int(st['distinct_pairs'])},
+           'cold_ms_first_assembly': cold_ms}
+    del op, A
+    state['op'] = state['A'] = None
+    builder.releaseScratch()
+    return out
 
 
 _REAL_STDOUT = None
@@ -458,6 +608,9 @@ def main():
     ap.add_argument('--workload', default='disc20k', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-seconds', type=float, default=15.)
+    ap.add_argument('--north-star', dest='north_star', action='store_true', default=True,
+                    help='also time a few assemblies of disc105k (BASELINE configs[4]) and report them under north_star')
+    ap.add_argument('--no-north-star', dest='north_star', action='store_false')
     args = ap.parse_args()
     # the reference arm is bounded: a few sampled slices per step
     args.steps_ref = min(args.steps, 2)

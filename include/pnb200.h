@@ -119,6 +119,13 @@ typedef struct {
 
 typedef struct pnb_problem pnb_problem;
 
+/* mesh.hVector, mesh.h, mesh.hmin (hdeltaCy, fem/PyNucleus_fem/meshCy.pyx:1654-1732): per cell the longest edge,
+ * h_max / h_min the longest / SHORTEST edge of the mesh; edge lengths are sqrt(mydot(e,e)) with mydot = BLAS ddot
+ * (base/PyNucleus_base/opt_true_blas.pxi:125-141), which accumulates with fused multiply-adds.  Host arithmetic,
+ * no device needed.  vertices: num_vertices x dim, cells: num_cells x (dim+1), h: num_cells (out). */
+int pnb_mesh_edge_lengths(int32_t dim, int32_t num_cells, const double *vertices, const int32_t *cells,
+                          double *h, double *h_max, double *h_min);
+
 const char *pnb_last_error(void);
 int pnb_version(void);
 int pnb_device_count(void);
@@ -173,13 +180,37 @@ int pnb_far_max_order(void);
 int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end,
                        double *A, int64_t ld, int a_on_device);
 
-/* 2D, several GPUs: exploits the symmetry across GPUs (the reference splits the cell loop over ranks and
- * Allreduces the matrix, nonlocalAssembly_{SCALAR}.pxi:1280-1285, 1449-1450).  Instance `part` of `nparts`
- * evaluates its share of the cell pairs into the full N x N device scratch dU (this share of the operator
- * without the cell-diagonal blocks).  The caller sums rows [row_begin,row_end) of all shares on their owner,
- * sums the cell-block buffers and calls pnb_dense_rows_end on the summed rows. */
-int pnb_dense_partial_begin(pnb_problem *p, int zero_exterior, int part, int nparts, int32_t row_begin, int32_t row_end,
-                            double *dU, int64_t ld);
+/* 2D, several GPUs of one node (one problem instance per GPU).  Replaces the reference's split of the cell loop over MPI
+ * ranks followed by an Allreduce of the whole N x N matrix (nonlocalAssembly_{SCALAR}.pxi:1280-1285, 1449-1450).
+ * Part `part` of `nparts` owns a contiguous range of cell groups (cells ordered along a Hilbert curve; the ranges are
+ * balanced by estimated work) and the rows of the dofs that first appear in its groups.  Every cell pair is evaluated
+ * exactly once over all parts: a unit of two groups by the part of its row group or of its column group, alternating.
+ * The unit block reaches the owners of its rows as row fragments stored into their staging buffers (peer memory over
+ * NVLink: plain stores, no read-modify-write, no atomics); the owner sums the fragments of its rows in a fixed order.
+ * Per GPU only num_rows x num_dofs entries and a staging buffer of about twice that size exist; no collective moves
+ * matrix entries.  The caller exchanges the per-cell diagonal blocks (pnb_dense_cell_blocks_copy, num_cells x 6 doubles)
+ * and one status word.
+ *   1. pnb_dist_plan      partition, schedules and tables; returns num_rows and the staging size of this part
+ *      pnb_dist_rows      global dof of every owned row (ascending)
+ *   2. pnb_dist_eval      asynchronous; stage_ptrs[o] = staging buffer of part o as seen from this device (own
+ *                         allocation, or peer memory opened with pnb_ipc_import)
+ *   3. pnb_dist_status    synchronises the device; order_needed > 0: a pair needs a regular rule beyond the supplied
+ *                         tables -- the caller takes the maximum over ALL parts, extends the tables on all of them
+ *                         (pnb_problem_set_rules) and repeats step 2
+ *   4. the caller sums the cell-block buffers over the parts, after which all parts are known to have finished step 2
+ *   5. pnb_dist_apply     A_rows (device, num_rows x num_dofs): row k = global row rows[k] */
+int pnb_dist_plan(pnb_problem *p, int32_t nparts, int32_t part, int32_t *num_rows, int64_t *staging_doubles);
+int pnb_dist_rows(pnb_problem *p, int32_t *rows);
+int pnb_dist_eval(pnb_problem *p, int zero_exterior, double *const *stage_ptrs);
+int pnb_dist_status(pnb_problem *p, int32_t *order_needed);
+int pnb_dist_apply(pnb_problem *p, int use_cell_blocks, double *A_rows, int64_t ld);
+/* plain device allocations and their CUDA IPC handles (64 bytes), so that the staging buffers of the other processes of
+ * the node can be written through peer memory */
+int pnb_device_alloc(int device, int64_t bytes, void **dptr);
+int pnb_device_free(int device, void *dptr);
+int pnb_ipc_export(int device, void *dptr, unsigned char *handle);
+int pnb_ipc_import(int device, const unsigned char *handle, void **dptr);
+int pnb_ipc_close(int device, void *dptr);
 
 /* Row-block (multi-GPU) form of pnb_dense_assemble: one problem instance per GPU assembles the rows
  * [row_begin, row_end) (multiples of pnb_row_granularity(), or num_dofs) into device memory A_rows of
@@ -188,6 +219,7 @@ int pnb_dense_partial_begin(pnb_problem *p, int zero_exterior, int part, int npa
  *   1. pnb_dense_rows_begin   all pair integrals that touch the owned rows
  *   2. the caller sums the buffers returned by pnb_dense_cell_blocks over all row blocks (NCCL allreduce;
  *      supports are disjoint, so the sum is exact and order independent).  Not needed for a single block.
+ * Used for 1D problems and explicit row ranges (DoF-tile kernels); 2D operators on several GPUs: pnb_dist_*.
  *   3. pnb_dense_rows_end     adds the cell-diagonal blocks to the owned rows */
 int pnb_row_granularity(void);
 int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *A_rows, int64_t ld);

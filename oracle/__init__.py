@@ -79,7 +79,7 @@ class Problem:
         self.bfacets = np.ascontiguousarray(mesh.boundary_facets() if bfacets is None else bfacets, dtype=np.int32)
         self.num_dofs = int(num_dofs)
         self.s = float(s)
-        hmin = float(self.h.min() if hmin is None else hmin)
+        hmin = float(mesh.hmin if hmin is None else hmin)
         diam = float(mesh.diam if diam is None else diam)
         self.H0 = diam/np.sqrt(8.)
         dim = self.dim

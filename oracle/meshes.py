@@ -35,16 +35,24 @@ class Mesh:
         return self.vertices.shape[0]
 
     # -- geometry ---------------------------------------------------------
+    def _edge_lengths(self):
+        """(hVector, h, hmin) as hdeltaCy rounds them (meshCy.pyx:1654-1732): orc_edge_lengths in nonlocal_oracle.c"""
+        import ctypes
+        from . import lib
+        if getattr(self, '_hcache', None) is None or self._hcache[0] is not self.vertices:
+            v = np.ascontiguousarray(self.vertices, dtype=np.float64)
+            c = np.ascontiguousarray(self.cells, dtype=np.int32)
+            h = np.empty(c.shape[0])
+            hmax, hmin = ctypes.c_double(0.), ctypes.c_double(0.)
+            lib().orc_edge_lengths(ctypes.c_int(self.dim), ctypes.c_int(c.shape[0]), ctypes.c_void_p(v.ctypes.data),
+                                   ctypes.c_void_p(c.ctypes.data), ctypes.c_void_p(h.ctypes.data), ctypes.byref(hmax),
+                                   ctypes.byref(hmin))
+            self._hcache = (self.vertices, h, float(hmax.value), float(hmin.value))
+        return self._hcache[1:]
+
     @property
     def hVector(self):
-        v, c = self.vertices, self.cells
-        h = np.zeros(c.shape[0])
-        nv = c.shape[1]
-        for i in range(nv):
-            for j in range(i+1, nv):
-                d = v[c[:, i]]-v[c[:, j]]
-                h = np.maximum(h, np.sqrt((d**2).sum(axis=1)))
-        return h
+        return self._edge_lengths()[0]
 
     @property
     def volVector(self):
@@ -57,11 +65,12 @@ class Mesh:
 
     @property
     def h(self):
-        return self.hVector.max()
+        return self._edge_lengths()[1]
 
     @property
     def hmin(self):
-        return self.hVector.min()
+        """shortest edge of the mesh (meshCy.pyx:1724)"""
+        return self._edge_lengths()[2]
 
     @property
     def diam(self):

@@ -676,3 +676,33 @@ int64_t orc_dense(const orc_problem *P, int start, int end, int zero_exterior, d
     }
     return npairs;
 }
+
+/* mesh.hVector / mesh.h / mesh.hmin, hdeltaCy (fem/PyNucleus_fem/meshCy.pyx:1654-1732): per cell the longest edge
+ * (hVec), over the mesh the longest (h) and the SHORTEST edge (hmin; :1724 takes the min over ALL edges).  An edge
+ * length is sqrt(mydot(e, e)); mydot is the BLAS ddot (base/PyNucleus_base/opt_true_blas.pxi:125-141) and the
+ * OpenBLAS behind scipy accumulates it with fused multiply-adds: e1*e1 + fl(e0*e0) rounded once.  Pinned against the
+ * hVector / hmin arrays of every fixture in tests/golden (tests/test_oracle_golden.py). */
+void orc_edge_lengths(int dim, int nc, const double *vertices, const int32_t *cells, double *h, double *hmax_out, double *hmin_out)
+{
+    double hmax = 0., hmin = 100.;
+    for (int c = 0; c < nc; c++) {
+        double hl = 0.;
+        if (dim == 1) {
+            hl = fabs(vertices[cells[2 * (size_t)c + 1]] - vertices[cells[2 * (size_t)c]]);
+            if (hl < hmin) hmin = hl;
+        } else {
+            const double *v0 = vertices + 2 * (size_t)cells[3 * (size_t)c], *v1 = vertices + 2 * (size_t)cells[3 * (size_t)c + 1],
+                         *v2 = vertices + 2 * (size_t)cells[3 * (size_t)c + 2];
+            const double e[3][2] = {{v2[0] - v1[0], v2[1] - v1[1]}, {v2[0] - v0[0], v2[1] - v0[1]}, {v1[0] - v0[0], v1[1] - v0[1]}};
+            for (int j = 0; j < 3; j++) {
+                const double hS = sqrt(fma(e[j][1], e[j][1], e[j][0] * e[j][0]));
+                if (hS < hmin) hmin = hS;
+                if (hS > hl) hl = hS;
+            }
+        }
+        if (hl > hmax) hmax = hl;
+        h[c] = hl;
+    }
+    *hmax_out = hmax;
+    *hmin_out = hmin;
+}

@@ -53,8 +53,10 @@ EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_cre
            'pnb_local_matrices', 'pnb_far_max_order', 'pnb_dense_assemble', 'pnb_dense_stats',
            'pnb_dense_timings', 'pnb_dense_matvec', 'pnb_fp64_peak', 'pnb_row_granularity', 'pnb_dense_rows_begin',
            'pnb_dense_cell_blocks', 'pnb_dense_cell_blocks_copy', 'pnb_dense_rows_end', 'pnb_farfield_blocks',
-           'pnb_release_cached_memory', 'pnb_dense_partial_begin', 'pnb_dense_kernel_timings',
-           'pnb_boundary_cell_blocks']
+           'pnb_release_cached_memory', 'pnb_dense_kernel_timings', 'pnb_dist_plan', 'pnb_dist_rows', 'pnb_dist_eval',
+           'pnb_dist_status', 'pnb_dist_apply', 'pnb_device_alloc', 'pnb_device_free', 'pnb_ipc_export', 'pnb_ipc_import',
+           'pnb_ipc_close',
+           'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths']
 
 _LIB = None
 
@@ -90,8 +92,16 @@ def lib():
                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
         L.pnb_dense_rows_begin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_void_p, ctypes.c_int64]
-        L.pnb_dense_partial_begin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int32,
-                                              ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64]
+        L.pnb_dist_plan.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_int32_p, c_int64_p]
+        L.pnb_dist_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_dist_eval.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.pnb_dist_status.argtypes = [ctypes.c_void_p, c_int32_p]
+        L.pnb_dist_apply.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]
+        L.pnb_device_alloc.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]
+        L.pnb_device_free.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        L.pnb_ipc_export.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_ipc_import.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.pnb_ipc_close.argtypes = [ctypes.c_int, ctypes.c_void_p]
         L.pnb_dense_rows_end.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64]
         L.pnb_dense_cell_blocks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), c_int64_p]
         L.pnb_dense_cell_blocks_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -105,6 +115,8 @@ def lib():
         L.pnb_dense_matvec.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.pnb_fp64_peak.argtypes = [ctypes.c_int, c_double_p]
+        L.pnb_mesh_edge_lengths.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            c_double_p, c_double_p]
         _LIB = L
     return _LIB
 

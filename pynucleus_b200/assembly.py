@@ -13,7 +13,7 @@ import warnings
 import numpy as np
 
 from . import _lib, quadrature
-from .linear_operators import Dense_LinearOperator
+from .linear_operators import Dense_LinearOperator, check_matrix_out
 
 IGNORED = -6
 COMMON_VERTEX, COMMON_EDGE, COMMON_FACE = -1, -2, -3
@@ -253,6 +253,8 @@ class nonlocalBuilder:
         dev = torch.device('cuda', prob.device)
         if self.dm2 is not None and out is not None:
             raise ValueError('out= is not supported together with dm2')
+        if out is not None:
+            check_matrix_out(out, N, N, dev)
         A = torch.empty((N, N), dtype=torch.float64, device=dev) if out is None else out
 
         def run():
@@ -278,6 +280,8 @@ class nonlocalBuilder:
             C['problems'] = [_Problem(self.dm, k, k.getBoundaryKernel(), self.orders, device, self.params.get('max_regular_order', 32),
                                       labels=C['labels'], blabels=C['blabels'], pair_class=C['pair_class'], active_class=i)
                              for i, k in enumerate(C['kernels'])]
+        if out is not None:
+            check_matrix_out(out, N, N, dev)
         A = torch.empty((N, N), dtype=torch.float64, device=dev) if out is None else out
         tmp = None
         for i, prob in enumerate(C['problems']):
@@ -305,90 +309,185 @@ class nonlocalBuilder:
             raise NotImplementedError('only getDense() supports two DoFMaps')
 
     def getDenseRowBlock(self, row_begin, row_end, out=None, process_group=None):
-        """Rows [row_begin, row_end) of getDense() on this process' GPU (row-block sharding over GPUs).
+        """Rows [row_begin, row_end) of getDense() on this process' GPU (contiguous row blocks: 1D problems and
+        explicit row ranges; 2D operators sharded over several GPUs go through getDenseDistributed, which owns rows by
+        cell groups and needs no work buffer).
 
-        The reference splits the cell loop over MPI ranks and Allreduces the whole matrix
-        (nonlocalAssembly_{SCALAR}.pxi:1280-1285, 1449-1450); here every rank owns a row block and the only
-        exchange is the sum of the per-cell diagonal blocks (num_cells x 6 doubles) over `process_group`.
+        Every rank assembles the pair integrals that touch its rows; the only exchange is the sum of the per-cell
+        diagonal blocks (num_cells x 6 doubles) over `process_group`.
         Returns a (row_end-row_begin) x N Dense_LinearOperator."""
         import torch
         self._no_dm2()
         N = self.dm.num_dofs
         prob = self.problem
         dev = torch.device('cuda', prob.device)
+        if out is not None and row_end > row_begin:
+            check_matrix_out(out, row_end-row_begin, N, dev)
         A = torch.empty((row_end-row_begin, N), dtype=torch.float64, device=dev) if out is None else out
         L = _lib.lib()
         nvc = self.mesh.dim+1
         empty = row_end <= row_begin
 
         import torch.distributed as dist
-        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        rank = dist.get_rank(process_group) if dist.is_initialized() else 0
-        gran = int(L.pnb_row_granularity())
-        blocks = row_partition(N, world, gran) if world > 1 else []
-        shared = self.mesh.dim == 2 and world > 1 and blocks[rank] == (row_begin, row_end)
-
-        def run_shared():
-            # 2D, standard partition: every rank evaluates 1/world of the cell pairs (each pair once over all ranks)
-            # into a full-size scratch, the owners of the rows sum the shares over NVLink (NCCL reduce)
-            U = self._scratch(N, dev)
-            _lib.check(L.pnb_dense_partial_begin(prob.handle, int(self.zeroExterior), rank, world, row_begin, row_end, U.data_ptr(), N))
-            works = []
-            for k, (a, b) in enumerate(blocks):
-                if b > a:
-                    dst = dist.get_global_rank(process_group, k) if process_group is not None else k
-                    works.append(dist.reduce(U[a:b], dst=dst, op=dist.ReduceOp.SUM, group=process_group, async_op=True))
-            for w in works:
-                w.wait()
-            if not empty:
-                A.copy_(U[row_begin:row_end])
-            D = exchange_cell_blocks(self.mesh.num_cells*(nvc*(nvc+1)//2), dev, process_group,
-                                     lambda buf: _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, buf.data_ptr(), 0)))
-            if not empty:
-                _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, D.data_ptr(), 1))
-                _lib.check(L.pnb_dense_rows_end(prob.handle, row_begin, row_end, A.data_ptr(), A.stride(0)))
+        multi = dist.is_initialized() and dist.get_world_size(process_group) > 1
 
         def run():
-            if shared:
-                return run_shared()
+            # returns the regular quadrature order that the supplied tables lack (0: none)
             D = None
+            rc = 0
             if not empty:
                 _lib.check(L.pnb_dense_rows_begin(prob.handle, int(self.zeroExterior), row_begin, row_end, A.data_ptr(), A.stride(0)))
-            if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            if multi:
                 # sum of the per-cell diagonal blocks over the row blocks (disjoint supports: exact)
                 D = exchange_cell_blocks(self.mesh.num_cells*(nvc*(nvc+1)//2), dev, process_group,
                                          None if empty else (lambda buf: _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, buf.data_ptr(), 0))))
             if not empty:
                 if D is not None:
                     _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, D.data_ptr(), 1))
-                _lib.check(L.pnb_dense_rows_end(prob.handle, row_begin, row_end, A.data_ptr(), A.stride(0)))
-        self._retry_on_order(run)
+                rc = L.pnb_dense_rows_end(prob.handle, row_begin, row_end, A.data_ptr(), A.stride(0))
+                if rc not in (0, -5):
+                    _lib.check(rc)
+            return 1 if rc == -5 else 0
+        self._collective_retry(run, multi, process_group, dev)
         return Dense_LinearOperator(A, prob.device) if not empty else None
 
-    def _scratch(self, N, dev):
+    def _collective_retry(self, run, multi, process_group, dev):
+        """`run()` returns nonzero when a pair asked for a regular rule beyond the supplied tables (the reference grows
+        its rule cache lazily, addQuadRule).  The ranks evaluate different pairs, so only some of them may see it, and
+        `run` contains collectives: the decision to extend the tables and run again is taken by ALL ranks together."""
         import torch
-        U = getattr(self, '_U', None)
-        if U is None or U.shape[0] != N or U.device != dev:
-            U = self._U = torch.empty((N, N), dtype=torch.float64, device=dev)
-        return U
+        import torch.distributed as dist
+        for attempt in range(3):
+            flag = int(run())
+            if multi:
+                t = torch.tensor([flag], dtype=torch.int32, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=process_group)
+                flag = int(t.item())
+            if flag == 0:
+                return
+            need = self.problem.required_max_order(self.zeroExterior)       # the same value on every rank (all pairs)
+            self.problem.set_max_order(max(need, self.problem.max_order+1))
+        raise _lib.PNBError(-5, 'regular quadrature tables still too small after extending them')
+
+    # -- several GPUs, 2D: rows owned by cell groups ---------------------------------
+    def _dist_state(self, world, rank, process_group, local_ptrs=None):
+        """plan + staging buffers of the distributed assembly (kept between assemblies).  local_ptrs: staging pointers of
+        all parts when they live in this process (tests emulate several parts on one GPU); else the buffers are
+        exchanged as CUDA IPC handles over `process_group` and written through NVLink peer memory."""
+        import torch
+        import torch.distributed as dist
+        st = getattr(self, '_dist', None)
+        if st is not None and st['key'] == (world, rank) and (local_ptrs is None or st['ptrs'] == list(local_ptrs)):
+            return st
+        self.releaseScratch()
+        L = _lib.lib()
+        prob = self.problem
+        nrows, nstage = ctypes.c_int32(0), ctypes.c_int64(0)
+        _lib.check(L.pnb_dist_plan(prob.handle, world, rank, ctypes.byref(nrows), ctypes.byref(nstage)))
+        rows = np.empty(nrows.value, dtype=np.int32)
+        _lib.check(L.pnb_dist_rows(prob.handle, rows.ctypes.data))
+        st = dict(key=(world, rank), rows=rows, nstage=int(nstage.value), own=None, opened=[], ptrs=None, all_rows=None)
+        if local_ptrs is not None:
+            st['ptrs'] = list(local_ptrs)
+        else:
+            own = ctypes.c_void_p()
+            _lib.check(L.pnb_device_alloc(prob.device, 8*max(st['nstage'], 1), ctypes.byref(own)))
+            st['own'] = own
+            ptrs = [None]*world
+            ptrs[rank] = own.value
+            if world > 1:
+                h = (ctypes.c_ubyte*64)()
+                _lib.check(L.pnb_ipc_export(prob.device, own, h))
+                handles = [None]*world
+                dist.all_gather_object(handles, bytes(h), group=process_group)
+                for r, hb in enumerate(handles):
+                    if r == rank:
+                        continue
+                    q = ctypes.c_void_p()
+                    _lib.check(L.pnb_ipc_import(prob.device, (ctypes.c_ubyte*64).from_buffer_copy(hb), ctypes.byref(q)))
+                    st['opened'].append(q)
+                    ptrs[r] = q.value
+                all_rows = [None]*world
+                dist.all_gather_object(all_rows, rows, group=process_group)
+                st['all_rows'] = all_rows
+            else:
+                st['all_rows'] = [rows]
+            st['ptrs'] = ptrs
+        self._dist = st
+        return st
 
     def releaseScratch(self):
-        """frees the N x N work buffer that getDenseRowBlock keeps between calls on several GPUs"""
-        self._U = None
+        """frees the staging buffer that the distributed assembly keeps between calls (collective: the other ranks hold
+        it open as peer memory, so all ranks release together)"""
+        st = getattr(self, '_dist', None)
+        self._dist = None
+        if st is None:
+            return
+        L = _lib.lib()
+        dev = self.problem.device
+        for q in st['opened']:
+            L.pnb_ipc_close(dev, q)
+        if st['own'] is not None:
+            import torch
+            torch.cuda.synchronize(dev)
+            L.pnb_device_free(dev, st['own'])
 
-    def getDenseDistributed(self, process_group=None):
-        """getDense() sharded by rows over the ranks of `process_group` (one process per GPU): returns a
-        DistributedDenseOperator whose matvec all-gathers the product (the reference's distributed operators
-        Allreduce instead, clusterMethodCy.pyx:3136-3142)."""
+    def getDenseDistributed(self, process_group=None, out=None):
+        """getDense() sharded over the ranks of `process_group` (one process per GPU).
+
+        2D: every rank owns a contiguous range of cell groups (Hilbert order) and the rows of their dofs; every cell
+        pair is evaluated once over all ranks, and a unit block reaches the owners of its rows through NVLink peer
+        stores into their staging buffers (no N x N work buffer, no collective over matrix entries; the reference
+        Allreduces the whole matrix, nonlocalAssembly_{SCALAR}.pxi:1449-1450).  What is exchanged collectively: the
+        per-cell diagonal blocks (num_cells x 6 doubles, one all-reduce) and one status word.
+        1D: contiguous row blocks (getDenseRowBlock).
+        Returns a DistributedDenseOperator whose matvec all-gathers the product."""
+        import torch
         import torch.distributed as dist
         from .solvers import DistributedDenseOperator
-        world = dist.get_world_size(process_group)
-        rank = dist.get_rank(process_group)
+        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        rank = dist.get_rank(process_group) if dist.is_initialized() else 0
         N = self.dm.num_dofs
-        blocks = row_partition(N, world, int(_lib.lib().pnb_row_granularity()))
-        a, b = blocks[rank]
-        rows = self.getDenseRowBlock(a, b, process_group=process_group)
-        return DistributedDenseOperator(rows, a, b, N, blocks, process_group)
+        if self.mesh.dim == 1:
+            blocks = row_partition(N, world, int(_lib.lib().pnb_row_granularity()))
+            a, b = blocks[rank]
+            rows = self.getDenseRowBlock(a, b, process_group=process_group)
+            return DistributedDenseOperator(rows, [np.arange(x, y, dtype=np.int32) for x, y in blocks], rank, N, process_group)
+        self._no_dm2()
+        prob = self.problem
+        dev = torch.device('cuda', prob.device)
+        st = self._dist_state(world, rank, process_group)
+        rows = st['rows']
+        if out is not None and rows.shape[0] > 0:
+            check_matrix_out(out, rows.shape[0], N, dev)
+        A = torch.empty((rows.shape[0], N), dtype=torch.float64, device=dev) if out is None else out
+        self._dist_run(st, A, process_group, world > 1)
+        return DistributedDenseOperator(Dense_LinearOperator(A, prob.device) if rows.shape[0] else None, st['all_rows'], rank, N,
+                                        process_group)
+
+    def _dist_run(self, st, A, process_group, multi):
+        """evaluation into the staging buffers, collective status / cell-block exchange, rows from the fragments"""
+        import torch
+        L = _lib.lib()
+        prob = self.problem
+        dev = torch.device('cuda', prob.device)
+        nvc = self.mesh.dim+1
+        world = st['key'][0]
+        ptrs = (ctypes.c_void_p*world)(*st['ptrs'])
+
+        def run():
+            _lib.check(L.pnb_dist_eval(prob.handle, int(self.zeroExterior), ptrs))
+            need = ctypes.c_int32(0)
+            _lib.check(L.pnb_dist_status(prob.handle, ctypes.byref(need)))
+            return 1 if need.value > 0 else 0
+        # the all-reduce of the status word is also the point where every rank knows that all fragments have arrived
+        self._collective_retry(run, multi, process_group, dev)
+        if multi:
+            D = exchange_cell_blocks(self.mesh.num_cells*(nvc*(nvc+1)//2), dev, process_group,
+                                     lambda buf: _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, buf.data_ptr(), 0)))
+            _lib.check(L.pnb_dense_cell_blocks_copy(prob.handle, D.data_ptr(), 1))
+        if st['rows'].shape[0] > 0:
+            _lib.check(L.pnb_dist_apply(prob.handle, 1, A.data_ptr(), A.stride(0)))
 
     def getDenseHost(self, out=None):
         """Same as getDense() but through the host-buffer C entry point: the result is written to host memory

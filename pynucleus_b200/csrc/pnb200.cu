@@ -56,6 +56,25 @@ static int fail(int code, const std::string &msg)
                         std::string(#call) + ": " + cudaGetErrorString(e_));                         \
     } while (0)
 
+// Entry points run on the problem's device and hand the calling thread its previous current device back on every
+// exit path (the caller -- torch -- keeps allocating on whatever device is current).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        err = cudaSetDevice(device);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ON_DEVICE(dev)          \
+    DeviceGuard device_guard_(dev); \
+    CK(device_guard_.err)
+
 extern "C" int pnb_device_count(void)
 {
     int n = 0;
@@ -160,8 +179,48 @@ template <class K> static void smem_optin(K kernel, int device)
     cudaFuncAttributes attr;
     if (smem_blk > 0 && cudaFuncGetAttributes(&attr, kernel) == cudaSuccess)
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_blk - (int)attr.sharedSizeBytes);
+    // all of the unified L1 as shared memory: two CTAs of ~100 KB must be resident per SM (with the default carve-out
+    // the driver kept a single CTA of the near evaluator and of the order-2 kernel on an SM: 8 warps instead of 16)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
     done[key] = true;
+}
+
+// ---------------------------------------------------------------------------
+// mesh.hVector / mesh.h / mesh.hmin as the reference computes them (hdeltaCy, fem/PyNucleus_fem/meshCy.pyx:1654-1732):
+// per cell the longest edge, over the mesh the longest and the SHORTEST edge, every edge length being
+// sqrt(mydot(e, e)) with mydot = BLAS ddot (base/PyNucleus_base/opt_true_blas.pxi:125-141).  The ddot of the BLAS the
+// reference links (OpenBLAS through scipy) accumulates with fused multiply-adds, x1*x1 + fl(x0*x0) in ONE rounding;
+// getQuadOrder takes logarithms of these numbers and rounds up, so the last bit decides the quadrature order of
+// some pairs on large meshes.  Host arithmetic only (no device needed).
+// ---------------------------------------------------------------------------
+extern "C" int pnb_mesh_edge_lengths(int32_t dim, int32_t num_cells, const double *vertices, const int32_t *cells,
+                                     double *h, double *h_max, double *h_min)
+{
+    if (!vertices || !cells || !h || !h_max || !h_min) return fail(PNB_ERR_ARG, "null argument");
+    if (dim != 1 && dim != 2) return fail(PNB_ERR_UNSUPPORTED, "pnb_mesh_edge_lengths: dim must be 1 or 2");
+    double hmax = 0., hmin = 100.;       // the reference starts from 100 (meshCy.pyx:1661)
+    for (int32_t c = 0; c < num_cells; c++) {
+        double hl = 0.;
+        if (dim == 1) {
+            hl = fabs(vertices[cells[2 * (size_t)c + 1]] - vertices[cells[2 * (size_t)c]]);
+            hmin = std::min(hmin, hl);
+        } else {
+            const double *v0 = vertices + 2 * (size_t)cells[3 * (size_t)c], *v1 = vertices + 2 * (size_t)cells[3 * (size_t)c + 1],
+                         *v2 = vertices + 2 * (size_t)cells[3 * (size_t)c + 2];
+            const double e[3][2] = {{v2[0] - v1[0], v2[1] - v1[1]}, {v2[0] - v0[0], v2[1] - v0[1]}, {v1[0] - v0[0], v1[1] - v0[1]}};
+            for (int j = 0; j < 3; j++) {
+                const double hS = sqrt(fma(e[j][1], e[j][1], e[j][0] * e[j][0]));
+                hmin = std::min(hmin, hS);
+                hl = std::max(hl, hS);
+            }
+        }
+        hmax = std::max(hmax, hl);
+        h[c] = hl;
+    }
+    *h_max = hmax;
+    *h_min = hmin;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -184,6 +243,7 @@ struct TileSched {
     int *err;               // [0]: max order requested beyond tables
     unsigned long long *counters;  // [0] evaluated pairs (far pass), [1] evaluated pairs (near pass)
     int own_t0, own_t1;     // row tiles [own_t0, own_t1) are owned (written) by this problem instance
+    const unsigned char *cell_mask;  // several GPUs (pnb_dist_plan): cells whose surface terms this instance computes; nullptr: by home tile
     int maxcells;           // largest cell list of a tile
     int *tileflag;          // ntiles x ntiles: tile holds pairs for the near pass
     int *unitflag;          // nunits: unit holds flagged tiles
@@ -207,7 +267,9 @@ struct pnb_problem {
     int pow_eoff = 240;      // PowTab::eoff of this problem
     std::vector<double> h_centers, h_h;
     std::vector<int4> h_grid;         // lane grids of the near evaluator per order
+    std::vector<int> h_reg_n;         // node count of the regular cell rule per order
     int part = 0, nparts = 1;         // share of the units this problem instance evaluates (multi-GPU)
+    bool dist = false;                // several GPUs: parts own groups (pnb_dist_plan)
     DProblem P{};
     TileSched S{};
     std::vector<void *> allocs;       // everything to free
@@ -282,7 +344,7 @@ static void build_powtab(PowTab *t, double scal, double expo, int eoff)
 extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
 {
     if (!p || !rules) return fail(PNB_ERR_ARG, "null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     for (void *d : p->rule_allocs) pool_free(d);
     p->rule_allocs.clear();
     const int nvc = p->dim + 1;
@@ -309,12 +371,12 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
     p->P.max_order = mo;
     p->P.reg_derived = nullptr; p->P.reg_doff = nullptr; p->P.reg_nmax = 0; p->P.reg_grid = nullptr;
     if (p->dim == 2) {
-        // per node: w, w*bary[0..2], w*bary[a]*bary[b] (a<=b), bary[0..2]
+        // per node PNB_DER2 double2: (w, w b0) (w b1, w b2) (q0,q1) (q2,q3) (q4,q5) with q = w b_a b_b (a<=b), (b0,b1) (b2,0)
         std::vector<int> doff(mo + 2, 0);
         std::vector<double> der;
         for (int o = 1; o <= mo; o++) {
             const pnb_rule_t &r = rules->cell[o];
-            doff[o] = (int)(der.size() / 13);
+            doff[o] = (int)(der.size() / (2 * PNB_DER2));
             p->P.reg_nmax = std::max(p->P.reg_nmax, r.n);
             for (int i = 0; i < r.n; i++) {
                 der.push_back(r.w[i]);
@@ -322,37 +384,35 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
                 for (int a = 0; a < 3; a++)
                     for (int b = a; b < 3; b++) der.push_back(r.w[i] * r.bary[a * r.n + i] * r.bary[b * r.n + i]);
                 for (int k = 0; k < 3; k++) der.push_back(r.bary[k * r.n + i]);
+                der.push_back(0.);
             }
         }
-        doff[mo + 1] = (int)(der.size() / 13);
-        // lane grid of the near evaluator per order: the smallest lane group (8, 16, 32) whose best RS x CS grid
-        // keeps >= 84 % of the lanes busy with <= 192 node pairs per lane, else the best grid found
-        std::vector<int4> grid(mo + 1, make_int4(32, 1, 32, 0));
+        doff[mo + 1] = (int)(der.size() / (2 * PNB_DER2));
+        // lane groups of the near evaluator per order: W lanes per item (they split the row tiles of PNB_NEAR_R rows),
+        // K = 32 / W items per warp; the pair (W, K) with the best lane utilisation whose column nodes fit the
+        // per-warp buffer of PNB_NEAR_WARP_POINTS points; ties: fewer lanes per item (longer loops, shorter reduction)
+        std::vector<int4> grid(mo + 1, make_int4(32, 1, 1, 0));
         for (int o = 1; o <= mo; o++) {
             const int n = rules->cell[o].n;
             if (n <= 0) continue;
             const int nsl = std::max(1, (n * n + 2047) / 2048), ncols = (n + nsl - 1) / nsl;
+            const int ntiles = (n + PNB_NEAR_R - 1) / PNB_NEAR_R;
             double best = -1.;
-            bool found = false;
-            for (int LPI = 8; LPI <= 32 && !found; LPI *= 2) {
-                if ((int64_t)n * (32 / LPI) > p->P.reg_nmax) continue;
-                double bu = -1.;
-                int4 bg = make_int4(LPI, 1, LPI, 0);
-                for (int RS = 1; RS <= LPI; RS++) {
-                    const int CS = LPI / RS;
-                    const int rp = (n + RS - 1) / RS, cp = (ncols + CS - 1) / CS;
-                    if (rp * cp > (LPI == 32 ? 1 << 30 : 192)) continue;
-                    const double u = ((double)n / (rp * RS)) * ((double)ncols / (cp * CS)) * ((double)RS * CS / LPI);
-                    if (u > bu) { bu = u; bg = make_int4(RS, CS, LPI, 0); }
-                }
-                if (bu > best) { best = bu; grid[o] = bg; }
-                if (bu >= 0.84) found = true;
+            for (int W = 1; W <= 32; W++) {
+                const int K = 32 / W;
+                if (K * (3 + ncols) > PNB_NEAR_WARP_POINTS) continue;
+                const int tp = (ntiles + W - 1) / W;
+                if ((int64_t)tp * PNB_NEAR_R * ncols > 4096) continue;        // bound on the work of one lane
+                const double u = (double)n / ((double)tp * W * PNB_NEAR_R) * ((double)K * W / 32.);
+                if (u > best + 1e-9) { best = u; grid[o] = make_int4(W, K, tp, 0); }
             }
         }
         if (upload(p, der.data(), der.size(), &p->P.reg_derived, true)) return PNB_ERR_CUDA;
         if (upload(p, doff.data(), doff.size(), &p->P.reg_doff, true)) return PNB_ERR_CUDA;
         if (upload(p, grid.data(), grid.size(), &p->P.reg_grid, true)) return PNB_ERR_CUDA;
         p->h_grid = grid;
+        p->h_reg_n.assign(mo + 1, 0);
+        for (int o = 1; o <= mo; o++) p->h_reg_n[o] = rules->cell[o].n;
     }
     // low-order 2D rules for the thread-per-pair evaluator (orders 2..5, node counts fixed at compile time)
     memset(p->far_rules, 0, sizeof(p->far_rules));
@@ -386,7 +446,7 @@ static void destroy_group_host(pnb_problem *p);
 extern "C" void pnb_problem_destroy(pnb_problem *p)
 {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard guard(p->device);
     for (void *d : p->allocs) pool_free(d);
     for (void *d : p->rule_allocs) pool_free(d);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
@@ -507,7 +567,7 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         return fail(PNB_ERR_NO_DEVICE, "no CUDA device: libpnb200 has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return fail(PNB_ERR_ARG, "invalid device index");
-    CK(cudaSetDevice(device));
+    ON_DEVICE(device);
 
     const double tc0 = wall_ms();
     pnb_problem *p = new pnb_problem();
@@ -742,7 +802,7 @@ __global__ void max_order_kernel(DProblem P, int zero_exterior, int *out, unsign
 extern "C" int pnb_max_order(pnb_problem *p, int zero_exterior, int32_t *max_order_out)
 {
     if (!p || !max_order_out) return fail(PNB_ERR_ARG, "null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     CK(cudaMemset(p->S.err, 0, sizeof(int) * 4));
     max_order_kernel<<<(p->nc + 127) / 128, 128>>>(p->P, zero_exterior, p->S.err + 1, nullptr);
     CK(cudaGetLastError());
@@ -755,7 +815,7 @@ extern "C" int pnb_max_order(pnb_problem *p, int zero_exterior, int32_t *max_ord
 extern "C" int pnb_panel_histogram(pnb_problem *p, int64_t *hist)
 {
     if (!p || !hist) return fail(PNB_ERR_ARG, "null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     unsigned long long *d = nullptr;
     CK(cudaMalloc(&d, 259 * sizeof(unsigned long long)));
     CK(cudaMemset(d, 0, 259 * sizeof(unsigned long long)));
@@ -771,7 +831,7 @@ extern "C" int pnb_classify_pairs(pnb_problem *p, int boundary, int64_t npairs, 
                                   int32_t *perm1, int32_t *perm2)
 {
     if (!p || !pairs || !panel) return fail(PNB_ERR_ARG, "null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int nvc = p->dim + 1;
     int *dpairs = nullptr, *dpanel = nullptr, *dp1 = nullptr, *dp2 = nullptr;
     const size_t n = (size_t)std::max<int64_t>(npairs, 1);
@@ -910,7 +970,7 @@ extern "C" int pnb_local_matrices(pnb_problem *p, int boundary, int path, int64_
 {
     if (!p || !pairs || !panel || !contrib) return fail(PNB_ERR_ARG, "null argument");
     if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int nvc = p->dim + 1;
     const int nloc = boundary ? nvc * (nvc + 1) / 2 : (2 * nvc) * (2 * nvc + 1) / 2;
     int *dpairs = nullptr, *dpanel = nullptr;
@@ -1472,7 +1532,7 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
     bool any = false;
     for (int m = 0; m < NV; m++) any |= P.dofs[(size_t)c1 * NV + m] >= 0;
     if (!any) return;
-    if (S.home[c1] < S.own_t0 || S.home[c1] >= S.own_t1) return;
+    if (S.cell_mask ? !S.cell_mask[c1] : (S.home[c1] < S.own_t0 || S.home[c1] >= S.own_t1)) return;
     double tot[ND];
 #pragma unroll
     for (int k = 0; k < ND; k++) tot[k] = 0.;
@@ -1804,6 +1864,18 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
 
 struct GroupHostFull : GroupHost {
     GroupGeom gg;
+    // several GPUs (pnb_dist_plan): part of every group, owner / position tables of the group-local dofs, rows of this part
+    std::vector<int> gr_part, rows, gcnt;
+    std::vector<unsigned char> gown, gpos;
+    std::vector<signed char> kinds;         // ngroups x ngroups (I <= J): unit kind, -1 = no pair of this problem instance
+    std::vector<int> ticket;                // ngroups x ngroups: list position | list << 30 of the units of this instance
+    bool dist = false;
+    std::vector<long long> uoff_all;        // ngroups x ngroups: start of the unit's fragments in THIS part's staging, -1 = none
+    long long stage_doubles = 0;
+    bool dist_ready = false;
+    std::vector<void *> dist_allocs;
+    DistApply apply{};
+    const unsigned char *d_cell_mask = nullptr;
     int far_mask = -1, max_order = -1, part = -1, nparts = -1;
     std::vector<void *> unit_allocs, near_allocs;
     const int2 *d_items = nullptr;
@@ -1811,6 +1883,7 @@ struct GroupHostFull : GroupHost {
     const int4 *d_chunks = nullptr;
     double *d_R = nullptr, *d_F = nullptr;
     int nitems = 0, npairs = 0, nchunks = 0;
+    int near_nmax = 1;                      // largest node count of a regular rule with near items
     bool near_ready = false;
 };
 
@@ -1886,7 +1959,10 @@ static int build_group_schedule(pnb_problem *p)
             fprintf(stderr, "group path: GC %d, %d groups, cap %d, maxld %d, %d colours, smem f2/mix/near %zu/%zu/%zu\n", gh->GC,
                     gg.ngroups, gg.cap, gg.maxld, gg.ncolors, gh->smem_f2, gh->smem_mix, gh->smem_near);
     }
-    if (gh->far_mask == p->far_mask && gh->max_order == p->P.max_order && gh->part == p->part && gh->nparts == p->nparts) return 0;
+    if (gh->far_mask == p->far_mask && gh->max_order == p->P.max_order && gh->part == p->part && gh->nparts == p->nparts &&
+        gh->dist == p->dist)
+        return 0;
+    gh->dist_ready = false;
     const double tw1 = wall_ms();
     // ---- unit kinds (depend on the tables) ----
     const GroupGeom &gg = gh->gg;
@@ -1900,8 +1976,8 @@ static int build_group_schedule(pnb_problem *p)
     std::vector<std::vector<GUnit>> f2(gh->nphase), mix(gh->nphase);
     gh->near_units.clear();
     int nslots = 0;
-    // several GPUs: the units of every (phase, kind) are dealt out round-robin
-    std::vector<int> dealt((size_t)gh->nphase * 3, 0);
+    // kind of every unit (depends on the tables)
+    gh->kinds.assign((size_t)gg.ngroups * gg.ngroups, -1);
     for (int I = 0; I < gg.ngroups; I++) {
         const double *b1 = &gg.box[(size_t)I * 7];
         for (int J = I; J < gg.ngroups; J++) {
@@ -1920,9 +1996,44 @@ static int build_group_schedule(pnb_problem *p)
                     if (!pnb_class_active(p->P, lI[0], lJ[0])) continue;      // no pair of this unit belongs to the class
                 } else if (kind == 0) kind = 1;                                // mixed labels: classified pair by pair
             }
+            gh->kinds[(size_t)I * gg.ngroups + J] = (signed char)kind;
+        }
+    }
+    if (gh->nparts != p->nparts) gh->gr_part.clear();
+    if (p->dist && gh->gr_part.empty()) {
+        // several GPUs: contiguous ranges of groups (Hilbert order) per part, balanced by the estimated work of the
+        // units in the group's row and column (a part evaluates about half of the units that touch its groups)
+        static const double kind_cost[3] = {1., 3.5, 9.};
+        std::vector<double> gcost(gg.ngroups, 0.);
+        double total = 0.;
+        for (int I = 0; I < gg.ngroups; I++)
+            for (int J = I; J < gg.ngroups; J++) {
+                const int k = gh->kinds[(size_t)I * gg.ngroups + J];
+                if (k < 0) continue;
+                const double c = kind_cost[k] * (I == J ? 0.5 : 1.);
+                gcost[I] += 0.5 * c; gcost[J] += 0.5 * c;
+                total += c;
+            }
+        gh->gr_part.assign(gg.ngroups, 0);
+        double acc = 0.;
+        for (int g = 0; g < gg.ngroups; g++) {
+            // the group goes to the part in whose share of the total its midpoint falls
+            const double mid = acc + 0.5 * gcost[g];
+            gh->gr_part[g] = total > 0. ? std::min(p->nparts - 1, (int)(mid / total * p->nparts)) : 0;
+            acc += gcost[g];
+        }
+    }
+    for (int I = 0; I < gg.ngroups; I++) {
+        for (int J = I; J < gg.ngroups; J++) {
+            const int kind = gh->kinds[(size_t)I * gg.ngroups + J];
+            if (kind < 0) continue;
             GUnit u{I, J, kind, -1};
             const int ph = gg.color[I] * ncol + gg.color[J];
-            if ((dealt[(size_t)ph * 3 + kind]++ % p->nparts) != p->part) continue;
+            if (p->dist) {
+                // the unit is evaluated by the part of its row group or of its column group, alternating
+                const int rI = gh->gr_part[I], rJ = gh->gr_part[J];
+                if ((((I + J) & 1) ? rJ : rI) != p->part) continue;
+            }
             if (kind == 2) { u.slot = nslots++; gh->near_units.push_back(u); }
             (kind == 0 ? f2 : mix)[ph].push_back(u);
         }
@@ -1947,7 +2058,8 @@ static int build_group_schedule(pnb_problem *p)
     if (up(gh->f2_units, &gh->d_f2) || up(gh->mix_units, &gh->d_mix) || up(gh->near_units, &gh->d_near)) return PNB_ERR_CUDA;
     {
         // list positions of the units (phase-major order: neighbours in the list never touch the same entries of U)
-        std::vector<int> ticket((size_t)gg.ngroups * gg.ngroups, -1);
+        std::vector<int> &ticket = gh->ticket;
+        ticket.assign((size_t)gg.ngroups * gg.ngroups, -1);
         for (size_t k = 0; k < gh->f2_units.size(); k++) ticket[(size_t)gh->f2_units[k].I * gg.ngroups + gh->f2_units[k].J] = (int)k;
         for (size_t k = 0; k < gh->mix_units.size(); k++)
             ticket[(size_t)gh->mix_units[k].I * gg.ngroups + gh->mix_units[k].J] = (int)k | (1 << 30);
@@ -1966,6 +2078,7 @@ static int build_group_schedule(pnb_problem *p)
     gh->max_order = p->P.max_order;
     gh->part = p->part;
     gh->nparts = p->nparts;
+    gh->dist = p->dist;
     if (getenv("PNB_BENCH_VERBOSE"))
         fprintf(stderr, "group path: units f2 %zu, mix %zu (near %zu), phases %d; host ms: groups %.1f, units %.1f\n",
                 gh->f2_units.size(), gh->mix_units.size(), gh->near_units.size(), gh->nphase, tw1 - tw0, wall_ms() - tw1);
@@ -2006,10 +2119,12 @@ static int build_near_list(pnb_problem *p)
         std::vector<int4> chunks;
         {
             int off = 0;
+            gh->near_nmax = 1;
             for (int t = 63; t >= 0; t--) {
                 const int key = t;
                 hbase[key] = off;
-                const int K = key >= 1 ? 32 / (key < (int)p->h_grid.size() ? p->h_grid[key].z : 32) : 1;
+                if (key >= 1 && hb[key] > 0 && key <= p->P.max_order) gh->near_nmax = std::max(gh->near_nmax, p->h_reg_n[key]);
+                const int K = key >= 1 ? (key < (int)p->h_grid.size() ? p->h_grid[key].y : 1) : 1;
                 const int per = (PNB_THREADS / 32) * K;
                 for (int q = 0; q < hb[key]; q += per) chunks.push_back(make_int4(key, off + q, std::min(per, hb[key] - q), 0));
                 off += hb[key];
@@ -2062,17 +2177,23 @@ static int build_near_list(pnb_problem *p)
 // part / nparts: share of the units evaluated by this instance (nparts > 1: dA is a full N x N scratch that holds
 // this share of U + U^T afterwards; the caller sums the shares of all instances).  own tiles: cells whose home
 // tile is owned get their boundary terms here.
-static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t ld, int part = 0, int nparts = 1, int own_t0 = 0, int own_t1 = -1)
+static int build_dist_tables(pnb_problem *p);
+static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t ld, int part = 0, int nparts = 1, int own_t0 = 0, int own_t1 = -1,
+                          bool dist = false)
 {
     p->part = part;
     p->nparts = nparts;
+    p->dist = dist;
     if (build_group_schedule(p)) return PNB_ERR_CUDA;
+    if (dist && build_dist_tables(p)) return PNB_ERR_CUDA;
+    if (!dist && p->G) p->G->dist.nparts = 0;
     GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
     GroupSched &G = *p->G;
     TileSched &S = p->S;
     const int nc = p->nc, N = p->N;
     S.own_t0 = own_t0;
     S.own_t1 = own_t1 < 0 ? S.ntiles : own_t1;
+    S.cell_mask = dist ? gh->d_cell_mask : nullptr;
     // unit slots of the other instances stay untouched: start from zero
     if (nparts > 1) cudaMemsetAsync(G.Dp, 0, (size_t)G.ngroups * nc * 6 * sizeof(double));
     for (auto &e : p->ev) if (!e) cudaEventCreate(&e);
@@ -2087,7 +2208,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
             for (int e = 0; e < 6; e++) R.qq[e][q] = F.qq[e][q];
         }
         R.c[0] = 1.;
-        for (int k = 1; k < 8; k++) R.c[k] = R.c[k - 1] * (p->P.expo - k + 1) / k;
+        for (int k = 1; k < 8; k++) R.c[k] = R.c[k - 1] * (p->P.expo - k + 1) / k;     // = PowTab::coef
         R.eoff = p->pow_eoff - 1023;
         R.pad = 0;
     }
@@ -2095,7 +2216,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
     cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * 6 * sizeof(double));
     cudaEventRecord(p->ev[0]);
-    cudaMemset2DAsync(dA, (size_t)ld * sizeof(double), 0, (size_t)N * sizeof(double), N);
+    if (!dist) cudaMemset2DAsync(dA, (size_t)ld * sizeof(double), 0, (size_t)N * sizeof(double), N);
     int launches = 0;
     const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
     {
@@ -2109,7 +2230,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         for (auto &e : p->kev) if (!e) cudaEventCreate(&e);
         cudaEventRecord(p->kev[0]);
         if (nf > 0 && !(dbg & 0x1000)) {
-            gf2_kernel<<<std::min(nf, nsm), PNB_GT, gh->smem_f2>>>(p->P, G, gh->d_f2, nf, dA, ld, R);
+            gf2_kernel<<<std::min(nf, 2 * nsm), PNB_F2T, gh->smem_f2>>>(p->P, G, gh->d_f2, nf, dA, ld, R);
             launches++;
         }
         cudaEventRecord(p->kev[1]);
@@ -2117,12 +2238,14 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         if (build_near_list(p)) return PNB_ERR_CUDA;
         if (gh->nitems > 0 && !(dbg & 0x100)) {
             const int wpb = PNB_THREADS / 32;
-            const size_t smem_eval = sizeof(PowTab) + ((size_t)13 + (size_t)wpb * 4) * p->P.reg_nmax * sizeof(double);
+            // rule table of the largest order that has items; per warp PNB_NEAR_WARP_POINTS points
+            const size_t smem_eval = sizeof(PowTabS) + ((size_t)PNB_DER2 * gh->near_nmax + (size_t)wpb * PNB_NEAR_WARP_POINTS) * sizeof(double2);
             smem_optin(gnear_eval_kernel, p->device);
             int nsm = 148;
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
             const int grid = std::min(gh->nchunks, 2 * nsm);
-            gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R);
+            gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R,
+                                                                gh->near_nmax, PNB_NEAR_WARP_POINTS);
             gnear_finalize_kernel<<<(gh->npairs + 255) / 256, 256>>>(p->P, G.npairs, gh->npairs, gh->d_R, gh->d_F);
             launches += 2;
         }
@@ -2133,7 +2256,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         }
     }
     cudaEventRecord(p->kev[3]);
-    {
+    if (!dist) {
         const unsigned nt = (unsigned)((N + 31) / 32);
         symmetrize_kernel<<<dim3(nt, nt), 256>>>(dA, ld, N);
         launches++;
@@ -2153,12 +2276,277 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// several GPUs: parts own groups and the rows of their dofs (no N x N scratch, no collective over matrix entries)
+// ---------------------------------------------------------------------------
+// Tables of the distributed assembly, built after the unit lists: which part owns every dof (the part of the first
+// group, in Hilbert order, that holds it), where the fragments of every unit start in the staging buffer of every
+// part, the rows of this part and the lookup tables of dist_apply_kernel.
+static int build_dist_tables(pnb_problem *p)
+{
+    GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+    GroupSched &G = *p->G;
+    if (gh->dist_ready) return 0;
+    const GroupGeom &gg = gh->gg;
+    const int ng = gg.ngroups, W = p->nparts, me = p->part, N = p->N, nc = p->nc;
+    if (W > PNB_MAX_PARTS) return fail(PNB_ERR_ARG, "too many parts");
+    const double tw0 = wall_ms();
+    for (void *d : gh->dist_allocs) pool_free(d);
+    gh->dist_allocs.clear();
+    // owner of every dof
+    std::vector<int> owner(N, -1);
+    std::vector<int> d2g_cnt(N + 1, 0);
+    for (int g = 0; g < ng; g++)
+        for (int k = gg.gdptr[g]; k < gg.gdptr[g + 1]; k++) {
+            const int d = gg.gdofs[k];
+            if (owner[d] < 0) owner[d] = gh->gr_part[g];
+            d2g_cnt[d + 1]++;
+        }
+    for (int d = 0; d < N; d++) d2g_cnt[d + 1] += d2g_cnt[d];
+    std::vector<int2> d2g(gg.gdofs.size());
+    {
+        std::vector<int> fill(d2g_cnt.begin(), d2g_cnt.end() - 1);
+        for (int g = 0; g < ng; g++)
+            for (int k = gg.gdptr[g]; k < gg.gdptr[g + 1]; k++) d2g[fill[gg.gdofs[k]]++] = make_int2(g, k - gg.gdptr[g]);
+    }
+    gh->gown.assign(gg.gdofs.size(), 0);
+    gh->gpos.assign(gg.gdofs.size(), 0);
+    gh->gcnt.assign((size_t)ng * W, 0);
+    for (int g = 0; g < ng; g++)
+        for (int k = gg.gdptr[g]; k < gg.gdptr[g + 1]; k++) {
+            const int o = owner[gg.gdofs[k]];
+            gh->gown[k] = (unsigned char)o;
+            gh->gpos[k] = (unsigned char)gh->gcnt[(size_t)g * W + o]++;
+        }
+    gh->rows.clear();
+    for (int d = 0; d < N; d++)
+        if (owner[d] == me) gh->rows.push_back(d);
+    // fragments of every unit in the staging buffer of part o: rows of I owned by o (nldJ values each), then rows of J
+    // owned by o (nldI values each); units in lexicographic order
+    const size_t nf2 = gh->f2_units.size(), nmix = gh->mix_units.size();
+    std::vector<long long> uoff_f2(std::max<size_t>(nf2, 1) * W, 0), uoff_mix(std::max<size_t>(nmix, 1) * W, 0);
+    gh->uoff_all.assign((size_t)ng * ng, -1);
+    std::vector<long long> run(W, 0);
+    for (int I = 0; I < ng; I++) {
+        const int nldI = gg.gdptr[I + 1] - gg.gdptr[I];
+        for (int J = I; J < ng; J++) {
+            if (gh->kinds[(size_t)I * ng + J] < 0) continue;
+            const int nldJ = gg.gdptr[J + 1] - gg.gdptr[J];
+            const int tk = gh->ticket[(size_t)I * ng + J];
+            long long *mine = tk < 0 ? nullptr : ((tk >> 30) ? &uoff_mix[(size_t)(tk & 0x3FFFFFFF) * W] : &uoff_f2[(size_t)tk * W]);
+            for (int o = 0; o < W; o++) {
+                const long long sz = (long long)gh->gcnt[(size_t)I * W + o] * nldJ + (long long)gh->gcnt[(size_t)J * W + o] * nldI;
+                if (mine) mine[o] = run[o];
+                if (o == me && sz > 0) gh->uoff_all[(size_t)I * ng + J] = run[o];
+                run[o] += sz;
+            }
+        }
+    }
+    gh->stage_doubles = run[me];
+    // groups by colour
+    std::vector<int> colptr(gg.ncolors + 1, 0), collist(ng);
+    for (int g = 0; g < ng; g++) colptr[gg.color[g] + 1]++;
+    for (int c = 0; c < gg.ncolors; c++) colptr[c + 1] += colptr[c];
+    {
+        std::vector<int> fill(colptr.begin(), colptr.end() - 1);
+        for (int g = 0; g < ng; g++) collist[fill[gg.color[g]]++] = g;
+    }
+    // cells whose surface terms this part computes: the cells of its groups
+    std::vector<unsigned char> mask(nc, 0);
+    for (int g = 0; g < ng; g++)
+        if (gh->gr_part[g] == me)
+            for (int k = gg.gptr[g]; k < gg.gptr[g + 1]; k++)
+                if (gg.gcells[k] >= 0) mask[gg.gcells[k]] = 1;
+    auto up = [&](const void *host, size_t bytes, const void **dev) -> int {
+        void *d = nullptr;
+        CK(pool_malloc(&d, std::max<size_t>(bytes, 16)));
+        gh->dist_allocs.push_back(d);
+        if (bytes) CK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+        *dev = d;
+        return 0;
+    };
+    DistSched &D = G.dist;
+    DistApply &X = gh->apply;
+    int rc = 0;
+    rc |= up(gh->gown.data(), gh->gown.size(), (const void **)&D.gown);
+    rc |= up(gh->gpos.data(), gh->gpos.size(), (const void **)&D.gpos);
+    rc |= up(gh->gcnt.data(), gh->gcnt.size() * sizeof(int), (const void **)&D.gcnt);
+    rc |= up(uoff_f2.data(), uoff_f2.size() * sizeof(long long), (const void **)&D.uoff_f2);
+    rc |= up(uoff_mix.data(), uoff_mix.size() * sizeof(long long), (const void **)&D.uoff_mix);
+    rc |= up(gh->rows.data(), gh->rows.size() * sizeof(int), (const void **)&X.rows);
+    rc |= up(d2g_cnt.data(), d2g_cnt.size() * sizeof(int), (const void **)&X.d2g_ptr);
+    rc |= up(d2g.data(), d2g.size() * sizeof(int2), (const void **)&X.d2g);
+    rc |= up(colptr.data(), colptr.size() * sizeof(int), (const void **)&X.colptr);
+    rc |= up(collist.data(), collist.size() * sizeof(int), (const void **)&X.collist);
+    rc |= up(gh->uoff_all.data(), gh->uoff_all.size() * sizeof(long long), (const void **)&X.uoff);
+    rc |= up(mask.data(), mask.size(), (const void **)&gh->d_cell_mask);
+    if (rc) return PNB_ERR_CUDA;
+    X.nrows = (int)gh->rows.size();
+    D.nparts = W;
+    D.part = me;
+    gh->dist_ready = true;
+    if (getenv("PNB_BENCH_VERBOSE"))
+        fprintf(stderr, "dist plan: part %d of %d, %d rows, staging %.2f GB; host ms %.1f\n", me, W, X.nrows, gh->stage_doubles * 8e-9,
+                wall_ms() - tw0);
+    return 0;
+}
+
+// Several GPUs, 2D.  Part `part` of `nparts` (one problem instance per GPU) owns a contiguous range of cell groups
+// (cells ordered along a Hilbert curve, ranges balanced by estimated work) and the rows of the dofs that first appear in
+// its groups.  Every cell pair is evaluated once over all parts: a unit of two groups by the part of its row group or
+// of its column group, alternating.  Replaces the reference's cell-range split + Allreduce of the N x N matrix
+// (nonlocalAssembly_{SCALAR}.pxi:1280-1285, 1449-1450): per GPU only the owned rows and a staging buffer of about
+// twice their size exist, and no collective moves matrix entries.
+extern "C" int pnb_dist_plan(pnb_problem *p, int32_t nparts, int32_t part, int32_t *num_rows, int64_t *staging_doubles)
+{
+    if (!p || !num_rows || !staging_doubles) return fail(PNB_ERR_ARG, "null argument");
+    if (p->dim != 2) return fail(PNB_ERR_UNSUPPORTED, "pnb_dist_plan: 2D only (1D problems use row blocks)");
+    if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
+    if (nparts < 1 || nparts > PNB_MAX_PARTS || part < 0 || part >= nparts) return fail(PNB_ERR_ARG, "invalid part");
+    ON_DEVICE(p->device);
+    p->part = part;
+    p->nparts = nparts;
+    p->dist = true;
+    if (build_group_schedule(p)) return PNB_ERR_CUDA;
+    if (build_dist_tables(p)) return PNB_ERR_CUDA;
+    GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+    *num_rows = (int32_t)gh->rows.size();
+    *staging_doubles = gh->stage_doubles;
+    return 0;
+}
+
+// global dof of every owned row, ascending (host, num_rows entries)
+extern "C" int pnb_dist_rows(pnb_problem *p, int32_t *rows)
+{
+    if (!p || !rows) return fail(PNB_ERR_ARG, "null argument");
+    GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+    if (!gh || !gh->dist_ready) return fail(PNB_ERR_ARG, "pnb_dist_rows: call pnb_dist_plan first");
+    memcpy(rows, gh->rows.data(), gh->rows.size() * sizeof(int));
+    return 0;
+}
+
+// Evaluates the units of this part and stores their blocks, row by row, into the staging buffers of the row owners.
+// stage_ptrs: host array of nparts device pointers, the staging buffer (staging_doubles of pnb_dist_plan) of every
+// part as seen from this device (own allocation, or peer memory opened with pnb_ipc_import).  Asynchronous; the
+// cell-diagonal blocks of this part's share are in the pnb_dense_cell_blocks buffer afterwards.
+extern "C" int pnb_dist_eval(pnb_problem *p, int zero_exterior, double *const *stage_ptrs)
+{
+    if (!p || !stage_ptrs) return fail(PNB_ERR_ARG, "null argument");
+    GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+    if (!gh || !p->dist) return fail(PNB_ERR_ARG, "pnb_dist_eval: call pnb_dist_plan first");
+    ON_DEVICE(p->device);
+    for (int o = 0; o < p->nparts; o++) p->G->dist.stage[o] = stage_ptrs[o];
+    return run_group_path(p, zero_exterior, nullptr, 0, p->part, p->nparts, 0, -1, true);
+}
+
+// largest regular quadrature order requested beyond the supplied tables by the last pnb_dist_eval (0: none).
+// Synchronises the device.  The caller takes the maximum over all parts and, if it is positive, raises the tables
+// on ALL parts (pnb_problem_set_rules) and repeats the evaluation: the decision must be collective.
+extern "C" int pnb_dist_status(pnb_problem *p, int32_t *order_needed)
+{
+    if (!p || !order_needed) return fail(PNB_ERR_ARG, "null argument");
+    ON_DEVICE(p->device);
+    CK(cudaDeviceSynchronize());
+    int herr[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(herr, p->S.err, sizeof(herr), cudaMemcpyDeviceToHost));
+    if (herr[1] > 0) return fail(PNB_ERR_CUDA, "internal error: a unit classified as far holds a near pair");
+    *order_needed = herr[0];
+    return 0;
+}
+
+// Owned rows of the operator from the staged fragments (all parts must have finished pnb_dist_eval: the caller
+// synchronises them) plus, if use_cell_blocks, the cell-diagonal blocks of the pnb_dense_cell_blocks buffer (summed
+// over the parts by the caller).  A_rows: device, num_rows x num_dofs, row k = global row rows[k].
+extern "C" int pnb_dist_apply(pnb_problem *p, int use_cell_blocks, double *A_rows, int64_t ld)
+{
+    if (!p || !A_rows) return fail(PNB_ERR_ARG, "null argument");
+    GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
+    if (!gh || !gh->dist_ready) return fail(PNB_ERR_ARG, "pnb_dist_apply: call pnb_dist_plan first");
+    if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
+    ON_DEVICE(p->device);
+    DistApply X = gh->apply;
+    X.stage = p->G->dist.stage[p->part];
+    if (X.nrows > 0) dist_apply_kernel<<<X.nrows, 256>>>(p->P, *p->G, X, p->S.dof_ptr, p->S.dof_cells, p->S.D, use_cell_blocks, A_rows, ld);
+    p->stats[2] += 1;
+    cudaEventRecord(p->ev[4]);
+    cudaError_t e = cudaEventSynchronize(p->ev[4]);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    unsigned long long hcnt[8] = {0};
+    if (e == cudaSuccess) e = cudaMemcpy(hcnt, p->S.counters, sizeof(hcnt), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(PNB_ERR_CUDA, std::string("distributed assembly: ") + cudaGetErrorString(e));
+    float ms;
+    for (int k = 0; k < 2; k++) { cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]); p->timings[k] = ms; }
+    cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]);
+    float ms2 = 0.f;
+    cudaEventElapsedTime(&ms2, p->ev[3], p->ev[4]);
+    p->timings[2] = ms + ms2;      // reduction of the cell blocks + (exchange by the caller) + apply
+    cudaEventElapsedTime(&ms, p->ev[0], p->ev[4]);
+    p->timings[3] = ms;
+    p->stats[0] = (int64_t)(hcnt[0] + hcnt[1] + hcnt[2]);
+    p->stats[3] = (int64_t)hcnt[1];
+    p->stats[4] = (int64_t)hcnt[2];
+    p->stats[1] = p->distinct_pairs;
+    if (p->kev[0])
+        for (int k = 0; k < 4; k++) {
+            float kms = 0.f;
+            if (cudaEventElapsedTime(&kms, p->kev[k], p->kev[k + 1]) == cudaSuccess) p->ktimings[k] = kms;
+            else { cudaGetLastError(); p->ktimings[k] = 0.; }
+        }
+    return 0;
+}
+
+// plain device allocations that can be shared with the other processes of the node (peer memory over NVLink)
+extern "C" int pnb_device_alloc(int device, int64_t bytes, void **dptr)
+{
+    if (!dptr || bytes < 0) return fail(PNB_ERR_ARG, "invalid argument");
+    ON_DEVICE(device);
+    CK(cudaMalloc(dptr, (size_t)std::max<int64_t>(bytes, 256)));
+    return 0;
+}
+
+extern "C" int pnb_device_free(int device, void *dptr)
+{
+    ON_DEVICE(device);
+    if (dptr) CK(cudaFree(dptr));
+    return 0;
+}
+
+// handle: 64 bytes (cudaIpcMemHandle_t) that another process of the node turns into a device pointer
+extern "C" int pnb_ipc_export(int device, void *dptr, unsigned char *handle)
+{
+    if (!dptr || !handle) return fail(PNB_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    ON_DEVICE(device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+extern "C" int pnb_ipc_import(int device, const unsigned char *handle, void **dptr)
+{
+    if (!dptr || !handle) return fail(PNB_ERR_ARG, "null argument");
+    ON_DEVICE(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int pnb_ipc_close(int device, void *dptr)
+{
+    ON_DEVICE(device);
+    if (dptr) CK(cudaIpcCloseMemHandle(dptr));
+    return 0;
+}
+
 static void destroy_group_host(pnb_problem *p)
 {
     if (p->gh) {
         GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
         for (void *d : gh->unit_allocs) pool_free(d);
         for (void *d : gh->near_allocs) pool_free(d);
+        for (void *d : gh->dist_allocs) pool_free(d);
         delete gh;
         p->gh = nullptr;
     }
@@ -2183,13 +2571,14 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
     if (check_rows(p, row_begin, row_end)) return PNB_ERR_ARG;
     if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
     TileSched &S = p->S;
     // 2D, whole operator: cell-group path (PNB_DEBUG bit 0x800 forces the DoF-tile path)
     if (p->dim == 2 && row_begin == 0 && row_end == p->N && !((getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0) & 0x800))
         return run_group_path(p, zero_exterior, dA, ld);
     if (build_tile_schedule(p)) return PNB_ERR_CUDA;
+    S.cell_mask = nullptr;
     S.own_t0 = row_begin / PNB_TD;
     S.own_t1 = (row_end + PNB_TD - 1) / PNB_TD;
     // units: group pairs (gr <= gc) that hold a tile touching an owned row tile, near-diagonal first
@@ -2253,24 +2642,6 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     return 0;
 }
 
-// Several GPUs, 2D: instance `part` of `nparts` evaluates its share of the group units (dealt out round-robin per
-// phase and kind, so that every pair is still evaluated exactly once over all instances) into the FULL N x N
-// device scratch dU, which afterwards holds this share of U + U^T.  The caller sums the rows [row_begin,
-// row_end) of all shares on the owner of those rows (reduce over NVLink), sums the cell-block buffers
-// (pnb_dense_cell_blocks_copy) and finishes with pnb_dense_rows_end on the summed rows.
-extern "C" int pnb_dense_partial_begin(pnb_problem *p, int zero_exterior, int part, int nparts, int32_t row_begin, int32_t row_end,
-                                       double *dU, int64_t ld)
-{
-    if (!p || !dU) return fail(PNB_ERR_ARG, "null argument");
-    if (p->dim != 2) return fail(PNB_ERR_UNSUPPORTED, "pnb_dense_partial_begin: 2D only (1D problems use row blocks)");
-    if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
-    if (nparts < 1 || part < 0 || part >= nparts) return fail(PNB_ERR_ARG, "invalid part");
-    if (row_begin != row_end && check_rows(p, row_begin, row_end)) return PNB_ERR_ARG;
-    if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
-    CK(cudaSetDevice(p->device));
-    return run_group_path(p, zero_exterior, dU, ld, part, nparts, row_begin / PNB_TD, (row_end + PNB_TD - 1) / PNB_TD);
-}
-
 // device buffer of the cell-diagonal blocks: num_cells x (dim+1)(dim+2)/2 doubles.  After _begin it holds the
 // complete blocks of the cells whose home row tile is owned and zeros elsewhere; with several row blocks the
 // caller sums the buffers of all owners (disjoint supports: the sum is exact) before calling _end.
@@ -2287,7 +2658,7 @@ extern "C" int pnb_dense_cell_blocks(pnb_problem *p, double **dptr, int64_t *cou
 extern "C" int pnb_dense_cell_blocks_copy(pnb_problem *p, double *device_buf, int to_problem)
 {
     if (!p || !device_buf) return fail(PNB_ERR_ARG, "null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int nvc = p->dim + 1;
     const size_t bytes = (size_t)p->nc * (nvc * (nvc + 1) / 2) * sizeof(double);
     if (to_problem) CK(cudaMemcpyAsync(p->S.D, device_buf, bytes, cudaMemcpyDeviceToDevice));
@@ -2302,11 +2673,12 @@ extern "C" int pnb_boundary_cell_blocks(pnb_problem *p, double *host_out)
 {
     if (!p || !host_out) return fail(PNB_ERR_ARG, "null argument");
     if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
     TileSched &S = p->S;
     S.own_t0 = 0;
     S.own_t1 = S.ntiles;
+    S.cell_mask = nullptr;
     CK(cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * ND * sizeof(double)));
     CK(cudaMemsetAsync(S.err, 0, 4 * sizeof(int)));
     if (p->nb > 0) {
@@ -2327,7 +2699,7 @@ extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row
 {
     if (!p || !dA) return fail(PNB_ERR_ARG, "null argument");
     if (check_rows(p, row_begin, row_end)) return PNB_ERR_ARG;
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     TileSched &S = p->S;
     if (S.own_t0 != row_begin / PNB_TD) return fail(PNB_ERR_ARG, "pnb_dense_rows_end does not match pnb_dense_rows_begin");
     const int nrows = row_end - row_begin;
@@ -2376,7 +2748,7 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
     if (row_begin != 0 || row_end != p->N)
         return fail(PNB_ERR_ARG, "pnb_dense_assemble builds the whole operator; row blocks go through pnb_dense_rows_begin/_end");
     if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int N = p->N;
     double *dA = A;
     if (!a_on_device) {
@@ -2471,7 +2843,7 @@ extern "C" int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *b
                                    const int32_t *eta_ptr, const int64_t *offsets, double *out)
 {
     if (!p || !boxes1 || !boxes2 || !m1 || !m2 || !eta || !eta_ptr || !offsets || !out) return fail(PNB_ERR_ARG, "null argument");
-    CK(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     if (nblk == 0) return 0;
     const int dim = p->dim;
     const int64_t total = offsets[nblk];
@@ -2554,7 +2926,7 @@ extern "C" int pnb_dense_matvec(int device, const double *A, int64_t num_rows, i
 {
     if (!A || !x || !y) return fail(PNB_ERR_ARG, "null argument");
     if (pnb_device_count() == 0) return fail(PNB_ERR_NO_DEVICE, "no CUDA device: libpnb200 has no CPU fallback");
-    CK(cudaSetDevice(device));
+    ON_DEVICE(device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const int64_t want = (num_rows * 32 + 255) / 256;
@@ -2659,7 +3031,7 @@ extern "C" int pnb_fp64_peak(int device, double *tflops)
     }
     if (!tflops) return fail(PNB_ERR_ARG, "null argument");
     if (pnb_device_count() == 0) return fail(PNB_ERR_NO_DEVICE, "no CUDA device");
-    CK(cudaSetDevice(device));
+    ON_DEVICE(device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const int blocks = sms * 8, threads = 256, iters = 20000;

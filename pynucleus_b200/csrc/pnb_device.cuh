@@ -13,6 +13,9 @@
 #define PNB_SB 16             // sub-batch: PNB_SB x PNB_SB cell pairs
 #define PNB_THREADS 256
 #define PNB_IGNORED_PANEL (-6)
+#define PNB_NEAR_R 4          // rows per register tile of the near evaluator
+#define PNB_NEAR_WARP_POINTS 288   // shared-memory points (double2) per warp of the near evaluator
+#define PNB_DER2 7            // double2 per node of the derived rule table (see DProblem::reg_derived)
 
 struct DRule {
     int n;
@@ -65,11 +68,12 @@ struct DProblem {
     int max_order;
     const DRule *reg_cell;
     const DRule *reg_facet;
-    // 2D cell rules, per node 10 doubles: w, w*bary[0..2], w*bary[a]*bary[b] (a<=b); rule o starts at node reg_doff[o]
+    // 2D cell rules, per node PNB_DER2 double2: (w, w b0) (w b1, w b2) (q0,q1) (q2,q3) (q4,q5) with q = w b_a b_b (a<=b),
+    // (b0,b1) (b2,0); rule o starts at node reg_doff[o]
     const double *reg_derived;
     const int *reg_doff;
     int reg_nmax;              // largest node count of a cell rule
-    const int4 *reg_grid;      // per order: lane grid of the near evaluator (row lanes, column lanes, lanes per pair, 0)
+    const int4 *reg_grid;      // per order: lane groups of the near evaluator (lanes per item W, items per warp K, row tiles per lane, 0)
     // piecewise constant variable kernels: this problem instance takes the pairs of one class (see pnb_kernel_t)
     const unsigned char *labels;   // nc, nullptr = constant kernel
     const unsigned char *blabels;  // nb

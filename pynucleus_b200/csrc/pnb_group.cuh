@@ -20,7 +20,24 @@
 // slot Dp[g][c] has exactly one writer, the unit (group(c), g).
 #pragma once
 
+// Several GPUs (row sets per part, see pnb_dist_plan in pnb200.cu): a unit does not add its block to the matrix but
+// stores it, row by row, into the staging buffer of the part that owns the row -- once as rows of I (columns dofs(J))
+// and once transposed as rows of J (columns dofs(I)).  Every (unit, row) fragment has its own place in the staging
+// buffer of its destination (plain stores through peer memory over NVLink: no read-modify-write, no atomics, no
+// collective); the owner sums the fragments of its rows in a fixed order afterwards (dist_apply_kernel).
+#define PNB_MAX_PARTS 16
+struct DistSched {
+    int nparts, part;
+    double *stage[PNB_MAX_PARTS];     // staging buffer of every part (peer-mapped device pointers)
+    const unsigned char *gown;        // per group-local dof (gdptr[g] + l): part that owns the row
+    const unsigned char *gpos;        // ... its position among the dofs of the group owned by that part
+    const int *gcnt;                  // ngroups x nparts: dofs of group g owned by part o
+    const long long *uoff_f2;         // per unit of the f2 list x nparts: start of its fragments in stage[o]
+    const long long *uoff_mix;        // the same for the mix list
+};
+
 struct GroupSched {
+    DistSched dist;
     int ngroups, cap, maxld, ldS, ncolors;
     const int *gptr;     // ngroups+1: first cell slot of a group (multiples of PNB_SB)
     const int *gcells;   // cell id per slot, -1 = padding; batches of PNB_SB slots share no vertex
@@ -57,22 +74,23 @@ struct F2Rule {
     int eoff, pad;       // PowTab::eoff minus the exponent bias
 };
 
-__device__ __forceinline__ double f2_pow(const PowTab *t, const F2Rule &R, double d2)
+// power function of the order-2 units: replicated shared-memory table (lane-private bank group, see PowTabS),
+// series coefficients as constant-bank operands; degree 6
+__device__ __forceinline__ double f2_pow(const double2 *__restrict__ itl, const double *__restrict__ T1, const F2Rule &R, double d2)
 {
     const int hi = __double2hiint(d2), lo = __double2loint(d2);
     const int E = min(max(((hi >> 20) & 0x7ff) + R.eoff, 0), 255);
-    const int idx = (hi >> 13) & 0x7f;
+    const int idx = (hi >> 10) & (0x7f * PNB_POW_REP);
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double2 it = t->IT[idx];
+    const double2 it = itl[idx];
     const double r = fma(m, it.x, -1.0);
-    double p = fma(R.c[7], r, R.c[6]);
-    p = fma(p, r, R.c[5]);
+    double p = fma(R.c[6], r, R.c[5]);
     p = fma(p, r, R.c[4]);
     p = fma(p, r, R.c[3]);
     p = fma(p, r, R.c[2]);
     p = fma(p, r, R.c[1]);
     p = fma(p, r, R.c[0]);
-    return t->T1[E] * (it.y * p);
+    return T1[E] * (it.y * p);
 }
 
 __device__ __forceinline__ unsigned char *carve(unsigned char *&p, size_t bytes)
@@ -123,56 +141,72 @@ __device__ __forceinline__ void g_flush_block(const GroupSched &G, const double 
     }
 }
 
+// several GPUs: the unit block goes to the staging buffers of the row owners (see DistSched).  Both passes write runs of
+// consecutive addresses (the transposed pass reads the block column by column: ldS is odd, no bank conflicts).
+__device__ __forceinline__ void g_flush_staged(const GroupSched &G, const long long *__restrict__ uoff, const double *S, int ldS, int I,
+                                               int dI, int nldI, int dJ, int nldJ, int tid, int nthreads)
+{
+    const DistSched &D = G.dist;
+    for (int e = tid; e < nldI * nldJ; e += nthreads) {
+        const int a = e / nldJ, b = e - a * nldJ;
+        const int o = D.gown[dI + a];
+        D.stage[o][uoff[o] + (long long)D.gpos[dI + a] * nldJ + b] = S[a * ldS + b];
+    }
+    for (int e = tid; e < nldI * nldJ; e += nthreads) {
+        const int b = e / nldI, a = e - b * nldI;
+        const int o = D.gown[dJ + b];
+        D.stage[o][uoff[o] + (long long)D.gcnt[I * D.nparts + o] * nldJ + (long long)D.gpos[dJ + b] * nldI + a] = S[a * ldS + b];
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
-// uniform order 2.  PNB_GT threads: two column batches per step (sub-batch = tid / 256), so that 16 warps
-// hide the latency of the dependent FP64 chains although the unit block limits the SM to one CTA.  The
-// evaluation needs no ordering; the two sub-batches add to the block one after the other.
+// uniform order 2.  PNB_F2T = 256 threads, two CTAs per SM, one 16 x 16 sub-batch per step (thread = cell pair).
+// Warp w holds the row cells 2w, 2w+1 of the row batch during the whole sweep over the column batches: the row cells of
+// a batch share no vertex, so no other warp touches its rows of the unit block, and the column cells of a step share
+// no vertex either -- the block updates need no barrier and no atomics.
 // Cell-diagonal blocks: xx[e] = sum_i qq[e][i] r_i and yy[e] = sum_j qq[e][j] c_j are linear in the row sums
 // r_i / column sums c_j of the kernel matrix, so only those (3 + 3 values per pair) are reduced over the
-// partner cells; qq is applied once per cell at the end.
+// partner cells; qq is applied once per cell at the end.  Row sums stay in registers over the sweep; the column sums
+// of a step are combined over the 8 warps through a double-buffered staging array: ONE barrier per step.
 // -------------------------------------------------------------------------------------------------
 #define PNB_GT 512
+#define PNB_F2T 256
 inline size_t gf2_smem_bytes(int cap, int maxld, int ldS)
 {
     size_t b = 0;
     auto add = [&](size_t x) { b += (x + 15) & ~(size_t)15; };
-    add(sizeof(PowTab));
+    add(sizeof(PowTabS));
     add((size_t)maxld * ldS * 8);
-    add((size_t)12 * cap * 8);        // nodes of both sides
-    add((size_t)2 * cap * 8);         // vol
-    add((size_t)4 * cap * 4);         // cell, loc (both sides)
-    add((size_t)2 * 8 * 16 * 3 * 8);  // Yw
+    add((size_t)6 * cap * 8);         // nodes of the column side
+    add((size_t)cap * 8);             // vol of the column side
+    add((size_t)2 * cap * 4);         // cell, loc of the column side
+    add((size_t)2 * 8 * 16 * 3 * 8);  // Yw: column sums of a step per warp, two buffers
     add((size_t)cap * 3 * 8);         // column sums
-    add((size_t)16 * 3 * 8);          // row sums of the second sub-batch
     return b;
 }
 
-__global__ void __launch_bounds__(PNB_GT, 1)
+__global__ void __launch_bounds__(PNB_F2T, 2)
 gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits, double *__restrict__ A, int64_t ld, F2Rule R)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
     const int cap = G.cap, ldS = G.ldS;
-    PowTab *pw = reinterpret_cast<PowTab *>(carve(sp, sizeof(PowTab)));
+    PowTabS *pw = reinterpret_cast<PowTabS *>(carve(sp, sizeof(PowTabS)));
     double *S = reinterpret_cast<double *>(carve(sp, (size_t)G.maxld * ldS * 8));
-    double *xi = reinterpret_cast<double *>(carve(sp, (size_t)12 * cap * 8));
-    double *yj = xi + 6 * cap;
-    double *voli = reinterpret_cast<double *>(carve(sp, (size_t)2 * cap * 8));
-    double *volj = voli + cap;
-    int *celli = reinterpret_cast<int *>(carve(sp, (size_t)4 * cap * 4));
-    int *cellj = celli + cap, *loci = celli + 2 * cap, *locj = celli + 3 * cap;
+    double *yj = reinterpret_cast<double *>(carve(sp, (size_t)6 * cap * 8));
+    double *volj = reinterpret_cast<double *>(carve(sp, (size_t)cap * 8));
+    int *cellj = reinterpret_cast<int *>(carve(sp, (size_t)2 * cap * 4));
+    int *locj = cellj + cap;
     double *Yw = reinterpret_cast<double *>(carve(sp, (size_t)2 * 8 * 16 * 3 * 8));
     double *CYs = reinterpret_cast<double *>(carve(sp, (size_t)cap * 3 * 8));
-    double *RX1 = reinterpret_cast<double *>(carve(sp, (size_t)16 * 3 * 8));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_ticket;
-    {
-        const double *src = reinterpret_cast<const double *>(P.pow_int);
-        double *dst = reinterpret_cast<double *>(pw);
-        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_GT) dst[e] = src[e];
-    }
+    powtab_stage(pw, P.pow_int, tid, PNB_F2T);
+    const double2 *itl = pw->IT + (lane & (PNB_POW_REP - 1));
+    const double *T1s = pw->T1;
     unsigned long long my_pairs = 0;
+    const int k1 = tid >> 4, k2 = tid & 15;
     for (;;) {
     __syncthreads();
     if (tid == 0) s_ticket = atomicAdd(G.counters_i, 1);
@@ -184,44 +218,57 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits
     const int ibeg = G.gptr[I], nI = G.gptr[I + 1] - ibeg, jbeg = G.gptr[J], nJ = G.gptr[J + 1] - jbeg;
     const int dI = G.gdptr[I], nldI = G.gdptr[I + 1] - dI, dJ = G.gdptr[J], nldJ = G.gdptr[J + 1] - dJ;
     {
-        for (int e = tid; e < nldI * ldS; e += PNB_GT) S[e] = 0.;
-        for (int e = tid; e < cap * 3; e += PNB_GT) CYs[e] = 0.;
-        for (int e = tid; e < nI + nJ; e += PNB_GT) {
-            const bool first = e < nI;
-            const int s = first ? e : e - nI;
-            const int c = G.gcells[(first ? ibeg : jbeg) + s];
-            double *nd = first ? xi : yj;
-            (first ? celli : cellj)[s] = c;
-            (first ? loci : locj)[s] = G.gloc[(first ? ibeg : jbeg) + s];
+        for (int e = tid; e < nldI * ldS; e += PNB_F2T) S[e] = 0.;
+        for (int e = tid; e < cap * 3; e += PNB_F2T) CYs[e] = 0.;
+        for (int s = tid; s < nJ; s += PNB_F2T) {
+            const int c = G.gcells[jbeg + s];
+            cellj[s] = c;
+            locj[s] = G.gloc[jbeg + s];
             if (c >= 0) {
                 const double *v = P.simplices + (size_t)c * 6;
-                (first ? voli : volj)[s] = P.vol[c];
+                volj[s] = P.vol[c];
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
-                    nd[(2 * q) * cap + s] = R.bary[0][q] * v[0] + R.bary[1][q] * v[2] + R.bary[2][q] * v[4];
-                    nd[(2 * q + 1) * cap + s] = R.bary[0][q] * v[1] + R.bary[1][q] * v[3] + R.bary[2][q] * v[5];
+                    yj[(2 * q) * cap + s] = R.bary[0][q] * v[0] + R.bary[1][q] * v[2] + R.bary[2][q] * v[4];
+                    yj[(2 * q + 1) * cap + s] = R.bary[0][q] * v[1] + R.bary[1][q] * v[3] + R.bary[2][q] * v[5];
                 }
             }
         }
     }
     __syncthreads();
-    const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15, wsub = warp & 7;
+    int step = 0;
     for (int rb = 0; rb < nI; rb += PNB_SB) {
         const int s1 = rb + k1;
-        const int c1 = celli[s1];
-        const int l1 = loci[s1];
+        const int c1 = G.gcells[ibeg + s1];
+        const int l1 = G.gloc[ibeg + s1];
         double x[3][2];
+        double v1 = 0.;
+        if (c1 >= 0) {
+            const double *v = P.simplices + (size_t)c1 * 6;
+            const double v0 = v[0], v1_ = v[1], v2 = v[2], v3 = v[3], v4 = v[4], v5 = v[5];
 #pragma unroll
-        for (int q = 0; q < 3; q++) { x[q][0] = xi[(2 * q) * cap + s1]; x[q][1] = xi[(2 * q + 1) * cap + s1]; }
-        const double v1 = c1 >= 0 ? 2.0 * voli[s1] : 0.;
+            for (int q = 0; q < 3; q++) {
+                x[q][0] = R.bary[0][q] * v0 + R.bary[1][q] * v2 + R.bary[2][q] * v4;
+                x[q][1] = R.bary[0][q] * v1_ + R.bary[1][q] * v3 + R.bary[2][q] * v5;
+            }
+            v1 = 2.0 * P.vol[c1];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 3; q++) x[q][0] = x[q][1] = 0.;
+        }
+        // rows of the unit block that belong to the three dofs of the row cell (-1: no dof)
+        int ro[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int ra = (l1 >> (8 * a)) & 0xFF;
+            ro[a] = ra == 0xFF ? -1 : ra * ldS;
+        }
         double rx[3] = {0., 0., 0.};
-        for (int cb0 = 0; cb0 < nJ; cb0 += 2 * PNB_SB) {
-            const int cb = cb0 + sub * PNB_SB;
+        for (int cb = 0; cb < nJ; cb += PNB_SB, step++) {
             const int s2 = cb + k2;
-            const int c2 = cb < nJ ? cellj[s2] : -1;
-            const int l2 = cb < nJ ? locj[s2] : 0x00FFFFFF;
+            const int c2 = cellj[s2];
+            const int l2 = locj[s2];
             double cy[3] = {0., 0., 0.};
-            double X[9];
             // a pair is skipped only when neither cell carries a dof (as the reference does)
             const bool live = c1 >= 0 && c2 >= 0 && !((l1 & 0x00FFFFFF) == 0x00FFFFFF && (l2 & 0x00FFFFFF) == 0x00FFFFFF);
             if (live) {
@@ -233,10 +280,11 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
                         const double a = x[i][0] - y0, b = x[i][1] - y1;
-                        g[i][j] = f2_pow(pw, R, a * a + b * b);
+                        g[i][j] = f2_pow(itl, T1s, R, a * a + b * b);
                     }
                 }
                 const double sc = v1 * volj[s2];
+                double X[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) X[k] = 0.;
 #pragma unroll
@@ -266,82 +314,58 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits
                     for (int i = 0; i < 3; i++) c = fma(g[i][j], R.w[i], c);
                     cy[j] = c * sc;
                 }
+                // conflict free: this warp owns its rows for the sweep, the 16 column cells of a step share no vertex
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const int cbk = (l2 >> (8 * b)) & 0xFF;
+                    if (cbk == 0xFF) continue;
+#pragma unroll
+                    for (int a = 0; a < 3; a++)
+                        if (ro[a] >= 0) S[ro[a] + cbk] += X[a * 3 + b];
+                }
             }
-            // column sums: the two half-warps, then the 8 warps of the sub-batch through shared memory
+            // column sums: the two row cells of the warp, then the 8 warps through shared memory
 #pragma unroll
             for (int e = 0; e < 3; e++) cy[e] += __shfl_xor_sync(0xffffffffu, cy[e], 16);
+            double *yw = Yw + (size_t)(step & 1) * (8 * 16 * 3);
             if (lane < 16) {
 #pragma unroll
-                for (int e = 0; e < 3; e++) Yw[((sub * 8 + wsub) * 16 + k2) * 3 + e] = cy[e];
+                for (int e = 0; e < 3; e++) yw[(warp * 16 + k2) * 3 + e] = cy[e];
             }
-            __syncthreads();     // orders the block updates of the previous step, publishes Yw
-            // conflict free inside a sub-batch: the 16 row cells share no vertex, neither do the 16 column cells
-            if (live && sub == 0) {
+            __syncthreads();     // the one barrier of the step: publishes yw (the other buffer is written in the next step)
+            if (lane < 6) {
+                const int t = warp * 6 + lane;        // 48 values: (column cell, node)
+                double s = 0.;
 #pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const int ra = (l1 >> (8 * a)) & 0xFF;
-                    if (ra == 0xFF) continue;
-#pragma unroll
-                    for (int b = 0; b < 3; b++) {
-                        const int cbk = (l2 >> (8 * b)) & 0xFF;
-                        if (cbk == 0xFF) continue;
-                        S[ra * ldS + cbk] += X[a * 3 + b];
-                    }
-                }
-            }
-            if (tid < 96) {
-                const int sb = tid / 48, t = tid - sb * 48, kk2 = t / 3, e = t - kk2 * 3;
-                if (cb0 + sb * PNB_SB < nJ) {
-                    double s = 0.;
-#pragma unroll
-                    for (int w = 0; w < 8; w++) s += Yw[((sb * 8 + w) * 16 + kk2) * 3 + e];
-                    CYs[(cb0 + sb * PNB_SB + kk2) * 3 + e] += s;
-                }
-            }
-            __syncthreads();
-            if (live && sub == 1) {
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const int ra = (l1 >> (8 * a)) & 0xFF;
-                    if (ra == 0xFF) continue;
-#pragma unroll
-                    for (int b = 0; b < 3; b++) {
-                        const int cbk = (l2 >> (8 * b)) & 0xFF;
-                        if (cbk == 0xFF) continue;
-                        S[ra * ldS + cbk] += X[a * 3 + b];
-                    }
-                }
+                for (int w = 0; w < 8; w++) s += yw[w * 48 + t];
+                CYs[cb * 3 + t] += s;
             }
         }
-        // row sums: over the 16 lanes (fixed tree), then the two sub-batches
+        // row sums over the 16 lanes of the row cell (fixed tree)
 #pragma unroll
         for (int off = 8; off > 0; off >>= 1) {
 #pragma unroll
             for (int e = 0; e < 3; e++) rx[e] += __shfl_xor_sync(0xffffffffu, rx[e], off);
         }
-        if (sub == 1 && k2 == 0) {
-#pragma unroll
-            for (int e = 0; e < 3; e++) RX1[k1 * 3 + e] = rx[e];
-        }
-        __syncthreads();
-        if (sub == 0 && k2 == 0 && c1 >= 0) {
-#pragma unroll
-            for (int e = 0; e < 3; e++) rx[e] += RX1[k1 * 3 + e];
+        if (k2 == 0 && c1 >= 0) {
 #pragma unroll
             for (int e = 0; e < 6; e++)
                 G.Dp[((size_t)J * P.nc + c1) * 6 + e] = R.qq[e][0] * rx[0] + R.qq[e][1] * rx[1] + R.qq[e][2] * rx[2];
         }
     }
     __syncthreads();
-    for (int e = tid; e < nJ * 6; e += PNB_GT) {
+    for (int e = tid; e < nJ * 6; e += PNB_F2T) {
         const int s2 = e / 6, k = e - s2 * 6;
         const int c2 = cellj[s2];
         if (c2 >= 0)
             G.Dp[((size_t)I * P.nc + c2) * 6 + k] = R.qq[k][0] * CYs[s2 * 3] + R.qq[k][1] * CYs[s2 * 3 + 1] + R.qq[k][2] * CYs[s2 * 3 + 2];
     }
-    g_wait_predecessors(G, 0, ticket, I, J, tid, PNB_GT);
-    g_flush_block(G, S, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_GT);
-    g_signal_done(G, 0, ticket, tid);
+    if (G.dist.nparts > 0) g_flush_staged(G, G.dist.uoff_f2 + (size_t)ticket * G.dist.nparts, S, ldS, I, dI, nldI, dJ, nldJ, tid, PNB_F2T);
+    else {
+        g_wait_predecessors(G, 0, ticket, I, J, tid, PNB_F2T);
+        g_flush_block(G, S, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_F2T);
+        g_signal_done(G, 0, ticket, tid);
+    }
     }
     for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
     if (lane == 0 && my_pairs) atomicAdd(G.counters + 2, my_pairs);
@@ -507,37 +531,35 @@ gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int
     }
 }
 
-// Regular near pair: one column slice of its n x n node pairs per lane group of LPI = 8, 16 or 32 lanes
-// (small rules: several pairs per warp).  Inside the group the lanes form an RS x CS grid: lane (ri, cj) takes
-// the rows i = ri, ri + RS, ... and the columns j = j0 + cj, j0 + cj + CS, ...; all lanes of a column group
-// read the same column data (shared-memory broadcast), and the row sums of
-// nonlocalOperator_{SCALAR}.pxi:769-789 are factored out (27 instead of ~60 FP64 operations per node pair).
+// Regular near pair: one column slice of its n x n node pairs per lane group of W lanes (K = 32 / W items per warp).
+// The lanes of a group split the ROWS in tiles of PNB_NEAR_R rows; every lane sweeps all columns of the slice with its
+// rows in registers, so that the column data (node, weights, products) is read once per PNB_NEAR_R node pairs and
+// by all lanes of the group at the same address (broadcast) -- round 1 read it once per node pair and ran at 80 % of
+// the shared-memory pipe against 33 % of the FP64 pipe (ncu).  The row sums of nonlocalOperator_{SCALAR}.pxi:769-789
+// are factored out: per node pair 5 (distance) + 11 (power) + 4 (row sums) + 1 (column sum) FP64 operations, per
+// column 6 more for the second cell's diagonal block, per row 15 for the cross block and the first cell's block.
 // The node coordinates are computed once per item, un-fused and in the reference's order (see
 // lanes_regular_interior), and kept in shared memory.
-__device__ __forceinline__ void near_regular_group(const DProblem &P, const PowCtx &kv, const double *__restrict__ der, int n, int Ka, int Kb,
-                                                   int slice, int nsl, double *xs, int gl, int4 grid, bool valid, double *acc)
+template <class KV>
+__device__ __forceinline__ void near_regular_group(const DProblem &P, const KV &kv, const double2 *__restrict__ der, int n, int Ka, int Kb,
+                                                   int slice, int nsl, double2 *xs, int gl, int W, bool valid, double *acc)
 {
-    const int RS = grid.x, CS = grid.y, LPI = grid.z;
+    constexpr int R = PNB_NEAR_R;
     const int per = (n + nsl - 1) / nsl;
-    const int j0 = slice * per, j1 = min(n, j0 + per);
+    const int j0 = slice * per, j1 = min(n, j0 + per), ncol = max(j1 - j0, 0);
+    // shared memory of the group: the vertices of the first cell (3 points), then the nodes of the column slice
+    double2 *V1 = xs, *Y = xs + 3;
     if (valid) {
-        double s1[3][2], s2[3][2];
-        load_simplex<2>(P.simplices, Ka, 3, s1);
+        if (gl < 3) V1[gl] = make_double2(P.simplices[(size_t)Ka * 6 + 2 * gl], P.simplices[(size_t)Ka * 6 + 2 * gl + 1]);
+        double s2[3][2];
         load_simplex<2>(P.simplices, Kb, 3, s2);
-        for (int k = gl; k < n; k += LPI) {
-            // barycentric coordinates from the derived table: bary[m] = (w bary[m]) / w is not bit-exact, so the
-            // table keeps the plain coordinates in slots 10..12
-            const double b0 = der[(size_t)k * 13 + 10], b1 = der[(size_t)k * 13 + 11], b2 = der[(size_t)k * 13 + 12];
-            double x0 = PNB_MUL(b0, s1[0][0]), x1 = PNB_MUL(b0, s1[0][1]);
-            x0 = PNB_ADD(x0, PNB_MUL(b1, s1[1][0])); x1 = PNB_ADD(x1, PNB_MUL(b1, s1[1][1]));
-            x0 = PNB_ADD(x0, PNB_MUL(b2, s1[2][0])); x1 = PNB_ADD(x1, PNB_MUL(b2, s1[2][1]));
-            xs[k] = x0; xs[n + k] = x1;
-            if (k >= j0 && k < j1) {
-                double y0 = PNB_MUL(b0, s2[0][0]), y1 = PNB_MUL(b0, s2[0][1]);
-                y0 = PNB_ADD(y0, PNB_MUL(b1, s2[1][0])); y1 = PNB_ADD(y1, PNB_MUL(b1, s2[1][1]));
-                y0 = PNB_ADD(y0, PNB_MUL(b2, s2[2][0])); y1 = PNB_ADD(y1, PNB_MUL(b2, s2[2][1]));
-                xs[2 * n + k] = y0; xs[3 * n + k] = y1;
-            }
+        for (int k = j0 + gl; k < j1; k += W) {
+            const double2 ba = der[k * PNB_DER2 + 5], bb = der[k * PNB_DER2 + 6];
+            const double b0 = ba.x, b1 = ba.y, b2 = bb.x;
+            double y0 = PNB_MUL(b0, s2[0][0]), y1 = PNB_MUL(b0, s2[0][1]);
+            y0 = PNB_ADD(y0, PNB_MUL(b1, s2[1][0])); y1 = PNB_ADD(y1, PNB_MUL(b1, s2[1][1]));
+            y0 = PNB_ADD(y0, PNB_MUL(b2, s2[2][0])); y1 = PNB_ADD(y1, PNB_MUL(b2, s2[2][1]));
+            Y[k - j0] = make_double2(y0, y1);
         }
     }
     __syncwarp();
@@ -546,35 +568,69 @@ __device__ __forceinline__ void near_regular_group(const DProblem &P, const PowC
     for (int k = 0; k < 9; k++) xy[k] = 0.;
 #pragma unroll
     for (int k = 0; k < 6; k++) xx[k] = yy[k] = 0.;
-    if (valid && gl < RS * CS) {
-        const int ri = gl % RS, cj = gl / RS;
-        for (int i = ri; i < n; i += RS) {
-            const double X0 = xs[i], X1 = xs[n + i];
-            const double *di = der + (size_t)i * 13;
-            const double wi = di[0];
-            double t0 = 0., t1 = 0., t2 = 0., rs = 0.;
-#pragma unroll 4
-            for (int j = j0 + cj; j < j1; j += CS) {
-                const double a = X0 - xs[2 * n + j], b = X1 - xs[3 * n + j];
-                const double g = kv(PNB_ADD(PNB_MUL(a, a), PNB_MUL(b, b)));
-                const double *dj = der + (size_t)j * 13;
-                rs = fma(g, dj[0], rs);
-                t0 = fma(g, dj[1], t0);
-                t1 = fma(g, dj[2], t1);
-                t2 = fma(g, dj[3], t2);
-                const double gw = g * wi;
+    if (valid) {
+        const int ntiles = (n + R - 1) / R;
+        const double2 *dcol = der + (size_t)j0 * PNB_DER2;
+        for (int tile = gl; tile < ntiles; tile += W) {
+            const int i0 = tile * R;
+            double X0[R], X1[R], wq[R], rs[R], t0[R], t1[R], t2[R];
+            {
+                // nodes of the row tile, un-fused and in the reference's order (nodesInGlobalCoords, quadrature.pyx:76-87)
+                const double2 va = V1[0], vb = V1[1], vc = V1[2];
 #pragma unroll
-                for (int e = 0; e < 6; e++) yy[e] = fma(gw, dj[4 + e], yy[e]);
+                for (int q = 0; q < R; q++) {
+                    const int i = min(i0 + q, n - 1);
+                    const double2 ba = der[i * PNB_DER2 + 5], bb = der[i * PNB_DER2 + 6];
+                    double x0 = PNB_MUL(ba.x, va.x), x1 = PNB_MUL(ba.x, va.y);
+                    x0 = PNB_ADD(x0, PNB_MUL(ba.y, vb.x)); x1 = PNB_ADD(x1, PNB_MUL(ba.y, vb.y));
+                    x0 = PNB_ADD(x0, PNB_MUL(bb.x, vc.x)); x1 = PNB_ADD(x1, PNB_MUL(bb.x, vc.y));
+                    X0[q] = x0; X1[q] = x1;
+                    wq[q] = i0 + q < n ? der[i * PNB_DER2].x : 0.;     // rows beyond the rule: weight 0
+                    rs[q] = t0[q] = t1[q] = t2[q] = 0.;
+                }
+            }
+#pragma unroll 2
+            for (int j = 0; j < ncol; j++) {
+                const double2 y = Y[j];
+                double g[R];
+#pragma unroll
+                for (int q = 0; q < R; q++) {
+                    const double a = X0[q] - y.x, b = X1[q] - y.y;
+                    g[q] = kv(PNB_ADD(PNB_MUL(a, a), PNB_MUL(b, b)));
+                }
+                const double2 *dj = dcol + j * PNB_DER2;
+                const double2 c0 = dj[0], c1 = dj[1];
+                double cw = 0.;
+#pragma unroll
+                for (int q = 0; q < R; q++) {
+                    rs[q] = fma(g[q], c0.x, rs[q]);
+                    t0[q] = fma(g[q], c0.y, t0[q]);
+                    t1[q] = fma(g[q], c1.x, t1[q]);
+                    t2[q] = fma(g[q], c1.y, t2[q]);
+                    cw = fma(g[q], wq[q], cw);
+                }
+                const double2 c2 = dj[2], c3 = dj[3], c4 = dj[4];
+                yy[0] = fma(cw, c2.x, yy[0]); yy[1] = fma(cw, c2.y, yy[1]);
+                yy[2] = fma(cw, c3.x, yy[2]); yy[3] = fma(cw, c3.y, yy[3]);
+                yy[4] = fma(cw, c4.x, yy[4]); yy[5] = fma(cw, c4.y, yy[5]);
             }
 #pragma unroll
-            for (int aa = 0; aa < 3; aa++) {
-                const double wp = di[1 + aa];
-                xy[aa * 3 + 0] = fma(-wp, t0, xy[aa * 3 + 0]);
-                xy[aa * 3 + 1] = fma(-wp, t1, xy[aa * 3 + 1]);
-                xy[aa * 3 + 2] = fma(-wp, t2, xy[aa * 3 + 2]);
-            }
+            for (int q = 0; q < R; q++) {
+                if (i0 + q < n) {
+                    const double2 *di = der + (size_t)(i0 + q) * PNB_DER2;
+                    const double2 d0 = di[0], d1 = di[1], d2 = di[2], d3 = di[3], d4 = di[4];
+                    const double wp[3] = {d0.y, d1.x, d1.y};
 #pragma unroll
-            for (int e = 0; e < 6; e++) xx[e] = fma(di[4 + e], rs, xx[e]);
+                    for (int aa = 0; aa < 3; aa++) {
+                        xy[aa * 3 + 0] = fma(-wp[aa], t0[q], xy[aa * 3 + 0]);
+                        xy[aa * 3 + 1] = fma(-wp[aa], t1[q], xy[aa * 3 + 1]);
+                        xy[aa * 3 + 2] = fma(-wp[aa], t2[q], xy[aa * 3 + 2]);
+                    }
+                    xx[0] = fma(d2.x, rs[q], xx[0]); xx[1] = fma(d2.y, rs[q], xx[1]);
+                    xx[2] = fma(d3.x, rs[q], xx[2]); xx[3] = fma(d3.y, rs[q], xx[3]);
+                    xx[4] = fma(d4.x, rs[q], xx[4]); xx[5] = fma(d4.y, rs[q], xx[5]);
+                }
+            }
         }
     }
     // the reference's flattened upper triangle of the 6 x 6 local matrix over (dofs of cell 1, dofs of cell 2)
@@ -588,24 +644,21 @@ __device__ __forceinline__ void near_regular_group(const DProblem &P, const PowC
 }
 
 // Persistent CTAs over chunks of items of one key (regular: the order; 0: singular pairs).  A chunk holds up to
-// 8 x (32 / LPI) items, one lane group each; the derived rule table of the key is staged in shared memory.
+// 8 x K items, one lane group each; the derived rule table of the key is staged in shared memory.
 __global__ void __launch_bounds__(PNB_THREADS, 2)
 gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__restrict__ items, const int *__restrict__ perm,
-                  const int4 *__restrict__ chunks, int nchunks, double *__restrict__ R)
+                  const int4 *__restrict__ chunks, int nchunks, double *__restrict__ R, int der_nodes, int warp_points)
 {
     constexpr int NV = 3, NL = PairDims<2>::NL, NRr = 2 * NV - 1, NA = NRr * (NRr + 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PowTab *pw = reinterpret_cast<PowTab *>(smem_raw);
-    double *der = reinterpret_cast<double *>(smem_raw + sizeof(PowTab));
-    double *xsw = der + (size_t)13 * P.reg_nmax + (size_t)(threadIdx.x >> 5) * 4 * P.reg_nmax;
-    {
-        const double *src = reinterpret_cast<const double *>(P.pow_int);
-        double *dst = reinterpret_cast<double *>(pw);
-        for (int e = threadIdx.x; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_THREADS) dst[e] = src[e];
-    }
+    PowTabS *pw = reinterpret_cast<PowTabS *>(smem_raw);
+    double2 *der = reinterpret_cast<double2 *>(smem_raw + sizeof(PowTabS));
+    // per warp: per item the vertices of the first cell and the nodes of the column slice (warp_points points)
+    double2 *xsw = der + (size_t)PNB_DER2 * der_nodes + (size_t)(threadIdx.x >> 5) * warp_points;
+    powtab_stage(pw, P.pow_int, threadIdx.x, PNB_THREADS);
     __syncthreads();
-    const PowCtx kv(pw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PowCtxS kv(pw, lane);
     int staged = -1;
     for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         const int4 c = chunks[ch];
@@ -613,31 +666,37 @@ gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__rest
         if (key >= 1 && key != staged) {
             __syncthreads();      // everybody is done with the previous table
             const int n = P.reg_cell[key].n;
-            const double *src = P.reg_derived + (size_t)P.reg_doff[key] * 13;
-            for (int e = threadIdx.x; e < n * 13; e += PNB_THREADS) der[e] = src[e];
+            const double2 *src = reinterpret_cast<const double2 *>(P.reg_derived) + (size_t)P.reg_doff[key] * PNB_DER2;
+            for (int e = threadIdx.x; e < n * PNB_DER2; e += PNB_THREADS) der[e] = src[e];
             staged = key;
             __syncthreads();
         }
         if (key >= 1) {
             const int4 grid = P.reg_grid[key];
-            const int LPI = grid.z, K = 32 / LPI, g = lane / LPI, gl = lane - g * LPI;
+            const int W = grid.x, K = grid.y, g = lane / W, gl = lane - g * W;
             const int idx = warp * K + g;
-            const bool valid = idx < c.z;
+            const bool valid = g < K && idx < c.z;
             const int item = valid ? perm[c.y + idx] : 0;
             const int2 it = items[item];
             const int4 pr = pairs[it.x];
             const int n = P.reg_cell[key].n;
+            const int nsl = near_slices(P, key);
+            const int per = (n + nsl - 1) / nsl;
             double acc[NL];
             __syncwarp();
-            near_regular_group(P, kv, der, n, pr.x, pr.y, it.y, near_slices(P, key), xsw + (size_t)g * 4 * n, gl, grid, valid, acc);
-            for (int off = LPI >> 1; off > 0; off >>= 1) {
+            near_regular_group(P, kv, der, n, pr.x, pr.y, it.y, nsl, xsw + (size_t)min(g, K - 1) * (3 + per), gl, W, valid, acc);
+            // fixed tree over the W lanes of the group (W need not be a power of two)
+            for (int off = 16; off > 0; off >>= 1) {
+                if (off >= W) continue;
 #pragma unroll
-                for (int k = 0; k < NL; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+                for (int k = 0; k < NL; k++) {
+                    const double v = __shfl_down_sync(0xffffffffu, acc[k], off);
+                    if (gl + off < W) acc[k] += v;
+                }
             }
-            if (valid) {
+            if (valid && gl == 0) {
 #pragma unroll
-                for (int k = 0; k < NL; k++)
-                    if ((k % LPI) == gl) R[(size_t)item * NL + k] = acc[k];
+                for (int k = 0; k < NL; k++) R[(size_t)item * NL + k] = acc[k];
             }
         } else {
             const int idx = warp;
@@ -744,7 +803,7 @@ __global__ void __launch_bounds__(256) gnear_finalize_kernel(DProblem P, const i
 // gnear_eval_kernel and is fetched here, so that all contributions of a unit are added in one fixed order
 // -------------------------------------------------------------------------------------------------
 struct GMixFixed {
-    PowTab pw;
+    PowTabS pw;
     FarRule far[PNB_FAR_MAX_ORDER - 1];      // orders 2..PNB_FAR_MAX_ORDER
     double dxy[2 * PNB_SB * PNB_SB][12];
     unsigned char slotD[2 * PNB_SB * PNB_SB];
@@ -825,9 +884,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_ticket;
     {
-        const double *src = reinterpret_cast<const double *>(P.pow_int);
-        double *dst = reinterpret_cast<double *>(&sm.pw);
-        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += PNB_GT) dst[e] = src[e];
+        powtab_stage(&sm.pw, P.pow_int, tid, PNB_GT);
         const double *fs = reinterpret_cast<const double *>(P.far_rules + 2);
         double *fd = reinterpret_cast<double *>(&sm.far[0]);
         for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_GT) fd[e] = fs[e];
@@ -835,7 +892,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
     unsigned long long my_pairs = 0, my_near = 0;
     PROF_DECL
     __syncthreads();        // the power table is complete before its coefficients go to registers
-    const PowCtx kv(&sm.pw);
+    const PowCtxS kv(&sm.pw, lane);
     const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15;
     for (;;) {
     __syncthreads();
@@ -1032,9 +1089,12 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
         double *dp = &G.Dp[((size_t)I * P.nc + cc) * ND + (e % ND)];
         *dp = diag ? *dp + DYs[e] : DYs[e];
     }
-    g_wait_predecessors(G, 1, ticket, I, J, tid, PNB_GT);
-    g_flush_block(G, S, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_GT);
-    g_signal_done(G, 1, ticket, tid);
+    if (G.dist.nparts > 0) g_flush_staged(G, G.dist.uoff_mix + (size_t)ticket * G.dist.nparts, S, ldS, I, dI, nldI, dJ, nldJ, tid, PNB_GT);
+    else {
+        g_wait_predecessors(G, 1, ticket, I, J, tid, PNB_GT);
+        g_flush_block(G, S, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_GT);
+        g_signal_done(G, 1, ticket, tid);
+    }
     PROF(4)
     }
 #ifdef PNB_PROFILE
@@ -1078,4 +1138,76 @@ __global__ void greduce_D_kernel(GroupSched G, double *D, const double *Dbnd, in
     for (int g = 0; g < G.ngroups; g++) s += G.Dp[(size_t)g * nc * 6 + e];
     if (use_bnd) s += Dbnd[e];
     D[e] = s;
+}
+
+// -------------------------------------------------------------------------------------------------
+// several GPUs: rows of the operator from the staged fragments.  One CTA per owned row a: for every group g that holds
+// a and every group h, the row of unit (min(g,h), max(g,h)) that belongs to a (as a row of I and / or of J) is added
+// to the columns dofs(h).  Groups of one colour share no dof, so the warps take different h of a colour without
+// synchronisation; colours, and the groups g of a, follow each other in a fixed order: every entry is summed in the
+// same order on every run (bitwise reproducible, no atomics).  The cell-diagonal blocks of the cells around a
+// (D, summed over the parts by the caller) are added last, like scatter_D_kernel does.
+// -------------------------------------------------------------------------------------------------
+struct DistApply {
+    int nrows;
+    const int *rows;            // owned rows (global dofs), ascending
+    const int *d2g_ptr;         // N+1: dof -> (group, local index in the group)
+    const int2 *d2g;
+    const int *colptr;          // ncolors+1: groups by colour
+    const int *collist;
+    const long long *uoff;      // ngroups x ngroups (I <= J): start of the unit's fragments in this part's staging, -1 = none
+    const double *stage;        // this part's staging buffer
+};
+
+__global__ void __launch_bounds__(256) dist_apply_kernel(DProblem P, GroupSched G, DistApply X, const int *__restrict__ dof_ptr,
+                                                         const int *__restrict__ dof_cells, const double *__restrict__ D, int use_D,
+                                                         double *__restrict__ A, int64_t ld)
+{
+    const int r = blockIdx.x;
+    if (r >= X.nrows) return;
+    const int a = X.rows[r];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int me = G.dist.part, np = G.dist.nparts, ng = G.ngroups;
+    double *row = A + (size_t)r * ld;
+    for (int c = tid; c < P.N; c += blockDim.x) row[c] = 0.;
+    __syncthreads();
+    for (int col = 0; col < G.ncolors; col++) {
+        const int h0 = X.colptr[col], nh = X.colptr[col + 1] - h0;
+        for (int k = X.d2g_ptr[a]; k < X.d2g_ptr[a + 1]; k++) {
+            const int g = X.d2g[k].x, la = X.d2g[k].y;
+            const int nldg = G.gdptr[g + 1] - G.gdptr[g];
+            const long long pos = G.dist.gpos[G.gdptr[g] + la];
+            for (int hi = warp; hi < nh; hi += nwarps) {
+                const int h = X.collist[h0 + hi];
+                const int nldh = G.gdptr[h + 1] - G.gdptr[h];
+                const int *cols = G.gdofs + G.gdptr[h];
+                if (g <= h) {       // a is a row of I = g, columns dofs(J = h)
+                    const long long off = X.uoff[(size_t)g * ng + h];
+                    if (off >= 0) {
+                        const double *f = X.stage + off + pos * nldh;
+                        for (int c = lane; c < nldh; c += 32) row[cols[c]] += f[c];
+                    }
+                }
+                if (g >= h) {       // a is a row of J = g of unit (I = h, J = g), columns dofs(I = h)
+                    const long long off = X.uoff[(size_t)h * ng + g];
+                    if (off >= 0) {
+                        const double *f = X.stage + off + (long long)G.dist.gcnt[h * np + me] * nldg + pos * nldh;
+                        for (int c = lane; c < nldh; c += 32) row[cols[c]] += f[c];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (use_D && tid == 0) {
+        for (int t = dof_ptr[a]; t < dof_ptr[a + 1]; t++) {
+            const int K = dof_cells[t] >> 2, pq = dof_cells[t] & 3;
+            for (int q = 0; q < 3; q++) {
+                const int Jd = P.dofs[(size_t)K * 3 + q];
+                if (Jd < 0) continue;
+                const int kk = pq <= q ? tri_idx(3, pq, q) : tri_idx(3, q, pq);
+                row[Jd] += D[(size_t)K * 6 + kk];
+            }
+        }
+    }
 }

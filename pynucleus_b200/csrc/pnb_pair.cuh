@@ -21,35 +21,69 @@ template <int DIM> struct PairDims {
 // gamma(x,y) = C |x-y|^(-d-2s)  (kernelsCy.pyx:159-183); boundary kernels :216-240,
 // evaluated from d2 = |x-y|^2 with the table-driven power (PowTab).
 
-// polynomial coefficients in registers, tables wherever `t` points (shared or global memory)
-struct PowCtx {
-    const PowTab *t;
-    double c0, c1, c2, c3, c4, c5, c6, c7;
+// Shared-memory copy of a PowTab with the 128 mantissa entries replicated 8 times: lane l reads copy l & 7, i.e. its
+// own group of four banks, so that the 16-byte lookups of a quarter warp never collide (a 128-bit shared load is
+// served per quarter warp).  With the compact table the random lookups were the largest source of bank conflicts
+// of all three pair kernels (ncu, round 1: 2.3e9 conflict cycles per assembly in the unit kernel alone).
+#define PNB_POW_REP 8
+struct PowTabS {
+    double2 IT[128 * PNB_POW_REP];
+    double T1[256];
+    double coef[8];
+    int eoff, pad;
+};
+
+__device__ __forceinline__ void powtab_stage(PowTabS *dst, const PowTab *__restrict__ src, int tid, int nthreads)
+{
+    for (int e = tid; e < 128 * PNB_POW_REP; e += nthreads) dst->IT[e] = src->IT[e / PNB_POW_REP];
+    for (int e = tid; e < 256; e += nthreads) dst->T1[e] = src->T1[e];
+    if (tid < 8) dst->coef[tid] = src->coef[tid];
+    if (tid == 0) { dst->eoff = src->eoff; dst->pad = 0; }
+}
+
+// polynomial coefficients in registers, tables wherever they live: REP = 1 compact table (global memory),
+// REP = PNB_POW_REP replicated shared-memory copy.  Degree 6: with |r| <= 2^-8 the truncation error is
+// binom(e,7) r^7 <= 1e-16 for the exponents that occur (|e| <= 2.5).
+template <int REP> struct PowCtxT {
+    const double2 *it;
+    const double *T1;
+    double c0, c1, c2, c3, c4, c5, c6;
     int eoff;          // table offset minus the exponent bias
-    __device__ __forceinline__ explicit PowCtx(const PowTab *tab) : t(tab)
+    __device__ __forceinline__ void init(const double *coef, int eo)
     {
-        eoff = tab->eoff - 1023;
-        c0 = tab->coef[0]; c1 = tab->coef[1]; c2 = tab->coef[2]; c3 = tab->coef[3];
-        c4 = tab->coef[4]; c5 = tab->coef[5]; c6 = tab->coef[6]; c7 = tab->coef[7];
+        eoff = eo - 1023;
+        c0 = coef[0]; c1 = coef[1]; c2 = coef[2]; c3 = coef[3];
+        c4 = coef[4]; c5 = coef[5]; c6 = coef[6];
+    }
+    __device__ __forceinline__ explicit PowCtxT(const PowTab *tab) : it(tab->IT), T1(tab->T1)
+    {
+        static_assert(REP == 1, "compact table");
+        init(tab->coef, tab->eoff);
+    }
+    __device__ __forceinline__ PowCtxT(const PowTabS *tab, int lane) : it(tab->IT + (lane & (PNB_POW_REP - 1))), T1(tab->T1)
+    {
+        static_assert(REP == PNB_POW_REP, "replicated table");
+        init(tab->coef, tab->eoff);
     }
     __device__ __forceinline__ double operator()(double d2) const
     {
         const int hi = __double2hiint(d2), lo = __double2loint(d2);
         const int E = min(max(((hi >> 20) & 0x7ff) + eoff, 0), 255);
-        const int idx = (hi >> 13) & 0x7f;
+        const int idx = REP == 1 ? ((hi >> 13) & 0x7f) : ((hi >> 10) & (0x7f * REP));
         const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-        const double2 it = t->IT[idx];
-        const double r = fma(m, it.x, -1.0);
-        double p = fma(c7, r, c6);
-        p = fma(p, r, c5);
+        const double2 iv = it[idx];
+        const double r = fma(m, iv.x, -1.0);
+        double p = fma(c6, r, c5);
         p = fma(p, r, c4);
         p = fma(p, r, c3);
         p = fma(p, r, c2);
         p = fma(p, r, c1);
         p = fma(p, r, c0);
-        return t->T1[E] * (it.y * p);
+        return T1[E] * (iv.y * p);
     }
 };
+typedef PowCtxT<1> PowCtx;
+typedef PowCtxT<PNB_POW_REP> PowCtxS;
 
 __device__ __forceinline__ double kernel_value(const PowTab *__restrict__ t, double d2)
 {
@@ -352,8 +386,9 @@ __host__ __device__ inline int far_expected_nodes(int order) { return order == 2
 // per-order instantiations were measured 2-3x slower: the tile kernel then no longer fits the instruction
 // cache and warps stall on instruction fetch.)  R lives in shared memory; all lanes of a warp that work on
 // the same order read the same addresses (broadcast).
+template <class KV>
 __device__ __forceinline__ void far_eval_2d(const FarRule &R, const double (*s1)[2], const double (*s2)[2],
-                                            const PowCtx &T, const bool with_d, double *xy, double *xx, double *yy)
+                                            const KV &T, const bool with_d, double *xy, double *xx, double *yy)
 {
     const int n = R.n;
 #pragma unroll
@@ -404,8 +439,8 @@ __device__ __forceinline__ void far_eval_2d(const FarRule &R, const double (*s1)
 // rolled, the body is small enough for the instruction cache), so that the nodes of the second cell and the
 // column sums c_j = sum_i w_i g_ij live in registers: 19 instead of 31 FP64 operations per node pair, and the
 // rule constants are read at fixed shared-memory offsets.
-template <int N>
-__device__ __forceinline__ void far_eval_n(const FarRule &R, const double (*s1)[2], const double (*s2)[2], const PowCtx &T,
+template <int N, class KV>
+__device__ __forceinline__ void far_eval_n(const FarRule &R, const double (*s1)[2], const double (*s2)[2], const KV &T,
                                            double *xy, double *xx, double *yy)
 {
     double Y0[N], Y1[N], c[N];

@@ -14,6 +14,26 @@ import torch
 from . import _lib
 
 
+def _check_vector(v, n, device, name):
+    """the matvec kernel reads / writes contiguous float64 device memory through raw pointers"""
+    if not isinstance(v, torch.Tensor) or v.dim() != 1 or v.shape[0] != n:
+        raise ValueError('{}: need a 1-D tensor of length {}'.format(name, n))
+    if v.dtype != torch.float64 or not v.is_cuda or v.device != device:
+        raise ValueError('{}: need a float64 tensor on {} (got {} on {})'.format(name, device, v.dtype, v.device))
+    if n > 1 and v.stride(0) != 1:
+        raise ValueError('{}: need a contiguous tensor (stride {})'.format(name, v.stride(0)))
+
+
+def check_matrix_out(out, rows, cols, device):
+    """`out=` targets of the assembly entry points: the kernels write row-major float64 device memory"""
+    if not isinstance(out, torch.Tensor) or out.dim() != 2 or tuple(out.shape) != (rows, cols):
+        raise ValueError('out: need a ({}, {}) tensor'.format(rows, cols))
+    if out.dtype != torch.float64 or not out.is_cuda or out.device != device:
+        raise ValueError('out: need a float64 tensor on {} (got {} on {})'.format(device, out.dtype, out.device))
+    if (cols > 1 and out.stride(1) != 1) or (rows > 1 and out.stride(0) < cols):
+        raise ValueError('out: need row-major storage (strides {})'.format(tuple(out.stride())))
+
+
 class Dense_LinearOperator:
     def __init__(self, data, device_index=None):
         if not isinstance(data, torch.Tensor):
@@ -60,8 +80,8 @@ class Dense_LinearOperator:
         """x, y: float64 CUDA tensors on the operator's device"""
         if y is None:
             y = torch.empty(self.num_rows, dtype=torch.float64, device=self._A.device)
-        if x.shape[0] != self.num_columns or y.shape[0] != self.num_rows:
-            raise ValueError('shape mismatch')
+        _check_vector(x, self.num_columns, self._A.device, 'x')
+        _check_vector(y, self.num_rows, self._A.device, 'y')
         if self.num_rows == 0 or self.num_columns == 0:
             return y.zero_()
         stream = torch.cuda.current_stream(self._A.device).cuda_stream

@@ -31,16 +31,24 @@ class meshNd:
     num_cells = property(lambda self: self.cells.shape[0])
 
     # ---- geometry -------------------------------------------------------
+    def _edge_lengths(self):
+        """hVector, h, hmin exactly as hdeltaCy rounds them (fem/PyNucleus_fem/meshCy.pyx:1654-1732): the host routine
+        pnb_mesh_edge_lengths of the library (edge lengths through a fused-multiply-add dot product like the BLAS ddot
+        behind the reference's mydot; getQuadOrder is sensitive to the last bit of h)"""
+        import ctypes
+        from . import _lib
+        h = np.empty(self.num_cells)
+        hmax, hmin = ctypes.c_double(0.), ctypes.c_double(0.)
+        _lib.check(_lib.lib().pnb_mesh_edge_lengths(self.manifold_dim, self.num_cells, self.vertices.ctypes.data,
+                                                    self.cells.ctypes.data, h.ctypes.data, ctypes.byref(hmax),
+                                                    ctypes.byref(hmin)))
+        self._h, self._hmax, self._hmin = h, float(hmax.value), float(hmin.value)
+
     @property
     def hVector(self):
+        """longest edge per cell"""
         if self._h is None:
-            v, c = self.vertices, self.cells
-            h2 = np.zeros(c.shape[0])
-            for i in range(c.shape[1]):
-                for j in range(i+1, c.shape[1]):
-                    d = v[c[:, j]]-v[c[:, i]]
-                    h2 = np.maximum(h2, (d*d).sum(axis=1))
-            self._h = np.sqrt(h2)
+            self._edge_lengths()
         return self._h
 
     @property
@@ -55,8 +63,20 @@ class meshNd:
                 self._vol = np.abs(a[:, 0]*b[:, 1]-a[:, 1]*b[:, 0])*0.5
         return self._vol
 
-    h = property(lambda self: float(self.hVector.max()))
-    hmin = property(lambda self: float(self.hVector.min()))
+    @property
+    def h(self):
+        """longest edge of the mesh"""
+        if self._h is None:
+            self._edge_lengths()
+        return self._hmax
+
+    @property
+    def hmin(self):
+        """SHORTEST edge of the mesh (meshCy.pyx:1724: min over all edges, not over the cells' longest edges)"""
+        if self._h is None:
+            self._edge_lengths()
+        return self._hmin
+
     volume = property(lambda self: float(self.volVector.sum()))
 
     @property

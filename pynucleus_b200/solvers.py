@@ -11,16 +11,25 @@ import torch
 
 
 class DistributedDenseOperator:
-    """Row block of a dense operator per rank; matvec = local rows of A x, then all-gather."""
+    """Rows of a dense operator per rank; matvec = local rows of A x, then all-gather of the pieces.
 
-    def __init__(self, A_rows, row_begin, row_end, num_dofs, blocks, process_group=None):
+    all_rows[r]: global row indices (ascending) held by rank r -- contiguous blocks (1D) or the rows of the dofs of a
+    range of cell groups (2D, nonlocalBuilder.getDenseDistributed).  A_rows: Dense_LinearOperator with
+    len(all_rows[rank]) rows and num_dofs columns (None on a rank without rows)."""
+
+    def __init__(self, A_rows, all_rows, rank, num_dofs, process_group=None):
         self.A_rows = A_rows
-        self.row_begin, self.row_end = row_begin, row_end
+        self.all_rows = [np.asarray(r, dtype=np.int64) for r in all_rows]
+        self.rank = rank
+        self.rows = self.all_rows[rank]
         self.num_rows = self.num_columns = num_dofs
-        self.blocks = blocks
         self.group = process_group
-        self._send = self._recv = None
+        self._send = self._recv = self._perm = None
         self.device = A_rows.device_data.device if A_rows is not None else torch.device('cuda', torch.cuda.current_device())
+        # contiguous blocks keep their bounds (1D row blocks)
+        r = self.rows
+        self.row_begin = int(r[0]) if r.shape[0] else 0
+        self.row_end = int(r[-1])+1 if r.shape[0] else 0
 
     shape = property(lambda self: (self.num_rows, self.num_columns))
 
@@ -28,17 +37,22 @@ class DistributedDenseOperator:
         import torch.distributed as dist
         if y is None:
             y = torch.empty(self.num_rows, dtype=torch.float64, device=self.device)
-        # blocks may differ in length (64-row granularity): gather fixed-size slots, then unpack
-        slot = max(b-a for a, b in self.blocks)
+        # the pieces differ in length: gather fixed-size slots, then scatter them to the global numbering
+        slot = max(r.shape[0] for r in self.all_rows)
         if self._send is None:
             self._send = torch.zeros(slot, dtype=torch.float64, device=self.device)
-            self._recv = torch.empty(slot*len(self.blocks), dtype=torch.float64, device=self.device)
-        n = self.row_end-self.row_begin
+            self._recv = torch.empty(slot*len(self.all_rows), dtype=torch.float64, device=self.device)
+            src = np.concatenate([k*slot+np.arange(r.shape[0]) for k, r in enumerate(self.all_rows)])
+            self._src = torch.as_tensor(src, device=self.device)
+            self._dst = torch.as_tensor(np.concatenate(self.all_rows), device=self.device)
+        n = self.rows.shape[0]
         if self.A_rows is not None and n > 0:
             self.A_rows.matvec_device(x, self._send[:n])
-        dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
-        for r, (a, b) in enumerate(self.blocks):
-            y[a:b] = self._recv[r*slot:r*slot+b-a]
+        if len(self.all_rows) > 1:
+            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        else:
+            self._recv.copy_(self._send)
+        y[self._dst] = self._recv[self._src]
         return y
 
     def diagonal_device(self):
@@ -46,9 +60,10 @@ class DistributedDenseOperator:
         d = torch.zeros(self.num_rows, dtype=torch.float64, device=self.device)
         if self.A_rows is not None:
             A = self.A_rows.device_data
-            idx = torch.arange(self.row_end-self.row_begin, device=self.device)
-            d[self.row_begin:self.row_end] = A[idx, idx+self.row_begin]
-        dist.all_reduce(d, group=self.group)
+            rows = torch.as_tensor(self.rows, device=self.device)
+            d[rows] = A[torch.arange(rows.shape[0], device=self.device), rows]
+        if len(self.all_rows) > 1:
+            dist.all_reduce(d, group=self.group)
         return d
 
 

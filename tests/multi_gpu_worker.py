@@ -23,12 +23,16 @@ def main():
     op = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5, 'device': local}).getDenseDistributed()
     A = full.device_data
     mine = op.A_rows.device_data
-    # every rank evaluates a share of the cell pairs and the shares are summed over NVLink: same terms as on
-    # one GPU, different summation order -> 1e-12 relative to the entry / diagonal scale
+    rows = torch.as_tensor(op.rows, device='cuda')
+    # every rank evaluates a share of the cell pairs and the blocks reach the row owners through NVLink peer stores: same
+    # terms as on one GPU, different summation order -> 1e-12 relative to the entry / diagonal scale
     d = torch.sqrt(torch.diagonal(A))
-    scale = torch.maximum(A[op.row_begin:op.row_end].abs(), 1e-2*torch.outer(d[op.row_begin:op.row_end], d))
-    err = float(((mine-A[op.row_begin:op.row_end]).abs()/scale).max())
-    assert err < 1e-12, 'row block differs from the single-GPU operator: %g' % err
+    scale = torch.maximum(A[rows].abs(), 1e-2*torch.outer(d[rows], d))
+    err = float(((mine-A[rows]).abs()/scale).max())
+    assert err < 1e-12, 'rows differ from the single-GPU operator: %g' % err
+    counts = [None]*dist.get_world_size()
+    dist.all_gather_object(counts, int(rows.shape[0]))
+    assert sum(counts) == dm.num_dofs
     x = torch.from_numpy(np.random.default_rng(3).standard_normal(dm.num_dofs)).cuda()
     y = op.matvec_device(x)
     y1 = full.matvec_device(x)

@@ -383,16 +383,18 @@ def test_two_gpus_row_blocks_matvec_cg():
     assert out.returncode == 0 and 'OK' in out.stdout, out.stdout[-2000:]+out.stderr[-4000:]
 
 
-@pytest.mark.parametrize('nparts', [2, 3])
-def test_unit_shares_sum_to_full_operator(nparts):
-    """several GPUs, 2D (pnb_dense_partial_begin), emulated on one GPU: every instance evaluates its share of the
-    cell pairs into a full-size scratch; the row owners sum the shares (what the NCCL reduce does) and add the
-    summed cell-diagonal blocks.  Every pair is evaluated exactly once over all instances."""
+@pytest.mark.parametrize('nparts,sides,noRef', [(2, 6, 4), (3, 6, 4), (4, 10, 5)])
+def test_distributed_parts_equal_full_operator(nparts, sides, noRef):
+    """several GPUs, 2D (pnb_dist_*), emulated on ONE GPU: one problem instance per part, all staging buffers in this
+    process (on several GPUs they are peer memory).  Every part evaluates its units into the staging buffers of the row
+    owners, the cell-diagonal blocks are summed (what the all-reduce does), every part builds its rows.  Every pair is
+    evaluated exactly once over all parts, the rows of the parts partition the dofs, and the rows equal the single-GPU
+    operator."""
+    import ctypes
     import torch
     import pynucleus_b200 as pb
     from pynucleus_b200 import _lib
-    from pynucleus_b200.assembly import row_partition
-    mesh = pb.refined(pb.uniform_disc(), 4)
+    mesh = pb.refined(pb.polygon_disc(sides), noRef)
     dm = pb.P1_DoFMap(mesh)
     N = dm.num_dofs
     kernel = pb.getFractionalKernel(2, 0.75)
@@ -400,30 +402,59 @@ def test_unit_shares_sum_to_full_operator(nparts):
     full = ref.getDense().data
     distinct = ref.getStats()['distinct_pairs']
     L = _lib.lib()
-    blocks = row_partition(N, nparts, L.pnb_row_granularity())
-    builders = [pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}) for _ in blocks]
-    Usum = torch.zeros((N, N), dtype=torch.float64, device='cuda')
+    builders = [pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}) for _ in range(nparts)]
+    rows, stages = [], []
+    for k, bld in enumerate(builders):
+        nrows, nstage = ctypes.c_int32(0), ctypes.c_int64(0)
+        _lib.check(L.pnb_dist_plan(bld.problem.handle, nparts, k, ctypes.byref(nrows), ctypes.byref(nstage)))
+        r = np.empty(nrows.value, dtype=np.int32)
+        _lib.check(L.pnb_dist_rows(bld.problem.handle, r.ctypes.data))
+        rows.append(r)
+        # NaN-filled: a fragment that is read without having been written shows up in the result
+        stages.append(torch.full((max(int(nstage.value), 1),), float('nan'), dtype=torch.float64, device='cuda'))
+    assert np.array_equal(np.sort(np.concatenate(rows)), np.arange(N))
+    ptrs = (ctypes.c_void_p*nparts)(*[t.data_ptr() for t in stages])
     Dsum = torch.zeros(mesh.num_cells*6, dtype=torch.float64, device='cuda')
-    evaluated = 0
-    for k, (bld, (a, b)) in enumerate(zip(builders, blocks)):
-        U = torch.empty((N, N), dtype=torch.float64, device='cuda')
-        _lib.check(L.pnb_dense_partial_begin(bld.problem.handle, 1, k, nparts, a, b, U.data_ptr(), N))
+    for bld in builders:
+        _lib.check(L.pnb_dist_eval(bld.problem.handle, 1, ptrs))
+        need = ctypes.c_int32(0)
+        _lib.check(L.pnb_dist_status(bld.problem.handle, ctypes.byref(need)))
+        assert need.value == 0
         D = torch.empty_like(Dsum)
         _lib.check(L.pnb_dense_cell_blocks_copy(bld.problem.handle, D.data_ptr(), 0))
         torch.cuda.synchronize()
-        Usum += U
         Dsum += D
-    outs = []
-    for bld, (a, b) in zip(builders, blocks):
-        out = Usum[a:b].clone()
+    A = np.zeros((N, N))
+    evaluated = 0
+    for bld, r in zip(builders, rows):
+        out = torch.empty((r.shape[0], N), dtype=torch.float64, device='cuda')
         _lib.check(L.pnb_dense_cell_blocks_copy(bld.problem.handle, Dsum.data_ptr(), 1))
-        _lib.check(L.pnb_dense_rows_end(bld.problem.handle, a, b, out.data_ptr(), out.stride(0)))
+        _lib.check(L.pnb_dist_apply(bld.problem.handle, 1, out.data_ptr(), out.stride(0)))
         evaluated += bld.getStats()['evaluated_pairs']
-        outs.append(out)
-    A = torch.cat(outs, dim=0).cpu().numpy()
+        A[r] = out.cpu().numpy()
     assert evaluated == distinct
     assert entry_err(A, full) < TOL
     assert np.abs(A-A.T).max() <= 1e-13*np.abs(A).max()
+    # work balance of the plan: no part evaluates more than 1.35 times its share
+    shares = [b.getStats()['evaluated_pairs'] for b in builders]
+    assert max(shares) < 1.35*distinct/nparts, shares
+
+
+def test_distributed_operator_single_process():
+    """getDenseDistributed without a process group (world size 1): same code path as on several GPUs, own staging buffer"""
+    import torch
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.uniform_disc(), 3)
+    dm = pb.P1_DoFMap(mesh)
+    kernel = pb.getFractionalKernel(2, 0.75)
+    full = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense()
+    b = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5})
+    op = b.getDenseDistributed()
+    assert np.array_equal(op.rows, np.arange(dm.num_dofs))
+    assert entry_err(op.A_rows.data, full.data) < TOL
+    x = torch.from_numpy(np.random.default_rng(1).standard_normal(dm.num_dofs)).cuda()
+    assert float((op.matvec_device(x)-full.matvec_device(x)).abs().max()) < 1e-12*float(full.matvec_device(x).abs().max())
+    b.releaseScratch()
 
 
 def test_group_path_equals_tile_path(monkeypatch):

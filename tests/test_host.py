@@ -254,3 +254,21 @@ def test_near_field_container_is_consistent():
     assert np.abs(near.matvec_device(x).numpy()-ref.dot(x.numpy())).max() < 1e-13
     assert np.abs(y_blocks-ref.dot(x.numpy())).max() < 1e-13
     assert np.abs(near.diagonal_device().numpy()-np.diag(ref)).max() < 1e-15
+
+
+def test_mesh_sizes_bit_exact_vs_reference(golden_dir):
+    """hVector / h / hmin from the reference's own vertex arrays must equal the reference's values to the last bit
+    (hdeltaCy, meshCy.pyx:1654-1732: longest edge per cell, hmin = SHORTEST edge of the mesh, edge lengths through a
+    fused dot product): getQuadOrder and the singular quadrature orders round logarithms of these numbers up"""
+    import glob
+    n = 0
+    for f in sorted(glob.glob(os.path.join(golden_dir, '*.npz'))):
+        g = np.load(f)
+        if 'hVector' not in g.files or 'cells' not in g.files:
+            continue
+        m = pb.meshNd(g['vertices'], g['cells'])
+        assert np.array_equal(m.hVector, g['hVector']), f
+        assert m.hmin == float(g['hmin']) and m.h == float(g['h']), f
+        assert np.array_equal(m.volVector, g['volVector']), f
+        n += 1
+    assert n >= 10

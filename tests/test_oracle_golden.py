@@ -237,3 +237,20 @@ def test_single_entries_match_reference(golden_dir, name):
         assert abs(entry(I, J)-ref) < 1e-12*max(abs(ref), 1e-2*scale)
     for I in range(0, N, max(1, N//8)):
         assert abs(entry(I, I)/g['diagonal'][I]-1) < 1e-12
+
+
+def test_oracle_mesh_sizes_bit_exact_vs_reference(golden_dir):
+    """the oracle's own hVector / h / hmin (orc_edge_lengths) against every fixture that stores the reference's"""
+    import glob
+    from oracle import meshes
+    n = 0
+    for f in sorted(glob.glob(os.path.join(golden_dir, '*.npz'))):
+        g = np.load(f)
+        if 'hVector' not in g.files or 'cells' not in g.files:
+            continue
+        m = meshes.Mesh(g['vertices'], g['cells'])
+        assert np.array_equal(m.hVector, g['hVector']), f
+        assert m.hmin == float(g['hmin']) and m.h == float(g['h']), f
+        assert np.array_equal(m.volVector, g['volVector']), f
+        n += 1
+    assert n >= 10
