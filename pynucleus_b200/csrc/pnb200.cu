@@ -1884,6 +1884,8 @@ struct GroupHostFull : GroupHost {
     double *d_R = nullptr, *d_F = nullptr;
     int nitems = 0, npairs = 0, nchunks = 0;
     int near_nmax = 1;                      // largest node count of a regular rule with near items
+    void *mix_scratch = nullptr;            // unit blocks of the resident CTAs of gmix_kernel
+    size_t mix_scratch_bytes = 0;
     bool near_ready = false;
 };
 
@@ -1925,7 +1927,9 @@ static int build_group_schedule(pnb_problem *p)
             build_group_geometry(p, GC, order, gh->gg);
             gh->GC = GC;
             const int ldS = gh->gg.maxld + 1;
-            if (forced > 0 || (gmix_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS) <= budget && gh->gg.maxld < 255)) break;
+            if (forced > 0 || (std::max(gf2_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS), gmix_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS)) <= budget &&
+                               gh->gg.maxld < 255))
+                break;
         }
         const GroupGeom &gg = gh->gg;
         if (gg.maxld >= 255) return fail(PNB_ERR_UNSUPPORTED, "cell group with more than 254 local dofs");
@@ -2251,7 +2255,17 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         }
         cudaEventRecord(p->kev[2]);
         if (nm > 0 && !(dbg & 0x200)) {
-            gmix_kernel<<<std::min(nm, nsm), PNB_GT, gh->smem_mix>>>(p->P, G, gh->d_mix, nm, dA, ld, p->far_mask);
+            // unit blocks of the resident CTAs (two per SM): global scratch, L2 resident
+            const int ncta = std::min(nm, 2 * nsm);
+            const size_t need = (size_t)ncta * G.maxld * G.ldS * sizeof(double);
+            if (gh->mix_scratch_bytes < need) {
+                if (gh->mix_scratch) pool_free(gh->mix_scratch);
+                gh->mix_scratch = nullptr;
+                gh->mix_scratch_bytes = 0;
+                CK(pool_malloc(&gh->mix_scratch, need));
+                gh->mix_scratch_bytes = need;
+            }
+            gmix_kernel<<<ncta, PNB_MT, gh->smem_mix>>>(p->P, G, gh->d_mix, nm, dA, ld, p->far_mask, (double *)gh->mix_scratch);
             launches++;
         }
     }
@@ -2547,6 +2561,7 @@ static void destroy_group_host(pnb_problem *p)
         for (void *d : gh->unit_allocs) pool_free(d);
         for (void *d : gh->near_allocs) pool_free(d);
         for (void *d : gh->dist_allocs) pool_free(d);
+        if (gh->mix_scratch) pool_free(gh->mix_scratch);
         delete gh;
         p->gh = nullptr;
     }

@@ -376,16 +376,17 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits
 // Returns the panel (order >= 1, or -(shared vertices) for touching pairs), 0 when the slot holds no pair.
 // -------------------------------------------------------------------------------------------------
 struct GCls {
-    const double *cxI, *cxJ;      // [2][cap]
+    const double *cxI, *cxJ;      // [2][capI], [2][cap]
     const float *lhI, *ahI, *lhJ, *ahJ;
     const int *cellI, *locI, *cellJ, *locJ;
     int cap;
+    int capI, ioff;               // row side: arrays of capI slots that start at slot ioff of the group (unit kernel: one row batch)
     float cf, sf;
 };
 
 __device__ __forceinline__ int g_classify(const DProblem &P, const GCls &c, bool diag, bool maybe_touching, int rb, int cb, int k1, int k2)
 {
-    const int s1 = rb + k1, s2 = cb + k2;
+    const int s1 = rb + k1 - c.ioff, s2 = cb + k2;
     const int K1 = c.cellI[s1], K2 = c.cellJ[s2];
     // diagonal units: every unordered pair once (batches rb <= cb; inside a batch k1 <= k2)
     if (!(K1 >= 0 && K2 >= 0 && K1 != K2 ? (!diag || rb < cb || k1 < k2) : (K1 >= 0 && K1 == K2 && diag))) return 0;
@@ -402,7 +403,7 @@ __device__ __forceinline__ int g_classify(const DProblem &P, const GCls &c, bool
         panel = -shared_vertices(v1, 3, v2, 3);
     }
     if (panel == 0) {
-        const double a = c.cxI[s1] - c.cxJ[s2], b = c.cxI[c.cap + s1] - c.cxJ[c.cap + s2];
+        const double a = c.cxI[s1] - c.cxJ[s2], b = c.cxI[c.capI + s1] - c.cxJ[c.cap + s2];
         panel = fast_order_2d(a * a + b * b, c.lhI[s1], c.lhJ[s2], c.ahI[s1], c.ahJ[s2], c.cf, c.sf);
         if (panel < 0) {
             // getPanelType evaluates (c1 <= c2): keep the operand order of the reference
@@ -467,7 +468,7 @@ gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int
     c.cxI = cxs; c.cxJ = cxs + 2 * cap;
     c.lhI = lhs; c.ahI = lhs + cap; c.lhJ = lhs + 2 * cap; c.ahJ = lhs + 3 * cap;
     c.cellI = ints; c.locI = ints + cap; c.cellJ = ints + 2 * cap; c.locJ = ints + 3 * cap;
-    c.cap = cap;
+    c.cap = cap; c.capI = cap; c.ioff = 0;
     c.cf = (float)P.c_int; c.sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
     g_load_cls_side(P, G, I, ints, ints + cap, cxs, lhs, lhs + cap, cap, tid);
     g_load_cls_side(P, G, J, ints + 2 * cap, ints + 3 * cap, cxs + 2 * cap, lhs + 2 * cap, lhs + 3 * cap, cap, tid);
@@ -550,7 +551,7 @@ __device__ __forceinline__ void near_regular_group(const DProblem &P, const KV &
     // shared memory of the group: the vertices of the first cell (3 points), then the nodes of the column slice
     double2 *V1 = xs, *Y = xs + 3;
     if (valid) {
-        if (gl < 3) V1[gl] = make_double2(P.simplices[(size_t)Ka * 6 + 2 * gl], P.simplices[(size_t)Ka * 6 + 2 * gl + 1]);
+        for (int k = gl; k < 3; k += W) V1[k] = make_double2(P.simplices[(size_t)Ka * 6 + 2 * k], P.simplices[(size_t)Ka * 6 + 2 * k + 1]);
         double s2[3][2];
         load_simplex<2>(P.simplices, Kb, 3, s2);
         for (int k = j0 + gl; k < j1; k += W) {
@@ -802,15 +803,20 @@ __global__ void __launch_bounds__(256) gnear_finalize_kernel(DProblem P, const i
 // unit kernel: regular pairs of order 2..5 thread-per-pair (binned by order); every other pair was evaluated by
 // gnear_eval_kernel and is fetched here, so that all contributions of a unit are added in one fixed order
 // -------------------------------------------------------------------------------------------------
+#define PNB_MT 256
 struct GMixFixed {
     PowTabS pw;
     FarRule far[PNB_FAR_MAX_ORDER - 1];      // orders 2..PNB_FAR_MAX_ORDER
-    double dxy[2 * PNB_SB * PNB_SB][12];
-    unsigned char slotD[2 * PNB_SB * PNB_SB];
-    int list[2 * PNB_SB * PNB_SB];
-    int clscnt[(PNB_FAR_MAX_ORDER - 1) * (PNB_GT / 32)];
-    int warpcnt[PNB_GT / 32];
+    double dxy[PNB_SB * PNB_SB][12];
+    unsigned char slotD[PNB_SB * PNB_SB];
+    int list[PNB_SB * PNB_SB];
+    int clscnt[(PNB_FAR_MAX_ORDER - 1) * (PNB_MT / 32)];
+    int warpcnt[PNB_MT / 32];
     int nlist, anyD;
+    // row batch of the current step
+    double sxI[6 * PNB_SB], cxI[2 * PNB_SB], volI[PNB_SB];
+    float lhI[PNB_SB], ahI[PNB_SB];
+    int cellI[PNB_SB], locI[PNB_SB];
 };
 
 inline size_t gmix_smem_bytes(int cap, int maxld, int ldS)
@@ -818,13 +824,14 @@ inline size_t gmix_smem_bytes(int cap, int maxld, int ldS)
     size_t b = 0;
     auto add = [&](size_t x) { b += (x + 15) & ~(size_t)15; };
     add(sizeof(GMixFixed));
-    add((size_t)maxld * ldS * 8);
-    add((size_t)2 * 6 * cap * 8);     // sx
-    add((size_t)2 * 2 * cap * 8);     // cx
-    add((size_t)2 * cap * 8);         // vol
-    add((size_t)2 * 2 * cap * 4);     // lh, ah
-    add((size_t)2 * 2 * cap * 4);     // cell, loc
+    add((size_t)3 * PNB_SB * ldS * 8);   // block of the row batch: (row cell, local vertex) x column dofs
+    add((size_t)6 * cap * 8);         // sx of the column side
+    add((size_t)2 * cap * 8);         // cx
+    add((size_t)cap * 8);             // vol
+    add((size_t)2 * cap * 4);         // lh, ah
+    add((size_t)2 * cap * 4);         // cell, loc
     add((size_t)cap * 6 * 8);         // DYs
+    (void)maxld;
     return b;
 }
 
@@ -838,62 +845,72 @@ inline size_t gnear_list_smem_bytes(int cap)
     return b;
 }
 
-// adds the 3 x 3 cross block of a pair to the unit block
-__device__ __forceinline__ void g_scatter(double *S, int ldS, int rl, int cl, const double *xy)
+// adds the 3 x 3 cross block of a pair to the block of the row batch: row = (row cell, local vertex)
+__device__ __forceinline__ void g_scatter(double *S, int ldS, int k1, int rl, int cl, const double *xy)
 {
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int a = (rl >> (8 * i)) & 0xFF;
-        if (a == 0xFF) continue;
+    for (int j = 0; j < 3; j++) {
+        const int b = (cl >> (8 * j)) & 0xFF;
+        if (b == 0xFF) continue;
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const int b = (cl >> (8 * j)) & 0xFF;
-            if (b == 0xFF) continue;
-            S[a * ldS + b] += xy[i * 3 + j];
-        }
+        for (int i = 0; i < 3; i++)
+            if (((rl >> (8 * i)) & 0xFF) != 0xFF) S[(k1 * 3 + i) * ldS + b] += xy[i * 3 + j];
     }
 }
 
-// PNB_GT threads, two column batches per step (sub-batch = slot / 256): classification, binning and evaluation
-// run over both; the block updates of the two sub-batches are separated by a barrier.
-__global__ void __launch_bounds__(PNB_GT, 1)
-gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits, double *__restrict__ A, int64_t ld, int far_mask)
+// -------------------------------------------------------------------------------------------------
+// unit kernel of all units that are not uniformly of order 2: PNB_MT = 256 threads, two CTAs per SM, one 16 x 16
+// sub-batch per step.  Every step: classify the 256 pairs (shared vertices only for adjacent groups; getQuadOrder in
+// FP32 with exact FP64 re-evaluation near an integer), bin the regular pairs of order 2..5 by order (ballots + warp
+// scan), evaluate them one per thread in list order (warps of equal order), fetch the pairs that gnear_eval_kernel
+// evaluated (touching pairs, higher orders) from F, add all cross blocks to the block of the ROW BATCH and reduce the
+// cell-diagonal blocks.  The block of a row batch has one row per (row cell, local vertex): the 256 pairs of a step hit
+// distinct entries whatever thread evaluates them.  After the sweep over the column batches the block is added to the
+// unit block, which lives in a CTA-private global scratch (L2 resident; dof-indexed rows); the unit block goes to the
+// matrix (or, several GPUs, to the staging buffers) once per unit, in ticket order, like in the order-2 kernel.
+// Round 1 kept the whole unit block in shared memory: one 512-thread CTA per SM whose 16 warps waited at five
+// barriers per step for the warps with the high-order pairs (ncu: 25 % of the stall samples); two independent CTAs
+// fill each other's waits.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PNB_MT, 2)
+gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits, double *__restrict__ A, int64_t ld, int far_mask,
+            double *__restrict__ scratch)
 {
-    constexpr int ND = 6, SB = PNB_SB, NW = PNB_GT / 32, NSL = 2 * SB * SB;
+    constexpr int ND = 6, SB = PNB_SB, NW = PNB_MT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
     const int cap = G.cap, ldS = G.ldS;
     GMixFixed &sm = *reinterpret_cast<GMixFixed *>(carve(sp, sizeof(GMixFixed)));
-    double *S = reinterpret_cast<double *>(carve(sp, (size_t)G.maxld * ldS * 8));
-    double *sx = reinterpret_cast<double *>(carve(sp, (size_t)2 * 6 * cap * 8));
-    double *cxs = reinterpret_cast<double *>(carve(sp, (size_t)2 * 2 * cap * 8));
-    double *vols = reinterpret_cast<double *>(carve(sp, (size_t)2 * cap * 8));
-    float *lhs = reinterpret_cast<float *>(carve(sp, (size_t)2 * 2 * cap * 4));
-    int *ints = reinterpret_cast<int *>(carve(sp, (size_t)2 * 2 * cap * 4));
+    double *S = reinterpret_cast<double *>(carve(sp, (size_t)3 * SB * ldS * 8));
+    double *sxJ = reinterpret_cast<double *>(carve(sp, (size_t)6 * cap * 8));
+    double *cxJ = reinterpret_cast<double *>(carve(sp, (size_t)2 * cap * 8));
+    double *volJ = reinterpret_cast<double *>(carve(sp, (size_t)cap * 8));
+    float *lhJ = reinterpret_cast<float *>(carve(sp, (size_t)2 * cap * 4));
+    int *cellJ = reinterpret_cast<int *>(carve(sp, (size_t)2 * cap * 4));
     double *DYs = reinterpret_cast<double *>(carve(sp, (size_t)cap * 6 * 8));
-    // side 0 = rows (I), side 1 = columns (J)
-    double *sxI = sx, *sxJ = sx + 6 * cap, *volI = vols, *volJ = vols + cap;
-    int *cellI = ints, *locI = ints + cap, *cellJ = ints + 2 * cap, *locJ = ints + 3 * cap;
+    float *ahJ = lhJ + cap;
+    int *locJ = cellJ + cap;
+    // the unit block of this CTA: maxld x ldS doubles of global memory
+    double *Sg = scratch + (size_t)blockIdx.x * G.maxld * ldS;
     GCls c;
-    c.cxI = cxs; c.cxJ = cxs + 2 * cap;
-    c.lhI = lhs; c.ahI = lhs + cap; c.lhJ = lhs + 2 * cap; c.ahJ = lhs + 3 * cap;
-    c.cellI = cellI; c.locI = locI; c.cellJ = cellJ; c.locJ = locJ;
-    c.cap = cap;
+    c.cxI = sm.cxI; c.cxJ = cxJ;
+    c.lhI = sm.lhI; c.ahI = sm.ahI; c.lhJ = lhJ; c.ahJ = ahJ;
+    c.cellI = sm.cellI; c.locI = sm.locI; c.cellJ = cellJ; c.locJ = locJ;
+    c.cap = cap; c.capI = SB;
     c.cf = (float)P.c_int; c.sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_ticket;
     {
-        powtab_stage(&sm.pw, P.pow_int, tid, PNB_GT);
+        powtab_stage(&sm.pw, P.pow_int, tid, PNB_MT);
         const double *fs = reinterpret_cast<const double *>(P.far_rules + 2);
         double *fd = reinterpret_cast<double *>(&sm.far[0]);
-        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_GT) fd[e] = fs[e];
+        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_MT) fd[e] = fs[e];
     }
     unsigned long long my_pairs = 0, my_near = 0;
-    PROF_DECL
     __syncthreads();        // the power table is complete before its coefficients go to registers
     const PowCtxS kv(&sm.pw, lane);
-    const int sub = tid >> 8, k1 = (tid >> 4) & 15, k2 = tid & 15;
+    const int k1 = tid >> 4, k2 = tid & 15;
     for (;;) {
     __syncthreads();
     if (tid == 0) s_ticket = atomicAdd(G.counters_i + 1, 1);
@@ -906,36 +923,49 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
     const int ibeg = G.gptr[I], nI = G.gptr[I + 1] - ibeg, jbeg = G.gptr[J], nJ = G.gptr[J + 1] - jbeg;
     const int dI = G.gdptr[I], nldI = G.gdptr[I + 1] - dI, dJ = G.gdptr[J], nldJ = G.gdptr[J + 1] - dJ;
     {
-        for (int e = tid; e < nldI * ldS; e += PNB_GT) S[e] = 0.;
-        for (int e = tid; e < cap * 6; e += PNB_GT) DYs[e] = 0.;
-        if (tid < PNB_THREADS) {
-            g_load_cls_side(P, G, I, cellI, locI, cxs, lhs, lhs + cap, cap, tid);
-            g_load_cls_side(P, G, J, cellJ, locJ, cxs + 2 * cap, lhs + 2 * cap, lhs + 3 * cap, cap, tid);
-        }
-        for (int e = tid; e < nI + nJ; e += PNB_GT) {
-            const bool first = e < nI;
-            const int s = first ? e : e - nI;
-            const int cc = G.gcells[(first ? ibeg : jbeg) + s];
+        for (int e = tid; e < nldI * ldS; e += PNB_MT) Sg[e] = 0.;
+        for (int e = tid; e < cap * 6; e += PNB_MT) DYs[e] = 0.;
+        for (int s = tid; s < nJ; s += PNB_MT) {
+            const int cc = G.gcells[jbeg + s];
+            cellJ[s] = cc;
+            locJ[s] = G.gloc[jbeg + s];
             if (cc >= 0) {
-                double *d = first ? sxI : sxJ;
+                cxJ[s] = P.centers[(size_t)cc * 2];
+                cxJ[cap + s] = P.centers[(size_t)cc * 2 + 1];
+                lhJ[s] = P.lhf[cc];
+                ahJ[s] = P.ahf[cc];
 #pragma unroll
-                for (int k = 0; k < 6; k++) d[k * cap + s] = P.simplices[(size_t)cc * 6 + k];
-                (first ? volI : volJ)[s] = P.vol[cc];
+                for (int k = 0; k < 6; k++) sxJ[k * cap + s] = P.simplices[(size_t)cc * 6 + k];
+                volJ[s] = P.vol[cc];
             }
         }
     }
-    __syncthreads();
-    PROF(0)
-
     for (int rb = 0; rb < nI; rb += SB) {
+        __syncthreads();        // the previous row batch is flushed, its row data no longer read
+        c.ioff = rb;
+        if (tid < SB) {
+            const int cc = G.gcells[ibeg + rb + tid];
+            sm.cellI[tid] = cc;
+            sm.locI[tid] = G.gloc[ibeg + rb + tid];
+            if (cc >= 0) {
+                sm.cxI[tid] = P.centers[(size_t)cc * 2];
+                sm.cxI[SB + tid] = P.centers[(size_t)cc * 2 + 1];
+                sm.lhI[tid] = P.lhf[cc];
+                sm.ahI[tid] = P.ahf[cc];
+#pragma unroll
+                for (int k = 0; k < 6; k++) sm.sxI[k * SB + tid] = P.simplices[(size_t)cc * 6 + k];
+                sm.volI[tid] = P.vol[cc];
+            }
+        }
+        for (int e = tid; e < 3 * SB * ldS; e += PNB_MT) S[e] = 0.;
         double dxacc = 0.;      // threads tid < SB*ND: entry (tid % ND) of the block of row cell rb + tid / ND
-        for (int cb0 = diag ? rb : 0; cb0 < nJ; cb0 += 2 * SB) {
-            const int cb = cb0 + sub * SB;
-            // ---- classify every pair of the two sub-batches ----
+        __syncthreads();
+        for (int cb = diag ? rb : 0; cb < nJ; cb += SB) {
+            // ---- classify the pairs of the sub-batch ----
             int cls = 0, todo = 0;
             sm.slotD[tid] = 0;
             if (tid == 0) sm.anyD = 0;
-            if (cb < nJ) {
+            {
                 const int panel = g_classify(P, c, diag, nearunit, rb, cb, k1, k2);
                 if (panel != 0) {
                     const bool is_far = panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1);
@@ -961,53 +991,47 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
             __syncthreads();    // B1
             int nnear = 0, npos = 0;
             {
-                // exclusive prefix over the (order, warp) counters: 64 entries, two per lane, warp scan
-                static_assert((PNB_FAR_MAX_ORDER - 1) * NW == 64, "counter scan assumes 64 entries");
+                // exclusive prefix over the (order, warp) counters: 32 entries, one per lane, warp scan
+                static_assert((PNB_FAR_MAX_ORDER - 1) * NW == 32, "counter scan assumes 32 entries");
                 const int me = (cls - 2) * NW + warp;
-                const int v0 = sm.clscnt[2 * lane], v1 = sm.clscnt[2 * lane + 1];
-                int incl = v0 + v1;
+                const int v0 = sm.clscnt[lane];
+                int incl = v0;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
                     const int t = __shfl_up_sync(0xffffffffu, incl, off);
                     if (lane >= off) incl += t;
                 }
                 const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                const int src = (me >> 1) & 31;
-                const int ex = __shfl_sync(0xffffffffu, incl - v0 - v1, src), a0 = __shfl_sync(0xffffffffu, v0, src);
-                const int pos = ex + ((me & 1) ? a0 : 0);
+                const int pos = __shfl_sync(0xffffffffu, incl - v0, me & 31);
                 if (cls != 0) sm.list[pos + __popc(mybal & ((1u << lane) - 1))] = tid | (cls << 12);
                 if (tid == 0) sm.nlist = tot;
                 if (nearunit) {
-                    // rank inside the own sub-batch (the list builder numbers every sub-batch separately)
+                    // rank inside the sub-batch (the list builder numbers every sub-batch separately)
                     for (int w = 0; w < NW; w++) {
-                        if (w < warp && (w >> 3) == sub) npos += sm.warpcnt[w];
+                        if (w < warp) npos += sm.warpcnt[w];
                         nnear += sm.warpcnt[w];
                     }
                     npos += __popc(nbal & ((1u << lane) - 1));
                 }
             }
             __syncthreads();    // B2
-            PROF(1)
             const int nlist = sm.nlist;
             if (nlist == 0 && nnear == 0) continue;     // uniform across the CTA
-            // ---- evaluate the far pairs (no ordering needed) ----
-            double xy[9];
-            int frl = 0x00FFFFFF, fcl = 0x00FFFFFF, fsub = -1;
+            // ---- evaluate the far pairs in list order; any thread may take any pair of the sub-batch ----
             if (tid < nlist) {
                 const int item = sm.list[tid];
-                const int slot = item & 0x1FF, order = item >> 12;
-                fsub = slot >> 8;
-                const int a1 = rb + ((slot >> 4) & 15), a2 = cb0 + fsub * SB + (slot & 15);
+                const int slot = item & 0xFF, order = item >> 12;
+                const int a1 = slot >> 4, a2 = cb + (slot & 15);
                 my_pairs++;
-                double s1v[3][2], s2v[3][2], xx[6], yy[6];
+                double s1v[3][2], s2v[3][2], xy[9], xx[6], yy[6];
 #pragma unroll
                 for (int m = 0; m < 3; m++) {
-                    s1v[m][0] = sxI[(2 * m) * cap + a1];
-                    s1v[m][1] = sxI[(2 * m + 1) * cap + a1];
+                    s1v[m][0] = sm.sxI[(2 * m) * SB + a1];
+                    s1v[m][1] = sm.sxI[(2 * m + 1) * SB + a1];
                     s2v[m][0] = sxJ[(2 * m) * cap + a2];
                     s2v[m][1] = sxJ[(2 * m + 1) * cap + a2];
                 }
-                const double sc = 2.0 * volI[a1] * volJ[a2];
+                const double sc = 2.0 * sm.volI[a1] * volJ[a2];
                 // node counts of the adopted rule family (far_expected_nodes): 3, 6, 6, 7
                 if (order == 2) far_eval_n<3>(sm.far[0], s1v, s2v, kv, xy, xx, yy);
                 else if (order == 5) far_eval_n<7>(sm.far[3], s1v, s2v, kv, xy, xx, yy);
@@ -1021,92 +1045,83 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
                 for (int k = 0; k < 9; k++) xy[k] *= sc;
                 sm.slotD[slot] = 1;
                 sm.anyD = 1;
-                frl = locI[a1];
-                fcl = locJ[a2];
+                g_scatter(S, ldS, a1, sm.locI[a1], locJ[a2], xy);
             }
-            PROF(2)
-            // ---- block updates: sub-batch 0, barrier, sub-batch 1; pairs of one sub-batch hit distinct entries ----
-#pragma unroll 1
-            for (int ph = 0; ph < 2; ph++) {
-                if (ph == 1) __syncthreads();
-                if (fsub == ph) g_scatter(S, ldS, frl, fcl, xy);
-                if (todo != 0 && sub == ph) {
-                    // pairs evaluated by gnear_eval_kernel
-                    const int pos = G.nearbase[((size_t)u.slot * G.nbmax + rb / SB) * G.nbmax + cb / SB] + npos;
-                    const int4 pr = G.npairs[pos];
-                    if (pr.x != cellI[rb + k1] || pr.y != cellJ[cb + k2] || pr.z != todo) atomicMax(G.err + 1, 2);
-                    else {
-                        const double *f = G.F + (size_t)pos * 21;
-                        double nxy[9];
+            if (todo != 0) {
+                // pairs evaluated by gnear_eval_kernel
+                const int pos = G.nearbase[((size_t)u.slot * G.nbmax + rb / SB) * G.nbmax + cb / SB] + npos;
+                const int4 pr = G.npairs[pos];
+                if (pr.x != sm.cellI[k1] || pr.y != cellJ[cb + k2] || pr.z != todo) atomicMax(G.err + 1, 2);
+                else {
+                    const double *f = G.F + (size_t)pos * 21;
+                    double nxy[9];
 #pragma unroll
-                        for (int k = 0; k < 9; k++) nxy[k] = __ldg(f + k);
-                        my_near++;
+                    for (int k = 0; k < 9; k++) nxy[k] = __ldg(f + k);
+                    my_near++;
 #pragma unroll
-                        for (int k = 0; k < 12; k++) sm.dxy[tid][k] = __ldg(f + 9 + k);
-                        sm.slotD[tid] = 1;
-                        sm.anyD = 1;
-                        g_scatter(S, ldS, locI[rb + k1], locJ[cb + k2], nxy);
-                    }
+                    for (int k = 0; k < 12; k++) sm.dxy[tid][k] = __ldg(f + 9 + k);
+                    sm.slotD[tid] = 1;
+                    sm.anyD = 1;
+                    g_scatter(S, ldS, k1, sm.locI[k1], locJ[cb + k2], nxy);
                 }
             }
             __syncthreads();    // B3
-            // ---- cell-diagonal blocks: reduce over the two sub-batches ----
+            // ---- cell-diagonal blocks: sums over the partners of the step ----
             if (sm.anyD) {
                 if (tid < SB * ND) {
                     const int kk1 = tid / ND, comp = tid - kk1 * ND;
                     double sacc = 0.;
-                    for (int q = 0; q < 2 * SB; q++) {
-                        const int slot = (q >> 4) * (SB * SB) + kk1 * SB + (q & 15);
+                    for (int q = 0; q < SB; q++) {
+                        const int slot = kk1 * SB + q;
                         if (sm.slotD[slot]) sacc += sm.dxy[slot][comp];
                     }
                     dxacc += sacc;
-                } else if (tid < 3 * SB * ND) {
+                } else if (tid < 2 * SB * ND) {
                     const int t2 = tid - SB * ND;
-                    const int sb = t2 / (SB * ND), t3 = t2 - sb * (SB * ND);
-                    const int kk2 = t3 / ND, comp = t3 - kk2 * ND;
+                    const int kk2 = t2 / ND, comp = t2 - kk2 * ND;
                     double sacc = 0.;
                     for (int kk1 = 0; kk1 < SB; kk1++) {
-                        const int slot = sb * (SB * SB) + kk1 * SB + kk2;
+                        const int slot = kk1 * SB + kk2;
                         if (sm.slotD[slot]) sacc += sm.dxy[slot][ND + comp];
                     }
-                    if (cb0 + sb * SB < nJ) DYs[(cb0 + sb * SB + kk2) * ND + comp] += sacc;
+                    DYs[(cb + kk2) * ND + comp] += sacc;
                 }
             }
             __syncthreads();    // B4: slotD / dxy reused by the next step
-            PROF(3)
         }
         if (tid < SB * ND) {
             const int kk1 = tid / ND, comp = tid - kk1 * ND;
-            const int cc = cellI[rb + kk1];
+            const int cc = sm.cellI[kk1];
             if (cc >= 0) G.Dp[((size_t)J * P.nc + cc) * ND + comp] = dxacc;
+        }
+        // the block of the row batch joins the unit block (private to this CTA; the row cells of a batch share no vertex)
+        for (int e = tid; e < 3 * SB * nldJ; e += PNB_MT) {
+            const int r = e / nldJ, b = e - r * nldJ;
+            const int la = (sm.locI[r / 3] >> (8 * (r % 3))) & 0xFF;
+            if (la != 0xFF && sm.cellI[r / 3] >= 0) Sg[la * ldS + b] += S[r * ldS + b];
         }
     }
     __syncthreads();
     // column-cell sums; same group on both sides: slot Dp[I][c] takes the row sums (written above) and these
-    for (int e = tid; e < nJ * ND; e += PNB_GT) {
+    for (int e = tid; e < nJ * ND; e += PNB_MT) {
         const int cc = cellJ[e / ND];
         if (cc < 0) continue;
         double *dp = &G.Dp[((size_t)I * P.nc + cc) * ND + (e % ND)];
         *dp = diag ? *dp + DYs[e] : DYs[e];
     }
-    if (G.dist.nparts > 0) g_flush_staged(G, G.dist.uoff_mix + (size_t)ticket * G.dist.nparts, S, ldS, I, dI, nldI, dJ, nldJ, tid, PNB_GT);
+    if (G.dist.nparts > 0) g_flush_staged(G, G.dist.uoff_mix + (size_t)ticket * G.dist.nparts, Sg, ldS, I, dI, nldI, dJ, nldJ, tid, PNB_MT);
     else {
-        g_wait_predecessors(G, 1, ticket, I, J, tid, PNB_GT);
-        g_flush_block(G, S, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_GT);
+        g_wait_predecessors(G, 1, ticket, I, J, tid, PNB_MT);
+        g_flush_block(G, Sg, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_MT);
         g_signal_done(G, 1, ticket, tid);
     }
-    PROF(4)
     }
-#ifdef PNB_PROFILE
-    if (tid == 0) { for (int k_ = 0; k_ < 5; k_++) atomicAdd(G.counters + 3 + k_, (unsigned long long)pt_[k_]); }
-#endif
     for (int off = 16; off > 0; off >>= 1) {
         my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
         my_near += __shfl_xor_sync(0xffffffffu, my_near, off);
     }
     if (lane == 0 && my_pairs) atomicAdd(G.counters, my_pairs);
     if (lane == 0 && my_near) atomicAdd(G.counters + 1, my_near);
-    (void)NSL;
 }
 
 // F = U + U^T in place, 32 x 32 tiles; bitwise symmetric by construction
