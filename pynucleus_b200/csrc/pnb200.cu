@@ -1884,6 +1884,7 @@ struct GroupHostFull : GroupHost {
     double *d_R = nullptr, *d_F = nullptr;
     int nitems = 0, npairs = 0, nchunks = 0;
     int near_nmax = 1;                      // largest node count of a regular rule with near items
+    int mix_warps = PNB_MW_MAX;             // warps per CTA of gmix_kernel (what fits into shared memory)
     void *mix_scratch = nullptr;            // unit blocks of the resident CTAs of gmix_kernel
     size_t mix_scratch_bytes = 0;
     bool near_ready = false;
@@ -1927,7 +1928,7 @@ static int build_group_schedule(pnb_problem *p)
             build_group_geometry(p, GC, order, gh->gg);
             gh->GC = GC;
             const int ldS = gh->gg.maxld + 1;
-            if (forced > 0 || (std::max(gf2_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS), gmix_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS)) <= budget &&
+            if (forced > 0 || (gf2_smem_bytes(gh->gg.cap, gh->gg.maxld, ldS) <= budget && gmix_warps(gh->gg.cap, gh->gg.maxld, budget) >= 4 &&
                                gh->gg.maxld < 255))
                 break;
         }
@@ -1956,7 +1957,32 @@ static int build_group_schedule(pnb_problem *p)
         G.err = p->S.err;
         G.counters = p->S.counters;
         gh->smem_f2 = gf2_smem_bytes(G.cap, G.maxld, G.ldS);
-        gh->smem_mix = gmix_smem_bytes(G.cap, G.maxld, G.ldS);
+        gh->mix_warps = std::max(1, gmix_warps(G.cap, G.maxld, budget));
+        if (getenv("PNB_MIX_WARPS")) gh->mix_warps = std::max(1, std::min(gh->mix_warps, atoi(getenv("PNB_MIX_WARPS"))));
+        gh->smem_mix = gmix_smem_bytes(G.cap, G.maxld, gh->mix_warps);
+        {
+            // incidence lists of the group-local dofs: (cell slot, local vertex) in ascending order
+            std::vector<int> iptr(1, 0);
+            std::vector<unsigned short> ilist;
+            for (int g = 0; g < gg.ngroups; g++) {
+                const int nld = gg.gdptr[g + 1] - gg.gdptr[g], ns = gg.gptr[g + 1] - gg.gptr[g];
+                std::vector<std::vector<unsigned short>> per(nld);
+                for (int sl = 0; sl < ns; sl++) {
+                    if (gg.gcells[gg.gptr[g] + sl] < 0) continue;
+                    const int packed = gg.gloc[gg.gptr[g] + sl];
+                    for (int m = 0; m < 3; m++) {
+                        const int l = (packed >> (8 * m)) & 0xFF;
+                        if (l != 0xFF) per[l].push_back((unsigned short)(sl * 4 + m));
+                    }
+                }
+                for (int l = 0; l < nld; l++) {
+                    ilist.insert(ilist.end(), per[l].begin(), per[l].end());
+                    iptr.push_back((int)ilist.size());
+                }
+            }
+            if (ilist.empty()) ilist.push_back(0);
+            if (upload(p, iptr.data(), iptr.size(), &G.gincptr) || upload(p, ilist.data(), ilist.size(), &G.ginc)) return PNB_ERR_CUDA;
+        }
         gh->smem_near = gnear_list_smem_bytes(G.cap);
         gh->ready = true;
         if (getenv("PNB_BENCH_VERBOSE"))
@@ -2114,7 +2140,7 @@ static int build_near_list(pnb_problem *p)
         CK(pool_malloc((void **)&binbase, 64 * sizeof(int)));
         gh->near_allocs.push_back(binbase);
         CK(cudaMemset(bins, 0, 128 * sizeof(int)));
-        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 0, cursor, nullptr, nullptr, nullptr, bins, nullptr, nullptr);
+        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 0, cursor, nullptr, nullptr, nullptr, nullptr, bins, nullptr, nullptr);
         int tot[2] = {0, 0};
         CK(cudaMemcpy(tot, cursor, sizeof(tot), cudaMemcpyDeviceToHost));
         int hb[64], hbase[64];
@@ -2148,6 +2174,10 @@ static int build_near_list(pnb_problem *p)
         gh->near_allocs.push_back(perm);
         CK(pool_malloc((void **)&nearbase, (size_t)nslots * G.nbmax * G.nbmax * sizeof(int)));
         gh->near_allocs.push_back(nearbase);
+        unsigned char *nearrow = nullptr;
+        CK(pool_malloc((void **)&nearrow, (size_t)nslots * G.nbmax * G.nbmax * PNB_SB));
+        gh->near_allocs.push_back(nearrow);
+        if (tot[0] >= (1 << 28)) return fail(PNB_ERR_UNSUPPORTED, "more than 2^28 near pairs");
         CK(pool_malloc((void **)&R, std::max<size_t>(tot[1], 1) * PairDims<2>::NL * sizeof(double)));
         gh->near_allocs.push_back(R);
         double *F = nullptr;
@@ -2159,13 +2189,14 @@ static int build_near_list(pnb_problem *p)
         gh->near_allocs.push_back(dchunks);
         if (!chunks.empty()) CK(cudaMemcpy(dchunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
         CK(cudaMemset(cursor, 0, 4 * sizeof(int)));
-        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 1, cursor, pairs, items, nearbase, bins, binbase, perm);
+        gnear_list_kernel<<<(unsigned)gh->near_units.size(), PNB_THREADS, gh->smem_near>>>(p->P, G, gh->d_near, p->far_mask, 1, cursor, pairs, items, nearbase, nearrow, bins, binbase, perm);
         CK(cudaDeviceSynchronize());
         gh->d_perm = perm;
         gh->d_chunks = dchunks;
         gh->nchunks = (int)chunks.size();
         G.npairs = pairs;
         G.nearbase = nearbase;
+        G.nearrow = nearrow;
         G.R = R;
         gh->d_items = items;
         gh->d_R = R;
@@ -2255,9 +2286,9 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         }
         cudaEventRecord(p->kev[2]);
         if (nm > 0 && !(dbg & 0x200)) {
-            // unit blocks of the resident CTAs (two per SM): global scratch, L2 resident
-            const int ncta = std::min(nm, 2 * nsm);
-            const size_t need = (size_t)ncta * G.maxld * G.ldS * sizeof(double);
+            // unit blocks of the resident CTAs (one per SM): global scratch, L2 resident
+            const int ncta = std::min(nm, nsm);
+            const size_t need = (size_t)ncta * gmix_scratch_doubles(G.cap, G.maxld, G.ldS) * sizeof(double);
             if (gh->mix_scratch_bytes < need) {
                 if (gh->mix_scratch) pool_free(gh->mix_scratch);
                 gh->mix_scratch = nullptr;
@@ -2265,7 +2296,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
                 CK(pool_malloc(&gh->mix_scratch, need));
                 gh->mix_scratch_bytes = need;
             }
-            gmix_kernel<<<ncta, PNB_MT, gh->smem_mix>>>(p->P, G, gh->d_mix, nm, dA, ld, p->far_mask, (double *)gh->mix_scratch);
+            gmix_kernel<<<ncta, gh->mix_warps * 32, gh->smem_mix>>>(p->P, G, gh->d_mix, nm, dA, ld, p->far_mask, (double *)gh->mix_scratch);
             launches++;
         }
     }

@@ -48,6 +48,9 @@ struct GroupSched {
     int nbmax;           // largest number of batches of a group
     const int4 *npairs;  // near pair list: (row cell, column cell, panel, first item)
     const int *nearbase; // [near slot][row batch][column batch]: position of the first pair of the sub-batch
+    const unsigned char *nearrow;   // ... x PNB_SB: pairs of the sub-batch in earlier rows
+    const int *gincptr;  // per group-local dof (gdptr[g] + l, one more at the end): its (cell slot, local vertex) incidences
+    const unsigned short *ginc;     // slot * 4 + vertex, ascending
     const double *R;     // results of the near items, NL doubles each
     const double *F;     // per near pair: finished cross block (9) and cell-diagonal blocks (6 + 6)
     // ordered updates of U: every unit list is processed by persistent CTAs in list order (tickets); a unit adds
@@ -274,14 +277,35 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits
             if (live) {
                 my_pairs++;
                 double g[3][3];
+                {
+                    // the nine powers stage by stage (see PowCtxT::batch): nine independent FMA chains in flight
+                    double rr[9], yv[9], tv[9], pp[9];
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const double y0 = yj[(2 * j) * cap + s2], y1 = yj[(2 * j + 1) * cap + s2];
+                    for (int j = 0; j < 3; j++) {
+                        const double y0 = yj[(2 * j) * cap + s2], y1 = yj[(2 * j + 1) * cap + s2];
 #pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        const double a = x[i][0] - y0, b = x[i][1] - y1;
-                        g[i][j] = f2_pow(itl, T1s, R, a * a + b * b);
+                        for (int i = 0; i < 3; i++) {
+                            const double a = x[i][0] - y0, b = x[i][1] - y1;
+                            const double d2 = a * a + b * b;
+                            const int hi = __double2hiint(d2), lo = __double2loint(d2);
+                            const int E = min(max(((hi >> 20) & 0x7ff) + R.eoff, 0), 255);
+                            const int idx = (hi >> 10) & (0x7f * PNB_POW_REP);
+                            const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+                            const double2 it = itl[idx];
+                            tv[i * 3 + j] = T1s[E];
+                            yv[i * 3 + j] = it.y;
+                            rr[i * 3 + j] = fma(m, it.x, -1.0);
+                        }
                     }
+#pragma unroll
+                    for (int k = 0; k < 9; k++) pp[k] = fma(R.c[6], rr[k], R.c[5]);
+#pragma unroll
+                    for (int q = 4; q >= 0; q--) {
+#pragma unroll
+                        for (int k = 0; k < 9; k++) pp[k] = fma(pp[k], rr[k], R.c[q]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 9; k++) g[k / 3][k % 3] = tv[k] * (yv[k] * pp[k]);
                 }
                 const double sc = v1 * volj[s2];
                 double X[9];
@@ -450,7 +474,7 @@ __device__ __forceinline__ void g_load_cls_side(const DProblem &P, const GroupSc
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PNB_THREADS)
 gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int far_mask, int fill, int *cursor, int4 *pairs, int2 *items,
-                  int *nearbase, int *bins, const int *binbase, int *perm)
+                  int *nearbase, unsigned char *nearrow, int *bins, const int *binbase, int *perm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
@@ -505,7 +529,10 @@ gnear_list_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int
                     if (w < warp) { pp += wcnt[w]; pi += wits[w]; }
                     tp += wcnt[w]; ti += wits[w];
                 }
-                if (tid == 0) nearbase[((size_t)u.slot * G.nbmax + rb / PNB_SB) * G.nbmax + cb / PNB_SB] = base[0] + run_pairs;
+                const size_t sbi = ((size_t)u.slot * G.nbmax + rb / PNB_SB) * G.nbmax + cb / PNB_SB;
+                if (tid == 0) nearbase[sbi] = base[0] + run_pairs;
+                // pairs of the sub-batch in the rows before k1 (the unit kernel works row by row)
+                if (k2 == 0) nearrow[sbi * PNB_SB + k1] = (unsigned char)(pp + __popc(bal & ((1u << lane) - 1)));
                 if (near) {
                     const int pos = base[0] + run_pairs + pp + __popc(bal & ((1u << lane) - 1));
                     const int it0 = base[1] + run_items + pi + inc - sl;
@@ -593,12 +620,13 @@ __device__ __forceinline__ void near_regular_group(const DProblem &P, const KV &
 #pragma unroll 2
             for (int j = 0; j < ncol; j++) {
                 const double2 y = Y[j];
-                double g[R];
+                double g[R], d2[R];
 #pragma unroll
                 for (int q = 0; q < R; q++) {
                     const double a = X0[q] - y.x, b = X1[q] - y.y;
-                    g[q] = kv(PNB_ADD(PNB_MUL(a, a), PNB_MUL(b, b)));
+                    d2[q] = PNB_ADD(PNB_MUL(a, a), PNB_MUL(b, b));
                 }
+                kv.template batch<R>(d2, g);
                 const double2 *dj = dcol + j * PNB_DER2;
                 const double2 c0 = dj[0], c1 = dj[1];
                 double cw = 0.;
@@ -803,37 +831,50 @@ __global__ void __launch_bounds__(256) gnear_finalize_kernel(DProblem P, const i
 // unit kernel: regular pairs of order 2..5 thread-per-pair (binned by order); every other pair was evaluated by
 // gnear_eval_kernel and is fetched here, so that all contributions of a unit are added in one fixed order
 // -------------------------------------------------------------------------------------------------
-#define PNB_MT 256
+#define PNB_MW_MAX 12          // warps of the unit kernel (one CTA per SM)
 struct GMixFixed {
     PowTabS pw;
     FarRule far[PNB_FAR_MAX_ORDER - 1];      // orders 2..PNB_FAR_MAX_ORDER
-    double dxy[PNB_SB * PNB_SB][12];
-    unsigned char slotD[PNB_SB * PNB_SB];
-    int list[PNB_SB * PNB_SB];
-    int clscnt[(PNB_FAR_MAX_ORDER - 1) * (PNB_MT / 32)];
-    int warpcnt[PNB_MT / 32];
-    int nlist, anyD;
-    // row batch of the current step
-    double sxI[6 * PNB_SB], cxI[2 * PNB_SB], volI[PNB_SB];
-    float lhI[PNB_SB], ahI[PNB_SB];
-    int cellI[PNB_SB], locI[PNB_SB];
 };
 
-inline size_t gmix_smem_bytes(int cap, int maxld, int ldS)
+// per warp: staged cross blocks of the pairs of the current row cell (9 x cap), column-cell sums (6 x cap),
+// classification result per column slot (cap ints) and the slots sorted by evaluation class (cap bytes)
+__host__ __device__ inline size_t gmix_warp_bytes_dev(int cap)
+{
+    return (size_t)cap * (9 * 8 + 6 * 8 + 4) + (((size_t)cap + 15) & ~(size_t)15);
+}
+inline size_t gmix_warp_bytes(int cap)
+{
+    return (size_t)cap * (9 * 8 + 6 * 8 + 4) + (((size_t)cap + 15) & ~(size_t)15);
+}
+
+inline size_t gmix_shared_bytes(int cap, int maxld)
 {
     size_t b = 0;
     auto add = [&](size_t x) { b += (x + 15) & ~(size_t)15; };
     add(sizeof(GMixFixed));
-    add((size_t)3 * PNB_SB * ldS * 8);   // block of the row batch: (row cell, local vertex) x column dofs
     add((size_t)6 * cap * 8);         // sx of the column side
     add((size_t)2 * cap * 8);         // cx
     add((size_t)cap * 8);             // vol
     add((size_t)2 * cap * 4);         // lh, ah
     add((size_t)2 * cap * 4);         // cell, loc
-    add((size_t)cap * 6 * 8);         // DYs
-    (void)maxld;
+    add((size_t)(maxld + 2) * 2);     // incidence lists of the column dofs: pointers
+    add((size_t)3 * cap * 2);         // ... entries
     return b;
 }
+
+// warps of the unit kernel that fit into the shared memory of an SM (0: none)
+inline int gmix_warps(int cap, int maxld, size_t budget)
+{
+    const size_t sh = gmix_shared_bytes(cap, maxld) + 64;
+    if (sh >= budget) return 0;
+    return (int)std::min<size_t>(PNB_MW_MAX, (budget - sh) / gmix_warp_bytes(cap));
+}
+
+inline size_t gmix_smem_bytes(int cap, int maxld, int nw) { return gmix_shared_bytes(cap, maxld) + (size_t)nw * gmix_warp_bytes(cap); }
+
+// doubles of global scratch per CTA: the unit block with one row per (row cell slot, local vertex), then dof-indexed
+inline size_t gmix_scratch_doubles(int cap, int maxld, int ldS) { return (size_t)(3 * cap + maxld) * ldS; }
 
 inline size_t gnear_list_smem_bytes(int cap)
 {
@@ -845,72 +886,65 @@ inline size_t gnear_list_smem_bytes(int cap)
     return b;
 }
 
-// adds the 3 x 3 cross block of a pair to the block of the row batch: row = (row cell, local vertex)
-__device__ __forceinline__ void g_scatter(double *S, int ldS, int k1, int rl, int cl, const double *xy)
-{
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int b = (cl >> (8 * j)) & 0xFF;
-        if (b == 0xFF) continue;
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            if (((rl >> (8 * i)) & 0xFF) != 0xFF) S[(k1 * 3 + i) * ldS + b] += xy[i * 3 + j];
-    }
-}
-
 // -------------------------------------------------------------------------------------------------
-// unit kernel of all units that are not uniformly of order 2: PNB_MT = 256 threads, two CTAs per SM, one 16 x 16
-// sub-batch per step.  Every step: classify the 256 pairs (shared vertices only for adjacent groups; getQuadOrder in
-// FP32 with exact FP64 re-evaluation near an integer), bin the regular pairs of order 2..5 by order (ballots + warp
-// scan), evaluate them one per thread in list order (warps of equal order), fetch the pairs that gnear_eval_kernel
-// evaluated (touching pairs, higher orders) from F, add all cross blocks to the block of the ROW BATCH and reduce the
-// cell-diagonal blocks.  The block of a row batch has one row per (row cell, local vertex): the 256 pairs of a step hit
-// distinct entries whatever thread evaluates them.  After the sweep over the column batches the block is added to the
-// unit block, which lives in a CTA-private global scratch (L2 resident; dof-indexed rows); the unit block goes to the
-// matrix (or, several GPUs, to the staging buffers) once per unit, in ticket order, like in the order-2 kernel.
-// Round 1 kept the whole unit block in shared memory: one 512-thread CTA per SM whose 16 warps waited at five
-// barriers per step for the warps with the high-order pairs (ncu: 25 % of the stall samples); two independent CTAs
-// fill each other's waits.
+// unit kernel of all units that are not uniformly of order 2.  One CTA per SM, ONE WARP PER ROW CELL: the warp classifies
+// the partners of its row cell in the column group (shared vertices only for adjacent groups; getQuadOrder in FP32 with
+// exact FP64 re-evaluation near an integer), sorts them by evaluation class with ballots (order 5, 2, 3, 4, then the
+// pairs that gnear_eval_kernel evaluated: touching pairs, higher orders), and evaluates them thread-per-pair in sorted
+// order, so that the lanes of a warp run the same evaluator except in the one or two chunks where the class changes.
+// There is no barrier inside a unit: rounds 1 and 2 binned 256 pairs per step over the whole CTA and waited at 4-5
+// barriers per step for the warps that held the high-order pairs (ncu: barrier 3.0-3.7 of ~10 stall cycles per issue).
+// Accumulation without atomics and in a fixed order:
+//  * cross blocks: every pair stores its 3 x 3 block into the warp's staging array (a private place per column slot);
+//    after the row the warp gathers them per column dof through the incidence lists of the column group (fixed order)
+//    and writes the three rows (row cell, local vertex) x column dofs of the unit block, which lives in CTA-private
+//    global scratch (L2 resident).  The rows of the dofs of the row group are gathered the same way before the block
+//    goes to the matrix (or, several GPUs, to the staging buffers) in ticket order;
+//  * row-cell diagonal blocks: per-lane registers over the row, fixed butterfly over the lanes;
+//  * column-cell diagonal blocks: per-warp sums over the rows of the warp (rows are dealt out statically), summed over
+//    the warps in warp order at the end of the unit.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PNB_MT, 2)
+__global__ void __launch_bounds__(PNB_MW_MAX * 32, 1)
 gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits, double *__restrict__ A, int64_t ld, int far_mask,
             double *__restrict__ scratch)
 {
-    constexpr int ND = 6, SB = PNB_SB, NW = PNB_MT / 32;
+    constexpr int ND = 6, SB = PNB_SB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
     const int cap = G.cap, ldS = G.ldS;
+    const int NT = blockDim.x, NW = NT >> 5;
     GMixFixed &sm = *reinterpret_cast<GMixFixed *>(carve(sp, sizeof(GMixFixed)));
-    double *S = reinterpret_cast<double *>(carve(sp, (size_t)3 * SB * ldS * 8));
     double *sxJ = reinterpret_cast<double *>(carve(sp, (size_t)6 * cap * 8));
     double *cxJ = reinterpret_cast<double *>(carve(sp, (size_t)2 * cap * 8));
     double *volJ = reinterpret_cast<double *>(carve(sp, (size_t)cap * 8));
     float *lhJ = reinterpret_cast<float *>(carve(sp, (size_t)2 * cap * 4));
     int *cellJ = reinterpret_cast<int *>(carve(sp, (size_t)2 * cap * 4));
-    double *DYs = reinterpret_cast<double *>(carve(sp, (size_t)cap * 6 * 8));
+    unsigned short *incptr = reinterpret_cast<unsigned short *>(carve(sp, (size_t)(G.maxld + 2) * 2));
+    unsigned short *inc = reinterpret_cast<unsigned short *>(carve(sp, (size_t)3 * cap * 2));
     float *ahJ = lhJ + cap;
     int *locJ = cellJ + cap;
-    // the unit block of this CTA: maxld x ldS doubles of global memory
-    double *Sg = scratch + (size_t)blockIdx.x * G.maxld * ldS;
-    GCls c;
-    c.cxI = sm.cxI; c.cxJ = cxJ;
-    c.lhI = sm.lhI; c.ahI = sm.ahI; c.lhJ = lhJ; c.ahJ = ahJ;
-    c.cellI = sm.cellI; c.locI = sm.locI; c.cellJ = cellJ; c.locJ = locJ;
-    c.cap = cap; c.capI = SB;
-    c.cf = (float)P.c_int; c.sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *wbase = sp + (size_t)warp * gmix_warp_bytes_dev(cap);
+    double *Sw = reinterpret_cast<double *>(wbase);                 // [9][cap]
+    double *DYw = Sw + (size_t)9 * cap;                             // [6][cap]
+    int *info = reinterpret_cast<int *>(DYw + (size_t)6 * cap);     // [cap]
+    unsigned char *list = reinterpret_cast<unsigned char *>(info + cap);
+    // the unit block of this CTA in global memory
+    double *Sg = scratch + (size_t)blockIdx.x * ((size_t)(3 * cap + G.maxld) * ldS);
+    double *Sd = Sg + (size_t)3 * cap * ldS;
+    const float cf = (float)P.c_int, sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
+
     __shared__ int s_ticket;
     {
-        powtab_stage(&sm.pw, P.pow_int, tid, PNB_MT);
+        powtab_stage(&sm.pw, P.pow_int, tid, NT);
         const double *fs = reinterpret_cast<const double *>(P.far_rules + 2);
         double *fd = reinterpret_cast<double *>(&sm.far[0]);
-        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += PNB_MT) fd[e] = fs[e];
+        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER - 1) * sizeof(FarRule) / sizeof(double)); e += NT) fd[e] = fs[e];
     }
     unsigned long long my_pairs = 0, my_near = 0;
     __syncthreads();        // the power table is complete before its coefficients go to registers
     const PowCtxS kv(&sm.pw, lane);
-    const int k1 = tid >> 4, k2 = tid & 15;
+    const unsigned lt = (1u << lane) - 1, half = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
     for (;;) {
     __syncthreads();
     if (tid == 0) s_ticket = atomicAdd(G.counters_i + 1, 1);
@@ -923,9 +957,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
     const int ibeg = G.gptr[I], nI = G.gptr[I + 1] - ibeg, jbeg = G.gptr[J], nJ = G.gptr[J + 1] - jbeg;
     const int dI = G.gdptr[I], nldI = G.gdptr[I + 1] - dI, dJ = G.gdptr[J], nldJ = G.gdptr[J + 1] - dJ;
     {
-        for (int e = tid; e < nldI * ldS; e += PNB_MT) Sg[e] = 0.;
-        for (int e = tid; e < cap * 6; e += PNB_MT) DYs[e] = 0.;
-        for (int s = tid; s < nJ; s += PNB_MT) {
+        for (int s = tid; s < nJ; s += NT) {
             const int cc = G.gcells[jbeg + s];
             cellJ[s] = cc;
             locJ[s] = G.gloc[jbeg + s];
@@ -939,180 +971,220 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
                 volJ[s] = P.vol[cc];
             }
         }
+        const int i0 = G.gincptr[dJ];
+        for (int b = tid; b <= nldJ; b += NT) incptr[b] = (unsigned short)(G.gincptr[dJ + b] - i0);
+        const int ninc = G.gincptr[dJ + nldJ] - i0;
+        for (int e = tid; e < ninc; e += NT) inc[e] = G.ginc[i0 + e];
+        for (int e = lane; e < 6 * cap; e += 32) DYw[e] = 0.;
     }
-    for (int rb = 0; rb < nI; rb += SB) {
-        __syncthreads();        // the previous row batch is flushed, its row data no longer read
-        c.ioff = rb;
-        if (tid < SB) {
-            const int cc = G.gcells[ibeg + rb + tid];
-            sm.cellI[tid] = cc;
-            sm.locI[tid] = G.gloc[ibeg + rb + tid];
-            if (cc >= 0) {
-                sm.cxI[tid] = P.centers[(size_t)cc * 2];
-                sm.cxI[SB + tid] = P.centers[(size_t)cc * 2 + 1];
-                sm.lhI[tid] = P.lhf[cc];
-                sm.ahI[tid] = P.ahf[cc];
+    __syncthreads();
+    for (int r1 = warp; r1 < nI; r1 += NW) {
+        const int K1 = G.gcells[ibeg + r1];
+        if (K1 < 0) continue;      // padding slot (warp uniform)
+        const int l1 = G.gloc[ibeg + r1];
+        const int rb = r1 & ~(SB - 1), k1 = r1 & (SB - 1);
+        const bool nodof1 = (l1 & 0x00FFFFFF) == 0x00FFFFFF;
+        double s1v[3][2];
 #pragma unroll
-                for (int k = 0; k < 6; k++) sm.sxI[k * SB + tid] = P.simplices[(size_t)cc * 6 + k];
-                sm.volI[tid] = P.vol[cc];
-            }
+        for (int m = 0; m < 3; m++) {
+            s1v[m][0] = P.simplices[(size_t)K1 * 6 + 2 * m];
+            s1v[m][1] = P.simplices[(size_t)K1 * 6 + 2 * m + 1];
         }
-        for (int e = tid; e < 3 * SB * ldS; e += PNB_MT) S[e] = 0.;
-        double dxacc = 0.;      // threads tid < SB*ND: entry (tid % ND) of the block of row cell rb + tid / ND
-        __syncthreads();
-        for (int cb = diag ? rb : 0; cb < nJ; cb += SB) {
-            // ---- classify the pairs of the sub-batch ----
-            int cls = 0, todo = 0;
-            sm.slotD[tid] = 0;
-            if (tid == 0) sm.anyD = 0;
-            {
-                const int panel = g_classify(P, c, diag, nearunit, rb, cb, k1, k2);
-                if (panel != 0) {
+        const double c10 = P.centers[(size_t)K1 * 2], c11 = P.centers[(size_t)K1 * 2 + 1];
+        const float lh1 = P.lhf[K1], ah1 = P.ahf[K1];
+        const double vol1 = 2.0 * P.vol[K1];
+        int v1[3] = {0, 0, 0};
+        if (nearunit) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) v1[m] = P.cells[(size_t)K1 * 3 + m];
+        }
+        const int lab1 = P.labels ? P.labels[K1] : 0;
+        // ---- classify the partners: info[slot] = 0 no pair, 2..5 order of the thread-per-pair evaluator, 6 | pos << 3 near ----
+        int c5 = 0, c2 = 0, c3 = 0, c4 = 0, cn = 0;
+        for (int s0 = 0; s0 < nJ; s0 += 32) {
+            const int s2 = s0 + lane;
+            int code = 0, todo = 0;
+            if (s2 < nJ) {
+                const int K2 = cellJ[s2];
+                const int cb = s2 & ~(SB - 1), k2 = s2 & (SB - 1);
+                // diagonal units: every unordered pair once (batches rb <= cb; inside a batch k1 <= k2)
+                bool live = K2 >= 0 && (K1 != K2 ? (!diag || rb < cb || (rb == cb && k1 < k2)) : diag);
+                // the reference skips pairs of cells without any dof
+                if (live && nodof1 && (locJ[s2] & 0x00FFFFFF) == 0x00FFFFFF) live = false;
+                // piecewise variable kernels: pairs of other classes belong to another problem instance
+                if (live && P.labels && !pnb_class_active(P, lab1, P.labels[K2])) live = false;
+                if (live) {
+                    int panel = 0;
+                    if (K1 == K2) panel = -3;
+                    else if (nearunit) {
+                        int v2[3];
+#pragma unroll
+                        for (int m = 0; m < 3; m++) v2[m] = P.cells[(size_t)K2 * 3 + m];
+                        panel = -shared_vertices(v1, 3, v2, 3);
+                    }
+                    if (panel == 0) {
+                        const double a = c10 - cxJ[s2], b = c11 - cxJ[cap + s2];
+                        panel = fast_order_2d(a * a + b * b, lh1, lhJ[s2], ah1, ahJ[s2], cf, sf);
+                        if (panel < 0) {
+                            // getPanelType evaluates (c1 <= c2): keep the operand order of the reference
+                            const int ca = min(K1, K2), cbb = max(K1, K2);
+                            const double d = center_distance(P.centers + (size_t)ca * 2, P.centers + (size_t)cbb * 2, 2);
+                            panel = quad_order_interior(P, P.h[ca], P.h[cbb], d);
+                        }
+                    }
                     const bool is_far = panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1);
                     if (panel > P.max_order) atomicMax(G.err, panel);
-                    else if (is_far) cls = panel;
+                    else if (is_far) code = panel;
                     else if (nearunit) todo = panel;
                     else atomicMax(G.err + 1, 1);   // host bound violated (never expected)
                 }
             }
-            // ---- ordered binning of the far pairs by order; rank of the other pairs in slot order ----
-            unsigned mybal = 0;
-#pragma unroll
-            for (int o = 2; o <= PNB_FAR_MAX_ORDER; o++) {
-                const unsigned bc = __ballot_sync(0xffffffffu, cls == o);
-                if (lane == 0) sm.clscnt[(o - 2) * NW + warp] = __popc(bc);
-                if (cls == o) mybal = bc;
-            }
-            unsigned nbal = 0;
             if (nearunit) {
-                nbal = __ballot_sync(0xffffffffu, todo != 0);
-                if (lane == 0) sm.warpcnt[warp] = __popc(nbal);
+                // position in the near pair list: sub-batch base + pairs of earlier rows of the sub-batch + rank in the row
+                const unsigned nbal = __ballot_sync(0xffffffffu, todo != 0);
+                if (todo != 0) {
+                    const size_t sbi = ((size_t)u.slot * G.nbmax + rb / SB) * G.nbmax + (s2 / SB);
+                    const int pos = G.nearbase[sbi] + G.nearrow[sbi * SB + k1] + __popc(nbal & half & lt);
+                    const int4 pr = G.npairs[pos];
+                    if (pr.x != K1 || pr.y != cellJ[s2] || pr.z != todo) atomicMax(G.err + 1, 2);
+                    else code = 6 | (pos << 3);
+                }
             }
-            __syncthreads();    // B1
-            int nnear = 0, npos = 0;
-            {
-                // exclusive prefix over the (order, warp) counters: 32 entries, one per lane, warp scan
-                static_assert((PNB_FAR_MAX_ORDER - 1) * NW == 32, "counter scan assumes 32 entries");
-                const int me = (cls - 2) * NW + warp;
-                const int v0 = sm.clscnt[lane];
-                int incl = v0;
+            if (s2 < nJ) {
+                info[s2] = code;
+                if (code == 0) {
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, off);
-                    if (lane >= off) incl += t;
-                }
-                const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                const int pos = __shfl_sync(0xffffffffu, incl - v0, me & 31);
-                if (cls != 0) sm.list[pos + __popc(mybal & ((1u << lane) - 1))] = tid | (cls << 12);
-                if (tid == 0) sm.nlist = tot;
-                if (nearunit) {
-                    // rank inside the sub-batch (the list builder numbers every sub-batch separately)
-                    for (int w = 0; w < NW; w++) {
-                        if (w < warp) npos += sm.warpcnt[w];
-                        nnear += sm.warpcnt[w];
-                    }
-                    npos += __popc(nbal & ((1u << lane) - 1));
+                    for (int k = 0; k < 9; k++) Sw[k * cap + s2] = 0.;
                 }
             }
-            __syncthreads();    // B2
-            const int nlist = sm.nlist;
-            if (nlist == 0 && nnear == 0) continue;     // uniform across the CTA
-            // ---- evaluate the far pairs in list order; any thread may take any pair of the sub-batch ----
-            if (tid < nlist) {
-                const int item = sm.list[tid];
-                const int slot = item & 0xFF, order = item >> 12;
-                const int a1 = slot >> 4, a2 = cb + (slot & 15);
-                my_pairs++;
-                double s1v[3][2], s2v[3][2], xy[9], xx[6], yy[6];
+            const int kind = code & 7;
+            c5 += __popc(__ballot_sync(0xffffffffu, kind == 5));
+            c2 += __popc(__ballot_sync(0xffffffffu, kind == 2));
+            c3 += __popc(__ballot_sync(0xffffffffu, kind == 3));
+            c4 += __popc(__ballot_sync(0xffffffffu, kind == 4));
+            cn += __popc(__ballot_sync(0xffffffffu, kind == 6));
+        }
+        // ---- slots sorted by class (counting sort, slot order inside a class) ----
+        const int ntot = c5 + c2 + c3 + c4 + cn;
+        {
+            int b5 = 0, b2 = c5, b3 = b2 + c2, b4 = b3 + c3, bn = b4 + c4;
+            for (int s0 = 0; s0 < nJ; s0 += 32) {
+                const int s2 = s0 + lane;
+                const int kind = s2 < nJ ? (info[s2] & 7) : 0;
+                const unsigned m5 = __ballot_sync(0xffffffffu, kind == 5), m2 = __ballot_sync(0xffffffffu, kind == 2);
+                const unsigned m3 = __ballot_sync(0xffffffffu, kind == 3), m4 = __ballot_sync(0xffffffffu, kind == 4);
+                const unsigned mn = __ballot_sync(0xffffffffu, kind == 6);
+                int pos = -1;
+                if (kind == 5) pos = b5 + __popc(m5 & lt);
+                else if (kind == 2) pos = b2 + __popc(m2 & lt);
+                else if (kind == 3) pos = b3 + __popc(m3 & lt);
+                else if (kind == 4) pos = b4 + __popc(m4 & lt);
+                else if (kind == 6) pos = bn + __popc(mn & lt);
+                if (pos >= 0) list[pos] = (unsigned char)s2;
+                b5 += __popc(m5); b2 += __popc(m2); b3 += __popc(m3); b4 += __popc(m4); bn += __popc(mn);
+            }
+        }
+        __syncwarp();
+        // ---- evaluate in sorted order ----
+        double xa[ND];
+#pragma unroll
+        for (int k = 0; k < ND; k++) xa[k] = 0.;
+        for (int p = lane; p < ntot; p += 32) {
+            const int slot = list[p];
+            const int inf = info[slot], kind = inf & 7;
+            double xy[9], xx[6], yy[6];
+            if (kind == 6) {
+                const double *f = G.F + (size_t)(inf >> 3) * 21;
+#pragma unroll
+                for (int k = 0; k < 9; k++) xy[k] = __ldg(f + k);
+#pragma unroll
+                for (int k = 0; k < 6; k++) { xx[k] = __ldg(f + 9 + k); yy[k] = __ldg(f + 15 + k); }
+                my_near++;
+            } else {
+                double s2v[3][2];
 #pragma unroll
                 for (int m = 0; m < 3; m++) {
-                    s1v[m][0] = sm.sxI[(2 * m) * SB + a1];
-                    s1v[m][1] = sm.sxI[(2 * m + 1) * SB + a1];
-                    s2v[m][0] = sxJ[(2 * m) * cap + a2];
-                    s2v[m][1] = sxJ[(2 * m + 1) * cap + a2];
+                    s2v[m][0] = sxJ[(2 * m) * cap + slot];
+                    s2v[m][1] = sxJ[(2 * m + 1) * cap + slot];
                 }
-                const double sc = 2.0 * sm.volI[a1] * volJ[a2];
+                const double sc = vol1 * volJ[slot];
                 // node counts of the adopted rule family (far_expected_nodes): 3, 6, 6, 7
-                if (order == 2) far_eval_n<3>(sm.far[0], s1v, s2v, kv, xy, xx, yy);
-                else if (order == 5) far_eval_n<7>(sm.far[3], s1v, s2v, kv, xy, xx, yy);
-                else far_eval_n<6>(sm.far[order - 2], s1v, s2v, kv, xy, xx, yy);
-#pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    sm.dxy[slot][k] = xx[k] * sc;
-                    sm.dxy[slot][6 + k] = yy[k] * sc;
-                }
+                if (kind == 2) far_eval_n<3>(sm.far[0], s1v, s2v, kv, xy, xx, yy);
+                else if (kind == 5) far_eval_n<7>(sm.far[3], s1v, s2v, kv, xy, xx, yy);
+                else far_eval_n<6>(sm.far[kind - 2], s1v, s2v, kv, xy, xx, yy);
 #pragma unroll
                 for (int k = 0; k < 9; k++) xy[k] *= sc;
-                sm.slotD[slot] = 1;
-                sm.anyD = 1;
-                g_scatter(S, ldS, a1, sm.locI[a1], locJ[a2], xy);
-            }
-            if (todo != 0) {
-                // pairs evaluated by gnear_eval_kernel
-                const int pos = G.nearbase[((size_t)u.slot * G.nbmax + rb / SB) * G.nbmax + cb / SB] + npos;
-                const int4 pr = G.npairs[pos];
-                if (pr.x != sm.cellI[k1] || pr.y != cellJ[cb + k2] || pr.z != todo) atomicMax(G.err + 1, 2);
-                else {
-                    const double *f = G.F + (size_t)pos * 21;
-                    double nxy[9];
 #pragma unroll
-                    for (int k = 0; k < 9; k++) nxy[k] = __ldg(f + k);
-                    my_near++;
+                for (int k = 0; k < 6; k++) { xx[k] *= sc; yy[k] *= sc; }
+                my_pairs++;
+            }
 #pragma unroll
-                    for (int k = 0; k < 12; k++) sm.dxy[tid][k] = __ldg(f + 9 + k);
-                    sm.slotD[tid] = 1;
-                    sm.anyD = 1;
-                    g_scatter(S, ldS, k1, sm.locI[k1], locJ[cb + k2], nxy);
-                }
+            for (int k = 0; k < 9; k++) Sw[k * cap + slot] = xy[k];
+#pragma unroll
+            for (int k = 0; k < ND; k++) {
+                xa[k] += xx[k];
+                DYw[k * cap + slot] += yy[k];
             }
-            __syncthreads();    // B3
-            // ---- cell-diagonal blocks: sums over the partners of the step ----
-            if (sm.anyD) {
-                if (tid < SB * ND) {
-                    const int kk1 = tid / ND, comp = tid - kk1 * ND;
-                    double sacc = 0.;
-                    for (int q = 0; q < SB; q++) {
-                        const int slot = kk1 * SB + q;
-                        if (sm.slotD[slot]) sacc += sm.dxy[slot][comp];
-                    }
-                    dxacc += sacc;
-                } else if (tid < 2 * SB * ND) {
-                    const int t2 = tid - SB * ND;
-                    const int kk2 = t2 / ND, comp = t2 - kk2 * ND;
-                    double sacc = 0.;
-                    for (int kk1 = 0; kk1 < SB; kk1++) {
-                        const int slot = kk1 * SB + kk2;
-                        if (sm.slotD[slot]) sacc += sm.dxy[slot][ND + comp];
-                    }
-                    DYs[(cb + kk2) * ND + comp] += sacc;
-                }
+        }
+        // ---- row-cell block: fixed butterfly over the lanes ----
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < ND; k++) xa[k] += __shfl_xor_sync(0xffffffffu, xa[k], off);
+        }
+        if (lane < ND) {
+            double v = xa[0];
+#pragma unroll
+            for (int k = 1; k < ND; k++) if (lane == k) v = xa[k];
+            G.Dp[((size_t)J * P.nc + K1) * ND + lane] = v;
+        }
+        __syncwarp();
+        // ---- cross blocks per column dof: rows (r1, local vertex) of the unit block ----
+        for (int b = lane; b < nldJ; b += 32) {
+            double o0 = 0., o1 = 0., o2 = 0.;
+            const int e1 = incptr[b + 1];
+            for (int e = incptr[b]; e < e1; e++) {
+                const int v = inc[e], sl = v >> 2, j = v & 3;
+                o0 += Sw[j * cap + sl];
+                o1 += Sw[(3 + j) * cap + sl];
+                o2 += Sw[(6 + j) * cap + sl];
             }
-            __syncthreads();    // B4: slotD / dxy reused by the next step
+            double *dst = Sg + (size_t)(r1 * 3) * ldS + b;
+            dst[0] = o0;
+            dst[ldS] = o1;
+            dst[2 * ldS] = o2;
         }
-        if (tid < SB * ND) {
-            const int kk1 = tid / ND, comp = tid - kk1 * ND;
-            const int cc = sm.cellI[kk1];
-            if (cc >= 0) G.Dp[((size_t)J * P.nc + cc) * ND + comp] = dxacc;
-        }
-        // the block of the row batch joins the unit block (private to this CTA; the row cells of a batch share no vertex)
-        for (int e = tid; e < 3 * SB * nldJ; e += PNB_MT) {
-            const int r = e / nldJ, b = e - r * nldJ;
-            const int la = (sm.locI[r / 3] >> (8 * (r % 3))) & 0xFF;
-            if (la != 0xFF && sm.cellI[r / 3] >= 0) Sg[la * ldS + b] += S[r * ldS + b];
-        }
+        __syncwarp();
     }
     __syncthreads();
-    // column-cell sums; same group on both sides: slot Dp[I][c] takes the row sums (written above) and these
-    for (int e = tid; e < nJ * ND; e += PNB_MT) {
-        const int cc = cellJ[e / ND];
+    // column-cell sums over the warps (warp order); same group on both sides: slot Dp[I][c] takes the row sums
+    // (written above) and these
+    for (int e = tid; e < nJ * ND; e += NT) {
+        const int s2 = e / ND, k = e - s2 * ND;
+        const int cc = cellJ[s2];
         if (cc < 0) continue;
-        double *dp = &G.Dp[((size_t)I * P.nc + cc) * ND + (e % ND)];
-        *dp = diag ? *dp + DYs[e] : DYs[e];
+        double s = 0.;
+        for (int w = 0; w < NW; w++)
+            s += reinterpret_cast<const double *>(sp + (size_t)w * gmix_warp_bytes_dev(cap))[(size_t)(9 + k) * cap + s2];
+        double *dp = &G.Dp[((size_t)I * P.nc + cc) * ND + k];
+        *dp = diag ? *dp + s : s;
     }
-    if (G.dist.nparts > 0) g_flush_staged(G, G.dist.uoff_mix + (size_t)ticket * G.dist.nparts, Sg, ldS, I, dI, nldI, dJ, nldJ, tid, PNB_MT);
+    // rows of the dofs of the row group, gathered over the (row cell, local vertex) rows in a fixed order
+    for (int e = tid; e < nldI * nldJ; e += NT) {
+        const int a = e / nldJ, b = e - a * nldJ;
+        double s = 0.;
+        const int q1 = G.gincptr[dI + a + 1];
+        for (int q = G.gincptr[dI + a]; q < q1; q++) {
+            const int v = G.ginc[q];
+            s += Sg[(size_t)((v >> 2) * 3 + (v & 3)) * ldS + b];
+        }
+        Sd[a * ldS + b] = s;
+    }
+    __syncthreads();
+    if (G.dist.nparts > 0) g_flush_staged(G, G.dist.uoff_mix + (size_t)ticket * G.dist.nparts, Sd, ldS, I, dI, nldI, dJ, nldJ, tid, NT);
     else {
-        g_wait_predecessors(G, 1, ticket, I, J, tid, PNB_MT);
-        g_flush_block(G, Sg, ldS, dI, nldI, dJ, nldJ, A, ld, tid, PNB_MT);
+        g_wait_predecessors(G, 1, ticket, I, J, tid, NT);
+        g_flush_block(G, Sd, ldS, dI, nldI, dJ, nldJ, A, ld, tid, NT);
         g_signal_done(G, 1, ticket, tid);
     }
     }

@@ -81,6 +81,38 @@ template <int REP> struct PowCtxT {
         p = fma(p, r, c0);
         return T1[E] * (iv.y * p);
     }
+    // N independent powers, written stage by stage: the polynomial is a chain of seven dependent FMAs, and ptxas
+    // interleaved at most two such chains when they came from separate calls (ncu, round 2: the dependent FMAs of the
+    // unit kernel carried 4-5x the stall samples of the independent ones).  Stage order keeps N chains in flight.
+    template <int N> __device__ __forceinline__ void batch(const double *d2, double *g) const
+    {
+        double r[N], y[N], t[N], p[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const int hi = __double2hiint(d2[j]), lo = __double2loint(d2[j]);
+            const int E = min(max(((hi >> 20) & 0x7ff) + eoff, 0), 255);
+            const int idx = REP == 1 ? ((hi >> 13) & 0x7f) : ((hi >> 10) & (0x7f * REP));
+            const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+            const double2 iv = it[idx];
+            t[j] = T1[E];
+            y[j] = iv.y;
+            r[j] = fma(m, iv.x, -1.0);
+        }
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = fma(c6, r[j], c5);
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = fma(p[j], r[j], c4);
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = fma(p[j], r[j], c3);
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = fma(p[j], r[j], c2);
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = fma(p[j], r[j], c1);
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = fma(p[j], r[j], c0);
+#pragma unroll
+        for (int j = 0; j < N; j++) g[j] = t[j] * (y[j] * p[j]);
+    }
 };
 typedef PowCtxT<1> PowCtx;
 typedef PowCtxT<PNB_POW_REP> PowCtxS;
@@ -464,17 +496,22 @@ __device__ __forceinline__ void far_eval_n(const FarRule &R, const double (*s1)[
         const double X1 = p0 * s1[0][1] + p1 * s1[1][1] + p2 * s1[2][1];
         const double wi = R.w[i];
         double r = 0., t0 = 0., t1 = 0., t2 = 0.;
+        double d2[N], g[N];
 #pragma unroll
         for (int j = 0; j < N; j++) {
             const double a = X0 - Y0[j], b = X1 - Y1[j];
-            const double g = T(a * a + b * b);
+            d2[j] = a * a + b * b;
+        }
+        T.template batch<N>(d2, g);
+#pragma unroll
+        for (int j = 0; j < N; j++) {
             // the rule constants are re-read from shared memory (broadcast) in every row: hoisted out of the row loop
             // they would not fit into the registers and come back from local memory instead
-            t0 = fma(g, RV.wb[0][j], t0);
-            t1 = fma(g, RV.wb[1][j], t1);
-            t2 = fma(g, RV.wb[2][j], t2);
-            r = fma(g, RV.w[j], r);
-            c[j] = fma(g, wi, c[j]);
+            t0 = fma(g[j], RV.wb[0][j], t0);
+            t1 = fma(g[j], RV.wb[1][j], t1);
+            t2 = fma(g[j], RV.wb[2][j], t2);
+            r = fma(g[j], RV.w[j], r);
+            c[j] = fma(g[j], wi, c[j]);
         }
         const double q0 = wi * p0, q1 = wi * p1, q2 = wi * p2;
         const double r0 = r * q0, r1 = r * q1, r2 = r * q2;
