@@ -137,10 +137,26 @@ __device__ __forceinline__ void g_signal_done(const GroupSched &G, int listid, i
 __device__ __forceinline__ void g_flush_block(const GroupSched &G, const double *S, int ldS, int dI, int nldI, int dJ, int nldJ, double *A,
                                               int64_t ld, int tid, int nthreads)
 {
-    for (int e = tid; e < nldI * nldJ; e += nthreads) {
-        const int a = e / nldJ, b = e - a * nldJ;
-        double *dst = &A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]];
-        __stcg(dst, __ldcg(dst) + S[a * ldS + b]);
+    // four independent read-modify-writes in flight per thread (L2 latency)
+    const int n = nldI * nldJ;
+    for (int e0 = tid; e0 < n; e0 += 4 * nthreads) {
+        double *dst[4];
+        double o[4], v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int e = e0 + t * nthreads;
+            dst[t] = nullptr;
+            o[t] = v[t] = 0.;
+            if (e < n) {
+                const int a = e / nldJ, b = e - a * nldJ;
+                dst[t] = &A[(size_t)G.gdofs[dI + a] * ld + G.gdofs[dJ + b]];
+                v[t] = S[a * ldS + b];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) if (dst[t]) o[t] = __ldcg(dst[t]);
+#pragma unroll
+        for (int t = 0; t < 4; t++) if (dst[t]) __stcg(dst[t], o[t] + v[t]);
     }
 }
 
@@ -1169,24 +1185,44 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
         double *dp = &G.Dp[((size_t)I * P.nc + cc) * ND + k];
         *dp = diag ? *dp + s : s;
     }
-    // rows of the dofs of the row group, gathered over the (row cell, local vertex) rows in a fixed order
-    for (int e = tid; e < nldI * nldJ; e += NT) {
-        const int a = e / nldJ, b = e - a * nldJ;
-        double s = 0.;
-        const int q1 = G.gincptr[dI + a + 1];
-        for (int q = G.gincptr[dI + a]; q < q1; q++) {
-            const int v = G.ginc[q];
-            s += Sg[(size_t)((v >> 2) * 3 + (v & 3)) * ldS + b];
+    // rows of the dofs of the row group, gathered over the (row cell, local vertex) rows in a fixed order: one warp per
+    // row a, lanes over the columns; the loads of up to eight incidences are issued together (L2 latency)
+    const bool staged = G.dist.nparts > 0;
+    if (!staged) g_wait_predecessors(G, 1, ticket, I, J, tid, NT);
+    for (int a = warp; a < nldI; a += NW) {
+        const int q0 = G.gincptr[dI + a], nq = G.gincptr[dI + a + 1] - q0;
+        double *arow = staged ? nullptr : A + (size_t)G.gdofs[dI + a] * ld;
+        for (int b0 = 0; b0 < nldJ; b0 += 64) {
+            const int b = b0 + lane, b2 = b + 32;
+            double s = 0., s2 = 0.;
+            for (int qq = 0; qq < nq; qq += 8) {
+                double v[8], w[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const int inc = qq + t < nq ? G.ginc[q0 + qq + t] : -1;
+                    const double *src = Sg + (size_t)((inc >> 2) * 3 + (inc & 3)) * ldS;
+                    v[t] = (inc >= 0 && b < nldJ) ? __ldcg(src + b) : 0.;
+                    w[t] = (inc >= 0 && b2 < nldJ) ? __ldcg(src + b2) : 0.;
+                }
+#pragma unroll
+                for (int t = 0; t < 8; t++) { s += v[t]; s2 += w[t]; }
+            }
+            if (staged) {
+                if (b < nldJ) Sd[a * ldS + b] = s;
+                if (b2 < nldJ) Sd[a * ldS + b2] = s2;
+            } else {
+                // the matrix (L2 operations: other SMs update neighbouring entries of the same lines)
+                double *d1 = b < nldJ ? arow + G.gdofs[dJ + b] : nullptr, *d2 = b2 < nldJ ? arow + G.gdofs[dJ + b2] : nullptr;
+                const double o1 = d1 ? __ldcg(d1) : 0., o2 = d2 ? __ldcg(d2) : 0.;
+                if (d1) __stcg(d1, o1 + s);
+                if (d2) __stcg(d2, o2 + s2);
+            }
         }
-        Sd[a * ldS + b] = s;
     }
-    __syncthreads();
-    if (G.dist.nparts > 0) g_flush_staged(G, G.dist.uoff_mix + (size_t)ticket * G.dist.nparts, Sd, ldS, I, dI, nldI, dJ, nldJ, tid, NT);
-    else {
-        g_wait_predecessors(G, 1, ticket, I, J, tid, NT);
-        g_flush_block(G, Sd, ldS, dI, nldI, dJ, nldJ, A, ld, tid, NT);
-        g_signal_done(G, 1, ticket, tid);
-    }
+    if (staged) {
+        __syncthreads();
+        g_flush_staged(G, G.dist.uoff_mix + (size_t)ticket * G.dist.nparts, Sd, ldS, I, dI, nldI, dJ, nldJ, tid, NT);
+    } else g_signal_done(G, 1, ticket, tid);
     }
     for (int off = 16; off > 0; off >>= 1) {
         my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);

@@ -90,7 +90,7 @@ template <int REP> struct PowCtxT {
 #pragma unroll
         for (int j = 0; j < N; j++) {
             const int hi = __double2hiint(d2[j]), lo = __double2loint(d2[j]);
-            const int E = min(max(((hi >> 20) & 0x7ff) + eoff, 0), 255);
+            const int E = min(max((int)((unsigned)hi >> 20) + eoff, 0), 255);      // d2 >= 0: no sign bit
             const int idx = REP == 1 ? ((hi >> 13) & 0x7f) : ((hi >> 10) & (0x7f * REP));
             const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
             const double2 iv = it[idx];
@@ -510,9 +510,10 @@ __device__ __forceinline__ void far_eval_n(const FarRule &R, const double (*s1)[
             t0 = fma(g[j], RV.wb[0][j], t0);
             t1 = fma(g[j], RV.wb[1][j], t1);
             t2 = fma(g[j], RV.wb[2][j], t2);
-            r = fma(g[j], RV.w[j], r);
             c[j] = fma(g[j], wi, c[j]);
         }
+        // row sum of the weighted kernel values: the barycentric coordinates of a node add up to one
+        r = (t0 + t1) + t2;
         const double q0 = wi * p0, q1 = wi * p1, q2 = wi * p2;
         const double r0 = r * q0, r1 = r * q1, r2 = r * q2;
         xx[0] += r0 * p0; xx[1] += r0 * p1; xx[2] += r0 * p2;
