@@ -41,6 +41,8 @@ extern "C" {
 
 /* kernel types, nl/PyNucleus_nl/kernel_params.pxi:87-98 */
 #define PNB_KERNEL_FRACTIONAL 0
+#define PNB_KERNEL_INDICATOR 1      /* constant kernel C chi(|x-y| <= delta), kernelsCy.pyx:273-295 */
+#define PNB_KERNEL_PERIDYNAMIC 2    /* C / |x-y| chi(|x-y| <= delta), kernelsCy.pyx:321-359 */
 
 /* Simplicial mesh: the arrays nonlocalBuilder reads from `dm.mesh`
  * (nonlocalOperator_{SCALAR}.pxi:111-126,144-152: vertices, cells, volVector,
@@ -69,14 +71,16 @@ typedef struct {
 /* Kernel parameter block, the device-side equivalent of
  * kernel_params.pxi:14-28 for piecewise-constant symmetric kernels. */
 typedef struct {
-    int32_t kernel_type;   /* PNB_KERNEL_FRACTIONAL */
+    int32_t kernel_type;   /* PNB_KERNEL_*: all are C |x-y|^singularity inside the horizon */
     int32_t dim;
     double s;              /* fS        */
     double scaling;        /* fSCALING of the interior kernel  C(d,s)          */
     double bscaling;       /* fSCALING of kernel.getBoundaryKernel() = C/s     */
     double singularity;    /* fSINGULARITY of the interior kernel, -d-2s       */
     double bsingularity;   /* of the boundary kernel, 1-d-2s                   */
-    double horizon2;       /* fHORIZON2; +inf for the infinite horizon         */
+    double horizon2;       /* fHORIZON2; +inf for the infinite horizon.  Finite: interaction domain = l2 ball
+                            * (ball2_retriangulation, interactionDomains.pyx:866-965): remote pairs are skipped, pairs cut
+                            * by the horizon are re-triangulated, no zero-exterior surface terms                */
     double target_order;   /* local_matrix.target_order                         */
     double btarget_order;  /* local_matrix_zeroExterior.target_order            */
     int32_t order_num_dofs; /* num_dofs entering getQuadOrder (local_matrix.num_dofs, fractionalLaplacian2D.pyx:629);

@@ -5,7 +5,8 @@ host-side mirror of the reference interface."""
 from .mesh import simpleInterval, uniform_disc, polygon_disc, refined, meshNd  # noqa: F401
 from .dofmap import P1_DoFMap  # noqa: F401
 from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder, variableConstFractionalOrder, leftRightFractionalOrder,  # noqa: F401
-                      constantFractionalLaplacianScaling, FRACTIONAL)
+                      constantFractionalLaplacianScaling, FRACTIONAL, INDICATOR, PERIDYNAMIC, Kernel, getIntegrableKernel,
+                      constantIntegrableScaling, constant)
 from .assembly import nonlocalBuilder, assembleNonlocalOperator  # noqa: F401
 from .linear_operators import Dense_LinearOperator, diagonalOperator  # noqa: F401
 from .solvers import cg, gmres, lu, DistributedDenseOperator  # noqa: F401

@@ -156,7 +156,7 @@ class nonlocalBuilder:
                                                        self.dm.polynomialOrder)
             self._problem = None
             return
-        if not kernel.symmetric or not isinstance(kernel.s, constFractionalOrder):
+        if not kernel.symmetric or not (kernel.s is None or isinstance(kernel.s, constFractionalOrder)):
             raise NotImplementedError('only symmetric kernels whose order is constant or piecewise constant (leftRight) are supported yet')
         self.kernel = kernel
         # nonlocalAssembly_{SCALAR}.pxi:918-921

@@ -264,6 +264,7 @@ struct pnb_problem {
     std::vector<int> h_cells, h_dofs, h_home; // host copies for the lazily built schedules
     std::vector<unsigned char> h_labels;      // cell labels of piecewise variable kernels (empty: constant kernel)
     bool tiles_ready = false;
+    bool finite = false;        // finite horizon: DoF-tile path only
     int pow_eoff = 240;      // PowTab::eoff of this problem
     std::vector<double> h_centers, h_h;
     std::vector<int4> h_grid;         // lane grids of the near evaluator per order
@@ -557,9 +558,15 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     if (!mesh || !dm || !kernel || !rules || !out) return fail(PNB_ERR_ARG, "null argument");
     if (mesh->dim != 1 && mesh->dim != 2) return fail(PNB_ERR_UNSUPPORTED, "only 1D and 2D meshes are supported");
     if (dm->dofs_per_element != mesh->dim + 1) return fail(PNB_ERR_UNSUPPORTED, "only P1 DoFMaps are supported");
-    if (kernel->kernel_type != PNB_KERNEL_FRACTIONAL) return fail(PNB_ERR_UNSUPPORTED, "kernel type not supported");
+    // kernels of the form C |x-y|^singularity chi(|x-y| <= horizon): fractional (singularity = -d-2s), constant /
+    // indicator (0), inverse distance / peridynamic (-1)  (kernelsCy.pyx:75-183, 273-386)
+    if (kernel->kernel_type != PNB_KERNEL_FRACTIONAL && kernel->kernel_type != PNB_KERNEL_INDICATOR &&
+        kernel->kernel_type != PNB_KERNEL_PERIDYNAMIC)
+        return fail(PNB_ERR_UNSUPPORTED, "kernel type not supported");
+    if (kernel->kernel_type != PNB_KERNEL_FRACTIONAL && !std::isfinite(kernel->horizon2))
+        return fail(PNB_ERR_UNSUPPORTED, "integrable kernels need a finite horizon");
     if (kernel->dim != mesh->dim) return fail(PNB_ERR_ARG, "Kernel dimension must match dm.mesh dimension");
-    if (std::isfinite(kernel->horizon2)) return fail(PNB_ERR_UNSUPPORTED, "finite horizon not supported yet");
+    if (kernel->horizon2 <= 0. || kernel->horizon2 != kernel->horizon2) return fail(PNB_ERR_ARG, "horizon must be positive");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -649,13 +656,16 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     {
         PowTab tabs[2];
         const double scal[2] = {kernel->scaling, kernel->bscaling};
-        const double expo[2] = {-0.5 * dim - kernel->s, -0.5 * (dim - 1) - kernel->s};
+        const double expo[2] = {0.5 * kernel->singularity, 0.5 * kernel->bsingularity};
         // exponent window of the tables: top above 4 diam^2 (no two points of the mesh are further apart than the
         // diagonal of its bounding box), 256 binary exponents down from there
         int ex = 0;
         frexp(4. * mesh->diam * mesh->diam, &ex);
         p->pow_eoff = 254 - ex;
-        for (int t = 0; t < 2; t++) build_powtab(&tabs[t], scal[t], expo[t], p->pow_eoff);
+        for (int t = 0; t < 2; t++) {
+            build_powtab(&tabs[t], scal[t], expo[t], p->pow_eoff);
+            tabs[t].horizon2 = std::isfinite(kernel->horizon2) ? kernel->horizon2 : INFINITY;
+        }
         const PowTab *dt = nullptr;
         rc |= upload(p, tabs, 2, &dt);
         P.pow_int = dt;
@@ -691,8 +701,10 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     }
     P.s = kernel->s; P.C = kernel->scaling; P.Cb = kernel->bscaling;
     P.sing = kernel->singularity; P.bsing = kernel->bsingularity;
-    P.expo = -0.5 * dim - kernel->s;            // kernelsCy.pyx:159-183
-    P.bexpo = -0.5 * (dim - 1) - kernel->s;     // kernelsCy.pyx:216-240
+    P.expo = 0.5 * kernel->singularity;         // kernelsCy.pyx:159-183: -d/2 - s for the fractional kernel
+    P.bexpo = 0.5 * kernel->bsingularity;       // kernelsCy.pyx:216-240
+    P.horizon2 = std::isfinite(kernel->horizon2) ? kernel->horizon2 : INFINITY;
+    p->finite = std::isfinite(kernel->horizon2);
     P.H0 = mesh->diam / sqrt(8.);               // nonlocalOperator_{SCALAR}.pxi:435
     const double Nord = kernel->order_num_dofs > 0 ? kernel->order_num_dofs : N;
     if (dim == 2) {
@@ -790,6 +802,7 @@ __global__ void max_order_kernel(DProblem P, int zero_exterior, int *out, unsign
         int p1[3], p2[3];
         for (int c2 = c1; c2 < P.nc; c2++) {
             const int pan = panel_interior(P, c1, c2, p1, p2);
+            if (pan == PNB_IGNORED_PANEL) continue;
             best = max(best, pan);
             if (hist && pan >= -3 && pan < 256) atomicAdd(&hist[3 + pan], 1ull);
         }
@@ -931,7 +944,8 @@ __global__ void local_matrices_kernel(DProblem P, int boundary, int path, int fa
     if (pan > P.max_order) { if (lane == 0) atomicMax(err, pan); return; }
     if (pan >= 1) {
         const double vol = P.vol[a] * P.vol[b];
-        if (path == 1 && DIM == 2 && pan >= 2 && pan <= PNB_FAR_MAX_ORDER && ((far_mask >> pan) & 1)) {
+        if (path == 1 && DIM == 2 && pan >= 2 && pan <= PNB_FAR_MAX_ORDER && ((far_mask >> pan) & 1) &&
+            !(P.horizon2 < INFINITY && pair_relative_position(P, a, b) == 2)) {
             if (lane == 0) {
                 double s1[3][2], s2[3][2], xy[9], xx[6], yy[6];
                 load_simplex<2>(P.simplices, a, 3, s1);
@@ -949,7 +963,8 @@ __global__ void local_matrices_kernel(DProblem P, int boundary, int path, int fa
             return;
         }
         double acc[NL];
-        lanes_regular_interior<DIM>(P, a, b, pan, lane, 32, acc);
+        if (P.horizon2 < INFINITY && pair_relative_position(P, a, b) == 2) lanes_cut_interior<DIM>(P, a, b, pan, lane, 32, acc);
+        else lanes_regular_interior<DIM>(P, a, b, pan, lane, 32, acc);
         warp_allreduce<NL>(acc);
 #pragma unroll
         for (int k = 0; k < NL; k++)
@@ -1132,6 +1147,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
     const int gr = S.units[2 * unit], gc = S.units[2 * unit + 1];
     unsigned long long my_pairs = 0;
     const float cf = (float)P.c_int, sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
+    const bool finite = P.horizon2 < INFINITY;
     {   // stage the power table
         const double *src = reinterpret_cast<const double *>(P.pow_int);
         double *dst = reinterpret_cast<double *>(&sm.pw);
@@ -1176,6 +1192,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                     const int k1 = tid / SB, k2 = tid % SB;
                     const int K1 = sm.rb.cell[k1], K2 = sm.cb.cell[k2];
                     int todo = 0;  // 0 nothing, >0 regular order (queued), <0 singular panel (queued)
+                    int relpos = 0;
                     int cls = 0;   // far pass: order 2..5 of a pair for the thread-per-pair evaluator, else 0
                     bool countD = false;
                     sm.slotD[tid] = 0;
@@ -1192,6 +1209,10 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
 #pragma unroll
                                 for (int m = 0; m < NV; m++) { v1[m] = sm.rb.v[m][k1]; v2[m] = sm.cb.v[m][k2]; }
                                 panel = -shared_vertices(v1, NV, v2, NV);
+                                if (panel == 0 && finite) {
+                                    relpos = pair_relative_position(P, min(K1, K2), max(K1, K2));
+                                    if (relpos == 1) panel = PNB_IGNORED_PANEL;      // REMOTE
+                                }
                                 if (panel == 0) {
                                     if (DIM == 2) {
                                         const double a = sm.rb.cx[0][k1] - sm.cb.cx[0][k2], b = sm.rb.cx[DIM - 1][k1] - sm.cb.cx[DIM - 1][k2];
@@ -1205,10 +1226,11 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                                     }
                                 }
                             }
-                            const bool is_far = DIM == 2 && panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1);
-                            if (panel > P.max_order) atomicMax(S.err, panel);
+                            const bool is_far = DIM == 2 && panel >= 2 && panel <= PNB_FAR_MAX_ORDER && ((far_mask >> panel) & 1) && relpos != 2;
+                            if (panel == PNB_IGNORED_PANEL) {}
+                            else if (panel > P.max_order) atomicMax(S.err, panel);
                             else if (is_far) cls = NEAR ? 0 : panel;
-                            else todo = panel;
+                            else todo = relpos == 2 ? panel + PNB_CUT_FLAG : panel;      // cut pairs: regular order + flag
                         }
                     }
                     // ---- ordered binning: far pass by order, near pass in slot order ----
@@ -1305,7 +1327,8 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                                 const int q = pass == 0 ? it / Sl : it, sl = pass == 0 ? it - q * Sl : 0;
                                 const int slot = sm.list[q] & 0xFF;
                                 const bool cD = (sm.list[q] & 0x100) != 0;
-                                const int panel = sm.listpanel[q];
+                                const bool cut = sm.listpanel[q] >= PNB_CUT_FLAG;
+                                const int panel = cut ? sm.listpanel[q] - PNB_CUT_FLAG : sm.listpanel[q];
                                 const int Ka = sm.rb.cell[slot / SB], Kb = sm.cb.cell[slot % SB];
                                 // reference orientation of singular pairs: smaller cell index first
                                 const bool swapped = panel < 0 && Ka > Kb;
@@ -1317,7 +1340,10 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                                 if (pass == 0) {
                                     if (lane == 0 && sl == 0) my_pairs++;
                                     if (panel >= 1) {
-                                        lanes_regular_interior<DIM>(P, Ka, Kb, panel, sl * 32 + lane, 32 * Sl, acc);
+                                        // cut pairs are evaluated in the reference's orientation (smaller cell first): the
+                                        // re-triangulation is not symmetric in its two arguments
+                                        if (cut) lanes_cut_interior<DIM>(P, min(Ka, Kb), max(Ka, Kb), panel, sl * 32 + lane, 32 * Sl, acc);
+                                        else lanes_regular_interior<DIM>(P, Ka, Kb, panel, sl * 32 + lane, 32 * Sl, acc);
                                         warp_allreduce<NL>(acc);
                                     } else {
                                         lanes_singular_interior<DIM>(P, c1, c2, pan, p1, p2, sl * 32 + lane, 32 * Sl, acc);
@@ -1336,6 +1362,19 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                                         for (int ss = 0; ss < Sl; ss++) v += sm.partial[q * Sl + ss][k];
                                         acc[k] = v;
                                     }
+                                }
+                                if (cut && Ka > Kb) {
+                                    // evaluated as (Kb, Ka): back to the local numbering of (Ka, Kb)
+                                    double t[NL];
+#pragma unroll
+                                    for (int k = 0; k < NL; k++) t[k] = acc[k];
+#pragma unroll
+                                    for (int I = 0; I < 2 * NV; I++)
+#pragma unroll
+                                        for (int J = I; J < 2 * NV; J++) {
+                                            const int i2 = (I + NV) % (2 * NV), j2 = (J + NV) % (2 * NV);
+                                            acc[tri_idx(2 * NV, I, J)] = t[i2 <= j2 ? tri_idx(2 * NV, i2, j2) : tri_idx(2 * NV, j2, i2)];
+                                        }
                                 }
                                 double myv = 0.;         // lane k < NX: entry k of the cross block
                                 double myd = 0.;         // lane k < 2*ND: entry k of (dx, dy)
@@ -2446,6 +2485,7 @@ extern "C" int pnb_dist_plan(pnb_problem *p, int32_t nparts, int32_t part, int32
 {
     if (!p || !num_rows || !staging_doubles) return fail(PNB_ERR_ARG, "null argument");
     if (p->dim != 2) return fail(PNB_ERR_UNSUPPORTED, "pnb_dist_plan: 2D only (1D problems use row blocks)");
+    if (p->finite) return fail(PNB_ERR_UNSUPPORTED, "pnb_dist_plan: finite horizon operators use row blocks (pnb_dense_rows_begin/_end)");
     if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
     if (nparts < 1 || nparts > PNB_MAX_PARTS || part < 0 || part >= nparts) return fail(PNB_ERR_ARG, "invalid part");
     ON_DEVICE(p->device);
@@ -2621,7 +2661,7 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     const int nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
     TileSched &S = p->S;
     // 2D, whole operator: cell-group path (PNB_DEBUG bit 0x800 forces the DoF-tile path)
-    if (p->dim == 2 && row_begin == 0 && row_end == p->N && !((getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0) & 0x800))
+    if (p->dim == 2 && !p->finite && row_begin == 0 && row_end == p->N && !((getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0) & 0x800))
         return run_group_path(p, zero_exterior, dA, ld);
     if (build_tile_schedule(p)) return PNB_ERR_CUDA;
     S.cell_mask = nullptr;

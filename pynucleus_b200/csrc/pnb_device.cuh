@@ -13,6 +13,7 @@
 #define PNB_SB 16             // sub-batch: PNB_SB x PNB_SB cell pairs
 #define PNB_THREADS 256
 #define PNB_IGNORED_PANEL (-6)
+#define PNB_CUT_FLAG 4096      // added to the regular order of a pair cut by the horizon (near pass of the tile kernel)
 #define PNB_NEAR_R 4          // rows per register tile of the near evaluator
 #define PNB_NEAR_WARP_POINTS 288   // shared-memory points (double2) per warp of the near evaluator
 #define PNB_DER2 7            // double2 per node of the derived rule table (see DProblem::reg_derived)
@@ -38,6 +39,7 @@ struct PowTab {
     double T1[256];
     double2 IT[128];   // x = 1/m0 (rounded), y = m0^e for the exact reciprocal of x
     double scal, expo;
+    double horizon2;   // finite horizon: the kernel vanishes for |x-y|^2 > horizon2 (+inf otherwise)
     int eoff, pad;     // T1[k] = scal * 2^((k - eoff) e)
 };
 
@@ -63,6 +65,7 @@ struct DProblem {
     const double *bh;          // nb   (get_h_surface_simplex)
     const double *hcell;       // nc   (get_h_simplex, used by the boundary class)
     double s, C, Cb, sing, bsing, expo, bexpo;
+    double horizon2;           // fHORIZON2, +inf for the infinite horizon
     double H0, c_int, c_bnd;   // c_* = target-order dependent log constants of getQuadOrder
     DRule q_id, q_edge, q_vertex, bq_edge, bq_vertex;
     int max_order;
@@ -221,6 +224,27 @@ __host__ __device__ inline double center_distance(const double *c1, const double
     return sqrt(d2);
 }
 
+// ball2_retriangulation.getRelativePosition (interactionDomains.pyx:875-898) of two cells:
+// 0 INTERACT (all vertex distances <= horizon), 1 REMOTE (all >= horizon), 2 CUT
+__host__ __device__ inline int pair_relative_position(const DProblem &P, int c1, int c2)
+{
+    const int nvc = P.dim + 1;
+    double dmin2 = INFINITY, dmax2 = 0.;
+    for (int i = 0; i < nvc; i++)
+        for (int k = 0; k < nvc; k++) {
+            double d2 = 0.;
+            for (int j = 0; j < P.dim; j++) {
+                const double t = PNB_SUB(P.simplices[((size_t)c1 * nvc + i) * P.dim + j], P.simplices[((size_t)c2 * nvc + k) * P.dim + j]);
+                d2 = PNB_ADD(d2, PNB_MUL(t, t));
+            }
+            dmin2 = fmin(dmin2, d2);
+            dmax2 = fmax(dmax2, d2);
+        }
+    if (dmin2 >= P.horizon2) return 1;
+    if (dmax2 <= P.horizon2) return 0;
+    return 2;
+}
+
 // getPanelType for an element pair c1<=c2 (nonlocalOperator_{SCALAR}.pxi:493-540).
 __host__ __device__ inline int panel_interior(const DProblem &P, int c1, int c2, int *perm1, int *perm2)
 {
@@ -228,6 +252,8 @@ __host__ __device__ inline int panel_interior(const DProblem &P, int c1, int c2,
     if (c1 > c2) return PNB_IGNORED_PANEL;
     int panel = proto_panel(P.cells + (size_t)c1 * nvc, nvc, P.cells + (size_t)c2 * nvc, nvc, c1 == c2, perm1, perm2);
     if (panel == 0) {
+        // finite horizon: pairs entirely outside each other's interaction ball are ignored (:516)
+        if (P.horizon2 < INFINITY && pair_relative_position(P, c1, c2) == 1) return PNB_IGNORED_PANEL;
         double d = center_distance(P.centers + (size_t)c1 * P.dim, P.centers + (size_t)c2 * P.dim, P.dim);
         panel = quad_order_interior(P, P.h[c1], P.h[c2], d);
     }

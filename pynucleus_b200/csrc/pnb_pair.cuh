@@ -48,6 +48,7 @@ template <int REP> struct PowCtxT {
     const double2 *it;
     const double *T1;
     double c0, c1, c2, c3, c4, c5, c6;
+    double horizon2 = INFINITY;
     int eoff;          // table offset minus the exponent bias
     __device__ __forceinline__ void init(const double *coef, int eo)
     {
@@ -59,6 +60,7 @@ template <int REP> struct PowCtxT {
     {
         static_assert(REP == 1, "compact table");
         init(tab->coef, tab->eoff);
+        horizon2 = tab->horizon2;
     }
     __device__ __forceinline__ PowCtxT(const PowTabS *tab, int lane) : it(tab->IT + (lane & (PNB_POW_REP - 1))), T1(tab->T1)
     {
@@ -79,7 +81,10 @@ template <int REP> struct PowCtxT {
         p = fma(p, r, c2);
         p = fma(p, r, c1);
         p = fma(p, r, c0);
-        return T1[E] * (iv.y * p);
+        const double v = T1[E] * (iv.y * p);
+        // finite horizon: indicator of the interaction ball (kernelsCy.pyx:75-114; compact table only -- the unit
+        // kernels of the cell-group path serve the infinite horizon)
+        return (REP != 1 || d2 <= horizon2) ? v : 0.;
     }
     // N independent powers, written stage by stage: the polynomial is a chain of seven dependent FMAs, and ptxas
     // interleaved at most two such chains when they came from separate calls (ncu, round 2: the dependent FMAs of the
@@ -379,6 +384,409 @@ __device__ void lanes_boundary(const DProblem &P, int c1, int f, int panel, cons
 
 // fixed-shape butterfly: every lane ends with the same, order-independent-of-
 // scheduling sum
+// ---------------------------------------------------------------------------
+// Finite horizon (interaction domain = l2 ball of radius delta; ball2_retriangulation, interactionDomains.pyx:866-965).
+// Relative position of two simplices from their vertex distances (:875-898).
+// ---------------------------------------------------------------------------
+#define PNB_REL_INTERACT 0
+#define PNB_REL_REMOTE 1
+#define PNB_REL_CUT 2
+template <int DIM>
+__host__ __device__ inline int relative_position(const double (*s1)[2], int n1, const double (*s2)[2], int n2, double horizon2)
+{
+    double dmin2 = INFINITY, dmax2 = 0.;
+    for (int i = 0; i < n1; i++)
+        for (int k = 0; k < n2; k++) {
+            double d2 = 0.;
+            for (int j = 0; j < DIM; j++) { const double t = PNB_SUB(s1[i][j], s2[k][j]); d2 = PNB_ADD(d2, PNB_MUL(t, t)); }
+            dmin2 = fmin(dmin2, d2);
+            dmax2 = fmax(dmax2, d2);
+        }
+    if (dmin2 >= horizon2) return PNB_REL_REMOTE;
+    if (dmax2 <= horizon2) return PNB_REL_INTERACT;
+    return PNB_REL_CUT;
+}
+
+// isInside (:900-909)
+template <int DIM> __host__ __device__ inline bool ball_inside(const double *x, const double *y, double horizon2)
+{
+    double d2 = 0.;
+    for (int j = 0; j < DIM; j++) { const double t = PNB_SUB(x[j], y[j]); d2 = PNB_ADD(d2, PNB_MUL(t, t)); }
+    return d2 <= horizon2;
+}
+
+// findIntersections (:911-937): parameters in [0,1] where the segment start -> end of the simplex meets the sphere around
+// x.  `out` keeps its old contents when fewer intersections are found, as in the reference.
+template <int DIM>
+__host__ __device__ inline int ball_intersections(const double *x, const double (*simplex)[2], int start, int end, double horizon2, double *out)
+{
+    double nn = 0., p = 0., q = 0.;
+    for (int k = 0; k < DIM; k++) {
+        const double A = PNB_SUB(simplex[end][k], simplex[start][k]);
+        const double B = PNB_SUB(simplex[start][k], x[k]);
+        nn = PNB_ADD(nn, PNB_MUL(A, A));
+        p = PNB_ADD(p, PNB_MUL(A, B));
+        q = PNB_ADD(q, PNB_MUL(B, B));
+    }
+    nn = 1. / nn;
+    p = PNB_MUL(p, PNB_MUL(2., nn));
+    q = PNB_MUL(PNB_SUB(q, horizon2), nn);
+    const double A = PNB_MUL(-p, 0.5);
+    const double B = sqrt(PNB_SUB(PNB_MUL(A, A), q));
+    int num = 0;
+    double c = PNB_SUB(A, B);
+    if (c >= 0. && c <= 1.) out[num++] = c;
+    c = PNB_ADD(A, B);
+    if (c >= 0. && c <= 1.) out[num++] = c;
+    return num;
+}
+
+// sub-simplices of the outer element: barycentric map lambda -> A lambda + b, volume factor
+struct CutOuter {
+    double A[3][3][3], b[3][3], vol[3];
+    int n;
+};
+// sub-simplices of the inner element for one outer node: lambda -> A lambda
+struct CutInner {
+    double A[3][3][3], vol[3];
+    int n;
+};
+
+// startLoopSubSimplices_Simplex (:406-566) together with nextSubSimplex_Simplex (:63-96)
+template <int DIM>
+__host__ __device__ inline void cut_outer(const double (*s1)[2], const double (*s2)[2], double horizon2, CutOuter &o)
+{
+    o.n = 0;
+    for (int t = 0; t < 3; t++) {
+        o.vol[t] = 0.;
+        for (int i = 0; i < 3; i++) { o.b[t][i] = 0.; for (int j = 0; j < 3; j++) o.A[t][i][j] = 0.; }
+    }
+    if (DIM == 1) {
+        const double horizon = sqrt(horizon2);
+        const bool lr = s1[0][0] < s2[0][0];
+        const double vol1 = fabs(PNB_SUB(s1[0][0], s1[1][0])), inv = 1. / vol1;
+        double iv[4];
+        iv[0] = PNB_MUL(s1[0][0], inv);
+        iv[3] = PNB_MUL(s1[1][0], inv);
+        int k0, k1;
+        if (lr) {
+            iv[1] = PNB_MUL(fmax(s1[0][0], PNB_SUB(s2[0][0], horizon)), inv);
+            iv[2] = PNB_MUL(fmin(s1[1][0], PNB_SUB(s2[1][0], horizon)), inv);
+            k0 = 1; k1 = 3;
+        } else {
+            iv[1] = PNB_MUL(fmax(s1[0][0], PNB_ADD(s2[0][0], horizon)), inv);
+            iv[2] = PNB_MUL(fmin(s1[1][0], PNB_ADD(s2[1][0], horizon)), inv);
+            k0 = 0; k1 = 2;
+        }
+        for (int k = k0; k < k1; k++) {
+            const double l = iv[k], r = iv[k + 1];
+            if (!(PNB_SUB(r, l) > 0.)) continue;
+            const int t = o.n++;
+            o.A[t][0][0] = PNB_SUB(r, l);
+            o.A[t][1][1] = PNB_SUB(r, l);
+            o.b[t][0] = PNB_SUB(iv[3], r);
+            o.b[t][1] = PNB_SUB(l, iv[0]);
+            o.vol[t] = PNB_SUB(r, l);
+        }
+        return;
+    }
+    bool inIJ[3][3], inI[3];
+    int numInside = 0;
+    for (int i = 0; i < 3; i++) {
+        bool any = false;
+        for (int k = 0; k < 3; k++) { inIJ[i][k] = ball_inside<DIM>(s1[i], s2[k], horizon2); any |= inIJ[i][k]; }
+        inI[i] = any;
+        numInside += any;
+    }
+    double isec[2] = {0., 0.};
+    if (numInside == 1) {
+        int in = 0;
+        while (!inI[in]) in++;
+        const int o1 = (in + 1) % 3, o2 = (in + 2) % 3;
+        double c1 = 0., c2 = 0.;
+        for (int j = 0; j < 3; j++)
+            if (inIJ[in][j]) {
+                ball_intersections<DIM>(s2[j], s1, in, o1, horizon2, isec);
+                c1 = fmax(c1, isec[0]);
+                ball_intersections<DIM>(s2[j], s1, in, o2, horizon2, isec);
+                c2 = fmax(c2, isec[0]);
+            }
+        if (PNB_MUL(c1, c2) > 0.) {
+            o.A[0][in][in] = PNB_ADD(c1, c2);
+            o.A[0][in][o1] = c2;
+            o.A[0][in][o2] = c1;
+            o.A[0][o1][o1] = c1;
+            o.A[0][o2][o2] = c2;
+            o.b[0][in] = PNB_SUB(PNB_SUB(1., c1), c2);
+            o.vol[0] = PNB_MUL(c1, c2);
+            o.n = 1;
+        }
+    } else if (numInside == 2) {
+        int out = 0;
+        while (inI[out]) out++;
+        const int i1 = (out + 1) % 3, i2 = (out + 2) % 3;
+        double c1 = 1., c2 = 1.;
+        for (int j = 0; j < 3; j++) {
+            if (inIJ[i1][j]) { ball_intersections<DIM>(s2[j], s1, out, i1, horizon2, isec); c1 = fmin(c1, isec[0]); }
+            if (inIJ[i2][j]) { ball_intersections<DIM>(s2[j], s1, out, i2, horizon2, isec); c2 = fmin(c2, isec[0]); }
+        }
+        // lengths of the two possible cuts; the reference takes them from the second simplex and leaves d2 un-squared
+        // (:513-518) -- kept for parity
+        double d1 = 0., d2 = 0.;
+        for (int k = 0; k < 2; k++) {
+            const double t1 = PNB_SUB(PNB_ADD(s2[out][k], PNB_MUL(c1, PNB_SUB(s2[i1][k], s2[out][k]))), s2[i2][k]);
+            d1 = PNB_ADD(d1, PNB_MUL(t1, t1));
+            d2 = PNB_ADD(d2, PNB_SUB(PNB_ADD(s2[out][k], PNB_MUL(c2, PNB_SUB(s2[i2][k], s2[out][k]))), s2[i1][k]));
+        }
+        if (d1 < d2) {
+            if (PNB_SUB(1., c1) > 0.) {
+                const int t = o.n++;
+                o.A[t][out][out] = PNB_SUB(1., c1);
+                o.A[t][i1][i1] = PNB_SUB(1., c1);
+                o.A[t][i1][i2] = -c1;
+                o.A[t][i2][i2] = 1.;
+                o.b[t][i1] = c1;
+                o.vol[t] = PNB_SUB(1., c1);
+            }
+            if (PNB_MUL(c1, PNB_SUB(1., c2)) > 0.) {
+                const int t = o.n++;
+                o.A[t][out][out] = PNB_SUB(1., c2);
+                o.A[t][i2][i2] = 1.;
+                o.A[t][i2][out] = c2;
+                o.A[t][out][i1] = PNB_SUB(1., c1);
+                o.A[t][i1][i1] = c1;
+                o.vol[t] = PNB_MUL(c1, PNB_SUB(1., c2));
+            }
+        } else {
+            if (PNB_SUB(1., c2) > 0.) {
+                const int t = o.n++;
+                o.A[t][out][out] = PNB_SUB(1., c2);
+                o.A[t][i2][i2] = PNB_SUB(1., c2);
+                o.A[t][i2][i1] = -c2;
+                o.A[t][i1][i1] = 1.;
+                o.b[t][i2] = c2;
+                o.vol[t] = PNB_SUB(1., c2);
+            }
+            if (PNB_MUL(c2, PNB_SUB(1., c1)) > 0.) {
+                const int t = o.n++;
+                o.A[t][out][out] = PNB_SUB(1., c1);
+                o.A[t][i1][i1] = 1.;
+                o.A[t][i1][out] = c1;
+                o.A[t][out][i2] = PNB_SUB(1., c2);
+                o.A[t][i2][i2] = c2;
+                o.vol[t] = PNB_MUL(c2, PNB_SUB(1., c1));
+            }
+        }
+    } else if (numInside == 3) {
+        o.A[0][0][0] = o.A[0][1][1] = o.A[0][2][2] = 1.;
+        o.vol[0] = 1.;
+        o.n = 1;
+    }
+    // numInside == 0 cannot happen for a CUT pair (the reference raises NotImplementedError)
+}
+
+// startLoopSubSimplices_Node (:568-826) with nextSubSimplex_Node (:101-112); the l2 ball has no special points
+template <int DIM>
+__host__ __device__ inline void cut_inner(const double *x, const double (*s2)[2], double horizon2, CutInner &o)
+{
+    o.n = 0;
+    for (int t = 0; t < 3; t++) {
+        o.vol[t] = 0.;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o.A[t][i][j] = 0.;
+    }
+    bool ind[3] = {false, false, false};
+    int numInside = 0;
+    for (int j = 0; j < DIM + 1; j++) { ind[j] = ball_inside<DIM>(x, s2[j], horizon2); numInside += ind[j]; }
+    double isec[2] = {0., 0.};
+    if (DIM == 1) {
+        if (numInside == 0) {
+            if (ball_intersections<DIM>(x, s2, 0, 1, horizon2, isec) == 2) {
+                o.A[0][0][0] = PNB_SUB(1., isec[0]);
+                o.A[0][1][0] = isec[0];
+                o.A[0][1][1] = isec[1];
+                o.A[0][0][1] = PNB_SUB(1., isec[1]);
+                o.vol[0] = PNB_SUB(isec[1], isec[0]);
+                o.n = 1;
+            }
+        } else if (numInside == 1) {
+            int in = 0;
+            while (!ind[in]) in++;
+            const int out = (in + 1) % 2;
+            ball_intersections<DIM>(x, s2, in, out, horizon2, isec);
+            o.A[0][in][in] = 1.;
+            o.A[0][out][out] = isec[0];
+            o.A[0][in][out] = PNB_SUB(1., isec[0]);
+            o.vol[0] = isec[0];
+            o.n = 1;
+        } else {
+            o.A[0][0][0] = o.A[0][1][1] = 1.;
+            o.vol[0] = 1.;
+            o.n = 1;
+        }
+        return;
+    }
+    if (numInside == 1) {
+        int in = 0;
+        while (!ind[in]) in++;
+        const int o1 = (in + 1) % 3, o2 = (in + 2) % 3;
+        ball_intersections<DIM>(x, s2, in, o1, horizon2, isec);
+        const double c1 = isec[0];
+        ball_intersections<DIM>(x, s2, in, o2, horizon2, isec);
+        const double c2 = isec[0];
+        const int ni = ball_intersections<DIM>(x, s2, o1, o2, horizon2, isec);
+        if (ni == 0) {
+            o.A[0][in][in] = 1.;
+            o.A[0][in][o1] = PNB_SUB(1., c1);
+            o.A[0][o1][o1] = c1;
+            o.A[0][o2][o2] = c2;
+            o.A[0][in][o2] = PNB_SUB(1., c2);
+            o.vol[0] = PNB_MUL(c1, c2);
+            o.n = 1;
+        } else if (ni == 2) {
+            o.A[0][in][in] = 1.;
+            o.A[0][o1][o1] = c1;
+            o.A[0][in][o1] = PNB_SUB(1., c1);
+            o.A[0][o2][o2] = isec[0];
+            o.A[0][o1][o2] = PNB_SUB(1., isec[0]);
+            o.vol[0] = PNB_MUL(c1, isec[0]);
+            o.A[1][in][in] = 1.;
+            o.A[1][o1][o1] = PNB_SUB(1., isec[0]);
+            o.A[1][o2][o1] = isec[0];
+            o.A[1][o1][o2] = PNB_SUB(1., isec[1]);
+            o.A[1][o2][o2] = isec[1];
+            o.vol[1] = PNB_SUB(isec[1], isec[0]);
+            o.A[2][in][in] = 1.;
+            o.A[2][o1][o1] = PNB_SUB(1., isec[1]);
+            o.A[2][o2][o1] = isec[1];
+            o.A[2][o2][o2] = c2;
+            o.A[2][in][o2] = PNB_SUB(1., c2);
+            o.vol[2] = PNB_MUL(c2, PNB_SUB(1., isec[1]));
+            o.n = 3;
+        } else {
+            o.A[0][in][in] = 1.;
+            o.A[0][o1][o1] = c1;
+            o.A[0][in][o1] = PNB_SUB(1., c1);
+            o.A[0][o2][o2] = isec[0];
+            o.A[0][o1][o2] = PNB_SUB(1., isec[0]);
+            o.vol[0] = PNB_MUL(c1, isec[0]);
+            o.A[1][in][in] = 1.;
+            o.A[1][o1][o1] = PNB_SUB(1., isec[0]);
+            o.A[1][o2][o1] = isec[0];
+            o.A[1][o2][o2] = c2;
+            o.A[1][in][o2] = PNB_SUB(1., c2);
+            o.vol[1] = PNB_MUL(c2, PNB_SUB(1., isec[0]));
+            o.n = 2;
+        }
+    } else if (numInside == 2) {
+        int out = 0;
+        while (ind[out]) out++;
+        const int i1 = (out + 1) % 3, i2 = (out + 2) % 3;
+        ball_intersections<DIM>(x, s2, out, i1, horizon2, isec);
+        const double c1 = isec[0];
+        ball_intersections<DIM>(x, s2, out, i2, horizon2, isec);
+        const double c2 = isec[0];
+        double d1 = 0., d2 = 0.;
+        for (int k = 0; k < DIM; k++) {
+            const double t1 = PNB_SUB(s2[i2][k], PNB_ADD(PNB_MUL(c1, s2[i1][k]), PNB_MUL(PNB_SUB(1., c1), s2[out][k])));
+            const double t2 = PNB_SUB(s2[i1][k], PNB_ADD(PNB_MUL(c2, s2[i2][k]), PNB_MUL(PNB_SUB(1., c2), s2[out][k])));
+            d1 = PNB_ADD(d1, PNB_MUL(t1, t1));
+            d2 = PNB_ADD(d2, PNB_MUL(t2, t2));
+        }
+        if (d1 < d2) {
+            o.A[0][i2][i2] = 1.;
+            o.A[0][out][out] = PNB_SUB(1., c2);
+            o.A[0][i2][out] = c2;
+            o.A[0][i1][i1] = c1;
+            o.A[0][out][i1] = PNB_SUB(1., c1);
+            o.vol[0] = PNB_MUL(c1, PNB_SUB(1., c2));
+            o.A[1][i1][i1] = 1.;
+            o.A[1][i2][i2] = 1.;
+            o.A[1][out][out] = PNB_SUB(1., c1);
+            o.A[1][i1][out] = c1;
+            o.vol[1] = PNB_SUB(1., c1);
+        } else {
+            o.A[0][i1][i1] = 1.;
+            o.A[0][i2][i2] = c2;
+            o.A[0][out][i2] = PNB_SUB(1., c2);
+            o.A[0][out][out] = PNB_SUB(1., c1);
+            o.A[0][i1][out] = c1;
+            o.vol[0] = PNB_MUL(c2, PNB_SUB(1., c1));
+            o.A[1][i1][i1] = 1.;
+            o.A[1][i2][i2] = 1.;
+            o.A[1][out][out] = PNB_SUB(1., c2);
+            o.A[1][i2][out] = c2;
+            o.vol[1] = PNB_SUB(1., c2);
+        }
+        o.n = 2;
+    } else if (numInside == 3) {
+        o.A[0][0][0] = o.A[0][1][1] = o.A[0][2][2] = 1.;
+        o.vol[0] = 1.;
+        o.n = 1;
+    }
+    // numInside == 0: no special point for the l2 ball, the intersection (if any) is ignored (:648-667)
+}
+
+// Regular element pair whose vertex distances straddle the horizon: cut branch of eval_distant
+// (nonlocalOperator_{SCALAR}.pxi:790-847).  The lanes split the (outer sub-simplex, outer node) items; every lane
+// re-triangulates the inner element for its outer nodes.  acc[NL] as in lanes_regular_interior (not yet multiplied
+// by vol1*vol2).
+template <int DIM>
+__device__ void lanes_cut_interior(const DProblem &P, int c1, int c2, int order, int lane, int nlanes, double *acc)
+{
+    constexpr int NV = PairDims<DIM>::NV, NL = PairDims<DIM>::NL;
+    double s1[3][2], s2[3][2];
+    load_simplex<DIM>(P.simplices, c1, NV, s1);
+    load_simplex<DIM>(P.simplices, c2, NV, s2);
+    const DRule r = P.reg_cell[order];
+    const int n = r.n;
+    const PowCtx kv(P.pow_int);
+    const double horizon2 = P.horizon2;
+#pragma unroll
+    for (int k = 0; k < NL; k++) acc[k] = 0.;
+    CutOuter co;
+    cut_outer<DIM>(s1, s2, horizon2, co);
+    CutInner ci;
+    for (int q = lane; q < co.n * n; q += nlanes) {
+        const int t = q / n, i = q - t * n;
+        // transformed outer node (transformQuadratureRule.compute, quadrature.pyx:197-206) and its global coordinates
+        double l1[3] = {0., 0., 0.}, x[2] = {0., 0.};
+        for (int k = 0; k < NV; k++) {
+            double v = co.b[t][k];
+            for (int j = 0; j < NV; j++) v = PNB_ADD(v, PNB_MUL(co.A[t][k][j], r.bary[j * n + i]));
+            l1[k] = v;
+        }
+        for (int k = 0; k < NV; k++)
+            for (int m = 0; m < DIM; m++) x[m] = PNB_ADD(x[m], PNB_MUL(l1[k], s1[k][m]));
+        cut_inner<DIM>(x, s2, horizon2, ci);
+        for (int u = 0; u < ci.n; u++) {
+            const double cc = PNB_MUL(co.vol[t], ci.vol[u]);
+            for (int jn = 0; jn < n; jn++) {
+                double l2[3] = {0., 0., 0.}, y[2] = {0., 0.};
+                for (int k = 0; k < NV; k++) {
+                    double v = 0.;
+                    for (int j = 0; j < NV; j++) v = PNB_ADD(v, PNB_MUL(ci.A[u][k][j], r.bary[j * n + jn]));
+                    l2[k] = v;
+                }
+                for (int k = 0; k < NV; k++)
+                    for (int m = 0; m < DIM; m++) y[m] = PNB_ADD(y[m], PNB_MUL(l2[k], s2[k][m]));
+                double d2 = 0.;
+                for (int m = 0; m < DIM; m++) { const double w = PNB_SUB(x[m], y[m]); d2 = PNB_ADD(d2, PNB_MUL(w, w)); }
+                const double g = (r.w[i] * r.w[jn]) * kv(d2) * cc;
+                double psi[2 * NV];
+#pragma unroll
+                for (int k = 0; k < NV; k++) { psi[k] = l1[k]; psi[NV + k] = -l2[k]; }
+                int k = 0;
+#pragma unroll
+                for (int I = 0; I < 2 * NV; I++) {
+                    const double tt = g * psi[I];
+#pragma unroll
+                    for (int J = I; J < 2 * NV; J++) acc[k++] += tt * psi[J];
+                }
+            }
+        }
+    }
+}
+
 template <int N> __device__ __forceinline__ void warp_allreduce(double *v)
 {
 #pragma unroll

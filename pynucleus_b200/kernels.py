@@ -168,6 +168,110 @@ class FractionalKernel:
                                                                          ', boundary' if self.boundary else '')
 
 
+INDICATOR, PERIDYNAMIC = 1, 2      # kernel_params.pxi:88-90
+
+
+def getKernelEnum(kernelTypeString):
+    """kernelsCy.pyx:49-59"""
+    k = kernelTypeString.upper()
+    if k == 'FRACTIONAL':
+        return FRACTIONAL
+    if k in ('INDICATOR', 'CONSTANT'):
+        return INDICATOR
+    if k in ('INVERSEDISTANCE', 'INVERSEOFDISTANCE', 'PERIDYNAMIC'):
+        return PERIDYNAMIC
+    raise NotImplementedError(kernelTypeString)
+
+
+def constantIntegrableScaling(kType, dim, horizon):
+    """normalisation of the integrable kernels on the l2 ball (kernelNormalization.pyx:225-251)"""
+    if horizon <= 0.:
+        return np.nan
+    if kType == INDICATOR:
+        if dim == 1:
+            return 3./horizon**3/2.
+        if dim == 2:
+            return 8./pi/horizon**4/2.
+    elif kType == PERIDYNAMIC:
+        if dim == 1:
+            return 2./horizon**2/2.
+        if dim == 2:
+            return 6./pi/horizon**3/2.
+    raise NotImplementedError()
+
+
+class Kernel:
+    """integrable kernels gamma(x,y) = C |x-y|^singularity chi(|x-y| <= delta): 'constant' / 'indicator'
+    (singularity 0, kernelsCy.pyx:273-295) and 'inverseDistance' / 'peridynamic' (singularity -1, :321-359) on the
+    l2 ball (ball2_retriangulation).  Attribute names follow kernelsCy.pyx:620-700."""
+    valueSize = 1
+    s = None
+    sValue = 0.
+
+    def __init__(self, dim, kType, horizon, scaling, boundary=False, phi=None, piecewise=True):
+        if kType not in (INDICATOR, PERIDYNAMIC):
+            raise NotImplementedError('kernel type {} is not supported yet'.format(kType))
+        self.dim = int(dim)
+        self.kernelType = kType
+        self.horizon = horizon
+        self.boundary = boundary
+        self.piecewise = piecewise
+        self.phi = phi
+        self.scalingPrePhi = scaling
+        self.scalingValue = scaling if phi is None else phi*scaling
+        self.variableOrder = self.variableHorizon = self.variableScaling = self.variable = False
+        self.symmetric = True
+        self.horizonValue = horizon.value
+        self.horizonValue2 = horizon.value**2
+        self.finiteHorizon = horizon.value != np.inf
+        if not self.finiteHorizon:
+            raise NotImplementedError('integrable kernels need a finite horizon')
+        self.complement = False
+        self.singularityValue = 0. if kType == INDICATOR else -1.
+        self.min_singularity = self.max_singularity = self.singularityValue
+
+    def getModifiedKernel(self, horizon=None, scaling=None):
+        horizon = self.horizon if horizon is None else horizon
+        return getIntegrableKernel(self.dim, self.kernelType, horizon, scaling=scaling, piecewise=self.piecewise)
+
+    def getBoundaryKernel(self):
+        """The surface forms of the integrable kernels (kernelsCy.pyx:297-318, 361-386) only enter operators with a zero
+        exterior, which a finite horizon rules out (nonlocalAssembly_{SCALAR}.pxi:918-921); this object only carries the
+        singularity the boundary tables are built for."""
+        bk = Kernel.__new__(Kernel)
+        bk.__dict__.update(self.__dict__)
+        bk.boundary = True
+        bk.scalingValue = 0.
+        bk.singularityValue = self.singularityValue+1.
+        bk.min_singularity = bk.max_singularity = bk.singularityValue
+        return bk
+
+    def __call__(self, x, y):
+        x = np.atleast_1d(np.asarray(x, dtype=float))
+        y = np.atleast_1d(np.asarray(y, dtype=float))
+        d2 = float(((x-y)**2).sum())
+        if d2 > self.horizonValue2:
+            return 0.
+        return self.scalingValue*pow(d2, 0.5*self.singularityValue)
+
+    def __repr__(self):
+        return 'kernel({}, horizon={}, scaling={})'.format({INDICATOR: 'indicator', PERIDYNAMIC: 'peridynamic'}[self.kernelType],
+                                                          self.horizonValue, self.scalingValue)
+
+
+def getIntegrableKernel(dim, kernel, horizon, scaling=None, interaction=None, normalized=True, piecewise=True, phi=None,
+                        boundary=False, **kwargs):
+    """kernels.py:172-202"""
+    dim = getattr(dim, 'dim', dim)
+    kType = getKernelEnum(kernel) if isinstance(kernel, str) else int(kernel)
+    horizonFun = _getHorizon(horizon)
+    if interaction is not None and interaction not in ('ball2', ):
+        raise NotImplementedError('only the l2 ball is supported as interaction domain')
+    if scaling is None:
+        scaling = constantIntegrableScaling(kType, dim, horizonFun.value) if normalized else 0.5
+    return Kernel(dim, kType, horizonFun, scaling, boundary=boundary, phi=phi, piecewise=piecewise)
+
+
 def _getFractionalOrder(s):
     if isinstance(s, (int, float)):
         return constFractionalOrder(s)
@@ -208,6 +312,8 @@ def getFractionalKernel(dim, s, horizon=None, interaction=None, scaling=None, no
 def getKernel(dim, s=None, horizon=None, scaling=None, interaction=None, normalized=True, piecewise=True, phi=None,
               kernel=FRACTIONAL, boundary=False, **kwargs):
     """kernels.py:213-231"""
-    if kernel in (FRACTIONAL, 'fractional', 'FRACTIONAL'):
+    kType = getKernelEnum(kernel) if isinstance(kernel, str) else int(kernel)
+    if kType == FRACTIONAL:
         return getFractionalKernel(dim, s, horizon, interaction, scaling, normalized, piecewise, phi, boundary)
-    raise NotImplementedError('kernel type {} is not supported yet'.format(kernel))
+    return getIntegrableKernel(dim, kType, horizon, scaling=scaling, interaction=interaction, normalized=normalized,
+                               piecewise=piecewise, phi=phi)
