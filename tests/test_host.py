@@ -272,3 +272,18 @@ def test_mesh_sizes_bit_exact_vs_reference(golden_dir):
         assert np.array_equal(m.volVector, g['volVector']), f
         n += 1
     assert n >= 10
+
+
+def test_cython_shim_builds_and_binds_the_c_abi():
+    """integration/pnb200_shim.pyx compiles against include/pnb200.h, links libpnb200.so and fails loudly without a
+    device (no compute here)"""
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+    sys.path.insert(0, root)
+    from integration.build_shim import build
+    so = build()
+    assert os.path.exists(so)
+    out = subprocess.run(['nm', '-D', '--undefined-only', so], capture_output=True, text=True).stdout
+    for sym in ('pnb_problem_create', 'pnb_dense_assemble', 'pnb_problem_destroy', 'pnb_max_order', 'pnb_last_error'):
+        assert sym in out
