@@ -145,6 +145,11 @@ int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm, const pnb
 int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules);
 void pnb_problem_destroy(pnb_problem *p);
 
+/* Assembly path of whole 2D operators with an infinite horizon: 0 (default) the cell-group kernels, 1 the DoF-tile
+ * kernels that also serve 1D problems, row blocks and finite horizons.  Both produce the same operator (summation
+ * order differs); the parity tests compare them. */
+int pnb_problem_set_path(pnb_problem *p, int path);
+
 /* Largest regular quadrature order any cell pair / cell-facet pair requests
  * (getQuadOrder, fractionalLaplacian2D.pyx:622-642,1226-1253;
  * fractionalLaplacian1D.pyx:234-253,644-669).  Lets the host build exactly the

@@ -110,7 +110,8 @@ class nonlocalBuilder:
     """nonlocalBuilder(dm, kernel, params={}, zeroExterior=True, comm=None, PLogger=None, dm2=None)
 
     `params`: 'target_order' (nonlocalAssembly_{SCALAR}.pxi:987), 'quadType' in
-    ('classical-refactored',), 'device' (CUDA device index, default current)."""
+    ('classical-refactored',), 'device' (CUDA device index, default current), 'assembly_path' ('default' | 'tiles': the
+    DoF-tile kernels instead of the cell-group kernels for whole 2D operators)."""
 
     def __init__(self, dm, kernel, params={}, zeroExterior=True, comm=None, PLogger=None, dm2=None, **kwargs):
         if 'boundary' in kwargs:
@@ -184,6 +185,8 @@ class nonlocalBuilder:
             self._problem = _Problem(self._dm_assembly, self.kernel, self.kernelBoundary, self.orders, device,
                                      self.params.get('max_regular_order', 32),
                                      order_num_dofs=self.dm.num_dofs if self.dm2 is not None else 0)
+            if self.params.get('assembly_path', 'default') == 'tiles':
+                _lib.check(_lib.lib().pnb_problem_set_path(self._problem.handle, 1))
         return self._problem
 
     def _retry_on_order(self, fn):

@@ -38,7 +38,6 @@ static double wall_ms()
 
 static thread_local std::string g_err;
 struct pnb_problem;
-static pnb_problem *g_bench_problem = nullptr;   // last created problem (debug micro-benchmarks only)
 extern "C" const char *pnb_last_error(void) { return g_err.c_str(); }
 extern "C" int pnb_version(void) { return 100; }
 extern "C" int pnb_far_max_order(void) { return PNB_FAR_MAX_ORDER; }
@@ -265,6 +264,7 @@ struct pnb_problem {
     std::vector<unsigned char> h_labels;      // cell labels of piecewise variable kernels (empty: constant kernel)
     bool tiles_ready = false;
     bool finite = false;        // finite horizon: DoF-tile path only
+    int path = 0;               // 0: default, 1: DoF-tile path for whole 2D operators too (pnb_problem_set_path)
     int pow_eoff = 240;      // PowTab::eoff of this problem
     std::vector<double> h_centers, h_h;
     std::vector<int4> h_grid;         // lane grids of the near evaluator per order
@@ -436,9 +436,6 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
             }
             p->far_mask |= 1 << o;
         }
-    // experiments: PNB_FAR_MASK restricts the orders taken by the thread-per-pair evaluator (the others go to the
-    // near evaluator)
-    if (getenv("PNB_FAR_MASK")) p->far_mask &= atoi(getenv("PNB_FAR_MASK"));
     if (upload(p, p->far_rules, (size_t)PNB_FAR_MAX_ORDER + 1, &p->P.far_rules, true)) return PNB_ERR_CUDA;
     return 0;
 }
@@ -453,7 +450,6 @@ extern "C" void pnb_problem_destroy(pnb_problem *p)
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     for (auto &e : p->kev) if (e) cudaEventDestroy(e);
     if (p->stage) pool_free(p->stage);
-    if (g_bench_problem == p) g_bench_problem = nullptr;
     destroy_group_host(p);
     delete p;
 }
@@ -771,7 +767,6 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     if (getenv("PNB_BENCH_VERBOSE"))
         fprintf(stderr, "pnb_problem_create: mesh + upload %.1f ms, tile schedule %.1f ms, tables %.1f ms\n", tc1 - tc0, tc2 - tc1, wall_ms() - tc2);
     *out = p;
-    g_bench_problem = p;
     return 0;
 }
 
@@ -810,6 +805,13 @@ __global__ void max_order_kernel(DProblem P, int zero_exterior, int *out, unsign
             for (int f = 0; f < P.nb; f++) best = max(best, panel_boundary(P, c1, f, p1, p2));
     }
     atomicMax(out, best);
+}
+
+extern "C" int pnb_problem_set_path(pnb_problem *p, int path)
+{
+    if (!p || path < 0 || path > 1) return fail(PNB_ERR_ARG, "invalid argument");
+    p->path = path;
+    return 0;
 }
 
 extern "C" int pnb_max_order(pnb_problem *p, int zero_exterior, int32_t *max_order_out)
@@ -1027,15 +1029,6 @@ template <int DIM> struct CellBatch {
     int cell[PNB_SB], loc[PNB_SB], home[PNB_SB], any[PNB_SB];
 };
 
-#ifdef PNB_PROFILE
-#define PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pc_ = clock64();
-#define PROF(k) { const long long now_ = clock64(); pt_[k] += now_ - pc_; pc_ = now_; }
-#define PROF_END if (tid == 0) { for (int k_ = 0; k_ < 8; k_++) atomicAdd(S.counters + 2 + (k_ % 6), (unsigned long long)pt_[k_]); }
-#else
-#define PROF_DECL
-#define PROF(k)
-#define PROF_END
-#endif
 
 template <int DIM, bool NEAR> struct TileSmem {
     static constexpr int NV = PairDims<DIM>::NV, NX = PairDims<DIM>::NX, ND = PairDims<DIM>::ND;
@@ -1161,7 +1154,6 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
     __syncthreads();
     const PowCtx kv(&sm.pw);
     bool unit_near = false;
-    PROF_DECL
 
     for (int rt = gr * S.G; rt < min((gr + 1) * S.G, S.ntiles); rt++)
         for (int ct = max(gc * S.G, rt); ct < min((gc + 1) * S.G, S.ntiles); ct++) {
@@ -1182,12 +1174,10 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                 __syncthreads();
                 load_batch<DIM>(P, S, sm.rb, rbeg, rb, tid);
                 for (int cb = diag ? rb : 0; cb < nC; cb += SB) {
-                    PROF(5)
                     __syncthreads();    // S0: previous sub-batch done
                     load_batch<DIM>(P, S, sm.cb, cbeg, cb, tid);
                     if (tid == 0) sm.anyD = 0;
                     __syncthreads();    // S1: batches visible
-                    PROF(0)
                     // ---- phase 1: classify every pair of the sub-batch ----
                     const int k1 = tid / SB, k2 = tid % SB;
                     const int K1 = sm.rb.cell[k1], K2 = sm.cb.cell[k2];
@@ -1247,7 +1237,6 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                         mybal = __ballot_sync(0xffffffffu, todo != 0);
                         if (lane == 0) sm.warpcnt[warp] = __popc(mybal);
                     }
-                    PROF(1)
                     __syncthreads();    // S2
                     if (!NEAR) {
                         const int me = (cls - 2) * NW + warp;
@@ -1274,7 +1263,6 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                         if (tid == 0) sm.nlist = tot;
                     }
                     __syncthreads();    // S3
-                    PROF(2)
                     const int nlist = sm.nlist;
                     if (nlist == 0) continue;     // uniform across the CTA
                     // ---- phase 2: evaluate ----
@@ -1431,7 +1419,6 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                         }
                     }
                     __syncthreads();    // S4: direct updates done
-                    PROF(4)
                     if (diag) {
                         // mirror image inside a diagonal tile: second conflict-free round
                         if (!NEAR) {
@@ -1504,7 +1491,6 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                 unit_near = true;
             }
         }
-    PROF_END
     if (!NEAR && unit_near && tid == 0) S.unitflag[unit] = 1;
     // pair counter (statistics only; integer atomics)
     for (int off = 16; off > 0; off >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, off);
@@ -1960,7 +1946,7 @@ static int build_group_schedule(pnb_problem *p)
         std::vector<int> order(nc);
         for (int c = 0; c < nc; c++) order[c] = c;
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
-        const int forced = getenv("PNB_GC") ? atoi(getenv("PNB_GC")) : 0;
+        const int forced = 0;
         const int cand[] = {128, 96, 64, 32};   // even numbers of full batches (two column batches per step)
         for (int GC : cand) {
             if (forced > 0) GC = forced;
@@ -1997,7 +1983,6 @@ static int build_group_schedule(pnb_problem *p)
         G.counters = p->S.counters;
         gh->smem_f2 = gf2_smem_bytes(G.cap, G.maxld, G.ldS);
         gh->mix_warps = std::max(1, gmix_warps(G.cap, G.maxld, budget));
-        if (getenv("PNB_MIX_WARPS")) gh->mix_warps = std::max(1, std::min(gh->mix_warps, atoi(getenv("PNB_MIX_WARPS"))));
         gh->smem_mix = gmix_smem_bytes(G.cap, G.maxld, gh->mix_warps);
         {
             // incidence lists of the group-local dofs: (cell slot, local vertex) in ascending order
@@ -2292,7 +2277,6 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
     cudaEventRecord(p->ev[0]);
     if (!dist) cudaMemset2DAsync(dA, (size_t)ld * sizeof(double), 0, (size_t)N * sizeof(double), N);
     int launches = 0;
-    const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
     {
         // one persistent launch per unit list; the units take tickets in list order and order their updates of U
         // among themselves (g_wait_predecessors)
@@ -2303,14 +2287,14 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         cudaMemsetAsync(G.done, 0, std::max<size_t>((size_t)nf + nm, 1) * sizeof(int));
         for (auto &e : p->kev) if (!e) cudaEventCreate(&e);
         cudaEventRecord(p->kev[0]);
-        if (nf > 0 && !(dbg & 0x1000)) {
+        if (nf > 0) {
             gf2_kernel<<<std::min(nf, 2 * nsm), PNB_F2T, gh->smem_f2>>>(p->P, G, gh->d_f2, nf, dA, ld, R);
             launches++;
         }
         cudaEventRecord(p->kev[1]);
         // the near pair list is built (first assembly only) while the f2 kernel runs; its results feed the mix kernel
         if (build_near_list(p)) return PNB_ERR_CUDA;
-        if (gh->nitems > 0 && !(dbg & 0x100)) {
+        if (gh->nitems > 0) {
             const int wpb = PNB_THREADS / 32;
             // rule table of the largest order that has items; per warp PNB_NEAR_WARP_POINTS points
             const size_t smem_eval = sizeof(PowTabS) + ((size_t)PNB_DER2 * gh->near_nmax + (size_t)wpb * PNB_NEAR_WARP_POINTS) * sizeof(double2);
@@ -2324,7 +2308,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
             launches += 2;
         }
         cudaEventRecord(p->kev[2]);
-        if (nm > 0 && !(dbg & 0x200)) {
+        if (nm > 0) {
             // unit blocks of the resident CTAs (one per SM): global scratch, L2 resident
             const int ncta = std::min(nm, nsm);
             const size_t need = (size_t)ncta * gmix_scratch_doubles(G.cap, G.maxld, G.ldS) * sizeof(double);
@@ -2660,8 +2644,8 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     ON_DEVICE(p->device);
     const int nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
     TileSched &S = p->S;
-    // 2D, whole operator: cell-group path (PNB_DEBUG bit 0x800 forces the DoF-tile path)
-    if (p->dim == 2 && !p->finite && row_begin == 0 && row_end == p->N && !((getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0) & 0x800))
+    // 2D, whole operator, infinite horizon: cell-group path (pnb_problem_set_path(p, 1) selects the DoF-tile path)
+    if (p->dim == 2 && !p->finite && row_begin == 0 && row_end == p->N && p->path == 0)
         return run_group_path(p, zero_exterior, dA, ld);
     if (build_tile_schedule(p)) return PNB_ERR_CUDA;
     S.cell_mask = nullptr;
@@ -2689,7 +2673,6 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     cudaMemsetAsync(S.unitflag, 0, (size_t)S.nunits_all * sizeof(int));
     cudaEventRecord(p->ev[0]);
     int launches = 0;
-    const int dbg = getenv("PNB_DEBUG") ? atoi(getenv("PNB_DEBUG")) : 0;
     int nnear_units = 0;
     if (p->dim == 2) {
         const size_t smem = sizeof(TileSmem<2, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
@@ -2699,7 +2682,7 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
         tile_kernel<2, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, p->far_mask);
         compact_units_kernel<<<1, 1024>>>(S);
         cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);
-        if (nnear_units > 0 && !(dbg & 0x100))
+        if (nnear_units > 0)
             tile_kernel<2, true><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, p->far_mask);
     } else {
         const size_t smem = sizeof(TileSmem<1, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
@@ -2819,10 +2802,6 @@ extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row
             else { cudaGetLastError(); p->ktimings[k] = 0.; }
         }
     }
-#ifdef PNB_PROFILE
-    if (p->kev[0]) fprintf(stderr, "PNB_PROFILE gmix cycles (thread 0 of every CTA, summed): unit setup %llu | classify+bin %llu | evaluate %llu | block update+D %llu | flush %llu\n", hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7]);
-    else fprintf(stderr, "PNB_PROFILE cycles(tid0 sums): load+S1 %llu | classify %llu | S2+list+S3 %llu | eval %llu | S4 %llu | mirror+D+loop %llu\n", hcnt[2], hcnt[3], hcnt[4], hcnt[5], hcnt[6], hcnt[7]);
-#endif
     p->stats[1] = p->distinct_pairs;
     return 0;
 }
@@ -3036,85 +3015,8 @@ __global__ void fp64_peak_kernel(double *out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
-// micro-benchmark of the thread-per-pair evaluator in isolation (debug aid, PNB_FAREVAL_BENCH)
-__global__ void __launch_bounds__(256, 2) fareval_bench_kernel(DProblem P, int order, int with_d, int iters, double *out)
-{
-    __shared__ PowTab pw;
-    __shared__ FarRule far[PNB_FAR_MAX_ORDER + 1];
-    const int tid = threadIdx.x;
-    {
-        const double *src = reinterpret_cast<const double *>(P.pow_int);
-        double *dst = reinterpret_cast<double *>(&pw);
-        for (int e = tid; e < (int)(sizeof(PowTab) / sizeof(double)); e += 256) dst[e] = src[e];
-        const double *fs = reinterpret_cast<const double *>(P.far_rules);
-        double *fd = reinterpret_cast<double *>(&far[0]);
-        for (int e = tid; e < (int)((PNB_FAR_MAX_ORDER + 1) * sizeof(FarRule) / sizeof(double)); e += 256) fd[e] = fs[e];
-    }
-    __syncthreads();
-    const PowCtx kv(&pw);
-    const int g = blockIdx.x * 256 + tid;
-    double s1[3][2], s2[3][2];
-    load_simplex<2>(P.simplices, g % P.nc, 3, s1);
-    load_simplex<2>(P.simplices, (g * 7 + P.nc / 2) % P.nc, 3, s2);
-    double acc = 0.;
-    for (int it = 0; it < iters; it++) {
-        double xy[9], xx[6], yy[6];
-        far_eval_2d(far[order], s1, s2, kv, with_d != 0, xy, xx, yy);
-        acc += xy[0] + xy[4] + xy[8] + xx[0] + yy[5];
-        s2[0][0] += 1e-9;
-    }
-    out[g] = acc;
-}
-
-__global__ void fp64_latency_kernel(double *out, long long *cyc, int iters)
-{
-    double a = threadIdx.x * 1e-9 + 1.0;
-    const double b = 1.0000001, c = 1e-9;
-    const long long t0 = clock64();
-    for (int i = 0; i < iters; i++) {
-        a = fma(a, b, c); a = fma(a, b, c); a = fma(a, b, c); a = fma(a, b, c);
-        a = fma(a, b, c); a = fma(a, b, c); a = fma(a, b, c); a = fma(a, b, c);
-    }
-    const long long t1 = clock64();
-    out[threadIdx.x] = a;
-    if (threadIdx.x == 0) cyc[0] = t1 - t0;
-}
-
 extern "C" int pnb_fp64_peak(int device, double *tflops)
 {
-    if (getenv("PNB_FAREVAL_BENCH") && g_bench_problem) {
-        pnb_problem *p = g_bench_problem;
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        double *d = nullptr;
-        const int blocks = sms * 2 * 8, iters = 200;
-        cudaMalloc(&d, (size_t)blocks * 256 * sizeof(double));
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int order = 2; order <= 5; order++)
-            for (int wd = 0; wd < 2; wd++) {
-                fareval_bench_kernel<<<blocks, 256>>>(p->P, order, wd, 10, d);
-                cudaEventRecord(e0);
-                fareval_bench_kernel<<<blocks, 256>>>(p->P, order, wd, iters, d);
-                cudaEventRecord(e1);
-                cudaEventSynchronize(e1);
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, e0, e1);
-                const double pairs = (double)blocks * 256 * iters;
-                const int n = p->far_rules[order].n;
-                fprintf(stderr, "PNB fareval order %d with_d %d: %.3f ms, %.3e pairs/s, %.3e node pairs/s (%s)\n", order, wd, ms, pairs / (ms * 1e-3), pairs * n * n / (ms * 1e-3), cudaGetErrorString(cudaGetLastError()));
-            }
-        cudaFree(d);
-    }
-    if (getenv("PNB_FP64_LATENCY")) {
-        double *d = nullptr; long long *c = nullptr, h = 0;
-        cudaMalloc(&d, 32 * sizeof(double)); cudaMalloc(&c, sizeof(long long));
-        fp64_latency_kernel<<<1, 32>>>(d, c, 1000);
-        fp64_latency_kernel<<<1, 32>>>(d, c, 1000);
-        cudaMemcpy(&h, c, sizeof(long long), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "PNB dependent DFMA latency: %.2f cycles\n", (double)h / 8000.);
-        cudaFree(d); cudaFree(c);
-    }
     if (!tflops) return fail(PNB_ERR_ARG, "null argument");
     if (pnb_device_count() == 0) return fail(PNB_ERR_NO_DEVICE, "no CUDA device");
     ON_DEVICE(device);

@@ -37,6 +37,24 @@ class P1_DoFMap:
         self.num_boundary_dofs = int(bv.shape[0])
         self._vertex2dof = num
 
+    @classmethod
+    def fromArrays(cls, mesh, dofs, num_dofs, num_boundary_dofs=None):
+        """DoFMap over `mesh` with a given cell -> DoF table (negative = boundary DoF -1-k), e.g. the `dofs` array of a
+        PyNucleus DoFMap built with an indicator tag (fem/PyNucleus_fem/DoFMaps.pyx:358-)"""
+        dm = cls.__new__(cls)
+        dm.mesh = mesh
+        dm.dim = mesh.dim
+        dm.dofs_per_vertex, dm.dofs_per_edge, dm.dofs_per_element = 1, 0, mesh.manifold_dim+1
+        dm.dofs = np.ascontiguousarray(dofs, dtype=INDEX)
+        assert dm.dofs.shape == mesh.cells.shape
+        dm.num_dofs = int(num_dofs)
+        v2d = np.zeros(mesh.num_vertices, dtype=np.int64)
+        v2d[mesh.cells.ravel()] = dm.dofs.ravel()
+        assert np.array_equal(v2d[mesh.cells], dm.dofs), 'P1: one DoF per vertex'
+        dm._vertex2dof = v2d
+        dm.num_boundary_dofs = int((v2d < 0).sum()) if num_boundary_dofs is None else int(num_boundary_dofs)
+        return dm
+
     def getComplementDoFMap(self):
         """DoFs and boundary DoFs swapped (fem/PyNucleus_fem/DoFMaps.pyx:1170-1184)"""
         from copy import copy

@@ -98,3 +98,45 @@ def test_dense_vs_reference(golden_dir, name):
     assert entry_err(A, g['A']) < TOL
     assert np.abs(A-A.T).max() <= 1e-15*np.abs(A).max()
     assert b.getStats()['evaluated_pairs'] > 0
+
+
+@pytest.mark.parametrize('ktype', ['constant', 'fractional'])
+def test_baseline_config2_square_finite_horizon(golden_dir, ktype):
+    """BASELINE configs[2]: runNonlocal.py --domain square --kernelType constant|fractional --problem poly-Dirichlet.
+    The reference's driver classes (structured variant of its square-with-collar mesh, see
+    oracle/refbuild/make_golden_nonlocal_driver.py) produced operator, Dirichlet coupling block, right-hand side and
+    solution; here the same mesh and DoFMaps go through the CUDA path.  With --matrixFormat H2 the reference itself falls
+    back to the dense operator on this configuration ("Cannot assemble H2 operator, assembling dense matrix instead")."""
+    import torch
+    import pynucleus_b200 as pb
+    g = load(golden_dir, 'nonlocal_square_'+ktype)
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'])
+    dmI = pb.P1_DoFMap.fromArrays(mesh, g['dofs'], int(g['num_dofs']))
+    dmBC = pb.P1_DoFMap.fromArrays(mesh, g['dofsBC'], int(g['num_dofsBC']))
+    assert np.array_equal(dmI.getComplementDoFMap().dofs, dmBC.dofs)
+    kernel = kernel_from_golden(g)
+    assert abs(kernel.scalingValue-float(g['scaling'])) <= 1e-15*float(g['scaling'])
+    params = {'target_order': float(g['target_order'])}
+    A = pb.nonlocalBuilder(dmI, kernel, params).getDense()
+    Ad = A.data
+    rows = g['rows']
+    dscale = np.sqrt(np.abs(g['diagonal']))
+    scale = np.maximum(np.abs(g['A_rows']), 1e-2*np.outer(dscale[rows], dscale))
+    assert (np.abs(Ad[rows]-g['A_rows'])/scale).max() < TOL
+    assert np.abs(np.diag(Ad)-g['diagonal']).max() < TOL*np.abs(g['diagonal']).max()
+    assert np.abs(Ad.dot(g['x'])-g['Ax']).max() < TOL*np.abs(g['Ax']).max()
+    assert abs(np.linalg.norm(Ad)-float(g['frobenius'])) < TOL*float(g['frobenius'])
+    # Dirichlet coupling block (two DoFMaps)
+    ABC = pb.nonlocalBuilder(dmI, kernel, params, dm2=dmBC).getDense().data
+    assert ABC.shape == (dmI.num_dofs, dmBC.num_dofs)
+    bscale = np.abs(g['ABC_rows']).max()
+    assert np.abs(ABC[rows]-g['ABC_rows']).max() < TOL*bscale
+    assert np.abs(ABC.dot(g['xb'])-g['ABCxb']).max() < TOL*np.abs(g['ABCxb']).max()
+    assert abs(np.linalg.norm(ABC)-float(g['ABC_frobenius'])) < TOL*float(g['ABC_frobenius'])
+    # the driver's linear system: same solution (the reference solved it with cg-mg to its tolerance)
+    b = torch.from_numpy(g['b']).cuda()
+    u, its, res = pb.cg(A, b, tol=1e-12, maxiter=2000)
+    uI = g['uI']
+    assert np.abs(u.cpu().numpy()-uI).max() < 1e-5*np.abs(uI).max()
+    r = Ad.dot(uI)-g['b']
+    assert np.abs(r).max() < 1e-4*np.abs(g['b']).max()

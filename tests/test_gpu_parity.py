@@ -457,9 +457,9 @@ def test_distributed_operator_single_process():
     b.releaseScratch()
 
 
-def test_group_path_equals_tile_path(monkeypatch):
-    """2D: the cell-group kernels (default) against the DoF-tile kernels (PNB_DEBUG bit 0x800), which share only the
-    per-pair evaluators: same operator to rounding, both bitwise symmetric"""
+def test_group_path_equals_tile_path():
+    """2D: the cell-group kernels (default) against the DoF-tile kernels (params['assembly_path'] = 'tiles'), which share
+    only the per-pair evaluators: same operator to rounding, both bitwise symmetric"""
     import pynucleus_b200 as pb
     mesh = pb.refined(pb.polygon_disc(7), 3)
     mesh.vertices[:] = mesh.vertices*np.array([1.3, 0.8])      # anisotropic: several mesh sizes and orders
@@ -467,8 +467,7 @@ def test_group_path_equals_tile_path(monkeypatch):
     dm = pb.P1_DoFMap(mesh)
     kernel = pb.getFractionalKernel(2, 0.4)
     A = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense().data
-    monkeypatch.setenv('PNB_DEBUG', '2048')
-    b = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5})
+    b = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5, 'assembly_path': 'tiles'})
     B = b.getDense().data
     assert b.getStats()['evaluated_pairs'] > b.getStats()['distinct_pairs']      # the tile path ran (halo pairs)
     assert entry_err(A, B) < TOL
