@@ -1754,6 +1754,13 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
             std::sort(uv.begin(), uv.end());
             uv.erase(std::unique(uv.begin(), uv.end()), uv.end());
             for (size_t e = 0; e < vids.size(); e++) lv[e] = (int)(std::lower_bound(uv.begin(), uv.end(), vids[e]) - uv.begin());
+            // the greedy choice occasionally needs one batch more than the minimum; a few restarts with a rotated scan
+            // order (deterministic) almost always find a minimal colouring, which keeps the slot count of the groups
+            // (shared memory per warp of the unit kernels) at its minimum
+            std::vector<std::vector<int>> bestb;
+            for (int attempt = 0; attempt < 12; attempt++) {
+            bcells.assign(B0, std::vector<int>());
+            const int rot = (int)(((long long)attempt * 37) % std::max(n, 1));
             std::vector<unsigned long long> vmask(uv.size(), 0ull);   // batches that hold a cell at this vertex
             std::vector<int> cnt(B0, 0);
             std::vector<char> done(n, 0);
@@ -1763,7 +1770,8 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
                 const unsigned long long all = cnt.size() >= 64 ? ~0ull : ((1ull << cnt.size()) - 1);
                 int best = -1, bestf = 1 << 30;
                 unsigned long long bestmask = 0;
-                for (int k = 0; k < n; k++) {
+                for (int k0 = 0; k0 < n; k0++) {
+                    const int k = k0 + rot < n ? k0 + rot : k0 + rot - n;
                     if (done[k]) continue;
                     const unsigned long long forb = vmask[lv[k * 3]] | vmask[lv[k * 3 + 1]] | vmask[lv[k * 3 + 2]] | full;
                     const unsigned long long feas = ~forb & all;
@@ -1789,6 +1797,10 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
                 for (int m = 0; m < 3; m++) vmask[lv[best * 3 + m]] |= 1ull << b;
                 done[best] = 1;
             }
+            if (bestb.empty() || bcells.size() < bestb.size()) bestb = bcells;
+            if ((int)bestb.size() <= B0) break;
+            }
+            bcells = bestb;
         }
         for (int k = c0; k < c1; k++) grp[order[k]] = g;
         // fullest batches first
