@@ -535,6 +535,7 @@ def run_cuda(args):
     if rank == 0:
         emit(line)
     if world > 1:
+        pb.release_staging_pool()
         dist.destroy_process_group()
 
 

@@ -7,7 +7,7 @@ from .dofmap import P1_DoFMap  # noqa: F401
 from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder, variableConstFractionalOrder, leftRightFractionalOrder,  # noqa: F401
                       constantFractionalLaplacianScaling, FRACTIONAL, INDICATOR, PERIDYNAMIC, Kernel, getIntegrableKernel,
                       constantIntegrableScaling, constant)
-from .assembly import nonlocalBuilder, assembleNonlocalOperator  # noqa: F401
+from .assembly import nonlocalBuilder, assembleNonlocalOperator, release_staging_pool  # noqa: F401
 from .linear_operators import Dense_LinearOperator, diagonalOperator  # noqa: F401
 from .solvers import cg, gmres, lu, DistributedDenseOperator  # noqa: F401
 

@@ -106,6 +106,30 @@ class _Problem:
             pass
 
 
+_STAGE_POOL = {}
+
+
+def _release_pool(pool):
+    import torch
+    L = _lib.lib()
+    dev = pool['device']
+    torch.cuda.synchronize(dev)
+    for q in pool['opened']:
+        L.pnb_ipc_close(dev, q)
+    pool['opened'] = []
+    if pool['own'] is not None:
+        L.pnb_device_free(dev, pool['own'])
+        pool['own'] = None
+    pool['capacity'] = -1
+
+
+def release_staging_pool():
+    """frees the staging buffers of the distributed assembly that builders left in the pool.  Collective: the other
+    ranks hold them open as peer memory, so all ranks call this together (e.g. before destroying the process group)."""
+    for key in list(_STAGE_POOL):
+        _release_pool(_STAGE_POOL.pop(key))
+
+
 class nonlocalBuilder:
     """nonlocalBuilder(dm, kernel, params={}, zeroExterior=True, comm=None, PLogger=None, dm2=None)
 
@@ -376,7 +400,14 @@ class nonlocalBuilder:
     def _dist_state(self, world, rank, process_group, local_ptrs=None):
         """plan + staging buffers of the distributed assembly (kept between assemblies).  local_ptrs: staging pointers of
         all parts when they live in this process (tests emulate several parts on one GPU); else the buffers are
-        exchanged as CUDA IPC handles over `process_group` and written through NVLink peer memory."""
+        exchanged as CUDA IPC handles over `process_group` and written through NVLink peer memory.
+
+        The staging buffers and their peer mappings outlive the builder (module-level pool, like the device memory pool
+        of the library): a new builder on the same ranks reuses them when they are large enough on every rank (one
+        all-reduce decides), so that the IPC handshake is paid once per process group and size."""
+        import os
+        import sys
+        import time
         import torch
         import torch.distributed as dist
         st = getattr(self, '_dist', None)
@@ -385,55 +416,79 @@ class nonlocalBuilder:
         self.releaseScratch()
         L = _lib.lib()
         prob = self.problem
+        t0 = time.perf_counter()
         nrows, nstage = ctypes.c_int32(0), ctypes.c_int64(0)
         _lib.check(L.pnb_dist_plan(prob.handle, world, rank, ctypes.byref(nrows), ctypes.byref(nstage)))
         rows = np.empty(nrows.value, dtype=np.int32)
         _lib.check(L.pnb_dist_rows(prob.handle, rows.ctypes.data))
-        st = dict(key=(world, rank), rows=rows, nstage=int(nstage.value), own=None, opened=[], ptrs=None, all_rows=None)
+        t1 = time.perf_counter()
+        st = dict(key=(world, rank), rows=rows, nstage=int(nstage.value), pool=None, ptrs=None, all_rows=None)
         if local_ptrs is not None:
             st['ptrs'] = list(local_ptrs)
-        else:
+        elif world == 1:
             own = ctypes.c_void_p()
             _lib.check(L.pnb_device_alloc(prob.device, 8*max(st['nstage'], 1), ctypes.byref(own)))
-            st['own'] = own
-            ptrs = [None]*world
-            ptrs[rank] = own.value
-            if world > 1:
+            st['pool'] = dict(own=own, opened=[], ptrs=[own.value], capacity=st['nstage'], device=prob.device, private=True)
+            st['ptrs'] = [own.value]
+            st['all_rows'] = [rows]
+        else:
+            dev = torch.device('cuda', prob.device)
+            key = (id(process_group) if process_group is not None else 0, world, rank, prob.device)
+            pool = _STAGE_POOL.get(key)
+            ok = torch.tensor([1 if (pool is not None and pool['capacity'] >= st['nstage']) else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 0:
+                if pool is not None:
+                    _release_pool(pool)
+                own = ctypes.c_void_p()
+                _lib.check(L.pnb_device_alloc(prob.device, 8*max(st['nstage'], 1), ctypes.byref(own)))
                 h = (ctypes.c_ubyte*64)()
                 _lib.check(L.pnb_ipc_export(prob.device, own, h))
-                handles = [None]*world
-                dist.all_gather_object(handles, bytes(h), group=process_group)
-                for r, hb in enumerate(handles):
+                mine = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(dev)
+                allh = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(allh, mine, group=process_group)
+                allh = allh.cpu().numpy()
+                ptrs = [None]*world
+                ptrs[rank] = own.value
+                opened = []
+                for r in range(world):
                     if r == rank:
                         continue
                     q = ctypes.c_void_p()
-                    _lib.check(L.pnb_ipc_import(prob.device, (ctypes.c_ubyte*64).from_buffer_copy(hb), ctypes.byref(q)))
-                    st['opened'].append(q)
+                    _lib.check(L.pnb_ipc_import(prob.device, (ctypes.c_ubyte*64).from_buffer_copy(allh[r].tobytes()), ctypes.byref(q)))
+                    opened.append(q)
                     ptrs[r] = q.value
-                all_rows = [None]*world
-                dist.all_gather_object(all_rows, rows, group=process_group)
-                st['all_rows'] = all_rows
-            else:
-                st['all_rows'] = [rows]
-            st['ptrs'] = ptrs
+                pool = dict(own=own, opened=opened, ptrs=ptrs, capacity=st['nstage'], device=prob.device, private=False)
+                _STAGE_POOL[key] = pool
+            st['pool'] = pool
+            st['ptrs'] = pool['ptrs']
+            # rows of all parts (layout of the all-gather in the distributed matvec): counts, then padded row lists
+            cnt = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+            cnts = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(cnts, cnt, group=process_group)
+            cnts = cnts.cpu().numpy()
+            mx = int(cnts.max())
+            mine = torch.zeros(max(mx, 1), dtype=torch.int32, device=dev)
+            if rows.shape[0]:
+                mine[:rows.shape[0]] = torch.from_numpy(rows).to(dev)
+            allr = torch.empty((world, max(mx, 1)), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(allr, mine, group=process_group)
+            allr = allr.cpu().numpy()
+            st['all_rows'] = [allr[r, :int(cnts[r])].copy() for r in range(world)]
+        if os.environ.get('PNB_BENCH_VERBOSE') and rank == 0:
+            print('dist state: plan %.1f ms, staging + handshake %.1f ms' % ((t1-t0)*1e3, (time.perf_counter()-t1)*1e3), file=sys.stderr)
         self._dist = st
         return st
 
     def releaseScratch(self):
-        """frees the staging buffer that the distributed assembly keeps between calls (collective: the other ranks hold
-        it open as peer memory, so all ranks release together)"""
+        """drops the distributed-assembly state of this builder.  Staging buffers shared through peer memory stay in the
+        module-level pool (release_staging_pool() frees them, collectively); a private buffer (one part) is freed."""
         st = getattr(self, '_dist', None)
         self._dist = None
-        if st is None:
+        if st is None or st['pool'] is None:
             return
-        L = _lib.lib()
-        dev = self.problem.device
-        for q in st['opened']:
-            L.pnb_ipc_close(dev, q)
-        if st['own'] is not None:
-            import torch
-            torch.cuda.synchronize(dev)
-            L.pnb_device_free(dev, st['own'])
+        if st['pool'].get('private'):
+            _release_pool(st['pool'])
 
     def getDenseDistributed(self, process_group=None, out=None):
         """getDense() sharded over the ranks of `process_group` (one process per GPU).

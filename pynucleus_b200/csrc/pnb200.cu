@@ -1055,7 +1055,9 @@ template <int DIM, bool NEAR> struct TileSmem {
 // and the caller repeats the selection with the reference's exact double arithmetic.
 __device__ __forceinline__ int fast_order_2d(double d2, float lh1, float lh2, float ah1, float ah2, float cf, float sf)
 {
-    const float MARGIN = 2e-3f;
+    // error of the FP32 evaluation: ~1e-6 absolute in the logarithms and 6e-8 relative in the divisions, numerators up to
+    // ~20 over denominators >= 0.4 -> below 1e-4; values closer than MARGIN to an integer are re-decided in FP64
+    const float MARGIN = 4e-4f;
     const float Ld = 0.5f * __logf((float)d2);
     const float l1 = Ld - lh1, l2 = Ld - lh2;
     const float m = fmaxf(ah1, ah2);
@@ -1534,7 +1536,9 @@ __global__ void compact_units_kernel(TileSched S)
 // handed to ceil() is within the error bound of an integer (the caller then repeats it in double precision)
 __device__ __forceinline__ int fast_order_boundary_2d(double d2, float lh1, float lh2, float ah1, float ah2, float cb, float sf)
 {
-    const float MARGIN = 2e-3f;
+    // error of the FP32 evaluation: ~1e-6 absolute in the logarithms and 6e-8 relative in the divisions, numerators up to
+    // ~20 over denominators >= 0.4 -> below 1e-4; values closer than MARGIN to an integer are re-decided in FP64
+    const float MARGIN = 4e-4f;
     const float Ld = 0.5f * __logf((float)d2);
     const float l1 = fmaxf(Ld - lh1, 0.f), l2 = fmaxf(Ld - lh2, 0.f);
     const float m = fmaxf(ah1, ah2);

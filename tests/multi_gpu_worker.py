@@ -45,6 +45,7 @@ def main():
     dist.barrier()
     if rank == 0:
         print('OK', dm.num_dofs, its)
+    pb.release_staging_pool()
     dist.destroy_process_group()
 
 
