@@ -145,6 +145,11 @@ int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm, const pnb
 int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules);
 void pnb_problem_destroy(pnb_problem *p);
 
+/* Sparsity pattern of nonlocalBuilder.getDense(trySparsification=True) (nonlocalAssembly_{SCALAR}.pxi:1293-1332): byte
+ * mask (device memory, num_dofs x num_dofs, leading dimension ld) with a one for every pair of DoFs of every cell pair
+ * that getPanelType does not ignore (finite horizon: pairs within reach of each other). */
+int pnb_sparsity_mask(pnb_problem *p, unsigned char *device_mask, int64_t ld);
+
 /* Assembly path of whole 2D operators with an infinite horizon: 0 (default) the cell-group kernels, 1 the DoF-tile
  * kernels that also serve 1D problems, row blocks and finite horizons.  Both produce the same operator (summation
  * order differs); the parity tests compare them. */

@@ -108,3 +108,30 @@ if __name__ == '__main__':
     case(2, 3, 'constant', 0., 0.7, 'finite_disc_constant_r3')
     case(2, 3, 'inverseDistance', 0., 0.7, 'finite_disc_invdist_r3')
     case(2, 4, 'fractional', 0.4, 0.45, 'finite_disc_frac0.4_r4', max_cut_pairs=40)
+
+
+def sparsified_case(dim, noRef, ktype, s, horizon, name):
+    """getDense(trySparsification=True) (nonlocalAssembly_{SCALAR}.pxi:1287-1348): symmetric sparse (SSS) operator whose
+    pattern holds every DoF pair of the cell pairs that are not ignored"""
+    mesh = simpleInterval(-1, 1) if dim == 1 else uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    kernel = make_kernel(dim, ktype, s, horizon)
+    params = {'target_order': 0.5} if dim == 2 else {}
+    A = nonlocalBuilder(dm, kernel, params).getDense(trySparsification=True)
+    out = dict(vertices=np.array(mesh.vertices), cells=np.array(mesh.cells), dofs=np.array(dm.dofs), num_dofs=dm.num_dofs,
+               kernel_type=ktype, s=s, horizon=horizon, target_order=0.5, operator_type=type(A).__name__,
+               indptr=np.array(A.indptr), indices=np.array(A.indices), data=np.array(A.data), diagonal=np.array(A.diagonal),
+               volume=mesh.volume)
+    if dim == 2:
+        out['boundaryEdges'] = np.array(mesh.boundaryEdges)
+    else:
+        out['boundaryVertices'] = np.array(mesh.boundaryVertices)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, type(A).__name__, A.shape, 'nnz', A.nnz)
+
+
+if __name__ == '__main__' and os.environ.get('SPARSIFIED', '1') == '1':
+    sparsified_case(2, 4, 'fractional', 0.4, 0.3, 'sparsified_disc_frac0.4_r4')
+    sparsified_case(1, 6, 'constant', 0., 0.25, 'sparsified_interval_constant_r6')

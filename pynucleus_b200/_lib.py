@@ -56,7 +56,7 @@ EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_cre
            'pnb_release_cached_memory', 'pnb_dense_kernel_timings', 'pnb_dist_plan', 'pnb_dist_rows', 'pnb_dist_eval',
            'pnb_dist_status', 'pnb_dist_apply', 'pnb_device_alloc', 'pnb_device_free', 'pnb_ipc_export', 'pnb_ipc_import',
            'pnb_ipc_close',
-           'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths', 'pnb_problem_set_path']
+           'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths', 'pnb_problem_set_path', 'pnb_sparsity_mask']
 
 _LIB = None
 
@@ -82,6 +82,7 @@ def lib():
         L.pnb_problem_set_rules.argtypes = [ctypes.c_void_p, ctypes.POINTER(pnb_rules_t)]
         L.pnb_problem_destroy.argtypes = [ctypes.c_void_p]
         L.pnb_problem_set_path.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.pnb_sparsity_mask.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         L.pnb_problem_destroy.restype = None
         L.pnb_max_order.argtypes = [ctypes.c_void_p, ctypes.c_int, c_int32_p]
         L.pnb_classify_pairs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,

@@ -269,6 +269,8 @@ class nonlocalBuilder:
         import torch
         if self._classes is not None:
             return self._getDenseClasses(out)
+        if trySparsification and self._sparsify():
+            return self._getSparsified()
         N = self._dm_assembly.num_dofs
         if N == 0:
             # no unknowns (e.g. a one-cell interval): empty operator, like the reference
@@ -292,6 +294,35 @@ class nonlocalBuilder:
             n1 = self.dm.num_dofs
             return Dense_LinearOperator(A[:n1, n1:].contiguous(), prob.device)
         return Dense_LinearOperator(A, prob.device)
+
+    def _sparsify(self, threshold=0.8):
+        """the reference's criterion for assembling into a sparse operator (nonlocalAssembly_{SCALAR}.pxi:1287-1292)"""
+        mesh = self.mesh
+        return (self.comm is None and not self.zeroExterior and self.dm2 is None and self.kernel.finiteHorizon
+                and self.dm.num_dofs > 0
+                and float(np.sum(mesh.volVector))*(1.-threshold) > self.kernel.horizonValue**mesh.dim)
+
+    def _getSparsified(self):
+        """getDense(trySparsification=True) for a horizon that is small against the domain: symmetric sparse operator over
+        the reference's pattern (every DoF pair of the cell pairs that are not ignored, :1293-1332).  The values are those
+        of the dense device assembly, gathered at the pattern."""
+        import torch
+        from .linear_operators import SSS_LinearOperator
+        N = self.dm.num_dofs
+        prob = self.problem
+        dev = torch.device('cuda', prob.device)
+        A = self.getDense().device_data
+        mask = torch.empty((N, N), dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().pnb_sparsity_mask(prob.handle, mask.data_ptr(), mask.stride(0)))
+        # The reference registers (I,J), (J,I) and (I,I) in the pattern it hands to the SSS operator (addToSparsityElemElemSym,
+        # :185-202) and only ever adds to the entries below the diagonal (SSS addToEntry): the stored pattern is the full
+        # one, with zeros on and above the diagonal.  Reproduced as is, so that indptr / indices / data are interchangeable.
+        idx = mask.nonzero()           # row-major: rows ascending, columns ascending inside a row
+        counts = torch.bincount(idx[:, 0], minlength=N)
+        indptr = torch.zeros(N+1, dtype=torch.int32, device=dev)
+        indptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        vals = torch.where(idx[:, 1] < idx[:, 0], A[idx[:, 0], idx[:, 1]], torch.zeros((), dtype=A.dtype, device=dev))
+        return SSS_LinearOperator(indptr, idx[:, 1].to(torch.int32).contiguous(), vals.contiguous(), torch.diagonal(A).clone())
 
     def _getDenseClasses(self, out=None):
         """piecewise constant variable order: sum over the classes of cell pairs, each assembled by the constant-order

@@ -827,6 +827,45 @@ extern "C" int pnb_max_order(pnb_problem *p, int zero_exterior, int32_t *max_ord
     return 0;
 }
 
+// sparsity pattern of getDense(trySparsification=True) (nonlocalAssembly_{SCALAR}.pxi:1293-1332): every pair of dofs of
+// every cell pair that is not ignored.  One thread per first cell; the stores of a one are idempotent.
+__global__ void sparsity_mask_kernel(DProblem P, unsigned char *mask, int64_t ld)
+{
+    const int c1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c1 >= P.nc) return;
+    const int nvc = P.dim + 1;
+    int d1[3], p1[3], p2[3];
+    bool any1 = false;
+    for (int m = 0; m < nvc; m++) { d1[m] = P.dofs[(size_t)c1 * nvc + m]; any1 |= d1[m] >= 0; }
+    for (int c2 = c1; c2 < P.nc; c2++) {
+        int d2[3];
+        bool any2 = false;
+        for (int m = 0; m < nvc; m++) { d2[m] = P.dofs[(size_t)c2 * nvc + m]; any2 |= d2[m] >= 0; }
+        if (!any1 && !any2) continue;
+        if (panel_interior(P, c1, c2, p1, p2) == PNB_IGNORED_PANEL) continue;
+        for (int a = 0; a < 2 * nvc; a++) {
+            const int I = a < nvc ? d1[a] : d2[a - nvc];
+            if (I < 0) continue;
+            for (int b = 0; b < 2 * nvc; b++) {
+                const int J = b < nvc ? d1[b] : d2[b - nvc];
+                if (J >= 0) mask[(size_t)I * ld + J] = 1;
+            }
+        }
+    }
+}
+
+extern "C" int pnb_sparsity_mask(pnb_problem *p, unsigned char *dmask, int64_t ld)
+{
+    if (!p || !dmask) return fail(PNB_ERR_ARG, "null argument");
+    if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
+    ON_DEVICE(p->device);
+    CK(cudaMemset2D(dmask, (size_t)ld, 0, (size_t)p->N, (size_t)p->N));
+    sparsity_mask_kernel<<<(p->nc + 127) / 128, 128>>>(p->P, dmask, ld);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
 extern "C" int pnb_panel_histogram(pnb_problem *p, int64_t *hist)
 {
     if (!p || !hist) return fail(PNB_ERR_ARG, "null argument");

@@ -166,3 +166,69 @@ class diagonalOperator:
 
     def getMemorySize(self):
         return self.data.nbytes
+
+
+class SSS_LinearOperator:
+    """symmetric sparse operator in the reference's SSS layout (base/PyNucleus_base/SSS_LinearOperator_{SCALAR}.pxi):
+    CSR arrays (`indptr`, `indices`, `data`, column indices ascending) whose entries below the diagonal carry the
+    operator, plus `diagonal`; y = L x + L^T x + diagonal * x.  The arrays live on the device; the product runs as two
+    sparse products and a diagonal scaling."""
+
+    def __init__(self, indptr, indices, data, diagonal):
+        import torch
+        self.indptr, self.indices, self._data, self._diagonal = indptr, indices, data, diagonal
+        n = diagonal.shape[0]
+        self.shape = (n, n)
+        self.num_rows = self.num_columns = n
+        self.device = diagonal.device
+        self._L = torch.sparse_csr_tensor(indptr.to(torch.int64), indices.to(torch.int64), data, size=(n, n))
+        self._LT = self._L.to_sparse_coo().t().to_sparse_csr()
+
+    @property
+    def nnz(self):
+        return int(self.indices.shape[0])
+
+    @property
+    def data(self):
+        return self._data.cpu().numpy()
+
+    @property
+    def diagonal(self):
+        return self._diagonal.cpu().numpy()
+
+    def isSparse(self):
+        return True
+
+    def getMemorySize(self):
+        return 8*(self.nnz+self.num_rows)+4*(self.nnz+self.num_rows+1)
+
+    def matvec_device(self, x, y=None):
+        import torch
+        _check_vector(x, self.num_columns, self.device, 'x')
+        r = torch.mv(self._L, x)+torch.mv(self._LT, x)+self._diagonal*x
+        if y is None:
+            return r
+        y.copy_(r)
+        return y
+
+    def matvec(self, x, y=None):
+        import torch
+        r = self.matvec_device(torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=self.device)).cpu().numpy()
+        if y is None:
+            return r
+        y[:] = r
+        return y
+
+    def dot(self, x):
+        return self.matvec(x)
+
+    def __mul__(self, x):
+        return self.matvec(x)
+
+    def toarray(self):
+        import torch
+        L = self._L.to_dense()
+        return (L+L.t()+torch.diag(self._diagonal)).cpu().numpy()
+
+    def __repr__(self):
+        return '<{}x{} SSS_LinearOperator with {} stored entries>'.format(self.num_rows, self.num_columns, self.nnz)

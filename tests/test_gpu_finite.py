@@ -140,3 +140,28 @@ def test_baseline_config2_square_finite_horizon(golden_dir, ktype):
     assert np.abs(u.cpu().numpy()-uI).max() < 1e-5*np.abs(uI).max()
     r = Ad.dot(uI)-g['b']
     assert np.abs(r).max() < 1e-4*np.abs(g['b']).max()
+
+
+@pytest.mark.parametrize('name', ['sparsified_disc_frac0.4_r4', 'sparsified_interval_constant_r6'])
+def test_try_sparsification_vs_reference(golden_dir, name):
+    """getDense(trySparsification=True), horizon small against the domain (nonlocalAssembly_{SCALAR}.pxi:1287-1348): the
+    reference returns a symmetric sparse (SSS) operator; same pattern, same entries, same products"""
+    g = load(golden_dir, name)
+    b = builder_from_golden(g)
+    A = b.getDense(trySparsification=True)
+    assert type(A).__name__ == str(g['operator_type']) == 'SSS_LinearOperator'
+    assert np.array_equal(A.indptr.cpu().numpy(), g['indptr'])
+    assert np.array_equal(A.indices.cpu().numpy(), g['indices'])
+    scale = np.abs(g['diagonal']).max()
+    assert np.abs(A.diagonal-g['diagonal']).max() < TOL*scale
+    assert np.abs(A.data-g['data']).max() < TOL*scale
+    # the sparse operator is the dense one
+    D = b.getDense().data
+    assert np.abs(A.toarray()-D).max() < 1e-15*scale
+    x = np.linspace(-1., 1., D.shape[0])
+    assert np.abs(A*x-D.dot(x)).max() < 1e-12*np.abs(D.dot(x)).max()
+    # a horizon that is not small against the domain: dense operator, as in the reference
+    import pynucleus_b200 as pb
+    dim = g['vertices'].shape[1]
+    bd = pb.nonlocalBuilder(b.dm, pb.getFractionalKernel(dim, 0.4, 1.5), {'target_order': 0.5})
+    assert type(bd.getDense(trySparsification=True)).__name__ == 'Dense_LinearOperator'
