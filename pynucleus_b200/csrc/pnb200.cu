@@ -2234,7 +2234,7 @@ static int build_near_list(pnb_problem *p)
                 hbase[key] = off;
                 if (key >= 1 && hb[key] > 0 && key <= p->P.max_order) gh->near_nmax = std::max(gh->near_nmax, p->h_reg_n[key]);
                 const int K = key >= 1 ? (key < (int)p->h_grid.size() ? p->h_grid[key].y : 1) : 1;
-                const int per = (PNB_THREADS / 32) * K;
+                const int per = (PNB_NEAR_THREADS / 32) * K;
                 for (int q = 0; q < hb[key]; q += per) chunks.push_back(make_int4(key, off + q, std::min(per, hb[key] - q), 0));
                 off += hb[key];
             }
@@ -2350,15 +2350,23 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         // the near pair list is built (first assembly only) while the f2 kernel runs; its results feed the mix kernel
         if (build_near_list(p)) return PNB_ERR_CUDA;
         if (gh->nitems > 0) {
-            const int wpb = PNB_THREADS / 32;
+            const int wpb = PNB_NEAR_THREADS / 32;
             // rule table of the largest order that has items; per warp PNB_NEAR_WARP_POINTS points
-            const size_t smem_eval = sizeof(PowTabS) + ((size_t)PNB_DER2 * gh->near_nmax + (size_t)wpb * PNB_NEAR_WARP_POINTS) * sizeof(double2);
+            // two CTAs per SM: the table holds at most the nodes that fit beside the power table and the warp buffers
+            int smem_sm = 0;
+            cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device);
+            if (smem_sm <= 0) smem_sm = 228 * 1024;
+            const size_t fixed = sizeof(PowTabS) + (size_t)wpb * PNB_NEAR_WARP_POINTS * sizeof(double2);
+            const size_t per_cta = (size_t)smem_sm / 2 - 1024 - 256;
+            const int fit = per_cta > fixed ? (int)((per_cta - fixed) / (PNB_DER2 * sizeof(double2))) : 0;
+            const int der_nodes = std::max(1, std::min(gh->near_nmax, fit));
+            const size_t smem_eval = fixed + (size_t)PNB_DER2 * der_nodes * sizeof(double2);
             smem_optin(gnear_eval_kernel, p->device);
             int nsm = 148;
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
             const int grid = std::min(gh->nchunks, 2 * nsm);
-            gnear_eval_kernel<<<grid, PNB_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R,
-                                                                gh->near_nmax, PNB_NEAR_WARP_POINTS);
+            gnear_eval_kernel<<<grid, PNB_NEAR_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R,
+                                                                der_nodes, PNB_NEAR_WARP_POINTS);
             gnear_finalize_kernel<<<(gh->npairs + 255) / 256, 256>>>(p->P, G.npairs, gh->npairs, gh->d_R, gh->d_F);
             launches += 2;
         }

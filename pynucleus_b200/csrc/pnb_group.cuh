@@ -688,9 +688,17 @@ __device__ __forceinline__ void near_regular_group(const DProblem &P, const KV &
         }
 }
 
+// the same with the rule table in global memory (not inlined: one extra copy of the loop, outside the hot path's registers)
+template <class KV>
+__device__ __noinline__ void near_regular_group_global(const DProblem &P, const KV &kv, const double2 *__restrict__ der, int n, int Ka, int Kb,
+                                                       int slice, int nsl, double2 *xs, int gl, int W, bool valid, double *acc)
+{
+    near_regular_group(P, kv, der, n, Ka, Kb, slice, nsl, xs, gl, W, valid, acc);
+}
+
 // Persistent CTAs over chunks of items of one key (regular: the order; 0: singular pairs).  A chunk holds up to
 // 8 x K items, one lane group each; the derived rule table of the key is staged in shared memory.
-__global__ void __launch_bounds__(PNB_THREADS, 2)
+__global__ void __launch_bounds__(PNB_NEAR_THREADS, 2)
 gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__restrict__ items, const int *__restrict__ perm,
                   const int4 *__restrict__ chunks, int nchunks, double *__restrict__ R, int der_nodes, int warp_points)
 {
@@ -700,7 +708,7 @@ gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__rest
     double2 *der = reinterpret_cast<double2 *>(smem_raw + sizeof(PowTabS));
     // per warp: per item the vertices of the first cell and the nodes of the column slice (warp_points points)
     double2 *xsw = der + (size_t)PNB_DER2 * der_nodes + (size_t)(threadIdx.x >> 5) * warp_points;
-    powtab_stage(pw, P.pow_int, threadIdx.x, PNB_THREADS);
+    powtab_stage(pw, P.pow_int, threadIdx.x, PNB_NEAR_THREADS);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PowCtxS kv(pw, lane);
@@ -708,11 +716,15 @@ gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__rest
     for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         const int4 c = chunks[ch];
         const int key = c.x;
-        if (key >= 1 && key != staged) {
+        // rules with more nodes than the shared-memory table holds (the few highest orders) are read from global memory
+        // (L1 / L2): sizing the table for them cost the second resident CTA of every SM (ncu, round 2: 125 KB per CTA,
+        // 8 warps per SM)
+        const bool in_smem = key >= 1 && P.reg_cell[key].n <= der_nodes;
+        if (in_smem && key != staged) {
             __syncthreads();      // everybody is done with the previous table
             const int n = P.reg_cell[key].n;
             const double2 *src = reinterpret_cast<const double2 *>(P.reg_derived) + (size_t)P.reg_doff[key] * PNB_DER2;
-            for (int e = threadIdx.x; e < n * PNB_DER2; e += PNB_THREADS) der[e] = src[e];
+            for (int e = threadIdx.x; e < n * PNB_DER2; e += PNB_NEAR_THREADS) der[e] = src[e];
             staged = key;
             __syncthreads();
         }
@@ -729,7 +741,10 @@ gnear_eval_kernel(DProblem P, const int4 *__restrict__ pairs, const int2 *__rest
             const int per = (n + nsl - 1) / nsl;
             double acc[NL];
             __syncwarp();
-            near_regular_group(P, kv, der, n, pr.x, pr.y, it.y, nsl, xsw + (size_t)min(g, K - 1) * (3 + per), gl, W, valid, acc);
+            if (in_smem) near_regular_group(P, kv, der, n, pr.x, pr.y, it.y, nsl, xsw + (size_t)min(g, K - 1) * (3 + per), gl, W, valid, acc);
+            else
+                near_regular_group_global(P, kv, reinterpret_cast<const double2 *>(P.reg_derived) + (size_t)P.reg_doff[key] * PNB_DER2, n, pr.x,
+                                          pr.y, it.y, nsl, xsw + (size_t)min(g, K - 1) * (3 + per), gl, W, valid, acc);
             // fixed tree over the W lanes of the group (W need not be a power of two)
             for (int off = 16; off > 0; off >>= 1) {
                 if (off >= W) continue;
