@@ -264,6 +264,11 @@ struct pnb_problem {
     std::vector<unsigned char> h_labels;      // cell labels of piecewise variable kernels (empty: constant kernel)
     bool tiles_ready = false;
     bool finite = false;        // finite horizon: DoF-tile path only
+    cudaStream_t copy_stream = nullptr;             // device -> host copies of finished row panels
+    cudaEvent_t pev[PNB_ROW_PANELS] = {};
+    cudaEvent_t bev[2] = {};                        // surface-term kernel launched ahead of the schedule
+    bool early_boundary = false;
+    bool host_panels = false;                       // the last assembly copied its rows panel by panel
     int path = 0;               // 0: default, 1: DoF-tile path for whole 2D operators too (pnb_problem_set_path)
     int pow_eoff = 240;      // PowTab::eoff of this problem
     std::vector<double> h_centers, h_h;
@@ -443,6 +448,15 @@ extern "C" int pnb_problem_set_rules(pnb_problem *p, const pnb_rules_t *rules)
 static void destroy_group_host(pnb_problem *p);
 extern "C" void pnb_problem_destroy(pnb_problem *p)
 {
+    if (p && p->copy_stream) {
+        cudaStreamSynchronize(p->copy_stream);
+        cudaStreamDestroy(p->copy_stream);
+        p->copy_stream = nullptr;
+    }
+    if (p)
+        for (auto &e : p->pev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (p)
+        for (auto &e : p->bev) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (!p) return;
     DeviceGuard guard(p->device);
     for (void *d : p->allocs) pool_free(d);
@@ -1801,10 +1815,20 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
             // order (deterministic) almost always find a minimal colouring, which keeps the slot count of the groups
             // (shared memory per warp of the unit kernels) at its minimum
             std::vector<std::vector<int>> bestb;
+            // cells around every group-local vertex: the batches forbidden to a cell are kept per cell and updated when a
+            // neighbour is assigned (the selection scans one word per cell)
+            std::vector<int> vptr(uv.size() + 1, 0), vlist((size_t)n * 3);
+            for (int e = 0; e < n * 3; e++) vptr[lv[e] + 1]++;
+            for (size_t v = 0; v < uv.size(); v++) vptr[v + 1] += vptr[v];
+            {
+                std::vector<int> pos(vptr.begin(), vptr.end() - 1);
+                for (int e = 0; e < n * 3; e++) vlist[pos[lv[e]]++] = e / 3;
+            }
+            std::vector<unsigned long long> forb(n);
             for (int attempt = 0; attempt < 12; attempt++) {
             bcells.assign(B0, std::vector<int>());
             const int rot = (int)(((long long)attempt * 37) % std::max(n, 1));
-            std::vector<unsigned long long> vmask(uv.size(), 0ull);   // batches that hold a cell at this vertex
+            std::fill(forb.begin(), forb.end(), 0ull);
             std::vector<int> cnt(B0, 0);
             std::vector<char> done(n, 0);
             for (int it = 0; it < n; it++) {
@@ -1816,8 +1840,7 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
                 for (int k0 = 0; k0 < n; k0++) {
                     const int k = k0 + rot < n ? k0 + rot : k0 + rot - n;
                     if (done[k]) continue;
-                    const unsigned long long forb = vmask[lv[k * 3]] | vmask[lv[k * 3 + 1]] | vmask[lv[k * 3 + 2]] | full;
-                    const unsigned long long feas = ~forb & all;
+                    const unsigned long long feas = ~(forb[k] | full) & all;
                     const int nf = __builtin_popcountll(feas);
                     if (nf < bestf) { bestf = nf; best = k; bestmask = feas; if (nf == 0) break; }
                 }
@@ -1837,7 +1860,10 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
                 }
                 cnt[b]++;
                 bcells[b].push_back(order[c0 + best]);
-                for (int m = 0; m < 3; m++) vmask[lv[best * 3 + m]] |= 1ull << b;
+                for (int m = 0; m < 3; m++) {
+                    const int v = lv[best * 3 + m];
+                    for (int e = vptr[v]; e < vptr[v + 1]; e++) forb[vlist[e]] |= 1ull << b;
+                }
                 done[best] = 1;
             }
             if (bestb.empty() || bcells.size() < bestb.size()) bestb = bcells;
@@ -1965,6 +1991,10 @@ struct GroupHostFull : GroupHost {
     int nitems = 0, npairs = 0, nchunks = 0;
     int near_nmax = 1;                      // largest node count of a regular rule with near items
     int mix_warps = PNB_MW_MAX;             // warps per CTA of gmix_kernel (what fits into shared memory)
+    // row panels: the unit lists are ordered by the first panel of rows (by dof index) that a unit touches, so that the rows
+    // of panel k are final once the units of the panels <= k are done (their copy to the host overlaps the later panels)
+    int npanels = 1, panel_tiles = 0;       // panel = panel_tiles row tiles of 32 rows
+    std::vector<int> f2_pbeg, mix_pbeg;     // npanels + 1: list positions
     void *mix_scratch = nullptr;            // unit blocks of the resident CTAs of gmix_kernel
     size_t mix_scratch_bytes = 0;
     bool near_ready = false;
@@ -2031,7 +2061,7 @@ static int build_group_schedule(pnb_problem *p)
             }
             rc |= upload(p, aptr.data(), aptr.size(), &G.adjptr);
             rc |= upload(p, alist.data(), alist.size(), &G.adj);
-            rc |= dalloc(p, 4, &G.counters_i);
+            rc |= dalloc(p, 2 * PNB_ROW_PANELS + 2, &G.counters_i);
         }
         if (rc) return PNB_ERR_CUDA;
         G.err = p->S.err;
@@ -2082,7 +2112,18 @@ static int build_group_schedule(pnb_problem *p)
     const bool far_2 = far_top >= 2;
     const int ncol = gg.ncolors;
     gh->nphase = ncol * ncol;
-    std::vector<std::vector<GUnit>> f2(gh->nphase), mix(gh->nphase);
+    // first row panel touched by the dofs of every group
+    const int NP = p->dist ? 1 : PNB_ROW_PANELS;
+    const int ntile32 = std::max(1, (p->N + 31) / 32);
+    gh->panel_tiles = (ntile32 + NP - 1) / NP;
+    gh->npanels = (ntile32 + gh->panel_tiles - 1) / gh->panel_tiles;
+    std::vector<int> gpanel(gg.ngroups, 0);
+    for (int g = 0; g < gg.ngroups; g++) {
+        int mn = p->N;
+        for (int k = gg.gdptr[g]; k < gg.gdptr[g + 1]; k++) mn = std::min(mn, gg.gdofs[k]);
+        gpanel[g] = std::min(gh->npanels - 1, (mn / 32) / gh->panel_tiles);
+    }
+    std::vector<std::vector<GUnit>> f2((size_t)gh->nphase * gh->npanels), mix((size_t)gh->nphase * gh->npanels);
     gh->near_units.clear();
     int nslots = 0;
     // kind of every unit (depends on the tables)
@@ -2137,7 +2178,7 @@ static int build_group_schedule(pnb_problem *p)
             const int kind = gh->kinds[(size_t)I * gg.ngroups + J];
             if (kind < 0) continue;
             GUnit u{I, J, kind, -1};
-            const int ph = gg.color[I] * ncol + gg.color[J];
+            const int ph = std::min(gpanel[I], gpanel[J]) * gh->nphase + gg.color[I] * ncol + gg.color[J];
             if (p->dist) {
                 // the unit is evaluated by the part of its row group or of its column group, alternating
                 const int rI = gh->gr_part[I], rJ = gh->gr_part[J];
@@ -2148,11 +2189,16 @@ static int build_group_schedule(pnb_problem *p)
         }
     }
     gh->f2_units.clear(); gh->mix_units.clear();
-    for (int ph = 0; ph < gh->nphase; ph++) {
+    gh->f2_pbeg.assign(1, 0); gh->mix_pbeg.assign(1, 0);
+    for (int ph = 0; ph < gh->nphase * gh->npanels; ph++) {
         // near units first: they are the longest
         std::stable_sort(mix[ph].begin(), mix[ph].end(), [](const GUnit &a, const GUnit &b) { return a.kind > b.kind; });
         gh->f2_units.insert(gh->f2_units.end(), f2[ph].begin(), f2[ph].end());
         gh->mix_units.insert(gh->mix_units.end(), mix[ph].begin(), mix[ph].end());
+        if ((ph + 1) % gh->nphase == 0) {
+            gh->f2_pbeg.push_back((int)gh->f2_units.size());
+            gh->mix_pbeg.push_back((int)gh->mix_units.size());
+        }
     }
     for (void *d : gh->unit_allocs) pool_free(d);
     gh->unit_allocs.clear();
@@ -2292,12 +2338,30 @@ static int build_near_list(pnb_problem *p)
 // this share of U + U^T afterwards; the caller sums the shares of all instances).  own tiles: cells whose home
 // tile is owned get their boundary terms here.
 static int build_dist_tables(pnb_problem *p);
+// host_out != nullptr (pinned host memory, leading dimension host_ld): the rows of a panel are copied to the host as soon
+// as the units that touch them are done, on a second stream, while the later panels are assembled
 static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t ld, int part = 0, int nparts = 1, int own_t0 = 0, int own_t1 = -1,
-                          bool dist = false)
+                          bool dist = false, double *host_out = nullptr, int64_t host_ld = 0)
 {
     p->part = part;
     p->nparts = nparts;
     p->dist = dist;
+    // one GPU: the surface terms do not depend on the unit schedule; their kernel runs while the host builds it
+    const bool early_boundary = !dist && nparts == 1;
+    p->early_boundary = early_boundary;
+    if (early_boundary) {
+        TileSched &S0 = p->S;
+        S0.own_t0 = own_t0;
+        S0.own_t1 = own_t1 < 0 ? S0.ntiles : own_t1;
+        S0.cell_mask = nullptr;
+        for (auto &e : p->bev) if (!e) cudaEventCreate(&e);
+        cudaMemsetAsync(S0.err, 0, 4 * sizeof(int));
+        cudaMemsetAsync(S0.counters, 0, 8 * sizeof(unsigned long long));
+        cudaMemsetAsync(S0.Dbnd, 0, (size_t)p->nc * 6 * sizeof(double));
+        cudaEventRecord(p->bev[0]);
+        if (zero_exterior && p->nb > 0) boundary_kernel<2><<<(unsigned)(((size_t)p->nc * 32 + 255) / 256), 256>>>(p->P, S0);
+        cudaEventRecord(p->bev[1]);
+    }
     if (build_group_schedule(p)) return PNB_ERR_CUDA;
     if (dist && build_dist_tables(p)) return PNB_ERR_CUDA;
     if (!dist && p->G) p->G->dist.nparts = 0;
@@ -2326,9 +2390,11 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         R.eoff = p->pow_eoff - 1023;
         R.pad = 0;
     }
-    cudaMemsetAsync(S.err, 0, 4 * sizeof(int));
-    cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
-    cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * 6 * sizeof(double));
+    if (!early_boundary) {
+        cudaMemsetAsync(S.err, 0, 4 * sizeof(int));
+        cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
+        cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * 6 * sizeof(double));
+    }
     cudaEventRecord(p->ev[0]);
     if (!dist) cudaMemset2DAsync(dA, (size_t)ld * sizeof(double), 0, (size_t)N * sizeof(double), N);
     int launches = 0;
@@ -2338,12 +2404,17 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         int nsm = 148;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
         const int nf = (int)gh->f2_units.size(), nm = (int)gh->mix_units.size();
-        cudaMemsetAsync(G.counters_i, 0, 4 * sizeof(int));
+        cudaMemsetAsync(G.counters_i, 0, (2 * PNB_ROW_PANELS + 2) * sizeof(int));
         cudaMemsetAsync(G.done, 0, std::max<size_t>((size_t)nf + nm, 1) * sizeof(int));
         for (auto &e : p->kev) if (!e) cudaEventCreate(&e);
         cudaEventRecord(p->kev[0]);
-        if (nf > 0) {
-            gf2_kernel<<<std::min(nf, 2 * nsm), PNB_F2T, gh->smem_f2>>>(p->P, G, gh->d_f2, nf, dA, ld, R);
+        // device output: one launch per list.  Host output: the order-2 units of the first panel, the near evaluator, then
+        // panel by panel (order-2 units, other units, symmetrisation of the panel's rows, copy on the second stream)
+        const bool panels = host_out != nullptr && !dist && gh->npanels > 1;
+        p->host_panels = panels;
+        const int f2_first_end = panels ? gh->f2_pbeg[1] : nf;
+        if (f2_first_end > 0) {
+            gf2_kernel<<<std::min(f2_first_end, 2 * nsm), PNB_F2T, gh->smem_f2>>>(p->P, G, gh->d_f2, 0, f2_first_end, G.counters_i, dA, ld, R);
             launches++;
         }
         cudaEventRecord(p->kev[1]);
@@ -2382,20 +2453,50 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
                 CK(pool_malloc(&gh->mix_scratch, need));
                 gh->mix_scratch_bytes = need;
             }
-            gmix_kernel<<<ncta, gh->mix_warps * 32, gh->smem_mix>>>(p->P, G, gh->d_mix, nm, dA, ld, p->far_mask, (double *)gh->mix_scratch);
-            launches++;
+            if (!panels) {
+                gmix_kernel<<<ncta, gh->mix_warps * 32, gh->smem_mix>>>(p->P, G, gh->d_mix, 0, nm, G.counters_i + 1, dA, ld, p->far_mask,
+                                                                        (double *)gh->mix_scratch);
+                launches++;
+            }
+        }
+        if (panels) {
+            if (!p->copy_stream) CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+            for (auto &e : p->pev) if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            const unsigned nt = (unsigned)((N + 31) / 32);
+            for (int k = 0; k < gh->npanels; k++) {
+                const int f0 = gh->f2_pbeg[k], f1 = gh->f2_pbeg[k + 1], m0 = gh->mix_pbeg[k], m1 = gh->mix_pbeg[k + 1];
+                if (k > 0 && f1 > f0) {
+                    gf2_kernel<<<std::min(f1 - f0, 2 * nsm), PNB_F2T, gh->smem_f2>>>(p->P, G, gh->d_f2, f0, f1, G.counters_i + 2 * k, dA, ld, R);
+                    launches++;
+                }
+                if (m1 > m0) {
+                    gmix_kernel<<<std::min(m1 - m0, nsm), gh->mix_warps * 32, gh->smem_mix>>>(p->P, G, gh->d_mix, m0, m1, G.counters_i + 2 * k + 1, dA,
+                                                                                              ld, p->far_mask, (double *)gh->mix_scratch);
+                    launches++;
+                }
+                // rows of the panel: U + U^T for the tiles right of the diagonal tile (both images), final from here on
+                const int t0 = k * gh->panel_tiles, t1 = std::min((int)nt, t0 + gh->panel_tiles);
+                symmetrize_kernel<<<dim3(nt, (unsigned)(t1 - t0)), 256>>>(dA, ld, N, t0);
+                launches++;
+                cudaEventRecord(p->pev[k]);
+                cudaStreamWaitEvent(p->copy_stream, p->pev[k], 0);
+                const int r0 = t0 * 32, r1 = std::min(N, t1 * 32);
+                CK(cudaMemcpy2DAsync(host_out + (size_t)r0 * host_ld, (size_t)host_ld * sizeof(double), dA + (size_t)r0 * ld, (size_t)ld * sizeof(double),
+                                     (size_t)N * sizeof(double), (size_t)(r1 - r0), cudaMemcpyDeviceToHost, p->copy_stream));
+            }
         }
     }
     cudaEventRecord(p->kev[3]);
-    if (!dist) {
+    const bool panels_done = p->host_panels;
+    if (!dist && !panels_done) {
         const unsigned nt = (unsigned)((N + 31) / 32);
-        symmetrize_kernel<<<dim3(nt, nt), 256>>>(dA, ld, N);
+        symmetrize_kernel<<<dim3(nt, nt), 256>>>(dA, ld, N, 0);
         launches++;
     }
     cudaEventRecord(p->kev[4]);
     cudaEventRecord(p->ev[1]);
     if (zero_exterior && p->nb > 0) {
-        boundary_kernel<2><<<(unsigned)(((size_t)nc * 32 + 255) / 256), 256>>>(p->P, S);
+        if (!early_boundary) boundary_kernel<2><<<(unsigned)(((size_t)nc * 32 + 255) / 256), 256>>>(p->P, S);
         launches++;
     }
     cudaEventRecord(p->ev[2]);
@@ -2698,9 +2799,18 @@ static int check_rows(pnb_problem *p, int32_t row_begin, int32_t row_end)
 extern "C" int pnb_row_granularity(void) { return PNB_TD; }
 
 // tile passes + boundary kernel + reduction of the cell-diagonal blocks of the owned cells
+static int dense_rows_begin_impl(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *dA, int64_t ld,
+                                 double *host_out, int64_t host_ld);
 extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *dA, int64_t ld)
 {
+    return dense_rows_begin_impl(p, zero_exterior, row_begin, row_end, dA, ld, nullptr, 0);
+}
+
+static int dense_rows_begin_impl(pnb_problem *p, int zero_exterior, int32_t row_begin, int32_t row_end, double *dA, int64_t ld,
+                                 double *host_out, int64_t host_ld)
+{
     if (!p || !dA) return fail(PNB_ERR_ARG, "null argument");
+    p->host_panels = false;
     if (!p->has_singular) return fail(PNB_ERR_ARG, "problem was created without quadrature tables");
     if (check_rows(p, row_begin, row_end)) return PNB_ERR_ARG;
     if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
@@ -2709,7 +2819,7 @@ extern "C" int pnb_dense_rows_begin(pnb_problem *p, int zero_exterior, int32_t r
     TileSched &S = p->S;
     // 2D, whole operator, infinite horizon: cell-group path (pnb_problem_set_path(p, 1) selects the DoF-tile path)
     if (p->dim == 2 && !p->finite && row_begin == 0 && row_end == p->N && p->path == 0)
-        return run_group_path(p, zero_exterior, dA, ld);
+        return run_group_path(p, zero_exterior, dA, ld, 0, 1, 0, -1, false, host_out, host_ld);
     if (build_tile_schedule(p)) return PNB_ERR_CUDA;
     S.cell_mask = nullptr;
     S.own_t0 = row_begin / PNB_TD;
@@ -2849,6 +2959,8 @@ extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row
     if (herr[1] > 0) return fail(PNB_ERR_CUDA, "internal error: a unit classified as far holds a near pair");
     float ms;
     for (int k = 0; k < 2; k++) { cudaEventElapsedTime(&ms, p->ev[k], p->ev[k + 1]); p->timings[k] = ms; }
+    if (p->early_boundary && p->bev[0] && cudaEventElapsedTime(&ms, p->bev[0], p->bev[1]) == cudaSuccess) p->timings[1] = ms;
+    p->early_boundary = false;
     cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]);
     float ms2;
     cudaEventElapsedTime(&ms2, p->ev[3], p->ev[4]);
@@ -2866,6 +2978,57 @@ extern "C" int pnb_dense_rows_end(pnb_problem *p, int32_t row_begin, int32_t row
         }
     }
     p->stats[1] = p->distinct_pairs;
+    return 0;
+}
+
+// entries of the matrix that receive cell-diagonal blocks (pairs of dofs of one cell): gathered after the scatter
+__global__ void gather_entries_kernel(const double *__restrict__ A, int64_t ld, const int2 *__restrict__ ij, int n, double *__restrict__ out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = A[(size_t)ij[e].x * ld + ij[e].y];
+}
+
+// Host output assembled panel by panel (run_group_path): the rows went to the host before the cell-diagonal blocks were
+// complete (they sum over all partner cells, i.e. are final only after the last unit).  The entries they touch -- the
+// pairs of dofs of one cell, ~7 per row -- are read back after the scatter and written over the copied values.
+static int fix_cell_block_entries(pnb_problem *p, const double *dA, int64_t ld, double *A, int64_t host_ld)
+{
+    const int nvc = p->dim + 1, nc = p->nc;
+    std::vector<int2> ij;
+    ij.reserve((size_t)nc * nvc * nvc);
+    for (int c = 0; c < nc; c++)
+        for (int a = 0; a < nvc; a++) {
+            const int I = p->h_dofs[(size_t)c * nvc + a];
+            if (I < 0) continue;
+            for (int b = 0; b < nvc; b++) {
+                const int J = p->h_dofs[(size_t)c * nvc + b];
+                if (J >= 0) ij.push_back(make_int2(I, J));
+            }
+        }
+    const int n = (int)ij.size();
+    if (n == 0) return 0;
+    int2 *dij = nullptr;
+    double *dv = nullptr;
+    CK(pool_malloc((void **)&dij, (size_t)n * sizeof(int2)));
+    CK(pool_malloc((void **)&dv, (size_t)n * sizeof(double)));
+    std::vector<double> v(n);
+    cudaError_t e = cudaMemcpy(dij, ij.data(), (size_t)n * sizeof(int2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        gather_entries_kernel<<<(n + 255) / 256, 256>>>(dA, ld, dij, n, dv);
+        e = cudaMemcpy(v.data(), dv, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    pool_free(dij);
+    pool_free(dv);
+    if (e != cudaSuccess) return fail(PNB_ERR_CUDA, std::string("cell block entries: ") + cudaGetErrorString(e));
+    // scattered writes into a large array: a few host threads (duplicates carry the same value)
+    const int nt = std::max(1, std::min(8, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&, t]() {
+            const int e0 = (int)((int64_t)n * t / nt), e1 = (int)((int64_t)n * (t + 1) / nt);
+            for (int q = e0; q < e1; q++) A[(size_t)ij[q].x * host_ld + ij[q].y] = v[q];
+        });
+    for (auto &x : th) x.join();
     return 0;
 }
 
@@ -2895,11 +3058,23 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
     const bool verbose = getenv("PNB_BENCH_VERBOSE") != nullptr;
     auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t0 = now();
-    int rc = pnb_dense_rows_begin(p, zero_exterior, 0, N, dA, dld);
+    // pinned host buffer: finished row panels are copied while the assembly continues (cell-group path)
+    bool pinned = false;
+    if (!a_on_device) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, A) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    int rc = dense_rows_begin_impl(p, zero_exterior, 0, N, dA, dld, pinned ? A : nullptr, ld);
     const double t1 = now();
     if (!rc) rc = pnb_dense_rows_end(p, 0, N, dA, dld);
     const double t2 = now();
-    if (!rc && !a_on_device) {
+    if (rc && p->host_panels && p->copy_stream) cudaStreamSynchronize(p->copy_stream);     // no copy may outlive a failed call
+    if (!rc && !a_on_device && p->host_panels) {
+        cudaError_t e = cudaStreamSynchronize(p->copy_stream);
+        if (e != cudaSuccess) rc = fail(PNB_ERR_CUDA, std::string("copy back: ") + cudaGetErrorString(e));
+        else rc = fix_cell_block_entries(p, dA, dld, A, ld);
+    } else if (!rc && !a_on_device) {
         cudaError_t e;
         if (ld == N) e = cudaMemcpy(A, dA, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost);
         else e = cudaMemcpy2D(A, (size_t)ld * sizeof(double), dA, (size_t)N * sizeof(double), (size_t)N * sizeof(double), N, cudaMemcpyDeviceToHost);

@@ -12,6 +12,7 @@
 #define PNB_TD 64             // DoFs per output tile
 #define PNB_SB 16             // sub-batch: PNB_SB x PNB_SB cell pairs
 #define PNB_THREADS 256
+#define PNB_ROW_PANELS 12      // row panels of the cell-group path (copy of finished rows overlaps the assembly)
 #define PNB_NEAR_THREADS 256    // near evaluator: two CTAs of eight warps per SM (six warps with 170 registers were measured slower)
 #define PNB_IGNORED_PANEL (-6)
 #define PNB_CUT_FLAG 4096      // added to the regular order of a pair cut by the horizon (near pass of the tile kernel)

@@ -59,7 +59,7 @@ struct GroupSched {
     const int *adj;
     const int *ticket;   // ngroups x ngroups: list position | (list << 30) of unit (I <= J), -1 = not evaluated here
     int *done;           // completion flags: list 0 (f2) at [0, nf2), list 1 (mix) at [nf2, nf2 + nmix)
-    int *counters_i;     // [0], [1]: next ticket of list 0 / 1
+    int *counters_i;     // ticket counters, one per launch: [2 * panel + list]
     int nlist0;
     int *err;
     unsigned long long *counters;
@@ -205,7 +205,8 @@ inline size_t gf2_smem_bytes(int cap, int maxld, int ldS)
 }
 
 __global__ void __launch_bounds__(PNB_F2T, 2)
-gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits, double *__restrict__ A, int64_t ld, F2Rule R)
+gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int first, int nunits, int *__restrict__ next,
+           double *__restrict__ A, int64_t ld, F2Rule R)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
@@ -228,7 +229,7 @@ gf2_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits
     const int k1 = tid >> 4, k2 = tid & 15;
     for (;;) {
     __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(G.counters_i, 1);
+    if (tid == 0) s_ticket = first + atomicAdd(next, 1);     // list positions [first, nunits) of this launch
     __syncthreads();
     const int ticket = s_ticket;
     if (ticket >= nunits) break;
@@ -936,8 +937,8 @@ inline size_t gnear_list_smem_bytes(int cap)
 //    the warps in warp order at the end of the unit.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PNB_MW_MAX * 32, 1)
-gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunits, double *__restrict__ A, int64_t ld, int far_mask,
-            double *__restrict__ scratch)
+gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int first, int nunits, int *__restrict__ next,
+            double *__restrict__ A, int64_t ld, int far_mask, double *__restrict__ scratch)
 {
     constexpr int ND = 6, SB = PNB_SB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -978,7 +979,7 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
     const unsigned lt = (1u << lane) - 1, half = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
     for (;;) {
     __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(G.counters_i + 1, 1);
+    if (tid == 0) s_ticket = first + atomicAdd(next, 1);     // list positions [first, nunits) of this launch
     __syncthreads();
     const int ticket = s_ticket;
     if (ticket >= nunits) break;
@@ -1248,10 +1249,10 @@ gmix_kernel(DProblem P, GroupSched G, const GUnit *__restrict__ units, int nunit
 }
 
 // F = U + U^T in place, 32 x 32 tiles; bitwise symmetric by construction
-__global__ void __launch_bounds__(256) symmetrize_kernel(double *A, int64_t ld, int N)
+__global__ void __launch_bounds__(256) symmetrize_kernel(double *A, int64_t ld, int N, int row_tile0)
 {
     __shared__ double T1[32][33], T2[32][33];
-    const int r = blockIdx.y, c = blockIdx.x;
+    const int r = row_tile0 + blockIdx.y, c = blockIdx.x;
     if (r > c) return;
     const int r0 = r * 32, c0 = c * 32;
     for (int e = threadIdx.x; e < 32 * 32; e += 256) {
