@@ -122,6 +122,27 @@ def test_dense_host_entry_point(golden_dir):
     assert np.array_equal(A, b.getDense().data)
 
 
+def test_order_retry_extends_the_tables(golden_dir):
+    """tables supplied up to an order below what the mesh needs: the library reports PNB_ERR_ORDER, the builder extends the
+    tables to pnb_max_order (the reference grows its rule cache lazily, addQuadRule) and the result is unchanged;
+    device, pageable-host and pinned-host outputs"""
+    import torch
+    g = load(golden_dir, 'disc_s0.75_r3')
+    ref = builder_from_golden(g).getDense().data
+    b = builder_from_golden(g)
+    b.params['max_regular_order'] = 3
+    assert b.problem.max_order == 3
+    A = b.getDense().data
+    assert b.problem.max_order > 3 and np.array_equal(A, ref)
+    b2 = builder_from_golden(g)
+    b2.params['max_regular_order'] = 3
+    assert np.array_equal(b2.getDenseHost(), ref)
+    b3 = builder_from_golden(g)
+    b3.params['max_regular_order'] = 3
+    pinned = torch.empty(ref.shape, dtype=torch.float64).pin_memory()
+    assert entry_err(b3.getDenseHost(out=pinned.numpy()), ref) < 1e-14
+
+
 def test_dense_host_pinned_buffer_overlapped_copy():
     """pinned host buffer: the rows are copied panel by panel while the assembly continues, the entries that receive
     cell-diagonal blocks are written last -- the result is bitwise the device operator"""
