@@ -438,16 +438,27 @@ def run_cuda(args):
         v['frac'] = v['tflops']/peak if peak else None
     dominant = max(('gmix_kernel', 'gnear_eval_kernel', 'gf2_kernel'), key=lambda k: per_kernel[k]['ms'])
     achieved = per_kernel[dominant]['tflops']
+    # dram bytes per launch of the dominant kernel: from the committed ncu capture of the same kernel on the same mesh
+    # (not measurable inside a timed run); None when the summary is absent or for another workload
+    traffic, traffic_src = None, 'no ncu summary for this workload'
+    try:
+        if args.workload == 'disc20k' and world == 1:
+            with open(os.path.join(ROOT, 'profiles', 'r2_final_ncu_summary.json')) as f:
+                summ = json.load(f)
+            traffic = float(summ[dominant]['dram_bytes'])
+            traffic_src = 'profiles/r2_final_ncu_summary.json ({})'.format(summ.get('_source', 'ncu --set full'))
+    except Exception:
+        pass
     roofline = {'bound': 'fp64', 'kernel': dominant, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': achieved/peak if peak else None,
-                'traffic': None,
+                'traffic': traffic,
                 'kernels': per_kernel,
                 'frac_all_pair_kernels': per_kernel['all pair kernels']['tflops']/peak if peak else None,
                 'note': 'algorithmic flops (SURVEY 8d: 70/node-pair regular, 49/61/76 singular; pow excluded) of the cell pairs '
                         'the kernel evaluates / its device time (CUDA events around the launch inside the C call, averaged '
                         'over the timed steps); peak = DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no '
-                        'FP64 figure); traffic: not measurable in-run (FP64-bound kernels; dram bytes per launch are in the '
-                        'ncu captures under profiles/); pow evaluations/s over all pair kernels = {:.3e}; evaluated/distinct '
+                        'FP64 figure); traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, '
+                        'taken from ' + traffic_src + ' (algorithmic output of the whole assembly: 8 N^2 bytes); pow evaluations/s over all pair kernels = {:.3e}; evaluated/distinct '
                         'pairs {:.3f}; pair-kernel share of step {:.3f}'.format(
                             pows_all*share/t_all, st['evaluated_pairs']/max(st['distinct_pairs'], 1), t_all*1e3/ms_step)}
 

@@ -1896,7 +1896,7 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
     };
     {
         // groups are independent: a few host threads (the colouring is quadratic in the group size)
-        const int nt = std::max(1, std::min(16, std::min((int)std::thread::hardware_concurrency(), gg.ngroups / 8)));
+        const int nt = std::max(1, std::min(8, std::min((int)std::thread::hardware_concurrency(), gg.ngroups / 8)));
         std::vector<std::thread> th;
         for (int t = 0; t < nt; t++)
             th.emplace_back([&, t]() { for (int g = t; g < gg.ngroups; g += nt) do_group(g); });
