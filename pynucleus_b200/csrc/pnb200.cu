@@ -230,6 +230,7 @@ struct TileSched {
     const int *tile_ptr;    // ntiles+1
     const int *tile_cells;  // cell ids per tile, ascending
     const int *tile_loc;    // packed tile-local dof index of each vertex (8 bits each, 0xFF = not in tile)
+    const double *tile_box; // ntiles x 2 x dim: bounding box (lo, hi per coordinate) of the vertices of the tile's cells
     const int *home;        // nc: home tile of a cell
     const int *units;       // 2 x nunits (row group, col group)
     int nunits;
@@ -261,6 +262,7 @@ struct pnb_problem {
     GroupSched *G = nullptr;          // 2D cell-group path (pnb_group.cuh)
     GroupHost *gh = nullptr;
     std::vector<int> h_cells, h_dofs, h_home; // host copies for the lazily built schedules
+    std::vector<double> h_vertices;           // mesh vertices (tile bounding boxes of the finite-horizon path)
     std::vector<unsigned char> h_labels;      // cell labels of piecewise variable kernels (empty: constant kernel)
     bool tiles_ready = false;
     bool finite = false;        // finite horizon: DoF-tile path only
@@ -537,6 +539,21 @@ static int build_tile_schedule(pnb_problem *p)
             tptr[t + 1] = (int)tlist.size();
         }
     }
+    {
+        const int dim = p->dim;
+        std::vector<double> box((size_t)S.ntiles * 2 * dim);
+        for (int t = 0; t < S.ntiles; t++) {
+            for (int l = 0; l < dim; l++) { box[((size_t)t * 2) * dim + l] = 1e300; box[((size_t)t * 2 + 1) * dim + l] = -1e300; }
+            for (int c : tcells[t])
+                for (int m = 0; m < nvc; m++)
+                    for (int l = 0; l < dim; l++) {
+                        const double v = p->h_vertices[(size_t)cells[(size_t)c * nvc + m] * dim + l];
+                        box[((size_t)t * 2) * dim + l] = std::min(box[((size_t)t * 2) * dim + l], v);
+                        box[((size_t)t * 2 + 1) * dim + l] = std::max(box[((size_t)t * 2 + 1) * dim + l], v);
+                    }
+        }
+        if (upload(p, box.data(), box.size(), &S.tile_box)) return PNB_ERR_CUDA;
+    }
     std::vector<int> units;
     // heavy (near-diagonal) units first
     for (int dg = 0; dg < S.ngroups; dg++)
@@ -642,6 +659,7 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         }
     }
     p->h_cells.assign(mesh->cells, mesh->cells + (size_t)nc * nvc);
+    p->h_vertices.assign(mesh->vertices, mesh->vertices + (size_t)mesh->num_vertices * dim);
     p->h_dofs.assign(dm->dofs, dm->dofs + (size_t)nc * nvc);
     if (dim == 2) {
         p->h_centers = centers;
@@ -1213,6 +1231,32 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
     for (int rt = gr * S.G; rt < min((gr + 1) * S.G, S.ntiles); rt++)
         for (int ct = max(gc * S.G, rt); ct < min((gc + 1) * S.G, S.ntiles); ct++) {
             if (NEAR && !S.tileflag[(size_t)rt * S.ntiles + ct]) continue;
+            if (finite && rt != ct) {
+                // finite horizon: tiles whose bounding boxes are further apart than the horizon hold only REMOTE pairs
+                double g2 = 0.;
+                for (int l = 0; l < DIM; l++) {
+                    const double lo1 = S.tile_box[((size_t)rt * 2) * DIM + l], hi1 = S.tile_box[((size_t)rt * 2 + 1) * DIM + l];
+                    const double lo2 = S.tile_box[((size_t)ct * 2) * DIM + l], hi2 = S.tile_box[((size_t)ct * 2 + 1) * DIM + l];
+                    const double g = fmax(0., fmax(lo2 - hi1, lo1 - hi2));
+                    g2 += g * g;
+                }
+                // strict margin: a pair is REMOTE when its smallest vertex distance is >= the horizon
+                if (g2 > P.horizon2 * (1. + 1e-12)) {
+                    // the far pass defines every entry of the matrix: a skipped tile (and its mirror image) is zero
+                    if (!NEAR) {
+                        const bool own_r = rt >= S.own_t0 && rt < S.own_t1, own_c = ct >= S.own_t0 && ct < S.own_t1;
+                        const int r0 = rt * TD, c0 = ct * TD;
+                        for (int e = tid; e < TD * TD; e += PNB_THREADS) {
+                            const int a = e / TD, b = e - a * TD;
+                            if (r0 + a < P.N && c0 + b < P.N) {
+                                if (own_r) A[(size_t)(r0 + a - S.own_t0 * TD) * ld + c0 + b] = 0.;
+                                if (own_c) A[(size_t)(c0 + b - S.own_t0 * TD) * ld + r0 + a] = 0.;
+                            }
+                        }
+                    }
+                    continue;
+                }
+            }
             const bool diag = rt == ct;
             // row-block ownership: the direct image belongs to the owner of row tile rt, the mirror image to the
             // owner of row tile ct; tiles that touch no owned row are not computed by this GPU
