@@ -59,6 +59,17 @@ typedef struct {
     double diam;             /* mesh.diam; H0 = diam/sqrt(8), nonlocalOperator_{SCALAR}.pxi:435 */
     int32_t num_bfacets;
     const int32_t *bfacets;  /* host, num_bfacets x dim: boundary vertices (1D) / oriented boundary edges (2D) */
+    /* Batch of independent sub-meshes in one problem (H2 near field: one block per near cluster pair,
+     * assembleClusters, nonlocalAssembly_{SCALAR}.pxi:1663-1889).  num_blocks > 0: the cells, DoFs and boundary facets
+     * of block k are the contiguous ranges [block_*_ptr[k], block_*_ptr[k+1]); cells of different blocks never
+     * interact, every block has its own surface terms.  DoF ranges start at multiples of pnb_block_alignment()
+     * (unused DoFs pad the range).  pnb_dense_assemble then writes, instead of one num_dofs x num_dofs matrix, the
+     * dense operators of the blocks one after the other (block k: n_k x n_k doubles, row-major, n_k = its DoF range,
+     * at offset sum_{j<k} n_j^2; device output only, ld is ignored).  num_blocks == 0: one mesh (default). */
+    int32_t num_blocks;
+    const int32_t *block_cell_ptr;   /* host, num_blocks+1 */
+    const int32_t *block_dof_ptr;    /* host, num_blocks+1 */
+    const int32_t *block_facet_ptr;  /* host, num_blocks+1 */
 } pnb_mesh_t;
 
 /* P1 DoFMap: dm.dofs, negative = boundary DoF (fem/PyNucleus_fem/DoFMaps.pyx:157-210) */
@@ -154,6 +165,9 @@ int pnb_sparsity_mask(pnb_problem *p, unsigned char *device_mask, int64_t ld);
  * kernels that also serve 1D problems, row blocks and finite horizons.  Both produce the same operator (summation
  * order differs); the parity tests compare them. */
 int pnb_problem_set_path(pnb_problem *p, int path);
+
+/* alignment of the DoF ranges of the blocks of a batched problem (pnb_mesh_t.num_blocks) */
+int pnb_block_alignment(void);
 
 /* Largest regular quadrature order any cell pair / cell-facet pair requests
  * (getQuadOrder, fractionalLaplacian2D.pyx:622-642,1226-1253;

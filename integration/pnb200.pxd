@@ -14,6 +14,10 @@ cdef extern from "pnb200.h":
         double diam
         int32_t num_bfacets
         const int32_t *bfacets
+        int32_t num_blocks
+        const int32_t *block_cell_ptr
+        const int32_t *block_dof_ptr
+        const int32_t *block_facet_ptr
     ctypedef struct pnb_dofmap_t:
         int32_t dofs_per_element
         int32_t num_dofs

@@ -21,7 +21,8 @@ class pnb_mesh_t(ctypes.Structure):
     _fields_ = [('dim', ctypes.c_int32), ('num_vertices', ctypes.c_int32), ('num_cells', ctypes.c_int32),
                 ('vertices', ctypes.c_void_p), ('cells', ctypes.c_void_p), ('vol', ctypes.c_void_p),
                 ('h', ctypes.c_void_p), ('diam', ctypes.c_double), ('num_bfacets', ctypes.c_int32),
-                ('bfacets', ctypes.c_void_p)]
+                ('bfacets', ctypes.c_void_p), ('num_blocks', ctypes.c_int32), ('block_cell_ptr', ctypes.c_void_p),
+                ('block_dof_ptr', ctypes.c_void_p), ('block_facet_ptr', ctypes.c_void_p)]
 
 
 class pnb_dofmap_t(ctypes.Structure):
@@ -56,7 +57,7 @@ EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_cre
            'pnb_release_cached_memory', 'pnb_dense_kernel_timings', 'pnb_dist_plan', 'pnb_dist_rows', 'pnb_dist_eval',
            'pnb_dist_status', 'pnb_dist_apply', 'pnb_device_alloc', 'pnb_device_free', 'pnb_ipc_export', 'pnb_ipc_import',
            'pnb_ipc_close',
-           'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths', 'pnb_problem_set_path', 'pnb_sparsity_mask']
+           'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths', 'pnb_problem_set_path', 'pnb_sparsity_mask', 'pnb_block_alignment']
 
 _LIB = None
 

@@ -23,7 +23,7 @@ class _Problem:
     """owner of a pnb_problem handle (device-resident mesh, DoFMap, kernel, tables)"""
 
     def __init__(self, dm, kernel, bkernel, orders, device, max_order, order_num_dofs=0, labels=None, blabels=None,
-                 pair_class=None, active_class=0, tables_from=None):
+                 pair_class=None, active_class=0, tables_from=None, blocks=None):
         mesh = dm.mesh
         self._keep = []
         self.dim = mesh.dim
@@ -39,6 +39,11 @@ class _Problem:
         m = _lib.pnb_mesh_t(mesh.dim, mesh.num_vertices, mesh.num_cells, self.vertices.ctypes.data,
                             self.cells.ctypes.data, self.vol.ctypes.data, self.h.ctypes.data, mesh.diam,
                             self.bfacets.shape[0], self.bfacets.ctypes.data)
+        if blocks is not None:
+            # batch of independent sub-meshes (H2 near field): contiguous cell / dof / facet ranges per block
+            self.blocks = [np.ascontiguousarray(b, dtype=np.int32) for b in blocks]
+            m.num_blocks = self.blocks[0].shape[0]-1
+            m.block_cell_ptr, m.block_dof_ptr, m.block_facet_ptr = (b.ctypes.data for b in self.blocks)
         d = _lib.pnb_dofmap_t(dm.dofs_per_element, dm.num_dofs, self.dofs.ctypes.data)
         k = _lib.pnb_kernel_t(kernel.kernelType, kernel.dim, kernel.sValue, kernel.scalingValue, bkernel.scalingValue,
                               kernel.singularityValue, bkernel.singularityValue,

@@ -231,6 +231,16 @@ struct TileSched {
     const int *tile_cells;  // cell ids per tile, ascending
     const int *tile_loc;    // packed tile-local dof index of each vertex (8 bits each, 0xFF = not in tile)
     const double *tile_box; // ntiles x 2 x dim: bounding box (lo, hi per coordinate) of the vertices of the tile's cells
+    // batched independent blocks (pnb_mesh_t.num_blocks > 0; nullptr otherwise): cells of different blocks never interact,
+    // the output holds one dense operator per block
+    const int *cell_block;  // nc: block of a cell
+    const int *tile_block;  // ntiles: block of a tile
+    const int *blk_tile0;   // nblocks: first tile
+    const int *blk_group0;  // nblocks: first tile group
+    const int *blk_n;       // nblocks: number of dofs (leading dimension of the block's operator)
+    const long long *blk_out;   // nblocks: offset of the block's operator in the output
+    const int *blk_fptr;    // nblocks+1: boundary facets of the block
+    int dgroups;            // first dimension of DXp / DYp (groups per block; ngroups without blocks)
     const int *home;        // nc: home tile of a cell
     const int *units;       // 2 x nunits (row group, col group)
     int nunits;
@@ -266,6 +276,10 @@ struct pnb_problem {
     std::vector<unsigned char> h_labels;      // cell labels of piecewise variable kernels (empty: constant kernel)
     bool tiles_ready = false;
     bool finite = false;        // finite horizon: DoF-tile path only
+    int nblocks = 0;            // batched independent blocks (pnb_mesh_t.num_blocks)
+    std::vector<int> h_blk_cell, h_blk_dof, h_blk_facet;    // block ranges (host)
+    std::vector<int> h_block_units;                          // unit list of the batched problem
+    long long blocks_out_doubles = 0;                        // size of the batched output
     cudaStream_t copy_stream = nullptr;             // device -> host copies of finished row panels
     cudaEvent_t pev[PNB_ROW_PANELS] = {};
     cudaEvent_t bev[2] = {};                        // surface-term kernel launched ahead of the schedule
@@ -555,6 +569,16 @@ static int build_tile_schedule(pnb_problem *p)
         if (upload(p, box.data(), box.size(), &S.tile_box)) return PNB_ERR_CUDA;
     }
     std::vector<int> units;
+    if (p->nblocks > 0) {
+        // batched blocks: the group pairs inside every block
+        const int align = S.G * TD;
+        for (int k = 0; k < p->nblocks; k++) {
+            const int g0 = p->h_blk_dof[k] / align, g1 = (p->h_blk_dof[k + 1] + align - 1) / align;
+            for (int gr = g0; gr < g1; gr++)
+                for (int gc = gr; gc < g1; gc++) { units.push_back(gr); units.push_back(gc); }
+        }
+        p->h_block_units = units;
+    } else
     // heavy (near-diagonal) units first
     for (int dg = 0; dg < S.ngroups; dg++)
         for (int gr = 0; gr + dg < S.ngroups; gr++) { units.push_back(gr); units.push_back(gr + dg); }
@@ -566,8 +590,8 @@ static int build_tile_schedule(pnb_problem *p)
     rc |= upload(p, tlist.data(), tlist.size(), &S.tile_cells);
     rc |= upload(p, tloc.data(), tloc.size(), &S.tile_loc);
     rc |= upload(p, units.data(), units.size(), &S.units);
-    rc |= dalloc(p, (size_t)S.ngroups * nc * ND, &S.DXp);
-    rc |= dalloc(p, (size_t)S.ngroups * nc * ND, &S.DYp);
+    rc |= dalloc(p, (size_t)S.dgroups * nc * ND, &S.DXp);
+    rc |= dalloc(p, (size_t)S.dgroups * nc * ND, &S.DYp);
     S.maxcells = PNB_SB;
     for (int t = 0; t < S.ntiles; t++) S.maxcells = std::max(S.maxcells, tptr[t + 1] - tptr[t]);
     rc |= dalloc(p, (size_t)S.ntiles * S.ntiles, &S.tileflag);
@@ -750,6 +774,50 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     S.ntiles = std::max(1, (N + TD - 1) / TD);
     S.G = 2;
     S.ngroups = (S.ntiles + S.G - 1) / S.G;
+    S.dgroups = S.ngroups;
+    S.cell_block = S.tile_block = S.blk_tile0 = S.blk_group0 = S.blk_n = S.blk_fptr = nullptr;
+    S.blk_out = nullptr;
+    std::vector<int> cell_block;
+    if (mesh->num_blocks > 0) {
+        // batched independent blocks: contiguous ranges of cells / dofs / boundary facets per block
+        const int nbk = mesh->num_blocks, align = S.G * TD;
+        if (!mesh->block_cell_ptr || !mesh->block_dof_ptr || !mesh->block_facet_ptr) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "block ranges missing"); }
+        p->nblocks = nbk;
+        p->h_blk_cell.assign(mesh->block_cell_ptr, mesh->block_cell_ptr + nbk + 1);
+        p->h_blk_dof.assign(mesh->block_dof_ptr, mesh->block_dof_ptr + nbk + 1);
+        p->h_blk_facet.assign(mesh->block_facet_ptr, mesh->block_facet_ptr + nbk + 1);
+        if (p->h_blk_cell[0] != 0 || p->h_blk_cell[nbk] != nc || p->h_blk_dof[0] != 0 || p->h_blk_dof[nbk] != N || p->h_blk_facet[0] != 0 ||
+            p->h_blk_facet[nbk] != nb) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "block ranges do not cover the mesh"); }
+        std::vector<int> tile_block(S.ntiles, 0), blk_tile0(nbk), blk_group0(nbk), blk_n(nbk);
+        std::vector<long long> blk_out(nbk);
+        cell_block.assign(nc, 0);
+        long long off = 0;
+        int dg = 1;
+        for (int k = 0; k < nbk; k++) {
+            const int d0 = p->h_blk_dof[k], d1 = p->h_blk_dof[k + 1];
+            if (d0 % align != 0 || d1 <= d0 || (d1 % align != 0 && k + 1 < nbk) || p->h_blk_cell[k + 1] < p->h_blk_cell[k] ||
+                p->h_blk_facet[k + 1] < p->h_blk_facet[k]) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "block dof ranges must be non-empty and start at multiples of pnb_block_alignment()"); }
+            blk_tile0[k] = d0 / TD;
+            blk_group0[k] = d0 / align;
+            blk_n[k] = d1 - d0;
+            blk_out[k] = off;
+            off += (long long)(d1 - d0) * (d1 - d0);
+            dg = std::max(dg, (d1 - d0 + align - 1) / align);
+            for (int t = d0 / TD; t < (d1 + TD - 1) / TD; t++) tile_block[t] = k;
+            for (int c = p->h_blk_cell[k]; c < p->h_blk_cell[k + 1]; c++) cell_block[c] = k;
+        }
+        p->blocks_out_doubles = off;
+        S.dgroups = dg;
+        rc |= upload(p, cell_block.data(), cell_block.size(), &S.cell_block);
+        rc |= upload(p, tile_block.data(), tile_block.size(), &S.tile_block);
+        rc |= upload(p, blk_tile0.data(), blk_tile0.size(), &S.blk_tile0);
+        rc |= upload(p, blk_group0.data(), blk_group0.size(), &S.blk_group0);
+        rc |= upload(p, blk_n.data(), blk_n.size(), &S.blk_n);
+        rc |= upload(p, blk_out.data(), blk_out.size(), &S.blk_out);
+        rc |= upload(p, p->h_blk_facet.data(), p->h_blk_facet.size(), &S.blk_fptr);
+        if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
+        p->path = 1;        // the DoF-tile kernels
+    }
     std::vector<int> home(nc);
     int64_t live = 0;
     for (int c = 0; c < nc; c++) {
@@ -759,9 +827,15 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
             if (d >= N) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "dof index out of range"); }
             if (d >= 0 && (mind < 0 || d < mind)) mind = d;
         }
-        if (mind >= 0) { home[c] = mind / TD; live++; }
-        // no dofs: spread such cells evenly; they only feed cell-diagonal blocks of other cells
-        else home[c] = (int)(((int64_t)c * S.ntiles) / std::max(nc, 1));
+        if (mind >= 0) {
+            home[c] = mind / TD; live++;
+            if (!cell_block.empty() && (mind < p->h_blk_dof[cell_block[c]] || mind >= p->h_blk_dof[cell_block[c] + 1])) {
+                pnb_problem_destroy(p);
+                return fail(PNB_ERR_ARG, "a cell refers to a dof outside its block");
+            }
+        }
+        // no dofs: spread such cells evenly (blocks: first tile of the block); they only feed cell-diagonal blocks of other cells
+        else home[c] = cell_block.empty() ? (int)(((int64_t)c * S.ntiles) / std::max(nc, 1)) : p->h_blk_dof[cell_block[c]] / TD;
     }
     // pairs c1<=c2 that the reference does not skip (at least one non-negative dof)
     {
@@ -839,9 +913,12 @@ __global__ void max_order_kernel(DProblem P, int zero_exterior, int *out, unsign
     atomicMax(out, best);
 }
 
+extern "C" int pnb_block_alignment(void) { return 2 * PNB_TD; }
+
 extern "C" int pnb_problem_set_path(pnb_problem *p, int path)
 {
     if (!p || path < 0 || path > 1) return fail(PNB_ERR_ARG, "invalid argument");
+    if (p->nblocks > 0 && path != 1) return fail(PNB_ERR_ARG, "batched blocks use the DoF-tile path");
     p->path = path;
     return 0;
 }
@@ -1174,6 +1251,18 @@ __device__ __forceinline__ void load_batch(const DProblem &P, const TileSched &S
     }
 }
 
+// address of entry (row, col) of the operator: one matrix with leading dimension ld whose first row is row tile own_t0,
+// or (batched blocks) the dense operator of the block that holds tile t
+__device__ __forceinline__ double *entry_ptr(const TileSched &S, double *A, int64_t ld, int t, int row, int col)
+{
+    if (S.tile_block) {
+        const int k = S.tile_block[t];
+        const int o = S.blk_tile0[k] * PNB_TD;
+        return A + S.blk_out[k] + (size_t)(row - o) * S.blk_n[k] + (col - o);
+    }
+    return A + (size_t)(row - S.own_t0 * PNB_TD) * ld + col;
+}
+
 // adds the NV x NV cross block X of the pair (row cell, column cell) to the tile; conflict free within a sub-batch
 template <int DIM>
 __device__ __forceinline__ void scatter_block(double (*acc)[PNB_TD + 1], int rloc, int cloc, const double *X, bool transposed)
@@ -1211,6 +1300,8 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int unit = NEAR ? S.nearunits[blockIdx.x] : blockIdx.x;
     const int gr = S.units[2 * unit], gc = S.units[2 * unit + 1];
+    // batched blocks: the cell-diagonal staging is indexed by the group inside the block
+    const int goff = S.tile_block ? S.blk_group0[S.tile_block[gr * S.G]] : 0;
     unsigned long long my_pairs = 0;
     const float cf = (float)P.c_int, sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
     const bool finite = P.horizon2 < INFINITY;
@@ -1231,6 +1322,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
     for (int rt = gr * S.G; rt < min((gr + 1) * S.G, S.ntiles); rt++)
         for (int ct = max(gc * S.G, rt); ct < min((gc + 1) * S.G, S.ntiles); ct++) {
             if (NEAR && !S.tileflag[(size_t)rt * S.ntiles + ct]) continue;
+            if (S.tile_block && S.tile_block[rt] != S.tile_block[ct]) continue;
             if (finite && rt != ct) {
                 // finite horizon: tiles whose bounding boxes are further apart than the horizon hold only REMOTE pairs
                 double g2 = 0.;
@@ -1249,8 +1341,8 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                         for (int e = tid; e < TD * TD; e += PNB_THREADS) {
                             const int a = e / TD, b = e - a * TD;
                             if (r0 + a < P.N && c0 + b < P.N) {
-                                if (own_r) A[(size_t)(r0 + a - S.own_t0 * TD) * ld + c0 + b] = 0.;
-                                if (own_c) A[(size_t)(c0 + b - S.own_t0 * TD) * ld + r0 + a] = 0.;
+                                if (own_r) *entry_ptr(S, A, ld, rt, r0 + a, c0 + b) = 0.;
+                                if (own_c) *entry_ptr(S, A, ld, rt, c0 + b, r0 + a) = 0.;
                             }
                         }
                     }
@@ -1562,7 +1654,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
             for (int e = tid; e < TD * TD; e += PNB_THREADS) {
                 const int a = e / TD, b = e - a * TD;
                 if (own_r && r0 + a < P.N && c0 + b < P.N) {
-                    double *dst = &A[(size_t)(r0 + a - S.own_t0 * TD) * ld + c0 + b];
+                    double *dst = entry_ptr(S, A, ld, rt, r0 + a, c0 + b);
                     // diagonal tiles: acc[a][b] and acc[b][a] hold the same terms summed in different orders;
                     // their mean is bitwise symmetric (and deterministic)
                     const double v = diag ? 0.5 * (sm.acc[a][b] + sm.acc[b][a]) : sm.acc[a][b];
@@ -1573,17 +1665,17 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                 for (int e = tid; e < TD * TD; e += PNB_THREADS) {
                     const int b = e / TD, a = e - b * TD;
                     if (r0 + a < P.N && c0 + b < P.N) {
-                        double *dst = &A[(size_t)(c0 + b - S.own_t0 * TD) * ld + r0 + a];
+                        double *dst = entry_ptr(S, A, ld, rt, c0 + b, r0 + a);
                         *dst = NEAR ? *dst + sm.acc[a][b] : sm.acc[a][b];
                     }
                 }
             for (int e = tid; e < nR * ND; e += PNB_THREADS) {
                 const int K = S.tile_cells[rbeg + e / ND];
-                if (K >= 0 && DXs[e] != 0.) S.DXp[((size_t)gc * P.nc + K) * ND + (e % ND)] += DXs[e];
+                if (K >= 0 && DXs[e] != 0.) S.DXp[((size_t)(gc - goff) * P.nc + K) * ND + (e % ND)] += DXs[e];
             }
             for (int e = tid; e < nC * ND; e += PNB_THREADS) {
                 const int K = S.tile_cells[cbeg + e / ND];
-                if (K >= 0 && DYs[e] != 0.) S.DYp[((size_t)gr * P.nc + K) * ND + (e % ND)] += DYs[e];
+                if (K >= 0 && DYs[e] != 0.) S.DYp[((size_t)(gr - goff) * P.nc + K) * ND + (e % ND)] += DYs[e];
             }
             if (!NEAR && sm.anynear) {
                 if (tid == 0) S.tileflag[(size_t)rt * S.ntiles + ct] = 1;
@@ -1662,12 +1754,14 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
     double tot[ND];
 #pragma unroll
     for (int k = 0; k < ND; k++) tot[k] = 0.;
+    // batched blocks: the surface of the cell's own block
+    const int fbeg = S.cell_block ? S.blk_fptr[S.cell_block[c1]] : 0, fend = S.cell_block ? S.blk_fptr[S.cell_block[c1] + 1] : P.nb;
     // regular facets: lane-per-facet
-    for (int f0 = 0; f0 < P.nb; f0 += 32) {
+    for (int f0 = fbeg; f0 < fend; f0 += 32) {
         const int f = f0 + lane;
         int pan = 0;
         int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
-        const bool mine = f < P.nb && (!P.labels || pnb_class_active(P, P.labels[c1], P.blabels[f]));
+        const bool mine = f < fend && (!P.labels || pnb_class_active(P, P.labels[c1], P.blabels[f]));
         if (mine) {
             if (DIM == 2) {
                 pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.bfacets + (size_t)f * 2, 2, false, p1, p2);
@@ -1736,8 +1830,8 @@ __global__ void reduce_D_kernel(TileSched S, int nc, int ND, int use_bnd)
     const int hm = S.home[e / ND];
     if (hm < S.own_t0 || hm >= S.own_t1) { S.D[e] = 0.; return; }
     double s = 0.;
-    for (int g = 0; g < S.ngroups; g++) s += S.DXp[(size_t)g * nc * ND + e];
-    for (int g = 0; g < S.ngroups; g++) s += S.DYp[(size_t)g * nc * ND + e];
+    for (int g = 0; g < S.dgroups; g++) s += S.DXp[(size_t)g * nc * ND + e];
+    for (int g = 0; g < S.dgroups; g++) s += S.DYp[(size_t)g * nc * ND + e];
     if (use_bnd) s += S.Dbnd[e];
     S.D[e] = s;
 }
@@ -1748,6 +1842,7 @@ __global__ void scatter_D_kernel(DProblem P, TileSched S, double *A, int64_t ld)
 {
     const int I = blockIdx.x * blockDim.x + threadIdx.x + S.own_t0 * PNB_TD;
     if (I >= P.N || I >= S.own_t1 * PNB_TD) return;
+    double *Ablk = A;
     A -= (size_t)S.own_t0 * PNB_TD * ld;
     const int NV = P.dim + 1, ND = NV * (NV + 1) / 2;
     for (int t = S.dof_ptr[I]; t < S.dof_ptr[I + 1]; t++) {
@@ -1756,7 +1851,8 @@ __global__ void scatter_D_kernel(DProblem P, TileSched S, double *A, int64_t ld)
             const int J = P.dofs[(size_t)K * NV + q];
             if (J < 0) continue;
             const int kk = p <= q ? tri_idx(NV, p, q) : tri_idx(NV, q, p);
-            A[(size_t)I * ld + J] += S.D[(size_t)K * ND + kk];
+            if (S.tile_block) *entry_ptr(S, Ablk, ld, I / PNB_TD, I, J) += S.D[(size_t)K * ND + kk];
+            else A[(size_t)I * ld + J] += S.D[(size_t)K * ND + kk];
         }
     }
 }
@@ -2862,6 +2958,7 @@ static int dense_rows_begin_impl(pnb_problem *p, int zero_exterior, int32_t row_
     const int nc = p->nc, nvc = p->dim + 1, ND = nvc * (nvc + 1) / 2;
     TileSched &S = p->S;
     // 2D, whole operator, infinite horizon: cell-group path (pnb_problem_set_path(p, 1) selects the DoF-tile path)
+    if (p->nblocks > 0 && (row_begin != 0 || row_end != p->N)) return fail(PNB_ERR_ARG, "batched blocks are assembled as a whole");
     if (p->dim == 2 && !p->finite && row_begin == 0 && row_end == p->N && p->path == 0)
         return run_group_path(p, zero_exterior, dA, ld, 0, 1, 0, -1, false, host_out, host_ld);
     if (build_tile_schedule(p)) return PNB_ERR_CUDA;
@@ -2872,6 +2969,8 @@ static int dense_rows_begin_impl(pnb_problem *p, int zero_exterior, int32_t row_
     {
         const int g0 = S.own_t0 / S.G, g1 = (S.own_t1 - 1) / S.G;
         std::vector<int> units;
+        if (p->nblocks > 0) units = p->h_block_units;
+        else
         for (int dg = 0; dg < S.ngroups; dg++)
             for (int gr = 0; gr + dg < S.ngroups; gr++) {
                 const int gc = gr + dg;
@@ -2881,8 +2980,8 @@ static int dense_rows_begin_impl(pnb_problem *p, int zero_exterior, int32_t row_
         CK(cudaMemcpy(const_cast<int *>(S.units), units.data(), units.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     for (auto &e : p->ev) if (!e) cudaEventCreate(&e);
-    cudaMemsetAsync(S.DXp, 0, (size_t)S.ngroups * nc * ND * sizeof(double));
-    cudaMemsetAsync(S.DYp, 0, (size_t)S.ngroups * nc * ND * sizeof(double));
+    cudaMemsetAsync(S.DXp, 0, (size_t)S.dgroups * nc * ND * sizeof(double));
+    cudaMemsetAsync(S.DYp, 0, (size_t)S.dgroups * nc * ND * sizeof(double));
     cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * ND * sizeof(double));
     cudaMemsetAsync(S.err, 0, 4 * sizeof(int));
     cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
@@ -3083,6 +3182,7 @@ extern "C" int pnb_dense_assemble(pnb_problem *p, int zero_exterior, int32_t row
     if (row_begin != 0 || row_end != p->N)
         return fail(PNB_ERR_ARG, "pnb_dense_assemble builds the whole operator; row blocks go through pnb_dense_rows_begin/_end");
     if (ld < p->N) return fail(PNB_ERR_ARG, "leading dimension smaller than num_dofs");
+    if (p->nblocks > 0 && !a_on_device) return fail(PNB_ERR_UNSUPPORTED, "batched blocks: device output only");
     ON_DEVICE(p->device);
     const int N = p->N;
     double *dA = A;

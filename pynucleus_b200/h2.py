@@ -356,7 +356,173 @@ class nearFieldBlocks:
         return A.cpu().numpy()
 
 
+class _BatchMesh:
+    """disjoint union of sub-meshes over the vertices of the parent mesh (cells of block k are contiguous)"""
+    manifold_dim = None
+
+    def __init__(self, parent, cells, vol, h, bfacets):
+        self.dim = self.manifold_dim = parent.dim
+        self.vertices = parent.vertices
+        self.num_vertices = parent.num_vertices
+        self.cells = cells
+        self.num_cells = cells.shape[0]
+        self.volVector, self.hVector, self.boundaryFacets = vol, h, bfacets
+        self.diam = parent.diam
+
+
+def _block_boundary_facets(mesh, cells, block_of_cell, nblocks, device=None):
+    """boundary facets of every block's sub-mesh (as meshNd.boundaryFacets finds them for one mesh: the edges that
+    belong to one cell of the block, oriented as in that cell; 1D: the vertices that belong to one cell), block by block.
+    Integer sorting only; runs on `device` when given (millions of edges for a large near field)."""
+    import torch
+    nv, ncv = mesh.num_vertices, cells.shape[0]
+    dev = torch.device('cpu') if device is None else device
+    C = torch.as_tensor(np.ascontiguousarray(cells), device=dev).to(torch.int64)
+    B = torch.as_tensor(np.ascontiguousarray(block_of_cell), device=dev).to(torch.int64)
+    if mesh.dim == 1:
+        v = C.reshape(-1)
+        Bv = B.repeat_interleave(2)
+        key = Bv*nv+v
+        _, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
+        sel = torch.nonzero(cnt[inv] == 1).reshape(-1)
+        # meshNd orders the boundary vertices of a mesh ascending; blocks are contiguous
+        sel = sel[torch.argsort(key[sel], stable=True)]
+        fac = v[sel].to(torch.int32).reshape(-1, 1)
+        fb = Bv[sel]
+    else:
+        e = torch.cat((C[:, [0, 1]], C[:, [1, 2]], C[:, [2, 0]]))
+        Be = B.repeat(3)
+        lo, hi = torch.minimum(e[:, 0], e[:, 1]), torch.maximum(e[:, 0], e[:, 1])
+        key = (Be*nv+lo)*nv+hi
+        _, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
+        sel = torch.nonzero(cnt[inv] == 1).reshape(-1)        # ascending: edge type major, then cell order
+        # per block (blocks are contiguous in the cell order): edge type major, then cell order -- the order
+        # meshNd.boundaryFacets produces for the sub-mesh
+        typ = sel//ncv
+        sel = sel[torch.argsort(Be[sel]*3+typ, stable=True)]
+        fac = e[sel].to(torch.int32)
+        fb = Be[sel]
+    fptr = np.zeros(nblocks+1, dtype=np.int32)
+    np.cumsum(torch.bincount(fb, minlength=nblocks).cpu().numpy(), out=fptr[1:])
+    return np.ascontiguousarray(fac.cpu().numpy()), fptr
+
+
 def assemble_clusters(builder, Pnear, entries=False):
+    """Near field of the H2 operator (assembleClusters, nonlocalAssembly_{SCALAR}.pxi:1663-1889, constant kernel).
+
+    For a near cluster pair (n1, n2) the reference integrates the bilinear form over D x D, D = the cells around the
+    DoFs of n1 and n2, and replaces the rest of the space by a surface integral over the boundary of D
+    (:1840-1889); it keeps the entries (i in n1, j in n2).  That is the dense operator of the sub-mesh D with the
+    zero-exterior surface terms on its own boundary, with the quadrature parameters of the whole problem.
+
+    All cluster pairs are assembled by ONE batched device problem (round 2; round 1 ran one small problem per pair, 3.1 s
+    at 12k DoFs, host-bound): the sub-meshes become the blocks of a disjoint union (pnb_mesh_t.num_blocks) whose cells
+    never interact across blocks, every block with its own surface, and the DoF-tile kernels write one dense operator
+    per block; the blocks (n1, n2) are gathered from them in one indexing operation.
+
+    entries=True: the getEntry flavour (:1539-1660) -- for the regional operator (zeroExterior=False) the reference
+    keeps the patch x patch part only, without surface terms and without the correction below."""
+    import torch
+    from .assembly import _Problem
+    from . import _lib
+    if not builder.params.get('near_field_batched', True):
+        return _assemble_clusters_one_by_one(builder, Pnear, entries)
+    mesh, dm = builder.mesh, builder.dm
+    dev_index = builder.problem.device
+    dev = torch.device('cuda', dev_index)
+    out = nearFieldBlocks(dm.num_dofs, dev)
+    d2c = dof_to_cells(dm)
+    node_cells = {}
+
+    def cells_of(n):
+        if n.id not in node_cells:
+            node_cells[n.id] = cells_of_dofs(dm, n.dofs, d2c)
+        return node_cells[n.id]
+    todo, seen = [], set()
+    for n1, n2 in Pnear:
+        if (n2.id, n1.id) not in seen and (n1.id, n2.id) not in seen:
+            seen.add((n1.id, n2.id))
+            todo.append((n1, n2))
+    if not todo:
+        return out
+    align = int(_lib.lib().pnb_block_alignment())
+    nb = len(todo)
+    cell_lists, sdof_lists, gather = [], [], []
+    cptr = np.zeros(nb+1, dtype=np.int64)
+    dptr = np.zeros(nb+1, dtype=np.int64)
+    out_off = 0
+    sizes = []
+    for k, (n1, n2) in enumerate(todo):
+        d1, d2 = n1.dofs, n2.dofs
+        union = np.union1d(d1, d2)
+        cells = np.union1d(cells_of(n1), cells_of(n2))       # cellsUnion
+        gd = dm.dofs[cells]
+        pos = np.minimum(np.searchsorted(union, np.maximum(gd, 0)), union.shape[0]-1)
+        inside = (gd >= 0) & (union[pos] == gd)
+        n = union.shape[0]
+        npad = -(-n//align)*align
+        sdof_lists.append(np.where(inside, pos+dptr[k], -1))
+        cell_lists.append(cells)
+        cptr[k+1] = cptr[k]+cells.shape[0]
+        dptr[k+1] = dptr[k]+npad
+        r, c = np.searchsorted(union, d1), np.searchsorted(union, d2)
+        gather.append((out_off+r[:, None]*npad+c[None, :]).ravel())
+        sizes.append((d1.shape[0], d2.shape[0]))
+        out_off += npad*npad
+    if dptr[-1] >= 2**31 or cptr[-1] >= 2**31:
+        raise MemoryError('near field batch too large for 32-bit indices; use params["near_field_batched"] = False')
+    cells_all = np.concatenate(cell_lists)
+    block_of_cell = np.repeat(np.arange(nb), np.diff(cptr))
+    vcells = np.ascontiguousarray(mesh.cells[cells_all], dtype=np.int32)
+    fac, fptr = _block_boundary_facets(mesh, vcells, block_of_cell, nb, dev)
+    bmesh = _BatchMesh(mesh, vcells, np.ascontiguousarray(mesh.volVector[cells_all]), np.ascontiguousarray(mesh.hVector[cells_all]), fac)
+    sdm = _SubDoFMap(bmesh, np.ascontiguousarray(np.concatenate(sdof_lists), dtype=np.int32), int(dptr[-1]))
+    surface = 0 if (entries and not builder.zeroExterior) else 1
+    prob = _Problem(sdm, builder.kernel, builder.kernelBoundary, builder.orders, dev_index, builder.problem.max_order,
+                    order_num_dofs=dm.num_dofs, tables_from=builder.problem, blocks=(cptr, dptr, fptr))
+    A = torch.empty(out_off, dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, surface, 0, sdm.num_dofs, A.data_ptr(), sdm.num_dofs, 1))
+    vals = A[torch.as_tensor(np.concatenate(gather), device=dev)]
+    del A, prob
+    cache = {}
+    o = 0
+    for (n1, n2), (a, b) in zip(todo, sizes):
+        cache[(n1.id, n2.id)] = vals[o:o+a*b].view(a, b)
+        o += a*b
+    for n1, n2 in Pnear:
+        B = cache.get((n1.id, n2.id))
+        if B is None:
+            # the local matrices are symmetric: block (n2, n1)^T
+            B = cache[(n2.id, n1.id)].t().contiguous()
+        out.add(n1.dofs, n2.dofs, B)
+    if not builder.zeroExterior and not entries:
+        out.correction = _regional_correction(builder)
+    return out
+
+
+def _regional_correction(builder):
+    """regional operator: the blocks hold the surface terms around the cluster unions, which stand for the whole
+    complement of the union; take the part Omega^c out again (:1889-1912): minus the surface terms of the domain
+    boundary, cell by cell, on the entries of the near pattern"""
+    import ctypes
+    from . import _lib
+    mesh, dm = builder.mesh, builder.dm
+    nv = mesh.dim+1
+    D = np.zeros((mesh.num_cells, nv*(nv+1)//2))
+    _lib.check(_lib.lib().pnb_boundary_cell_blocks(builder.problem.handle, D.ctypes.data_as(ctypes.c_void_p)))
+    rows, cols, vals = [], [], []
+    k = 0
+    for p in range(nv):
+        for q in range(p, nv):
+            ok = (dm.dofs[:, p] >= 0) & (dm.dofs[:, q] >= 0) & (D[:, k] != 0)
+            rows.append(dm.dofs[ok, p]); cols.append(dm.dofs[ok, q]); vals.append(-D[ok, k])
+            if p != q:
+                rows.append(dm.dofs[ok, q]); cols.append(dm.dofs[ok, p]); vals.append(-D[ok, k])
+            k += 1
+    return (np.concatenate(rows).astype(np.int64), np.concatenate(cols).astype(np.int64), np.concatenate(vals))
+
+
+def _assemble_clusters_one_by_one(builder, Pnear, entries=False):
     """Near field of the H2 operator (assembleClusters, nonlocalAssembly_{SCALAR}.pxi:1663-1889, constant kernel).
 
     For a near cluster pair (n1, n2) the reference integrates the bilinear form over D x D, D = the cells around the
