@@ -135,3 +135,28 @@ def sparsified_case(dim, noRef, ktype, s, horizon, name):
 if __name__ == '__main__' and os.environ.get('SPARSIFIED', '1') == '1':
     sparsified_case(2, 4, 'fractional', 0.4, 0.3, 'sparsified_disc_frac0.4_r4')
     sparsified_case(1, 6, 'constant', 0., 0.25, 'sparsified_interval_constant_r6')
+
+
+def rows_case(noRef, ktype, s, horizon, name, nrows=16):
+    """larger mesh (disc, N = 2977 at noRef 5): sampled rows, the diagonal and products of the reference's operator"""
+    mesh = uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    kernel = make_kernel(2, ktype, s, horizon)
+    A = np.array(nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense().data)
+    rng = np.random.default_rng(9)
+    rows = np.sort(rng.choice(dm.num_dofs, nrows, replace=False))
+    x = rng.standard_normal(dm.num_dofs)
+    out = dict(vertices=np.array(mesh.vertices), cells=np.array(mesh.cells), dofs=np.array(dm.dofs), num_dofs=dm.num_dofs,
+               boundaryEdges=np.array(mesh.boundaryEdges), kernel_type=ktype, s=s, horizon=horizon, target_order=0.5,
+               scaling=kernel.scalingValue, singularity=kernel.singularityValue,
+               rows=rows, A_rows=A[rows], diagonal=np.diag(A).copy(), x=x, Ax=A.dot(x), frobenius=np.linalg.norm(A),
+               nonzeros=int(np.count_nonzero(A)))
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, dm.num_dofs, 'nonzeros %.1f%%' % (100.*np.count_nonzero(A)/A.size))
+
+
+if __name__ == '__main__' and os.environ.get('ROWS', '0') == '1':
+    rows_case(5, 'fractional', 0.4, 0.3, 'finite_disc_frac0.4_r5_rows')
+    rows_case(5, 'constant', 0., 0.25, 'finite_disc_constant_r5_rows')

@@ -255,7 +255,9 @@ struct TileSched {
     int own_t0, own_t1;     // row tiles [own_t0, own_t1) are owned (written) by this problem instance
     const unsigned char *cell_mask;  // several GPUs (pnb_dist_plan): cells whose surface terms this instance computes; nullptr: by home tile
     int maxcells;           // largest cell list of a tile
-    int *tileflag;          // ntiles x ntiles: tile holds pairs for the near pass
+    int *tileflag;          // ntiles x tf_width: tile pair holds pairs for the near pass (batched blocks: column tile counted
+                            // from the first tile of the block, tf_width = most tiles of a block)
+    int tf_width;
     int *unitflag;          // nunits: unit holds flagged tiles
     int *nearunits;         // compacted list of flagged units, [nunits] = count
 };
@@ -594,7 +596,7 @@ static int build_tile_schedule(pnb_problem *p)
     rc |= dalloc(p, (size_t)S.dgroups * nc * ND, &S.DYp);
     S.maxcells = PNB_SB;
     for (int t = 0; t < S.ntiles; t++) S.maxcells = std::max(S.maxcells, tptr[t + 1] - tptr[t]);
-    rc |= dalloc(p, (size_t)S.ntiles * S.ntiles, &S.tileflag);
+    rc |= dalloc(p, (size_t)S.ntiles * S.tf_width, &S.tileflag);
     rc |= dalloc(p, (size_t)S.nunits, &S.unitflag);
     rc |= dalloc(p, (size_t)S.nunits + 1, &S.nearunits);
     if (rc) return PNB_ERR_CUDA;
@@ -775,6 +777,7 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
     S.G = 2;
     S.ngroups = (S.ntiles + S.G - 1) / S.G;
     S.dgroups = S.ngroups;
+    S.tf_width = S.ntiles;
     S.cell_block = S.tile_block = S.blk_tile0 = S.blk_group0 = S.blk_n = S.blk_fptr = nullptr;
     S.blk_out = nullptr;
     std::vector<int> cell_block;
@@ -808,6 +811,7 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         }
         p->blocks_out_doubles = off;
         S.dgroups = dg;
+        S.tf_width = dg * S.G;
         rc |= upload(p, cell_block.data(), cell_block.size(), &S.cell_block);
         rc |= upload(p, tile_block.data(), tile_block.size(), &S.tile_block);
         rc |= upload(p, blk_tile0.data(), blk_tile0.size(), &S.blk_tile0);
@@ -1321,8 +1325,9 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
 
     for (int rt = gr * S.G; rt < min((gr + 1) * S.G, S.ntiles); rt++)
         for (int ct = max(gc * S.G, rt); ct < min((gc + 1) * S.G, S.ntiles); ct++) {
-            if (NEAR && !S.tileflag[(size_t)rt * S.ntiles + ct]) continue;
             if (S.tile_block && S.tile_block[rt] != S.tile_block[ct]) continue;
+            const size_t tfi = (size_t)rt * S.tf_width + (S.tile_block ? ct - S.blk_tile0[S.tile_block[rt]] : ct);
+            if (NEAR && !S.tileflag[tfi]) continue;
             if (finite && rt != ct) {
                 // finite horizon: tiles whose bounding boxes are further apart than the horizon hold only REMOTE pairs
                 double g2 = 0.;
@@ -1678,7 +1683,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                 if (K >= 0 && DYs[e] != 0.) S.DYp[((size_t)(gr - goff) * P.nc + K) * ND + (e % ND)] += DYs[e];
             }
             if (!NEAR && sm.anynear) {
-                if (tid == 0) S.tileflag[(size_t)rt * S.ntiles + ct] = 1;
+                if (tid == 0) S.tileflag[tfi] = 1;
                 unit_near = true;
             }
         }
@@ -2985,7 +2990,7 @@ static int dense_rows_begin_impl(pnb_problem *p, int zero_exterior, int32_t row_
     cudaMemsetAsync(S.Dbnd, 0, (size_t)nc * ND * sizeof(double));
     cudaMemsetAsync(S.err, 0, 4 * sizeof(int));
     cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long));
-    cudaMemsetAsync(S.tileflag, 0, (size_t)S.ntiles * S.ntiles * sizeof(int));
+    cudaMemsetAsync(S.tileflag, 0, (size_t)S.ntiles * S.tf_width * sizeof(int));
     cudaMemsetAsync(S.unitflag, 0, (size_t)S.nunits_all * sizeof(int));
     cudaEventRecord(p->ev[0]);
     int launches = 0;

@@ -165,3 +165,21 @@ def test_try_sparsification_vs_reference(golden_dir, name):
     dim = g['vertices'].shape[1]
     bd = pb.nonlocalBuilder(b.dm, pb.getFractionalKernel(dim, 0.4, 1.5), {'target_order': 0.5})
     assert type(bd.getDense(trySparsification=True)).__name__ == 'Dense_LinearOperator'
+
+
+@pytest.mark.parametrize('name', ['finite_disc_frac0.4_r5_rows', 'finite_disc_constant_r5_rows'])
+def test_sampled_rows_at_2977_dofs(golden_dir, name):
+    """a larger finite-horizon operator (6 144 cells, ~1.2e5 pairs cut by the horizon) against rows, diagonal, a product,
+    the Frobenius norm and the number of non-zeros of the reference's own operator"""
+    g = load(golden_dir, name)
+    b = builder_from_golden(g)
+    A = b.getDense().data
+    rows = g['rows']
+    d = np.sqrt(np.abs(g['diagonal']))
+    scale = np.maximum(np.abs(g['A_rows']), 1e-2*np.outer(d[rows], d))
+    assert (np.abs(A[rows]-g['A_rows'])/scale).max() < TOL
+    assert np.abs(np.diag(A)-g['diagonal']).max() < TOL*np.abs(g['diagonal']).max()
+    assert np.abs(A.dot(g['x'])-g['Ax']).max() < TOL*np.abs(g['Ax']).max()
+    assert abs(np.linalg.norm(A)-float(g['frobenius'])) < TOL*float(g['frobenius'])
+    assert int(np.count_nonzero(A)) == int(g['nonzeros'])
+    assert np.abs(A-A.T).max() <= 1e-15*np.abs(A).max()
