@@ -650,6 +650,19 @@ class nonlocalBuilder:
         import torch
         from .cluster_tree import admissible_clusters
         from . import h2
+        if self.kernel.finiteHorizon:
+            # The cluster code here follows the reference's infinite-horizon branches only (queryAdmissibility with a
+            # horizon, clusterMethodCy.pyx:4019-4033, and the horizon-cut surface terms of the near field are not built).
+            # On the configurations the reference's own tests cover (BASELINE configs[2]) it finds no admissible pair
+            # either and assembles the dense operator (nonlocalAssembly_{SCALAR}.pxi:3200-3209); do that always.
+            H = self.getDense()
+            if returnNearField and returnTree:
+                return H, [], None
+            if returnNearField:
+                return H, []
+            if returnTree:
+                return H, None
+            return H
         root = self.getTree()
         Pnear, Pfar_nodes = admissible_clusters(root, trim=self.params.get('trim', True))
         if sum(len(v) for v in Pfar_nodes.values()) == 0:

@@ -183,3 +183,18 @@ def test_sampled_rows_at_2977_dofs(golden_dir, name):
     assert abs(np.linalg.norm(A)-float(g['frobenius'])) < TOL*float(g['frobenius'])
     assert int(np.count_nonzero(A)) == int(g['nonzeros'])
     assert np.abs(A-A.T).max() <= 1e-15*np.abs(A).max()
+
+
+def test_h2_with_finite_horizon_is_the_dense_operator(golden_dir):
+    """matrixFormat H2 on BASELINE configs[2]: the reference finds no admissible cluster pair and assembles the dense
+    operator ("Cannot assemble H2 operator, assembling dense matrix instead"); getH2 returns the dense operator for every
+    finite-horizon kernel (far field with a horizon is not built -- never a silently wrong H2 operator)"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, 'nonlocal_square_constant')
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'])
+    dmI = pb.P1_DoFMap.fromArrays(mesh, g['dofs'], int(g['num_dofs']))
+    b = pb.nonlocalBuilder(dmI, kernel_from_golden(g), {'target_order': float(g['target_order'])})
+    H = b.getH2()
+    assert type(H).__name__ == 'Dense_LinearOperator'
+    rows = g['rows']
+    assert np.abs(H.data[rows]-g['A_rows']).max() < TOL*np.abs(g['diagonal']).max()
