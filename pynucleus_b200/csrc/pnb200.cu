@@ -708,22 +708,24 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
 
     // table-driven power for both kernels, per-cell logs for the fast order selection
     {
-        PowTab tabs[2];
-        const double scal[2] = {kernel->scaling, kernel->bscaling};
-        const double expo[2] = {0.5 * kernel->singularity, 0.5 * kernel->bsingularity};
+        // third table: boundary kernel divided by |x-y| (the unit vector of the surface form folded into the power)
+        PowTab tabs[3];
+        const double scal[3] = {kernel->scaling, kernel->bscaling, kernel->bscaling};
+        const double expo[3] = {0.5 * kernel->singularity, 0.5 * kernel->bsingularity, 0.5 * kernel->bsingularity - 0.5};
         // exponent window of the tables: top above 4 diam^2 (no two points of the mesh are further apart than the
         // diagonal of its bounding box), 256 binary exponents down from there
         int ex = 0;
         frexp(4. * mesh->diam * mesh->diam, &ex);
         p->pow_eoff = 254 - ex;
-        for (int t = 0; t < 2; t++) {
+        for (int t = 0; t < 3; t++) {
             build_powtab(&tabs[t], scal[t], expo[t], p->pow_eoff);
             tabs[t].horizon2 = std::isfinite(kernel->horizon2) ? kernel->horizon2 : INFINITY;
         }
         const PowTab *dt = nullptr;
-        rc |= upload(p, tabs, 2, &dt);
+        rc |= upload(p, tabs, 3, &dt);
         P.pow_int = dt;
         P.pow_bnd = dt + 1;
+        P.pow_bnd_unit = dt + 2;
         std::vector<float> lhf(nc), ahf(nc);
         const double H0 = mesh->diam / sqrt(8.);
         for (int c = 0; c < nc; c++) {

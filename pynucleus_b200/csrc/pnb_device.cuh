@@ -49,6 +49,7 @@ struct DProblem {
     int dim, nc, nv, N, nb;
     const PowTab *pow_int;     // interior kernel  C |x-y|^(-d-2s)   as a function of |x-y|^2
     const PowTab *pow_bnd;     // boundary kernel
+    const PowTab *pow_bnd_unit;    // boundary kernel / |x-y|: gamma_b(x,y) n.(y-x)/|y-x| = pow_bnd_unit(|x-y|^2) n.(y-x)
     const struct FarRule *far_rules;   // PNB_FAR_MAX_ORDER+1 low-order 2D rules for the thread-per-pair evaluator
     const float *lhf;          // nc: (float) log(h)
     const float *ahf;          // nc: (float) |log(h/H0)|

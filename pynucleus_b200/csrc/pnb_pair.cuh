@@ -287,7 +287,8 @@ __device__ void lanes_boundary(const DProblem &P, int c1, int f, int panel, cons
         nx *= inv;
         ny *= inv;
     }
-    const PowCtx kv(P.pow_bnd);
+    // 2D: the power carries the 1/|x-y| of the unit vector (no reciprocal square root per node pair); 1D: plain kernel
+    const PowCtx kv(DIM == 2 ? P.pow_bnd_unit : P.pow_bnd);
 #pragma unroll
     for (int k = 0; k < ND; k++) acc[k] = 0.;
     if (panel >= 1) {
@@ -314,8 +315,7 @@ __device__ void lanes_boundary(const DProblem &P, int c1, int f, int panel, cons
             double nw = 1.;
             if (DIM == 2) {
                 d2 = PNB_ADD(d2, PNB_MUL(w1, w1));
-                const double inv = 1. / sqrt(d2);
-                nw = nx * (w0 * inv) + ny * (w1 * inv);
+                nw = nx * w0 + ny * w1;
             }
             const double g = (r0.w[i] * r1.w[m]) * nw * kv(d2);
             int k = 0;
@@ -367,8 +367,7 @@ __device__ void lanes_boundary(const DProblem &P, int c1, int f, int panel, cons
             double nw = 1.;
             if (DIM == 2) {
                 d2 = PNB_ADD(d2, PNB_MUL(w1, w1));
-                const double inv = 1. / sqrt(d2);
-                nw = nx * (w0 * inv) + ny * (w1 * inv);
+                nw = nx * w0 + ny * w1;
             }
             const double g = r.w[q] * nw * kv(d2);
             int k = 0;
