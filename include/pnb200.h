@@ -104,7 +104,17 @@ typedef struct {
     const uint8_t *cell_labels;    /* host, num_cells, values 0..3 */
     const uint8_t *bfacet_labels;  /* host, num_bfacets */
     int32_t active_class;
-    uint8_t pair_class[16];        /* [label1 * 4 + label2] -> class */
+    uint8_t pair_class[16];        /* [label of the cell with the SMALLER index * 4 + label of the other cell] -> class of a
+                                    * cell pair.  An unsymmetric table (or pair_orientation != 0) sends the problem to the
+                                    * DoF-tile kernels; the cell-group kernels look the class up in either order */
+    uint8_t bpair_class[16];       /* [cell label * 4 + facet label] -> class of a (cell, boundary facet) pair of the
+                                    * zero-exterior surface terms (kernel.evalParams(cell centre, facet centre)); need not
+                                    * be symmetric.  Unsymmetric piecewise orders s(x,y) != s(y,x) are assembled as sums of
+                                    * such instances, see nonlocalBuilder._getDenseClasses */
+    int32_t pair_orientation;      /* singular (touching) cell pairs: 0 = evaluated as (smaller cell index, larger), the
+                                    * order of the reference's symmetric assembly loop; 1 = as (larger, smaller), the second
+                                    * visit of its unsymmetric loop (nonlocalAssembly_{SCALAR}.pxi:1419-1428).  The singular
+                                    * rules are not symmetric in their two cells: the results differ by the quadrature error */
 } pnb_kernel_t;
 
 /* One quadrature table: rows x n barycentric coordinates (x point first, then

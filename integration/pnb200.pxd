@@ -38,6 +38,8 @@ cdef extern from "pnb200.h":
         const uint8_t *bfacet_labels
         int32_t active_class
         uint8_t pair_class[16]
+        uint8_t bpair_class[16]
+        int32_t pair_orientation
     ctypedef struct pnb_rule_t:
         int32_t n
         int32_t rows

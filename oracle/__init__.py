@@ -38,7 +38,7 @@ class _Problem(ctypes.Structure):
                 ('max_order', ctypes.c_int),
                 ('reg_cell', ctypes.c_void_p), ('reg_facet', ctypes.c_void_p), ('order_num_dofs', ctypes.c_int),
                 ('labels', ctypes.c_void_p), ('blabels', ctypes.c_void_p), ('active_class', ctypes.c_int),
-                ('pair_class', ctypes.c_ubyte*16)]
+                ('pair_class', ctypes.c_ubyte*16), ('bpair_class', ctypes.c_ubyte*16), ('pair_orientation', ctypes.c_int)]
 
 
 def build():
@@ -67,7 +67,8 @@ class Problem:
 
     def __init__(self, vertices, cells, dofs, num_dofs, s, bfacets=None, target_order=None,
                  hVector=None, volVector=None, hmin=None, diam=None, max_order=None, order_num_dofs=None,
-                 s_max=None, labels=None, blabels=None, pair_class=None, active_class=0):
+                 s_max=None, labels=None, blabels=None, pair_class=None, active_class=0, bpair_class=None,
+                 pair_orientation=0, s_min=None):
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         self.dofs = np.ascontiguousarray(dofs, dtype=np.int32)
@@ -91,8 +92,10 @@ class Problem:
         self.order_num_dofs = int(order_num_dofs) if order_num_dofs else self.num_dofs
         # variable kernels: the singular quadrature orders follow the largest order s.max (fractionalLaplacian2D.pyx:606)
         sm = self.s if s_max is None else float(s_max)
+        smn = sm if s_min is None else float(s_min)
         self.orders = tables.diag_orders(dim, -dim-2*sm, 1.-dim-2*sm, hmin, self.H0,
-                                         self.order_num_dofs, target_order)
+                                         self.order_num_dofs, target_order, min_singularity=-dim-2*smn,
+                                         min_boundary_singularity=1.-dim-2*smn)
         self.near = tables.near_rules(dim, self.singularity, self.bsingularity, self.orders)
         self._keep = []
         P = _Problem()
@@ -113,6 +116,9 @@ class Problem:
             P.active_class = int(active_class)
             for i, v in enumerate(np.asarray(pair_class, dtype=np.uint8).ravel()):
                 P.pair_class[i] = int(v)
+            for i, v in enumerate(np.asarray(pair_class if bpair_class is None else bpair_class, dtype=np.uint8).ravel()):
+                P.bpair_class[i] = int(v)
+            P.pair_orientation = int(pair_orientation)
         P.nb = self.bfacets.shape[0]
         P.bfacets = self.bfacets.ctypes.data
         P.H0 = self.H0

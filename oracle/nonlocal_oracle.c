@@ -70,7 +70,11 @@ typedef struct {
     const unsigned char *labels;   /* nc */
     const unsigned char *blabels;  /* nb */
     int active_class;
-    unsigned char pair_class[16];  /* [label1 * 4 + label2] */
+    unsigned char pair_class[16];  /* [label of cell c1 * 4 + label of cell c2], c1 <= c2 */
+    unsigned char bpair_class[16]; /* [cell label * 4 + boundary facet label] */
+    /* Unsymmetric piecewise orders: the reference visits (c1,c2) and (c2,c1) (NA.pxi:1412-1428); pair_orientation 1
+     * evaluates the second visit, i.e. the touching pair with the cell of the larger index as first cell of the rule */
+    int pair_orientation;
 } orc_problem;
 #define ORDN(P) ((P)->order_num_dofs > 0 ? (P)->order_num_dofs : (P)->num_dofs)
 
@@ -204,10 +208,17 @@ static double kernel_boundary(const orc_problem *P, const double *x, const doubl
 /* ---------------------------------------------------------------------- */
 /* panel type of a cell pair (symmetric cells: c1 <= c2)                   */
 /* ---------------------------------------------------------------------- */
+static int orc_panel_interior_any(const orc_problem *P, int c1, int c2, int *perm1, int *perm2);
 int orc_panel_interior(const orc_problem *P, int c1, int c2, int *perm1, int *perm2)
 {
-    int nvc = P->dim + 1, panel;
     if (c1 > c2) return IGNORED;
+    return orc_panel_interior_any(P, c1, c2, perm1, perm2);
+}
+
+/* unsymmetric cells (NO.pxi:296: no c1 > c2 test) */
+static int orc_panel_interior_any(const orc_problem *P, int c1, int c2, int *perm1, int *perm2)
+{
+    int nvc = P->dim + 1, panel;
     panel = proto_panel(P->cells + (size_t)c1 * nvc, nvc, P->cells + (size_t)c2 * nvc, nvc, c1 == c2, perm1, perm2);
     if (panel == 0) {
         double s1[MAXV][2], s2[MAXV][2], m1[2], m2[2], d2 = 0.;
@@ -596,9 +607,20 @@ int64_t orc_dense(const orc_problem *P, int start, int end, int zero_exterior, d
                 }
                 if (skip) continue;
                 if (P->labels && P->pair_class[P->labels[c1] * 4 + P->labels[c2]] != P->active_class) continue;
+                if (P->labels && P->pair_orientation && c1 != c2) {
+                    /* second visit of the unsymmetric loop: (c2, c1) */
+                    for (k = 0; k < nvc; k++) {
+                        ldofs[k] = P->dofs[(size_t)c2 * nvc + k];
+                        ldofs[nvc + k] = P->dofs[(size_t)c1 * nvc + k];
+                    }
+                    panel = orc_panel_interior_any(P, c2, c1, p1, p2);
+                    if (panel == IGNORED) continue;
+                    orc_local_interior(P, c2, c1, panel, p1, p2, contrib);
+                } else {
                 panel = orc_panel_interior(P, c1, c2, p1, p2);
                 if (panel == IGNORED) continue;
                 orc_local_interior(P, c1, c2, panel, p1, p2, contrib);
+                }
                 npairs++;
                 if (use_atomic) {
                     /* same scatter, atomic adds */
@@ -634,7 +656,7 @@ int64_t orc_dense(const orc_problem *P, int start, int end, int zero_exterior, d
                 for (k = 0; k < nvc; k++) ldofs[k] = P->dofs[(size_t)c1 * nvc + k];
                 for (f = 0; f < P->nb; f++) {
                     int panel;
-                    if (P->labels && P->pair_class[P->labels[c1] * 4 + P->blabels[f]] != P->active_class) continue;
+                    if (P->labels && P->bpair_class[P->labels[c1] * 4 + P->blabels[f]] != P->active_class) continue;
                     panel = orc_panel_boundary(P, c1, f, p1, p2);
                     orc_local_boundary(P, c1, f, panel, p1, p2, bcontrib);
                     if (use_atomic) {

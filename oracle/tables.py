@@ -190,11 +190,18 @@ def regular_rule(order, manifold_dim):
 # order heuristics
 # --------------------------------------------------------------------------
 
-def diag_orders(dim, singularity, boundary_singularity, hmin, H0, num_dofs, target_order=None, poly_order=1):
+def diag_orders(dim, singularity, boundary_singularity, hmin, H0, num_dofs, target_order=None, poly_order=1,
+                min_singularity=None, min_boundary_singularity=None):
     """Returns dict with target orders and the quadrature orders of the
     singular rules for the interior and the boundary local matrices."""
     out = {}
     lg = abs(log(hmin/H0))
+    # variable orders (fractionalLaplacian1D.pyx:218-222, 629-633): smax from kernel.max_singularity, smin from
+    # kernel.min_singularity
+    if min_singularity is None:
+        min_singularity = singularity
+    if min_boundary_singularity is None:
+        min_boundary_singularity = boundary_singularity
     if dim == 2:
         to = 0.5 if target_order is None else target_order
         smax = max(-0.5*(singularity+2), 0.)
@@ -205,11 +212,13 @@ def diag_orders(dim, singularity, boundary_singularity, hmin, H0, num_dofs, targ
         out['b_target_order'] = to
         out['b_qod'] = int(max(ceil((to+0.5+smaxb)/0.35*lg), 2))
     elif dim == 1:
-        smin = smax = max(-0.5*(singularity+1), 0.)
+        smax = max(-0.5*(singularity+1), 0.)
+        smin = max(-0.5*(min_singularity+1), 0.)
         to = poly_order+1-smin if target_order is None else target_order
         out['target_order'] = to
         out['qod'] = int(max(ceil(((to+2.)*log(num_dofs*H0)+(2.*smax-1.)*lg)/0.8), 2))
-        sminb = smaxb = max(0.5*(-boundary_singularity), 0.)
+        smaxb = max(0.5*(-boundary_singularity), 0.)
+        sminb = max(0.5*(-min_boundary_singularity), 0.)
         tob = poly_order+1-sminb if target_order is None else target_order
         out['b_target_order'] = tob
         out['b_qod'] = int(max(ceil(((tob+1.)*log(num_dofs*H0)+(2.*smaxb-1.)*lg)/0.8), 2))

@@ -23,7 +23,7 @@ class _Problem:
     """owner of a pnb_problem handle (device-resident mesh, DoFMap, kernel, tables)"""
 
     def __init__(self, dm, kernel, bkernel, orders, device, max_order, order_num_dofs=0, labels=None, blabels=None,
-                 pair_class=None, active_class=0, tables_from=None, blocks=None):
+                 pair_class=None, active_class=0, tables_from=None, blocks=None, bpair_class=None, pair_orientation=0):
         mesh = dm.mesh
         self._keep = []
         self.dim = mesh.dim
@@ -58,6 +58,9 @@ class _Problem:
             k.active_class = int(active_class)
             for i, v in enumerate(np.asarray(pair_class, dtype=np.uint8).ravel()):
                 k.pair_class[i] = int(v)
+            for i, v in enumerate(np.asarray(pair_class if bpair_class is None else bpair_class, dtype=np.uint8).ravel()):
+                k.bpair_class[i] = int(v)
+            k.pair_orientation = int(pair_orientation)
         if tables_from is not None:
             # same kernel, orders and table range as another problem (H2 near field: one problem per cluster pair):
             # share its host-side table structure instead of converting the tables again
@@ -163,31 +166,67 @@ class nonlocalBuilder:
     def setKernel(self, kernel, zeroExterior=True):
         from .kernels import constFractionalOrder, getFractionalKernel
         self._classes = None
-        if kernel.symmetric and hasattr(kernel.s, 'classes'):
-            # piecewise constant order s(x,y): one constant-order problem instance per class of cell pairs, the
-            # operator is their sum; quadrature orders follow s.max like the reference's setKernel
-            # (fractionalLaplacian2D.pyx:606-611, 1217-1219)
+        if hasattr(kernel.s, 'blockOrders'):
+            # piecewise constant order s(x,y) = sVals[block(x), block(y)], evaluated at the cell centres once per ordered
+            # cell pair (kernel.evalParams, nonlocalOperator_{SCALAR}.pxi:509-513).  One constant-order problem instance
+            # per pass, each restricted to a class of cell pairs; the operator is their sum.  Quadrature orders follow
+            # s.max like the reference's setKernel (fractionalLaplacian2D.pyx:606-611, 1217-1219).
+            #
+            # Symmetric orders: pass k takes the pairs with s = v_k.  Unsymmetric orders: the reference visits both
+            # orientations of a pair (nonlocalAssembly_{SCALAR}.pxi:1412-1428), each with the parameters of ITS ordered pair
+            # and without the factor 2 of the symmetric loop; with piecewise parameters both kernel evaluations of the
+            # unsymmetric local matrix (fractionalLaplacian2D.pyx:1155-1184: temp, temp2) use the same s, so the
+            # orientation (c1, c2) contributes the symmetric local matrix of s(c1, c2) -- evaluated with c1 as the first
+            # cell of the singular rule, which matters at the level of the quadrature error (1e-7).  Hence two passes per
+            # order v_k, each at half weight (a power of two: exact): the orientations (smaller cell index, larger) of class
+            # k, and the orientations (larger, smaller) of class k.  The surface terms (cell, facet) of
+            # s(cell centre, facet centre) = v_k ride along with both halves.
             if self.dm2 is not None:
                 raise NotImplementedError('two DoFMaps with a variable order')
-            svals, pair_class = kernel.s.classes()
+            if getattr(kernel, 'finiteHorizon', False):
+                raise NotImplementedError('piecewise variable orders with a finite horizon')
             mesh = self.mesh
+            sVals = np.asarray(kernel.s.blockOrders(), dtype=np.float64)
+            nb_ = sVals.shape[0]
+            if nb_ > 4:
+                raise NotImplementedError('piecewise constant orders with more than 4 blocks')
+            vals = sorted(set(sVals.ravel().tolist()))
+            pc = np.array([[vals.index(sVals[i, j]) for j in range(nb_)] for i in range(nb_)])
             centers = mesh.vertices[mesh.cells].mean(axis=1)
             bf = np.asarray(mesh.boundaryFacets).reshape(-1, mesh.dim)
             bcenters = mesh.vertices[bf].mean(axis=1)
-            self._classes = dict(kernels=[getFractionalKernel(mesh.dim, sv) for sv in svals], pair_class=pair_class,
-                                 labels=kernel.s.labels(centers), blabels=kernel.s.labels(bcenters), problems=None)
+            passes = []
+            for k_, v in enumerate(vals):
+                fwd = pc == k_
+                if kernel.s.symmetric:
+                    todo = ((fwd, 0, 1.), )
+                else:
+                    # table[label of the smaller cell][label of the larger cell]
+                    todo = ((fwd, 0, 0.5), (fwd.T, 1, 0.5))
+                for M, orientation, weight in todo:
+                    P4, B4 = np.zeros((4, 4), dtype=np.uint8), np.zeros((4, 4), dtype=np.uint8)
+                    P4[:nb_, :nb_] = M
+                    B4[:nb_, :nb_] = fwd
+                    passes.append(dict(kernel=getFractionalKernel(mesh.dim, v), pair_class=P4, bpair_class=B4, weight=weight,
+                                       orientation=orientation))
+            self._classes = dict(passes=passes, labels=kernel.s.labels(centers), blabels=kernel.s.labels(bcenters), problems=None)
             self.kernel = kernel
             self.zeroExterior = zeroExterior
             kmax = getFractionalKernel(mesh.dim, kernel.s.max)
             self.kernelBoundary = kernel.getBoundaryKernel()
             H0 = mesh.diam/np.sqrt(8.)
+            # the unsymmetric local matrix ignores params['target_order'] (fractionalLaplacian2D.pyx:911 hands num_dofs
+            # to the base class in the place of target_order: both None)
+            target_order = self.params.get('target_order', None) if kernel.symmetric else None
             self.orders = quadrature.localMatrixOrders(mesh.dim, kmax.singularityValue, kmax.getBoundaryKernel().singularityValue,
-                                                       mesh.hmin, H0, self.dm.num_dofs, self.params.get('target_order', None),
-                                                       self.dm.polynomialOrder)
+                                                       mesh.hmin, H0, self.dm.num_dofs, target_order,
+                                                       self.dm.polynomialOrder, min_singularity=kernel.min_singularity,
+                                                       min_bsingularity=self.kernelBoundary.min_singularity)
             self._problem = None
             return
         if not kernel.symmetric or not (kernel.s is None or isinstance(kernel.s, constFractionalOrder)):
-            raise NotImplementedError('only symmetric kernels whose order is constant or piecewise constant (leftRight) are supported yet')
+            raise NotImplementedError('only kernels whose order is constant or piecewise constant are supported (orders that vary inside a '
+                                      'cell need a singular rule per cell pair)')
         self.kernel = kernel
         # nonlocalAssembly_{SCALAR}.pxi:918-921
         self.zeroExterior = False if kernel.finiteHorizon else zeroExterior
@@ -340,22 +379,24 @@ class nonlocalBuilder:
         dev = torch.device('cuda', device)
         N = self.dm.num_dofs
         if C['problems'] is None:
-            C['problems'] = [_Problem(self.dm, k, k.getBoundaryKernel(), self.orders, device, self.params.get('max_regular_order', 32),
-                                      labels=C['labels'], blabels=C['blabels'], pair_class=C['pair_class'], active_class=i)
-                             for i, k in enumerate(C['kernels'])]
+            C['problems'] = [_Problem(self.dm, q['kernel'], q['kernel'].getBoundaryKernel(), self.orders, device,
+                                      self.params.get('max_regular_order', 32), labels=C['labels'], blabels=C['blabels'],
+                                      pair_class=q['pair_class'], bpair_class=q['bpair_class'], active_class=1,
+                                      pair_orientation=q['orientation'])
+                             for q in C['passes']]
         if out is not None:
             check_matrix_out(out, N, N, dev)
         A = torch.empty((N, N), dtype=torch.float64, device=dev) if out is None else out
         tmp = None
-        for i, prob in enumerate(C['problems']):
+        for i, (prob, q) in enumerate(zip(C['problems'], C['passes'])):
             target = A
             if i > 0:
                 tmp = torch.empty_like(A) if tmp is None else tmp
                 target = tmp
 
             def run():
-                _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, target.data_ptr(),
-                                                         target.stride(0), 1))
+                _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior and q['bpair_class'].any()), 0, N,
+                                                         target.data_ptr(), target.stride(0), 1))
             try:
                 run()
             except _lib.PNBError as e:
@@ -363,8 +404,11 @@ class nonlocalBuilder:
                     raise
                 prob.set_max_order(max(prob.required_max_order(self.zeroExterior), prob.max_order+1))
                 run()
-            if i > 0:
-                A += tmp
+            if i == 0:
+                if q['weight'] != 1.:
+                    A *= q['weight']
+            else:
+                A.add_(tmp, alpha=q['weight'])
         return Dense_LinearOperator(A, device)
 
     def _no_dm2(self):

@@ -287,6 +287,7 @@ struct pnb_problem {
     cudaEvent_t bev[2] = {};                        // surface-term kernel launched ahead of the schedule
     bool early_boundary = false;
     bool host_panels = false;                       // the last assembly copied its rows panel by panel
+    bool ordered_classes = false;   // piecewise kernels with an unsymmetric class table or reversed singular pairs: DoF-tile path only
     int path = 0;               // 0: default, 1: DoF-tile path for whole 2D operators too (pnb_problem_set_path)
     int pow_eoff = 240;      // PowTab::eoff of this problem
     std::vector<double> h_centers, h_h;
@@ -743,8 +744,8 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         rc |= upload(p, ahb.data(), (size_t)nb, &P.ahbf);
         if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
     }
-    P.labels = nullptr; P.blabels = nullptr; P.active_class = 0;
-    for (int l = 0; l < 4; l++) P.pair_class[l] = 0;
+    P.labels = nullptr; P.blabels = nullptr; P.active_class = 0; P.pair_orientation = 0;
+    for (int l = 0; l < 4; l++) P.pair_class[l] = P.bpair_class[l] = 0;
     if (kernel->cell_labels) {
         if (nb > 0 && !kernel->bfacet_labels) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "cell labels without boundary facet labels"); }
         rc |= upload(p, kernel->cell_labels, (size_t)nc, &P.labels);
@@ -752,8 +753,15 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
         P.active_class = kernel->active_class;
         for (int l1 = 0; l1 < 4; l1++)
-            for (int l2 = 0; l2 < 4; l2++) P.pair_class[l1] |= (unsigned)kernel->pair_class[l1 * 4 + l2] << (8 * l2);
+            for (int l2 = 0; l2 < 4; l2++) {
+                if (kernel->pair_class[l1 * 4 + l2] != kernel->pair_class[l2 * 4 + l1]) p->path = 1;
+                P.pair_class[l1] |= (unsigned)kernel->pair_class[l1 * 4 + l2] << (8 * l2);
+                P.bpair_class[l1] |= (unsigned)kernel->bpair_class[l1 * 4 + l2] << (8 * l2);
+            }
         p->h_labels.assign(kernel->cell_labels, kernel->cell_labels + nc);
+        P.pair_orientation = kernel->pair_orientation ? 1 : 0;
+        if (P.pair_orientation) p->path = 1;
+        p->ordered_classes = p->path == 1;
     }
     P.s = kernel->s; P.C = kernel->scaling; P.Cb = kernel->bscaling;
     P.sing = kernel->singularity; P.bsing = kernel->bsingularity;
@@ -925,6 +933,7 @@ extern "C" int pnb_problem_set_path(pnb_problem *p, int path)
 {
     if (!p || path < 0 || path > 1) return fail(PNB_ERR_ARG, "invalid argument");
     if (p->nblocks > 0 && path != 1) return fail(PNB_ERR_ARG, "batched blocks use the DoF-tile path");
+    if (p->ordered_classes && path != 1) return fail(PNB_ERR_ARG, "ordered pair classes / pair orientation use the DoF-tile path");
     p->path = path;
     return 0;
 }
@@ -1389,7 +1398,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                         countD = sm.rb.home[k1] == rt && sm.cb.home[k2] == ct;
                         const bool rin = (sm.rb.loc[k1] & 0x00FFFFFF) != 0x00FFFFFF, cin = (sm.cb.loc[k2] & 0x00FFFFFF) != 0x00FFFFFF;
                         if ((sm.rb.any[k1] || sm.cb.any[k2]) && (countD || (rin && cin)) &&
-                            (!P.labels || pnb_class_active(P, P.labels[K1], P.labels[K2]))) {
+                            (!P.labels || pnb_class_active(P, P.labels[min(K1, K2)], P.labels[max(K1, K2)]))) {
                             int panel;
                             if (K1 == K2) panel = -NV;
                             else {
@@ -1517,7 +1526,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                                 const int panel = cut ? sm.listpanel[q] - PNB_CUT_FLAG : sm.listpanel[q];
                                 const int Ka = sm.rb.cell[slot / SB], Kb = sm.cb.cell[slot % SB];
                                 // reference orientation of singular pairs: smaller cell index first
-                                const bool swapped = panel < 0 && Ka > Kb;
+                                const bool swapped = panel < 0 && (P.pair_orientation ? Ka < Kb : Ka > Kb);
                                 const int c1 = swapped ? Kb : Ka, c2 = swapped ? Ka : Kb;
                                 int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
                                 int pan = panel;
@@ -1768,7 +1777,7 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
         const int f = f0 + lane;
         int pan = 0;
         int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
-        const bool mine = f < fend && (!P.labels || pnb_class_active(P, P.labels[c1], P.blabels[f]));
+        const bool mine = f < fend && (!P.labels || pnb_bclass_active(P, P.labels[c1], P.blabels[f]));
         if (mine) {
             if (DIM == 2) {
                 pan = proto_panel(P.cells + (size_t)c1 * NV, NV, P.bfacets + (size_t)f * 2, 2, false, p1, p2);

@@ -85,12 +85,19 @@ struct DProblem {
     const unsigned char *blabels;  // nb
     int active_class;
     unsigned int pair_class[4];    // packed: byte l2 of word l1
+    unsigned int bpair_class[4];   // (cell label, boundary facet label)
+    int pair_orientation;          // singular pairs: 0 smaller cell index first, 1 larger first
 };
 
 // does the pair of labels belong to this problem instance?
 __host__ __device__ inline bool pnb_class_active(const DProblem &P, int l1, int l2)
 {
     return (int)((P.pair_class[l1 & 3] >> (8 * (l2 & 3))) & 0xFF) == P.active_class;
+}
+
+__host__ __device__ inline bool pnb_bclass_active(const DProblem &P, int lc, int lf)
+{
+    return (int)((P.bpair_class[lc & 3] >> (8 * (lf & 3))) & 0xFF) == P.active_class;
 }
 
 __host__ __device__ inline int tri_idx(int n, int i, int j) { return n * i - ((i * (i + 1)) >> 1) + j; }

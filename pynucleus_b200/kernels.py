@@ -41,14 +41,45 @@ class variableConstFractionalOrder(constFractionalOrder):
     pass
 
 
-class leftRightFractionalOrder:
-    """s(x,y) piecewise constant with an interface x_0 = const (fractionalOrders.pyx:285-335): sll / srr for both points
-    left / right of it, slr (= srl for a symmetric kernel) across.  A piecewise order: the reference evaluates it at the
-    cell centres, once per cell pair (kernel.evalParams, nonlocalOperator_{SCALAR}.pxi:509-513).
+class _blockFractionalOrder:
+    """piecewise constant order s(x,y) = sVals[block(x), block(y)].  The reference evaluates such an order at the cell
+    centres, once per ORDERED cell pair (kernel.evalParams, nonlocalOperator_{SCALAR}.pxi:509-513), and visits both
+    orientations of a pair when sVals is not symmetric (nonlocalAssembly_{SCALAR}.pxi:1412-1428).
 
-    `labels(points)` / `classes()` describe it to the device path: cells get the label 0 (left) or 1 (right), the pair
-    class of two labels selects one of the constant orders."""
+    `labels(points)` (block of every point, uint8 < 4) and `blockOrders()` (the matrix sVals) describe the order to the
+    device path, see nonlocalBuilder.setKernel."""
     numParameters = 1
+
+    def _finish(self, sVals):
+        self.sVals = np.array(sVals, dtype=np.float64)
+        self.min = float(self.sVals.min())
+        self.max = float(self.sVals.max())
+
+    def blockOrders(self):
+        return self.sVals
+
+    def classes(self):
+        """symmetric orders: (distinct orders, pair_class[4][4]) -- pass k takes the cell pairs of class k"""
+        assert self.symmetric
+        vals = []
+        for v in self.sVals.ravel().tolist():
+            if v not in vals:
+                vals.append(v)
+        pc = np.zeros((4, 4), dtype=np.uint8)
+        n = self.sVals.shape[0]
+        for i in range(n):
+            for j in range(n):
+                pc[i, j] = vals.index(self.sVals[i, j])
+        return vals, pc
+
+    def __call__(self, x, y):
+        lx, ly = self.labels(np.atleast_2d(np.asarray(x, dtype=float)))[0], self.labels(np.atleast_2d(np.asarray(y, dtype=float)))[0]
+        return float(self.sVals[lx, ly])
+
+
+class leftRightFractionalOrder(_blockFractionalOrder):
+    """interface x_0 = const (fractionalOrders.pyx:285-335): sll / srr for both points left / right of it, slr / srl across
+    (x left and y right / x right and y left); symmetric iff slr == srl"""
 
     def __init__(self, sll, srr, slr=np.nan, srl=np.nan, interface=0.):
         if not np.isfinite(slr):
@@ -57,28 +88,122 @@ class leftRightFractionalOrder:
             srl = 0.5*(sll+srr)
         self.sll, self.srr, self.slr, self.srl, self.interface = float(sll), float(srr), float(slr), float(srl), float(interface)
         self.symmetric = self.slr == self.srl
-        self.min = min(self.sll, self.srr, self.slr, self.srl)
-        self.max = max(self.sll, self.srr, self.slr, self.srl)
-
-    def __call__(self, x, y):
-        x0, y0 = np.atleast_1d(x)[0], np.atleast_1d(y)[0]
-        if x0 < self.interface:
-            return self.sll if y0 < self.interface else self.slr
-        return self.srl if y0 < self.interface else self.srr
+        self._finish([[self.sll, self.slr], [self.srl, self.srr]])
 
     def labels(self, points):
         return (np.asarray(points)[:, 0] >= self.interface).astype(np.uint8)
 
-    def classes(self):
-        """(orders per class, pair_class[4][4])"""
-        pc = np.zeros((4, 4), dtype=np.uint8)
-        pc[0, 1] = pc[1, 0] = 1
-        pc[1, 1] = 2
-        return [self.sll, self.slr, self.srr], pc
-
     def __repr__(self):
         return 'leftRightFractionalOrder(ll={},rr={},lr={},rl={},interface={},sym={})'.format(self.sll, self.srr, self.slr, self.srl,
                                                                                             self.interface, int(self.symmetric))
+
+
+class piecewiseConstantFractionalOrder(_blockFractionalOrder):
+    """blocks given by an indicator function x -> block number (fractionalOrders.pyx:218-283); off-diagonal orders that
+    are not finite default to the mean of the two diagonal ones; symmetric iff |sVals - sVals^T| < 1e-10"""
+
+    def __init__(self, dim, blockIndicator, sVals):
+        sVals = np.array(sVals, dtype=np.float64)
+        assert sVals.shape[0] == sVals.shape[1]
+        n = sVals.shape[0]
+        for i in range(n):
+            for j in range(n):
+                if i == j:
+                    assert np.isfinite(sVals[i, j])
+                elif not np.isfinite(sVals[i, j]):
+                    sVals[i, j] = 0.5*(sVals[i, i]+sVals[j, j])
+        self.dim = dim
+        self.blockIndicator = blockIndicator
+        self.symmetric = bool(np.absolute(sVals-sVals.T).max() < 1e-10)
+        self._finish(sVals)
+
+    @property
+    def numBlocks(self):
+        return self.sVals.shape[0]
+
+    def labels(self, points):
+        lab = np.array([int(self.blockIndicator(np.asarray(q, dtype=float))) for q in np.asarray(points)], dtype=np.int64)
+        if lab.size and (lab.min() < 0 or lab.max() >= self.numBlocks):
+            raise ValueError('block indicator outside [0, numBlocks)')
+        return lab.astype(np.uint8)
+
+    def __repr__(self):
+        return 'piecewiseConstantFractionalOrder(numBlocks={},sym={})'.format(self.numBlocks, self.symmetric)
+
+
+class layersFractionalOrder(_blockFractionalOrder):
+    """layers along the last coordinate (fractionalOrders.pyx:822-893): layer i = [b_i, b_{i+1}], the first match wins,
+    points outside fall into the first / last layer"""
+
+    def __init__(self, dim, layerBoundaries, layerOrders):
+        self.dim = dim
+        self.layerBoundaries = np.array(layerBoundaries, dtype=np.float64)
+        layerOrders = np.array(layerOrders, dtype=np.float64)
+        n = self.layerBoundaries.shape[0]-1
+        assert layerOrders.shape == (n, n)
+        self.layerOrders = layerOrders
+        self.symmetric = bool((layerOrders == layerOrders.T).all())
+        self._finish(layerOrders)
+
+    def labels(self, points):
+        c = np.asarray(points)[:, self.dim-1]
+        b = self.layerBoundaries
+        n = b.shape[0]-1
+        # first i with b_i <= c <= b_{i+1}
+        lab = np.searchsorted(b[1:], c, side='left')
+        lab = np.where(c <= b[0], 0, np.where(c >= b[n], n-1, np.minimum(lab, n-1)))
+        return lab.astype(np.uint8)
+
+    def __repr__(self):
+        return 'layersFractionalOrder(numLayers={})'.format(self.layerOrders.shape[0])
+
+
+class innerOuterFractionalOrder(_blockFractionalOrder):
+    """ball |x-center| < r and its complement (fractionalOrders.pyx:675-733)"""
+
+    def __init__(self, dim, sii, soo, r, center, sio=np.nan, soi=np.nan):
+        if not np.isfinite(sio):
+            sio = 0.5*(sii+soo)
+        if not np.isfinite(soi):
+            soi = 0.5*(sii+soo)
+        self.dim, self.r2, self.center = dim, float(r)*float(r), np.array(center, dtype=np.float64)
+        self.sii, self.soo, self.sio, self.soi = float(sii), float(soo), float(sio), float(soi)
+        self.symmetric = self.sio == self.soi
+        self._finish([[self.sii, self.sio], [self.soi, self.soo]])
+
+    def labels(self, points):
+        p = np.asarray(points)
+        r2 = np.zeros(p.shape[0])
+        for i in range(self.dim):
+            r2 = r2+(p[:, i]-self.center[i])**2
+        return (r2 >= self.r2).astype(np.uint8)
+
+    def __repr__(self):
+        return 'innerOuterFractionalOrder(ii={},oo={},io={},oi={},r={},sym={})'.format(self.sii, self.soo, self.sio, self.soi,
+                                                                                     np.sqrt(self.r2), self.symmetric)
+
+
+class islandsFractionalOrder(_blockFractionalOrder):
+    """islands r <= |x_i| <= r2 in every coordinate (fractionalOrders.pyx:737-819, 2D)"""
+
+    def __init__(self, sii, soo, r, r2, sio=np.nan, soi=np.nan):
+        if not np.isfinite(sio):
+            sio = 0.5*(sii+soo)
+        if not np.isfinite(soi):
+            soi = 0.5*(sii+soo)
+        self.r, self.r2 = float(r), float(r2)
+        self.sii, self.soo, self.sio, self.soi = float(sii), float(soo), float(sio), float(soi)
+        self.symmetric = self.sio == self.soi
+        self._finish([[self.sii, self.sio], [self.soi, self.soo]])
+
+    def labels(self, points):
+        p = np.absolute(np.asarray(points)[:, :2])
+        inside = ((p >= self.r) & (p <= self.r2)).all(axis=1)
+        return (~inside).astype(np.uint8)
+
+    def __repr__(self):
+        return 'islandsFractionalOrder(ii={},oo={},io={},oi={},r={},r2={},sym={})'.format(self.sii, self.soo, self.sio, self.soi,
+                                                                                        self.r, self.r2, self.symmetric)
 
 
 class constant:
@@ -294,9 +419,11 @@ def getFractionalKernel(dim, s, horizon=None, interaction=None, scaling=None, no
     horizonFun = _getHorizon(horizon)
     if derivative != 0 or tempered != 0. or manifold:
         raise NotImplementedError('derivative / tempered / manifold kernels are outside the accelerated path')
-    if isinstance(sFun, leftRightFractionalOrder):
-        if not sFun.symmetric or horizonFun.value != np.inf or not normalized or scaling is not None:
-            raise NotImplementedError('piecewise orders: symmetric, infinite horizon, normalised kernels only')
+    if isinstance(sFun, _blockFractionalOrder):
+        if horizonFun.value != np.inf or not normalized or scaling is not None:
+            raise NotImplementedError('piecewise orders: infinite horizon, normalised kernels only')
+        if not piecewise:
+            raise NotImplementedError('orders evaluated per quadrature node (piecewise=False) are outside the accelerated path')
         # the scaling is a function of s(x,y) (variableFractionalLaplacianScaling, kernelNormalization.pyx:421-499):
         # evaluated per class by the builder
         return FractionalKernel(dim, sFun, horizonFun, np.nan, boundary=boundary, phi=phi, piecewise=piecewise)

@@ -119,8 +119,13 @@ class localMatrixOrders:
     """target order and singular quadrature orders of the interior and boundary
     local matrices (setKernel of fractionalLaplacian{1,2}D[_boundary])."""
 
-    def __init__(self, dim, singularity, bsingularity, hmin, H0, num_dofs, target_order=None, polynomialOrder=1):
+    def __init__(self, dim, singularity, bsingularity, hmin, H0, num_dofs, target_order=None, polynomialOrder=1,
+                 min_singularity=None, min_bsingularity=None):
+        # variable orders: `singularity` is kernel.max_singularity (from s.max), `min_singularity` kernel.min_singularity
+        # (from s.min); they only differ in the 1D default target order
         lg = abs(log(hmin/H0))
+        min_singularity = singularity if min_singularity is None else min_singularity
+        min_bsingularity = bsingularity if min_bsingularity is None else min_bsingularity
         if dim == 2:
             # fractionalLaplacian2D.pyx:600-615, 1210-1220
             to = 0.5 if target_order is None else target_order
@@ -133,12 +138,14 @@ class localMatrixOrders:
             self.bquad_order_diagonal = int(max(ceil((to+0.5+smaxb)/0.35*lg), 2))
         else:
             # fractionalLaplacian1D.pyx:218-228, 629-639
-            smin = smax = max(-0.5*(singularity+1), 0.)
+            smax = max(-0.5*(singularity+1), 0.)
+            smin = max(-0.5*(min_singularity+1), 0.)
             to = polynomialOrder+1-smin if target_order is None else target_order
             self.target_order = to
             self.quad_order_diagonal = int(max(ceil(((to+2.)*log(num_dofs*H0)+(2.*smax-1.)*lg)/0.8), 2))
             self.quad_order_diagonalV = self.quad_order_diagonal
-            sminb = smaxb = max(0.5*(-bsingularity), 0.)
+            smaxb = max(0.5*(-bsingularity), 0.)
+            sminb = max(0.5*(-min_bsingularity), 0.)
             tob = polynomialOrder+1-sminb if target_order is None else target_order
             self.btarget_order = tob
             self.bquad_order_diagonal = int(max(ceil(((tob+1.)*log(num_dofs*H0)+(2.*smaxb-1.)*lg)/0.8), 2))

@@ -826,3 +826,27 @@ def test_mesh_without_unknowns():
     A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(1, 0.25), {}).getDense()
     assert A.shape == (0, 0) and A.data.shape == (0, 0)
     assert A.matvec(np.zeros(0)).shape == (0, )
+
+
+@pytest.mark.parametrize('name', ['nonsym_disc_leftright_r2', 'nonsym_disc_leftright_r3', 'nonsym_interval_leftright_r5',
+                                  'nonsym_disc_layers_r3', 'disc_layers_sym_r2', 'nonsym_interval_innerouter_r5'])
+def test_unsymmetric_piecewise_order_vs_reference(golden_dir, name):
+    """Unsymmetric piecewise constant orders s(x,y) != s(y,x) (the reference switches to
+    fractionalLaplacian{1,2}D_nonsym and visits both orientations of every cell pair,
+    nonlocalAssembly_{SCALAR}.pxi:1412-1428): two half-weight passes per order over the two orientations; leftRight,
+    layers (3 blocks) and innerOuter orders, 1D and 2D, with and without the surface terms"""
+    import pynucleus_b200 as pb
+    from test_oracle_golden import order_from_fixture
+    g = load(golden_dir, name)
+    dim = g['vertices'].shape[1]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'])
+    dm = pb.P1_DoFMap(mesh)
+    s = order_from_fixture(g)
+    kernel = pb.getFractionalKernel(dim, s)
+    assert kernel.variable and kernel.symmetric == bool(g['symmetric'])
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = pb.nonlocalBuilder(dm, kernel, params, zeroExterior=ze)
+        assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+        A = b.getDense().data
+        assert entry_err(A, g[key]) < TOL

@@ -254,3 +254,60 @@ def test_oracle_mesh_sizes_bit_exact_vs_reference(golden_dir):
         assert np.array_equal(m.volVector, g['volVector']), f
         n += 1
     assert n >= 10
+
+
+NONSYM = ['nonsym_disc_leftright_r2', 'nonsym_disc_leftright_r3', 'nonsym_interval_leftright_r5', 'nonsym_disc_layers_r3',
+          'disc_layers_sym_r2', 'nonsym_interval_innerouter_r5']
+
+
+def order_from_fixture(g):
+    import pynucleus_b200 as pb
+    kind = str(g['kind'])
+    dim = g['vertices'].shape[1]
+    if kind == 'leftRight':
+        return pb.leftRightFractionalOrder(float(g['sll']), float(g['srr']), float(g['slr']), float(g['srl']), float(g['interface']))
+    if kind == 'layers':
+        return pb.layersFractionalOrder(dim, g['layerBoundaries'], g['layerOrders'])
+    if kind == 'innerOuter':
+        return pb.innerOuterFractionalOrder(dim, float(g['sii']), float(g['soo']), float(g['r']), g['center'], float(g['sio']), float(g['soi']))
+    raise NotImplementedError(kind)
+
+
+@pytest.mark.parametrize('name', NONSYM)
+def test_unsymmetric_piecewise_order_matches_reference(golden_dir, name):
+    """Unsymmetric piecewise orders (fractionalLaplacian{1,2}D_nonsym, fractionalLaplacian2D.pyx:894-1184; both
+    orientations of a pair visited, nonlocalAssembly_{SCALAR}.pxi:1412-1428).  With piecewise parameters the orientation
+    (c1, c2) contributes the symmetric local matrix of s(c1, c2) at weight 1, with c1 as first cell of the singular rule:
+    restated as two constant-order passes per order at half weight, over the orientations (smaller, larger cell index)
+    and (larger, smaller) of that order."""
+    g = load(golden_dir, name)
+    sFun = order_from_fixture(g)
+    dim = g['vertices'].shape[1]
+    assert bool(g['symmetric']) == sFun.symmetric
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices'].reshape(-1, 1)
+    labels = sFun.labels(g['vertices'][g['cells']].mean(axis=1))
+    blabels = sFun.labels(g['vertices'][bf].mean(axis=1))
+    sV = sFun.blockOrders()
+    nb = sV.shape[0]
+    vals = sorted(set(sV.ravel().tolist()))
+    pc = np.array([[vals.index(sV[i, j]) for j in range(nb)] for i in range(nb)])
+    kw = dict(bfacets=bf, hVector=g['hVector'], volVector=g['volVector'], hmin=float(g['hmin']), diam=float(g['diam']),
+              s_max=max(vals), s_min=min(vals), labels=labels, blabels=blabels, active_class=1, max_order=40)
+    if dim == 2:
+        kw['target_order'] = 0.5
+
+    def problem(k, M, orientation):
+        P4, B4 = np.zeros((4, 4), dtype=np.uint8), np.zeros((4, 4), dtype=np.uint8)
+        P4[:nb, :nb] = M
+        B4[:nb, :nb] = pc == k
+        return oracle.Problem(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), vals[k], pair_class=P4, bpair_class=B4,
+                              pair_orientation=orientation, **kw)
+
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        A = 0.
+        for k in range(len(vals)):
+            if sFun.symmetric:
+                A = A+problem(k, pc == k, 0).dense(ze)
+            else:
+                A = A+0.5*problem(k, pc == k, 0).dense(ze)+0.5*problem(k, (pc == k).T, 1).dense(ze)
+        assert np.abs(A-g[key]).max() < 1e-13*np.abs(g[key]).max()
