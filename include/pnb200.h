@@ -296,6 +296,67 @@ int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, cons
                         const int32_t *m1, const int32_t *m2, int32_t max_m, const double *eta,
                         const int32_t *eta_ptr, const int64_t *offsets, double *out);
 
+/* ---- H2 operator on the device -------------------------------------------------------------------------
+ * Replaces H2Matrix.matvec (nl/PyNucleus_nl/clusterMethodCy.pyx:2269-2295) with its upwardPass / downwardPass
+ * (:1093-1176) and tree_node.enterLeafValues (:1205-1325).  The caller describes the cluster tree node by node
+ * (ids = positions in the arrays; the root has parent -1), hands over the transfer operators, the far-field kernel blocks
+ * (pnb_farfield_blocks) and the near field as a CSR matrix; the leaf moments are either supplied or computed on the
+ * device from the mesh.  All arrays are host memory unless stated; the library copies what it keeps. */
+typedef struct pnb_h2 pnb_h2;
+typedef struct {
+    int32_t dim, num_dofs, num_nodes;
+    const int32_t *coef_ptr;       /* num_nodes+1: node n owns coef_ptr[n+1]-coef_ptr[n] = m_n^dim coefficients */
+    const int32_t *parent;         /* num_nodes, -1 for the root */
+    const int32_t *level;          /* num_nodes, root = 0 */
+    /* leaves */
+    int32_t num_leaves;
+    const int32_t *leaf_node;      /* num_leaves: node id */
+    const int32_t *leaf_dof_ptr;   /* num_leaves+1 */
+    const int32_t *leaf_dofs;      /* dofs of the leaves (every dof in exactly one leaf) */
+    const double *leaf_values;     /* V[dof][alpha] of all leaves back to back (row-major), or NULL: computed on the
+                                    * device from the fields below */
+    const int32_t *leaf_cell_ptr;  /* num_leaves+1: cells around the dofs of a leaf, ascending */
+    const int32_t *leaf_cells;
+    const int32_t *leaf_cell_pos;  /* (dim+1) per listed cell: position of its dofs in the leaf's dof list, -1 = elsewhere */
+    const double *leaf_boxes;      /* num_leaves x dim x 2 */
+    const int32_t *leaf_orders;    /* num_leaves: interpolation order m */
+    int32_t num_vertices, num_cells;
+    const double *vertices;        /* num_vertices x dim */
+    const int32_t *cells;          /* num_cells x (dim+1) */
+    const double *vol;             /* num_cells */
+    int32_t max_m;                 /* largest interpolation order */
+    const int32_t *rule_n;         /* max_m+1: nodes of the rule of order m+2 on the reference simplex used by leaves of
+                                    * interpolation order m (0 where no leaf has that order) */
+    const int64_t *rule_bary_ptr;  /* max_m+1: start of the (dim+1) x rule_n[m] barycentric coordinates in rule_bary */
+    const int64_t *rule_w_ptr;     /* max_m+1: start of the rule_n[m] weights in rule_w */
+    const double *rule_bary;
+    const double *rule_w;
+    int64_t rule_bary_size, rule_w_size;
+    const double *eta;             /* 1D Chebyshev nodes as in pnb_farfield_blocks */
+    const int32_t *eta_ptr;        /* max_m+2 */
+    /* transfer operators: T[m_parent^dim][m_node^dim] (row-major) at transfer_ptr[n]; -1 for the root */
+    const int64_t *transfer_ptr;
+    const double *transfer;
+    int64_t transfer_size;
+    /* admissible pairs (n1, n2) with their blocks K[m1^dim][m2^dim] at far_ptr[k] */
+    int32_t num_far;
+    const int32_t *far_n1, *far_n2;
+    const int64_t *far_ptr;
+    const double *far_blocks;
+    int64_t far_size;
+    /* near field, CSR, DEVICE memory (kept by the caller while the handle lives is NOT required: copied) */
+    const int64_t *near_indptr;    /* device, num_dofs+1, or NULL */
+    const int64_t *near_indices;   /* device */
+    const double *near_data;       /* device */
+} pnb_h2_desc_t;
+
+int pnb_h2_create(int device, const pnb_h2_desc_t *desc, pnb_h2 **out);
+/* leaf moments as computed or supplied: host buffer of the size of all V blocks */
+int pnb_h2_leaf_values(pnb_h2 *h, double *out);
+/* y = H x; x, y device memory, stream a cudaStream_t.  far_only != 0: without the near field */
+int pnb_h2_matvec(pnb_h2 *h, const double *x, double *y, int far_only, void *stream);
+int pnb_h2_destroy(pnb_h2 *h);
+
 /* Dense_LinearOperator.matvec (base/PyNucleus_base/DenseLinearOperator_{SCALAR}.pxi:14-18
  * -> dgemv, opt_true_blas.pxi:159): y = A x for a row block.  All pointers are
  * device memory on `device`; stream is a cudaStream_t (0 = default stream). */

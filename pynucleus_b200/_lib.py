@@ -48,6 +48,24 @@ class pnb_rules_t(ctypes.Structure):
                 ('cell', ctypes.POINTER(pnb_rule_t)), ('facet', ctypes.POINTER(pnb_rule_t))]
 
 
+class pnb_h2_desc_t(ctypes.Structure):
+    _fields_ = [('dim', ctypes.c_int32), ('num_dofs', ctypes.c_int32), ('num_nodes', ctypes.c_int32),
+                ('coef_ptr', ctypes.c_void_p), ('parent', ctypes.c_void_p), ('level', ctypes.c_void_p),
+                ('num_leaves', ctypes.c_int32), ('leaf_node', ctypes.c_void_p), ('leaf_dof_ptr', ctypes.c_void_p),
+                ('leaf_dofs', ctypes.c_void_p), ('leaf_values', ctypes.c_void_p), ('leaf_cell_ptr', ctypes.c_void_p),
+                ('leaf_cells', ctypes.c_void_p), ('leaf_cell_pos', ctypes.c_void_p), ('leaf_boxes', ctypes.c_void_p),
+                ('leaf_orders', ctypes.c_void_p), ('num_vertices', ctypes.c_int32), ('num_cells', ctypes.c_int32),
+                ('vertices', ctypes.c_void_p), ('cells', ctypes.c_void_p), ('vol', ctypes.c_void_p),
+                ('max_m', ctypes.c_int32), ('rule_n', ctypes.c_void_p), ('rule_bary_ptr', ctypes.c_void_p),
+                ('rule_w_ptr', ctypes.c_void_p), ('rule_bary', ctypes.c_void_p), ('rule_w', ctypes.c_void_p),
+                ('rule_bary_size', ctypes.c_int64), ('rule_w_size', ctypes.c_int64),
+                ('eta', ctypes.c_void_p), ('eta_ptr', ctypes.c_void_p),
+                ('transfer_ptr', ctypes.c_void_p), ('transfer', ctypes.c_void_p), ('transfer_size', ctypes.c_int64),
+                ('num_far', ctypes.c_int32), ('far_n1', ctypes.c_void_p), ('far_n2', ctypes.c_void_p),
+                ('far_ptr', ctypes.c_void_p), ('far_blocks', ctypes.c_void_p), ('far_size', ctypes.c_int64),
+                ('near_indptr', ctypes.c_void_p), ('near_indices', ctypes.c_void_p), ('near_data', ctypes.c_void_p)]
+
+
 # every symbol include/pnb200.h declares
 EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_create', 'pnb_problem_set_rules',
            'pnb_problem_destroy', 'pnb_max_order', 'pnb_classify_pairs', 'pnb_panel_histogram',
@@ -57,7 +75,8 @@ EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_cre
            'pnb_release_cached_memory', 'pnb_dense_kernel_timings', 'pnb_dist_plan', 'pnb_dist_rows', 'pnb_dist_eval',
            'pnb_dist_status', 'pnb_dist_apply', 'pnb_device_alloc', 'pnb_device_free', 'pnb_ipc_export', 'pnb_ipc_import',
            'pnb_ipc_close',
-           'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths', 'pnb_problem_set_path', 'pnb_sparsity_mask', 'pnb_block_alignment']
+           'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths', 'pnb_problem_set_path', 'pnb_sparsity_mask', 'pnb_block_alignment',
+           'pnb_h2_create', 'pnb_h2_leaf_values', 'pnb_h2_matvec', 'pnb_h2_destroy']
 
 _LIB = None
 
@@ -120,6 +139,10 @@ def lib():
         L.pnb_fp64_peak.argtypes = [ctypes.c_int, c_double_p]
         L.pnb_mesh_edge_lengths.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             c_double_p, c_double_p]
+        L.pnb_h2_create.argtypes = [ctypes.c_int, ctypes.POINTER(pnb_h2_desc_t), ctypes.POINTER(ctypes.c_void_p)]
+        L.pnb_h2_leaf_values.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.pnb_h2_matvec.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.pnb_h2_destroy.argtypes = [ctypes.c_void_p]
         _LIB = L
     return _LIB
 

@@ -712,9 +712,10 @@ class nonlocalBuilder:
         if sum(len(v) for v in Pfar_nodes.values()) == 0:
             H = self.getDense()
         else:
-            d2c = h2.dof_to_cells(self.dm)
+            host_leaves = not self.params.get('h2_device_engine', True)
+            d2c = h2.dof_to_cells(self.dm) if host_leaves else None
             for n in root.get_tree_nodes():
-                if n.isLeaf:
+                if n.isLeaf and host_leaves:
                     n.value = h2.leaf_values(n, self.mesh, self.dm, d2c)
                 if n.parent is not None:
                     n.transferOperator = h2.transfer_operator(n.parent, n)
@@ -729,7 +730,11 @@ class nonlocalBuilder:
             near = self.assembleClusters(Pnear)
             near.compile()
             H = h2.H2Matrix(root, Pfar, near, self.dm.num_dofs, dev)
-            H.compile()
+            if host_leaves:
+                H.compile()         # library sparse products (validation path)
+            else:
+                # leaf moments, the three passes and the near-field product by the library's own kernels
+                H.build_engine(self.mesh, self.dm)
         out = (H, )
         if returnNearField:
             out += (Pnear, )

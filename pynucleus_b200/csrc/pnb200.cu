@@ -3443,3 +3443,5 @@ extern "C" int pnb_fp64_peak(int device, double *tflops)
     *tflops = best;
     return 0;
 }
+
+#include "pnb_h2.cuh"

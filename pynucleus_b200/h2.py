@@ -225,7 +225,149 @@ class H2Matrix:
             down = down+torch.mv(Ut, down)
         return torch.mv(self._Bt, down)
 
+    # ---- device engine: own kernels for the three passes and the near field (pnb_h2_*, csrc/pnb_h2.cuh) -------------
+    def build_engine(self, mesh=None, dm=None, leaf_values_on_device=True):
+        """Hands the tree, the transfer operators, the far-field blocks and the near field (CSR) to libpnb200.  With a
+        mesh the leaf moments V (enterLeafValues, clusterMethodCy.pyx:1205-1325) are computed by the device kernel and
+        written back to `node.value`; otherwise the values already attached to the leaves are uploaded."""
+        import ctypes
+        from . import _lib
+        nodes = list(self.tree.get_tree_nodes())
+        index = {n.id: k for k, n in enumerate(nodes)}
+        dim = self.tree.dim
+        nn = len(nodes)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)      # noqa: E731
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)      # noqa: E731
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)    # noqa: E731
+        mm = np.array([n.interpolation_order**dim for n in nodes], dtype=np.int64)
+        coef_ptr = i32(np.concatenate(([0], np.cumsum(mm))))
+        parent = i32([index[n.parent.id] if n.parent is not None else -1 for n in nodes])
+        level = i32([n.levelNo-self.tree.levelNo for n in nodes])
+        leaves = [n for n in nodes if n.isLeaf]
+        leaf_node = i32([index[n.id] for n in leaves])
+        leaf_dof_ptr = i32(np.concatenate(([0], np.cumsum([n.dofs.shape[0] for n in leaves]))))
+        leaf_dofs = i32(np.concatenate([n.dofs for n in leaves])) if leaves else i32([])
+        if leaf_dofs.shape[0] != np.unique(leaf_dofs).shape[0]:
+            raise ValueError('the leaves of the cluster tree must partition the dofs')
+        keep = [coef_ptr, parent, level, leaf_node, leaf_dof_ptr, leaf_dofs]
+        D = _lib.pnb_h2_desc_t()
+        D.dim, D.num_dofs, D.num_nodes = dim, self.num_rows, nn
+        D.coef_ptr, D.parent, D.level = coef_ptr.ctypes.data, parent.ctypes.data, level.ctypes.data
+        D.num_leaves = len(leaves)
+        D.leaf_node, D.leaf_dof_ptr, D.leaf_dofs = leaf_node.ctypes.data, leaf_dof_ptr.ctypes.data, leaf_dofs.ctypes.data
+        on_device = leaf_values_on_device and mesh is not None
+        if on_device:
+            # cells around the dofs of every leaf (ascending) and the positions of their dofs in the leaf
+            N = self.num_rows
+            dof_leaf = np.full(N, -1, dtype=np.int64)
+            dof_pos = np.zeros(N, dtype=np.int64)
+            for k, n in enumerate(leaves):
+                dof_leaf[n.dofs] = k
+                dof_pos[n.dofs] = np.arange(n.dofs.shape[0])
+            cd = np.asarray(dm.dofs)
+            nv = cd.shape[1]
+            cl = np.where(cd >= 0, dof_leaf[np.maximum(cd, 0)], -1)                 # leaf of every cell dof
+            key = (cl.astype(np.int64)*mesh.num_cells+np.arange(mesh.num_cells)[:, None])[cl >= 0]
+            key = np.unique(key)                                                    # (leaf, cell) ascending
+            lc_leaf, lc_cell = key//mesh.num_cells, key % mesh.num_cells
+            leaf_cell_ptr = i32(np.concatenate(([0], np.cumsum(np.bincount(lc_leaf, minlength=len(leaves))))))
+            pos = np.where(cl[lc_cell] == lc_leaf[:, None], dof_pos[np.maximum(cd[lc_cell], 0)], -1)
+            leaf_cells, leaf_cell_pos = i32(lc_cell), i32(pos.reshape(-1, nv))
+            boxes = f64(np.stack([n.box for n in leaves])) if leaves else f64(np.zeros((0, dim, 2)))
+            orders = i32([n.interpolation_order for n in leaves])
+            max_m = int(orders.max()) if leaves else 1
+            rule_n = np.zeros(max_m+1, dtype=np.int32)
+            bptr, wptr = np.zeros(max_m+1, dtype=np.int64), np.zeros(max_m+1, dtype=np.int64)
+            barys, ws = [], []
+            for m in sorted(set(orders.tolist())):
+                bary, w = quadrature.regular(m+2, dim)          # P1: quadOrder = order+2 (Sauter/Schwab p. 428)
+                rule_n[m] = w.shape[0]
+                bptr[m] = sum(b.size for b in barys)
+                wptr[m] = sum(x.size for x in ws)
+                barys.append(f64(bary).ravel())
+                ws.append(f64(w))
+            rule_bary, rule_w = f64(np.concatenate(barys)), f64(np.concatenate(ws))
+            eta_ptr = np.zeros(max_m+2, dtype=np.int32)
+            etas = []
+            for m in range(max_m+1):
+                eta_ptr[m] = sum(e.shape[0] for e in etas)
+                etas.append(np.cos((2.0*np.arange(m, 0, -1)-1.0)/(2.0*m)*np.pi) if m > 0 else np.zeros(0))
+            eta_ptr[max_m+1] = sum(e.shape[0] for e in etas)
+            eta = f64(np.concatenate(etas))
+            vertices, cells, vol = f64(mesh.vertices), i32(mesh.cells), f64(mesh.volVector)
+            keep += [leaf_cell_ptr, leaf_cells, leaf_cell_pos, boxes, orders, rule_n, bptr, wptr, rule_bary, rule_w, eta_ptr, eta,
+                     vertices, cells, vol]
+            D.leaf_values = None
+            D.leaf_cell_ptr, D.leaf_cells, D.leaf_cell_pos = leaf_cell_ptr.ctypes.data, leaf_cells.ctypes.data, leaf_cell_pos.ctypes.data
+            D.leaf_boxes, D.leaf_orders = boxes.ctypes.data, orders.ctypes.data
+            D.num_vertices, D.num_cells = mesh.num_vertices, mesh.num_cells
+            D.vertices, D.cells, D.vol = vertices.ctypes.data, cells.ctypes.data, vol.ctypes.data
+            D.max_m, D.rule_n, D.rule_bary_ptr, D.rule_w_ptr = max_m, rule_n.ctypes.data, bptr.ctypes.data, wptr.ctypes.data
+            D.rule_bary, D.rule_w, D.rule_bary_size, D.rule_w_size = rule_bary.ctypes.data, rule_w.ctypes.data, rule_bary.size, rule_w.size
+            D.eta, D.eta_ptr = eta.ctypes.data, eta_ptr.ctypes.data
+        else:
+            V = f64(np.concatenate([np.asarray(n.value).ravel() for n in leaves])) if leaves else f64([])
+            keep.append(V)
+            D.leaf_values = V.ctypes.data
+        tsz = np.array([0 if n.parent is None else n.parent.interpolation_order**dim*n.interpolation_order**dim for n in nodes],
+                       dtype=np.int64)
+        tstart = np.concatenate(([0], np.cumsum(tsz)))
+        transfer_ptr = i64(np.where(tsz > 0, tstart[:-1], -1))
+        transfer = f64(np.concatenate([np.asarray(n.transferOperator).ravel() for n in nodes if n.parent is not None])
+                       if nn > 1 else [])
+        pairs = [cp for lvl in self.Pfar for cp in self.Pfar[lvl]]
+        far_n1, far_n2 = i32([index[cp.n1.id] for cp in pairs]), i32([index[cp.n2.id] for cp in pairs])
+        fsz = np.array([cp.kernelInterpolant.size for cp in pairs], dtype=np.int64)
+        far_ptr = i64(np.concatenate(([0], np.cumsum(fsz))))
+        far_blocks = f64(np.concatenate([np.asarray(cp.kernelInterpolant).ravel() for cp in pairs]) if pairs else [])
+        keep += [transfer_ptr, transfer, far_n1, far_n2, far_ptr, far_blocks]
+        D.transfer_ptr, D.transfer, D.transfer_size = transfer_ptr.ctypes.data, transfer.ctypes.data, transfer.size
+        D.num_far, D.far_n1, D.far_n2 = len(pairs), far_n1.ctypes.data, far_n2.ctypes.data
+        D.far_ptr, D.far_blocks, D.far_size = far_ptr.ctypes.data, far_blocks.ctypes.data, far_blocks.size
+        csr = getattr(self.Anear, '_csr', None)
+        if csr is not None:
+            crow, col, val = csr.crow_indices(), csr.col_indices(), csr.values()
+            keep += [crow, col, val]
+            D.near_indptr, D.near_indices, D.near_data = crow.data_ptr(), col.data_ptr(), val.data_ptr()
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().pnb_h2_create(self.device.index if self.device.index is not None else 0, ctypes.byref(D),
+                                            ctypes.byref(handle)))
+        self._engine = handle
+        self._engine_near = csr is not None
+        if on_device:
+            nV = int(sum(n.dofs.shape[0]*n.interpolation_order**dim for n in leaves))
+            V = np.empty(nV)
+            _lib.check(_lib.lib().pnb_h2_leaf_values(handle, V.ctypes.data))
+            o = 0
+            for n in leaves:
+                sz = n.dofs.shape[0]*n.interpolation_order**dim
+                n.value = V[o:o+sz].reshape(n.dofs.shape[0], -1)
+                o += sz
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, '_engine', None):
+                from . import _lib
+                _lib.lib().pnb_h2_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
     def matvec_device(self, x, y=None):
+        import torch
+        if getattr(self, '_engine', None):
+            from . import _lib
+            from .linear_operators import _check_vector
+            if y is None:
+                y = torch.empty(self.num_rows, dtype=torch.float64, device=self.device)
+            _check_vector(x, self.num_columns, self.device, 'x')
+            _check_vector(y, self.num_rows, self.device, 'y')
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib().pnb_h2_matvec(self._engine, x.data_ptr(), y.data_ptr(), 0 if self._engine_near else 1, stream))
+            if not self._engine_near and self.Anear is not None:
+                y += self.Anear.matvec_device(x)
+            return y
         out = self.farfield_compiled(x) if getattr(self, '_compiled', False) else self.farfield_device(x)
         if self.Anear is not None:
             out += self.Anear.matvec_device(x)

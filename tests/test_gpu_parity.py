@@ -850,3 +850,38 @@ def test_unsymmetric_piecewise_order_vs_reference(golden_dir, name):
         assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
         A = b.getDense().data
         assert entry_err(A, g[key]) < TOL
+
+
+@pytest.mark.parametrize('name', ['h2_interval_s0.25_r8', 'h2_disc_s0.75_r4'])
+def test_h2_device_engine(golden_dir, name):
+    """The library's own H2 kernels (pnb_h2_*: leaf moments, upward / far-field / downward passes, CSR near field;
+    clusterMethodCy.pyx:1093-1325, 2269-2295): leaf moments against the host restatement, far field and whole product
+    against the reference's H2 matvec and against the node-by-node torch recursion, bitwise reproducible"""
+    import scipy.sparse as sp
+    import torch
+    from pynucleus_b200 import h2, _lib
+    g = load(golden_dir, name)
+    b = builder_from_golden(g)
+    H = b.getH2()
+    assert getattr(H, '_engine', None), 'the device engine must be the path that runs'
+    d2c = h2.dof_to_cells(b.dm)
+    for n in H.tree.get_tree_nodes():
+        if n.isLeaf:
+            V = h2.leaf_values(n, b.mesh, b.dm, d2c)
+            assert np.abs(V-n.value).max() < 1e-13*np.abs(V).max()
+    x = torch.as_tensor(g['x']).cuda()
+    N = b.dm.num_dofs
+    yfar = torch.empty(N, dtype=torch.float64, device='cuda')
+    _lib.check(_lib.lib().pnb_h2_matvec(H._engine, x.data_ptr(), yfar.data_ptr(), 1, torch.cuda.current_stream().cuda_stream))
+    low = sp.csr_matrix((g['Anear_data'], g['Anear_indices'], g['Anear_indptr']), shape=(N, N))
+    ref_far = g['Hx']-(low+low.T+sp.diags(g['Anear_diagonal'])).dot(g['x'])
+    assert np.abs(yfar.cpu().numpy()-ref_far).max() < 1e-11*np.abs(ref_far).max()
+    ytorch = H.farfield_device(x)
+    assert float((yfar-ytorch).abs().max()) < 1e-13*float(ytorch.abs().max())
+    y1, y2 = H.matvec_device(x), H.matvec_device(x)
+    assert torch.equal(y1, y2)
+    assert np.abs(y1.cpu().numpy()-g['Hx']).max() < 1e-11*np.abs(g['Hx']).max()
+    # the library-SpMV formulation gives the same product
+    H.compile()
+    yc = H.farfield_compiled(x)+H.Anear.matvec_device(x)
+    assert float((y1-yc).abs().max()) < 1e-12*float(yc.abs().max())
