@@ -296,6 +296,16 @@ int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, cons
                         const int32_t *m1, const int32_t *m2, int32_t max_m, const double *eta,
                         const int32_t *eta_ptr, const int64_t *offsets, double *out);
 
+/* Dense operator for a DoFMap that is not P1 (P2 on intervals and triangles; P1 accepted for cross-checks): the
+ * reference runs the same assembly loop with (2 dpe)(2 dpe + 1)/2 local entries built from the DoFMap's shape functions
+ * (nonlocalAssembly_{SCALAR}.pxi:1386-1448 with fractionalLaplacian2D.pyx:644-891).  `p` carries the mesh, the kernel and
+ * the tables (create it with the vertex dofs of the map as a P1 table and kernel.order_num_dofs = num_dofs); `dofs` is the
+ * element's cell -> dof table (host, num_cells x dofs_per_element, the reference's local order: vertices, then edges
+ * (0,1), (1,2), (0,2); 1D: vertices, then the cell).  One warp owns one row of the operator (no atomics, bitwise
+ * reproducible); infinite horizon, constant kernels.  A: device, num_dofs x num_dofs, row-major. */
+int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
+                               int zero_exterior, double *A, int64_t ld);
+
 /* ---- H2 operator on the device -------------------------------------------------------------------------
  * Replaces H2Matrix.matvec (nl/PyNucleus_nl/clusterMethodCy.pyx:2269-2295) with its upwardPass / downwardPass
  * (:1093-1176) and tree_node.enterLeafValues (:1205-1325).  The caller describes the cluster tree node by node

@@ -166,6 +166,12 @@ class nonlocalBuilder:
     def setKernel(self, kernel, zeroExterior=True):
         from .kernels import constFractionalOrder, getFractionalKernel
         self._classes = None
+        self._element = self.dm.polynomialOrder != 1
+        if self._element:
+            if self.dm.polynomialOrder != 2:
+                raise NotImplementedError('P1 and P2 elements')
+            if self.dm2 is not None or hasattr(kernel.s, 'blockOrders') or kernel.finiteHorizon:
+                raise NotImplementedError('P2 elements: one DoFMap, constant kernels with infinite horizon')
         if hasattr(kernel.s, 'blockOrders'):
             # piecewise constant order s(x,y) = sVals[block(x), block(y)], evaluated at the cell centres once per ordered
             # cell pair (kernel.evalParams, nonlocalOperator_{SCALAR}.pxi:509-513).  One constant-order problem instance
@@ -250,9 +256,13 @@ class nonlocalBuilder:
             if not torch.cuda.is_available():
                 raise RuntimeError('pynucleus_b200 needs a CUDA device; there is no CPU fallback')
             device = self.params.get('device', torch.cuda.current_device())
-            self._problem = _Problem(self._dm_assembly, self.kernel, self.kernelBoundary, self.orders, device,
-                                     self.params.get('max_regular_order', 32),
-                                     order_num_dofs=self.dm.num_dofs if self.dm2 is not None else 0)
+            dm_dev, ond = self._dm_assembly, (self.dm.num_dofs if self.dm2 is not None else 0)
+            if self._element:
+                # P2: the device problem holds mesh, kernel and tables behind the vertex dofs; the element's table goes to
+                # pnb_dense_assemble_element (row-owner kernel, csrc/pnb_element.cuh)
+                dm_dev, ond = self.dm.vertexPart(), self.dm.num_dofs
+            self._problem = _Problem(dm_dev, self.kernel, self.kernelBoundary, self.orders, device,
+                                     self.params.get('max_regular_order', 32), order_num_dofs=ond)
             if self.params.get('assembly_path', 'default') == 'tiles':
                 _lib.check(_lib.lib().pnb_problem_set_path(self._problem.handle, 1))
         return self._problem
@@ -331,8 +341,13 @@ class nonlocalBuilder:
         A = torch.empty((N, N), dtype=torch.float64, device=dev) if out is None else out
 
         def run():
-            _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.data_ptr(),
-                                                     A.stride(0), 1))
+            if self._element:
+                ed = np.ascontiguousarray(self.dm.dofs, dtype=np.int32)
+                _lib.check(_lib.lib().pnb_dense_assemble_element(prob.handle, self.dm.polynomialOrder, self.dm.dofs_per_element, N,
+                                                                 ed.ctypes.data, int(self.zeroExterior), A.data_ptr(), A.stride(0)))
+            else:
+                _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.data_ptr(),
+                                                         A.stride(0), 1))
         self._retry_on_order(run)
         if self.dm2 is not None:
             n1 = self.dm.num_dofs
@@ -414,6 +429,8 @@ class nonlocalBuilder:
     def _no_dm2(self):
         if self.dm2 is not None:
             raise NotImplementedError('only getDense() supports two DoFMaps')
+        if self._element:
+            raise NotImplementedError('only getDense() supports P2 elements')
 
     def getDenseRowBlock(self, row_begin, row_end, out=None, process_group=None):
         """Rows [row_begin, row_end) of getDense() on this process' GPU (contiguous row blocks: 1D problems and

@@ -3445,3 +3445,4 @@ extern "C" int pnb_fp64_peak(int device, double *tflops)
 }
 
 #include "pnb_h2.cuh"
+#include "pnb_element.cuh"

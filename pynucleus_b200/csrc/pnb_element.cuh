@@ -1,0 +1,442 @@
+// Dense assembly for finite elements other than P1 (P2 in 1D and 2D; P1 for cross-checking): row-owner kernel.
+//
+// The reference treats every element through the same local matrices, built from the shape functions of the DoFMap
+// (getLocalShapeFunction, fractionalLaplacian2D.pyx:644-813 / fractionalLaplacian1D.pyx:255-339 for the singular PSI
+// tables, nonlocalOperator_{SCALAR}.pxi:549-600 for the regular ones, :988-1020 / fractionalLaplacian2D.pyx:1255-1314
+// for the surface terms), with (2 dpe)(2 dpe + 1)/2 = 78 local entries for P2 triangles.  Here ONE WARP OWNS ONE ROW I of
+// the operator: for every cell c1 around dof I and every cell c2 it evaluates, with the lanes over the quadrature nodes,
+// only row I of the local matrix of the pair,
+//      a(I, slot) = sum_q w_q gamma(x_q, y_q) psi_I(q) * { phi_slot(x_q) for the slots of the first cell,
+//                                                          -phi_slot(y_q) for the slots of the second cell },
+// psi_I = phi_I|first(x) - phi_I|second(y), and adds it to the row -- first the slots of the first cell, then those of the
+// second (the dofs of one cell are distinct), pair after pair: every entry has one writer and a fixed summation order
+// (no atomics, bitwise reproducible).  Dofs shared by the two cells need no special PSI rows: their two parts land on the
+// same entry.  Pairs are classified lane-per-partner (32 at a time) with the same panel / order functions as the P1 path
+// and evaluated in the reference's orientation (smaller cell index first) with its permutations of the shared vertices.
+// The kernel value is re-evaluated for every row dof of a pair (2 dpe times): this path trades speed for generality and
+// is meant for the problem sizes P2 is used at; the P1 production path is pnb_group.cuh.
+#pragma once
+
+template <int DIM, int PORD> struct ElemDims {
+    static constexpr int NV = DIM + 1;
+    static constexpr int DPE = PORD == 1 ? NV : (DIM == 1 ? 3 : 6);
+};
+
+// shape functions in the cell's own vertex order (DoFMaps.pyx:1854-1880 P1, :1932-2005 P2: vertices, then the edges
+// (0,1), (1,2), (0,2); 1D: the two vertices, then the cell)
+template <int DIM, int PORD> __device__ __forceinline__ void elem_shape(const double *lam, double *phi)
+{
+    if (PORD == 1) {
+#pragma unroll
+        for (int k = 0; k <= DIM; k++) phi[k] = lam[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k <= DIM; k++) phi[k] = lam[k] * (2. * lam[k] - 1.);
+        phi[DIM + 1] = 4. * lam[0] * lam[1];
+        if (DIM == 2) {
+            phi[4] = 4. * lam[1] * lam[2];
+            phi[5] = 4. * lam[0] * lam[2];
+        }
+    }
+}
+
+// row of dof slots (sLo in the first cell, sHi in the second; -1 = the dof is not in that cell) of the local matrix of
+// the cell pair (lo, hi), lo <= hi.  acc[0..DPE) first-cell slots, acc[DPE..2 DPE) second-cell slots; NOT yet multiplied
+// by the volume factor; partial sums of this lane.
+template <int DIM, int PORD>
+__device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, const int *perm1, const int *perm2, int sLo, int sHi,
+                              int lane, double *acc)
+{
+    constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
+    double t1[3][2], t2[3][2];
+    load_simplex<DIM>(P.simplices, lo, NV, t1);
+    load_simplex<DIM>(P.simplices, hi, NV, t2);
+    const PowCtx kv(P.pow_int);
+#pragma unroll
+    for (int k = 0; k < 2 * DPE; k++) acc[k] = 0.;
+    if (panel >= 1) {
+        const DRule r = P.reg_cell[panel];
+        const int n = r.n;
+        for (int q = lane; q < n * n; q += 32) {
+            const int i = q / n, j = q - i * n;
+            double lx[NV], ly[NV], px[DPE], py[DPE];
+            double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                lx[k] = r.bary[k * n + i];
+                ly[k] = r.bary[k * n + j];
+                // un-fused, in the reference's order (nodesInGlobalCoords, quadrature.pyx:76-87)
+                x0 = PNB_ADD(x0, PNB_MUL(lx[k], t1[k][0]));
+                y0 = PNB_ADD(y0, PNB_MUL(ly[k], t2[k][0]));
+                if (DIM == 2) {
+                    x1 = PNB_ADD(x1, PNB_MUL(lx[k], t1[k][1]));
+                    y1 = PNB_ADD(y1, PNB_MUL(ly[k], t2[k][1]));
+                }
+            }
+            double d2 = PNB_MUL(x0 - y0, x0 - y0);
+            if (DIM == 2) d2 = PNB_ADD(d2, PNB_MUL(x1 - y1, x1 - y1));
+            elem_shape<DIM, PORD>(lx, px);
+            elem_shape<DIM, PORD>(ly, py);
+            double psiI = 0.;
+#pragma unroll
+            for (int k = 0; k < DPE; k++) {
+                if (k == sLo) psiI += px[k];
+                if (k == sHi) psiI -= py[k];
+            }
+            const double g = (r.w[i] * r.w[j]) * kv(d2) * psiI;
+#pragma unroll
+            for (int k = 0; k < DPE; k++) {
+                acc[k] = fma(g, px[k], acc[k]);
+                acc[DPE + k] = fma(-g, py[k], acc[DPE + k]);
+            }
+        }
+    } else {
+        // singular pair: rule nodes in barycentric coordinates over the PERMUTED vertices (shared vertices first)
+        double s1[3][2], s2[3][2];
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+#pragma unroll
+            for (int m = 0; m < NV; m++) {
+                if (perm1[k] == m) { s1[k][0] = t1[m][0]; s1[k][1] = t1[m][1]; }
+                if (perm2[k] == m) { s2[k][0] = t2[m][0]; s2[k][1] = t2[m][1]; }
+            }
+        }
+        DRule r;
+        if (DIM == 2) r = panel == -3 ? P.q_id : (panel == -2 ? P.q_edge : P.q_vertex);
+        else r = panel == -2 ? P.q_id : P.q_vertex;
+        const int n = r.n;
+        for (int q = lane; q < n; q += 32) {
+            double lx[NV], ly[NV], px[DPE], py[DPE];
+            double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                const double bx = r.bary[k * n + q], by = r.bary[(NV + k) * n + q];
+                // un-fused and left to right as in fractionalLaplacian2D.pyx:858-863
+                if (k == 0) {
+                    x0 = PNB_MUL(s1[k][0], bx);
+                    y0 = PNB_MUL(s2[k][0], by);
+                    if (DIM == 2) { x1 = PNB_MUL(s1[k][1], bx); y1 = PNB_MUL(s2[k][1], by); }
+                } else {
+                    x0 = PNB_ADD(x0, PNB_MUL(s1[k][0], bx));
+                    y0 = PNB_ADD(y0, PNB_MUL(s2[k][0], by));
+                    if (DIM == 2) { x1 = PNB_ADD(x1, PNB_MUL(s1[k][1], bx)); y1 = PNB_ADD(y1, PNB_MUL(s2[k][1], by)); }
+                }
+                // back to the cells' own vertex order
+#pragma unroll
+                for (int m = 0; m < NV; m++) {
+                    if (perm1[k] == m) lx[m] = bx;
+                    if (perm2[k] == m) ly[m] = by;
+                }
+            }
+            double d2 = PNB_MUL(x0 - y0, x0 - y0);
+            if (DIM == 2) d2 = PNB_ADD(d2, PNB_MUL(x1 - y1, x1 - y1));
+            elem_shape<DIM, PORD>(lx, px);
+            elem_shape<DIM, PORD>(ly, py);
+            double psiI = 0.;
+#pragma unroll
+            for (int k = 0; k < DPE; k++) {
+                if (k == sLo) psiI += px[k];
+                if (k == sHi) psiI -= py[k];
+            }
+            const double g = r.w[q] * kv(d2) * psiI;
+#pragma unroll
+            for (int k = 0; k < DPE; k++) {
+                acc[k] = fma(g, px[k], acc[k]);
+                acc[DPE + k] = fma(-g, py[k], acc[DPE + k]);
+            }
+        }
+    }
+}
+
+// row of dof slot sI of the surface-term local matrix of (cell c1, boundary facet f)
+// (eval_distant_boundary, nonlocalOperator_{SCALAR}.pxi:1069-1108; singular: fractionalLaplacian2D.pyx:1356-1407,
+// fractionalLaplacian1D.pyx:753-781); NOT yet multiplied by the volume factor
+template <int DIM, int PORD>
+__device__ void elem_boundary_row(const DProblem &P, int c1, int f, int panel, const int *perm1, const int *perm2, int sI, int lane,
+                                  double *acc)
+{
+    constexpr int NV = DIM + 1, NF = DIM, DPE = ElemDims<DIM, PORD>::DPE;
+    double t1[3][2], t2[3][2];
+    load_simplex<DIM>(P.simplices, c1, NV, t1);
+    load_simplex<DIM>(P.bsimplices, f, NF, t2);
+    double nx = 0., ny = 0.;
+    if (DIM == 2) {
+        nx = t2[1][1] - t2[0][1];
+        ny = t2[0][0] - t2[1][0];
+        const double inv = 1. / sqrt(nx * nx + ny * ny);
+        nx *= inv;
+        ny *= inv;
+    }
+    const PowCtx kv(DIM == 2 ? P.pow_bnd_unit : P.pow_bnd);
+#pragma unroll
+    for (int k = 0; k < DPE; k++) acc[k] = 0.;
+    if (panel >= 1) {
+        const DRule r0 = P.reg_cell[panel], r1 = P.reg_facet[panel];
+        const int n0 = r0.n, n1 = r1.n;
+        for (int q = lane; q < n0 * n1; q += 32) {
+            const int i = q / n1, m = q - i * n1;
+            double lx[NV], px[DPE];
+            double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                lx[k] = r0.bary[k * n0 + i];
+                x0 = PNB_ADD(x0, PNB_MUL(lx[k], t1[k][0]));
+                if (DIM == 2) x1 = PNB_ADD(x1, PNB_MUL(lx[k], t1[k][1]));
+            }
+#pragma unroll
+            for (int k = 0; k < NF; k++) {
+                const double b = r1.bary[k * n1 + m];
+                y0 = PNB_ADD(y0, PNB_MUL(b, t2[k][0]));
+                if (DIM == 2) y1 = PNB_ADD(y1, PNB_MUL(b, t2[k][1]));
+            }
+            const double w0 = y0 - x0, w1 = y1 - x1;
+            double d2 = PNB_MUL(w0, w0);
+            double nw = 1.;
+            if (DIM == 2) {
+                d2 = PNB_ADD(d2, PNB_MUL(w1, w1));
+                nw = nx * w0 + ny * w1;
+            }
+            elem_shape<DIM, PORD>(lx, px);
+            double pI = 0.;
+#pragma unroll
+            for (int k = 0; k < DPE; k++)
+                if (k == sI) pI = px[k];
+            const double g = (r0.w[i] * r1.w[m]) * nw * kv(d2) * pI;
+#pragma unroll
+            for (int k = 0; k < DPE; k++) acc[k] = fma(g, px[k], acc[k]);
+        }
+    } else {
+        double s1[3][2], s2[3][2];
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+#pragma unroll
+            for (int m = 0; m < NV; m++) {
+                if (perm1[k] == m) { s1[k][0] = t1[m][0]; s1[k][1] = t1[m][1]; }
+                if (k < NF && m < NF && perm2[k] == m) { s2[k][0] = t2[m][0]; s2[k][1] = t2[m][1]; }
+            }
+        const DRule r = (DIM == 2 && panel == -2) ? P.bq_edge : P.bq_vertex;
+        const int n = r.n;
+        for (int q = lane; q < n; q += 32) {
+            double lx[NV], px[DPE];
+            double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                const double b = r.bary[k * n + q];
+                if (k == 0) {
+                    x0 = PNB_MUL(s1[k][0], b);
+                    if (DIM == 2) x1 = PNB_MUL(s1[k][1], b);
+                } else {
+                    x0 = PNB_ADD(x0, PNB_MUL(s1[k][0], b));
+                    if (DIM == 2) x1 = PNB_ADD(x1, PNB_MUL(s1[k][1], b));
+                }
+#pragma unroll
+                for (int m = 0; m < NV; m++)
+                    if (perm1[k] == m) lx[m] = b;
+            }
+#pragma unroll
+            for (int k = 0; k < NF; k++) {
+                const double b = r.bary[(NV + k) * n + q];
+                if (k == 0) {
+                    y0 = PNB_MUL(s2[k][0], b);
+                    if (DIM == 2) y1 = PNB_MUL(s2[k][1], b);
+                } else {
+                    y0 = PNB_ADD(y0, PNB_MUL(s2[k][0], b));
+                    if (DIM == 2) y1 = PNB_ADD(y1, PNB_MUL(s2[k][1], b));
+                }
+            }
+            const double w0 = x0 - y0, w1 = x1 - y1;
+            double d2 = PNB_MUL(w0, w0);
+            double nw = 1.;
+            if (DIM == 2) {
+                d2 = PNB_ADD(d2, PNB_MUL(w1, w1));
+                nw = nx * w0 + ny * w1;
+            }
+            elem_shape<DIM, PORD>(lx, px);
+            double pI = 0.;
+#pragma unroll
+            for (int k = 0; k < DPE; k++)
+                if (k == sI) pI = px[k];
+            const double g = r.w[q] * nw * kv(d2) * pI;
+#pragma unroll
+            for (int k = 0; k < DPE; k++) acc[k] = fma(g, px[k], acc[k]);
+        }
+    }
+}
+
+struct ElemJob {
+    int N, dpe;
+    const int *edofs;       // nc x dpe: cell -> dof (negative: boundary dof)
+    const int *dof_ptr;     // N+1: dof -> (cell, slot) list, cells ascending
+    const int *dof_cells;   // cell * 8 + slot
+    int *err;               // [0]: regular order missing in the tables
+};
+
+template <int DIM, int PORD>
+__global__ void __launch_bounds__(128) elem_rows_kernel(DProblem P, ElemJob J, int zero_exterior, double *__restrict__ A, int64_t ld)
+{
+    constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
+    const int lane = threadIdx.x & 31;
+    const int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (I >= J.N) return;
+    double *row = A + (size_t)I * ld;
+    for (int j = lane; j < J.N; j += 32) row[j] = 0.;
+    __syncwarp();
+    for (int t = J.dof_ptr[I]; t < J.dof_ptr[I + 1]; t++) {
+        const int c1 = J.dof_cells[t] >> 3, sI1 = J.dof_cells[t] & 7;
+        // ---- Omega x Omega: all partner cells, 32 classified at a time
+        for (int c20 = 0; c20 < P.nc; c20 += 32) {
+            const int c2 = c20 + lane;
+            int pan = PNB_IGNORED_PANEL, sI2 = -1;
+            int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
+            if (c2 < P.nc) {
+#pragma unroll
+                for (int k = 0; k < DPE; k++)
+                    if (J.edofs[(size_t)c2 * DPE + k] == I) sI2 = k;
+                // a pair of two cells around I is visited from its smaller cell only
+                const bool skip = c2 != c1 && sI2 >= 0 && c2 < c1;
+                if (!skip) pan = panel_interior(P, min(c1, c2), max(c1, c2), p1, p2);
+                if (pan != PNB_IGNORED_PANEL && pan > P.max_order) { atomicMax(J.err, pan); pan = PNB_IGNORED_PANEL; }
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, pan != PNB_IGNORED_PANEL);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int c2s = c20 + src;
+                const int pans = __shfl_sync(0xffffffffu, pan, src), sI2s = __shfl_sync(0xffffffffu, sI2, src);
+                int q1[3], q2[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    q1[k] = __shfl_sync(0xffffffffu, p1[k], src);
+                    q2[k] = __shfl_sync(0xffffffffu, p2[k], src);
+                }
+                const int lo = min(c1, c2s), hi = max(c1, c2s);
+                const int sLo = lo == c1 ? sI1 : sI2s, sHi = hi == c1 ? sI1 : sI2s;
+                double acc[2 * DPE];
+                elem_pair_row<DIM, PORD>(P, lo, hi, pans, q1, q2, sLo, sHi, lane, acc);
+                warp_allreduce<2 * DPE>(acc);
+                // volume factors: vol1 vol2 (nonlocalOperator_{SCALAR}.pxi:756), 4 vol1 vol2 for the singular 2D rules
+                // (fractionalLaplacian2D.pyx:851); off-diagonal pairs count twice (nonlocalAssembly_{SCALAR}.pxi:1404-1410)
+                const double sc = (lo == hi ? 1.0 : 2.0) * ((pans < 0 && DIM == 2) ? 4.0 : 1.0) * P.vol[lo] * P.vol[hi];
+                double mine = 0.;
+#pragma unroll
+                for (int k = 0; k < DPE; k++)
+                    if (k == lane) mine = acc[k];
+                if (lane < DPE) {
+                    const int d = J.edofs[(size_t)lo * DPE + lane];
+                    if (d >= 0) row[d] += sc * mine;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < DPE; k++)
+                    if (k == lane) mine = acc[DPE + k];
+                if (lane < DPE) {
+                    const int d = J.edofs[(size_t)hi * DPE + lane];
+                    if (d >= 0) row[d] += sc * mine;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- Omega x Omega^c: surface terms of the cell with all boundary facets
+        if (zero_exterior) {
+            for (int f0 = 0; f0 < P.nb; f0 += 32) {
+                const int f = f0 + lane;
+                int pan = PNB_IGNORED_PANEL;
+                int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
+                if (f < P.nb) {
+                    pan = panel_boundary(P, c1, f, p1, p2);
+                    if (pan > P.max_order) { atomicMax(J.err, pan); pan = PNB_IGNORED_PANEL; }
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, pan != PNB_IGNORED_PANEL);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int fs = f0 + src;
+                    const int pans = __shfl_sync(0xffffffffu, pan, src);
+                    int q1[3], q2[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        q1[k] = __shfl_sync(0xffffffffu, p1[k], src);
+                        q2[k] = __shfl_sync(0xffffffffu, p2[k], src);
+                    }
+                    double acc[DPE];
+                    elem_boundary_row<DIM, PORD>(P, c1, fs, pans, q1, q2, sI1, lane, acc);
+                    warp_allreduce<DPE>(acc);
+                    const double sc = pans >= 1 ? P.vol[c1] * P.bvol[fs] : (DIM == 2 ? -2.0 * P.vol[c1] * P.bvol[fs] : P.vol[c1]);
+                    double mine = 0.;
+#pragma unroll
+                    for (int k = 0; k < DPE; k++)
+                        if (k == lane) mine = acc[k];
+                    if (lane < DPE) {
+                        const int d = J.edofs[(size_t)c1 * DPE + lane];
+                        if (d >= 0) row[d] += sc * mine;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+}
+
+extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
+                                          int zero_exterior, double *A, int64_t ld)
+{
+    if (!p || !dofs || !A) return fail(PNB_ERR_ARG, "null argument");
+    if (polynomial_order < 1 || polynomial_order > 2) return fail(PNB_ERR_UNSUPPORTED, "elements: P1 and P2");
+    const int dpe = polynomial_order == 1 ? p->dim + 1 : (p->dim == 1 ? 3 : 6);
+    if (dofs_per_element != dpe) return fail(PNB_ERR_ARG, "dofs_per_element does not match the element");
+    if (p->finite) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: infinite horizon only");
+    if (!p->h_labels.empty()) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: constant kernels only");
+    if (p->nblocks > 0) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: no batched blocks");
+    if (ld < num_dofs) return fail(PNB_ERR_ARG, "leading dimension too small");
+    ON_DEVICE(p->device);
+    if (num_dofs == 0) return 0;
+    const int nc = p->nc;
+    std::vector<int> dptr(num_dofs + 1, 0), dcells;
+    for (int c = 0; c < nc; c++)
+        for (int m = 0; m < dpe; m++) {
+            const int d = dofs[(size_t)c * dpe + m];
+            if (d >= num_dofs) return fail(PNB_ERR_ARG, "dof index out of range");
+            if (d >= 0) dptr[d + 1]++;
+        }
+    for (int i = 0; i < num_dofs; i++) dptr[i + 1] += dptr[i];
+    dcells.resize(dptr[num_dofs]);
+    {
+        std::vector<int> pos(dptr.begin(), dptr.end() - 1);
+        for (int c = 0; c < nc; c++)
+            for (int m = 0; m < dpe; m++) {
+                const int d = dofs[(size_t)c * dpe + m];
+                if (d >= 0) dcells[pos[d]++] = c * 8 + m;
+            }
+    }
+    ElemJob J;
+    J.N = num_dofs;
+    J.dpe = dpe;
+    int *d_edofs = nullptr, *d_ptr = nullptr, *d_cells = nullptr, *d_err = nullptr;
+    CK(cudaMalloc(&d_edofs, (size_t)nc * dpe * sizeof(int)));
+    CK(cudaMalloc(&d_ptr, ((size_t)num_dofs + 1) * sizeof(int)));
+    CK(cudaMalloc(&d_cells, std::max<size_t>(dcells.size(), 1) * sizeof(int)));
+    CK(cudaMalloc(&d_err, sizeof(int)));
+    cudaMemcpy(d_edofs, dofs, (size_t)nc * dpe * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_ptr, dptr.data(), dptr.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_cells, dcells.data(), dcells.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemset(d_err, 0, sizeof(int));
+    J.edofs = d_edofs; J.dof_ptr = d_ptr; J.dof_cells = d_cells; J.err = d_err;
+    const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
+    if (p->dim == 2) {
+        if (polynomial_order == 2) elem_rows_kernel<2, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+        else elem_rows_kernel<2, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+    } else {
+        if (polynomial_order == 2) elem_rows_kernel<1, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+        else elem_rows_kernel<1, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    int herr = 0;
+    cudaMemcpy(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err);
+    CK(e);
+    if (herr > 0) {
+        return fail(PNB_ERR_ORDER, "regular quadrature order " + std::to_string(herr) + " exceeds the supplied tables");
+    }
+    return 0;
+}

@@ -1,5 +1,5 @@
-"""P1 DoFMap: the cell -> DoF table consumed by the assembly path
-(fem/PyNucleus_fem/DoFMaps.pyx:61-330; numbering :157-210)."""
+"""P1 / P2 DoFMaps: the cell -> DoF table consumed by the assembly path
+(fem/PyNucleus_fem/DoFMaps.pyx:61-330; numbering :157-322)."""
 import numpy as np
 
 from .mesh import INDEX
@@ -86,6 +86,95 @@ class P1_DoFMap:
         coords = np.zeros((self.num_dofs, self.dim))
         m = self._vertex2dof >= 0
         coords[self._vertex2dof[m]] = self.mesh.vertices[m]
+        return coords
+
+    def ones(self):
+        return np.ones(self.num_dofs)
+
+    def zeros(self):
+        return np.zeros(self.num_dofs)
+
+
+class P2_DoFMap:
+    """continuous piecewise quadratic elements (DoFMaps.pyx:1978-2031): one dof per vertex and per edge (1D: per vertex
+    and per cell).  Local order on a cell: vertices, then the edges (0,1), (1,2), (0,2).  Numbering as in the reference's
+    constructor (:157-322): boundary vertices -1, -2, ... in the order of mesh.boundaryVertices, boundary edges continue
+    the negative numbers in the order of mesh.boundaryEdges; the other dofs are numbered cell by cell by first appearance,
+    the vertices of a cell before its edges."""
+    polynomialOrder = 2
+
+    def __init__(self, mesh, tag=None):
+        if tag is not None:
+            raise NotImplementedError('P2_DoFMap: default tag (whole boundary) only')
+        self.mesh = mesh
+        self.dim = mesh.dim
+        self.dofs_per_vertex = 1
+        nvc = mesh.manifold_dim+1
+        cells = np.asarray(mesh.cells)
+        nc = cells.shape[0]
+        vdof = {}
+        nb = -1
+        for v in np.asarray(mesh.boundaryVertices).tolist():
+            vdof[v] = nb
+            nb -= 1
+        if mesh.manifold_dim == 1:
+            self.dofs_per_edge, self.dofs_per_element = 0, 3
+            dofs = np.empty((nc, 3), dtype=np.int64)
+            n = 0
+            for i in range(nc):
+                for k in range(2):
+                    v = int(cells[i, k])
+                    if v not in vdof:
+                        vdof[v] = n
+                        n += 1
+                    dofs[i, k] = vdof[v]
+                dofs[i, 2] = n
+                n += 1
+        else:
+            self.dofs_per_edge, self.dofs_per_element = 1, 6
+            edof = {}
+            for e in np.asarray(mesh.boundaryFacets).reshape(-1, 2).tolist():
+                edof[(min(e), max(e))] = nb
+                nb -= 1
+            dofs = np.empty((nc, 6), dtype=np.int64)
+            n = 0
+            for i in range(nc):
+                c = [int(x) for x in cells[i]]
+                for k in range(3):
+                    if c[k] not in vdof:
+                        vdof[c[k]] = n
+                        n += 1
+                    dofs[i, k] = vdof[c[k]]
+                for k, (a, b) in enumerate(((0, 1), (1, 2), (0, 2))):
+                    e = (min(c[a], c[b]), max(c[a], c[b]))
+                    if e not in edof:
+                        edof[e] = n
+                        n += 1
+                    dofs[i, 3+k] = edof[e]
+        self.dofs = np.ascontiguousarray(dofs, dtype=INDEX)
+        self.num_dofs = int(n)
+        self.num_boundary_dofs = int(-nb-1)
+        self._nvc = nvc
+
+    def vertexPart(self):
+        """the vertex dofs as a P1-shaped table over the same numbering (the device problem keeps the mesh, the kernel and
+        the tables behind it; the element's own table goes to pnb_dense_assemble_element)"""
+        from copy import copy
+        v = copy(self)
+        v.dofs = np.ascontiguousarray(self.dofs[:, :self._nvc], dtype=INDEX)
+        v.dofs_per_element = self._nvc
+        return v
+
+    def __repr__(self):
+        return 'P2 DoFMap with {} DoFs and {} boundary DoFs.'.format(self.num_dofs, self.num_boundary_dofs)
+
+    def getDoFCoordinates(self):
+        nodes = (np.array([[1., 0.], [0., 1.], [0.5, 0.5]]) if self.mesh.manifold_dim == 1 else
+                 np.array([[1., 0., 0.], [0., 1., 0.], [0., 0., 1.], [0.5, 0.5, 0.], [0., 0.5, 0.5], [0.5, 0., 0.5]]))
+        coords = np.zeros((self.num_dofs, self.dim))
+        x = np.einsum('kv,cvd->ckd', nodes, self.mesh.vertices[self.mesh.cells])
+        m = self.dofs >= 0
+        coords[self.dofs[m]] = x[m]
         return coords
 
     def ones(self):

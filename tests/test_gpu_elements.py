@@ -1,0 +1,93 @@
+"""P2 elements (SURVEY 8, row N1 of the round-1 verdict): the row-owner kernel of csrc/pnb_element.cuh against fixtures
+produced by the reference's P2_DoFMap + nonlocalBuilder.getDense (oracle/refbuild/make_golden_p2.py)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def entry_err(A, Aref):
+    d = np.sqrt(np.abs(np.diag(Aref))) if Aref.shape[0] == Aref.shape[1] else None
+    scale = np.abs(Aref) if d is None else np.maximum(np.abs(Aref), 1e-2*np.outer(d, d))
+    return (np.abs(A-Aref)/scale).max()
+
+
+def setup(name):
+    import pynucleus_b200 as pb
+    g = dict(np.load(os.path.join(GOLDEN, name+'.npz')))
+    dim = g['vertices'].shape[1]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'],
+                     boundaryVertices=g['boundaryVertices'])
+    return g, dim, mesh
+
+
+@pytest.mark.parametrize('name', ['p2_interval_s0.25_r4', 'p2_interval_s0.75_r5', 'p2_disc_s0.75_r1', 'p2_disc_s0.75_r2',
+                                  'p2_disc_s0.25_r2'])
+def test_p2_dense_vs_reference(name):
+    """getDense on a P2_DoFMap: entries 1e-12 against the reference's (78 local entries per triangle pair there, one row
+    per warp here), with and without the surface terms; symmetric to rounding, bitwise reproducible"""
+    import pynucleus_b200 as pb
+    g, dim, mesh = setup(name)
+    dm = pb.P2_DoFMap(mesh)
+    assert np.array_equal(dm.dofs, g['dofs'])
+    kernel = pb.getFractionalKernel(dim, float(g['s']))
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = pb.nonlocalBuilder(dm, kernel, params, zeroExterior=ze)
+        assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+        assert abs(b.orders.target_order-float(g['target_order_used'])) < 1e-14
+        A = b.getDense().data
+        assert A.shape == g[key].shape
+        assert entry_err(A, g[key]) < TOL
+        assert np.abs(A-A.T).max() < 1e-13*np.abs(A).max()
+        assert np.array_equal(A, b.getDense().data)
+
+
+def test_p2_dense_rows_larger_mesh_vs_reference():
+    """721 P2 dofs (384 triangles): every 8th row and the diagonal of the reference's operator"""
+    import pynucleus_b200 as pb
+    g, dim, mesh = setup('p2_disc_s0.75_r3')
+    dm = pb.P2_DoFMap(mesh)
+    assert np.array_equal(dm.dofs, g['dofs'])
+    kernel = pb.getFractionalKernel(2, 0.75)
+    rows = g['rows']
+    for ze, key in ((True, 'A_rows'), (False, 'A_interior_rows')):
+        A = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}, zeroExterior=ze).getDense().data
+        dscale = np.sqrt(np.abs(g['A_diagonal']))
+        scale = np.maximum(np.abs(g[key]), 1e-2*np.outer(dscale[rows], dscale))
+        assert (np.abs(A[rows]-g[key])/scale).max() < TOL
+        if ze:
+            assert np.abs(np.diag(A)-g['A_diagonal']).max() < TOL*np.abs(g['A_diagonal']).max()
+
+
+@pytest.mark.parametrize('dim', [1, 2])
+def test_element_kernel_with_p1_equals_production_path(dim):
+    """the row-owner kernel run with P1 shape functions against the production P1 kernels (same tables, same pairs)"""
+    import torch
+    import pynucleus_b200 as pb
+    from pynucleus_b200 import _lib
+    mesh = pb.refined(pb.uniform_disc(), 3) if dim == 2 else pb.refined(pb.simpleInterval(-1, 1), 6)
+    dm = pb.P1_DoFMap(mesh)
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, 0.75), {'target_order': 0.5} if dim == 2 else {})
+    A = b.getDense().data
+    N = dm.num_dofs
+    B = torch.empty((N, N), dtype=torch.float64, device='cuda')
+    ed = np.ascontiguousarray(dm.dofs, dtype=np.int32)
+    _lib.check(_lib.lib().pnb_dense_assemble_element(b.problem.handle, 1, dim+1, N, ed.ctypes.data, 1, B.data_ptr(), B.stride(0)))
+    assert entry_err(B.cpu().numpy(), A) < TOL
+
+
+def test_p2_unsupported_combinations_raise():
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.uniform_disc(), 1)
+    dm = pb.P2_DoFMap(mesh)
+    with pytest.raises(NotImplementedError):
+        pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75, horizon=0.5), {})
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'target_order': 0.5})
+    with pytest.raises(NotImplementedError):
+        b.getH2()

@@ -287,3 +287,17 @@ def test_cython_shim_builds_and_binds_the_c_abi():
     out = subprocess.run(['nm', '-D', '--undefined-only', so], capture_output=True, text=True).stdout
     for sym in ('pnb_problem_create', 'pnb_dense_assemble', 'pnb_problem_destroy', 'pnb_max_order', 'pnb_last_error'):
         assert sym in out
+
+
+@pytest.mark.parametrize('name', ['p2_interval_s0.25_r4', 'p2_disc_s0.75_r1', 'p2_disc_s0.75_r2', 'p2_disc_s0.75_r3'])
+def test_p2_dofmap_numbering_matches_reference(name):
+    """P2_DoFMap (fem/PyNucleus_fem/DoFMaps.pyx:157-322, 1978-2031): cell -> dof table equal to the reference's"""
+    import pynucleus_b200 as pb
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), 'golden', name+'.npz')))
+    dim = g['vertices'].shape[1]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'],
+                     boundaryVertices=g['boundaryVertices'])
+    dm = pb.P2_DoFMap(mesh)
+    assert dm.num_dofs == int(g['num_dofs']) and dm.num_boundary_dofs == int(g['num_boundary_dofs'])
+    assert np.array_equal(dm.dofs, g['dofs'])
+    assert np.array_equal(dm.vertexPart().dofs, g['dofs'][:, :dim+1])
