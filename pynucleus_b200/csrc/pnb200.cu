@@ -25,6 +25,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <mutex>
+#include <map>
 
 // ---------------------------------------------------------------------------
 // error handling
@@ -54,6 +56,20 @@ static int fail(int code, const std::string &msg)
             return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? PNB_ERR_NO_DEVICE : PNB_ERR_CUDA, \
                         std::string(#call) + ": " + cudaGetErrorString(e_));                         \
     } while (0)
+
+// device attributes are queried once per device and attribute (some of the queries take a millisecond)
+static int device_attr(cudaDeviceAttr attr, int device)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({(int)attr, device});
+    if (it != cache.end()) return it->second;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, attr, device) != cudaSuccess) { cudaGetLastError(); v = 0; }
+    cache[{(int)attr, device}] = v;
+    return v;
+}
 
 // Entry points run on the problem's device and hand the calling thread its previous current device back on every
 // exit path (the caller -- torch -- keeps allocating on whatever device is current).
@@ -174,7 +190,7 @@ template <class K> static void smem_optin(K kernel, int device)
     const auto key = std::make_pair((const void *)kernel, device);
     if (done.count(key)) return;
     int smem_blk = 0;
-    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    smem_blk = device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaFuncAttributes attr;
     if (smem_blk > 0 && cudaFuncGetAttributes(&attr, kernel) == cudaSuccess)
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_blk - (int)attr.sharedSizeBytes);
@@ -2052,7 +2068,7 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
     };
     {
         // groups are independent: a few host threads (the colouring is quadratic in the group size)
-        const int nt = std::max(1, std::min(8, std::min((int)std::thread::hardware_concurrency(), gg.ngroups / 8)));
+        const int nt = std::max(1, std::min(16, std::min((int)std::thread::hardware_concurrency(), gg.ngroups / 8)));
         std::vector<std::thread> th;
         for (int t = 0; t < nt; t++)
             th.emplace_back([&, t]() { for (int g = t; g < gg.ngroups; g += nt) do_group(g); });
@@ -2071,14 +2087,25 @@ static void build_group_geometry(const pnb_problem *p, int GC, const std::vector
     // adjacency through shared vertices
     gg.adj.assign(gg.ngroups, std::vector<int>());
     {
-        std::vector<std::vector<int>> vg(p->P.nv);
+        // groups around every vertex (CSR), then all pairs of groups that meet at a vertex
+        const int nv = p->P.nv;
+        std::vector<int> vptr(nv + 1, 0), vgrp((size_t)nc * 3);
         for (int c = 0; c < nc; c++)
-            for (int m = 0; m < 3; m++) vg[cells[(size_t)c * 3 + m]].push_back(grp[c]);
-        for (auto &l : vg) {
-            std::sort(l.begin(), l.end());
-            l.erase(std::unique(l.begin(), l.end()), l.end());
-            for (int a : l)
-                for (int b : l) gg.adj[a].push_back(b);
+            for (int m = 0; m < 3; m++) vptr[cells[(size_t)c * 3 + m] + 1]++;
+        for (int v = 0; v < nv; v++) vptr[v + 1] += vptr[v];
+        {
+            std::vector<int> pos(vptr.begin(), vptr.end() - 1);
+            for (int c = 0; c < nc; c++)
+                for (int m = 0; m < 3; m++) vgrp[pos[cells[(size_t)c * 3 + m]]++] = grp[c];
+        }
+        for (int v = 0; v < nv; v++) {
+            int *b = &vgrp[vptr[v]], *e = &vgrp[vptr[v + 1]];
+            if (e - b < 2) continue;
+            std::sort(b, e);
+            e = std::unique(b, e);
+            if (e - b < 2) continue;
+            for (int *a = b; a < e; a++)
+                for (int *q = b; q < e; q++) gg.adj[*a].push_back(*q);
         }
         for (int g = 0; g < gg.ngroups; g++) {
             auto &l = gg.adj[g];
@@ -2165,10 +2192,10 @@ static int build_group_schedule(pnb_problem *p)
     GroupHostFull *gh = static_cast<GroupHostFull *>(p->gh);
     GroupSched &G = *p->G;
     int smem_sm = 0;
-    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device);
+    smem_sm = device_attr(cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device);
     if (smem_sm <= 0) smem_sm = 228 * 1024;
     int smem_blk = 0;
-    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+    smem_blk = device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
     const size_t budget = smem_blk > 0 ? (size_t)smem_blk : (size_t)smem_sm - 1024;     // one 512-thread CTA per SM
     if (!gh->ready) {
         // Hilbert order of the cell centers
@@ -2184,10 +2211,17 @@ static int build_group_schedule(pnb_problem *p)
             }
             key[c] = hilbert_index(q[0], q[1]);
         }
+        // stable order by key = order of the packed (key, cell) words (keys are below 2^32)
         std::vector<int> order(nc);
-        for (int c = 0; c < nc; c++) order[c] = c;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
-        const int forced = 0;
+        {
+            std::vector<uint64_t> packed(nc);
+            for (int c = 0; c < nc; c++) packed[c] = (key[c] << 32) | (uint32_t)c;
+            std::sort(packed.begin(), packed.end());
+            for (int c = 0; c < nc; c++) order[c] = (int)(packed[c] & 0xFFFFFFFFu);
+        }
+        const double tg0 = wall_ms();
+        // PNB_GROUP_CELLS: cells per group (experiments; a multiple of 32)
+        const int forced = getenv("PNB_GROUP_CELLS") ? atoi(getenv("PNB_GROUP_CELLS")) : 0;
         const int cand[] = {128, 96, 64, 32};   // even numbers of full batches (two column batches per step)
         for (int GC : cand) {
             if (forced > 0) GC = forced;
@@ -2199,6 +2233,7 @@ static int build_group_schedule(pnb_problem *p)
                 break;
         }
         const GroupGeom &gg = gh->gg;
+        const double tg1 = wall_ms();
         if (gg.maxld >= 255) return fail(PNB_ERR_UNSUPPORTED, "cell group with more than 254 local dofs");
         G.ngroups = gg.ngroups; G.cap = gg.cap; G.maxld = gg.maxld; G.ldS = gg.maxld + 1; G.ncolors = gg.ncolors;
         G.nbmax = gg.cap / PNB_SB;
@@ -2220,29 +2255,40 @@ static int build_group_schedule(pnb_problem *p)
             rc |= dalloc(p, 2 * PNB_ROW_PANELS + 2, &G.counters_i);
         }
         if (rc) return PNB_ERR_CUDA;
+        const double tg2 = wall_ms();
         G.err = p->S.err;
         G.counters = p->S.counters;
         gh->smem_f2 = gf2_smem_bytes(G.cap, G.maxld, G.ldS);
         gh->mix_warps = std::max(1, gmix_warps(G.cap, G.maxld, budget));
         gh->smem_mix = gmix_smem_bytes(G.cap, G.maxld, gh->mix_warps);
         {
-            // incidence lists of the group-local dofs: (cell slot, local vertex) in ascending order
+            // incidence lists of the group-local dofs: (cell slot, local vertex) in ascending order (counting sort per group)
             std::vector<int> iptr(1, 0);
             std::vector<unsigned short> ilist;
+            ilist.reserve(gg.gcells.size() * 3);
+            std::vector<int> cnt;
             for (int g = 0; g < gg.ngroups; g++) {
                 const int nld = gg.gdptr[g + 1] - gg.gdptr[g], ns = gg.gptr[g + 1] - gg.gptr[g];
-                std::vector<std::vector<unsigned short>> per(nld);
+                cnt.assign(nld + 1, 0);
                 for (int sl = 0; sl < ns; sl++) {
                     if (gg.gcells[gg.gptr[g] + sl] < 0) continue;
                     const int packed = gg.gloc[gg.gptr[g] + sl];
                     for (int m = 0; m < 3; m++) {
                         const int l = (packed >> (8 * m)) & 0xFF;
-                        if (l != 0xFF) per[l].push_back((unsigned short)(sl * 4 + m));
+                        if (l != 0xFF) cnt[l + 1]++;
                     }
                 }
-                for (int l = 0; l < nld; l++) {
-                    ilist.insert(ilist.end(), per[l].begin(), per[l].end());
-                    iptr.push_back((int)ilist.size());
+                for (int l = 0; l < nld; l++) cnt[l + 1] += cnt[l];
+                const size_t base = ilist.size();
+                ilist.resize(base + cnt[nld]);
+                for (int l = 0; l < nld; l++) iptr.push_back((int)(base + cnt[l + 1]));
+                for (int sl = 0; sl < ns; sl++) {
+                    if (gg.gcells[gg.gptr[g] + sl] < 0) continue;
+                    const int packed = gg.gloc[gg.gptr[g] + sl];
+                    for (int m = 0; m < 3; m++) {
+                        const int l = (packed >> (8 * m)) & 0xFF;
+                        if (l != 0xFF) ilist[base + cnt[l]++] = (unsigned short)(sl * 4 + m);
+                    }
                 }
             }
             if (ilist.empty()) ilist.push_back(0);
@@ -2251,8 +2297,10 @@ static int build_group_schedule(pnb_problem *p)
         gh->smem_near = gnear_list_smem_bytes(G.cap);
         gh->ready = true;
         if (getenv("PNB_BENCH_VERBOSE"))
-            fprintf(stderr, "group path: GC %d, %d groups, cap %d, maxld %d, %d colours, smem f2/mix/near %zu/%zu/%zu\n", gh->GC,
-                    gg.ngroups, gg.cap, gg.maxld, gg.ncolors, gh->smem_f2, gh->smem_mix, gh->smem_near);
+            fprintf(stderr, "group path: GC %d, %d groups, cap %d, maxld %d, %d colours, smem f2/mix/near %zu/%zu/%zu; host ms: hilbert %.1f, "
+                    "geometry %.1f, uploads %.1f, incidences %.1f\n", gh->GC,
+                    gg.ngroups, gg.cap, gg.maxld, gg.ncolors, gh->smem_f2, gh->smem_mix, gh->smem_near, tg0 - tw0, tg1 - tg0, tg2 - tg1,
+                    wall_ms() - tg2);
     }
     if (gh->far_mask == p->far_mask && gh->max_order == p->P.max_order && gh->part == p->part && gh->nparts == p->nparts &&
         gh->dist == p->dist)
@@ -2558,7 +2606,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
         // one persistent launch per unit list; the units take tickets in list order and order their updates of U
         // among themselves (g_wait_predecessors)
         int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
+        nsm = device_attr(cudaDevAttrMultiProcessorCount, p->device);
         const int nf = (int)gh->f2_units.size(), nm = (int)gh->mix_units.size();
         cudaMemsetAsync(G.counters_i, 0, (2 * PNB_ROW_PANELS + 2) * sizeof(int));
         cudaMemsetAsync(G.done, 0, std::max<size_t>((size_t)nf + nm, 1) * sizeof(int));
@@ -2581,7 +2629,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
             // rule table of the largest order that has items; per warp PNB_NEAR_WARP_POINTS points
             // two CTAs per SM: the table holds at most the nodes that fit beside the power table and the warp buffers
             int smem_sm = 0;
-            cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device);
+            smem_sm = device_attr(cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device);
             if (smem_sm <= 0) smem_sm = 228 * 1024;
             const size_t fixed = sizeof(PowTabS) + (size_t)wpb * PNB_NEAR_WARP_POINTS * sizeof(double2);
             const size_t per_cta = (size_t)smem_sm / 2 - 1024 - 256;
@@ -2590,7 +2638,7 @@ static int run_group_path(pnb_problem *p, int zero_exterior, double *dA, int64_t
             const size_t smem_eval = fixed + (size_t)PNB_DER2 * der_nodes * sizeof(double2);
             smem_optin(gnear_eval_kernel, p->device);
             int nsm = 148;
-            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
+            nsm = device_attr(cudaDevAttrMultiProcessorCount, p->device);
             const int grid = std::min(gh->nchunks, 2 * nsm);
             gnear_eval_kernel<<<grid, PNB_NEAR_THREADS, smem_eval>>>(p->P, G.npairs, gh->d_items, gh->d_perm, gh->d_chunks, gh->nchunks, gh->d_R,
                                                                 der_nodes, PNB_NEAR_WARP_POINTS);
@@ -3391,7 +3439,7 @@ extern "C" int pnb_dense_matvec(int device, const double *A, int64_t num_rows, i
     if (pnb_device_count() == 0) return fail(PNB_ERR_NO_DEVICE, "no CUDA device: libpnb200 has no CPU fallback");
     ON_DEVICE(device);
     int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    sms = device_attr(cudaDevAttrMultiProcessorCount, device);
     const int64_t want = (num_rows * 32 + 255) / 256;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 8));
     matvec_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A, num_rows, num_cols, ld, x, y);
@@ -3419,7 +3467,7 @@ extern "C" int pnb_fp64_peak(int device, double *tflops)
     if (pnb_device_count() == 0) return fail(PNB_ERR_NO_DEVICE, "no CUDA device");
     ON_DEVICE(device);
     int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    sms = device_attr(cudaDevAttrMultiProcessorCount, device);
     const int blocks = sms * 8, threads = 256, iters = 20000;
     double *d = nullptr;
     CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));

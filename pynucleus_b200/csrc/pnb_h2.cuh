@@ -540,7 +540,7 @@ extern "C" int pnb_h2_matvec(pnb_h2 *h, const double *x, double *y, int far_only
     const bool near = !far_only && h->near_indptr;
     if (near) {
         int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        sms = device_attr(cudaDevAttrMultiProcessorCount, h->device);
         const int blocks = std::max(1, std::min((h->num_dofs * 32 + 255) / 256, sms * 8));
         csr_matvec_kernel<<<blocks, 256, 0, st>>>(h->num_dofs, h->near_indptr, h->near_indices, h->near_data, x, y);
     }
