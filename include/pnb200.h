@@ -302,9 +302,10 @@ int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, cons
  * the tables (create it with the vertex dofs of the map as a P1 table and kernel.order_num_dofs = num_dofs); `dofs` is the
  * element's cell -> dof table (host, num_cells x dofs_per_element, the reference's local order: vertices, then edges
  * (0,1), (1,2), (0,2); 1D: vertices, then the cell).  One warp owns one row of the operator (no atomics, bitwise
- * reproducible); infinite horizon, constant kernels.  A: device, num_dofs x num_dofs, row-major. */
+ * reproducible); infinite horizon, constant kernels.  A: num_dofs x num_dofs, row-major, leading dimension ld; device
+ * memory if a_on_device != 0, else host memory (assembled on the device and copied back). */
 int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
-                               int zero_exterior, double *A, int64_t ld);
+                               int zero_exterior, double *A, int64_t ld, int a_on_device);
 
 /* ---- H2 operator on the device -------------------------------------------------------------------------
  * Replaces H2Matrix.matvec (nl/PyNucleus_nl/clusterMethodCy.pyx:2269-2295) with its upwardPass / downwardPass

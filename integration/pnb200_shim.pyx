@@ -10,7 +10,7 @@ one call into the CUDA library.  The result is written straight into the `data` 
     from pnb200_shim import nonlocalBuilderB200          # subclass of PyNucleus_nl.nonlocalBuilder
     A = nonlocalBuilderB200(dm, kernel, params).getDense()
 
-Unsupported configurations (non-symmetric or variable kernels, two DoFMaps, P0/P2, vector-valued kernels) fall through
+Unsupported configurations (non-symmetric or variable kernels, two DoFMaps, P0 / P3, vector-valued kernels) fall through
 to the reference's own getDense, so the subclass is a drop-in.
 """
 import numpy as np
@@ -56,9 +56,11 @@ def _regular_rules(int dim, int max_order):
 
 def supported(builder):
     """configurations the accelerated path covers (everything else stays with the reference's Cython loops)"""
-    from PyNucleus_fem.DoFMaps import P1_DoFMap
+    from PyNucleus_fem.DoFMaps import P1_DoFMap, P2_DoFMap
     k = builder.kernel
-    return (builder.dm2 is None and isinstance(builder.dm, P1_DoFMap) and k.symmetric and not k.variable
+    if isinstance(builder.dm, P2_DoFMap) and (k.finiteHorizon or int(k.kernelType) != 0):
+        return False        # P2: fractional kernels with infinite horizon (row-owner kernel)
+    return (builder.dm2 is None and isinstance(builder.dm, (P1_DoFMap, P2_DoFMap)) and k.symmetric and not k.variable
             and k.valueSize == 1 and builder.dm.mesh.dim in (1, 2) and builder.dm.mesh.manifold_dim == builder.dm.mesh.dim
             and (builder.comm is None or builder.comm.size == 1) and int(k.kernelType) in (0, 1, 2)
             and not k.complement and (int(k.kernelType) == 0 or k.finiteHorizon))
@@ -76,7 +78,8 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
         pnb_problem *prob = NULL
         pnb_rule_t *cell = NULL
         pnb_rule_t *facet = NULL
-        int rc, o, dim, N, zero_exterior
+        int rc, o, dim, N, zero_exterior, porder, dpe
+        int32_t[:, ::1] edofs
         int32_t need = 0
         double[:, ::1] vertices, nodes
         double[::1] vol, h, weights
@@ -93,7 +96,12 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
     N = dm.num_dofs
     vertices = np.ascontiguousarray(mesh.vertices, dtype=np.float64)
     cells = np.ascontiguousarray(mesh.cells, dtype=np.int32)
-    dofs = np.ascontiguousarray(dm.dofs, dtype=np.int32)
+    # P2: the problem is created over the vertex dofs (first dim+1 columns of the table); the element's whole table goes
+    # to pnb_dense_assemble_element
+    porder = dm.polynomialOrder
+    dpe = dm.dofs_per_element
+    edofs = np.ascontiguousarray(dm.dofs, dtype=np.int32)
+    dofs = np.ascontiguousarray(np.asarray(dm.dofs)[:, :dim+1], dtype=np.int32)
     vol = np.ascontiguousarray(mesh.volVector, dtype=np.float64)
     h = np.ascontiguousarray(mesh.hVector, dtype=np.float64)
     if dim == 2:
@@ -115,7 +123,7 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
     m.diam = mesh.diam
     m.num_bfacets = <int32_t>bfacets.shape[0]
     m.bfacets = &bfacets[0, 0] if bfacets.shape[0] > 0 else NULL
-    d.dofs_per_element = dm.dofs_per_element
+    d.dofs_per_element = dim+1
     d.num_dofs = N
     d.dofs = &dofs[0, 0]
     k.kernel_type = int(kernel.kernelType)
@@ -125,6 +133,7 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
     k.singularity = kernel.singularityValue
     k.horizon2 = kernel.horizonValue**2 if kernel.finiteHorizon else np.inf
     k.target_order = lm.target_order
+    k.order_num_dofs = N
     if k.kernel_type == 0:
         k.bscaling = lmb.kernel.scalingValue
         k.bsingularity = lmb.kernel.singularityValue
@@ -180,7 +189,10 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
             if rc != 0:
                 raise PNB200Error(_last_error())
             with nogil:
-                rc = pnb_dense_assemble(prob, zero_exterior, 0, N, &data[0, 0], N, 0)
+                if porder == 1:
+                    rc = pnb_dense_assemble(prob, zero_exterior, 0, N, &data[0, 0], N, 0)
+                else:
+                    rc = pnb_dense_assemble_element(prob, porder, dpe, N, &edofs[0, 0], zero_exterior, &data[0, 0], N, 0)
             if rc == 0:
                 break
             if rc != -5 or attempt == 1:       # PNB_ERR_ORDER: the reference grows its rule cache lazily (addQuadRule)

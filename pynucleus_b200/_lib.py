@@ -144,7 +144,7 @@ def lib():
         L.pnb_h2_matvec.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.pnb_h2_destroy.argtypes = [ctypes.c_void_p]
         L.pnb_dense_assemble_element.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
-                                                 ctypes.c_void_p, ctypes.c_int64]
+                                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
         _LIB = L
     return _LIB
 

@@ -344,7 +344,7 @@ class nonlocalBuilder:
             if self._element:
                 ed = np.ascontiguousarray(self.dm.dofs, dtype=np.int32)
                 _lib.check(_lib.lib().pnb_dense_assemble_element(prob.handle, self.dm.polynomialOrder, self.dm.dofs_per_element, N,
-                                                                 ed.ctypes.data, int(self.zeroExterior), A.data_ptr(), A.stride(0)))
+                                                                 ed.ctypes.data, int(self.zeroExterior), A.data_ptr(), A.stride(0), 1))
             else:
                 _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.data_ptr(),
                                                          A.stride(0), 1))

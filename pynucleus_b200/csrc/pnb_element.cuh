@@ -378,18 +378,25 @@ __global__ void __launch_bounds__(128) elem_rows_kernel(DProblem P, ElemJob J, i
 }
 
 extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
-                                          int zero_exterior, double *A, int64_t ld)
+                                          int zero_exterior, double *A_out, int64_t ld_out, int a_on_device)
 {
-    if (!p || !dofs || !A) return fail(PNB_ERR_ARG, "null argument");
+    if (!p || !dofs || !A_out) return fail(PNB_ERR_ARG, "null argument");
     if (polynomial_order < 1 || polynomial_order > 2) return fail(PNB_ERR_UNSUPPORTED, "elements: P1 and P2");
     const int dpe = polynomial_order == 1 ? p->dim + 1 : (p->dim == 1 ? 3 : 6);
     if (dofs_per_element != dpe) return fail(PNB_ERR_ARG, "dofs_per_element does not match the element");
     if (p->finite) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: infinite horizon only");
     if (!p->h_labels.empty()) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: constant kernels only");
     if (p->nblocks > 0) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: no batched blocks");
-    if (ld < num_dofs) return fail(PNB_ERR_ARG, "leading dimension too small");
+    if (ld_out < num_dofs) return fail(PNB_ERR_ARG, "leading dimension too small");
     ON_DEVICE(p->device);
     if (num_dofs == 0) return 0;
+    // host output: assembled in a device buffer and copied back
+    double *A = A_out;
+    int64_t ld = ld_out;
+    if (!a_on_device) {
+        ld = num_dofs;
+        CK(pool_malloc((void **)&A, (size_t)num_dofs * num_dofs * sizeof(double)));
+    }
     const int nc = p->nc;
     std::vector<int> dptr(num_dofs + 1, 0), dcells;
     for (int c = 0; c < nc; c++)
@@ -412,10 +419,13 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     J.N = num_dofs;
     J.dpe = dpe;
     int *d_edofs = nullptr, *d_ptr = nullptr, *d_cells = nullptr, *d_err = nullptr;
-    CK(cudaMalloc(&d_edofs, (size_t)nc * dpe * sizeof(int)));
-    CK(cudaMalloc(&d_ptr, ((size_t)num_dofs + 1) * sizeof(int)));
-    CK(cudaMalloc(&d_cells, std::max<size_t>(dcells.size(), 1) * sizeof(int)));
-    CK(cudaMalloc(&d_err, sizeof(int)));
+    if (cudaMalloc(&d_edofs, (size_t)nc * dpe * sizeof(int)) != cudaSuccess || cudaMalloc(&d_ptr, ((size_t)num_dofs + 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&d_cells, std::max<size_t>(dcells.size(), 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&d_err, sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err);
+        if (!a_on_device) pool_free(A);
+        return fail(PNB_ERR_CUDA, "out of device memory");
+    }
     cudaMemcpy(d_edofs, dofs, (size_t)nc * dpe * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemcpy(d_ptr, dptr.data(), dptr.size() * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemcpy(d_cells, dcells.data(), dcells.size() * sizeof(int), cudaMemcpyHostToDevice);
@@ -434,6 +444,12 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     int herr = 0;
     cudaMemcpy(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost);
     cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err);
+    if (!a_on_device) {
+        if (e == cudaSuccess && herr == 0)
+            e = cudaMemcpy2D(A_out, (size_t)ld_out * sizeof(double), A, (size_t)ld * sizeof(double), (size_t)num_dofs * sizeof(double),
+                             (size_t)num_dofs, cudaMemcpyDeviceToHost);
+        pool_free(A);
+    }
     CK(e);
     if (herr > 0) {
         return fail(PNB_ERR_ORDER, "regular quadrature order " + std::to_string(herr) + " exceeds the supplied tables");

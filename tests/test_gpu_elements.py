@@ -78,7 +78,7 @@ def test_element_kernel_with_p1_equals_production_path(dim):
     N = dm.num_dofs
     B = torch.empty((N, N), dtype=torch.float64, device='cuda')
     ed = np.ascontiguousarray(dm.dofs, dtype=np.int32)
-    _lib.check(_lib.lib().pnb_dense_assemble_element(b.problem.handle, 1, dim+1, N, ed.ctypes.data, 1, B.data_ptr(), B.stride(0)))
+    _lib.check(_lib.lib().pnb_dense_assemble_element(b.problem.handle, 1, dim+1, N, ed.ctypes.data, 1, B.data_ptr(), B.stride(0), 1))
     assert entry_err(B.cpu().numpy(), A) < TOL
 
 

@@ -100,3 +100,25 @@ def test_unsupported_configuration_falls_through(shim):
     assert not shim.supported(b)
     A = b.getDense()
     assert A.shape == (dm.num_dofs, dm2.num_dofs)
+
+
+@pytest.mark.parametrize('dim,noRef,s', [(1, 5, 0.75), (2, 2, 0.75), (2, 2, 0.25)])
+def test_reference_builder_vs_shim_p2(shim, dim, noRef, s):
+    """P2_DoFMap of the reference through the shim (pnb_dense_assemble_element) against its own Cython getDense"""
+    from PyNucleus_fem.mesh import simpleInterval, uniform_disc
+    from PyNucleus_fem.DoFMaps import P2_DoFMap
+    from PyNucleus_nl.kernels import getFractionalKernel
+    from PyNucleus_nl.fractionalOrders import constFractionalOrder
+    from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder
+    mesh = simpleInterval(-1, 1) if dim == 1 else uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P2_DoFMap(mesh)
+    kernel = getFractionalKernel(dim, constFractionalOrder(s), np.inf)
+    params = {'target_order': 0.5} if dim == 2 else {}
+    Aref = np.array(nonlocalBuilder(dm, kernel, dict(params)).getDense().data)
+    b = shim.builder_class()(dm, kernel, dict(params))
+    assert shim.supported(b)
+    A = b.getDense()
+    assert A.shape == Aref.shape
+    assert entry_err(np.array(A.data), Aref) < TOL
