@@ -91,6 +91,13 @@ def diam_box(b):
     return sqrt(d)
 
 
+class dofArray(np.ndarray):
+    """sorted dof indices of a cluster with the `toSet()` of the reference's indexSet (tests/test_fracLapl.py:174)"""
+
+    def toSet(self):
+        return set(self.tolist())
+
+
 class tree_node:
     def __init__(self, parent, dofs, data, mixed_node=False):
         self.parent = parent
@@ -122,8 +129,8 @@ class tree_node:
     @property
     def dofs(self):
         if self.isLeaf:
-            return self._dofs
-        return np.unique(np.concatenate([c.dofs for c in self.children]))
+            return self._dofs.view(dofArray)
+        return np.unique(np.concatenate([c.dofs for c in self.children])).view(dofArray)
 
     def root(self):
         n = self
@@ -144,6 +151,54 @@ class tree_node:
         yield self
         for c in self.children:
             yield from c.get_tree_nodes()
+
+    # ---- the passes of the H2 product, node by node (tree_node.upwardPass / downwardPass / resetCoefficientsDown,
+    # clusterMethodCy.pyx:1093-1176), for callers that drive them by hand like tests/test_fracLapl.py:176-186 of the
+    # reference.  Device tensors throughout (the cluster bases are attached by H2Matrix); H2Matrix.matvec itself runs
+    # the batched kernels of csrc/pnb_h2.cuh.
+    def _dev(self, array, key):
+        import torch
+        cache = self.__dict__.setdefault('_tensors', {})
+        if key not in cache:
+            cache[key] = torch.as_tensor(np.ascontiguousarray(array), device=self.root()._device)
+        return cache[key]
+
+    def upwardPass_py(self, x, componentNo=0, skip_leaves=False):
+        import torch
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=self.root()._device)
+        if self.isLeaf:
+            if not skip_leaves:
+                self.coefficientsUp = self._dev(self.value, 'V').t().mv(x[self._dev(self.dofs, 'dofs')])
+        else:
+            acc = None
+            for c in self.children:
+                c.upwardPass_py(x, componentNo, skip_leaves)
+                t = c._dev(c.transferOperator, 'T').mv(c.coefficientsUp)
+                acc = t if acc is None else acc+t
+            self.coefficientsUp = acc
+
+    def resetCoefficientsDown_py(self, vecValued=False):
+        import torch
+        for n in self.get_tree_nodes():
+            n.coefficientsDown = torch.zeros(n.interpolation_order**n.dim, dtype=torch.float64, device=self.root()._device)
+
+    def downwardPass_py(self, y, componentNo=0):
+        """adds the far-field part to y (host array: in place through a device copy; device tensor: in place)"""
+        import torch
+        host = not isinstance(y, torch.Tensor)
+        yt = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64), device=self.root()._device) if host else y
+        self._down(yt)
+        if host:
+            y[:] = yt.cpu().numpy()
+
+    def _down(self, yt):
+        if self.isLeaf:
+            yt[self._dev(self.dofs, 'dofs')] += self._dev(self.value, 'V').mv(self.coefficientsDown)
+        else:
+            for c in self.children:
+                c.coefficientsDown += c._dev(c.transferOperator, 'T').t().mv(self.coefficientsDown)
+                c._down(yt)
 
     def get_tree_nodes_up_to_level(self, level):
         yield self

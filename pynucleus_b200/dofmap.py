@@ -5,6 +5,35 @@ import numpy as np
 from .mesh import INDEX
 
 
+def _shape_values(polynomialOrder, manifold_dim, bary):
+    """local shape functions at barycentric points, [dofs_per_element, n] (DoFMaps.pyx:1854-1880, 1932-2005)"""
+    lam = np.asarray(bary)
+    if polynomialOrder == 1:
+        return lam.copy()
+    phi = [lam[k]*(2.*lam[k]-1.) for k in range(manifold_dim+1)]
+    phi.append(4.*lam[0]*lam[1])
+    if manifold_dim == 2:
+        phi += [4.*lam[1]*lam[2], 4.*lam[0]*lam[2]]
+    return np.array(phi)
+
+
+def _assembleRHS(dm, fun, qr_order=None):
+    """b_i = int f phi_i (DoFMap.assembleRHS, DoFMaps.pyx:905-): simplex rule of order 2 p + 2 per cell, host side"""
+    from . import quadrature
+    mesh = dm.mesh
+    md = mesh.manifold_dim
+    bary, w = quadrature.regular(2*dm.polynomialOrder+2 if qr_order is None else qr_order, md)
+    phi = _shape_values(dm.polynomialOrder, md, bary)                          # [dpe, nq]
+    x = np.einsum('kq,ckd->cqd', bary, mesh.vertices[mesh.cells])                # [nc, nq, dim]
+    f = np.array([[fun(x[c, q]) for q in range(x.shape[1])] for c in range(x.shape[0])]) if callable(fun) else \
+        np.full(x.shape[:2], float(fun))
+    loc = mesh.volVector[:, None]*np.einsum('cq,q,kq->ck', f, w, phi)            # [nc, dpe]
+    b = np.zeros(dm.num_dofs)
+    m = dm.dofs >= 0
+    np.add.at(b, dm.dofs[m], loc[m])
+    return b
+
+
 class P1_DoFMap:
     polynomialOrder = 1
 
@@ -94,6 +123,9 @@ class P1_DoFMap:
     def zeros(self):
         return np.zeros(self.num_dofs)
 
+    def assembleRHS(self, fun, qr_order=None):
+        return _assembleRHS(self, fun, qr_order)
+
 
 class P2_DoFMap:
     """continuous piecewise quadratic elements (DoFMaps.pyx:1978-2031): one dof per vertex and per edge (1D: per vertex
@@ -182,3 +214,6 @@ class P2_DoFMap:
 
     def zeros(self):
         return np.zeros(self.num_dofs)
+
+    def assembleRHS(self, fun, qr_order=None):
+        return _assembleRHS(self, fun, qr_order)

@@ -126,6 +126,13 @@ class farFieldClusterPair:
     def __init__(self, n1, n2, kernelInterpolant):
         self.n1, self.n2, self.kernelInterpolant = n1, n2, kernelInterpolant
 
+    def apply(self, x, y):
+        """y += kernelInterpolant x (farFieldClusterPair.apply, clusterMethodCy.pyx:1968-1974); device tensors"""
+        import torch
+        if getattr(self, '_K', None) is None or self._K.device != x.device:
+            self._K = torch.as_tensor(np.ascontiguousarray(self.kernelInterpolant), device=x.device)
+        y += self._K.mv(x)
+
 
 class H2Matrix:
     """y = Anear x + far field; `Anear` any object with a device matvec (or None), x / y float64 CUDA tensors"""
@@ -136,6 +143,7 @@ class H2Matrix:
         self.num_rows = self.num_columns = num_dofs
         self.device = device
         self._dev = {}
+        tree._device = device
         for n in tree.get_tree_nodes():
             n._dofs_t = torch.as_tensor(n.dofs, device=device) if n.isLeaf else None
 

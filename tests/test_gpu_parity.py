@@ -885,3 +885,52 @@ def test_h2_device_engine(golden_dir, name):
     H.compile()
     yc = H.farfield_compiled(x)+H.Anear.matvec_device(x)
     assert float((y1-yc).abs().max()) < 1e-12*float(yc.abs().max())
+
+
+@pytest.mark.parametrize('dim,s,errBnd', [(1, 0.3, 1e-4), (1, 0.7, 1e-2), (2, 0.3, 1.2e-4), (2, 0.7, 1e-2)])
+def test_h2_like_the_reference_test(dim, s, errBnd):
+    """tests/test_fracLapl.py:141-237 of the reference (`h2` / `testH2`), statement for statement and with its parameters
+    (orders, error bounds, refinements, eta, maxLevels, the DoFMap tag) against this package's objects: near field against
+    the dense operator outside the admissible blocks, the far field through the tree's own upwardPass_py /
+    resetCoefficientsDown_py / clusterPair.apply / downwardPass_py, and the whole product.  The 2D mesh is the 10-gon fan
+    instead of `circle(10)` (meshpy is not available offline)."""
+    import pynucleus_b200 as pb
+    from pynucleus_b200.h2 import H2Matrix
+    if dim == 1:
+        mesh, refinements, eta, maxLevels = pb.simpleInterval(-1, 1), 6, 1, None
+    else:
+        fan = pb.polygon_disc(10)
+        mesh, refinements, eta, maxLevels = pb.meshNd(fan.vertices, fan.cells), 3, 3, 4
+    for _ in range(refinements):
+        mesh = mesh.refine()
+    # tag=-1 (no Dirichlet vertices) for s < 0.5, the whole boundary otherwise
+    dm = pb.P1_DoFMap(mesh, tag=np.zeros(mesh.num_vertices, dtype=bool) if s < 0.5 else None)
+    params = {'eta': eta, 'maxLevels': maxLevels}
+    builder = pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, s), params=params, zeroExterior=True)
+    A_d = np.array(builder.getDense().data)
+    A_h2 = builder.getH2()
+    assert isinstance(A_h2, H2Matrix)
+    n = A_d.shape[0]
+    Afar = np.zeros((n, n))
+    for level in A_h2.Pfar:
+        for c in A_h2.Pfar[level]:
+            Afar[np.ix_(list(c.n1.dofs.toSet()), list(c.n2.dofs.toSet()))] = A_d[np.ix_(list(c.n1.dofs.toSet()), list(c.n2.dofs.toSet()))]
+    Anear = A_d-Afar
+    errNear = np.absolute(Anear-A_h2.Anear.toarray()).max()
+    x = np.ones((A_d.shape[0]))
+    y_d = np.dot(Afar, x)
+    y_h2 = np.zeros_like(y_d)
+    assert len(A_h2.Pfar) > 0
+    A_h2.tree.upwardPass_py(x)
+    A_h2.tree.resetCoefficientsDown_py()
+    for level in A_h2.Pfar:
+        for clusterPair in A_h2.Pfar[level]:
+            n1, n2 = clusterPair.n1, clusterPair.n2
+            clusterPair.apply(n2.coefficientsUp, n1.coefficientsDown)
+    A_h2.tree.downwardPass_py(y_h2)
+    errFar = np.absolute(y_d-y_h2).max()
+    y_d = np.dot(A_d, x)
+    y_h2 = A_h2*x
+    errAll = np.absolute(y_d-y_h2).max()
+    # the reference asserts errNear < errBnd, errFar < errBnd, errAll < errBnd (tests/test_fracLapl.py:191-200)
+    assert errNear < errBnd and errFar < errBnd and errAll < errBnd, (errNear, errFar, errAll)
