@@ -521,6 +521,15 @@ def run_cuda(args):
         except Exception as e:       # e.g. out of memory on a small part count: reported, not fatal
             north = {'workload': 'disc105k', 'error': '{}: {}'.format(type(e).__name__, str(e)[:300])}
 
+    # the rows next to the hot path (SURVEY 8f / verdict rows): H2 product on the library's kernels, P2 elements, an
+    # unsymmetric piecewise order -- small sizes, a few seconds, one GPU only
+    widening = None
+    if rank == 0 and world == 1 and not args.no_widening:
+        try:
+            widening = widening_leg(dev)
+        except Exception as e:
+            widening = {'error': '{}: {}'.format(type(e).__name__, str(e)[:300])}
+
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
         cpu = reference_throughput(args.workload, target_seconds=args.ref_seconds)
@@ -540,6 +549,7 @@ def run_cuda(args):
             'roofline': roofline,
             'matvec': matvec,
             'north_star': north,
+            'widening': widening,
             'cpu_baseline': cpu,
             'phases_ms': {'tiles': st['ms_tiles'], 'boundary': st['ms_boundary'], 'reduce_scatter': st['ms_reduce_scatter']},
             'pairs': {'distinct': st['distinct_pairs'], 'evaluated': st['evaluated_pairs']}}
@@ -548,6 +558,68 @@ def run_cuda(args):
     if world > 1:
         pb.release_staging_pool()
         dist.destroy_process_group()
+
+
+def _event_ms(fn, n, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)/n
+
+
+def widening_leg(dev):
+    """H2 operator (N = 12 097): assembly time, product on the library's own kernels against the dense product; P2 elements
+    (2 977 dofs) and an unsymmetric leftRight order (2 977 dofs): dense assembly time and symmetry of the result"""
+    import torch
+    import pynucleus_b200 as pb
+    out = {}
+    params = {'target_order': TARGET_ORDER, 'device': dev.index}
+    mesh = pb.refined(pb.uniform_disc(), 6)
+    dm = pb.P1_DoFMap(mesh)
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, S_ORDER), params)
+    A = b.getDense()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    H = b.getH2()
+    torch.cuda.synchronize()
+    t_h2 = time.perf_counter()-t0
+    x = torch.as_tensor(np.sin(np.arange(dm.num_dofs)*0.37)+0.1, device=dev)
+    y = torch.empty_like(x)
+    yh, yd = H.matvec_device(x).clone(), A.matvec_device(x).clone()
+    out['h2'] = {'workload': 'disc r=6, N={}, s={}'.format(dm.num_dofs, S_ORDER), 'getH2_s': t_h2,
+                 'near_nnz_frac': H.Anear.nnz/float(dm.num_dofs)**2, 'far_pairs': sum(len(v) for v in H.Pfar.values()),
+                 'matvec_ms': _event_ms(lambda: H.matvec_device(x, y), 50), 'dense_matvec_ms': _event_ms(lambda: A.matvec_device(x, y), 50),
+                 'rel_diff_vs_dense_product': float((yh-yd).abs().max()/yd.abs().max()),
+                 'kernels': 'pnb_h2_matvec (csr_matvec, h2_leaf_up, h2_transfer_up, h2_far, h2_far_sum, h2_transfer_down, h2_leaf_down)'}
+    del H, A, b
+    mesh = pb.refined(pb.uniform_disc(), 4)
+    dm2 = pb.P2_DoFMap(mesh)
+    b2 = pb.nonlocalBuilder(dm2, pb.getFractionalKernel(2, S_ORDER), params)
+    A2 = b2.getDense()
+    ms = _event_ms(lambda: b2.getDense(out=A2.device_data), 3, warm=1)
+    d = A2.device_data
+    out['p2'] = {'workload': 'disc r=4, P2, {} dofs ({} cells), s={}'.format(dm2.num_dofs, mesh.num_cells, S_ORDER), 'ms_per_assembly': ms,
+                 'entries_per_s': dm2.num_dofs**2/(ms*1e-3), 'symmetry_rel': float((d-d.t()).abs().max()/d.abs().max()),
+                 'min_diagonal': float(torch.diagonal(d).min()), 'kernel': 'elem_rows_kernel<2,2>'}
+    del A2, b2
+    mesh = pb.refined(pb.uniform_disc(), 5)
+    dm = pb.P1_DoFMap(mesh)
+    s = pb.leftRightFractionalOrder(0.25, 0.75, 0.6, 0.4)
+    b3 = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, s), params)
+    A3 = b3.getDense()
+    ms = _event_ms(lambda: b3.getDense(out=A3.device_data), 3, warm=1)
+    d = A3.device_data
+    out['unsymmetric_order'] = {'workload': 'disc r=5, N={}, leftRight(0.25, 0.75, 0.6, 0.4)'.format(dm.num_dofs), 'ms_per_assembly': ms,
+                                'passes': len(b3._classes['passes']), 'symmetry_rel': float((d-d.t()).abs().max()/d.abs().max()),
+                                'min_diagonal': float(torch.diagonal(d).min())}
+    return out
 
 
 def north_star_leg(args, world, rank, local_rank, dev, flush, peak):
@@ -623,6 +695,8 @@ def main():
     ap.add_argument('--north-star', dest='north_star', action='store_true', default=True,
                     help='also time a few assemblies of disc105k (BASELINE configs[4]) and report them under north_star')
     ap.add_argument('--no-north-star', dest='north_star', action='store_false')
+    ap.add_argument('--no-widening', dest='no_widening', action='store_true', default=False,
+                    help='skip the H2 / P2 / unsymmetric-order legs (a few seconds on one GPU)')
     args = ap.parse_args()
     # the reference arm is bounded: a few sampled slices per step
     args.steps_ref = min(args.steps, 2)
