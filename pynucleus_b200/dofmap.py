@@ -17,12 +17,13 @@ def _shape_values(polynomialOrder, manifold_dim, bary):
     return np.array(phi)
 
 
-def _assembleRHS(dm, fun, qr_order=None):
-    """b_i = int f phi_i (DoFMap.assembleRHS, DoFMaps.pyx:905-): simplex rule of order 2 p + 2 per cell, host side"""
+def _assembleRHS(dm, fun, qr_order=None, rule=None):
+    """b_i = int f phi_i (DoFMap.assembleRHS, DoFMaps.pyx:766-785): simplex rule of order 2 p + 2 per cell unless a rule
+    (barycentric nodes [dim+1, n], weights) is given; host side"""
     from . import quadrature
     mesh = dm.mesh
     md = mesh.manifold_dim
-    bary, w = quadrature.regular(2*dm.polynomialOrder+2 if qr_order is None else qr_order, md)
+    bary, w = quadrature.regular(2*dm.polynomialOrder+2 if qr_order is None else qr_order, md) if rule is None else rule
     phi = _shape_values(dm.polynomialOrder, md, bary)                          # [dpe, nq]
     x = np.einsum('kq,ckd->cqd', bary, mesh.vertices[mesh.cells])                # [nc, nq, dim]
     f = np.array([[fun(x[c, q]) for q in range(x.shape[1])] for c in range(x.shape[0])]) if callable(fun) else \
@@ -123,8 +124,8 @@ class P1_DoFMap:
     def zeros(self):
         return np.zeros(self.num_dofs)
 
-    def assembleRHS(self, fun, qr_order=None):
-        return _assembleRHS(self, fun, qr_order)
+    def assembleRHS(self, fun, qr_order=None, rule=None):
+        return _assembleRHS(self, fun, qr_order, rule)
 
 
 class P2_DoFMap:
@@ -215,5 +216,5 @@ class P2_DoFMap:
     def zeros(self):
         return np.zeros(self.num_dofs)
 
-    def assembleRHS(self, fun, qr_order=None):
-        return _assembleRHS(self, fun, qr_order)
+    def assembleRHS(self, fun, qr_order=None, rule=None):
+        return _assembleRHS(self, fun, qr_order, rule)

@@ -118,3 +118,45 @@ def test_fracLapl_like_the_reference_test(dim, s, element, errBnd):
     else:
         err = np.sqrt(abs(np.dot(rhs, u)-2*np.pi*2**(-2*s)*gamma(1)/gamma(1+s)**2/2/(s+1)))
     assert err < errBnd, '{} not smaller than {}'.format(err, errBnd)
+
+
+@pytest.mark.parametrize('s,ref', [(0.25, (0.08454379705489531, 0.022920865169740616)), (0.75, (0.03250922885004246, 0.0009589826276423743))])
+def test_p2_driver_known_answers(s, ref):
+    """runFractional.py --domain interval --s const(s) --problem constant --element P2 --matrixFormat dense at the driver's
+    default size (5 refinements of its two-cell interval: 127 P2 dofs): Hs and L2 errors against the reference's cached
+    results (tests/cache_runFractional.py--domaininterval--sconst(*)--problemconstant--elementP2--solvercg-mg--matrixFormatdense;
+    formulas nl/PyNucleus_nl/discretizedProblems.py:77-110, exact values nonlocalProblems.py:741-749).  The linear system is
+    solved directly here (the driver's cg-mg stops at 1e-6); the L2 error also carries the quadrature of the exact solution,
+    so it is held to the reference's own rTol = 3e-2."""
+    from math import gamma
+    import pynucleus_b200 as pb
+    from pynucleus_b200.dofmap import _shape_values
+    from pynucleus_b200 import quadrature
+    mesh = pb.refined(pb.simpleInterval(-1, 1), 6)
+    dm = pb.P2_DoFMap(mesh)
+    assert dm.num_dofs == 127
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(1, s), {}).getDense().data
+    b = dm.assembleRHS(1.)
+    u = np.linalg.solve(A, b)
+    C = 2.**(-2.*s)*gamma(0.5)/gamma(0.5+s)/gamma(1.+s)
+    Hs_ex2 = C*np.sqrt(np.pi)*gamma(s+1)/gamma(s+1.5)
+    L2_ex2 = C**2*np.sqrt(np.pi)*gamma(2*s+1)/gamma(2*s+1.5)
+    Hs = np.sqrt(abs(b.dot(u)-Hs_ex2))
+    assert abs(Hs/ref[0]-1) < 1e-5, (Hs, ref[0])
+    # L2 error: ||u_ex||^2 - 2 (u_ex, u_h) + (u_h, u_h) with the P2 mass matrix
+    # default rule of assembleRHS for P2 in 1D: Gauss1D(order=5), three Gauss-Legendre nodes (fem/PyNucleus_fem/femCy.pyx:2644,
+    # quadrature.pyx:303-316)
+    t, wg = np.polynomial.legendre.leggauss(3)
+    z = dm.assembleRHS(lambda x: C*max(1.-x[0]**2, 0.)**s, rule=(np.stack(((t+1)/2, 1-(t+1)/2)), wg/2))
+    bary, w = quadrature.regular(6, 1)
+    phi = _shape_values(2, 1, bary)
+    Mloc = np.einsum('q,iq,jq->ij', w, phi, phi)
+    M = np.zeros((dm.num_dofs, dm.num_dofs))
+    for c in range(mesh.num_cells):
+        d = dm.dofs[c]
+        for i in range(3):
+            for j in range(3):
+                if d[i] >= 0 and d[j] >= 0:
+                    M[d[i], d[j]] += mesh.volVector[c]*Mloc[i, j]
+    L2 = np.sqrt(abs(L2_ex2-2*z.dot(u)+u.dot(M.dot(u))))
+    assert abs(L2/ref[1]-1) < 3e-2, (L2, ref[1])
