@@ -268,6 +268,7 @@ struct ElemJob {
     const int *edofs;       // nc x dpe: cell -> dof (negative: boundary dof)
     const int *dof_ptr;     // N+1: dof -> (cell, slot) list, cells ascending
     const int *dof_cells;   // cell * 8 + slot
+    const int *row_order;   // rows by descending number of cells around the dof (vertex dofs before edge dofs): long rows first
     int *err;               // [0]: regular order missing in the tables
 };
 
@@ -276,8 +277,9 @@ __global__ void __launch_bounds__(128) elem_rows_kernel(DProblem P, ElemJob J, i
 {
     constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
     const int lane = threadIdx.x & 31;
-    const int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (I >= J.N) return;
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (widx >= J.N) return;
+    const int I = J.row_order[widx];
     double *row = A + (size_t)I * ld;
     for (int j = lane; j < J.N; j += 32) row[j] = 0.;
     __syncwarp();
@@ -418,11 +420,15 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     ElemJob J;
     J.N = num_dofs;
     J.dpe = dpe;
-    int *d_edofs = nullptr, *d_ptr = nullptr, *d_cells = nullptr, *d_err = nullptr;
+    std::vector<int> row_order(num_dofs);
+    for (int i = 0; i < num_dofs; i++) row_order[i] = i;
+    std::stable_sort(row_order.begin(), row_order.end(), [&](int a, int b) { return dptr[a + 1] - dptr[a] > dptr[b + 1] - dptr[b]; });
+    int *d_edofs = nullptr, *d_ptr = nullptr, *d_cells = nullptr, *d_err = nullptr, *d_order = nullptr;
     if (cudaMalloc(&d_edofs, (size_t)nc * dpe * sizeof(int)) != cudaSuccess || cudaMalloc(&d_ptr, ((size_t)num_dofs + 1) * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&d_cells, std::max<size_t>(dcells.size(), 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&d_err, sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&d_cells, std::max<size_t>(dcells.size(), 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&d_err, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&d_order, (size_t)num_dofs * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
-        cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err);
+        cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order);
         if (!a_on_device) pool_free(A);
         return fail(PNB_ERR_CUDA, "out of device memory");
     }
@@ -430,7 +436,8 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     cudaMemcpy(d_ptr, dptr.data(), dptr.size() * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemcpy(d_cells, dcells.data(), dcells.size() * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemset(d_err, 0, sizeof(int));
-    J.edofs = d_edofs; J.dof_ptr = d_ptr; J.dof_cells = d_cells; J.err = d_err;
+    cudaMemcpy(d_order, row_order.data(), row_order.size() * sizeof(int), cudaMemcpyHostToDevice);
+    J.edofs = d_edofs; J.dof_ptr = d_ptr; J.dof_cells = d_cells; J.err = d_err; J.row_order = d_order;
     const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
     if (p->dim == 2) {
         if (polynomial_order == 2) elem_rows_kernel<2, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
@@ -443,7 +450,7 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     int herr = 0;
     cudaMemcpy(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err);
+    cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order);
     if (!a_on_device) {
         if (e == cudaSuccess && herr == 0)
             e = cudaMemcpy2D(A_out, (size_t)ld_out * sizeof(double), A, (size_t)ld * sizeof(double), (size_t)num_dofs * sizeof(double),
