@@ -73,3 +73,33 @@ if __name__ == '__main__':
         # uninitialised parameter slot, so its 2D innerOuter order is not reproducible
         case(1, 5, innerOuterFractionalOrder(1, 0.3, 0.7, 0.5, np.array([0.1]), 0.55, 0.35), 'nonsym_interval_innerouter_r5',
              {}, dict(kind='innerOuter', sii=0.3, soo=0.7, r=0.5, center=np.array([0.1]), sio=0.55, soi=0.35))
+
+
+def case_constant_nonsym(dim, noRef, s, name, params):
+    """constantNonSymFractionalOrder: s(x,y) = const flagged as unsymmetric (fractionalOrders.pyx:631-638); the kernel cannot
+    be piecewise (kernels.py:147-149), so the reference evaluates order and scaling per quadrature node
+    (updateAndEvalFractional, kernelsCy.pyx:596-622) inside the unsymmetric local matrices"""
+    from PyNucleus_nl.fractionalOrders import constantNonSymFractionalOrder
+    import warnings
+    mesh = uniform_disc() if dim == 2 else simpleInterval(-1, 1)
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        kernel = getFractionalKernel(dim, constantNonSymFractionalOrder(s), np.inf)
+    assert kernel.variable and not kernel.piecewise and not kernel.symmetric
+    out = mesh_arrays(mesh, dm)
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = nonlocalBuilder(dm, kernel, dict(params), zeroExterior=ze)
+        out[key] = np.array(b.getDense().data)
+    out.update(symmetric=0, local_matrix=type(b.local_matrix).__name__, target_order_used=b.local_matrix.target_order,
+               quad_order_diagonal=b.local_matrix.quad_order_diagonal, kind='constantNonSym', s=s)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, out['A'].shape, type(b.local_matrix).__name__, 'asym of A: %.3e' % np.abs(out['A']-out['A'].T).max())
+
+
+if __name__ == '__main__' and ('all' in (sys.argv[1:] or ['all']) or 'constant' in sys.argv[1:]):
+    case_constant_nonsym(2, 2, 0.75, 'nonsym_disc_constant0.75_r2', {'target_order': 0.5})
+    case_constant_nonsym(2, 3, 0.25, 'nonsym_disc_constant0.25_r3', {'target_order': 0.5})
+    case_constant_nonsym(1, 5, 0.75, 'nonsym_interval_constant0.75_r5', {})

@@ -5,7 +5,7 @@ host-side mirror of the reference interface."""
 from .mesh import simpleInterval, uniform_disc, polygon_disc, refined, meshNd  # noqa: F401
 from .dofmap import P1_DoFMap, P2_DoFMap  # noqa: F401
 from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder, variableConstFractionalOrder, leftRightFractionalOrder,  # noqa: F401
-                      piecewiseConstantFractionalOrder, layersFractionalOrder, innerOuterFractionalOrder, islandsFractionalOrder,
+                      piecewiseConstantFractionalOrder, constantNonSymFractionalOrder, layersFractionalOrder, innerOuterFractionalOrder, islandsFractionalOrder,
                       constantFractionalLaplacianScaling, FRACTIONAL, INDICATOR, PERIDYNAMIC, Kernel, getIntegrableKernel,
                       constantIntegrableScaling, constant)
 from .assembly import nonlocalBuilder, assembleNonlocalOperator, release_staging_pool  # noqa: F401

@@ -98,6 +98,25 @@ class leftRightFractionalOrder(_blockFractionalOrder):
                                                                                             self.interface, int(self.symmetric))
 
 
+class constantNonSymFractionalOrder(_blockFractionalOrder):
+    """s(x,y) = const declared as an UNSYMMETRIC order (fractionalOrders.pyx:631-638): the reference then runs its
+    unsymmetric code path -- fractionalLaplacian*_nonsym, both orientations of every cell pair, order and scaling evaluated
+    per quadrature node (the kernel cannot be piecewise, kernels.py:147-149) -- on a constant.  One block, two half-weight
+    passes over the two orientations; the per-node scaling equals the constant one (same formula,
+    kernelNormalization.pyx:438-439)."""
+    symmetric = False
+
+    def __init__(self, s):
+        self.value_ = float(s)
+        self._finish([[float(s)]])
+
+    def labels(self, points):
+        return np.zeros(np.asarray(points).shape[0], dtype=np.uint8)
+
+    def __repr__(self):
+        return 'constantNonSymFractionalOrder({})'.format(self.value_)
+
+
 class piecewiseConstantFractionalOrder(_blockFractionalOrder):
     """blocks given by an indicator function x -> block number (fractionalOrders.pyx:218-283); off-diagonal orders that
     are not finite default to the mean of the two diagonal ones; symmetric iff |sVals - sVals^T| < 1e-10"""
@@ -422,7 +441,9 @@ def getFractionalKernel(dim, s, horizon=None, interaction=None, scaling=None, no
     if isinstance(sFun, _blockFractionalOrder):
         if horizonFun.value != np.inf or not normalized or scaling is not None:
             raise NotImplementedError('piecewise orders: infinite horizon, normalised kernels only')
-        if not piecewise:
+        if isinstance(sFun, constantNonSymFractionalOrder):
+            piecewise = False       # kernels.py:147-149: single-variable unsymmetric orders cannot be piecewise
+        elif not piecewise:
             raise NotImplementedError('orders evaluated per quadrature node (piecewise=False) are outside the accelerated path')
         # the scaling is a function of s(x,y) (variableFractionalLaplacianScaling, kernelNormalization.pyx:421-499):
         # evaluated per class by the builder

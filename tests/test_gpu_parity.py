@@ -763,7 +763,7 @@ def _driver_errors(domain, s, fmt, noRef, params, solver, variable=False):
     dim = 1 if domain == 'interval' else 2
     mesh = pb.refined(pb.simpleInterval(-1, 1) if dim == 1 else pb.uniform_disc(), noRef)
     dm = pb.P1_DoFMap(mesh)
-    order = pb.variableConstFractionalOrder(s) if variable else s
+    order = pb.constantNonSymFractionalOrder(s) if variable == 'nonsym' else (pb.variableConstFractionalOrder(s) if variable else s)
     builder = pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, order), params)
     A = builder.getH2() if fmt == 'H2' else builder.getDense()
     b = _p1_load_vector(mesh, dm)
@@ -806,10 +806,17 @@ DRIVER_CASES = [
     (('interval', 0.75, 'H2', 7, {}, 'gmres', False), (0.041849732677658555, 0.001458788789368659), (3e-2, 3e-2)),
     (('disc', 0.25, 'dense', 5, {'target_order': 0.5}, 'cg', False), (0.1839933908571473, 0.057885119791182965), (1e-4, 1e-4)),
     (('disc', 0.75, 'H2', 5, {'target_order': 0.5}, 'cg', False), (0.059725648882225826, 0.0022274080583107514), (3e-2, 3e-2)),
+    # --s constantNonSym(s): the reference's unsymmetric code path on a constant order (both orientations of every cell
+    # pair); cached under ...--sconstantNonSym(*)--problemconstant--elementP1--solvergmres-jacobi--matrixFormatdense.  The
+    # driver stops gmres-jacobi at a relative residual of 1e-6, which shows in the 7th digit of the Hs error for s = 0.75
+    # (the systems here are solved to 1e-12); the operators themselves are pinned entry by entry (nonsym_*_constant*).
+    (('interval', 0.25, 'dense', 7, {}, 'gmres', 'nonsym'), (0.09611243700814974, 0.0266553185536795), (1e-9, 1e-6)),
+    (('interval', 0.75, 'dense', 7, {}, 'gmres', 'nonsym'), (0.04184297664965481, 0.0014584875781664202), (1e-6, 1e-5)),
+    (('disc', 0.25, 'dense', 5, {'target_order': 0.5}, 'gmres', 'nonsym'), (0.18399339204392906, 0.05788512423832981), (1e-4, 1e-4)),
 ]
 
 
-@pytest.mark.parametrize('case,ref,tol', DRIVER_CASES, ids=['-'.join(str(v) for v in c[0][:4])+'-'+c[0][5] for c in DRIVER_CASES])
+@pytest.mark.parametrize('case,ref,tol', DRIVER_CASES, ids=['-'.join(str(v) for v in c[0][:4])+'-'+c[0][5]+('-'+str(c[0][6]) if c[0][6] else '') for c in DRIVER_CASES])
 def test_driver_known_answers(case, ref, tol):
     """BASELINE configs 0 / 1 / 3 at the sizes of the reference's own cached driver tests"""
     Hs, L2 = _driver_errors(*case)
@@ -829,7 +836,8 @@ def test_mesh_without_unknowns():
 
 
 @pytest.mark.parametrize('name', ['nonsym_disc_leftright_r2', 'nonsym_disc_leftright_r3', 'nonsym_interval_leftright_r5',
-                                  'nonsym_disc_layers_r3', 'disc_layers_sym_r2', 'nonsym_interval_innerouter_r5'])
+                                  'nonsym_disc_layers_r3', 'disc_layers_sym_r2', 'nonsym_interval_innerouter_r5',
+                                  'nonsym_disc_constant0.75_r2', 'nonsym_disc_constant0.25_r3', 'nonsym_interval_constant0.75_r5'])
 def test_unsymmetric_piecewise_order_vs_reference(golden_dir, name):
     """Unsymmetric piecewise constant orders s(x,y) != s(y,x) (the reference switches to
     fractionalLaplacian{1,2}D_nonsym and visits both orientations of every cell pair,

@@ -257,7 +257,8 @@ def test_oracle_mesh_sizes_bit_exact_vs_reference(golden_dir):
 
 
 NONSYM = ['nonsym_disc_leftright_r2', 'nonsym_disc_leftright_r3', 'nonsym_interval_leftright_r5', 'nonsym_disc_layers_r3',
-          'disc_layers_sym_r2', 'nonsym_interval_innerouter_r5']
+          'disc_layers_sym_r2', 'nonsym_interval_innerouter_r5', 'nonsym_disc_constant0.75_r2', 'nonsym_disc_constant0.25_r3',
+          'nonsym_interval_constant0.75_r5']
 
 
 def order_from_fixture(g):
@@ -270,6 +271,8 @@ def order_from_fixture(g):
         return pb.layersFractionalOrder(dim, g['layerBoundaries'], g['layerOrders'])
     if kind == 'innerOuter':
         return pb.innerOuterFractionalOrder(dim, float(g['sii']), float(g['soo']), float(g['r']), g['center'], float(g['sio']), float(g['soi']))
+    if kind == 'constantNonSym':
+        return pb.constantNonSymFractionalOrder(float(g['s']))
     raise NotImplementedError(kind)
 
 
