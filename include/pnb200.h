@@ -115,6 +115,10 @@ typedef struct {
                                     * order of the reference's symmetric assembly loop; 1 = as (larger, smaller), the second
                                     * visit of its unsymmetric loop (nonlocalAssembly_{SCALAR}.pxi:1419-1428).  The singular
                                     * rules are not symmetric in their two cells: the results differ by the quadrature error */
+    int32_t pair_filter;           /* 0 = all cell pairs of the class; 1 = only the touching (singular) ones: the orientation
+                                    * of a pair only matters for those, so an unsymmetric order takes the bulk of the pairs from
+                                    * ONE instance on the fast path and corrects the touching pairs with two cheap instances
+                                    * (+1/2 orientation 1, -1/2 orientation 0), see nonlocalBuilder.setKernel */
 } pnb_kernel_t;
 
 /* One quadrature table: rows x n barycentric coordinates (x point first, then

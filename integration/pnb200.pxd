@@ -40,6 +40,7 @@ cdef extern from "pnb200.h":
         uint8_t pair_class[16]
         uint8_t bpair_class[16]
         int32_t pair_orientation
+        int32_t pair_filter
     ctypedef struct pnb_rule_t:
         int32_t n
         int32_t rows

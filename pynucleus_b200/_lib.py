@@ -35,7 +35,7 @@ class pnb_kernel_t(ctypes.Structure):
                 ('bsingularity', ctypes.c_double), ('horizon2', ctypes.c_double),
                 ('target_order', ctypes.c_double), ('btarget_order', ctypes.c_double), ('order_num_dofs', ctypes.c_int32),
                 ('cell_labels', ctypes.c_void_p), ('bfacet_labels', ctypes.c_void_p), ('active_class', ctypes.c_int32),
-                ('pair_class', ctypes.c_uint8*16), ('bpair_class', ctypes.c_uint8*16), ('pair_orientation', ctypes.c_int32)]
+                ('pair_class', ctypes.c_uint8*16), ('bpair_class', ctypes.c_uint8*16), ('pair_orientation', ctypes.c_int32), ('pair_filter', ctypes.c_int32)]
 
 
 class pnb_rule_t(ctypes.Structure):

@@ -23,7 +23,7 @@ class _Problem:
     """owner of a pnb_problem handle (device-resident mesh, DoFMap, kernel, tables)"""
 
     def __init__(self, dm, kernel, bkernel, orders, device, max_order, order_num_dofs=0, labels=None, blabels=None,
-                 pair_class=None, active_class=0, tables_from=None, blocks=None, bpair_class=None, pair_orientation=0):
+                 pair_class=None, active_class=0, tables_from=None, blocks=None, bpair_class=None, pair_orientation=0, pair_filter=0):
         mesh = dm.mesh
         self._keep = []
         self.dim = mesh.dim
@@ -61,6 +61,7 @@ class _Problem:
             for i, v in enumerate(np.asarray(pair_class if bpair_class is None else bpair_class, dtype=np.uint8).ravel()):
                 k.bpair_class[i] = int(v)
             k.pair_orientation = int(pair_orientation)
+            k.pair_filter = int(pair_filter)
         if tables_from is not None:
             # same kernel, orders and table range as another problem (H2 near field: one problem per cluster pair):
             # share its host-side table structure instead of converting the tables again
@@ -183,10 +184,12 @@ class nonlocalBuilder:
             # and without the factor 2 of the symmetric loop; with piecewise parameters both kernel evaluations of the
             # unsymmetric local matrix (fractionalLaplacian2D.pyx:1155-1184: temp, temp2) use the same s, so the
             # orientation (c1, c2) contributes the symmetric local matrix of s(c1, c2) -- evaluated with c1 as the first
-            # cell of the singular rule, which matters at the level of the quadrature error (1e-7).  Hence two passes per
-            # order v_k, each at half weight (a power of two: exact): the orientations (smaller cell index, larger) of class
-            # k, and the orientations (larger, smaller) of class k.  The surface terms (cell, facet) of
-            # s(cell centre, facet centre) = v_k ride along with both halves.
+            # cell of the singular rule, which matters at the level of the quadrature error (1e-7) for touching pairs and
+            # not at all for the others.  Hence per order v_k: the pairs with both orientations of that order in ONE pass on
+            # the fast path (first cell = smaller index) plus two cheap passes over the touching pairs only (+1/2 with the
+            # larger cell first, -1/2 with the smaller: the mean of the two orientations); the pairs with one orientation of
+            # that order at half weight in that orientation (factors 1/2: exact).  The surface terms (cell, facet) of
+            # s(cell centre, facet centre) = v_k ride along with the first pass.
             if self.dm2 is not None:
                 raise NotImplementedError('two DoFMaps with a variable order')
             if getattr(kernel, 'finiteHorizon', False):
@@ -202,19 +205,29 @@ class nonlocalBuilder:
             bf = np.asarray(mesh.boundaryFacets).reshape(-1, mesh.dim)
             bcenters = mesh.vertices[bf].mean(axis=1)
             passes = []
+
+            def add(M, Mb, weight, orientation, pair_filter=0):
+                if not (M.any() or Mb.any()):
+                    return
+                P4, B4 = np.zeros((4, 4), dtype=np.uint8), np.zeros((4, 4), dtype=np.uint8)
+                P4[:nb_, :nb_] = M
+                B4[:nb_, :nb_] = Mb
+                passes.append(dict(kernel=getFractionalKernel(mesh.dim, v), pair_class=P4, bpair_class=B4, weight=weight,
+                                   orientation=orientation, filter=pair_filter))
+            none = np.zeros((nb_, nb_), dtype=bool)
             for k_, v in enumerate(vals):
-                fwd = pc == k_
+                fwd = pc == k_          # table[label of the smaller cell][label of the larger cell]
                 if kernel.s.symmetric:
-                    todo = ((fwd, 0, 1.), )
-                else:
-                    # table[label of the smaller cell][label of the larger cell]
-                    todo = ((fwd, 0, 0.5), (fwd.T, 1, 0.5))
-                for M, orientation, weight in todo:
-                    P4, B4 = np.zeros((4, 4), dtype=np.uint8), np.zeros((4, 4), dtype=np.uint8)
-                    P4[:nb_, :nb_] = M
-                    B4[:nb_, :nb_] = fwd
-                    passes.append(dict(kernel=getFractionalKernel(mesh.dim, v), pair_class=P4, bpair_class=B4, weight=weight,
-                                       orientation=orientation))
+                    add(fwd, fwd, 1., 0)
+                    continue
+                # both orientations of order v: all pairs once on the fast path (orientation 0), then the touching pairs
+                # corrected to the mean of the two orientations; one orientation only: half weight in that orientation
+                both, only_fwd, only_bwd = fwd & fwd.T, fwd & ~fwd.T, ~fwd & fwd.T
+                add(both, fwd, 1., 0)
+                add(both, none, 0.5, 1, pair_filter=1)
+                add(both, none, -0.5, 0, pair_filter=1)
+                add(only_fwd, none, 0.5, 0)
+                add(only_bwd, none, 0.5, 1)
             self._classes = dict(passes=passes, labels=kernel.s.labels(centers), blabels=kernel.s.labels(bcenters), problems=None)
             self.kernel = kernel
             self.zeroExterior = zeroExterior
@@ -397,7 +410,7 @@ class nonlocalBuilder:
             C['problems'] = [_Problem(self.dm, q['kernel'], q['kernel'].getBoundaryKernel(), self.orders, device,
                                       self.params.get('max_regular_order', 32), labels=C['labels'], blabels=C['blabels'],
                                       pair_class=q['pair_class'], bpair_class=q['bpair_class'], active_class=1,
-                                      pair_orientation=q['orientation'])
+                                      pair_orientation=q['orientation'], pair_filter=q['filter'])
                              for q in C['passes']]
         if out is not None:
             check_matrix_out(out, N, N, dev)

@@ -760,7 +760,7 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
         rc |= upload(p, ahb.data(), (size_t)nb, &P.ahbf);
         if (rc) { pnb_problem_destroy(p); return PNB_ERR_CUDA; }
     }
-    P.labels = nullptr; P.blabels = nullptr; P.active_class = 0; P.pair_orientation = 0;
+    P.labels = nullptr; P.blabels = nullptr; P.active_class = 0; P.pair_orientation = 0; P.pair_filter = 0;
     for (int l = 0; l < 4; l++) P.pair_class[l] = P.bpair_class[l] = 0;
     if (kernel->cell_labels) {
         if (nb > 0 && !kernel->bfacet_labels) { pnb_problem_destroy(p); return fail(PNB_ERR_ARG, "cell labels without boundary facet labels"); }
@@ -776,7 +776,8 @@ extern "C" int pnb_problem_create(const pnb_mesh_t *mesh, const pnb_dofmap_t *dm
             }
         p->h_labels.assign(kernel->cell_labels, kernel->cell_labels + nc);
         P.pair_orientation = kernel->pair_orientation ? 1 : 0;
-        if (P.pair_orientation) p->path = 1;
+        P.pair_filter = kernel->pair_filter == 1 ? 1 : 0;
+        if (P.pair_orientation || P.pair_filter) p->path = 1;
         p->ordered_classes = p->path == 1;
     }
     P.s = kernel->s; P.C = kernel->scaling; P.Cb = kernel->bscaling;
@@ -1355,8 +1356,9 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
             if (S.tile_block && S.tile_block[rt] != S.tile_block[ct]) continue;
             const size_t tfi = (size_t)rt * S.tf_width + (S.tile_block ? ct - S.blk_tile0[S.tile_block[rt]] : ct);
             if (NEAR && !S.tileflag[tfi]) continue;
-            if (finite && rt != ct) {
-                // finite horizon: tiles whose bounding boxes are further apart than the horizon hold only REMOTE pairs
+            if ((finite || P.pair_filter == 1) && rt != ct) {
+                // finite horizon: tiles whose bounding boxes are further apart than the horizon hold only REMOTE pairs;
+                // touching pairs only (pair_filter 1): cells that share a vertex sit in tiles whose boxes share that point
                 double g2 = 0.;
                 for (int l = 0; l < DIM; l++) {
                     const double lo1 = S.tile_box[((size_t)rt * 2) * DIM + l], hi1 = S.tile_box[((size_t)rt * 2 + 1) * DIM + l];
@@ -1365,7 +1367,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                     g2 += g * g;
                 }
                 // strict margin: a pair is REMOTE when its smallest vertex distance is >= the horizon
-                if (g2 > P.horizon2 * (1. + 1e-12)) {
+                if (P.pair_filter == 1 ? g2 > 0. : g2 > P.horizon2 * (1. + 1e-12)) {
                     // the far pass defines every entry of the matrix: a skipped tile (and its mirror image) is zero
                     if (!NEAR) {
                         const bool own_r = rt >= S.own_t0 && rt < S.own_t1, own_c = ct >= S.own_t0 && ct < S.own_t1;
@@ -1422,6 +1424,8 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
 #pragma unroll
                                 for (int m = 0; m < NV; m++) { v1[m] = sm.rb.v[m][k1]; v2[m] = sm.cb.v[m][k2]; }
                                 panel = -shared_vertices(v1, NV, v2, NV);
+                                // pair filter 1: touching pairs only (see pnb_kernel_t.pair_filter)
+                                if (panel == 0 && P.pair_filter == 1) panel = PNB_IGNORED_PANEL;
                                 if (panel == 0 && finite) {
                                     relpos = pair_relative_position(P, min(K1, K2), max(K1, K2));
                                     if (relpos == 1) panel = PNB_IGNORED_PANEL;      // REMOTE

@@ -87,6 +87,7 @@ struct DProblem {
     unsigned int pair_class[4];    // packed: byte l2 of word l1
     unsigned int bpair_class[4];   // (cell label, boundary facet label)
     int pair_orientation;          // singular pairs: 0 smaller cell index first, 1 larger first
+    int pair_filter;               // 1: touching (singular) pairs only
 };
 
 // does the pair of labels belong to this problem instance?
