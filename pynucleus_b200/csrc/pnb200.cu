@@ -1319,7 +1319,10 @@ __device__ __forceinline__ void scatter_block(double (*acc)[PNB_TD + 1], int rlo
 // NEAR = true:  near pass over the flagged units.  Evaluates singular pairs and the remaining regular pairs one
 //               per warp and adds to the tiles (A += ...).  Same CTA <-> tile ownership in both passes: no
 //               atomics on floating point data anywhere.
-template <int DIM, bool NEAR>
+// FIN: finite horizon (REMOTE / CUT classes, re-triangulated pairs).  The infinite-horizon instantiation of the near pass
+// does not carry the registers and the stack of the re-triangulation (236 registers, 720 bytes of stack).  (Forcing two
+// CTAs per SM on it -- 128 registers, spills -- doubled its time: measured.)
+template <int DIM, bool NEAR, bool FIN>
 __global__ void __launch_bounds__(PNB_THREADS, NEAR ? 1 : 2)
 tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
 {
@@ -1336,7 +1339,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
     const int goff = S.tile_block ? S.blk_group0[S.tile_block[gr * S.G]] : 0;
     unsigned long long my_pairs = 0;
     const float cf = (float)P.c_int, sf = (float)fmax(-0.5 * (P.sing + 2), 0.);
-    const bool finite = P.horizon2 < INFINITY;
+    constexpr bool finite = FIN;
     {   // stage the power table
         const double *src = reinterpret_cast<const double *>(P.pow_int);
         double *dst = reinterpret_cast<double *>(&sm.pw);
@@ -1542,7 +1545,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                                 const int q = pass == 0 ? it / Sl : it, sl = pass == 0 ? it - q * Sl : 0;
                                 const int slot = sm.list[q] & 0xFF;
                                 const bool cD = (sm.list[q] & 0x100) != 0;
-                                const bool cut = sm.listpanel[q] >= PNB_CUT_FLAG;
+                                const bool cut = FIN && sm.listpanel[q] >= PNB_CUT_FLAG;
                                 const int panel = cut ? sm.listpanel[q] - PNB_CUT_FLAG : sm.listpanel[q];
                                 const int Ka = sm.rb.cell[slot / SB], Kb = sm.cb.cell[slot % SB];
                                 // reference orientation of singular pairs: smaller cell index first
@@ -1557,7 +1560,7 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                                     if (panel >= 1) {
                                         // cut pairs are evaluated in the reference's orientation (smaller cell first): the
                                         // re-triangulation is not symmetric in its two arguments
-                                        if (cut) lanes_cut_interior<DIM>(P, min(Ka, Kb), max(Ka, Kb), panel, sl * 32 + lane, 32 * Sl, acc);
+                                        if (FIN && cut) lanes_cut_interior<DIM>(P, min(Ka, Kb), max(Ka, Kb), panel, sl * 32 + lane, 32 * Sl, acc);
                                         else lanes_regular_interior<DIM>(P, Ka, Kb, panel, sl * 32 + lane, 32 * Sl, acc);
                                         warp_allreduce<NL>(acc);
                                     } else {
@@ -3061,22 +3064,39 @@ static int dense_rows_begin_impl(pnb_problem *p, int zero_exterior, int32_t row_
     if (p->dim == 2) {
         const size_t smem = sizeof(TileSmem<2, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
         const size_t smem_far = sizeof(TileSmem<2, false>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
-        smem_optin(tile_kernel<2, false>, p->device);
-        smem_optin(tile_kernel<2, true>, p->device);
-        tile_kernel<2, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, p->far_mask);
+        if (p->finite) {
+            smem_optin(tile_kernel<2, false, true>, p->device);
+            smem_optin(tile_kernel<2, true, true>, p->device);
+            tile_kernel<2, false, true><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, p->far_mask);
+        } else {
+            smem_optin(tile_kernel<2, false, false>, p->device);
+            smem_optin(tile_kernel<2, true, false>, p->device);
+            tile_kernel<2, false, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, p->far_mask);
+        }
         compact_units_kernel<<<1, 1024>>>(S);
         cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);
-        if (nnear_units > 0)
-            tile_kernel<2, true><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, p->far_mask);
+        if (nnear_units > 0) {
+            if (p->finite) tile_kernel<2, true, true><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, p->far_mask);
+            else tile_kernel<2, true, false><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, p->far_mask);
+        }
     } else {
         const size_t smem = sizeof(TileSmem<1, true>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
         const size_t smem_far = sizeof(TileSmem<1, false>) + 2 * (size_t)S.maxcells * ND * sizeof(double);
-        smem_optin(tile_kernel<1, false>, p->device);
-        smem_optin(tile_kernel<1, true>, p->device);
-        tile_kernel<1, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, 0);
+        if (p->finite) {
+            smem_optin(tile_kernel<1, false, true>, p->device);
+            smem_optin(tile_kernel<1, true, true>, p->device);
+            tile_kernel<1, false, true><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, 0);
+        } else {
+            smem_optin(tile_kernel<1, false, false>, p->device);
+            smem_optin(tile_kernel<1, true, false>, p->device);
+            tile_kernel<1, false, false><<<S.nunits, PNB_THREADS, smem_far>>>(p->P, S, dA, ld, 0);
+        }
         compact_units_kernel<<<1, 1024>>>(S);
         cudaMemcpy(&nnear_units, S.nearunits + S.nunits, sizeof(int), cudaMemcpyDeviceToHost);
-        if (nnear_units > 0) tile_kernel<1, true><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, 0);
+        if (nnear_units > 0) {
+            if (p->finite) tile_kernel<1, true, true><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, 0);
+            else tile_kernel<1, true, false><<<nnear_units, PNB_THREADS, smem>>>(p->P, S, dA, ld, 0);
+        }
     }
     launches += nnear_units > 0 ? 3 : 2;
     cudaEventRecord(p->ev[1]);
