@@ -942,3 +942,34 @@ def test_h2_like_the_reference_test(dim, s, errBnd):
     errAll = np.absolute(y_d-y_h2).max()
     # the reference asserts errNear < errBnd, errFar < errBnd, errAll < errBnd (tests/test_fracLapl.py:191-200)
     assert errNear < errBnd and errFar < errBnd and errAll < errBnd, (errNear, errFar, errAll)
+
+
+def test_unsymmetric_order_larger_mesh_vs_oracle():
+    """an unsymmetric leftRight order on a mesh with uniformly far units on both sides of the interface (cell-group path for
+    the pairs with both orientations of an order, filtered DoF-tile passes for the touching pairs, half-weight passes across
+    the interface) against the oracle's two-orientation restatement (pinned to the reference by
+    test_unsymmetric_piecewise_order_matches_reference)"""
+    import oracle
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.polygon_disc(7), 4)
+    dm = pb.P1_DoFMap(mesh)
+    s = pb.leftRightFractionalOrder(0.3, 0.7, 0.55, 0.4, 0.1)
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, s), {'target_order': 0.5})
+    A = b.getDense().data
+    assert len(b._classes['passes']) == 12
+    labels = s.labels(mesh.vertices[mesh.cells].mean(axis=1))
+    blabels = s.labels(mesh.vertices[mesh.boundaryFacets].mean(axis=1))
+    sV = s.blockOrders()
+    vals = sorted(set(sV.ravel().tolist()))
+    pc = np.array([[vals.index(sV[i, j]) for j in range(2)] for i in range(2)])
+    ref = 0.
+    for k, sv in enumerate(vals):
+        for M, orientation in ((pc == k, 0), ((pc == k).T, 1)):
+            P4, B4 = np.zeros((4, 4), dtype=np.uint8), np.zeros((4, 4), dtype=np.uint8)
+            P4[:2, :2] = M
+            B4[:2, :2] = pc == k
+            P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, sv, bfacets=mesh.boundaryFacets, target_order=0.5,
+                               s_max=max(vals), s_min=min(vals), labels=labels, blabels=blabels, pair_class=P4, bpair_class=B4,
+                               pair_orientation=orientation, active_class=1, max_order=40)
+            ref = ref+0.5*P.dense(True)
+    assert entry_err(A, ref) < TOL
