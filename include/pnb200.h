@@ -300,12 +300,13 @@ int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, cons
                         const int32_t *m1, const int32_t *m2, int32_t max_m, const double *eta,
                         const int32_t *eta_ptr, const int64_t *offsets, double *out);
 
-/* Dense operator for a DoFMap that is not P1 (P2 on intervals and triangles; P1 accepted for cross-checks): the
+/* Dense operator for a DoFMap that is not P1 (P0 and P2 on intervals and triangles; P1 accepted for cross-checks): the
  * reference runs the same assembly loop with (2 dpe)(2 dpe + 1)/2 local entries built from the DoFMap's shape functions
  * (nonlocalAssembly_{SCALAR}.pxi:1386-1448 with fractionalLaplacian2D.pyx:644-891).  `p` carries the mesh, the kernel and
  * the tables (create it with the vertex dofs of the map as a P1 table and kernel.order_num_dofs = num_dofs); `dofs` is the
  * element's cell -> dof table (host, num_cells x dofs_per_element, the reference's local order: vertices, then edges
- * (0,1), (1,2), (0,2); 1D: vertices, then the cell).  One warp owns one row of the operator (no atomics, bitwise
+ * (0,1), (1,2), (0,2); 1D: vertices, then the cell; P0: the cell).  polynomial_order 0 expects singular tables built for
+ * discontinuous elements (no cancellation across elements, fractionalLaplacian2D.pyx:595-600).  One warp owns one row of the operator (no atomics, bitwise
  * reproducible); infinite horizon, constant kernels.  A: num_dofs x num_dofs, row-major, leading dimension ld; device
  * memory if a_on_device != 0, else host memory (assembled on the device and copied back). */
 int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,

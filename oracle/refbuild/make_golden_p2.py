@@ -15,17 +15,17 @@ ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
 OUT = os.path.join(ROOT, 'tests', 'golden')
 
 from PyNucleus_fem.mesh import simpleInterval, uniform_disc  # noqa: E402
-from PyNucleus_fem.DoFMaps import P2_DoFMap  # noqa: E402
+from PyNucleus_fem.DoFMaps import P2_DoFMap, P0_DoFMap  # noqa: E402
 from PyNucleus_nl.kernels import getFractionalKernel  # noqa: E402
 from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder  # noqa: E402
 from PyNucleus_nl.fractionalOrders import constFractionalOrder  # noqa: E402
 
 
-def case(dim, noRef, s, name, params):
+def case(dim, noRef, s, name, params, DoFMap=None):
     mesh = uniform_disc() if dim == 2 else simpleInterval(-1, 1)
     for _ in range(noRef):
         mesh = mesh.refine()
-    dm = P2_DoFMap(mesh)
+    dm = (P2_DoFMap if DoFMap is None else DoFMap)(mesh)
     kernel = getFractionalKernel(dim, constFractionalOrder(s), np.inf)
     out = dict(vertices=np.array(mesh.vertices), cells=np.array(mesh.cells), dofs=np.array(dm.dofs), num_dofs=dm.num_dofs,
                num_boundary_dofs=dm.num_boundary_dofs, hVector=np.array(mesh.hVector), volVector=np.array(mesh.volVector),
@@ -61,3 +61,8 @@ if __name__ == '__main__':
         case(2, 2, 0.75, 'p2_disc_s0.75_r2', {'target_order': 0.5})
         case(2, 2, 0.25, 'p2_disc_s0.25_r2', {'target_order': 0.5})
         case(2, 3, 0.75, 'p2_disc_s0.75_r3', {'target_order': 0.5})
+    if 'all' in which or 'p0' in which:
+        # piecewise constants: s < 1/2 only (fractionalLaplacian2D.pyx:596-598)
+        case(1, 5, 0.25, 'p0_interval_s0.25_r5', {}, DoFMap=P0_DoFMap)
+        case(2, 2, 0.25, 'p0_disc_s0.25_r2', {'target_order': 0.5}, DoFMap=P0_DoFMap)
+        case(2, 3, 0.4, 'p0_disc_s0.4_r3', {'target_order': 0.5}, DoFMap=P0_DoFMap)

@@ -169,10 +169,14 @@ class nonlocalBuilder:
         self._classes = None
         self._element = self.dm.polynomialOrder != 1
         if self._element:
-            if self.dm.polynomialOrder != 2:
-                raise NotImplementedError('P1 and P2 elements')
+            if self.dm.polynomialOrder not in (0, 2):
+                raise NotImplementedError('P0, P1 and P2 elements')
             if self.dm2 is not None or hasattr(kernel.s, 'blockOrders') or kernel.finiteHorizon:
-                raise NotImplementedError('P2 elements: one DoFMap, constant kernels with infinite horizon')
+                raise NotImplementedError('P0 / P2 elements: one DoFMap, constant kernels with infinite horizon')
+            if self.dm.polynomialOrder == 0 and not kernel.max_singularity > -1.-self.mesh.dim:
+                # fractionalLaplacian2D.pyx:596-598, fractionalLaplacian1D.pyx:212-214
+                raise AssertionError('Discontinuous finite elements are not conforming for singularity order {} <= {}.'.format(
+                    kernel.max_singularity, -1-self.mesh.dim))
         if hasattr(kernel.s, 'blockOrders'):
             # piecewise constant order s(x,y) = sVals[block(x), block(y)], evaluated at the cell centres once per ordered
             # cell pair (kernel.evalParams, nonlocalOperator_{SCALAR}.pxi:509-513).  One constant-order problem instance

@@ -1,4 +1,4 @@
-// Dense assembly for finite elements other than P1 (P2 in 1D and 2D; P1 for cross-checking): row-owner kernel.
+// Dense assembly for finite elements other than P1 (P0 and P2 in 1D and 2D; P1 for cross-checking): row-owner kernel.
 //
 // The reference treats every element through the same local matrices, built from the shape functions of the DoFMap
 // (getLocalShapeFunction, fractionalLaplacian2D.pyx:644-813 / fractionalLaplacian1D.pyx:255-339 for the singular PSI
@@ -19,14 +19,15 @@
 
 template <int DIM, int PORD> struct ElemDims {
     static constexpr int NV = DIM + 1;
-    static constexpr int DPE = PORD == 1 ? NV : (DIM == 1 ? 3 : 6);
+    static constexpr int DPE = PORD == 0 ? 1 : (PORD == 1 ? NV : (DIM == 1 ? 3 : 6));
 };
 
 // shape functions in the cell's own vertex order (DoFMaps.pyx:1854-1880 P1, :1932-2005 P2: vertices, then the edges
 // (0,1), (1,2), (0,2); 1D: the two vertices, then the cell)
 template <int DIM, int PORD> __device__ __forceinline__ void elem_shape(const double *lam, double *phi)
 {
-    if (PORD == 1) {
+    if (PORD == 0) phi[0] = 1.;      // piecewise constants (DoFMaps.pyx:1776-1786)
+    else if (PORD == 1) {
 #pragma unroll
         for (int k = 0; k <= DIM; k++) phi[k] = lam[k];
     } else {
@@ -383,8 +384,8 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
                                           int zero_exterior, double *A_out, int64_t ld_out, int a_on_device)
 {
     if (!p || !dofs || !A_out) return fail(PNB_ERR_ARG, "null argument");
-    if (polynomial_order < 1 || polynomial_order > 2) return fail(PNB_ERR_UNSUPPORTED, "elements: P1 and P2");
-    const int dpe = polynomial_order == 1 ? p->dim + 1 : (p->dim == 1 ? 3 : 6);
+    if (polynomial_order < 0 || polynomial_order > 2) return fail(PNB_ERR_UNSUPPORTED, "elements: P0, P1 and P2");
+    const int dpe = polynomial_order == 0 ? 1 : (polynomial_order == 1 ? p->dim + 1 : (p->dim == 1 ? 3 : 6));
     if (dofs_per_element != dpe) return fail(PNB_ERR_ARG, "dofs_per_element does not match the element");
     if (p->finite) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: infinite horizon only");
     if (!p->h_labels.empty()) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: constant kernels only");
@@ -441,10 +442,12 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
     if (p->dim == 2) {
         if (polynomial_order == 2) elem_rows_kernel<2, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
-        else elem_rows_kernel<2, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+        else if (polynomial_order == 1) elem_rows_kernel<2, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+        else elem_rows_kernel<2, 0><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
     } else {
         if (polynomial_order == 2) elem_rows_kernel<1, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
-        else elem_rows_kernel<1, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+        else if (polynomial_order == 1) elem_rows_kernel<1, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+        else elem_rows_kernel<1, 0><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();

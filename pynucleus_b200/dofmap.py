@@ -8,6 +8,8 @@ from .mesh import INDEX
 def _shape_values(polynomialOrder, manifold_dim, bary):
     """local shape functions at barycentric points, [dofs_per_element, n] (DoFMaps.pyx:1854-1880, 1932-2005)"""
     lam = np.asarray(bary)
+    if polynomialOrder == 0:
+        return np.ones((1, lam.shape[1]))
     if polynomialOrder == 1:
         return lam.copy()
     phi = [lam[k]*(2.*lam[k]-1.) for k in range(manifold_dim+1)]
@@ -126,6 +128,50 @@ class P1_DoFMap:
 
     def assembleRHS(self, fun, qr_order=None, rule=None):
         return _assembleRHS(self, fun, qr_order, rule)
+
+
+class P0_DoFMap:
+    """piecewise constants (DoFMaps.pyx:1788-1806): one dof per cell, numbered like the cells; no boundary dofs.  The reference
+    accepts them for kernels with s < 1/2 (the space is not conforming otherwise, fractionalLaplacian2D.pyx:596-598)."""
+    polynomialOrder = 0
+
+    def __init__(self, mesh, tag=None):
+        if tag is not None:
+            raise NotImplementedError('P0_DoFMap: default tag only')
+        self.mesh = mesh
+        self.dim = mesh.dim
+        self.dofs_per_vertex = self.dofs_per_edge = 0
+        self.dofs_per_element = 1
+        self.dofs = np.ascontiguousarray(np.arange(mesh.num_cells).reshape(-1, 1), dtype=INDEX)
+        self.num_dofs = int(mesh.num_cells)
+        self.num_boundary_dofs = 0
+
+    def vertexPart(self):
+        """a P1-shaped table for the device problem behind the element kernel (mesh, kernel, tables): the cell's dof in the
+        first slot, nothing in the others -- the element kernel never reads it"""
+        from copy import copy
+        v = copy(self)
+        nvc = self.mesh.manifold_dim+1
+        t = np.full((self.mesh.num_cells, nvc), -1, dtype=INDEX)
+        t[:, 0] = np.arange(self.mesh.num_cells)
+        v.dofs = np.ascontiguousarray(t)
+        v.dofs_per_element = nvc
+        return v
+
+    def __repr__(self):
+        return 'P0 DoFMap with {} DoFs and {} boundary DoFs.'.format(self.num_dofs, self.num_boundary_dofs)
+
+    def getDoFCoordinates(self):
+        return self.mesh.vertices[self.mesh.cells].mean(axis=1)
+
+    def assembleRHS(self, fun, qr_order=None, rule=None):
+        return _assembleRHS(self, fun, qr_order, rule)
+
+    def ones(self):
+        return np.ones(self.num_dofs)
+
+    def zeros(self):
+        return np.zeros(self.num_dofs)
 
 
 class P2_DoFMap:

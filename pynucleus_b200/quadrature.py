@@ -154,18 +154,21 @@ class localMatrixOrders:
 def singular_tables(dim, singularity, bsingularity, orders, polynomialOrder=1):
     """dict name -> (bary, w) for the five singular tables of pnb_rules_t"""
     out = {}
-    sg = 2.+singularity   # cancellation orders: fractionalLaplacian2D.pyx:591-598, fractionalLaplacian1D.pyx:209-216
+    # cancellation orders (fractionalLaplacian2D.pyx:591-600, fractionalLaplacian1D.pyx:209-216): the integrand cancels two
+    # orders of the singularity within an element, and two across elements for continuous elements (none for P0)
+    sg = 2.+singularity
+    sga = singularity if polynomialOrder == 0 else 2.+singularity
     if dim == 2:
         out['identical'] = singular2d(COMMON_FACE, sg, orders.quad_order_diagonal, orders.quad_order_diagonalV)
-        out['edge'] = singular2d(COMMON_EDGE, sg, orders.quad_order_diagonal, orders.quad_order_diagonalV)
-        out['vertex'] = singular2d(COMMON_VERTEX, sg, orders.quad_order_diagonal, orders.quad_order_diagonalV)
+        out['edge'] = singular2d(COMMON_EDGE, sga, orders.quad_order_diagonal, orders.quad_order_diagonalV)
+        out['vertex'] = singular2d(COMMON_VERTEX, sga, orders.quad_order_diagonal, orders.quad_order_diagonalV)
         sgb = bsingularity if bsingularity > -2.+1e-3 else 2.+bsingularity   # fractionalLaplacian2D.pyx:1271-1274
         out['bedge'] = singular2d_boundary(COMMON_EDGE, sgb, orders.bquad_order_diagonal)
         out['bvertex'] = singular2d_boundary(COMMON_VERTEX, bsingularity, orders.bquad_order_diagonal)
     else:
         qor = 2*max(polynomialOrder, 1)
         out['identical'] = singular1d(COMMON_EDGE, sg, orders.quad_order_diagonal, qor)
-        out['vertex'] = singular1d(COMMON_VERTEX, sg, orders.quad_order_diagonal, qor)
+        out['vertex'] = singular1d(COMMON_VERTEX, sga, orders.quad_order_diagonal, qor)
         sgb = bsingularity if bsingularity > -1.+1e-3 else 2.+bsingularity   # fractionalLaplacian1D.pyx:688-691
         out['bvertex'] = singular1d_boundary(sgb, orders.bquad_order_diagonal)
     return out

@@ -48,6 +48,28 @@ def test_p2_dense_vs_reference(name):
         assert np.array_equal(A, b.getDense().data)
 
 
+@pytest.mark.parametrize('name', ['p0_interval_s0.25_r5', 'p0_disc_s0.25_r2', 'p0_disc_s0.4_r3'])
+def test_p0_dense_vs_reference(name):
+    """piecewise constants (P0_DoFMap, s < 1/2): no cancellation of the singularity across elements, so the edge / vertex
+    rules are built for the bare kernel singularity (fractionalLaplacian2D.pyx:595-600); entries 1e-12 against the
+    reference's operator, with and without the surface terms"""
+    import pynucleus_b200 as pb
+    g, dim, mesh = setup(name)
+    dm = pb.P0_DoFMap(mesh)
+    assert np.array_equal(dm.dofs, g['dofs']) and dm.num_dofs == int(g['num_dofs'])
+    kernel = pb.getFractionalKernel(dim, float(g['s']))
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = pb.nonlocalBuilder(dm, kernel, params, zeroExterior=ze)
+        assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+        assert abs(b.orders.target_order-float(g['target_order_used'])) < 1e-14
+        A = b.getDense().data
+        assert entry_err(A, g[key]) < TOL
+        assert np.abs(A-A.T).max() < 1e-13*np.abs(A).max()
+    with pytest.raises(AssertionError):
+        pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, 0.75), params)
+
+
 def test_p2_dense_rows_larger_mesh_vs_reference():
     """721 P2 dofs (384 triangles): every 8th row and the diagonal of the reference's operator"""
     import pynucleus_b200 as pb
@@ -160,3 +182,25 @@ def test_p2_driver_known_answers(s, ref):
                     M[d[i], d[j]] += mesh.volVector[c]*Mloc[i, j]
     L2 = np.sqrt(abs(L2_ex2-2*z.dot(u)+u.dot(M.dot(u))))
     assert abs(L2/ref[1]-1) < 3e-2, (L2, ref[1])
+
+
+@pytest.mark.parametrize('domain,noRef,ref,tol', [('interval', 7, 0.0863469994893122, 1e-6), ('disc', 5, 0.1403179566911808, 1e-4)])
+def test_p0_driver_known_answers(domain, noRef, ref, tol):
+    """runFractional.py --domain interval|disc --s const(0.25) --problem constant --element P0 --matrixFormat dense at the
+    driver's default sizes (128 cells on the interval, 6144 on the disc): Hs error against the reference's cached result
+    (tests/cache_runFractional.py--domain*--sconst(0.25)--problemconstant--elementP0--solvercg-mg--matrixFormatdense).  The 2D
+    run carries the substituted regular triangle rules, hence 1e-4 there."""
+    from math import gamma
+    import pynucleus_b200 as pb
+    s = 0.25
+    dim = 1 if domain == 'interval' else 2
+    mesh = pb.refined(pb.simpleInterval(-1, 1) if dim == 1 else pb.uniform_disc(), noRef)
+    dm = pb.P0_DoFMap(mesh)
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, s), {'target_order': 0.5} if dim == 2 else {}).getDense().data
+    b = dm.assembleRHS(1.)
+    assert np.abs(b-mesh.volVector).max() < 1e-15
+    u = np.linalg.solve(A, b)
+    C = 2.**(-2.*s)*gamma(dim/2.)/gamma(dim/2.+s)/gamma(1.+s)
+    Hs_ex2 = C*np.sqrt(np.pi)*gamma(s+1)/gamma(s+1.5) if dim == 1 else C*np.pi/(s+1)
+    Hs = np.sqrt(abs(b.dot(u)-Hs_ex2))
+    assert abs(Hs/ref-1) < tol, (Hs, ref)
