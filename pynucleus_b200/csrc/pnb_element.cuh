@@ -274,7 +274,7 @@ struct ElemJob {
 };
 
 template <int DIM, int PORD>
-__global__ void __launch_bounds__(128) elem_rows_kernel(DProblem P, ElemJob J, int zero_exterior, double *__restrict__ A, int64_t ld)
+__global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J, int zero_exterior, double *__restrict__ A, int64_t ld)
 {
     constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
     const int lane = threadIdx.x & 31;
