@@ -11,11 +11,14 @@
 // psi_I = phi_I|first(x) - phi_I|second(y), and adds it to the row -- first the slots of the first cell, then those of the
 // second (the dofs of one cell are distinct), pair after pair: every entry has one writer and a fixed summation order
 // (no atomics, bitwise reproducible).  Dofs shared by the two cells need no special PSI rows: their two parts land on the
-// same entry.  Pairs are classified lane-per-partner (32 at a time) with the same panel / order functions as the P1 path
-// and evaluated in the reference's orientation (smaller cell index first) with its permutations of the shared vertices.
+// same entry.  Pairs are classified lane-per-partner (32 at a time, partner cells that share no vertex and hence no dof)
+// with the same panel / order functions as the P1 path and evaluated in the reference's orientation (smaller cell index
+// first) with its permutations of the shared vertices; regular pairs of low order are evaluated one per lane.
 // The kernel value is re-evaluated for every row dof of a pair (2 dpe times): this path trades speed for generality and
 // is meant for the problem sizes P2 is used at; the P1 production path is pnb_group.cuh.
 #pragma once
+
+#define PNB_ELEM_THREAD_ORDER 5    // regular pairs up to this order are evaluated one per lane (<= 49 node pairs)
 
 template <int DIM, int PORD> struct ElemDims {
     static constexpr int NV = DIM + 1;
@@ -46,7 +49,7 @@ template <int DIM, int PORD> __device__ __forceinline__ void elem_shape(const do
 // by the volume factor; partial sums of this lane.
 template <int DIM, int PORD>
 __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, const int *perm1, const int *perm2, int sLo, int sHi,
-                              int lane, double *acc)
+                              int lane, int nlanes, double *acc)
 {
     constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
     double t1[3][2], t2[3][2];
@@ -58,7 +61,7 @@ __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, cons
     if (panel >= 1) {
         const DRule r = P.reg_cell[panel];
         const int n = r.n;
-        for (int q = lane; q < n * n; q += 32) {
+        for (int q = lane; q < n * n; q += nlanes) {
             const int i = q / n, j = q - i * n;
             double lx[NV], ly[NV], px[DPE], py[DPE];
             double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
@@ -106,7 +109,7 @@ __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, cons
         if (DIM == 2) r = panel == -3 ? P.q_id : (panel == -2 ? P.q_edge : P.q_vertex);
         else r = panel == -2 ? P.q_id : P.q_vertex;
         const int n = r.n;
-        for (int q = lane; q < n; q += 32) {
+        for (int q = lane; q < n; q += nlanes) {
             double lx[NV], ly[NV], px[DPE], py[DPE];
             double x0 = 0., x1 = 0., y0 = 0., y1 = 0.;
 #pragma unroll
@@ -270,6 +273,8 @@ struct ElemJob {
     const int *dof_ptr;     // N+1: dof -> (cell, slot) list, cells ascending
     const int *dof_cells;   // cell * 8 + slot
     const int *row_order;   // rows by descending number of cells around the dof (vertex dofs before edge dofs): long rows first
+    const int *partners;    // all cells in batches of 32 that share no vertex (-1: padding), colour by colour
+    int npartners;          // length of `partners` (a multiple of 32)
     int *err;               // [0]: regular order missing in the tables
 };
 
@@ -286,12 +291,15 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
     __syncwarp();
     for (int t = J.dof_ptr[I]; t < J.dof_ptr[I + 1]; t++) {
         const int c1 = J.dof_cells[t] >> 3, sI1 = J.dof_cells[t] & 7;
-        // ---- Omega x Omega: all partner cells, 32 classified at a time
-        for (int c20 = 0; c20 < P.nc; c20 += 32) {
-            const int c2 = c20 + lane;
+        // ---- Omega x Omega: all partner cells, 32 at a time.  The partners of a step share no vertex, hence no dof: the
+        // regular pairs of low order are evaluated one per lane and added to the row without conflicts (the entries of
+        // the cell c1 itself, common to all lanes, through a fixed butterfly); singular pairs and high orders follow,
+        // one after the other, with the lanes over the quadrature nodes
+        for (int c20 = 0; c20 < J.npartners; c20 += 32) {
+            const int c2 = J.partners[c20 + lane];
             int pan = PNB_IGNORED_PANEL, sI2 = -1;
             int p1[3] = {0, 1, 2}, p2[3] = {0, 1, 2};
-            if (c2 < P.nc) {
+            if (c2 >= 0) {
 #pragma unroll
                 for (int k = 0; k < DPE; k++)
                     if (J.edofs[(size_t)c2 * DPE + k] == I) sI2 = k;
@@ -300,11 +308,44 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
                 if (!skip) pan = panel_interior(P, min(c1, c2), max(c1, c2), p1, p2);
                 if (pan != PNB_IGNORED_PANEL && pan > P.max_order) { atomicMax(J.err, pan); pan = PNB_IGNORED_PANEL; }
             }
-            unsigned todo = __ballot_sync(0xffffffffu, pan != PNB_IGNORED_PANEL);
+            // regular pairs of order <= PNB_ELEM_THREAD_ORDER: one per lane (c2 does not touch c1, so dof I is not in c2)
+            const bool mine_far = pan >= 1 && pan <= PNB_ELEM_THREAD_ORDER;
+            if (__any_sync(0xffffffffu, mine_far)) {
+                double c1side[DPE], c2side[DPE];
+#pragma unroll
+                for (int k = 0; k < DPE; k++) c1side[k] = c2side[k] = 0.;
+                if (mine_far) {
+                    const int lo = min(c1, c2), hi = max(c1, c2);
+                    double acc[2 * DPE];
+                    elem_pair_row<DIM, PORD>(P, lo, hi, pan, p1, p2, lo == c1 ? sI1 : -1, hi == c1 ? sI1 : -1, 0, 1, acc);
+                    const double sc = 2.0 * P.vol[lo] * P.vol[hi];
+#pragma unroll
+                    for (int k = 0; k < DPE; k++) {
+                        c1side[k] = sc * (lo == c1 ? acc[k] : acc[DPE + k]);
+                        c2side[k] = sc * (lo == c1 ? acc[DPE + k] : acc[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < DPE; k++) {
+                        const int d = J.edofs[(size_t)c2 * DPE + k];
+                        if (d >= 0) row[d] += c2side[k];
+                    }
+                }
+                warp_allreduce<DPE>(c1side);
+                double mine = 0.;
+#pragma unroll
+                for (int k = 0; k < DPE; k++)
+                    if (k == lane) mine = c1side[k];
+                if (lane < DPE) {
+                    const int d = J.edofs[(size_t)c1 * DPE + lane];
+                    if (d >= 0) row[d] += mine;
+                }
+                __syncwarp();
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, pan != PNB_IGNORED_PANEL && !mine_far);
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int c2s = c20 + src;
+                const int c2s = __shfl_sync(0xffffffffu, c2, src);
                 const int pans = __shfl_sync(0xffffffffu, pan, src), sI2s = __shfl_sync(0xffffffffu, sI2, src);
                 int q1[3], q2[3];
 #pragma unroll
@@ -315,7 +356,7 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
                 const int lo = min(c1, c2s), hi = max(c1, c2s);
                 const int sLo = lo == c1 ? sI1 : sI2s, sHi = hi == c1 ? sI1 : sI2s;
                 double acc[2 * DPE];
-                elem_pair_row<DIM, PORD>(P, lo, hi, pans, q1, q2, sLo, sHi, lane, acc);
+                elem_pair_row<DIM, PORD>(P, lo, hi, pans, q1, q2, sLo, sHi, lane, 32, acc);
                 warp_allreduce<2 * DPE>(acc);
                 // volume factors: vol1 vol2 (nonlocalOperator_{SCALAR}.pxi:756), 4 vol1 vol2 for the singular 2D rules
                 // (fractionalLaplacian2D.pyx:851); off-diagonal pairs count twice (nonlocalAssembly_{SCALAR}.pxi:1404-1410)
@@ -424,12 +465,51 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     std::vector<int> row_order(num_dofs);
     for (int i = 0; i < num_dofs; i++) row_order[i] = i;
     std::stable_sort(row_order.begin(), row_order.end(), [&](int a, int b) { return dptr[a + 1] - dptr[a] > dptr[b + 1] - dptr[b]; });
-    int *d_edofs = nullptr, *d_ptr = nullptr, *d_cells = nullptr, *d_err = nullptr, *d_order = nullptr;
+    // partner cells in steps of 32 that share no vertex: greedy colouring of the cells (two cells are adjacent when they
+    // share a vertex), the cells of a colour in ascending order, every colour padded to a multiple of 32
+    std::vector<int> partners;
+    {
+        const int nvc = p->dim + 1, nv = p->P.nv;
+        const int *cells = p->h_cells.data();
+        std::vector<int> vptr(nv + 1, 0), vcell((size_t)nc * nvc);
+        for (int c = 0; c < nc; c++)
+            for (int m = 0; m < nvc; m++) vptr[cells[(size_t)c * nvc + m] + 1]++;
+        for (int v = 0; v < nv; v++) vptr[v + 1] += vptr[v];
+        {
+            std::vector<int> pos(vptr.begin(), vptr.end() - 1);
+            for (int c = 0; c < nc; c++)
+                for (int m = 0; m < nvc; m++) vcell[pos[cells[(size_t)c * nvc + m]]++] = c;
+        }
+        std::vector<int> color(nc, -1);
+        std::vector<std::vector<int>> byc;
+        std::vector<char> used;
+        for (int c = 0; c < nc; c++) {
+            used.assign(byc.size() + 1, 0);
+            for (int m = 0; m < nvc; m++) {
+                const int v = cells[(size_t)c * nvc + m];
+                for (int e = vptr[v]; e < vptr[v + 1]; e++) {
+                    const int k = color[vcell[e]];
+                    if (k >= 0) used[k] = 1;
+                }
+            }
+            int k = 0;
+            while (used[k]) k++;
+            if (k == (int)byc.size()) byc.emplace_back();
+            color[c] = k;
+            byc[k].push_back(c);
+        }
+        for (auto &l : byc) {
+            partners.insert(partners.end(), l.begin(), l.end());
+            while (partners.size() % 32) partners.push_back(-1);
+        }
+    }
+    int *d_edofs = nullptr, *d_ptr = nullptr, *d_cells = nullptr, *d_err = nullptr, *d_order = nullptr, *d_partners = nullptr;
     if (cudaMalloc(&d_edofs, (size_t)nc * dpe * sizeof(int)) != cudaSuccess || cudaMalloc(&d_ptr, ((size_t)num_dofs + 1) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&d_cells, std::max<size_t>(dcells.size(), 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&d_err, sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&d_order, (size_t)num_dofs * sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&d_order, (size_t)num_dofs * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&d_partners, std::max<size_t>(partners.size(), 1) * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
-        cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order);
+        cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order); cudaFree(d_partners);
         if (!a_on_device) pool_free(A);
         return fail(PNB_ERR_CUDA, "out of device memory");
     }
@@ -438,7 +518,9 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     cudaMemcpy(d_cells, dcells.data(), dcells.size() * sizeof(int), cudaMemcpyHostToDevice);
     cudaMemset(d_err, 0, sizeof(int));
     cudaMemcpy(d_order, row_order.data(), row_order.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_partners, partners.data(), partners.size() * sizeof(int), cudaMemcpyHostToDevice);
     J.edofs = d_edofs; J.dof_ptr = d_ptr; J.dof_cells = d_cells; J.err = d_err; J.row_order = d_order;
+    J.partners = d_partners; J.npartners = (int)partners.size();
     const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
     if (p->dim == 2) {
         if (polynomial_order == 2) elem_rows_kernel<2, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
@@ -453,7 +535,7 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     int herr = 0;
     cudaMemcpy(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order);
+    cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order); cudaFree(d_partners);
     if (!a_on_device) {
         if (e == cudaSuccess && herr == 0)
             e = cudaMemcpy2D(A_out, (size_t)ld_out * sizeof(double), A, (size_t)ld * sizeof(double), (size_t)num_dofs * sizeof(double),
