@@ -1779,6 +1779,8 @@ __device__ __forceinline__ int fast_order_boundary_2d(double d2, float lh1, floa
     return -1;
 }
 
+#define PNB_BND_LANE_ORDER 5
+
 template <int DIM>
 __global__ void boundary_kernel(DProblem P, TileSched S)
 {
@@ -1812,18 +1814,18 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
                 }
             } else pan = panel_boundary(P, c1, f, p1, p2);
         }
-        if (mine && pan >= 1) {
-            if (pan > P.max_order) atomicMax(S.err, pan);
-            else {
-                double acc[ND];
-                lanes_boundary<DIM>(P, c1, f, pan, p1, p2, 0, 1, acc);
-                const double sc = P.vol[c1] * P.bvol[f];
+        // regular facets of low order: one per lane; the few facets close to the cell (orders above PNB_BND_LANE_ORDER,
+        // up to ~1500 node pairs) would keep one lane busy while the others idle: they go to the whole warp below
+        if (mine && pan > P.max_order) { atomicMax(S.err, pan); pan = 0; }
+        if (mine && pan >= 1 && pan <= PNB_BND_LANE_ORDER) {
+            double acc[ND];
+            lanes_boundary<DIM>(P, c1, f, pan, p1, p2, 0, 1, acc);
+            const double sc = P.vol[c1] * P.bvol[f];
 #pragma unroll
-                for (int k = 0; k < ND; k++) tot[k] += acc[k] * sc;
-            }
+            for (int k = 0; k < ND; k++) tot[k] += acc[k] * sc;
         }
-        // singular facets of this chunk: whole warp per facet, in facet order
-        unsigned sing = __ballot_sync(0xffffffffu, mine && pan < 0);
+        // singular facets and regular facets of high order of this chunk: whole warp per facet, in facet order
+        unsigned sing = __ballot_sync(0xffffffffu, mine && (pan < 0 || pan > PNB_BND_LANE_ORDER));
         while (sing) {
             const int src = __ffs(sing) - 1;
             sing &= sing - 1;
@@ -1837,8 +1839,8 @@ __global__ void boundary_kernel(DProblem P, TileSched S)
             }
             double acc[ND];
             lanes_boundary<DIM>(P, c1, fs, pans, q1, q2, lane, 32, acc);
-            const double sc = DIM == 2 ? -2.0 * P.vol[c1] * P.bvol[fs] : P.vol[c1];
-            // entry (I,J) over permuted dofs -> local (perm1[I], perm1[J])
+            const double sc = pans >= 1 ? P.vol[c1] * P.bvol[fs] : (DIM == 2 ? -2.0 * P.vol[c1] * P.bvol[fs] : P.vol[c1]);
+            // entry (I,J) over permuted dofs -> local (perm1[I], perm1[J]) (regular facets: identity)
             int k = 0;
 #pragma unroll
             for (int I = 0; I < NV; I++)
