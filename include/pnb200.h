@@ -379,6 +379,19 @@ int pnb_h2_destroy(pnb_h2 *h);
 int pnb_dense_matvec(int device, const double *A, int64_t num_rows, int64_t num_cols, int64_t ld,
                      const double *x, double *y, void *stream);
 
+/* ---- BLAS-1 of the device CG loop (cg_solver.solve, base/PyNucleus_base/solvers.pyx:364-445), fused; all vectors and the
+ * workspace are device memory, stream a cudaStream_t.  The workspace holds the scalars of the iteration: work[0] = <r,z> of
+ * the previous iteration, work[1] = <p,Ap>, work[2] = <r,z>, work[3] = <r,r>; pnb_krylov_workspace_doubles() doubles.
+ * Reductions have a fixed shape: bitwise reproducible. */
+int pnb_krylov_workspace_doubles(void);
+int pnb_krylov_dot(int device, int64_t n, const double *a, const double *b, double *work, double *out, void *stream);
+/* alpha = work[0] / <p,Ap>;  x += alpha p;  r -= alpha Ap;  z = Minv .* r (Minv == NULL: z = r, z may alias r);
+ * work[2] = <r,z>, work[3] = <r,r> */
+int pnb_krylov_cg_update(int device, int64_t n, const double *p, const double *Ap, const double *Minv, double *x, double *r,
+                         double *z, double *work, void *stream);
+/* p = z + (work[2] / work[0]) p;  work[0] = work[2] */
+int pnb_krylov_cg_direction(int device, int64_t n, const double *z, double *p, double *work, void *stream);
+
 /* FP64 FMA throughput microbenchmark (roofline denominator): returns TFLOP/s */
 int pnb_fp64_peak(int device, double *tflops);
 

@@ -3520,3 +3520,4 @@ extern "C" int pnb_fp64_peak(int device, double *tflops)
 
 #include "pnb_h2.cuh"
 #include "pnb_element.cuh"
+#include "pnb_krylov.cuh"

@@ -96,12 +96,15 @@ def _setup(A, b, x0, precond, jacobi):
     return host, bt, x, precond
 
 
-def cg(A, b, x0=None, tol=1e-8, maxiter=1000, jacobi=True, relative=False, use2norm=False, precond=None):
+def cg(A, b, x0=None, tol=1e-8, maxiter=1000, jacobi=True, relative=False, use2norm=False, precond=None, fused=True):
     """Preconditioned conjugate gradients on the device, following cg_solver.solve step by step
     (base/PyNucleus_base/solvers.pyx:364-445): stopping rule on sqrt(<r, M^-1 r>) (or the 2-norm with use2norm),
     absolute tolerance or relative to the initial residual (relative=True, :296-301), residual recomputed every 50
     iterations.  b, x0: float64 CUDA tensors or numpy arrays (copied); precond: callable on device vectors (default:
     Jacobi when jacobi=True).  Returns (x, iterations, residuals) with the reference's return value and history."""
+    if fused and precond is None and not hasattr(A, 'all_rows'):
+        # single GPU, no or diagonal preconditioner: the BLAS-1 of the iteration runs in the library's fused kernels
+        return _cg_fused(A, b, x0, tol, maxiter, jacobi, relative, use2norm)
     host, bt, x, precond = _setup(A, b, x0, precond, jacobi)
     r = bt-A.matvec_device(x) if x0 is not None else bt.clone()
     if relative:
@@ -142,6 +145,70 @@ def cg(A, b, x0=None, tol=1e-8, maxiter=1000, jacobi=True, relative=False, use2n
                 break
             p = z+(beta/beta_old)*p
             beta_old = beta
+            k += 1
+    return (x.cpu().numpy() if host else x), its, res
+
+
+def _cg_fused(A, b, x0, tol, maxiter, jacobi, relative, use2norm):
+    """cg() with the vector updates and inner products of an iteration in three fused library kernels
+    (pnb_krylov_cg_update / pnb_krylov_cg_direction, csrc/pnb_krylov.cuh): the scalars stay on the device, the host reads
+    <r,z> and <r,r> once per iteration for the stopping rule.  Same recurrences, stopping rule and residual history as the
+    loop above."""
+    from . import _lib
+    L = _lib.lib()
+    host, bt, x, _ = _setup(A, b, x0, None, False)
+    dev = bt.device
+    n = bt.shape[0]
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    Minv = _jacobi(A, dev).contiguous() if jacobi else None
+    x = x.contiguous()
+    r = (bt-A.matvec_device(x) if x0 is not None else bt.clone()).contiguous()
+    if relative:
+        tol = tol*float(torch.linalg.vector_norm(r))
+    z = Minv*r if Minv is not None else r
+    p = z.clone()
+    work = torch.zeros(int(L.pnb_krylov_workspace_doubles()), dtype=torch.float64, device=dev)
+    stream = lambda: torch.cuda.current_stream(dev).cuda_stream      # noqa: E731
+
+    def dots():
+        # work[2] = <r,z>, work[3] = <r,r>
+        _lib.check(L.pnb_krylov_dot(index, n, r.data_ptr(), z.data_ptr(), work.data_ptr(), work[2:].data_ptr(), stream()))
+        _lib.check(L.pnb_krylov_dot(index, n, r.data_ptr(), r.data_ptr(), work.data_ptr(), work[3:].data_ptr(), stream()))
+
+    def criterion():
+        rz, rr = work[2:4].tolist()
+        if Minv is None or use2norm:
+            return float(np.sqrt(rr))
+        return float(np.sqrt(abs(rz)))
+    dots()
+    work[0] = work[2]
+    crit = criterion()
+    res = [crit]
+    its, k = maxiter, 0
+    Ap = torch.empty_like(p)
+    if crit <= tol:
+        its = 0
+    else:
+        for i in range(maxiter):
+            try:
+                Ap = A.matvec_device(p, Ap)
+            except TypeError:
+                Ap = A.matvec_device(p)
+            _lib.check(L.pnb_krylov_cg_update(index, n, p.data_ptr(), Ap.data_ptr(), Minv.data_ptr() if Minv is not None else None,
+                                              x.data_ptr(), r.data_ptr(), z.data_ptr(), work.data_ptr(), stream()))
+            if k == 50:
+                # residual recomputed from the iterate (solvers.pyx:420-424)
+                r.copy_(bt-A.matvec_device(x))
+                if Minv is not None:
+                    torch.mul(Minv, r, out=z)
+                dots()
+                k = 0
+            crit = criterion()
+            res.append(crit)
+            if crit <= tol:
+                its = i
+                break
+            _lib.check(L.pnb_krylov_cg_direction(index, n, z.data_ptr(), p.data_ptr(), work.data_ptr(), stream()))
             k += 1
     return (x.cpu().numpy() if host else x), its, res
 

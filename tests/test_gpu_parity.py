@@ -973,3 +973,39 @@ def test_unsymmetric_order_larger_mesh_vs_oracle():
                                pair_orientation=orientation, active_class=1, max_order=40)
             ref = ref+0.5*P.dense(True)
     assert entry_err(A, ref) < TOL
+
+
+def test_fused_cg_kernels(golden_dir):
+    """the fused BLAS-1 kernels of the CG loop (pnb_krylov_*, csrc/pnb_krylov.cuh) against the reference's histories (above,
+    through the default path of pb.cg) and against the step-by-step torch formulation: same iteration counts, histories to
+    1e-9, bitwise reproducible; the 50-iteration residual refresh is exercised on the larger operator"""
+    import torch
+    import pynucleus_b200 as pb
+    from pynucleus_b200 import _lib
+    # the dot product kernel alone
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    a, c = rng.standard_normal(100003), rng.standard_normal(100003)
+    at, ct = torch.as_tensor(a).cuda(), torch.as_tensor(c).cuda()
+    work = torch.zeros(int(L.pnb_krylov_workspace_doubles()), dtype=torch.float64, device='cuda')
+    out = torch.zeros(1, dtype=torch.float64, device='cuda')
+    _lib.check(L.pnb_krylov_dot(0, a.shape[0], at.data_ptr(), ct.data_ptr(), work.data_ptr(), out.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream))
+    assert abs(float(out)-a.dot(c)) < 1e-12*np.abs(a*c).sum()
+    for noRef, maxiter in ((3, 200), (5, 400)):
+        mesh = pb.refined(pb.uniform_disc(), noRef)
+        dm = pb.P1_DoFMap(mesh)
+        A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.75), {'target_order': 0.5}).getDense()
+        rhs = torch.ones(dm.num_dofs, dtype=torch.float64, device='cuda')
+        for jac in (True, False):
+            for kw in ({}, {'use2norm': True}, {'relative': True}):
+                x1, i1, r1 = pb.cg(A, rhs, tol=1e-12, maxiter=maxiter, jacobi=jac, **kw)
+                x0, i0, r0 = pb.cg(A, rhs, tol=1e-12, maxiter=maxiter, jacobi=jac, fused=False, **kw)
+                assert i1 == i0 and len(r1) == len(r0)
+                # histories agree to rounding until the residual reaches the noise floor of the recurrences (~1e-13 of its start)
+                assert (np.abs(np.array(r1)-np.array(r0)) < 1e-9*np.array(r0)+1e-12*r0[0]).all()
+                assert float((x1-x0).abs().max()) < 1e-9*float(x0.abs().max())
+                x2, i2, r2 = pb.cg(A, rhs, tol=1e-12, maxiter=maxiter, jacobi=jac, **kw)
+                assert torch.equal(x1, x2) and r1 == r2
+        if noRef == 5:
+            assert i1 > 50      # the residual refresh of iteration 50 ran
