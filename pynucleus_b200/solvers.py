@@ -102,7 +102,7 @@ def cg(A, b, x0=None, tol=1e-8, maxiter=1000, jacobi=True, relative=False, use2n
     absolute tolerance or relative to the initial residual (relative=True, :296-301), residual recomputed every 50
     iterations.  b, x0: float64 CUDA tensors or numpy arrays (copied); precond: callable on device vectors (default:
     Jacobi when jacobi=True).  Returns (x, iterations, residuals) with the reference's return value and history."""
-    if fused and precond is None and not hasattr(A, 'all_rows'):
+    if fused and precond is None and not hasattr(A, 'all_rows') and _device_of(A).type == 'cuda':
         # single GPU, no or diagonal preconditioner: the BLAS-1 of the iteration runs in the library's fused kernels
         return _cg_fused(A, b, x0, tol, maxiter, jacobi, relative, use2norm)
     host, bt, x, precond = _setup(A, b, x0, precond, jacobi)
