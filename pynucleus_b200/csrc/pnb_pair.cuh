@@ -757,6 +757,13 @@ __device__ void lanes_cut_interior(const DProblem &P, int c1, int c2, int order,
         for (int k = 0; k < NV; k++)
             for (int m = 0; m < DIM; m++) x[m] = PNB_ADD(x[m], PNB_MUL(l1[k], s1[k][m]));
         cut_inner<DIM>(x, s2, horizon2, ci);
+        // the outer node is fixed over the inner loops: row sum rs = sum g, tJ = sum g l2, yy = sum g l2 l2^T are
+        // accumulated per inner node, the products with l1 formed once per outer node
+        double rs = 0., tJ[NV], yy[NV * (NV + 1) / 2];
+#pragma unroll
+        for (int k = 0; k < NV; k++) tJ[k] = 0.;
+#pragma unroll
+        for (int k = 0; k < NV * (NV + 1) / 2; k++) yy[k] = 0.;
         for (int u = 0; u < ci.n; u++) {
             const double cc = PNB_MUL(co.vol[t], ci.vol[u]);
             for (int jn = 0; jn < n; jn++) {
@@ -771,17 +778,28 @@ __device__ void lanes_cut_interior(const DProblem &P, int c1, int c2, int order,
                 double d2 = 0.;
                 for (int m = 0; m < DIM; m++) { const double w = PNB_SUB(x[m], y[m]); d2 = PNB_ADD(d2, PNB_MUL(w, w)); }
                 const double g = (r.w[i] * r.w[jn]) * kv(d2) * cc;
-                double psi[2 * NV];
+                rs += g;
+                int kk = 0;
 #pragma unroll
-                for (int k = 0; k < NV; k++) { psi[k] = l1[k]; psi[NV + k] = -l2[k]; }
-                int k = 0;
+                for (int a = 0; a < NV; a++) {
+                    const double ga = g * l2[a];
+                    tJ[a] += ga;
 #pragma unroll
-                for (int I = 0; I < 2 * NV; I++) {
-                    const double tt = g * psi[I];
-#pragma unroll
-                    for (int J = I; J < 2 * NV; J++) acc[k++] += tt * psi[J];
+                    for (int b = a; b < NV; b++) { yy[kk] = fma(ga, l2[b], yy[kk]); kk++; }
                 }
             }
+        }
+        {
+            int k = 0;
+#pragma unroll
+            for (int I = 0; I < 2 * NV; I++)
+#pragma unroll
+                for (int J = I; J < 2 * NV; J++) {
+                    if (J < NV) acc[k] = fma(rs * l1[I], l1[J], acc[k]);
+                    else if (I < NV) acc[k] = fma(-l1[I], tJ[J - NV], acc[k]);
+                    else acc[k] += yy[tri_idx(NV, I - NV, J - NV)];
+                    k++;
+                }
         }
     }
 }
