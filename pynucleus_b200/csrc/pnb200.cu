@@ -1227,6 +1227,7 @@ template <int DIM, bool NEAR> struct TileSmem {
     int nlist;
     int anynear;
     int anyD;
+    int cursor[2];      // near pass: next item of the sub-batch (items are taken by the warps as they become free)
     // followed by DXs[maxcells][ND], DYs[maxcells][ND] (dynamic)
 };
 
@@ -1454,7 +1455,8 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                         }
                     }
                     // ---- ordered binning: far pass by order, near pass in slot order ----
-                    unsigned mybal = 0;
+                    unsigned mybal = 0, mybalx = 0;
+                    bool heavy = false;
                     if (!NEAR) {
                         if (todo != 0) sm.anynear = 1;
 #pragma unroll
@@ -1464,8 +1466,12 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                             if (cls == c) mybal = bc;
                         }
                     } else {
+                        // expensive items (pairs cut by the horizon, regular orders above 8) go to the front of the list: the
+                        // warps take the items in list order, so the long ones start first
+                        heavy = todo >= PNB_CUT_FLAG || (todo > 8 && todo < PNB_CUT_FLAG);
                         mybal = __ballot_sync(0xffffffffu, todo != 0);
-                        if (lane == 0) sm.warpcnt[warp] = __popc(mybal);
+                        mybalx = __ballot_sync(0xffffffffu, heavy);
+                        if (lane == 0) { sm.warpcnt[warp] = __popc(mybal); sm.clscnt[warp] = __popc(mybalx); }
                     }
                     __syncthreads();    // S2
                     if (!NEAR) {
@@ -1480,17 +1486,19 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                         if (cls != 0) sm.list[pos + __popc(mybal & ((1u << lane) - 1))] = tid | (countD ? 0x100 : 0) | (cls << 12);
                         if (tid == 0) sm.nlist = tot;
                     } else {
-                        int pos = 0, tot = 0;
+                        int posx = 0, posl = 0, tot = 0, totx = 0;
                         for (int w = 0; w < NW; w++) {
-                            if (w < warp) pos += sm.warpcnt[w];
+                            if (w < warp) { posx += sm.clscnt[w]; posl += sm.warpcnt[w] - sm.clscnt[w]; }
                             tot += sm.warpcnt[w];
+                            totx += sm.clscnt[w];
                         }
                         if (todo != 0) {
-                            pos += __popc(mybal & ((1u << lane) - 1));
+                            const unsigned lt = (1u << lane) - 1;
+                            const int pos = heavy ? posx + __popc(mybalx & lt) : totx + posl + __popc(mybal & ~mybalx & lt);
                             sm.list[pos] = tid | (countD ? 0x100 : 0);
                             sm.listpanel[pos] = todo;
                         }
-                        if (tid == 0) sm.nlist = tot;
+                        if (tid == 0) { sm.nlist = tot; sm.cursor[0] = sm.cursor[1] = 0; }
                     }
                     __syncthreads();    // S3
                     const int nlist = sm.nlist;
@@ -1541,7 +1549,16 @@ tile_kernel(DProblem P, TileSched S, double *A, int64_t ld, int far_mask)
                         for (int pass = 0; pass < (Sl > 1 ? 2 : 1); pass++) {
                             if (pass == 1) __syncthreads();
                             const int nitems = pass == 0 ? nlist * Sl : nlist;
-                            for (int it = warp; it < nitems; it += NW) {
+                            // The items of a sub-batch differ in cost by orders of magnitude (cut pairs, high orders);
+                            // dealt round robin, the warps waited at the closing barrier for the unlucky one (ncu: barrier
+                            // 3.4 of the stall cycles per issue).  They are taken from a counter instead: every pair
+                            // of a sub-batch updates entries of its own (the cells of a batch share no vertex), so the
+                            // result does not depend on which warp takes which item.
+                            for (;;) {
+                                int it = 0;
+                                if (lane == 0) it = atomicAdd(&sm.cursor[pass], 1);
+                                it = __shfl_sync(0xffffffffu, it, 0);
+                                if (it >= nitems) break;
                                 const int q = pass == 0 ? it / Sl : it, sl = pass == 0 ? it - q * Sl : 0;
                                 const int slot = sm.list[q] & 0xFF;
                                 const bool cD = (sm.list[q] & 0x100) != 0;
