@@ -300,7 +300,8 @@ int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, cons
                         const int32_t *m1, const int32_t *m2, int32_t max_m, const double *eta,
                         const int32_t *eta_ptr, const int64_t *offsets, double *out);
 
-/* Dense operator for a DoFMap that is not P1 (P0 and P2 on intervals and triangles; P1 accepted for cross-checks): the
+/* Dense operator for a DoFMap that is not P1 (P0 and P2 on intervals and triangles, P3 on intervals; P1 accepted for
+ * cross-checks): the
  * reference runs the same assembly loop with (2 dpe)(2 dpe + 1)/2 local entries built from the DoFMap's shape functions
  * (nonlocalAssembly_{SCALAR}.pxi:1386-1448 with fractionalLaplacian2D.pyx:644-891).  `p` carries the mesh, the kernel and
  * the tables (create it with the vertex dofs of the map as a P1 table and kernel.order_num_dofs = num_dofs); `dofs` is the

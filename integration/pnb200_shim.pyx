@@ -10,7 +10,7 @@ one call into the CUDA library.  The result is written straight into the `data` 
     from pnb200_shim import nonlocalBuilderB200          # subclass of PyNucleus_nl.nonlocalBuilder
     A = nonlocalBuilderB200(dm, kernel, params).getDense()
 
-Unsupported configurations (non-symmetric or variable kernels, two DoFMaps, P3, vector-valued kernels) fall through
+Unsupported configurations (non-symmetric or variable kernels, two DoFMaps, P3 on triangles, vector-valued kernels) fall through
 to the reference's own getDense, so the subclass is a drop-in.
 """
 import numpy as np
@@ -56,11 +56,13 @@ def _regular_rules(int dim, int max_order):
 
 def supported(builder):
     """configurations the accelerated path covers (everything else stays with the reference's Cython loops)"""
-    from PyNucleus_fem.DoFMaps import P0_DoFMap, P1_DoFMap, P2_DoFMap
+    from PyNucleus_fem.DoFMaps import P0_DoFMap, P1_DoFMap, P2_DoFMap, P3_DoFMap
     k = builder.kernel
-    if isinstance(builder.dm, (P0_DoFMap, P2_DoFMap)) and (k.finiteHorizon or int(k.kernelType) != 0):
-        return False        # P0 / P2: fractional kernels with infinite horizon (row-owner kernel)
-    return (builder.dm2 is None and isinstance(builder.dm, (P0_DoFMap, P1_DoFMap, P2_DoFMap)) and k.symmetric and not k.variable
+    if isinstance(builder.dm, (P0_DoFMap, P2_DoFMap, P3_DoFMap)) and (k.finiteHorizon or int(k.kernelType) != 0):
+        return False        # P0 / P2 / P3: fractional kernels with infinite horizon (row-owner kernel)
+    if isinstance(builder.dm, P3_DoFMap) and builder.dm.mesh.dim != 1:
+        return False        # cubic elements: intervals only
+    return (builder.dm2 is None and isinstance(builder.dm, (P0_DoFMap, P1_DoFMap, P2_DoFMap, P3_DoFMap)) and k.symmetric and not k.variable
             and k.valueSize == 1 and builder.dm.mesh.dim in (1, 2) and builder.dm.mesh.manifold_dim == builder.dm.mesh.dim
             and (builder.comm is None or builder.comm.size == 1) and int(k.kernelType) in (0, 1, 2)
             and not k.complement and (int(k.kernelType) == 0 or k.finiteHorizon))

@@ -15,7 +15,7 @@ ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
 OUT = os.path.join(ROOT, 'tests', 'golden')
 
 from PyNucleus_fem.mesh import simpleInterval, uniform_disc  # noqa: E402
-from PyNucleus_fem.DoFMaps import P2_DoFMap, P0_DoFMap  # noqa: E402
+from PyNucleus_fem.DoFMaps import P2_DoFMap, P0_DoFMap, P3_DoFMap  # noqa: E402
 from PyNucleus_nl.kernels import getFractionalKernel  # noqa: E402
 from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder  # noqa: E402
 from PyNucleus_nl.fractionalOrders import constFractionalOrder  # noqa: E402
@@ -66,3 +66,6 @@ if __name__ == '__main__':
         case(1, 5, 0.25, 'p0_interval_s0.25_r5', {}, DoFMap=P0_DoFMap)
         case(2, 2, 0.25, 'p0_disc_s0.25_r2', {'target_order': 0.5}, DoFMap=P0_DoFMap)
         case(2, 3, 0.4, 'p0_disc_s0.4_r3', {'target_order': 0.5}, DoFMap=P0_DoFMap)
+    if 'all' in which or 'p3' in which:
+        case(1, 4, 0.25, 'p3_interval_s0.25_r4', {}, DoFMap=P3_DoFMap)
+        case(1, 4, 0.75, 'p3_interval_s0.75_r4', {}, DoFMap=P3_DoFMap)

@@ -3,7 +3,7 @@ nonlocalBuilder API.  The compute path is hand-written CUDA for
 sm_100a in libpnb200.so (C ABI: include/pnb200.h); this package is the
 host-side mirror of the reference interface."""
 from .mesh import simpleInterval, uniform_disc, polygon_disc, refined, meshNd  # noqa: F401
-from .dofmap import P0_DoFMap, P1_DoFMap, P2_DoFMap  # noqa: F401
+from .dofmap import P0_DoFMap, P1_DoFMap, P2_DoFMap, P3_DoFMap  # noqa: F401
 from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder, variableConstFractionalOrder, leftRightFractionalOrder,  # noqa: F401
                       piecewiseConstantFractionalOrder, constantNonSymFractionalOrder, layersFractionalOrder, innerOuterFractionalOrder, islandsFractionalOrder,
                       constantFractionalLaplacianScaling, FRACTIONAL, INDICATOR, PERIDYNAMIC, Kernel, getIntegrableKernel,

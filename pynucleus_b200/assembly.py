@@ -169,8 +169,8 @@ class nonlocalBuilder:
         self._classes = None
         self._element = self.dm.polynomialOrder != 1
         if self._element:
-            if self.dm.polynomialOrder not in (0, 2):
-                raise NotImplementedError('P0, P1 and P2 elements')
+            if self.dm.polynomialOrder not in (0, 2, 3):
+                raise NotImplementedError('P0, P1, P2 and (intervals) P3 elements')
             if self.dm2 is not None or hasattr(kernel.s, 'blockOrders') or kernel.finiteHorizon:
                 raise NotImplementedError('P0 / P2 elements: one DoFMap, constant kernels with infinite horizon')
             if self.dm.polynomialOrder == 0 and not kernel.max_singularity > -1.-self.mesh.dim:

@@ -22,7 +22,7 @@
 
 template <int DIM, int PORD> struct ElemDims {
     static constexpr int NV = DIM + 1;
-    static constexpr int DPE = PORD == 0 ? 1 : (PORD == 1 ? NV : (DIM == 1 ? 3 : 6));
+    static constexpr int DPE = PORD == 0 ? 1 : (PORD == 1 ? NV : (PORD == 2 ? (DIM == 1 ? 3 : 6) : 4));     // P3: intervals only
 };
 
 // shape functions in the cell's own vertex order (DoFMaps.pyx:1854-1880 P1, :1932-2005 P2: vertices, then the edges
@@ -33,7 +33,7 @@ template <int DIM, int PORD> __device__ __forceinline__ void elem_shape(const do
     else if (PORD == 1) {
 #pragma unroll
         for (int k = 0; k <= DIM; k++) phi[k] = lam[k];
-    } else {
+    } else if (PORD == 2) {
 #pragma unroll
         for (int k = 0; k <= DIM; k++) phi[k] = lam[k] * (2. * lam[k] - 1.);
         phi[DIM + 1] = 4. * lam[0] * lam[1];
@@ -41,6 +41,12 @@ template <int DIM, int PORD> __device__ __forceinline__ void elem_shape(const do
             phi[4] = 4. * lam[1] * lam[2];
             phi[5] = 4. * lam[0] * lam[2];
         }
+    } else {
+        // cubic elements on an interval (DoFMaps.pyx:2034-2078, 2113-2122): the two vertices, then the cell dofs at 1/3, 2/3
+        phi[0] = 4.5 * lam[0] * (lam[0] - 1. / 3.) * (lam[0] - 2. / 3.);
+        phi[1] = 4.5 * lam[1] * (lam[1] - 1. / 3.) * (lam[1] - 2. / 3.);
+        phi[2] = 13.5 * lam[0] * lam[1] * (lam[0] - 1. / 3.);
+        phi[3] = 13.5 * lam[1] * lam[0] * (lam[1] - 1. / 3.);
     }
 }
 
@@ -425,8 +431,9 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
                                           int zero_exterior, double *A_out, int64_t ld_out, int a_on_device)
 {
     if (!p || !dofs || !A_out) return fail(PNB_ERR_ARG, "null argument");
-    if (polynomial_order < 0 || polynomial_order > 2) return fail(PNB_ERR_UNSUPPORTED, "elements: P0, P1 and P2");
-    const int dpe = polynomial_order == 0 ? 1 : (polynomial_order == 1 ? p->dim + 1 : (p->dim == 1 ? 3 : 6));
+    if (polynomial_order < 0 || polynomial_order > 3 || (polynomial_order == 3 && p->dim != 1))
+        return fail(PNB_ERR_UNSUPPORTED, "elements: P0, P1, P2; P3 on intervals");
+    const int dpe = polynomial_order == 0 ? 1 : (polynomial_order == 1 ? p->dim + 1 : (polynomial_order == 2 ? (p->dim == 1 ? 3 : 6) : 4));
     if (dofs_per_element != dpe) return fail(PNB_ERR_ARG, "dofs_per_element does not match the element");
     if (p->finite) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: infinite horizon only");
     if (!p->h_labels.empty()) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: constant kernels only");
@@ -527,7 +534,8 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
         else if (polynomial_order == 1) elem_rows_kernel<2, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
         else elem_rows_kernel<2, 0><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
     } else {
-        if (polynomial_order == 2) elem_rows_kernel<1, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+        if (polynomial_order == 3) elem_rows_kernel<1, 3><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
+        else if (polynomial_order == 2) elem_rows_kernel<1, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
         else if (polynomial_order == 1) elem_rows_kernel<1, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
         else elem_rows_kernel<1, 0><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
     }

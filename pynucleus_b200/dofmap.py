@@ -12,6 +12,10 @@ def _shape_values(polynomialOrder, manifold_dim, bary):
         return np.ones((1, lam.shape[1]))
     if polynomialOrder == 1:
         return lam.copy()
+    if polynomialOrder == 3:
+        assert manifold_dim == 1
+        return np.array([4.5*lam[0]*(lam[0]-1./3.)*(lam[0]-2./3.), 4.5*lam[1]*(lam[1]-1./3.)*(lam[1]-2./3.),
+                         13.5*lam[0]*lam[1]*(lam[0]-1./3.), 13.5*lam[1]*lam[0]*(lam[1]-1./3.)])
     phi = [lam[k]*(2.*lam[k]-1.) for k in range(manifold_dim+1)]
     phi.append(4.*lam[0]*lam[1])
     if manifold_dim == 2:
@@ -163,6 +167,59 @@ class P0_DoFMap:
 
     def getDoFCoordinates(self):
         return self.mesh.vertices[self.mesh.cells].mean(axis=1)
+
+    def assembleRHS(self, fun, qr_order=None, rule=None):
+        return _assembleRHS(self, fun, qr_order, rule)
+
+    def ones(self):
+        return np.ones(self.num_dofs)
+
+    def zeros(self):
+        return np.zeros(self.num_dofs)
+
+
+class P3_DoFMap:
+    """continuous piecewise cubic elements on intervals (DoFMaps.pyx:2106-2122): one dof per vertex, two per cell (at 1/3 and
+    2/3 of the cell); numbered cell by cell, the vertices of a cell before its own two dofs.  (Triangles: not built.)"""
+    polynomialOrder = 3
+
+    def __init__(self, mesh, tag=None):
+        if tag is not None or mesh.manifold_dim != 1:
+            raise NotImplementedError('P3_DoFMap: intervals, default tag')
+        self.mesh = mesh
+        self.dim = mesh.dim
+        self.dofs_per_vertex, self.dofs_per_edge, self.dofs_per_element = 1, 0, 4
+        cells = np.asarray(mesh.cells)
+        nc = cells.shape[0]
+        vdof = {}
+        nb = -1
+        for v in np.asarray(mesh.boundaryVertices).tolist():
+            vdof[v] = nb
+            nb -= 1
+        dofs = np.empty((nc, 4), dtype=np.int64)
+        n = 0
+        for i in range(nc):
+            for k in range(2):
+                v = int(cells[i, k])
+                if v not in vdof:
+                    vdof[v] = n
+                    n += 1
+                dofs[i, k] = vdof[v]
+            dofs[i, 2], dofs[i, 3] = n, n+1
+            n += 2
+        self.dofs = np.ascontiguousarray(dofs, dtype=INDEX)
+        self.num_dofs = int(n)
+        self.num_boundary_dofs = int(-nb-1)
+
+    def vertexPart(self):
+        from copy import copy
+        v = copy(self)
+        v.dofs = np.ascontiguousarray(self.dofs[:, :2], dtype=INDEX)
+        v.dofs_per_element = 2
+        return v
+
+    def __repr__(self):
+        return 'P3 DoFMap with {} DoFs and {} boundary DoFs.'.format(self.num_dofs, self.num_boundary_dofs)
 
     def assembleRHS(self, fun, qr_order=None, rule=None):
         return _assembleRHS(self, fun, qr_order, rule)

@@ -70,6 +70,22 @@ def test_p0_dense_vs_reference(name):
         pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, 0.75), params)
 
 
+@pytest.mark.parametrize('name', ['p3_interval_s0.25_r4', 'p3_interval_s0.75_r4'])
+def test_p3_interval_dense_vs_reference(name):
+    """cubic elements on the interval (P3_DoFMap: 4 dofs per cell): numbering and operator against the reference's"""
+    import pynucleus_b200 as pb
+    g, dim, mesh = setup(name)
+    dm = pb.P3_DoFMap(mesh)
+    assert np.array_equal(dm.dofs, g['dofs']) and dm.num_dofs == int(g['num_dofs'])
+    kernel = pb.getFractionalKernel(1, float(g['s']))
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = pb.nonlocalBuilder(dm, kernel, {}, zeroExterior=ze)
+        assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+        assert abs(b.orders.target_order-float(g['target_order_used'])) < 1e-14
+        A = b.getDense().data
+        assert entry_err(A, g[key]) < TOL
+
+
 def test_p2_dense_rows_larger_mesh_vs_reference():
     """721 P2 dofs (384 triangles): every 8th row and the diagonal of the reference's operator"""
     import pynucleus_b200 as pb
@@ -204,3 +220,21 @@ def test_p0_driver_known_answers(domain, noRef, ref, tol):
     Hs_ex2 = C*np.sqrt(np.pi)*gamma(s+1)/gamma(s+1.5) if dim == 1 else C*np.pi/(s+1)
     Hs = np.sqrt(abs(b.dot(u)-Hs_ex2))
     assert abs(Hs/ref-1) < tol, (Hs, ref)
+
+
+@pytest.mark.parametrize('s,ref', [(0.25, 0.061422967833697564), (0.75, 0.02241204241913628)])
+def test_p3_driver_known_answers(s, ref):
+    """runFractional.py --domain interval --s const(s) --problem constant --element P3 --matrixFormat dense at the driver's
+    default size (5 refinements of its two-cell interval: 191 P3 dofs): Hs error against the reference's cached result
+    (tests/cache_runFractional.py--domaininterval--sconst(*)--problemconstant--elementP3--solvercg-mg--matrixFormatdense)"""
+    from math import gamma
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.simpleInterval(-1, 1), 6)
+    dm = pb.P3_DoFMap(mesh)
+    assert dm.num_dofs == 191
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(1, s), {}).getDense().data
+    b = dm.assembleRHS(1.)
+    u = np.linalg.solve(A, b)
+    C = 2.**(-2.*s)*gamma(0.5)/gamma(0.5+s)/gamma(1.+s)
+    Hs = np.sqrt(abs(b.dot(u)-C*np.sqrt(np.pi)*gamma(s+1)/gamma(s+1.5)))
+    assert abs(Hs/ref-1) < 1e-5, (Hs, ref)

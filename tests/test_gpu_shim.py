@@ -103,18 +103,18 @@ def test_unsupported_configuration_falls_through(shim):
 
 
 @pytest.mark.parametrize('dim,noRef,s,element', [(1, 5, 0.75, 'P2'), (2, 2, 0.75, 'P2'), (2, 2, 0.25, 'P2'), (1, 5, 0.25, 'P0'),
-                                                 (2, 2, 0.3, 'P0')])
+                                                 (2, 2, 0.3, 'P0'), (1, 4, 0.75, 'P3')])
 def test_reference_builder_vs_shim_p2(shim, dim, noRef, s, element):
     """P2_DoFMap / P0_DoFMap of the reference through the shim (pnb_dense_assemble_element) against its own Cython getDense"""
     from PyNucleus_fem.mesh import simpleInterval, uniform_disc
-    from PyNucleus_fem.DoFMaps import P0_DoFMap, P2_DoFMap
+    from PyNucleus_fem.DoFMaps import P0_DoFMap, P2_DoFMap, P3_DoFMap
     from PyNucleus_nl.kernels import getFractionalKernel
     from PyNucleus_nl.fractionalOrders import constFractionalOrder
     from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder
     mesh = simpleInterval(-1, 1) if dim == 1 else uniform_disc()
     for _ in range(noRef):
         mesh = mesh.refine()
-    dm = P2_DoFMap(mesh) if element == 'P2' else P0_DoFMap(mesh)
+    dm = {'P2': P2_DoFMap, 'P0': P0_DoFMap, 'P3': P3_DoFMap}[element](mesh)
     kernel = getFractionalKernel(dim, constFractionalOrder(s), np.inf)
     params = {'target_order': 0.5} if dim == 2 else {}
     Aref = np.array(nonlocalBuilder(dm, kernel, dict(params)).getDense().data)
