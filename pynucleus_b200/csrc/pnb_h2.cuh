@@ -46,6 +46,12 @@ struct pnb_h2 {
     const int *parent = nullptr;
     std::vector<int> h_level_ptr;
     int max_mm = 0, max_leaf_dofs = 0;
+    // the launch sequence of a product as a CUDA graph over internal input / output vectors (one per flavour: with /
+    // without the near field); built on first use
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    cudaStream_t cap_stream = nullptr;
+    double *xin = nullptr, *yout = nullptr;
+    bool graph_failed = false;
 };
 
 template <class T> static int h2_upload(pnb_h2 *h, const T *host, size_t count, const T **dev)
@@ -347,6 +353,8 @@ extern "C" int pnb_h2_destroy(pnb_h2 *h)
     if (!h) return 0;
     {
         DeviceGuard g(h->device);
+        for (auto &e : h->gexec) if (e) cudaGraphExecDestroy(e);
+        if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
         for (void *d : h->allocs) cudaFree(d);
     }
     delete h;
@@ -532,15 +540,12 @@ extern "C" int pnb_h2_leaf_values(pnb_h2 *h, double *out)
     return 0;
 }
 
-extern "C" int pnb_h2_matvec(pnb_h2 *h, const double *x, double *y, int far_only, void *stream)
+// the kernels of one product, in order, on stream st
+static void h2_enqueue(pnb_h2 *h, const double *x, double *y, bool near, cudaStream_t st)
 {
-    if (!h || !x || !y) return fail(PNB_ERR_ARG, "null argument");
-    ON_DEVICE(h->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool near = !far_only && h->near_indptr;
     if (near) {
-        int sms = 148;
-        sms = device_attr(cudaDevAttrMultiProcessorCount, h->device);
+        int sms = device_attr(cudaDevAttrMultiProcessorCount, h->device);
+        if (sms <= 0) sms = 148;
         const int blocks = std::max(1, std::min((h->num_dofs * 32 + 255) / 256, sms * 8));
         csr_matvec_kernel<<<blocks, 256, 0, st>>>(h->num_dofs, h->near_indptr, h->near_indices, h->near_data, x, y);
     }
@@ -565,6 +570,51 @@ extern "C" int pnb_h2_matvec(pnb_h2 *h, const double *x, double *y, int far_only
         h2_leaf_down_kernel<<<h->num_leaves, 256, 0, st>>>(h->leaf_node, h->coef_ptr, h->leaf_dof_ptr, h->leaf_dofs, h->leaf_val_ptr,
                                                           h->leaf_values, h->down, y, near ? 1 : 0);
     }
+}
+
+// captures the launch sequence over the internal vectors xin / yout (2 L + 5 dependent launches: the launch gaps are a third
+// of the product at 12k DoFs)
+static void h2_build_graph(pnb_h2 *h, bool near)
+{
+    const int gi = near ? 0 : 1;
+    const char *env = getenv("PNB_H2_GRAPH");
+    if (env && atoi(env) == 0) { h->graph_failed = true; return; }
+    if (!h->xin) {
+        void *d = nullptr;
+        if (cudaMalloc(&d, std::max<size_t>(h->num_dofs, 1) * sizeof(double) * 2) != cudaSuccess) { cudaGetLastError(); h->graph_failed = true; return; }
+        h->allocs.push_back(d);
+        h->xin = (double *)d;
+        h->yout = h->xin + h->num_dofs;
+    }
+    if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError(); h->graph_failed = true; return;
+    }
+    device_attr(cudaDevAttrMultiProcessorCount, h->device);      // cached before the capture
+    cudaGraph_t g = nullptr;
+    bool ok = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+        h2_enqueue(h, h->xin, h->yout, near, h->cap_stream);
+        ok = cudaStreamEndCapture(h->cap_stream, &g) == cudaSuccess && g != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&h->gexec[gi], g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    if (!ok) { cudaGetLastError(); h->gexec[gi] = nullptr; h->graph_failed = true; }
+}
+
+extern "C" int pnb_h2_matvec(pnb_h2 *h, const double *x, double *y, int far_only, void *stream)
+{
+    if (!h || !x || !y) return fail(PNB_ERR_ARG, "null argument");
+    ON_DEVICE(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool near = !far_only && h->near_indptr;
+    const int gi = near ? 0 : 1;
+    if (!h->gexec[gi] && !h->graph_failed) h2_build_graph(h, near);
+    if (h->gexec[gi]) {
+        const size_t bytes = (size_t)h->num_dofs * sizeof(double);
+        CK(cudaMemcpyAsync(h->xin, x, bytes, cudaMemcpyDeviceToDevice, st));
+        CK(cudaGraphLaunch(h->gexec[gi], st));
+        CK(cudaMemcpyAsync(y, h->yout, bytes, cudaMemcpyDeviceToDevice, st));
+    } else h2_enqueue(h, x, y, near, st);
     CK(cudaGetLastError());
     return 0;
 }
