@@ -69,3 +69,9 @@ if __name__ == '__main__':
     if 'all' in which or 'p3' in which:
         case(1, 4, 0.25, 'p3_interval_s0.25_r4', {}, DoFMap=P3_DoFMap)
         case(1, 4, 0.75, 'p3_interval_s0.75_r4', {}, DoFMap=P3_DoFMap)
+    if 'all' in which or 'tiny' in which:
+        # smallest meshes: one hexagon (6 cells), two intervals
+        case(2, 0, 0.75, 'p2_disc_s0.75_r0', {'target_order': 0.5})
+        case(2, 0, 0.25, 'p0_disc_s0.25_r0', {'target_order': 0.5}, DoFMap=P0_DoFMap)
+        case(1, 1, 0.75, 'p2_interval_s0.75_r1', {})
+        case(1, 1, 0.25, 'p3_interval_s0.25_r1', {}, DoFMap=P3_DoFMap)

@@ -238,3 +238,17 @@ def test_p3_driver_known_answers(s, ref):
     C = 2.**(-2.*s)*gamma(0.5)/gamma(0.5+s)/gamma(1.+s)
     Hs = np.sqrt(abs(b.dot(u)-C*np.sqrt(np.pi)*gamma(s+1)/gamma(s+1.5)))
     assert abs(Hs/ref-1) < 1e-5, (Hs, ref)
+
+
+@pytest.mark.parametrize('name,element', [('p2_disc_s0.75_r0', 'P2'), ('p0_disc_s0.25_r0', 'P0'), ('p2_interval_s0.75_r1', 'P2'),
+                                          ('p3_interval_s0.25_r1', 'P3')])
+def test_elements_on_the_smallest_meshes(name, element):
+    """one hexagon of six triangles / two intervals: every pair touching, fewer rows than lanes"""
+    import pynucleus_b200 as pb
+    g, dim, mesh = setup(name)
+    dm = {'P0': pb.P0_DoFMap, 'P2': pb.P2_DoFMap, 'P3': pb.P3_DoFMap}[element](mesh)
+    assert np.array_equal(dm.dofs, g['dofs'])
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, float(g['s'])), params, zeroExterior=ze).getDense().data
+        assert A.shape == g[key].shape and entry_err(A, g[key]) < TOL

@@ -1009,3 +1009,20 @@ def test_fused_cg_kernels(golden_dir):
                 assert torch.equal(x1, x2) and r1 == r2
         if noRef == 5:
             assert i1 > 50      # the residual refresh of iteration 50 ran
+
+
+def test_piecewise_order_with_a_single_block_in_the_mesh():
+    """an interface outside the domain: every cell carries the same label, the passes of the other orders are empty, and
+    the operator equals the constant-order one (symmetric order) / the constantNonSym one (unsymmetric order)"""
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.uniform_disc(), 3)
+    dm = pb.P1_DoFMap(mesh)
+    params = {'target_order': 0.5}
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, 0.3), params).getDense().data
+    # singular quadrature orders follow s.max = 0.3 in both
+    As = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, pb.leftRightFractionalOrder(0.3, 0.2, 0.25, 0.25, interface=5.)), params).getDense().data
+    assert entry_err(As, A) < TOL
+    An = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, pb.leftRightFractionalOrder(0.3, 0.2, 0.25, 0.1, interface=5.)), params).getDense().data
+    Ac = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, pb.constantNonSymFractionalOrder(0.3)), params).getDense().data
+    assert entry_err(An, Ac) < TOL
+    assert 1e-9 < entry_err(Ac, A) < 1e-5      # the two orientations of the singular rules differ by their quadrature error
