@@ -619,6 +619,20 @@ def widening_leg(dev):
     out['unsymmetric_order'] = {'workload': 'disc r=5, N={}, leftRight(0.25, 0.75, 0.6, 0.4)'.format(dm.num_dofs), 'ms_per_assembly': ms,
                                 'passes': len(b3._classes['passes']), 'symmetry_rel': float((d-d.t()).abs().max()/d.abs().max()),
                                 'min_diagonal': float(torch.diagonal(d).min())}
+    del A3, b3
+    # BASELINE configs[2] flavour at size: finite horizon (l2 ball), fractional and constant kernels, dense operator
+    mesh = pb.refined(pb.uniform_disc(), 6)
+    dm = pb.P1_DoFMap(mesh)
+    fin = {}
+    for name, k in (('fractional s=0.4', pb.getFractionalKernel(2, 0.4, 0.15)), ('constant', pb.getIntegrableKernel(2, 'constant', 0.15))):
+        b4 = pb.nonlocalBuilder(dm, k, params)
+        A4 = b4.getDense()
+        ms = _event_ms(lambda: b4.getDense(out=A4.device_data), 2, warm=1)
+        d = A4.device_data
+        fin[name] = {'ms_per_assembly': ms, 'nonzero_frac': float((d != 0).sum())/d.numel(), 'symmetric': bool(torch.equal(d, d.t())),
+                     'min_diagonal': float(torch.diagonal(d).min())}
+        del A4, b4
+    out['finite_horizon'] = {'workload': 'disc r=6, N={}, horizon 0.15 (l2 ball), P1, dense'.format(dm.num_dofs), **fin}
     return out
 
 
