@@ -222,10 +222,11 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps_ref, 'warmup': args.warmup_ref, 'ms_per_step': 1e3*N*N/v, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_string(args.workload, N, mesh.num_cells),
-                       'note': ('CPU: reference Cython getDense (stub-built, oracle/_ref)' if last['kind'] == 'reference' else
-                                'CPU: C restatement of the reference algorithm (oracle/; oracle/_ref is absent)')
-                               + '; ms_per_step extrapolated from the sampled slices to the full matrix'},
+            'config': config_block(args.workload, N, mesh.num_cells, max(1, args.gpus)),
+            'note': ('CPU: reference Cython getDense (stub-built, oracle/_ref)' if last['kind'] == 'reference' else
+                     'CPU: C restatement of the reference algorithm (oracle/; oracle/_ref is absent)')
+                    + '; ms_per_step extrapolated from the sampled slices to the full matrix; `config` describes the workload and is '
+                      'the CUDA arm\'s (l2 / parallelism refer to that arm)',
             'cpu_baseline': dict(last, value=v),
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
@@ -234,6 +235,14 @@ def run_reference(args):
 # --------------------------------------------------------------------------
 # CUDA arm
 # --------------------------------------------------------------------------
+def config_block(workload, N, nc, world):
+    """the `config` of the JSON line: identical in both arms at the same number of GPUs (the driver compares them)"""
+    return {'workload': workload_string(workload, N, nc),
+            'l2': 'output ({:.2f} GB/step) exceeds L2; 512 MB flush written between steps (untimed)'.format(N*N*8/1e9),
+            'parallelism': 'single GPU' if world == 1 else
+                           'rows owned by cell groups x{} (peer-memory fragments, no matrix collective)'.format(world)}
+
+
 def workload_string(workload, N, nc):
     """the same description in both arms (the driver compares the config of the two lines)"""
     return ('{}: 2D disc ({}-gon fan, {} radial refinements), s={}, P1, infinite horizon, zero exterior, dense, N={} ({} cells), '
@@ -536,10 +545,7 @@ def run_cuda(args):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_string(args.workload, N, mesh.num_cells),
-                       'l2': 'output ({:.2f} GB/step) exceeds L2; 512 MB flush written between steps (untimed)'.format(N*N*8/1e9),
-                       'parallelism': 'single GPU' if world == 1 else
-                                      'rows owned by cell groups x{} (peer-memory fragments, no matrix collective)'.format(world)},
+            'config': config_block(args.workload, N, mesh.num_cells, world),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d)*world, 'd2h_bytes_per_step': int(N*N*8),
                     'ms_per_step': float(np.mean(e2e_ms)), 'checksum_A00': checksum},
