@@ -718,10 +718,12 @@ def main():
     ap.add_argument('--no-widening', dest='no_widening', action='store_true', default=False,
                     help='skip the H2 / P2 / unsymmetric-order legs (a few seconds on one GPU)')
     args = ap.parse_args()
-    # the reference arm is bounded: a few sampled slices per step
-    args.steps_ref = min(args.steps, 2)
-    args.warmup_ref = min(args.warmup, 0)
+    # the reference arm runs the same W + K steps; every step is a bounded sample of the workload (rank slices of the
+    # reference's own cell partition), sized so that the whole run takes about two minutes of CPU work plus process start-up
+    args.steps_ref = max(1, args.steps)
+    args.warmup_ref = max(0, args.warmup)
     if args.impl == 'reference':
+        args.ref_seconds = min(args.ref_seconds, 120./(args.steps_ref+args.warmup_ref))
         run_reference(args)
     else:
         run_cuda(args)
