@@ -313,6 +313,36 @@ int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, cons
 int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
                                int zero_exterior, double *A, int64_t ld, int a_on_device);
 
+/* Dense operator for a fractional order that VARIES INSIDE A CELL: s(x, y) = sFun(x), kernel.piecewise == False
+ * (singleVariableUnsymmetricFractionalOrder, fractionalOrders.pyx:153-183; smoothedLeftRightFractionalOrder :641-645 is the
+ * driver's `--s twoDomainNonSym(sl,sr)`).  The reference then assembles with the unsymmetric local matrices
+ * fractionalLaplacian{1,2}D_nonsym over both orientations of every cell pair (nonlocalAssembly_{SCALAR}.pxi:1412-1428),
+ * re-evaluates order, scaling constant and kernel at every quadrature node (updateAndEvalFractional, kernelsCy.pyx:596-622;
+ * variableFractionalLaplacianScaling.evalPtr, kernelNormalization.pyx:421-440) and uses, per cell pair, the singularity
+ * -d - 2 max(s) over the centres and vertices of both cells (evalParamsOnSimplices, kernelsCy.pyx:1826-1850) for the
+ * regular order and for a singular rule of its own (getNearQuadRule).  The caller evaluates s at the centres and vertices
+ * and hands over the distinct maxima with one set of singular tables per value. */
+#define PNB_ORDERFUN_CONST 0
+#define PNB_ORDERFUN_SMOOTHSTEP 1          /* smoothStep, fractionalOrders.pyx:389-416 (first coordinate) */
+#define PNB_ORDERFUN_LINEARSTEP 2          /* linearStep, :447-470 */
+#define PNB_ORDERFUN_SMOOTHSTEP_RADIAL 3   /* smoothStepRadial, :497-535 (interface = radius) */
+typedef struct {
+    int32_t fun;                   /* PNB_ORDERFUN_* */
+    double sl, sr, r, slope, interface;
+    int32_t num_values;            /* distinct values of max(s) over a cell (centre and vertices) or boundary facet */
+    const double *values;          /* host, num_values, ascending */
+    const int32_t *cell_value;     /* host, num_cells: index into values */
+    const int32_t *bfacet_value;   /* host, num_bfacets */
+    /* singular tables for the singularities -d - 2 values[k] (boundary: 1 - d - 2 values[k]); host, num_values entries each;
+     * edge / bedge: 2D only (may be NULL in 1D) */
+    const pnb_rule_t *identical, *edge, *vertex, *bedge, *bvertex;
+} pnb_varorder_t;
+/* `p`: mesh, regular tables and the quadrature-order constants (target orders, order_num_dofs) of the local matrices; its
+ * own kernel parameters and singular tables are not used.  Elements as in pnb_dense_assemble_element.  One warp owns one
+ * row (no atomics, bitwise reproducible); normalised kernels with infinite horizon. */
+int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t *order, int polynomial_order, int dofs_per_element,
+                                int num_dofs, const int32_t *dofs, int zero_exterior, double *A, int64_t ld, int a_on_device);
+
 /* ---- H2 operator on the device -------------------------------------------------------------------------
  * Replaces H2Matrix.matvec (nl/PyNucleus_nl/clusterMethodCy.pyx:2269-2295) with its upwardPass / downwardPass
  * (:1093-1176) and tree_node.enterLeafValues (:1205-1325).  The caller describes the cluster tree node by node

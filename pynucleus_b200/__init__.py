@@ -7,7 +7,8 @@ from .dofmap import P0_DoFMap, P1_DoFMap, P2_DoFMap, P3_DoFMap  # noqa: F401
 from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFractionalOrder, variableConstFractionalOrder, leftRightFractionalOrder,  # noqa: F401
                       piecewiseConstantFractionalOrder, constantNonSymFractionalOrder, layersFractionalOrder, innerOuterFractionalOrder, islandsFractionalOrder,
                       constantFractionalLaplacianScaling, FRACTIONAL, INDICATOR, PERIDYNAMIC, Kernel, getIntegrableKernel,
-                      constantIntegrableScaling, constant)
+                      constantIntegrableScaling, constant, singleVariableUnsymmetricFractionalOrder,
+                      smoothedLeftRightFractionalOrder, linearLeftRightFractionalOrder, variableFractionalLaplacianScaling)
 from .assembly import nonlocalBuilder, assembleNonlocalOperator, release_staging_pool  # noqa: F401
 from .linear_operators import Dense_LinearOperator, diagonalOperator  # noqa: F401
 from .solvers import cg, gmres, lu, DistributedDenseOperator  # noqa: F401

@@ -48,6 +48,15 @@ class pnb_rules_t(ctypes.Structure):
                 ('cell', ctypes.POINTER(pnb_rule_t)), ('facet', ctypes.POINTER(pnb_rule_t))]
 
 
+class pnb_varorder_t(ctypes.Structure):
+    _fields_ = [('fun', ctypes.c_int32), ('sl', ctypes.c_double), ('sr', ctypes.c_double), ('r', ctypes.c_double),
+                ('slope', ctypes.c_double), ('interface', ctypes.c_double), ('num_values', ctypes.c_int32),
+                ('values', ctypes.c_void_p), ('cell_value', ctypes.c_void_p), ('bfacet_value', ctypes.c_void_p),
+                ('identical', ctypes.POINTER(pnb_rule_t)), ('edge', ctypes.POINTER(pnb_rule_t)),
+                ('vertex', ctypes.POINTER(pnb_rule_t)), ('bedge', ctypes.POINTER(pnb_rule_t)),
+                ('bvertex', ctypes.POINTER(pnb_rule_t))]
+
+
 class pnb_h2_desc_t(ctypes.Structure):
     _fields_ = [('dim', ctypes.c_int32), ('num_dofs', ctypes.c_int32), ('num_nodes', ctypes.c_int32),
                 ('coef_ptr', ctypes.c_void_p), ('parent', ctypes.c_void_p), ('level', ctypes.c_void_p),
@@ -76,7 +85,7 @@ EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_cre
            'pnb_dist_status', 'pnb_dist_apply', 'pnb_device_alloc', 'pnb_device_free', 'pnb_ipc_export', 'pnb_ipc_import',
            'pnb_ipc_close',
            'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths', 'pnb_problem_set_path', 'pnb_sparsity_mask', 'pnb_block_alignment',
-           'pnb_h2_create', 'pnb_h2_leaf_values', 'pnb_h2_matvec', 'pnb_h2_destroy', 'pnb_dense_assemble_element',
+           'pnb_h2_create', 'pnb_h2_leaf_values', 'pnb_h2_matvec', 'pnb_h2_destroy', 'pnb_dense_assemble_element', 'pnb_dense_assemble_varorder',
            'pnb_krylov_workspace_doubles', 'pnb_krylov_dot', 'pnb_krylov_cg_update', 'pnb_krylov_cg_direction']
 
 _LIB = None
@@ -146,6 +155,8 @@ def lib():
         L.pnb_h2_destroy.argtypes = [ctypes.c_void_p]
         L.pnb_dense_assemble_element.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
+        L.pnb_dense_assemble_varorder.argtypes = [ctypes.c_void_p, ctypes.POINTER(pnb_varorder_t), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
         L.pnb_krylov_dot.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p]
         L.pnb_krylov_cg_update.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

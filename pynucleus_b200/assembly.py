@@ -165,7 +165,7 @@ class nonlocalBuilder:
         self.setKernel(kernel, zeroExterior)
 
     def setKernel(self, kernel, zeroExterior=True):
-        from .kernels import constFractionalOrder, getFractionalKernel
+        from .kernels import constFractionalOrder, getFractionalKernel, singleVariableUnsymmetricFractionalOrder
         self._classes = None
         self._element = self.dm.polynomialOrder != 1
         if self._element:
@@ -177,6 +177,47 @@ class nonlocalBuilder:
                 # fractionalLaplacian2D.pyx:596-598, fractionalLaplacian1D.pyx:212-214
                 raise AssertionError('Discontinuous finite elements are not conforming for singularity order {} <= {}.'.format(
                     kernel.max_singularity, -1-self.mesh.dim))
+        self._varorder = None
+        if isinstance(getattr(kernel, 's', None), singleVariableUnsymmetricFractionalOrder):
+            # order that varies inside the cells: s(x, y) = sFun(x), kernel.piecewise == False.  The reference assembles with
+            # the unsymmetric local matrices over both orientations of every cell pair, evaluates order, scaling and kernel
+            # per quadrature node and takes, per cell pair, the singularity -d - 2 max(s) over the centres and vertices of
+            # both cells (evalParamsOnSimplices, kernelsCy.pyx:1826-1850) for the regular order and for a singular rule of
+            # its own.  Device path: pnb_dense_assemble_varorder (csrc/pnb_varorder.cuh); here: s at the centres and
+            # vertices, the distinct maxima and one set of singular tables per value.
+            if self.dm2 is not None or self.dm.polynomialOrder != 1:
+                raise NotImplementedError('orders varying inside a cell: one P1 DoFMap')
+            if kernel.finiteHorizon:
+                raise NotImplementedError('orders varying inside a cell: infinite horizon')
+            mesh = self.mesh
+            self.kernel = kernel
+            self.zeroExterior = zeroExterior
+            self.kernelBoundary = kernel.getBoundaryKernel()
+            kmax = getFractionalKernel(mesh.dim, kernel.s.max)
+            H0 = mesh.diam/np.sqrt(8.)
+            # the unsymmetric local matrix never sees params['target_order'] (fractionalLaplacian2D.pyx:911 hands num_dofs
+            # to the base class in its place); the boundary local matrix does (nonlocalAssembly_{SCALAR}.pxi:1045-1053)
+            args = (mesh.dim, kmax.singularityValue, kmax.getBoundaryKernel().singularityValue, mesh.hmin, H0, self.dm.num_dofs)
+            kw = dict(polynomialOrder=self.dm.polynomialOrder, min_singularity=kernel.min_singularity,
+                      min_bsingularity=self.kernelBoundary.min_singularity)
+            self.orders = quadrature.localMatrixOrders(*args, target_order=None, **kw)
+            ob = quadrature.localMatrixOrders(*args, target_order=self.params.get('target_order', None), **kw)
+            self.orders.btarget_order, self.orders.bquad_order_diagonal = ob.btarget_order, ob.bquad_order_diagonal
+            T = mesh.vertices[mesh.cells]
+            centers = np.zeros((mesh.num_cells, mesh.dim))
+            for k in range(mesh.dim+1):
+                centers += T[:, k]
+            centers /= mesh.dim+1
+            smax_cell = np.maximum(kernel.s.evaluate(centers), kernel.s.evaluate(T).max(axis=1))
+            bf = np.asarray(mesh.boundaryFacets).reshape(-1, mesh.dim)
+            F = mesh.vertices[bf]
+            smax_facet = np.maximum(kernel.s.evaluate(F.mean(axis=1)), kernel.s.evaluate(F).max(axis=1))
+            vals, inv = np.unique(np.concatenate((smax_cell, smax_facet)), return_inverse=True)
+            self._varorder = dict(base=kmax, values=np.ascontiguousarray(vals),
+                                  cell_value=np.ascontiguousarray(inv[:mesh.num_cells], dtype=np.int32),
+                                  bfacet_value=np.ascontiguousarray(inv[mesh.num_cells:], dtype=np.int32), struct=None)
+            self._problem = None
+            return
         if hasattr(kernel.s, 'blockOrders'):
             # piecewise constant order s(x,y) = sVals[block(x), block(y)], evaluated at the cell centres once per ordered
             # cell pair (kernel.evalParams, nonlocalOperator_{SCALAR}.pxi:509-513).  One constant-order problem instance
@@ -245,6 +286,13 @@ class nonlocalBuilder:
                                                        mesh.hmin, H0, self.dm.num_dofs, target_order,
                                                        self.dm.polynomialOrder, min_singularity=kernel.min_singularity,
                                                        min_bsingularity=self.kernelBoundary.min_singularity)
+            if not kernel.symmetric and self.params.get('target_order', None) is not None:
+                # ... but the boundary local matrix does see it (nonlocalAssembly_{SCALAR}.pxi:1045-1053)
+                ob = quadrature.localMatrixOrders(mesh.dim, kmax.singularityValue, kmax.getBoundaryKernel().singularityValue,
+                                                  mesh.hmin, H0, self.dm.num_dofs, self.params['target_order'],
+                                                  self.dm.polynomialOrder, min_singularity=kernel.min_singularity,
+                                                  min_bsingularity=self.kernelBoundary.min_singularity)
+                self.orders.btarget_order, self.orders.bquad_order_diagonal = ob.btarget_order, ob.bquad_order_diagonal
             self._problem = None
             return
         if not kernel.symmetric or not (kernel.s is None or isinstance(kernel.s, constFractionalOrder)):
@@ -268,6 +316,9 @@ class nonlocalBuilder:
     def problem(self):
         if self._classes is not None:
             raise NotImplementedError('only getDense() supports piecewise variable orders')
+        if self._varorder is not None and not getattr(self, '_varorder_access', False):
+            # the device problem of this path carries a constant stand-in kernel: nothing but getDense() may use it
+            raise NotImplementedError('only getDense() supports orders that vary inside a cell')
         if self._problem is None:
             import torch
             if not torch.cuda.is_available():
@@ -278,7 +329,12 @@ class nonlocalBuilder:
                 # P2: the device problem holds mesh, kernel and tables behind the vertex dofs; the element's table goes to
                 # pnb_dense_assemble_element (row-owner kernel, csrc/pnb_element.cuh)
                 dm_dev, ond = self.dm.vertexPart(), self.dm.num_dofs
-            self._problem = _Problem(dm_dev, self.kernel, self.kernelBoundary, self.orders, device,
+            kern, bkern = self.kernel, self.kernelBoundary
+            if self._varorder is not None:
+                # mesh, regular tables and order constants; the kernel values come from pnb_varorder_t
+                kern = self._varorder['base']
+                bkern = kern.getBoundaryKernel()
+            self._problem = _Problem(dm_dev, kern, bkern, self.orders, device,
                                      self.params.get('max_regular_order', 32), order_num_dofs=ond)
             if self.params.get('assembly_path', 'default') == 'tiles':
                 _lib.check(_lib.lib().pnb_problem_set_path(self._problem.handle, 1))
@@ -349,13 +405,20 @@ class nonlocalBuilder:
                 raise RuntimeError('pynucleus_b200 needs a CUDA device; there is no CPU fallback')
             dev = torch.device('cuda', self.params.get('device', torch.cuda.current_device()))
             return Dense_LinearOperator(torch.empty((0, 0), dtype=torch.float64, device=dev), dev.index)
-        prob = self.problem
+        self._varorder_access = self._varorder is not None
+        try:
+            prob = self.problem
+        finally:
+            self._varorder_access = False
         dev = torch.device('cuda', prob.device)
         if self.dm2 is not None and out is not None:
             raise ValueError('out= is not supported together with dm2')
         if out is not None:
             check_matrix_out(out, N, N, dev)
         A = torch.empty((N, N), dtype=torch.float64, device=dev) if out is None else out
+
+        if self._varorder is not None:
+            return self._getDenseVarOrder(prob, A, N)
 
         def run():
             if self._element:
@@ -369,6 +432,51 @@ class nonlocalBuilder:
         if self.dm2 is not None:
             n1 = self.dm.num_dofs
             return Dense_LinearOperator(A[:n1, n1:].contiguous(), prob.device)
+        return Dense_LinearOperator(A, prob.device)
+
+    def _varorder_struct(self):
+        """pnb_varorder_t of the kernel's order: the order function, the distinct pair maxima of s and one set of singular
+        tables per value (what getNearQuadRule caches per singularity, fractionalLaplacian1D.pyx:452-547)"""
+        V = self._varorder
+        if V['struct'] is None:
+            dim = self.mesh.dim
+            keep = []
+            n = V['values'].shape[0]
+            names = ('identical', 'edge', 'vertex', 'bedge', 'bvertex')
+            arrays = {name: (_lib.pnb_rule_t*n)() for name in names}
+            for k, v in enumerate(V['values'].tolist()):
+                tabs = quadrature.singular_tables(dim, -dim-2.*v, 1.-dim-2.*v, self.orders, self.dm.polynomialOrder)
+                for name in names:
+                    if name in tabs:
+                        arrays[name][k] = _lib.as_rule(*tabs[name], keep)
+            fun, sl, sr, r, slope, interface = self.kernel.s.orderFunction()
+            st = _lib.pnb_varorder_t(int(fun), sl, sr, r, slope, interface, n, V['values'].ctypes.data,
+                                     V['cell_value'].ctypes.data, V['bfacet_value'].ctypes.data)
+            for name in names:
+                if name in ('edge', 'bedge') and dim == 1:
+                    continue
+                setattr(st, name, arrays[name])
+            V['struct'] = (st, arrays, keep)
+        return V['struct'][0]
+
+    def _getDenseVarOrder(self, prob, A, N):
+        import re
+        st = self._varorder_struct()
+        ed = np.ascontiguousarray(self.dm.dofs, dtype=np.int32)
+
+        def run():
+            _lib.check(_lib.lib().pnb_dense_assemble_varorder(prob.handle, ctypes.byref(st), self.dm.polynomialOrder,
+                                                              self.dm.dofs_per_element, N, ed.ctypes.data, int(self.zeroExterior),
+                                                              A.data_ptr(), A.stride(0), 1))
+        try:
+            run()
+        except _lib.PNBError as e:
+            # the pair singularities differ from the base problem's: the library reports the order it needs
+            m = re.search(r'order (\d+) exceeds', str(e))
+            if e.code != -5 or m is None:
+                raise
+            prob.set_max_order(int(m.group(1)))
+            run()
         return Dense_LinearOperator(A, prob.device)
 
     def _sparsify(self, threshold=0.8):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'pnb200.cu')
 OUT = os.path.join(HERE, 'libpnb200.so')
 DEPS = [SRC, os.path.join(HERE, 'csrc', 'pnb_device.cuh'), os.path.join(HERE, 'csrc', 'pnb_pair.cuh'),
-        os.path.join(HERE, 'csrc', 'pnb_group.cuh'), os.path.join(HERE, 'csrc', 'pnb_h2.cuh'), os.path.join(HERE, 'csrc', 'pnb_element.cuh'), os.path.join(HERE, 'csrc', 'pnb_krylov.cuh'),
+        os.path.join(HERE, 'csrc', 'pnb_group.cuh'), os.path.join(HERE, 'csrc', 'pnb_h2.cuh'), os.path.join(HERE, 'csrc', 'pnb_element.cuh'), os.path.join(HERE, 'csrc', 'pnb_krylov.cuh'), os.path.join(HERE, 'csrc', 'pnb_varorder.cuh'),
         os.path.join(HERE, '..', 'include', 'pnb200.h')]
 
 # per-thread default streams: host threads that assemble independent problems (H2 near field) overlap on the device

@@ -3537,4 +3537,5 @@ extern "C" int pnb_fp64_peak(int device, double *tflops)
 
 #include "pnb_h2.cuh"
 #include "pnb_element.cuh"
+#include "pnb_varorder.cuh"
 #include "pnb_krylov.cuh"

@@ -427,27 +427,16 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
     }
 }
 
-extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
-                                          int zero_exterior, double *A_out, int64_t ld_out, int a_on_device)
+// host side of ElemJob: dof -> (cell, slot) lists, rows by length, partner cells coloured into vertex-disjoint steps of 32;
+// everything is uploaded, `dev` receives the device allocations (release with elem_job_free)
+static void elem_job_free(std::vector<void *> &dev)
 {
-    if (!p || !dofs || !A_out) return fail(PNB_ERR_ARG, "null argument");
-    if (polynomial_order < 0 || polynomial_order > 3 || (polynomial_order == 3 && p->dim != 1))
-        return fail(PNB_ERR_UNSUPPORTED, "elements: P0, P1, P2; P3 on intervals");
-    const int dpe = polynomial_order == 0 ? 1 : (polynomial_order == 1 ? p->dim + 1 : (polynomial_order == 2 ? (p->dim == 1 ? 3 : 6) : 4));
-    if (dofs_per_element != dpe) return fail(PNB_ERR_ARG, "dofs_per_element does not match the element");
-    if (p->finite) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: infinite horizon only");
-    if (!p->h_labels.empty()) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: constant kernels only");
-    if (p->nblocks > 0) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: no batched blocks");
-    if (ld_out < num_dofs) return fail(PNB_ERR_ARG, "leading dimension too small");
-    ON_DEVICE(p->device);
-    if (num_dofs == 0) return 0;
-    // host output: assembled in a device buffer and copied back
-    double *A = A_out;
-    int64_t ld = ld_out;
-    if (!a_on_device) {
-        ld = num_dofs;
-        CK(pool_malloc((void **)&A, (size_t)num_dofs * num_dofs * sizeof(double)));
-    }
+    for (void *d : dev) cudaFree(d);
+    dev.clear();
+}
+
+static int elem_job_build(pnb_problem *p, int dpe, int num_dofs, const int32_t *dofs, ElemJob &J, std::vector<void *> &dev)
+{
     const int nc = p->nc;
     std::vector<int> dptr(num_dofs + 1, 0), dcells;
     for (int c = 0; c < nc; c++)
@@ -466,7 +455,6 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
                 if (d >= 0) dcells[pos[d]++] = c * 8 + m;
             }
     }
-    ElemJob J;
     J.N = num_dofs;
     J.dpe = dpe;
     std::vector<int> row_order(num_dofs);
@@ -517,7 +505,6 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
         cudaMalloc(&d_partners, std::max<size_t>(partners.size(), 1) * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order); cudaFree(d_partners);
-        if (!a_on_device) pool_free(A);
         return fail(PNB_ERR_CUDA, "out of device memory");
     }
     cudaMemcpy(d_edofs, dofs, (size_t)nc * dpe * sizeof(int), cudaMemcpyHostToDevice);
@@ -528,6 +515,40 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     cudaMemcpy(d_partners, partners.data(), partners.size() * sizeof(int), cudaMemcpyHostToDevice);
     J.edofs = d_edofs; J.dof_ptr = d_ptr; J.dof_cells = d_cells; J.err = d_err; J.row_order = d_order;
     J.partners = d_partners; J.npartners = (int)partners.size();
+    dev = {d_edofs, d_ptr, d_cells, d_err, d_order, d_partners};
+    return 0;
+}
+
+extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
+                                          int zero_exterior, double *A_out, int64_t ld_out, int a_on_device)
+{
+    if (!p || !dofs || !A_out) return fail(PNB_ERR_ARG, "null argument");
+    if (polynomial_order < 0 || polynomial_order > 3 || (polynomial_order == 3 && p->dim != 1))
+        return fail(PNB_ERR_UNSUPPORTED, "elements: P0, P1, P2; P3 on intervals");
+    const int dpe = polynomial_order == 0 ? 1 : (polynomial_order == 1 ? p->dim + 1 : (polynomial_order == 2 ? (p->dim == 1 ? 3 : 6) : 4));
+    if (dofs_per_element != dpe) return fail(PNB_ERR_ARG, "dofs_per_element does not match the element");
+    if (p->finite) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: infinite horizon only");
+    if (!p->h_labels.empty()) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: constant kernels only");
+    if (p->nblocks > 0) return fail(PNB_ERR_UNSUPPORTED, "elements other than P1: no batched blocks");
+    if (ld_out < num_dofs) return fail(PNB_ERR_ARG, "leading dimension too small");
+    ON_DEVICE(p->device);
+    if (num_dofs == 0) return 0;
+    // host output: assembled in a device buffer and copied back
+    double *A = A_out;
+    int64_t ld = ld_out;
+    if (!a_on_device) {
+        ld = num_dofs;
+        CK(pool_malloc((void **)&A, (size_t)num_dofs * num_dofs * sizeof(double)));
+    }
+    ElemJob J;
+    std::vector<void *> dev;
+    {
+        const int rc = elem_job_build(p, dpe, num_dofs, dofs, J, dev);
+        if (rc) {
+            if (!a_on_device) pool_free(A);
+            return rc;
+        }
+    }
     const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
     if (p->dim == 2) {
         if (polynomial_order == 2) elem_rows_kernel<2, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
@@ -542,8 +563,8 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     int herr = 0;
-    cudaMemcpy(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order); cudaFree(d_partners);
+    cudaMemcpy(&herr, J.err, sizeof(int), cudaMemcpyDeviceToHost);
+    elem_job_free(dev);
     if (!a_on_device) {
         if (e == cudaSuccess && herr == 0)
             e = cudaMemcpy2D(A_out, (size_t)ld_out * sizeof(double), A, (size_t)ld * sizeof(double), (size_t)num_dofs * sizeof(double),

@@ -225,6 +225,66 @@ class islandsFractionalOrder(_blockFractionalOrder):
                                                                                         self.r, self.r2, self.symmetric)
 
 
+class singleVariableUnsymmetricFractionalOrder:
+    """s(x, y) = sFun(x): an order that varies INSIDE the cells (fractionalOrders.pyx:153-183).  The kernel cannot be
+    piecewise (kernels.py:147-149): the reference evaluates order, scaling constant and kernel at every quadrature node
+    (updateAndEvalFractional, kernelsCy.pyx:596-622) inside the unsymmetric local matrices.  Device path:
+    pnb_dense_assemble_varorder; `orderFunction()` describes sFun to it (PNB_ORDERFUN_*)."""
+    symmetric = False
+    numParameters = 2
+    ORDERFUN_CONST, ORDERFUN_SMOOTHSTEP, ORDERFUN_LINEARSTEP, ORDERFUN_SMOOTHSTEP_RADIAL = 0, 1, 2, 3
+
+    def orderFunction(self):
+        return self.fun, self.sl, self.sr, self.r, self.slope, self.interface
+
+    def evaluate(self, points):
+        """s at an array of points (..., dim), the reference's formulas (fractionalOrders.pyx:389-416, 447-470)"""
+        t = np.asarray(points, dtype=np.float64)[..., 0]
+        if self.fun == self.ORDERFUN_LINEARSTEP:
+            v = self.sl+self.slope*(t-self.interface+self.r)
+        else:
+            u = (t-self.interface)*self.slope+0.5
+            v = self.sl+(self.sr-self.sl)*(3.0*u**2-2.0*u**3)
+        return np.where(t < self.interface-self.r, self.sl, np.where(t > self.interface+self.r, self.sr, v))
+
+    def __call__(self, x, y):
+        return float(self.evaluate(np.atleast_2d(np.asarray(x, dtype=float)))[0])
+
+
+class smoothedLeftRightFractionalOrder(singleVariableUnsymmetricFractionalOrder):
+    """sl left of interface - r, sr right of interface + r, a cubic step in between (fractionalOrders.pyx:641-645 with
+    smoothStep :389-416); the order of the driver flag `--s twoDomainNonSym(sl,sr)` (nonlocalProblems.py:95)"""
+    fun = singleVariableUnsymmetricFractionalOrder.ORDERFUN_SMOOTHSTEP
+
+    def __init__(self, sl, sr, r=0.1, slope=200., interface=0.):
+        self.sl, self.sr, self.r, self.interface = float(sl), float(sr), float(r), float(interface)
+        self.slope = 0.5/self.r
+        self.min, self.max = min(self.sl, self.sr), max(self.sl, self.sr)
+
+    def __repr__(self):
+        return 'smoothedLeftRightFractionalOrder(sl={},sr={},r={},interface={})'.format(self.sl, self.sr, self.r, self.interface)
+
+
+class linearLeftRightFractionalOrder(singleVariableUnsymmetricFractionalOrder):
+    """the same with a linear ramp (fractionalOrders.pyx:648-651 with linearStep :447-470)"""
+    fun = singleVariableUnsymmetricFractionalOrder.ORDERFUN_LINEARSTEP
+
+    def __init__(self, sl, sr, r=0.1, interface=0.):
+        self.sl, self.sr, self.r, self.interface = float(sl), float(sr), float(r), float(interface)
+        self.slope = 0.5*(self.sr-self.sl)/self.r
+        self.min, self.max = min(self.sl, self.sr), max(self.sl, self.sr)
+
+    def __repr__(self):
+        return 'linearLeftRightFractionalOrder(sl={},sr={},r={},interface={})'.format(self.sl, self.sr, self.r, self.interface)
+
+
+def variableFractionalLaplacianScaling(dim, s):
+    """C(d, s(x,y)) / 2 of a normalised kernel with infinite horizon (kernelNormalization.pyx:438-439); s may be an array"""
+    from scipy.special import gamma as gamma_
+    s = np.asarray(s, dtype=np.float64)
+    return 2.0**(2.0*s)*s*gamma_(s+0.5*dim)*pi**(-0.5*dim)/gamma_(1.0-s)*0.5
+
+
 class constant:
     """constant function, used for the horizon (fem functions.pyx)"""
 
@@ -303,6 +363,13 @@ class FractionalKernel:
         d2 = float(((x-y)**2).sum())
         if self.finiteHorizon and d2 > self.horizonValue2:
             return 0.
+        if isinstance(self.s, singleVariableUnsymmetricFractionalOrder):
+            # order and scaling per point (updateAndEvalFractional, kernelsCy.pyx:596-622); boundary form: phi = 1/s
+            sv = self.s(x, y)
+            C = float(variableFractionalLaplacianScaling(self.dim, sv))
+            if not self.boundary:
+                return C*pow(d2, -0.5*self.dim-sv)
+            return C/sv*pow(d2, -0.5*(self.dim-1)-sv)
         if not self.boundary:
             return self.scalingValue*pow(d2, -0.5*self.dim-self.sValue)
         return self.scalingValue*pow(d2, -0.5*(self.dim-1)-self.sValue)
@@ -448,6 +515,11 @@ def getFractionalKernel(dim, s, horizon=None, interaction=None, scaling=None, no
         # the scaling is a function of s(x,y) (variableFractionalLaplacianScaling, kernelNormalization.pyx:421-499):
         # evaluated per class by the builder
         return FractionalKernel(dim, sFun, horizonFun, np.nan, boundary=boundary, phi=phi, piecewise=piecewise)
+    if isinstance(sFun, singleVariableUnsymmetricFractionalOrder):
+        if horizonFun.value != np.inf or not normalized or scaling is not None or phi is not None:
+            raise NotImplementedError('orders varying inside a cell: infinite horizon, normalised kernels only')
+        # kernels.py:147-149: "Variable s kernels cannot be piecewise. Switching to piecewise == False."
+        return FractionalKernel(dim, sFun, horizonFun, np.nan, boundary=boundary, phi=None, piecewise=False)
     if not isinstance(sFun, constFractionalOrder):
         raise NotImplementedError('this variable fractional order is not supported yet')
     if scaling is None:

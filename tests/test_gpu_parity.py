@@ -1026,3 +1026,61 @@ def test_piecewise_order_with_a_single_block_in_the_mesh():
     Ac = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, pb.constantNonSymFractionalOrder(0.3)), params).getDense().data
     assert entry_err(An, Ac) < TOL
     assert 1e-9 < entry_err(Ac, A) < 1e-5      # the two orientations of the singular rules differ by their quadrature error
+
+
+def _varorder_from_fixture(pb, g):
+    kind = str(g['kind'])
+    if kind == 'smoothedLeftRight':
+        return pb.smoothedLeftRightFractionalOrder(float(g['sl']), float(g['sr']), r=float(g['r']), interface=float(g['interface']))
+    assert kind == 'linearLeftRight'
+    return pb.linearLeftRightFractionalOrder(float(g['sl']), float(g['sr']), r=float(g['r']), interface=float(g['interface']))
+
+
+@pytest.mark.parametrize('name', ['varorder_interval_smoothed_r5', 'varorder_interval_smoothed_r6', 'varorder_interval_linear_r5',
+                                  'varorder_disc_smoothed_r2', 'varorder_disc_smoothed_r3'])
+def test_order_varying_inside_cells_vs_reference(golden_dir, name):
+    """Orders that vary inside a cell, s(x,y) = sFun(x) (SURVEY 8 a12 updateAndEvalFractional, a13 variable scaling, a14
+    singleVariableUnsymmetricFractionalOrder; the driver's --s twoDomainNonSym): the reference's unsymmetric local matrices
+    over both orientations, order / scaling / kernel per quadrature node, a singular rule per pair singularity
+    (csrc/pnb_varorder.cuh) against operators assembled by the reference itself (make_golden_varorder.py)"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    dim = g['vertices'].shape[1]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'])
+    dm = pb.P1_DoFMap(mesh)
+    kernel = pb.getFractionalKernel(dim, _varorder_from_fixture(pb, g))
+    assert kernel.variable and not kernel.symmetric and not kernel.piecewise
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = pb.nonlocalBuilder(dm, kernel, params, zeroExterior=ze)
+        assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+        assert b.orders.bquad_order_diagonal == int(g['bquad_order_diagonal'])
+        A = b.getDense().data
+        assert entry_err(A, g[key]) < TOL
+        # bitwise reproducible (one writer per entry, fixed summation order)
+        assert np.array_equal(A, b.getDense().data)
+    with pytest.raises(NotImplementedError):
+        b.getH2()
+
+
+def test_order_varying_inside_cells_vs_oracle():
+    """the same path on meshes / orders without a reference fixture, against the numpy restatement oracle/varorder.py
+    (itself pinned to the reference's fixtures in test_oracle_golden.py): a linear ramp across the disc, an interface off
+    the mesh lines, a small max_regular_order so that the table retry runs"""
+    import pynucleus_b200 as pb
+    from oracle import varorder
+    mesh = pb.refined(pb.uniform_disc(), 2)
+    dm = pb.P1_DoFMap(mesh)
+    order = pb.linearLeftRightFractionalOrder(0.35, 0.65, r=0.4, interface=0.13)
+    b = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, order), {'target_order': 0.5, 'max_regular_order': 3})
+    A = b.getDense().data
+    Aref = varorder.dense(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, varorder.linearStep(0.35, 0.65, 0.4, 0.13),
+                          mesh.boundaryFacets, hmin=mesh.hmin, diam=mesh.diam)
+    assert entry_err(A, Aref) < TOL
+    mesh = pb.refined(pb.simpleInterval(-1, 1), 6)
+    dm = pb.P1_DoFMap(mesh)
+    order = pb.smoothedLeftRightFractionalOrder(0.2, 0.8, r=0.33, interface=-0.21)
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(1, order), {}).getDense().data
+    Aref = varorder.dense(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, varorder.smoothStep(0.2, 0.8, 0.33, -0.21),
+                          mesh.boundaryFacets, hmin=mesh.hmin, diam=mesh.diam)
+    assert entry_err(A, Aref) < TOL

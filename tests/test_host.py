@@ -301,3 +301,41 @@ def test_p2_dofmap_numbering_matches_reference(name):
     assert dm.num_dofs == int(g['num_dofs']) and dm.num_boundary_dofs == int(g['num_boundary_dofs'])
     assert np.array_equal(dm.dofs, g['dofs'])
     assert np.array_equal(dm.vertexPart().dofs, g['dofs'][:, :dim+1])
+
+
+@pytest.mark.parametrize('name', ['varorder_interval_smoothed_r6', 'varorder_interval_linear_r5', 'varorder_disc_smoothed_r3'])
+def test_orders_varying_inside_cells_host_side(golden_dir, name):
+    """host side of the path for orders s(x,y) = sFun(x) (no GPU needed): the order function and the kernel objects against
+    values of the reference's own objects, the quadrature orders against the reference's local matrices, the ranking of the
+    pair singularities against the oracle's evalParamsOnSimplices restatement"""
+    from oracle import varorder
+    g = np.load(os.path.join(golden_dir, name+'.npz'))
+    dim = g['vertices'].shape[1]
+    cls, ocls = ((pb.smoothedLeftRightFractionalOrder, varorder.smoothStep) if str(g['kind']) == 'smoothedLeftRight'
+                 else (pb.linearLeftRightFractionalOrder, varorder.linearStep))
+    order = cls(float(g['sl']), float(g['sr']), r=float(g['r']), interface=float(g['interface']))
+    sF = ocls(float(g['sl']), float(g['sr']), float(g['r']), float(g['interface']))
+    X, Y = g['points_x'], g['points_y']
+    assert np.abs(order.evaluate(X)-g['s_values']).max() < 1e-15
+    kernel = pb.getFractionalKernel(dim, order)
+    assert not kernel.piecewise and not kernel.symmetric and kernel.variable
+    kb = kernel.getBoundaryKernel()
+    for i in range(X.shape[0]):
+        assert abs(kernel(X[i], Y[i])/g['kernel_values'][i]-1) < 1e-14
+        assert abs(kb(X[i], Y[i])/g['bkernel_values'][i]-1) < 1e-14
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'])
+    dm = pb.P1_DoFMap(mesh)
+    b = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5} if dim == 2 else {})
+    assert b.orders.target_order == float(g['target_order_used']) and b.orders.btarget_order == float(g['btarget_order_used'])
+    assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+    assert b.orders.bquad_order_diagonal == int(g['bquad_order_diagonal'])
+    V = b._varorder
+    T = mesh.vertices[mesh.cells]
+    smax = np.maximum(sF(T.mean(axis=1)), sF(T).max(axis=1))
+    assert np.abs(V['values'][V['cell_value']]-smax).max() < 1e-15
+    assert (np.diff(V['values']) > 0).all() and V['values'][0] >= order.min and V['values'][-1] <= order.max
+    st = b._varorder_struct()
+    assert st.num_values == V['values'].shape[0] and st.identical[0].n > 0 and st.bvertex[st.num_values-1].n > 0
+    # nothing but getDense() may use the stand-in device problem of this path
+    with pytest.raises(NotImplementedError):
+        b.getEntry(0, 0)

@@ -314,3 +314,29 @@ def test_unsymmetric_piecewise_order_matches_reference(golden_dir, name):
             else:
                 A = A+0.5*problem(k, pc == k, 0).dense(ze)+0.5*problem(k, (pc == k).T, 1).dense(ze)
         assert np.abs(A-g[key]).max() < 1e-13*np.abs(g[key]).max()
+
+
+def _varorder_fun(g):
+    from oracle import varorder
+    cls = varorder.smoothStep if str(g['kind']) == 'smoothedLeftRight' else varorder.linearStep
+    return cls(float(g['sl']), float(g['sr']), float(g['r']), float(g['interface']))
+
+
+@pytest.mark.parametrize('name', ['varorder_interval_smoothed_r5', 'varorder_interval_linear_r5', 'varorder_interval_smoothed_r6',
+                                  'varorder_disc_smoothed_r2'])
+def test_order_varying_inside_cells_matches_reference(golden_dir, name):
+    """orders that vary inside a cell (kernel.piecewise == False; the driver's twoDomainNonSym): the numpy restatement
+    oracle/varorder.py against operators assembled by the reference itself (make_golden_varorder.py)"""
+    from oracle import varorder
+    g = np.load(os.path.join(golden_dir, name+'.npz'))
+    sF = _varorder_fun(g)
+    dim = g['vertices'].shape[1]
+    X, Y = g['points_x'], g['points_y']
+    assert np.abs(sF(X)-g['s_values']).max() < 1e-15
+    assert np.abs(varorder.kernel_value(dim, sF, X, Y)/g['kernel_values']-1).max() < 1e-14
+    assert np.abs(varorder.kernel_value(dim, sF, X, Y, True)/g['bkernel_values']-1).max() < 1e-14
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices']
+    for ze, key in ((False, 'A_interior'), (True, 'A')):
+        A = varorder.dense(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), sF, bf, zero_exterior=ze,
+                           hmin=float(g['hmin']), diam=float(g['diam']))
+        assert np.abs(A-g[key]).max() < 1e-12*np.abs(g[key]).max()
