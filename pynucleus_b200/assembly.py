@@ -783,8 +783,13 @@ class nonlocalBuilder:
         return A
 
     # -- H2 format ----------------------------------------------------------------
+    def _no_varorder(self):
+        if getattr(self, '_varorder', None) is not None:
+            raise NotImplementedError('only getDense() supports orders that vary inside a cell')
+
     def getTree(self):
         """root of the cluster tree (nonlocalAssembly_{SCALAR}.pxi:2541-2664, serial branch)"""
+        self._no_varorder()
         from .cluster_tree import build_tree
         self._no_dm2()
         return build_tree(self.mesh, self.dm, self.kernel, self.orders.target_order, self.params)
@@ -833,6 +838,7 @@ class nonlocalBuilder:
         operators as in the reference (node for node), far-field kernel blocks from the CUDA kernel, near field per
         near cluster pair from the dense device path on the cluster-union sub-mesh (h2.assemble_clusters).
         Falls back to getDense() when there is no admissible pair, like the reference (:3200-3209)."""
+        self._no_varorder()
         import torch
         from .cluster_tree import admissible_clusters
         from . import h2
