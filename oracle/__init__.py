@@ -38,7 +38,8 @@ class _Problem(ctypes.Structure):
                 ('max_order', ctypes.c_int),
                 ('reg_cell', ctypes.c_void_p), ('reg_facet', ctypes.c_void_p), ('order_num_dofs', ctypes.c_int),
                 ('labels', ctypes.c_void_p), ('blabels', ctypes.c_void_p), ('active_class', ctypes.c_int),
-                ('pair_class', ctypes.c_ubyte*16), ('bpair_class', ctypes.c_ubyte*16), ('pair_orientation', ctypes.c_int)]
+                ('pair_class', ctypes.c_ubyte*16), ('bpair_class', ctypes.c_ubyte*16), ('pair_orientation', ctypes.c_int),
+                ('tempered', ctypes.c_double)]
 
 
 def build():
@@ -68,7 +69,7 @@ class Problem:
     def __init__(self, vertices, cells, dofs, num_dofs, s, bfacets=None, target_order=None,
                  hVector=None, volVector=None, hmin=None, diam=None, max_order=None, order_num_dofs=None,
                  s_max=None, labels=None, blabels=None, pair_class=None, active_class=0, bpair_class=None,
-                 pair_orientation=0, s_min=None):
+                 pair_orientation=0, s_min=None, tempered=0.):
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         self.dofs = np.ascontiguousarray(dofs, dtype=np.int32)
@@ -86,7 +87,7 @@ class Problem:
         dim = self.dim
         self.singularity = -dim-2*s
         self.bsingularity = 1.-dim-2*s
-        self.C = tables.fractional_scaling(dim, s)
+        self.C = tables.fractional_scaling(dim, s, tempered=tempered)
         self.Cb = self.C*(1./s)      # phi = 1/s, kernels.py:151-160, kernelsCy.pyx:1990-1995
         # two DoFMaps: the local matrices (orders, getQuadOrder) keep the DoF count of the first map
         self.order_num_dofs = int(order_num_dofs) if order_num_dofs else self.num_dofs
@@ -119,6 +120,7 @@ class Problem:
             for i, v in enumerate(np.asarray(pair_class if bpair_class is None else bpair_class, dtype=np.uint8).ravel()):
                 P.bpair_class[i] = int(v)
             P.pair_orientation = int(pair_orientation)
+        P.tempered = float(tempered)
         P.nb = self.bfacets.shape[0]
         P.bfacets = self.bfacets.ctypes.data
         P.H0 = self.H0

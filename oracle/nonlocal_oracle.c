@@ -75,6 +75,10 @@ typedef struct {
     /* Unsymmetric piecewise orders: the reference visits (c1,c2) and (c2,c1) (NA.pxi:1412-1428); pair_orientation 1
      * evaluates the second visit, i.e. the touching pair with the cell of the larger index as first cell of the rule */
     int pair_orientation;
+    /* tempered fractional kernel (temperedFracKernelInfinite*, kernelsCy.pyx:186-213): interior kernel times
+     * exp(-tempered |x-y|); the boundary kernel stays the plain power law (getBoundaryKernel, kernelsCy.pyx:2011-2020,
+     * does not hand `tempered` on).  0 = not tempered */
+    double tempered;
 } orc_problem;
 #define ORDN(P) ((P)->order_num_dofs > 0 ? (P)->order_num_dofs : (P)->num_dofs)
 
@@ -189,8 +193,10 @@ static double kernel_interior(const orc_problem *P, const double *x, const doubl
     double d2 = (x[0] - y[0]) * (x[0] - y[0]);
     if (P->dim == 2) {
         d2 += (x[1] - y[1]) * (x[1] - y[1]);
+        if (P->tempered != 0.) return P->C * pow(d2, -1. - P->s) * exp(-P->tempered * sqrt(d2));
         return P->C * pow(d2, -1. - P->s);
     }
+    if (P->tempered != 0.) return P->C * pow(d2, -0.5 - P->s) * exp(-P->tempered * sqrt(d2));
     return P->C * pow(d2, -0.5 - P->s);
 }
 

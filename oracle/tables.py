@@ -257,12 +257,14 @@ def near_rules(dim, singularity, boundary_singularity, orders, poly_order=1):
     return rules
 
 
-def fractional_scaling(dim, s, horizon=np.inf):
-    """kernelNormalization.pyx:70-89 (untempered)."""
+def fractional_scaling(dim, s, horizon=np.inf, tempered=0.):
+    """kernelNormalization.pyx:70-89"""
     from scipy.special import gamma
     from math import pi
     if horizon < np.inf:
         return (2.-2*s) * pow(horizon, 2*s-2.) * dim * gamma(0.5*dim)/pow(pi, 0.5*dim) * 0.5
+    if tempered != 0. and s != 0.5:
+        return gamma(0.5*dim) / abs(gamma(-2*s))/pow(pi, 0.5*dim) * 0.5 * 0.5
     return 2.0**(2.0*s) * s * gamma(s+0.5*dim)/pow(pi, 0.5*dim)/gamma(1.0-s) * 0.5
 
 

@@ -340,3 +340,35 @@ def test_order_varying_inside_cells_matches_reference(golden_dir, name):
         A = varorder.dense(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), sF, bf, zero_exterior=ze,
                            hmin=float(g['hmin']), diam=float(g['diam']))
         assert np.abs(A-g[key]).max() < 1e-12*np.abs(g[key]).max()
+
+
+def test_order_varying_inside_cells_reproduces_cached_driver_run():
+    """oracle/varorder.py against the reference's cached driver result
+    tests/cache_runFractional.py--domaininterval--stwoDomainNonSym(0.25,0.75)--problemknownSolution--elementP1--solverlu--matrixFormatdense
+    (127 DoFs, u = (1-x^2)^0.7): interpolated L2 and Linf errors of the discrete solution"""
+    from scipy.special import hyp2f1, gamma as Gamma
+    from oracle import varorder
+    m = meshes.interval(-1., 1., 7)
+    dofs, n = meshes.p1_dofs(m)
+    assert n == 127
+    sF = varorder.smoothStep(0.25, 0.75, 0.1, 0.)
+    A = varorder.dense(m.vertices, m.cells, dofs, n, sF, m.boundary_facets())
+    beta = 0.7
+    bary, w = tables.regular_rule(3, 1)            # simplexXiaoGimbutas(3, 1), discretizedProblems.py:561
+    T = m.vertices[m.cells][:, :, 0]
+    pts = np.einsum('kq,ck->cq', bary, T)
+    s = sF(pts[..., None])
+    f = 2**(2*s)*Gamma(s+0.5)*Gamma(beta+1.)/np.sqrt(np.pi)/Gamma(beta+1.-s)*hyp2f1(s+0.5, -beta+s, 0.5, pts**2)
+    vol = np.abs(T[:, 1]-T[:, 0])
+    b, M, xs = np.zeros(n), np.zeros((n, n)), np.zeros(n)
+    for k in range(2):
+        ok = dofs[:, k] >= 0
+        np.add.at(b, dofs[ok, k], (vol[:, None]*f*w*bary[k]).sum(axis=1)[ok])
+        xs[dofs[ok, k]] = T[ok, k]
+        for l in range(2):
+            ok2 = ok & (dofs[:, l] >= 0)
+            np.add.at(M, (dofs[ok2, k], dofs[ok2, l]), (2. if k == l else 1.)*vol[ok2]/6.)
+    u = np.linalg.solve(A, b)
+    e = u-(1-xs**2)**beta
+    assert abs(np.abs(e).max()/0.003599161364716205-1) < 1e-8
+    assert abs(np.sqrt(e.dot(M.dot(e)))/0.001265060713568335-1) < 1e-8
