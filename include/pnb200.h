@@ -312,6 +312,14 @@ int pnb_farfield_blocks(pnb_problem *p, int64_t nblk, const double *boxes1, cons
  * memory if a_on_device != 0, else host memory (assembled on the device and copied back). */
 int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
                                int zero_exterior, double *A, int64_t ld, int a_on_device);
+/* The same for TEMPERED fractional kernels gamma(x,y) = C |x-y|^(-d-2s) exp(-tempered |x-y|) (temperedFracKernelInfinite*,
+ * kernelsCy.pyx:186-213; any element incl. P1).  `p` carries the power law with the tempered scaling constant
+ * (constantFractionalLaplacianScaling, kernelNormalization.pyx:84-88) as kernel.scaling; the surface terms use the boundary
+ * kernel of `p` as it is: the reference's getBoundaryKernel (kernelsCy.pyx:1982-2027) does not hand the tempering on, so its
+ * zero-exterior terms are the untempered power law with the tempered constant / s.  tempered = 0: the plain kernel. */
+int pnb_dense_assemble_element_tempered(pnb_problem *p, double tempered, int polynomial_order, int dofs_per_element,
+                                        int num_dofs, const int32_t *dofs, int zero_exterior, double *A, int64_t ld,
+                                        int a_on_device);
 
 /* Dense operator for a fractional order that VARIES INSIDE A CELL: s(x, y) = sFun(x), kernel.piecewise == False
  * (singleVariableUnsymmetricFractionalOrder, fractionalOrders.pyx:153-183; smoothedLeftRightFractionalOrder :641-645 is the

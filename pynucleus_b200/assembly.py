@@ -167,12 +167,14 @@ class nonlocalBuilder:
     def setKernel(self, kernel, zeroExterior=True):
         from .kernels import constFractionalOrder, getFractionalKernel, singleVariableUnsymmetricFractionalOrder
         self._classes = None
-        self._element = self.dm.polynomialOrder != 1
+        # tempered kernels run on the row-owner kernel of the element path for every element, P1 included
+        self._tempered = float(getattr(kernel, 'tempered', 0.))
+        self._element = self.dm.polynomialOrder != 1 or self._tempered != 0.
         if self._element:
-            if self.dm.polynomialOrder not in (0, 2, 3):
+            if self.dm.polynomialOrder not in (0, 1, 2, 3):
                 raise NotImplementedError('P0, P1, P2 and (intervals) P3 elements')
             if self.dm2 is not None or hasattr(kernel.s, 'blockOrders') or kernel.finiteHorizon:
-                raise NotImplementedError('P0 / P2 elements: one DoFMap, constant kernels with infinite horizon')
+                raise NotImplementedError('P0 / P2 elements and tempered kernels: one DoFMap, constant orders with infinite horizon')
             if self.dm.polynomialOrder == 0 and not kernel.max_singularity > -1.-self.mesh.dim:
                 # fractionalLaplacian2D.pyx:596-598, fractionalLaplacian1D.pyx:212-214
                 raise AssertionError('Discontinuous finite elements are not conforming for singularity order {} <= {}.'.format(
@@ -328,7 +330,7 @@ class nonlocalBuilder:
             if self._element:
                 # P2: the device problem holds mesh, kernel and tables behind the vertex dofs; the element's table goes to
                 # pnb_dense_assemble_element (row-owner kernel, csrc/pnb_element.cuh)
-                dm_dev, ond = self.dm.vertexPart(), self.dm.num_dofs
+                dm_dev, ond = (self.dm.vertexPart() if self.dm.polynomialOrder != 1 else self.dm), self.dm.num_dofs
             kern, bkern = self.kernel, self.kernelBoundary
             if self._varorder is not None:
                 # mesh, regular tables and order constants; the kernel values come from pnb_varorder_t
@@ -371,6 +373,8 @@ class nonlocalBuilder:
     def getLocalMatrices(self, pairs, boundary=False, path=0):
         """local_matrix.eval(contrib, panel) for the given pairs -> (panel, contrib[n, nloc])"""
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        if getattr(self, '_tempered', 0.) != 0. and not boundary:
+            raise NotImplementedError('only getDense() supports tempered kernels')
         n = pairs.shape[0]
         nvc = self.mesh.dim+1
         nloc = nvc*(nvc+1)//2 if boundary else (2*nvc)*(2*nvc+1)//2
@@ -423,8 +427,9 @@ class nonlocalBuilder:
         def run():
             if self._element:
                 ed = np.ascontiguousarray(self.dm.dofs, dtype=np.int32)
-                _lib.check(_lib.lib().pnb_dense_assemble_element(prob.handle, self.dm.polynomialOrder, self.dm.dofs_per_element, N,
-                                                                 ed.ctypes.data, int(self.zeroExterior), A.data_ptr(), A.stride(0), 1))
+                _lib.check(_lib.lib().pnb_dense_assemble_element_tempered(prob.handle, self._tempered, self.dm.polynomialOrder,
+                                                                          self.dm.dofs_per_element, N, ed.ctypes.data,
+                                                                          int(self.zeroExterior), A.data_ptr(), A.stride(0), 1))
             else:
                 _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.data_ptr(),
                                                          A.stride(0), 1))
@@ -555,7 +560,7 @@ class nonlocalBuilder:
         if self.dm2 is not None:
             raise NotImplementedError('only getDense() supports two DoFMaps')
         if self._element:
-            raise NotImplementedError('only getDense() supports P2 elements')
+            raise NotImplementedError('only getDense() supports P0 / P2 / P3 elements and tempered kernels')
 
     def getDenseRowBlock(self, row_begin, row_end, out=None, process_group=None):
         """Rows [row_begin, row_end) of getDense() on this process' GPU (contiguous row blocks: 1D problems and

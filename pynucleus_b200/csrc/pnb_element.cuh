@@ -55,7 +55,7 @@ template <int DIM, int PORD> __device__ __forceinline__ void elem_shape(const do
 // by the volume factor; partial sums of this lane.
 template <int DIM, int PORD>
 __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, const int *perm1, const int *perm2, int sLo, int sHi,
-                              int lane, int nlanes, double *acc)
+                              int lane, int nlanes, double *acc, double tempered = 0.)
 {
     constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
     double t1[3][2], t2[3][2];
@@ -93,7 +93,8 @@ __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, cons
                 if (k == sLo) psiI += px[k];
                 if (k == sHi) psiI -= py[k];
             }
-            const double g = (r.w[i] * r.w[j]) * kv(d2) * psiI;
+            // tempered kernels: times exp(-lambda |x-y|) (temperedFracKernelInfinite*, kernelsCy.pyx:186-213)
+            const double g = (r.w[i] * r.w[j]) * (tempered != 0. ? kv(d2) * exp(-tempered * sqrt(d2)) : kv(d2)) * psiI;
 #pragma unroll
             for (int k = 0; k < DPE; k++) {
                 acc[k] = fma(g, px[k], acc[k]);
@@ -148,7 +149,7 @@ __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, cons
                 if (k == sLo) psiI += px[k];
                 if (k == sHi) psiI -= py[k];
             }
-            const double g = r.w[q] * kv(d2) * psiI;
+            const double g = r.w[q] * (tempered != 0. ? kv(d2) * exp(-tempered * sqrt(d2)) : kv(d2)) * psiI;
 #pragma unroll
             for (int k = 0; k < DPE; k++) {
                 acc[k] = fma(g, px[k], acc[k]);
@@ -282,6 +283,7 @@ struct ElemJob {
     const int *partners;    // all cells in batches of 32 that share no vertex (-1: padding), colour by colour
     int npartners;          // length of `partners` (a multiple of 32)
     int *err;               // [0]: regular order missing in the tables
+    double tempered;        // tempered fractional kernel: interior kernel times exp(-tempered |x-y|); 0 = not tempered
 };
 
 template <int DIM, int PORD>
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
                 if (mine_far) {
                     const int lo = min(c1, c2), hi = max(c1, c2);
                     double acc[2 * DPE];
-                    elem_pair_row<DIM, PORD>(P, lo, hi, pan, p1, p2, lo == c1 ? sI1 : -1, hi == c1 ? sI1 : -1, 0, 1, acc);
+                    elem_pair_row<DIM, PORD>(P, lo, hi, pan, p1, p2, lo == c1 ? sI1 : -1, hi == c1 ? sI1 : -1, 0, 1, acc, J.tempered);
                     const double sc = 2.0 * P.vol[lo] * P.vol[hi];
 #pragma unroll
                     for (int k = 0; k < DPE; k++) {
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
                 const int lo = min(c1, c2s), hi = max(c1, c2s);
                 const int sLo = lo == c1 ? sI1 : sI2s, sHi = hi == c1 ? sI1 : sI2s;
                 double acc[2 * DPE];
-                elem_pair_row<DIM, PORD>(P, lo, hi, pans, q1, q2, sLo, sHi, lane, 32, acc);
+                elem_pair_row<DIM, PORD>(P, lo, hi, pans, q1, q2, sLo, sHi, lane, 32, acc, J.tempered);
                 warp_allreduce<2 * DPE>(acc);
                 // volume factors: vol1 vol2 (nonlocalOperator_{SCALAR}.pxi:756), 4 vol1 vol2 for the singular 2D rules
                 // (fractionalLaplacian2D.pyx:851); off-diagonal pairs count twice (nonlocalAssembly_{SCALAR}.pxi:1404-1410)
@@ -457,6 +459,7 @@ static int elem_job_build(pnb_problem *p, int dpe, int num_dofs, const int32_t *
     }
     J.N = num_dofs;
     J.dpe = dpe;
+    J.tempered = 0.;
     std::vector<int> row_order(num_dofs);
     for (int i = 0; i < num_dofs; i++) row_order[i] = i;
     std::stable_sort(row_order.begin(), row_order.end(), [&](int a, int b) { return dptr[a + 1] - dptr[a] > dptr[b + 1] - dptr[b]; });
@@ -522,7 +525,16 @@ static int elem_job_build(pnb_problem *p, int dpe, int num_dofs, const int32_t *
 extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_per_element, int num_dofs, const int32_t *dofs,
                                           int zero_exterior, double *A_out, int64_t ld_out, int a_on_device)
 {
+    return pnb_dense_assemble_element_tempered(p, 0., polynomial_order, dofs_per_element, num_dofs, dofs, zero_exterior, A_out, ld_out,
+                                               a_on_device);
+}
+
+extern "C" int pnb_dense_assemble_element_tempered(pnb_problem *p, double tempered, int polynomial_order, int dofs_per_element,
+                                                   int num_dofs, const int32_t *dofs, int zero_exterior, double *A_out, int64_t ld_out,
+                                                   int a_on_device)
+{
     if (!p || !dofs || !A_out) return fail(PNB_ERR_ARG, "null argument");
+    if (!(tempered >= 0.) || !(tempered < INFINITY)) return fail(PNB_ERR_ARG, "the tempering rate must be finite and >= 0");
     if (polynomial_order < 0 || polynomial_order > 3 || (polynomial_order == 3 && p->dim != 1))
         return fail(PNB_ERR_UNSUPPORTED, "elements: P0, P1, P2; P3 on intervals");
     const int dpe = polynomial_order == 0 ? 1 : (polynomial_order == 1 ? p->dim + 1 : (polynomial_order == 2 ? (p->dim == 1 ? 3 : 6) : 4));
@@ -549,6 +561,7 @@ extern "C" int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, 
             return rc;
         }
     }
+    J.tempered = tempered;
     const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
     if (p->dim == 2) {
         if (polynomial_order == 2) elem_rows_kernel<2, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);

@@ -315,10 +315,12 @@ class FractionalKernel:
     kernelType = FRACTIONAL
     valueSize = 1
 
-    def __init__(self, dim, s, horizon, scaling, boundary=False, phi=None, piecewise=True):
+    def __init__(self, dim, s, horizon, scaling, boundary=False, phi=None, piecewise=True, tempered=0.):
         self.dim = int(dim)
         self.s = s
         self.horizon = horizon
+        # tempered kernel C |x-y|^(-d-2s) exp(-tempered |x-y|) (temperedFracKernelInfinite*, kernelsCy.pyx:186-213)
+        self.tempered = float(tempered)
         self.boundary = boundary
         self.piecewise = piecewise
         self.phi = phi
@@ -354,6 +356,8 @@ class FractionalKernel:
     def getBoundaryKernel(self):
         """kernel of the Gauss-theorem surface term, scaled by 1/s (kernelsCy.pyx:1982-2027)"""
         phi = 1./self.s.value if hasattr(self.s, 'value') else None
+        # `tempered` is not handed on (kernelsCy.pyx:2011-2020): the surface terms of a tempered kernel are the plain power
+        # law with the tempered scaling constant
         return FractionalKernel(self.dim, self.s, self.horizon, self.scalingPrePhi, boundary=True,
                                 phi=phi, piecewise=self.piecewise)
 
@@ -371,12 +375,16 @@ class FractionalKernel:
                 return C*pow(d2, -0.5*self.dim-sv)
             return C/sv*pow(d2, -0.5*(self.dim-1)-sv)
         if not self.boundary:
+            if self.tempered != 0.:
+                return self.scalingValue*pow(d2, -0.5*self.dim-self.sValue)*np.exp(-self.tempered*np.sqrt(d2))
             return self.scalingValue*pow(d2, -0.5*self.dim-self.sValue)
         return self.scalingValue*pow(d2, -0.5*(self.dim-1)-self.sValue)
 
     def __repr__(self):
-        return 'kernel(fractional, s={}, horizon={}, scaling={}{})'.format(self.s, self.horizonValue, self.scalingValue,
-                                                                         ', boundary' if self.boundary else '')
+        return 'kernel({}fractional, s={}, horizon={}, scaling={}{}{})'.format('tempered-' if self.tempered != 0. else '', self.s,
+                                                                             self.horizonValue, self.scalingValue,
+                                                                             ', tempered={}'.format(self.tempered) if self.tempered != 0. else '',
+                                                                             ', boundary' if self.boundary else '')
 
 
 INDICATOR, PERIDYNAMIC = 1, 2      # kernel_params.pxi:88-90
@@ -503,8 +511,11 @@ def getFractionalKernel(dim, s, horizon=None, interaction=None, scaling=None, no
     dim = getattr(dim, 'dim', dim)
     sFun = _getFractionalOrder(s)
     horizonFun = _getHorizon(horizon)
-    if derivative != 0 or tempered != 0. or manifold:
-        raise NotImplementedError('derivative / tempered / manifold kernels are outside the accelerated path')
+    if derivative != 0 or manifold:
+        raise NotImplementedError('derivative / manifold kernels are outside the accelerated path')
+    if tempered != 0. and (not isinstance(sFun, constFractionalOrder) or isinstance(sFun, variableConstFractionalOrder)
+                           or horizonFun.value != np.inf or boundary):
+        raise NotImplementedError('tempered kernels: constant order, infinite horizon')
     if isinstance(sFun, _blockFractionalOrder):
         if horizonFun.value != np.inf or not normalized or scaling is not None:
             raise NotImplementedError('piecewise orders: infinite horizon, normalised kernels only')
@@ -526,7 +537,7 @@ def getFractionalKernel(dim, s, horizon=None, interaction=None, scaling=None, no
         scaling = constantFractionalLaplacianScaling(dim, sFun.value, horizonFun.value, tempered) if normalized else 0.5
     if boundary and phi is None:
         phi = 1./sFun.value
-    return FractionalKernel(dim, sFun, horizonFun, scaling, boundary=boundary, phi=phi, piecewise=piecewise)
+    return FractionalKernel(dim, sFun, horizonFun, scaling, boundary=boundary, phi=phi, piecewise=piecewise, tempered=tempered)
 
 
 def getKernel(dim, s=None, horizon=None, scaling=None, interaction=None, normalized=True, piecewise=True, phi=None,

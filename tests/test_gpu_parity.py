@@ -1144,3 +1144,51 @@ def test_driver_known_answer_two_domain_nonsym(domain, noRef, ref, tol):
     print(domain, dm.num_dofs, L2, L2i, Linf)
     assert abs(L2i/ref[1]-1) < tol and abs(Linf/ref[2]-1) < tol
     assert abs(L2/ref[0]-1) < max(tol, 1e-6)
+
+
+TEMPERED_CASES = ['tempered_interval_s0.75_l2_r5', 'tempered_interval_s0.25_l0.5_r6', 'tempered_disc_s0.75_l2_r2',
+                  'tempered_disc_s0.25_l1_r3', 'tempered_p2_interval_s0.75_l1.5_r4', 'tempered_p2_disc_s0.75_l1.5_r1']
+
+
+@pytest.mark.parametrize('name', TEMPERED_CASES)
+def test_tempered_kernel_vs_reference(golden_dir, name):
+    """tempered fractional kernels C |x-y|^(-d-2s) exp(-lambda |x-y|) (SURVEY 8 a12 temperedFracKernelInfinite*, a13 the
+    tempered scaling constant) on the row-owner kernel (P1 and P2), against operators assembled by the reference itself
+    (make_golden_tempered.py); the surface terms are the untempered power law, as in the reference"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    dim = g['vertices'].shape[1]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'])
+    dm = pb.P2_DoFMap(mesh) if str(g['element']) == 'P2' else pb.P1_DoFMap(mesh)
+    assert dm.num_dofs == int(g['num_dofs'])
+    kernel = pb.getFractionalKernel(dim, float(g['s']), tempered=float(g['tempered']))
+    assert abs(kernel.scalingValue/float(g['scaling'])-1) < 1e-14
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = pb.nonlocalBuilder(dm, kernel, params, zeroExterior=ze)
+        assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+        A = b.getDense().data
+        assert entry_err(A, g[key]) < TOL
+        assert np.array_equal(A, A.T)
+    with pytest.raises(NotImplementedError):
+        b.getH2()
+    with pytest.raises(NotImplementedError):
+        b.getEntry(0, 0)
+
+
+def test_tempered_kernel_larger_mesh_vs_oracle():
+    """tempered kernel on a mesh without a fixture against the C oracle (pinned to the fixtures in test_oracle_golden.py);
+    lambda -> 0 recovers the production path's operator up to the scaling constant"""
+    import pynucleus_b200 as pb
+    import oracle
+    mesh = pb.refined(pb.uniform_disc(), 4)
+    dm = pb.P1_DoFMap(mesh)
+    s, lam = 0.6, 3.0
+    A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(2, s, tempered=lam), {'target_order': 0.5}).getDense().data
+    P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, s, bfacets=mesh.boundaryFacets, target_order=0.5,
+                       tempered=lam)
+    assert entry_err(A, P.dense(True)) < TOL
+    k0, kt = pb.getFractionalKernel(2, s), pb.getFractionalKernel(2, s, tempered=1e-300)
+    A0 = pb.nonlocalBuilder(dm, k0, {'target_order': 0.5}).getDense().data
+    At = pb.nonlocalBuilder(dm, kt, {'target_order': 0.5}).getDense().data
+    assert entry_err(At*(k0.scalingValue/kt.scalingValue), A0) < TOL

@@ -339,3 +339,21 @@ def test_orders_varying_inside_cells_host_side(golden_dir, name):
     # nothing but getDense() may use the stand-in device problem of this path
     with pytest.raises(NotImplementedError):
         b.getEntry(0, 0)
+
+
+@pytest.mark.parametrize('name', ['tempered_interval_s0.75_l2_r5', 'tempered_disc_s0.25_l1_r3'])
+def test_tempered_kernel_objects_match_reference(golden_dir, name):
+    """kernel objects of the tempered fractional kernels against values of the reference's own objects: interior kernel with
+    the exponential factor, boundary kernel without it (getBoundaryKernel does not hand `tempered` on)"""
+    g = np.load(os.path.join(golden_dir, name+'.npz'))
+    dim = g['vertices'].shape[1]
+    kernel = pb.getFractionalKernel(dim, float(g['s']), tempered=float(g['tempered']))
+    kb = kernel.getBoundaryKernel()
+    assert kernel.tempered == float(g['tempered']) and kb.tempered == 0.
+    assert abs(kernel.scalingValue/float(g['scaling'])-1) < 1e-14 and abs(kb.scalingValue/float(g['bscaling'])-1) < 1e-14
+    X, Y = g['points_x'], g['points_y']
+    for i in range(X.shape[0]):
+        assert abs(kernel(X[i], Y[i])/g['kernel_values'][i]-1) < 1e-14
+        assert abs(kb(X[i], Y[i])/g['bkernel_values'][i]-1) < 1e-14
+    with pytest.raises(NotImplementedError):
+        pb.getFractionalKernel(dim, float(g['s']), horizon=0.3, tempered=1.)

@@ -372,3 +372,18 @@ def test_order_varying_inside_cells_reproduces_cached_driver_run():
     e = u-(1-xs**2)**beta
     assert abs(np.abs(e).max()/0.003599161364716205-1) < 1e-8
     assert abs(np.sqrt(e.dot(M.dot(e)))/0.001265060713568335-1) < 1e-8
+
+
+@pytest.mark.parametrize('name', ['tempered_interval_s0.75_l2_r5', 'tempered_interval_s0.25_l0.5_r6', 'tempered_disc_s0.75_l2_r2',
+                                  'tempered_disc_s0.25_l1_r3'])
+def test_tempered_kernel_matches_reference(golden_dir, name):
+    """tempered fractional kernels in the C restatement against operators assembled by the reference (make_golden_tempered.py)"""
+    g = np.load(os.path.join(golden_dir, name+'.npz'))
+    dim = g['vertices'].shape[1]
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices'].reshape(-1, 1)
+    P = oracle.Problem(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), float(g['s']), bfacets=bf,
+                       target_order=0.5 if dim == 2 else None, hVector=g['hVector'], volVector=g['volVector'],
+                       hmin=float(g['hmin']), diam=float(g['diam']), tempered=float(g['tempered']))
+    assert abs(P.C/float(g['scaling'])-1) < 1e-14 and abs(P.Cb/float(g['bscaling'])-1) < 1e-14
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        assert np.abs(P.dense(ze)-g[key]).max() < 1e-13*np.abs(g[key]).max()
