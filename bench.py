@@ -639,6 +639,23 @@ def widening_leg(dev):
                      'min_diagonal': float(torch.diagonal(d).min())}
         del A4, b4
     out['finite_horizon'] = {'workload': 'disc r=6, N={}, horizon 0.15 (l2 ball), P1, dense'.format(dm.num_dofs), **fin}
+    # kernels outside the power-table path, on the row-owner kernels: an order that varies inside the cells (the driver's
+    # twoDomainNonSym: order, scaling constant and a general power per quadrature node) and a tempered kernel
+    mesh = pb.refined(pb.uniform_disc(), 5)
+    dm = pb.P1_DoFMap(mesh)
+    for name, k, kern in (('order_inside_cells', pb.getFractionalKernel(2, pb.smoothedLeftRightFractionalOrder(0.25, 0.75)), 'varorder_rows_kernel<2,1>'),
+                          ('tempered', pb.getFractionalKernel(2, S_ORDER, tempered=2.), 'elem_rows_kernel<2,1>')):
+        try:
+            b5 = pb.nonlocalBuilder(dm, k, params)
+            A5 = b5.getDense()
+            ms = _event_ms(lambda: b5.getDense(out=A5.device_data), 2, warm=1)
+            d = A5.device_data
+            out[name] = {'workload': 'disc r=5, N={}, {}'.format(dm.num_dofs, k), 'ms_per_assembly': ms,
+                         'entries_per_s': dm.num_dofs**2/(ms*1e-3), 'asymmetry_rel': float((d-d.t()).abs().max()/d.abs().max()),
+                         'min_diagonal': float(torch.diagonal(d).min()), 'kernel': kern}
+            del A5, b5
+        except Exception as e:
+            out[name] = {'error': '{}: {}'.format(type(e).__name__, str(e)[:200])}
     return out
 
 
