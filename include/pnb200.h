@@ -320,6 +320,22 @@ int pnb_dense_assemble_element(pnb_problem *p, int polynomial_order, int dofs_pe
 int pnb_dense_assemble_element_tempered(pnb_problem *p, double tempered, int polynomial_order, int dofs_per_element,
                                         int num_dofs, const int32_t *dofs, int zero_exterior, double *A, int64_t ld,
                                         int a_on_device);
+/* The general form: kernels gamma(x,y) = C |x-y|^e f(|x-y|) whose power law (C, e) is the interior kernel of `p` and whose
+ * boundary kernel is the boundary power law of `p` times another smooth factor.  Serves the integrable kernels with infinite
+ * horizon of the reference's driver tests (tests/test_drivers_intFracLapl.py:42-43), with e = 0:
+ *   Gaussian    C exp(-a r^2), a = 1/(2 variance^d) (gaussianKernel*, kernelsCy.pyx:388-415; Kernel.__init__ :690-695);
+ *               boundary 1D  C sqrt(pi/a) erfc(sqrt(a) r)  (:418-430),  2D  C/a exp(-a r^2)/r  (:433-445)
+ *   exponential C exp(-a r), boundary 2C/a exp(-a r)  (:448-477)
+ * Create `p` as a fractional problem with singularity = bsingularity = 0, scaling = C, bscaling = the constant of the
+ * boundary form, infinite horizon. */
+#define PNB_SMOOTH_NONE 0
+#define PNB_SMOOTH_EXP_R 1          /* exp(-a |x-y|)   */
+#define PNB_SMOOTH_EXP_R2 2         /* exp(-a |x-y|^2) */
+#define PNB_SMOOTH_ERFC_R 3         /* erfc(sqrt(a) |x-y|): boundary factor only */
+#define PNB_SMOOTH_EXP_R2_OVER_R 4  /* exp(-a |x-y|^2) / |x-y|: boundary factor only (2D) */
+int pnb_dense_assemble_element_smooth(pnb_problem *p, int mode, double a, int bmode, double ba, int polynomial_order,
+                                      int dofs_per_element, int num_dofs, const int32_t *dofs, int zero_exterior, double *A,
+                                      int64_t ld, int a_on_device);
 
 /* Dense operator for a fractional order that VARIES INSIDE A CELL: s(x, y) = sFun(x), kernel.piecewise == False
  * (singleVariableUnsymmetricFractionalOrder, fractionalOrders.pyx:153-183; smoothedLeftRightFractionalOrder :641-645 is the

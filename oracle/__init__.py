@@ -39,7 +39,8 @@ class _Problem(ctypes.Structure):
                 ('reg_cell', ctypes.c_void_p), ('reg_facet', ctypes.c_void_p), ('order_num_dofs', ctypes.c_int),
                 ('labels', ctypes.c_void_p), ('blabels', ctypes.c_void_p), ('active_class', ctypes.c_int),
                 ('pair_class', ctypes.c_ubyte*16), ('bpair_class', ctypes.c_ubyte*16), ('pair_orientation', ctypes.c_int),
-                ('tempered', ctypes.c_double)]
+                ('tempered', ctypes.c_double), ('smode', ctypes.c_int), ('bmode', ctypes.c_int),
+                ('sa', ctypes.c_double), ('ba', ctypes.c_double)]
 
 
 def build():
@@ -69,7 +70,7 @@ class Problem:
     def __init__(self, vertices, cells, dofs, num_dofs, s, bfacets=None, target_order=None,
                  hVector=None, volVector=None, hmin=None, diam=None, max_order=None, order_num_dofs=None,
                  s_max=None, labels=None, blabels=None, pair_class=None, active_class=0, bpair_class=None,
-                 pair_orientation=0, s_min=None, tempered=0.):
+                 pair_orientation=0, s_min=None, tempered=0., smooth=None):
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         self.dofs = np.ascontiguousarray(dofs, dtype=np.int32)
@@ -89,14 +90,22 @@ class Problem:
         self.bsingularity = 1.-dim-2*s
         self.C = tables.fractional_scaling(dim, s, tempered=tempered)
         self.Cb = self.C*(1./s)      # phi = 1/s, kernels.py:151-160, kernelsCy.pyx:1990-1995
+        if smooth is not None:
+            # Gaussian / exponential kernels on the full space: smooth = (C, smode, sa, Cb, bmode, ba); singularity 0 for
+            # the kernel and its boundary form (Kernel.__init__, kernelsCy.pyx:657-664); `s` is not used
+            self.C, self.Cb = float(smooth[0]), float(smooth[3])
+            self.singularity = self.bsingularity = 0.
         # two DoFMaps: the local matrices (orders, getQuadOrder) keep the DoF count of the first map
         self.order_num_dofs = int(order_num_dofs) if order_num_dofs else self.num_dofs
         # variable kernels: the singular quadrature orders follow the largest order s.max (fractionalLaplacian2D.pyx:606)
         sm = self.s if s_max is None else float(s_max)
         smn = sm if s_min is None else float(s_min)
-        self.orders = tables.diag_orders(dim, -dim-2*sm, 1.-dim-2*sm, hmin, self.H0,
-                                         self.order_num_dofs, target_order, min_singularity=-dim-2*smn,
-                                         min_boundary_singularity=1.-dim-2*smn)
+        if smooth is not None:
+            self.orders = tables.diag_orders(dim, 0., 0., hmin, self.H0, self.order_num_dofs, target_order)
+        else:
+            self.orders = tables.diag_orders(dim, -dim-2*sm, 1.-dim-2*sm, hmin, self.H0,
+                                             self.order_num_dofs, target_order, min_singularity=-dim-2*smn,
+                                             min_boundary_singularity=1.-dim-2*smn)
         self.near = tables.near_rules(dim, self.singularity, self.bsingularity, self.orders)
         self._keep = []
         P = _Problem()
@@ -121,6 +130,8 @@ class Problem:
                 P.bpair_class[i] = int(v)
             P.pair_orientation = int(pair_orientation)
         P.tempered = float(tempered)
+        if smooth is not None:
+            P.smode, P.sa, P.bmode, P.ba = int(smooth[1]), float(smooth[2]), int(smooth[4]), float(smooth[5])
         P.nb = self.bfacets.shape[0]
         P.bfacets = self.bfacets.ctypes.data
         P.H0 = self.H0

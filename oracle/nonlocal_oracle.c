@@ -79,6 +79,11 @@ typedef struct {
      * exp(-tempered |x-y|); the boundary kernel stays the plain power law (getBoundaryKernel, kernelsCy.pyx:2011-2020,
      * does not hand `tempered` on).  0 = not tempered */
     double tempered;
+    /* integrable kernels on the full space (gaussianKernel*, exponentialKernel, kernelsCy.pyx:388-477): C f(|x-y|) with
+     * smode 1: f = exp(-sa r), 2: f = exp(-sa r^2); boundary forms Cb fb(|x-y|) with bmode 1: exp(-ba r),
+     * 3: erfc(sqrt(ba) r), 4: exp(-ba r^2)/r.  0 = power-law kernels */
+    int smode, bmode;
+    double sa, ba;
 } orc_problem;
 #define ORDN(P) ((P)->order_num_dofs > 0 ? (P)->order_num_dofs : (P)->num_dofs)
 
@@ -191,6 +196,10 @@ static void get_simplex(const orc_problem *P, const int32_t *verts, int n, doubl
 static double kernel_interior(const orc_problem *P, const double *x, const double *y)
 {
     double d2 = (x[0] - y[0]) * (x[0] - y[0]);
+    if (P->smode) {
+        if (P->dim == 2) d2 += (x[1] - y[1]) * (x[1] - y[1]);
+        return P->C * (P->smode == 1 ? exp(-P->sa * sqrt(d2)) : exp(-d2 * P->sa));
+    }
     if (P->dim == 2) {
         d2 += (x[1] - y[1]) * (x[1] - y[1]);
         if (P->tempered != 0.) return P->C * pow(d2, -1. - P->s) * exp(-P->tempered * sqrt(d2));
@@ -204,6 +213,12 @@ static double kernel_interior(const orc_problem *P, const double *x, const doubl
 static double kernel_boundary(const orc_problem *P, const double *x, const double *y)
 {
     double d2 = (x[0] - y[0]) * (x[0] - y[0]);
+    if (P->bmode) {
+        if (P->dim == 2) d2 += (x[1] - y[1]) * (x[1] - y[1]);
+        if (P->bmode == 1) return P->Cb * exp(-P->ba * sqrt(d2));
+        if (P->bmode == 3) return P->Cb * erfc(sqrt(P->ba * d2));
+        return P->Cb * exp(-P->ba * d2) / sqrt(d2);
+    }
     if (P->dim == 2) {
         d2 += (x[1] - y[1]) * (x[1] - y[1]);
         return P->Cb * pow(d2, -0.5 - P->s);

@@ -167,9 +167,20 @@ class nonlocalBuilder:
     def setKernel(self, kernel, zeroExterior=True):
         from .kernels import constFractionalOrder, getFractionalKernel, singleVariableUnsymmetricFractionalOrder
         self._classes = None
-        # tempered kernels run on the row-owner kernel of the element path for every element, P1 included
+        # kernels with a smooth factor on top of the power law (tempered fractional, Gaussian, exponential) run on the
+        # row-owner kernel of the element path for every element, P1 included: (mode, a, boundary mode, boundary a)
         self._tempered = float(getattr(kernel, 'tempered', 0.))
-        self._element = self.dm.polynomialOrder != 1 or self._tempered != 0.
+        self._smooth = (1, self._tempered, 0, 0.) if self._tempered != 0. else (0, 0., 0, 0.)
+        self._standin = None
+        if hasattr(kernel, 'exponentInverse'):
+            from types import SimpleNamespace
+            mode, a, bmode, ba, bconst = kernel.smoothFactors()
+            self._smooth = (mode, a, bmode, ba)
+            # device problem: the power law C |x-y|^0 behind the smooth factors (pnb_dense_assemble_element_smooth)
+            base = dict(kernelType=0, dim=kernel.dim, sValue=-0.5*kernel.dim, horizonValue2=np.inf, finiteHorizon=False)
+            self._standin = (SimpleNamespace(scalingValue=kernel.scalingValue, singularityValue=0., **base),
+                             SimpleNamespace(scalingValue=bconst, singularityValue=0., **base))
+        self._element = self.dm.polynomialOrder != 1 or self._smooth[0] != 0
         if self._element:
             if self.dm.polynomialOrder not in (0, 1, 2, 3):
                 raise NotImplementedError('P0, P1, P2 and (intervals) P3 elements')
@@ -336,6 +347,8 @@ class nonlocalBuilder:
                 # mesh, regular tables and order constants; the kernel values come from pnb_varorder_t
                 kern = self._varorder['base']
                 bkern = kern.getBoundaryKernel()
+            if getattr(self, '_standin', None) is not None:
+                kern, bkern = self._standin
             self._problem = _Problem(dm_dev, kern, bkern, self.orders, device,
                                      self.params.get('max_regular_order', 32), order_num_dofs=ond)
             if self.params.get('assembly_path', 'default') == 'tiles':
@@ -373,8 +386,8 @@ class nonlocalBuilder:
     def getLocalMatrices(self, pairs, boundary=False, path=0):
         """local_matrix.eval(contrib, panel) for the given pairs -> (panel, contrib[n, nloc])"""
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
-        if getattr(self, '_tempered', 0.) != 0. and not boundary:
-            raise NotImplementedError('only getDense() supports tempered kernels')
+        if getattr(self, '_smooth', (0, ))[0] != 0:
+            raise NotImplementedError('only getDense() supports tempered / Gaussian / exponential kernels')
         n = pairs.shape[0]
         nvc = self.mesh.dim+1
         nloc = nvc*(nvc+1)//2 if boundary else (2*nvc)*(2*nvc+1)//2
@@ -427,9 +440,10 @@ class nonlocalBuilder:
         def run():
             if self._element:
                 ed = np.ascontiguousarray(self.dm.dofs, dtype=np.int32)
-                _lib.check(_lib.lib().pnb_dense_assemble_element_tempered(prob.handle, self._tempered, self.dm.polynomialOrder,
-                                                                          self.dm.dofs_per_element, N, ed.ctypes.data,
-                                                                          int(self.zeroExterior), A.data_ptr(), A.stride(0), 1))
+                mode, a, bmode, ba = self._smooth
+                _lib.check(_lib.lib().pnb_dense_assemble_element_smooth(prob.handle, mode, a, bmode, ba, self.dm.polynomialOrder,
+                                                                        self.dm.dofs_per_element, N, ed.ctypes.data,
+                                                                        int(self.zeroExterior), A.data_ptr(), A.stride(0), 1))
             else:
                 _lib.check(_lib.lib().pnb_dense_assemble(prob.handle, int(self.zeroExterior), 0, N, A.data_ptr(),
                                                          A.stride(0), 1))

@@ -50,12 +50,29 @@ template <int DIM, int PORD> __device__ __forceinline__ void elem_shape(const do
     }
 }
 
+// Smooth factor on top of the power law C |x-y|^e of the problem's tables, as a function of |x-y|^2:
+//   1  exp(-a |x-y|)        tempered fractional kernels (kernelsCy.pyx:186-213), exponential kernel and its boundary form (:448-477)
+//   2  exp(-a |x-y|^2)      Gaussian kernel (:388-415)
+//   3  erfc(sqrt(a) |x-y|)  1D boundary form of the Gaussian kernel (:418-430: Gamma(1/2, a r^2) = sqrt(pi) erfc(sqrt(a) r))
+//   4  exp(-a |x-y|^2)/|x-y|  2D boundary form of the Gaussian kernel (:433-445: Gamma(1, a r^2) = exp(-a r^2)) over the
+//                           table of the boundary kernel divided by |x-y|
+__device__ __forceinline__ double elem_smooth(int mode, double a, double d2)
+{
+    switch (mode) {
+    case 1: return exp(-a * sqrt(d2));
+    case 2: return exp(-a * d2);
+    case 3: return erfc(sqrt(a * d2));
+    case 4: return exp(-a * d2) * rsqrt(d2);
+    default: return 1.;
+    }
+}
+
 // row of dof slots (sLo in the first cell, sHi in the second; -1 = the dof is not in that cell) of the local matrix of
 // the cell pair (lo, hi), lo <= hi.  acc[0..DPE) first-cell slots, acc[DPE..2 DPE) second-cell slots; NOT yet multiplied
 // by the volume factor; partial sums of this lane.
 template <int DIM, int PORD>
 __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, const int *perm1, const int *perm2, int sLo, int sHi,
-                              int lane, int nlanes, double *acc, double tempered = 0.)
+                              int lane, int nlanes, double *acc, int smode = 0, double sa = 0.)
 {
     constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
     double t1[3][2], t2[3][2];
@@ -93,8 +110,7 @@ __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, cons
                 if (k == sLo) psiI += px[k];
                 if (k == sHi) psiI -= py[k];
             }
-            // tempered kernels: times exp(-lambda |x-y|) (temperedFracKernelInfinite*, kernelsCy.pyx:186-213)
-            const double g = (r.w[i] * r.w[j]) * (tempered != 0. ? kv(d2) * exp(-tempered * sqrt(d2)) : kv(d2)) * psiI;
+            const double g = (r.w[i] * r.w[j]) * (smode ? kv(d2) * elem_smooth(smode, sa, d2) : kv(d2)) * psiI;
 #pragma unroll
             for (int k = 0; k < DPE; k++) {
                 acc[k] = fma(g, px[k], acc[k]);
@@ -149,7 +165,7 @@ __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, cons
                 if (k == sLo) psiI += px[k];
                 if (k == sHi) psiI -= py[k];
             }
-            const double g = r.w[q] * (tempered != 0. ? kv(d2) * exp(-tempered * sqrt(d2)) : kv(d2)) * psiI;
+            const double g = r.w[q] * (smode ? kv(d2) * elem_smooth(smode, sa, d2) : kv(d2)) * psiI;
 #pragma unroll
             for (int k = 0; k < DPE; k++) {
                 acc[k] = fma(g, px[k], acc[k]);
@@ -164,7 +180,7 @@ __device__ void elem_pair_row(const DProblem &P, int lo, int hi, int panel, cons
 // fractionalLaplacian1D.pyx:753-781); NOT yet multiplied by the volume factor
 template <int DIM, int PORD>
 __device__ void elem_boundary_row(const DProblem &P, int c1, int f, int panel, const int *perm1, const int *perm2, int sI, int lane,
-                                  double *acc)
+                                  double *acc, int bmode = 0, double ba = 0.)
 {
     constexpr int NV = DIM + 1, NF = DIM, DPE = ElemDims<DIM, PORD>::DPE;
     double t1[3][2], t2[3][2];
@@ -212,7 +228,7 @@ __device__ void elem_boundary_row(const DProblem &P, int c1, int f, int panel, c
 #pragma unroll
             for (int k = 0; k < DPE; k++)
                 if (k == sI) pI = px[k];
-            const double g = (r0.w[i] * r1.w[m]) * nw * kv(d2) * pI;
+            const double g = (r0.w[i] * r1.w[m]) * nw * (bmode ? kv(d2) * elem_smooth(bmode, ba, d2) : kv(d2)) * pI;
 #pragma unroll
             for (int k = 0; k < DPE; k++) acc[k] = fma(g, px[k], acc[k]);
         }
@@ -267,7 +283,7 @@ __device__ void elem_boundary_row(const DProblem &P, int c1, int f, int panel, c
 #pragma unroll
             for (int k = 0; k < DPE; k++)
                 if (k == sI) pI = px[k];
-            const double g = r.w[q] * nw * kv(d2) * pI;
+            const double g = r.w[q] * nw * (bmode ? kv(d2) * elem_smooth(bmode, ba, d2) : kv(d2)) * pI;
 #pragma unroll
             for (int k = 0; k < DPE; k++) acc[k] = fma(g, px[k], acc[k]);
         }
@@ -283,7 +299,8 @@ struct ElemJob {
     const int *partners;    // all cells in batches of 32 that share no vertex (-1: padding), colour by colour
     int npartners;          // length of `partners` (a multiple of 32)
     int *err;               // [0]: regular order missing in the tables
-    double tempered;        // tempered fractional kernel: interior kernel times exp(-tempered |x-y|); 0 = not tempered
+    int smode, bmode;       // smooth factors of the interior and the boundary kernel (elem_smooth), 0 = none
+    double sa, ba;
 };
 
 template <int DIM, int PORD>
@@ -325,7 +342,7 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
                 if (mine_far) {
                     const int lo = min(c1, c2), hi = max(c1, c2);
                     double acc[2 * DPE];
-                    elem_pair_row<DIM, PORD>(P, lo, hi, pan, p1, p2, lo == c1 ? sI1 : -1, hi == c1 ? sI1 : -1, 0, 1, acc, J.tempered);
+                    elem_pair_row<DIM, PORD>(P, lo, hi, pan, p1, p2, lo == c1 ? sI1 : -1, hi == c1 ? sI1 : -1, 0, 1, acc, J.smode, J.sa);
                     const double sc = 2.0 * P.vol[lo] * P.vol[hi];
 #pragma unroll
                     for (int k = 0; k < DPE; k++) {
@@ -364,7 +381,7 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
                 const int lo = min(c1, c2s), hi = max(c1, c2s);
                 const int sLo = lo == c1 ? sI1 : sI2s, sHi = hi == c1 ? sI1 : sI2s;
                 double acc[2 * DPE];
-                elem_pair_row<DIM, PORD>(P, lo, hi, pans, q1, q2, sLo, sHi, lane, 32, acc, J.tempered);
+                elem_pair_row<DIM, PORD>(P, lo, hi, pans, q1, q2, sLo, sHi, lane, 32, acc, J.smode, J.sa);
                 warp_allreduce<2 * DPE>(acc);
                 // volume factors: vol1 vol2 (nonlocalOperator_{SCALAR}.pxi:756), 4 vol1 vol2 for the singular 2D rules
                 // (fractionalLaplacian2D.pyx:851); off-diagonal pairs count twice (nonlocalAssembly_{SCALAR}.pxi:1404-1410)
@@ -411,7 +428,7 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
                         q2[k] = __shfl_sync(0xffffffffu, p2[k], src);
                     }
                     double acc[DPE];
-                    elem_boundary_row<DIM, PORD>(P, c1, fs, pans, q1, q2, sI1, lane, acc);
+                    elem_boundary_row<DIM, PORD>(P, c1, fs, pans, q1, q2, sI1, lane, acc, J.bmode, J.ba);
                     warp_allreduce<DPE>(acc);
                     const double sc = pans >= 1 ? P.vol[c1] * P.bvol[fs] : (DIM == 2 ? -2.0 * P.vol[c1] * P.bvol[fs] : P.vol[c1]);
                     double mine = 0.;
@@ -459,7 +476,8 @@ static int elem_job_build(pnb_problem *p, int dpe, int num_dofs, const int32_t *
     }
     J.N = num_dofs;
     J.dpe = dpe;
-    J.tempered = 0.;
+    J.smode = J.bmode = 0;
+    J.sa = J.ba = 0.;
     std::vector<int> row_order(num_dofs);
     for (int i = 0; i < num_dofs; i++) row_order[i] = i;
     std::stable_sort(row_order.begin(), row_order.end(), [&](int a, int b) { return dptr[a + 1] - dptr[a] > dptr[b + 1] - dptr[b]; });
@@ -533,8 +551,20 @@ extern "C" int pnb_dense_assemble_element_tempered(pnb_problem *p, double temper
                                                    int num_dofs, const int32_t *dofs, int zero_exterior, double *A_out, int64_t ld_out,
                                                    int a_on_device)
 {
-    if (!p || !dofs || !A_out) return fail(PNB_ERR_ARG, "null argument");
     if (!(tempered >= 0.) || !(tempered < INFINITY)) return fail(PNB_ERR_ARG, "the tempering rate must be finite and >= 0");
+    return pnb_dense_assemble_element_smooth(p, tempered != 0. ? PNB_SMOOTH_EXP_R : PNB_SMOOTH_NONE, tempered, PNB_SMOOTH_NONE, 0.,
+                                             polynomial_order, dofs_per_element, num_dofs, dofs, zero_exterior, A_out, ld_out, a_on_device);
+}
+
+extern "C" int pnb_dense_assemble_element_smooth(pnb_problem *p, int mode, double a, int bmode, double ba, int polynomial_order,
+                                                 int dofs_per_element, int num_dofs, const int32_t *dofs, int zero_exterior,
+                                                 double *A_out, int64_t ld_out, int a_on_device)
+{
+    if (!p || !dofs || !A_out) return fail(PNB_ERR_ARG, "null argument");
+    if (mode < PNB_SMOOTH_NONE || mode > PNB_SMOOTH_EXP_R2 || bmode < PNB_SMOOTH_NONE || bmode > PNB_SMOOTH_EXP_R2_OVER_R)
+        return fail(PNB_ERR_ARG, "unknown smooth factor");
+    if ((mode != PNB_SMOOTH_NONE && !(a >= 0. && a < INFINITY)) || (bmode != PNB_SMOOTH_NONE && !(ba >= 0. && ba < INFINITY)))
+        return fail(PNB_ERR_ARG, "the rate of a smooth factor must be finite and >= 0");
     if (polynomial_order < 0 || polynomial_order > 3 || (polynomial_order == 3 && p->dim != 1))
         return fail(PNB_ERR_UNSUPPORTED, "elements: P0, P1, P2; P3 on intervals");
     const int dpe = polynomial_order == 0 ? 1 : (polynomial_order == 1 ? p->dim + 1 : (polynomial_order == 2 ? (p->dim == 1 ? 3 : 6) : 4));
@@ -561,7 +591,8 @@ extern "C" int pnb_dense_assemble_element_tempered(pnb_problem *p, double temper
             return rc;
         }
     }
-    J.tempered = tempered;
+    J.smode = mode; J.sa = a;
+    J.bmode = bmode; J.ba = ba;
     const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
     if (p->dim == 2) {
         if (polynomial_order == 2) elem_rows_kernel<2, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);

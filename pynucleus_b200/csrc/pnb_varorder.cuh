@@ -30,6 +30,7 @@ struct VarOrderDev {
     const int *cell_val;            // nc: rank of max s over the cell's centre and vertices
     const int *facet_val;           // nb
     const DRule *rules;             // 5 x nvals: identical | edge | vertex | bedge | bvertex
+    const PowTab *pt;               // power tables of the two plateaus: interior sl | sr, boundary sl | sr
 };
 
 __device__ __forceinline__ double vo_order(const VarOrderDev &V, double x0, double x1)
@@ -51,6 +52,19 @@ template <int DIM> __device__ __forceinline__ double vo_scaling(const VarOrderDe
     if (s == V.sr) return V.Cr;
     const double ipi = DIM == 1 ? 0.56418958354775628 : 0.31830988618379067;    // pi^(-d/2)
     return exp2(2.0 * s) * s * tgamma(s + 0.5 * DIM) * ipi / tgamma(1.0 - s) * 0.5;
+}
+
+// kernel value at squared distance d2 for the order s of the first argument.  Most nodes lie on one of the two plateaus of
+// the order: there the power comes from the table of that constant order (pnb_device.cuh), elsewhere from tgamma / pow.
+// boundary: C(s)/s |x-y|^(1-d-2s), in 2D divided by |x-y| (the normal factor of the surface form is not normalised)
+template <int DIM> __device__ __forceinline__ double vo_kernel(const VarOrderDev &V, double d2, double s, bool boundary)
+{
+    if (s == V.sl || s == V.sr) {
+        const PowCtx kv(V.pt + (boundary ? 2 : 0) + (s == V.sl ? 0 : 1));
+        return kv(d2);
+    }
+    const double C = vo_scaling<DIM>(V, s);
+    return boundary ? C / s * pow(d2, (DIM == 2 ? -1. : 0.) - s) : C * pow(d2, -0.5 * DIM - s);
 }
 
 // getQuadOrder of the unsymmetric local matrices (fractionalLaplacian2D.pyx:915-934, fractionalLaplacian1D.pyx:431-450)
@@ -183,11 +197,11 @@ __device__ void vo_pair_row(const DProblem &P, const VarOrderDev &V, int cA, int
         double tI = 0.;
         if (sA >= 0) {
             const double sx = vo_order(V, x0, x1);
-            tI = vo_scaling<DIM>(V, sx) * pow(d2, -0.5 * DIM - sx) * pIx;
+            tI = vo_kernel<DIM>(V, d2, sx, false) * pIx;
         }
         if (sB >= 0) {
             const double sy = vo_order(V, y0, y1);
-            tI -= vo_scaling<DIM>(V, sy) * pow(d2, -0.5 * DIM - sy) * pIy;
+            tI -= vo_kernel<DIM>(V, d2, sy, false) * pIy;
         }
         tI *= w;
 #pragma unroll
@@ -301,8 +315,7 @@ __device__ void vo_boundary_row(const DProblem &P, const VarOrderDev &V, int c1,
             if (k == sI) pI = px[k];
         // boundary kernel (2D: divided by |x-y|, the normal factor nw is not normalised)
         const double sx = vo_order(V, x0, x1);
-        const double kv = vo_scaling<DIM>(V, sx) / sx * pow(d2, (DIM == 2 ? -1. : 0.) - sx);
-        const double g = w * nw * kv * pI;
+        const double g = w * nw * vo_kernel<DIM>(V, d2, sx, true) * pI;
 #pragma unroll
         for (int k = 0; k < DPE; k++) acc[k] = fma(g, px[k], acc[k]);
     }
@@ -520,19 +533,21 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
             pack.insert(pack.end(), s.w, s.w + s.n);
         }
     double *d_pack = nullptr, *d_vals = nullptr;
+    PowTab *d_pt = nullptr;
     DRule *d_rules = nullptr;
     int *d_cv = nullptr, *d_fv = nullptr;
     std::vector<void *> dev;
     double *A = A_out;
     int64_t ld = ld_out;
     auto cleanup = [&]() {
-        cudaFree(d_pack); cudaFree(d_vals); cudaFree(d_rules); cudaFree(d_cv); cudaFree(d_fv);
+        cudaFree(d_pack); cudaFree(d_vals); cudaFree(d_rules); cudaFree(d_cv); cudaFree(d_fv); cudaFree(d_pt);
         elem_job_free(dev);
         if (!a_on_device && A != A_out) pool_free(A);
     };
     if (cudaMalloc(&d_pack, std::max<size_t>(pack.size(), 1) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&d_vals, (size_t)nvals * sizeof(double)) != cudaSuccess || cudaMalloc(&d_rules, hr.size() * sizeof(DRule)) != cudaSuccess ||
-        cudaMalloc(&d_cv, (size_t)p->nc * sizeof(int)) != cudaSuccess || cudaMalloc(&d_fv, std::max<size_t>(p->nb, 1) * sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&d_cv, (size_t)p->nc * sizeof(int)) != cudaSuccess || cudaMalloc(&d_fv, std::max<size_t>(p->nb, 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&d_pt, 4 * sizeof(PowTab)) != cudaSuccess) {
         cudaGetLastError();
         cleanup();
         return fail(PNB_ERR_CUDA, "out of device memory");
@@ -555,7 +570,18 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
         V.Cl = exp2(2.0 * V.sl) * V.sl * tgamma(V.sl + 0.5 * dim) * ipi / tgamma(1.0 - V.sl) * 0.5;
         V.Cr = exp2(2.0 * V.sr) * V.sr * tgamma(V.sr + 0.5 * dim) * ipi / tgamma(1.0 - V.sr) * 0.5;
     }
-    V.nvals = nvals; V.vals = d_vals; V.cell_val = d_cv; V.facet_val = d_fv; V.rules = d_rules;
+    {
+        // power tables of the two plateaus, over the exponent window of the problem's own tables
+        std::vector<PowTab> tabs(4);
+        const double sv[2] = {V.sl, V.sr}, Cv[2] = {V.Cl, V.Cr};
+        for (int k = 0; k < 2; k++) {
+            build_powtab(&tabs[k], Cv[k], -0.5 * dim - sv[k], p->pow_eoff);
+            build_powtab(&tabs[2 + k], Cv[k] / sv[k], (dim == 2 ? -1. : 0.) - sv[k], p->pow_eoff);
+        }
+        for (auto &t : tabs) t.horizon2 = INFINITY;
+        cudaMemcpy(d_pt, tabs.data(), 4 * sizeof(PowTab), cudaMemcpyHostToDevice);
+    }
+    V.nvals = nvals; V.vals = d_vals; V.cell_val = d_cv; V.facet_val = d_fv; V.rules = d_rules; V.pt = d_pt;
     if (!a_on_device) {
         ld = num_dofs;
         A = nullptr;

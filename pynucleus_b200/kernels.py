@@ -388,6 +388,9 @@ class FractionalKernel:
 
 
 INDICATOR, PERIDYNAMIC = 1, 2      # kernel_params.pxi:88-90
+GAUSSIAN, EXPONENTIAL = 3, 8
+# smooth factors of pnb_dense_assemble_element_smooth (include/pnb200.h)
+SMOOTH_NONE, SMOOTH_EXP_R, SMOOTH_EXP_R2, SMOOTH_ERFC_R, SMOOTH_EXP_R2_OVER_R = 0, 1, 2, 3, 4
 
 
 def getKernelEnum(kernelTypeString):
@@ -399,13 +402,25 @@ def getKernelEnum(kernelTypeString):
         return INDICATOR
     if k in ('INVERSEDISTANCE', 'INVERSEOFDISTANCE', 'PERIDYNAMIC'):
         return PERIDYNAMIC
+    if k == 'GAUSSIAN':
+        return GAUSSIAN
+    if k == 'EXPONENTIAL':
+        return EXPONENTIAL
     raise NotImplementedError(kernelTypeString)
 
 
-def constantIntegrableScaling(kType, dim, horizon):
-    """normalisation of the integrable kernels on the l2 ball (kernelNormalization.pyx:225-251)"""
+def constantIntegrableScaling(kType, dim, horizon, gaussian_variance=1., exponentialRate=1.):
+    """normalisation of the integrable kernels on the l2 ball, and of the Gaussian / exponential kernels on the full space
+    (kernelNormalization.pyx:225-283)"""
     if horizon <= 0.:
         return np.nan
+    if kType == GAUSSIAN and horizon == np.inf:
+        if dim == 1:
+            return 1.0/np.sqrt(2.0*pi*gaussian_variance)/2.
+        if dim == 2:
+            return 1.0/(2.0*pi*gaussian_variance)/2.
+    if kType == EXPONENTIAL and horizon == np.inf and dim == 1:
+        return exponentialRate**3/2.0/2.
     if kType == INDICATOR:
         if dim == 1:
             return 3./horizon**3/2.
@@ -427,8 +442,8 @@ class Kernel:
     s = None
     sValue = 0.
 
-    def __init__(self, dim, kType, horizon, scaling, boundary=False, phi=None, piecewise=True):
-        if kType not in (INDICATOR, PERIDYNAMIC):
+    def __init__(self, dim, kType, horizon, scaling, boundary=False, phi=None, piecewise=True, variance=1., exponentialRate=1.):
+        if kType not in (INDICATOR, PERIDYNAMIC, GAUSSIAN, EXPONENTIAL):
             raise NotImplementedError('kernel type {} is not supported yet'.format(kType))
         self.dim = int(dim)
         self.kernelType = kType
@@ -443,15 +458,26 @@ class Kernel:
         self.horizonValue = horizon.value
         self.horizonValue2 = horizon.value**2
         self.finiteHorizon = horizon.value != np.inf
-        if not self.finiteHorizon:
+        if kType in (GAUSSIAN, EXPONENTIAL):
+            # Gaussian C exp(-|x-y|^2 / (2 variance^d)) and exponential C exp(-rate |x-y|) on the full space
+            # (gaussianKernel*, exponentialKernel: kernelsCy.pyx:388-477; fEXPONENTINVERSE: Kernel.__init__ :690-697), the
+            # kernels of the reference's driver tests `--interaction fullSpace --horizon inf`
+            if self.finiteHorizon:
+                raise NotImplementedError('Gaussian / exponential kernels: infinite horizon (interaction fullSpace)')
+            if kType == EXPONENTIAL and self.dim != 1:
+                raise NotImplementedError('exponential kernel: 1D (the reference has no normalisation for 2D)')
+            self.variance, self.exponentialRate = float(variance), float(exponentialRate)
+            self.exponentInverse = 0.5/self.variance**self.dim if kType == GAUSSIAN else self.exponentialRate
+        elif not self.finiteHorizon:
             raise NotImplementedError('integrable kernels need a finite horizon')
         self.complement = False
-        self.singularityValue = 0. if kType == INDICATOR else -1.
+        self.singularityValue = -1. if kType == PERIDYNAMIC else 0.
         self.min_singularity = self.max_singularity = self.singularityValue
 
     def getModifiedKernel(self, horizon=None, scaling=None):
         horizon = self.horizon if horizon is None else horizon
-        return getIntegrableKernel(self.dim, self.kernelType, horizon, scaling=scaling, piecewise=self.piecewise)
+        return getIntegrableKernel(self.dim, self.kernelType, horizon, scaling=scaling, piecewise=self.piecewise,
+                                   variance=getattr(self, 'variance', 1.), exponentialRate=getattr(self, 'exponentialRate', 1.))
 
     def getBoundaryKernel(self):
         """The surface forms of the integrable kernels (kernelsCy.pyx:297-318, 361-386) only enter operators with a zero
@@ -460,10 +486,24 @@ class Kernel:
         bk = Kernel.__new__(Kernel)
         bk.__dict__.update(self.__dict__)
         bk.boundary = True
+        if self.kernelType in (GAUSSIAN, EXPONENTIAL):
+            # surface forms gaussianKernel{1,2}Dboundary / exponentialKernelBoundary (kernelsCy.pyx:418-445, 463-477): same
+            # scaling and singularity entries as the interior kernel
+            return bk
         bk.scalingValue = 0.
         bk.singularityValue = self.singularityValue+1.
         bk.min_singularity = bk.max_singularity = bk.singularityValue
         return bk
+
+    def smoothFactors(self):
+        """(mode, a, boundary mode, boundary a, constant of the boundary power law) for pnb_dense_assemble_element_smooth"""
+        from scipy.special import erfc  # noqa: F401
+        C, a = self.scalingValue, self.exponentInverse
+        if self.kernelType == EXPONENTIAL:
+            return SMOOTH_EXP_R, a, SMOOTH_EXP_R, a, 2.0*C/a
+        if self.dim == 1:
+            return SMOOTH_EXP_R2, a, SMOOTH_ERFC_R, a, C*np.sqrt(pi/a)
+        return SMOOTH_EXP_R2, a, SMOOTH_EXP_R2_OVER_R, a, C/a
 
     def __call__(self, x, y):
         x = np.atleast_1d(np.asarray(x, dtype=float))
@@ -471,24 +511,38 @@ class Kernel:
         d2 = float(((x-y)**2).sum())
         if d2 > self.horizonValue2:
             return 0.
+        if self.kernelType in (GAUSSIAN, EXPONENTIAL):
+            from scipy.special import erfc
+            C, a = self.scalingValue, self.exponentInverse
+            if self.kernelType == EXPONENTIAL:
+                return (2.0*C/a if self.boundary else C)*np.exp(-a*np.sqrt(d2))
+            if not self.boundary:
+                return C*np.exp(-d2*a)
+            if self.dim == 1:
+                return C*np.sqrt(pi/a)*erfc(np.sqrt(d2*a))
+            return C/(d2*a)*np.exp(-d2*a)*np.sqrt(d2)
         return self.scalingValue*pow(d2, 0.5*self.singularityValue)
 
     def __repr__(self):
-        return 'kernel({}, horizon={}, scaling={})'.format({INDICATOR: 'indicator', PERIDYNAMIC: 'peridynamic'}[self.kernelType],
-                                                          self.horizonValue, self.scalingValue)
+        name = {INDICATOR: 'indicator', PERIDYNAMIC: 'peridynamic', GAUSSIAN: 'Gaussian', EXPONENTIAL: 'exponential'}[self.kernelType]
+        return 'kernel({}, horizon={}, scaling={})'.format(name, self.horizonValue, self.scalingValue)
 
 
 def getIntegrableKernel(dim, kernel, horizon, scaling=None, interaction=None, normalized=True, piecewise=True, phi=None,
-                        boundary=False, **kwargs):
+                        boundary=False, variance=1., exponentialRate=1., **kwargs):
     """kernels.py:172-202"""
     dim = getattr(dim, 'dim', dim)
     kType = getKernelEnum(kernel) if isinstance(kernel, str) else int(kernel)
     horizonFun = _getHorizon(horizon)
-    if interaction is not None and interaction not in ('ball2', ):
-        raise NotImplementedError('only the l2 ball is supported as interaction domain')
+    if interaction is not None and interaction not in ('ball2', 'fullSpace'):
+        raise NotImplementedError('interaction domains: the l2 ball, the full space for an infinite horizon')
+    if interaction == 'fullSpace' and horizonFun.value != np.inf:
+        raise NotImplementedError('the full space needs an infinite horizon')
     if scaling is None:
-        scaling = constantIntegrableScaling(kType, dim, horizonFun.value) if normalized else 0.5
-    return Kernel(dim, kType, horizonFun, scaling, boundary=boundary, phi=phi, piecewise=piecewise)
+        scaling = (constantIntegrableScaling(kType, dim, horizonFun.value, gaussian_variance=variance, exponentialRate=exponentialRate)
+                   if normalized else 0.5)
+    return Kernel(dim, kType, horizonFun, scaling, boundary=boundary, phi=phi, piecewise=piecewise, variance=variance,
+                  exponentialRate=exponentialRate)
 
 
 def _getFractionalOrder(s):
@@ -547,4 +601,4 @@ def getKernel(dim, s=None, horizon=None, scaling=None, interaction=None, normali
     if kType == FRACTIONAL:
         return getFractionalKernel(dim, s, horizon, interaction, scaling, normalized, piecewise, phi, boundary)
     return getIntegrableKernel(dim, kType, horizon, scaling=scaling, interaction=interaction, normalized=normalized,
-                               piecewise=piecewise, phi=phi)
+                               piecewise=piecewise, phi=phi, **{k: v for k, v in kwargs.items() if k in ('variance', 'exponentialRate')})

@@ -1218,3 +1218,48 @@ def test_order_varying_inside_cells_rows_vs_reference(golden_dir, name):
     x = g['x']
     assert np.abs(A.dot(x)-g['Ax']).max() < TOL*np.abs(g['Ax']).max()
     assert np.abs(A.T.dot(x)-g['ATx']).max() < TOL*np.abs(g['ATx']).max()
+
+
+SMOOTH_CASES = ['gaussian_interval_v0.1_r5', 'gaussian_interval_v0.02_r6', 'exponential_interval_a8_r5', 'exponential_interval_a2.5_r6',
+                'gaussian_disc_v0.1_r2', 'gaussian_disc_v0.3_r3', 'gaussian_p2_interval_v0.1_r4']
+
+
+@pytest.mark.parametrize('name', SMOOTH_CASES)
+def test_gaussian_and_exponential_kernels_vs_reference(golden_dir, name):
+    """Gaussian and exponential kernels on the full space (SURVEY 8 a12 gaussianKernel* / exponentialKernel* with their
+    boundary forms, a13 their constantIntegrableScaling; the kernels of the reference's driver tests `--kernelType gaussian /
+    exponential --interaction fullSpace`): pnb_dense_assemble_element_smooth against operators assembled by the reference
+    itself (make_golden_smooth.py), with and without the surface terms"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    dim = g['vertices'].shape[1]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'])
+    dm = pb.P2_DoFMap(mesh) if str(g['element']) == 'P2' else pb.P1_DoFMap(mesh)
+    assert dm.num_dofs == int(g['num_dofs'])
+    kw = {'variance': float(g['variance'])} if str(g['kernelType']) == 'gaussian' else {'exponentialRate': float(g['exponentialRate'])}
+    kernel = pb.getIntegrableKernel(dim, str(g['kernelType']), np.inf, interaction='fullSpace', **kw)
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = pb.nonlocalBuilder(dm, kernel, params, zeroExterior=ze)
+        A = b.getDense().data
+        assert entry_err(A, g[key]) < TOL
+        assert np.array_equal(A, b.getDense().data)
+    with pytest.raises(NotImplementedError):
+        b.getH2()
+
+
+def test_gaussian_kernel_larger_mesh_vs_oracle(golden_dir):
+    """Gaussian kernel on a finer disc (705 DoFs) than the fixtures, against the C oracle (pinned to the fixtures)"""
+    import pynucleus_b200 as pb
+    import oracle
+    from math import pi
+    mesh = pb.refined(pb.uniform_disc(), 4)
+    dm = pb.P1_DoFMap(mesh)
+    var = 0.05
+    kernel = pb.getIntegrableKernel(2, 'gaussian', np.inf, variance=var)
+    A = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5}).getDense().data
+    C, a = kernel.scalingValue, 0.5/var**2
+    assert abs(C-1./(2*pi*var)/2) < 1e-15
+    P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, -1., bfacets=mesh.boundaryFacets, target_order=0.5,
+                       smooth=(C, 2, a, C/a, 4, a))
+    assert entry_err(A, P.dense(True)) < TOL

@@ -387,3 +387,31 @@ def test_tempered_kernel_matches_reference(golden_dir, name):
     assert abs(P.C/float(g['scaling'])-1) < 1e-14 and abs(P.Cb/float(g['bscaling'])-1) < 1e-14
     for ze, key in ((True, 'A'), (False, 'A_interior')):
         assert np.abs(P.dense(ze)-g[key]).max() < 1e-13*np.abs(g[key]).max()
+
+
+def smooth_oracle_problem(g, **kw):
+    """oracle problem of a Gaussian / exponential fixture (make_golden_smooth.py)"""
+    from math import pi, sqrt
+    dim = g['vertices'].shape[1]
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices'].reshape(-1, 1)
+    C = float(g['scaling'])
+    if str(g['kernelType']) == 'gaussian':
+        a = 0.5/float(g['variance'])**dim           # fEXPONENTINVERSE, kernelsCy.pyx:693-695
+        sm = (C, 2, a, C*sqrt(pi/a), 3, a) if dim == 1 else (C, 2, a, C/a, 4, a)
+    else:
+        a = float(g['exponentialRate'])
+        sm = (C, 1, a, 2*C/a, 1, a)
+    return oracle.Problem(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), -0.5*dim, bfacets=bf,
+                          target_order=0.5 if dim == 2 else None, hVector=g['hVector'], volVector=g['volVector'],
+                          hmin=float(g['hmin']), diam=float(g['diam']), smooth=sm, **kw)
+
+
+@pytest.mark.parametrize('name', ['gaussian_interval_v0.1_r5', 'gaussian_interval_v0.02_r6', 'exponential_interval_a8_r5',
+                                  'exponential_interval_a2.5_r6', 'gaussian_disc_v0.1_r2', 'gaussian_disc_v0.3_r3'])
+def test_gaussian_and_exponential_kernels_match_reference(golden_dir, name):
+    """Gaussian / exponential kernels on the full space in the C restatement against operators assembled by the reference"""
+    g = np.load(os.path.join(golden_dir, name+'.npz'))
+    P = smooth_oracle_problem(g)
+    assert P.orders['qod'] == int(g['quad_order_diagonal']) and P.orders['b_qod'] == int(g['bquad_order_diagonal'])
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        assert np.abs(P.dense(ze)-g[key]).max() < 1e-13*np.abs(g[key]).max()
