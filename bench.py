@@ -644,7 +644,8 @@ def widening_leg(dev):
     mesh = pb.refined(pb.uniform_disc(), 5)
     dm = pb.P1_DoFMap(mesh)
     for name, k, kern in (('order_inside_cells', pb.getFractionalKernel(2, pb.smoothedLeftRightFractionalOrder(0.25, 0.75)), 'varorder_rows_kernel<2,1>'),
-                          ('tempered', pb.getFractionalKernel(2, S_ORDER, tempered=2.), 'elem_rows_kernel<2,1>')):
+                          ('tempered', pb.getFractionalKernel(2, S_ORDER, tempered=2.), 'elem_rows_kernel<2,1>'),
+                          ('gaussian', pb.getIntegrableKernel(2, 'gaussian', np.inf, variance=0.1), 'elem_rows_kernel<2,1>')):
         try:
             b5 = pb.nonlocalBuilder(dm, k, params)
             A5 = b5.getDense()

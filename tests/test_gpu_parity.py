@@ -1263,3 +1263,19 @@ def test_gaussian_kernel_larger_mesh_vs_oracle(golden_dir):
     P = oracle.Problem(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, -1., bfacets=mesh.boundaryFacets, target_order=0.5,
                        smooth=(C, 2, a, C/a, 4, a))
     assert entry_err(A, P.dense(True)) < TOL
+
+
+@pytest.mark.parametrize('kt', ['gaussian', 'exponential'])
+def test_driver_known_answers_gaussian_and_exponential(kt):
+    """the reference's cached driver runs `runNonlocal.py --domain interval --kernelType gaussian --gaussianVariance 0.1` /
+    `--kernelType exponential --exponentialRate 8` with `--interaction fullSpace --horizon inf` (tests/test_drivers_intFracLapl.py:42-43;
+    511 unknowns): operator from pnb_dense_assemble_element_smooth, the errors as the driver reports them"""
+    import pynucleus_b200 as pb
+    from test_oracle_golden import SMOOTH_DRIVER_CASES, smooth_driver_setup, smooth_driver_errors
+    mesh = pb.refined(pb.simpleInterval(-1, 1), 9)
+    dm = pb.P1_DoFMap(mesh)
+    kw, _, f, u_ex = smooth_driver_setup(kt)
+    kernel = pb.getIntegrableKernel(1, kt, np.inf, interaction='fullSpace', **kw)
+    A = pb.nonlocalBuilder(dm, kernel, {}).getDense().data
+    L2i, Linf = smooth_driver_errors(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, A, f, u_ex)
+    assert abs(L2i/SMOOTH_DRIVER_CASES[kt][0]-1) < 1e-6 and abs(Linf/SMOOTH_DRIVER_CASES[kt][1]-1) < 1e-12
