@@ -10,7 +10,8 @@ one call into the CUDA library.  The result is written straight into the `data` 
     from pnb200_shim import nonlocalBuilderB200          # subclass of PyNucleus_nl.nonlocalBuilder
     A = nonlocalBuilderB200(dm, kernel, params).getDense()
 
-Unsupported configurations (non-symmetric or variable kernels, two DoFMaps, P3 on triangles, vector-valued kernels) fall through
+Tempered fractional kernels go to the row-owner kernel with their rate.  Unsupported configurations (non-symmetric or variable
+kernels, Gaussian / exponential kernels, two DoFMaps, P3 on triangles, vector-valued kernels) fall through
 to the reference's own getDense, so the subclass is a drop-in.
 """
 import numpy as np
@@ -54,10 +55,19 @@ def _regular_rules(int dim, int max_order):
     return cell, facet
 
 
+def _tempered(kernel):
+    """tempering rate of a fractional kernel (temperedFracKernelInfinite*, kernelsCy.pyx:186-213), 0 for all others"""
+    if int(kernel.kernelType) != 0:
+        return 0.
+    return float(getattr(kernel, 'temperedValue', 0.) or 0.)
+
+
 def supported(builder):
     """configurations the accelerated path covers (everything else stays with the reference's Cython loops)"""
     from PyNucleus_fem.DoFMaps import P0_DoFMap, P1_DoFMap, P2_DoFMap, P3_DoFMap
     k = builder.kernel
+    if _tempered(k) != 0. and k.finiteHorizon:
+        return False        # tempered kernels: infinite horizon (row-owner kernel)
     if isinstance(builder.dm, (P0_DoFMap, P2_DoFMap, P3_DoFMap)) and (k.finiteHorizon or int(k.kernelType) != 0):
         return False        # P0 / P2 / P3: fractional kernels with infinite horizon (row-owner kernel)
     if isinstance(builder.dm, P3_DoFMap) and builder.dm.mesh.dim != 1:
@@ -83,6 +93,7 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
         int rc, o, dim, N, zero_exterior, porder, dpe
         int32_t[:, ::1] edofs
         int32_t need = 0
+        double tempered
         double[:, ::1] vertices, nodes
         double[::1] vol, h, weights
         int32_t[:, ::1] cells, dofs, bfacets
@@ -92,6 +103,9 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
     mesh = builder.dm.mesh
     dm = builder.dm
     kernel = builder.kernel
+    # tempered kernels: the power law with the tempered constant in the problem, the exponential factor in the row-owner
+    # kernel; the surface terms stay as they are (the reference's boundary kernel is not tempered, kernelsCy.pyx:2011-2020)
+    tempered = _tempered(kernel)
     lm = builder.local_matrix
     lmb = builder.local_matrix_zeroExterior
     dim = mesh.dim
@@ -197,10 +211,11 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
             if rc != 0:
                 raise PNB200Error(_last_error())
             with nogil:
-                if porder == 1:
+                if porder == 1 and tempered == 0.:
                     rc = pnb_dense_assemble(prob, zero_exterior, 0, N, &data[0, 0], N, 0)
                 else:
-                    rc = pnb_dense_assemble_element(prob, porder, dpe, N, &edofs[0, 0], zero_exterior, &data[0, 0], N, 0)
+                    rc = pnb_dense_assemble_element_tempered(prob, tempered, porder, dpe, N, &edofs[0, 0], zero_exterior,
+                                                             &data[0, 0], N, 0)
             if rc == 0:
                 break
             if rc != -5 or attempt == 1:       # PNB_ERR_ORDER: the reference grows its rule cache lazily (addQuadRule)

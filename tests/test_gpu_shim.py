@@ -123,3 +123,24 @@ def test_reference_builder_vs_shim_p2(shim, dim, noRef, s, element):
     A = b.getDense()
     assert A.shape == Aref.shape
     assert entry_err(np.array(A.data), Aref) < TOL
+
+
+@pytest.mark.parametrize('dim,noRef,s,lam,element', [(1, 5, 0.75, 2.0, 'P1'), (2, 2, 0.25, 1.0, 'P1'), (1, 4, 0.75, 1.5, 'P2')])
+def test_reference_builder_vs_shim_tempered(shim, dim, noRef, s, lam, element):
+    """a tempered fractional kernel of the reference (kernelType FRACTIONAL with temperedValue != 0) through the shim: the row-owner
+    kernel with the rate (pnb_dense_assemble_element_tempered), not the plain power law, against the reference's Cython getDense"""
+    from PyNucleus_fem.mesh import simpleInterval, uniform_disc
+    from PyNucleus_fem.DoFMaps import P1_DoFMap, P2_DoFMap
+    from PyNucleus_nl.kernels import getFractionalKernel
+    from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder
+    mesh = simpleInterval(-1, 1) if dim == 1 else uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = {'P1': P1_DoFMap, 'P2': P2_DoFMap}[element](mesh)
+    kernel = getFractionalKernel(dim, s, np.inf, tempered=lam)
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze in (True, False):
+        Aref = np.array(nonlocalBuilder(dm, kernel, dict(params), zeroExterior=ze).getDense().data)
+        b = shim.builder_class()(dm, kernel, dict(params), zeroExterior=ze)
+        assert shim.supported(b)
+        assert entry_err(np.array(b.getDense().data), Aref) < TOL
