@@ -71,5 +71,8 @@ cdef extern from "pnb200.h":
                                    int zero_exterior, double *A, int64_t ld, int a_on_device) nogil
     int pnb_dense_assemble_element_tempered(pnb_problem *, double tempered, int polynomial_order, int dofs_per_element, int num_dofs,
                                             const int32_t *dofs, int zero_exterior, double *A, int64_t ld, int a_on_device) nogil
+    int pnb_dense_assemble_element_smooth(pnb_problem *, int mode, double a, int bmode, double ba, int polynomial_order,
+                                          int dofs_per_element, int num_dofs, const int32_t *dofs, int zero_exterior, double *A,
+                                          int64_t ld, int a_on_device) nogil
     int pnb_dense_matvec(int device, const double *A, int64_t num_rows, int64_t num_cols, int64_t ld, const double *x,
                          double *y) nogil

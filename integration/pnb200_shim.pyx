@@ -10,8 +10,9 @@ one call into the CUDA library.  The result is written straight into the `data` 
     from pnb200_shim import nonlocalBuilderB200          # subclass of PyNucleus_nl.nonlocalBuilder
     A = nonlocalBuilderB200(dm, kernel, params).getDense()
 
-Tempered fractional kernels go to the row-owner kernel with their rate.  Unsupported configurations (non-symmetric or variable
-kernels, Gaussian / exponential kernels, two DoFMaps, P3 on triangles, vector-valued kernels) fall through
+Tempered fractional kernels and the Gaussian / exponential kernels on the full space go to the row-owner kernel with their smooth
+factors (pnb_dense_assemble_element_smooth).  Unsupported configurations (non-symmetric or variable
+kernels, two DoFMaps, P3 on triangles, vector-valued kernels) fall through
 to the reference's own getDense, so the subclass is a drop-in.
 """
 import numpy as np
@@ -62,10 +63,31 @@ def _tempered(kernel):
     return float(getattr(kernel, 'temperedValue', 0.) or 0.)
 
 
+def _smooth(kernel):
+    """(mode, a, boundary mode, boundary a, constant of the boundary form) of a Gaussian / exponential kernel on the full space
+    (gaussianKernel*, exponentialKernel*: kernelsCy.pyx:388-477; fEXPONENTINVERSE: Kernel.__init__ :690-697), None otherwise"""
+    kt = int(kernel.kernelType)
+    if kt not in (3, 8) or kernel.finiteHorizon:
+        return None
+    C = kernel.scalingValue
+    if kt == 8:
+        a = float(kernel.getKernelParam('exponentialRate'))
+        return 1, a, 1, a, 2.0*C/a
+    a = 0.5/float(kernel.getKernelParam('variance'))**kernel.dim
+    if kernel.dim == 1:
+        return 2, a, 3, a, C*np.sqrt(np.pi/a)
+    return 2, a, 4, a, C/a
+
+
 def supported(builder):
     """configurations the accelerated path covers (everything else stays with the reference's Cython loops)"""
     from PyNucleus_fem.DoFMaps import P0_DoFMap, P1_DoFMap, P2_DoFMap, P3_DoFMap
     k = builder.kernel
+    if int(k.kernelType) in (3, 8):
+        # Gaussian (1D / 2D) and exponential (1D) kernels on the full space, P1 / P2 (row-owner kernel with smooth factors)
+        return (not k.finiteHorizon and builder.dm2 is None and isinstance(builder.dm, (P1_DoFMap, P2_DoFMap)) and k.symmetric
+                and not k.variable and k.valueSize == 1 and builder.dm.mesh.dim in (1, 2) and builder.dm.mesh.manifold_dim == builder.dm.mesh.dim
+                and (builder.comm is None or builder.comm.size == 1) and not k.complement)
     if _tempered(k) != 0. and k.finiteHorizon:
         return False        # tempered kernels: infinite horizon (row-owner kernel)
     if isinstance(builder.dm, (P0_DoFMap, P2_DoFMap, P3_DoFMap)) and (k.finiteHorizon or int(k.kernelType) != 0):
@@ -93,7 +115,8 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
         int rc, o, dim, N, zero_exterior, porder, dpe
         int32_t[:, ::1] edofs
         int32_t need = 0
-        double tempered
+        double tempered, sa = 0., sba = 0.
+        int smode = 0, sbmode = 0
         double[:, ::1] vertices, nodes
         double[::1] vol, h, weights
         int32_t[:, ::1] cells, dofs, bfacets
@@ -106,6 +129,9 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
     # tempered kernels: the power law with the tempered constant in the problem, the exponential factor in the row-owner
     # kernel; the surface terms stay as they are (the reference's boundary kernel is not tempered, kernelsCy.pyx:2011-2020)
     tempered = _tempered(kernel)
+    smooth = _smooth(kernel)
+    if tempered != 0.:
+        smode, sa = 1, tempered
     lm = builder.local_matrix
     lmb = builder.local_matrix_zeroExterior
     dim = mesh.dim
@@ -156,7 +182,15 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
     k.horizon2 = kernel.horizonValue**2 if kernel.finiteHorizon else np.inf
     k.target_order = lm.target_order
     k.order_num_dofs = N
-    if k.kernel_type == 0:
+    if smooth is not None:
+        # the library sees the power law C |x-y|^0 (a fractional problem with singularity 0) and the smooth factors
+        smode, sa, sbmode, sba, bconst = smooth
+        k.kernel_type = 0
+        k.s = -0.5*kernel.dim
+        k.bscaling = bconst
+        k.bsingularity = lmb.kernel.singularityValue
+        k.btarget_order = lmb.target_order
+    elif k.kernel_type == 0:
         k.bscaling = lmb.kernel.scalingValue
         k.bsingularity = lmb.kernel.singularityValue
         k.btarget_order = lmb.target_order
@@ -211,11 +245,11 @@ def getDense(builder, zeroExterior=True, int device=0, int max_regular_order=24)
             if rc != 0:
                 raise PNB200Error(_last_error())
             with nogil:
-                if porder == 1 and tempered == 0.:
+                if porder == 1 and smode == 0:
                     rc = pnb_dense_assemble(prob, zero_exterior, 0, N, &data[0, 0], N, 0)
                 else:
-                    rc = pnb_dense_assemble_element_tempered(prob, tempered, porder, dpe, N, &edofs[0, 0], zero_exterior,
-                                                             &data[0, 0], N, 0)
+                    rc = pnb_dense_assemble_element_smooth(prob, smode, sa, sbmode, sba, porder, dpe, N, &edofs[0, 0], zero_exterior,
+                                                           &data[0, 0], N, 0)
             if rc == 0:
                 break
             if rc != -5 or attempt == 1:       # PNB_ERR_ORDER: the reference grows its rule cache lazily (addQuadRule)

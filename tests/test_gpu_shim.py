@@ -144,3 +144,25 @@ def test_reference_builder_vs_shim_tempered(shim, dim, noRef, s, lam, element):
         b = shim.builder_class()(dm, kernel, dict(params), zeroExterior=ze)
         assert shim.supported(b)
         assert entry_err(np.array(b.getDense().data), Aref) < TOL
+
+
+@pytest.mark.parametrize('dim,noRef,ktype,kw,element', [(1, 5, 'gaussian', {'variance': 0.1}, 'P1'), (1, 5, 'exponential', {'exponentialRate': 8.0}, 'P1'),
+                                                        (2, 2, 'gaussian', {'variance': 0.2}, 'P1'), (1, 4, 'gaussian', {'variance': 0.1}, 'P2')])
+def test_reference_builder_vs_shim_gaussian_exponential(shim, dim, noRef, ktype, kw, element):
+    """the Gaussian / exponential kernels of the reference's driver tests (full space) through the shim
+    (pnb_dense_assemble_element_smooth) against the reference's Cython getDense, with and without the surface terms"""
+    from PyNucleus_fem.mesh import simpleInterval, uniform_disc
+    from PyNucleus_fem.DoFMaps import P1_DoFMap, P2_DoFMap
+    from PyNucleus_nl.kernels import getIntegrableKernel
+    from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder
+    mesh = simpleInterval(-1, 1) if dim == 1 else uniform_disc()
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = {'P1': P1_DoFMap, 'P2': P2_DoFMap}[element](mesh)
+    kernel = getIntegrableKernel(dim, ktype, np.inf, **kw)
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze in (True, False):
+        Aref = np.array(nonlocalBuilder(dm, kernel, dict(params), zeroExterior=ze).getDense().data)
+        b = shim.builder_class()(dm, kernel, dict(params), zeroExterior=ze)
+        assert shim.supported(b)
+        assert entry_err(np.array(b.getDense().data), Aref) < TOL
