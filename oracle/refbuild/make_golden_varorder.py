@@ -18,18 +18,18 @@ ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
 OUT = os.path.join(ROOT, 'tests', 'golden')
 
 from PyNucleus_fem.mesh import simpleInterval, uniform_disc  # noqa: E402
-from PyNucleus_fem.DoFMaps import P1_DoFMap  # noqa: E402
+from PyNucleus_fem.DoFMaps import P0_DoFMap, P1_DoFMap, P2_DoFMap  # noqa: E402
 from PyNucleus_nl.kernels import getFractionalKernel  # noqa: E402
 from PyNucleus_nl.nonlocalAssembly import nonlocalBuilder  # noqa: E402
 from PyNucleus_nl.fractionalOrders import smoothedLeftRightFractionalOrder, linearLeftRightFractionalOrder  # noqa: E402
 from make_golden_nonsym import mesh_arrays  # noqa: E402
 
 
-def case(dim, noRef, sFun, name, params, extra):
+def case(dim, noRef, sFun, name, params, extra, element='P1'):
     mesh = uniform_disc() if dim == 2 else simpleInterval(-1, 1)
     for _ in range(noRef):
         mesh = mesh.refine()
-    dm = P1_DoFMap(mesh)
+    dm = {'P0': P0_DoFMap, 'P1': P1_DoFMap, 'P2': P2_DoFMap}[element](mesh)
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         kernel = getFractionalKernel(dim, sFun, np.inf)
@@ -47,7 +47,7 @@ def case(dim, noRef, sFun, name, params, extra):
     out['kernel_values'] = np.array([kernel(X[i], Y[i]) for i in range(64)])
     kb = kernel.getBoundaryKernel()
     out['bkernel_values'] = np.array([kb(X[i], Y[i]) for i in range(64)])
-    out.update(symmetric=0, local_matrix=type(b.local_matrix).__name__, target_order_used=b.local_matrix.target_order,
+    out.update(symmetric=0, element=element, local_matrix=type(b.local_matrix).__name__, target_order_used=b.local_matrix.target_order,
                quad_order_diagonal=b.local_matrix.quad_order_diagonal,
                btarget_order_used=b.local_matrix_zeroExterior.target_order,
                bquad_order_diagonal=b.local_matrix_zeroExterior.quad_order_diagonal, **extra)
@@ -64,10 +64,17 @@ if __name__ == '__main__':
              dict(kind='smoothedLeftRight', sl=0.75, sr=0.25, r=0.3, interface=0.2))
         case(1, 5, linearLeftRightFractionalOrder(0.3, 0.6, r=0.25), 'varorder_interval_linear_r5', {},
              dict(kind='linearLeftRight', sl=0.3, sr=0.6, r=0.25, interface=0.))
+    if 'all' in which or 'elements' in which:
+        case(1, 4, smoothedLeftRightFractionalOrder(0.25, 0.75, r=0.3), 'varorder_p2_interval_smoothed_r4', {},
+             dict(kind='smoothedLeftRight', sl=0.25, sr=0.75, r=0.3, interface=0.), element='P2')
     if 'all' in which or '2d' in which:
         case(2, 2, smoothedLeftRightFractionalOrder(0.25, 0.75), 'varorder_disc_smoothed_r2', {'target_order': 0.5},
              dict(kind='smoothedLeftRight', sl=0.25, sr=0.75, r=0.1, interface=0.))
         case(2, 3, smoothedLeftRightFractionalOrder(0.75, 0.25, r=0.3), 'varorder_disc_smoothed_r3', {'target_order': 0.5},
              dict(kind='smoothedLeftRight', sl=0.75, sr=0.25, r=0.3, interface=0.))
+        case(2, 1, smoothedLeftRightFractionalOrder(0.25, 0.75, r=0.3), 'varorder_p2_disc_smoothed_r1', {'target_order': 0.5},
+             dict(kind='smoothedLeftRight', sl=0.25, sr=0.75, r=0.3, interface=0.), element='P2')
+        case(2, 2, smoothedLeftRightFractionalOrder(0.2, 0.4, r=0.3), 'varorder_p0_disc_smoothed_r2', {'target_order': 0.5},
+             dict(kind='smoothedLeftRight', sl=0.2, sr=0.4, r=0.3, interface=0.), element='P0')
         # smoothedInnerOuterFractionalOrder cannot be constructed in the reference (fractionalOrders.pyx:657 passes
         # numParameters = 0, which fractionalOrderBase.__init__ :51 rejects): no fixture

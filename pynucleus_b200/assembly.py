@@ -198,8 +198,8 @@ class nonlocalBuilder:
             # both cells (evalParamsOnSimplices, kernelsCy.pyx:1826-1850) for the regular order and for a singular rule of
             # its own.  Device path: pnb_dense_assemble_varorder (csrc/pnb_varorder.cuh); here: s at the centres and
             # vertices, the distinct maxima and one set of singular tables per value.
-            if self.dm2 is not None or self.dm.polynomialOrder != 1:
-                raise NotImplementedError('orders varying inside a cell: one P1 DoFMap')
+            if self.dm2 is not None:
+                raise NotImplementedError('orders varying inside a cell: one DoFMap')
             if kernel.finiteHorizon:
                 raise NotImplementedError('orders varying inside a cell: infinite horizon')
             mesh = self.mesh

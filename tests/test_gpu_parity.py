@@ -1037,7 +1037,8 @@ def _varorder_from_fixture(pb, g):
 
 
 @pytest.mark.parametrize('name', ['varorder_interval_smoothed_r5', 'varorder_interval_smoothed_r6', 'varorder_interval_linear_r5',
-                                  'varorder_disc_smoothed_r2', 'varorder_disc_smoothed_r3'])
+                                  'varorder_disc_smoothed_r2', 'varorder_disc_smoothed_r3', 'varorder_p2_interval_smoothed_r4',
+                                  'varorder_p2_disc_smoothed_r1', 'varorder_p0_disc_smoothed_r2'])
 def test_order_varying_inside_cells_vs_reference(golden_dir, name):
     """Orders that vary inside a cell, s(x,y) = sFun(x) (SURVEY 8 a12 updateAndEvalFractional, a13 variable scaling, a14
     singleVariableUnsymmetricFractionalOrder; the driver's --s twoDomainNonSym): the reference's unsymmetric local matrices
@@ -1046,8 +1047,11 @@ def test_order_varying_inside_cells_vs_reference(golden_dir, name):
     import pynucleus_b200 as pb
     g = load(golden_dir, name)
     dim = g['vertices'].shape[1]
+    element = str(g['element']) if 'element' in g.files else 'P1'
     mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'])
-    dm = pb.P1_DoFMap(mesh)
+    dm = {'P0': pb.P0_DoFMap, 'P1': pb.P1_DoFMap, 'P2': pb.P2_DoFMap}[element](mesh)
+    # the unknowns are numbered like the reference's (the numbering of the boundary dofs, all negative, does not matter)
+    assert dm.num_dofs == int(g['num_dofs']) and np.array_equal(np.where(dm.dofs >= 0, dm.dofs, -1), np.where(g['dofs'] >= 0, g['dofs'], -1))
     kernel = pb.getFractionalKernel(dim, _varorder_from_fixture(pb, g))
     assert kernel.variable and not kernel.symmetric and not kernel.piecewise
     params = {'target_order': 0.5} if dim == 2 else {}
