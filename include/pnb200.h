@@ -350,6 +350,8 @@ int pnb_dense_assemble_element_smooth(pnb_problem *p, int mode, double a, int bm
 #define PNB_ORDERFUN_SMOOTHSTEP 1          /* smoothStep, fractionalOrders.pyx:389-416 (first coordinate) */
 #define PNB_ORDERFUN_LINEARSTEP 2          /* linearStep, :447-470 */
 #define PNB_ORDERFUN_SMOOTHSTEP_RADIAL 3   /* smoothStepRadial, :497-535 (interface = radius) */
+#define PNB_ORDERFUN_FE 4                  /* feFractionalOrder, :660-668: a P1 function on the assembly mesh (vertex_values);
+                                            * sl / sr = bounds of the order (values equal to them use the power tables) */
 typedef struct {
     int32_t fun;                   /* PNB_ORDERFUN_* */
     double sl, sr, r, slope, interface;
@@ -360,6 +362,7 @@ typedef struct {
     /* singular tables for the singularities -d - 2 values[k] (boundary: 1 - d - 2 values[k]); host, num_values entries each;
      * edge / bedge: 2D only (may be NULL in 1D) */
     const pnb_rule_t *identical, *edge, *vertex, *bedge, *bvertex;
+    const double *vertex_values;   /* host, num_vertices: PNB_ORDERFUN_FE only (else NULL) */
 } pnb_varorder_t;
 /* `p`: mesh, regular tables and the quadrature-order constants (target orders, order_num_dofs) of the local matrices; its
  * own kernel parameters and singular tables are not used.  Elements as in pnb_dense_assemble_element.  One warp owns one

@@ -78,3 +78,36 @@ if __name__ == '__main__':
              dict(kind='smoothedLeftRight', sl=0.2, sr=0.4, r=0.3, interface=0.), element='P0')
         # smoothedInnerOuterFractionalOrder cannot be constructed in the reference (fractionalOrders.pyx:657 passes
         # numParameters = 0, which fractionalOrderBase.__init__ :51 rejects): no fixture
+
+
+def case_fe(dim, noRef, fun, smin, smax, name, params):
+    """feFractionalOrder (fractionalOrders.pyx:660-668): the order is a P1 finite element function on the mesh of the operator"""
+    from PyNucleus_fem import NO_BOUNDARY
+    from PyNucleus_fem.functions import Lambda
+    from PyNucleus_nl.fractionalOrders import feFractionalOrder
+    mesh = uniform_disc() if dim == 2 else simpleInterval(-1, 1)
+    for _ in range(noRef):
+        mesh = mesh.refine()
+    dm = P1_DoFMap(mesh)
+    dms = P1_DoFMap(mesh, NO_BOUNDARY)
+    vec = dms.interpolate(Lambda(fun))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        kernel = getFractionalKernel(dim, feFractionalOrder(vec, smin, smax), np.inf)
+    assert kernel.variable and not kernel.piecewise and not kernel.symmetric
+    out = mesh_arrays(mesh, dm)
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = nonlocalBuilder(dm, kernel, dict(params), zeroExterior=ze)
+        out[key] = np.array(b.getDense().data)
+    out.update(symmetric=0, element='P1', kind='fe', order_dofs=np.array(dms.dofs), order_values=np.array(vec), smin=smin, smax=smax,
+               target_order_used=b.local_matrix.target_order, quad_order_diagonal=b.local_matrix.quad_order_diagonal,
+               btarget_order_used=b.local_matrix_zeroExterior.target_order,
+               bquad_order_diagonal=b.local_matrix_zeroExterior.quad_order_diagonal)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, out['A'].shape, type(b.local_matrix).__name__, 'asym of A: %.3e' % np.abs(out['A']-out['A'].T).max(), flush=True)
+
+
+if __name__ == '__main__' and ('all' in (sys.argv[1:] or ['all']) or 'fe' in sys.argv[1:]):
+    case_fe(1, 5, lambda x: 0.5+0.2*np.sin(2*x[0]), 0.3, 0.7, 'varorder_fe_interval_r5', {})
+    case_fe(2, 2, lambda x: 0.5+0.2*np.sin(2*x[0])*np.cos(x[1]), 0.3, 0.7, 'varorder_fe_disc_r2', {'target_order': 0.5})
+    case_fe(2, 3, lambda x: 0.45+0.3*x[0]*x[1], 0.25, 0.65, 'varorder_fe_disc_r3', {'target_order': 0.5})

@@ -55,14 +55,25 @@ class linearStep(smoothStep):
         return np.where(x0 < self.interface-self.r, self.sl, np.where(x0 > self.interface+self.r, self.sr, v))
 
 
+class feOrder:
+    """feFractionalOrder (fractionalOrders.pyx:660-668) on the mesh of the operator: P1 function given by its vertex values;
+    at a point of cell c with barycentric coordinates lam the order is sum_k lam_k u[vertex k of c]"""
+
+    def __init__(self, vertex_values, smin=None, smax=None):
+        self.vertex_values = np.asarray(vertex_values, dtype=np.float64)
+        self.min = float(self.vertex_values.min() if smin is None else smin)
+        self.max = float(self.vertex_values.max() if smax is None else smax)
+
+
 def scaling(dim, s):
     """variableFractionalLaplacianScaling, normalized, infinite horizon (kernelNormalization.pyx:438-439)"""
     return 2.0**(2.0*s)*s*gamma(s+0.5*dim)*pi**(-0.5*dim)/gamma(1.0-s)*0.5
 
 
-def kernel_value(dim, sFun, x, y, boundary=False):
-    """gamma(x, y) (fracKernelInfinite*, kernelsCy.pyx:159-183; boundary form with phi = 1/s)"""
-    s = sFun(x)
+def kernel_value(dim, sFun, x, y, boundary=False, s=None):
+    """gamma(x, y) (fracKernelInfinite*, kernelsCy.pyx:159-183; boundary form with phi = 1/s); s: the order at x if known"""
+    if s is None:
+        s = sFun(x)
     d2 = ((x-y)**2).sum(axis=-1)
     if boundary:
         return scaling(dim, s)/s*d2**(0.5*(1-dim)-s)
@@ -123,7 +134,15 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
     orders = tables.diag_orders(dim, -dim-2*sFun.max, 1.-dim-2*sFun.max, hmin, H0, num_dofs, None,
                                 min_singularity=-dim-2*sFun.min, min_boundary_singularity=1.-dim-2*sFun.min)
     to, tob = orders['target_order'], orders['b_target_order']
-    smax_cell = np.maximum(sFun(centers), sFun(T).max(axis=1))
+    fe = hasattr(sFun, 'vertex_values')
+    if fe:
+        smax_cell = sFun.vertex_values[cells].max(axis=1)
+    else:
+        smax_cell = np.maximum(sFun(centers), sFun(T).max(axis=1))
+
+    def order_at(c, lam, x):
+        """the order at the points x of cell c (barycentric coordinates lam, nvc x nq, in the cell's own vertex order)"""
+        return lam.T.dot(sFun.vertex_values[cells[c]]) if fe else sFun(x)
     near_cache = {}
 
     def near(smax):
@@ -179,8 +198,8 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
                     A[idx[i], idx[j]] += M[i, j]
 
     def local(cA, cB, lamx, lamy, w, x, y):
-        gxy = kernel_value(dim, sFun, x, y)
-        gyx = kernel_value(dim, sFun, y, x)
+        gxy = kernel_value(dim, sFun, x, y, s=order_at(cA, lamx, x))
+        gyx = kernel_value(dim, sFun, y, x, s=order_at(cB, lamy, y))
         px, py = shape(lamx), shape(lamy)             # nvc x nq
         rowI = np.vstack((px*(w*gxy), -py*(w*gyx)))    # temp PHI[I,0] - temp2 PHI[I,1]
         colJ = np.vstack((px, -py))
@@ -221,7 +240,10 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
             for f in range(bfacets.shape[0]):
                 F = vertices[bfacets[f]]
                 fc = F.mean(axis=0) if nvf > 1 else F[0]
-                smax = max(smax_cell[c1], float(sFun(fc[None])[0]), float(sFun(F).max()))
+                if fe:
+                    smax = max(smax_cell[c1], float(sFun.vertex_values[bfacets[f]].max()))
+                else:
+                    smax = max(smax_cell[c1], float(sFun(fc[None])[0]), float(sFun(F).max()))
                 panel, p1, p2 = _proto(cells[c1], bfacets[f], False)
                 if dim == 2:
                     nrm = np.array([F[1, 1]-F[0, 1], F[0, 0]-F[1, 0]])
@@ -239,7 +261,7 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
                     x = lamx.T.dot(T[c1])
                     y = np.tile(bf, (1, n)).T.dot(F)
                     w = np.repeat(w1, m)*np.tile(wf, n)
-                    g = kernel_value(dim, sFun, x, y, boundary=True)
+                    g = kernel_value(dim, sFun, x, y, boundary=True, s=order_at(c1, lamx, x))
                     if dim == 2:
                         # gamma_b n.(y-x)/|y-x| (eval_distant_boundary, nonlocalOperator_{SCALAR}.pxi:1069-1108)
                         g = g*((y-x).dot(nrm))/np.sqrt(((x-y)**2).sum(axis=1))
@@ -251,7 +273,7 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
                     y = bary[nvc:nvc+nvf].T.dot(SF)
                     lamx = np.zeros((nvc, bary.shape[1]))
                     lamx[p1] = bary[:nvc]
-                    g = kernel_value(dim, sFun, x, y, boundary=True)
+                    g = kernel_value(dim, sFun, x, y, boundary=True, s=order_at(c1, lamx, x))
                     if dim == 2:
                         # fractionalLaplacian2D.pyx:1356-1407: n.(x-y)/|x-y| and the factor -2 vol1 vol2
                         g = g*((x-y).dot(nrm))/np.sqrt(((x-y)**2).sum(axis=1))

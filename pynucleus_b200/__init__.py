@@ -8,7 +8,8 @@ from .kernels import (getFractionalKernel, getKernel, FractionalKernel, constFra
                       piecewiseConstantFractionalOrder, constantNonSymFractionalOrder, layersFractionalOrder, innerOuterFractionalOrder, islandsFractionalOrder,
                       constantFractionalLaplacianScaling, FRACTIONAL, INDICATOR, PERIDYNAMIC, Kernel, getIntegrableKernel,
                       constantIntegrableScaling, constant, singleVariableUnsymmetricFractionalOrder,
-                      smoothedLeftRightFractionalOrder, linearLeftRightFractionalOrder, variableFractionalLaplacianScaling)
+                      smoothedLeftRightFractionalOrder, linearLeftRightFractionalOrder, feFractionalOrder,
+                      variableFractionalLaplacianScaling)
 from .assembly import nonlocalBuilder, assembleNonlocalOperator, release_staging_pool  # noqa: F401
 from .linear_operators import Dense_LinearOperator, diagonalOperator  # noqa: F401
 from .solvers import cg, gmres, lu, DistributedDenseOperator  # noqa: F401

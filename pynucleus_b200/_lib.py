@@ -54,7 +54,7 @@ class pnb_varorder_t(ctypes.Structure):
                 ('values', ctypes.c_void_p), ('cell_value', ctypes.c_void_p), ('bfacet_value', ctypes.c_void_p),
                 ('identical', ctypes.POINTER(pnb_rule_t)), ('edge', ctypes.POINTER(pnb_rule_t)),
                 ('vertex', ctypes.POINTER(pnb_rule_t)), ('bedge', ctypes.POINTER(pnb_rule_t)),
-                ('bvertex', ctypes.POINTER(pnb_rule_t))]
+                ('bvertex', ctypes.POINTER(pnb_rule_t)), ('vertex_values', ctypes.c_void_p)]
 
 
 class pnb_h2_desc_t(ctypes.Structure):

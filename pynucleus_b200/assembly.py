@@ -216,19 +216,27 @@ class nonlocalBuilder:
             self.orders = quadrature.localMatrixOrders(*args, target_order=None, **kw)
             ob = quadrature.localMatrixOrders(*args, target_order=self.params.get('target_order', None), **kw)
             self.orders.btarget_order, self.orders.bquad_order_diagonal = ob.btarget_order, ob.bquad_order_diagonal
-            T = mesh.vertices[mesh.cells]
-            centers = np.zeros((mesh.num_cells, mesh.dim))
-            for k in range(mesh.dim+1):
-                centers += T[:, k]
-            centers /= mesh.dim+1
-            smax_cell = np.maximum(kernel.s.evaluate(centers), kernel.s.evaluate(T).max(axis=1))
             bf = np.asarray(mesh.boundaryFacets).reshape(-1, mesh.dim)
-            F = mesh.vertices[bf]
-            smax_facet = np.maximum(kernel.s.evaluate(F.mean(axis=1)), kernel.s.evaluate(F).max(axis=1))
+            vertex_values = None
+            if hasattr(kernel.s, 'vertexValues'):
+                # P1 function on the mesh: its maximum over a cell or facet (centre included) is the largest vertex value
+                vertex_values = np.ascontiguousarray(kernel.s.vertexValues(mesh))
+                smax_cell = vertex_values[mesh.cells].max(axis=1)
+                smax_facet = vertex_values[bf].max(axis=1)
+            else:
+                T = mesh.vertices[mesh.cells]
+                centers = np.zeros((mesh.num_cells, mesh.dim))
+                for k in range(mesh.dim+1):
+                    centers += T[:, k]
+                centers /= mesh.dim+1
+                smax_cell = np.maximum(kernel.s.evaluate(centers), kernel.s.evaluate(T).max(axis=1))
+                F = mesh.vertices[bf]
+                smax_facet = np.maximum(kernel.s.evaluate(F.mean(axis=1)), kernel.s.evaluate(F).max(axis=1))
             vals, inv = np.unique(np.concatenate((smax_cell, smax_facet)), return_inverse=True)
             self._varorder = dict(base=kmax, values=np.ascontiguousarray(vals),
                                   cell_value=np.ascontiguousarray(inv[:mesh.num_cells], dtype=np.int32),
-                                  bfacet_value=np.ascontiguousarray(inv[mesh.num_cells:], dtype=np.int32), struct=None)
+                                  bfacet_value=np.ascontiguousarray(inv[mesh.num_cells:], dtype=np.int32), struct=None,
+                                  vertex_values=vertex_values)
             self._problem = None
             return
         if hasattr(kernel.s, 'blockOrders'):
@@ -475,6 +483,8 @@ class nonlocalBuilder:
                 if name in ('edge', 'bedge') and dim == 1:
                     continue
                 setattr(st, name, arrays[name])
+            if V['vertex_values'] is not None:
+                st.vertex_values = V['vertex_values'].ctypes.data
             V['struct'] = (st, arrays, keep)
         return V['struct'][0]
 

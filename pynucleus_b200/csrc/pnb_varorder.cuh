@@ -31,9 +31,25 @@ struct VarOrderDev {
     const int *facet_val;           // nb
     const DRule *rules;             // 5 x nvals: identical | edge | vertex | bedge | bvertex
     const PowTab *pt;               // power tables of the two plateaus: interior sl | sr, boundary sl | sr
+    const double *vert_s;           // PNB_ORDERFUN_FE: the order at the mesh vertices (P1 function on the assembly mesh)
 };
 
-__device__ __forceinline__ double vo_order(const VarOrderDev &V, double x0, double x1)
+__device__ __forceinline__ double vo_order_fun(const VarOrderDev &V, double x0, double x1);
+
+// order at a point of cell `cellv` (its vertex ids) with barycentric coordinates lam (the cell's own vertex order)
+template <int NV> __device__ __forceinline__ double vo_order(const VarOrderDev &V, double x0, double x1, const int *cellv, const double *lam)
+{
+    if (V.fun == PNB_ORDERFUN_FE) {
+        // feFractionalOrder (fractionalOrders.pyx:660-668): sum_k phi_k(x) u[dof_k], lookupExtended.evalPtr :573-586
+        double v = 0.;
+#pragma unroll
+        for (int k = 0; k < NV; k++) v += lam[k] * V.vert_s[cellv[k]];
+        return v;
+    }
+    return vo_order_fun(V, x0, x1);
+}
+
+__device__ __forceinline__ double vo_order_fun(const VarOrderDev &V, double x0, double x1)
 {
     // smoothStep / linearStep / smoothStepRadial (fractionalOrders.pyx:389-416, 447-470, 497-535)
     double t = x0;
@@ -196,11 +212,11 @@ __device__ void vo_pair_row(const DProblem &P, const VarOrderDev &V, int cA, int
         // a kernel value is only needed where the row's shape function does not vanish
         double tI = 0.;
         if (sA >= 0) {
-            const double sx = vo_order(V, x0, x1);
+            const double sx = vo_order<NV>(V, x0, x1, P.cells + (size_t)cA * NV, lx);
             tI = vo_kernel<DIM>(V, d2, sx, false) * pIx;
         }
         if (sB >= 0) {
-            const double sy = vo_order(V, y0, y1);
+            const double sy = vo_order<NV>(V, y0, y1, P.cells + (size_t)cB * NV, ly);
             tI -= vo_kernel<DIM>(V, d2, sy, false) * pIy;
         }
         tI *= w;
@@ -314,7 +330,7 @@ __device__ void vo_boundary_row(const DProblem &P, const VarOrderDev &V, int c1,
         for (int k = 0; k < DPE; k++)
             if (k == sI) pI = px[k];
         // boundary kernel (2D: divided by |x-y|, the normal factor nw is not normalised)
-        const double sx = vo_order(V, x0, x1);
+        const double sx = vo_order<NV>(V, x0, x1, P.cells + (size_t)c1 * NV, lx);
         const double g = w * nw * vo_kernel<DIM>(V, d2, sx, true) * pI;
 #pragma unroll
         for (int k = 0; k < DPE; k++) acc[k] = fma(g, px[k], acc[k]);
@@ -499,7 +515,8 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
     if (dofs_per_element != dpe) return fail(PNB_ERR_ARG, "dofs_per_element does not match the element");
     if (p->finite) return fail(PNB_ERR_UNSUPPORTED, "orders varying inside a cell: infinite horizon only");
     if (p->nblocks > 0) return fail(PNB_ERR_UNSUPPORTED, "orders varying inside a cell: no batched blocks");
-    if (order->fun < PNB_ORDERFUN_CONST || order->fun > PNB_ORDERFUN_SMOOTHSTEP_RADIAL) return fail(PNB_ERR_ARG, "unknown order function");
+    if (order->fun < PNB_ORDERFUN_CONST || order->fun > PNB_ORDERFUN_FE) return fail(PNB_ERR_ARG, "unknown order function");
+    if (order->fun == PNB_ORDERFUN_FE && !order->vertex_values) return fail(PNB_ERR_ARG, "PNB_ORDERFUN_FE needs vertex_values");
     if (order->num_values <= 0 || !order->values || !order->cell_value || !order->identical || !order->vertex || !order->bvertex ||
         (p->dim == 2 && (!order->edge || !order->bedge)) || (p->nb > 0 && !order->bfacet_value))
         return fail(PNB_ERR_ARG, "incomplete order description");
@@ -532,7 +549,7 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
             pack.insert(pack.end(), s.bary, s.bary + (size_t)s.rows * s.n);
             pack.insert(pack.end(), s.w, s.w + s.n);
         }
-    double *d_pack = nullptr, *d_vals = nullptr;
+    double *d_pack = nullptr, *d_vals = nullptr, *d_vs = nullptr;
     PowTab *d_pt = nullptr;
     DRule *d_rules = nullptr;
     int *d_cv = nullptr, *d_fv = nullptr;
@@ -540,14 +557,15 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
     double *A = A_out;
     int64_t ld = ld_out;
     auto cleanup = [&]() {
-        cudaFree(d_pack); cudaFree(d_vals); cudaFree(d_rules); cudaFree(d_cv); cudaFree(d_fv); cudaFree(d_pt);
+        cudaFree(d_pack); cudaFree(d_vals); cudaFree(d_rules); cudaFree(d_cv); cudaFree(d_fv); cudaFree(d_pt); cudaFree(d_vs);
         elem_job_free(dev);
         if (!a_on_device && A != A_out) pool_free(A);
     };
     if (cudaMalloc(&d_pack, std::max<size_t>(pack.size(), 1) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&d_vals, (size_t)nvals * sizeof(double)) != cudaSuccess || cudaMalloc(&d_rules, hr.size() * sizeof(DRule)) != cudaSuccess ||
         cudaMalloc(&d_cv, (size_t)p->nc * sizeof(int)) != cudaSuccess || cudaMalloc(&d_fv, std::max<size_t>(p->nb, 1) * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&d_pt, 4 * sizeof(PowTab)) != cudaSuccess) {
+        cudaMalloc(&d_pt, 4 * sizeof(PowTab)) != cudaSuccess ||
+        (order->fun == PNB_ORDERFUN_FE && cudaMalloc(&d_vs, (size_t)p->P.nv * sizeof(double)) != cudaSuccess)) {
         cudaGetLastError();
         cleanup();
         return fail(PNB_ERR_CUDA, "out of device memory");
@@ -562,6 +580,7 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
     cudaMemcpy(d_rules, hr.data(), hr.size() * sizeof(DRule), cudaMemcpyHostToDevice);
     cudaMemcpy(d_cv, order->cell_value, (size_t)p->nc * sizeof(int), cudaMemcpyHostToDevice);
     if (p->nb > 0) cudaMemcpy(d_fv, order->bfacet_value, (size_t)p->nb * sizeof(int), cudaMemcpyHostToDevice);
+    if (d_vs) cudaMemcpy(d_vs, order->vertex_values, (size_t)p->P.nv * sizeof(double), cudaMemcpyHostToDevice);
     VarOrderDev V;
     V.fun = order->fun;
     V.sl = order->sl; V.sr = order->sr; V.r = order->r; V.slope = order->slope; V.interface = order->interface;
@@ -581,7 +600,7 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
         for (auto &t : tabs) t.horizon2 = INFINITY;
         cudaMemcpy(d_pt, tabs.data(), 4 * sizeof(PowTab), cudaMemcpyHostToDevice);
     }
-    V.nvals = nvals; V.vals = d_vals; V.cell_val = d_cv; V.facet_val = d_fv; V.rules = d_rules; V.pt = d_pt;
+    V.nvals = nvals; V.vals = d_vals; V.cell_val = d_cv; V.facet_val = d_fv; V.rules = d_rules; V.pt = d_pt; V.vert_s = d_vs;
     if (!a_on_device) {
         ld = num_dofs;
         A = nullptr;

@@ -278,6 +278,44 @@ class linearLeftRightFractionalOrder(singleVariableUnsymmetricFractionalOrder):
         return 'linearLeftRightFractionalOrder(sl={},sr={},r={},interface={})'.format(self.sl, self.sr, self.r, self.interface)
 
 
+class feFractionalOrder(singleVariableUnsymmetricFractionalOrder):
+    """s(x, y) = s_h(x) for a P1 finite element function s_h = sum_i u_i phi_i (fractionalOrders.pyx:660-668; dofs of the
+    map that are boundary dofs contribute nothing, lookupExtended.evalPtr :573-586).  The reference takes an fe_vector and looks
+    the cell of every point up; here the function lives on the ASSEMBLY mesh (`dm.mesh` must be the mesh of the operator's
+    DoFMap), so that the cell of a quadrature node is known and the order is `sum_k lambda_k(x) u[dof_k]` on the device
+    (PNB_ORDERFUN_FE).  Any order that varies smoothly over the mesh can be supplied this way through its nodal values."""
+    fun = 4
+
+    def __init__(self, dm, u, smin=None, smax=None):
+        if dm.polynomialOrder != 1:
+            raise NotImplementedError('feFractionalOrder: P1 functions')
+        self.dm = dm
+        self.u = np.ascontiguousarray(u, dtype=np.float64)
+        assert self.u.shape == (dm.num_dofs, )
+        self.min = float(self.u.min() if smin is None else smin)
+        self.max = float(self.u.max() if smax is None else smax)
+        # the bounds double as the two values whose powers come from tables on the device
+        self.sl, self.sr, self.r, self.slope, self.interface = self.min, self.max, 0., 0., 0.
+
+    def vertexValues(self, mesh):
+        """the order at the vertices of `mesh` (which must be the function's own mesh)"""
+        m = self.dm.mesh
+        if m is not mesh and not (m.vertices.shape == mesh.vertices.shape and np.array_equal(m.vertices, mesh.vertices)
+                                  and np.array_equal(m.cells, mesh.cells)):
+            raise NotImplementedError('feFractionalOrder: the order must be given on the mesh of the operator')
+        v = np.zeros(mesh.num_vertices)
+        for k in range(self.dm.dofs.shape[1]):
+            ok = self.dm.dofs[:, k] >= 0
+            v[mesh.cells[ok, k]] = self.u[self.dm.dofs[ok, k]]
+        return v
+
+    def evaluate(self, points):
+        raise NotImplementedError('feFractionalOrder is evaluated cell by cell on the device (no point lookup on the host)')
+
+    def __repr__(self):
+        return 'feFractionalOrder({} dofs, min={}, max={})'.format(self.u.shape[0], self.min, self.max)
+
+
 def variableFractionalLaplacianScaling(dim, s):
     """C(d, s(x,y)) / 2 of a normalised kernel with infinite horizon (kernelNormalization.pyx:438-439); s may be an array"""
     from scipy.special import gamma as gamma_

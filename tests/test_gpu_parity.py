@@ -1283,3 +1283,33 @@ def test_driver_known_answers_gaussian_and_exponential(kt):
     A = pb.nonlocalBuilder(dm, kernel, {}).getDense().data
     L2i, Linf = smooth_driver_errors(mesh.vertices, mesh.cells, dm.dofs, dm.num_dofs, A, f, u_ex)
     assert abs(L2i/SMOOTH_DRIVER_CASES[kt][0]-1) < 1e-6 and abs(Linf/SMOOTH_DRIVER_CASES[kt][1]-1) < 1e-12
+
+
+@pytest.mark.parametrize('name', ['varorder_fe_interval_r5', 'varorder_fe_disc_r2', 'varorder_fe_disc_r3'])
+def test_order_given_by_a_fe_function_vs_reference(golden_dir, name):
+    """feFractionalOrder (the order is a P1 finite element function, evaluated per quadrature node from the
+    barycentric coordinates of the node's cell; every cell has a pair singularity of its own, hence as many sets of singular
+    tables as cells) against operators assembled by the reference itself"""
+    import pynucleus_b200 as pb
+    from test_oracle_golden import fe_order_vertex_values
+    g = load(golden_dir, name)
+    dim = g['vertices'].shape[1]
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'] if dim == 2 else g['boundaryVertices'])
+    dm = pb.P1_DoFMap(mesh)
+    # the order lives on a map without boundary dofs (NO_BOUNDARY in the reference): every vertex carries a value
+    dms = pb.P1_DoFMap(mesh, tag=np.zeros(mesh.num_vertices, dtype=bool))
+    vs = fe_order_vertex_values(g)
+    u = np.zeros(dms.num_dofs)
+    for k in range(dim+1):
+        u[dms.dofs[:, k]] = vs[mesh.cells[:, k]]
+    order = pb.feFractionalOrder(dms, u, float(g['smin']), float(g['smax']))
+    assert np.array_equal(order.vertexValues(mesh), vs)
+    kernel = pb.getFractionalKernel(dim, order)
+    assert kernel.variable and not kernel.symmetric and not kernel.piecewise
+    params = {'target_order': 0.5} if dim == 2 else {}
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        b = pb.nonlocalBuilder(dm, kernel, params, zeroExterior=ze)
+        assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+        assert b.orders.bquad_order_diagonal == int(g['bquad_order_diagonal'])
+        A = b.getDense().data
+        assert entry_err(A, g[key]) < TOL

@@ -398,3 +398,26 @@ def test_gaussian_and_exponential_kernel_objects_match_reference(golden_dir, nam
     assert b.orders.bquad_order_diagonal == int(g['bquad_order_diagonal'])
     with pytest.raises(NotImplementedError):
         pb.getIntegrableKernel(dim, str(g['kernelType']), 0.3)
+
+
+def test_fe_order_host_side(golden_dir):
+    """feFractionalOrder on the host: vertex values through the order's own DoFMap, ranking of the pair singularities (largest
+    vertex value per cell / facet), quadrature orders as in the reference's local matrices; a mesh other than the order's is refused"""
+    from test_oracle_golden import fe_order_vertex_values
+    g = np.load(os.path.join(golden_dir, 'varorder_fe_disc_r2.npz'))
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'])
+    dms = pb.P1_DoFMap(mesh, tag=np.zeros(mesh.num_vertices, dtype=bool))
+    assert dms.num_dofs == mesh.num_vertices
+    vs = fe_order_vertex_values(g)
+    u = np.zeros(dms.num_dofs)
+    for k in range(3):
+        u[dms.dofs[:, k]] = vs[mesh.cells[:, k]]
+    order = pb.feFractionalOrder(dms, u, float(g['smin']), float(g['smax']))
+    b = pb.nonlocalBuilder(pb.P1_DoFMap(mesh), pb.getFractionalKernel(2, order), {'target_order': 0.5})
+    assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal']) and b.orders.bquad_order_diagonal == int(g['bquad_order_diagonal'])
+    V = b._varorder
+    assert np.array_equal(V['values'][V['cell_value']], vs[mesh.cells].max(axis=1))
+    assert np.array_equal(V['values'][V['bfacet_value']], vs[np.asarray(mesh.boundaryFacets)].max(axis=1))
+    assert b._varorder_struct().vertex_values
+    with pytest.raises(NotImplementedError):
+        pb.nonlocalBuilder(pb.P1_DoFMap(pb.refined(mesh, 1)), pb.getFractionalKernel(2, order), {'target_order': 0.5})

@@ -474,3 +474,28 @@ def test_gaussian_and_exponential_kernels_reproduce_cached_driver_runs(kt):
     A = oracle.Problem(m.vertices, m.cells, dofs, n, -0.5, smooth=sm).dense(True)
     L2i, Linf = smooth_driver_errors(m.vertices, m.cells, dofs, n, A, f, u_ex)
     assert abs(L2i/SMOOTH_DRIVER_CASES[kt][0]-1) < 1e-6 and abs(Linf/SMOOTH_DRIVER_CASES[kt][1]-1) < 1e-12
+
+
+def fe_order_vertex_values(g):
+    """vertex values of the P1 order function stored in a varorder_fe_* fixture"""
+    vs = np.zeros(g['vertices'].shape[0])
+    od = g['order_dofs']
+    for k in range(od.shape[1]):
+        ok = od[:, k] >= 0
+        vs[g['cells'][ok, k]] = g['order_values'][od[ok, k]]
+    return vs
+
+
+@pytest.mark.parametrize('name', ['varorder_fe_interval_r5', 'varorder_fe_disc_r2'])
+def test_order_given_by_a_fe_function_matches_reference(golden_dir, name):
+    """feFractionalOrder (the order is a P1 function on the mesh of the operator) in oracle/varorder.py against operators
+    assembled by the reference itself (make_golden_varorder.py fe)"""
+    from oracle import varorder
+    g = np.load(os.path.join(golden_dir, name+'.npz'))
+    dim = g['vertices'].shape[1]
+    sF = varorder.feOrder(fe_order_vertex_values(g), float(g['smin']), float(g['smax']))
+    bf = g['boundaryEdges'] if dim == 2 else g['boundaryVertices']
+    for ze, key in ((True, 'A'), (False, 'A_interior')):
+        A = varorder.dense(g['vertices'], g['cells'], g['dofs'], int(g['num_dofs']), sF, bf, zero_exterior=ze,
+                           hmin=float(g['hmin']), diam=float(g['diam']))
+        assert np.abs(A-g[key]).max() < 1e-12*np.abs(g[key]).max()
