@@ -922,6 +922,9 @@ class nonlocalBuilder:
     def getFarFieldBlocks(self, boxes1, boxes2, m1, m2):
         """kernelInterpolant blocks of admissible cluster pairs (assembleFarFieldInteractions,
         clusterMethodCy.pyx:2153-2238): list of (m1^d x m2^d) arrays  -2 gamma(xi_i, xi_j)."""
+        if getattr(self, '_smooth', (0, ))[0] != 0:
+            # the device problem of these kernels carries the power law without its smooth factor
+            raise NotImplementedError('only getDense() supports tempered / Gaussian / exponential kernels')
         dim = self.mesh.dim
         boxes1 = np.ascontiguousarray(boxes1, dtype=np.float64).reshape(-1, dim, 2)
         boxes2 = np.ascontiguousarray(boxes2, dtype=np.float64).reshape(-1, dim, 2)
