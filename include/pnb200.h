@@ -370,6 +370,16 @@ typedef struct {
 int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t *order, int polynomial_order, int dofs_per_element,
                                 int num_dofs, const int32_t *dofs, int zero_exterior, double *A, int64_t ld, int a_on_device);
 
+/* Several GPUs for the row-owner kernels (pnb_dense_assemble_element / _tempered / _smooth / _varorder): one problem instance per
+ * GPU assembles the rows of one part.  The rows, sorted by descending number of cells around their dof, are dealt to the parts
+ * in turn; a row is complete on its owner (one warp per row, no exchange of matrix entries, no collective).  After
+ * pnb_problem_set_row_part(p, part, nparts) the assembly calls write num_rows x num_dofs entries (device memory only):
+ * row k of the output = global row rows[k] of pnb_element_rows (ascending).  nparts = 1 restores the whole operator.
+ * pnb_element_rows is host arithmetic (rows may be NULL to query the count). */
+int pnb_problem_set_row_part(pnb_problem *p, int32_t part, int32_t nparts);
+int pnb_element_rows(pnb_problem *p, int dofs_per_element, int num_dofs, const int32_t *dofs, int32_t part, int32_t nparts,
+                     int32_t *rows, int32_t *num_rows);
+
 /* ---- H2 operator on the device -------------------------------------------------------------------------
  * Replaces H2Matrix.matvec (nl/PyNucleus_nl/clusterMethodCy.pyx:2269-2295) with its upwardPass / downwardPass
  * (:1093-1176) and tree_node.enterLeafValues (:1205-1325).  The caller describes the cluster tree node by node

@@ -508,6 +508,59 @@ class nonlocalBuilder:
             run()
         return Dense_LinearOperator(A, prob.device)
 
+    def _element_problem(self):
+        self._varorder_access = self._varorder is not None
+        try:
+            return self.problem
+        finally:
+            self._varorder_access = False
+
+    def rowsOfPart(self, part, nparts):
+        """global rows (ascending) that part `part` of `nparts` assembles on the row-owner kernels (pnb_element_rows)"""
+        if not (self._element or self._varorder is not None):
+            raise NotImplementedError('row parts exist for the row-owner kernels only; P1 production path: getDenseDistributed')
+        prob = self._element_problem()
+        ed = np.ascontiguousarray(self.dm.dofs, dtype=np.int32)
+        n = ctypes.c_int32(0)
+        L = _lib.lib()
+        _lib.check(L.pnb_element_rows(prob.handle, self.dm.dofs_per_element, self.dm.num_dofs, ed.ctypes.data, part, nparts, None,
+                                      ctypes.byref(n)))
+        rows = np.zeros(n.value, dtype=np.int32)
+        _lib.check(L.pnb_element_rows(prob.handle, self.dm.dofs_per_element, self.dm.num_dofs, ed.ctypes.data, part, nparts,
+                                      rows.ctypes.data, ctypes.byref(n)))
+        return rows
+
+    def getDenseRowsOfPart(self, part, nparts, out=None):
+        """the rows `rowsOfPart(part, nparts)` of getDense() on this process' GPU (row-owner kernels; one warp per row, so a
+        part needs nothing from the others: no collective, per GPU only its rows).  Returns a Dense_LinearOperator with
+        len(rows) x num_dofs entries."""
+        import torch
+        rows = self.rowsOfPart(part, nparts)
+        prob = self._element_problem()
+        dev = torch.device('cuda', prob.device)
+        N = self.dm.num_dofs
+        n = max(int(rows.shape[0]), 1)
+        if out is not None:
+            check_matrix_out(out, rows.shape[0], N, dev)
+        A = torch.empty((n, N), dtype=torch.float64, device=dev) if out is None else out
+        L = _lib.lib()
+        _lib.check(L.pnb_problem_set_row_part(prob.handle, part, nparts))
+        try:
+            if self._varorder is not None:
+                self._getDenseVarOrder(prob, A, N)
+            else:
+                ed = np.ascontiguousarray(self.dm.dofs, dtype=np.int32)
+                mode, a, bmode, ba = self._smooth
+
+                def run():
+                    _lib.check(L.pnb_dense_assemble_element_smooth(prob.handle, mode, a, bmode, ba, self.dm.polynomialOrder,
+                                                                   self.dm.dofs_per_element, N, ed.ctypes.data,
+                                                                   int(self.zeroExterior), A.data_ptr(), A.stride(0), 1))
+                self._retry_on_order(run)
+        finally:
+            _lib.check(L.pnb_problem_set_row_part(prob.handle, 0, 1))
+        return Dense_LinearOperator(A[:rows.shape[0]], prob.device)
+
     def _sparsify(self, threshold=0.8):
         """the reference's criterion for assembling into a sparse operator (nonlocalAssembly_{SCALAR}.pxi:1287-1292)"""
         mesh = self.mesh
@@ -757,6 +810,12 @@ class nonlocalBuilder:
         world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         rank = dist.get_rank(process_group) if dist.is_initialized() else 0
         N = self.dm.num_dofs
+        if self._element or self._varorder is not None:
+            # row-owner kernels (P0 / P2 / P3 elements, kernels with a smooth factor, orders that vary inside a cell): rows
+            # dealt to the ranks, every row complete on its owner -- nothing is exchanged during the assembly
+            all_rows = [self.rowsOfPart(r, world) for r in range(world)]
+            A = self.getDenseRowsOfPart(rank, world, out=out)
+            return DistributedDenseOperator(A if all_rows[rank].shape[0] else None, all_rows, rank, N, process_group)
         if self.mesh.dim == 1:
             blocks = row_partition(N, world, int(_lib.lib().pnb_row_granularity()))
             a, b = blocks[rank]

@@ -306,6 +306,7 @@ struct pnb_problem {
     bool ordered_classes = false;   // piecewise kernels with an unsymmetric class table or reversed singular pairs: DoF-tile path only
     int path = 0;               // 0: default, 1: DoF-tile path for whole 2D operators too (pnb_problem_set_path)
     int pow_eoff = 240;      // PowTab::eoff of this problem
+    int row_part = 0, row_nparts = 1;   // row-owner kernels: this instance assembles the rows of one part (pnb_problem_set_row_part)
     std::vector<double> h_centers, h_h;
     std::vector<int4> h_grid;         // lane grids of the near evaluator per order
     std::vector<int> h_reg_n;         // node count of the regular cell rule per order

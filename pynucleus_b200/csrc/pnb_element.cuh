@@ -301,6 +301,8 @@ struct ElemJob {
     int *err;               // [0]: regular order missing in the tables
     int smode, bmode;       // smooth factors of the interior and the boundary kernel (elem_smooth), 0 = none
     double sa, ba;
+    int nrows;              // rows of this launch: length of row_order (all N rows, or the rows of one part)
+    const int *row_slot;    // several parts (pnb_problem_set_row_part): global row -> row of the local output; nullptr: identity
 };
 
 template <int DIM, int PORD>
@@ -309,9 +311,9 @@ __global__ void __launch_bounds__(128, 3) elem_rows_kernel(DProblem P, ElemJob J
     constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
     const int lane = threadIdx.x & 31;
     const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (widx >= J.N) return;
+    if (widx >= J.nrows) return;
     const int I = J.row_order[widx];
-    double *row = A + (size_t)I * ld;
+    double *row = A + (size_t)(J.row_slot ? J.row_slot[I] : I) * ld;
     for (int j = lane; j < J.N; j += 32) row[j] = 0.;
     __syncwarp();
     for (int t = J.dof_ptr[I]; t < J.dof_ptr[I + 1]; t++) {
@@ -454,6 +456,60 @@ static void elem_job_free(std::vector<void *> &dev)
     dev.clear();
 }
 
+// rows of part `part` of `nparts` of the row-owner kernels: the rows sorted by descending number of cells around their dof are
+// dealt to the parts in turn (equal shares of long and short rows); `local` keeps that order (long rows first), `slot` maps a
+// global row to its position among the part's rows in ASCENDING order (-1: not owned)
+static void elem_rows_of_part(const std::vector<int> &row_order, int part, int nparts, std::vector<int> &local, std::vector<int> &slot)
+{
+    local.clear();
+    for (size_t k = (size_t)part; k < row_order.size(); k += (size_t)nparts) local.push_back(row_order[k]);
+    std::vector<int> sorted(local);
+    std::sort(sorted.begin(), sorted.end());
+    slot.assign(row_order.size(), -1);
+    for (size_t k = 0; k < sorted.size(); k++) slot[sorted[k]] = (int)k;
+}
+
+static int elem_row_order(int nc, int dpe, int num_dofs, const int32_t *dofs, std::vector<int> &row_order)
+{
+    std::vector<int> cnt(num_dofs, 0);
+    for (int c = 0; c < nc; c++)
+        for (int m = 0; m < dpe; m++) {
+            const int d = dofs[(size_t)c * dpe + m];
+            if (d >= num_dofs) return fail(PNB_ERR_ARG, "dof index out of range");
+            if (d >= 0) cnt[d]++;
+        }
+    row_order.resize(num_dofs);
+    for (int i = 0; i < num_dofs; i++) row_order[i] = i;
+    std::stable_sort(row_order.begin(), row_order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+    return 0;
+}
+
+extern "C" int pnb_problem_set_row_part(pnb_problem *p, int32_t part, int32_t nparts)
+{
+    if (!p) return fail(PNB_ERR_ARG, "null argument");
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(PNB_ERR_ARG, "part out of range");
+    p->row_part = part;
+    p->row_nparts = nparts;
+    return 0;
+}
+
+extern "C" int pnb_element_rows(pnb_problem *p, int dofs_per_element, int num_dofs, const int32_t *dofs, int32_t part, int32_t nparts,
+                                int32_t *rows, int32_t *num_rows)
+{
+    if (!p || !dofs || !num_rows) return fail(PNB_ERR_ARG, "null argument");
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(PNB_ERR_ARG, "part out of range");
+    std::vector<int> order, local, slot;
+    const int rc = elem_row_order(p->nc, dofs_per_element, num_dofs, dofs, order);
+    if (rc) return rc;
+    elem_rows_of_part(order, part, nparts, local, slot);
+    *num_rows = (int32_t)local.size();
+    if (rows) {
+        std::sort(local.begin(), local.end());
+        for (size_t k = 0; k < local.size(); k++) rows[k] = local[k];
+    }
+    return 0;
+}
+
 static int elem_job_build(pnb_problem *p, int dpe, int num_dofs, const int32_t *dofs, ElemJob &J, std::vector<void *> &dev)
 {
     const int nc = p->nc;
@@ -478,9 +534,16 @@ static int elem_job_build(pnb_problem *p, int dpe, int num_dofs, const int32_t *
     J.dpe = dpe;
     J.smode = J.bmode = 0;
     J.sa = J.ba = 0.;
-    std::vector<int> row_order(num_dofs);
+    std::vector<int> row_order(num_dofs), row_slot;
     for (int i = 0; i < num_dofs; i++) row_order[i] = i;
     std::stable_sort(row_order.begin(), row_order.end(), [&](int a, int b) { return dptr[a + 1] - dptr[a] > dptr[b + 1] - dptr[b]; });
+    if (p->row_nparts > 1) {
+        std::vector<int> local;
+        elem_rows_of_part(row_order, p->row_part, p->row_nparts, local, row_slot);
+        row_order.swap(local);
+    }
+    J.nrows = (int)row_order.size();
+    J.row_slot = nullptr;
     // partner cells in steps of 32 that share no vertex: greedy colouring of the cells (two cells are adjacent when they
     // share a vertex), the cells of a colour in ascending order, every colour padded to a multiple of 32
     std::vector<int> partners;
@@ -519,13 +582,13 @@ static int elem_job_build(pnb_problem *p, int dpe, int num_dofs, const int32_t *
             while (partners.size() % 32) partners.push_back(-1);
         }
     }
-    int *d_edofs = nullptr, *d_ptr = nullptr, *d_cells = nullptr, *d_err = nullptr, *d_order = nullptr, *d_partners = nullptr;
-    if (cudaMalloc(&d_edofs, (size_t)nc * dpe * sizeof(int)) != cudaSuccess || cudaMalloc(&d_ptr, ((size_t)num_dofs + 1) * sizeof(int)) != cudaSuccess ||
+    int *d_edofs = nullptr, *d_ptr = nullptr, *d_cells = nullptr, *d_err = nullptr, *d_order = nullptr, *d_partners = nullptr, *d_slot = nullptr;
+    if (cudaMalloc(&d_slot, std::max<size_t>(row_slot.size(), 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&d_edofs, (size_t)nc * dpe * sizeof(int)) != cudaSuccess || cudaMalloc(&d_ptr, ((size_t)num_dofs + 1) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&d_cells, std::max<size_t>(dcells.size(), 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&d_err, sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&d_order, (size_t)num_dofs * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&d_order, std::max<size_t>(row_order.size(), 1) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&d_partners, std::max<size_t>(partners.size(), 1) * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
-        cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order); cudaFree(d_partners);
+        cudaFree(d_edofs); cudaFree(d_ptr); cudaFree(d_cells); cudaFree(d_err); cudaFree(d_order); cudaFree(d_partners); cudaFree(d_slot);
         return fail(PNB_ERR_CUDA, "out of device memory");
     }
     cudaMemcpy(d_edofs, dofs, (size_t)nc * dpe * sizeof(int), cudaMemcpyHostToDevice);
@@ -536,7 +599,11 @@ static int elem_job_build(pnb_problem *p, int dpe, int num_dofs, const int32_t *
     cudaMemcpy(d_partners, partners.data(), partners.size() * sizeof(int), cudaMemcpyHostToDevice);
     J.edofs = d_edofs; J.dof_ptr = d_ptr; J.dof_cells = d_cells; J.err = d_err; J.row_order = d_order;
     J.partners = d_partners; J.npartners = (int)partners.size();
-    dev = {d_edofs, d_ptr, d_cells, d_err, d_order, d_partners};
+    if (!row_slot.empty()) {
+        cudaMemcpy(d_slot, row_slot.data(), row_slot.size() * sizeof(int), cudaMemcpyHostToDevice);
+        J.row_slot = d_slot;
+    }
+    dev = {d_edofs, d_ptr, d_cells, d_err, d_order, d_partners, d_slot};
     return 0;
 }
 
@@ -578,6 +645,7 @@ extern "C" int pnb_dense_assemble_element_smooth(pnb_problem *p, int mode, doubl
     // host output: assembled in a device buffer and copied back
     double *A = A_out;
     int64_t ld = ld_out;
+    if (!a_on_device && p->row_nparts > 1) return fail(PNB_ERR_UNSUPPORTED, "row parts: device output only");
     if (!a_on_device) {
         ld = num_dofs;
         CK(pool_malloc((void **)&A, (size_t)num_dofs * num_dofs * sizeof(double)));
@@ -593,7 +661,7 @@ extern "C" int pnb_dense_assemble_element_smooth(pnb_problem *p, int mode, doubl
     }
     J.smode = mode; J.sa = a;
     J.bmode = bmode; J.ba = ba;
-    const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
+    const unsigned blocks = (unsigned)std::max<size_t>(((size_t)J.nrows * 32 + 127) / 128, 1);
     if (p->dim == 2) {
         if (polynomial_order == 2) elem_rows_kernel<2, 2><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);
         else if (polynomial_order == 1) elem_rows_kernel<2, 1><<<blocks, 128>>>(p->P, J, zero_exterior, A, ld);

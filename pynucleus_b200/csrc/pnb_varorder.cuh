@@ -367,9 +367,9 @@ __global__ void __launch_bounds__(128, 2) varorder_rows_kernel(DProblem P, VarOr
     constexpr int NV = DIM + 1, DPE = ElemDims<DIM, PORD>::DPE;
     const int lane = threadIdx.x & 31;
     const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (widx >= J.N) return;
+    if (widx >= J.nrows) return;
     const int I = J.row_order[widx];
-    double *row = A + (size_t)I * ld;
+    double *row = A + (size_t)(J.row_slot ? J.row_slot[I] : I) * ld;
     for (int j = lane; j < J.N; j += 32) row[j] = 0.;
     __syncwarp();
     for (int t = J.dof_ptr[I]; t < J.dof_ptr[I + 1]; t++) {
@@ -522,6 +522,7 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
         return fail(PNB_ERR_ARG, "incomplete order description");
     if (!(order->sl > 0. && order->sl < 1. && order->sr > 0. && order->sr < 1.)) return fail(PNB_ERR_ARG, "orders must lie in (0, 1)");
     if (ld_out < num_dofs) return fail(PNB_ERR_ARG, "leading dimension too small");
+    if (!a_on_device && p->row_nparts > 1) return fail(PNB_ERR_UNSUPPORTED, "row parts: device output only");
     const int nvals = order->num_values;
     for (int c = 0; c < p->nc; c++)
         if (order->cell_value[c] < 0 || order->cell_value[c] >= nvals) return fail(PNB_ERR_ARG, "cell_value out of range");
@@ -619,7 +620,7 @@ extern "C" int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t 
             return rc;
         }
     }
-    const unsigned blocks = (unsigned)(((size_t)num_dofs * 32 + 127) / 128);
+    const unsigned blocks = (unsigned)std::max<size_t>(((size_t)J.nrows * 32 + 127) / 128, 1);
     if (dim == 2) {
         if (polynomial_order == 2) varorder_rows_kernel<2, 2><<<blocks, 128>>>(p->P, V, J, zero_exterior, A, ld);
         else if (polynomial_order == 1) varorder_rows_kernel<2, 1><<<blocks, 128>>>(p->P, V, J, zero_exterior, A, ld);

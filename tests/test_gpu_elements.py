@@ -252,3 +252,44 @@ def test_elements_on_the_smallest_meshes(name, element):
     for ze, key in ((True, 'A'), (False, 'A_interior')):
         A = pb.nonlocalBuilder(dm, pb.getFractionalKernel(dim, float(g['s'])), params, zeroExterior=ze).getDense().data
         assert A.shape == g[key].shape and entry_err(A, g[key]) < TOL
+
+
+@pytest.mark.parametrize('case', ['p2', 'varorder', 'gaussian'])
+def test_row_parts_of_the_row_owner_kernels_equal_the_full_operator(case):
+    """several GPUs for the row-owner kernels: the rows are dealt to the parts (pnb_problem_set_row_part / pnb_element_rows),
+    every row is complete on its owner.  The parts, assembled one after the other on one GPU, are a partition of the rows and
+    reproduce the full operator bit for bit; the distributed operator of a single process multiplies like the dense one"""
+    import torch
+    import pynucleus_b200 as pb
+    mesh = pb.refined(pb.uniform_disc(), 2)
+    params = {'target_order': 0.5}
+    if case == 'p2':
+        dm, kernel = pb.P2_DoFMap(mesh), pb.getFractionalKernel(2, 0.75)
+    elif case == 'varorder':
+        dm, kernel = pb.P1_DoFMap(mesh), pb.getFractionalKernel(2, pb.smoothedLeftRightFractionalOrder(0.25, 0.75, r=0.3))
+    else:
+        dm, kernel = pb.P1_DoFMap(mesh), pb.getIntegrableKernel(2, 'gaussian', np.inf, variance=0.1)
+    b = pb.nonlocalBuilder(dm, kernel, params)
+    A = b.getDense().data
+    N = dm.num_dofs
+    for nparts in (2, 3):
+        seen = np.zeros(N, dtype=int)
+        for part in range(nparts):
+            rows = b.rowsOfPart(part, nparts)
+            assert (np.diff(rows) > 0).all()
+            seen[rows] += 1
+            Ap = b.getDenseRowsOfPart(part, nparts).data
+            assert Ap.shape == (rows.shape[0], N) and np.array_equal(Ap, A[rows])
+        assert (seen == 1).all()
+    # more parts than rows of a kind: empty parts are fine
+    assert sum(b.rowsOfPart(p_, N+3).shape[0] for p_ in range(N+3)) == N
+    assert b.getDenseRowsOfPart(N+2, N+3).data.shape == (0, N)
+    # afterwards the builder assembles whole operators again
+    assert np.array_equal(b.getDense().data, A)
+    op = b.getDenseDistributed()
+    x = torch.as_tensor(np.cos(np.arange(N)*0.3), device=op.device)
+    y = op.matvec_device(x).cpu().numpy()
+    assert np.abs(y-A.dot(x.cpu().numpy())).max() < 1e-13*np.abs(y).max()
+    # the production path keeps its own sharding
+    with pytest.raises(NotImplementedError):
+        pb.nonlocalBuilder(pb.P1_DoFMap(mesh), pb.getFractionalKernel(2, 0.75), params).rowsOfPart(0, 2)

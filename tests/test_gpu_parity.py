@@ -1313,3 +1313,29 @@ def test_order_given_by_a_fe_function_vs_reference(golden_dir, name):
         assert b.orders.bquad_order_diagonal == int(g['bquad_order_diagonal'])
         A = b.getDense().data
         assert entry_err(A, g[key]) < TOL
+
+
+@pytest.mark.parametrize('name', ['tempered_disc_s0.75_l2_r5_rows', 'gaussian_disc_v0.05_r5_rows'])
+def test_smooth_factor_kernels_rows_vs_reference_at_2977_dofs(golden_dir, name):
+    """a tempered and a Gaussian kernel at 2 977 DoFs against sampled rows, the diagonal and the product A x of the reference's
+    own operator (make_golden_smooth_rows.py)"""
+    import pynucleus_b200 as pb
+    g = load(golden_dir, name)
+    mesh = pb.meshNd(g['vertices'], g['cells'], boundary=g['boundaryEdges'])
+    dm = pb.P1_DoFMap(mesh)
+    assert dm.num_dofs == int(g['num_dofs'])
+    if name.startswith('tempered'):
+        kernel = pb.getFractionalKernel(2, float(g['s']), tempered=float(g['tempered']))
+    else:
+        kernel = pb.getIntegrableKernel(2, 'gaussian', np.inf, variance=float(g['variance']))
+    assert abs(kernel.scalingValue/float(g['scaling'])-1) < 1e-14
+    b = pb.nonlocalBuilder(dm, kernel, {'target_order': 0.5})
+    assert b.orders.quad_order_diagonal == int(g['quad_order_diagonal'])
+    assert b.orders.bquad_order_diagonal == int(g['bquad_order_diagonal'])
+    A = b.getDense().data
+    rows = g['rows']
+    d = np.sqrt(np.abs(g['diag']))
+    scale = np.maximum(np.abs(g['A_rows']), 1e-2*np.outer(d[rows], d))
+    assert (np.abs(A[rows]-g['A_rows'])/scale).max() < TOL
+    assert np.abs(np.diag(A)/g['diag']-1).max() < TOL
+    assert np.abs(A.dot(g['x'])-g['Ax']).max() < TOL*np.abs(g['Ax']).max()
