@@ -379,6 +379,9 @@ int pnb_dense_assemble_varorder(pnb_problem *p, const pnb_varorder_t *order, int
 int pnb_problem_set_row_part(pnb_problem *p, int32_t part, int32_t nparts);
 int pnb_element_rows(pnb_problem *p, int dofs_per_element, int num_dofs, const int32_t *dofs, int32_t part, int32_t nparts,
                      int32_t *rows, int32_t *num_rows);
+/* the same without a problem instance (no device needed): every rank can list the rows of all parts */
+int pnb_element_rows_host(int32_t num_cells, int dofs_per_element, int num_dofs, const int32_t *dofs, int32_t part,
+                          int32_t nparts, int32_t *rows, int32_t *num_rows);
 
 /* ---- H2 operator on the device -------------------------------------------------------------------------
  * Replaces H2Matrix.matvec (nl/PyNucleus_nl/clusterMethodCy.pyx:2269-2295) with its upwardPass / downwardPass

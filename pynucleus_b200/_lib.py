@@ -85,7 +85,7 @@ EXPORTS = ['pnb_last_error', 'pnb_version', 'pnb_device_count', 'pnb_problem_cre
            'pnb_dist_status', 'pnb_dist_apply', 'pnb_device_alloc', 'pnb_device_free', 'pnb_ipc_export', 'pnb_ipc_import',
            'pnb_ipc_close',
            'pnb_boundary_cell_blocks', 'pnb_mesh_edge_lengths', 'pnb_problem_set_path', 'pnb_sparsity_mask', 'pnb_block_alignment',
-           'pnb_h2_create', 'pnb_h2_leaf_values', 'pnb_h2_matvec', 'pnb_h2_destroy', 'pnb_dense_assemble_element', 'pnb_dense_assemble_element_tempered', 'pnb_dense_assemble_element_smooth', 'pnb_dense_assemble_varorder', 'pnb_problem_set_row_part', 'pnb_element_rows',
+           'pnb_h2_create', 'pnb_h2_leaf_values', 'pnb_h2_matvec', 'pnb_h2_destroy', 'pnb_dense_assemble_element', 'pnb_dense_assemble_element_tempered', 'pnb_dense_assemble_element_smooth', 'pnb_dense_assemble_varorder', 'pnb_problem_set_row_part', 'pnb_element_rows', 'pnb_element_rows_host',
            'pnb_krylov_workspace_doubles', 'pnb_krylov_dot', 'pnb_krylov_cg_update', 'pnb_krylov_cg_direction']
 
 _LIB = None
@@ -163,6 +163,8 @@ def lib():
         L.pnb_problem_set_row_part.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
         L.pnb_element_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.c_void_p, c_int32_p]
+        L.pnb_element_rows_host.argtypes = [ctypes.c_int32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                            ctypes.c_void_p, c_int32_p]
         L.pnb_dense_assemble_varorder.argtypes = [ctypes.c_void_p, ctypes.POINTER(pnb_varorder_t), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
         L.pnb_krylov_dot.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -1032,6 +1032,22 @@ def exchange_cell_blocks(count, device, process_group=None, fill=None):
     return D
 
 
+def element_row_parts(dm, nparts):
+    """rows (ascending) of every part of the row-owner kernels for a DoFMap: host arithmetic of the library
+    (pnb_element_rows_host), so that every rank knows the rows of all ranks without a device"""
+    ed = np.ascontiguousarray(dm.dofs, dtype=np.int32)
+    L = _lib.lib()
+    out = []
+    for part in range(nparts):
+        n = ctypes.c_int32(0)
+        _lib.check(L.pnb_element_rows_host(ed.shape[0], ed.shape[1], dm.num_dofs, ed.ctypes.data, part, nparts, None, ctypes.byref(n)))
+        rows = np.zeros(n.value, dtype=np.int32)
+        _lib.check(L.pnb_element_rows_host(ed.shape[0], ed.shape[1], dm.num_dofs, ed.ctypes.data, part, nparts, rows.ctypes.data,
+                                           ctypes.byref(n)))
+        out.append(rows)
+    return out
+
+
 def row_partition(num_dofs, world_size, granularity=64):
     """contiguous row blocks [begin, end) per rank, aligned to the tile granularity of the device code"""
     ntiles = (num_dofs+granularity-1)//granularity

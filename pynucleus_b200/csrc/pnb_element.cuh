@@ -496,10 +496,17 @@ extern "C" int pnb_problem_set_row_part(pnb_problem *p, int32_t part, int32_t np
 extern "C" int pnb_element_rows(pnb_problem *p, int dofs_per_element, int num_dofs, const int32_t *dofs, int32_t part, int32_t nparts,
                                 int32_t *rows, int32_t *num_rows)
 {
-    if (!p || !dofs || !num_rows) return fail(PNB_ERR_ARG, "null argument");
+    if (!p) return fail(PNB_ERR_ARG, "null argument");
+    return pnb_element_rows_host(p->nc, dofs_per_element, num_dofs, dofs, part, nparts, rows, num_rows);
+}
+
+extern "C" int pnb_element_rows_host(int32_t num_cells, int dofs_per_element, int num_dofs, const int32_t *dofs, int32_t part,
+                                     int32_t nparts, int32_t *rows, int32_t *num_rows)
+{
+    if (!dofs || !num_rows || num_cells < 0 || dofs_per_element < 1 || num_dofs < 0) return fail(PNB_ERR_ARG, "bad argument");
     if (nparts < 1 || part < 0 || part >= nparts) return fail(PNB_ERR_ARG, "part out of range");
     std::vector<int> order, local, slot;
-    const int rc = elem_row_order(p->nc, dofs_per_element, num_dofs, dofs, order);
+    const int rc = elem_row_order(num_cells, dofs_per_element, num_dofs, dofs, order);
     if (rc) return rc;
     elem_rows_of_part(order, part, nparts, local, slot);
     *num_rows = (int32_t)local.size();

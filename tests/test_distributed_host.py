@@ -180,3 +180,68 @@ def test_multigrid_follows_the_reference(golden_dir):
     assert its == int(g['cg2_iterations']) == int(g['cgmg_iterations'])
     assert np.abs(np.array(res)/g['cg2_residuals']-1).max() < 1e-6
     assert np.abs(x.numpy()-g['u']).max() < 1e-8*np.abs(g['u']).max()
+
+
+def _row_parts_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import pynucleus_b200 as pb
+    from pynucleus_b200.assembly import element_row_parts
+    from pynucleus_b200.solvers import DistributedDenseOperator, gmres
+    # the rows of the row-owner kernels (here: a P2 map) as every rank lists them for all ranks, without a device
+    dm = pb.P2_DoFMap(pb.refined(pb.uniform_disc(), 2))
+    N = dm.num_dofs
+    all_rows = element_row_parts(dm, world)
+    rng = np.random.default_rng(9)
+    A = torch.from_numpy(rng.standard_normal((N, N))+N*np.eye(N))       # unsymmetric, like the operators of these kernels
+    mine = torch.from_numpy(all_rows[rank].astype(np.int64))
+    op = DistributedDenseOperator(_HostRows(A[mine].contiguous()), all_rows, rank, N)
+    x = torch.from_numpy(rng.standard_normal(N))
+    ok_mv = torch.allclose(op.matvec_device(x), A.mv(x), rtol=1e-13, atol=1e-11)
+    rhs = torch.from_numpy(rng.standard_normal(N))
+    v, its, res = gmres(op, rhs, tol=1e-11, maxiter=30, restarts=20)
+    ok_solve = float((A.mv(v)-rhs).abs().max()) < 1e-8
+    q.put((rank, [r.tolist() for r in all_rows], bool(ok_mv), bool(ok_solve)))
+    dist.destroy_process_group()
+
+
+def test_row_parts_of_the_row_owner_kernels_gloo():
+    """N > 1 for the row-owner kernels on the host: both ranks list the same rows for all parts (pnb_element_rows_host), the parts
+    partition the rows with long and short rows shared out evenly, and the distributed operator over these interleaved row sets
+    multiplies and solves (GMRES: the operators of these kernels need not be symmetric) like the full matrix"""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500+os.getpid() % 1000
+    procs = [ctx.Process(target=_row_parts_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[2] and r[3] for r in res), [r[2:] for r in res]
+    assert res[0][1] == res[1][1]
+    rows0, rows1 = (np.array(r) for r in res[0][1])
+    N = rows0.shape[0]+rows1.shape[0]
+    assert np.array_equal(np.sort(np.concatenate((rows0, rows1))), np.arange(N)) and abs(rows0.shape[0]-rows1.shape[0]) <= 1
+    assert (np.diff(rows0) > 0).all() and (np.diff(rows1) > 0).all()
+
+
+def test_element_row_parts_properties():
+    import pynucleus_b200 as pb
+    from pynucleus_b200.assembly import element_row_parts
+    mesh = pb.refined(pb.uniform_disc(), 2)
+    for dm in (pb.P1_DoFMap(mesh), pb.P2_DoFMap(mesh), pb.P0_DoFMap(mesh)):
+        cells_around = np.bincount(dm.dofs[dm.dofs >= 0].ravel(), minlength=dm.num_dofs)
+        for nparts in (1, 2, 3, 8, dm.num_dofs+5):
+            parts = element_row_parts(dm, nparts)
+            assert len(parts) == nparts
+            assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(dm.num_dofs))
+            sizes = [p.shape[0] for p in parts]
+            assert max(sizes)-min(sizes) <= 1
+            if nparts in (2, 3):
+                # rows are dealt in the order of their length: the work (cells around the dofs) is shared out evenly
+                work = [cells_around[p].sum() for p in parts]
+                assert max(work)-min(work) <= cells_around.max()
