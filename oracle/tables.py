@@ -234,10 +234,13 @@ def near_rules(dim, singularity, boundary_singularity, orders, poly_order=1):
     boundary: getNearQuadRule  (2D :1255-1314, 1D :671-709)
     Returns {('interior'|'boundary', panel): (bary, w)}."""
     rules = {}
+    # cancellation across elements: two orders for continuous elements, none for P0 (fractionalLaplacian2D.pyx:591-600,
+    # fractionalLaplacian1D.pyx:209-216)
+    sga = singularity if poly_order == 0 else 2.+singularity
     if dim == 2:
         sg = 2.+singularity
         for p in (COMMON_FACE, COMMON_EDGE, COMMON_VERTEX):
-            rules[('interior', p)] = singular_rule_2d(p, sg, orders['qod'], orders['qodV'])
+            rules[('interior', p)] = singular_rule_2d(p, sg if p == COMMON_FACE else sga, orders['qod'], orders['qodV'])
         if boundary_singularity > -2.+1e-3:
             sgb = boundary_singularity
         else:
@@ -248,7 +251,7 @@ def near_rules(dim, singularity, boundary_singularity, orders, poly_order=1):
         sg = 2.+singularity
         qor = 2*max(poly_order, 1)
         rules[('interior', COMMON_EDGE)] = singular_rule_1d(COMMON_EDGE, sg, orders['qod'], qor)
-        rules[('interior', COMMON_VERTEX)] = singular_rule_1d(COMMON_VERTEX, sg, orders['qod'], qor)
+        rules[('interior', COMMON_VERTEX)] = singular_rule_1d(COMMON_VERTEX, sga, orders['qod'], qor)
         if boundary_singularity > -1.+1e-3:
             sgb = boundary_singularity
         else:

@@ -108,12 +108,30 @@ def _h_simplex(X):
     return max(sqrt(((X[i]-X[j])**2).sum()) for i in range(n) for j in range(i+1, n))
 
 
+def shape_functions(dim, dpe, lam):
+    """local shape functions at barycentric coordinates lam (nvc x nq) in the reference's local order (DoFMaps.pyx:1776-2005):
+    P0 (one dof per cell), P1 (the vertices), P2 (vertices, then the edges (0,1), (1,2), (0,2); 1D: vertices, then the cell)"""
+    nvc = dim+1
+    if dpe == 1:
+        return np.ones((1, lam.shape[1]))
+    if dpe == nvc:
+        return lam
+    assert dpe == (3 if dim == 1 else 6)
+    out = [lam[k]*(2.*lam[k]-1.) for k in range(nvc)]
+    out.append(4.*lam[0]*lam[1])
+    if dim == 2:
+        out += [4.*lam[1]*lam[2], 4.*lam[0]*lam[2]]
+    return np.vstack(out)
+
+
 def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, target_order=None, hmin=None, diam=None):
     vertices = np.asarray(vertices, dtype=np.float64)
     cells = np.asarray(cells)
     dofs = np.asarray(dofs)
     dim = vertices.shape[1]
     nc, nvc = cells.shape
+    dpe = dofs.shape[1]
+    poly_order = {1: 0, nvc: 1}.get(dpe, 2)
     T = vertices[cells]                      # nc x nvc x dim
     centers = np.zeros((nc, dim))
     for k in range(nvc):                     # precomputeSimplices: running sum, then the mean
@@ -131,7 +149,7 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
     H0 = diam/sqrt(8.)
     # the unsymmetric local matrices never see params['target_order'] (fractionalLaplacian2D.pyx:911)
     del target_order
-    orders = tables.diag_orders(dim, -dim-2*sFun.max, 1.-dim-2*sFun.max, hmin, H0, num_dofs, None,
+    orders = tables.diag_orders(dim, -dim-2*sFun.max, 1.-dim-2*sFun.max, hmin, H0, num_dofs, None, poly_order=poly_order,
                                 min_singularity=-dim-2*sFun.min, min_boundary_singularity=1.-dim-2*sFun.min)
     to, tob = orders['target_order'], orders['b_target_order']
     fe = hasattr(sFun, 'vertex_values')
@@ -147,7 +165,7 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
 
     def near(smax):
         if smax not in near_cache:
-            near_cache[smax] = tables.near_rules(dim, -dim-2*smax, 1.-dim-2*smax, orders)
+            near_cache[smax] = tables.near_rules(dim, -dim-2*smax, 1.-dim-2*smax, orders, poly_order=poly_order)
         return near_cache[smax]
 
     def quad_order(h1, h2, d, smax):
@@ -184,16 +202,16 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
         return int(max(p1, p2))
 
     def shape(lam):
-        return lam                           # P1: the barycentric coordinates, rows = local dofs
+        return shape_functions(dim, dpe, lam)
 
     A = np.zeros((num_dofs, num_dofs))
 
     def scatter(dA, dB, M):
         idx = np.concatenate((dA, dB))
-        for i in range(2*nvc):
+        for i in range(2*dpe):
             if idx[i] < 0:
                 continue
-            for j in range(2*nvc):
+            for j in range(2*dpe):
                 if idx[j] >= 0:
                     A[idx[i], idx[j]] += M[i, j]
 
@@ -265,7 +283,8 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
                     if dim == 2:
                         # gamma_b n.(y-x)/|y-x| (eval_distant_boundary, nonlocalOperator_{SCALAR}.pxi:1069-1108)
                         g = g*((y-x).dot(nrm))/np.sqrt(((x-y)**2).sum(axis=1))
-                    M = (lamx*(w*g)).dot(lamx.T)*(vol[c1]*bvol)
+                    px = shape(lamx)
+                    M = (px*(w*g)).dot(px.T)*(vol[c1]*bvol)
                 else:
                     bary, w = near(smax)[('boundary', panel)]
                     SA, SF = T[c1][p1], F[p2[:nvf]]
@@ -277,12 +296,14 @@ def dense(vertices, cells, dofs, num_dofs, sFun, bfacets, zero_exterior=True, ta
                     if dim == 2:
                         # fractionalLaplacian2D.pyx:1356-1407: n.(x-y)/|x-y| and the factor -2 vol1 vol2
                         g = g*((x-y).dot(nrm))/np.sqrt(((x-y)**2).sum(axis=1))
-                        M = (lamx*(w*g)).dot(lamx.T)*(-2.*vol[c1]*bvol)
+                        px = shape(lamx)
+                        M = (px*(w*g)).dot(px.T)*(-2.*vol[c1]*bvol)
                     else:
-                        M = (lamx*(w*g)).dot(lamx.T)*vol[c1]
+                        px = shape(lamx)
+                        M = (px*(w*g)).dot(px.T)*vol[c1]
                 idx = dofs[c1]
-                for i in range(nvc):
-                    for j in range(nvc):
+                for i in range(dpe):
+                    for j in range(dpe):
                         if idx[i] >= 0 and idx[j] >= 0:
                             A[idx[i], idx[j]] += M[i, j]
     return A

@@ -535,7 +535,6 @@ class Kernel:
 
     def smoothFactors(self):
         """(mode, a, boundary mode, boundary a, constant of the boundary power law) for pnb_dense_assemble_element_smooth"""
-        from scipy.special import erfc  # noqa: F401
         C, a = self.scalingValue, self.exponentInverse
         if self.kernelType == EXPONENTIAL:
             return SMOOTH_EXP_R, a, SMOOTH_EXP_R, a, 2.0*C/a

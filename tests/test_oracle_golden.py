@@ -323,7 +323,8 @@ def _varorder_fun(g):
 
 
 @pytest.mark.parametrize('name', ['varorder_interval_smoothed_r5', 'varorder_interval_linear_r5', 'varorder_interval_smoothed_r6',
-                                  'varorder_disc_smoothed_r2'])
+                                  'varorder_disc_smoothed_r2', 'varorder_p2_interval_smoothed_r4', 'varorder_p2_disc_smoothed_r1',
+                                  'varorder_p0_disc_smoothed_r2'])
 def test_order_varying_inside_cells_matches_reference(golden_dir, name):
     """orders that vary inside a cell (kernel.piecewise == False; the driver's twoDomainNonSym): the numpy restatement
     oracle/varorder.py against operators assembled by the reference itself (make_golden_varorder.py)"""
